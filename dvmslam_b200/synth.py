@@ -1,0 +1,120 @@
+"""Seeded synthetic inputs for parity tests and bench.py.
+
+Nothing here is on the product path: it only manufactures the 8-bit grey
+images, the plane-sweep camera stream and the bundle-adjustment scene that
+BASELINE.json's configs name ("synthetic frame", "synthetic stream").
+"""
+from __future__ import annotations
+
+import numpy as np
+
+# rpi_cam.yaml intrinsics with the distortion zeroed
+# (reference: src/slam_system/configs/rpi_cam.yaml:23-26)
+RPI_K = (994.3, 993.4, 638.0, 372.6)
+
+
+def _box(a: np.ndarray, r: int) -> np.ndarray:
+    """(2r+1)^2 box filter with edge replication, float32, via integral image."""
+    if r <= 0:
+        return a
+    p = np.pad(a, r, mode="edge").astype(np.float64)
+    ii = np.zeros((p.shape[0] + 1, p.shape[1] + 1))
+    ii[1:, 1:] = p.cumsum(0).cumsum(1)
+    k = 2 * r + 1
+    s = ii[k:, k:] - ii[:-k, k:] - ii[k:, :-k] + ii[:-k, :-k]
+    return (s / (k * k)).astype(np.float32)
+
+
+def texture(w: int, h: int, seed: int = 0, n_shapes: int = 400, flat_frac: float = 0.06) -> np.ndarray:
+    """8-bit grey texture: 3 octaves of box-filtered uniform noise plus random filled
+    rectangles/discs (corners for FAST at several scales) and a few flat patches so
+    that the minThFAST fallback and empty cells are exercised."""
+    rng = np.random.default_rng(seed)
+    img = np.zeros((h, w), np.float32)
+    for r, amp in ((1, 38.0), (3, 52.0), (8, 64.0)):
+        img += amp * (_box(rng.random((h, w), dtype=np.float32), r) - 0.5) * (2 * r + 1) * 0.55
+    img += 128.0
+    yy, xx = np.mgrid[0:h, 0:w]
+    n_shapes = int(n_shapes * (w * h) / (640.0 * 480.0))
+    for _ in range(n_shapes):
+        cx, cy = rng.integers(0, w), rng.integers(0, h)
+        s = int(rng.integers(4, max(5, min(w, h) // 8)))
+        val = float(rng.integers(20, 236))
+        x0, x1 = max(cx - s, 0), min(cx + s, w)
+        y0, y1 = max(cy - s, 0), min(cy + s, h)
+        if rng.random() < 0.6:
+            sub = img[y0:y1, x0:x1]
+            sub[...] = 0.35 * sub + 0.65 * val
+        else:
+            m = (xx[y0:y1, x0:x1] - cx) ** 2 + (yy[y0:y1, x0:x1] - cy) ** 2 <= s * s
+            sub = img[y0:y1, x0:x1]
+            sub[m] = 0.35 * sub[m] + 0.65 * val
+    # fine speckle: small high-contrast blobs, the bulk of the FAST-20 corners
+    n_speck = int(0.012 * w * h)
+    sx = rng.integers(2, w - 8, n_speck)
+    sy = rng.integers(2, h - 8, n_speck)
+    ss = rng.integers(2, 7, n_speck)
+    sv = rng.integers(-90, 91, n_speck).astype(np.float32)
+    for x, y, q, v in zip(sx, sy, ss, sv):
+        img[y:y + q, x:x + q] += v
+    n_flat = int(flat_frac * 10)
+    for _ in range(n_flat):
+        fw, fh = int(rng.integers(w // 16, w // 6)), int(rng.integers(h // 16, h // 6))
+        x0, y0 = int(rng.integers(0, w - fw)), int(rng.integers(0, h - fh))
+        base = float(rng.integers(60, 200))
+        # low-contrast patch: only FAST-7 corners (or none) survive here
+        img[y0:y0 + fh, x0:x0 + fw] = base + 0.08 * (img[y0:y0 + fh, x0:x0 + fw] - 128.0)
+    return np.clip(np.rint(img), 0, 255).astype(np.uint8)
+
+
+def frame(w: int = 640, h: int = 480, seed: int = 0) -> np.ndarray:
+    """Config C1: one synthetic frame."""
+    return texture(w, h, seed)
+
+
+class PlaneStream:
+    """Config C2: camera translating 2 cm and yawing 0.2 deg per frame over a textured
+    plane at 3 m (plane z = 3 in the first camera's frame), 1280x720 crop of a 2x master
+    texture, warped with cv2.warpPerspective(INTER_LINEAR)."""
+
+    def __init__(self, w: int = 1280, h: int = 720, seed: int = 0, K=RPI_K, depth: float = 3.0):
+        self.w, self.h, self.K, self.depth = w, h, K, depth
+        self.master = texture(2 * w, 2 * h, seed)
+        fx, fy, cx, cy = K
+        self.Km = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1.0]])
+
+    def pose(self, k: int):
+        """World-to-camera (Rcw, tcw) of frame k; world = frame-0 camera frame."""
+        yaw = np.deg2rad(0.2) * k
+        c, s = np.cos(yaw), np.sin(yaw)
+        Rwc = np.array([[c, 0, s], [0, 1, 0], [-s, 0, c]])
+        twc = np.array([0.02 * k, 0.0, 0.0])
+        Rcw = Rwc.T
+        return Rcw, -Rcw @ twc
+
+    def plane_to_world(self, u, v):
+        """Master-texture pixel (u,v) -> 3-D world point on the plane.  Frame 0 sees the
+        master region [w/2, 3w/2) x [h/2, 3h/2) one to one."""
+        fx, fy, cx, cy = self.K
+        u = np.asarray(u, np.float64)
+        v = np.asarray(v, np.float64)
+        X = (u - self.w / 2 - cx) * self.depth / fx
+        Y = (v - self.h / 2 - cy) * self.depth / fy
+        return np.stack([X, Y, np.full_like(X, self.depth)], -1)
+
+    def homography(self, k: int) -> np.ndarray:
+        """Maps master pixels to frame-k pixels."""
+        Rcw, tcw = self.pose(k)
+        # master pixel -> world: Xw = A @ [u, v, 1]
+        p00 = self.plane_to_world(0.0, 0.0)
+        p10 = self.plane_to_world(1.0, 0.0)
+        p01 = self.plane_to_world(0.0, 1.0)
+        A = np.stack([p10 - p00, p01 - p00, p00], 1)
+        return self.Km @ (Rcw @ A + np.outer(tcw, [0, 0, 1.0]))
+
+    def frame(self, k: int) -> np.ndarray:
+        import cv2
+
+        H = self.homography(k)
+        return cv2.warpPerspective(self.master, H, (self.w, self.h), flags=cv2.INTER_LINEAR,
+                                   borderMode=cv2.BORDER_REFLECT_101)

@@ -1,0 +1,37 @@
+"""CPU oracle for the DVM-SLAM hot path -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs may import this package.  The product (dvmslam_b200) never does.
+
+Parity status: the reference holds no tests or golden vectors for this path
+(SURVEY.md section 8c).  The oracle is pinned instead against (1) the cv2 4.13.0
+primitives the reference calls (tests/test_oracle_cv2.py, golden vectors under
+tests/golden/ made by tests/golden/make_golden.py) and (2) the reference's own
+ORBextractor.cc compiled against oracle/cvshim into oracle/_ref/ (`make ref`).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build(ref: bool = False) -> None:
+    subprocess.run(["make", "-C", _HERE] + (["ref"] if ref else []), check=True, capture_output=True)
+
+
+def lib() -> ctypes.CDLL:
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "_build", "liboracle.so")
+        if not os.path.exists(path):
+            build()
+        try:
+            _LIB = ctypes.CDLL(path)
+        except OSError:
+            build()
+            _LIB = ctypes.CDLL(path)
+    return _LIB
