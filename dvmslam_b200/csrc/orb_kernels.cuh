@@ -1,0 +1,75 @@
+// orb_kernels.cuh -- device-side configuration and kernel entry points of the ORB extractor.
+#pragma once
+#include "common.cuh"
+
+namespace dvm {
+
+constexpr int kMaxLevels = 12;
+constexpr int kBorder = 16;        // EDGE_THRESHOLD - 3   (O3/src/ORBextractor.cc:618)
+constexpr int kEdge = 19;          // EDGE_THRESHOLD
+constexpr int kHalfPatch = 15;     // HALF_PATCH_SIZE
+constexpr int kCellTilePitch = 96; // smem pitch of one FAST cell tile (sub-image <= 88 px wide)
+constexpr int kCellMaxDim = 88;
+
+struct ResizeX { int sx0, sx1; short a0, a1; };       // per destination column
+struct ResizeY { int sy0, sy1; short b0, b1; };       // per destination row
+
+struct OrbLevel {
+    const uint8_t* img;   // level image (level 0 may alias the caller's device image)
+    int w, h, pitch;
+    int width, height;    // maxBorder - minBorder = (w - 32, h - 32)
+    int nCols, nRows, wCell, hCell;
+    int cell_base;        // index of this level's first cell in the flattened cell grid
+    int quota;            // mnFeaturesPerLevel[level]
+    int nIni;             // root nodes of the octree
+    float hX;
+    int cand_off, cand_cap; // slice of the candidate array
+    int node_cap;           // capacity of the node list == of the per-level selection
+    int sel_off;            // slice of the selection array
+    float scale;            // mvScaleFactor[level]
+    float size;             // (int)(31 * scale)
+    int xtab_off, ytab_off; // resize tables (levels >= 1)
+};
+
+struct OrbCfg {
+    int nlevels;
+    int total_cells;
+    int ini_th, min_th;
+    int max_kp;           // sum of node_cap
+    OrbLevel lv[kMaxLevels];
+};
+
+// packed keypoint: response << 24 | y << 12 | x   (x, y relative to the 16-px border origin)
+__host__ __device__ inline uint32_t pack_kp(int x, int y, int resp) { return ((uint32_t)resp << 24) | ((uint32_t)y << 12) | (uint32_t)x; }
+__host__ __device__ inline int kp_x(uint32_t p) { return p & 0xfff; }
+__host__ __device__ inline int kp_y(uint32_t p) { return (p >> 12) & 0xfff; }
+__host__ __device__ inline int kp_resp(uint32_t p) { return p >> 24; }
+
+struct OrbBuffers {
+    uint32_t* cand;        // [sum cand_cap] packed candidates, unordered within a level
+    int* cand_count;       // [2*kMaxLevels]: live counters, then a copy of the last frame's
+    uint16_t* pnode;       // [sum cand_cap] node id of each candidate (octree scratch)
+    uint32_t* sel;         // [max_kp] packed selection per level, octree list order
+    int* sel_count;        // [kMaxLevels]
+    uint32_t* work_kp;     // [max_kp] level-major sequence: packed kp
+    uint32_t* work_meta;   // [max_kp] level << 24 | destination row
+    int* counts;           // [2] = {n keypoints, monoIndex}
+    int* status;           // [1] sticky error bits (1 = candidate overflow, 2 = node overflow)
+    unsigned int* ticket;  // [1]
+    dvm_keypoint* out_kps; // [max_kp]
+    uint8_t* out_desc;     // [max_kp * 32]
+    const ResizeX* xtab;
+    const ResizeY* ytab;
+    const int8_t* pattern; // [256*4] device copy of the rBRIEF pattern
+};
+
+// launches (all on `stream`)
+void launch_resize_level(const OrbCfg& cfg, const OrbBuffers& b, int level, uint8_t* dst, cudaStream_t stream);
+void launch_fast_cells(const OrbCfg& cfg, const OrbBuffers& b, cudaStream_t stream);
+int octree_smem_bytes(const OrbCfg& cfg);
+int prepare_octree_kernel(int smem_bytes);
+void launch_octree(const OrbCfg& cfg, const OrbBuffers& b, int lap0, int lap1, int smem_bytes, cudaStream_t stream);
+void launch_describe(const OrbCfg& cfg, const OrbBuffers& b, cudaStream_t stream);
+void launch_blur_level_debug(const uint8_t* src, int w, int h, int spitch, uint8_t* dst, int dpitch, cudaStream_t stream);
+
+} // namespace dvm
