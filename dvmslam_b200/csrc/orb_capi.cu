@@ -43,6 +43,11 @@ struct dvm_orb {
     uint8_t* h_out = nullptr; // pinned mirror of d_out
     int8_t* d_pattern = nullptr;
     bool level0_aliased = false;
+    // per-stage profiling (bench.py roofline)
+    bool profiling = false;
+    cudaEvent_t ev[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
+    int prof_frames = 0;
+    float prof_ms[4] = { 0, 0, 0, 0 };
 };
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -63,6 +68,7 @@ static void free_all(dvm_orb* h)
     cudaFree(h->buf.cand); cudaFree(h->buf.cand_count); cudaFree(h->buf.pnode); cudaFree(h->buf.sel);
     cudaFree(h->buf.sel_count); cudaFree(h->buf.work_kp); cudaFree(h->buf.work_meta); cudaFree(h->buf.ticket);
     if (h->h_out) cudaFreeHost(h->h_out);
+    for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -103,7 +109,8 @@ static int configure(dvm_orb* h, int w, int hgt)
         DVM_REQUIRE(L.nIni >= 1 && L.nIni <= 32, "aspect ratio outside the supported 1:2 .. 32:1 range");
         L.hX = (float)L.width / L.nIni;
         L.cand_off = cand_off;
-        L.cand_cap = L.w * L.h / 12 + 64;
+        // strict 3x3 maxima cannot be 8-adjacent: at most ceil(cw/2)*ceil(ch/2) per cell, so this never overflows
+        L.cand_cap = ((L.width + 1) / 2 + L.nCols) * ((L.height + 1) / 2 + L.nRows);
         cand_off += L.cand_cap;
         L.node_cap = std::max(L.quota + 4, 4 * L.nIni + 4);
         DVM_REQUIRE(L.node_cap < 65535, "per-level feature quota too large");
@@ -134,10 +141,9 @@ static int configure(dvm_orb* h, int w, int hgt)
     DVM_REQUIRE(xt.size() <= h->xtab_cap && yt.size() <= h->ytab_cap, "resize table too small");
     h->oct_smem = octree_smem_bytes(c);
     DVM_REQUIRE(h->oct_smem <= 227 * 1024, "per-level feature quota needs more shared memory than one SM has");
-    if (h->oct_smem > h->oct_smem_prepared) {
+    {
         int rc = prepare_octree_kernel(h->oct_smem);
         if (rc != DVM_OK) return rc;
-        h->oct_smem_prepared = h->oct_smem;
     }
     DVM_CUDA(cudaStreamSynchronize(h->stream)); // nothing in flight may still read the old tables
     if (!xt.empty()) {
@@ -215,7 +221,7 @@ int dvm_orb_create(dvm_orb** out, int device, int nfeatures, float scale_factor,
         h->lvl_off[l] = off;
         off += align_up(lw, 128) * (size_t)(lh + 1) + 256;
         xt_n += lw + 8; yt_n += lh + 8;
-        cand += (size_t)(lw + 1) * (lh + 1) / 12 + 64 + 16;
+        cand += (size_t)(lw / 2 + 64) * (lh / 2 + 64);
     }
     h->pyr_bytes = off;
     h->dbg_bytes = align_up(max_width, 128) * (size_t)max_height;
@@ -279,11 +285,45 @@ int dvm_orb_max_keypoints(const dvm_orb* h) { return h ? h->max_kp : DVM_ERR_INV
 static int enqueue_pipeline(dvm_orb* h, int lap0, int lap1)
 {
     const OrbCfg& c = h->cfg;
+    const bool prof = h->profiling;
+    if (prof) DVM_CUDA(cudaEventRecord(h->ev[0], h->stream));
     for (int l = 1; l < c.nlevels; l++) launch_resize_level(c, h->buf, l, const_cast<uint8_t*>(c.lv[l].img), h->stream);
+    if (prof) DVM_CUDA(cudaEventRecord(h->ev[1], h->stream));
     launch_fast_cells(c, h->buf, h->stream);
+    if (prof) DVM_CUDA(cudaEventRecord(h->ev[2], h->stream));
     launch_octree(c, h->buf, lap0, lap1, h->oct_smem, h->stream);
+    if (prof) DVM_CUDA(cudaEventRecord(h->ev[3], h->stream));
     launch_describe(c, h->buf, h->stream);
+    if (prof) DVM_CUDA(cudaEventRecord(h->ev[4], h->stream));
     DVM_CUDA(cudaGetLastError());
+    if (prof) {
+        DVM_CUDA(cudaStreamSynchronize(h->stream));
+        for (int i = 0; i < 4; i++) {
+            float ms = 0;
+            DVM_CUDA(cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]));
+            h->prof_ms[i] += ms;
+        }
+        h->prof_frames++;
+    }
+    return DVM_OK;
+}
+
+int dvm_orb_set_profiling(dvm_orb* h, int enable)
+{
+    DVM_REQUIRE(h != nullptr, "null handle");
+    DVM_CUDA(cudaSetDevice(h->device));
+    if (enable && !h->ev[0])
+        for (auto& e : h->ev) DVM_CUDA(cudaEventCreate(&e));
+    h->profiling = enable != 0;
+    return DVM_OK;
+}
+
+int dvm_orb_get_profile(dvm_orb* h, int* n_frames, float* stage_ms_sum)
+{
+    DVM_REQUIRE(h != nullptr && n_frames != nullptr && stage_ms_sum != nullptr, "null argument");
+    *n_frames = h->prof_frames;
+    for (int i = 0; i < 4; i++) { stage_ms_sum[i] = h->prof_ms[i]; h->prof_ms[i] = 0; }
+    h->prof_frames = 0;
     return DVM_OK;
 }
 

@@ -9,6 +9,7 @@
 //                          43x43 window                          (:75-143, :919-925)
 #include "orb_kernels.cuh"
 #include "orb_math.cuh"
+#include <mutex>
 
 namespace dvm {
 
@@ -486,11 +487,19 @@ octree_kernel(const __grid_constant__ OrbCfg cfg, OrbBuffers b, int lap0, int la
 
 int prepare_octree_kernel(int smem_bytes)
 {
+    // the attribute is per (function, device) and shared by every handle in the process: only raise it
+    static std::mutex mu;
+    static int prepared[64] = { 0 };
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    if (dev >= 0 && dev < 64 && smem_bytes <= prepared[dev]) return DVM_OK;
     cudaError_t e = cudaFuncSetAttribute(octree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) {
         set_error("octree kernel needs %d bytes of shared memory: %s", smem_bytes, cudaGetErrorString(e));
         return DVM_ERR_CUDA;
     }
+    if (dev >= 0 && dev < 64) prepared[dev] = smem_bytes;
     return DVM_OK;
 }
 

@@ -36,6 +36,8 @@ def _bind(L):
                                         C.POINTER(C.c_void_p)]
     L.dvm_orb_stream.argtypes = [C.c_void_p]
     L.dvm_orb_stream.restype = C.c_void_p
+    L.dvm_orb_set_profiling.argtypes = [C.c_void_p, C.c_int]
+    L.dvm_orb_get_profile.argtypes = [C.c_void_p, _ip, C.c_void_p]
     L.dvm_orb_debug_level_size.argtypes = [C.c_void_p, C.c_int, _ip, _ip]
     L.dvm_orb_debug_level_image.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     L.dvm_orb_debug_level_keypoints.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -127,6 +129,16 @@ class ORBextractor:
         k, d, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
         check(self.L.dvm_orb_result_device(self.h, C.byref(k), C.byref(d), C.byref(c)))
         return k.value, d.value, c.value
+
+    def set_profiling(self, enable: bool):
+        check(self.L.dvm_orb_set_profiling(self.h, int(enable)))
+
+    def get_profile(self):
+        """(frames, summed ms per stage [pyramid, fast, octree, describe]); resets the counters."""
+        n = C.c_int()
+        ms = np.zeros(4, np.float32)
+        check(self.L.dvm_orb_get_profile(self.h, C.byref(n), ms.ctypes.data))
+        return n.value, ms
 
     # ---- stage read-back used by the parity tests ----
     def level_image(self, level: int, blurred: bool = False) -> np.ndarray:

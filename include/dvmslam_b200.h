@@ -95,6 +95,13 @@ DVM_API int dvm_orb_result_device(const dvm_orb* h, const dvm_keypoint** kps_dev
 /* The CUDA stream (cudaStream_t) the handle launches on, for CUDA-event timing by the caller. */
 DVM_API void* dvm_orb_stream(const dvm_orb* h);
 
+/* Per-stage device timing for bench.py's roofline: with profiling enabled every extract call records
+ * CUDA events on the handle's stream around its four stages {pyramid resize chain, per-cell FAST,
+ * octree + output ordering, orientation + blur + rBRIEF} and synchronises; dvm_orb_get_profile returns
+ * the number of profiled frames and the summed milliseconds per stage (and resets both). */
+DVM_API int dvm_orb_set_profiling(dvm_orb* h, int enable);
+DVM_API int dvm_orb_get_profile(dvm_orb* h, int* n_frames, float* stage_ms_sum /* [4] */);
+
 /* Stage read-back for parity tests (valid after an extract; synchronises).
  *  dvm_orb_debug_level_image: mvImagePyramid[level] (O3/include/ORBextractor.h:69), or with
  *    blurred=1 the GaussianBlur'ed working copy the descriptors are sampled from

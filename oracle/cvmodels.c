@@ -98,29 +98,111 @@ int cvm_fast_measure(const uint8_t* img, int stride, int x, int y)
     return best;
 }
 
+/* Segment test at threshold th: is there a contiguous arc of >= 9 ring pixels all brighter than
+ * c + th or all darker than c - th?  Ring comparisons are packed into 16-bit masks; a run of >= 9
+ * set bits in the (wrapped) mask is found by shift-and-and. */
+static inline int has_run9(uint32_t m16)
+{
+    uint32_t x = m16 | (m16 << 16);
+    uint32_t t = x & (x >> 1);
+    t &= t >> 2;
+    t &= t >> 4;
+    t &= x >> 8;
+    return t != 0;
+}
+
+static int fast_is_corner(const uint8_t* p, const int* off, int th)
+{
+    const int c = p[0], hi = c + th, lo = c - th;
+    uint32_t b = 0, d = 0;
+    for (int k = 0; k < 16; k++) {
+        const int v = p[off[k]];
+        b |= (uint32_t)(v > hi) << k;
+        d |= (uint32_t)(v < lo) << k;
+    }
+    return has_run9(b) || has_run9(d);
+}
+
+/* same value as cvm_fast_measure, with shared partial minima (3-windows, then 9 = 3+3+3) */
+static int fast_measure_quick(const uint8_t* p, const int* off)
+{
+    int r[16], lo3[16], hi3[16];
+    for (int k = 0; k < 16; k++) r[k] = p[off[k]];
+    for (int i = 0; i < 16; i++) {
+        const int a = r[i], b = r[(i + 1) & 15], e = r[(i + 2) & 15];
+        int mn = a < b ? a : b; mn = mn < e ? mn : e;
+        int mx = a > b ? a : b; mx = mx > e ? mx : e;
+        lo3[i] = mn; hi3[i] = mx;
+    }
+    int best_lo = 0, best_hi = 255;
+    for (int i = 0; i < 16; i++) {
+        int mn = lo3[i], mx = hi3[i];
+        const int l1 = lo3[(i + 3) & 15], l2 = lo3[(i + 6) & 15], h1 = hi3[(i + 3) & 15], h2 = hi3[(i + 6) & 15];
+        mn = mn < l1 ? mn : l1; mn = mn < l2 ? mn : l2;
+        mx = mx > h1 ? mx : h1; mx = mx > h2 ? mx : h2;
+        if (mn > best_lo) best_lo = mn;
+        if (mx < best_hi) best_hi = mx;
+    }
+    const int c = p[0];
+    const int a = best_lo - c, b = c - best_hi;
+    return a > b ? a : b;
+}
+
+/* Row-wise quick reject, written so the compiler vectorises it (u8 saturating arithmetic): a corner
+ * needs, on the same side, one pixel of every opposing pair (k, k+8). */
+static void fast_row_mask(const uint8_t* p, int w, int stride, int th, uint8_t* mask)
+{
+    const uint8_t* r[16];
+    for (int k = 0; k < 16; k++) r[k] = p + ring_dy[k] * stride + ring_dx[k];
+    for (int x = 3; x < w - 3; x++) {
+        const int c = p[x];
+        const uint8_t hi = (uint8_t)(c + th > 255 ? 255 : c + th), lo = (uint8_t)(c - th < 0 ? 0 : c - th);
+        uint8_t br = 1, dk = 1;
+        for (int k = 0; k < 8; k++) {
+            const uint8_t a = r[k][x], b = r[k + 8][x];
+            br &= (uint8_t)((a > hi) | (b > hi));
+            dk &= (uint8_t)((a < lo) | (b < lo));
+        }
+        mask[x] = (uint8_t)(br | dk);
+    }
+}
+
 int cvm_fast_detect(const uint8_t* img, int w, int h, int stride, int th,
                     cvm_fast_kp* out, int cap)
 {
     if (w < 7 || h < 7) return 0;
-    int* score = (int*)calloc((size_t)w * h, sizeof(int));
-    for (int y = 3; y < h - 3; y++)
-        for (int x = 3; x < w - 3; x++) {
-            int m = cvm_fast_measure(img, stride, x, y);
-            score[(size_t)y * w + x] = m > th ? m - 1 : 0;
-        }
+    int off[16];
+    for (int k = 0; k < 16; k++) off[k] = ring_dy[k] * stride + ring_dx[k];
+    /* three-row rolling score buffer, like cv::FAST: non-corners score 0 */
+    uint8_t* buf = (uint8_t*)calloc((size_t)4 * (w + 2), 1);
+    uint8_t* rows[3] = { buf + 1, buf + (w + 2) + 1, buf + 2 * (w + 2) + 1 };
+    uint8_t* mask = buf + 3 * (w + 2);
     int n = 0;
-    for (int y = 3; y < h - 3; y++)
+    for (int y = 3; y <= h - 3; y++) {
+        uint8_t* cur = rows[(y - 3) % 3];
+        memset(cur - 1, 0, w + 2);
+        if (y < h - 3) {
+            const uint8_t* p = img + (size_t)y * stride;
+            fast_row_mask(p, w, stride, th, mask);
+            for (int x = 3; x < w - 3; x++)
+                if (mask[x] && fast_is_corner(p + x, off, th))
+                    cur[x] = (uint8_t)(fast_measure_quick(p + x, off) - 1);
+        }
+        if (y == 3) continue;
+        /* non-max suppression of row y-1 against rows y-2, y-1, y (strictly greater than all 8) */
+        const uint8_t* prev = rows[(y - 4) % 3];
+        const uint8_t* pprev = rows[(y - 2) % 3]; /* == (y-5) mod 3: row y-2 */
         for (int x = 3; x < w - 3; x++) {
-            int s = score[(size_t)y * w + x];
-            if (s <= 0) continue;
-            const int* p = score + (size_t)y * w + x;
-            if (s > p[-1] && s > p[1] && s > p[-w - 1] && s > p[-w] && s > p[-w + 1] &&
-                s > p[w - 1] && s > p[w] && s > p[w + 1]) {
-                if (n < cap) { out[n].x = x; out[n].y = y; out[n].response = s; }
+            const int s = prev[x];
+            if (!s) continue;
+            if (s > prev[x - 1] && s > prev[x + 1] && s > pprev[x - 1] && s > pprev[x] && s > pprev[x + 1] &&
+                s > cur[x - 1] && s > cur[x] && s > cur[x + 1]) {
+                if (n < cap) { out[n].x = x; out[n].y = y - 1; out[n].response = s; }
                 n++;
             }
         }
-    free(score);
+    }
+    free(buf);
     return n;
 }
 
@@ -140,25 +222,32 @@ static inline int reflect101(int p, int n)
 
 void cvm_gaussian7_u8(const uint8_t* src, int w, int h, int sstride, uint8_t* dst, int dstride)
 {
-    static const int k[7] = { 18, 34, 48, 56, 48, 34, 18 };
-    uint32_t* tmp = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)w * h);
+    uint16_t* tmp = (uint16_t*)malloc(sizeof(uint16_t) * (size_t)w * h);
+    uint8_t* pad = (uint8_t*)malloc((size_t)w + 6);
     for (int y = 0; y < h; y++) {
         const uint8_t* S = src + (size_t)y * sstride;
-        for (int x = 0; x < w; x++) {
-            uint32_t acc = 0;
-            for (int i = 0; i < 7; i++) acc += k[i] * S[reflect101(x + i - 3, w)];
-            tmp[(size_t)y * w + x] = acc;
+        for (int i = 0; i < 3; i++) {
+            pad[i] = S[reflect101(i - 3, w)];
+            pad[w + 3 + i] = S[reflect101(w + i, w)];
         }
+        memcpy(pad + 3, S, w);
+        uint16_t* T = tmp + (size_t)y * w;
+        for (int x = 0; x < w; x++) /* <= 256*255, fits 16 bits */
+            T[x] = (uint16_t)(18 * (pad[x] + pad[x + 6]) + 34 * (pad[x + 1] + pad[x + 5]) +
+                              48 * (pad[x + 2] + pad[x + 4]) + 56 * pad[x + 3]);
     }
     for (int y = 0; y < h; y++) {
+        const uint16_t* r[7];
+        for (int j = 0; j < 7; j++) r[j] = tmp + (size_t)reflect101(y + j - 3, h) * w;
         uint8_t* D = dst + (size_t)y * dstride;
         for (int x = 0; x < w; x++) {
-            uint32_t acc = 0;
-            for (int j = 0; j < 7; j++) acc += k[j] * tmp[(size_t)reflect101(y + j - 3, h) * w + x];
+            const uint32_t acc = 18u * ((uint32_t)r[0][x] + r[6][x]) + 34u * ((uint32_t)r[1][x] + r[5][x]) +
+                                 48u * ((uint32_t)r[2][x] + r[4][x]) + 56u * (uint32_t)r[3][x];
             D[x] = (uint8_t)((acc + 32768u) >> 16);
         }
     }
     free(tmp);
+    free(pad);
 }
 
 /* --------------------------------------------------------------- fastAtan2
