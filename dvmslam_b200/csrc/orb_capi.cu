@@ -200,7 +200,7 @@ int dvm_orb_create(dvm_orb** out, int device, int nfeatures, float scale_factor,
     }
     int quota_sum = 0;
     for (int q : h->perLevel) quota_sum += q;
-    h->max_kp = quota_sum + nlevels * (4 + 4 * 32);
+    h->max_kp = (quota_sum + nlevels * (4 + 4 * 32) + 3) & ~3; // multiple of 4: keeps the descriptor block 16-byte aligned
 
 #define DVM_CREATE_CUDA(call)                                                                        \
     do {                                                                                             \

@@ -118,3 +118,68 @@ class PlaneStream:
         H = self.homography(k)
         return cv2.warpPerspective(self.master, H, (self.w, self.h), flags=cv2.INTER_LINEAR,
                                    borderMode=cv2.BORDER_REFLECT_101)
+
+
+def backproject_to_plane(stream: "PlaneStream", k: int, xy: np.ndarray) -> np.ndarray:
+    """World points (float32 [n,3]) where the pixel rays of frame k hit the textured plane."""
+    fx, fy, cx, cy = stream.K
+    Rcw, tcw = stream.pose(k)
+    Rwc, twc = Rcw.T, -Rcw.T @ tcw
+    rays = np.stack([(xy[:, 0] - cx) / fx, (xy[:, 1] - cy) / fy, np.ones(len(xy))], 1) @ Rwc.T
+    d = (stream.depth - twc[2]) / rays[:, 2]
+    return (twc[None, :] + rays * d[:, None]).astype(np.float32)
+
+
+def quat_from_R(R: np.ndarray) -> np.ndarray:
+    """(x, y, z, w) unit quaternion of a rotation matrix."""
+    t = np.trace(R)
+    if t > 0:
+        s = np.sqrt(t + 1.0) * 2
+        q = np.array([(R[2, 1] - R[1, 2]) / s, (R[0, 2] - R[2, 0]) / s, (R[1, 0] - R[0, 1]) / s, 0.25 * s])
+    else:
+        i = int(np.argmax(np.diag(R)))
+        j, k = (i + 1) % 3, (i + 2) % 3
+        s = np.sqrt(R[i, i] - R[j, j] - R[k, k] + 1.0) * 2
+        q = np.zeros(4)
+        q[i] = 0.25 * s
+        q[j] = (R[j, i] + R[i, j]) / s
+        q[k] = (R[k, i] + R[i, k]) / s
+        q[3] = (R[k, j] - R[j, k]) / s
+    if q[3] < 0:
+        q = -q
+    return q / np.linalg.norm(q)
+
+
+def tracking_case(stream: "PlaneStream", k: int, extract, n_local: int = 4000, seed: int = 0,
+                  pose_noise=(0.004, 0.002)):
+    """Inputs of one tracked frame (SURVEY.md 8d "tracking-only workload"): frame k-1 with a map point
+    behind every keypoint (plane geometry is known), frame k, a perturbed pose prior for frame k, and
+    a local map of `n_local` plane points observed from frame max(k-8, 0) (descriptor = that first
+    observation).  `extract(img) -> (kps, desc, mono)` is either the oracle's or the GPU extractor."""
+    rng = np.random.default_rng(seed * 1000 + k)
+    last_img, cur_img = stream.frame(k - 1), stream.frame(k)
+    lk, ld, _ = extract(last_img)
+    ck, cd, _ = extract(cur_img)
+    Xw = backproject_to_plane(stream, k - 1, np.stack([lk["x"], lk["y"]], 1).astype(np.float64))
+    n_last = len(lk)
+    has_mp = (rng.random(n_last) < 0.85).astype(np.uint8)       # not every keypoint holds a map point
+    outlier = (rng.random(n_last) < 0.03).astype(np.uint8)      # a few flagged by the previous PoseOptimization
+    obs_pos = (rng.random(n_last) < 0.97).astype(np.uint8)      # Observations() > 0 for nearly all
+    Rcw, tcw = stream.pose(k)
+    # motion-model prior: true pose with a small perturbation
+    w = rng.normal(0, pose_noise[1], 3)
+    th = np.linalg.norm(w)
+    Kx = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]])
+    dR = np.eye(3) + np.sin(th) / th * Kx + (1 - np.cos(th)) / th ** 2 * Kx @ Kx
+    Rp = (dR @ Rcw).astype(np.float32)
+    tp = (tcw + rng.normal(0, pose_noise[0], 3)).astype(np.float32)
+    # local map: keypoints of an earlier frame lifted to the plane
+    k0 = max(k - 8, 0)
+    mk, md, _ = extract(stream.frame(k0))
+    sel = rng.permutation(len(mk))[:n_local]
+    sel.sort()
+    Xm = backproject_to_plane(stream, k0, np.stack([mk["x"][sel], mk["y"][sel]], 1).astype(np.float64))
+    return dict(last_kps=lk, last_desc=ld, cur_kps=ck, cur_desc=cd, cur_img=cur_img, last_Xw=Xw, has_mp=has_mp,
+                outlier=outlier, obs_pos=obs_pos, Rcw_prior=Rp, tcw_prior=tp, Rcw_true=Rcw, tcw_true=tcw,
+                K=np.array(stream.K, np.float32), map_Xw=Xm, map_desc=md[sel].copy(), map_octave=mk["octave"][sel].copy(),
+                bounds=(0.0, 0.0, float(stream.w), float(stream.h)))

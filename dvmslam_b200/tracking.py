@@ -1,0 +1,136 @@
+"""Python mirrors of the per-frame tracking operators over the C-ABI: Frame (grid),
+ORBmatcher.SearchByProjection (both overloads) and Optimizer.PoseOptimization.  Argument meaning
+follows the reference (O3/include/ORBmatcher.h:40-95, O3/include/Optimizer.h:59); the pointer-graph
+arguments (Frame&, vector<MapPoint*>) are flattened to arrays as include/dvmslam_b200.h documents."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from ._lib import check, lib
+from .extractor import KP_DTYPE
+
+_vp = C.c_void_p
+_ip = C.POINTER(C.c_int)
+
+
+def _bind(L):
+    if getattr(L, "_trk_bound", False):
+        return
+    L.dvm_frame_create.argtypes = [C.POINTER(_vp), C.c_int, _vp, C.c_int, C.c_int, _vp, _vp]
+    L.dvm_frame_destroy.argtypes = [_vp]
+    L.dvm_frame_destroy.restype = None
+    L.dvm_frame_assign.argtypes = [_vp, _vp, _vp, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float]
+    L.dvm_frame_assign_from_orb.argtypes = [_vp, _vp, C.c_float, C.c_float, C.c_float, C.c_float]
+    L.dvm_frame_features_in_area.argtypes = [_vp, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, _vp, C.c_int, _ip]
+    L.dvm_frame_grid_cell.argtypes = [_vp, C.c_int, C.c_int, _vp, C.c_int, _ip]
+    L.dvm_match_by_projection_last.argtypes = [_vp, _vp, _vp, _vp, C.c_int] + [_vp] * 7 + [C.c_float, C.c_int, _vp, _ip]
+    L.dvm_match_by_projection_map.argtypes = [_vp, C.c_int] + [_vp] * 6 + [C.c_float, C.c_float, _vp, _vp, _ip]
+    L.dvm_match_last_rounds.argtypes = [_vp]
+    L.dvm_pose_optimization.argtypes = [_vp, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _ip, _vp]
+    L._trk_bound = True
+
+
+def _c(a, dt):
+    return np.ascontiguousarray(a, dt)
+
+
+class Frame:
+    """Mono Frame: undistorted keypoints + descriptors + 64x48 grid, resident on one B200."""
+
+    def __init__(self, max_keypoints: int, scale_factors, inv_level_sigma2, device: int = 0, stream: int = 0):
+        self.L = lib()
+        _bind(self.L)
+        self.h = _vp()
+        sf, isg = _c(scale_factors, np.float32), _c(inv_level_sigma2, np.float32)
+        check(self.L.dvm_frame_create(C.byref(self.h), device, _vp(stream) if stream else None, max_keypoints,
+                                      len(sf), sf.ctypes.data, isg.ctypes.data))
+        self.cap = (max_keypoints + 3) & ~3
+        self.n = 0
+
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            self.L.dvm_frame_destroy(self.h)
+            self.h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def assign(self, kps_un, desc, bounds):
+        k, d = _c(kps_un, KP_DTYPE), _c(desc, np.uint8)
+        self.n = len(k)
+        check(self.L.dvm_frame_assign(self.h, k.ctypes.data, d.ctypes.data, self.n, *map(float, bounds)))
+
+    def assign_from_orb(self, extractor, bounds):
+        check(self.L.dvm_frame_assign_from_orb(self.h, extractor.h, *map(float, bounds)))
+        self.n = self.cap
+
+    def GetFeaturesInArea(self, x, y, r, minLevel=-1, maxLevel=-1):
+        out = np.zeros(self.cap, np.int32)
+        n = C.c_int()
+        check(self.L.dvm_frame_features_in_area(self.h, x, y, r, minLevel, maxLevel, out.ctypes.data, self.cap,
+                                                C.byref(n)))
+        return out[:n.value].copy()
+
+    def grid_cell(self, ix, iy):
+        out = np.zeros(self.cap, np.int32)
+        n = C.c_int()
+        check(self.L.dvm_frame_grid_cell(self.h, ix, iy, out.ctypes.data, self.cap, C.byref(n)))
+        return out[:n.value].copy()
+
+
+class ORBmatcher:
+    TH_LOW, TH_HIGH, HISTO_LENGTH = 50, 100, 30
+
+    def __init__(self, nnratio: float = 0.6, checkOri: bool = True):
+        self.mfNNratio, self.mbCheckOrientation = nnratio, checkOri
+        self.L = lib()
+        _bind(self.L)
+
+    def SearchByProjectionLast(self, cur: Frame, Rcw, tcw, K, has_mp, outlier, Xw, mp_desc, obs_pos, last_octave,
+                               last_angle, th):
+        """SearchByProjection(CurrentFrame, LastFrame, th, bMono=True) -> (nmatches, cur_mp)."""
+        a = [_c(Rcw, np.float32), _c(tcw, np.float32), _c(K, np.float32)]
+        b = [_c(has_mp, np.uint8), _c(outlier, np.uint8), _c(Xw, np.float32), _c(mp_desc, np.uint8),
+             _c(obs_pos, np.uint8), _c(last_octave, np.int32), _c(last_angle, np.float32)]
+        cur_mp = np.full(cur.cap, -1, np.int32)
+        n = C.c_int()
+        check(self.L.dvm_match_by_projection_last(cur.h, *(x.ctypes.data for x in a), len(b[0]),
+                                                  *(x.ctypes.data for x in b), float(th),
+                                                  int(self.mbCheckOrientation), cur_mp.ctypes.data, C.byref(n)))
+        return n.value, cur_mp[:cur.n]
+
+    def SearchByProjectionMap(self, cur: Frame, projX, projY, level, view_cos, mp_desc, obs_pos, th, cur_blocked=None):
+        """SearchByProjection(F, vpMapPoints, th) -> (nmatches, cur_mp)."""
+        b = [_c(projX, np.float32), _c(projY, np.float32), _c(level, np.int32), _c(view_cos, np.float32),
+             _c(mp_desc, np.uint8), _c(obs_pos, np.uint8)]
+        blk = _c(cur_blocked, np.uint8) if cur_blocked is not None else None
+        cur_mp = np.full(cur.cap, -1, np.int32)
+        n = C.c_int()
+        check(self.L.dvm_match_by_projection_map(cur.h, len(b[0]), *(x.ctypes.data for x in b), float(th),
+                                                 float(self.mfNNratio), blk.ctypes.data if blk is not None else None,
+                                                 cur_mp.ctypes.data, C.byref(n)))
+        return n.value, cur_mp[:cur.n]
+
+    def rounds(self, cur: Frame) -> int:
+        return self.L.dvm_match_last_rounds(cur.h)
+
+
+def PoseOptimization(frame: Frame, q, t, K, Xw, kp_xy, inv_sigma2):
+    """Optimizer::PoseOptimization -> (n_inliers, q, t, outlier, (lm_iterations, lm_trials))."""
+    L = lib()
+    _bind(L)
+    q, t = _c(q, np.float32).copy(), _c(t, np.float32).copy()
+    Xw, kp_xy, w = _c(Xw, np.float32), _c(kp_xy, np.float32), _c(inv_sigma2, np.float32)
+    n = len(w)
+    out = np.zeros(max(n, 1), np.uint8)
+    stats = np.zeros(2, np.int32)
+    ninl = C.c_int()
+    check(L.dvm_pose_optimization(frame.h, q.ctypes.data, t.ctypes.data, _c(K, np.float32).ctypes.data, n,
+                                  Xw.ctypes.data, kp_xy.ctypes.data, w.ctypes.data, out.ctypes.data, C.byref(ninl),
+                                  stats.ctypes.data))
+    return ninl.value, q, t, out[:n], tuple(int(s) for s in stats)

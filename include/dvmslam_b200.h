@@ -114,6 +114,79 @@ DVM_API int dvm_orb_debug_level_image(dvm_orb* h, int level, int blurred, uint8_
 DVM_API int dvm_orb_debug_level_keypoints(dvm_orb* h, int level, int which, int* xs, int* ys, int* responses,
                                           int cap, int* n_out);
 
+/* ------------------------------------------------------------------------------------------------
+ * Frame (mono)   -- replaces the parts of ORB_SLAM3::Frame the matchers need
+ *                   (O3/src/Frame.cc:371-506 mono constructor, :712-782 grid queries)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct dvm_frame dvm_frame;
+
+/* scale_factors / inv_level_sigma2: the extractor's GetScaleFactors() / GetInverseScaleSigmaSquares()
+ * that Frame copies (O3/src/Frame.cc:399-405).  cuda_stream: a cudaStream_t to launch on (e.g.
+ * dvm_orb_stream() so that frame building is stream-ordered after extraction), or NULL for a private
+ * stream. */
+DVM_API int dvm_frame_create(dvm_frame** out, int device, void* cuda_stream, int max_keypoints, int nlevels,
+                             const float* scale_factors, const float* inv_level_sigma2);
+DVM_API void dvm_frame_destroy(dvm_frame* f);
+/* UndistortKeyPoints (identity: the caller passes undistorted keypoints; with k1 == 0 they are the
+ * extractor's output, O3/src/Frame.cc:791-795) + ComputeImageBounds result (minX..maxY) +
+ * AssignFeaturesToGrid.  Host arrays; synchronous. */
+DVM_API int dvm_frame_assign(dvm_frame* f, const dvm_keypoint* kps_un, const uint8_t* desc, int n, float min_x,
+                             float min_y, float max_x, float max_y);
+/* Same, taking the keypoints/descriptors of the extractor's last result straight from HBM
+ * (device to device, enqueued on the frame's stream; no synchronisation). */
+DVM_API int dvm_frame_assign_from_orb(dvm_frame* f, const dvm_orb* orb, float min_x, float min_y, float max_x,
+                                      float max_y);
+/* Frame::GetFeaturesInArea(x, y, r, minLevel, maxLevel) (O3/src/Frame.cc:712-770); indices in the
+ * reference's order.  *n_out may exceed cap (then only cap entries were written). */
+DVM_API int dvm_frame_features_in_area(dvm_frame* f, float x, float y, float r, int min_level, int max_level,
+                                       int32_t* out, int cap, int* n_out);
+/* mGrid[ix][iy] (O3/include/Frame.h:290) for parity tests. */
+DVM_API int dvm_frame_grid_cell(dvm_frame* f, int ix, int iy, int32_t* out, int cap, int* n_out);
+
+/* ------------------------------------------------------------------------------------------------
+ * ORBmatcher   -- replaces the projection matchers of ORB_SLAM3::ORBmatcher
+ *                 (O3/include/ORBmatcher.h:40-95; TH_HIGH = 100, HISTO_LENGTH = 30)
+ * Map points are passed as flat arrays; results are indices into those arrays (-1 = no map point).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* int ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, float th, bool bMono=true)
+ * (O3/src/ORBmatcher.cc:1553-1748).  One entry per last-frame keypoint i: has_mp (mvpMapPoints[i] !=
+ * NULL), outlier (mvbOutlier[i]), Xw (GetWorldPos), mp_desc (GetDescriptor, 32 B), mp_obs_pos
+ * (Observations() > 0), last_octave (mvKeys[i].octave), last_angle (mvKeysUn[i].angle).
+ * Rcw (row-major 3x3), tcw: CurrentFrame.GetPose(); K = fx, fy, cx, cy.
+ * cur_mp[cur n] receives, per current keypoint, the last-frame index whose map point it now holds
+ * (CurrentFrame.mvpMapPoints, which the caller cleared before the call); *nmatches = return value. */
+DVM_API int dvm_match_by_projection_last(dvm_frame* cur, const float* Rcw, const float* tcw, const float* K,
+                                         int last_n, const uint8_t* has_mp, const uint8_t* outlier, const float* Xw,
+                                         const uint8_t* mp_desc, const uint8_t* mp_obs_pos,
+                                         const int32_t* last_octave, const float* last_angle, float th,
+                                         int check_orientation, int32_t* cur_mp, int* nmatches);
+
+/* int ORBmatcher::SearchByProjection(Frame& F, const vector<MapPoint*>& vpMapPoints, float th, ...)
+ * (O3/src/ORBmatcher.cc:44-205; bFarPoints = false).  The caller lists, in vpMapPoints order, the map
+ * points with mbTrackInView set and !isBad(): proj_x/proj_y (mTrackProjX/Y), level
+ * (mnTrackScaleLevel), view_cos (mTrackViewCos), descriptor, Observations() > 0.  cur_blocked[i] != 0:
+ * keypoint i already holds a map point with Observations() > 0 (NULL = none).  nnratio = mfNNratio.
+ * cur_mp[cur n]: index of the map point assigned by THIS call, or -1. */
+DVM_API int dvm_match_by_projection_map(dvm_frame* cur, int m, const float* proj_x, const float* proj_y,
+                                        const int32_t* level, const float* view_cos, const uint8_t* mp_desc,
+                                        const uint8_t* mp_obs_pos, float th, float nnratio,
+                                        const uint8_t* cur_blocked, int32_t* cur_mp, int* nmatches);
+/* Number of Jacobi rounds the last matcher call on this frame needed (diagnostic). */
+DVM_API int dvm_match_last_rounds(dvm_frame* cur);
+
+/* ------------------------------------------------------------------------------------------------
+ * Optimizer::PoseOptimization   (O3/src/Optimizer.cc:744-1028, mono observations)
+ * ---------------------------------------------------------------------------------------------- */
+/* pose_q (x,y,z,w of Tcw.unit_quaternion()) and pose_t (Tcw.translation()) are in/out (float, like
+ * Frame::GetPose/SetPose); K = fx,fy,cx,cy; per correspondence the map point's world position, the
+ * undistorted keypoint and mvInvLevelSigma2[octave].  outlier[n] receives mvbOutlier; *n_inliers the
+ * return value (nInitialCorrespondences - nBad; 0 when n < 3).  stats (may be NULL): [0] LM
+ * iterations, [1] LM trials summed over the 4 rounds. */
+DVM_API int dvm_pose_optimization(dvm_frame* ctx, float* pose_q, float* pose_t, const float* K, int n,
+                                  const float* Xw, const float* kp_xy, const float* inv_sigma2, uint8_t* outlier,
+                                  int* n_inliers, int* stats);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,154 @@
+"""GPU parity of the per-frame tracking operators against the oracle: grid, window query, both
+projection matchers (bit-exact match indices) and PoseOptimization (stated fp tolerance)."""
+import numpy as np
+import pytest
+
+from dvmslam_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+POSE_T_TOL = 1e-5      # metres (scene depth 3 m)
+POSE_Q_TOL = 1e-6      # quaternion component
+
+
+@pytest.fixture(scope="module")
+def world():
+    from oracle.orb import OrbOracle
+
+    S = synth.PlaneStream(seed=0)
+    orc = OrbOracle(2000)
+    T = orc.tables()
+    cases = {k: synth.tracking_case(S, k, orc.extract) for k in (3, 12)}
+    return dict(S=S, T=T, cases=cases)
+
+
+def _frames(world, case):
+    from dvmslam_b200.tracking import Frame
+    from oracle.track import FrameOracle
+
+    T = world["T"]
+    F0 = FrameOracle(case["cur_kps"], case["cur_desc"], case["bounds"], T["scale"])
+    F1 = Frame(len(case["cur_kps"]) + 16, T["scale"], T["inv_sigma2"])
+    F1.assign(case["cur_kps"], case["cur_desc"], case["bounds"])
+    return F0, F1
+
+
+@pytest.mark.parametrize("k", [3, 12])
+def test_grid_and_area_queries(world, k):
+    case = world["cases"][k]
+    F0, F1 = _frames(world, case)
+    rng = np.random.default_rng(k)
+    for ix, iy in [(0, 0), (63, 47), (10, 20), (32, 24)] + [tuple(rng.integers(0, [64, 48])) for _ in range(40)]:
+        assert np.array_equal(F0.grid_cell(int(ix), int(iy)), F1.grid_cell(int(ix), int(iy))), (ix, iy)
+    for _ in range(60):
+        x, y = float(rng.uniform(-50, 1330)), float(rng.uniform(-50, 770))
+        r = float(rng.choice([5.0, 15.0, 37.3, 120.0]))
+        lv = int(rng.integers(0, 8))
+        for (a, b) in [(-1, -1), (lv - 1, lv + 1), (lv - 1, lv), (0, lv), (lv, -1)]:
+            assert np.array_equal(F0.features_in_area(x, y, r, a, b), F1.GetFeaturesInArea(x, y, r, a, b)), (x, y, r, a, b)
+    F1.close()
+
+
+@pytest.mark.parametrize("k,th", [(3, 15.0), (3, 30.0), (12, 15.0), (12, 7.0)])
+def test_search_by_projection_last(world, k, th):
+    from dvmslam_b200.tracking import ORBmatcher
+
+    case = world["cases"][k]
+    F0, F1 = _frames(world, case)
+    lk = case["last_kps"]
+    args = (case["Rcw_prior"], case["tcw_prior"], case["K"], case["has_mp"], case["outlier"], case["last_Xw"],
+            case["last_desc"], case["obs_pos"], lk["octave"], lk["angle"], th)
+    n0, m0 = F0.search_by_projection_last(*args)
+    for ori in (True, False):
+        n0, m0 = F0.search_by_projection_last(*args, check_ori=ori)
+        mt = ORBmatcher(0.9, ori)
+        n1, m1 = mt.SearchByProjectionLast(F1, *args)
+        assert n0 == n1, (ori, mt.rounds(F1))
+        assert np.array_equal(m0, m1), ori
+        assert n0 > 300
+    F1.close()
+
+
+def test_search_by_projection_last_heavy_contention(world):
+    """Many map points per keypoint (all last-frame points squeezed onto a few targets): the greedy
+    order dependence is what is being tested."""
+    from dvmslam_b200.tracking import ORBmatcher
+
+    case = world["cases"][3]
+    F0, F1 = _frames(world, case)
+    lk = case["last_kps"]
+    rng = np.random.default_rng(1)
+    Xw = case["last_Xw"].copy()
+    Xw[:, :2] = Xw[rng.integers(0, 40, len(Xw)), :2] + rng.normal(0, 0.01, (len(Xw), 2)).astype(np.float32)
+    obs = (rng.random(len(Xw)) < 0.7).astype(np.uint8)
+    args = (case["Rcw_prior"], case["tcw_prior"], case["K"], np.ones_like(case["has_mp"]), np.zeros_like(case["outlier"]),
+            Xw, case["last_desc"], obs, lk["octave"], lk["angle"], 30.0)
+    n0, m0 = F0.search_by_projection_last(*args)
+    mt = ORBmatcher(0.9, True)
+    n1, m1 = mt.SearchByProjectionLast(F1, *args)
+    assert n0 == n1 and np.array_equal(m0, m1), mt.rounds(F1)
+    assert mt.rounds(F1) >= 3
+    F1.close()
+
+
+def _project_map(case, Rcw, tcw, T):
+    X = case["map_Xw"].astype(np.float32)
+    Xc = X @ Rcw.T.astype(np.float32) + tcw.astype(np.float32)
+    K = case["K"]
+    u = K[0] * Xc[:, 0] / Xc[:, 2] + K[2]
+    v = K[1] * Xc[:, 1] / Xc[:, 2] + K[3]
+    ok = (Xc[:, 2] > 0) & (u >= 0) & (u < 1280) & (v >= 0) & (v < 720)
+    return ok, u.astype(np.float32), v.astype(np.float32)
+
+
+@pytest.mark.parametrize("k,th,nnratio", [(3, 1.0, 0.8), (12, 1.0, 0.8), (12, 5.0, 0.8), (3, 3.0, 0.6)])
+def test_search_by_projection_map(world, k, th, nnratio):
+    from dvmslam_b200.tracking import ORBmatcher
+
+    case = world["cases"][k]
+    F0, F1 = _frames(world, case)
+    ok, u, v = _project_map(case, case["Rcw_true"], case["tcw_true"], world["T"])
+    rng = np.random.default_rng(k)
+    level = case["map_octave"][ok].astype(np.int32)
+    cosv = rng.choice([0.9995, 0.9], ok.sum()).astype(np.float32)
+    obs = (rng.random(ok.sum()) < 0.95).astype(np.uint8)
+    blocked = (rng.random(len(case["cur_kps"])) < 0.3).astype(np.uint8)
+    args = (u[ok], v[ok], level, cosv, case["map_desc"][ok], obs, th, nnratio, blocked)
+    n0, m0 = F0.search_by_projection_map(*args)
+    mt = ORBmatcher(nnratio, True)
+    n1, m1 = mt.SearchByProjectionMap(F1, *args[:7], cur_blocked=blocked)
+    assert n0 == n1 and np.array_equal(m0, m1), mt.rounds(F1)
+    assert n0 > 100
+    assert not (blocked[m1 >= 0]).any()
+    F1.close()
+
+
+@pytest.mark.parametrize("k", [3, 12])
+def test_pose_optimization(world, k):
+    from dvmslam_b200.tracking import PoseOptimization
+    from oracle.track import pose_optimization
+
+    case = world["cases"][k]
+    F0, F1 = _frames(world, case)
+    lk, ck = case["last_kps"], case["cur_kps"]
+    n, cur_mp = F0.search_by_projection_last(case["Rcw_prior"], case["tcw_prior"], case["K"], case["has_mp"],
+                                             case["outlier"], case["last_Xw"], case["last_desc"], case["obs_pos"],
+                                             lk["octave"], lk["angle"], 15.0)
+    idx = np.nonzero(cur_mp >= 0)[0]
+    Xw = case["last_Xw"][cur_mp[idx]]
+    xy = np.stack([ck["x"][idx], ck["y"][idx]], 1)
+    w = world["T"]["inv_sigma2"][ck["octave"][idx]]
+    q = synth.quat_from_R(case["Rcw_prior"].astype(np.float64)).astype(np.float32)
+    r0, q0, t0, o0, s0 = pose_optimization(q, case["tcw_prior"], case["K"], Xw, xy, w)
+    r1, q1, t1, o1, s1 = PoseOptimization(F1, q, case["tcw_prior"], case["K"], Xw, xy, w)
+    assert s0 == s1, "same LM iteration / trial counts"
+    assert np.abs(t0 - t1).max() < POSE_T_TOL and np.abs(q0 - q1).max() < POSE_Q_TOL
+    assert r0 == r1 and np.array_equal(o0, o1)
+    assert r1 > 0.8 * len(idx)
+    # degenerate sizes
+    for m in (0, 2, 5, 9):
+        r0, q0, t0, o0, _ = pose_optimization(q, case["tcw_prior"], case["K"], Xw[:m], xy[:m], w[:m])
+        r1, q1, t1, o1, _ = PoseOptimization(F1, q, case["tcw_prior"], case["K"], Xw[:m], xy[:m], w[:m])
+        assert r0 == r1 and np.array_equal(o0, o1), m
+        assert np.abs(t0 - t1).max() < POSE_T_TOL and np.abs(q0 - q1).max() < POSE_Q_TOL, m
+    F1.close()
