@@ -1,0 +1,929 @@
+// lba.cu -- Optimizer::LocalBundleAdjustment on one B200 (O3/src/Optimizer.cc:1030-1387).
+//
+// One persistent cooperative kernel (one CTA per SM, grid.sync between phases) runs the whole of
+// g2o's optimize(10): the Levenberg-Marquardt control flow (lambda, accept/reject, Raul's stop rule,
+// g2o/core/optimization_algorithm_levenberg.cpp:59-165) is evaluated redundantly and identically by
+// every thread from deterministic partial sums, so the host is never consulted between trials.
+//
+//   L1  point-major linearisation: error, Huber weight, Jacobians, Hll, bl, Hpl   (block_solver.hpp:502-560,
+//       base_binary_edge.hpp:55-120, OptimizableTypes.cpp:136-155)
+//   L2  camera-major accumulation of Hpp, bp
+//   S0  per-landmark (Hll + lambda I)^-1 and Dinv*bl                               (block_solver.hpp:381-400)
+//   S1  Schur complement, one CTA per free camera row, shared-memory accumulation  (:402-437)
+//   C   dense reduced-camera solve: blocked Cholesky on one CTA, trailing updates on the FP64 tensor
+//       pipe (DMMA m8n8k4)                                                          (linear_solver_eigen.h:89-121)
+//   B1  landmark back-substitution, pose/point update into the trial buffers       (:459-483, se3quat.h:212-240)
+//   B2  errors and robust chi2 at the trial estimate
+#include "common.cuh"
+#include <cooperative_groups.h>
+#include <algorithm>
+#include <vector>
+
+namespace cg = cooperative_groups;
+using namespace dvm;
+
+namespace {
+
+constexpr int kLbaThreads = 512;
+constexpr int kLbaWarps = kLbaThreads / 32;
+constexpr int kNB = 32; // Cholesky block size
+
+struct LbaDev {
+    int nc, nf, np, ne, dimP, iterations;
+    double fx, fy, cx, cy, delta, dsqr;
+    double* camq[2]; double* camt[2];
+    const int* cam_col; const int* free_cam;
+    double* pts[2];
+    const int* ecam; const int* ept; const float* eobs; const float* einfo;
+    const int* pt_start; const int* pt_edges;
+    const int* cam_start; const int* cam_edges;
+    double* err; double* Hpl; double* Hll; double* bl; double* Dinv; double* db;
+    double* Hpp; double* bp; double* Hs; double* bs; double* x;
+    double* part;  // [gridDim * 4]
+    int* flags;    // [0] Cholesky ok
+    const volatile int* abort_flag;
+    float* out_camq; float* out_camt; float* out_pts; double* out_chi2; uint8_t* out_bad; double* out_stats;
+};
+
+// ---- SE3 helpers (same formulas as the pose-only optimiser; g2o/types/se3quat.h) ----
+struct Quat { double x, y, z, w; };
+__device__ inline void quat_normalize(Quat& q)
+{
+    if (q.w < 0) { q.x = -q.x; q.y = -q.y; q.z = -q.z; q.w = -q.w; }
+    const double n = sqrt(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
+    q.x /= n; q.y /= n; q.z /= n; q.w /= n;
+}
+__device__ inline Quat quat_mul(const Quat& a, const Quat& b)
+{
+    Quat r;
+    r.w = a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z;
+    r.x = a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y;
+    r.y = a.w * b.y + a.y * b.w + a.z * b.x - a.x * b.z;
+    r.z = a.w * b.z + a.z * b.w + a.x * b.y - a.y * b.x;
+    return r;
+}
+__device__ inline void quat_rotate(const Quat& q, const double v[3], double out[3])
+{
+    double uv[3] = { q.y * v[2] - q.z * v[1], q.z * v[0] - q.x * v[2], q.x * v[1] - q.y * v[0] };
+    uv[0] += uv[0]; uv[1] += uv[1]; uv[2] += uv[2];
+    out[0] = v[0] + q.w * uv[0] + (q.y * uv[2] - q.z * uv[1]);
+    out[1] = v[1] + q.w * uv[1] + (q.z * uv[0] - q.x * uv[2]);
+    out[2] = v[2] + q.w * uv[2] + (q.x * uv[1] - q.y * uv[0]);
+}
+__device__ inline void quat_to_matrix(const Quat& q, double R[9])
+{
+    const double tx = 2 * q.x, ty = 2 * q.y, tz = 2 * q.z;
+    const double twx = tx * q.w, twy = ty * q.w, twz = tz * q.w;
+    const double txx = tx * q.x, txy = ty * q.x, txz = tz * q.x;
+    const double tyy = ty * q.y, tyz = tz * q.y, tzz = tz * q.z;
+    R[0] = 1 - (tyy + tzz); R[1] = txy - twz; R[2] = txz + twy;
+    R[3] = txy + twz; R[4] = 1 - (txx + tzz); R[5] = tyz - twx;
+    R[6] = txz - twy; R[7] = tyz + twx; R[8] = 1 - (txx + tyy);
+}
+__device__ inline Quat quat_from_matrix(const double R[9])
+{
+    Quat q;
+    double t = R[0] + R[4] + R[8];
+    if (t > 0) {
+        t = sqrt(t + 1.0);
+        q.w = 0.5 * t;
+        t = 0.5 / t;
+        q.x = (R[7] - R[5]) * t; q.y = (R[2] - R[6]) * t; q.z = (R[3] - R[1]) * t;
+    } else {
+        int i = 0;
+        if (R[4] > R[0]) i = 1;
+        if (R[8] > R[i * 4]) i = 2;
+        const int j = (i + 1) % 3, k = (j + 1) % 3;
+        t = sqrt(R[i * 4] - R[j * 4] - R[k * 4] + 1.0);
+        double v[3];
+        v[i] = 0.5 * t;
+        t = 0.5 / t;
+        q.w = (R[k * 3 + j] - R[j * 3 + k]) * t;
+        v[j] = (R[j * 3 + i] + R[i * 3 + j]) * t;
+        v[k] = (R[k * 3 + i] + R[i * 3 + k]) * t;
+        q.x = v[0]; q.y = v[1]; q.z = v[2];
+    }
+    return q;
+}
+// T' = exp(u) * T
+__device__ inline void se3_update(const double u[6], const double* q_in, const double* t_in, double* q_out, double* t_out)
+{
+    const double w0 = u[0], w1 = u[1], w2 = u[2];
+    const double theta = sqrt(w0 * w0 + w1 * w1 + w2 * w2);
+    const double O[9] = { 0, -w2, w1, w2, 0, -w0, -w1, w0, 0 };
+    double O2[9], R[9], V[9];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) O2[i * 3 + j] = O[i * 3] * O[j] + O[i * 3 + 1] * O[3 + j] + O[i * 3 + 2] * O[6 + j];
+    if (theta < 0.00001) {
+#pragma unroll
+        for (int i = 0; i < 9; i++) { R[i] = ((i % 4 == 0) ? 1.0 : 0.0) + O[i] + O2[i]; V[i] = R[i]; }
+    } else {
+        const double sa = sin(theta) / theta, sb = (1 - cos(theta)) / (theta * theta);
+        const double sc = (theta - sin(theta)) / pow(theta, 3.0);
+#pragma unroll
+        for (int i = 0; i < 9; i++) {
+            const double I = (i % 4 == 0) ? 1.0 : 0.0;
+            R[i] = I + sa * O[i] + sb * O2[i];
+            V[i] = I + sb * O[i] + sc * O2[i];
+        }
+    }
+    Quat e = quat_from_matrix(R);
+    quat_normalize(e);
+    double et[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) et[i] = V[i * 3] * u[3] + V[i * 3 + 1] * u[4] + V[i * 3 + 2] * u[5];
+    const Quat T = { q_in[0], q_in[1], q_in[2], q_in[3] };
+    const double tt[3] = { t_in[0], t_in[1], t_in[2] };
+    double rt[3];
+    quat_rotate(e, tt, rt);
+    Quat r = quat_mul(e, T);
+    quat_normalize(r);
+    q_out[0] = r.x; q_out[1] = r.y; q_out[2] = r.z; q_out[3] = r.w;
+    t_out[0] = et[0] + rt[0]; t_out[1] = et[1] + rt[1]; t_out[2] = et[2] + rt[2];
+}
+
+__device__ inline double huber_rho0(const LbaDev& P, double e) { return e <= P.dsqr ? e : 2 * sqrt(e) * P.delta - P.dsqr; }
+__device__ inline double huber_rho1(const LbaDev& P, double e) { return e <= P.dsqr ? 1.0 : P.delta / sqrt(e); }
+
+// camera-frame point and reprojection error of edge e at estimate buffer `cur`
+__device__ inline void edge_residual(const LbaDev& P, int cur, int e, double xc[3], double r[2], Quat* qout)
+{
+    const int c = P.ecam[e], l = P.ept[e];
+    const double* q = P.camq[cur] + 4 * c;
+    const double* t = P.camt[cur] + 3 * c;
+    const Quat Q = { q[0], q[1], q[2], q[3] };
+    const double X[3] = { P.pts[cur][3 * l], P.pts[cur][3 * l + 1], P.pts[cur][3 * l + 2] };
+    quat_rotate(Q, X, xc);
+    xc[0] += t[0]; xc[1] += t[1]; xc[2] += t[2];
+    r[0] = (double)P.eobs[2 * e] - (P.fx * xc[0] / xc[2] + P.cx);
+    r[1] = (double)P.eobs[2 * e + 1] - (P.fy * xc[1] / xc[2] + P.cy);
+    if (qout) *qout = Q;
+}
+
+// deterministic sum of NV doubles per thread over the CTA; result in out[0..NV) for all threads
+template <int NV>
+__device__ inline void cta_sum(double (&v)[NV], double* warp_buf, double* out)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+        double s = v[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+        if (lane == 0) warp_buf[wid * NV + i] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < NV) {
+        double s = 0;
+        for (int w = 0; w < kLbaWarps; w++) s += warp_buf[w * NV + threadIdx.x];
+        out[threadIdx.x] = s;
+    }
+    __syncthreads();
+}
+
+__device__ inline double warp_sum(double s)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    return s;
+}
+__device__ inline double warp_max(double s)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s = fmax(s, __shfl_xor_sync(0xffffffffu, s, o));
+    return s;
+}
+
+// D = C - A * B for one m8n8k4 FP64 tensor-core tile step (a: A[r=lane/4][k=lane%4], b: B[k=lane%4][c=lane/4])
+__device__ inline void dmma_m8n8k4(double& c0, double& c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// ---- dense SPD solve Hs x = bs on ONE CTA: blocked right-looking Cholesky (lower), then L y = b, L^T x = y.
+// smem: panel [n][kNB] doubles + diag [kNB][kNB+1] doubles.  Returns false if a pivot is not positive.
+__device__ bool cta_cholesky_solve(int n, double* __restrict__ A, const double* __restrict__ b, double* __restrict__ x,
+                                   double* smem, int* s_flag)
+{
+    double* panel = smem;                      // [n][kNB]
+    double* diag = smem + (size_t)n * kNB;     // [kNB][kNB+1]
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) *s_flag = 1;
+    __syncthreads();
+    for (int k0 = 0; k0 < n; k0 += kNB) {
+        const int nb = min(kNB, n - k0);
+        // diagonal block -> smem
+        for (int i = tid; i < nb * nb; i += kLbaThreads) {
+            const int r = i / nb, c = i - r * nb;
+            diag[r * (kNB + 1) + c] = A[(size_t)(k0 + r) * n + k0 + c];
+        }
+        __syncthreads();
+        if (wid == 0) { // unblocked Cholesky of the nb x nb block by one warp, lane = row
+            for (int j = 0; j < nb; j++) {
+                double d = diag[j * (kNB + 1) + j];
+                const bool bad = !(d > 0) || !isfinite(d);
+                d = sqrt(d);
+                if (bad) { if (lane == 0) *s_flag = 0; d = 1.0; }
+                __syncwarp();
+                if (lane == j) diag[j * (kNB + 1) + j] = d;
+                if (lane > j && lane < nb) diag[lane * (kNB + 1) + j] /= d;
+                __syncwarp();
+                if (lane > j && lane < nb) {
+                    const double lij = diag[lane * (kNB + 1) + j];
+                    for (int k = j + 1; k <= lane; k++) diag[lane * (kNB + 1) + k] -= lij * diag[k * (kNB + 1) + j];
+                }
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < nb * nb; i += kLbaThreads) { // write L_kk back (lower part)
+            const int r = i / nb, c = i - r * nb;
+            if (c <= r) A[(size_t)(k0 + r) * n + k0 + c] = diag[r * (kNB + 1) + c];
+        }
+        const int r0 = k0 + nb; // first row below the diagonal block
+        // panel: L[i][k0..k0+nb) = A[i][..] * L_kk^-T, one row per thread
+        for (int i = r0 + tid; i < n; i += kLbaThreads) {
+            double row[kNB];
+            for (int c = 0; c < nb; c++) row[c] = A[(size_t)i * n + k0 + c];
+            for (int c = 0; c < nb; c++) {
+                double s = row[c];
+                for (int k = 0; k < c; k++) s -= row[k] * diag[c * (kNB + 1) + k];
+                row[c] = s / diag[c * (kNB + 1) + c];
+            }
+            for (int c = 0; c < nb; c++) { A[(size_t)i * n + k0 + c] = row[c]; panel[(size_t)(i - r0) * kNB + c] = row[c]; }
+            for (int c = nb; c < kNB; c++) panel[(size_t)(i - r0) * kNB + c] = 0.0;
+        }
+        __syncthreads();
+        // trailing update A22 -= L21 * L21^T (lower triangle), 8x8 tiles on the FP64 tensor pipe
+        const int m = n - r0;
+        if (m > 0) {
+            const int mt = (m + 7) / 8;
+            const int ntiles = mt * (mt + 1) / 2;
+            for (int t = wid; t < ntiles; t += kLbaWarps) {
+                // tile (ti, tj), tj <= ti, from the triangular index t
+                int ti = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+                while (ti * (ti + 1) / 2 > t) ti--;
+                while ((ti + 1) * (ti + 2) / 2 <= t) ti++;
+                const int tj = t - ti * (ti + 1) / 2;
+                const int ar = ti * 8 + (lane >> 2), bc = tj * 8 + (lane >> 2);
+                double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+                for (int kk = 0; kk < kNB; kk += 4) {
+                    const double a = ar < m ? panel[(size_t)ar * kNB + kk + (lane & 3)] : 0.0;
+                    const double bb = bc < m ? panel[(size_t)bc * kNB + kk + (lane & 3)] : 0.0;
+                    dmma_m8n8k4(c0, c1, a, bb);
+                }
+                const int cr = ti * 8 + (lane >> 2), cc = tj * 8 + (lane & 3) * 2;
+                if (cr < m) {
+                    double* dst = A + (size_t)(r0 + cr) * n + r0 + cc;
+                    if (cc < m && cc <= cr) dst[0] -= c0;
+                    if (cc + 1 < m && cc + 1 <= cr) dst[1] -= c1;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    const bool ok = *s_flag != 0;
+    // forward substitution L y = b (y kept in smem), blocked by kNB
+    double* y = smem; // reuse panel storage: n doubles
+    for (int i = tid; i < n; i += kLbaThreads) y[i] = b[i];
+    __syncthreads();
+    for (int k0 = 0; k0 < n; k0 += kNB) {
+        const int nb = min(kNB, n - k0);
+        if (wid == 0) {
+            for (int j = 0; j < nb; j++) {
+                if (lane == 0) y[k0 + j] /= A[(size_t)(k0 + j) * n + k0 + j];
+                __syncwarp();
+                const double yj = y[k0 + j];
+                if (lane > j && lane < nb) y[k0 + lane] -= A[(size_t)(k0 + lane) * n + k0 + j] * yj;
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        for (int i = k0 + nb + tid; i < n; i += kLbaThreads) {
+            double s = 0;
+            for (int c = 0; c < nb; c++) s += A[(size_t)i * n + k0 + c] * y[k0 + c];
+            y[i] -= s;
+        }
+        __syncthreads();
+    }
+    // backward substitution L^T x = y
+    for (int kb = (n - 1) / kNB; kb >= 0; kb--) {
+        const int k0 = kb * kNB, nb = min(kNB, n - k0);
+        if (wid == 0) {
+            for (int j = nb - 1; j >= 0; j--) {
+                if (lane == 0) y[k0 + j] /= A[(size_t)(k0 + j) * n + k0 + j];
+                __syncwarp();
+                const double yj = y[k0 + j];
+                if (lane < j) y[k0 + lane] -= A[(size_t)(k0 + j) * n + k0 + lane] * yj;
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < k0; i += kLbaThreads) {
+            double s = 0;
+            for (int c = 0; c < nb; c++) s += A[(size_t)(k0 + c) * n + i] * y[k0 + c];
+            y[i] -= s;
+        }
+        __syncthreads();
+    }
+    for (int i = tid; i < n; i += kLbaThreads) x[i] = ok ? y[i] : 0.0;
+    __syncthreads();
+    return ok;
+}
+
+__global__ void __launch_bounds__(kLbaThreads, 1) lba_kernel(LbaDev P)
+{
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ __align__(16) double smem[];
+    __shared__ double warp_buf[kLbaWarps * 28];
+    __shared__ double red[28];
+    __shared__ int s_flag;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int G = gridDim.x;
+    const int gwarp = blockIdx.x * kLbaWarps + wid, nwarps = G * kLbaWarps;
+    const int gtid = blockIdx.x * kLbaThreads + tid, nthreads = G * kLbaThreads;
+
+    int cur = 0; // index of the accepted estimate buffers
+    double lambda = -1, ni = 2;
+    int nBad = 0, done = 0, trials = 0;
+    double first_chi = 0, last_chi = 0;
+    bool stop = false;
+
+    // pbStopFlag lives in mapped host memory: thread 0 samples it and the whole grid adopts that value,
+    // so that every thread leaves the loops at the same point
+    auto agree_abort = [&]() -> bool {
+        if (!P.abort_flag) return false;
+        if (gtid == 0) P.flags[1] = (*P.abort_flag) ? 1 : 0;
+        grid.sync();
+        const bool a = P.flags[1] != 0;
+        grid.sync();
+        return a;
+    };
+
+    for (int it = 0; it < P.iterations && !stop; it++) {
+        if (agree_abort()) break;
+        // ---------------- L1: point-major linearisation ----------------
+        double chi_part = 0, maxd = 0;
+        for (int l = gwarp; l < P.np; l += nwarps) {
+            double h[6] = { 0, 0, 0, 0, 0, 0 }, g[3] = { 0, 0, 0 };
+            const int s = P.pt_start[l], e_end = P.pt_start[l + 1];
+            for (int k = s + lane; k < e_end; k += 32) {
+                const int e = P.pt_edges[k];
+                double xc[3], r[2];
+                Quat Q;
+                edge_residual(P, cur, e, xc, r, &Q);
+                P.err[2 * e] = r[0]; P.err[2 * e + 1] = r[1];
+                const double om = (double)P.einfo[e];
+                const double chi = r[0] * (om * r[0]) + r[1] * (om * r[1]);
+                chi_part += huber_rho0(P, chi);
+                const double w = huber_rho1(P, chi);
+                const double X = xc[0], Y = xc[1], Z = xc[2];
+                const double pj[6] = { -(P.fx / Z), 0.0, P.fx * X / (Z * Z), 0.0, -(P.fy / Z), P.fy * Y / (Z * Z) };
+                double R[9];
+                quat_to_matrix(Q, R);
+                double A[6];
+#pragma unroll
+                for (int rr = 0; rr < 2; rr++)
+#pragma unroll
+                    for (int kk = 0; kk < 3; kk++)
+                        A[rr * 3 + kk] = pj[rr * 3] * R[kk] + pj[rr * 3 + 1] * R[3 + kk] + pj[rr * 3 + 2] * R[6 + kk];
+                const double wo = w * om;
+                const double r0 = -om * r[0] * w, r1 = -om * r[1] * w;
+                g[0] += A[0] * r0 + A[3] * r1; g[1] += A[1] * r0 + A[4] * r1; g[2] += A[2] * r0 + A[5] * r1;
+                h[0] += A[0] * wo * A[0] + A[3] * wo * A[3];
+                h[1] += A[0] * wo * A[1] + A[3] * wo * A[4];
+                h[2] += A[0] * wo * A[2] + A[3] * wo * A[5];
+                h[3] += A[1] * wo * A[1] + A[4] * wo * A[4];
+                h[4] += A[1] * wo * A[2] + A[4] * wo * A[5];
+                h[5] += A[2] * wo * A[2] + A[5] * wo * A[5];
+                if (P.cam_col[P.ecam[e]] >= 0) {
+                    const double Dv[18] = { 0, Z, -Y, 1, 0, 0, -Z, 0, X, 0, 1, 0, Y, -X, 0, 0, 0, 1 };
+                    double* hp = P.Hpl + (size_t)e * 18;
+#pragma unroll
+                    for (int a = 0; a < 6; a++) {
+                        const double B0 = pj[0] * Dv[a] + pj[1] * Dv[6 + a] + pj[2] * Dv[12 + a];
+                        const double B1 = pj[3] * Dv[a] + pj[4] * Dv[6 + a] + pj[5] * Dv[12 + a];
+#pragma unroll
+                        for (int b2 = 0; b2 < 3; b2++) hp[a * 3 + b2] = B0 * wo * A[b2] + B1 * wo * A[3 + b2];
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 6; i++) h[i] = warp_sum(h[i]);
+#pragma unroll
+            for (int i = 0; i < 3; i++) g[i] = warp_sum(g[i]);
+            if (lane == 0) {
+#pragma unroll
+                for (int i = 0; i < 6; i++) P.Hll[(size_t)l * 6 + i] = h[i];
+#pragma unroll
+                for (int i = 0; i < 3; i++) P.bl[(size_t)l * 3 + i] = g[i];
+                maxd = fmax(maxd, fmax(fabs(h[0]), fmax(fabs(h[3]), fabs(h[5]))));
+            }
+        }
+        {
+            double v[1] = { chi_part };
+            cta_sum<1>(v, warp_buf, red);
+            maxd = warp_max(maxd);
+            if (lane == 0) warp_buf[wid] = maxd;
+            __syncthreads();
+            if (tid == 0) {
+                double m = 0;
+                for (int w2 = 0; w2 < kLbaWarps; w2++) m = fmax(m, warp_buf[w2]);
+                P.part[blockIdx.x * 4 + 0] = red[0];
+                P.part[blockIdx.x * 4 + 2] = m;
+            }
+            __syncthreads();
+        }
+        grid.sync();
+        // ---------------- L2: camera-major Hpp, bp ----------------
+        double maxdp = 0;
+        for (int cf = blockIdx.x; cf < P.nf; cf += G) {
+            double acc[27];
+#pragma unroll
+            for (int i = 0; i < 27; i++) acc[i] = 0;
+            const int s = P.cam_start[cf], e_end = P.cam_start[cf + 1];
+            for (int k = s + tid; k < e_end; k += kLbaThreads) {
+                const int e = P.cam_edges[k];
+                double xc[3], r[2];
+                edge_residual(P, cur, e, xc, r, nullptr);
+                const double om = (double)P.einfo[e];
+                const double chi = r[0] * (om * r[0]) + r[1] * (om * r[1]);
+                const double w = huber_rho1(P, chi);
+                const double X = xc[0], Y = xc[1], Z = xc[2];
+                const double pj[6] = { -(P.fx / Z), 0.0, P.fx * X / (Z * Z), 0.0, -(P.fy / Z), P.fy * Y / (Z * Z) };
+                const double Dv[18] = { 0, Z, -Y, 1, 0, 0, -Z, 0, X, 0, 1, 0, Y, -X, 0, 0, 0, 1 };
+                double B[12];
+#pragma unroll
+                for (int a = 0; a < 6; a++) {
+                    B[a] = pj[0] * Dv[a] + pj[1] * Dv[6 + a] + pj[2] * Dv[12 + a];
+                    B[6 + a] = pj[3] * Dv[a] + pj[4] * Dv[6 + a] + pj[5] * Dv[12 + a];
+                }
+                const double wo = w * om;
+                const double r0 = -om * r[0] * w, r1 = -om * r[1] * w;
+                int idx = 0;
+#pragma unroll
+                for (int a = 0; a < 6; a++) {
+                    acc[21 + a] += B[a] * r0 + B[6 + a] * r1;
+#pragma unroll
+                    for (int b2 = a; b2 < 6; b2++) acc[idx++] += B[a] * wo * B[b2] + B[6 + a] * wo * B[6 + b2];
+                }
+            }
+            cta_sum<27>(acc, warp_buf, red);
+            if (tid < 36) {
+                const int a = tid / 6, b2 = tid % 6;
+                const int lo = min(a, b2), hi = max(a, b2);
+                const int idx = lo * 6 - lo * (lo - 1) / 2 + (hi - lo);
+                P.Hpp[(size_t)cf * 36 + tid] = red[idx];
+            }
+            if (tid < 6) P.bp[cf * 6 + tid] = red[21 + tid];
+            if (tid == 0)
+                for (int a = 0; a < 6; a++) maxdp = fmax(maxdp, fabs(red[a * 6 - a * (a - 1) / 2]));
+            __syncthreads();
+        }
+        if (tid == 0) P.part[blockIdx.x * 4 + 3] = maxdp;
+        grid.sync();
+        double currentChi = 0;
+        {
+            double m = 0;
+            for (int b2 = 0; b2 < G; b2++) {
+                currentChi += P.part[b2 * 4 + 0];
+                m = fmax(m, fmax(P.part[b2 * 4 + 2], P.part[b2 * 4 + 3]));
+            }
+            if (it == 0) { lambda = 1e-5 * m; ni = 2; nBad = 0; first_chi = currentChi; }
+        }
+        const double iniChi = currentChi;
+        double rho = 0;
+        int qmax = 0;
+        bool aborted = false;
+        do {
+            const int trial = cur ^ 1;
+            // ---------------- S0: landmark inverses, clear Hs ----------------
+            for (int l = gtid; l < P.np; l += nthreads) {
+                const double* h = P.Hll + (size_t)l * 6;
+                const double d00 = h[0] + lambda, d01 = h[1], d02 = h[2], d11 = h[3] + lambda, d12 = h[4], d22 = h[5] + lambda;
+                const double c00 = d11 * d22 - d12 * d12, c01 = d12 * d02 - d01 * d22, c02 = d01 * d12 - d11 * d02;
+                const double det = d00 * c00 + d01 * c01 + d02 * c02;
+                const double id = 1.0 / det;
+                double* Di = P.Dinv + (size_t)l * 6;
+                const double i00 = c00 * id, i01 = c01 * id, i02 = c02 * id;
+                const double i11 = (d00 * d22 - d02 * d02) * id, i12 = (d02 * d01 - d00 * d12) * id, i22 = (d00 * d11 - d01 * d01) * id;
+                Di[0] = i00; Di[1] = i01; Di[2] = i02; Di[3] = i11; Di[4] = i12; Di[5] = i22;
+                const double* g = P.bl + (size_t)l * 3;
+                double* d = P.db + (size_t)l * 3;
+                d[0] = i00 * g[0] + i01 * g[1] + i02 * g[2];
+                d[1] = i01 * g[0] + i11 * g[1] + i12 * g[2];
+                d[2] = i02 * g[0] + i12 * g[1] + i22 * g[2];
+            }
+            for (size_t i = gtid; i < (size_t)P.dimP * P.dimP; i += nthreads) P.Hs[i] = 0.0;
+            grid.sync();
+            // ---------------- S1: Schur complement rows ----------------
+            for (int c1 = blockIdx.x; c1 < P.nf; c1 += G) {
+                double* row = smem;               // [nf][36]
+                double* bacc = smem + (size_t)P.nf * 36; // [6]
+                for (int i = tid; i < P.nf * 36 + 6; i += kLbaThreads) smem[i] = 0.0;
+                __syncthreads();
+                const int s = P.cam_start[c1], e_end = P.cam_start[c1 + 1];
+                for (int k = s + tid; k < e_end; k += kLbaThreads) {
+                    const int e1 = P.cam_edges[k];
+                    const int l = P.ept[e1];
+                    const double* B1 = P.Hpl + (size_t)e1 * 18;
+                    const double* Di = P.Dinv + (size_t)l * 6;
+                    const double* d = P.db + (size_t)l * 3;
+                    double BD[18];
+#pragma unroll
+                    for (int a = 0; a < 6; a++) {
+                        const double b0 = B1[a * 3], b1 = B1[a * 3 + 1], b2 = B1[a * 3 + 2];
+                        BD[a * 3] = b0 * Di[0] + b1 * Di[1] + b2 * Di[2];
+                        BD[a * 3 + 1] = b0 * Di[1] + b1 * Di[3] + b2 * Di[4];
+                        BD[a * 3 + 2] = b0 * Di[2] + b1 * Di[4] + b2 * Di[5];
+                        atomicAdd(&bacc[a], -(b0 * d[0] + b1 * d[1] + b2 * d[2]));
+                    }
+                    const int ps = P.pt_start[l], pe = P.pt_start[l + 1];
+                    for (int k2 = ps; k2 < pe; k2++) {
+                        const int e2 = P.pt_edges[k2];
+                        const int c2 = P.cam_col[P.ecam[e2]];
+                        if (c2 < c1) continue; // fixed (-1) or already covered by the symmetric block
+                        const double* B2 = P.Hpl + (size_t)e2 * 18;
+                        double* dst = row + (size_t)c2 * 36;
+#pragma unroll
+                        for (int a = 0; a < 6; a++)
+#pragma unroll
+                            for (int b2 = 0; b2 < 6; b2++)
+                                atomicAdd(&dst[a * 6 + b2],
+                                          -(BD[a * 3] * B2[b2 * 3] + BD[a * 3 + 1] * B2[b2 * 3 + 1] + BD[a * 3 + 2] * B2[b2 * 3 + 2]));
+                    }
+                }
+                __syncthreads();
+                // lower-triangular block column: Hs[(6*c2+b), (6*c1+a)] = S(c1,c2)[a][b]
+                for (int i = tid; i < (P.nf - c1) * 36; i += kLbaThreads) {
+                    const int c2 = c1 + i / 36, a = (i % 36) / 6, b2 = i % 6;
+                    double v = row[(size_t)c2 * 36 + a * 6 + b2];
+                    if (c2 == c1) v += P.Hpp[(size_t)c1 * 36 + a * 6 + b2] + (a == b2 ? lambda : 0.0);
+                    P.Hs[(size_t)(6 * c2 + b2) * P.dimP + 6 * c1 + a] = v;
+                }
+                if (tid < 6) P.bs[6 * c1 + tid] = P.bp[6 * c1 + tid] + bacc[tid];
+                __syncthreads();
+            }
+            grid.sync();
+            // ---------------- C: reduced camera system on one CTA ----------------
+            if (blockIdx.x == 0) {
+                bool ok = true;
+                if (P.dimP > 0) ok = cta_cholesky_solve(P.dimP, P.Hs, P.bs, P.x, smem, &s_flag);
+                if (tid == 0) P.flags[0] = ok ? 1 : 0;
+            }
+            grid.sync();
+            const bool ok2 = P.flags[0] != 0;
+            // ---------------- B1: landmark back-substitution and update into the trial buffers ----------------
+            double scale_part = 0;
+            for (int l = gwarp; l < P.np; l += nwarps) {
+                double cl[3] = { 0, 0, 0 };
+                const int s = P.pt_start[l], e_end = P.pt_start[l + 1];
+                for (int k = s + lane; k < e_end; k += 32) {
+                    const int e = P.pt_edges[k];
+                    const int c1 = P.cam_col[P.ecam[e]];
+                    if (c1 < 0) continue;
+                    const double* B1 = P.Hpl + (size_t)e * 18;
+                    const double* xp = P.x + 6 * c1;
+#pragma unroll
+                    for (int a = 0; a < 6; a++) { cl[0] -= B1[a * 3] * xp[a]; cl[1] -= B1[a * 3 + 1] * xp[a]; cl[2] -= B1[a * 3 + 2] * xp[a]; }
+                }
+                cl[0] = warp_sum(cl[0]); cl[1] = warp_sum(cl[1]); cl[2] = warp_sum(cl[2]);
+                if (lane == 0) {
+                    const double* g = P.bl + (size_t)l * 3;
+                    const double* Di = P.Dinv + (size_t)l * 6;
+                    const double c0 = g[0] + cl[0], c1v = g[1] + cl[1], c2v = g[2] + cl[2];
+                    double xl[3];
+                    xl[0] = Di[0] * c0 + Di[1] * c1v + Di[2] * c2v;
+                    xl[1] = Di[1] * c0 + Di[3] * c1v + Di[4] * c2v;
+                    xl[2] = Di[2] * c0 + Di[4] * c1v + Di[5] * c2v;
+                    if (!ok2) { xl[0] = xl[1] = xl[2] = 0.0; }
+#pragma unroll
+                    for (int a = 0; a < 3; a++) {
+                        P.x[P.dimP + 3 * l + a] = xl[a];
+                        P.pts[trial][3 * l + a] = P.pts[cur][3 * l + a] + xl[a];
+                        scale_part += xl[a] * (lambda * xl[a] + g[a]);
+                    }
+                }
+            }
+            for (int c = gtid; c < P.nc; c += nthreads) {
+                const int cf = P.cam_col[c];
+                if (cf >= 0) {
+                    const double* xp = P.x + 6 * cf;
+                    se3_update(xp, P.camq[cur] + 4 * c, P.camt[cur] + 3 * c, P.camq[trial] + 4 * c, P.camt[trial] + 3 * c);
+#pragma unroll
+                    for (int a = 0; a < 6; a++) scale_part += xp[a] * (lambda * xp[a] + P.bp[6 * cf + a]);
+                } else {
+                    for (int a = 0; a < 4; a++) P.camq[trial][4 * c + a] = P.camq[cur][4 * c + a];
+                    for (int a = 0; a < 3; a++) P.camt[trial][3 * c + a] = P.camt[cur][3 * c + a];
+                }
+            }
+            {
+                double v[1] = { scale_part };
+                cta_sum<1>(v, warp_buf, red);
+                if (tid == 0) P.part[blockIdx.x * 4 + 1] = red[0];
+            }
+            grid.sync();
+            // ---------------- B2: errors at the trial estimate ----------------
+            double chi_t = 0;
+            for (int e = gtid; e < P.ne; e += nthreads) {
+                double xc[3], r[2];
+                edge_residual(P, trial, e, xc, r, nullptr);
+                P.err[2 * e] = r[0]; P.err[2 * e + 1] = r[1];
+                const double om = (double)P.einfo[e];
+                chi_t += huber_rho0(P, r[0] * (om * r[0]) + r[1] * (om * r[1]));
+            }
+            {
+                double v[1] = { chi_t };
+                cta_sum<1>(v, warp_buf, red);
+                if (tid == 0) P.part[blockIdx.x * 4 + 0] = red[0];
+            }
+            grid.sync();
+            double tempChi = 0, scale = 0;
+            for (int b2 = 0; b2 < G; b2++) { tempChi += P.part[b2 * 4 + 0]; scale += P.part[b2 * 4 + 1]; }
+            if (!ok2) tempChi = 1.7976931348623157e308;
+            rho = currentChi - tempChi;
+            scale += 1e-3;
+            rho /= scale;
+            if (rho > 0 && isfinite(tempChi)) {
+                double alpha = 1. - pow((2 * rho - 1), 3.0);
+                alpha = fmin(alpha, 2. / 3.);
+                lambda *= fmax(1. / 3., alpha);
+                ni = 2;
+                currentChi = tempChi;
+                cur = trial; // discardTop: the trial buffers become the estimate
+            } else {
+                lambda *= ni;
+                ni *= 2; // pop: keep `cur`
+            }
+            qmax++;
+            trials++;
+            aborted = agree_abort();
+        } while (rho < 0 && qmax < 10 && !aborted);
+        done++;
+        last_chi = currentChi;
+        if (qmax == 10 || rho == 0) stop = true;
+        else {
+            if ((iniChi - currentChi) * 1e3 < iniChi) nBad++;
+            else nBad = 0;
+            if (nBad >= 3) stop = true;
+        }
+        if (aborted) stop = true;
+    }
+    // ---------------- outlier test and write-back (O3/src/Optimizer.cc:1313-1386) ----------------
+    for (int e = gtid; e < P.ne; e += nthreads) {
+        const double om = (double)P.einfo[e];
+        const double r0 = P.err[2 * e], r1 = P.err[2 * e + 1];
+        const double chi = r0 * (om * r0) + r1 * (om * r1);
+        double xc[3], r[2];
+        edge_residual(P, cur, e, xc, r, nullptr);
+        if (P.out_chi2) P.out_chi2[e] = chi;
+        P.out_bad[e] = (chi > 5.991 || !(xc[2] > 0.0)) ? 1 : 0;
+    }
+    for (int c = gtid; c < P.nc; c += nthreads) {
+        for (int a = 0; a < 4; a++) P.out_camq[4 * c + a] = (float)P.camq[cur][4 * c + a];
+        for (int a = 0; a < 3; a++) P.out_camt[3 * c + a] = (float)P.camt[cur][3 * c + a];
+    }
+    for (int i = gtid; i < P.np * 3; i += nthreads) P.out_pts[i] = (float)P.pts[cur][i];
+    if (gtid == 0) {
+        P.out_stats[0] = done; P.out_stats[1] = trials; P.out_stats[2] = first_chi; P.out_stats[3] = last_chi;
+    }
+}
+
+} // namespace
+
+struct dvm_lba {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int max_free = 0;
+    int grid = 0;
+    size_t smem_bytes = 0;
+    uint8_t* d_buf = nullptr; size_t d_cap = 0;
+    uint8_t* h_buf = nullptr; size_t h_cap = 0;
+    int* h_abort = nullptr; int* d_abort = nullptr; // mapped pinned
+    float last_ms = 0;
+};
+
+static void lba_free(dvm_lba* h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaFree(h->d_buf);
+    if (h->h_buf) cudaFreeHost(h->h_buf);
+    if (h->h_abort) cudaFreeHost(h->h_abort);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+extern "C" {
+
+int dvm_lba_create(dvm_lba** out, int device, int max_free_cameras)
+{
+    DVM_REQUIRE(out != nullptr, "null output handle");
+    *out = nullptr;
+    DVM_REQUIRE(max_free_cameras >= 1 && max_free_cameras <= 128, "max_free_cameras must be in 1..128");
+    int rc = select_device(device);
+    if (rc != DVM_OK) return rc;
+    dvm_lba* h = new dvm_lba;
+    h->device = device;
+    h->max_free = max_free_cameras;
+#define DVM_LCREATE(call)                                                                  \
+    do {                                                                                   \
+        cudaError_t e__ = (call);                                                          \
+        if (e__ != cudaSuccess) {                                                          \
+            set_error("%s failed in dvm_lba_create: %s", #call, cudaGetErrorString(e__));  \
+            lba_free(h);                                                                   \
+            return DVM_ERR_CUDA;                                                           \
+        }                                                                                  \
+    } while (0)
+    DVM_LCREATE(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    DVM_LCREATE(cudaEventCreate(&h->ev0));
+    DVM_LCREATE(cudaEventCreate(&h->ev1));
+    DVM_LCREATE(cudaHostAlloc(&h->h_abort, sizeof(int), cudaHostAllocMapped));
+    *h->h_abort = 0;
+    DVM_LCREATE(cudaHostGetDevicePointer(&h->d_abort, h->h_abort, 0));
+    // shared memory: max(Schur row [nf*36+6], Cholesky panel [n*kNB] + diag [kNB*(kNB+1)]) doubles
+    const size_t n = (size_t)6 * max_free_cameras;
+    h->smem_bytes = std::max((size_t)max_free_cameras * 36 + 6, n * kNB + (size_t)kNB * (kNB + 1)) * sizeof(double);
+    DVM_REQUIRE(h->smem_bytes <= 227 * 1024, "max_free_cameras needs more shared memory than one SM has");
+    DVM_LCREATE(cudaFuncSetAttribute(lba_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+    int sms = 0, per_sm = 0;
+    DVM_LCREATE(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    DVM_LCREATE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lba_kernel, kLbaThreads, h->smem_bytes));
+    DVM_REQUIRE(per_sm >= 1, "lba kernel does not fit on an SM");
+    h->grid = sms; // one persistent CTA per SM
+#undef DVM_LCREATE
+    *out = h;
+    return DVM_OK;
+}
+
+void dvm_lba_destroy(dvm_lba* h) { lba_free(h); }
+
+float dvm_lba_last_kernel_ms(const dvm_lba* h) { return h ? h->last_ms : -1.f; }
+
+int dvm_local_ba(dvm_lba* h, int nc, float* cam_q, float* cam_t, const uint8_t* cam_fixed, int np, float* pts, int ne,
+                 const int32_t* edge_cam, const int32_t* edge_pt, const float* edge_obs, const float* edge_inv_sigma2,
+                 const float* K, int iterations, const volatile int* abort_flag, double* edge_chi2, uint8_t* edge_bad,
+                 double* stats, int* iters_done)
+{
+    DVM_REQUIRE(h != nullptr && iters_done != nullptr, "null argument");
+    *iters_done = -1;
+    if (stats) stats[0] = stats[1] = stats[2] = stats[3] = 0;
+    DVM_REQUIRE(nc >= 0 && np >= 0 && ne >= 0 && iterations >= 0, "negative size");
+    DVM_REQUIRE(nc == 0 || (cam_q && cam_t && cam_fixed), "null camera arrays");
+    DVM_REQUIRE(np == 0 || pts, "null point array");
+    DVM_REQUIRE(ne == 0 || (edge_cam && edge_pt && edge_obs && edge_inv_sigma2 && edge_bad), "null edge arrays");
+    DVM_REQUIRE(K != nullptr, "null intrinsics");
+    // host-side structure building (the analogue of BlockSolver::buildStructure, block_solver.hpp:143-295)
+    std::vector<int> cam_col(nc, -1), free_cam;
+    int nfixed = 0;
+    for (int c = 0; c < nc; c++) {
+        if (cam_fixed[c]) nfixed++;
+        else { cam_col[c] = (int)free_cam.size(); free_cam.push_back(c); }
+    }
+    const int nf = (int)free_cam.size();
+    if (nfixed == 0) return DVM_OK;                 // "LBA aborted": no fixed keyframe (:1088-1091)
+    if (abort_flag && *abort_flag) return DVM_OK;   // :1306-1308
+    if (ne == 0 || nf + np == 0) return DVM_OK;
+    DVM_REQUIRE(nf <= h->max_free, "more free cameras than dvm_lba_create allowed");
+    for (int e = 0; e < ne; e++)
+        DVM_REQUIRE(edge_cam[e] >= 0 && edge_cam[e] < nc && edge_pt[e] >= 0 && edge_pt[e] < np, "edge index out of range");
+    std::vector<int> pt_start(np + 1, 0), pt_edges(ne), cam_start(nf + 1, 0), cam_edges;
+    for (int e = 0; e < ne; e++) pt_start[edge_pt[e] + 1]++;
+    for (int l = 0; l < np; l++) pt_start[l + 1] += pt_start[l];
+    {
+        std::vector<int> fill(pt_start.begin(), pt_start.end() - 1);
+        for (int e = 0; e < ne; e++) pt_edges[fill[edge_pt[e]]++] = e;
+    }
+    for (int e = 0; e < ne; e++)
+        if (cam_col[edge_cam[e]] >= 0) cam_start[cam_col[edge_cam[e]] + 1]++;
+    for (int c = 0; c < nf; c++) cam_start[c + 1] += cam_start[c];
+    cam_edges.resize(cam_start[nf] > 0 ? cam_start[nf] : 1);
+    {
+        std::vector<int> fill(cam_start.begin(), cam_start.end() - 1);
+        for (int e = 0; e < ne; e++) {
+            const int cf = cam_col[edge_cam[e]];
+            if (cf >= 0) cam_edges[fill[cf]++] = e;
+        }
+    }
+    DVM_CUDA(cudaSetDevice(h->device));
+    const int dimP = 6 * nf;
+    // ---- device layout ----
+    size_t off = 0;
+    auto take = [&](size_t bytes) { off = (off + 255) & ~(size_t)255; size_t o = off; off += bytes; return o; };
+    // uploaded block
+    const size_t o_camq = take((size_t)nc * 4 * 8), o_camt = take((size_t)nc * 3 * 8), o_pts = take((size_t)np * 3 * 8);
+    const size_t o_col = take((size_t)nc * 4), o_free = take((size_t)std::max(nf, 1) * 4);
+    const size_t o_ecam = take((size_t)ne * 4), o_ept = take((size_t)ne * 4), o_obs = take((size_t)ne * 8), o_info = take((size_t)ne * 4);
+    const size_t o_pst = take((size_t)(np + 1) * 4), o_ped = take((size_t)ne * 4);
+    const size_t o_cst = take((size_t)(nf + 1) * 4), o_ced = take(cam_edges.size() * 4);
+    const size_t upload_bytes = off;
+    // work block
+    const size_t o_camq1 = take((size_t)nc * 4 * 8), o_camt1 = take((size_t)nc * 3 * 8), o_pts1 = take((size_t)np * 3 * 8);
+    const size_t o_err = take((size_t)ne * 2 * 8), o_hpl = take((size_t)ne * 18 * 8);
+    const size_t o_hll = take((size_t)np * 6 * 8), o_bl = take((size_t)np * 3 * 8), o_dinv = take((size_t)np * 6 * 8), o_db = take((size_t)np * 3 * 8);
+    const size_t o_hpp = take((size_t)std::max(nf, 1) * 36 * 8), o_bp = take((size_t)std::max(dimP, 1) * 8);
+    const size_t o_hs = take((size_t)std::max(dimP * dimP, 1) * 8), o_bs = take((size_t)std::max(dimP, 1) * 8);
+    const size_t o_x = take((size_t)(dimP + np * 3 + 1) * 8);
+    const size_t o_part = take((size_t)h->grid * 4 * 8), o_flags = take(4 * 4);
+    // output block (contiguous, one D2H)
+    const size_t out_begin = (off + 255) & ~(size_t)255;
+    const size_t o_oq = take((size_t)nc * 4 * 4), o_ot = take((size_t)nc * 3 * 4), o_op = take((size_t)np * 3 * 4);
+    const size_t o_ochi = take((size_t)ne * 8), o_obad = take((size_t)ne), o_ostats = take(4 * 8);
+    const size_t total = off + 256;
+    if (total > h->d_cap) {
+        DVM_CUDA(cudaStreamSynchronize(h->stream));
+        cudaFree(h->d_buf); h->d_buf = nullptr;
+        if (h->h_buf) { cudaFreeHost(h->h_buf); h->h_buf = nullptr; }
+        const size_t cap = total + total / 4;
+        DVM_CUDA(cudaMalloc(&h->d_buf, cap));
+        DVM_CUDA(cudaHostAlloc(&h->h_buf, cap, cudaHostAllocDefault));
+        h->d_cap = h->h_cap = cap;
+    }
+    // ---- stage inputs (float -> double conversions as the reference's .cast<double>()) ----
+    uint8_t* hb = h->h_buf;
+    {
+        double* q = (double*)(hb + o_camq); double* t = (double*)(hb + o_camt); double* p = (double*)(hb + o_pts);
+        for (int c = 0; c < nc; c++) {
+            double x = cam_q[4 * c], y = cam_q[4 * c + 1], z = cam_q[4 * c + 2], w = cam_q[4 * c + 3];
+            if (w < 0) { x = -x; y = -y; z = -z; w = -w; }           // SE3Quat ctor: normalizeRotation()
+            const double n = std::sqrt(x * x + y * y + z * z + w * w);
+            q[4 * c] = x / n; q[4 * c + 1] = y / n; q[4 * c + 2] = z / n; q[4 * c + 3] = w / n;
+            for (int i = 0; i < 3; i++) t[3 * c + i] = cam_t[3 * c + i];
+        }
+        for (int i = 0; i < np * 3; i++) p[i] = pts[i];
+        memcpy(hb + o_col, cam_col.data(), (size_t)nc * 4);
+        memcpy(hb + o_free, free_cam.data(), (size_t)nf * 4);
+        memcpy(hb + o_ecam, edge_cam, (size_t)ne * 4);
+        memcpy(hb + o_ept, edge_pt, (size_t)ne * 4);
+        memcpy(hb + o_obs, edge_obs, (size_t)ne * 8);
+        memcpy(hb + o_info, edge_inv_sigma2, (size_t)ne * 4);
+        memcpy(hb + o_pst, pt_start.data(), (size_t)(np + 1) * 4);
+        memcpy(hb + o_ped, pt_edges.data(), (size_t)ne * 4);
+        memcpy(hb + o_cst, cam_start.data(), (size_t)(nf + 1) * 4);
+        memcpy(hb + o_ced, cam_edges.data(), cam_edges.size() * 4);
+    }
+    DVM_CUDA(cudaMemcpyAsync(h->d_buf, hb, upload_bytes, cudaMemcpyHostToDevice, h->stream));
+    uint8_t* db = h->d_buf;
+    LbaDev P;
+    memset(&P, 0, sizeof(P));
+    P.nc = nc; P.nf = nf; P.np = np; P.ne = ne; P.dimP = dimP; P.iterations = iterations;
+    P.fx = K[0]; P.fy = K[1]; P.cx = K[2]; P.cy = K[3];
+    P.delta = (double)(float)std::sqrt(5.991); // const float thHuberMono = sqrt(5.991), :1178
+    P.dsqr = P.delta * P.delta;
+    P.camq[0] = (double*)(db + o_camq); P.camq[1] = (double*)(db + o_camq1);
+    P.camt[0] = (double*)(db + o_camt); P.camt[1] = (double*)(db + o_camt1);
+    P.pts[0] = (double*)(db + o_pts); P.pts[1] = (double*)(db + o_pts1);
+    P.cam_col = (const int*)(db + o_col); P.free_cam = (const int*)(db + o_free);
+    P.ecam = (const int*)(db + o_ecam); P.ept = (const int*)(db + o_ept);
+    P.eobs = (const float*)(db + o_obs); P.einfo = (const float*)(db + o_info);
+    P.pt_start = (const int*)(db + o_pst); P.pt_edges = (const int*)(db + o_ped);
+    P.cam_start = (const int*)(db + o_cst); P.cam_edges = (const int*)(db + o_ced);
+    P.err = (double*)(db + o_err); P.Hpl = (double*)(db + o_hpl); P.Hll = (double*)(db + o_hll);
+    P.bl = (double*)(db + o_bl); P.Dinv = (double*)(db + o_dinv); P.db = (double*)(db + o_db);
+    P.Hpp = (double*)(db + o_hpp); P.bp = (double*)(db + o_bp); P.Hs = (double*)(db + o_hs); P.bs = (double*)(db + o_bs);
+    P.x = (double*)(db + o_x); P.part = (double*)(db + o_part); P.flags = (int*)(db + o_flags);
+    P.out_camq = (float*)(db + o_oq); P.out_camt = (float*)(db + o_ot); P.out_pts = (float*)(db + o_op);
+    P.out_chi2 = (double*)(db + o_ochi); P.out_bad = db + o_obad; P.out_stats = (double*)(db + o_ostats);
+    *h->h_abort = 0;
+    P.abort_flag = abort_flag ? h->d_abort : nullptr;
+    DVM_CUDA(cudaMemsetAsync(db + o_flags, 0, 16, h->stream));
+    DVM_CUDA(cudaMemsetAsync(db + o_err, 0, (size_t)ne * 2 * 8, h->stream));
+    void* args[] = { &P };
+    DVM_CUDA(cudaEventRecord(h->ev0, h->stream));
+    DVM_CUDA(cudaLaunchCooperativeKernel((void*)lba_kernel, dim3(h->grid), dim3(kLbaThreads), args, h->smem_bytes, h->stream));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    DVM_CUDA(cudaEventRecord(h->ev1, h->stream));
+    const size_t out_bytes = off - out_begin;
+    DVM_CUDA(cudaMemcpyAsync(hb + out_begin, db + out_begin, out_bytes, cudaMemcpyDeviceToHost, h->stream));
+    if (abort_flag) { // mirror the caller's pbStopFlag into mapped memory while the kernel runs
+        while (cudaEventQuery(h->ev1) == cudaErrorNotReady)
+            if (*abort_flag) *h->h_abort = 1;
+    }
+    DVM_CUDA(cudaStreamSynchronize(h->stream));
+    DVM_CUDA(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+    const double* ost = (const double*)(hb + o_ostats);
+    const float* oq = (const float*)(hb + o_oq);
+    const float* ot = (const float*)(hb + o_ot);
+    for (int c = 0; c < nc; c++) {
+        if (cam_col[c] < 0) continue; // only optimised keyframes are written back
+        for (int i = 0; i < 4; i++) cam_q[4 * c + i] = oq[4 * c + i];
+        for (int i = 0; i < 3; i++) cam_t[3 * c + i] = ot[3 * c + i];
+    }
+    memcpy(pts, hb + o_op, (size_t)np * 3 * 4);
+    if (edge_chi2) memcpy(edge_chi2, hb + o_ochi, (size_t)ne * 8);
+    memcpy(edge_bad, hb + o_obad, (size_t)ne);
+    if (stats) for (int i = 0; i < 4; i++) stats[i] = ost[i];
+    *iters_done = (int)ost[0];
+    if (!std::isfinite(ost[3])) { set_error("local BA produced a non-finite chi2"); return DVM_ERR_NUMERIC; }
+    return DVM_OK;
+}
+
+} // extern "C"

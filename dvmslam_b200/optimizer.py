@@ -1,0 +1,66 @@
+"""Python mirror of Optimizer::LocalBundleAdjustment (O3/include/Optimizer.h:56-57) over the C-ABI."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from ._lib import check, lib
+
+_vp = C.c_void_p
+_ip = C.POINTER(C.c_int)
+
+
+def _c(a, dt):
+    return np.ascontiguousarray(a, dt)
+
+
+class LocalBA:
+    """One solver context per agent/GPU (dvm_lba)."""
+
+    def __init__(self, max_free_cameras: int = 64, device: int = 0):
+        self.L = lib()
+        L = self.L
+        L.dvm_lba_create.argtypes = [C.POINTER(_vp), C.c_int, C.c_int]
+        L.dvm_lba_destroy.argtypes = [_vp]
+        L.dvm_lba_destroy.restype = None
+        L.dvm_local_ba.argtypes = [_vp, C.c_int, _vp, _vp, _vp, C.c_int, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, C.c_int,
+                                   _vp, _vp, _vp, _vp, _ip]
+        L.dvm_lba_last_kernel_ms.argtypes = [_vp]
+        L.dvm_lba_last_kernel_ms.restype = C.c_float
+        self.h = _vp()
+        check(L.dvm_lba_create(C.byref(self.h), device, max_free_cameras))
+
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            self.L.dvm_lba_destroy(self.h)
+            self.h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def LocalBundleAdjustment(self, cam_q, cam_t, cam_fixed, pts, edge_cam, edge_pt, edge_obs, edge_w, K, iterations=10,
+                              abort=None):
+        q, t = _c(cam_q, np.float32).copy(), _c(cam_t, np.float32).copy()
+        p = _c(pts, np.float32).copy()
+        fx = _c(cam_fixed, np.uint8)
+        ec, ep = _c(edge_cam, np.int32), _c(edge_pt, np.int32)
+        eo, ew = _c(edge_obs, np.float32), _c(edge_w, np.float32)
+        ne = len(ec)
+        chi2 = np.zeros(max(ne, 1), np.float64)
+        bad = np.zeros(max(ne, 1), np.uint8)
+        stats = np.zeros(4, np.float64)
+        iters = C.c_int()
+        ab = _c([abort], np.int32) if abort is not None else None
+        check(self.L.dvm_local_ba(self.h, len(fx), q.ctypes.data, t.ctypes.data, fx.ctypes.data, len(p), p.ctypes.data,
+                                  ne, ec.ctypes.data, ep.ctypes.data, eo.ctypes.data, ew.ctypes.data,
+                                  _c(K, np.float32).ctypes.data, iterations, ab.ctypes.data if ab is not None else None,
+                                  chi2.ctypes.data, bad.ctypes.data, stats.ctypes.data, C.byref(iters)))
+        return dict(cam_q=q, cam_t=t, pts=p, chi2=chi2[:ne], bad=bad[:ne], iters=int(stats[0]), trials=int(stats[1]),
+                    chi_first=stats[2], chi_last=stats[3], rc=iters.value, kernel_ms=self.kernel_ms())
+
+    def kernel_ms(self) -> float:
+        return float(self.L.dvm_lba_last_kernel_ms(self.h))

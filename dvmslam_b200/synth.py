@@ -183,3 +183,80 @@ def tracking_case(stream: "PlaneStream", k: int, extract, n_local: int = 4000, s
                 outlier=outlier, obs_pos=obs_pos, Rcw_prior=Rp, tcw_prior=tp, Rcw_true=Rcw, tcw_true=tcw,
                 K=np.array(stream.K, np.float32), map_Xw=Xm, map_desc=md[sel].copy(), map_octave=mk["octave"][sel].copy(),
                 bounds=(0.0, 0.0, float(stream.w), float(stream.h)))
+
+
+def ba_scene(n_free: int = 50, n_fixed: int = 10, n_points: int = 5000, seed: int = 0, K=RPI_K, w: int = 1280,
+             h: int = 720, max_obs: int = 12, pix_sigma: float = 1.0, outlier_frac: float = 0.05,
+             pose_noise=(0.02, np.deg2rad(0.5)), point_noise: float = 0.05):
+    """Config C4: cameras on a 12 m circle looking inward, points uniform in a 6 m cube,
+    every point observed by up to `max_obs` of the cameras that see it, pixel noise sigma*1.2^octave with
+    octave ~ U{0..7}, gross outliers, perturbed initial poses/points.  Returns flat float32 arrays in the
+    layout dvm_local_ba takes; cameras [0, n_free) are free, the rest fixed."""
+    rng = np.random.default_rng(seed)
+    fx, fy, cx, cy = K
+    nc = n_free + n_fixed
+    ang = np.sort(rng.uniform(0, 2 * np.pi, nc))
+    rng.shuffle(ang)
+    Rs, ts = [], []
+    for a in ang:
+        C = np.array([6.0 * np.cos(a), rng.uniform(-0.5, 0.5), 6.0 * np.sin(a)])
+        z = -C / np.linalg.norm(C)                      # look at the origin
+        x = np.cross(np.array([0.0, 1.0, 0.0]), z)
+        x /= np.linalg.norm(x)
+        y = np.cross(z, x)
+        Rcw = np.stack([x, y, z], 0)
+        Rs.append(Rcw)
+        ts.append(-Rcw @ C)
+    P = rng.uniform(-3.0, 3.0, (n_points, 3))
+    e_cam, e_pt, e_obs, e_w = [], [], [], []
+    for j in range(n_points):
+        vis = []
+        for c in range(nc):
+            Xc = Rs[c] @ P[j] + ts[c]
+            if Xc[2] < 0.5:
+                continue
+            u, v = fx * Xc[0] / Xc[2] + cx, fy * Xc[1] / Xc[2] + cy
+            if 0 <= u < w and 0 <= v < h:
+                vis.append((c, u, v))
+        if len(vis) > max_obs:
+            idx = rng.choice(len(vis), max_obs, replace=False)
+            vis = [vis[i] for i in sorted(idx)]
+        for c, u, v in vis:
+            octv = int(rng.integers(0, 8))
+            s = pix_sigma * 1.2 ** octv
+            du, dv = rng.normal(0, s, 2)
+            if rng.random() < outlier_frac:
+                du, dv = rng.uniform(-50, 50, 2)
+            e_cam.append(c)
+            e_pt.append(j)
+            e_obs.append((u + du, v + dv))
+            e_w.append(np.float32(1.0) / (np.float32(1.2) ** octv) ** 2)
+    # drop points nobody sees (they would make Hll singular, which the reference never builds)
+    e_pt = np.array(e_pt, np.int32)
+    seen = np.unique(e_pt)
+    remap = -np.ones(n_points, np.int64)
+    remap[seen] = np.arange(len(seen))
+    e_pt = remap[e_pt].astype(np.int32)
+    P = P[seen]
+    q = np.zeros((nc, 4), np.float32)
+    t = np.zeros((nc, 3), np.float32)
+    q_true = np.zeros((nc, 4))
+    t_true = np.zeros((nc, 3))
+    for c in range(nc):
+        q_true[c], t_true[c] = quat_from_R(Rs[c]), ts[c]
+        R, tt = Rs[c], ts[c]
+        if c < n_free:
+            wv = rng.normal(0, 1, 3)
+            wv *= pose_noise[1] / np.linalg.norm(wv)
+            th = np.linalg.norm(wv)
+            Kx = np.array([[0, -wv[2], wv[1]], [wv[2], 0, -wv[0]], [-wv[1], wv[0], 0]])
+            dR = np.eye(3) + np.sin(th) / th * Kx + (1 - np.cos(th)) / th ** 2 * Kx @ Kx
+            R = dR @ R
+            tt = tt + rng.normal(0, pose_noise[0] / np.sqrt(3), 3)
+        q[c], t[c] = quat_from_R(R), tt
+    fixed = np.zeros(nc, np.uint8)
+    fixed[n_free:] = 1
+    pts = (P + rng.normal(0, point_noise / np.sqrt(3), P.shape)).astype(np.float32)
+    return dict(cam_q=q, cam_t=t, cam_fixed=fixed, pts=pts, edge_cam=np.array(e_cam, np.int32), edge_pt=e_pt,
+                edge_obs=np.array(e_obs, np.float32), edge_w=np.array(e_w, np.float32), K=np.array(K, np.float32),
+                q_true=q_true, t_true=t_true, pts_true=P)

@@ -187,6 +187,36 @@ DVM_API int dvm_pose_optimization(dvm_frame* ctx, float* pose_q, float* pose_t, 
                                   const float* Xw, const float* kp_xy, const float* inv_sigma2, uint8_t* outlier,
                                   int* n_inliers, int* stats);
 
+/* ------------------------------------------------------------------------------------------------
+ * Optimizer::LocalBundleAdjustment   (O3/src/Optimizer.cc:1030-1387, mono observations)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct dvm_lba dvm_lba;
+
+/* One solver context per agent/GPU; buffers grow on demand.  max_free_cameras bounds the reduced
+ * camera system (6 * max_free_cameras unknowns, dense). */
+DVM_API int dvm_lba_create(dvm_lba** out, int device, int max_free_cameras);
+DVM_API void dvm_lba_destroy(dvm_lba* h);
+
+/* The flattened local window that LocalBundleAdjustment assembles (O3/src/Optimizer.cc:1033-1304):
+ *   cam_q[nc*4] (x,y,z,w) / cam_t[nc*3]: keyframe poses Tcw as float (KeyFrame::GetPose), in/out;
+ *   cam_fixed[nc]: 1 for lFixedCameras and for the map's initial keyframe (vSE3->setFixed);
+ *   pts[np*3]: MapPoint::GetWorldPos as float, in/out;
+ *   one mono observation per edge: edge_cam, edge_pt (indices into the arrays above), edge_obs
+ *   (kpUn.pt), edge_inv_sigma2 (mvInvLevelSigma2[octave]);  K = fx, fy, cx, cy.
+ * Runs optimizer.optimize(iterations) (the reference passes 10) of g2o's Levenberg-Marquardt with the
+ * Schur complement, entirely on the GPU.  abort_flag (may be NULL) is the reference's pbStopFlag: it
+ * is checked before starting and polled between LM iterations and trials.
+ * Outputs: updated cam_q/cam_t (free cameras) and pts as float; edge_chi2[ne] (may be NULL);
+ * edge_bad[ne] = chi2 > 5.991 || depth <= 0, i.e. the observations the caller must erase
+ * (:1313-1329); stats[4] (may be NULL) = {LM iterations, LM trials, initial robust chi2, final robust
+ * chi2}.  *iters_done = -1 when the call was a no-op (no fixed camera, abort already set). */
+DVM_API int dvm_local_ba(dvm_lba* h, int nc, float* cam_q, float* cam_t, const uint8_t* cam_fixed, int np, float* pts,
+                         int ne, const int32_t* edge_cam, const int32_t* edge_pt, const float* edge_obs,
+                         const float* edge_inv_sigma2, const float* K, int iterations, const volatile int* abort_flag,
+                         double* edge_chi2, uint8_t* edge_bad, double* stats, int* iters_done);
+/* Device time of the last dvm_local_ba kernel in milliseconds (CUDA events on the solver's stream). */
+DVM_API float dvm_lba_last_kernel_ms(const dvm_lba* h);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,60 @@
+"""Self-checks of the local-BA oracle (it has no upstream fixtures to pin against):
+finite-difference Jacobians, zero-noise convergence, monotone chi2, no-op conditions."""
+import numpy as np
+
+from dvmslam_b200 import synth
+from oracle.lba import edge_error_perturbed, edge_jacobians, local_ba
+
+
+def _args(S):
+    return (S["cam_q"], S["cam_t"], S["cam_fixed"], S["pts"], S["edge_cam"], S["edge_pt"], S["edge_obs"], S["edge_w"], S["K"])
+
+
+def test_jacobians_match_finite_differences():
+    S = synth.ba_scene(8, 2, 200, seed=1)
+    rng = np.random.default_rng(0)
+    for e in rng.choice(len(S["edge_cam"]), 20, replace=False):
+        q, t, X = S["cam_q"][S["edge_cam"][e]], S["cam_t"][S["edge_cam"][e]], S["pts"][S["edge_pt"][e]]
+        A, B = edge_jacobians(q, t, X, S["K"])
+        obs = S["edge_obs"][e]
+        h = 1e-6
+        Bn, An = np.zeros((2, 6)), np.zeros((2, 3))
+        for k in range(6):
+            d = np.zeros(6); d[k] = h
+            Bn[:, k] = (edge_error_perturbed(q, t, X, S["K"], obs, d, np.zeros(3)) -
+                        edge_error_perturbed(q, t, X, S["K"], obs, -d, np.zeros(3))) / (2 * h)
+        for k in range(3):
+            d = np.zeros(3); d[k] = h
+            An[:, k] = (edge_error_perturbed(q, t, X, S["K"], obs, np.zeros(6), d) -
+                        edge_error_perturbed(q, t, X, S["K"], obs, np.zeros(6), -d)) / (2 * h)
+        assert np.abs(B - Bn).max() < 1e-5 * max(1.0, np.abs(B).max())
+        assert np.abs(A - An).max() < 1e-5 * max(1.0, np.abs(A).max())
+
+
+def test_zero_noise_scene_converges():
+    S = synth.ba_scene(10, 3, 400, seed=2, pix_sigma=0.0, outlier_frac=0.0)
+    r = local_ba(*_args(S))
+    assert r["chi_last"] < 1e-6 * r["chi_first"]
+    assert np.abs(r["cam_t"] - S["t_true"]).max() < 1e-4
+    assert np.median(np.abs(r["pts"] - S["pts_true"]).max(1)) < 1e-4  # (points seen once keep their depth ambiguity)
+    assert r["bad"].sum() == 0
+
+
+def test_noisy_scene_reduces_chi2_and_flags_outliers():
+    S = synth.ba_scene(12, 4, 600, seed=3)
+    r = local_ba(*_args(S))
+    assert r["chi_last"] < r["chi_first"] and r["iters"] >= 2 and r["trials"] >= r["iters"]
+    assert 0.02 < r["bad"].mean() < 0.25
+    assert np.abs(r["cam_t"] - S["t_true"]).max() < np.abs(S["cam_t"] - S["t_true"]).max()
+    fixed = S["cam_fixed"].astype(bool)
+    assert np.array_equal(r["cam_q"][fixed], S["cam_q"][fixed]) and np.array_equal(r["cam_t"][fixed], S["cam_t"][fixed])
+
+
+def test_noop_conditions():
+    S = synth.ba_scene(6, 2, 100, seed=4)
+    a = list(_args(S))
+    a[2] = np.zeros_like(S["cam_fixed"])          # no fixed keyframe -> "LBA aborted"
+    r = local_ba(*a)
+    assert r["rc"] == -1 and np.array_equal(r["pts"], S["pts"])
+    r = local_ba(*_args(S), abort=1)              # pbStopFlag already set
+    assert r["rc"] == -1 and np.array_equal(r["cam_t"], S["cam_t"])
