@@ -1,39 +1,10 @@
 // track_capi.cu -- C-ABI of the Frame grid, the projection matchers and PoseOptimization.
 // Host-array entry points upload their flat inputs, run the kernels on the frame's stream and
 // read the results back (synchronous, like the reference's calls).
-#include "track_kernels.cuh"
+#include "track_internal.cuh"
 #include <vector>
 
 using namespace dvm;
-
-struct dvm_frame {
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    bool own_stream = false;
-    cudaEvent_t ev = nullptr;
-    int cap = 0;
-    FrameDev dev;
-    // device storage
-    dvm_keypoint* d_kps = nullptr;
-    uint8_t* d_desc = nullptr;
-    int* d_n = nullptr;
-    int* d_cell_start = nullptr;
-    int* d_cell_items = nullptr;
-    // matcher / optimiser scratch, grown on demand
-    uint8_t* d_in = nullptr;   // uploaded inputs
-    size_t in_cap = 0;
-    uint8_t* h_in = nullptr;   // pinned staging for uploads
-    size_t h_in_cap = 0;
-    MatchScratch ms;
-    int q_cap = 0;
-    int* d_cur_mp = nullptr;   // [cap + 8]: cur_mp, then {nmatches}
-    double* d_err = nullptr;
-    int err_cap = 0;
-    uint8_t* h_out = nullptr;  // pinned read-back
-    size_t h_out_cap = 0;
-    int last_rounds = 0;
-    int host_n = 0;
-};
 
 static void frame_free(dvm_frame* f)
 {
@@ -50,7 +21,7 @@ static void frame_free(dvm_frame* f)
     delete f;
 }
 
-static int ensure_query_cap(dvm_frame* f, int nq)
+int dvm_frame_ensure_query_cap(dvm_frame* f, int nq)
 {
     if (nq <= f->q_cap) return DVM_OK;
     const int cap = nq + nq / 4 + 256;
@@ -66,7 +37,7 @@ static int ensure_query_cap(dvm_frame* f, int nq)
     return DVM_OK;
 }
 
-static int ensure_bytes(dvm_frame* f, size_t in_bytes, size_t out_bytes)
+int dvm_frame_ensure_bytes(dvm_frame* f, size_t in_bytes, size_t out_bytes)
 {
     if (in_bytes > f->in_cap) {
         DVM_CUDA(cudaStreamSynchronize(f->stream));
@@ -223,7 +194,7 @@ int dvm_frame_features_in_area(dvm_frame* f, float x, float y, float r, int min_
 {
     DVM_REQUIRE(f != nullptr && n_out != nullptr && cap >= 0, "bad argument");
     DVM_CUDA(cudaSetDevice(f->device));
-    int rc = ensure_bytes(f, 0, (size_t)(f->cap + 8) * sizeof(int));
+    int rc = dvm_frame_ensure_bytes(f, 0, (size_t)(f->cap + 8) * sizeof(int));
     if (rc != DVM_OK) return rc;
     int* d_out = f->d_cur_mp;
     launch_features_in_area(f->dev, x, y, r, min_level, max_level, d_out, f->cap, d_out + f->cap, f->stream);
@@ -277,11 +248,12 @@ int dvm_match_by_projection_last(dvm_frame* cur, const float* Rcw, const float* 
     DVM_REQUIRE(last_n == 0 || (has_mp && outlier && Xw && mp_desc && mp_obs_pos && last_octave && last_angle), "null last-frame arrays");
     DVM_CUDA(cudaSetDevice(cur->device));
     const size_t n = (size_t)last_n;
-    int rc = ensure_bytes(cur, Packer::need({ n, n, n * 12, n * 32, n, n * 4, n * 4 }), (size_t)(cur->cap + 8) * sizeof(int));
+    int rc = dvm_frame_ensure_bytes(cur, Packer::need({ n, n, n * 12, n * 32, n, n * 4, n * 4 }), (size_t)(cur->cap + 8) * sizeof(int));
     if (rc != DVM_OK) return rc;
-    rc = ensure_query_cap(cur, last_n);
+    rc = dvm_frame_ensure_query_cap(cur, last_n);
     if (rc != DVM_OK) return rc;
     MatchLastArgs a;
+    memset(&a, 0, sizeof(a));
     memcpy(a.R, Rcw, sizeof(a.R)); memcpy(a.t, tcw, sizeof(a.t)); memcpy(a.K, K, sizeof(a.K));
     a.last_n = last_n; a.th = th; a.check_ori = check_orientation;
     Packer p(cur);
@@ -310,12 +282,13 @@ int dvm_match_by_projection_map(dvm_frame* cur, int m, const float* proj_x, cons
     DVM_REQUIRE(m == 0 || (proj_x && proj_y && level && view_cos && mp_desc && mp_obs_pos), "null map-point arrays");
     DVM_CUDA(cudaSetDevice(cur->device));
     const size_t n = (size_t)m, nc = (size_t)cur->host_n;
-    int rc = ensure_bytes(cur, Packer::need({ n * 4, n * 4, n * 4, n * 4, n * 32, n, nc }), (size_t)(cur->cap + 8) * sizeof(int));
+    int rc = dvm_frame_ensure_bytes(cur, Packer::need({ n * 4, n * 4, n * 4, n * 4, n * 32, n, nc }), (size_t)(cur->cap + 8) * sizeof(int));
     if (rc != DVM_OK) return rc;
-    rc = ensure_query_cap(cur, m);
+    rc = dvm_frame_ensure_query_cap(cur, m);
     if (rc != DVM_OK) return rc;
     for (int i = 0; i < m; i++) DVM_REQUIRE(level[i] >= 0 && level[i] < cur->dev.nlevels, "predicted level out of range");
     MatchMapArgs a;
+    memset(&a, 0, sizeof(a));
     a.m = m; a.th = th; a.nnratio = nnratio;
     Packer p(cur);
     a.projX = p.add(proj_x, n);
@@ -341,7 +314,7 @@ int dvm_pose_optimization(dvm_frame* ctx, float* pose_q, float* pose_t, const fl
     DVM_CUDA(cudaSetDevice(ctx->device));
     const size_t sn = (size_t)n;
     // device layout: inputs | pose[7] | result[4] | outlier[n]
-    int rc = ensure_bytes(ctx, Packer::need({ sn * 12, sn * 8, sn * 4, 7 * 4, 4 * 4, sn }), sn + 2048);
+    int rc = dvm_frame_ensure_bytes(ctx, Packer::need({ sn * 12, sn * 8, sn * 4, 7 * 4, 4 * 4, sn }), sn + 2048);
     if (rc != DVM_OK) return rc;
     if (n > ctx->err_cap) {
         DVM_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -369,7 +342,7 @@ int dvm_pose_optimization(dvm_frame* ctx, float* pose_q, float* pose_t, const fl
     launch_pose_opt(a, ctx->stream);
     DVM_CUDA(cudaGetLastError());
     const size_t out_bytes = p.off - out_begin;
-    rc = ensure_bytes(ctx, 0, out_bytes);
+    rc = dvm_frame_ensure_bytes(ctx, 0, out_bytes);
     if (rc != DVM_OK) return rc;
     DVM_CUDA(cudaMemcpyAsync(ctx->h_out, ctx->d_in + out_begin, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
     DVM_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -167,14 +167,26 @@ match_last_kernel(FrameDev cur, MatchLastArgs a, MatchScratch s, int* __restrict
     __shared__ int histo[kHistoLength];
     __shared__ int s_ind[3], s_events, s_bad;
     const int tid = threadIdx.x;
+    if (a.guard && *a.guard >= 20) return; // enough matches at th: the wider retry is not run
     const int ncur = min(*cur.n, cur.cap);
-    const int nq = a.last_n;
+    const int nq = a.n_ptr ? *a.n_ptr : a.last_n;
+    if (a.pose) { // pose prior held on the device
+        float Rm[9];
+        quat_to_R_f32(a.pose, Rm);
+        for (int i = 0; i < 9; i++) a.R[i] = Rm[i];
+        a.t[0] = a.pose[4]; a.t[1] = a.pose[5]; a.t[2] = a.pose[6];
+    }
+    auto mp_of = [&](int i) { return a.mp_index ? a.mp_index[i] : (a.has_mp[i] ? i : -1); };
+    auto desc_of = [&](int i) { return a.mp_desc + (size_t)(a.mp_index ? a.mp_index[i] : i) * 32; };
+    auto obs_of = [&](int i) { return a.obs_pos ? a.obs_pos[i] != 0 : true; };
+    auto angle_of = [&](int i) { return a.last_kps ? a.last_kps[i].angle : a.angle[i]; };
 
     // project every last-frame map point with the current pose prior
     for (int i = tid; i < nq; i += kMatchThreads) {
         int lv = -1;
-        if (a.has_mp[i] && !a.outlier[i]) {
-            const float X = a.Xw[3 * i], Y = a.Xw[3 * i + 1], Z = a.Xw[3 * i + 2];
+        const int mi = mp_of(i);
+        if (mi >= 0 && !a.outlier[i]) {
+            const float X = a.Xw[3 * mi], Y = a.Xw[3 * mi + 1], Z = a.Xw[3 * mi + 2];
             const float xc = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a.R[0], X), __fmul_rn(a.R[1], Y)), __fmul_rn(a.R[2], Z)), a.t[0]);
             const float yc = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a.R[3], X), __fmul_rn(a.R[4], Y)), __fmul_rn(a.R[5], Z)), a.t[1]);
             const float zc = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a.R[6], X), __fmul_rn(a.R[7], Y)), __fmul_rn(a.R[8], Z)), a.t[2]);
@@ -183,7 +195,7 @@ match_last_kernel(FrameDev cur, MatchLastArgs a, MatchScratch s, int* __restrict
                 const float u = __fadd_rn(__fdiv_rn(__fmul_rn(a.K[0], xc), zc), a.K[2]);
                 const float v = __fadd_rn(__fdiv_rn(__fmul_rn(a.K[1], yc), zc), a.K[3]);
                 if (!(u < cur.minX || u > cur.maxX) && !(v < cur.minY || v > cur.maxY)) {
-                    const int oct = a.octave[i];
+                    const int oct = a.last_kps ? a.last_kps[i].octave : a.octave[i];
                     s.pu[i] = u; s.pv[i] = v;
                     s.pr[i] = __fmul_rn(a.th, cur.scale[oct]);
                     lv = ((oct - 1) << 16) | ((oct + 1) & 0xffff);
@@ -205,7 +217,7 @@ match_last_kernel(FrameDev cur, MatchLastArgs a, MatchScratch s, int* __restrict
             const int lv = s.plevels[i];
             if (lv == -1) continue;
             uint32_t d[8];
-            load_desc(d, a.mp_desc + (size_t)i * 32);
+            load_desc(d, desc_of(i));
             int bestDist = 256, bestIdx = -1;
             walk_area(cur, s.pu[i], s.pv[i], s.pr[i], lv >> 16, (int)(short)(lv & 0xffff), [&](int idx, int) {
                 if (claim_prev[idx] < i) return; // taken by an earlier map point with observations
@@ -221,7 +233,7 @@ match_last_kernel(FrameDev cur, MatchLastArgs a, MatchScratch s, int* __restrict
         __syncthreads();
         for (int i = tid; i < nq; i += kMatchThreads) {
             const int k = s.choice[i];
-            if (k >= 0 && a.obs_pos[i]) atomicMin(&claim_next[k], i);
+            if (k >= 0 && obs_of(i)) atomicMin(&claim_next[k], i);
         }
         __syncthreads();
         int* t = claim_prev; claim_prev = claim_next; claim_next = t;
@@ -240,7 +252,7 @@ match_last_kernel(FrameDev cur, MatchLastArgs a, MatchScratch s, int* __restrict
         if (k < 0) continue;
         atomicMax(&owner[k], i);
         atomicAdd(&s_events, 1);
-        if (a.check_ori) atomicAdd(&histo[rot_bin(a.angle[i], cur.kps[k].angle)], 1);
+        if (a.check_ori) atomicAdd(&histo[rot_bin(angle_of(i), cur.kps[k].angle)], 1);
     }
     __syncthreads();
     if (tid == 0) {
@@ -253,7 +265,7 @@ match_last_kernel(FrameDev cur, MatchLastArgs a, MatchScratch s, int* __restrict
         for (int i = tid; i < nq; i += kMatchThreads) {
             const int k = s.choice[i];
             if (k < 0) continue;
-            const int bin = rot_bin(a.angle[i], cur.kps[k].angle);
+            const int bin = rot_bin(angle_of(i), cur.kps[k].angle);
             if (bin != s_ind[0] && bin != s_ind[1] && bin != s_ind[2]) {
                 nulled[k] = 1;
                 atomicAdd(&s_bad, 1);
@@ -278,8 +290,11 @@ match_map_kernel(FrameDev cur, MatchMapArgs a, MatchScratch s, int* __restrict__
     __shared__ int s_events;
     const int tid = threadIdx.x;
     const int ncur = min(*cur.n, cur.cap);
-    const int nq = a.m;
+    const int nq = a.m_ptr ? *a.m_ptr : a.m;
     const bool bFactor = a.th != 1.0f;
+    auto desc_of = [&](int i) { return a.mp_desc + (size_t)(a.q_index ? a.q_index[i] : i) * 32; };
+    auto obs_of = [&](int i) { return a.obs_pos ? a.obs_pos[i] != 0 : true; };
+    auto blocked = [&](int k) { return a.cur_map ? a.cur_map[k] >= 0 : (a.cur_blocked && a.cur_blocked[k]); };
     for (int i = tid; i < nq; i += kMatchThreads) {
         const int lvl = a.level[i];
         float r = a.view_cos[i] > 0.998f ? 2.5f : 4.0f; // RadiusByViewingCos
@@ -289,7 +304,7 @@ match_map_kernel(FrameDev cur, MatchMapArgs a, MatchScratch s, int* __restrict__
     }
     int* claim_prev = s.claim_a;
     int* claim_next = s.claim_b;
-    for (int k = tid; k < ncur; k += kMatchThreads) claim_prev[k] = (a.cur_blocked && a.cur_blocked[k]) ? -1 : kNoClaim;
+    for (int k = tid; k < ncur; k += kMatchThreads) claim_prev[k] = blocked(k) ? -1 : kNoClaim;
     if (tid == 0) s_events = 0;
     __syncthreads();
 
@@ -299,7 +314,7 @@ match_map_kernel(FrameDev cur, MatchMapArgs a, MatchScratch s, int* __restrict__
         for (int i = tid; i < nq; i += kMatchThreads) {
             const int lvl = a.level[i];
             uint32_t d[8];
-            load_desc(d, a.mp_desc + (size_t)i * 32);
+            load_desc(d, desc_of(i));
             int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
             walk_area(cur, a.projX[i], a.projY[i], s.pr[i], lvl - 1, lvl, [&](int idx, int oct) {
                 if (claim_prev[idx] < i) return; // held by a map point with observations
@@ -323,11 +338,11 @@ match_map_kernel(FrameDev cur, MatchMapArgs a, MatchScratch s, int* __restrict__
         }
         rounds++;
         if (!__syncthreads_or(changed)) break;
-        for (int k = tid; k < ncur; k += kMatchThreads) claim_next[k] = (a.cur_blocked && a.cur_blocked[k]) ? -1 : kNoClaim;
+        for (int k = tid; k < ncur; k += kMatchThreads) claim_next[k] = blocked(k) ? -1 : kNoClaim;
         __syncthreads();
         for (int i = tid; i < nq; i += kMatchThreads) {
             const int k = s.choice[i];
-            if (k >= 0 && a.obs_pos[i]) atomicMin(&claim_next[k], i);
+            if (k >= 0 && obs_of(i)) atomicMin(&claim_next[k], i);
         }
         __syncthreads();
         int* t = claim_prev; claim_prev = claim_next; claim_next = t;
@@ -525,7 +540,16 @@ __global__ void __launch_bounds__(kPoseThreads, 1) pose_opt_kernel(PoseOptArgs a
     __shared__ double warp_buf[kPoseWarps * 28];
     __shared__ double red[28];
     const int tid = threadIdx.x;
-    const int n = a.n;
+    const int n = a.n_ptr ? min(*a.n_ptr, a.n) : a.n;
+    auto edge_valid = [&](int k) { return a.map_index ? a.map_index[k] >= 0 : (a.valid ? a.valid[k] != 0 : true); };
+    auto edge_X = [&](int k) { return a.Xw + 3 * (size_t)(a.map_index ? a.map_index[k] : k); };
+    auto edge_info = [&](int k) { return (double)(a.kps ? a.inv_sigma2_table[a.kps[k].octave] : a.inv_sigma2[k]); };
+    auto edge_err = [&](const PoseCam& c, const SE3d& T, int k, double e[2], double xc[3]) {
+        float o[2];
+        if (a.kps) { o[0] = a.kps[k].x; o[1] = a.kps[k].y; }
+        else { o[0] = a.kp_xy[2 * k]; o[1] = a.kp_xy[2 * k + 1]; }
+        pose_edge_error(c, T, edge_X(k), o, e, xc);
+    };
     PoseCam cam;
     cam.fx = a.K[0]; cam.fy = a.K[1]; cam.cx = a.K[2]; cam.cy = a.K[3];
     cam.delta = (double)(float)sqrt(5.991);
@@ -535,7 +559,7 @@ __global__ void __launch_bounds__(kPoseThreads, 1) pose_opt_kernel(PoseOptArgs a
     // kept in a.outlier's byte until the end
     int nedges_local = 0;
     for (int k = tid; k < n; k += kPoseThreads) {
-        const bool valid = a.valid ? a.valid[k] != 0 : true;
+        const bool valid = edge_valid(k);
         a.outlier[k] = valid ? 0 : 4; // 4 = not an edge
         nedges_local += valid;
     }
@@ -568,9 +592,9 @@ __global__ void __launch_bounds__(kPoseThreads, 1) pose_opt_kernel(PoseOptArgs a
                     if (st & 5) continue;
                     nact++;
                     double e[2], xc[3];
-                    pose_edge_error(cam, T, a.Xw + 3 * k, a.kp_xy + 2 * k, e, xc);
+                    edge_err(cam, T, k, e, xc);
                     a.err[2 * k] = e[0]; a.err[2 * k + 1] = e[1];
-                    const double om = (double)a.inv_sigma2[k];
+                    const double om = edge_info(k);
                     const double chi = pose_chi2(e, om);
                     const bool robust = !(st & 2);
                     acc[27] += robust ? huber_rho0(cam, chi) : chi;
@@ -631,9 +655,9 @@ __global__ void __launch_bounds__(kPoseThreads, 1) pose_opt_kernel(PoseOptArgs a
                         const int st = a.outlier[k];
                         if (st & 5) continue;
                         double e[2], xc[3];
-                        pose_edge_error(cam, T, a.Xw + 3 * k, a.kp_xy + 2 * k, e, xc);
+                        edge_err(cam, T, k, e, xc);
                         a.err[2 * k] = e[0]; a.err[2 * k + 1] = e[1];
-                        const double c2 = pose_chi2(e, (double)a.inv_sigma2[k]);
+                        const double c2 = pose_chi2(e, edge_info(k));
                         chi[0] += (st & 2) ? c2 : huber_rho0(cam, c2);
                     }
                     block_sum<1>(chi, warp_buf, red);
@@ -672,8 +696,8 @@ __global__ void __launch_bounds__(kPoseThreads, 1) pose_opt_kernel(PoseOptArgs a
                 int st = a.outlier[k];
                 if (st & 4) continue;
                 double e[2] = { a.err[2 * k], a.err[2 * k + 1] };
-                if (st & 1) { double xc[3]; pose_edge_error(cam, T, a.Xw + 3 * k, a.kp_xy + 2 * k, e, xc); a.err[2 * k] = e[0]; a.err[2 * k + 1] = e[1]; }
-                const float chi2 = (float)pose_chi2(e, (double)a.inv_sigma2[k]);
+                if (st & 1) { double xc[3]; edge_err(cam, T, k, e, xc); a.err[2 * k] = e[0]; a.err[2 * k + 1] = e[1]; }
+                const float chi2 = (float)pose_chi2(e, edge_info(k));
                 if (chi2 > 5.991f) { st |= 1; bad[0] += 1; }
                 else st &= ~1;
                 if (round == 2) st |= 2;

@@ -38,6 +38,12 @@ struct MatchLastArgs {
     const float* angle;      // LastFrame.mvKeysUn[i].angle
     float th;
     int check_ori;
+    // ---- optional device-resident forms (dvm_tracker): all may be NULL ----
+    const int* n_ptr;              // last_n read from the device
+    const int* mp_index;           // per last keypoint: index into Xw / mp_desc (map arrays), -1 = no map point
+    const dvm_keypoint* last_kps;  // octave / angle source instead of the two arrays
+    const float* pose;             // qx,qy,qz,qw,tx,ty,tz on the device instead of R,t
+    const int* guard;              // skip the whole search if *guard >= 20 (the 2*th retry, Tracking.cc:2614)
 };
 
 // SearchByProjection(F, vpMapPoints): flat in-view map points (device pointers)
@@ -51,6 +57,10 @@ struct MatchMapArgs {
     const uint8_t* obs_pos;
     float th, nnratio;
     const uint8_t* cur_blocked; // [cur n] or nullptr
+    // ---- optional device-resident forms ----
+    const int* m_ptr;           // m read from the device
+    const int* q_index;         // per query: index into mp_desc (map array)
+    const int* cur_map;         // blocked = cur_map[k] >= 0 (instead of cur_blocked)
 };
 
 struct MatchScratch {
@@ -75,6 +85,11 @@ struct PoseOptArgs {
     uint8_t* outlier;        // [n] out
     int* result;             // [4] out: n_inliers, n_edges, lm iterations, lm trials
     double* err;             // [n*2] scratch (the edges' _error)
+    // ---- optional device-resident forms: one potential edge per keypoint of a frame ----
+    const int* n_ptr;                // number of keypoints on the device
+    const int* map_index;            // [n] map point of keypoint k (-1 none); Xw then indexes the map array
+    const dvm_keypoint* kps;         // observation and octave source
+    float inv_sigma2_table[kTrackMaxLevels]; // mvInvLevelSigma2 (with kps)
 };
 
 void launch_grid_build(const FrameDev& f, cudaStream_t stream);
@@ -83,6 +98,22 @@ void launch_match_last(const FrameDev& cur, const MatchLastArgs& a, const MatchS
 void launch_match_map(const FrameDev& cur, const MatchMapArgs& a, const MatchScratch& s, int* cur_mp, int* nmatches,
                       cudaStream_t stream);
 void launch_pose_opt(const PoseOptArgs& a, cudaStream_t stream);
+// quaternion (x,y,z,w, float) -> row-major rotation matrix, Eigen's toRotationMatrix in float32 after
+// normalisation: the convention shared with oracle/track_oracle.cpp (trko_is_in_frustum)
+__device__ inline void quat_to_R_f32(const float* q_in, float R[9])
+{
+    const float n = __fsqrt_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(q_in[0], q_in[0]), __fmul_rn(q_in[1], q_in[1])),
+                                                   __fmul_rn(q_in[2], q_in[2])), __fmul_rn(q_in[3], q_in[3])));
+    const float x = __fdiv_rn(q_in[0], n), y = __fdiv_rn(q_in[1], n), z = __fdiv_rn(q_in[2], n), w = __fdiv_rn(q_in[3], n);
+    const float tx = __fmul_rn(2.f, x), ty = __fmul_rn(2.f, y), tz = __fmul_rn(2.f, z);
+    const float twx = __fmul_rn(tx, w), twy = __fmul_rn(ty, w), twz = __fmul_rn(tz, w);
+    const float txx = __fmul_rn(tx, x), txy = __fmul_rn(ty, x), txz = __fmul_rn(tz, x);
+    const float tyy = __fmul_rn(ty, y), tyz = __fmul_rn(tz, y), tzz = __fmul_rn(tz, z);
+    R[0] = __fsub_rn(1.f, __fadd_rn(tyy, tzz)); R[1] = __fsub_rn(txy, twz); R[2] = __fadd_rn(txz, twy);
+    R[3] = __fadd_rn(txy, twz); R[4] = __fsub_rn(1.f, __fadd_rn(txx, tzz)); R[5] = __fsub_rn(tyz, twx);
+    R[6] = __fsub_rn(txz, twy); R[7] = __fadd_rn(tyz, twx); R[8] = __fsub_rn(1.f, __fadd_rn(txx, tyy));
+}
+
 void launch_features_in_area(const FrameDev& f, float x, float y, float r, int minLevel, int maxLevel, int* out, int cap,
                              int* n_out, cudaStream_t stream);
 

@@ -260,3 +260,50 @@ def ba_scene(n_free: int = 50, n_fixed: int = 10, n_points: int = 5000, seed: in
     return dict(cam_q=q, cam_t=t, cam_fixed=fixed, pts=pts, edge_cam=np.array(e_cam, np.int32), edge_pt=e_pt,
                 edge_obs=np.array(e_obs, np.float32), edge_w=np.array(e_w, np.float32), K=np.array(K, np.float32),
                 q_true=q_true, t_true=t_true, pts_true=P)
+
+
+class OrbitStream(PlaneStream):
+    """Bounded variant of the C2 stream for long runs: the camera sways over the same textured plane
+    (x = A sin, yaw = B sin, period `period` frames) so that frame `period` equals frame 0 and the
+    resident frame set of bench.py can be cycled.  Peak per-frame motion is 2 cm / 0.2 deg like C2."""
+
+    def __init__(self, w: int = 1280, h: int = 720, seed: int = 0, K=RPI_K, depth: float = 3.0, period: int = 320):
+        super().__init__(w, h, seed, K, depth)
+        self.period = period
+        self.amp_t = 0.02 * period / (2 * np.pi)
+        self.amp_yaw = np.deg2rad(0.2) * period / (2 * np.pi)
+
+    def pose(self, k: int):
+        ph = 2 * np.pi * k / self.period
+        yaw = self.amp_yaw * np.sin(ph + 1.0)
+        c, s = np.cos(yaw), np.sin(yaw)
+        Rwc = np.array([[c, 0, s], [0, 1, 0], [-s, 0, c]])
+        twc = np.array([self.amp_t * np.sin(ph), 0.05 * np.sin(2 * ph), 0.1 * np.sin(ph + 0.5)])
+        Rcw = Rwc.T
+        return Rcw, -Rcw @ twc
+
+
+def plane_map(stream: "PlaneStream", extract, keyframes, scale_factors, max_points: int = 6000, seed: int = 0):
+    """Ground-truth local map for the tracking-only workload: keypoints of the given keyframes lifted to
+    the plane; descriptor = first observation; normal / distance limits as MapPoint::UpdateNormalAndDepth
+    computes them (O3/src/MapPoint.cc:469-520) for a single observation."""
+    rng = np.random.default_rng(seed)
+    Xs, Ds, Ns, mind, maxd = [], [], [], [], []
+    nlev = len(scale_factors)
+    for k in keyframes:
+        kps, desc, _ = extract(stream.frame(k))
+        X = backproject_to_plane(stream, k, np.stack([kps["x"], kps["y"]], 1).astype(np.float64))
+        Rcw, tcw = stream.pose(k)
+        Ow = (-Rcw.T @ tcw).astype(np.float32)
+        PC = X - Ow[None, :]
+        dist = np.linalg.norm(PC, axis=1).astype(np.float32)
+        mx = dist * scale_factors[kps["octave"]]
+        Xs.append(X); Ds.append(desc); Ns.append(PC / dist[:, None])
+        maxd.append(mx); mind.append(mx / scale_factors[nlev - 1])
+    X, D, N = np.concatenate(Xs), np.concatenate(Ds), np.concatenate(Ns)
+    mind, maxd = np.concatenate(mind), np.concatenate(maxd)
+    if len(X) > max_points:
+        sel = np.sort(rng.permutation(len(X))[:max_points])
+        X, D, N, mind, maxd = X[sel], D[sel], N[sel], mind[sel], maxd[sel]
+    return dict(xw=X.astype(np.float32), desc=np.ascontiguousarray(D), normal=N.astype(np.float32),
+                min_dist=mind.astype(np.float32), max_dist=maxd.astype(np.float32))

@@ -134,3 +134,94 @@ def PoseOptimization(frame: Frame, q, t, K, Xw, kp_xy, inv_sigma2):
                                   Xw.ctypes.data, kp_xy.ctypes.data, w.ctypes.data, out.ctypes.data, C.byref(ninl),
                                   stats.ctypes.data))
     return ninl.value, q, t, out[:n], tuple(int(s) for s in stats)
+
+
+def is_in_frustum(frame: Frame, q, t, K, xw, normal, min_dist, max_dist, skip=None, cos_limit=0.5):
+    """Frame::isInFrustum + MapPoint::PredictScale over a batch -> (in_view, projX, projY, level, viewCos)."""
+    L = lib()
+    _bind(L)
+    L.dvm_frame_is_in_frustum.argtypes = [_vp, _vp, _vp, _vp, C.c_int] + [_vp] * 5 + [C.c_float] + [_vp] * 5
+    xw, normal = _c(xw, np.float32), _c(normal, np.float32)
+    m = len(xw)
+    inv, px, py = np.zeros(max(m, 1), np.uint8), np.zeros(max(m, 1), np.float32), np.zeros(max(m, 1), np.float32)
+    lv, vc = np.zeros(max(m, 1), np.int32), np.zeros(max(m, 1), np.float32)
+    sk = _c(skip, np.uint8) if skip is not None else None
+    check(L.dvm_frame_is_in_frustum(frame.h, _c(q, np.float32).ctypes.data, _c(t, np.float32).ctypes.data,
+                                    _c(K, np.float32).ctypes.data, m, xw.ctypes.data, normal.ctypes.data,
+                                    _c(min_dist, np.float32).ctypes.data, _c(max_dist, np.float32).ctypes.data,
+                                    sk.ctypes.data if sk is not None else None, float(cos_limit), inv.ctypes.data,
+                                    px.ctypes.data, py.ctypes.data, lv.ctypes.data, vc.ctypes.data))
+    return inv[:m], px[:m], py[:m], lv[:m], vc[:m]
+
+
+class Tracker:
+    """dvm_tracker: ExtractORB -> Frame -> TrackWithMotionModel -> TrackLocalMap chained on the GPU."""
+
+    def __init__(self, extractor, K, bounds, world_map):
+        self.L = lib()
+        _bind(self.L)
+        L = self.L
+        L.dvm_tracker_create.argtypes = [C.POINTER(_vp), _vp, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp]
+        L.dvm_tracker_destroy.argtypes = [_vp]
+        L.dvm_tracker_destroy.restype = None
+        L.dvm_tracker_bootstrap.argtypes = [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _ip]
+        L.dvm_tracker_track.argtypes = [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_int, _vp, _vp]
+        L.dvm_tracker_result.argtypes = [_vp, _vp, _vp]
+        L.dvm_tracker_debug_matches.argtypes = [_vp, _vp, _vp, C.c_int, _ip]
+        self.ext = extractor
+        self.h = _vp()
+        m = world_map
+        self._keep = [_c(K, np.float32), _c(bounds, np.float32), _c(m["xw"], np.float32), _c(m["desc"], np.uint8),
+                      _c(m["normal"], np.float32), _c(m["min_dist"], np.float32), _c(m["max_dist"], np.float32)]
+        k = self._keep
+        check(L.dvm_tracker_create(C.byref(self.h), extractor.h, k[0].ctypes.data, k[1].ctypes.data, len(k[2]),
+                                   k[2].ctypes.data, k[3].ctypes.data, k[4].ctypes.data, k[5].ctypes.data,
+                                   k[6].ctypes.data))
+        self._pose = np.zeros(7, np.float32)
+        self._counts = np.zeros(4, np.int32)
+
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            self.L.dvm_tracker_destroy(self.h)
+            self.h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def bootstrap(self, img, q, t):
+        img = np.ascontiguousarray(img, np.uint8)
+        n = C.c_int()
+        check(self.L.dvm_tracker_bootstrap(self.h, img.ctypes.data, img.shape[1], img.shape[0], img.strides[0],
+                                           _c(q, np.float32).ctypes.data, _c(t, np.float32).ctypes.data, C.byref(n)))
+        return n.value
+
+    def track(self, img, prior_q=None, prior_t=None, sync=True):
+        """img: host uint8 array, or (device_ptr, width, height, stride) for an image already in HBM."""
+        if isinstance(img, tuple):
+            ptr, w, h, stride = img
+            dev = 1
+        else:
+            img = np.ascontiguousarray(img, np.uint8)
+            ptr, w, h, stride, dev = img.ctypes.data, img.shape[1], img.shape[0], img.strides[0], 0
+        pq = _c(prior_q, np.float32) if prior_q is not None else None
+        pt = _c(prior_t, np.float32) if prior_t is not None else None
+        check(self.L.dvm_tracker_track(self.h, _vp(ptr), dev, w, h, stride, pq.ctypes.data if pq is not None else None,
+                                       pt.ctypes.data if pt is not None else None, int(sync), self._pose.ctypes.data,
+                                       self._counts.ctypes.data))
+        if sync:
+            return self._pose[:4].copy(), self._pose[4:].copy(), tuple(int(c) for c in self._counts)
+        return None
+
+    def result(self):
+        check(self.L.dvm_tracker_result(self.h, self._pose.ctypes.data, self._counts.ctypes.data))
+        return self._pose[:4].copy(), self._pose[4:].copy(), tuple(int(c) for c in self._counts)
+
+    def debug_matches(self):
+        cap = self.ext.cap
+        cm, ol = np.zeros(cap, np.int32), np.zeros(cap, np.uint8)
+        n = C.c_int()
+        check(self.L.dvm_tracker_debug_matches(self.h, cm.ctypes.data, ol.ctypes.data, cap, C.byref(n)))
+        return cm[:n.value].copy(), ol[:n.value].copy()

@@ -188,6 +188,51 @@ DVM_API int dvm_pose_optimization(dvm_frame* ctx, float* pose_q, float* pose_t, 
                                   int* n_inliers, int* stats);
 
 /* ------------------------------------------------------------------------------------------------
+ * Per-frame tracker: the call order of Tracking::TrackWithMotionModel + TrackLocalMap
+ * (O3/src/Tracking.cc:2584-2666, 2668-2768, 3041-3106) with every operator above chained on the GPU.
+ * The pointer-graph state machine itself (keyframe decisions, relocalisation, map management) stays
+ * on the host, as in the reference; this object only removes the host round trips between
+ * ExtractORB -> Frame -> SearchByProjection(last) -> PoseOptimization -> isInFrustum /
+ * SearchByProjection(local map) -> PoseOptimization for a map snapshot resident in HBM.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct dvm_tracker dvm_tracker;
+
+/* map snapshot (the local map, flattened): world position, representative descriptor, mean viewing
+ * direction (GetNormal) and mfMinDistance / mfMaxDistance of each map point.  K = fx, fy, cx, cy;
+ * bounds = mnMinX, mnMinY, mnMaxX, mnMaxY.  The tracker launches on the extractor's stream. */
+DVM_API int dvm_tracker_create(dvm_tracker** out, dvm_orb* orb, const float* K, const float* bounds, int map_n,
+                               const float* map_xw, const uint8_t* map_desc, const float* map_normal,
+                               const float* map_min_dist, const float* map_max_dist);
+DVM_API void dvm_tracker_destroy(dvm_tracker* t);
+/* Bootstrap: extract `gray` (host image), set the frame's pose (q = x,y,z,w; t) and associate its
+ * keypoints with map points by projection + descriptor search around the given pose (what the
+ * reference's initialisation / relocalisation leaves behind: a last frame with map points). */
+DVM_API int dvm_tracker_bootstrap(dvm_tracker* t, const uint8_t* gray, int width, int height, int stride,
+                                  const float* pose_q, const float* pose_t, int* n_matched);
+/* Track one frame.  gray_is_device != 0: the image is already in HBM.  prior_q/prior_t: the pose
+ * prior mVelocity * mLastFrame.GetPose() computed by the caller, or NULL to let the tracker apply the
+ * same constant-velocity model on the device from its last two poses.  With sync == 0 the call only
+ * enqueues (results are read later with dvm_tracker_result); with sync != 0 it returns the pose
+ * (pose_out[7] = qx,qy,qz,qw,tx,ty,tz) and counts[4] = {keypoints, matches after
+ * TrackWithMotionModel, inliers of the first PoseOptimization, mnMatchesInliers}. */
+DVM_API int dvm_tracker_track(dvm_tracker* t, const uint8_t* gray, int gray_is_device, int width, int height,
+                              int stride, const float* prior_q, const float* prior_t, int sync, float* pose_out,
+                              int32_t* counts);
+DVM_API int dvm_tracker_result(dvm_tracker* t, float* pose_out, int32_t* counts);
+/* Current frame's association after the last track call, for parity tests: cur_map[n] = map point
+ * index per keypoint (-1 none), outlier[n] = mvbOutlier. */
+DVM_API int dvm_tracker_debug_matches(dvm_tracker* t, int32_t* cur_map, uint8_t* outlier, int cap, int* n_out);
+
+/* Frame::isInFrustum (O3/src/Frame.cc:575-636) + MapPoint::PredictScale (O3/src/MapPoint.cc:573-587)
+ * for a batch of map points, through the frame's device context.  pose q,t = the frame's Tcw (float).
+ * skip[m] != 0 marks points to leave out (mnLastFrameSeen == frame id, isBad).  Outputs per point:
+ * in_view, proj_x, proj_y, level, view_cos (as the reference stores them in the MapPoint). */
+DVM_API int dvm_frame_is_in_frustum(dvm_frame* f, const float* pose_q, const float* pose_t, const float* K, int m,
+                                    const float* xw, const float* normal, const float* min_dist,
+                                    const float* max_dist, const uint8_t* skip, float viewing_cos_limit,
+                                    uint8_t* in_view, float* proj_x, float* proj_y, int32_t* level, float* view_cos);
+
+/* ------------------------------------------------------------------------------------------------
  * Optimizer::LocalBundleAdjustment   (O3/src/Optimizer.cc:1030-1387, mono observations)
  * ---------------------------------------------------------------------------------------------- */
 typedef struct dvm_lba dvm_lba;

@@ -80,6 +80,22 @@ class FrameOracle:
         return n, cur_mp[:self.n]
 
 
+def is_in_frustum(q, t, K, bounds, nlevels, scale_factor, xw, normal, min_dist, max_dist, skip=None, cos_limit=0.5):
+    L = _L()
+    L.trko_is_in_frustum.argtypes = [_vp, _vp, _vp, _vp, C.c_int, C.c_float, C.c_int] + [_vp] * 5 + [C.c_float] + [_vp] * 5
+    xw, normal = _c(xw, np.float32), _c(normal, np.float32)
+    m = len(xw)
+    inv, px, py = np.zeros(max(m, 1), np.uint8), np.zeros(max(m, 1), np.float32), np.zeros(max(m, 1), np.float32)
+    lv, vc = np.zeros(max(m, 1), np.int32), np.zeros(max(m, 1), np.float32)
+    sk = _c(skip, np.uint8) if skip is not None else None
+    L.trko_is_in_frustum(_c(q, np.float32).ctypes.data, _c(t, np.float32).ctypes.data, _c(K, np.float32).ctypes.data,
+                         _c(bounds, np.float32).ctypes.data, nlevels, float(scale_factor), m, xw.ctypes.data,
+                         normal.ctypes.data, _c(min_dist, np.float32).ctypes.data, _c(max_dist, np.float32).ctypes.data,
+                         sk.ctypes.data if sk is not None else None, float(cos_limit), inv.ctypes.data, px.ctypes.data,
+                         py.ctypes.data, lv.ctypes.data, vc.ctypes.data)
+    return inv[:m], px[:m], py[:m], lv[:m], vc[:m]
+
+
 def descriptor_distance(a, b):
     return _L().trko_descriptor_distance(_c(a, np.uint8).ctypes.data, _c(b, np.uint8).ctypes.data)
 
@@ -96,3 +112,78 @@ def pose_optimization(q, t, K, Xw, kp_xy, inv_sigma2):
     r = L.trko_pose_optimization(q.ctypes.data, t.ctypes.data, _c(K, np.float32).ctypes.data, n, Xw.ctypes.data,
                                  kp_xy.ctypes.data, w.ctypes.data, out.ctypes.data, stats.ctypes.data)
     return r, q, t, out[:n], tuple(stats)
+
+
+class TrackerOracle:
+    """The per-frame chain of Tracking::TrackWithMotionModel + TrackLocalMap (O3/src/Tracking.cc:2584-2768,
+    3041-3106) composed from the oracle operators, for a map snapshot given as flat arrays.  Mirrors
+    dvm_tracker step by step so that the GPU pipeline can be compared frame by frame."""
+
+    def __init__(self, extract, tables, K, bounds, world_map):
+        self.extract, self.T, self.K, self.bounds, self.map = extract, tables, np.asarray(K, np.float32), bounds, world_map
+        self.last = None
+
+    @staticmethod
+    def _R(q):
+        q = np.asarray(q, np.float32)
+        n = np.float32(np.sqrt(np.float32(np.float32(np.float32(q[0] * q[0] + q[1] * q[1]) + q[2] * q[2]) + q[3] * q[3])))
+        x, y, z, w = (q / n).astype(np.float32)
+        f = np.float32
+        tx, ty, tz = f(2) * x, f(2) * y, f(2) * z
+        twx, twy, twz = tx * w, ty * w, tz * w
+        txx, txy, txz = tx * x, ty * x, tz * x
+        tyy, tyz, tzz = ty * y, tz * y, tz * z
+        return np.array([f(1) - (tyy + tzz), txy - twz, txz + twy, txy + twz, f(1) - (txx + tzz), tyz - twx,
+                         txz - twy, tyz + twx, f(1) - (txx + tyy)], np.float32)
+
+    def _local_map_search(self, F, q, t, cur_map, th, nnratio, seen):
+        M = self.map
+        inv, px, py, lv, vc = is_in_frustum(q, t, self.K, self.bounds, len(self.T["scale"]), self.T["scale"][1],
+                                            M["xw"], M["normal"], M["min_dist"], M["max_dist"], seen, 0.5)
+        qi = np.nonzero(inv)[0]
+        blocked = (cur_map >= 0).astype(np.uint8)
+        n, m2 = F.search_by_projection_map(px[qi], py[qi], lv[qi], vc[qi], M["desc"][qi], np.ones(len(qi), np.uint8), th,
+                                           nnratio, blocked)
+        out = cur_map.copy()
+        take = (out < 0) & (m2 >= 0)
+        out[take] = qi[m2[take]]
+        return out, n
+
+    def bootstrap(self, img, q, t):
+        kps, desc, _ = self.extract(img)
+        F = FrameOracle(kps, desc, self.bounds, self.T["scale"])
+        cur_map = np.full(len(kps), -1, np.int64)
+        cur_map, n = self._local_map_search(F, q, t, cur_map, 3.0, 0.8, np.zeros(len(self.map["xw"]), np.uint8))
+        self.last = dict(kps=kps, mp=cur_map, outlier=np.zeros(len(kps), np.uint8), q=np.asarray(q, np.float32),
+                         t=np.asarray(t, np.float32))
+        return n
+
+    def track(self, img, prior_q, prior_t):
+        M, L = self.map, self.last
+        kps, desc, _ = self.extract(img)
+        F = FrameOracle(kps, desc, self.bounds, self.T["scale"])
+        R = self._R(prior_q)
+        lm = L["mp"]
+        has = (lm >= 0).astype(np.uint8)
+        lidx = np.where(lm >= 0, lm, 0)
+        args = (R, prior_t, self.K, has, L["outlier"], M["xw"][lidx], M["desc"][lidx], np.ones(len(lm), np.uint8),
+                L["kps"]["octave"], L["kps"]["angle"])
+        nm, cur_mp = F.search_by_projection_last(*args, 15.0)
+        if nm < 20:
+            nm, cur_mp = F.search_by_projection_last(*args, 30.0)
+        cur_map = np.where(cur_mp >= 0, lm[np.where(cur_mp >= 0, cur_mp, 0)], -1).astype(np.int64)
+        idx = np.nonzero(cur_map >= 0)[0]
+        xy = np.stack([kps["x"], kps["y"]], 1)
+        w = self.T["inv_sigma2"][kps["octave"]]
+        r1, q1, t1, o1, _ = pose_optimization(prior_q, prior_t, self.K, M["xw"][cur_map[idx]], xy[idx], w[idx])
+        seen = np.zeros(len(M["xw"]), np.uint8)
+        seen[cur_map[idx]] = 1
+        cur_map[idx[o1 != 0]] = -1
+        cur_map, n2 = self._local_map_search(F, q1, t1, cur_map, 1.0, 0.8, seen)
+        idx = np.nonzero(cur_map >= 0)[0]
+        r2, q2, t2, o2, _ = pose_optimization(q1, t1, self.K, M["xw"][cur_map[idx]], xy[idx], w[idx])
+        outl = np.zeros(len(kps), np.uint8)
+        outl[idx] = o2
+        inl = int(((cur_map >= 0) & (outl == 0)).sum())
+        self.last = dict(kps=kps, mp=cur_map, outlier=outl, q=q2, t=t2)
+        return dict(q=q2, t=t2, counts=(len(kps), nm, r1, inl), cur_map=cur_map, outlier=outl)

@@ -520,6 +520,58 @@ int trko_search_by_projection_map(void* fcur, int M, const float* projX, const f
     return nmatches;
 }
 
+/* Frame::isInFrustum (mono branch, O3/src/Frame.cc:576-636) + MapPoint::PredictScale
+ * (O3/src/MapPoint.cc:573-587) over a batch.  Conventions fixed by this oracle: Rcw is the float
+ * rotation matrix of the (normalised) float quaternion, Eigen's toRotationMatrix formula; products are
+ * ((a*x + b*y) + c*z) + t; Ow = R^T * (-t); log() is taken in double and rounded to float. */
+void trko_is_in_frustum(const float* q_in, const float* t, const float* K, const float* bounds, int nlevels,
+                        float scaleFactor, int m, const float* xw, const float* normal, const float* min_dist,
+                        const float* max_dist, const uint8_t* skip, float cosLimit, uint8_t* in_view, float* px,
+                        float* py, int* level, float* viewCos)
+{
+    float q[4] = { q_in[0], q_in[1], q_in[2], q_in[3] };
+    const float qn = std::sqrt(((q[0] * q[0] + q[1] * q[1]) + q[2] * q[2]) + q[3] * q[3]);
+    for (int i = 0; i < 4; i++) q[i] = q[i] / qn;
+    float R[9];
+    {
+        const float tx = 2 * q[0], ty = 2 * q[1], tz = 2 * q[2];
+        const float twx = tx * q[3], twy = ty * q[3], twz = tz * q[3];
+        const float txx = tx * q[0], txy = ty * q[0], txz = tz * q[0];
+        const float tyy = ty * q[1], tyz = tz * q[1], tzz = tz * q[2];
+        R[0] = 1 - (tyy + tzz); R[1] = txy - twz; R[2] = txz + twy;
+        R[3] = txy + twz; R[4] = 1 - (txx + tzz); R[5] = tyz - twx;
+        R[6] = txz - twy; R[7] = tyz + twx; R[8] = 1 - (txx + tyy);
+    }
+    float Ow[3];
+    for (int i = 0; i < 3; i++) Ow[i] = (R[i] * (-t[0]) + R[3 + i] * (-t[1])) + R[6 + i] * (-t[2]);
+    const float logScale = (float)std::log((double)scaleFactor);
+    for (int k = 0; k < m; k++) {
+        in_view[k] = 0; px[k] = -1; py[k] = -1; level[k] = -1; viewCos[k] = 0;
+        if (skip && skip[k]) continue;
+        const float X = xw[3 * k], Y = xw[3 * k + 1], Z = xw[3 * k + 2];
+        const float xc = ((R[0] * X + R[1] * Y) + R[2] * Z) + t[0];
+        const float yc = ((R[3] * X + R[4] * Y) + R[5] * Z) + t[1];
+        const float zc = ((R[6] * X + R[7] * Y) + R[8] * Z) + t[2];
+        if (zc < 0.0f) continue;
+        const float u = K[0] * xc / zc + K[2];
+        const float v = K[1] * yc / zc + K[3];
+        if (u < bounds[0] || u > bounds[2]) continue;
+        if (v < bounds[1] || v > bounds[3]) continue;
+        px[k] = u; py[k] = v;
+        const float maxD = 1.2f * max_dist[k], minD = 0.8f * min_dist[k];
+        const float PO[3] = { X - Ow[0], Y - Ow[1], Z - Ow[2] };
+        const float dist = std::sqrt((PO[0] * PO[0] + PO[1] * PO[1]) + PO[2] * PO[2]);
+        if (dist < minD || dist > maxD) continue;
+        const float vc = ((PO[0] * normal[3 * k] + PO[1] * normal[3 * k + 1]) + PO[2] * normal[3 * k + 2]) / dist;
+        if (vc < cosLimit) continue;
+        const float ratio = max_dist[k] / dist;
+        int nScale = (int)std::ceil((float)std::log((double)ratio) / logScale);
+        if (nScale < 0) nScale = 0;
+        else if (nScale >= nlevels) nScale = nlevels - 1;
+        in_view[k] = 1; level[k] = nScale; viewCos[k] = vc;
+    }
+}
+
 /* Optimizer::PoseOptimization, mono observations only.
  * pose_q = (x,y,z,w) of Tcw.unit_quaternion(), pose_t = Tcw.translation() (float, in/out);
  * K = fx,fy,cx,cy (float); per correspondence: world point (float), undistorted keypoint (float),

@@ -153,3 +153,80 @@ def test_pose_optimization(world, k):
         assert r0 == r1 and np.array_equal(o0, o1), m
         assert np.abs(t0 - t1).max() < POSE_T_TOL and np.abs(q0 - q1).max() < POSE_Q_TOL, m
     F1.close()
+
+
+def test_is_in_frustum(world):
+    from dvmslam_b200.tracking import Frame, is_in_frustum
+    from oracle.track import is_in_frustum as frustum_oracle
+
+    S, T = world["S"], world["T"]
+    case = world["cases"][12]
+    rng = np.random.default_rng(0)
+    m = len(case["map_Xw"])
+    X = case["map_Xw"]
+    Ow = (-case["Rcw_true"].T @ case["tcw_true"]).astype(np.float32)
+    nrm = X - Ow
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    nrm += rng.normal(0, 0.6, nrm.shape).astype(np.float32)       # some fail the viewing-angle test
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    dist = np.linalg.norm(X - Ow, axis=1).astype(np.float32)
+    maxd = (dist * rng.uniform(0.6, 4.0, m)).astype(np.float32)   # some outside the scale-invariance range
+    mind = (maxd / T["scale"][7]).astype(np.float32)
+    skip = (rng.random(m) < 0.1).astype(np.uint8)
+    q = synth.quat_from_R(case["Rcw_prior"].astype(np.float64)).astype(np.float32)
+    F = Frame(64, T["scale"], T["inv_sigma2"])
+    F.assign(case["cur_kps"][:32], case["cur_desc"][:32], case["bounds"])
+    a = frustum_oracle(q, case["tcw_prior"], case["K"], case["bounds"], 8, T["scale"][1], X, nrm, mind, maxd, skip, 0.5)
+    b = is_in_frustum(F, q, case["tcw_prior"], case["K"], X, nrm, mind, maxd, skip, 0.5)
+    F.close()
+    assert 0.1 < a[0].mean() < 0.95
+    for x, y, name in zip(a, b, ("in_view", "projX", "projY", "level", "viewCos")):
+        assert np.array_equal(x, y), name
+
+
+def test_tracker_pipeline_matches_oracle_chain():
+    """ExtractORB -> Frame -> SearchByProjection(last) -> PoseOptimization -> isInFrustum +
+    SearchByProjection(map) -> PoseOptimization, eight consecutive frames: the device-resident chain
+    must reproduce the oracle chain's associations exactly and its poses within tolerance."""
+    from dvmslam_b200.extractor import ORBextractor
+    from dvmslam_b200.tracking import Tracker
+    from oracle.orb import OrbOracle
+    from oracle.track import TrackerOracle
+
+    S = synth.OrbitStream(seed=1, period=320)
+    orc = OrbOracle(2000)
+    T = orc.tables()
+    M = synth.plane_map(S, orc.extract, [0, 40, 80, 120, 160, 200, 240, 280], T["scale"], 6000)
+    bounds = (0.0, 0.0, 1280.0, 720.0)
+    t0 = TrackerOracle(orc.extract, T, S.K, bounds, M)
+    ext = ORBextractor(2000, 1.2, 8, 20, 7, max_width=1280, max_height=720)
+    t1 = Tracker(ext, S.K, bounds, M)
+    R, t = S.pose(0)
+    q = synth.quat_from_R(R).astype(np.float32)
+    n0 = t0.bootstrap(S.frame(0), q, t)
+    n1 = t1.bootstrap(S.frame(0), q, t)
+    assert n0 == n1 and n0 > 50
+    cm, ol = t1.debug_matches()
+    assert np.array_equal(cm, t0.last["mp"])
+    pq, pt = q, np.asarray(t, np.float32)
+    for k in range(1, 9):
+        img = S.frame(k)
+        r0 = t0.track(img, pq, pt)
+        q1, tt1, c1 = t1.track(img, pq, pt)
+        cm, ol = t1.debug_matches()
+        assert c1 == tuple(int(c) for c in r0["counts"]), (k, c1, r0["counts"])
+        assert np.array_equal(cm, r0["cur_map"]), k
+        assert np.array_equal(ol, r0["outlier"]), k
+        assert np.abs(tt1 - r0["t"]).max() < POSE_T_TOL and np.abs(q1 - r0["q"]).max() < POSE_Q_TOL, k
+        assert c1[3] > 800
+        Rk, tk = S.pose(k)
+        assert np.abs(tt1 - tk).max() < 5e-3
+        pq, pt = r0["q"], r0["t"]   # zero-velocity prior from the oracle's result (identical to ours within tol)
+    # free-running mode: constant-velocity prior on the device, no host sync between frames
+    for k in range(9, 17):
+        t1.track(S.frame(k), sync=False)
+    q1, tt1, c1 = t1.result()
+    Rk, tk = S.pose(16)
+    assert c1[3] > 800 and np.abs(tt1 - tk).max() < 5e-3
+    t1.close()
+    ext.close()
