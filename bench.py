@@ -4,13 +4,19 @@
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
   (N > 1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...)
 
-Workload (config C2 of BASELINE.json): one agent per GPU, a 1280x720 synthetic plane-sweep stream,
-2000 features per frame.  One "step" = one batch of FRAMES_PER_STEP consecutive frames pushed through
-the per-frame hot path.  `value` = frames/sec over all agents with the frames already resident in
-HBM (320 distinct frames = 295 MB per agent, larger than the 126 MB L2, cycled); `e2e` = the same
-frames through the reference-facing C-ABI call with pinned HOST buffers (H2D image copy and D2H
-result copy inside the timed region).  `--impl reference` times the CPU oracle (the restated
-reference path) on the host cores.  Prints ONE JSON line on rank 0.
+Workload (config C2 of BASELINE.json, "tracking only"): one agent per GPU, a 1280x720 synthetic
+stream over a textured plane, 2000 features per frame, a pre-built local map of 6000 points.  One
+"step" = one batch of FRAMES_PER_STEP consecutive frames, each pushed through the whole per-frame hot
+path in the reference's order: ExtractORB -> Frame grid -> SearchByProjection(last frame) ->
+PoseOptimization -> isInFrustum + SearchByProjection(local map) -> PoseOptimization.
+`value` = tracked frames/sec over all agents with the frames already resident in HBM (320 distinct
+frames = 281 MB per agent, larger than the 126 MB L2, cycled; constant-velocity prior computed on the
+device, no host synchronisation inside a step); `e2e` = the same frames through the C-ABI call with
+pinned HOST images, the pose and inlier counts read back every frame (H2D and D2H inside the timed
+region).  The line also carries `lba`: local-BA LM iterations/sec on config C4 (50 free + 10 fixed
+keyframes, ~4900 points, ~57k observations) through dvm_local_ba with host arrays.
+`--impl reference` times the CPU oracle (the restated reference path) on the host cores.
+Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
@@ -30,7 +36,7 @@ sys.path.insert(0, ROOT)
 W, H, NFEAT = 1280, 720, 2000
 FRAMES_PER_STEP = 64
 RESIDENT_FRAMES = 320
-METRIC = "frames/sec/agent tracked (ORB front end, 1280x720, 2000 features)"
+METRIC = "frames/sec/agent tracked (1280x720, 2000 features, tracking only) + local-BA iter/sec in `lba`"
 UNIT = "frames/s"
 WORKLOAD = "C2: single agent per GPU, 1280x720 synthetic stream, 2000 feats/frame"
 
@@ -100,29 +106,83 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_frames(seed: int, n: int) -> np.ndarray:
+MAP_KEYFRAMES = list(range(0, RESIDENT_FRAMES, 40))
+MAP_POINTS = 6000
+BOUNDS = (0.0, 0.0, float(W), float(H))
+
+
+def make_stream(seed: int):
     from dvmslam_b200 import synth
 
-    s = synth.PlaneStream(W, H, seed=seed)
+    return synth.OrbitStream(W, H, seed=seed, period=RESIDENT_FRAMES)
+
+
+def make_frames(seed: int, n: int, stream=None) -> np.ndarray:
+    s = stream or make_stream(seed)
     out = np.empty((n, H, W), np.uint8)
     for k in range(n):
         out[k] = s.frame(k)
     return out
 
 
+def lba_scene(seed: int = 0):
+    from dvmslam_b200 import synth
+
+    S = synth.ba_scene(50, 10, 5000, seed=seed)
+    return S, (S["cam_q"], S["cam_t"], S["cam_fixed"], S["pts"], S["edge_cam"], S["edge_pt"], S["edge_obs"], S["edge_w"], S["K"])
+
+
 # ------------------------------------------------------------------------------------ reference arm
 def _ref_worker(args):
+    """One CPU agent: builds its map, bootstraps, then tracks n_frames frames with the oracle chain."""
     seed, n_frames, reps = args
+    from dvmslam_b200 import synth
     from oracle.orb import OrbOracle
+    from oracle.track import TrackerOracle
 
-    frames = make_frames(seed, n_frames)
+    S = make_stream(seed)
     o = OrbOracle(NFEAT)
-    o.extract(frames[0])
-    t = time.perf_counter()
+    T = o.tables()
+    M = synth.plane_map(S, o.extract, MAP_KEYFRAMES, T["scale"], MAP_POINTS)
+    trk = TrackerOracle(o.extract, T, S.K, BOUNDS, M)
+    R, t = S.pose(0)
+    q = synth.quat_from_R(R).astype(np.float32)
+    frames = make_frames(seed, n_frames + 1, S)
+    trk.bootstrap(frames[0], q, t)
+    pq, pt = q, np.asarray(t, np.float32)
+    dt = 0.0
     for _ in range(reps):
-        for f in frames:
-            o.extract(f)
-    return time.perf_counter() - t, n_frames * reps
+        for k in range(1, n_frames + 1):
+            t0 = time.perf_counter()
+            r = trk.track(frames[k], pq, pt)
+            dt += time.perf_counter() - t0
+            pq, pt = r["q"], r["t"]
+    return dt, n_frames * reps
+
+
+def _lba_worker(args):
+    seed, reps = args
+    from oracle.lba import local_ba
+
+    _, a = lba_scene(seed)
+    its, dt = 0, 0.0
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        r = local_ba(*a)
+        dt += time.perf_counter() - t0
+        its += r["iters"]
+    return dt, its
+
+
+def cpu_lba_iters_per_sec(cores: int, reps: int = 1):
+    import multiprocessing as mp
+
+    if cores == 1:
+        dt, n = _lba_worker((0, reps))
+        return n / dt
+    with mp.get_context("fork").Pool(cores) as pool:
+        res = pool.map(_lba_worker, [(i % 3, reps) for i in range(cores)])
+    return sum(n / dt for dt, n in res)
 
 
 def cpu_oracle_fps(cores: int, frames_per_core: int, reps: int = 1):
@@ -146,20 +206,23 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    per_step = 2  # frames per core per step: a bounded sample of the same workload
+    per_step = 2  # tracked frames per core per step: a bounded sample of the same workload
     for _ in range(args.warmup and 1):
         cpu_oracle_fps(cores, 1)
     t = time.perf_counter()
     vals = [cpu_oracle_fps(cores, per_step) for _ in range(args.steps)]
     wall = time.perf_counter() - t
     v = float(np.mean(vals))
+    lba_v = cpu_lba_iters_per_sec(cores, 1)
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": WORKLOAD, "frames_per_step": per_step * cores},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{per_step} frames/core/step x {args.steps} steps, one oracle process per core"},
-            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "lba": {"value": lba_v, "unit": "LM iterations/s", "cores": cores, "kind": "port",
+                    "sample": "one C4 local BA per core (oracle/lba_oracle.cpp)"}}
     print(json.dumps(line), flush=True)
 
 
@@ -167,8 +230,10 @@ def run_reference(args):
 def run_ours(args):
     import torch
 
-    from dvmslam_b200 import launch_count
+    from dvmslam_b200 import launch_count, synth
     from dvmslam_b200.extractor import ORBextractor
+    from dvmslam_b200.optimizer import LocalBA
+    from dvmslam_b200.tracking import Tracker
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -188,31 +253,44 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # synthetic stream of this agent, resident in HBM and mirrored in pinned host memory
-    frames_np = make_frames(seed=rank, n=RESIDENT_FRAMES)
+    # this agent's synthetic stream, resident in HBM and mirrored in pinned host memory
+    S = make_stream(seed=rank)
+    frames_np = make_frames(rank, RESIDENT_FRAMES, S)
     host = torch.from_numpy(frames_np).pin_memory()
     dev = host.cuda(non_blocking=False)
     host_np = host.numpy()
     frame_bytes = W * H
 
     ext = ORBextractor(NFEAT, 1.2, 8, 20, 7, max_width=W, max_height=H, device=local_rank)
+    T = ext.tables()
+    world_map = synth.plane_map(S, lambda im: ext(im), MAP_KEYFRAMES, T["scale"], MAP_POINTS)
+    trk = Tracker(ext, S.K, BOUNDS, world_map)
     stream = torch.cuda.ExternalStream(ext.stream(), device=local_rank)
     base = dev.data_ptr()
+    R0, t0 = S.pose(0)
+    q0 = synth.quat_from_R(R0).astype(np.float32)
+
+    def bootstrap():
+        return trk.bootstrap(host_np[0], q0, t0)
+
+    inliers = []
 
     def step_device(s):
         for i in range(FRAMES_PER_STEP):
-            k = (s * FRAMES_PER_STEP + i) % RESIDENT_FRAMES
-            ext.extract_device(base + k * frame_bytes, W, H, W)
+            k = (1 + s * FRAMES_PER_STEP + i) % RESIDENT_FRAMES
+            trk.track((base + k * frame_bytes, W, H, W), sync=False)
 
     def step_host(s):
         for i in range(FRAMES_PER_STEP):
-            k = (s * FRAMES_PER_STEP + i) % RESIDENT_FRAMES
-            ext(host_np[k], copy=False)
+            k = (1 + s * FRAMES_PER_STEP + i) % RESIDENT_FRAMES
+            _, _, c = trk.track(host_np[k], sync=True)
+            inliers.append(c[3])
 
     # ---- device-resident throughput (`value`) ----
+    bootstrap()
     for s in range(args.warmup):
         step_device(s)
-    ext.sync()
+    q, t, c = trk.result()
     barrier()
     clocks = ClockSampler(local_rank)
     if rank == 0:
@@ -223,7 +301,7 @@ def run_ours(args):
     for s in range(args.steps):
         step_device(args.warmup + s)
     e1.record(stream)
-    ext.sync()
+    q, t, c_dev = trk.result()
     barrier()
     launches = launch_count() - n0
     ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
@@ -232,26 +310,55 @@ def run_ours(args):
     ms_total = float(ms.item())
 
     # ---- end to end through the C-ABI host call (`e2e`) ----
+    bootstrap()
     for s in range(min(args.warmup, 1)):
         step_host(s)
+    inliers.clear()
     barrier()
-    t0 = time.perf_counter()
+    tw0 = time.perf_counter()
     for s in range(args.steps):
-        step_host(args.warmup + s)
+        step_host(1 + s)
     torch.cuda.synchronize()
-    e2e_s = torch.tensor([time.perf_counter() - t0], device="cuda")
+    e2e_s = torch.tensor([time.perf_counter() - tw0], device="cuda")
     if dist is not None:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     clock_info = clocks.stop() if rank == 0 else None
     e2e_total = float(e2e_s.item())
+    tracked_ok = float(np.mean(np.array(inliers) >= 30)) if inliers else 0.0
 
-    # ---- per-stage device time for the roofline (separate profiled pass, not part of `value`) ----
+    # ---- per-stage device time of the extractor for the roofline (separate profiled pass) ----
     ext.set_profiling(True)
     for i in range(FRAMES_PER_STEP):
         ext.extract_device(base + (i % RESIDENT_FRAMES) * frame_bytes, W, H, W)
     nprof, stage_ms = ext.get_profile()
     ext.set_profiling(False)
     stage_us = [1e3 * float(m) / max(nprof, 1) for m in stage_ms]
+
+    # ---- local BA (config C4) ----
+    lba = None
+    if rank == 0 or world > 1:
+        solver = LocalBA(64, device=local_rank)
+        _, a = lba_scene(rank % 3)
+        for _ in range(3):
+            solver.LocalBundleAdjustment(*a)
+        barrier()
+        reps, its, kern_ms = 20, 0, 0.0
+        tl0 = time.perf_counter()
+        for _ in range(reps):
+            r = solver.LocalBundleAdjustment(*a)
+            its += r["iters"]
+            kern_ms += r["kernel_ms"]
+        lba_s = torch.tensor([time.perf_counter() - tl0], device="cuda")
+        if dist is not None:
+            dist.all_reduce(lba_s, op=dist.ReduceOp.MAX)
+        ne = len(a[4])
+        lba = {"value": world * its / float(lba_s.item()), "unit": "LM iterations/s", "iterations_per_ba": its / reps,
+               "ms_per_ba_e2e": 1e3 * float(lba_s.item()) / reps, "ms_per_ba_kernel": kern_ms / reps,
+               "workload": f"C4: 50 free + 10 fixed keyframes, {len(a[3])} points, {ne} observations",
+               "kernel_iters_per_s": its / (kern_ms * 1e-3),
+               # ~29 MB and ~75 MFLOP per LM iteration at this size: latency-bound regime
+               "achieved_GBps_kernel": 29e6 * its / (kern_ms * 1e-3) / 1e9}
+        solver.close()
 
     if rank == 0:
         frames = args.steps * FRAMES_PER_STEP
@@ -263,28 +370,36 @@ def run_ours(args):
         if dom_bytes is None:  # octree: candidates read + selection written; latency-bound by construction
             dom_bytes = 4 * 40000 + 4 * NFEAT
         achieved = dom_bytes / (stage_us[dom] * 1e-6) / 1e9
+        frame_us = 1e3 * ms_total / frames
         roofline = {"bound": "hbm", "kernel": STAGE_NAMES[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": dom_bytes, "avg_launch_us": stage_us[dom],
                     "stage_us": dict(zip(STAGE_NAMES, stage_us)),
+                    "frame_us": frame_us, "tracking_us": frame_us - sum(stage_us),
                     "whole_frame": {"algorithmic_bytes": FRAME_BYTES_TOTAL,
                                     "achieved_GBps": FRAME_BYTES_TOTAL * value / world / 1e9}}
         cpu = None
         if world == 1:
-            t = time.perf_counter()
-            cpu_fps = cpu_oracle_fps(1, 24)
+            tc = time.perf_counter()
+            cpu_fps = cpu_oracle_fps(1, 16)
+            cpu_lba = cpu_lba_iters_per_sec(1, 2)
             cpu = {"value": cpu_fps, "unit": UNIT, "cores": 1, "kind": "port",
-                   "sample": f"24 frames of the same stream, single thread, {time.perf_counter() - t:.1f} s"}
+                   "sample": f"16 tracked frames of the same stream + 2 C4 local BAs, single thread, "
+                             f"{time.perf_counter() - tc:.1f} s", "lba_iters_per_s": cpu_lba}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "frames_per_step": FRAMES_PER_STEP,
+                "scaling": "weak", "vs_baseline": None, "dtype": "u8 (extract/match) + f64 (pose, BA)",
+                "data": "synthetic",
+                "config": {"workload": WORKLOAD, "frames_per_step": FRAMES_PER_STEP, "local_map_points": MAP_POINTS,
                            "l2": f"{RESIDENT_FRAMES} distinct resident frames ({RESIDENT_FRAMES * frame_bytes >> 20} MB) "
                                  "cycled: inputs larger than L2"},
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": FRAMES_PER_STEP * frame_bytes,
-                        "d2h_bytes_per_step": FRAMES_PER_STEP * (32 + ext.cap * 60)},
-                "gpu_launches": int(launches), "clocks": clock_info, "roofline": roofline, "cpu_baseline": cpu}
+                        "d2h_bytes_per_step": FRAMES_PER_STEP * 48, "tracked_ok_frac": tracked_ok,
+                        "median_inliers": float(np.median(inliers)) if inliers else 0.0},
+                "gpu_launches": int(launches), "clocks": clock_info, "roofline": roofline, "cpu_baseline": cpu,
+                "lba": lba, "last_counts_device_run": list(c_dev)}
         print(json.dumps(line), flush=True)
+    trk.close()
     ext.close()
     if dist is not None:
         dist.destroy_process_group()
