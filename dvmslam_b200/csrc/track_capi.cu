@@ -12,7 +12,7 @@ static void frame_free(dvm_frame* f)
     cudaSetDevice(f->device);
     cudaFree(f->d_kps); cudaFree(f->d_desc); cudaFree(f->d_n); cudaFree(f->d_cell_start); cudaFree(f->d_cell_items);
     cudaFree(f->d_in); cudaFree(f->ms.pu); cudaFree(f->ms.pv); cudaFree(f->ms.pr); cudaFree(f->ms.plevels);
-    cudaFree(f->ms.choice); cudaFree(f->ms.claim_a); cudaFree(f->ms.claim_b); cudaFree(f->ms.iters);
+    cudaFree(f->ms.choice); cudaFree(f->ms.cache); cudaFree(f->ms.ncand); cudaFree(f->ms.claim_a); cudaFree(f->ms.claim_b); cudaFree(f->ms.iters);
     cudaFree(f->d_cur_mp); cudaFree(f->d_err);
     if (f->h_in) cudaFreeHost(f->h_in);
     if (f->h_out) cudaFreeHost(f->h_out);
@@ -27,12 +27,15 @@ int dvm_frame_ensure_query_cap(dvm_frame* f, int nq)
     const int cap = nq + nq / 4 + 256;
     DVM_CUDA(cudaStreamSynchronize(f->stream));
     cudaFree(f->ms.pu); cudaFree(f->ms.pv); cudaFree(f->ms.pr); cudaFree(f->ms.plevels); cudaFree(f->ms.choice);
-    f->ms.pu = f->ms.pv = f->ms.pr = nullptr; f->ms.plevels = f->ms.choice = nullptr;
+    cudaFree(f->ms.cache); cudaFree(f->ms.ncand);
+    f->ms.pu = f->ms.pv = f->ms.pr = nullptr; f->ms.plevels = f->ms.choice = nullptr; f->ms.cache = nullptr; f->ms.ncand = nullptr;
     DVM_CUDA(cudaMalloc(&f->ms.pu, cap * sizeof(float)));
     DVM_CUDA(cudaMalloc(&f->ms.pv, cap * sizeof(float)));
     DVM_CUDA(cudaMalloc(&f->ms.pr, cap * sizeof(float)));
     DVM_CUDA(cudaMalloc(&f->ms.plevels, cap * sizeof(int)));
     DVM_CUDA(cudaMalloc(&f->ms.choice, cap * sizeof(int)));
+    DVM_CUDA(cudaMalloc(&f->ms.cache, (size_t)cap * kMatchCacheK * sizeof(unsigned long long)));
+    DVM_CUDA(cudaMalloc(&f->ms.ncand, cap * sizeof(int)));
     f->q_cap = cap;
     return DVM_OK;
 }

@@ -211,6 +211,25 @@ __device__ inline int rot_bin(float last_angle, float cur_angle)
     return bin;
 }
 
+// ---- candidate cache: the window of every query is walked ONCE; its best kMatchCacheK candidates are
+// kept sorted by (Hamming distance, walk order) -- the reference's preference order: strict '<' keeps
+// the first of equal distances.  The greedy rounds then only consult the cache; a query whose cached
+// candidates are all taken while it had more falls back to a full walk.
+__device__ inline unsigned long long pack_cand(int dist, int ord, int oct, int idx)
+{
+    return ((unsigned long long)(((unsigned)dist << 16) | (unsigned)min(ord, 0xffff)) << 32) | ((unsigned)oct << 16) | (unsigned)idx;
+}
+__device__ inline int cand_idx(unsigned long long e) { return (int)(e & 0xffffu); }
+__device__ inline int cand_oct(unsigned long long e) { return (int)((e >> 16) & 0xffu); }
+__device__ inline int cand_dist(unsigned long long e) { return (int)(e >> 48); }
+
+__device__ inline void topk_insert(unsigned long long (&top)[kMatchCacheK], unsigned long long v)
+{
+#pragma unroll
+    for (int p = 0; p < kMatchCacheK; p++)
+        if (v < top[p]) { const unsigned long long t = top[p]; top[p] = v; v = t; }
+}
+
 __global__ void __launch_bounds__(kMatchThreads, 1)
 match_last_kernel(FrameDev cur, MatchLastArgs a, MatchScratch s, int* __restrict__ cur_mp, int* __restrict__ nmatches,
                   int use_smem)
@@ -263,20 +282,55 @@ match_last_kernel(FrameDev cur, MatchLastArgs a, MatchScratch s, int* __restrict
     for (int k = tid; k < ncur; k += kMatchThreads) claim_prev[k] = kNoClaim;
     __syncthreads();
 
+    // walk every window once, fill the candidate cache
+    for (int i = tid; i < nq; i += kMatchThreads) {
+        const int lv = s.plevels[i];
+        if (lv == -1) continue;
+        uint32_t d[8];
+        load_desc(d, desc_of(i));
+        unsigned long long top[kMatchCacheK];
+#pragma unroll
+        for (int p = 0; p < kMatchCacheK; p++) top[p] = ~0ull;
+        int nc = 0;
+        walk_area(fl, s.pu[i], s.pv[i], s.pr[i], lv >> 16, (int)(short)(lv & 0xffff), [&](int idx, int oct) {
+            const int dist = hamming256(d, fl.desc + (size_t)idx * 32);
+            topk_insert(top, pack_cand(dist, nc, oct, idx));
+            nc++;
+        });
+#pragma unroll
+        for (int p = 0; p < kMatchCacheK; p++) s.cache[(size_t)i * kMatchCacheK + p] = top[p];
+        s.ncand[i] = nc;
+    }
+    __syncthreads();
+
     int rounds = 0;
     while (true) {
         int changed = 0;
         for (int i = tid; i < nq; i += kMatchThreads) {
             const int lv = s.plevels[i];
             if (lv == -1) continue;
-            uint32_t d[8];
-            load_desc(d, desc_of(i));
+            const int nc = s.ncand[i];
             int bestDist = 256, bestIdx = -1;
-            walk_area(fl, s.pu[i], s.pv[i], s.pr[i], lv >> 16, (int)(short)(lv & 0xffff), [&](int idx, int) {
-                if (claim_prev[idx] < i) return; // taken by an earlier map point with observations
-                const int dist = hamming256(d, fl.desc + (size_t)idx * 32);
-                if (dist < bestDist) { bestDist = dist; bestIdx = idx; }
-            });
+            bool found = false;
+            unsigned long long e[kMatchCacheK];
+#pragma unroll
+            for (int p = 0; p < kMatchCacheK; p++) e[p] = s.cache[(size_t)i * kMatchCacheK + p];
+#pragma unroll
+            for (int p = 0; p < kMatchCacheK; p++) {
+                if (found || p >= nc) continue;
+                const int idx = cand_idx(e[p]);
+                if (claim_prev[idx] < i) continue; // taken by an earlier map point with observations
+                bestDist = cand_dist(e[p]); bestIdx = idx; found = true;
+            }
+            if (!found && nc > kMatchCacheK) { // cache exhausted: full walk against the current claims
+                uint32_t d[8];
+                load_desc(d, desc_of(i));
+                walk_area(fl, s.pu[i], s.pv[i], s.pr[i], lv >> 16, (int)(short)(lv & 0xffff), [&](int idx, int) {
+                    if (claim_prev[idx] < i) return;
+                    const int dist = hamming256(d, fl.desc + (size_t)idx * 32);
+                    if (dist < bestDist) { bestDist = dist; bestIdx = idx; }
+                });
+            }
             const int pick = bestDist <= kThHigh ? bestIdx : -1;
             if (pick != s.choice[i]) { s.choice[i] = pick; changed = 1; }
         }
@@ -370,26 +424,66 @@ match_map_kernel(FrameDev cur, MatchMapArgs a, MatchScratch s, int* __restrict__
     if (tid == 0) s_events = 0;
     __syncthreads();
 
+    // walk every window once, fill the candidate cache (keypoints blocked before the call never qualify)
+    for (int i = tid; i < nq; i += kMatchThreads) {
+        const int lvl = a.level[i];
+        uint32_t d[8];
+        load_desc(d, desc_of(i));
+        unsigned long long top[kMatchCacheK];
+#pragma unroll
+        for (int p = 0; p < kMatchCacheK; p++) top[p] = ~0ull;
+        int nc = 0;
+        walk_area(fl, a.projX[i], a.projY[i], s.pr[i], lvl - 1, lvl, [&](int idx, int oct) {
+            if (claim_prev[idx] < 0) return; // blocked from the start
+            const int dist = hamming256(d, fl.desc + (size_t)idx * 32);
+            topk_insert(top, pack_cand(dist, nc, oct, idx));
+            nc++;
+        });
+#pragma unroll
+        for (int p = 0; p < kMatchCacheK; p++) s.cache[(size_t)i * kMatchCacheK + p] = top[p];
+        s.ncand[i] = nc;
+    }
+    __syncthreads();
+
     int rounds = 0;
     while (true) {
         int changed = 0;
         for (int i = tid; i < nq; i += kMatchThreads) {
-            const int lvl = a.level[i];
-            uint32_t d[8];
-            load_desc(d, desc_of(i));
+            const int nc = s.ncand[i];
             int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
-            walk_area(fl, a.projX[i], a.projY[i], s.pr[i], lvl - 1, lvl, [&](int idx, int oct) {
-                if (claim_prev[idx] < i) return; // held by a map point with observations
-                const int dist = hamming256(d, fl.desc + (size_t)idx * 32);
-                if (dist < bestDist) {
-                    bestDist2 = bestDist; bestDist = dist;
-                    bestLevel2 = bestLevel; bestLevel = oct;
-                    bestIdx = idx;
-                } else if (dist < bestDist2) {
-                    bestLevel2 = oct;
-                    bestDist2 = dist;
-                }
-            });
+            int found = 0;
+            unsigned long long e[kMatchCacheK];
+#pragma unroll
+            for (int p = 0; p < kMatchCacheK; p++) e[p] = s.cache[(size_t)i * kMatchCacheK + p];
+            // sorted by (distance, walk order): the first two free entries are the reference's best and
+            // second best (its scan keeps the earliest of equal distances)
+#pragma unroll
+            for (int p = 0; p < kMatchCacheK; p++) {
+                if (found >= 2 || p >= nc) continue;
+                const int idx = cand_idx(e[p]);
+                if (claim_prev[idx] < i) continue; // held by a map point with observations
+                if (found == 0) { bestDist = cand_dist(e[p]); bestLevel = cand_oct(e[p]); bestIdx = idx; }
+                else { bestDist2 = cand_dist(e[p]); bestLevel2 = cand_oct(e[p]); }
+                found++;
+            }
+            if (found < 2 && nc > kMatchCacheK) { // cache exhausted: full walk against the current claims
+                const int lvl = a.level[i];
+                uint32_t d[8];
+                load_desc(d, desc_of(i));
+                bestDist = 256; bestLevel = -1; bestDist2 = 256; bestLevel2 = -1; bestIdx = -1;
+                walk_area(fl, a.projX[i], a.projY[i], s.pr[i], lvl - 1, lvl, [&](int idx, int oct) {
+                    if (claim_prev[idx] < i) return;
+                    const int dist = hamming256(d, fl.desc + (size_t)idx * 32);
+                    if (dist < bestDist) {
+                        bestDist2 = bestDist; bestDist = dist;
+                        bestLevel2 = bestLevel; bestLevel = oct;
+                        bestIdx = idx;
+                    } else if (dist < bestDist2) {
+                        bestLevel2 = oct;
+                        bestDist2 = dist;
+                    }
+                });
+            }
             int pick = -1;
             if (bestDist <= kThHigh) {
                 const float lim = __fmul_rn(a.nnratio, (float)bestDist2);

@@ -72,7 +72,10 @@ struct MatchScratch {
     int* claim_a;   // [cap_kp]
     int* claim_b;   // [cap_kp]
     int* iters;     // [1] fixed-point rounds used (diagnostic)
+    unsigned long long* cache; // [cap_q * kMatchCacheK] best candidates of each query, sorted by (distance, walk order)
+    int* ncand;     // [cap_q] candidates seen by the window walk
 };
+constexpr int kMatchCacheK = 8;
 
 struct PoseOptArgs {
     int n;                   // correspondences (<= cap)
