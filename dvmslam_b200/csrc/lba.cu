@@ -29,7 +29,7 @@ constexpr int kLbaWarps = kLbaThreads / 32;
 constexpr int kNB = 32; // Cholesky block size
 
 struct LbaDev {
-    int nc, nf, np, ne, dimP, iterations;
+    int nc, nf, np, ne, dimP, dimPad, iterations; // dimPad = dimP rounded up to the Cholesky block size
     double fx, fy, cx, cy, delta, dsqr;
     double* camq[2]; double* camt[2];
     const int* cam_col; const int* free_cam;
@@ -204,67 +204,72 @@ __device__ inline void dmma_m8n8k4(double& c0, double& c1, double a, double b)
                  : "d"(a), "d"(b));
 }
 
-// ---- dense SPD solve Hs x = bs on ONE CTA: blocked right-looking Cholesky (lower), then L y = b, L^T x = y.
-// smem: panel [n][kNB] doubles + diag [kNB][kNB+1] doubles.  Returns false if a pivot is not positive.
+// ---- dense SPD solve Hs x = bs on ONE CTA: blocked right-looking Cholesky (lower triangle), then
+// L y = b, L^T x = y.  n is a multiple of kNB (the caller pads the system with an identity block), so
+// every block is a full 32x32.  smem: panel [n][kNB] + diag [kNB][kNB+1] doubles.
+// Returns false if a pivot is not positive (LinearSolver "failed": the LM trial is rejected).
 __device__ bool cta_cholesky_solve(int n, double* __restrict__ A, const double* __restrict__ b, double* __restrict__ x,
                                    double* smem, int* s_flag)
 {
     double* panel = smem;                      // [n][kNB]
     double* diag = smem + (size_t)n * kNB;     // [kNB][kNB+1]
+    constexpr int LD = kNB + 1;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (tid == 0) *s_flag = 1;
     __syncthreads();
     for (int k0 = 0; k0 < n; k0 += kNB) {
-        const int nb = min(kNB, n - k0);
-        // diagonal block -> smem
-        for (int i = tid; i < nb * nb; i += kLbaThreads) {
-            const int r = i / nb, c = i - r * nb;
-            diag[r * (kNB + 1) + c] = A[(size_t)(k0 + r) * n + k0 + c];
+        for (int i = tid; i < kNB * kNB; i += kLbaThreads) {
+            const int r = i >> 5, c = i & 31;
+            diag[r * LD + c] = A[(size_t)(k0 + r) * n + k0 + c];
         }
         __syncthreads();
-        if (wid == 0) { // unblocked Cholesky of the nb x nb block by one warp, lane = row
-            for (int j = 0; j < nb; j++) {
-                double d = diag[j * (kNB + 1) + j];
+        if (wid == 0) { // unblocked Cholesky of the 32x32 block by one warp, lane = row
+            for (int j = 0; j < kNB; j++) {
+                double d = diag[j * LD + j];
                 const bool bad = !(d > 0) || !isfinite(d);
                 d = sqrt(d);
                 if (bad) { if (lane == 0) *s_flag = 0; d = 1.0; }
                 __syncwarp();
-                if (lane == j) diag[j * (kNB + 1) + j] = d;
-                if (lane > j && lane < nb) diag[lane * (kNB + 1) + j] /= d;
+                if (lane == j) diag[j * LD + j] = d;
+                double lij = 0;
+                if (lane > j) { lij = diag[lane * LD + j] / d; diag[lane * LD + j] = lij; }
                 __syncwarp();
-                if (lane > j && lane < nb) {
-                    const double lij = diag[lane * (kNB + 1) + j];
-                    for (int k = j + 1; k <= lane; k++) diag[lane * (kNB + 1) + k] -= lij * diag[k * (kNB + 1) + j];
-                }
+                if (lane > j)
+                    for (int k = j + 1; k <= lane; k++) diag[lane * LD + k] -= lij * diag[k * LD + j];
                 __syncwarp();
             }
         }
         __syncthreads();
-        for (int i = tid; i < nb * nb; i += kLbaThreads) { // write L_kk back (lower part)
-            const int r = i / nb, c = i - r * nb;
-            if (c <= r) A[(size_t)(k0 + r) * n + k0 + c] = diag[r * (kNB + 1) + c];
+        for (int i = tid; i < kNB * kNB; i += kLbaThreads) { // write L_kk back (lower part)
+            const int r = i >> 5, c = i & 31;
+            if (c <= r) A[(size_t)(k0 + r) * n + k0 + c] = diag[r * LD + c];
         }
-        const int r0 = k0 + nb; // first row below the diagonal block
-        // panel: L[i][k0..k0+nb) = A[i][..] * L_kk^-T, one row per thread
+        const int r0 = k0 + kNB; // first row below the diagonal block
+        // panel: L[i][k0..k0+32) = A[i][..] * L_kk^-T, one row per thread, row held in registers
         for (int i = r0 + tid; i < n; i += kLbaThreads) {
             double row[kNB];
-            for (int c = 0; c < nb; c++) row[c] = A[(size_t)i * n + k0 + c];
-            for (int c = 0; c < nb; c++) {
-                double s = row[c];
-                for (int k = 0; k < c; k++) s -= row[k] * diag[c * (kNB + 1) + k];
-                row[c] = s / diag[c * (kNB + 1) + c];
+            const double* src = A + (size_t)i * n + k0;
+#pragma unroll
+            for (int c = 0; c < kNB; c++) row[c] = src[c];
+#pragma unroll
+            for (int c = 0; c < kNB; c++) {
+                double sacc = row[c];
+#pragma unroll
+                for (int k = 0; k < c; k++) sacc -= row[k] * diag[c * LD + k];
+                row[c] = sacc / diag[c * LD + c];
             }
-            for (int c = 0; c < nb; c++) { A[(size_t)i * n + k0 + c] = row[c]; panel[(size_t)(i - r0) * kNB + c] = row[c]; }
-            for (int c = nb; c < kNB; c++) panel[(size_t)(i - r0) * kNB + c] = 0.0;
+            double* dst = A + (size_t)i * n + k0;
+            double* pdst = panel + (size_t)(i - r0) * kNB;
+#pragma unroll
+            for (int c = 0; c < kNB; c++) { dst[c] = row[c]; pdst[c] = row[c]; }
         }
         __syncthreads();
         // trailing update A22 -= L21 * L21^T (lower triangle), 8x8 tiles on the FP64 tensor pipe
         const int m = n - r0;
         if (m > 0) {
-            const int mt = (m + 7) / 8;
+            const int mt = m / 8;
             const int ntiles = mt * (mt + 1) / 2;
             for (int t = wid; t < ntiles; t += kLbaWarps) {
-                // tile (ti, tj), tj <= ti, from the triangular index t
                 int ti = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
                 while (ti * (ti + 1) / 2 > t) ti--;
                 while ((ti + 1) * (ti + 2) / 2 <= t) ti++;
@@ -273,61 +278,71 @@ __device__ bool cta_cholesky_solve(int n, double* __restrict__ A, const double* 
                 double c0 = 0.0, c1 = 0.0;
 #pragma unroll
                 for (int kk = 0; kk < kNB; kk += 4) {
-                    const double a = ar < m ? panel[(size_t)ar * kNB + kk + (lane & 3)] : 0.0;
-                    const double bb = bc < m ? panel[(size_t)bc * kNB + kk + (lane & 3)] : 0.0;
+                    const double a = panel[(size_t)ar * kNB + kk + (lane & 3)];
+                    const double bb = panel[(size_t)bc * kNB + kk + (lane & 3)];
                     dmma_m8n8k4(c0, c1, a, bb);
                 }
-                const int cr = ti * 8 + (lane >> 2), cc = tj * 8 + (lane & 3) * 2;
-                if (cr < m) {
-                    double* dst = A + (size_t)(r0 + cr) * n + r0 + cc;
-                    if (cc < m && cc <= cr) dst[0] -= c0;
-                    if (cc + 1 < m && cc + 1 <= cr) dst[1] -= c1;
-                }
+                const int cc = tj * 8 + (lane & 3) * 2;
+                double* dst = A + (size_t)(r0 + ar) * n + r0 + cc;
+                if (cc <= ar) dst[0] -= c0;
+                if (cc + 1 <= ar) dst[1] -= c1;
             }
         }
         __syncthreads();
     }
     const bool ok = *s_flag != 0;
-    // forward substitution L y = b (y kept in smem), blocked by kNB
-    double* y = smem; // reuse panel storage: n doubles
+    // forward substitution L y = b: diagonal blocks staged in shared memory, off-diagonal GEMV by all threads
+    double* y = smem; // reuse the panel storage: n doubles
     for (int i = tid; i < n; i += kLbaThreads) y[i] = b[i];
     __syncthreads();
     for (int k0 = 0; k0 < n; k0 += kNB) {
-        const int nb = min(kNB, n - k0);
-        if (wid == 0) {
-            for (int j = 0; j < nb; j++) {
-                if (lane == 0) y[k0 + j] /= A[(size_t)(k0 + j) * n + k0 + j];
-                __syncwarp();
-                const double yj = y[k0 + j];
-                if (lane > j && lane < nb) y[k0 + lane] -= A[(size_t)(k0 + lane) * n + k0 + j] * yj;
-                __syncwarp();
-            }
+        for (int i = tid; i < kNB * kNB; i += kLbaThreads) {
+            const int r = i >> 5, c = i & 31;
+            diag[r * LD + c] = A[(size_t)(k0 + r) * n + k0 + c];
         }
         __syncthreads();
-        for (int i = k0 + nb + tid; i < n; i += kLbaThreads) {
-            double s = 0;
-            for (int c = 0; c < nb; c++) s += A[(size_t)i * n + k0 + c] * y[k0 + c];
-            y[i] -= s;
+        if (wid == 0) {
+            double yi = y[k0 + lane];
+            for (int j = 0; j < kNB; j++) {
+                const double yj = __shfl_sync(0xffffffffu, yi, j) / diag[j * LD + j];
+                if (lane == j) yi = yj;
+                if (lane > j) yi -= diag[lane * LD + j] * yj;
+            }
+            y[k0 + lane] = yi;
+        }
+        __syncthreads();
+        for (int i = k0 + kNB + tid; i < n; i += kLbaThreads) {
+            const double* Ai = A + (size_t)i * n + k0;
+            double sacc = 0;
+#pragma unroll 8
+            for (int c = 0; c < kNB; c++) sacc += Ai[c] * y[k0 + c];
+            y[i] -= sacc;
         }
         __syncthreads();
     }
     // backward substitution L^T x = y
-    for (int kb = (n - 1) / kNB; kb >= 0; kb--) {
-        const int k0 = kb * kNB, nb = min(kNB, n - k0);
-        if (wid == 0) {
-            for (int j = nb - 1; j >= 0; j--) {
-                if (lane == 0) y[k0 + j] /= A[(size_t)(k0 + j) * n + k0 + j];
-                __syncwarp();
-                const double yj = y[k0 + j];
-                if (lane < j) y[k0 + lane] -= A[(size_t)(k0 + j) * n + k0 + lane] * yj;
-                __syncwarp();
-            }
+    for (int k0 = n - kNB; k0 >= 0; k0 -= kNB) {
+        for (int i = tid; i < kNB * kNB; i += kLbaThreads) {
+            const int r = i >> 5, c = i & 31;
+            diag[r * LD + c] = A[(size_t)(k0 + r) * n + k0 + c];
         }
         __syncthreads();
+        if (wid == 0) {
+            double yi = y[k0 + lane];
+            for (int j = kNB - 1; j >= 0; j--) {
+                const double yj = __shfl_sync(0xffffffffu, yi, j) / diag[j * LD + j];
+                if (lane == j) yi = yj;
+                if (lane < j) yi -= diag[j * LD + lane] * yj;
+            }
+            y[k0 + lane] = yi;
+        }
+        __syncthreads();
+        // y[i] -= sum_c L[k0+c][i] * y[k0+c] for i < k0: thread i reads column i (coalesced across threads)
         for (int i = tid; i < k0; i += kLbaThreads) {
-            double s = 0;
-            for (int c = 0; c < nb; c++) s += A[(size_t)(k0 + c) * n + i] * y[k0 + c];
-            y[i] -= s;
+            double sacc = 0;
+#pragma unroll 8
+            for (int c = 0; c < kNB; c++) sacc += A[(size_t)(k0 + c) * n + i] * y[k0 + c];
+            y[i] -= sacc;
         }
         __syncthreads();
     }
@@ -519,61 +534,68 @@ __global__ void __launch_bounds__(kLbaThreads, 1) lba_kernel(LbaDev P)
                 d[1] = i01 * g[0] + i11 * g[1] + i12 * g[2];
                 d[2] = i02 * g[0] + i12 * g[1] + i22 * g[2];
             }
-            for (size_t i = gtid; i < (size_t)P.dimP * P.dimP; i += nthreads) P.Hs[i] = 0.0;
+            // Hs (lower triangle, padded to dimPad) starts as Hpp + lambda I, identity on the padding
+            for (size_t i = gtid; i < (size_t)P.dimPad * P.dimPad; i += nthreads) {
+                const int r = (int)(i / P.dimPad), c = (int)(i - (size_t)r * P.dimPad);
+                double v = 0.0;
+                if (r >= P.dimP) v = (r == c) ? 1.0 : 0.0;
+                else if (c < P.dimP && r / 6 == c / 6) v = P.Hpp[(size_t)(r / 6) * 36 + (r % 6) * 6 + (c % 6)] + (r == c ? lambda : 0.0);
+                P.Hs[i] = v;
+            }
+            for (int i = gtid; i < P.dimPad; i += nthreads) P.bs[i] = i < P.dimP ? P.bp[i] : 0.0;
             grid.sync();
-            // ---------------- S1: Schur complement rows ----------------
-            for (int c1 = blockIdx.x; c1 < P.nf; c1 += G) {
-                double* row = smem;               // [nf][36]
-                double* bacc = smem + (size_t)P.nf * 36; // [6]
-                for (int i = tid; i < P.nf * 36 + 6; i += kLbaThreads) smem[i] = 0.0;
-                __syncthreads();
-                const int s = P.cam_start[c1], e_end = P.cam_start[c1 + 1];
-                for (int k = s + tid; k < e_end; k += kLbaThreads) {
-                    const int e1 = P.cam_edges[k];
-                    const int l = P.ept[e1];
+            // ---------------- S1: Schur complement, point-major ----------------
+            // For landmark l with observing free cameras {c_i}: Hs(c_i, c_j) -= Hpl_i Dinv Hpl_j^T and
+            // bs(c_i) -= Hpl_i Dinv bl.  One warp per landmark, lanes over the (i, j >= i) pairs; the
+            // 6x6 products are added with FP64 reductions at L2 (no return value needed).
+            for (int l = gwarp; l < P.np; l += nwarps) {
+                const int ps = P.pt_start[l], k = P.pt_start[l + 1] - ps;
+                const double* Di = P.Dinv + (size_t)l * 6;
+                const double* d = P.db + (size_t)l * 3;
+                const double D0 = Di[0], D1 = Di[1], D2 = Di[2], D3 = Di[3], D4 = Di[4], D5 = Di[5];
+                const int npairs = k * (k + 1) / 2;
+                for (int p = lane; p < npairs; p += 32) {
+                    // p -> (i, j) with j <= i  (triangular index)
+                    int i = (int)((sqrt(8.0 * p + 1.0) - 1.0) * 0.5);
+                    while (i * (i + 1) / 2 > p) i--;
+                    while ((i + 1) * (i + 2) / 2 <= p) i++;
+                    const int j = p - i * (i + 1) / 2;
+                    int e1 = P.pt_edges[ps + i], e2 = P.pt_edges[ps + j];
+                    int c1 = P.cam_col[P.ecam[e1]], c2 = P.cam_col[P.ecam[e2]];
+                    if (c1 < 0 || c2 < 0) continue;
+                    if (c1 > c2) { int t = c1; c1 = c2; c2 = t; t = e1; e1 = e2; e2 = t; } // c1 <= c2: block stored at (c2, c1)
                     const double* B1 = P.Hpl + (size_t)e1 * 18;
-                    const double* Di = P.Dinv + (size_t)l * 6;
-                    const double* d = P.db + (size_t)l * 3;
+                    const double* B2 = P.Hpl + (size_t)e2 * 18;
                     double BD[18];
 #pragma unroll
                     for (int a = 0; a < 6; a++) {
                         const double b0 = B1[a * 3], b1 = B1[a * 3 + 1], b2 = B1[a * 3 + 2];
-                        BD[a * 3] = b0 * Di[0] + b1 * Di[1] + b2 * Di[2];
-                        BD[a * 3 + 1] = b0 * Di[1] + b1 * Di[3] + b2 * Di[4];
-                        BD[a * 3 + 2] = b0 * Di[2] + b1 * Di[4] + b2 * Di[5];
-                        atomicAdd(&bacc[a], -(b0 * d[0] + b1 * d[1] + b2 * d[2]));
+                        BD[a * 3] = b0 * D0 + b1 * D1 + b2 * D2;
+                        BD[a * 3 + 1] = b0 * D1 + b1 * D3 + b2 * D4;
+                        BD[a * 3 + 2] = b0 * D2 + b1 * D4 + b2 * D5;
                     }
-                    const int ps = P.pt_start[l], pe = P.pt_start[l + 1];
-                    for (int k2 = ps; k2 < pe; k2++) {
-                        const int e2 = P.pt_edges[k2];
-                        const int c2 = P.cam_col[P.ecam[e2]];
-                        if (c2 < c1) continue; // fixed (-1) or already covered by the symmetric block
-                        const double* B2 = P.Hpl + (size_t)e2 * 18;
-                        double* dst = row + (size_t)c2 * 36;
+                    if (i == j) { // once per observation: the gradient part
 #pragma unroll
                         for (int a = 0; a < 6; a++)
+                            atomicAdd(&P.bs[6 * c1 + a], -(B1[a * 3] * d[0] + B1[a * 3 + 1] * d[1] + B1[a * 3 + 2] * d[2]));
+                    }
+                    double* dst = P.Hs + (size_t)(6 * c2) * P.dimPad + 6 * c1;
 #pragma unroll
-                            for (int b2 = 0; b2 < 6; b2++)
-                                atomicAdd(&dst[a * 6 + b2],
-                                          -(BD[a * 3] * B2[b2 * 3] + BD[a * 3 + 1] * B2[b2 * 3 + 1] + BD[a * 3 + 2] * B2[b2 * 3 + 2]));
+                    for (int b2 = 0; b2 < 6; b2++) {
+                        const double q0 = B2[b2 * 3], q1 = B2[b2 * 3 + 1], q2 = B2[b2 * 3 + 2];
+#pragma unroll
+                        for (int a = 0; a < 6; a++) {
+                            if (i == j && a > b2) continue; // diagonal block: lower triangle only (a <= b2 <-> col <= row)
+                            atomicAdd(&dst[(size_t)b2 * P.dimPad + a], -(BD[a * 3] * q0 + BD[a * 3 + 1] * q1 + BD[a * 3 + 2] * q2));
+                        }
                     }
                 }
-                __syncthreads();
-                // lower-triangular block column: Hs[(6*c2+b), (6*c1+a)] = S(c1,c2)[a][b]
-                for (int i = tid; i < (P.nf - c1) * 36; i += kLbaThreads) {
-                    const int c2 = c1 + i / 36, a = (i % 36) / 6, b2 = i % 6;
-                    double v = row[(size_t)c2 * 36 + a * 6 + b2];
-                    if (c2 == c1) v += P.Hpp[(size_t)c1 * 36 + a * 6 + b2] + (a == b2 ? lambda : 0.0);
-                    P.Hs[(size_t)(6 * c2 + b2) * P.dimP + 6 * c1 + a] = v;
-                }
-                if (tid < 6) P.bs[6 * c1 + tid] = P.bp[6 * c1 + tid] + bacc[tid];
-                __syncthreads();
             }
             grid.sync();
             // ---------------- C: reduced camera system on one CTA ----------------
             if (blockIdx.x == 0) {
                 bool ok = true;
-                if (P.dimP > 0) ok = cta_cholesky_solve(P.dimP, P.Hs, P.bs, P.x, smem, &s_flag);
+                if (P.dimP > 0) ok = cta_cholesky_solve(P.dimPad, P.Hs, P.bs, P.x, smem, &s_flag);
                 if (tid == 0) P.flags[0] = ok ? 1 : 0;
             }
             grid.sync();
@@ -750,7 +772,7 @@ int dvm_lba_create(dvm_lba** out, int device, int max_free_cameras)
     *h->h_abort = 0;
     DVM_LCREATE(cudaHostGetDevicePointer(&h->d_abort, h->h_abort, 0));
     // shared memory: max(Schur row [nf*36+6], Cholesky panel [n*kNB] + diag [kNB*(kNB+1)]) doubles
-    const size_t n = (size_t)6 * max_free_cameras;
+    const size_t n = ((size_t)6 * max_free_cameras + kNB - 1) / kNB * kNB;
     h->smem_bytes = std::max((size_t)max_free_cameras * 36 + 6, n * kNB + (size_t)kNB * (kNB + 1)) * sizeof(double);
     DVM_REQUIRE(h->smem_bytes <= 227 * 1024, "max_free_cameras needs more shared memory than one SM has");
     DVM_LCREATE(cudaFuncSetAttribute(lba_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
@@ -815,6 +837,7 @@ int dvm_local_ba(dvm_lba* h, int nc, float* cam_q, float* cam_t, const uint8_t* 
     }
     DVM_CUDA(cudaSetDevice(h->device));
     const int dimP = 6 * nf;
+    const int dimPad = (dimP + kNB - 1) / kNB * kNB;
     // ---- device layout ----
     size_t off = 0;
     auto take = [&](size_t bytes) { off = (off + 255) & ~(size_t)255; size_t o = off; off += bytes; return o; };
@@ -830,8 +853,8 @@ int dvm_local_ba(dvm_lba* h, int nc, float* cam_q, float* cam_t, const uint8_t* 
     const size_t o_err = take((size_t)ne * 2 * 8), o_hpl = take((size_t)ne * 18 * 8);
     const size_t o_hll = take((size_t)np * 6 * 8), o_bl = take((size_t)np * 3 * 8), o_dinv = take((size_t)np * 6 * 8), o_db = take((size_t)np * 3 * 8);
     const size_t o_hpp = take((size_t)std::max(nf, 1) * 36 * 8), o_bp = take((size_t)std::max(dimP, 1) * 8);
-    const size_t o_hs = take((size_t)std::max(dimP * dimP, 1) * 8), o_bs = take((size_t)std::max(dimP, 1) * 8);
-    const size_t o_x = take((size_t)(dimP + np * 3 + 1) * 8);
+    const size_t o_hs = take((size_t)std::max(dimPad * dimPad, 1) * 8), o_bs = take((size_t)std::max(dimPad, 1) * 8);
+    const size_t o_x = take((size_t)(dimPad + np * 3 + 1) * 8);
     const size_t o_part = take((size_t)h->grid * 4 * 8), o_flags = take(4 * 4);
     // output block (contiguous, one D2H)
     const size_t out_begin = (off + 255) & ~(size_t)255;
@@ -874,7 +897,7 @@ int dvm_local_ba(dvm_lba* h, int nc, float* cam_q, float* cam_t, const uint8_t* 
     uint8_t* db = h->d_buf;
     LbaDev P;
     memset(&P, 0, sizeof(P));
-    P.nc = nc; P.nf = nf; P.np = np; P.ne = ne; P.dimP = dimP; P.iterations = iterations;
+    P.nc = nc; P.nf = nf; P.np = np; P.ne = ne; P.dimP = dimP; P.dimPad = dimPad; P.iterations = iterations;
     P.fx = K[0]; P.fy = K[1]; P.cx = K[2]; P.cy = K[3];
     P.delta = (double)(float)std::sqrt(5.991); // const float thHuberMono = sqrt(5.991), :1178
     P.dsqr = P.delta * P.delta;
