@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include <cooperative_groups.h>
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 namespace cg = cooperative_groups;
@@ -38,11 +39,12 @@ struct LbaDev {
     const int* pt_start; const int* pt_edges;
     const int* cam_start; const int* cam_edges;
     double* err; double* Hpl; double* Hll; double* bl; double* Dinv; double* db;
-    double* Hpp; double* bp; double* Hs; double* bs; double* x;
+    double* Hpp; double* bp; double* Hs; double* bs; double* x; double* Linv;
     double* part;  // [gridDim * 4]
     int* flags;    // [0] Cholesky ok
     const volatile int* abort_flag;
     float* out_camq; float* out_camt; float* out_pts; double* out_chi2; uint8_t* out_bad; double* out_stats;
+    unsigned long long* prof; // [8] ns per phase (L1, L2, S0, S1, C, B1, B2, other), written by thread 0
 };
 
 // ---- SE3 helpers (same formulas as the pose-only optimiser; g2o/types/se3quat.h) ----
@@ -204,82 +206,128 @@ __device__ inline void dmma_m8n8k4(double& c0, double& c1, double a, double b)
                  : "d"(a), "d"(b));
 }
 
-// ---- dense SPD solve Hs x = bs on ONE CTA: blocked right-looking Cholesky (lower triangle), then
-// L y = b, L^T x = y.  n is a multiple of kNB (the caller pads the system with an identity block), so
-// every block is a full 32x32.  smem: panel [n][kNB] + diag [kNB][kNB+1] doubles.
-// Returns false if a pivot is not positive (LinearSolver "failed": the LM trial is rejected).
-__device__ bool cta_cholesky_solve(int n, double* __restrict__ A, const double* __restrict__ b, double* __restrict__ x,
-                                   double* smem, int* s_flag)
+// ---- dense SPD solve Hs x = bs on ONE 8-CTA CLUSTER ------------------------------------------------
+// Blocked right-looking Cholesky (lower triangle, kNB = 32) of the n x n reduced camera matrix A
+// (n a multiple of 32: the caller pads with an identity block), with the right-hand side carried as an
+// extra matrix row (row n): after the factorisation that row holds y = L^-1 b, so only the backward
+// substitution L^T x = y remains.  Per block column:
+//   (a) every CTA factors the 32x32 diagonal block redundantly in registers of one warp (lane = row,
+//       shuffles for the column broadcasts) and inverts it (lane = column) -- no broadcast needed;
+//   (b) the panel rows are split over the 8 CTAs:  L21 = A21 * L11^-T  as a small GEMM with the inverse;
+//   (c) after a cluster barrier every CTA stages the whole panel in shared memory and takes its share
+//       of the 8x8 trailing tiles  A22 -= L21 L21^T  on the FP64 tensor pipe (DMMA m8n8k4).
+// A has n + 8 rows of leading dimension n.  Linv_g [n/32][32*32] receives the inverted diagonal blocks.
+constexpr int kClusterCtas = 8;
+constexpr int kPanelLd = 36;   // shared-memory row stride of the panel (doubles): conflict-free 8-byte fragment loads
+constexpr int kDiagLd = kNB + 1;
+
+__device__ inline size_t chol_smem_doubles(int n) { return (size_t)(n + 8) * kPanelLd + 2 * kNB * kDiagLd + 64 * kNB; }
+
+__device__ bool cluster_cholesky_solve(int n, double* __restrict__ A, const double* __restrict__ b, double* __restrict__ x,
+                                       double* __restrict__ Linv_g, double* smem, int* s_flag)
 {
-    double* panel = smem;                      // [n][kNB]
-    double* diag = smem + (size_t)n * kNB;     // [kNB][kNB+1]
-    constexpr int LD = kNB + 1;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    double* panel = smem;                                 // [(n + 8)][kPanelLd]
+    double* Ld = panel + (size_t)(n + 8) * kPanelLd;      // [kNB][kDiagLd]  factored diagonal block
+    double* Li = Ld + kNB * kDiagLd;                      // [kNB][kDiagLd]  its inverse
+    double* stage = Li + kNB * kDiagLd;                   // [64][kNB]       this CTA's panel rows before the TRSM
+    const int M = n + 8;                                  // rows including the right-hand-side row group
     if (tid == 0) *s_flag = 1;
-    __syncthreads();
+    // right-hand side as row n, zero rows n+1 .. n+7
+    if (rank == 0)
+        for (int i = tid; i < 8 * n; i += kLbaThreads) A[(size_t)n * n + i] = (i < n) ? b[i] : 0.0;
+    cluster.sync();
     for (int k0 = 0; k0 < n; k0 += kNB) {
-        for (int i = tid; i < kNB * kNB; i += kLbaThreads) {
-            const int r = i >> 5, c = i & 31;
-            diag[r * LD + c] = A[(size_t)(k0 + r) * n + k0 + c];
-        }
-        __syncthreads();
-        if (wid == 0) { // unblocked Cholesky of the 32x32 block by one warp, lane = row
-            for (int j = 0; j < kNB; j++) {
-                double d = diag[j * LD + j];
-                const bool bad = !(d > 0) || !isfinite(d);
-                d = sqrt(d);
-                if (bad) { if (lane == 0) *s_flag = 0; d = 1.0; }
-                __syncwarp();
-                if (lane == j) diag[j * LD + j] = d;
-                double lij = 0;
-                if (lane > j) { lij = diag[lane * LD + j] / d; diag[lane * LD + j] = lij; }
-                __syncwarp();
-                if (lane > j)
-                    for (int k = j + 1; k <= lane; k++) diag[lane * LD + k] -= lij * diag[k * LD + j];
-                __syncwarp();
-            }
-        }
-        __syncthreads();
-        for (int i = tid; i < kNB * kNB; i += kLbaThreads) { // write L_kk back (lower part)
-            const int r = i >> 5, c = i & 31;
-            if (c <= r) A[(size_t)(k0 + r) * n + k0 + c] = diag[r * LD + c];
-        }
-        const int r0 = k0 + kNB; // first row below the diagonal block
-        // panel: L[i][k0..k0+32) = A[i][..] * L_kk^-T, one row per thread, row held in registers
-        for (int i = r0 + tid; i < n; i += kLbaThreads) {
+        const int r0 = k0 + kNB;
+        // ---- (a) diagonal block: factor + invert, redundantly in every CTA ----
+        if (wid == 0) {
             double row[kNB];
-            const double* src = A + (size_t)i * n + k0;
 #pragma unroll
-            for (int c = 0; c < kNB; c++) row[c] = src[c];
+            for (int c = 0; c < kNB; c++) row[c] = A[(size_t)(k0 + lane) * n + k0 + c];
+            bool bad = false;
 #pragma unroll
-            for (int c = 0; c < kNB; c++) {
-                double sacc = row[c];
+            for (int j = 0; j < kNB; j++) {
+                const double djj = __shfl_sync(0xffffffffu, row[j], j);
+                bad = bad || !(djj > 0) || !isfinite(djj);
+                const double d = bad ? 1.0 : sqrt(djj);
+                const double lij = row[j] / d;
+                if (lane == j) row[j] = d;
+                else if (lane > j) row[j] = lij;
 #pragma unroll
-                for (int k = 0; k < c; k++) sacc -= row[k] * diag[c * LD + k];
-                row[c] = sacc / diag[c * LD + c];
+                for (int k = j + 1; k < kNB; k++) {
+                    const double lkj = __shfl_sync(0xffffffffu, row[j], k);
+                    if (lane >= k) row[k] -= lij * lkj;
+                }
             }
-            double* dst = A + (size_t)i * n + k0;
-            double* pdst = panel + (size_t)(i - r0) * kNB;
+            if (bad && lane == 0) *s_flag = 0;
 #pragma unroll
-            for (int c = 0; c < kNB; c++) { dst[c] = row[c]; pdst[c] = row[c]; }
+            for (int c = 0; c < kNB; c++) Ld[lane * kDiagLd + c] = (c <= lane) ? row[c] : 0.0;
+            __syncwarp();
+            // inverse of the lower-triangular block: lane = column j of L^-1
+            double xi[kNB];
+#pragma unroll
+            for (int i = 0; i < kNB; i++) {
+                double s0 = (i == lane) ? 1.0 : 0.0, s1 = 0.0;
+#pragma unroll
+                for (int k = 0; k < i; k += 2) {
+                    s0 -= Ld[i * kDiagLd + k] * xi[k];
+                    if (k + 1 < i) s1 -= Ld[i * kDiagLd + k + 1] * xi[k + 1];
+                }
+                xi[i] = (i >= lane) ? (s0 + s1) / Ld[i * kDiagLd + i] : 0.0;
+            }
+#pragma unroll
+            for (int i = 0; i < kNB; i++) Li[i * kDiagLd + lane] = xi[i];
+            if (rank == 0) {
+#pragma unroll
+                for (int c = 0; c < kNB; c++) {
+                    if (c <= lane) A[(size_t)(k0 + lane) * n + k0 + c] = row[c];
+                    Linv_g[(size_t)(k0 / kNB) * kNB * kNB + c * kNB + lane] = xi[c]; // Linv[c][lane]
+                }
+            }
         }
         __syncthreads();
-        // trailing update A22 -= L21 * L21^T (lower triangle), 8x8 tiles on the FP64 tensor pipe
-        const int m = n - r0;
-        if (m > 0) {
-            const int mt = m / 8;
-            const int ntiles = mt * (mt + 1) / 2;
-            for (int t = wid; t < ntiles; t += kLbaWarps) {
-                int ti = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
-                while (ti * (ti + 1) / 2 > t) ti--;
-                while ((ti + 1) * (ti + 2) / 2 <= t) ti++;
-                const int tj = t - ti * (ti + 1) / 2;
+        // ---- (b) panel rows of this CTA: L21 = A21 * L11^-T ----
+        const int mrows = M - r0;
+        const int chunk = (mrows + kClusterCtas - 1) / kClusterCtas;
+        const int i0 = r0 + rank * chunk, i1 = min(i0 + chunk, M);
+        for (int base = i0; base < i1; base += 64) {
+            const int cnt = min(64, i1 - base);
+            for (int t = tid; t < cnt * kNB; t += kLbaThreads) stage[t] = A[(size_t)(base + (t >> 5)) * n + k0 + (t & 31)];
+            __syncthreads();
+            for (int t = tid; t < cnt * kNB; t += kLbaThreads) {
+                const int r = t >> 5, c = t & 31;
+                double acc = 0.0;
+                for (int k = 0; k <= c; k++) acc += stage[r * kNB + k] * Li[c * kDiagLd + k];
+                A[(size_t)(base + r) * n + k0 + c] = acc;
+            }
+            __syncthreads();
+        }
+        cluster.sync();
+        // ---- (c) trailing update ----
+        const int mcols = n - r0;
+        if (mcols > 0) {
+            for (int t = tid; t < mrows * kNB; t += kLbaThreads)
+                panel[(size_t)(t >> 5) * kPanelLd + (t & 31)] = A[(size_t)(r0 + (t >> 5)) * n + k0 + (t & 31)];
+            __syncthreads();
+            const int mtc = mcols / 8;
+            const int tri = mtc * (mtc + 1) / 2;
+            const int ntiles = tri + mtc; // + the right-hand-side row group against every column tile
+            for (int t = rank * kLbaWarps + wid; t < ntiles; t += kClusterCtas * kLbaWarps) {
+                int ti, tj;
+                if (t < tri) {
+                    ti = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+                    while (ti * (ti + 1) / 2 > t) ti--;
+                    while ((ti + 1) * (ti + 2) / 2 <= t) ti++;
+                    tj = t - ti * (ti + 1) / 2;
+                } else { ti = mtc; tj = t - tri; }
                 const int ar = ti * 8 + (lane >> 2), bc = tj * 8 + (lane >> 2);
                 double c0 = 0.0, c1 = 0.0;
 #pragma unroll
                 for (int kk = 0; kk < kNB; kk += 4) {
-                    const double a = panel[(size_t)ar * kNB + kk + (lane & 3)];
-                    const double bb = panel[(size_t)bc * kNB + kk + (lane & 3)];
+                    const double a = panel[(size_t)ar * kPanelLd + kk + (lane & 3)];
+                    const double bb = panel[(size_t)bc * kPanelLd + kk + (lane & 3)];
                     dmma_m8n8k4(c0, c1, a, bb);
                 }
                 const int cc = tj * 8 + (lane & 3) * 2;
@@ -288,70 +336,46 @@ __device__ bool cta_cholesky_solve(int n, double* __restrict__ A, const double* 
                 if (cc + 1 <= ar) dst[1] -= c1;
             }
         }
-        __syncthreads();
+        cluster.sync();
     }
     const bool ok = *s_flag != 0;
-    // forward substitution L y = b: diagonal blocks staged in shared memory, off-diagonal GEMV by all threads
-    double* y = smem; // reuse the panel storage: n doubles
-    for (int i = tid; i < n; i += kLbaThreads) y[i] = b[i];
-    __syncthreads();
-    for (int k0 = 0; k0 < n; k0 += kNB) {
-        for (int i = tid; i < kNB * kNB; i += kLbaThreads) {
-            const int r = i >> 5, c = i & 31;
-            diag[r * LD + c] = A[(size_t)(k0 + r) * n + k0 + c];
-        }
+    // ---- backward substitution L^T x = y on CTA 0 (y = row n of A) ----
+    if (rank == 0) {
+        double* y = panel;          // [n]
+        double* part = panel + n;   // [16][kNB] partial sums
+        double* rhs = part + 16 * kNB;
+        for (int i = tid; i < n; i += kLbaThreads) y[i] = A[(size_t)n * n + i];
         __syncthreads();
-        if (wid == 0) {
-            double yi = y[k0 + lane];
-            for (int j = 0; j < kNB; j++) {
-                const double yj = __shfl_sync(0xffffffffu, yi, j) / diag[j * LD + j];
-                if (lane == j) yi = yj;
-                if (lane > j) yi -= diag[lane * LD + j] * yj;
+        for (int k0 = n - kNB; k0 >= 0; k0 -= kNB) {
+            // rhs[c] = y[k0+c] - sum_{i >= k0+32} L[i][k0+c] * x[i]
+            {
+                const int c = tid & 31, g = tid >> 5;
+                double acc = 0.0;
+                for (int i = k0 + kNB + g; i < n; i += kLbaWarps) acc += A[(size_t)i * n + k0 + c] * y[i];
+                part[g * kNB + c] = acc;
             }
-            y[k0 + lane] = yi;
+            __syncthreads();
+            if (tid < kNB) {
+                double acc = y[k0 + tid];
+                for (int g = 0; g < kLbaWarps; g++) acc -= part[g * kNB + tid];
+                rhs[tid] = acc;
+            }
+            __syncthreads();
+            if (tid < kNB) { // x_k = L_kk^-T rhs
+                const double* Lg = Linv_g + (size_t)(k0 / kNB) * kNB * kNB;
+                double acc = 0.0;
+                for (int c = tid; c < kNB; c++) acc += Lg[c * kNB + tid] * rhs[c];
+                y[k0 + tid] = acc;
+            }
+            __syncthreads();
         }
-        __syncthreads();
-        for (int i = k0 + kNB + tid; i < n; i += kLbaThreads) {
-            const double* Ai = A + (size_t)i * n + k0;
-            double sacc = 0;
-#pragma unroll 8
-            for (int c = 0; c < kNB; c++) sacc += Ai[c] * y[k0 + c];
-            y[i] -= sacc;
-        }
+        for (int i = tid; i < n; i += kLbaThreads) x[i] = ok ? y[i] : 0.0;
         __syncthreads();
     }
-    // backward substitution L^T x = y
-    for (int k0 = n - kNB; k0 >= 0; k0 -= kNB) {
-        for (int i = tid; i < kNB * kNB; i += kLbaThreads) {
-            const int r = i >> 5, c = i & 31;
-            diag[r * LD + c] = A[(size_t)(k0 + r) * n + k0 + c];
-        }
-        __syncthreads();
-        if (wid == 0) {
-            double yi = y[k0 + lane];
-            for (int j = kNB - 1; j >= 0; j--) {
-                const double yj = __shfl_sync(0xffffffffu, yi, j) / diag[j * LD + j];
-                if (lane == j) yi = yj;
-                if (lane < j) yi -= diag[j * LD + lane] * yj;
-            }
-            y[k0 + lane] = yi;
-        }
-        __syncthreads();
-        // y[i] -= sum_c L[k0+c][i] * y[k0+c] for i < k0: thread i reads column i (coalesced across threads)
-        for (int i = tid; i < k0; i += kLbaThreads) {
-            double sacc = 0;
-#pragma unroll 8
-            for (int c = 0; c < kNB; c++) sacc += A[(size_t)(k0 + c) * n + i] * y[k0 + c];
-            y[i] -= sacc;
-        }
-        __syncthreads();
-    }
-    for (int i = tid; i < n; i += kLbaThreads) x[i] = ok ? y[i] : 0.0;
-    __syncthreads();
     return ok;
 }
 
-__global__ void __launch_bounds__(kLbaThreads, 1) lba_kernel(LbaDev P)
+__global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kLbaThreads, 1) lba_kernel(LbaDev P)
 {
     cg::grid_group grid = cg::this_grid();
     extern __shared__ __align__(16) double smem[];
@@ -363,6 +387,16 @@ __global__ void __launch_bounds__(kLbaThreads, 1) lba_kernel(LbaDev P)
     const int gwarp = blockIdx.x * kLbaWarps + wid, nwarps = G * kLbaWarps;
     const int gtid = blockIdx.x * kLbaThreads + tid, nthreads = G * kLbaThreads;
 
+    unsigned long long t_prev = 0;
+    auto tick = [&](int slot) { // phase timer (thread 0 of CTA 0 only; the grid.sync before it makes it meaningful)
+        if (gtid == 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (slot >= 0) P.prof[slot] += t - t_prev;
+            t_prev = t;
+        }
+    };
+    tick(-1);
     int cur = 0; // index of the accepted estimate buffers
     double lambda = -1, ni = 2;
     int nBad = 0, done = 0, trials = 0;
@@ -455,6 +489,7 @@ __global__ void __launch_bounds__(kLbaThreads, 1) lba_kernel(LbaDev P)
             __syncthreads();
         }
         grid.sync();
+        tick(0);
         // ---------------- L2: camera-major Hpp, bp ----------------
         double maxdp = 0;
         for (int cf = blockIdx.x; cf < P.nf; cf += G) {
@@ -502,6 +537,7 @@ __global__ void __launch_bounds__(kLbaThreads, 1) lba_kernel(LbaDev P)
         }
         if (tid == 0) P.part[blockIdx.x * 4 + 3] = maxdp;
         grid.sync();
+        tick(1);
         double currentChi = 0;
         {
             double m = 0;
@@ -544,6 +580,7 @@ __global__ void __launch_bounds__(kLbaThreads, 1) lba_kernel(LbaDev P)
             }
             for (int i = gtid; i < P.dimPad; i += nthreads) P.bs[i] = i < P.dimP ? P.bp[i] : 0.0;
             grid.sync();
+            tick(2);
             // ---------------- S1: Schur complement, point-major ----------------
             // For landmark l with observing free cameras {c_i}: Hs(c_i, c_j) -= Hpl_i Dinv Hpl_j^T and
             // bs(c_i) -= Hpl_i Dinv bl.  One warp per landmark, lanes over the (i, j >= i) pairs; the
@@ -592,13 +629,15 @@ __global__ void __launch_bounds__(kLbaThreads, 1) lba_kernel(LbaDev P)
                 }
             }
             grid.sync();
+            tick(3);
             // ---------------- C: reduced camera system on one CTA ----------------
-            if (blockIdx.x == 0) {
+            if (blockIdx.x < kClusterCtas) { // the first cluster
                 bool ok = true;
-                if (P.dimP > 0) ok = cta_cholesky_solve(P.dimPad, P.Hs, P.bs, P.x, smem, &s_flag);
-                if (tid == 0) P.flags[0] = ok ? 1 : 0;
+                if (P.dimP > 0) ok = cluster_cholesky_solve(P.dimPad, P.Hs, P.bs, P.x, P.Linv, smem, &s_flag);
+                if (blockIdx.x == 0 && tid == 0) P.flags[0] = ok ? 1 : 0;
             }
             grid.sync();
+            tick(4);
             const bool ok2 = P.flags[0] != 0;
             // ---------------- B1: landmark back-substitution and update into the trial buffers ----------------
             double scale_part = 0;
@@ -650,6 +689,7 @@ __global__ void __launch_bounds__(kLbaThreads, 1) lba_kernel(LbaDev P)
                 if (tid == 0) P.part[blockIdx.x * 4 + 1] = red[0];
             }
             grid.sync();
+            tick(5);
             // ---------------- B2: errors at the trial estimate ----------------
             double chi_t = 0;
             for (int e = gtid; e < P.ne; e += nthreads) {
@@ -665,6 +705,7 @@ __global__ void __launch_bounds__(kLbaThreads, 1) lba_kernel(LbaDev P)
                 if (tid == 0) P.part[blockIdx.x * 4 + 0] = red[0];
             }
             grid.sync();
+            tick(6);
             double tempChi = 0, scale = 0;
             for (int b2 = 0; b2 < G; b2++) { tempChi += P.part[b2 * 4 + 0]; scale += P.part[b2 * 4 + 1]; }
             if (!ok2) tempChi = 1.7976931348623157e308;
@@ -750,7 +791,7 @@ int dvm_lba_create(dvm_lba** out, int device, int max_free_cameras)
 {
     DVM_REQUIRE(out != nullptr, "null output handle");
     *out = nullptr;
-    DVM_REQUIRE(max_free_cameras >= 1 && max_free_cameras <= 128, "max_free_cameras must be in 1..128");
+    DVM_REQUIRE(max_free_cameras >= 1 && max_free_cameras <= 100, "max_free_cameras must be in 1..100");
     int rc = select_device(device);
     if (rc != DVM_OK) return rc;
     dvm_lba* h = new dvm_lba;
@@ -773,14 +814,14 @@ int dvm_lba_create(dvm_lba** out, int device, int max_free_cameras)
     DVM_LCREATE(cudaHostGetDevicePointer(&h->d_abort, h->h_abort, 0));
     // shared memory: max(Schur row [nf*36+6], Cholesky panel [n*kNB] + diag [kNB*(kNB+1)]) doubles
     const size_t n = ((size_t)6 * max_free_cameras + kNB - 1) / kNB * kNB;
-    h->smem_bytes = std::max((size_t)max_free_cameras * 36 + 6, n * kNB + (size_t)kNB * (kNB + 1)) * sizeof(double);
+    h->smem_bytes = ((n + 8) * kPanelLd + 2 * kNB * kDiagLd + 64 * kNB) * sizeof(double);
     DVM_REQUIRE(h->smem_bytes <= 227 * 1024, "max_free_cameras needs more shared memory than one SM has");
     DVM_LCREATE(cudaFuncSetAttribute(lba_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
     int sms = 0, per_sm = 0;
     DVM_LCREATE(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
     DVM_LCREATE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lba_kernel, kLbaThreads, h->smem_bytes));
     DVM_REQUIRE(per_sm >= 1, "lba kernel does not fit on an SM");
-    h->grid = sms; // one persistent CTA per SM
+    h->grid = sms / kClusterCtas * kClusterCtas; // persistent CTAs in clusters of 8 (144 on a 148-SM B200)
 #undef DVM_LCREATE
     *out = h;
     return DVM_OK;
@@ -853,9 +894,10 @@ int dvm_local_ba(dvm_lba* h, int nc, float* cam_q, float* cam_t, const uint8_t* 
     const size_t o_err = take((size_t)ne * 2 * 8), o_hpl = take((size_t)ne * 18 * 8);
     const size_t o_hll = take((size_t)np * 6 * 8), o_bl = take((size_t)np * 3 * 8), o_dinv = take((size_t)np * 6 * 8), o_db = take((size_t)np * 3 * 8);
     const size_t o_hpp = take((size_t)std::max(nf, 1) * 36 * 8), o_bp = take((size_t)std::max(dimP, 1) * 8);
-    const size_t o_hs = take((size_t)std::max(dimPad * dimPad, 1) * 8), o_bs = take((size_t)std::max(dimPad, 1) * 8);
+    const size_t o_hs = take((size_t)std::max((dimPad + 8) * dimPad, 1) * 8), o_bs = take((size_t)std::max(dimPad, 1) * 8);
+    const size_t o_linv = take((size_t)std::max(dimPad * kNB, 1) * 8);
     const size_t o_x = take((size_t)(dimPad + np * 3 + 1) * 8);
-    const size_t o_part = take((size_t)h->grid * 4 * 8), o_flags = take(4 * 4);
+    const size_t o_part = take((size_t)h->grid * 4 * 8), o_flags = take(4 * 4), o_prof = take(8 * 8);
     // output block (contiguous, one D2H)
     const size_t out_begin = (off + 255) & ~(size_t)255;
     const size_t o_oq = take((size_t)nc * 4 * 4), o_ot = take((size_t)nc * 3 * 4), o_op = take((size_t)np * 3 * 4);
@@ -912,12 +954,15 @@ int dvm_local_ba(dvm_lba* h, int nc, float* cam_q, float* cam_t, const uint8_t* 
     P.err = (double*)(db + o_err); P.Hpl = (double*)(db + o_hpl); P.Hll = (double*)(db + o_hll);
     P.bl = (double*)(db + o_bl); P.Dinv = (double*)(db + o_dinv); P.db = (double*)(db + o_db);
     P.Hpp = (double*)(db + o_hpp); P.bp = (double*)(db + o_bp); P.Hs = (double*)(db + o_hs); P.bs = (double*)(db + o_bs);
+    P.Linv = (double*)(db + o_linv);
     P.x = (double*)(db + o_x); P.part = (double*)(db + o_part); P.flags = (int*)(db + o_flags);
     P.out_camq = (float*)(db + o_oq); P.out_camt = (float*)(db + o_ot); P.out_pts = (float*)(db + o_op);
     P.out_chi2 = (double*)(db + o_ochi); P.out_bad = db + o_obad; P.out_stats = (double*)(db + o_ostats);
     *h->h_abort = 0;
     P.abort_flag = abort_flag ? h->d_abort : nullptr;
     DVM_CUDA(cudaMemsetAsync(db + o_flags, 0, 16, h->stream));
+    DVM_CUDA(cudaMemsetAsync(db + o_prof, 0, 64, h->stream));
+    P.prof = (unsigned long long*)(db + o_prof);
     DVM_CUDA(cudaMemsetAsync(db + o_err, 0, (size_t)ne * 2 * 8, h->stream));
     void* args[] = { &P };
     DVM_CUDA(cudaEventRecord(h->ev0, h->stream));
@@ -932,6 +977,12 @@ int dvm_local_ba(dvm_lba* h, int nc, float* cam_q, float* cam_t, const uint8_t* 
     }
     DVM_CUDA(cudaStreamSynchronize(h->stream));
     DVM_CUDA(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+    if (getenv("DVM_LBA_PROFILE")) {
+        unsigned long long pr[8];
+        cudaMemcpy(pr, db + o_prof, 64, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[lba phases us] L1 %.1f L2 %.1f S0 %.1f S1 %.1f C %.1f B1 %.1f B2 %.1f total %.1f\n", pr[0] * 1e-3, pr[1] * 1e-3,
+                pr[2] * 1e-3, pr[3] * 1e-3, pr[4] * 1e-3, pr[5] * 1e-3, pr[6] * 1e-3, h->last_ms * 1e3);
+    }
     const double* ost = (const double*)(hb + o_ostats);
     const float* oq = (const float*)(hb + o_oq);
     const float* ot = (const float*)(hb + o_ot);
