@@ -221,11 +221,82 @@ constexpr int kClusterCtas = 8;
 constexpr int kPanelLd = 36;   // shared-memory row stride of the panel (doubles): conflict-free 8-byte fragment loads
 constexpr int kDiagLd = kNB + 1;
 
+// One warp: Cholesky of the 32x32 block at A (leading dimension ld, lower triangle) held in registers
+// (lane = row, column broadcasts by shuffle), then its inverse (lane = column).  Writes L to Ld and
+// L^-1 to Li (shared, stride kDiagLd); with write_back also L into A and L^-1 (row-major) into Linv_out.
+// Kept out of line so that its 64-register row does not compete with the caller's live state.
+__device__ __noinline__ bool warp_factor_invert_32(double* __restrict__ A, int ld, double* __restrict__ Ld,
+                                                   double* __restrict__ Li, bool write_back, double* __restrict__ Linv_out)
+{
+    const int lane = threadIdx.x & 31;
+    double row[kNB];
+#pragma unroll
+    for (int c = 0; c < kNB; c++) row[c] = A[(size_t)lane * ld + c];
+    bool bad = false;
+    double my_rinv = 1.0; // 1 / L[lane][lane]
+#pragma unroll
+    for (int j = 0; j < kNB; j++) {
+        const double djj = __shfl_sync(0xffffffffu, row[j], j);
+        bad = bad || !(djj > 0) || !isfinite(djj);
+        // IEEE sqrt and division are ~600-cycle software sequences and sit on the critical path of every
+        // column: one rsqrt (1-2 ulp) replaces both, well inside the solver's tolerance
+        const double rinv = bad ? 1.0 : rsqrt(djj);
+        const double lij = row[j] * rinv;
+        if (lane == j) { row[j] = djj * rinv; my_rinv = rinv; }
+        else if (lane > j) row[j] = lij;
+        // column j is exchanged through shared memory (Li is free until the inverse is written): the
+        // 31 broadcast loads pipeline, where 31 dependent shuffle pairs would serialise
+        Li[j * kDiagLd + lane] = row[j];
+        __syncwarp();
+#pragma unroll
+        for (int k = j + 1; k < kNB; k++) {
+            const double lkj = Li[j * kDiagLd + k];
+            if (lane >= k) row[k] -= lij * lkj;
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < kNB; c++) {
+        Ld[lane * kDiagLd + c] = (c <= lane) ? row[c] : 0.0;
+        if (write_back && c <= lane) A[(size_t)lane * ld + c] = row[c];
+    }
+    __syncwarp();
+    // inverse of the lower-triangular block: lane = column j of L^-1, forward substitution on e_j
+    double xi[kNB];
+#pragma unroll
+    for (int i = 0; i < kNB; i++) {
+        double s0 = (i == lane) ? 1.0 : 0.0, s1 = 0.0;
+#pragma unroll
+        for (int k = 0; k < i; k += 2) {
+            s0 -= Ld[i * kDiagLd + k] * xi[k];
+            if (k + 1 < i) s1 -= Ld[i * kDiagLd + k + 1] * xi[k + 1];
+        }
+        const double ri = __shfl_sync(0xffffffffu, my_rinv, i); // outside the select: every lane must take part
+        xi[i] = (i >= lane) ? (s0 + s1) * ri : 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < kNB; i++) {
+        Li[i * kDiagLd + lane] = xi[i];
+        if (write_back) Linv_out[i * kNB + lane] = xi[i];
+    }
+    return bad;
+}
+
 __device__ inline size_t chol_smem_doubles(int n) { return (size_t)(n + 8) * kPanelLd + 2 * kNB * kDiagLd + 64 * kNB; }
 
 __device__ bool cluster_cholesky_solve(int n, double* __restrict__ A, const double* __restrict__ b, double* __restrict__ x,
-                                       double* __restrict__ Linv_g, double* smem, int* s_flag)
+                                       double* __restrict__ Linv_g, double* smem, int* s_flag, unsigned long long* prof)
 {
+    unsigned long long tp = 0;
+    auto tk = [&](int slot) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (slot >= 0) prof[slot] += t - tp;
+            tp = t;
+        }
+    };
+    tk(-1);
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -243,51 +314,12 @@ __device__ bool cluster_cholesky_solve(int n, double* __restrict__ A, const doub
         const int r0 = k0 + kNB;
         // ---- (a) diagonal block: factor + invert, redundantly in every CTA ----
         if (wid == 0) {
-            double row[kNB];
-#pragma unroll
-            for (int c = 0; c < kNB; c++) row[c] = A[(size_t)(k0 + lane) * n + k0 + c];
-            bool bad = false;
-#pragma unroll
-            for (int j = 0; j < kNB; j++) {
-                const double djj = __shfl_sync(0xffffffffu, row[j], j);
-                bad = bad || !(djj > 0) || !isfinite(djj);
-                const double d = bad ? 1.0 : sqrt(djj);
-                const double lij = row[j] / d;
-                if (lane == j) row[j] = d;
-                else if (lane > j) row[j] = lij;
-#pragma unroll
-                for (int k = j + 1; k < kNB; k++) {
-                    const double lkj = __shfl_sync(0xffffffffu, row[j], k);
-                    if (lane >= k) row[k] -= lij * lkj;
-                }
-            }
+            const bool bad = warp_factor_invert_32(A + (size_t)k0 * n + k0, n, Ld, Li, rank == 0, Linv_g + (size_t)(k0 / kNB) * kNB * kNB);
             if (bad && lane == 0) *s_flag = 0;
-#pragma unroll
-            for (int c = 0; c < kNB; c++) Ld[lane * kDiagLd + c] = (c <= lane) ? row[c] : 0.0;
-            __syncwarp();
-            // inverse of the lower-triangular block: lane = column j of L^-1
-            double xi[kNB];
-#pragma unroll
-            for (int i = 0; i < kNB; i++) {
-                double s0 = (i == lane) ? 1.0 : 0.0, s1 = 0.0;
-#pragma unroll
-                for (int k = 0; k < i; k += 2) {
-                    s0 -= Ld[i * kDiagLd + k] * xi[k];
-                    if (k + 1 < i) s1 -= Ld[i * kDiagLd + k + 1] * xi[k + 1];
-                }
-                xi[i] = (i >= lane) ? (s0 + s1) / Ld[i * kDiagLd + i] : 0.0;
-            }
-#pragma unroll
-            for (int i = 0; i < kNB; i++) Li[i * kDiagLd + lane] = xi[i];
-            if (rank == 0) {
-#pragma unroll
-                for (int c = 0; c < kNB; c++) {
-                    if (c <= lane) A[(size_t)(k0 + lane) * n + k0 + c] = row[c];
-                    Linv_g[(size_t)(k0 / kNB) * kNB * kNB + c * kNB + lane] = xi[c]; // Linv[c][lane]
-                }
-            }
+            tk(8);
         }
         __syncthreads();
+        tk(9);
         // ---- (b) panel rows of this CTA: L21 = A21 * L11^-T ----
         const int mrows = M - r0;
         const int chunk = (mrows + kClusterCtas - 1) / kClusterCtas;
@@ -304,13 +336,16 @@ __device__ bool cluster_cholesky_solve(int n, double* __restrict__ A, const doub
             }
             __syncthreads();
         }
+        tk(10);
         cluster.sync();
+        tk(11);
         // ---- (c) trailing update ----
         const int mcols = n - r0;
         if (mcols > 0) {
             for (int t = tid; t < mrows * kNB; t += kLbaThreads)
                 panel[(size_t)(t >> 5) * kPanelLd + (t & 31)] = A[(size_t)(r0 + (t >> 5)) * n + k0 + (t & 31)];
             __syncthreads();
+            tk(12);
             const int mtc = mcols / 8;
             const int tri = mtc * (mtc + 1) / 2;
             const int ntiles = tri + mtc; // + the right-hand-side row group against every column tile
@@ -336,7 +371,9 @@ __device__ bool cluster_cholesky_solve(int n, double* __restrict__ A, const doub
                 if (cc + 1 <= ar) dst[1] -= c1;
             }
         }
+        tk(13);
         cluster.sync();
+        tk(14);
     }
     const bool ok = *s_flag != 0;
     // ---- backward substitution L^T x = y on CTA 0 (y = row n of A) ----
@@ -372,6 +409,7 @@ __device__ bool cluster_cholesky_solve(int n, double* __restrict__ A, const doub
         for (int i = tid; i < n; i += kLbaThreads) x[i] = ok ? y[i] : 0.0;
         __syncthreads();
     }
+    tk(15);
     return ok;
 }
 
@@ -633,7 +671,7 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kLbaThrea
             // ---------------- C: reduced camera system on one CTA ----------------
             if (blockIdx.x < kClusterCtas) { // the first cluster
                 bool ok = true;
-                if (P.dimP > 0) ok = cluster_cholesky_solve(P.dimPad, P.Hs, P.bs, P.x, P.Linv, smem, &s_flag);
+                if (P.dimP > 0) ok = cluster_cholesky_solve(P.dimPad, P.Hs, P.bs, P.x, P.Linv, smem, &s_flag, P.prof);
                 if (blockIdx.x == 0 && tid == 0) P.flags[0] = ok ? 1 : 0;
             }
             grid.sync();
@@ -817,11 +855,23 @@ int dvm_lba_create(dvm_lba** out, int device, int max_free_cameras)
     h->smem_bytes = ((n + 8) * kPanelLd + 2 * kNB * kDiagLd + 64 * kNB) * sizeof(double);
     DVM_REQUIRE(h->smem_bytes <= 227 * 1024, "max_free_cameras needs more shared memory than one SM has");
     DVM_LCREATE(cudaFuncSetAttribute(lba_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
-    int sms = 0, per_sm = 0;
-    DVM_LCREATE(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-    DVM_LCREATE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lba_kernel, kLbaThreads, h->smem_bytes));
-    DVM_REQUIRE(per_sm >= 1, "lba kernel does not fit on an SM");
-    h->grid = sms / kClusterCtas * kClusterCtas; // persistent CTAs in clusters of 8 (144 on a 148-SM B200)
+    {   // persistent CTAs in clusters of 8: as many clusters as can be co-resident (cooperative launch)
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(kClusterCtas * 64);
+        cfg.blockDim = dim3(kLbaThreads);
+        cfg.dynamicSmemBytes = h->smem_bytes;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = kClusterCtas; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int nclusters = 0;
+        DVM_LCREATE(cudaOccupancyMaxActiveClusters(&nclusters, lba_kernel, &cfg));
+        int sms = 0;
+        DVM_LCREATE(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+        nclusters = std::min(nclusters, sms / kClusterCtas);
+        if (nclusters < 1) { set_error("lba kernel: no 8-CTA cluster fits on this device"); lba_free(h); return DVM_ERR_CUDA; }
+        h->grid = nclusters * kClusterCtas;
+    }
 #undef DVM_LCREATE
     *out = h;
     return DVM_OK;
@@ -897,7 +947,7 @@ int dvm_local_ba(dvm_lba* h, int nc, float* cam_q, float* cam_t, const uint8_t* 
     const size_t o_hs = take((size_t)std::max((dimPad + 8) * dimPad, 1) * 8), o_bs = take((size_t)std::max(dimPad, 1) * 8);
     const size_t o_linv = take((size_t)std::max(dimPad * kNB, 1) * 8);
     const size_t o_x = take((size_t)(dimPad + np * 3 + 1) * 8);
-    const size_t o_part = take((size_t)h->grid * 4 * 8), o_flags = take(4 * 4), o_prof = take(8 * 8);
+    const size_t o_part = take((size_t)h->grid * 4 * 8), o_flags = take(4 * 4), o_prof = take(16 * 8);
     // output block (contiguous, one D2H)
     const size_t out_begin = (off + 255) & ~(size_t)255;
     const size_t o_oq = take((size_t)nc * 4 * 4), o_ot = take((size_t)nc * 3 * 4), o_op = take((size_t)np * 3 * 4);
@@ -961,7 +1011,7 @@ int dvm_local_ba(dvm_lba* h, int nc, float* cam_q, float* cam_t, const uint8_t* 
     *h->h_abort = 0;
     P.abort_flag = abort_flag ? h->d_abort : nullptr;
     DVM_CUDA(cudaMemsetAsync(db + o_flags, 0, 16, h->stream));
-    DVM_CUDA(cudaMemsetAsync(db + o_prof, 0, 64, h->stream));
+    DVM_CUDA(cudaMemsetAsync(db + o_prof, 0, 128, h->stream));
     P.prof = (unsigned long long*)(db + o_prof);
     DVM_CUDA(cudaMemsetAsync(db + o_err, 0, (size_t)ne * 2 * 8, h->stream));
     void* args[] = { &P };
@@ -978,8 +1028,10 @@ int dvm_local_ba(dvm_lba* h, int nc, float* cam_q, float* cam_t, const uint8_t* 
     DVM_CUDA(cudaStreamSynchronize(h->stream));
     DVM_CUDA(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
     if (getenv("DVM_LBA_PROFILE")) {
-        unsigned long long pr[8];
-        cudaMemcpy(pr, db + o_prof, 64, cudaMemcpyDeviceToHost);
+        unsigned long long pr[16];
+        cudaMemcpy(pr, db + o_prof, 128, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[chol us] factor %.1f inverse %.1f trsm %.1f sync %.1f stage %.1f tiles %.1f sync %.1f backsub %.1f\n", pr[8] * 1e-3,
+                pr[9] * 1e-3, pr[10] * 1e-3, pr[11] * 1e-3, pr[12] * 1e-3, pr[13] * 1e-3, pr[14] * 1e-3, pr[15] * 1e-3);
         fprintf(stderr, "[lba phases us] L1 %.1f L2 %.1f S0 %.1f S1 %.1f C %.1f B1 %.1f B2 %.1f total %.1f\n", pr[0] * 1e-3, pr[1] * 1e-3,
                 pr[2] * 1e-3, pr[3] * 1e-3, pr[4] * 1e-3, pr[5] * 1e-3, pr[6] * 1e-3, h->last_ms * 1e3);
     }
