@@ -1,0 +1,90 @@
+"""Regenerates the committed golden vectors (run in the build container, where cv2 4.13.0 is importable):
+
+    python tests/golden/make_golden.py
+
+  cv2_primitives.npz  outputs of the REAL OpenCV primitives the reference calls (cv::resize INTER_LINEAR,
+                      cv::GaussianBlur 7x7 sigma 2, cv::FAST 9-16 with NMS, cv::fastAtan2) on small seeded
+                      inputs -- the oracle's C models must reproduce them bit for bit;
+  orb_small.npz       ORBextractor::operator() outputs (keypoints, descriptors, monoIndex) on a 320x240 frame,
+                      produced by the cv2-backed pipeline (oracle/orb.py: extract_with_cv2), i.e. OpenCV
+                      primitives + the restated in-tree logic;
+  track_small.npz     matcher / pose-optimisation / local-BA results of the oracle on small seeded cases
+                      (no upstream fixture exists for these: they pin the oracle against regressions).
+The reference repository holds no fixtures for this path; these are ours.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def main():
+    import cv2
+
+    from dvmslam_b200 import synth
+    from oracle.lba import local_ba
+    from oracle.orb import OrbOracle, extract_with_cv2
+    from oracle.track import FrameOracle, pose_optimization
+
+    cv2.setNumThreads(1)
+    cv2.ipp.setUseIPP(False)
+    rng = np.random.default_rng(2026)
+
+    # ---- OpenCV primitives ----
+    img = synth.texture(200, 150, seed=7)
+    inv = np.float32(1) / np.float32(1.2)
+    dw, dh = int(np.rint(np.float32(200) * inv)), int(np.rint(np.float32(150) * inv))
+    resized = cv2.resize(img, (dw, dh), interpolation=cv2.INTER_LINEAR)
+    blurred = cv2.GaussianBlur(img, (7, 7), 2, sigmaY=2, borderType=cv2.BORDER_REFLECT_101)
+    fast = {}
+    for th in (20, 7):
+        det = cv2.FastFeatureDetector_create(th, True, cv2.FAST_FEATURE_DETECTOR_TYPE_9_16)
+        fast[th] = np.array([(k.pt[0], k.pt[1], k.response) for k in det.detect(img)], np.int32)
+    yx = rng.integers(-3000000, 3000000, (4000, 2))
+    yx[:50, 0] = 0
+    yx[50:100, 1] = 0
+    yx[100:150, 0] = yx[100:150, 1]
+    at = np.array([cv2.fastAtan2(float(y), float(x)) for y, x in yx], np.float32)
+    np.savez_compressed(os.path.join(HERE, "cv2_primitives.npz"), img=img, resized=resized, blurred=blurred,
+                        fast20=fast[20], fast7=fast[7], atan_yx=yx.astype(np.int32), atan_deg=at,
+                        cv2_version=np.array(cv2.__version__))
+
+    # ---- whole extractor on a small frame ----
+    frame = synth.frame(320, 240, seed=11)
+    kps, desc, mono = extract_with_cv2(frame, 500)
+    np.savez_compressed(os.path.join(HERE, "orb_small.npz"), frame=frame, kps=kps, desc=desc, mono=np.int32(mono),
+                        nfeatures=np.int32(500))
+
+    # ---- tracking operators and local BA on small cases ----
+    S = synth.PlaneStream(640, 480, seed=3, K=(500.0, 500.0, 320.0, 240.0))
+    orc = OrbOracle(800)
+    T = orc.tables()
+    case = synth.tracking_case(S, 4, orc.extract, n_local=1500)
+    F = FrameOracle(case["cur_kps"], case["cur_desc"], case["bounds"], T["scale"])
+    lk = case["last_kps"]
+    n, cur_mp = F.search_by_projection_last(case["Rcw_prior"], case["tcw_prior"], case["K"], case["has_mp"],
+                                            case["outlier"], case["last_Xw"], case["last_desc"], case["obs_pos"],
+                                            lk["octave"], lk["angle"], 15.0)
+    idx = np.nonzero(cur_mp >= 0)[0]
+    ck = case["cur_kps"]
+    q = synth.quat_from_R(case["Rcw_prior"].astype(np.float64)).astype(np.float32)
+    r, q2, t2, outl, _ = pose_optimization(q, case["tcw_prior"], case["K"], case["last_Xw"][cur_mp[idx]],
+                                           np.stack([ck["x"][idx], ck["y"][idx]], 1), T["inv_sigma2"][ck["octave"][idx]])
+    B = synth.ba_scene(6, 2, 120, seed=5)
+    ba = local_ba(B["cam_q"], B["cam_t"], B["cam_fixed"], B["pts"], B["edge_cam"], B["edge_pt"], B["edge_obs"],
+                  B["edge_w"], B["K"])
+    np.savez_compressed(os.path.join(HERE, "track_small.npz"), nmatches=np.int32(n), cur_mp=cur_mp, pose_q=q2,
+                        pose_t=t2, pose_inliers=np.int32(r), pose_outlier=outl, ba_cam_q=ba["cam_q"],
+                        ba_cam_t=ba["cam_t"], ba_pts=ba["pts"], ba_bad=ba["bad"], ba_iters=np.int32(ba["iters"]),
+                        ba_chi=np.array([ba["chi_first"], ba["chi_last"]]))
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")
+
+
+if __name__ == "__main__":
+    main()
