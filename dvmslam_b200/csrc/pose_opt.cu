@@ -1,4 +1,4 @@
-// pose_opt.cu -- Optimizer::PoseOptimization on one CTA (O3/src/Optimizer.cc:744-1028).
+// pose_opt.cu -- Optimizer::PoseOptimization on one 8-CTA cluster (O3/src/Optimizer.cc:744-1028).
 // Float64 work inside the stated tolerance: this file is compiled with FMA contraction enabled.
 #include "track_kernels.cuh"
 #include <cooperative_groups.h>
@@ -76,7 +76,7 @@ __device__ inline SE3d se3_exp(const double u[6])
         for (int i = 0; i < 9; i++) { R[i] = ((i % 4 == 0) ? 1.0 : 0.0) + O[i] + O2[i]; V[i] = R[i]; }
     } else {
         const double sa = sin(theta) / theta, sb = (1 - cos(theta)) / (theta * theta);
-        const double sc = (theta - sin(theta)) / pow(theta, 3.0);
+        const double sc = (theta - sin(theta)) / (theta * theta * theta);
 #pragma unroll
         for (int i = 0; i < 9; i++) {
             const double I = (i % 4 == 0) ? 1.0 : 0.0;
@@ -105,26 +105,36 @@ __device__ inline SE3d se3_mul(const SE3d& a, const SE3d& b)
 // unpivoted LDL^T of a symmetric 6x6 system (full storage); false if a pivot is not positive
 __device__ inline bool ldlt6_solve(const double* A, const double* b, double* x)
 {
-    double L[36], D[6], y[6];
+    double L[36], D[6], Dinv[6], y[6];
+    bool ok = true;
 #pragma unroll
     for (int j = 0; j < 6; j++) {
         double d = A[j * 6 + j];
+#pragma unroll
         for (int k = 0; k < j; k++) d -= L[j * 6 + k] * L[j * 6 + k] * D[k];
-        if (!(d > 0)) return false;
+        ok = ok && (d > 0);
         D[j] = d;
+        Dinv[j] = 1.0 / d;
+#pragma unroll
         for (int i = j + 1; i < 6; i++) {
             double s = A[i * 6 + j];
+#pragma unroll
             for (int k = 0; k < j; k++) s -= L[i * 6 + k] * L[j * 6 + k] * D[k];
-            L[i * 6 + j] = s / d;
+            L[i * 6 + j] = s * Dinv[j];
         }
     }
+    if (!ok) return false;
+#pragma unroll
     for (int i = 0; i < 6; i++) {
         double s = b[i];
+#pragma unroll
         for (int k = 0; k < i; k++) s -= L[i * 6 + k] * y[k];
         y[i] = s;
     }
+#pragma unroll
     for (int i = 5; i >= 0; i--) {
-        double s = y[i] / D[i];
+        double s = y[i] * Dinv[i];
+#pragma unroll
         for (int k = i + 1; k < 6; k++) s -= L[k * 6 + i] * x[k];
         x[i] = s;
     }
@@ -133,105 +143,120 @@ __device__ inline bool ldlt6_solve(const double* A, const double* b, double* x)
 
 struct PoseCam { double fx, fy, cx, cy, delta, dsqr; };
 
-__device__ inline void pose_edge_error(const PoseCam& c, const SE3d& T, const float* Xw, const float* obs, double e[2], double xc[3])
+__device__ inline void quat_to_matrix(const Quat& q, double R[9])
 {
-    const double X[3] = { (double)Xw[0], (double)Xw[1], (double)Xw[2] };
-    quat_rotate(T.r, X, xc);
-    xc[0] += T.t[0]; xc[1] += T.t[1]; xc[2] += T.t[2];
-    e[0] = (double)obs[0] - (c.fx * xc[0] / xc[2] + c.cx);
-    e[1] = (double)obs[1] - (c.fy * xc[1] / xc[2] + c.cy);
+    const double tx = 2 * q.x, ty = 2 * q.y, tz = 2 * q.z;
+    const double twx = tx * q.w, twy = ty * q.w, twz = tz * q.w;
+    const double txx = tx * q.x, txy = ty * q.x, txz = tz * q.x;
+    const double tyy = ty * q.y, tyz = tz * q.y, tzz = tz * q.z;
+    R[0] = 1 - (tyy + tzz); R[1] = txy - twz; R[2] = txz + twy;
+    R[3] = txy + twz; R[4] = 1 - (txx + tzz); R[5] = tyz - twx;
+    R[6] = txz - twy; R[7] = tyz + twx; R[8] = 1 - (txx + tyy);
 }
-__device__ inline double pose_chi2(const double e[2], double info) { return e[0] * (info * e[0]) + e[1] * (info * e[1]); }
-__device__ inline double huber_rho0(const PoseCam& c, double e) { return e <= c.dsqr ? e : 2 * sqrt(e) * c.delta - c.dsqr; }
-__device__ inline double huber_rho1(const PoseCam& c, double e) { return e <= c.dsqr ? 1.0 : c.delta / sqrt(e); }
 
-// One thread-block CLUSTER (8 CTAs x 128 threads, one edge per thread up to 1024 edges) runs the whole
-// of Optimizer::PoseOptimization: 4 rounds x optimize(10) of g2o's LM on one SE3 vertex with outlier
-// re-classification between rounds.  Every thread carries the pose and the 6x6 system redundantly
-// (identical arithmetic), so nothing is broadcast; per-edge terms are reduced in a fixed order
-// (warp shuffle -> CTA -> the 8 CTA partials exchanged through distributed shared memory), so the
-// result is deterministic.  Each LM trial is ONE pass over the edges: errors, robust chi2 and the
-// linearisation at the trial estimate are accumulated together; if the trial is accepted the next
-// iteration's buildSystem() is already there (same values g2o would recompute).
+// One thread-block CLUSTER (8 CTAs x 128 threads) runs the whole of Optimizer::PoseOptimization:
+// 4 rounds x optimize(10) of g2o's LM on one SE3 vertex with outlier re-classification between
+// rounds.  Every thread keeps its edges (world point, observation, information, state, last error) in
+// REGISTERS -- EPT edges per thread, edge k of the frame lives in thread k % 1024, slot k / 1024 -- so
+// the ~50 dependent passes of one call touch no global memory.  Every thread carries the pose and the
+// 6x6 system redundantly (identical arithmetic), so nothing is broadcast; per-edge terms are reduced in
+// a fixed order (transposed warp butterfly -> CTA -> the 8 CTA partials exchanged through distributed
+// shared memory), so the result is deterministic.  Each LM trial is ONE pass over the edges: errors,
+// robust chi2 and the linearisation at the trial estimate are accumulated together; if the trial is
+// accepted the next iteration's buildSystem() is already there (same values g2o would recompute).
 constexpr int kPoseCtas = 8;
 constexpr int kPoseThreads = 128;
 constexpr int kPoseWarps = kPoseThreads / 32;
-constexpr int kPoseNV = 30; // 21 H + 6 b + chi + active count + spare
+constexpr int kPoseStride = kPoseCtas * kPoseThreads;
+// reduction slots: 0..20 H upper triangle (row-major), 21..26 b, 27 robust chi2, 28 active edges
+constexpr int kPoseNV = 32;
 
 struct PoseShared {
     double warp_buf[kPoseWarps][kPoseNV];
     double recv[2][kPoseCtas][kPoseNV]; // partials of every CTA of the cluster, double-buffered
-    double tot[kPoseNV];
 };
 
-// sums v over all threads of the cluster; result in sh.tot (valid until the next call)
+// Sums v[s] over all threads of the cluster; on return v[s] holds the total of slot s in every thread
+// (same summation tree everywhere).  v is clobbered during the exchange.
 __device__ inline void cluster_sum(double (&v)[kPoseNV], PoseShared& sh, int& parity)
 {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned rank = cluster.block_rank();
+    // transposed butterfly: after the 5 steps lane l holds the warp total of slot l (31 shuffles)
 #pragma unroll
-    for (int i = 0; i < kPoseNV; i++) {
-        double s = v[i];
+    for (int off = 16; off >= 1; off >>= 1) {
+        const bool upper = (lane & off) != 0;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-        if (lane == 0) sh.warp_buf[wid][i] = s;
-    }
-    __syncthreads();
-    if (threadIdx.x < kPoseNV) {
-        double s = 0;
-#pragma unroll
-        for (int w = 0; w < kPoseWarps; w++) s += sh.warp_buf[w][threadIdx.x];
-        for (unsigned r = 0; r < kPoseCtas; r++) {
-            double* dst = cluster.map_shared_rank(&sh.recv[parity][rank][threadIdx.x], r);
-            *dst = s;
+        for (int i = 0; i < off; i++) {
+            const double send = upper ? v[i] : v[i + off];
+            const double keep = upper ? v[i + off] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
         }
     }
-    cluster.sync();
-    if (threadIdx.x < kPoseNV) {
-        double s = 0;
-#pragma unroll
-        for (int r = 0; r < kPoseCtas; r++) s += sh.recv[parity][r][threadIdx.x];
-        sh.tot[threadIdx.x] = s;
-    }
+    sh.warp_buf[wid][lane] = v[0];
     __syncthreads();
+    if (wid == 0) {
+        double s = sh.warp_buf[0][lane];
+#pragma unroll
+        for (int w = 1; w < kPoseWarps; w++) s += sh.warp_buf[w][lane];
+#pragma unroll
+        for (unsigned r = 0; r < kPoseCtas; r++) *cluster.map_shared_rank(&sh.recv[parity][rank][lane], r) = s;
+    }
+    cluster.sync();
+    double tot = sh.recv[parity][0][lane];
+#pragma unroll
+    for (int r = 1; r < kPoseCtas; r++) tot += sh.recv[parity][r][lane];
+#pragma unroll
+    for (int i = 0; i < 29; i++) v[i] = __shfl_sync(0xffffffffu, tot, i);
     parity ^= 1;
 }
 
+template <int EPT>
 __global__ void __cluster_dims__(kPoseCtas, 1, 1) __launch_bounds__(kPoseThreads, 1) pose_opt_kernel(PoseOptArgs a)
 {
     __shared__ PoseShared sh;
     const int tid = blockIdx.x * kPoseThreads + threadIdx.x;
-    constexpr int kStride = kPoseCtas * kPoseThreads;
     int parity = 0;
     const int n = a.n_ptr ? min(*a.n_ptr, a.n) : a.n;
-    auto edge_valid = [&](int k) { return a.map_index ? a.map_index[k] >= 0 : (a.valid ? a.valid[k] != 0 : true); };
-    auto edge_X = [&](int k) { return a.Xw + 3 * (size_t)(a.map_index ? a.map_index[k] : k); };
-    auto edge_info = [&](int k) { return (double)(a.kps ? a.inv_sigma2_table[a.kps[k].octave] : a.inv_sigma2[k]); };
-    auto edge_err = [&](const PoseCam& c, const SE3d& T, int k, double e[2], double xc[3]) {
-        float o[2];
-        if (a.kps) { o[0] = a.kps[k].x; o[1] = a.kps[k].y; }
-        else { o[0] = a.kp_xy[2 * k]; o[1] = a.kp_xy[2 * k + 1]; }
-        pose_edge_error(c, T, edge_X(k), o, e, xc);
-    };
     PoseCam cam;
     cam.fx = a.K[0]; cam.fy = a.K[1]; cam.cx = a.K[2]; cam.cy = a.K[3];
     cam.delta = (double)(float)sqrt(5.991);
     cam.dsqr = cam.delta * cam.delta;
 
-    // edge state byte (kept in a.outlier until the end): bit0 excluded (level 1), bit1 robust kernel
-    // removed, bit2 not an edge
+    // ---- gather this thread's edges into registers ----
+    // state: bit0 excluded (level 1), bit1 robust kernel removed, bit2 not an edge
+    double X[EPT][3], ox[EPT], oy[EPT], om[EPT], e0[EPT], e1[EPT];
+    int st[EPT], mis[EPT];
     double acc[kPoseNV];
 #pragma unroll
     for (int i = 0; i < kPoseNV; i++) acc[i] = 0;
-    for (int k = tid; k < n; k += kStride) {
-        const bool valid = edge_valid(k);
-        a.outlier[k] = valid ? 0 : 4;
-        acc[28] += valid;
+#pragma unroll
+    for (int s = 0; s < EPT; s++) {
+        const int k = tid + s * kPoseStride;
+        st[s] = 4; mis[s] = -1;
+        X[s][0] = X[s][1] = X[s][2] = 0; ox[s] = oy[s] = om[s] = 0; e0[s] = e1[s] = 0;
+        if (k < n) {
+            const int mi = a.map_index ? a.map_index[k] : k;
+            const bool valid = a.map_index ? mi >= 0 : (a.valid ? a.valid[k] != 0 : true);
+            if (valid) {
+                st[s] = 0; mis[s] = mi;
+                const float* xp = a.Xw + 3 * (size_t)mi;
+                X[s][0] = (double)xp[0]; X[s][1] = (double)xp[1]; X[s][2] = (double)xp[2];
+                if (a.kps) {
+                    ox[s] = (double)a.kps[k].x; oy[s] = (double)a.kps[k].y;
+                    om[s] = (double)a.inv_sigma2_table[a.kps[k].octave];
+                } else {
+                    ox[s] = (double)a.kp_xy[2 * k]; oy[s] = (double)a.kp_xy[2 * k + 1];
+                    om[s] = (double)a.inv_sigma2[k];
+                }
+                acc[28] += 1;
+            }
+        }
     }
     cluster_sum(acc, sh, parity);
-    const int nedges = (int)sh.tot[28];
+    const int nedges = (int)acc[28];
 
     SE3d T0;
     T0.r.x = a.pose[0]; T0.r.y = a.pose[1]; T0.r.z = a.pose[2]; T0.r.w = a.pose[3];
@@ -240,47 +265,63 @@ __global__ void __cluster_dims__(kPoseCtas, 1, 1) __launch_bounds__(kPoseThreads
     SE3d T = T0;
     int nBadEdges = 0, total_iters = 0, total_trials = 0;
 
-    // errors + robust chi2 + linearisation of every active edge at estimate Tx -> sh.tot
-    // (tot[0..20] H upper, [21..26] b, [27] robust chi2, [28] active edges)
+    // errors + robust chi2 + linearisation of every active edge at estimate Tx -> acc (all threads)
     auto linearize_at = [&](const SE3d& Tx) {
+        double R[9];
+        quat_to_matrix(Tx.r, R);
 #pragma unroll
         for (int i = 0; i < kPoseNV; i++) acc[i] = 0;
-        for (int k = tid; k < n; k += kStride) {
-            const int st = a.outlier[k];
-            if (st & 5) continue;
+#pragma unroll
+        for (int s = 0; s < EPT; s++) {
+            if (st[s] & 5) continue;
+            const double x = R[0] * X[s][0] + R[1] * X[s][1] + R[2] * X[s][2] + Tx.t[0];
+            const double y = R[3] * X[s][0] + R[4] * X[s][1] + R[5] * X[s][2] + Tx.t[1];
+            const double z = R[6] * X[s][0] + R[7] * X[s][1] + R[8] * X[s][2] + Tx.t[2];
+            const double iz = 1.0 / z;
+            const double ax = cam.fx * iz, ay = cam.fy * iz;      // d u / d x, d v / d y
+            const double bx = -ax * x * iz, by = -ay * y * iz;    // d u / d z, d v / d z
+            const double ex = ox[s] - (ax * x + cam.cx), ey = oy[s] - (ay * y + cam.cy);
+            e0[s] = ex; e1[s] = ey;
+            const double chi = om[s] * (ex * ex + ey * ey);
+            const bool robust = !(st[s] & 2);
+            double w = 1.0, rho = chi;
+            if (robust && chi > cam.dsqr) {
+                const double sq = sqrt(chi);
+                rho = 2 * sq * cam.delta - cam.dsqr;
+                w = cam.delta / sq;
+            }
+            acc[27] += rho;
             acc[28] += 1;
-            double e[2], xc[3];
-            edge_err(cam, Tx, k, e, xc);
-            a.err[2 * k] = e[0]; a.err[2 * k + 1] = e[1];
-            const double om = edge_info(k);
-            const double chi = pose_chi2(e, om);
-            const bool robust = !(st & 2);
-            acc[27] += robust ? huber_rho0(cam, chi) : chi;
-            const double w = robust ? huber_rho1(cam, chi) : 1.0;
-            const double x = xc[0], y = xc[1], z = xc[2];
-            const double pj[6] = { cam.fx / z, 0, -cam.fx * x / (z * z), 0, cam.fy / z, -cam.fy * y / (z * z) };
-            const double D[18] = { 0, z, -y, 1, 0, 0, -z, 0, x, 0, 1, 0, y, -x, 0, 0, 0, 1 };
-            double J[12];
+            // J = -dproj * [ -[Xc]x | I ]  (O3/src/OptimizableTypes.cpp:51-63); J0[4] = J1[3] = 0
+            const double J0[6] = { -bx * y, bx * x - ax * z, ax * y, -ax, 0.0, -bx };
+            const double J1[6] = { ay * z - by * y, by * x, -ay * x, 0.0, -ay, -by };
+            const double sw = w * om[s];
+            double S0[6], S1[6];
 #pragma unroll
-            for (int r = 0; r < 2; r++)
-#pragma unroll
-                for (int c = 0; c < 6; c++)
-                    J[r * 6 + c] = -(pj[r * 3] * D[c] + pj[r * 3 + 1] * D[6 + c] + pj[r * 3 + 2] * D[12 + c]);
+            for (int c = 0; c < 6; c++) { S0[c] = sw * J0[c]; S1[c] = sw * J1[c]; }
             int idx = 0;
 #pragma unroll
             for (int c = 0; c < 6; c++) {
-                acc[21 + c] -= w * (J[c] * (om * e[0]) + J[6 + c] * (om * e[1]));
+                if (c != 4) acc[21 + c] -= S0[c] * ex;
+                if (c != 3) acc[21 + c] -= S1[c] * ey;
 #pragma unroll
-                for (int d = c; d < 6; d++) acc[idx++] += J[c] * (w * om) * J[d] + J[6 + c] * (w * om) * J[6 + d];
+                for (int d = c; d < 6; d++) {
+                    if (c != 4 && d != 4) acc[idx] += S0[c] * J0[d];
+                    if (c != 3 && d != 3) acc[idx] += S1[c] * J1[d];
+                    idx++;
+                }
             }
         }
         cluster_sum(acc, sh, parity);
     };
     auto unpack = [&](double* H, double* b) {
         int idx = 0;
+#pragma unroll
         for (int c = 0; c < 6; c++)
-            for (int d = c; d < 6; d++) { H[c * 6 + d] = sh.tot[idx]; H[d * 6 + c] = sh.tot[idx]; idx++; }
-        for (int c = 0; c < 6; c++) b[c] = sh.tot[21 + c];
+#pragma unroll
+            for (int d = c; d < 6; d++) { H[c * 6 + d] = acc[idx]; H[d * 6 + c] = acc[idx]; idx++; }
+#pragma unroll
+        for (int c = 0; c < 6; c++) b[c] = acc[21 + c];
     };
 
     if (nedges >= 3) {
@@ -294,13 +335,14 @@ __global__ void __cluster_dims__(kPoseCtas, 1, 1) __launch_bounds__(kPoseThreads
             for (int it = 0; it < 10; it++) {
                 if (!have_system) {
                     linearize_at(T);
-                    if ((int)sh.tot[28] == 0) break; // no active edge: optimize() returns without touching anything
+                    if ((int)acc[28] == 0) break; // no active edge: optimize() returns without touching anything
                     unpack(H, b);
-                    currentChi = sh.tot[27];
+                    currentChi = acc[27];
                 }
                 const double iniChi = currentChi;
                 if (it == 0) {
                     double mx = 0;
+#pragma unroll
                     for (int j = 0; j < 6; j++) mx = fmax(fabs(H[j * 6 + j]), mx);
                     lambda = 1e-5 * mx; // computeLambdaInit, tau = 1e-5
                     ni = 2;
@@ -312,21 +354,28 @@ __global__ void __cluster_dims__(kPoseCtas, 1, 1) __launch_bounds__(kPoseThreads
                 do {
                     const SE3d backup = T;
                     double Hl[36], x[6];
+#pragma unroll
                     for (int j = 0; j < 36; j++) Hl[j] = H[j];
+#pragma unroll
                     for (int j = 0; j < 6; j++) Hl[j * 6 + j] += lambda;
                     const bool ok2 = ldlt6_solve(Hl, b, x);
-                    if (!ok2) for (int j = 0; j < 6; j++) x[j] = 0;
+                    if (!ok2) {
+#pragma unroll
+                        for (int j = 0; j < 6; j++) x[j] = 0;
+                    }
                     T = se3_mul(se3_exp(x), T);
                     linearize_at(T); // computeActiveErrors at the trial (+ speculative buildSystem)
-                    double tempChi = sh.tot[27];
+                    double tempChi = acc[27];
                     if (!ok2) tempChi = 1.7976931348623157e308;
                     rho = currentChi - tempChi;
                     double scale = 0;
+#pragma unroll
                     for (int j = 0; j < 6; j++) scale += x[j] * (lambda * x[j] + b[j]);
                     scale += 1e-3;
                     rho /= scale;
                     if (rho > 0 && isfinite(tempChi)) {
-                        double alpha = 1. - pow((2 * rho - 1), 3.0);
+                        const double c = 2 * rho - 1;
+                        double alpha = 1. - c * c * c;
                         alpha = fmin(alpha, 2. / 3.);
                         const double sf = fmax(1. / 3., alpha);
                         lambda *= sf;
@@ -348,26 +397,44 @@ __global__ void __cluster_dims__(kPoseCtas, 1, 1) __launch_bounds__(kPoseThreads
                 else nBadIter = 0;
                 if (nBadIter >= 3) break;
             }
-            // ---- re-classify every edge (O3/src/Optimizer.cc:941-965) ----
+            // ---- re-classify every edge (O3/src/Optimizer.cc:941-965): inliers keep the error of the
+            // last computeActiveErrors(), outliers are re-evaluated at the final estimate ----
+            double R[9];
+            quat_to_matrix(T.r, R);
 #pragma unroll
             for (int i = 0; i < kPoseNV; i++) acc[i] = 0;
-            for (int k = tid; k < n; k += kStride) {
-                int st = a.outlier[k];
-                if (st & 4) continue;
-                double e[2] = { a.err[2 * k], a.err[2 * k + 1] };
-                if (st & 1) { double xc[3]; edge_err(cam, T, k, e, xc); a.err[2 * k] = e[0]; a.err[2 * k + 1] = e[1]; }
-                const float chi2 = (float)pose_chi2(e, edge_info(k));
-                if (chi2 > 5.991f) { st |= 1; acc[0] += 1; }
-                else st &= ~1;
-                if (round == 2) st |= 2;
-                a.outlier[k] = (uint8_t)st;
+#pragma unroll
+            for (int s = 0; s < EPT; s++) {
+                if (st[s] & 4) continue;
+                if (st[s] & 1) {
+                    const double x = R[0] * X[s][0] + R[1] * X[s][1] + R[2] * X[s][2] + T.t[0];
+                    const double y = R[3] * X[s][0] + R[4] * X[s][1] + R[5] * X[s][2] + T.t[1];
+                    const double z = R[6] * X[s][0] + R[7] * X[s][1] + R[8] * X[s][2] + T.t[2];
+                    const double iz = 1.0 / z;
+                    e0[s] = ox[s] - (cam.fx * iz * x + cam.cx);
+                    e1[s] = oy[s] - (cam.fy * iz * y + cam.cy);
+                }
+                const float chi2 = (float)(om[s] * (e0[s] * e0[s] + e1[s] * e1[s]));
+                if (chi2 > 5.991f) { st[s] |= 1; acc[0] += 1; }
+                else st[s] &= ~1;
+                if (round == 2) st[s] |= 2;
             }
             cluster_sum(acc, sh, parity);
-            nBadEdges = (int)sh.tot[0];
+            nBadEdges = (int)acc[0];
             if (nedges < 10) break;
         }
     }
-    for (int k = tid; k < n; k += kStride) a.outlier[k] = (a.outlier[k] & 4) ? 0 : (a.outlier[k] & 1);
+#pragma unroll
+    for (int s = 0; s < EPT; s++) {
+        const int k = tid + s * kPoseStride;
+        if (k >= n) continue;
+        int out = (st[s] & 4) ? 0 : (st[s] & 1);
+        if (a.seen && !(st[s] & 4)) { // "discard outliers": Tracking.cc:2634-2654
+            a.seen[mis[s]] = 1;
+            if (out) { a.map_index_rw[k] = -1; out = 0; }
+        }
+        a.outlier[k] = (uint8_t)out;
+    }
     if (tid == 0) {
         if (nedges >= 3) {
             a.pose[0] = (float)T.r.x; a.pose[1] = (float)T.r.y; a.pose[2] = (float)T.r.z; a.pose[3] = (float)T.r.w;
@@ -377,10 +444,34 @@ __global__ void __cluster_dims__(kPoseCtas, 1, 1) __launch_bounds__(kPoseThreads
         a.result[1] = nedges;
         a.result[2] = total_iters;
         a.result[3] = total_trials;
+        if (a.out_pose) { // frame hand-over: pose history for the constant-velocity prior + result block
+            for (int i = 0; i < 7; i++) {
+                const float v = a.pose[i];
+                a.pose_prev[i] = a.pose_last[i];
+                a.pose_last[i] = v;
+                a.out_pose[i] = v;
+            }
+            a.out_counts[0] = n;
+            a.out_counts[1] = *a.nm_last;
+            a.out_counts[2] = a.res_first[0];
+            a.out_counts[3] = nedges >= 3 ? nedges - nBadEdges : nedges; // mnMatchesInliers
+        }
     }
     cooperative_groups::this_cluster().sync(); // no CTA may exit while peers can still write into its shared memory
 }
 
-void launch_pose_opt(const PoseOptArgs& a, cudaStream_t stream) { DVM_LAUNCH(pose_opt_kernel, kPoseCtas, kPoseThreads, 0, stream, a); }
+int launch_pose_opt(const PoseOptArgs& a, cudaStream_t stream)
+{
+    // a.n bounds the number of potential edges (the device count may be smaller): pick the register tile
+    if (a.n <= 2 * kPoseStride) DVM_LAUNCH(pose_opt_kernel<2>, kPoseCtas, kPoseThreads, 0, stream, a);
+    else if (a.n <= 4 * kPoseStride) DVM_LAUNCH(pose_opt_kernel<4>, kPoseCtas, kPoseThreads, 0, stream, a);
+    else if (a.n <= 8 * kPoseStride) DVM_LAUNCH(pose_opt_kernel<8>, kPoseCtas, kPoseThreads, 0, stream, a);
+    else if (a.n <= 16 * kPoseStride) DVM_LAUNCH(pose_opt_kernel<16>, kPoseCtas, kPoseThreads, 0, stream, a);
+    else {
+        set_error("PoseOptimization: %d correspondences exceed the supported %d", a.n, 16 * kPoseStride);
+        return DVM_ERR_CAPACITY;
+    }
+    return DVM_OK;
+}
 
 } // namespace dvm

@@ -182,12 +182,8 @@ int dvm_frame_assign_from_orb(dvm_frame* f, const dvm_orb* orb, float min_x, flo
         DVM_CUDA(cudaEventRecord(f->ev, os));
         DVM_CUDA(cudaStreamWaitEvent(f->stream, f->ev, 0));
     }
-    const int m = dvm_orb_max_keypoints(orb);
-    DVM_CUDA(cudaMemcpyAsync(f->d_kps, k, (size_t)m * sizeof(dvm_keypoint), cudaMemcpyDeviceToDevice, f->stream));
-    DVM_CUDA(cudaMemcpyAsync(f->d_desc, d, (size_t)m * 32, cudaMemcpyDeviceToDevice, f->stream));
-    DVM_CUDA(cudaMemcpyAsync(f->d_n, c, sizeof(int), cudaMemcpyDeviceToDevice, f->stream));
-    f->host_n = m;
-    launch_grid_build(f->dev, f->stream);
+    f->host_n = dvm_orb_max_keypoints(orb);
+    launch_frame_assign(f->dev, k, d, c, f->stream); // copy + AssignFeaturesToGrid in one launch
     DVM_CUDA(cudaGetLastError());
     return DVM_OK;
 }
@@ -342,7 +338,7 @@ int dvm_pose_optimization(dvm_frame* ctx, float* pose_q, float* pose_t, const fl
     a.valid = nullptr;
     a.err = ctx->d_err;
     DVM_CUDA(cudaMemcpyAsync(ctx->d_in, ctx->h_in, p.off, cudaMemcpyHostToDevice, ctx->stream));
-    launch_pose_opt(a, ctx->stream);
+    { const int prc = launch_pose_opt(a, ctx->stream); if (prc != DVM_OK) return prc; }
     DVM_CUDA(cudaGetLastError());
     const size_t out_bytes = p.off - out_begin;
     rc = dvm_frame_ensure_bytes(ctx, 0, out_bytes);

@@ -34,8 +34,7 @@ __device__ inline void load_desc(uint32_t a[8], const uint8_t* d)
     a[4] = v1.x; a[5] = v1.y; a[6] = v1.z; a[7] = v1.w;
 }
 
-// Where the matchers read the current frame from: global memory (FrameDev as is) or a copy staged in
-// shared memory (grid, keypoint x/y/octave records, descriptors) when the frame fits.
+// How the matchers read the current frame (global memory through L1/L2; the frame is ~200 KB).
 struct FrameLook {
     const int* cell_start;
     const int* cell_items;
@@ -54,33 +53,6 @@ __device__ inline FrameLook look_global(const FrameDev& f)
     v.cell_start = f.cell_start; v.cell_items = f.cell_items;
     v.kbase = reinterpret_cast<const char*>(f.kps); v.kstride = (int)sizeof(dvm_keypoint); v.oct_off = 20;
     v.desc = f.desc;
-    v.minX = f.minX; v.minY = f.minY; v.gwInv = f.gwInv; v.ghInv = f.ghInv;
-    return v;
-}
-
-__host__ __device__ inline size_t frame_smem_bytes(int cap) { return (size_t)(kGridCells + 4) * 4 + (size_t)cap * (4 + 12 + 32); }
-
-// copies the frame into shared memory (all threads of the CTA) and returns the view
-__device__ inline FrameLook look_shared(const FrameDev& f, int n, unsigned char* smem)
-{
-    uint4* sdesc = reinterpret_cast<uint4*>(smem);                              // [cap*2] (16-byte aligned first)
-    int* scell = reinterpret_cast<int*>(smem + (size_t)f.cap * 32);             // [kGridCells + 4]
-    int* sitems = scell + kGridCells + 4;                                       // [cap]
-    int* skp = sitems + f.cap;                                                  // [cap * 3]
-    for (int i = threadIdx.x; i <= kGridCells; i += blockDim.x) scell[i] = f.cell_start[i];
-    const int nitems = f.cell_start[kGridCells];
-    for (int i = threadIdx.x; i < nitems; i += blockDim.x) sitems[i] = f.cell_items[i];
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const dvm_keypoint* kp = f.kps + i;
-        skp[3 * i] = __float_as_int(kp->x); skp[3 * i + 1] = __float_as_int(kp->y); skp[3 * i + 2] = kp->octave;
-    }
-    const uint4* gdesc = reinterpret_cast<const uint4*>(f.desc);
-    for (int i = threadIdx.x; i < n * 2; i += blockDim.x) sdesc[i] = __ldg(gdesc + i);
-    __syncthreads();
-    FrameLook v;
-    v.cell_start = scell; v.cell_items = sitems;
-    v.kbase = reinterpret_cast<const char*>(skp); v.kstride = 12; v.oct_off = 8;
-    v.desc = reinterpret_cast<const uint8_t*>(sdesc);
     v.minX = f.minX; v.minY = f.minY; v.gwInv = f.gwInv; v.ghInv = f.ghInv;
     return v;
 }
@@ -117,12 +89,25 @@ __device__ inline void walk_area(const FrameLook& f, float x, float y, float r, 
 }
 
 // -------------------------------------------------------------------------------------- grid build
-__global__ void __launch_bounds__(1024) grid_build_kernel(FrameDev f)
+// src_kps != nullptr: first copy an extractor result (keypoints, descriptors, count) into the frame's buffers
+__global__ void __launch_bounds__(1024) grid_build_kernel(FrameDev f, const dvm_keypoint* __restrict__ src_kps,
+                                                          const uint8_t* __restrict__ src_desc, const int* __restrict__ src_n)
 {
     __shared__ int counts[kGridCells];
     __shared__ int warp_sums[33];
     const int tid = threadIdx.x;
-    const int n = min(*f.n, f.cap);
+    if (src_kps) {
+        const int ns = min(*src_n, f.cap);
+        const int* sk = reinterpret_cast<const int*>(src_kps);
+        int* dk = reinterpret_cast<int*>(const_cast<dvm_keypoint*>(f.kps));
+        for (int i = tid; i < ns * 7; i += 1024) dk[i] = sk[i];
+        const uint4* sd = reinterpret_cast<const uint4*>(src_desc);
+        uint4* dd = reinterpret_cast<uint4*>(const_cast<uint8_t*>(f.desc));
+        for (int i = tid; i < ns * 2; i += 1024) dd[i] = sd[i];
+        if (tid == 0) *const_cast<int*>(f.n) = *src_n;
+        __syncthreads();
+    }
+    const int n = min(src_kps ? *src_n : *f.n, f.cap);
     for (int c = tid; c < kGridCells; c += 1024) counts[c] = 0;
     __syncthreads();
     for (int i = tid; i < n; i += 1024) {
@@ -164,7 +149,29 @@ __global__ void __launch_bounds__(1024) grid_build_kernel(FrameDev f)
     }
 }
 
-void launch_grid_build(const FrameDev& f, cudaStream_t stream) { DVM_LAUNCH(grid_build_kernel, 1, 1024, 0, stream, f); }
+void launch_grid_build(const FrameDev& f, cudaStream_t stream)
+{
+    DVM_LAUNCH(grid_build_kernel, 1, 1024, 0, stream, f, (const dvm_keypoint*)nullptr, (const uint8_t*)nullptr, (const int*)nullptr);
+}
+void launch_frame_assign(const FrameDev& f, const dvm_keypoint* src_kps, const uint8_t* src_desc, const int* src_n,
+                         cudaStream_t stream)
+{
+    DVM_LAUNCH(grid_build_kernel, 1, 1024, 0, stream, f, src_kps, src_desc, src_n);
+}
+
+// Frame::isInFrustum for a batch of map points, one thread per point
+__global__ void __launch_bounds__(256) frustum_kernel(FrustumArgs a)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= a.m) return;
+    float R[9];
+    quat_to_R_f32(a.pose, R);
+    float u, v, vc;
+    int lvl;
+    const bool vis = frustum_eval(a, R, k, u, v, lvl, vc);
+    a.in_view[k] = vis ? 1 : 0; a.px[k] = u; a.py[k] = v; a.level[k] = lvl; a.view_cos[k] = vc;
+}
+void launch_frustum(const FrustumArgs& a, cudaStream_t stream) { DVM_LAUNCH(frustum_kernel, div_up(a.m, 256), 256, 0, stream, a); }
 
 __global__ void features_in_area_kernel(FrameDev f, float x, float y, float r, int minLevel, int maxLevel, int* out,
                                         int cap, int* n_out)
@@ -230,77 +237,82 @@ __device__ inline void topk_insert(unsigned long long (&top)[kMatchCacheK], unsi
         if (v < top[p]) { const unsigned long long t = top[p]; top[p] = v; v = t; }
 }
 
+constexpr int kWalkThreads = 128;
+
+// ---- SearchByProjection(cur, last), phase 1: one thread per last-frame keypoint projects its map point
+// with the pose prior and walks its window once (many CTAs; the frame is read through L1/L2) ----
+__global__ void __launch_bounds__(kWalkThreads) match_last_walk_kernel(FrameDev cur, MatchLastArgs a, MatchScratch s)
+{
+    if (a.guard && *a.guard >= 20) return; // enough matches at th: the wider retry is not run
+    const int nq = a.n_ptr ? *a.n_ptr : a.last_n;
+    const int i = blockIdx.x * kWalkThreads + threadIdx.x;
+    if (i >= nq) return;
+    if (a.pose) { // pose prior held on the device
+        float Rm[9];
+        quat_to_R_f32(a.pose, Rm);
+        for (int k = 0; k < 9; k++) a.R[k] = Rm[k];
+        a.t[0] = a.pose[4]; a.t[1] = a.pose[5]; a.t[2] = a.pose[6];
+    }
+    const FrameLook fl = look_global(cur);
+    const int mi = a.mp_index ? a.mp_index[i] : (a.has_mp[i] ? i : -1);
+    int lv = -1, nc = 0;
+    unsigned long long top[kMatchCacheK];
+#pragma unroll
+    for (int p = 0; p < kMatchCacheK; p++) top[p] = ~0ull;
+    if (mi >= 0 && !a.outlier[i]) {
+        const float X = a.Xw[3 * mi], Y = a.Xw[3 * mi + 1], Z = a.Xw[3 * mi + 2];
+        const float xc = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a.R[0], X), __fmul_rn(a.R[1], Y)), __fmul_rn(a.R[2], Z)), a.t[0]);
+        const float yc = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a.R[3], X), __fmul_rn(a.R[4], Y)), __fmul_rn(a.R[5], Z)), a.t[1]);
+        const float zc = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a.R[6], X), __fmul_rn(a.R[7], Y)), __fmul_rn(a.R[8], Z)), a.t[2]);
+        const float invzc = (float)(1.0 / (double)zc);
+        if (!(invzc < 0)) {
+            const float u = __fadd_rn(__fdiv_rn(__fmul_rn(a.K[0], xc), zc), a.K[2]);
+            const float v = __fadd_rn(__fdiv_rn(__fmul_rn(a.K[1], yc), zc), a.K[3]);
+            if (!(u < cur.minX || u > cur.maxX) && !(v < cur.minY || v > cur.maxY)) {
+                const int oct = a.last_kps ? a.last_kps[i].octave : a.octave[i];
+                const float r = __fmul_rn(a.th, cur.scale[oct]);
+                s.pu[i] = u; s.pv[i] = v; s.pr[i] = r;
+                lv = ((oct - 1) << 16) | ((oct + 1) & 0xffff);
+                uint32_t d[8];
+                load_desc(d, a.mp_desc + (size_t)mi * 32);
+                walk_area(fl, u, v, r, oct - 1, oct + 1, [&](int idx, int o) {
+                    const int dist = hamming256(d, fl.desc + (size_t)idx * 32);
+                    topk_insert(top, pack_cand(dist, nc, o, idx));
+                    nc++;
+                });
+            }
+        }
+    }
+    s.plevels[i] = lv;
+    if (lv != -1) {
+#pragma unroll
+        for (int p = 0; p < kMatchCacheK; p++) s.cache[(size_t)i * kMatchCacheK + p] = top[p];
+        s.ncand[i] = nc;
+    }
+}
+
+// ---- phase 2: the sequential-greedy outcome as a Jacobi fixed point on ONE CTA (claims in shared
+// memory), then the rotation-consistency check ----
 __global__ void __launch_bounds__(kMatchThreads, 1)
 match_last_kernel(FrameDev cur, MatchLastArgs a, MatchScratch s, int* __restrict__ cur_mp, int* __restrict__ nmatches,
                   int use_smem)
 {
-    extern __shared__ __align__(16) unsigned char frame_smem[];
+    extern __shared__ __align__(16) unsigned char claim_smem[];
     __shared__ int histo[kHistoLength];
     __shared__ int s_ind[3], s_events, s_bad;
     const int tid = threadIdx.x;
     if (a.guard && *a.guard >= 20) return; // enough matches at th: the wider retry is not run
     const int ncur = min(*cur.n, cur.cap);
     const int nq = a.n_ptr ? *a.n_ptr : a.last_n;
-    if (a.pose) { // pose prior held on the device
-        float Rm[9];
-        quat_to_R_f32(a.pose, Rm);
-        for (int i = 0; i < 9; i++) a.R[i] = Rm[i];
-        a.t[0] = a.pose[4]; a.t[1] = a.pose[5]; a.t[2] = a.pose[6];
-    }
-    const FrameLook fl = use_smem ? look_shared(cur, ncur, frame_smem) : look_global(cur);
-    auto mp_of = [&](int i) { return a.mp_index ? a.mp_index[i] : (a.has_mp[i] ? i : -1); };
+    const FrameLook fl = look_global(cur);
     auto desc_of = [&](int i) { return a.mp_desc + (size_t)(a.mp_index ? a.mp_index[i] : i) * 32; };
     auto obs_of = [&](int i) { return a.obs_pos ? a.obs_pos[i] != 0 : true; };
     auto angle_of = [&](int i) { return a.last_kps ? a.last_kps[i].angle : a.angle[i]; };
 
-    // project every last-frame map point with the current pose prior
-    for (int i = tid; i < nq; i += kMatchThreads) {
-        int lv = -1;
-        const int mi = mp_of(i);
-        if (mi >= 0 && !a.outlier[i]) {
-            const float X = a.Xw[3 * mi], Y = a.Xw[3 * mi + 1], Z = a.Xw[3 * mi + 2];
-            const float xc = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a.R[0], X), __fmul_rn(a.R[1], Y)), __fmul_rn(a.R[2], Z)), a.t[0]);
-            const float yc = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a.R[3], X), __fmul_rn(a.R[4], Y)), __fmul_rn(a.R[5], Z)), a.t[1]);
-            const float zc = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a.R[6], X), __fmul_rn(a.R[7], Y)), __fmul_rn(a.R[8], Z)), a.t[2]);
-            const float invzc = (float)(1.0 / (double)zc);
-            if (!(invzc < 0)) {
-                const float u = __fadd_rn(__fdiv_rn(__fmul_rn(a.K[0], xc), zc), a.K[2]);
-                const float v = __fadd_rn(__fdiv_rn(__fmul_rn(a.K[1], yc), zc), a.K[3]);
-                if (!(u < cur.minX || u > cur.maxX) && !(v < cur.minY || v > cur.maxY)) {
-                    const int oct = a.last_kps ? a.last_kps[i].octave : a.octave[i];
-                    s.pu[i] = u; s.pv[i] = v;
-                    s.pr[i] = __fmul_rn(a.th, cur.scale[oct]);
-                    lv = ((oct - 1) << 16) | ((oct + 1) & 0xffff);
-                }
-            }
-        }
-        s.plevels[i] = lv;
-        s.choice[i] = -1;
-    }
-    int* claim_prev = s.claim_a;
-    int* claim_next = s.claim_b;
+    int* claim_prev = use_smem ? reinterpret_cast<int*>(claim_smem) : s.claim_a;
+    int* claim_next = use_smem ? reinterpret_cast<int*>(claim_smem) + cur.cap : s.claim_b;
+    for (int i = tid; i < nq; i += kMatchThreads) s.choice[i] = -1;
     for (int k = tid; k < ncur; k += kMatchThreads) claim_prev[k] = kNoClaim;
-    __syncthreads();
-
-    // walk every window once, fill the candidate cache
-    for (int i = tid; i < nq; i += kMatchThreads) {
-        const int lv = s.plevels[i];
-        if (lv == -1) continue;
-        uint32_t d[8];
-        load_desc(d, desc_of(i));
-        unsigned long long top[kMatchCacheK];
-#pragma unroll
-        for (int p = 0; p < kMatchCacheK; p++) top[p] = ~0ull;
-        int nc = 0;
-        walk_area(fl, s.pu[i], s.pv[i], s.pr[i], lv >> 16, (int)(short)(lv & 0xffff), [&](int idx, int oct) {
-            const int dist = hamming256(d, fl.desc + (size_t)idx * 32);
-            topk_insert(top, pack_cand(dist, nc, oct, idx));
-            nc++;
-        });
-#pragma unroll
-        for (int p = 0; p < kMatchCacheK; p++) s.cache[(size_t)i * kMatchCacheK + p] = top[p];
-        s.ncand[i] = nc;
-    }
     __syncthreads();
 
     int rounds = 0;
@@ -312,15 +324,13 @@ match_last_kernel(FrameDev cur, MatchLastArgs a, MatchScratch s, int* __restrict
             const int nc = s.ncand[i];
             int bestDist = 256, bestIdx = -1;
             bool found = false;
-            unsigned long long e[kMatchCacheK];
-#pragma unroll
-            for (int p = 0; p < kMatchCacheK; p++) e[p] = s.cache[(size_t)i * kMatchCacheK + p];
-#pragma unroll
-            for (int p = 0; p < kMatchCacheK; p++) {
-                if (found || p >= nc) continue;
-                const int idx = cand_idx(e[p]);
+            const unsigned long long* e = s.cache + (size_t)i * kMatchCacheK;
+            for (int p = 0; p < kMatchCacheK && p < nc; p++) {
+                const unsigned long long ev = e[p];
+                const int idx = cand_idx(ev);
                 if (claim_prev[idx] < i) continue; // taken by an earlier map point with observations
-                bestDist = cand_dist(e[p]); bestIdx = idx; found = true;
+                bestDist = cand_dist(ev); bestIdx = idx; found = true;
+                break;
             }
             if (!found && nc > kMatchCacheK) { // cache exhausted: full walk against the current claims
                 uint32_t d[8];
@@ -381,97 +391,109 @@ match_last_kernel(FrameDev cur, MatchLastArgs a, MatchScratch s, int* __restrict
     }
     __syncthreads();
     for (int k = tid; k < ncur; k += kMatchThreads) cur_mp[k] = nulled[k] ? -1 : owner[k];
+    if (a.map_out) // CurrentFrame.mvpMapPoints as map indices (device-resident tracker)
+        for (int k = tid; k < cur.cap; k += kMatchThreads)
+            a.map_out[k] = (k < ncur && !nulled[k] && owner[k] >= 0) ? a.mp_index[owner[k]] : -1;
     if (tid == 0) { *nmatches = s_events - s_bad; *s.iters = rounds; }
 }
 
 constexpr size_t kMatchSmemLimit = 200 * 1024;
 static bool prepare_match_kernels(); // raises the dynamic shared memory limit of both matcher kernels once
+__host__ inline size_t claim_smem_bytes(int cap) { return (size_t)cap * 8; }
 
 void launch_match_last(const FrameDev& cur, const MatchLastArgs& a, const MatchScratch& s, int* cur_mp, int* nmatches,
                        cudaStream_t stream)
 {
-    const size_t smem = frame_smem_bytes(cur.cap);
+    const size_t smem = claim_smem_bytes(cur.cap);
     const int use_smem = smem <= kMatchSmemLimit ? 1 : 0;
     prepare_match_kernels();
+    DVM_LAUNCH(match_last_walk_kernel, div_up(max(a.last_n, 1), kWalkThreads), kWalkThreads, 0, stream, cur, a, s);
     DVM_LAUNCH(match_last_kernel, 1, kMatchThreads, use_smem ? smem : 0, stream, cur, a, s, cur_mp, nmatches, use_smem);
 }
 
 // --------------------------------------------------------------- SearchByProjection(F, mapPoints)
+// phase 1: one thread per in-view map point walks its window once
+__global__ void __launch_bounds__(kWalkThreads) match_map_walk_kernel(FrameDev cur, MatchMapArgs a, MatchScratch s)
+{
+    const int nq = a.m_ptr ? *a.m_ptr : a.m;
+    const int i = blockIdx.x * kWalkThreads + threadIdx.x;
+    if (i >= nq) return;
+    const FrameLook fl = look_global(cur);
+    int lvl;
+    float px, py, vcos;
+    if (a.use_frustum) { // SearchLocalPoints: isInFrustum decides whether map point i takes part at all
+        float R[9];
+        quat_to_R_f32(a.fr.pose, R);
+        if (!frustum_eval(a.fr, R, i, px, py, lvl, vcos)) { s.plevels[i] = -1; s.ncand[i] = 0; return; }
+    } else {
+        lvl = a.level[i]; px = a.projX[i]; py = a.projY[i]; vcos = a.view_cos[i];
+    }
+    float r = vcos > 0.998f ? 2.5f : 4.0f; // RadiusByViewingCos
+    if (a.th != 1.0f) r = __fmul_rn(r, a.th);
+    r = __fmul_rn(r, cur.scale[lvl]);
+    s.pu[i] = px; s.pv[i] = py; s.pr[i] = r; s.plevels[i] = lvl;
+    uint32_t d[8];
+    load_desc(d, a.mp_desc + (size_t)(a.q_index ? a.q_index[i] : i) * 32);
+    unsigned long long top[kMatchCacheK];
+#pragma unroll
+    for (int p = 0; p < kMatchCacheK; p++) top[p] = ~0ull;
+    int nc = 0;
+    walk_area(fl, px, py, r, lvl - 1, lvl, [&](int idx, int oct) {
+        if (a.cur_map ? a.cur_map[idx] >= 0 : (a.cur_blocked && a.cur_blocked[idx])) return; // blocked from the start
+        const int dist = hamming256(d, fl.desc + (size_t)idx * 32);
+        topk_insert(top, pack_cand(dist, nc, oct, idx));
+        nc++;
+    });
+#pragma unroll
+    for (int p = 0; p < kMatchCacheK; p++) s.cache[(size_t)i * kMatchCacheK + p] = top[p];
+    s.ncand[i] = nc;
+}
+
 __global__ void __launch_bounds__(kMatchThreads, 1)
 match_map_kernel(FrameDev cur, MatchMapArgs a, MatchScratch s, int* __restrict__ cur_mp, int* __restrict__ nmatches,
                  int use_smem)
 {
-    extern __shared__ __align__(16) unsigned char frame_smem[];
+    extern __shared__ __align__(16) unsigned char claim_smem[];
     __shared__ int s_events;
     const int tid = threadIdx.x;
     const int ncur = min(*cur.n, cur.cap);
     const int nq = a.m_ptr ? *a.m_ptr : a.m;
-    const bool bFactor = a.th != 1.0f;
-    const FrameLook fl = use_smem ? look_shared(cur, ncur, frame_smem) : look_global(cur);
+    const FrameLook fl = look_global(cur);
     auto desc_of = [&](int i) { return a.mp_desc + (size_t)(a.q_index ? a.q_index[i] : i) * 32; };
     auto obs_of = [&](int i) { return a.obs_pos ? a.obs_pos[i] != 0 : true; };
     auto blocked = [&](int k) { return a.cur_map ? a.cur_map[k] >= 0 : (a.cur_blocked && a.cur_blocked[k]); };
-    for (int i = tid; i < nq; i += kMatchThreads) {
-        const int lvl = a.level[i];
-        float r = a.view_cos[i] > 0.998f ? 2.5f : 4.0f; // RadiusByViewingCos
-        if (bFactor) r = __fmul_rn(r, a.th);
-        s.pr[i] = __fmul_rn(r, cur.scale[lvl]);
-        s.choice[i] = -1;
-    }
-    int* claim_prev = s.claim_a;
-    int* claim_next = s.claim_b;
+    int* claim_prev = use_smem ? reinterpret_cast<int*>(claim_smem) : s.claim_a;
+    int* claim_next = use_smem ? reinterpret_cast<int*>(claim_smem) + cur.cap : s.claim_b;
+    for (int i = tid; i < nq; i += kMatchThreads) s.choice[i] = -1;
     for (int k = tid; k < ncur; k += kMatchThreads) claim_prev[k] = blocked(k) ? -1 : kNoClaim;
     if (tid == 0) s_events = 0;
-    __syncthreads();
-
-    // walk every window once, fill the candidate cache (keypoints blocked before the call never qualify)
-    for (int i = tid; i < nq; i += kMatchThreads) {
-        const int lvl = a.level[i];
-        uint32_t d[8];
-        load_desc(d, desc_of(i));
-        unsigned long long top[kMatchCacheK];
-#pragma unroll
-        for (int p = 0; p < kMatchCacheK; p++) top[p] = ~0ull;
-        int nc = 0;
-        walk_area(fl, a.projX[i], a.projY[i], s.pr[i], lvl - 1, lvl, [&](int idx, int oct) {
-            if (claim_prev[idx] < 0) return; // blocked from the start
-            const int dist = hamming256(d, fl.desc + (size_t)idx * 32);
-            topk_insert(top, pack_cand(dist, nc, oct, idx));
-            nc++;
-        });
-#pragma unroll
-        for (int p = 0; p < kMatchCacheK; p++) s.cache[(size_t)i * kMatchCacheK + p] = top[p];
-        s.ncand[i] = nc;
-    }
     __syncthreads();
 
     int rounds = 0;
     while (true) {
         int changed = 0;
         for (int i = tid; i < nq; i += kMatchThreads) {
+            const int lvl = s.plevels[i];
+            if (lvl < 0) continue; // not in the frustum
             const int nc = s.ncand[i];
             int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
             int found = 0;
-            unsigned long long e[kMatchCacheK];
-#pragma unroll
-            for (int p = 0; p < kMatchCacheK; p++) e[p] = s.cache[(size_t)i * kMatchCacheK + p];
             // sorted by (distance, walk order): the first two free entries are the reference's best and
             // second best (its scan keeps the earliest of equal distances)
-#pragma unroll
-            for (int p = 0; p < kMatchCacheK; p++) {
-                if (found >= 2 || p >= nc) continue;
-                const int idx = cand_idx(e[p]);
+            const unsigned long long* e = s.cache + (size_t)i * kMatchCacheK;
+            for (int p = 0; p < kMatchCacheK && p < nc && found < 2; p++) {
+                const unsigned long long ev = e[p];
+                const int idx = cand_idx(ev);
                 if (claim_prev[idx] < i) continue; // held by a map point with observations
-                if (found == 0) { bestDist = cand_dist(e[p]); bestLevel = cand_oct(e[p]); bestIdx = idx; }
-                else { bestDist2 = cand_dist(e[p]); bestLevel2 = cand_oct(e[p]); }
+                if (found == 0) { bestDist = cand_dist(ev); bestLevel = cand_oct(ev); bestIdx = idx; }
+                else { bestDist2 = cand_dist(ev); bestLevel2 = cand_oct(ev); }
                 found++;
             }
             if (found < 2 && nc > kMatchCacheK) { // cache exhausted: full walk against the current claims
-                const int lvl = a.level[i];
                 uint32_t d[8];
                 load_desc(d, desc_of(i));
                 bestDist = 256; bestLevel = -1; bestDist2 = 256; bestLevel2 = -1; bestIdx = -1;
-                walk_area(fl, a.projX[i], a.projY[i], s.pr[i], lvl - 1, lvl, [&](int idx, int oct) {
+                walk_area(fl, s.pu[i], s.pv[i], s.pr[i], lvl - 1, lvl, [&](int idx, int oct) {
                     if (claim_prev[idx] < i) return;
                     const int dist = hamming256(d, fl.desc + (size_t)idx * 32);
                     if (dist < bestDist) {
@@ -514,16 +536,20 @@ match_map_kernel(FrameDev cur, MatchMapArgs a, MatchScratch s, int* __restrict__
         atomicAdd(&s_events, 1);
     }
     __syncthreads();
-    for (int k = tid; k < ncur; k += kMatchThreads) cur_mp[k] = owner[k];
+    for (int k = tid; k < ncur; k += kMatchThreads) {
+        cur_mp[k] = owner[k];
+        if (a.merge_into && owner[k] >= 0) a.merge_into[k] = a.q_index ? a.q_index[owner[k]] : owner[k];
+    }
     if (tid == 0) { *nmatches = s_events; *s.iters = rounds; }
 }
 
 void launch_match_map(const FrameDev& cur, const MatchMapArgs& a, const MatchScratch& s, int* cur_mp, int* nmatches,
                       cudaStream_t stream)
 {
-    const size_t smem = frame_smem_bytes(cur.cap);
+    const size_t smem = claim_smem_bytes(cur.cap);
     const int use_smem = smem <= kMatchSmemLimit ? 1 : 0;
     prepare_match_kernels();
+    DVM_LAUNCH(match_map_walk_kernel, div_up(max(a.m, 1), kWalkThreads), kWalkThreads, 0, stream, cur, a, s);
     DVM_LAUNCH(match_map_kernel, 1, kMatchThreads, use_smem ? smem : 0, stream, cur, a, s, cur_mp, nmatches, use_smem);
 }
 

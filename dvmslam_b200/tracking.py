@@ -167,6 +167,9 @@ class Tracker:
         L.dvm_tracker_bootstrap.argtypes = [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _ip]
         L.dvm_tracker_track.argtypes = [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_int, _vp, _vp]
         L.dvm_tracker_result.argtypes = [_vp, _vp, _vp]
+        L.dvm_tracker_prefetch.argtypes = [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.dvm_tracker_stream.argtypes = [_vp]
+        L.dvm_tracker_stream.restype = _vp
         L.dvm_tracker_debug_matches.argtypes = [_vp, _vp, _vp, C.c_int, _ip]
         self.ext = extractor
         self.h = _vp()
@@ -198,14 +201,29 @@ class Tracker:
                                            _c(q, np.float32).ctypes.data, _c(t, np.float32).ctypes.data, C.byref(n)))
         return n.value
 
-    def track(self, img, prior_q=None, prior_t=None, sync=True):
-        """img: host uint8 array, or (device_ptr, width, height, stride) for an image already in HBM."""
+    @staticmethod
+    def _image_args(img):
+        if img is None:
+            return None, 0, 0, 0, 0
         if isinstance(img, tuple):
             ptr, w, h, stride = img
-            dev = 1
-        else:
-            img = np.ascontiguousarray(img, np.uint8)
-            ptr, w, h, stride, dev = img.ctypes.data, img.shape[1], img.shape[0], img.strides[0], 0
+            return ptr, w, h, stride, 1
+        assert img.dtype == np.uint8 and img.strides[1] == 1, "CV_8UC1 rows expected"
+        return img.ctypes.data, img.shape[1], img.shape[0], img.strides[0], 0
+
+    def stream(self) -> int:
+        """cudaStream_t of the tracking chain (the extractor runs on its own stream)."""
+        return int(self.L.dvm_tracker_stream(self.h) or 0)
+
+    def prefetch(self, img):
+        """Enqueue upload + ExtractORB of the NEXT frame; the next track() call then takes img=None."""
+        ptr, w, h, stride, dev = self._image_args(img)
+        check(self.L.dvm_tracker_prefetch(self.h, _vp(ptr), dev, w, h, stride))
+
+    def track(self, img, prior_q=None, prior_t=None, sync=True):
+        """img: host uint8 array, (device_ptr, width, height, stride) for an image already in HBM, or None
+        when the frame was handed over with prefetch()."""
+        ptr, w, h, stride, dev = self._image_args(img)
         pq = _c(prior_q, np.float32) if prior_q is not None else None
         pt = _c(prior_t, np.float32) if prior_t is not None else None
         check(self.L.dvm_tracker_track(self.h, _vp(ptr), dev, w, h, stride, pq.ctypes.data if pq is not None else None,

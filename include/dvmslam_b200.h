@@ -219,6 +219,16 @@ DVM_API int dvm_tracker_track(dvm_tracker* t, const uint8_t* gray, int gray_is_d
                               int stride, const float* prior_q, const float* prior_t, int sync, float* pose_out,
                               int32_t* counts);
 DVM_API int dvm_tracker_result(dvm_tracker* t, float* pose_out, int32_t* counts);
+/* Frame pipelining: ExtractORB does not depend on the previous frame's pose, so the tracker runs it on
+ * the extractor's stream while the tracking chain of the previous frame runs on its own stream.
+ * dvm_tracker_prefetch enqueues the upload + extraction of the NEXT frame (call it after
+ * dvm_tracker_track(..., sync = 0) of the current frame and before dvm_tracker_result); the following
+ * dvm_tracker_track call then ignores its image arguments (gray may be NULL) and uses the prefetched
+ * frame.  With sync == 0 and no prefetch the same overlap happens whenever the host runs ahead. */
+DVM_API int dvm_tracker_prefetch(dvm_tracker* t, const uint8_t* gray, int gray_is_device, int width, int height,
+                                 int stride);
+/* The CUDA stream (cudaStream_t) of the tracking chain, for CUDA-event timing by the caller. */
+DVM_API void* dvm_tracker_stream(const dvm_tracker* t);
 /* Current frame's association after the last track call, for parity tests: cur_map[n] = map point
  * index per keypoint (-1 none), outlier[n] = mvbOutlier. */
 DVM_API int dvm_tracker_debug_matches(dvm_tracker* t, int32_t* cur_map, uint8_t* outlier, int cap, int* n_out);

@@ -230,3 +230,40 @@ def test_tracker_pipeline_matches_oracle_chain():
     assert c1[3] > 800 and np.abs(tt1 - tk).max() < 5e-3
     t1.close()
     ext.close()
+
+
+def test_tracker_prefetch_overlap_is_identical():
+    """dvm_tracker_prefetch (next frame's upload + extraction on the extractor's stream while the current
+    frame's chain runs) must not change any result: same poses, counts and associations as the plain
+    synchronous loop, bit for bit."""
+    from dvmslam_b200.extractor import ORBextractor
+    from dvmslam_b200.tracking import Tracker
+
+    S = synth.OrbitStream(seed=2, period=320)
+    bounds = (0.0, 0.0, 1280.0, 720.0)
+    exts = [ORBextractor(2000, 1.2, 8, 20, 7, max_width=1280, max_height=720) for _ in range(2)]
+    T = exts[0].tables()
+    M = synth.plane_map(S, lambda im: exts[0](im), [0, 40, 80, 120], T["scale"], 6000)
+    trk = [Tracker(e, S.K, bounds, M) for e in exts]
+    R, t = S.pose(0)
+    q = synth.quat_from_R(R).astype(np.float32)
+    frames = [S.frame(k) for k in range(0, 8)]
+    for tr in trk:
+        assert tr.bootstrap(frames[0], q, t) > 50
+    ref = []
+    for k in range(1, 7):
+        ref.append(trk[0].track(frames[k]) + trk[0].debug_matches())
+    pending = False
+    for k in range(1, 7):
+        trk[1].track(None if pending else frames[k], sync=False)
+        trk[1].prefetch(frames[k + 1])
+        pending = True
+        got = trk[1].result() + trk[1].debug_matches()
+        r = ref[k - 1]
+        assert got[2] == r[2], (k, got[2], r[2])
+        assert np.array_equal(got[0], r[0]) and np.array_equal(got[1], r[1]), k
+        assert np.array_equal(got[3], r[3]) and np.array_equal(got[4], r[4]), k
+    for tr in trk:
+        tr.close()
+    for e in exts:
+        e.close()
