@@ -327,17 +327,34 @@ int dvm_orb_get_profile(dvm_orb* h, int* n_frames, float* stage_ms_sum)
     return DVM_OK;
 }
 
-int dvm_orb_extract_device(dvm_orb* h, const uint8_t* gray_dev, int width, int height, int stride, int lap0, int lap1)
+// where the next extract leaves its result: the handle's own block (default) or caller-provided HBM
+static void set_outputs(dvm_orb* h, dvm_keypoint* kps, uint8_t* desc, int32_t* counts)
+{
+    h->buf.counts = counts ? counts : (int*)h->d_out;
+    h->buf.out_kps = kps ? kps : (dvm_keypoint*)(h->d_out + 32);
+    h->buf.out_desc = desc ? desc : h->d_out + 32 + (size_t)h->max_kp * sizeof(dvm_keypoint);
+}
+
+int dvm_orb_extract_device_to(dvm_orb* h, const uint8_t* gray_dev, int width, int height, int stride, int lap0, int lap1,
+                              dvm_keypoint* kps_dev, uint8_t* desc_dev, int32_t* counts_dev)
 {
     DVM_REQUIRE(h != nullptr && gray_dev != nullptr, "null argument");
     DVM_REQUIRE(width > 0 && height > 0 && stride >= width, "bad image geometry");
+    DVM_REQUIRE((kps_dev == nullptr) == (desc_dev == nullptr) && (kps_dev == nullptr) == (counts_dev == nullptr),
+                "kps_dev, desc_dev and counts_dev go together");
     DVM_CUDA(cudaSetDevice(h->device));
     int rc = configure(h, width, height);
     if (rc != DVM_OK) return rc;
     h->cfg.lv[0].img = gray_dev; // level 0 is the caller's image, read in place
     h->cfg.lv[0].pitch = stride;
     h->level0_aliased = true;
+    set_outputs(h, kps_dev, desc_dev, counts_dev);
     return enqueue_pipeline(h, lap0, lap1);
+}
+
+int dvm_orb_extract_device(dvm_orb* h, const uint8_t* gray_dev, int width, int height, int stride, int lap0, int lap1)
+{
+    return dvm_orb_extract_device_to(h, gray_dev, width, height, stride, lap0, lap1, nullptr, nullptr, nullptr);
 }
 
 int dvm_orb_sync(dvm_orb* h)
@@ -376,6 +393,7 @@ int dvm_orb_extract(dvm_orb* h, const uint8_t* gray, int width, int height, int 
     L0.img = h->d_pyr + h->lvl_off[0];
     L0.pitch = (int)align_up(L0.w, 128);
     h->level0_aliased = false;
+    set_outputs(h, nullptr, nullptr, nullptr);
     DVM_CUDA(cudaMemcpy2DAsync(h->d_pyr + h->lvl_off[0], L0.pitch, gray, stride, width, height, cudaMemcpyHostToDevice,
                                h->stream));
     rc = enqueue_pipeline(h, lap0, lap1);

@@ -10,7 +10,7 @@ static void frame_free(dvm_frame* f)
 {
     if (!f) return;
     cudaSetDevice(f->device);
-    cudaFree(f->d_kps); cudaFree(f->d_desc); cudaFree(f->d_n); cudaFree(f->d_cell_start); cudaFree(f->d_cell_items);
+    cudaFree(f->d_kps); cudaFree(f->d_desc); cudaFree(f->d_n); cudaFree(f->d_cell_start); cudaFree(f->d_cell_items); cudaFree(f->d_kxyo);
     cudaFree(f->d_in); cudaFree(f->ms.pu); cudaFree(f->ms.pv); cudaFree(f->ms.pr); cudaFree(f->ms.plevels);
     cudaFree(f->ms.choice); cudaFree(f->ms.cache); cudaFree(f->ms.ncand); cudaFree(f->ms.claim_a); cudaFree(f->ms.claim_b); cudaFree(f->ms.iters);
     cudaFree(f->d_cur_mp); cudaFree(f->d_err);
@@ -117,11 +117,14 @@ int dvm_frame_create(dvm_frame** out, int device, void* cuda_stream, int max_key
     DVM_FCREATE(cudaEventCreateWithFlags(&f->ev, cudaEventDisableTiming));
     DVM_FCREATE(cudaMalloc(&f->d_kps, f->cap * sizeof(dvm_keypoint)));
     DVM_FCREATE(cudaMalloc(&f->d_desc, (size_t)f->cap * 32));
-    DVM_FCREATE(cudaMalloc(&f->d_n, sizeof(int)));
-    DVM_FCREATE(cudaMemset(f->d_n, 0, sizeof(int)));
-    DVM_FCREATE(cudaMalloc(&f->d_cell_start, (kGridCells + 1) * sizeof(int)));
-    DVM_FCREATE(cudaMemset(f->d_cell_start, 0, (kGridCells + 1) * sizeof(int)));
+    DVM_FCREATE(cudaMalloc(&f->d_n, 4 * sizeof(int))); // {n, monoIndex} as the extractor writes them
+    DVM_FCREATE(cudaMemset(f->d_n, 0, 4 * sizeof(int)));
+    DVM_FCREATE(cudaMalloc(&f->d_cell_start, (kGridCells + 4) * sizeof(int)));
+    DVM_FCREATE(cudaMemset(f->d_cell_start, 0, (kGridCells + 4) * sizeof(int)));
     DVM_FCREATE(cudaMalloc(&f->d_cell_items, f->cap * sizeof(int)));
+    DVM_FCREATE(cudaMemset(f->d_cell_items, 0, f->cap * sizeof(int)));
+    DVM_FCREATE(cudaMalloc(&f->d_kxyo, (size_t)f->cap * 3 * sizeof(int)));
+    DVM_FCREATE(cudaMemset(f->d_kxyo, 0, (size_t)f->cap * 3 * sizeof(int)));
     DVM_FCREATE(cudaMalloc(&f->ms.claim_a, f->cap * sizeof(int)));
     DVM_FCREATE(cudaMalloc(&f->ms.claim_b, f->cap * sizeof(int)));
     DVM_FCREATE(cudaMalloc(&f->ms.iters, sizeof(int)));
@@ -130,7 +133,7 @@ int dvm_frame_create(dvm_frame** out, int device, void* cuda_stream, int max_key
     FrameDev& d = f->dev;
     memset(&d, 0, sizeof(d));
     d.kps = f->d_kps; d.desc = f->d_desc; d.n = f->d_n; d.cap = f->cap;
-    d.cell_start = f->d_cell_start; d.cell_items = f->d_cell_items;
+    d.cell_start = f->d_cell_start; d.cell_items = f->d_cell_items; d.kxyo = f->d_kxyo;
     d.nlevels = nlevels;
     for (int i = 0; i < nlevels; i++) { d.scale[i] = scale_factors[i]; d.inv_sigma2[i] = inv_level_sigma2[i]; }
     *out = f;
@@ -184,6 +187,22 @@ int dvm_frame_assign_from_orb(dvm_frame* f, const dvm_orb* orb, float min_x, flo
     }
     f->host_n = dvm_orb_max_keypoints(orb);
     launch_frame_assign(f->dev, k, d, c, f->stream); // copy + AssignFeaturesToGrid in one launch
+    DVM_CUDA(cudaGetLastError());
+    return DVM_OK;
+}
+
+int dvm_frame_construct_device(dvm_frame* f, dvm_orb* orb, const uint8_t* gray_dev, int width, int height, int stride,
+                               float min_x, float min_y, float max_x, float max_y)
+{
+    DVM_REQUIRE(f != nullptr && orb != nullptr && gray_dev != nullptr, "null argument");
+    DVM_REQUIRE(dvm_orb_max_keypoints(orb) <= f->cap, "frame capacity below the extractor's maximum");
+    DVM_REQUIRE(max_x > min_x && max_y > min_y, "empty image bounds");
+    DVM_CUDA(cudaSetDevice(f->device));
+    set_bounds(f, min_x, min_y, max_x, max_y);
+    int rc = dvm_orb_extract_device_to(orb, gray_dev, width, height, stride, 0, 1000, f->d_kps, f->d_desc, f->d_n);
+    if (rc != DVM_OK) return rc;
+    f->host_n = dvm_orb_max_keypoints(orb);
+    launch_grid_build(f->dev, (cudaStream_t)dvm_orb_stream(orb));
     DVM_CUDA(cudaGetLastError());
     return DVM_OK;
 }

@@ -18,6 +18,7 @@ struct dvm_frame {
     int* d_n = nullptr;
     int* d_cell_start = nullptr;
     int* d_cell_items = nullptr;
+    int* d_kxyo = nullptr;
     // matcher / optimiser scratch, grown on demand
     uint8_t* d_in = nullptr;   // uploaded inputs
     size_t in_cap = 0;

@@ -57,6 +57,54 @@ __device__ inline FrameLook look_global(const FrameDev& f)
     return v;
 }
 
+// ---- frame staged in shared memory by TMA bulk copies (cp.async.bulk, one mbarrier) ----
+__host__ __device__ inline size_t frame_smem_bytes(int cap) { return (size_t)cap * (32 + 12 + 4) + (size_t)(kGridCells + 4) * 4; }
+__device__ inline uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// all threads of the CTA call this; returns once descriptors, {x,y,octave} records and the CSR grid of
+// the frame are in `smem` (layout: desc | kxyo | cell_start | cell_items, every part 16-byte aligned)
+__device__ inline FrameLook look_shared_tma(const FrameDev& f, int n, unsigned char* smem, unsigned long long* bar)
+{
+    unsigned char* sdesc = smem;
+    unsigned char* skxyo = sdesc + (size_t)f.cap * 32;
+    unsigned char* scell = skxyo + (size_t)f.cap * 12;
+    unsigned char* sitems = scell + (size_t)(kGridCells + 4) * 4;
+    const uint32_t b = smem_u32(bar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(b), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t bytes_desc = (uint32_t)n * 32u;
+        const uint32_t bytes_kxyo = min(((uint32_t)n * 12u + 15u) & ~15u, (uint32_t)f.cap * 12u);
+        const uint32_t bytes_cell = (uint32_t)(kGridCells + 4) * 4u;
+        const uint32_t bytes_items = min(((uint32_t)n * 4u + 15u) & ~15u, (uint32_t)f.cap * 4u);
+        const uint32_t total = bytes_desc + bytes_kxyo + bytes_cell + bytes_items;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(total) : "memory");
+        auto bulk = [&](unsigned char* dst, const void* src, uint32_t bytes) {
+            if (bytes == 0) return;
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(b) : "memory");
+        };
+        bulk(sdesc, f.desc, bytes_desc);
+        bulk(skxyo, f.kxyo, bytes_kxyo);
+        bulk(scell, f.cell_start, bytes_cell);
+        bulk(sitems, f.cell_items, bytes_items);
+    }
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(b), "r"(0) : "memory");
+    }
+    FrameLook v;
+    v.cell_start = reinterpret_cast<const int*>(scell); v.cell_items = reinterpret_cast<const int*>(sitems);
+    v.kbase = reinterpret_cast<const char*>(skxyo); v.kstride = 12; v.oct_off = 8;
+    v.desc = sdesc;
+    v.minX = f.minX; v.minY = f.minY; v.gwInv = f.gwInv; v.ghInv = f.ghInv;
+    return v;
+}
+
 // Frame::GetFeaturesInArea: calls fn(idx, octave) for every keypoint of the window, in the
 // reference's traversal order (ix outer, iy inner, insertion order inside a cell).
 template <class Fn>
@@ -112,6 +160,7 @@ __global__ void __launch_bounds__(1024) grid_build_kernel(FrameDev f, const dvm_
     __syncthreads();
     for (int i = tid; i < n; i += 1024) {
         const dvm_keypoint* kp = f.kps + i;
+        f.kxyo[3 * i] = __float_as_int(kp->x); f.kxyo[3 * i + 1] = __float_as_int(kp->y); f.kxyo[3 * i + 2] = kp->octave;
         const int px = (int)roundf(__fmul_rn(__fsub_rn(kp->x, f.minX), f.gwInv));
         const int py = (int)roundf(__fmul_rn(__fsub_rn(kp->y, f.minY), f.ghInv));
         if (px < 0 || px >= kGridCols || py < 0 || py >= kGridRows) continue;
@@ -241,10 +290,14 @@ constexpr int kWalkThreads = 128;
 
 // ---- SearchByProjection(cur, last), phase 1: one thread per last-frame keypoint projects its map point
 // with the pose prior and walks its window once (many CTAs; the frame is read through L1/L2) ----
-__global__ void __launch_bounds__(kWalkThreads) match_last_walk_kernel(FrameDev cur, MatchLastArgs a, MatchScratch s)
+__global__ void __launch_bounds__(kWalkThreads) match_last_walk_kernel(FrameDev cur, MatchLastArgs a, MatchScratch s, int use_smem)
 {
+    extern __shared__ __align__(128) unsigned char frame_smem[];
+    __shared__ __align__(8) unsigned long long s_bar;
     if (a.guard && *a.guard >= 20) return; // enough matches at th: the wider retry is not run
     const int nq = a.n_ptr ? *a.n_ptr : a.last_n;
+    if ((int)(blockIdx.x * kWalkThreads) >= nq) return;
+    const FrameLook fl = use_smem ? look_shared_tma(cur, min(*cur.n, cur.cap), frame_smem, &s_bar) : look_global(cur);
     const int i = blockIdx.x * kWalkThreads + threadIdx.x;
     if (i >= nq) return;
     if (a.pose) { // pose prior held on the device
@@ -253,7 +306,6 @@ __global__ void __launch_bounds__(kWalkThreads) match_last_walk_kernel(FrameDev 
         for (int k = 0; k < 9; k++) a.R[k] = Rm[k];
         a.t[0] = a.pose[4]; a.t[1] = a.pose[5]; a.t[2] = a.pose[6];
     }
-    const FrameLook fl = look_global(cur);
     const int mi = a.mp_index ? a.mp_index[i] : (a.has_mp[i] ? i : -1);
     int lv = -1, nc = 0;
     unsigned long long top[kMatchCacheK];
@@ -407,18 +459,23 @@ void launch_match_last(const FrameDev& cur, const MatchLastArgs& a, const MatchS
     const size_t smem = claim_smem_bytes(cur.cap);
     const int use_smem = smem <= kMatchSmemLimit ? 1 : 0;
     prepare_match_kernels();
-    DVM_LAUNCH(match_last_walk_kernel, div_up(max(a.last_n, 1), kWalkThreads), kWalkThreads, 0, stream, cur, a, s);
+    const size_t fsm = frame_smem_bytes(cur.cap);
+    const int stage = fsm <= kMatchSmemLimit ? 1 : 0;
+    DVM_LAUNCH(match_last_walk_kernel, div_up(max(a.last_n, 1), kWalkThreads), kWalkThreads, stage ? fsm : 0, stream, cur, a, s, stage);
     DVM_LAUNCH(match_last_kernel, 1, kMatchThreads, use_smem ? smem : 0, stream, cur, a, s, cur_mp, nmatches, use_smem);
 }
 
 // --------------------------------------------------------------- SearchByProjection(F, mapPoints)
 // phase 1: one thread per in-view map point walks its window once
-__global__ void __launch_bounds__(kWalkThreads) match_map_walk_kernel(FrameDev cur, MatchMapArgs a, MatchScratch s)
+__global__ void __launch_bounds__(kWalkThreads) match_map_walk_kernel(FrameDev cur, MatchMapArgs a, MatchScratch s, int use_smem)
 {
+    extern __shared__ __align__(128) unsigned char frame_smem[];
+    __shared__ __align__(8) unsigned long long s_bar;
     const int nq = a.m_ptr ? *a.m_ptr : a.m;
+    if ((int)(blockIdx.x * kWalkThreads) >= nq) return;
+    const FrameLook fl = use_smem ? look_shared_tma(cur, min(*cur.n, cur.cap), frame_smem, &s_bar) : look_global(cur);
     const int i = blockIdx.x * kWalkThreads + threadIdx.x;
     if (i >= nq) return;
-    const FrameLook fl = look_global(cur);
     int lvl;
     float px, py, vcos;
     if (a.use_frustum) { // SearchLocalPoints: isInFrustum decides whether map point i takes part at all
@@ -549,7 +606,9 @@ void launch_match_map(const FrameDev& cur, const MatchMapArgs& a, const MatchScr
     const size_t smem = claim_smem_bytes(cur.cap);
     const int use_smem = smem <= kMatchSmemLimit ? 1 : 0;
     prepare_match_kernels();
-    DVM_LAUNCH(match_map_walk_kernel, div_up(max(a.m, 1), kWalkThreads), kWalkThreads, 0, stream, cur, a, s);
+    const size_t fsm = frame_smem_bytes(cur.cap);
+    const int stage = fsm <= kMatchSmemLimit ? 1 : 0;
+    DVM_LAUNCH(match_map_walk_kernel, div_up(max(a.m, 1), kWalkThreads), kWalkThreads, stage ? fsm : 0, stream, cur, a, s, stage);
     DVM_LAUNCH(match_map_kernel, 1, kMatchThreads, use_smem ? smem : 0, stream, cur, a, s, cur_mp, nmatches, use_smem);
 }
 
@@ -562,6 +621,8 @@ static bool prepare_match_kernels()
     if (dev < 0 || dev >= 64 || done[dev].load()) return true;
     cudaFuncSetAttribute(match_last_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMatchSmemLimit);
     cudaFuncSetAttribute(match_map_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMatchSmemLimit);
+    cudaFuncSetAttribute(match_last_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMatchSmemLimit);
+    cudaFuncSetAttribute(match_map_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMatchSmemLimit);
     done[dev].store(true);
     return true;
 }

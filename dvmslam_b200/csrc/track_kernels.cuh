@@ -18,8 +18,9 @@ struct FrameDev {
     const int* n;          // device int: number of keypoints
     int cap;
     float minX, minY, maxX, maxY, gwInv, ghInv;
-    int* cell_start;       // [kGridCells + 1]
+    int* cell_start;       // [kGridCells + 1] (allocated kGridCells + 4)
     int* cell_items;       // [cap]
+    int* kxyo;             // [cap * 3] compact {x bits, y bits, octave} records written by the grid build
     int nlevels;
     float scale[kTrackMaxLevels];       // mvScaleFactors
     float inv_sigma2[kTrackMaxLevels];  // mvInvLevelSigma2

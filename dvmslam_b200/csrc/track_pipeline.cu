@@ -52,28 +52,30 @@ __global__ void __launch_bounds__(1024) begin_frame_kernel(const float* last, co
 } // namespace
 
 // ------------------------------------------------------------------------------------------------
-// Two streams per agent: `es` (the extractor handle's stream) runs ExtractORB, `stream` runs the
-// dependency chain of the tracked frame.  Extraction of frame k+1 does not depend on frame k's pose, so
-// it overlaps frame k's chain; ev_extracted / ev_copied order the hand-over of the extractor's result
-// buffers (the chain copies them into the frame at its very start).
+// Two streams per agent: `es` (the extractor handle's stream) runs the Frame constructor (ExtractORB
+// straight into the frame's buffers + AssignFeaturesToGrid), `stream` runs the dependency chain of the
+// tracked frame.  Frame i+1 does not depend on frame i's pose until the chain starts, so its
+// construction overlaps frame i's chain.  Frames live in a ring of three (current, last, next being
+// built); ev_extracted[slot] / ev_done[slot] order the hand-over between the two streams.
+constexpr int kRing = 3;
 struct dvm_tracker {
     int device = 0;
     cudaStream_t stream = nullptr;  // tracking chain
     cudaStream_t es = nullptr;      // extraction (owned by the extractor handle)
-    cudaEvent_t ev_extracted = nullptr, ev_copied = nullptr;
-    bool have_copied = false;       // ev_copied has been recorded at least once
-    bool prefetched = false;        // the next frame's extraction is already enqueued
+    cudaEvent_t ev_extracted[kRing] = { nullptr, nullptr, nullptr };
+    cudaEvent_t ev_done[kRing] = { nullptr, nullptr, nullptr };
+    long long n_extracted = 0;      // frames whose construction has been enqueued
+    long long n_tracked = 0;        // frames whose chain has been enqueued (frame 0 = bootstrap)
     dvm_orb* orb = nullptr;
-    dvm_frame* frames[2] = { nullptr, nullptr };
-    int idx = 0; // frames[idx] is the last frame
+    dvm_frame* frames[kRing] = { nullptr, nullptr, nullptr };
     int cap = 0, map_n = 0, nlevels = 0;
     float K[4], bounds[4], logScale = 0;
     std::vector<float> inv_sigma2;
     // map snapshot
     float* d_xw = nullptr; uint8_t* d_desc = nullptr; float* d_normal = nullptr; float* d_mind = nullptr; float* d_maxd = nullptr;
-    // per-frame association (ping-pong with the frames)
-    int* d_mp[2] = { nullptr, nullptr };
-    uint8_t* d_outl[2] = { nullptr, nullptr };
+    // per-frame association (same ring as the frames)
+    int* d_mp[kRing] = { nullptr, nullptr, nullptr };
+    uint8_t* d_outl[kRing] = { nullptr, nullptr, nullptr };
     // scratch
     uint8_t* d_seen = nullptr;
     int* d_cur_mp = nullptr; int* d_cur_mp2 = nullptr;
@@ -93,13 +95,13 @@ static void tracker_free(dvm_tracker* t)
     if (t->stream) cudaStreamSynchronize(t->stream);
     if (t->es) cudaStreamSynchronize(t->es);
     for (auto f : t->frames) if (f) dvm_frame_destroy(f);
-    void* ptrs[] = { t->d_xw, t->d_desc, t->d_normal, t->d_mind, t->d_maxd, t->d_mp[0], t->d_mp[1], t->d_outl[0], t->d_outl[1],
-                     t->d_seen, t->d_cur_mp, t->d_cur_mp2, t->d_cnt, t->d_pose, t->d_pose_last, t->d_pose_prev, t->d_res1,
-                     t->d_res2, t->d_result, t->d_img };
+    void* ptrs[] = { t->d_xw, t->d_desc, t->d_normal, t->d_mind, t->d_maxd, t->d_mp[0], t->d_mp[1], t->d_mp[2], t->d_outl[0],
+                     t->d_outl[1], t->d_outl[2], t->d_seen, t->d_cur_mp, t->d_cur_mp2, t->d_cnt, t->d_pose, t->d_pose_last,
+                     t->d_pose_prev, t->d_res1, t->d_res2, t->d_result, t->d_img };
     for (void* p : ptrs) cudaFree(p);
     if (t->h_result) cudaFreeHost(t->h_result);
-    if (t->ev_extracted) cudaEventDestroy(t->ev_extracted);
-    if (t->ev_copied) cudaEventDestroy(t->ev_copied);
+    for (auto e : t->ev_extracted) if (e) cudaEventDestroy(e);
+    for (auto e : t->ev_done) if (e) cudaEventDestroy(e);
     if (t->stream) cudaStreamDestroy(t->stream);
     delete t;
 }
@@ -191,9 +193,11 @@ int dvm_tracker_create(dvm_tracker** out, dvm_orb* orb, const float* K, const fl
         }                                                                                      \
     } while (0)
     DVM_TCREATE(cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking));
-    DVM_TCREATE(cudaEventCreateWithFlags(&t->ev_extracted, cudaEventDisableTiming));
-    DVM_TCREATE(cudaEventCreateWithFlags(&t->ev_copied, cudaEventDisableTiming));
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < kRing; i++) {
+        DVM_TCREATE(cudaEventCreateWithFlags(&t->ev_extracted[i], cudaEventDisableTiming));
+        DVM_TCREATE(cudaEventCreateWithFlags(&t->ev_done[i], cudaEventDisableTiming));
+    }
+    for (int i = 0; i < kRing; i++) {
         int rc = dvm_frame_create(&t->frames[i], t->device, t->stream, t->cap, t->nlevels, sc, is2);
         if (rc != DVM_OK) { tracker_free(t); return rc; }
         rc = dvm_frame_ensure_query_cap(t->frames[i], std::max(map_n, t->cap));
@@ -207,7 +211,7 @@ int dvm_tracker_create(dvm_tracker** out, dvm_orb* orb, const float* K, const fl
     DVM_TCREATE(cudaMemcpy(t->d_normal, map_normal, M * 12, cudaMemcpyHostToDevice));
     DVM_TCREATE(cudaMemcpy(t->d_mind, map_min_dist, M * 4, cudaMemcpyHostToDevice));
     DVM_TCREATE(cudaMemcpy(t->d_maxd, map_max_dist, M * 4, cudaMemcpyHostToDevice));
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < kRing; i++) {
         DVM_TCREATE(cudaMalloc(&t->d_mp[i], C * 4)); DVM_TCREATE(cudaMemset(t->d_mp[i], 0xff, C * 4));
         DVM_TCREATE(cudaMalloc(&t->d_outl[i], C)); DVM_TCREATE(cudaMemset(t->d_outl[i], 0, C));
     }
@@ -242,11 +246,15 @@ static int enqueue_local_map_search(dvm_tracker* t, dvm_frame* cur, int* cur_map
     return DVM_OK;
 }
 
-// H2D staging (if the image is on the host) + ExtractORB on the extraction stream
+// Frame construction on the extraction stream: H2D staging (if the image is on the host), ExtractORB
+// into the ring slot of frame n_extracted, AssignFeaturesToGrid
 static int enqueue_extract(dvm_tracker* t, const uint8_t* gray, int gray_is_device, int width, int height, int stride)
 {
-    // the extractor's result buffers are free again once the previous frame's chain has copied them
-    if (t->have_copied) DVM_CUDA(cudaStreamWaitEvent(t->es, t->ev_copied, 0));
+    const long long i = t->n_extracted;
+    const int slot = (int)(i % kRing);
+    // the slot was the "last frame" of chain i-2: it is free again once that chain has finished
+    if (i >= 2 && i - 2 < t->n_tracked) DVM_CUDA(cudaStreamWaitEvent(t->es, t->ev_done[(i - 2) % kRing], 0));
+    DVM_REQUIRE(i - 2 < t->n_tracked || i < 2, "extraction may run at most one frame ahead of tracking");
     const uint8_t* img = gray;
     int istride = stride;
     if (!gray_is_device) {
@@ -260,20 +268,11 @@ static int enqueue_extract(dvm_tracker* t, const uint8_t* gray, int gray_is_devi
         DVM_CUDA(cudaMemcpy2DAsync(t->d_img, width, gray, stride, width, height, cudaMemcpyHostToDevice, t->es));
         img = t->d_img; istride = width;
     }
-    int rc = dvm_orb_extract_device(t->orb, img, width, height, istride, 0, 1000);   // Frame::ExtractORB(0, im, 0, 1000)
+    int rc = dvm_frame_construct_device(t->frames[slot], t->orb, img, width, height, istride, t->bounds[0], t->bounds[1],
+                                        t->bounds[2], t->bounds[3]);
     if (rc != DVM_OK) return rc;
-    DVM_CUDA(cudaEventRecord(t->ev_extracted, t->es));
-    return DVM_OK;
-}
-
-// Frame construction on the tracking stream: copy the extractor's result, build the grid
-static int enqueue_frame(dvm_tracker* t, dvm_frame* cur)
-{
-    DVM_CUDA(cudaStreamWaitEvent(t->stream, t->ev_extracted, 0));
-    int rc = dvm_frame_assign_from_orb(cur, t->orb, t->bounds[0], t->bounds[1], t->bounds[2], t->bounds[3]);
-    if (rc != DVM_OK) return rc;
-    DVM_CUDA(cudaEventRecord(t->ev_copied, t->stream));
-    t->have_copied = true;
+    DVM_CUDA(cudaEventRecord(t->ev_extracted[slot], t->es));
+    t->n_extracted = i + 1;
     return DVM_OK;
 }
 
@@ -282,14 +281,15 @@ int dvm_tracker_bootstrap(dvm_tracker* t, const uint8_t* gray, int width, int he
 {
     DVM_REQUIRE(t && gray && pose_q && pose_t, "null argument");
     DVM_CUDA(cudaSetDevice(t->device));
-    t->prefetched = false;
+    DVM_CUDA(cudaStreamSynchronize(t->es));
+    DVM_CUDA(cudaStreamSynchronize(t->stream));
+    t->n_extracted = 0;
+    t->n_tracked = 0;
     int rc = enqueue_extract(t, gray, 0, width, height, stride);
     if (rc != DVM_OK) return rc;
-    dvm_frame* cur = t->frames[t->idx];
-    rc = enqueue_frame(t, cur);
-    if (rc != DVM_OK) return rc;
+    dvm_frame* cur = t->frames[0];
+    DVM_CUDA(cudaStreamWaitEvent(t->stream, t->ev_extracted[0], 0));
     float* pose = reinterpret_cast<float*>(t->h_result + 64);
-    DVM_CUDA(cudaStreamSynchronize(t->stream)); // the pinned staging block may still be in flight
     for (int i = 0; i < 4; i++) pose[i] = pose_q[i];
     for (int i = 0; i < 3; i++) pose[4 + i] = pose_t[i];
     DVM_CUDA(cudaMemcpyAsync(t->d_pose, pose, 28, cudaMemcpyHostToDevice, t->stream));
@@ -297,11 +297,13 @@ int dvm_tracker_bootstrap(dvm_tracker* t, const uint8_t* gray, int width, int he
     DVM_CUDA(cudaMemcpyAsync(t->d_pose_prev, pose, 28, cudaMemcpyHostToDevice, t->stream));
     DVM_CUDA(cudaMemsetAsync(t->d_seen, 0, t->map_n, t->stream));
     DVM_CUDA(cudaMemsetAsync(t->d_cnt, 0, 32, t->stream));
-    DVM_CUDA(cudaMemsetAsync(t->d_mp[t->idx], 0xff, (size_t)t->cap * 4, t->stream));
-    DVM_CUDA(cudaMemsetAsync(t->d_outl[t->idx], 0, t->cap, t->stream));
-    rc = enqueue_local_map_search(t, cur, t->d_mp[t->idx], 3.0f, 0.8f);
+    DVM_CUDA(cudaMemsetAsync(t->d_mp[0], 0xff, (size_t)t->cap * 4, t->stream));
+    DVM_CUDA(cudaMemsetAsync(t->d_outl[0], 0, t->cap, t->stream));
+    rc = enqueue_local_map_search(t, cur, t->d_mp[0], 3.0f, 0.8f);
     if (rc != DVM_OK) return rc;
     DVM_CUDA(cudaGetLastError());
+    DVM_CUDA(cudaEventRecord(t->ev_done[0], t->stream));
+    t->n_tracked = 1;
     int nm = 0;
     DVM_CUDA(cudaMemcpyAsync(&nm, t->d_cnt + 3, 4, cudaMemcpyDeviceToHost, t->stream));
     DVM_CUDA(cudaStreamSynchronize(t->stream));
@@ -312,32 +314,31 @@ int dvm_tracker_bootstrap(dvm_tracker* t, const uint8_t* gray, int width, int he
 int dvm_tracker_prefetch(dvm_tracker* t, const uint8_t* gray, int gray_is_device, int width, int height, int stride)
 {
     DVM_REQUIRE(t && gray, "null argument");
-    DVM_REQUIRE(!t->prefetched, "a prefetched frame is already pending");
+    DVM_REQUIRE(t->n_tracked >= 1, "bootstrap the tracker first");
+    DVM_REQUIRE(t->n_extracted == t->n_tracked, "a prefetched frame is already pending");
     DVM_CUDA(cudaSetDevice(t->device));
-    int rc = enqueue_extract(t, gray, gray_is_device, width, height, stride);
-    if (rc != DVM_OK) return rc;
-    t->prefetched = true;
-    return DVM_OK;
+    return enqueue_extract(t, gray, gray_is_device, width, height, stride);
 }
 
 int dvm_tracker_track(dvm_tracker* t, const uint8_t* gray, int gray_is_device, int width, int height, int stride,
                       const float* prior_q, const float* prior_t, int sync, float* pose_out, int32_t* counts)
 {
     DVM_REQUIRE(t != nullptr, "null handle");
-    DVM_REQUIRE(gray != nullptr || t->prefetched, "null image and no prefetched frame");
+    DVM_REQUIRE(t->n_tracked >= 1, "bootstrap the tracker first");
+    const bool prefetched = t->n_extracted > t->n_tracked;
+    DVM_REQUIRE(gray != nullptr || prefetched, "null image and no prefetched frame");
     DVM_REQUIRE((prior_q == nullptr) == (prior_t == nullptr), "prior_q and prior_t go together");
     DVM_CUDA(cudaSetDevice(t->device));
-    const int li = t->idx, ci = t->idx ^ 1;
-    dvm_frame* last = t->frames[li];
-    dvm_frame* cur = t->frames[ci];
     int rc;
-    if (!t->prefetched) {
+    if (!prefetched) {
         rc = enqueue_extract(t, gray, gray_is_device, width, height, stride);
         if (rc != DVM_OK) return rc;
     }
-    t->prefetched = false;
-    rc = enqueue_frame(t, cur);
-    if (rc != DVM_OK) return rc;
+    const long long fi = t->n_tracked;
+    const int ci = (int)(fi % kRing), li = (int)((fi - 1) % kRing);
+    dvm_frame* last = t->frames[li];
+    dvm_frame* cur = t->frames[ci];
+    DVM_CUDA(cudaStreamWaitEvent(t->stream, t->ev_extracted[ci], 0));
     // mCurrentFrame.SetPose(mVelocity * mLastFrame.GetPose()); reset of the per-frame marks and counters
     if (prior_q) {
         float* pose = reinterpret_cast<float*>(t->h_result + 64);
@@ -381,7 +382,8 @@ int dvm_tracker_track(dvm_tracker* t, const uint8_t* gray, int gray_is_device, i
     rc = launch_pose_opt(pa, t->stream);
     if (rc != DVM_OK) return rc;
     DVM_CUDA(cudaGetLastError());
-    t->idx = ci;
+    DVM_CUDA(cudaEventRecord(t->ev_done[ci], t->stream));
+    t->n_tracked = fi + 1;
     if (sync) return dvm_tracker_result(t, pose_out, counts);
     return DVM_OK;
 }
@@ -403,12 +405,13 @@ int dvm_tracker_debug_matches(dvm_tracker* t, int32_t* cur_map, uint8_t* outlier
     DVM_CUDA(cudaSetDevice(t->device));
     DVM_CUDA(cudaStreamSynchronize(t->stream));
     int n = 0;
-    DVM_CUDA(cudaMemcpy(&n, t->frames[t->idx]->d_n, 4, cudaMemcpyDeviceToHost));
+    const int li = (int)((t->n_tracked - 1) % kRing);
+    DVM_CUDA(cudaMemcpy(&n, t->frames[li]->d_n, 4, cudaMemcpyDeviceToHost));
     n = std::min(n, t->cap);
     *n_out = n;
     const int m = std::min(n, cap);
-    if (cur_map && m > 0) DVM_CUDA(cudaMemcpy(cur_map, t->d_mp[t->idx], (size_t)m * 4, cudaMemcpyDeviceToHost));
-    if (outlier && m > 0) DVM_CUDA(cudaMemcpy(outlier, t->d_outl[t->idx], (size_t)m, cudaMemcpyDeviceToHost));
+    if (cur_map && m > 0) DVM_CUDA(cudaMemcpy(cur_map, t->d_mp[li], (size_t)m * 4, cudaMemcpyDeviceToHost));
+    if (outlier && m > 0) DVM_CUDA(cudaMemcpy(outlier, t->d_outl[li], (size_t)m, cudaMemcpyDeviceToHost));
     return DVM_OK;
 }
 

@@ -87,6 +87,11 @@ DVM_API int dvm_orb_extract(dvm_orb* h, const uint8_t* gray, int width, int heig
  * bench.py's device-resident `value` use. */
 DVM_API int dvm_orb_extract_device(dvm_orb* h, const uint8_t* gray_dev, int width, int height, int stride, int lap0,
                                    int lap1);
+/* Same, leaving the result in caller-provided HBM: kps_dev[dvm_orb_max_keypoints()], desc_dev[max*32],
+ * counts_dev[2] = {n, mono_index} (all three or none; none = the handle's own buffers).  Lets a Frame own
+ * its keypoints without a copy while the handle already extracts the next image. */
+DVM_API int dvm_orb_extract_device_to(dvm_orb* h, const uint8_t* gray_dev, int width, int height, int stride, int lap0,
+                                      int lap1, dvm_keypoint* kps_dev, uint8_t* desc_dev, int32_t* counts_dev);
 DVM_API int dvm_orb_sync(dvm_orb* h);
 /* Device pointers to the last result: kps (dvm_keypoint[cap]), desc (u8[cap*32]),
  * counts (int32[2] = {n, mono_index}). */
@@ -136,6 +141,12 @@ DVM_API int dvm_frame_assign(dvm_frame* f, const dvm_keypoint* kps_un, const uin
  * (device to device, enqueued on the frame's stream; no synchronisation). */
 DVM_API int dvm_frame_assign_from_orb(dvm_frame* f, const dvm_orb* orb, float min_x, float min_y, float max_x,
                                       float max_y);
+/* The mono Frame constructor on the device (O3/src/Frame.cc:371-479 with zero distortion): ExtractORB(0, im,
+ * 0, 1000) straight into the frame's own buffers, then AssignFeaturesToGrid -- all enqueued on the
+ * EXTRACTOR's stream, no synchronisation.  The frame's own stream must be ordered after it by the caller
+ * (cudaStreamWaitEvent; dvm_tracker does this). */
+DVM_API int dvm_frame_construct_device(dvm_frame* f, dvm_orb* orb, const uint8_t* gray_dev, int width, int height,
+                                       int stride, float min_x, float min_y, float max_x, float max_y);
 /* Frame::GetFeaturesInArea(x, y, r, minLevel, maxLevel) (O3/src/Frame.cc:712-770); indices in the
  * reference's order.  *n_out may exceed cap (then only cap entries were written). */
 DVM_API int dvm_frame_features_in_area(dvm_frame* f, float x, float y, float r, int min_level, int max_level,
