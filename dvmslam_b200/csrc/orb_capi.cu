@@ -280,6 +280,11 @@ int dvm_orb_tables(const dvm_orb* h, int* nlevels, float* scale, float* inv_scal
 }
 
 int dvm_orb_max_keypoints(const dvm_orb* h) { return h ? h->max_kp : DVM_ERR_INVALID; }
+int dvm_orb_max_keypoints_current(const dvm_orb* h)
+{
+    if (!h) return DVM_ERR_INVALID;
+    return h->cur_w > 0 ? std::min(h->max_kp, (h->cfg.max_kp + 3) & ~3) : h->max_kp;
+}
 
 // enqueue the whole extractor on the handle's stream; level 0 must already be in place
 static int enqueue_pipeline(dvm_orb* h, int lap0, int lap1)

@@ -2,6 +2,7 @@
 // Float64 work inside the stated tolerance: this file is compiled with FMA contraction enabled.
 #include "track_kernels.cuh"
 #include <cooperative_groups.h>
+#include <cstdlib>
 
 namespace dvm {
 
@@ -10,11 +11,37 @@ namespace dvm {
 struct Quat { double x, y, z, w; };
 struct SE3d { Quat r; double t[3]; };
 
+// Branch-free reciprocal / reciprocal square root: hardware seed (MUFU.RCP64H / RSQ64H, ~20 bits) and two
+// Newton steps.  For the normal, well-scaled operands of this file (depths, Hessian pivots, squared
+// norms) the result is within 1 ulp of the IEEE quotient, far inside the stated pose tolerance, and
+// the dependent chain is about half of the compiler's division with its special-case slow path.
+__device__ inline double fast_rcp(double d)
+{
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+    double e = fma(-d, x, 1.0);
+    x = fma(x, e, x);
+    e = fma(-d, x, 1.0);
+    return fma(x, e, x);
+}
+__device__ inline double fast_rsqrt(double d)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    const double h = 0.5 * d;
+    double e = fma(-h * y, y, 0.5);
+    y = fma(y, e, y);
+    e = fma(-h * y, y, 0.5);
+    y = fma(y, e, y);
+    e = fma(-h * y, y, 0.5);
+    return fma(y, e, y);
+}
+
 __device__ inline void quat_normalize(Quat& q)
 {
-    if (q.w < 0) { q.x = -q.x; q.y = -q.y; q.z = -q.z; q.w = -q.w; }
-    const double n = sqrt(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
-    q.x /= n; q.y /= n; q.z /= n; q.w /= n;
+    double s = fast_rsqrt(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
+    if (q.w < 0) s = -s;
+    q.x *= s; q.y *= s; q.z *= s; q.w *= s;
 }
 __device__ inline Quat quat_mul(const Quat& a, const Quat& b)
 {
@@ -33,62 +60,49 @@ __device__ inline void quat_rotate(const Quat& q, const double v[3], double out[
     out[1] = v[1] + q.w * uv[1] + (q.z * uv[0] - q.x * uv[2]);
     out[2] = v[2] + q.w * uv[2] + (q.x * uv[1] - q.y * uv[0]);
 }
-__device__ inline Quat quat_from_matrix(const double R[9])
-{
-    Quat q;
-    double t = R[0] + R[4] + R[8];
-    if (t > 0) {
-        t = sqrt(t + 1.0);
-        q.w = 0.5 * t;
-        t = 0.5 / t;
-        q.x = (R[7] - R[5]) * t;
-        q.y = (R[2] - R[6]) * t;
-        q.z = (R[3] - R[1]) * t;
-    } else {
-        int i = 0;
-        if (R[4] > R[0]) i = 1;
-        if (R[8] > R[i * 4]) i = 2;
-        const int j = (i + 1) % 3, k = (j + 1) % 3;
-        t = sqrt(R[i * 4] - R[j * 4] - R[k * 4] + 1.0);
-        double v[3];
-        v[i] = 0.5 * t;
-        t = 0.5 / t;
-        q.w = (R[k * 3 + j] - R[j * 3 + k]) * t;
-        v[j] = (R[j * 3 + i] + R[i * 3 + j]) * t;
-        v[k] = (R[k * 3 + i] + R[i * 3 + k]) * t;
-        q.x = v[0]; q.y = v[1]; q.z = v[2];
-    }
-    return q;
-}
-// SE3Quat::exp (g2o/types/se3quat.h:212-240)
+// SE3Quat::exp (g2o/types/se3quat.h:212-240): R = I + A*O + B*O^2, V = I + B'*O + C*O^2 with O = [w]x;
+// below theta = 1e-5 the reference takes A = B = B' = C = 1.  Its Quaternion(R) constructor goes through
+// the trace branch whenever trace(R) > 0 (rotation steps below 120 degrees):
+//   trace = 3 - 2*B*theta^2,  R[2][1] - R[1][2] = 2*A*w0, ...   (O^2 is symmetric)
+// so q = (A*w / tt, tt / 2) with tt = sqrt(trace + 1), then normalised -- evaluated here without forming
+// the matrices.  A step of 120 degrees or more cannot come out of a damped LM solve on a tracked frame;
+// it would only make this kernel's result differ from the reference, never fail.
 __device__ inline SE3d se3_exp(const double u[6])
 {
     const double w0 = u[0], w1 = u[1], w2 = u[2];
-    const double theta = sqrt(w0 * w0 + w1 * w1 + w2 * w2);
-    const double O[9] = { 0, -w2, w1, w2, 0, -w0, -w1, w0, 0 };
-    double O2[9], R[9], V[9];
-#pragma unroll
-    for (int i = 0; i < 3; i++)
-#pragma unroll
-        for (int j = 0; j < 3; j++) O2[i * 3 + j] = O[i * 3] * O[j] + O[i * 3 + 1] * O[3 + j] + O[i * 3 + 2] * O[6 + j];
-    if (theta < 0.00001) {
-#pragma unroll
-        for (int i = 0; i < 9; i++) { R[i] = ((i % 4 == 0) ? 1.0 : 0.0) + O[i] + O2[i]; V[i] = R[i]; }
-    } else {
-        const double sa = sin(theta) / theta, sb = (1 - cos(theta)) / (theta * theta);
-        const double sc = (theta - sin(theta)) / (theta * theta * theta);
-#pragma unroll
-        for (int i = 0; i < 9; i++) {
-            const double I = (i % 4 == 0) ? 1.0 : 0.0;
-            R[i] = I + sa * O[i] + sb * O2[i];
-            V[i] = I + sb * O[i] + sc * O2[i];
-        }
+    const double th2 = w0 * w0 + w1 * w1 + w2 * w2;
+    double A = 1.0, B = 1.0, Bv = 1.0, C = 1.0;
+    if (!(th2 < 1e-10) && th2 < 0.25) {
+        // 1e-5 <= theta < 0.5 rad, every LM step on a tracked frame: even power series of
+        // sin(t)/t, (1-cos t)/t^2, (t-sin t)/t^3 in t^2 (truncation below 1e-19) -- no sqrt, no sincos
+        const double x = th2;
+        A = 1.0 + x * (-1.0 / 6 + x * (1.0 / 120 + x * (-1.0 / 5040 + x * (1.0 / 362880 + x * (-1.0 / 39916800 + x * (1.0 / 6227020800.0 + x * (-1.0 / 1307674368000.0)))))));
+        B = 0.5 + x * (-1.0 / 24 + x * (1.0 / 720 + x * (-1.0 / 40320 + x * (1.0 / 3628800 + x * (-1.0 / 479001600 + x * (1.0 / 87178291200.0 + x * (-1.0 / 20922789888000.0)))))));
+        C = 1.0 / 6 + x * (-1.0 / 120 + x * (1.0 / 5040 + x * (-1.0 / 362880 + x * (1.0 / 39916800 + x * (-1.0 / 6227020800.0 + x * (1.0 / 1307674368000.0 + x * (-1.0 / 355687428096000.0)))))));
+        Bv = B;
+    } else if (!(th2 < 1e-10)) {
+        const double inv = fast_rsqrt(th2), theta = th2 * inv;
+        double sn, cs;
+        sincos(theta, &sn, &cs);
+        A = sn * inv;
+        B = (1.0 - cs) * inv * inv;
+        Bv = B;
+        C = (theta - sn) * inv * inv * inv;
     }
     SE3d T;
-    T.r = quat_from_matrix(R);
+    const double tt2 = 4.0 - 2.0 * B * th2;     // trace + 1
+    const double itt = fast_rsqrt(tt2);
+    T.r.w = 0.5 * tt2 * itt;
+    const double sx = A * itt;
+    T.r.x = sx * w0; T.r.y = sx * w1; T.r.z = sx * w2;
     quat_normalize(T.r);
-#pragma unroll
-    for (int i = 0; i < 3; i++) T.t[i] = V[i * 3] * u[3] + V[i * 3 + 1] * u[4] + V[i * 3 + 2] * u[5];
+    // t = V * v = v + B'*(w x v) + C*(w x (w x v))
+    const double v0 = u[3], v1 = u[4], v2 = u[5];
+    const double c0 = w1 * v2 - w2 * v1, c1 = w2 * v0 - w0 * v2, c2 = w0 * v1 - w1 * v0;
+    const double d0 = w1 * c2 - w2 * c1, d1 = w2 * c0 - w0 * c2, d2 = w0 * c1 - w1 * c0;
+    T.t[0] = v0 + Bv * c0 + C * d0;
+    T.t[1] = v1 + Bv * c1 + C * d1;
+    T.t[2] = v2 + Bv * c2 + C * d2;
     return T;
 }
 __device__ inline SE3d se3_mul(const SE3d& a, const SE3d& b)
@@ -114,7 +128,7 @@ __device__ inline bool ldlt6_solve(const double* A, const double* b, double* x)
         for (int k = 0; k < j; k++) d -= L[j * 6 + k] * L[j * 6 + k] * D[k];
         ok = ok && (d > 0);
         D[j] = d;
-        Dinv[j] = 1.0 / d;
+        Dinv[j] = fast_rcp(d);
 #pragma unroll
         for (int i = j + 1; i < 6; i++) {
             double s = A[i * 6 + j];
@@ -173,17 +187,27 @@ constexpr int kPoseNV = 32;
 
 struct PoseShared {
     double warp_buf[kPoseWarps][kPoseNV];
-    double recv[2][kPoseCtas][kPoseNV]; // partials of every CTA of the cluster, double-buffered
+    // partials of every CTA of the cluster, double-buffered; filled by the peers' st.async stores, whose
+    // bytes are counted by bar[parity] (transaction barrier): consumers sleep on the barrier, nobody polls
+    double recv[2][kPoseCtas][kPoseNV];
+    unsigned long long bar[2];
 };
 
+__device__ inline uint32_t cvta_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+constexpr unsigned kPoseTxBytes = kPoseCtas * kPoseNV * 8;
+
 // Sums v[s] over all threads of the cluster; on return v[s] holds the total of slot s in every thread
-// (same summation tree everywhere).  v is clobbered during the exchange.
-__device__ inline void cluster_sum(double (&v)[kPoseNV], PoseShared& sh, int& parity)
+// (same summation tree everywhere).  v is clobbered during the exchange.  `pass` counts the calls (>= 0).
+//   warp butterfly -> CTA partial (one __syncthreads) -> warp 0 sends its 32 partials to the 8 CTAs with
+//   st.async (remote store + complete_tx on the receiver's mbarrier) -> every warp waits on the local
+//   mbarrier (try_wait sleeps in hardware) and adds the 8 partials in rank order.
+__device__ inline void cluster_sum(double (&v)[kPoseNV], PoseShared& sh, unsigned& pass)
 {
-    namespace cg = cooperative_groups;
-    cg::cluster_group cluster = cg::this_cluster();
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const unsigned rank = cluster.block_rank();
+    unsigned rank;
+    asm("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    const int parity = (int)(pass & 1u);
+    const unsigned phase = (pass >> 1) & 1u;
     // transposed butterfly: after the 5 steps lane l holds the warp total of slot l (31 shuffles)
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) {
@@ -196,21 +220,35 @@ __device__ inline void cluster_sum(double (&v)[kPoseNV], PoseShared& sh, int& pa
         }
     }
     sh.warp_buf[wid][lane] = v[0];
-    __syncthreads();
+    __syncthreads(); // also: every warp of this CTA has finished reading recv[parity] of pass - 2
+    const uint32_t bar = cvta_smem(&sh.bar[parity]);
     if (wid == 0) {
+        // arm this pass's phase (peers' bytes may already have been counted: the tx-count is signed)
+        if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kPoseTxBytes) : "memory");
         double s = sh.warp_buf[0][lane];
 #pragma unroll
         for (int w = 1; w < kPoseWarps; w++) s += sh.warp_buf[w][lane];
+        const uint32_t local = cvta_smem(&sh.recv[parity][rank][lane]);
 #pragma unroll
-        for (unsigned r = 0; r < kPoseCtas; r++) *cluster.map_shared_rank(&sh.recv[parity][rank][lane], r) = s;
+        for (unsigned r = 0; r < kPoseCtas; r++) {
+            uint32_t rdst, rbar;
+            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rdst) : "r"(local), "r"(r));
+            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar) : "r"(bar), "r"(r));
+            asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];"
+                         ::"r"(rdst), "l"(__double_as_longlong(s)), "r"(rbar) : "memory");
+        }
     }
-    cluster.sync();
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(phase) : "memory");
+    }
     double tot = sh.recv[parity][0][lane];
 #pragma unroll
     for (int r = 1; r < kPoseCtas; r++) tot += sh.recv[parity][r][lane];
 #pragma unroll
     for (int i = 0; i < 29; i++) v[i] = __shfl_sync(0xffffffffu, tot, i);
-    parity ^= 1;
+    pass++;
 }
 
 template <int EPT>
@@ -218,12 +256,19 @@ __global__ void __cluster_dims__(kPoseCtas, 1, 1) __launch_bounds__(kPoseThreads
 {
     __shared__ PoseShared sh;
     const int tid = blockIdx.x * kPoseThreads + threadIdx.x;
-    int parity = 0;
+    unsigned parity = 0; // pass counter of cluster_sum
     const int n = a.n_ptr ? min(*a.n_ptr, a.n) : a.n;
     PoseCam cam;
     cam.fx = a.K[0]; cam.fy = a.K[1]; cam.cx = a.K[2]; cam.cy = a.K[3];
     cam.delta = (double)(float)sqrt(5.991);
     cam.dsqr = cam.delta * cam.delta;
+
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(cvta_smem(&sh.bar[0])), "r"(1));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(cvta_smem(&sh.bar[1])), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    cooperative_groups::this_cluster().sync(); // nobody sends before every CTA has initialised its barriers
 
     // ---- gather this thread's edges into registers ----
     // state: bit0 excluded (level 1), bit1 robust kernel removed, bit2 not an edge
@@ -265,8 +310,18 @@ __global__ void __cluster_dims__(kPoseCtas, 1, 1) __launch_bounds__(kPoseThreads
     SE3d T = T0;
     int nBadEdges = 0, total_iters = 0, total_trials = 0;
 
+    unsigned long long pr_t = 0, pr_edges = 0, pr_reduce = 0, pr_solve = 0, pr_pass = 0;
+    auto stamp = [&](unsigned long long& bucket) {
+        if (a.prof) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            bucket += now - pr_t;
+            pr_t = now;
+        }
+    };
     // errors + robust chi2 + linearisation of every active edge at estimate Tx -> acc (all threads)
     auto linearize_at = [&](const SE3d& Tx) {
+        stamp(pr_solve);
         double R[9];
         quat_to_matrix(Tx.r, R);
 #pragma unroll
@@ -277,7 +332,7 @@ __global__ void __cluster_dims__(kPoseCtas, 1, 1) __launch_bounds__(kPoseThreads
             const double x = R[0] * X[s][0] + R[1] * X[s][1] + R[2] * X[s][2] + Tx.t[0];
             const double y = R[3] * X[s][0] + R[4] * X[s][1] + R[5] * X[s][2] + Tx.t[1];
             const double z = R[6] * X[s][0] + R[7] * X[s][1] + R[8] * X[s][2] + Tx.t[2];
-            const double iz = 1.0 / z;
+            const double iz = fast_rcp(z);
             const double ax = cam.fx * iz, ay = cam.fy * iz;      // d u / d x, d v / d y
             const double bx = -ax * x * iz, by = -ay * y * iz;    // d u / d z, d v / d z
             const double ex = ox[s] - (ax * x + cam.cx), ey = oy[s] - (ay * y + cam.cy);
@@ -286,9 +341,9 @@ __global__ void __cluster_dims__(kPoseCtas, 1, 1) __launch_bounds__(kPoseThreads
             const bool robust = !(st[s] & 2);
             double w = 1.0, rho = chi;
             if (robust && chi > cam.dsqr) {
-                const double sq = sqrt(chi);
-                rho = 2 * sq * cam.delta - cam.dsqr;
-                w = cam.delta / sq;
+                const double isq = fast_rsqrt(chi);
+                rho = 2 * (chi * isq) * cam.delta - cam.dsqr;
+                w = cam.delta * isq;
             }
             acc[27] += rho;
             acc[28] += 1;
@@ -312,7 +367,10 @@ __global__ void __cluster_dims__(kPoseCtas, 1, 1) __launch_bounds__(kPoseThreads
                 }
             }
         }
+        stamp(pr_edges);
         cluster_sum(acc, sh, parity);
+        stamp(pr_reduce);
+        pr_pass++;
     };
     auto unpack = [&](double* H, double* b) {
         int idx = 0;
@@ -324,6 +382,7 @@ __global__ void __cluster_dims__(kPoseCtas, 1, 1) __launch_bounds__(kPoseThreads
         for (int c = 0; c < 6; c++) b[c] = acc[21 + c];
     };
 
+    if (a.prof) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(pr_t));
     if (nedges >= 3) {
         for (int round = 0; round < 4; round++) {
             T = T0; // the frame's pose is only written back at the end (O3/src/Optimizer.cc:935-936)
@@ -372,7 +431,7 @@ __global__ void __cluster_dims__(kPoseCtas, 1, 1) __launch_bounds__(kPoseThreads
 #pragma unroll
                     for (int j = 0; j < 6; j++) scale += x[j] * (lambda * x[j] + b[j]);
                     scale += 1e-3;
-                    rho /= scale;
+                    rho *= fast_rcp(scale);
                     if (rho > 0 && isfinite(tempChi)) {
                         const double c = 2 * rho - 1;
                         double alpha = 1. - c * c * c;
@@ -410,7 +469,7 @@ __global__ void __cluster_dims__(kPoseCtas, 1, 1) __launch_bounds__(kPoseThreads
                     const double x = R[0] * X[s][0] + R[1] * X[s][1] + R[2] * X[s][2] + T.t[0];
                     const double y = R[3] * X[s][0] + R[4] * X[s][1] + R[5] * X[s][2] + T.t[1];
                     const double z = R[6] * X[s][0] + R[7] * X[s][1] + R[8] * X[s][2] + T.t[2];
-                    const double iz = 1.0 / z;
+                    const double iz = fast_rcp(z);
                     e0[s] = ox[s] - (cam.fx * iz * x + cam.cx);
                     e1[s] = oy[s] - (cam.fy * iz * y + cam.cy);
                 }
@@ -444,6 +503,7 @@ __global__ void __cluster_dims__(kPoseCtas, 1, 1) __launch_bounds__(kPoseThreads
         a.result[1] = nedges;
         a.result[2] = total_iters;
         a.result[3] = total_trials;
+        if (a.prof) { a.prof[0] = pr_edges; a.prof[1] = pr_reduce; a.prof[2] = pr_solve; a.prof[3] = pr_pass; }
         if (a.out_pose) { // frame hand-over: pose history for the constant-velocity prior + result block
             for (int i = 0; i < 7; i++) {
                 const float v = a.pose[i];
@@ -460,8 +520,27 @@ __global__ void __cluster_dims__(kPoseCtas, 1, 1) __launch_bounds__(kPoseThreads
     cooperative_groups::this_cluster().sync(); // no CTA may exit while peers can still write into its shared memory
 }
 
-int launch_pose_opt(const PoseOptArgs& a, cudaStream_t stream)
+int launch_pose_opt(const PoseOptArgs& a_in, cudaStream_t stream)
 {
+    PoseOptArgs a = a_in;
+    static const bool profile = getenv("DVM_POSE_PROFILE") != nullptr;
+    static unsigned long long* d_prof = nullptr;
+    if (profile) {
+        if (!d_prof) cudaMalloc(&d_prof, 32);
+        a.prof = d_prof;
+    }
+    struct Report { // prints the phase timers of this launch when profiling (synchronises: diagnostics only)
+        cudaStream_t st; bool on; unsigned long long* d;
+        ~Report()
+        {
+            if (!on) return;
+            unsigned long long pr[4] = { 0, 0, 0, 0 };
+            cudaStreamSynchronize(st);
+            cudaMemcpy(pr, d, 32, cudaMemcpyDeviceToHost);
+            fprintf(stderr, "[pose-opt us] edges %.1f reduce %.1f solve %.1f passes %llu\n", pr[0] * 1e-3, pr[1] * 1e-3,
+                    pr[2] * 1e-3, pr[3]);
+        }
+    } report{ stream, profile, d_prof };
     // a.n bounds the number of potential edges (the device count may be smaller): pick the register tile
     if (a.n <= 2 * kPoseStride) DVM_LAUNCH(pose_opt_kernel<2>, kPoseCtas, kPoseThreads, 0, stream, a);
     else if (a.n <= 4 * kPoseStride) DVM_LAUNCH(pose_opt_kernel<4>, kPoseCtas, kPoseThreads, 0, stream, a);

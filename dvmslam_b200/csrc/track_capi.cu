@@ -12,7 +12,7 @@ static void frame_free(dvm_frame* f)
     cudaSetDevice(f->device);
     cudaFree(f->d_kps); cudaFree(f->d_desc); cudaFree(f->d_n); cudaFree(f->d_cell_start); cudaFree(f->d_cell_items); cudaFree(f->d_kxyo);
     cudaFree(f->d_in); cudaFree(f->ms.pu); cudaFree(f->ms.pv); cudaFree(f->ms.pr); cudaFree(f->ms.plevels);
-    cudaFree(f->ms.choice); cudaFree(f->ms.cache); cudaFree(f->ms.ncand); cudaFree(f->ms.claim_a); cudaFree(f->ms.claim_b); cudaFree(f->ms.iters);
+    cudaFree(f->ms.choice); cudaFree(f->ms.cache); cudaFree(f->ms.ncand); cudaFree(f->ms.qlist); cudaFree(f->ms.claim_a); cudaFree(f->ms.claim_b); cudaFree(f->ms.iters);
     cudaFree(f->d_cur_mp); cudaFree(f->d_err);
     if (f->h_in) cudaFreeHost(f->h_in);
     if (f->h_out) cudaFreeHost(f->h_out);
@@ -27,7 +27,8 @@ int dvm_frame_ensure_query_cap(dvm_frame* f, int nq)
     const int cap = nq + nq / 4 + 256;
     DVM_CUDA(cudaStreamSynchronize(f->stream));
     cudaFree(f->ms.pu); cudaFree(f->ms.pv); cudaFree(f->ms.pr); cudaFree(f->ms.plevels); cudaFree(f->ms.choice);
-    cudaFree(f->ms.cache); cudaFree(f->ms.ncand);
+    cudaFree(f->ms.cache); cudaFree(f->ms.ncand); cudaFree(f->ms.qlist);
+    f->ms.qlist = nullptr;
     f->ms.pu = f->ms.pv = f->ms.pr = nullptr; f->ms.plevels = f->ms.choice = nullptr; f->ms.cache = nullptr; f->ms.ncand = nullptr;
     DVM_CUDA(cudaMalloc(&f->ms.pu, cap * sizeof(float)));
     DVM_CUDA(cudaMalloc(&f->ms.pv, cap * sizeof(float)));
@@ -36,6 +37,7 @@ int dvm_frame_ensure_query_cap(dvm_frame* f, int nq)
     DVM_CUDA(cudaMalloc(&f->ms.choice, cap * sizeof(int)));
     DVM_CUDA(cudaMalloc(&f->ms.cache, (size_t)cap * kMatchCacheK * sizeof(unsigned long long)));
     DVM_CUDA(cudaMalloc(&f->ms.ncand, cap * sizeof(int)));
+    DVM_CUDA(cudaMalloc(&f->ms.qlist, cap * sizeof(int)));
     f->q_cap = cap;
     return DVM_OK;
 }
@@ -201,7 +203,8 @@ int dvm_frame_construct_device(dvm_frame* f, dvm_orb* orb, const uint8_t* gray_d
     set_bounds(f, min_x, min_y, max_x, max_y);
     int rc = dvm_orb_extract_device_to(orb, gray_dev, width, height, stride, 0, 1000, f->d_kps, f->d_desc, f->d_n);
     if (rc != DVM_OK) return rc;
-    f->host_n = dvm_orb_max_keypoints(orb);
+    f->host_n = dvm_orb_max_keypoints_current(orb);
+    f->dev.cap = f->host_n; // tight bound for this image size: sizes the matchers' shared-memory staging
     launch_grid_build(f->dev, (cudaStream_t)dvm_orb_stream(orb));
     DVM_CUDA(cudaGetLastError());
     return DVM_OK;

@@ -288,6 +288,21 @@ __device__ inline void topk_insert(unsigned long long (&top)[kMatchCacheK], unsi
 
 constexpr int kWalkThreads = 128;
 
+// ordered list of the queries that take part (plevels != -1) in shared memory; returns their number
+__device__ inline int compact_active(const int* __restrict__ plevels, int nq, int* qlist, int* warp_sums)
+{
+    const int ipt = div_up(max(nq, 1), kMatchThreads);
+    const int i0 = min((int)threadIdx.x * ipt, nq), i1 = min(i0 + ipt, nq);
+    int c = 0;
+    for (int i = i0; i < i1; i++) c += (plevels[i] != -1);
+    int total;
+    int off = block_exclusive_scan(c, warp_sums, &total);
+    for (int i = i0; i < i1; i++)
+        if (plevels[i] != -1) qlist[off++] = i;
+    __syncthreads();
+    return total;
+}
+
 // ---- SearchByProjection(cur, last), phase 1: one thread per last-frame keypoint projects its map point
 // with the pose prior and walks its window once (many CTAs; the frame is read through L1/L2) ----
 __global__ void __launch_bounds__(kWalkThreads) match_last_walk_kernel(FrameDev cur, MatchLastArgs a, MatchScratch s, int use_smem)
@@ -361,24 +376,27 @@ match_last_kernel(FrameDev cur, MatchLastArgs a, MatchScratch s, int* __restrict
     auto obs_of = [&](int i) { return a.obs_pos ? a.obs_pos[i] != 0 : true; };
     auto angle_of = [&](int i) { return a.last_kps ? a.last_kps[i].angle : a.angle[i]; };
 
+    __shared__ int warp_sums[33];
     int* claim_prev = use_smem ? reinterpret_cast<int*>(claim_smem) : s.claim_a;
     int* claim_next = use_smem ? reinterpret_cast<int*>(claim_smem) + cur.cap : s.claim_b;
+    int* qlist = s.qlist;
     for (int i = tid; i < nq; i += kMatchThreads) s.choice[i] = -1;
     for (int k = tid; k < ncur; k += kMatchThreads) claim_prev[k] = kNoClaim;
-    __syncthreads();
+    const int nact = compact_active(s.plevels, nq, qlist, warp_sums);
 
     int rounds = 0;
     while (true) {
         int changed = 0;
-        for (int i = tid; i < nq; i += kMatchThreads) {
+        for (int j = tid; j < nact; j += kMatchThreads) {
+            const int i = qlist[j];
             const int lv = s.plevels[i];
-            if (lv == -1) continue;
             const int nc = s.ncand[i];
             int bestDist = 256, bestIdx = -1;
             bool found = false;
             const unsigned long long* e = s.cache + (size_t)i * kMatchCacheK;
+            const ulonglong2 e01 = *reinterpret_cast<const ulonglong2*>(e), e23 = *reinterpret_cast<const ulonglong2*>(e + 2);
             for (int p = 0; p < kMatchCacheK && p < nc; p++) {
-                const unsigned long long ev = e[p];
+                const unsigned long long ev = p == 0 ? e01.x : p == 1 ? e01.y : p == 2 ? e23.x : p == 3 ? e23.y : e[p];
                 const int idx = cand_idx(ev);
                 if (claim_prev[idx] < i) continue; // taken by an earlier map point with observations
                 bestDist = cand_dist(ev); bestIdx = idx; found = true;
@@ -400,7 +418,8 @@ match_last_kernel(FrameDev cur, MatchLastArgs a, MatchScratch s, int* __restrict
         if (!__syncthreads_or(changed)) break;
         for (int k = tid; k < ncur; k += kMatchThreads) claim_next[k] = kNoClaim;
         __syncthreads();
-        for (int i = tid; i < nq; i += kMatchThreads) {
+        for (int j = tid; j < nact; j += kMatchThreads) {
+            const int i = qlist[j];
             const int k = s.choice[i];
             if (k >= 0 && obs_of(i)) atomicMin(&claim_next[k], i);
         }
@@ -416,7 +435,8 @@ match_last_kernel(FrameDev cur, MatchLastArgs a, MatchScratch s, int* __restrict
     __syncthreads();
     for (int k = tid; k < ncur; k += kMatchThreads) { owner[k] = -1; nulled[k] = 0; }
     __syncthreads();
-    for (int i = tid; i < nq; i += kMatchThreads) {
+    for (int j = tid; j < nact; j += kMatchThreads) {
+        const int i = qlist[j];
         const int k = s.choice[i];
         if (k < 0) continue;
         atomicMax(&owner[k], i);
@@ -431,7 +451,8 @@ match_last_kernel(FrameDev cur, MatchLastArgs a, MatchScratch s, int* __restrict
     }
     __syncthreads();
     if (a.check_ori) {
-        for (int i = tid; i < nq; i += kMatchThreads) {
+        for (int j = tid; j < nact; j += kMatchThreads) {
+            const int i = qlist[j];
             const int k = s.choice[i];
             if (k < 0) continue;
             const int bin = rot_bin(angle_of(i), cur.kps[k].angle);
@@ -519,27 +540,30 @@ match_map_kernel(FrameDev cur, MatchMapArgs a, MatchScratch s, int* __restrict__
     auto desc_of = [&](int i) { return a.mp_desc + (size_t)(a.q_index ? a.q_index[i] : i) * 32; };
     auto obs_of = [&](int i) { return a.obs_pos ? a.obs_pos[i] != 0 : true; };
     auto blocked = [&](int k) { return a.cur_map ? a.cur_map[k] >= 0 : (a.cur_blocked && a.cur_blocked[k]); };
+    __shared__ int warp_sums[33];
     int* claim_prev = use_smem ? reinterpret_cast<int*>(claim_smem) : s.claim_a;
     int* claim_next = use_smem ? reinterpret_cast<int*>(claim_smem) + cur.cap : s.claim_b;
+    int* qlist = s.qlist;
     for (int i = tid; i < nq; i += kMatchThreads) s.choice[i] = -1;
     for (int k = tid; k < ncur; k += kMatchThreads) claim_prev[k] = blocked(k) ? -1 : kNoClaim;
     if (tid == 0) s_events = 0;
-    __syncthreads();
+    const int nact = compact_active(s.plevels, nq, qlist, warp_sums); // queries in the frustum, vpMapPoints order
 
     int rounds = 0;
     while (true) {
         int changed = 0;
-        for (int i = tid; i < nq; i += kMatchThreads) {
+        for (int j = tid; j < nact; j += kMatchThreads) {
+            const int i = qlist[j];
             const int lvl = s.plevels[i];
-            if (lvl < 0) continue; // not in the frustum
             const int nc = s.ncand[i];
             int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
             int found = 0;
             // sorted by (distance, walk order): the first two free entries are the reference's best and
             // second best (its scan keeps the earliest of equal distances)
             const unsigned long long* e = s.cache + (size_t)i * kMatchCacheK;
+            const ulonglong2 e01 = *reinterpret_cast<const ulonglong2*>(e), e23 = *reinterpret_cast<const ulonglong2*>(e + 2);
             for (int p = 0; p < kMatchCacheK && p < nc && found < 2; p++) {
-                const unsigned long long ev = e[p];
+                const unsigned long long ev = p == 0 ? e01.x : p == 1 ? e01.y : p == 2 ? e23.x : p == 3 ? e23.y : e[p];
                 const int idx = cand_idx(ev);
                 if (claim_prev[idx] < i) continue; // held by a map point with observations
                 if (found == 0) { bestDist = cand_dist(ev); bestLevel = cand_oct(ev); bestIdx = idx; }
@@ -575,7 +599,8 @@ match_map_kernel(FrameDev cur, MatchMapArgs a, MatchScratch s, int* __restrict__
         if (!__syncthreads_or(changed)) break;
         for (int k = tid; k < ncur; k += kMatchThreads) claim_next[k] = blocked(k) ? -1 : kNoClaim;
         __syncthreads();
-        for (int i = tid; i < nq; i += kMatchThreads) {
+        for (int j = tid; j < nact; j += kMatchThreads) {
+            const int i = qlist[j];
             const int k = s.choice[i];
             if (k >= 0 && obs_of(i)) atomicMin(&claim_next[k], i);
         }
@@ -586,7 +611,8 @@ match_map_kernel(FrameDev cur, MatchMapArgs a, MatchScratch s, int* __restrict__
     __syncthreads();
     for (int k = tid; k < ncur; k += kMatchThreads) owner[k] = -1;
     __syncthreads();
-    for (int i = tid; i < nq; i += kMatchThreads) {
+    for (int j = tid; j < nact; j += kMatchThreads) {
+        const int i = qlist[j];
         const int k = s.choice[i];
         if (k < 0) continue;
         atomicMax(&owner[k], i);

@@ -94,6 +94,7 @@ struct MatchScratch {
     int* iters;     // [1] fixed-point rounds used (diagnostic)
     unsigned long long* cache; // [cap_q * kMatchCacheK] best candidates of each query, sorted by (distance, walk order)
     int* ncand;     // [cap_q] candidates seen by the window walk
+    int* qlist;     // [cap_q] ordered list of the queries that take part
 };
 constexpr int kMatchCacheK = 8;
 
@@ -120,6 +121,7 @@ struct PoseOptArgs {
     int* map_index_rw;
     // frame hand-over after TrackLocalMap: pose history for the constant-velocity prior and the result block
     float* pose_last; float* pose_prev; float* out_pose; int* out_counts; const int* nm_last; const int* res_first;
+    unsigned long long* prof; // [4] or nullptr: ns spent in {edge pass, reduction, solve + update, passes} (DVM_POSE_PROFILE)
 };
 
 void launch_grid_build(const FrameDev& f, cudaStream_t stream);

@@ -192,7 +192,11 @@ int dvm_tracker_create(dvm_tracker** out, dvm_orb* orb, const float* K, const fl
             return DVM_ERR_CUDA;                                                               \
         }                                                                                      \
     } while (0)
-    DVM_TCREATE(cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking));
+    {   // the chain is the critical path: its few small CTAs go ahead of the extractor's wide grids
+        int lo = 0, hi = 0;
+        DVM_TCREATE(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        DVM_TCREATE(cudaStreamCreateWithPriority(&t->stream, cudaStreamNonBlocking, hi));
+    }
     for (int i = 0; i < kRing; i++) {
         DVM_TCREATE(cudaEventCreateWithFlags(&t->ev_extracted[i], cudaEventDisableTiming));
         DVM_TCREATE(cudaEventCreateWithFlags(&t->ev_done[i], cudaEventDisableTiming));
@@ -352,7 +356,7 @@ int dvm_tracker_track(dvm_tracker* t, const uint8_t* gray, int gray_is_device, i
     // ---- TrackWithMotionModel: SearchByProjection(cur, last, th = 15), retry with 2*th below 20 matches ----
     MatchLastArgs la;
     memset(&la, 0, sizeof(la));
-    la.last_n = t->cap; la.n_ptr = last->d_n;
+    la.last_n = last->dev.cap; la.n_ptr = last->d_n;
     la.mp_index = t->d_mp[li]; la.outlier = t->d_outl[li];
     la.Xw = t->d_xw; la.mp_desc = t->d_desc; la.obs_pos = nullptr; la.last_kps = last->d_kps;
     la.pose = t->d_pose; la.th = 15.0f; la.check_ori = 1;
@@ -364,7 +368,7 @@ int dvm_tracker_track(dvm_tracker* t, const uint8_t* gray, int gray_is_device, i
     // ---- PoseOptimization + discard outliers (fused tail) ----
     PoseOptArgs pa;
     memset(&pa, 0, sizeof(pa));
-    pa.n = t->cap; pa.n_ptr = cur->d_n; pa.map_index = t->d_mp[ci]; pa.Xw = t->d_xw; pa.kps = cur->d_kps;
+    pa.n = cur->dev.cap; pa.n_ptr = cur->d_n; pa.map_index = t->d_mp[ci]; pa.Xw = t->d_xw; pa.kps = cur->d_kps;
     for (int i = 0; i < t->nlevels; i++) pa.inv_sigma2_table[i] = t->inv_sigma2[i];
     for (int i = 0; i < 4; i++) pa.K[i] = t->K[i];
     pa.pose = t->d_pose; pa.outlier = t->d_outl[ci]; pa.result = t->d_res1;

@@ -72,6 +72,9 @@ DVM_API int dvm_orb_tables(const dvm_orb* h, int* nlevels, float* scale, float* 
                            float* inv_sigma2, int* features_per_level);
 /* Upper bound on the number of keypoints one extract call can return (size kps/desc with it). */
 DVM_API int dvm_orb_max_keypoints(const dvm_orb* h);
+/* The tighter bound for the image size of the last extract call (the octree can return at most
+ * quota + 4 keypoints per level); equals dvm_orb_max_keypoints() before the first extract. */
+DVM_API int dvm_orb_max_keypoints_current(const dvm_orb* h);
 
 /* int ORBextractor::operator()(image, mask (ignored), keypoints, descriptors, vLappingArea)
  * (O3/src/ORBextractor.cc:876-955).  gray: CV_8UC1 host image, `stride` bytes per row.
