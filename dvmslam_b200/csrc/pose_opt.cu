@@ -32,8 +32,6 @@ __device__ inline double fast_rsqrt(double d)
     double e = fma(-h * y, y, 0.5);
     y = fma(y, e, y);
     e = fma(-h * y, y, 0.5);
-    y = fma(y, e, y);
-    e = fma(-h * y, y, 0.5);
     return fma(y, e, y);
 }
 
@@ -116,43 +114,54 @@ __device__ inline SE3d se3_mul(const SE3d& a, const SE3d& b)
     return r;
 }
 
-// unpivoted LDL^T of a symmetric 6x6 system (full storage); false if a pivot is not positive
-__device__ inline bool ldlt6_solve(const double* A, const double* b, double* x)
+// Symmetric positive-definite 6x6 solve by 3x3 blocks (rotation block A11, translation block A22):
+//   S = A22 - A12^T A11^-1 A12,  x2 = S^-1 (b2 - A12^T A11^-1 b1),  x1 = A11^-1 b1 - A11^-1 A12 x2
+// with closed-form (adjugate) 3x3 inverses.  Same solution as the LDL^T the reference's dense solver
+// computes (g2o/solvers/linear_solver_dense.h:57-104) up to rounding, but the dependent chain is a third
+// as long, which is what bounds one LM trial here.  Returns false unless the matrix is positive definite
+// (all six leading principal minors positive <=> A11 and its Schur complement positive definite).
+struct Sym3 { double m00, m01, m02, m11, m12, m22; };
+__device__ inline bool sym3_inverse(const Sym3& m, Sym3& inv)
 {
-    double L[36], D[6], Dinv[6], y[6];
-    bool ok = true;
+    const double c00 = m.m11 * m.m22 - m.m12 * m.m12, c01 = m.m02 * m.m12 - m.m01 * m.m22, c02 = m.m01 * m.m12 - m.m02 * m.m11;
+    const double c11 = m.m00 * m.m22 - m.m02 * m.m02, c12 = m.m01 * m.m02 - m.m00 * m.m12, c22 = m.m00 * m.m11 - m.m01 * m.m01;
+    const double det = m.m00 * c00 + m.m01 * c01 + m.m02 * c02;
+    const double id = fast_rcp(det);
+    inv.m00 = c00 * id; inv.m01 = c01 * id; inv.m02 = c02 * id; inv.m11 = c11 * id; inv.m12 = c12 * id; inv.m22 = c22 * id;
+    return m.m00 > 0 && c22 > 0 && det > 0;
+}
+__device__ inline bool spd6_solve(const double* A, const double* b, double* x)
+{
+    const Sym3 A11 = { A[0], A[1], A[2], A[7], A[8], A[14] };
+    Sym3 I1;
+    const bool ok1 = sym3_inverse(A11, I1);
+    const double i1[9] = { I1.m00, I1.m01, I1.m02, I1.m01, I1.m11, I1.m12, I1.m02, I1.m12, I1.m22 };
+    double W[9], u[3]; // W = A11^-1 A12, u = A11^-1 b1
 #pragma unroll
-    for (int j = 0; j < 6; j++) {
-        double d = A[j * 6 + j];
+    for (int r = 0; r < 3; r++) {
 #pragma unroll
-        for (int k = 0; k < j; k++) d -= L[j * 6 + k] * L[j * 6 + k] * D[k];
-        ok = ok && (d > 0);
-        D[j] = d;
-        Dinv[j] = fast_rcp(d);
-#pragma unroll
-        for (int i = j + 1; i < 6; i++) {
-            double s = A[i * 6 + j];
-#pragma unroll
-            for (int k = 0; k < j; k++) s -= L[i * 6 + k] * L[j * 6 + k] * D[k];
-            L[i * 6 + j] = s * Dinv[j];
-        }
+        for (int c = 0; c < 3; c++) W[r * 3 + c] = i1[r * 3] * A[0 * 6 + 3 + c] + i1[r * 3 + 1] * A[1 * 6 + 3 + c] + i1[r * 3 + 2] * A[2 * 6 + 3 + c];
+        u[r] = i1[r * 3] * b[0] + i1[r * 3 + 1] * b[1] + i1[r * 3 + 2] * b[2];
     }
-    if (!ok) return false;
+    auto a12 = [&](int r, int c) { return A[r * 6 + 3 + c]; };
+    Sym3 S;
+    S.m00 = A[21] - (a12(0, 0) * W[0] + a12(1, 0) * W[3] + a12(2, 0) * W[6]);
+    S.m01 = A[22] - (a12(0, 0) * W[1] + a12(1, 0) * W[4] + a12(2, 0) * W[7]);
+    S.m02 = A[23] - (a12(0, 0) * W[2] + a12(1, 0) * W[5] + a12(2, 0) * W[8]);
+    S.m11 = A[28] - (a12(0, 1) * W[1] + a12(1, 1) * W[4] + a12(2, 1) * W[7]);
+    S.m12 = A[29] - (a12(0, 1) * W[2] + a12(1, 1) * W[5] + a12(2, 1) * W[8]);
+    S.m22 = A[35] - (a12(0, 2) * W[2] + a12(1, 2) * W[5] + a12(2, 2) * W[8]);
+    double r2[3];
 #pragma unroll
-    for (int i = 0; i < 6; i++) {
-        double s = b[i];
+    for (int c = 0; c < 3; c++) r2[c] = b[3 + c] - (a12(0, c) * u[0] + a12(1, c) * u[1] + a12(2, c) * u[2]);
+    Sym3 IS;
+    const bool ok2 = sym3_inverse(S, IS);
+    x[3] = IS.m00 * r2[0] + IS.m01 * r2[1] + IS.m02 * r2[2];
+    x[4] = IS.m01 * r2[0] + IS.m11 * r2[1] + IS.m12 * r2[2];
+    x[5] = IS.m02 * r2[0] + IS.m12 * r2[1] + IS.m22 * r2[2];
 #pragma unroll
-        for (int k = 0; k < i; k++) s -= L[i * 6 + k] * y[k];
-        y[i] = s;
-    }
-#pragma unroll
-    for (int i = 5; i >= 0; i--) {
-        double s = y[i] * Dinv[i];
-#pragma unroll
-        for (int k = i + 1; k < 6; k++) s -= L[k * 6 + i] * x[k];
-        x[i] = s;
-    }
-    return true;
+    for (int r = 0; r < 3; r++) x[r] = u[r] - (W[r * 3] * x[3] + W[r * 3 + 1] * x[4] + W[r * 3 + 2] * x[5]);
+    return ok1 && ok2;
 }
 
 struct PoseCam { double fx, fy, cx, cy, delta, dsqr; };
@@ -417,7 +426,7 @@ __global__ void __cluster_dims__(kPoseCtas, 1, 1) __launch_bounds__(kPoseThreads
                     for (int j = 0; j < 36; j++) Hl[j] = H[j];
 #pragma unroll
                     for (int j = 0; j < 6; j++) Hl[j * 6 + j] += lambda;
-                    const bool ok2 = ldlt6_solve(Hl, b, x);
+                    const bool ok2 = spd6_solve(Hl, b, x);
                     if (!ok2) {
 #pragma unroll
                         for (int j = 0; j < 6; j++) x[j] = 0;
