@@ -209,6 +209,7 @@ octree_kernel(const __grid_constant__ OrbCfg cfg, OrbBuffers b, int lap0, int la
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int warp_sums[33];
     __shared__ int s_size, s_M, s_nc, s_finish, s_phase, s_Meff, s_ticket;
+    __shared__ int s_stk[192];
 
     const int level = blockIdx.x;
     const OrbLevel& L = cfg.lv[level];
@@ -284,16 +285,18 @@ octree_kernel(const __grid_constant__ OrbCfg cfg, OrbBuffers b, int lap0, int la
                 if (A[i].cnt > 1) proc[off++] = i;
             if (tid == 0) s_M = tot;
         } else {
+            // sort (size, UL.x) ascending exactly as libstdc++ would, walk it backwards
+            // (O3/src/ORBextractor.cc:544-547); cc is dead here and serves as scratch
             const int M0 = s_nc;
-            if (tid == 0) { // sort (size, UL.x) ascending exactly as libstdc++ would, walk it backwards
-                for (int k = 0; k < M0; k++) {
-                    const Node& nd = A[cands[k]];
-                    sortbuf[k] = ((unsigned long long)(((unsigned)nd.cnt << 12) | (unsigned)nd.x0) << 32) | (unsigned)cands[k];
-                }
-                libstdcxx_sort(sortbuf, M0, KeyHi32Less());
-                for (int k = 0; k < M0; k++) proc[k] = (int)(unsigned)sortbuf[M0 - 1 - k];
-                s_M = M0;
+            for (int k = tid; k < M0; k += kOctThreads) {
+                const Node& nd = A[cands[k]];
+                sortbuf[k] = ((unsigned long long)(((unsigned)nd.cnt << 12) | (unsigned)nd.x0) << 32) | (unsigned)cands[k];
             }
+            __syncthreads();
+            libstdcxx_sort_cta(sortbuf, (unsigned long long*)cc, cc + 2 * capmax, cc + 3 * capmax, s_stk, M0, KeyHi32Less());
+            for (int k = tid; k < M0; k += kOctThreads) proc[k] = (int)(unsigned)sortbuf[M0 - 1 - k];
+            if (tid == 0) s_M = M0;
+            __syncthreads();
         }
         for (int i = tid; i < sizeA * 4; i += kOctThreads) cc[i] = 0;
         for (int i = tid; i < sizeA; i += kOctThreads) removed[i] = 0;

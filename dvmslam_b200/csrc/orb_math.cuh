@@ -358,4 +358,160 @@ __host__ __device__ inline void libstdcxx_sort(T* a, int n, Less less)
     }
 }
 
+
+// Scalar model of libstdcxx_sort_cta below (same stopper-pairing partition, same rank-based final pass);
+// tests/host_math_check.cu runs it against std::sort on the CPU.
+template <typename T, typename Less>
+__host__ inline void libstdcxx_sort_stopper_model(T* a, T* tmp, int* li, int* ri, int n, Less less)
+{
+    if (n <= 0) return;
+    if (n > 16) {
+        int st_first[64], st_last[64], st_depth[64], sp = 0, lg = 0;
+        for (int t = n; t > 1; t >>= 1) lg++;
+        st_first[0] = 0; st_last[0] = n; st_depth[0] = 2 * lg; sp = 1;
+        while (sp > 0) {
+            --sp;
+            int first = st_first[sp], last = st_last[sp], depth = st_depth[sp];
+            while (last - first > 16) {
+                if (depth == 0) { stdsort_heapsort(a + first, last - first, less); break; }
+                --depth;
+                {
+                    const int ia = first + 1, ib = first + (last - first) / 2, ic = last - 1;
+                    int pick;
+                    if (less(a[ia], a[ib])) {
+                        if (less(a[ib], a[ic])) pick = ib;
+                        else if (less(a[ia], a[ic])) pick = ic;
+                        else pick = ia;
+                    } else if (less(a[ia], a[ic])) pick = ia;
+                    else if (less(a[ib], a[ic])) pick = ic;
+                    else pick = ib;
+                    const T t = a[first]; a[first] = a[pick]; a[pick] = t;
+                }
+                const T P = a[first];
+                const int lo = first + 1, hi = last;
+                int nL = 0, nR = 0;
+                for (int i = lo; i < hi; i++) if (!less(a[i], P)) li[nL++] = i;
+                for (int i = hi - 1; i >= lo; i--) if (!less(P, a[i])) ri[nR++] = i;
+                ri[nR++] = first;
+                int K = 0;
+                const int kmax = nL < nR ? nL : nR;
+                for (int k = 0; k < kmax; k++) K += li[k] < ri[k];
+                for (int k = 0; k < K; k++) { const T t = a[li[k]]; a[li[k]] = a[ri[k]]; a[ri[k]] = t; }
+                int cut;
+                if (K < nL) cut = K > 0 ? (li[K] < ri[K - 1] ? li[K] : ri[K - 1]) : li[K];
+                else cut = ri[K - 1];
+                st_first[sp] = cut; st_last[sp] = last; st_depth[sp] = depth; sp++;
+                last = cut;
+            }
+        }
+    }
+    for (int i = 0; i < n; i++) {
+        int rank = 0;
+        for (int j = 0; j < n; j++) rank += (less(a[j], a[i]) || (!less(a[i], a[j]) && j < i)) ? 1 : 0;
+        tmp[rank] = a[i];
+    }
+    for (int i = 0; i < n; i++) a[i] = tmp[i];
+}
+
+#ifdef __CUDACC__
+// ---- the same std::sort, cooperatively on one CTA -------------------------------------------------
+// Result identical to libstdcxx_sort (element for element, ties included):
+//  * __introsort_loop is run by warp 0 with the Hoare partition evaluated in parallel.  The
+//    sequential scan "left pointer stops at the next element >= pivot, right pointer at the next element
+//    <= pivot, swap, repeat until they cross" pairs the k-th left stopper l_k with the k-th right stopper
+//    r_k of the ORIGINAL segment for every k with l_k < r_k (the pointers never re-visit a swapped
+//    position before they cross), so the K swaps are independent and the cut is min(l_K, r_{K-1}).
+//  * __final_insertion_sort is a stable insertion sort of the whole range, i.e. a stable sort by key:
+//    every thread ranks its elements directly.
+// a, tmp: n elements each in shared memory; li, ri: n + 1 ints each; stk: 192 ints.  All threads call.
+template <typename T, typename Less>
+__device__ inline void libstdcxx_sort_cta(T* a, T* tmp, int* li, int* ri, int* stk, int n, Less less)
+{
+    if (n <= 0) return;
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (tid < 32 && n > 16) {
+        int* st_first = stk; int* st_last = stk + 64; int* st_depth = stk + 128;
+        int sp = 0, lg = 0;
+        for (int t = n; t > 1; t >>= 1) lg++;
+        if (lane == 0) { st_first[0] = 0; st_last[0] = n; st_depth[0] = 2 * lg; }
+        sp = 1;
+        __syncwarp();
+        while (sp > 0) {
+            --sp;
+            int first = st_first[sp], last = st_last[sp], depth = st_depth[sp];
+            __syncwarp();
+            while (last - first > 16) {
+                if (depth == 0) {
+                    if (lane == 0) stdsort_heapsort(a + first, last - first, less);
+                    __syncwarp();
+                    break;
+                }
+                --depth;
+                if (lane == 0) { // __move_median_to_first(first, first + 1, mid, last - 1)
+                    const int ia = first + 1, ib = first + (last - first) / 2, ic = last - 1;
+                    int pick;
+                    if (less(a[ia], a[ib])) {
+                        if (less(a[ib], a[ic])) pick = ib;
+                        else if (less(a[ia], a[ic])) pick = ic;
+                        else pick = ia;
+                    } else if (less(a[ia], a[ic])) pick = ia;
+                    else if (less(a[ib], a[ic])) pick = ic;
+                    else pick = ib;
+                    const T t = a[first]; a[first] = a[pick]; a[pick] = t;
+                }
+                __syncwarp();
+                const T P = a[first];
+                const int lo = first + 1, hi = last;
+                int nL = 0, nR = 0;
+                for (int c = 0; c < hi - lo; c += 32) {
+                    const int il = lo + c + lane, ir = hi - 1 - c - lane;
+                    const bool fl = il < hi && !less(a[il], P);
+                    const bool fr = ir >= lo && !less(P, a[ir]);
+                    const unsigned ml = __ballot_sync(0xffffffffu, fl), mr = __ballot_sync(0xffffffffu, fr);
+                    const unsigned below = (1u << lane) - 1u;
+                    if (fl) li[nL + __popc(ml & below)] = il;
+                    if (fr) ri[nR + __popc(mr & below)] = ir;
+                    nL += __popc(ml); nR += __popc(mr);
+                }
+                if (lane == 0) ri[nR] = first; // the pivot itself stops the right pointer
+                nR++;
+                __syncwarp();
+                int K = 0;
+                const int kmax = min(nL, nR);
+                for (int c = 0; c < kmax; c += 32) {
+                    const int k = c + lane;
+                    const bool sw = k < kmax && li[k] < ri[k];
+                    K += __popc(__ballot_sync(0xffffffffu, sw));
+                }
+                for (int k = lane; k < K; k += 32) {
+                    const int x = li[k], y = ri[k];
+                    const T t = a[x]; a[x] = a[y]; a[y] = t;
+                }
+                int cut;
+                if (K < nL) cut = K > 0 ? min(li[K], ri[K - 1]) : li[K];
+                else cut = ri[K - 1];
+                __syncwarp();
+                if (lane == 0) { st_first[sp] = cut; st_last[sp] = last; st_depth[sp] = depth; }
+                sp++;
+                last = cut;
+                __syncwarp();
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += blockDim.x) {
+        const T v = a[i];
+        int rank = 0;
+        for (int j = 0; j < n; j++) {
+            const T w = a[j];
+            rank += (less(w, v) || (!less(v, w) && j < i)) ? 1 : 0;
+        }
+        tmp[rank] = v;
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += blockDim.x) a[i] = tmp[i];
+    __syncthreads();
+}
+#endif
+
 } // namespace dvm

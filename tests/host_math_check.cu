@@ -99,9 +99,13 @@ int main()
             std::vector<unsigned long long> mine(v.size());
             for (size_t i = 0; i < v.size(); i++) mine[i] = ((unsigned long long)(unsigned)v[i].first << 32) | (unsigned)v[i].second;
             std::sort(v.begin(), v.end(), [](P& a, P& b) { return a.first < b.first; });
+            std::vector<unsigned long long> coop(mine), tmp(v.size());
+            std::vector<int> li(v.size() + 1), ri(v.size() + 1);
             libstdcxx_sort(mine.data(), (int)mine.size(), KeyHi32Less());
+            // the stopper-pairing form the GPU runs cooperatively (libstdcxx_sort_cta)
+            libstdcxx_sort_stopper_model(coop.data(), tmp.data(), li.data(), ri.data(), (int)coop.size(), KeyHi32Less());
             for (size_t i = 0; i < v.size(); i++)
-                if ((int)(mine[i] & 0xffffffffu) != v[i].second) return false;
+                if ((int)(mine[i] & 0xffffffffu) != v[i].second || coop[i] != mine[i]) return false;
             return true;
         };
         int cases = 0;
