@@ -48,6 +48,18 @@ STAGE_BYTES = [2781331 + 1931488, 2853088, None, 5706176 + 1498000 + 1024000 + 1
 FRAME_BYTES_TOTAL = 15914083
 
 
+STAGE_KERNELS = [None, "fast_cells_kernel", "octree_kernel", "describe_kernel"]
+
+
+def ncu_traffic(stage):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the stage's kernel, from the committed
+    `ncu --set full` capture (profiles/traffic.json, written by profiles/summarize_ncu.py); None if absent."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(STAGE_KERNELS[stage])
+    except Exception:
+        return None
+
+
 def measured_peak_hbm():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -380,7 +392,7 @@ def run_ours(args):
         achieved = dom_bytes / (stage_us[dom] * 1e-6) / 1e9
         frame_us = 1e3 * ms_total / frames
         roofline = {"bound": "hbm", "kernel": STAGE_NAMES[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "frac": achieved / peak, "traffic": ncu_traffic(dom), "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": dom_bytes, "avg_launch_us": stage_us[dom],
                     "stage_us": dict(zip(STAGE_NAMES, stage_us)),
                     "frame_us": frame_us, "tracking_us": frame_us - sum(stage_us),

@@ -1,0 +1,229 @@
+// bow_kernels.cu -- sm_100a kernels of the descriptor matchers that do not project a map point.
+//
+//   bow_node_kernel / bow_finish_kernel    ORBmatcher::SearchByBoW(KF, Frame)  (O3/src/ORBmatcher.cc:214-393)
+//                                          ORBmatcher::SearchByBoW(KF, KF)     (O3/src/ORBmatcher.cc:709-834)
+//   init_match_kernel                      ORBmatcher::SearchForInitialization (O3/src/ORBmatcher.cc:605-707)
+//
+// SearchByBoW walks the vocabulary nodes the two feature vectors share; inside a node it is a sequential
+// greedy loop (a feature of side 2 taken by an earlier feature of side 1 is skipped), but a feature
+// belongs to exactly one node, so nodes are independent: one warp per shared node, the side-1 features of
+// the node in order, the side-2 features across the lanes, nearest / second-nearest by warp reduction.
+//
+// SearchForInitialization is sequential over the whole first frame (vMatchedDistance is live state).
+// As in the projection matchers, the sequential outcome is reached as the fixed point of
+//     choice[i1] = best candidate i2 with  min{ dist[j] : j < i1, choice[j] = i2 } > dist(i1, i2)
+// iterated from "nothing matched" on one CTA; at a fixed point the rule holds for i1 = 0, 1, 2, ... in
+// turn, which is the reference's loop.
+#include "bow_kernels.cuh"
+#include "track_device.cuh"
+
+namespace dvm {
+
+// ------------------------------------------------------------------------------------- SearchByBoW
+constexpr int kBowWarps = 4;
+
+__device__ inline int find_node(const uint32_t* ids, int n, uint32_t key)
+{
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (ids[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    return (lo < n && ids[lo] == key) ? lo : -1;
+}
+
+// key of a candidate: distance in the high bits, position in the node's list below -- the minimum is the
+// reference's "first of the nearest" (strict '<' keeps the earlier of equal distances)
+constexpr unsigned kPosBits = 20;
+constexpr unsigned kNoKey = (256u << kPosBits);
+
+__global__ void __launch_bounds__(kBowWarps * 32) bow_node_kernel(BowArgs g)
+{
+    const int lane = threadIdx.x & 31;
+    const int ia = blockIdx.x * kBowWarps + (threadIdx.x >> 5);
+    if (ia >= g.a.n_nodes) return;
+    const int ib = find_node(g.b.node_id, g.b.n_nodes, g.a.node_id[ia]);
+    if (ib < 0) return;
+    const int a0 = g.a.node_start[ia], a1 = g.a.node_start[ia + 1];
+    const int b0 = g.b.node_start[ib], nb = g.b.node_start[ib + 1] - b0;
+    if (nb <= 0) return;
+    // first chunk of side 2 kept in registers (nodes hold ~20 features at 2000 features / 100 nodes)
+    int r2_0 = -1;
+    uint32_t d2_0[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+    if (lane < nb) {
+        r2_0 = (int)g.b.feat_idx[b0 + lane];
+        if (g.kf_kf && g.b.valid && !g.b.valid[r2_0]) r2_0 = -1;   // !pMP2 || pMP2->isBad()
+        if (r2_0 >= 0) load_desc(d2_0, g.b.desc + (size_t)r2_0 * 32);
+    }
+    bool taken_0 = false;
+    for (int p = a0; p < a1; p++) {
+        const int r1 = (int)g.a.feat_idx[p];
+        if (g.a.valid && !g.a.valid[r1]) continue;
+        uint32_t d1[8];
+        load_desc(d1, g.a.desc + (size_t)r1 * 32);
+        unsigned k1 = kNoKey, dist2 = 256;   // lane-local nearest key / second-nearest distance
+        if (r2_0 >= 0 && !taken_0) {
+            const unsigned dist = __popc(d1[0] ^ d2_0[0]) + __popc(d1[1] ^ d2_0[1]) + __popc(d1[2] ^ d2_0[2]) +
+                                  __popc(d1[3] ^ d2_0[3]) + __popc(d1[4] ^ d2_0[4]) + __popc(d1[5] ^ d2_0[5]) +
+                                  __popc(d1[6] ^ d2_0[6]) + __popc(d1[7] ^ d2_0[7]);
+            if (dist < 256) k1 = (dist << kPosBits) | (unsigned)lane;
+        }
+        for (int q = 32 + lane; q < nb; q += 32) {   // larger nodes: the rest through L1
+            const int r2 = (int)g.b.feat_idx[b0 + q];
+            if (g.match21[r2] >= 0) continue;
+            if (g.kf_kf && g.b.valid && !g.b.valid[r2]) continue;
+            const unsigned dist = (unsigned)hamming256(d1, g.b.desc + (size_t)r2 * 32);
+            const unsigned key = (dist << kPosBits) | (unsigned)q;
+            if (dist < (k1 >> kPosBits)) { dist2 = k1 >> kPosBits; k1 = key; }
+            else if (dist < dist2) dist2 = dist;
+        }
+        const unsigned best = __reduce_min_sync(0xffffffffu, k1);
+        const unsigned mine = (k1 == best) ? dist2 : min(k1 >> kPosBits, 256u);
+        const unsigned bestDist2 = __reduce_min_sync(0xffffffffu, mine);
+        const unsigned bestDist1 = best >> kPosBits;
+        const bool near = g.kf_kf ? bestDist1 < (unsigned)kThLow : bestDist1 <= (unsigned)kThLow;
+        if (near && (float)bestDist1 < __fmul_rn(g.nnratio, (float)bestDist2)) {
+            const int q = (int)(best & ((1u << kPosBits) - 1));
+            if (q < 32) { if (lane == q) taken_0 = true; }
+            const int r2 = __shfl_sync(0xffffffffu, q < 32 ? r2_0 : 0, q & 31);
+            if (lane == 0) {
+                const int rr = q < 32 ? r2 : (int)g.b.feat_idx[b0 + q];
+                g.match21[rr] = r1;
+                g.match12[r1] = rr;
+                atomicAdd(&g.counters[0], 1);
+                if (g.check_ori) atomicAdd(&g.histo[rot_bin(g.a.angle[r1], g.b.angle[rr])], 1);
+            }
+            __syncwarp(); // the write to match21 is visible to the lanes that read it for the next feature
+        }
+    }
+}
+
+// rotation-consistency check over all accepted pairs + the match count
+__global__ void __launch_bounds__(1024) bow_finish_kernel(BowArgs g)
+{
+    __shared__ int s_ind[3], s_bad;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        int i1 = -1, i2 = -1, i3 = -1;
+        if (g.check_ori) three_maxima(g.histo, kHistoLength, i1, i2, i3);
+        s_ind[0] = i1; s_ind[1] = i2; s_ind[2] = i3;
+        s_bad = 0;
+    }
+    __syncthreads();
+    if (g.check_ori) {
+        int bad = 0;
+        for (int r1 = tid; r1 < g.a.n; r1 += 1024) {
+            const int r2 = g.match12[r1];
+            if (r2 < 0) continue;
+            const int bin = rot_bin(g.a.angle[r1], g.b.angle[r2]);
+            if (bin != s_ind[0] && bin != s_ind[1] && bin != s_ind[2]) { g.match12[r1] = -1; g.match21[r2] = -1; bad++; }
+        }
+        if (bad) atomicAdd(&s_bad, bad);
+    }
+    __syncthreads();
+    if (tid == 0) g.counters[1] = g.counters[0] - s_bad;
+}
+
+void launch_bow_match(const BowArgs& g, cudaStream_t stream)
+{
+    if (g.a.n_nodes > 0 && g.b.n_nodes > 0)
+        DVM_LAUNCH(bow_node_kernel, div_up(g.a.n_nodes, kBowWarps), kBowWarps * 32, 0, stream, g);
+    DVM_LAUNCH(bow_finish_kernel, 1, 1024, 0, stream, g);
+}
+
+// --------------------------------------------------------------------------- SearchForInitialization
+constexpr int kInitThreads = 1024;
+
+__global__ void __launch_bounds__(kInitThreads, 1) init_match_kernel(FrameDev f2, InitMatchArgs a)
+{
+    __shared__ int histo[kHistoLength];
+    __shared__ int s_ind[3], s_n;
+    const int tid = threadIdx.x;
+    const int n2 = min(*f2.n, f2.cap);
+    const FrameLook fl = look_global(f2);
+    int* choice_prev = a.choice_a;  int* choice_next = a.choice_b;
+    int* cdist_prev = a.cdist_a;    int* cdist_next = a.cdist_b;
+    for (int i = tid; i < a.n1; i += kInitThreads) { choice_prev[i] = -1; cdist_prev[i] = 0; }
+    __syncthreads();
+    int rounds = 0;
+    while (true) {
+        // claim lists of the previous round: head[i2] -> i1 -> next[i1] -> ...
+        for (int k = tid; k < n2; k += kInitThreads) a.head[k] = -1;
+        __syncthreads();
+        for (int i = tid; i < a.n1; i += kInitThreads) {
+            const int k = choice_prev[i];
+            if (k >= 0) a.next[i] = atomicExch(&a.head[k], i);
+        }
+        __syncthreads();
+        int changed = 0;
+        for (int i1 = tid; i1 < a.n1; i1 += kInitThreads) {
+            int pick = -1, pickDist = 0;
+            if (a.kps1[i1].octave <= 0) {     // level1 > 0: continue
+                uint32_t d1[8];
+                load_desc(d1, a.desc1 + (size_t)i1 * 32);
+                int bestDist = INT_MAX, bestDist2 = INT_MAX, bestIdx2 = -1;
+                const int level1 = a.kps1[i1].octave;
+                walk_area(fl, a.prev_matched[2 * i1], a.prev_matched[2 * i1 + 1], (float)a.window, level1, level1,
+                          [&](int i2, int) {
+                              const int dist = hamming256(d1, fl.desc + (size_t)i2 * 32);
+                              // vMatchedDistance[i2] as the sequential loop sees it at i1
+                              for (int j = a.head[i2]; j >= 0; j = a.next[j])
+                                  if (j < i1 && cdist_prev[j] <= dist) return;
+                              if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestIdx2 = i2; }
+                              else if (dist < bestDist2) bestDist2 = dist;
+                          });
+                if (bestDist <= kThLow && (float)bestDist < __fmul_rn((float)bestDist2, a.nnratio)) { pick = bestIdx2; pickDist = bestDist; }
+            }
+            choice_next[i1] = pick; cdist_next[i1] = pickDist;
+            if (pick != choice_prev[i1]) changed = 1;
+        }
+        rounds++;
+        const int any = __syncthreads_or(changed);
+        int* t = choice_prev; choice_prev = choice_next; choice_next = t;
+        t = cdist_prev; cdist_prev = cdist_next; cdist_next = t;
+        if (!any) break;
+    }
+    // vnMatches21[i2] = the last query that took i2; every accepted query left one histogram entry
+    if (tid < kHistoLength) histo[tid] = 0;
+    if (tid == 0) s_n = 0;
+    for (int k = tid; k < n2; k += kInitThreads) a.head[k] = -1;
+    __syncthreads();
+    for (int i = tid; i < a.n1; i += kInitThreads) {
+        const int k = choice_prev[i];
+        if (k < 0) continue;
+        atomicMax(&a.head[k], i);
+        if (a.check_ori) atomicAdd(&histo[rot_bin(a.kps1[i].angle, f2.kps[k].angle)], 1);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int i1 = -1, i2 = -1, i3 = -1;
+        if (a.check_ori) three_maxima(histo, kHistoLength, i1, i2, i3);
+        s_ind[0] = i1; s_ind[1] = i2; s_ind[2] = i3;
+    }
+    __syncthreads();
+    int cnt = 0;
+    for (int i = tid; i < a.n1; i += kInitThreads) {
+        int k = choice_prev[i];
+        if (k >= 0 && a.head[k] != i) k = -1;   // displaced by a later query
+        if (k >= 0 && a.check_ori) {
+            const int bin = rot_bin(a.kps1[i].angle, f2.kps[k].angle);
+            if (bin != s_ind[0] && bin != s_ind[1] && bin != s_ind[2]) k = -1;
+        }
+        a.matches12[i] = k;
+        if (k >= 0) {
+            cnt++;
+            a.prev_matched[2 * i] = f2.kps[k].x;
+            a.prev_matched[2 * i + 1] = f2.kps[k].y;
+        }
+    }
+    if (cnt) atomicAdd(&s_n, cnt);
+    __syncthreads();
+    if (tid == 0) { a.result[0] = s_n; a.result[1] = rounds; }
+}
+
+void launch_init_match(const FrameDev& f2, const InitMatchArgs& a, cudaStream_t stream)
+{
+    DVM_LAUNCH(init_match_kernel, 1, kInitThreads, 0, stream, f2, a);
+}
+
+} // namespace dvm

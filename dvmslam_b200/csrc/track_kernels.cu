@@ -13,128 +13,9 @@
 // i = 0, 1, 2, ... in turn, so it is exactly the sequential result; typical frames need 3-5 rounds.
 #include "track_kernels.cuh"
 #include "orb_math.cuh"
+#include "track_device.cuh"
 
 namespace dvm {
-
-// --------------------------------------------------------------------------------------- helpers
-__device__ inline int hamming256(const uint32_t a[8], const uint8_t* b)
-{
-    // ORBmatcher::DescriptorDistance: popcount of the 256-bit XOR
-    const uint4* p = reinterpret_cast<const uint4*>(b);
-    const uint4 v0 = p[0], v1 = p[1];
-    return __popc(a[0] ^ v0.x) + __popc(a[1] ^ v0.y) + __popc(a[2] ^ v0.z) + __popc(a[3] ^ v0.w) +
-           __popc(a[4] ^ v1.x) + __popc(a[5] ^ v1.y) + __popc(a[6] ^ v1.z) + __popc(a[7] ^ v1.w);
-}
-
-__device__ inline void load_desc(uint32_t a[8], const uint8_t* d)
-{
-    const uint4* p = reinterpret_cast<const uint4*>(d);
-    const uint4 v0 = __ldg(p), v1 = __ldg(p + 1);
-    a[0] = v0.x; a[1] = v0.y; a[2] = v0.z; a[3] = v0.w;
-    a[4] = v1.x; a[5] = v1.y; a[6] = v1.z; a[7] = v1.w;
-}
-
-// How the matchers read the current frame (global memory through L1/L2; the frame is ~200 KB).
-struct FrameLook {
-    const int* cell_start;
-    const int* cell_items;
-    const char* kbase;   // keypoint records: x at +0, y at +4, octave at +oct_off
-    int kstride, oct_off;
-    const uint8_t* desc;
-    float minX, minY, gwInv, ghInv;
-    __device__ float x(int i) const { return *reinterpret_cast<const float*>(kbase + (size_t)i * kstride); }
-    __device__ float y(int i) const { return *reinterpret_cast<const float*>(kbase + (size_t)i * kstride + 4); }
-    __device__ int oct(int i) const { return *reinterpret_cast<const int*>(kbase + (size_t)i * kstride + oct_off); }
-};
-
-__device__ inline FrameLook look_global(const FrameDev& f)
-{
-    FrameLook v;
-    v.cell_start = f.cell_start; v.cell_items = f.cell_items;
-    v.kbase = reinterpret_cast<const char*>(f.kps); v.kstride = (int)sizeof(dvm_keypoint); v.oct_off = 20;
-    v.desc = f.desc;
-    v.minX = f.minX; v.minY = f.minY; v.gwInv = f.gwInv; v.ghInv = f.ghInv;
-    return v;
-}
-
-// ---- frame staged in shared memory by TMA bulk copies (cp.async.bulk, one mbarrier) ----
-__host__ __device__ inline size_t frame_smem_bytes(int cap) { return (size_t)cap * (32 + 12 + 4) + (size_t)(kGridCells + 4) * 4; }
-__device__ inline uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-// all threads of the CTA call this; returns once descriptors, {x,y,octave} records and the CSR grid of
-// the frame are in `smem` (layout: desc | kxyo | cell_start | cell_items, every part 16-byte aligned)
-__device__ inline FrameLook look_shared_tma(const FrameDev& f, int n, unsigned char* smem, unsigned long long* bar)
-{
-    unsigned char* sdesc = smem;
-    unsigned char* skxyo = sdesc + (size_t)f.cap * 32;
-    unsigned char* scell = skxyo + (size_t)f.cap * 12;
-    unsigned char* sitems = scell + (size_t)(kGridCells + 4) * 4;
-    const uint32_t b = smem_u32(bar);
-    if (threadIdx.x == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(b), "r"(1));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const uint32_t bytes_desc = (uint32_t)n * 32u;
-        const uint32_t bytes_kxyo = min(((uint32_t)n * 12u + 15u) & ~15u, (uint32_t)f.cap * 12u);
-        const uint32_t bytes_cell = (uint32_t)(kGridCells + 4) * 4u;
-        const uint32_t bytes_items = min(((uint32_t)n * 4u + 15u) & ~15u, (uint32_t)f.cap * 4u);
-        const uint32_t total = bytes_desc + bytes_kxyo + bytes_cell + bytes_items;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(total) : "memory");
-        auto bulk = [&](unsigned char* dst, const void* src, uint32_t bytes) {
-            if (bytes == 0) return;
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(b) : "memory");
-        };
-        bulk(sdesc, f.desc, bytes_desc);
-        bulk(skxyo, f.kxyo, bytes_kxyo);
-        bulk(scell, f.cell_start, bytes_cell);
-        bulk(sitems, f.cell_items, bytes_items);
-    }
-    uint32_t done = 0;
-    while (!done) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done) : "r"(b), "r"(0) : "memory");
-    }
-    FrameLook v;
-    v.cell_start = reinterpret_cast<const int*>(scell); v.cell_items = reinterpret_cast<const int*>(sitems);
-    v.kbase = reinterpret_cast<const char*>(skxyo); v.kstride = 12; v.oct_off = 8;
-    v.desc = sdesc;
-    v.minX = f.minX; v.minY = f.minY; v.gwInv = f.gwInv; v.ghInv = f.ghInv;
-    return v;
-}
-
-// Frame::GetFeaturesInArea: calls fn(idx, octave) for every keypoint of the window, in the
-// reference's traversal order (ix outer, iy inner, insertion order inside a cell).
-template <class Fn>
-__device__ inline void walk_area(const FrameLook& f, float x, float y, float r, int minLevel, int maxLevel, Fn fn)
-{
-    const float dxm = __fsub_rn(x, f.minX), dym = __fsub_rn(y, f.minY);
-    const int nMinCellX = max(0, (int)floorf(__fmul_rn(__fsub_rn(dxm, r), f.gwInv)));
-    if (nMinCellX >= kGridCols) return;
-    const int nMaxCellX = min(kGridCols - 1, (int)ceilf(__fmul_rn(__fadd_rn(dxm, r), f.gwInv)));
-    if (nMaxCellX < 0) return;
-    const int nMinCellY = max(0, (int)floorf(__fmul_rn(__fsub_rn(dym, r), f.ghInv)));
-    if (nMinCellY >= kGridRows) return;
-    const int nMaxCellY = min(kGridRows - 1, (int)ceilf(__fmul_rn(__fadd_rn(dym, r), f.ghInv)));
-    if (nMaxCellY < 0) return;
-    const bool bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
-    for (int ix = nMinCellX; ix <= nMaxCellX; ix++) {
-        // cells of one grid column are contiguous: one range covers iy = nMinCellY .. nMaxCellY
-        const int j0 = f.cell_start[ix * kGridRows + nMinCellY], j1 = f.cell_start[ix * kGridRows + nMaxCellY + 1];
-        for (int j = j0; j < j1; j++) {
-            const int idx = f.cell_items[j];
-            const int oct = f.oct(idx);
-            if (bCheckLevels) {
-                if (oct < minLevel) continue;
-                if (maxLevel >= 0 && oct > maxLevel) continue;
-            }
-            const float distx = __fsub_rn(f.x(idx), x), disty = __fsub_rn(f.y(idx), y);
-            if (fabsf(distx) < r && fabsf(disty) < r) fn(idx, oct);
-        }
-    }
-}
 
 // -------------------------------------------------------------------------------------- grid build
 // src_kps != nullptr: first copy an extractor result (keypoints, descriptors, count) into the frame's buffers
@@ -243,29 +124,6 @@ void launch_features_in_area(const FrameDev& f, float x, float y, float r, int m
 // ----------------------------------------------------------------- SearchByProjection(cur, last)
 constexpr int kMatchThreads = 1024;
 constexpr int kNoClaim = 0x7fffffff;
-
-// ORBmatcher::ComputeThreeMaxima
-__device__ inline void three_maxima(const int* histo, int L, int& ind1, int& ind2, int& ind3)
-{
-    int max1 = 0, max2 = 0, max3 = 0;
-    for (int i = 0; i < L; i++) {
-        const int s = histo[i];
-        if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
-        else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
-        else if (s > max3) { max3 = s; ind3 = i; }
-    }
-    if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { ind2 = -1; ind3 = -1; }
-    else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) { ind3 = -1; }
-}
-
-__device__ inline int rot_bin(float last_angle, float cur_angle)
-{
-    float rot = __fsub_rn(last_angle, cur_angle);
-    if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
-    int bin = (int)roundf(__fmul_rn(rot, 1.0f / kHistoLength)); // factor = 1/30: the reference's bug, kept
-    if (bin == kHistoLength) bin = 0;
-    return bin;
-}
 
 // ---- candidate cache: the window of every query is walked ONCE; its best kMatchCacheK candidates are
 // kept sorted by (Hamming distance, walk order) -- the reference's preference order: strict '<' keeps

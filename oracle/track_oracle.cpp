@@ -7,6 +7,7 @@
  *   ORBmatcher::DescriptorDistance                                  O3/src/ORBmatcher.cc:1900-1914
  *   ORBmatcher::SearchByProjection(Frame&, const Frame&, th, mono)  O3/src/ORBmatcher.cc:1553-1748
  *   ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>&, th)  O3/src/ORBmatcher.cc:44-212
+ *   ORBmatcher::SearchForInitialization                             O3/src/ORBmatcher.cc:605-707
  *   ORBmatcher::ComputeThreeMaxima                                  O3/src/ORBmatcher.cc:1862-1896
  *   Optimizer::PoseOptimization                                     O3/src/Optimizer.cc:744-1028
  *     with g2o's Levenberg-Marquardt (g2o/core/optimization_algorithm_levenberg.cpp:59-188),
@@ -618,6 +619,68 @@ int trko_pose_optimization(float* pose_q, float* pose_t, const float* K, int n, 
     pose_q[0] = (float)T.r.x; pose_q[1] = (float)T.r.y; pose_q[2] = (float)T.r.z; pose_q[3] = (float)T.r.w;
     pose_t[0] = (float)T.t[0]; pose_t[1] = (float)T.t[1]; pose_t[2] = (float)T.t[2];
     return n - nBad;
+}
+
+/* SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize)  (O3/src/ORBmatcher.cc:605-707).
+ * f2 = F2 (grid queries); F1 is given by its undistorted keypoints and descriptors.  prev_matched[n1*2]
+ * (in/out) = vbPrevMatched; matches12[n1] receives vnMatches12.  Returns nmatches. */
+int trko_search_for_initialization(int n1, const void* kps1_, const uint8_t* desc1, void* f2, float* prev_matched,
+                                   int windowSize, float nnratio, int checkOri, int* matches12)
+{
+    const KeyPt* kps1 = (const KeyPt*)kps1_;
+    Frame& F2 = *(Frame*)f2;
+    int nmatches = 0;
+    for (int i = 0; i < n1; i++) matches12[i] = -1;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    const float factor = 1.0f / HISTO_LENGTH;
+    std::vector<int> vMatchedDistance(F2.n, std::numeric_limits<int>::max());
+    std::vector<int> vnMatches21(F2.n, -1);
+    std::vector<int> idx;
+    for (int i1 = 0; i1 < n1; i1++) {
+        const int level1 = kps1[i1].octave;
+        if (level1 > 0) continue;
+        features_in_area(F2, prev_matched[2 * i1], prev_matched[2 * i1 + 1], (float)windowSize, level1, level1, idx);
+        if (idx.empty()) continue;
+        const uint8_t* d1 = desc1 + (size_t)i1 * 32;
+        int bestDist = std::numeric_limits<int>::max(), bestDist2 = std::numeric_limits<int>::max(), bestIdx2 = -1;
+        for (int i2 : idx) {
+            const int dist = descriptor_distance(d1, &F2.desc[(size_t)i2 * 32]);
+            if (vMatchedDistance[i2] <= dist) continue;
+            if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestIdx2 = i2; }
+            else if (dist < bestDist2) { bestDist2 = dist; }
+        }
+        if (bestDist <= TH_LOW) {
+            if (bestDist < (float)bestDist2 * nnratio) {
+                if (vnMatches21[bestIdx2] >= 0) { matches12[vnMatches21[bestIdx2]] = -1; nmatches--; }
+                matches12[i1] = bestIdx2;
+                vnMatches21[bestIdx2] = i1;
+                vMatchedDistance[bestIdx2] = bestDist;
+                nmatches++;
+                if (checkOri) {
+                    float rot = kps1[i1].angle - F2.kps[bestIdx2].angle;
+                    if (rot < 0.0) rot += 360.0f;
+                    int bin = (int)std::round(rot * factor);
+                    if (bin == HISTO_LENGTH) bin = 0;
+                    rotHist[bin].push_back(i1);
+                }
+            }
+        }
+    }
+    if (checkOri) {
+        int ind1 = -1, ind2 = -1, ind3 = -1, sizes[HISTO_LENGTH];
+        for (int i = 0; i < HISTO_LENGTH; i++) sizes[i] = (int)rotHist[i].size();
+        three_maxima(sizes, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++)
+            if (i != ind1 && i != ind2 && i != ind3)
+                for (int j : rotHist[i])
+                    if (matches12[j] >= 0) { matches12[j] = -1; nmatches--; }
+    }
+    for (int i1 = 0; i1 < n1; i1++)
+        if (matches12[i1] >= 0) {
+            prev_matched[2 * i1] = F2.kps[matches12[i1]].x;
+            prev_matched[2 * i1 + 1] = F2.kps[matches12[i1]].y;
+        }
+    return nmatches;
 }
 
 } // extern "C"
