@@ -1,0 +1,258 @@
+// bow_capi.cu -- C-ABI of SearchByBoW, SearchForInitialization and the exhaustive Hamming search.
+// Host-array entry points stage their flat inputs in the frame's pinned buffer, upload them with one
+// copy, run the kernels on the frame's stream and read the results back (synchronous, like the
+// reference's calls).
+#include "bow_kernels.cuh"
+#include "track_internal.cuh"
+#include <vector>
+
+using namespace dvm;
+
+namespace {
+
+// packs host arrays into the frame's pinned staging buffer at 256-byte aligned offsets
+struct Stage {
+    dvm_frame* f;
+    size_t off = 0;
+    explicit Stage(dvm_frame* f_) : f(f_) { }
+    template <typename T>
+    T* add(const T* src, size_t count)
+    {
+        off = (off + 255) & ~(size_t)255;
+        if (src && count) memcpy(f->h_in + off, src, count * sizeof(T));
+        T* d = reinterpret_cast<T*>(f->d_in + off);
+        off += count * sizeof(T);
+        return d;
+    }
+};
+
+size_t padded(std::initializer_list<size_t> sizes)
+{
+    size_t t = 0;
+    for (size_t s : sizes) t = ((t + 255) & ~(size_t)255) + s;
+    return t + 256;
+}
+
+int check_side(const dvm_bow_features* s, std::vector<uint8_t>& seen)
+{
+    DVM_REQUIRE(s != nullptr && s->n >= 0 && s->n_nodes >= 0, "bad feature set");
+    DVM_REQUIRE(s->n == 0 || (s->desc && s->angle), "null descriptors / angles");
+    DVM_REQUIRE(s->n_nodes == 0 || (s->node_id && s->node_start && s->feat_idx), "null feature vector");
+    seen.assign((size_t)s->n, 0);
+    for (int i = 0; i < s->n_nodes; i++) {
+        DVM_REQUIRE(i == 0 || s->node_id[i - 1] < s->node_id[i], "feature-vector nodes must ascend");
+        DVM_REQUIRE(s->node_start[i] <= s->node_start[i + 1] && s->node_start[i] >= 0, "node_start must not decrease");
+    }
+    const int total = s->n_nodes ? s->node_start[s->n_nodes] : 0;
+    for (int p = s->n_nodes ? s->node_start[0] : 0; p < total; p++) {
+        const uint32_t r = s->feat_idx[p];
+        DVM_REQUIRE(r < (uint32_t)s->n, "feature index out of range");
+        DVM_REQUIRE(!seen[r], "a feature belongs to one vocabulary node only");
+        seen[r] = 1;
+    }
+    return DVM_OK;
+}
+
+} // namespace
+
+struct dvm_hamming {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    KnnScratch scratch;
+    uint8_t* d_buf = nullptr; size_t d_cap = 0;   // host-call staging: a | b | key1 | key2
+    uint8_t* h_buf = nullptr; size_t h_cap = 0;
+};
+
+extern "C" {
+
+int dvm_match_by_bow(dvm_frame* ctx, int kf_kf, const dvm_bow_features* a, const dvm_bow_features* b, float nnratio,
+                     int check_orientation, int32_t* match12, int32_t* match21, int* nmatches)
+{
+    DVM_REQUIRE(ctx != nullptr && nmatches != nullptr, "null argument");
+    std::vector<uint8_t> seen;
+    int rc = check_side(a, seen);
+    if (rc != DVM_OK) return rc;
+    rc = check_side(b, seen);
+    if (rc != DVM_OK) return rc;
+    DVM_CUDA(cudaSetDevice(ctx->device));
+    const dvm_bow_features* S[2] = { a, b };
+    size_t in_bytes = 0;
+    for (int k = 0; k < 2; k++) {
+        const size_t n = (size_t)S[k]->n, nn = (size_t)S[k]->n_nodes, tot = nn ? (size_t)S[k]->node_start[nn] : 0;
+        in_bytes += padded({ n * 32, n * 4, n, nn * 4, (nn + 1) * 4, tot * 4 });
+    }
+    const size_t out_ints = (size_t)a->n + (size_t)b->n + kHistoLength + 2;
+    in_bytes += padded({ out_ints * 4 });
+    rc = dvm_frame_ensure_bytes(ctx, in_bytes, out_ints * 4 + 256);
+    if (rc != DVM_OK) return rc;
+    Stage st(ctx);
+    BowArgs g;
+    memset(&g, 0, sizeof(g));
+    BowSide* D[2] = { &g.a, &g.b };
+    for (int k = 0; k < 2; k++) {
+        const size_t n = (size_t)S[k]->n, nn = (size_t)S[k]->n_nodes, tot = nn ? (size_t)S[k]->node_start[nn] : 0;
+        D[k]->n = S[k]->n; D[k]->n_nodes = S[k]->n_nodes;
+        D[k]->desc = st.add(S[k]->desc, n * 32);
+        D[k]->angle = st.add(S[k]->angle, n);
+        D[k]->valid = S[k]->has_mp ? st.add(S[k]->has_mp, n) : nullptr;
+        D[k]->node_id = st.add(S[k]->node_id, nn);
+        D[k]->node_start = st.add(S[k]->node_start, nn + 1);
+        D[k]->feat_idx = st.add(S[k]->feat_idx, tot);
+    }
+    if (!kf_kf) g.b.valid = nullptr;
+    g.kf_kf = kf_kf ? 1 : 0; g.nnratio = nnratio; g.check_ori = check_orientation;
+    const size_t in_end = st.off;
+    int* d_out = st.add((const int*)nullptr, out_ints);   // match12 | match21 | histo | counters
+    g.match12 = d_out; g.match21 = d_out + a->n; g.histo = g.match21 + b->n; g.counters = g.histo + kHistoLength;
+    DVM_CUDA(cudaMemcpyAsync(ctx->d_in, ctx->h_in, in_end, cudaMemcpyHostToDevice, ctx->stream));
+    DVM_CUDA(cudaMemsetAsync(d_out, 0xff, ((size_t)a->n + (size_t)b->n) * 4, ctx->stream));
+    DVM_CUDA(cudaMemsetAsync(g.histo, 0, (kHistoLength + 2) * 4, ctx->stream));
+    launch_bow_match(g, ctx->stream);
+    DVM_CUDA(cudaGetLastError());
+    DVM_CUDA(cudaMemcpyAsync(ctx->h_out, d_out, out_ints * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    DVM_CUDA(cudaStreamSynchronize(ctx->stream));
+    const int* h = (const int*)ctx->h_out;
+    if (match12 && a->n) memcpy(match12, h, (size_t)a->n * 4);
+    if (match21 && b->n) memcpy(match21, h + a->n, (size_t)b->n * 4);
+    *nmatches = h[(size_t)a->n + b->n + kHistoLength + 1];
+    return DVM_OK;
+}
+
+int dvm_match_for_initialization(dvm_frame* f2, int n1, const dvm_keypoint* kps1_un, const uint8_t* desc1,
+                                 float* prev_matched, int window_size, float nnratio, int check_orientation,
+                                 int32_t* matches12, int* nmatches)
+{
+    DVM_REQUIRE(f2 != nullptr && nmatches != nullptr && n1 >= 0 && window_size >= 0, "bad argument");
+    DVM_REQUIRE(n1 == 0 || (kps1_un && desc1 && prev_matched && matches12), "null first-frame arrays");
+    DVM_CUDA(cudaSetDevice(f2->device));
+    const size_t n = (size_t)n1;
+    const size_t out_bytes = n * 8 + n * 4 + 8;   // prev_matched | matches12 | result
+    int rc = dvm_frame_ensure_bytes(f2, padded({ n * sizeof(dvm_keypoint), n * 32, out_bytes + 512, n * 4, n * 4, n * 4, n * 4, n * 4,
+                                                 (size_t)f2->cap * 4 }), out_bytes + 512);
+    if (rc != DVM_OK) return rc;
+    Stage st(f2);
+    InitMatchArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n1 = n1; a.window = window_size; a.nnratio = nnratio; a.check_ori = check_orientation;
+    a.kps1 = st.add(kps1_un, n);
+    a.desc1 = st.add(desc1, n * 32);
+    const size_t out_begin = (st.off + 255) & ~(size_t)255;
+    a.prev_matched = st.add(prev_matched, n * 2);
+    const size_t in_end = st.off;
+    a.matches12 = st.add((const int*)nullptr, n);
+    a.result = st.add((const int*)nullptr, 2);
+    const size_t out_end = st.off;
+    a.choice_a = st.add((const int*)nullptr, n); a.choice_b = st.add((const int*)nullptr, n);
+    a.cdist_a = st.add((const int*)nullptr, n); a.cdist_b = st.add((const int*)nullptr, n);
+    a.next = st.add((const int*)nullptr, n);
+    a.head = st.add((const int*)nullptr, (size_t)f2->cap);
+    DVM_CUDA(cudaMemcpyAsync(f2->d_in, f2->h_in, in_end, cudaMemcpyHostToDevice, f2->stream));
+    launch_init_match(f2->dev, a, f2->stream);
+    DVM_CUDA(cudaGetLastError());
+    DVM_CUDA(cudaMemcpyAsync(f2->h_out, f2->d_in + out_begin, out_end - out_begin, cudaMemcpyDeviceToHost, f2->stream));
+    DVM_CUDA(cudaStreamSynchronize(f2->stream));
+    const uint8_t* h = f2->h_out;
+    auto at = [&](const void* dptr) { return h + ((const uint8_t*)dptr - (f2->d_in + out_begin)); };
+    if (n1) {
+        memcpy(prev_matched, at(a.prev_matched), n * 8);
+        memcpy(matches12, at(a.matches12), n * 4);
+    }
+    const int* r = (const int*)at(a.result);
+    *nmatches = r[0];
+    f2->last_rounds = r[1];
+    return DVM_OK;
+}
+
+int dvm_hamming_create(dvm_hamming** out, int device, void* cuda_stream)
+{
+    DVM_REQUIRE(out != nullptr, "null output handle");
+    *out = nullptr;
+    int rc = select_device(device);
+    if (rc != DVM_OK) return rc;
+    dvm_hamming* h = new dvm_hamming;
+    h->device = device;
+    if (cuda_stream) h->stream = (cudaStream_t)cuda_stream;
+    else {
+        cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) { set_error("cudaStreamCreate failed: %s", cudaGetErrorString(e)); delete h; return DVM_ERR_CUDA; }
+        h->own_stream = true;
+    }
+    *out = h;
+    return DVM_OK;
+}
+
+void dvm_hamming_destroy(dvm_hamming* h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    cudaFree(h->scratch.part[0]); cudaFree(h->scratch.part[1]); cudaFree(h->d_buf);
+    if (h->h_buf) cudaFreeHost(h->h_buf);
+    if (h->own_stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int dvm_hamming_knn_device(dvm_hamming* h, const uint8_t* a_dev, int ba, int na, const uint8_t* b_dev, int bb, int nb,
+                           uint32_t* key1_dev, uint32_t* key2_dev, int32_t* counts_dev, int th_low, float nnratio)
+{
+    DVM_REQUIRE(h != nullptr && ba >= 0 && bb >= 0 && na >= 0 && nb >= 0 && nb < (1 << 20), "bad sizes");
+    DVM_REQUIRE((long long)ba * bb < (1LL << 31), "too many block pairs");
+    DVM_REQUIRE(ba * bb * na == 0 || (a_dev && key1_dev && key2_dev && (nb == 0 || b_dev)), "null device arrays");
+    DVM_CUDA(cudaSetDevice(h->device));
+    KnnArgs k;
+    k.a = a_dev; k.ba = ba; k.na = na; k.b = b_dev; k.bb = bb; k.nb = nb;
+    k.key1 = key1_dev; k.key2 = key2_dev; k.counts = counts_dev; k.th_low = th_low; k.nnratio = nnratio;
+    return launch_hamming_knn(k, h->scratch, h->stream);
+}
+
+int dvm_hamming_sync(dvm_hamming* h)
+{
+    DVM_REQUIRE(h != nullptr, "null handle");
+    DVM_CUDA(cudaSetDevice(h->device));
+    DVM_CUDA(cudaStreamSynchronize(h->stream));
+    return DVM_OK;
+}
+
+int dvm_hamming_knn(dvm_hamming* h, const uint8_t* a, int na, const uint8_t* b, int nb, int32_t* best_idx,
+                    int32_t* best_dist, int32_t* second_dist)
+{
+    DVM_REQUIRE(h != nullptr && na >= 0 && nb >= 0 && nb < (1 << 20), "bad sizes");
+    DVM_REQUIRE(na == 0 || (a && best_idx && best_dist && second_dist), "null query arrays");
+    DVM_REQUIRE(nb == 0 || b, "null database");
+    if (na == 0) return DVM_OK;
+    DVM_CUDA(cudaSetDevice(h->device));
+    const size_t ab = ((size_t)na * 32 + 255) & ~(size_t)255, bbytes = ((size_t)nb * 32 + 255) & ~(size_t)255;
+    const size_t kb = ((size_t)na * 4 + 255) & ~(size_t)255;
+    const size_t need = ab + bbytes + 2 * kb;
+    if (need > h->d_cap) {
+        DVM_CUDA(cudaStreamSynchronize(h->stream));
+        cudaFree(h->d_buf); h->d_buf = nullptr;
+        if (h->h_buf) { cudaFreeHost(h->h_buf); h->h_buf = nullptr; }
+        h->d_cap = h->h_cap = 0;
+        const size_t cap = need + need / 4;
+        DVM_CUDA(cudaMalloc(&h->d_buf, cap));
+        DVM_CUDA(cudaHostAlloc(&h->h_buf, cap, cudaHostAllocDefault));
+        h->d_cap = h->h_cap = cap;
+    }
+    memcpy(h->h_buf, a, (size_t)na * 32);
+    if (nb) memcpy(h->h_buf + ab, b, (size_t)nb * 32);
+    DVM_CUDA(cudaMemcpyAsync(h->d_buf, h->h_buf, ab + bbytes, cudaMemcpyHostToDevice, h->stream));
+    uint32_t* k1 = reinterpret_cast<uint32_t*>(h->d_buf + ab + bbytes);
+    uint32_t* k2 = reinterpret_cast<uint32_t*>(h->d_buf + ab + bbytes + kb);
+    int rc = dvm_hamming_knn_device(h, h->d_buf, 1, na, h->d_buf + ab, 1, nb, k1, k2, nullptr, 0, 0.f);
+    if (rc != DVM_OK) return rc;
+    DVM_CUDA(cudaMemcpyAsync(h->h_buf + ab + bbytes, k1, 2 * kb, cudaMemcpyDeviceToHost, h->stream));
+    DVM_CUDA(cudaStreamSynchronize(h->stream));
+    const uint32_t* hk1 = reinterpret_cast<const uint32_t*>(h->h_buf + ab + bbytes);
+    const uint32_t* hk2 = reinterpret_cast<const uint32_t*>(h->h_buf + ab + bbytes + kb);
+    for (int i = 0; i < na; i++) {
+        const uint32_t d1 = hk1[i] >> 20, d2 = hk2[i] >> 20;
+        best_dist[i] = (int32_t)(d1 < 256 ? d1 : 256);
+        best_idx[i] = d1 < 256 ? (int32_t)(hk1[i] & 0xfffffu) : -1;
+        second_dist[i] = (int32_t)(d2 < 256 ? d2 : 256);
+    }
+    return DVM_OK;
+}
+
+} // extern "C"

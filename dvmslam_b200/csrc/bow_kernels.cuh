@@ -1,0 +1,67 @@
+// bow_kernels.cuh -- device structures and launchers of SearchByBoW, SearchForInitialization and the
+// exhaustive Hamming search (bow_kernels.cu, hamming.cu).
+#pragma once
+#include "track_kernels.cuh"
+
+namespace dvm {
+
+// One side of SearchByBoW: descriptors, keypoint angles, map-point validity and the DBoW2 FeatureVector
+// in CSR form (node ids ascending = std::map order; feat_idx in push_back order).  Device pointers.
+struct BowSide {
+    int n;
+    const uint8_t* desc;
+    const float* angle;
+    const uint8_t* valid;      // may be nullptr: every feature takes part
+    int n_nodes;
+    const uint32_t* node_id;
+    const int* node_start;
+    const uint32_t* feat_idx;
+};
+
+struct BowArgs {
+    BowSide a, b;
+    int kf_kf;        // 0: SearchByBoW(KF, Frame)   1: SearchByBoW(KF, KF)
+    float nnratio;
+    int check_ori;
+    int* match12;     // [a.n] partner in b or -1 (preset to -1)
+    int* match21;     // [b.n] partner in a or -1 (preset to -1)
+    int* histo;       // [kHistoLength] preset to 0
+    int* counters;    // [2]: accepted pairs (preset 0), nmatches (out)
+};
+
+void launch_bow_match(const BowArgs& g, cudaStream_t stream);
+
+// SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize); F2 is the FrameDev
+struct InitMatchArgs {
+    int n1;
+    const dvm_keypoint* kps1;  // F1.mvKeysUn
+    const uint8_t* desc1;      // F1.mDescriptors
+    float* prev_matched;       // [n1 * 2] in/out
+    int window;
+    float nnratio;
+    int check_ori;
+    int* matches12;            // [n1] out
+    int* result;               // [2] out: nmatches, fixed-point rounds
+    // scratch
+    int* choice_a; int* choice_b; int* cdist_a; int* cdist_b; int* next;  // [n1] each
+    int* head;                                                            // [F2 cap]
+};
+
+void launch_init_match(const FrameDev& f2, const InitMatchArgs& a, cudaStream_t stream);
+
+// Exhaustive nearest / second-nearest search, batched over blocks (keyframes):
+//   a [ba][na][32], b [bb][nb][32]  ->  key1 / key2 [ba][bb][na]
+// key = distance << 20 | index in the b block; key1 = nearest (first of equal distances), key2 = the
+// second smallest key (its distance is the reference's bestDist2); 256 << 20 when absent.
+// counts (may be nullptr) [ba][bb]: rows with dist1 <= th_low and dist1 < nnratio * dist2.
+struct KnnArgs {
+    const uint8_t* a; int ba, na;
+    const uint8_t* b; int bb, nb;
+    uint32_t* key1; uint32_t* key2;
+    int* counts;   // preset to 0 by the launcher
+    int th_low; float nnratio;
+};
+struct KnnScratch { uint32_t* part[2] = { nullptr, nullptr }; size_t cap = 0; }; // per-split partial keys
+int launch_hamming_knn(const KnnArgs& k, KnnScratch& scratch, cudaStream_t stream);
+
+} // namespace dvm

@@ -307,3 +307,43 @@ def plane_map(stream: "PlaneStream", extract, keyframes, scale_factors, max_poin
         X, D, N, mind, maxd = X[sel], D[sel], N[sel], mind[sel], maxd[sel]
     return dict(xw=X.astype(np.float32), desc=np.ascontiguousarray(D), normal=N.astype(np.float32),
                 min_dist=mind.astype(np.float32), max_dist=maxd.astype(np.float32))
+
+
+# ------------------------------------------------------------------ inputs of the descriptor matchers
+def toy_feature_vector(desc: np.ndarray, bits: int = 7) -> dict:
+    """A stand-in for DBoW2's FeatureVector (node id at level L-4 -> feature indices in index order): the
+    node of a descriptor is the majority bit of `bits` disjoint groups of its 256 bits, so that noisy
+    copies of a descriptor mostly share a node, as words under a common vocabulary ancestor do.  The
+    matchers take the feature vector as an input; only its structure matters for parity."""
+    d = np.unpackbits(np.ascontiguousarray(desc, np.uint8), axis=1, bitorder="little")
+    g = 256 // bits
+    node = np.zeros(len(d), np.int64)
+    for b in range(bits):
+        node |= (d[:, b * g:(b + 1) * g].sum(1) * 2 > g).astype(np.int64) << b
+    fv: dict = {}
+    for i, n in enumerate(node):
+        fv.setdefault(int(n) * 3 + 11, []).append(i)   # sparse, non-contiguous node ids like a real vocabulary
+    return fv
+
+
+def noisy_copy(desc: np.ndarray, flip_p: float, rng) -> np.ndarray:
+    """Bernoulli(flip_p) bit flips of 32-byte descriptors."""
+    flips = np.packbits(rng.random((len(desc), 256)) < flip_p, axis=1, bitorder="little")
+    return np.ascontiguousarray(desc ^ flips)
+
+
+def keyframe_blocks(n_kf: int, n_feat: int, seed: int, shared_from: np.ndarray | None = None, shared_frac: float = 0.3,
+                    flip_p: float = 0.08) -> np.ndarray:
+    """Config C3 input: `n_kf` keyframes x `n_feat` descriptors u8[n_kf, n_feat, 32].  With
+    `shared_from` (another agent's blocks of the same shape) the first `shared_frac` of every keyframe's
+    descriptors are noisy copies of that agent's keyframe with the same index (true matches, expected
+    distance 256 * flip_p), placed at shuffled positions; the rest is uniform random (expected 128)."""
+    rng = np.random.default_rng(seed)
+    out = rng.integers(0, 256, (n_kf, n_feat, 32), dtype=np.uint8)
+    if shared_from is not None:
+        ns = int(shared_frac * n_feat)
+        for k in range(n_kf):
+            src = rng.choice(n_feat, ns, replace=False)
+            dst = rng.choice(n_feat, ns, replace=False)
+            out[k, dst] = noisy_copy(shared_from[k, src], flip_p, rng)
+    return out

@@ -190,6 +190,72 @@ DVM_API int dvm_match_by_projection_map(dvm_frame* cur, int m, const float* proj
 DVM_API int dvm_match_last_rounds(dvm_frame* cur);
 
 /* ------------------------------------------------------------------------------------------------
+ * ORBmatcher, descriptor matchers without projection
+ *   SearchByBoW(KeyFrame*, Frame&, ...)      O3/src/ORBmatcher.cc:214-393  (TrackReferenceKeyFrame, Relocalization)
+ *   SearchByBoW(KeyFrame*, KeyFrame*, ...)   O3/src/ORBmatcher.cc:709-834  (loop closing / map merging, the
+ *                                            reference's inter-agent descriptor comparison)
+ *   SearchForInitialization(F1, F2, ...)     O3/src/ORBmatcher.cc:605-707  (monocular initialisation)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* One side of SearchByBoW (host arrays).  The DBoW2::FeatureVector (std::map<NodeId, vector<unsigned>>,
+ * O3/Thirdparty/DBoW2/DBoW2/FeatureVector.h) is flattened to CSR form in the map's iteration order:
+ * node_id ascending, node_start[n_nodes + 1], feat_idx = each node's indices in push_back order (every
+ * feature index appears at most once, as DBoW2 guarantees). */
+typedef struct dvm_bow_features {
+    int32_t n;                 /* number of features (keypoints) */
+    const uint8_t* desc;       /* [n * 32]  mDescriptors */
+    const float* angle;        /* [n]       mvKeysUn[i].angle (== mvKeys[i].angle) */
+    const uint8_t* has_mp;     /* [n]       map point present && !isBad(); NULL = every feature */
+    int32_t n_nodes;           /* mFeatVec.size() */
+    const uint32_t* node_id;   /* [n_nodes] */
+    const int32_t* node_start; /* [n_nodes + 1] */
+    const uint32_t* feat_idx;  /* [node_start[n_nodes]] */
+} dvm_bow_features;
+
+/* kf_kf == 0: SearchByBoW(pKF = a, F = b): a.has_mp = vpMapPointsKF[i] && !isBad(); b.has_mp is ignored
+ *             (every unmatched feature of F is a candidate); a match needs bestDist1 <= TH_LOW.
+ * kf_kf != 0: SearchByBoW(pKF1 = a, pKF2 = b): both sides need a map point; bestDist1 < TH_LOW.
+ * match12[a.n] / match21[b.n] (either may be NULL) receive the partner's index or -1:
+ * vpMapPointMatches[i] of the Frame form is "the map point of a's feature match21[i]", vpMatches12[i] of
+ * the KeyFrame form is "the map point of b's feature match12[i]".  ctx: any frame handle (device and
+ * stream to run on, staging buffers). */
+DVM_API int dvm_match_by_bow(dvm_frame* ctx, int kf_kf, const dvm_bow_features* a, const dvm_bow_features* b,
+                             float nnratio, int check_orientation, int32_t* match12, int32_t* match21,
+                             int* nmatches);
+
+/* int ORBmatcher::SearchForInitialization(Frame& F1, Frame& F2, vector<cv::Point2f>& vbPrevMatched,
+ * vector<int>& vnMatches12, int windowSize).  f2 = F2 (assigned frame: grid queries); F1 by its
+ * undistorted keypoints and descriptors; prev_matched[n1 * 2] is vbPrevMatched, updated in place;
+ * matches12[n1] receives vnMatches12; *nmatches the return value. */
+DVM_API int dvm_match_for_initialization(dvm_frame* f2, int n1, const dvm_keypoint* kps1_un, const uint8_t* desc1,
+                                         float* prev_matched, int window_size, float nnratio,
+                                         int check_orientation, int32_t* matches12, int* nmatches);
+
+/* ------------------------------------------------------------------------------------------------
+ * Exhaustive nearest / second-nearest Hamming search (DescriptorDistance, O3/src/ORBmatcher.cc:1900-1914)
+ * -- the inter-agent loop-closure exchange of config C3: every received keyframe's descriptors against
+ * every local keyframe's, without the vocabulary prefilter (see csrc/hamming.cu).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct dvm_hamming dvm_hamming;
+/* cuda_stream: a cudaStream_t to launch on, or NULL for a private stream. */
+DVM_API int dvm_hamming_create(dvm_hamming** out, int device, void* cuda_stream);
+DVM_API void dvm_hamming_destroy(dvm_hamming* h);
+/* Host arrays a[na * 32], b[nb * 32].  Per row of a: best_idx (first of the nearest rows of b, -1 if
+ * none is closer than 256), best_dist, second_dist (256 when absent) -- the matchers' bestIdx /
+ * bestDist1 / bestDist2 over all of b.  Synchronous. */
+DVM_API int dvm_hamming_knn(dvm_hamming* h, const uint8_t* a, int na, const uint8_t* b, int nb, int32_t* best_idx,
+                            int32_t* best_dist, int32_t* second_dist);
+/* Batched, device-resident: a_dev [ba][na][32] against b_dev [bb][nb][32] (nb < 2^20).  key1_dev /
+ * key2_dev [ba][bb][na] receive distance << 20 | index of the nearest row and the second-smallest
+ * such key ((256 << 20) when absent); counts_dev [ba][bb] (may be NULL) the number of rows with
+ * best_dist <= th_low && best_dist < nnratio * second_dist -- the score by which the exchange ranks
+ * keyframe pairs.  Enqueues on the handle's stream; no synchronisation. */
+DVM_API int dvm_hamming_knn_device(dvm_hamming* h, const uint8_t* a_dev, int ba, int na, const uint8_t* b_dev, int bb,
+                                   int nb, uint32_t* key1_dev, uint32_t* key2_dev, int32_t* counts_dev, int th_low,
+                                   float nnratio);
+DVM_API int dvm_hamming_sync(dvm_hamming* h);
+
+/* ------------------------------------------------------------------------------------------------
  * Optimizer::PoseOptimization   (O3/src/Optimizer.cc:744-1028, mono observations)
  * ---------------------------------------------------------------------------------------------- */
 /* pose_q (x,y,z,w of Tcw.unit_quaternion()) and pose_t (Tcw.translation()) are in/out (float, like

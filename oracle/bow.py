@@ -1,0 +1,75 @@
+"""Bindings of oracle/bow_oracle.cpp and trko_search_for_initialization -- TEST INFRASTRUCTURE, NOT PRODUCT CODE."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import lib
+from .orb import KP_DTYPE
+
+_vp = C.c_void_p
+
+
+def _L():
+    L = lib()
+    if getattr(L, "_bow_bound", False):
+        return L
+    L.bowo_search_by_bow.argtypes = [C.c_int] + [C.c_int, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp] * 2 + [C.c_float, C.c_int, _vp, _vp]
+    L.bowo_hamming_knn.argtypes = [_vp, C.c_int, _vp, C.c_int, _vp, _vp, _vp]
+    L.bowo_hamming_knn.restype = None
+    L.trko_search_for_initialization.argtypes = [C.c_int, _vp, _vp, _vp, _vp, C.c_int, C.c_float, C.c_int, _vp]
+    L._bow_bound = True
+    return L
+
+
+def _c(a, dt):
+    return np.ascontiguousarray(a, dt)
+
+
+def _csr(fv):
+    nodes = sorted(fv)
+    node_id = np.array(nodes, np.uint32)
+    start = np.zeros(len(nodes) + 1, np.int32)
+    for i, k in enumerate(nodes):
+        start[i + 1] = start[i] + len(fv[k])
+    idx = np.concatenate([np.asarray(fv[k], np.uint32) for k in nodes]) if nodes else np.zeros(0, np.uint32)
+    return node_id, start, _c(idx, np.uint32)
+
+
+def search_by_bow(kf_kf, desc1, angle1, valid1, fv1, desc2, angle2, valid2, fv2, nnratio=0.6, check_ori=True):
+    """-> (nmatches, match12, match21); fv = {node: [feature indices]}"""
+    L = _L()
+    sides = []
+    for d, a, v, fv in ((desc1, angle1, valid1, fv1), (desc2, angle2, valid2, fv2)):
+        d, a = _c(d, np.uint8), _c(a, np.float32)
+        v = None if v is None else _c(v, np.uint8)
+        nid, st, idx = _csr(fv)
+        sides.append((len(a), d, a, v, len(nid), nid, st, idx))
+    m12 = np.full(max(sides[0][0], 1), -1, np.int32)
+    m21 = np.full(max(sides[1][0], 1), -1, np.int32)
+    args = []
+    for n, d, a, v, nn, nid, st, idx in sides:
+        args += [n, d.ctypes.data, a.ctypes.data, v.ctypes.data if v is not None else None, nn, nid.ctypes.data,
+                 st.ctypes.data, idx.ctypes.data]
+    n = L.bowo_search_by_bow(int(kf_kf), *args, float(nnratio), int(check_ori), m12.ctypes.data, m21.ctypes.data)
+    return n, m12[:sides[0][0]], m21[:sides[1][0]]
+
+
+def hamming_knn(a, b):
+    L = _L()
+    a, b = _c(a, np.uint8), _c(b, np.uint8)
+    out = [np.zeros(max(len(a), 1), np.int32) for _ in range(3)]
+    L.bowo_hamming_knn(a.ctypes.data, len(a), b.ctypes.data, len(b), *(o.ctypes.data for o in out))
+    return tuple(o[:len(a)] for o in out)
+
+
+def search_for_initialization(kps1, desc1, frame2_oracle, prev_matched, window=100, nnratio=0.9, check_ori=True):
+    """frame2_oracle: oracle.track.FrameOracle of F2 -> (nmatches, matches12, prev_matched)"""
+    L = _L()
+    k1, d1 = _c(kps1, KP_DTYPE), _c(desc1, np.uint8)
+    pm = _c(prev_matched, np.float32).copy()
+    m12 = np.full(max(len(k1), 1), -1, np.int32)
+    n = L.trko_search_for_initialization(len(k1), k1.ctypes.data, d1.ctypes.data, frame2_oracle.h, pm.ctypes.data,
+                                         int(window), float(nnratio), int(check_ori), m12.ctypes.data)
+    return n, m12[:len(k1)], pm

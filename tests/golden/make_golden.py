@@ -10,6 +10,9 @@
                       primitives + the restated in-tree logic;
   track_small.npz     matcher / pose-optimisation / local-BA results of the oracle on small seeded cases
                       (no upstream fixture exists for these: they pin the oracle against regressions).
+  bow_small.npz       SearchByBoW (both overloads), SearchForInitialization and exhaustive nearest/second-nearest
+                      results of the oracle on the seeded cases of tests/bow_cases.py (regression pins, no upstream
+                      fixture).
 The reference repository holds no fixtures for this path; these are ours.
 """
 import os
@@ -81,6 +84,24 @@ def main():
                         pose_t=t2, pose_inliers=np.int32(r), pose_outlier=outl, ba_cam_q=ba["cam_q"],
                         ba_cam_t=ba["cam_t"], ba_pts=ba["pts"], ba_bad=ba["bad"], ba_iters=np.int32(ba["iters"]),
                         ba_chi=np.array([ba["chi_first"], ba["chi_last"]]))
+    # ---- descriptor matchers without projection ----
+    from oracle.bow import hamming_knn, search_by_bow, search_for_initialization
+    from tests import bow_cases
+
+    orc = OrbOracle(600)
+    T = orc.tables()
+    c = bow_cases.bow_pair(orc.extract)
+    out = {}
+    for kf_kf in (0, 1):
+        n, m12, m21 = search_by_bow(kf_kf, c["desc1"], c["angle1"], c["valid1"], c["fv1"], c["desc2"], c["angle2"],
+                                    c["valid2"], c["fv2"], 0.7, True)
+        out[f"bow{kf_kf}_n"], out[f"bow{kf_kf}_m12"], out[f"bow{kf_kf}_m21"] = np.int32(n), m12, m21
+    ci = bow_cases.init_pair(orc.extract)
+    F2 = FrameOracle(ci["kps2"], ci["desc2"], ci["bounds"], T["scale"])
+    n, m12, pm = search_for_initialization(ci["kps1"], ci["desc1"], F2, ci["prev"], 100, 0.9, True)
+    out["init_n"], out["init_m12"], out["init_prev"] = np.int32(n), m12, pm
+    out["knn"] = np.stack(hamming_knn(c["desc1"], c["desc2"]))
+    np.savez_compressed(os.path.join(HERE, "bow_small.npz"), **out)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")
