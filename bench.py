@@ -36,6 +36,7 @@ sys.path.insert(0, ROOT)
 W, H, NFEAT = 1280, 720, 2000
 FRAMES_PER_STEP = 64
 RESIDENT_FRAMES = 320
+C3_KEYFRAMES = 64   # keyframes per agent in the inter-agent exchange step
 METRIC = "frames/sec/agent tracked (1280x720, 2000 features, tracking only) + local-BA iter/sec in `lba`"
 UNIT = "frames/s"
 WORKLOAD = "C2: single agent per GPU, 1280x720 synthetic stream, 2000 feats/frame"
@@ -380,6 +381,47 @@ def run_ours(args):
                "achieved_GBps_kernel": 29e6 * its / (kern_ms * 1e-3) / 1e9}
         solver.close()
 
+    # ---- inter-agent loop-closure exchange step (config C3): all-to-all of new keyframe descriptor blocks +
+    # exhaustive Hamming matching against the local keyframe database; at N = 1 the matching alone ----
+    from dvmslam_b200.exchange import LoopClosureExchange, pair_owner
+
+    base = synth.keyframe_blocks(C3_KEYFRAMES, NFEAT, seed=100)
+    own = base if rank == 0 else synth.keyframe_blocks(C3_KEYFRAMES, NFEAT, seed=100 + rank, shared_from=base)
+    own_dev = torch.from_numpy(own).cuda()
+    x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    xms, ncand, nl0 = [], 0, launch_count()
+    for rep in range(4):   # first repetition = warm-up (NCCL channel setup, buffer growth)
+        ex = LoopClosureExchange(n_feat=NFEAT, max_keyframes=C3_KEYFRAMES, device=torch.device("cuda", local_rank),
+                                 owner="balanced")
+        ex.add_keyframes(own_dev)
+        barrier()
+        x0.record()
+        if world > 1:
+            cands = ex.exchange()
+        else:
+            cnt = ex.match_counts(ex.db[:ex.n_kf], ex.db[:ex.n_kf])
+            cands = np.argwhere(cnt >= ex.min_matches)
+        x1.record()
+        torch.cuda.synchronize()
+        if rep:
+            xms.append(x0.elapsed_time(x1))
+            ncand = len(cands)
+        ex.close()
+    xt = torch.tensor([float(np.mean(xms))], device="cuda")
+    if dist is not None:
+        dist.all_reduce(xt, op=dist.ReduceOp.MAX)
+    kf_pairs = C3_KEYFRAMES * C3_KEYFRAMES * (world * (world - 1) // 2 if world > 1 else 1)
+    my_pairs = sum(1 for p in range(world) if p != rank and pair_owner(rank, p, "balanced") == rank) if world > 1 else 1
+    exchange = {"value": kf_pairs / (float(xt.item()) * 1e-3), "unit": "keyframe pairs/s", "ms_per_round": float(xt.item()),
+                "workload": f"C3: {C3_KEYFRAMES} keyframes x {NFEAT} descriptors per agent, every agent pair matched once "
+                            f"(balanced ownership), {'all-to-all over NCCL + ' if world > 1 else ''}exhaustive Hamming",
+                "descriptor_pairs_per_s": kf_pairs * NFEAT * NFEAT / (float(xt.item()) * 1e-3),
+                # popcount-bound: 8 POPC per descriptor pair; the quarter-rate pipe issues 16 lanes/clk/SM
+                "popc_per_clk_per_sm_rank0": my_pairs * C3_KEYFRAMES ** 2 * NFEAT * NFEAT * 8 / (float(np.mean(xms)) * 1e-3)
+                                             / 148 / 1.965e9,
+                "bytes_exchanged_per_rank": C3_KEYFRAMES * NFEAT * 32 if world > 1 else 0,
+                "candidates_rank0": int(ncand), "gpu_launches": int(launch_count() - nl0)}
+
     if rank == 0:
         frames = args.steps * FRAMES_PER_STEP
         value = world * frames / (ms_total * 1e-3)
@@ -417,7 +459,7 @@ def run_ours(args):
                         "d2h_bytes_per_step": FRAMES_PER_STEP * 48, "tracked_ok_frac": tracked_ok,
                         "median_inliers": float(np.median(inliers)) if inliers else 0.0},
                 "gpu_launches": int(launches), "clocks": clock_info, "roofline": roofline, "cpu_baseline": cpu,
-                "lba": lba, "last_counts_device_run": list(c_dev)}
+                "lba": lba, "exchange": exchange, "last_counts_device_run": list(c_dev)}
         print(json.dumps(line), flush=True)
     trk.close()
     ext.close()

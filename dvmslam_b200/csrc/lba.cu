@@ -883,7 +883,7 @@ float dvm_lba_last_kernel_ms(const dvm_lba* h) { return h ? h->last_ms : -1.f; }
 
 int dvm_local_ba(dvm_lba* h, int nc, float* cam_q, float* cam_t, const uint8_t* cam_fixed, int np, float* pts, int ne,
                  const int32_t* edge_cam, const int32_t* edge_pt, const float* edge_obs, const float* edge_inv_sigma2,
-                 const float* K, int iterations, const volatile int* abort_flag, double* edge_chi2, uint8_t* edge_bad,
+                 const float* K, int iterations, const volatile uint8_t* abort_flag, double* edge_chi2, uint8_t* edge_bad,
                  double* stats, int* iters_done)
 {
     DVM_REQUIRE(h != nullptr && iters_done != nullptr, "null argument");

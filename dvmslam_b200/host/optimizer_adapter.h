@@ -1,0 +1,191 @@
+// optimizer_adapter.h -- the bodies of ORB_SLAM3::Optimizer::PoseOptimization and ::LocalBundleAdjustment
+// (O3/include/Optimizer.h:56-59) over the C-ABI.  Templates over the reference's own Frame / KeyFrame /
+// MapPoint / Map types; the pointer-graph part (which keyframes and map points form the window, what is
+// erased and written back afterwards) is the reference's own logic, restated around one GPU call.
+// Mono observations only (mvuRight < 0, no second camera), like the C-ABI.
+#pragma once
+#include <list>
+#include <map>
+#include <mutex>
+#include <tuple>
+#include <unordered_map>
+#include <utility>
+#include <vector>
+
+#include "orb_matcher_adapter.h"
+
+namespace dvm_host {
+
+// pose <-> (qx, qy, qz, qw, tx, ty, tz) through the accessors Sophus::SE3f / Eigen offer
+template <class PoseT>
+void pose_to_floats(const PoseT& Tcw, float q[4], float t[3])
+{
+    const auto uq = Tcw.unit_quaternion();
+    q[0] = uq.x(); q[1] = uq.y(); q[2] = uq.z(); q[3] = uq.w();
+    const auto tr = Tcw.translation();
+    for (int k = 0; k < 3; k++) t[k] = tr(k);
+}
+
+template <class PoseT>
+PoseT pose_from_floats(const PoseT& like, const float q[4], const float t[3])
+{
+    auto uq = like.unit_quaternion();
+    uq.x() = q[0]; uq.y() = q[1]; uq.z() = q[2]; uq.w() = q[3];
+    auto tr = like.translation();
+    for (int k = 0; k < 3; k++) tr(k) = t[k];
+    return PoseT(uq, tr);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// int Optimizer::PoseOptimization(Frame* pFrame)                          O3/src/Optimizer.cc:744-1028
+// ---------------------------------------------------------------------------------------------------
+template <class FrameT, class MapPointT>
+int PoseOptimization(FrameT* pFrame)
+{
+    const int N = pFrame->N;
+    std::vector<float> Xw, xy, w;
+    std::vector<int> index;         // vnIndexEdgeMono
+    Xw.reserve(3 * N); xy.reserve(2 * N); w.reserve(N); index.reserve(N);
+    {
+        std::unique_lock<std::mutex> lock(MapPointT::mGlobalMutex);                      // :785
+        for (int i = 0; i < N; i++) {
+            MapPointT* pMP = pFrame->mvpMapPoints[i];
+            if (!pMP) continue;
+            pFrame->mvbOutlier[i] = false;                                               // :794
+            const auto& kpUn = pFrame->mvKeysUn[i];
+            const auto p = pMP->GetWorldPos();
+            for (int k = 0; k < 3; k++) Xw.push_back(p(k));
+            xy.push_back(kpUn.pt.x); xy.push_back(kpUn.pt.y);
+            w.push_back(pFrame->mvInvLevelSigma2[kpUn.octave]);                          // :806
+            index.push_back(i);
+        }
+    }
+    const int n = static_cast<int>(index.size());   // nInitialCorrespondences
+    if (n < 3) return 0;                                                                 // :923-924
+    float q[4], t[3];
+    const auto Tcw = pFrame->GetPose();
+    pose_to_floats(Tcw, q, t);
+    const float K[4] = { pFrame->fx, pFrame->fy, pFrame->cx, pFrame->cy };
+    std::vector<uint8_t> outlier(n);
+    int inliers = 0;
+    check(dvm_pose_optimization(device_frame(*pFrame).frame.h, q, t, K, n, Xw.data(), xy.data(), w.data(), outlier.data(),
+                                &inliers, nullptr),
+          "Optimizer::PoseOptimization");
+    for (int k = 0; k < n; k++) pFrame->mvbOutlier[index[k]] = outlier[k] != 0;          // :951-961
+    pFrame->SetPose(pose_from_floats(Tcw, q, t));                                        // :1021-1025
+    return inliers;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// void Optimizer::LocalBundleAdjustment(KeyFrame* pKF, bool* pbStopFlag, Map* pMap, int& num_fixedKF,
+//                                       int& num_OptKF, int& num_MPs, int& num_edges)   :1030-1387
+// solver: one dvm_lba context per local-mapping thread (dvm_lba_create).
+// ---------------------------------------------------------------------------------------------------
+template <class KeyFrameT, class MapPointT, class MapT>
+void LocalBundleAdjustment(dvm_lba* solver, KeyFrameT* pKF, bool* pbStopFlag, MapT* pMap, int& num_fixedKF, int& num_OptKF,
+                           int& num_MPs, int& num_edges)
+{
+    // ---- window assembly: the reference's breadth-first search, :1033-1091 ----
+    std::list<KeyFrameT*> lLocalKeyFrames;
+    lLocalKeyFrames.push_back(pKF);
+    pKF->mnBALocalForKF = pKF->mnId;
+    auto* pCurrentMap = pKF->GetMap();
+    for (KeyFrameT* pKFi : pKF->GetVectorCovisibleKeyFrames()) {
+        pKFi->mnBALocalForKF = pKF->mnId;
+        if (!pKFi->isBad() && pKFi->GetMap() == pCurrentMap) lLocalKeyFrames.push_back(pKFi);
+    }
+    num_fixedKF = 0;
+    std::list<MapPointT*> lLocalMapPoints;
+    for (KeyFrameT* pKFi : lLocalKeyFrames) {
+        if (pKFi->mnId == pMap->GetInitKFid()) num_fixedKF = 1;
+        for (MapPointT* pMP : pKFi->GetMapPointMatches())
+            if (pMP && !pMP->isBad() && pMP->GetMap() == pCurrentMap && pMP->mnBALocalForKF != pKF->mnId) {
+                lLocalMapPoints.push_back(pMP);
+                pMP->mnBALocalForKF = pKF->mnId;
+            }
+    }
+    std::list<KeyFrameT*> lFixedCameras;
+    for (MapPointT* pMP : lLocalMapPoints)
+        for (const auto& ob : pMP->GetObservations()) {
+            KeyFrameT* pKFi = ob.first;
+            if (pKFi->mnBALocalForKF != pKF->mnId && pKFi->mnBAFixedForKF != pKF->mnId) {
+                pKFi->mnBAFixedForKF = pKF->mnId;
+                if (!pKFi->isBad() && pKFi->GetMap() == pCurrentMap) lFixedCameras.push_back(pKFi);
+            }
+        }
+    num_fixedKF += static_cast<int>(lFixedCameras.size());
+    if (num_fixedKF == 0) return;                                                        // :1088-1091
+
+    // ---- flatten: cameras (local first, then fixed), points, one edge per mono observation ----
+    std::vector<KeyFrameT*> cams(lLocalKeyFrames.begin(), lLocalKeyFrames.end());
+    cams.insert(cams.end(), lFixedCameras.begin(), lFixedCameras.end());
+    const int nLocal = static_cast<int>(lLocalKeyFrames.size());
+    std::unordered_map<KeyFrameT*, int> camIndex;
+    std::vector<float> cam_q(cams.size() * 4), cam_t(cams.size() * 3);
+    std::vector<uint8_t> cam_fixed(cams.size());
+    for (size_t c = 0; c < cams.size(); c++) {
+        camIndex[cams[c]] = static_cast<int>(c);
+        pose_to_floats(cams[c]->GetPose(), &cam_q[4 * c], &cam_t[3 * c]);
+        cam_fixed[c] = static_cast<int>(c) >= nLocal || cams[c]->mnId == pMap->GetInitKFid();   // :1124, :1140
+    }
+    num_OptKF = nLocal;
+    std::vector<MapPointT*> pts(lLocalMapPoints.begin(), lLocalMapPoints.end());
+    std::vector<float> xyz(pts.size() * 3), edge_obs, edge_w;
+    std::vector<int32_t> edge_cam, edge_pt;
+    std::vector<std::pair<KeyFrameT*, MapPointT*>> edge_owner;
+    for (size_t j = 0; j < pts.size(); j++) {
+        const auto p = pts[j]->GetWorldPos();
+        for (int k = 0; k < 3; k++) xyz[3 * j + k] = p(k);
+        for (const auto& ob : pts[j]->GetObservations()) {                               // :1196-1232
+            KeyFrameT* pKFi = ob.first;
+            if (pKFi->isBad() || pKFi->GetMap() != pCurrentMap) continue;
+            const int leftIndex = std::get<0>(ob.second);
+            if (leftIndex == -1 || !(pKFi->mvuRight[leftIndex] < 0)) continue;           // mono observation only
+            const auto it = camIndex.find(pKFi);
+            if (it == camIndex.end()) continue;
+            const auto& kpUn = pKFi->mvKeysUn[leftIndex];
+            edge_cam.push_back(it->second);
+            edge_pt.push_back(static_cast<int32_t>(j));
+            edge_obs.push_back(kpUn.pt.x); edge_obs.push_back(kpUn.pt.y);
+            edge_w.push_back(pKFi->mvInvLevelSigma2[kpUn.octave]);
+            edge_owner.emplace_back(pKFi, pts[j]);
+        }
+    }
+    num_MPs = static_cast<int>(pts.size());
+    num_edges = static_cast<int>(edge_cam.size());
+    if (pbStopFlag && *pbStopFlag) return;                                               // :1306-1308
+
+    // ---- optimizer.initializeOptimization(); optimizer.optimize(10);  :1310-1311 ----
+    // pbStopFlag (a bool set by the tracking thread, O3/src/LocalMapping.cc:359) is polled by the library while
+    // the solver runs and forwarded to the device, like g2o's forceStopFlag
+    static_assert(sizeof(bool) == 1, "pbStopFlag is read as one byte");
+    const float K[4] = { pKF->fx, pKF->fy, pKF->cx, pKF->cy };   // KeyFrame::fx.. are per-object constants
+    std::vector<uint8_t> edge_bad(edge_cam.size() ? edge_cam.size() : 1);
+    int iters = 0;
+    check(dvm_local_ba(solver, static_cast<int>(cams.size()), cam_q.data(), cam_t.data(), cam_fixed.data(),
+                       static_cast<int>(pts.size()), xyz.data(), static_cast<int>(edge_cam.size()), edge_cam.data(),
+                       edge_pt.data(), edge_obs.data(), edge_w.data(), K, 10,
+                       reinterpret_cast<const volatile uint8_t*>(pbStopFlag), nullptr, edge_bad.data(),
+                       nullptr, &iters),
+          "Optimizer::LocalBundleAdjustment");
+    if (iters < 0) return;
+
+    // ---- cull and write back, :1313-1387 ----
+    std::unique_lock<std::mutex> lock(pMap->mMutexMapUpdate);
+    for (size_t e = 0; e < edge_owner.size(); e++) {
+        MapPointT* pMP = edge_owner[e].second;
+        if (pMP->isBad() || !edge_bad[e]) continue;
+        edge_owner[e].first->EraseMapPointMatch(pMP);
+        pMP->EraseObservation(edge_owner[e].first);
+    }
+    for (int c = 0; c < nLocal; c++) cams[c]->SetPose(pose_from_floats(cams[c]->GetPose(), &cam_q[4 * c], &cam_t[3 * c]));
+    for (size_t j = 0; j < pts.size(); j++) {
+        auto p = pts[j]->GetWorldPos();
+        for (int k = 0; k < 3; k++) p(k) = xyz[3 * j + k];
+        pts[j]->SetWorldPos(p);
+        pts[j]->UpdateNormalAndDepth();
+    }
+    pMap->IncreaseChangeIndex();
+}
+
+} // namespace dvm_host

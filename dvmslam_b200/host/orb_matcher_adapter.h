@@ -1,0 +1,257 @@
+// orb_matcher_adapter.h -- the bodies of ORB_SLAM3::ORBmatcher's hot methods (O3/include/ORBmatcher.h:40-95)
+// over the C-ABI.  Templates over the reference's own Frame / KeyFrame / MapPoint types: they read exactly
+// the members the reference's implementation reads, flatten the pointer graph to the flat arrays of
+// include/dvmslam_b200.h, call the library and write the result back where the reference writes it.
+// In O3/src/ORBmatcher.cc every replaced body becomes one line.
+//
+// Mono path only (Frame::Nleft == -1, no right camera), like the C-ABI.
+#pragma once
+#include <cstring>
+#include <list>
+#include <memory>
+#include <vector>
+
+#include "dvm_host.h"
+
+namespace dvm_host {
+
+// ---------------------------------------------------------------------------------------------------
+// A Frame's device twin (keypoints, descriptors, 64x48 grid in HBM).  Created on first use and kept in a
+// small per-thread LRU keyed by Frame::mnId, so that the 2-3 matcher calls and the PoseOptimization calls of
+// one tracked frame upload it once.  (A maintainer who prefers an explicit member adds
+// `std::shared_ptr<dvm_host::DeviceFrame>` to Frame and calls device_frame_create in the mono constructor,
+// O3/src/Frame.cc:411-479.)
+// ---------------------------------------------------------------------------------------------------
+struct DeviceFrame {
+    FrameHandle frame;
+    long unsigned int id = ~0ul;
+    int n = 0;
+};
+
+template <class FrameT>
+std::shared_ptr<DeviceFrame> device_frame_create(const FrameT& F)
+{
+    auto d = std::make_shared<DeviceFrame>();
+    const int n = static_cast<int>(F.mvKeysUn.size());
+    check(dvm_frame_create(&d->frame.h, device_from_env(), nullptr, n > 0 ? n : 1, static_cast<int>(F.mvScaleFactors.size()),
+                           F.mvScaleFactors.data(), F.mvInvLevelSigma2.data()),
+          "dvm_frame_create");
+    // mvKeysUn is what AssignFeaturesToGrid and every matcher read (O3/src/Frame.cc:481-506)
+    std::vector<uint8_t> desc(static_cast<size_t>(n) * 32);
+    for (int i = 0; i < n; i++) std::memcpy(&desc[static_cast<size_t>(i) * 32], F.mDescriptors.ptr(i), 32);
+    check(dvm_frame_assign(d->frame.h, reinterpret_cast<const dvm_keypoint*>(F.mvKeysUn.data()), desc.data(), n,
+                           F.mnMinX, F.mnMinY, F.mnMaxX, F.mnMaxY),
+          "dvm_frame_assign");
+    d->id = F.mnId;
+    d->n = n;
+    return d;
+}
+
+template <class FrameT>
+DeviceFrame& device_frame(const FrameT& F)
+{
+    thread_local std::list<std::shared_ptr<DeviceFrame>> lru;
+    for (auto it = lru.begin(); it != lru.end(); ++it)
+        if ((*it)->id == F.mnId && (*it)->n == static_cast<int>(F.mvKeysUn.size())) {
+            lru.splice(lru.begin(), lru, it);
+            return *lru.front();
+        }
+    lru.push_front(device_frame_create(F));
+    if (lru.size() > 4) lru.pop_back();
+    return *lru.front();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// int ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono)
+// O3/src/ORBmatcher.cc:1553-1748.  Call sites clear CurrentFrame.mvpMapPoints first
+// (O3/src/Tracking.cc:2603, 2618); entries that are already set are kept and block nothing here.
+// ---------------------------------------------------------------------------------------------------
+template <class FrameT>
+int SearchByProjectionLast(FrameT& Cur, const FrameT& Last, float th, bool checkOrientation)
+{
+    DeviceFrame& dev = device_frame(Cur);
+    const auto Tcw = Cur.GetPose();
+    const auto R = Tcw.rotationMatrix();
+    const auto t = Tcw.translation();
+    float Rcw[9], tcw[3];
+    for (int r = 0; r < 3; r++) {
+        for (int c = 0; c < 3; c++) Rcw[3 * r + c] = R(r, c);
+        tcw[r] = t(r);
+    }
+    const float K[4] = { Cur.fx, Cur.fy, Cur.cx, Cur.cy };
+    const int n = Last.N;
+    std::vector<uint8_t> has_mp(n), outlier(n), obs_pos(n), desc(static_cast<size_t>(n) * 32);
+    std::vector<float> Xw(static_cast<size_t>(n) * 3), angle(n);
+    std::vector<int32_t> octave(n);
+    for (int i = 0; i < n; i++) {
+        auto* pMP = Last.mvpMapPoints[i];
+        has_mp[i] = pMP != nullptr;
+        outlier[i] = Last.mvbOutlier[i];
+        octave[i] = Last.mvKeys[i].octave;
+        angle[i] = Last.mvKeysUn[i].angle;
+        if (!pMP) continue;
+        const auto x3Dw = pMP->GetWorldPos();
+        for (int k = 0; k < 3; k++) Xw[static_cast<size_t>(i) * 3 + k] = x3Dw(k);
+        const auto d = pMP->GetDescriptor();
+        std::memcpy(&desc[static_cast<size_t>(i) * 32], d.ptr(0), 32);
+        obs_pos[i] = pMP->Observations() > 0;
+    }
+    std::vector<int32_t> cur_mp(Cur.N > 0 ? Cur.N : 1, -1);
+    int nmatches = 0;
+    check(dvm_match_by_projection_last(dev.frame.h, Rcw, tcw, K, n, has_mp.data(), outlier.data(), Xw.data(), desc.data(),
+                                       obs_pos.data(), octave.data(), angle.data(), th, checkOrientation ? 1 : 0,
+                                       cur_mp.data(), &nmatches),
+          "ORBmatcher::SearchByProjection(Frame&, const Frame&)");
+    for (int i = 0; i < Cur.N; i++)
+        if (cur_mp[i] >= 0) Cur.mvpMapPoints[i] = Last.mvpMapPoints[cur_mp[i]];
+    return nmatches;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// int ORBmatcher::SearchByProjection(Frame& F, const vector<MapPoint*>& vpMapPoints, const float th,
+//                                    const bool bFarPoints, const float thFarPoints)
+// O3/src/ORBmatcher.cc:44-205 (+ RadiusByViewingCos :207-212, applied on the device)
+// ---------------------------------------------------------------------------------------------------
+template <class FrameT, class MapPointT>
+int SearchByProjectionMap(FrameT& F, const std::vector<MapPointT*>& vpMapPoints, float th, float nnratio,
+                          bool bFarPoints = false, float thFarPoints = 50.0f)
+{
+    DeviceFrame& dev = device_frame(F);
+    std::vector<int> sel;            // vpMapPoints indices that take part, in order
+    sel.reserve(vpMapPoints.size());
+    for (size_t i = 0; i < vpMapPoints.size(); i++) {
+        MapPointT* pMP = vpMapPoints[i];
+        if (!pMP->mbTrackInView) continue;                             // :52-53 (mono: no mbTrackInViewR)
+        if (bFarPoints && pMP->mTrackDepth > thFarPoints) continue;    // :55-56
+        if (pMP->isBad()) continue;                                    // :58-59
+        sel.push_back(static_cast<int>(i));
+    }
+    const int m = static_cast<int>(sel.size());
+    std::vector<float> px(m), py(m), vc(m);
+    std::vector<int32_t> lvl(m);
+    std::vector<uint8_t> desc(static_cast<size_t>(m) * 32), obs_pos(m), blocked(F.N > 0 ? F.N : 1);
+    for (int k = 0; k < m; k++) {
+        MapPointT* pMP = vpMapPoints[sel[k]];
+        px[k] = pMP->mTrackProjX; py[k] = pMP->mTrackProjY; lvl[k] = pMP->mnTrackScaleLevel; vc[k] = pMP->mTrackViewCos;
+        const auto d = pMP->GetDescriptor();
+        std::memcpy(&desc[static_cast<size_t>(k) * 32], d.ptr(0), 32);
+        obs_pos[k] = pMP->Observations() > 0;
+    }
+    for (int i = 0; i < F.N; i++) blocked[i] = F.mvpMapPoints[i] && F.mvpMapPoints[i]->Observations() > 0;   // :86-88
+    std::vector<int32_t> cur_mp(F.N > 0 ? F.N : 1, -1);
+    int nmatches = 0;
+    check(dvm_match_by_projection_map(dev.frame.h, m, px.data(), py.data(), lvl.data(), vc.data(), desc.data(),
+                                      obs_pos.data(), th, nnratio, blocked.data(), cur_mp.data(), &nmatches),
+          "ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&)");
+    for (int i = 0; i < F.N; i++)
+        if (cur_mp[i] >= 0) F.mvpMapPoints[i] = vpMapPoints[sel[cur_mp[i]]];
+    return nmatches;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// SearchByBoW: a DBoW2::FeatureVector (std::map<NodeId, std::vector<unsigned>>) flattened to CSR form
+// ---------------------------------------------------------------------------------------------------
+struct FlatFeatures {
+    std::vector<uint8_t> desc, has_mp;
+    std::vector<float> angle;
+    std::vector<uint32_t> node_id, feat_idx;
+    std::vector<int32_t> node_start;
+    dvm_bow_features view() const
+    {
+        dvm_bow_features v;
+        v.n = static_cast<int32_t>(angle.size());
+        v.desc = desc.data(); v.angle = angle.data(); v.has_mp = has_mp.empty() ? nullptr : has_mp.data();
+        v.n_nodes = static_cast<int32_t>(node_id.size());
+        v.node_id = node_id.data(); v.node_start = node_start.data(); v.feat_idx = feat_idx.data();
+        return v;
+    }
+};
+
+template <class KeyPointVec, class MatT, class FeatVecT, class MapPointT>
+FlatFeatures flatten_features(const KeyPointVec& keysUn, const MatT& descriptors, const FeatVecT& featVec,
+                              const std::vector<MapPointT*>* mapPoints)
+{
+    FlatFeatures f;
+    const size_t n = keysUn.size();
+    f.desc.resize(n * 32);
+    f.angle.resize(n);
+    for (size_t i = 0; i < n; i++) {
+        std::memcpy(&f.desc[i * 32], descriptors.ptr(static_cast<int>(i)), 32);
+        f.angle[i] = keysUn[i].angle;
+    }
+    if (mapPoints) {
+        f.has_mp.resize(n);
+        for (size_t i = 0; i < n; i++) f.has_mp[i] = (*mapPoints)[i] && !(*mapPoints)[i]->isBad();
+    }
+    f.node_start.push_back(0);
+    for (const auto& kv : featVec) {               // std::map iteration = ascending node id
+        f.node_id.push_back(static_cast<uint32_t>(kv.first));
+        for (unsigned idx : kv.second) f.feat_idx.push_back(idx);
+        f.node_start.push_back(static_cast<int32_t>(f.feat_idx.size()));
+    }
+    return f;
+}
+
+// int ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, vector<MapPoint*>& vpMapPointMatches)   :214-393
+template <class KeyFrameT, class FrameT, class MapPointT>
+int SearchByBoW(KeyFrameT* pKF, FrameT& F, std::vector<MapPointT*>& vpMapPointMatches, float nnratio, bool checkOrientation)
+{
+    const std::vector<MapPointT*> vpMapPointsKF = pKF->GetMapPointMatches();
+    vpMapPointMatches.assign(static_cast<size_t>(F.N), static_cast<MapPointT*>(nullptr));
+    const FlatFeatures a = flatten_features(pKF->mvKeysUn, pKF->mDescriptors, pKF->mFeatVec, &vpMapPointsKF);
+    const FlatFeatures b = flatten_features(F.mvKeys, F.mDescriptors, F.mFeatVec, static_cast<const std::vector<MapPointT*>*>(nullptr));
+    const dvm_bow_features va = a.view(), vb = b.view();
+    std::vector<int32_t> match21(F.N > 0 ? F.N : 1, -1);
+    int nmatches = 0;
+    check(dvm_match_by_bow(device_frame(F).frame.h, 0, &va, &vb, nnratio, checkOrientation ? 1 : 0, nullptr, match21.data(),
+                           &nmatches),
+          "ORBmatcher::SearchByBoW(KeyFrame*, Frame&)");
+    for (int i = 0; i < F.N; i++)
+        if (match21[i] >= 0) vpMapPointMatches[i] = vpMapPointsKF[match21[i]];
+    return nmatches;
+}
+
+// int ORBmatcher::SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, vector<MapPoint*>& vpMatches12)   :709-834
+// ctx: any device frame (e.g. device_frame(currentFrame)); it only provides the GPU stream and staging buffers.
+template <class KeyFrameT, class MapPointT>
+int SearchByBoW(KeyFrameT* pKF1, KeyFrameT* pKF2, std::vector<MapPointT*>& vpMatches12, float nnratio, bool checkOrientation,
+                dvm_frame* ctx)
+{
+    const std::vector<MapPointT*> mp1 = pKF1->GetMapPointMatches(), mp2 = pKF2->GetMapPointMatches();
+    vpMatches12.assign(mp1.size(), static_cast<MapPointT*>(nullptr));
+    const FlatFeatures a = flatten_features(pKF1->mvKeysUn, pKF1->mDescriptors, pKF1->mFeatVec, &mp1);
+    const FlatFeatures b = flatten_features(pKF2->mvKeysUn, pKF2->mDescriptors, pKF2->mFeatVec, &mp2);
+    const dvm_bow_features va = a.view(), vb = b.view();
+    std::vector<int32_t> match12(mp1.empty() ? 1 : mp1.size(), -1);
+    int nmatches = 0;
+    check(dvm_match_by_bow(ctx, 1, &va, &vb, nnratio, checkOrientation ? 1 : 0, match12.data(), nullptr, &nmatches),
+          "ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*)");
+    for (size_t i = 0; i < mp1.size(); i++)
+        if (match12[i] >= 0) vpMatches12[i] = mp2[match12[i]];
+    return nmatches;
+}
+
+// int ORBmatcher::SearchForInitialization(Frame& F1, Frame& F2, vector<cv::Point2f>& vbPrevMatched,
+//                                         vector<int>& vnMatches12, int windowSize)            :605-707
+template <class FrameT, class Point2fT>
+int SearchForInitialization(FrameT& F1, FrameT& F2, std::vector<Point2fT>& vbPrevMatched, std::vector<int>& vnMatches12,
+                            int windowSize, float nnratio, bool checkOrientation)
+{
+    const int n1 = static_cast<int>(F1.mvKeysUn.size());
+    vnMatches12.assign(static_cast<size_t>(n1), -1);
+    std::vector<uint8_t> desc1(static_cast<size_t>(n1) * 32);
+    std::vector<float> prev(static_cast<size_t>(n1) * 2);
+    for (int i = 0; i < n1; i++) {
+        std::memcpy(&desc1[static_cast<size_t>(i) * 32], F1.mDescriptors.ptr(i), 32);
+        prev[2 * i] = vbPrevMatched[i].x; prev[2 * i + 1] = vbPrevMatched[i].y;
+    }
+    int nmatches = 0;
+    check(dvm_match_for_initialization(device_frame(F2).frame.h, n1, reinterpret_cast<const dvm_keypoint*>(F1.mvKeysUn.data()),
+                                       desc1.data(), prev.data(), windowSize, nnratio, checkOrientation ? 1 : 0,
+                                       vnMatches12.data(), &nmatches),
+          "ORBmatcher::SearchForInitialization");
+    for (int i = 0; i < n1; i++) { vbPrevMatched[i].x = prev[2 * i]; vbPrevMatched[i].y = prev[2 * i + 1]; }
+    return nmatches;
+}
+
+} // namespace dvm_host

@@ -114,11 +114,14 @@ class HammingKnn:
     """Exhaustive nearest / second-nearest Hamming search on one B200 (dvm_hamming_*)."""
     NO_KEY = 256 << 20
 
-    def __init__(self, device: int = 0, stream: int = 0):
+    def __init__(self, device: int = 0, stream=None):
+        """stream: None = a private stream; an integer cudaStream_t to launch on (0, CUDA's legacy default
+        stream -- what torch.cuda.current_stream().cuda_stream returns by default -- is passed as
+        cudaStreamLegacy, since a NULL handle means "private stream" in the C-ABI)."""
         self.L = lib()
         _bind(self.L)
         self.h = _vp()
-        check(self.L.dvm_hamming_create(C.byref(self.h), device, _vp(stream) if stream else None))
+        check(self.L.dvm_hamming_create(C.byref(self.h), device, None if stream is None else _vp(stream if stream else 1)))
 
     def close(self):
         if getattr(self, "h", None) and self.h.value:

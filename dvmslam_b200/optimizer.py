@@ -54,7 +54,7 @@ class LocalBA:
         bad = np.zeros(max(ne, 1), np.uint8)
         stats = np.zeros(4, np.float64)
         iters = C.c_int()
-        ab = _c([abort], np.int32) if abort is not None else None
+        ab = _c([abort], np.uint8) if abort is not None else None   # pbStopFlag: a one-byte bool
         check(self.L.dvm_local_ba(self.h, len(fx), q.ctypes.data, t.ctypes.data, fx.ctypes.data, len(p), p.ctypes.data,
                                   ne, ec.ctypes.data, ep.ctypes.data, eo.ctypes.data, ew.ctypes.data,
                                   _c(K, np.float32).ctypes.data, iterations, ab.ctypes.data if ab is not None else None,

@@ -339,15 +339,16 @@ DVM_API void dvm_lba_destroy(dvm_lba* h);
  *   one mono observation per edge: edge_cam, edge_pt (indices into the arrays above), edge_obs
  *   (kpUn.pt), edge_inv_sigma2 (mvInvLevelSigma2[octave]);  K = fx, fy, cx, cy.
  * Runs optimizer.optimize(iterations) (the reference passes 10) of g2o's Levenberg-Marquardt with the
- * Schur complement, entirely on the GPU.  abort_flag (may be NULL) is the reference's pbStopFlag: it
- * is checked before starting and polled between LM iterations and trials.
+ * Schur complement, entirely on the GPU.  abort_flag (may be NULL) is the reference's pbStopFlag (a
+ * one-byte `bool` written by the tracking thread): it is checked before starting and polled between LM
+ * iterations and trials.
  * Outputs: updated cam_q/cam_t (free cameras) and pts as float; edge_chi2[ne] (may be NULL);
  * edge_bad[ne] = chi2 > 5.991 || depth <= 0, i.e. the observations the caller must erase
  * (:1313-1329); stats[4] (may be NULL) = {LM iterations, LM trials, initial robust chi2, final robust
  * chi2}.  *iters_done = -1 when the call was a no-op (no fixed camera, abort already set). */
 DVM_API int dvm_local_ba(dvm_lba* h, int nc, float* cam_q, float* cam_t, const uint8_t* cam_fixed, int np, float* pts,
                          int ne, const int32_t* edge_cam, const int32_t* edge_pt, const float* edge_obs,
-                         const float* edge_inv_sigma2, const float* K, int iterations, const volatile int* abort_flag,
+                         const float* edge_inv_sigma2, const float* K, int iterations, const volatile uint8_t* abort_flag,
                          double* edge_chi2, uint8_t* edge_bad, double* stats, int* iters_done);
 /* Device time of the last dvm_local_ba kernel in milliseconds (CUDA events on the solver's stream). */
 DVM_API float dvm_lba_last_kernel_ms(const dvm_lba* h);

@@ -1,0 +1,294 @@
+// adapter_harness.cpp -- TEST INFRASTRUCTURE.  Builds mock Frame / KeyFrame / MapPoint graphs from flat
+// arrays, drives the C++ adapters of dvmslam_b200/host/ exactly as the reference's call sites would, and
+// hands the results back flat, so that tests/test_host_adapters.py can compare them with the direct C-ABI
+// calls and the oracle.
+#include <cstring>
+#include <memory>
+#include <string>
+
+#include "mock_slam.h"
+#include "optimizer_adapter.h"
+#include "orb_matcher_adapter.h"
+
+namespace mock {
+std::mutex MapPoint::mGlobalMutex;
+float Frame::fx, Frame::fy, Frame::cx, Frame::cy, Frame::mnMinX, Frame::mnMinY, Frame::mnMaxX, Frame::mnMaxY;
+float g_K[4];
+}
+using namespace mock;
+
+namespace {
+std::string g_err;
+long unsigned int g_next_frame_id = 1;
+
+void fill_frame(Frame& F, const dvm_keypoint* kps, const uint8_t* desc, int n, const float* scale, const float* invsig2, int nlevels)
+{
+    F.mnId = g_next_frame_id++;
+    F.N = n;
+    F.mvKeysUn.resize(n);
+    if (n) std::memcpy((void*)F.mvKeysUn.data(), kps, sizeof(dvm_keypoint) * n);
+    F.mvKeys = F.mvKeysUn;
+    F.mvuRight.assign(n, -1.f);
+    F.mDescriptors.create(n > 0 ? n : 1, 32, CV_8U);
+    for (int i = 0; i < n; i++) std::memcpy(F.mDescriptors.ptr(i), desc + (size_t)i * 32, 32);
+    F.mvpMapPoints.assign(n, nullptr);
+    F.mvbOutlier.assign(n, false);
+    F.mvScaleFactors.assign(scale, scale + nlevels);
+    F.mvInvLevelSigma2.assign(invsig2, invsig2 + nlevels);
+}
+
+void set_pose(SE3f& T, const float* q, const float* t)
+{
+    for (int k = 0; k < 4; k++) T.q.q[k] = q[k];
+    for (int k = 0; k < 3; k++) T.t.v[k] = t[k];
+}
+
+FeatureVector to_fv(int nn, const uint32_t* node, const int32_t* start, const uint32_t* idx)
+{
+    FeatureVector fv;
+    for (int i = 0; i < nn; i++) fv[node[i]] = std::vector<unsigned>(idx + start[i], idx + start[i + 1]);
+    return fv;
+}
+
+template <class Fn>
+int guarded(Fn fn)
+{
+    try { return fn(); }
+    catch (const dvm_host::Error& e) { g_err = e.what(); return -1000 + e.code; }
+}
+} // namespace
+
+extern "C" {
+
+const char* hm_last_error() { return g_err.c_str(); }
+
+void hm_set_camera(const float* K, const float* bounds)
+{
+    Frame::fx = K[0]; Frame::fy = K[1]; Frame::cx = K[2]; Frame::cy = K[3];
+    for (int k = 0; k < 4; k++) g_K[k] = K[k];
+    Frame::mnMinX = bounds[0]; Frame::mnMinY = bounds[1]; Frame::mnMaxX = bounds[2]; Frame::mnMaxY = bounds[3];
+}
+
+// TrackWithMotionModel's matcher call: Cur (pose prior set), Last (map points per keypoint)
+int hm_search_by_projection_last(const dvm_keypoint* ckps, const uint8_t* cdesc, int nc, const float* scale, const float* invsig2,
+                                 int nlevels, const float* q, const float* t, const dvm_keypoint* lkps, int nl,
+                                 const uint8_t* has_mp, const uint8_t* outlier, const float* Xw, const uint8_t* mp_desc,
+                                 const uint8_t* obs_pos, float th, int checkOri, int* cur_mp)
+{
+    Frame Cur, Last;
+    fill_frame(Cur, ckps, cdesc, nc, scale, invsig2, nlevels);
+    std::vector<uint8_t> zero((size_t)(nl > 0 ? nl : 1) * 32);
+    fill_frame(Last, lkps, zero.data(), nl, scale, invsig2, nlevels);
+    set_pose(Cur.mTcw, q, t);
+    std::vector<std::unique_ptr<MapPoint>> mps(nl);
+    for (int i = 0; i < nl; i++) {
+        Last.mvbOutlier[i] = outlier[i] != 0;
+        if (!has_mp[i]) continue;
+        mps[i].reset(new MapPoint);
+        for (int k = 0; k < 3; k++) mps[i]->pos(k) = Xw[3 * i + k];
+        std::memcpy(mps[i]->desc.ptr(0), mp_desc + (size_t)i * 32, 32);
+        mps[i]->nObs = obs_pos[i] ? 1 : 0;
+        Last.mvpMapPoints[i] = mps[i].get();
+    }
+    return guarded([&] {
+        const int n = dvm_host::SearchByProjectionLast(Cur, Last, th, checkOri != 0);
+        for (int i = 0; i < nc; i++) {
+            cur_mp[i] = -1;
+            if (Cur.mvpMapPoints[i])
+                for (int j = 0; j < nl; j++) if (mps[j].get() == Cur.mvpMapPoints[i]) cur_mp[i] = j;
+        }
+        return n;
+    });
+}
+
+// SearchLocalPoints' matcher call: vpMapPoints with the fields isInFrustum stored; in_view[m] = mbTrackInView
+int hm_search_by_projection_map(const dvm_keypoint* ckps, const uint8_t* cdesc, int nc, const float* scale, const float* invsig2,
+                                int nlevels, int m, const uint8_t* in_view, const float* px, const float* py, const int* level,
+                                const float* vcos, const uint8_t* mp_desc, const uint8_t* obs_pos, const uint8_t* cur_blocked,
+                                float th, float nnratio, int* cur_mp)
+{
+    Frame F;
+    fill_frame(F, ckps, cdesc, nc, scale, invsig2, nlevels);
+    std::vector<std::unique_ptr<MapPoint>> mps(m);
+    std::vector<MapPoint*> vp(m);
+    for (int i = 0; i < m; i++) {
+        mps[i].reset(new MapPoint);
+        MapPoint& p = *mps[i];
+        p.mbTrackInView = in_view[i] != 0; p.mTrackProjX = px[i]; p.mTrackProjY = py[i]; p.mnTrackScaleLevel = level[i];
+        p.mTrackViewCos = vcos[i];
+        std::memcpy(p.desc.ptr(0), mp_desc + (size_t)i * 32, 32);
+        p.nObs = obs_pos[i] ? 1 : 0;
+        vp[i] = &p;
+    }
+    MapPoint held;   // keypoints that already hold a map point with observations
+    held.nObs = 1;
+    for (int i = 0; i < nc; i++) if (cur_blocked && cur_blocked[i]) F.mvpMapPoints[i] = &held;
+    return guarded([&] {
+        const int n = dvm_host::SearchByProjectionMap(F, vp, th, nnratio);
+        for (int i = 0; i < nc; i++) {
+            cur_mp[i] = -1;
+            if (F.mvpMapPoints[i] && F.mvpMapPoints[i] != &held)
+                for (int j = 0; j < m; j++) if (vp[j] == F.mvpMapPoints[i]) cur_mp[i] = j;
+        }
+        return n;
+    });
+}
+
+// Optimizer::PoseOptimization(Frame*): one map point per listed keypoint
+int hm_pose_optimization(const dvm_keypoint* kps, int n, const float* scale, const float* invsig2, int nlevels, float* q, float* t,
+                         const int* mp_of_kp /* [n]: index into Xw or -1 */, const float* Xw, uint8_t* outlier)
+{
+    Frame F;
+    std::vector<uint8_t> desc((size_t)(n > 0 ? n : 1) * 32);
+    fill_frame(F, kps, desc.data(), n, scale, invsig2, nlevels);
+    set_pose(F.mTcw, q, t);
+    std::vector<std::unique_ptr<MapPoint>> mps(n);
+    for (int i = 0; i < n; i++) {
+        if (mp_of_kp[i] < 0) continue;
+        mps[i].reset(new MapPoint);
+        for (int k = 0; k < 3; k++) mps[i]->pos(k) = Xw[3 * mp_of_kp[i] + k];
+        F.mvpMapPoints[i] = mps[i].get();
+    }
+    return guarded([&] {
+        const int inl = dvm_host::PoseOptimization<Frame, MapPoint>(&F);
+        for (int k = 0; k < 4; k++) q[k] = F.mTcw.q.q[k];
+        for (int k = 0; k < 3; k++) t[k] = F.mTcw.t.v[k];
+        for (int i = 0; i < n; i++) outlier[i] = F.mvbOutlier[i];
+        return inl;
+    });
+}
+
+// both SearchByBoW overloads; out[i]: for kf_kf == 0 per feature of side 2 the side-1 feature whose map point it
+// received, for kf_kf != 0 per feature of side 1 the side-2 feature whose map point it received (-1 none)
+int hm_search_by_bow(int kf_kf, int n1, const uint8_t* d1, const float* a1, const uint8_t* v1, int nn1, const uint32_t* node1,
+                     const int32_t* st1, const uint32_t* idx1, int n2, const uint8_t* d2, const float* a2, const uint8_t* v2,
+                     int nn2, const uint32_t* node2, const int32_t* st2, const uint32_t* idx2, float nnratio, int checkOri, int* out)
+{
+    const float one[1] = { 1.f };
+    auto make_kps = [](int n, const float* ang) {
+        std::vector<dvm_keypoint> k(n);
+        for (int i = 0; i < n; i++) { k[i] = dvm_keypoint{ float(i % 640), float(i / 640), 31.f, ang[i], 1.f, 0, -1 }; }
+        return k;
+    };
+    KeyFrame K1, K2;
+    Frame F;
+    std::vector<std::unique_ptr<MapPoint>> m1(n1), m2(n2);
+    auto fill_kf = [&](KeyFrame& K, int n, const uint8_t* d, const float* ang, const uint8_t* v, std::vector<std::unique_ptr<MapPoint>>& mp,
+                       const FeatureVector& fv) {
+        const std::vector<dvm_keypoint> k = make_kps(n, ang);
+        K.N = n;
+        K.mvKeysUn.resize(n);
+        if (n) std::memcpy((void*)K.mvKeysUn.data(), k.data(), sizeof(dvm_keypoint) * n);
+        K.mDescriptors.create(n > 0 ? n : 1, 32, CV_8U);
+        for (int i = 0; i < n; i++) std::memcpy(K.mDescriptors.ptr(i), d + (size_t)i * 32, 32);
+        K.mapPoints.assign(n, nullptr);
+        for (int i = 0; i < n; i++)
+            if (!v || v[i]) { mp[i].reset(new MapPoint); K.mapPoints[i] = mp[i].get(); }
+        K.mFeatVec = fv;
+    };
+    fill_kf(K1, n1, d1, a1, v1, m1, to_fv(nn1, node1, st1, idx1));
+    // a context frame for the GPU call (SearchByBoW itself has no grid to consult)
+    const std::vector<dvm_keypoint> k2 = make_kps(n2, a2);
+    fill_frame(F, k2.data(), d2, n2, one, one, 1);
+    F.mFeatVec = to_fv(nn2, node2, st2, idx2);
+    if (kf_kf) fill_kf(K2, n2, d2, a2, v2, m2, F.mFeatVec);
+    return guarded([&] {
+        std::vector<MapPoint*> res;
+        int n;
+        if (!kf_kf) {
+            n = dvm_host::SearchByBoW(&K1, F, res, nnratio, checkOri != 0);
+            for (int i = 0; i < n2; i++) {
+                out[i] = -1;
+                if (res[i]) for (int j = 0; j < n1; j++) if (m1[j].get() == res[i]) out[i] = j;
+            }
+        } else {
+            n = dvm_host::SearchByBoW(&K1, &K2, res, nnratio, checkOri != 0, dvm_host::device_frame(F).frame.h);
+            for (int i = 0; i < n1; i++) {
+                out[i] = -1;
+                if (res[i]) for (int j = 0; j < n2; j++) if (m2[j].get() == res[i]) out[i] = j;
+            }
+        }
+        return n;
+    });
+}
+
+int hm_search_for_initialization(const dvm_keypoint* k1, const uint8_t* d1, int n1, const dvm_keypoint* k2, const uint8_t* d2, int n2,
+                                 const float* scale, const float* invsig2, int nlevels, float* prev, int window, float nnratio,
+                                 int checkOri, int* matches12)
+{
+    Frame F1, F2;
+    fill_frame(F1, k1, d1, n1, scale, invsig2, nlevels);
+    fill_frame(F2, k2, d2, n2, scale, invsig2, nlevels);
+    std::vector<cv::Point2f> vbPrev(n1);
+    for (int i = 0; i < n1; i++) vbPrev[i] = cv::Point2f(prev[2 * i], prev[2 * i + 1]);
+    return guarded([&] {
+        std::vector<int> m12;
+        const int n = dvm_host::SearchForInitialization(F1, F2, vbPrev, m12, window, nnratio, checkOri != 0);
+        for (int i = 0; i < n1; i++) { matches12[i] = m12[i]; prev[2 * i] = vbPrev[i].x; prev[2 * i + 1] = vbPrev[i].y; }
+        return n;
+    });
+}
+
+// Optimizer::LocalBundleAdjustment on a flat scene: free cameras become pKF (camera 0) and its covisible keyframes,
+// fixed cameras exist only as observers of the local map points.  counts[4] = num_fixedKF, num_OptKF, num_MPs,
+// num_edges; erased[ne] = the observation was culled.
+int hm_local_ba(int nc, float* cam_q, float* cam_t, const uint8_t* cam_fixed, int np, float* pts, int ne, const int* edge_cam,
+                const int* edge_pt, const float* edge_obs, const int* edge_octave, const float* invsig2, int nlevels,
+                int stop_flag_mode /* 0 none, 1 present and clear, 2 already set */, int* counts, uint8_t* erased)
+{
+    Map map;
+    std::vector<std::unique_ptr<KeyFrame>> kfs(nc);
+    std::vector<std::unique_ptr<MapPoint>> mps(np);
+    std::vector<int> next_kp(nc, 0);
+    for (int c = 0; c < nc; c++) {
+        kfs[c].reset(new KeyFrame);
+        kfs[c]->mnId = 100 + c;
+        kfs[c]->map = &map;
+        kfs[c]->fx = g_K[0]; kfs[c]->fy = g_K[1]; kfs[c]->cx = g_K[2]; kfs[c]->cy = g_K[3];
+        set_pose(kfs[c]->Tcw, cam_q + 4 * c, cam_t + 3 * c);
+        kfs[c]->mvInvLevelSigma2.assign(invsig2, invsig2 + nlevels);
+    }
+    map.initKFid = 1;   // not in the window: the fixed set is exactly the non-covisible observers
+    for (int j = 0; j < np; j++) {
+        mps[j].reset(new MapPoint);
+        mps[j]->mnId = j;
+        mps[j]->map = &map;
+        for (int k = 0; k < 3; k++) mps[j]->pos(k) = pts[3 * j + k];
+    }
+    std::vector<int> edge_kp(ne);
+    for (int e = 0; e < ne; e++) {
+        KeyFrame& K = *kfs[edge_cam[e]];
+        const int kp = next_kp[edge_cam[e]]++;
+        edge_kp[e] = kp;
+        cv::KeyPoint k(edge_obs[2 * e], edge_obs[2 * e + 1], 31.f, 0.f, 1.f, edge_octave[e]);
+        K.mvKeysUn.push_back(k);
+        K.mvuRight.push_back(-1.f);
+        K.mapPoints.push_back(mps[edge_pt[e]].get());
+        K.N++;
+        mps[edge_pt[e]]->observations[&K] = std::make_tuple(kp, -1);
+    }
+    int first_free = -1;
+    for (int c = 0; c < nc; c++)
+        if (!cam_fixed[c]) {
+            if (first_free < 0) first_free = c;
+            else kfs[first_free]->covisible.push_back(kfs[c].get());
+        }
+    if (first_free < 0) return -1;
+    dvm_host::LbaHandle solver;
+    bool stop = stop_flag_mode == 2;
+    return guarded([&] {
+        dvm_host::check(dvm_lba_create(&solver.h, dvm_host::device_from_env(), 64), "dvm_lba_create");
+        counts[0] = counts[1] = counts[2] = counts[3] = -7;
+        dvm_host::LocalBundleAdjustment<KeyFrame, MapPoint, Map>(solver.h, kfs[first_free].get(), stop_flag_mode ? &stop : nullptr, &map,
+                                                                 counts[0], counts[1], counts[2], counts[3]);
+        for (int c = 0; c < nc; c++) {
+            for (int k = 0; k < 4; k++) cam_q[4 * c + k] = kfs[c]->Tcw.q.q[k];
+            for (int k = 0; k < 3; k++) cam_t[3 * c + k] = kfs[c]->Tcw.t.v[k];
+        }
+        for (int j = 0; j < np; j++) for (int k = 0; k < 3; k++) pts[3 * j + k] = mps[j]->pos(k);
+        for (int e = 0; e < ne; e++) erased[e] = kfs[edge_cam[e]]->mapPoints[edge_kp[e]] == nullptr;
+        return map.changeIndex;
+    });
+}
+
+} // extern "C"

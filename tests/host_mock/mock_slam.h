@@ -1,0 +1,131 @@
+// mock_slam.h -- TEST INFRASTRUCTURE.  Stand-ins for the reference's Frame / KeyFrame / MapPoint / Map /
+// Sophus::SE3f types with exactly the members dvmslam_b200/host/*.h read or write (names and meaning as in
+// O3/include/{Frame,KeyFrame,MapPoint,Map}.h), so the adapters can be compiled and driven without Eigen,
+// Sophus, DBoW2 and the rest of ORB-SLAM3.
+#pragma once
+#include <map>
+#include <mutex>
+#include <opencv2/opencv.hpp>
+#include <set>
+#include <tuple>
+#include <vector>
+
+namespace mock {
+
+struct Vec3 {
+    float v[3] = { 0, 0, 0 };
+    float& operator()(int i) { return v[i]; }
+    float operator()(int i) const { return v[i]; }
+};
+struct Mat3 {
+    float m[9] = { 1, 0, 0, 0, 1, 0, 0, 0, 1 };
+    float operator()(int r, int c) const { return m[3 * r + c]; }
+};
+struct Quat {
+    float q[4] = { 0, 0, 0, 1 };
+    float& x() { return q[0]; } float& y() { return q[1]; } float& z() { return q[2]; } float& w() { return q[3]; }
+    float x() const { return q[0]; } float y() const { return q[1]; } float z() const { return q[2]; } float w() const { return q[3]; }
+};
+// Sophus::SE3<float>: unit_quaternion(), translation(), rotationMatrix(), SE3(quaternion, translation)
+struct SE3f {
+    Quat q; Vec3 t;
+    SE3f() { }
+    SE3f(const Quat& q_, const Vec3& t_) : q(q_), t(t_) { }
+    Quat unit_quaternion() const { return q; }
+    Vec3 translation() const { return t; }
+    Mat3 rotationMatrix() const
+    {   // Eigen's Quaternion::toRotationMatrix
+        const float x = q.q[0], y = q.q[1], z = q.q[2], w = q.q[3];
+        const float tx = 2 * x, ty = 2 * y, tz = 2 * z, twx = tx * w, twy = ty * w, twz = tz * w, txx = tx * x, txy = ty * x,
+                    txz = tz * x, tyy = ty * y, tyz = tz * y, tzz = tz * z;
+        Mat3 R;
+        R.m[0] = 1 - (tyy + tzz); R.m[1] = txy - twz; R.m[2] = txz + twy;
+        R.m[3] = txy + twz; R.m[4] = 1 - (txx + tzz); R.m[5] = tyz - twx;
+        R.m[6] = txz - twy; R.m[7] = tyz + twx; R.m[8] = 1 - (txx + tyy);
+        return R;
+    }
+};
+
+struct Map;
+struct KeyFrame;
+
+struct MapPoint {
+    static std::mutex mGlobalMutex;
+    unsigned long mnId = 0;
+    Vec3 pos;
+    cv::Mat desc = cv::Mat(1, 32, CV_8U);
+    int nObs = 1;
+    bool bad = false;
+    Map* map = nullptr;
+    // tracking fields written by Frame::isInFrustum
+    bool mbTrackInView = false, mbTrackInViewR = false;
+    float mTrackProjX = 0, mTrackProjY = 0, mTrackViewCos = 0, mTrackDepth = 0;
+    int mnTrackScaleLevel = 0;
+    unsigned long mnBALocalForKF = ~0ul;
+    std::map<KeyFrame*, std::tuple<int, int>> observations;
+    int normalUpdates = 0;
+
+    Vec3 GetWorldPos() const { return pos; }
+    void SetWorldPos(const Vec3& p) { pos = p; }
+    cv::Mat GetDescriptor() const { return desc; }
+    int Observations() const { return nObs; }
+    bool isBad() const { return bad; }
+    Map* GetMap() const { return map; }
+    std::map<KeyFrame*, std::tuple<int, int>> GetObservations() const { return observations; }
+    void EraseObservation(KeyFrame* kf) { observations.erase(kf); }
+    void UpdateNormalAndDepth() { normalUpdates++; }
+};
+
+typedef std::map<unsigned int, std::vector<unsigned int>> FeatureVector;   // DBoW2::FeatureVector
+
+struct Frame {
+    static float fx, fy, cx, cy, mnMinX, mnMinY, mnMaxX, mnMaxY;
+    long unsigned int mnId = 0;
+    int N = 0, Nleft = -1;
+    std::vector<cv::KeyPoint> mvKeys, mvKeysUn;
+    std::vector<float> mvuRight;
+    cv::Mat mDescriptors;
+    std::vector<MapPoint*> mvpMapPoints;
+    std::vector<bool> mvbOutlier;
+    std::vector<float> mvScaleFactors, mvInvLevelSigma2;
+    FeatureVector mFeatVec;
+    SE3f mTcw;
+    SE3f GetPose() const { return mTcw; }
+    void SetPose(const SE3f& T) { mTcw = T; }
+};
+
+struct KeyFrame {
+    float fx = 0, fy = 0, cx = 0, cy = 0;   // per-object constants in the reference (O3/include/KeyFrame.h)
+    long unsigned int mnId = 0;
+    unsigned long mnBALocalForKF = ~0ul, mnBAFixedForKF = ~0ul;
+    int N = 0, NLeft = -1;
+    std::vector<cv::KeyPoint> mvKeysUn;
+    std::vector<float> mvuRight, mvInvLevelSigma2;
+    cv::Mat mDescriptors;
+    std::vector<MapPoint*> mapPoints;
+    std::vector<KeyFrame*> covisible;
+    FeatureVector mFeatVec;
+    SE3f Tcw;
+    bool bad = false;
+    Map* map = nullptr;
+    std::vector<MapPoint*> GetMapPointMatches() const { return mapPoints; }
+    std::vector<KeyFrame*> GetVectorCovisibleKeyFrames() const { return covisible; }
+    SE3f GetPose() const { return Tcw; }
+    void SetPose(const SE3f& T) { Tcw = T; }
+    bool isBad() const { return bad; }
+    Map* GetMap() const { return map; }
+    void EraseMapPointMatch(MapPoint* mp)
+    {
+        for (auto& p : mapPoints) if (p == mp) p = nullptr;
+    }
+};
+
+struct Map {
+    std::mutex mMutexMapUpdate;
+    unsigned long initKFid = 0;
+    int changeIndex = 0;
+    unsigned long GetInitKFid() const { return initKFid; }
+    void IncreaseChangeIndex() { changeIndex++; }
+};
+
+} // namespace mock
