@@ -305,16 +305,21 @@ def run_ours(args):
             k = (1 + s * FRAMES_PER_STEP + i) % RESIDENT_FRAMES
             trk.track((base + k * frame_bytes, W, H, W), sync=False)
 
-    pending = [False]  # the next frame's upload + extraction is already enqueued (dvm_tracker_prefetch)
+    pending = [0]  # frames whose upload + extraction is already enqueued (dvm_tracker_prefetch; at most two)
 
     def step_host(s):
-        # a camera-driven loop: frame k+1 is handed to the extraction stream while frame k's chain runs;
-        # every frame's pose and counts are read back to the host before the next frame is tracked
+        # a camera-driven loop: frames k+1 and k+2 are handed to the two extraction streams while frame k's chain
+        # runs; every frame's pose and counts are read back to the host before the next frame is tracked
         for i in range(FRAMES_PER_STEP):
             k = (1 + s * FRAMES_PER_STEP + i) % RESIDENT_FRAMES
-            trk.track(None if pending[0] else host_np[k], sync=False)
-            trk.prefetch(host_np[(k + 1) % RESIDENT_FRAMES])
-            pending[0] = True
+            if pending[0] == 0:
+                trk.track(host_np[k], sync=False)
+            else:
+                trk.track(None, sync=False)
+                pending[0] -= 1
+            while pending[0] < 2:
+                trk.prefetch(host_np[(k + 1 + pending[0]) % RESIDENT_FRAMES])
+                pending[0] += 1
             _, _, c = trk.result()
             inliers.append(c[3])
 
@@ -343,7 +348,7 @@ def run_ours(args):
 
     # ---- end to end through the C-ABI host call (`e2e`) ----
     bootstrap()
-    pending[0] = False
+    pending[0] = 0
     for s in range(min(args.warmup, 1)):
         step_host(s)
     inliers.clear()

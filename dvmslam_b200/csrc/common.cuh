@@ -41,6 +41,25 @@ extern std::atomic<uint64_t> g_launches;
         ::dvm::g_launches.fetch_add(1, std::memory_order_relaxed);                           \
     } while (0)
 
+// Programmatic dependent launch for chains of small dependent kernels on one stream: the kernel is scheduled
+// while its predecessor still runs (the predecessor calls pdl_trigger() at its top) and blocks in pdl_wait() until
+// the predecessor has completed and its memory is visible, which takes the launch latency off the dependency
+// chain.  Both device calls are no-ops in a launch without the attribute.
+#define DVM_LAUNCH_PDL(kernel, grid_, block_, smem_, stream_, ...)                              \
+    do {                                                                                     \
+        cudaLaunchConfig_t cfg__ = {};                                                       \
+        cfg__.gridDim = dim3(grid_); cfg__.blockDim = dim3(block_);                        \
+        cfg__.dynamicSmemBytes = (smem_); cfg__.stream = (stream_);                        \
+        cudaLaunchAttribute at__[1];                                                         \
+        at__[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                     \
+        at__[0].val.programmaticStreamSerializationAllowed = 1;                              \
+        cfg__.attrs = at__; cfg__.numAttrs = 1;                                              \
+        cudaLaunchKernelEx(&cfg__, kernel, __VA_ARGS__);                                     \
+        ::dvm::g_launches.fetch_add(1, std::memory_order_relaxed);                           \
+    } while (0)
+__device__ inline void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ inline void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 int select_device(int device); // validates sm_100, returns dvm_status
 
 constexpr int kNumSMs = 148; // B200

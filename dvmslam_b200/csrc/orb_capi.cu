@@ -262,6 +262,13 @@ int dvm_orb_create(dvm_orb** out, int device, int nfeatures, float scale_factor,
     return DVM_OK;
 }
 
+int dvm_orb_clone(const dvm_orb* src, dvm_orb** out)
+{
+    DVM_REQUIRE(src != nullptr && out != nullptr, "null argument");
+    return dvm_orb_create(out, src->device, src->nfeatures, (float)src->scaleFactor, src->nlevels, src->iniTh, src->minTh,
+                          src->max_w, src->max_h);
+}
+
 void dvm_orb_destroy(dvm_orb* h) { free_all(h); }
 
 int dvm_orb_tables(const dvm_orb* h, int* nlevels, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2,

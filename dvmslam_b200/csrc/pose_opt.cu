@@ -263,6 +263,7 @@ __device__ inline void cluster_sum(double (&v)[kPoseNV], PoseShared& sh, unsigne
 template <int EPT>
 __global__ void __cluster_dims__(kPoseCtas, 1, 1) __launch_bounds__(kPoseThreads, 1) pose_opt_kernel(PoseOptArgs a)
 {
+    pdl_trigger(); pdl_wait();
     __shared__ PoseShared sh;
     const int tid = blockIdx.x * kPoseThreads + threadIdx.x;
     unsigned parity = 0; // pass counter of cluster_sum
@@ -551,10 +552,10 @@ int launch_pose_opt(const PoseOptArgs& a_in, cudaStream_t stream)
         }
     } report{ stream, profile, d_prof };
     // a.n bounds the number of potential edges (the device count may be smaller): pick the register tile
-    if (a.n <= 2 * kPoseStride) DVM_LAUNCH(pose_opt_kernel<2>, kPoseCtas, kPoseThreads, 0, stream, a);
-    else if (a.n <= 4 * kPoseStride) DVM_LAUNCH(pose_opt_kernel<4>, kPoseCtas, kPoseThreads, 0, stream, a);
-    else if (a.n <= 8 * kPoseStride) DVM_LAUNCH(pose_opt_kernel<8>, kPoseCtas, kPoseThreads, 0, stream, a);
-    else if (a.n <= 16 * kPoseStride) DVM_LAUNCH(pose_opt_kernel<16>, kPoseCtas, kPoseThreads, 0, stream, a);
+    if (a.n <= 2 * kPoseStride) DVM_LAUNCH_PDL(pose_opt_kernel<2>, kPoseCtas, kPoseThreads, 0, stream, a);
+    else if (a.n <= 4 * kPoseStride) DVM_LAUNCH_PDL(pose_opt_kernel<4>, kPoseCtas, kPoseThreads, 0, stream, a);
+    else if (a.n <= 8 * kPoseStride) DVM_LAUNCH_PDL(pose_opt_kernel<8>, kPoseCtas, kPoseThreads, 0, stream, a);
+    else if (a.n <= 16 * kPoseStride) DVM_LAUNCH_PDL(pose_opt_kernel<16>, kPoseCtas, kPoseThreads, 0, stream, a);
     else {
         set_error("PoseOptimization: %d correspondences exceed the supported %d", a.n, 16 * kPoseStride);
         return DVM_ERR_CAPACITY;

@@ -144,6 +144,66 @@ __device__ inline void topk_insert(unsigned long long (&top)[kMatchCacheK], unsi
         if (v < top[p]) { const unsigned long long t = top[p]; top[p] = v; v = t; }
 }
 
+
+// ---- one WARP per query: the lanes share the window's candidates, every lane keeps its own sorted
+// top-K, and the K best of the warp are merged by K rounds of a 64-bit warp minimum.  The order key of a
+// candidate is its position in the window's traversal (cells in the reference's order, unfiltered), which
+// is monotone in the reference's visiting order, so (distance, key) ranks candidates exactly as the
+// sequential scan does. ----
+template <class Fn>
+__device__ inline void walk_area_warp(const FrameLook& f, float x, float y, float r, int minLevel, int maxLevel, int lane, Fn fn)
+{
+    const float dxm = __fsub_rn(x, f.minX), dym = __fsub_rn(y, f.minY);
+    const int nMinCellX = max(0, (int)floorf(__fmul_rn(__fsub_rn(dxm, r), f.gwInv)));
+    if (nMinCellX >= kGridCols) return;
+    const int nMaxCellX = min(kGridCols - 1, (int)ceilf(__fmul_rn(__fadd_rn(dxm, r), f.gwInv)));
+    if (nMaxCellX < 0) return;
+    const int nMinCellY = max(0, (int)floorf(__fmul_rn(__fsub_rn(dym, r), f.ghInv)));
+    if (nMinCellY >= kGridRows) return;
+    const int nMaxCellY = min(kGridRows - 1, (int)ceilf(__fmul_rn(__fadd_rn(dym, r), f.ghInv)));
+    if (nMaxCellY < 0) return;
+    const bool bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
+    int base = 0;
+    for (int ix = nMinCellX; ix <= nMaxCellX; ix++) {
+        const int j0 = f.cell_start[ix * kGridRows + nMinCellY], j1 = f.cell_start[ix * kGridRows + nMaxCellY + 1];
+        for (int j = j0 + lane; j < j1; j += 32) {
+            const int idx = f.cell_items[j];
+            const int oct = f.oct(idx);
+            if (bCheckLevels) {
+                if (oct < minLevel) continue;
+                if (maxLevel >= 0 && oct > maxLevel) continue;
+            }
+            const float distx = __fsub_rn(f.x(idx), x), disty = __fsub_rn(f.y(idx), y);
+            if (fabsf(distx) < r && fabsf(disty) < r) fn(idx, oct, base + (j - j0));
+        }
+        base += j1 - j0;
+    }
+}
+
+__device__ inline unsigned long long warp_min_u64(unsigned long long v)
+{
+    const unsigned hi = __reduce_min_sync(0xffffffffu, (unsigned)(v >> 32));
+    const unsigned lo = __reduce_min_sync(0xffffffffu, (unsigned)(v >> 32) == hi ? (unsigned)v : 0xffffffffu);
+    return ((unsigned long long)hi << 32) | lo;
+}
+
+// merges the lanes' sorted top-K lists; lane p < K returns the p-th best of the warp (~0 when absent)
+__device__ inline unsigned long long warp_topk_merge(unsigned long long (&top)[kMatchCacheK], int lane)
+{
+    unsigned long long mine = ~0ull;
+#pragma unroll
+    for (int p = 0; p < kMatchCacheK; p++) {
+        const unsigned long long m = warp_min_u64(top[0]);
+        if (lane == p) mine = m;
+        if (top[0] == m && m != ~0ull) { // keys are unique: exactly one lane pops
+#pragma unroll
+            for (int q = 0; q + 1 < kMatchCacheK; q++) top[q] = top[q + 1];
+            top[kMatchCacheK - 1] = ~0ull;
+        }
+    }
+    return mine;
+}
+
 constexpr int kWalkThreads = 128;
 
 // ordered list of the queries that take part (plevels != -1) in shared memory; returns their number
@@ -161,18 +221,17 @@ __device__ inline int compact_active(const int* __restrict__ plevels, int nq, in
     return total;
 }
 
-// ---- SearchByProjection(cur, last), phase 1: one thread per last-frame keypoint projects its map point
+// ---- SearchByProjection(cur, last), phase 1: one WARP per last-frame keypoint projects its map point
 // with the pose prior and walks its window once (many CTAs; the frame is read through L1/L2) ----
-__global__ void __launch_bounds__(kWalkThreads) match_last_walk_kernel(FrameDev cur, MatchLastArgs a, MatchScratch s, int use_smem)
+__global__ void __launch_bounds__(kWalkThreads) match_last_walk_kernel(FrameDev cur, MatchLastArgs a, MatchScratch s)
 {
-    extern __shared__ __align__(128) unsigned char frame_smem[];
-    __shared__ __align__(8) unsigned long long s_bar;
+    pdl_trigger(); pdl_wait();
     if (a.guard && *a.guard >= 20) return; // enough matches at th: the wider retry is not run
     const int nq = a.n_ptr ? *a.n_ptr : a.last_n;
-    if ((int)(blockIdx.x * kWalkThreads) >= nq) return;
-    const FrameLook fl = use_smem ? look_shared_tma(cur, min(*cur.n, cur.cap), frame_smem, &s_bar) : look_global(cur);
-    const int i = blockIdx.x * kWalkThreads + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int i = (blockIdx.x * kWalkThreads + threadIdx.x) >> 5;
     if (i >= nq) return;
+    const FrameLook fl = look_global(cur);
     if (a.pose) { // pose prior held on the device
         float Rm[9];
         quat_to_R_f32(a.pose, Rm);
@@ -196,23 +255,25 @@ __global__ void __launch_bounds__(kWalkThreads) match_last_walk_kernel(FrameDev 
             if (!(u < cur.minX || u > cur.maxX) && !(v < cur.minY || v > cur.maxY)) {
                 const int oct = a.last_kps ? a.last_kps[i].octave : a.octave[i];
                 const float r = __fmul_rn(a.th, cur.scale[oct]);
-                s.pu[i] = u; s.pv[i] = v; s.pr[i] = r;
+                if (lane == 0) { s.pu[i] = u; s.pv[i] = v; s.pr[i] = r; }
                 lv = ((oct - 1) << 16) | ((oct + 1) & 0xffff);
                 uint32_t d[8];
                 load_desc(d, a.mp_desc + (size_t)mi * 32);
-                walk_area(fl, u, v, r, oct - 1, oct + 1, [&](int idx, int o) {
+                walk_area_warp(fl, u, v, r, oct - 1, oct + 1, lane, [&](int idx, int o, int ord) {
                     const int dist = hamming256(d, fl.desc + (size_t)idx * 32);
-                    topk_insert(top, pack_cand(dist, nc, o, idx));
+                    topk_insert(top, pack_cand(dist, ord, o, idx));
                     nc++;
                 });
             }
         }
     }
-    s.plevels[i] = lv;
+    // the branch conditions above depend on the query only: the whole warp is here together
+    if (lane == 0) s.plevels[i] = lv;
     if (lv != -1) {
-#pragma unroll
-        for (int p = 0; p < kMatchCacheK; p++) s.cache[(size_t)i * kMatchCacheK + p] = top[p];
-        s.ncand[i] = nc;
+        nc = __reduce_add_sync(0xffffffffu, nc);
+        const unsigned long long e = warp_topk_merge(top, lane);
+        if (lane < kMatchCacheK) s.cache[(size_t)i * kMatchCacheK + lane] = e;
+        if (lane == 0) s.ncand[i] = nc;
     }
 }
 
@@ -222,6 +283,7 @@ __global__ void __launch_bounds__(kMatchThreads, 1)
 match_last_kernel(FrameDev cur, MatchLastArgs a, MatchScratch s, int* __restrict__ cur_mp, int* __restrict__ nmatches,
                   int use_smem)
 {
+    pdl_trigger(); pdl_wait();
     extern __shared__ __align__(16) unsigned char claim_smem[];
     __shared__ int histo[kHistoLength];
     __shared__ int s_ind[3], s_events, s_bad;
@@ -338,57 +400,59 @@ void launch_match_last(const FrameDev& cur, const MatchLastArgs& a, const MatchS
     const size_t smem = claim_smem_bytes(cur.cap);
     const int use_smem = smem <= kMatchSmemLimit ? 1 : 0;
     prepare_match_kernels();
-    const size_t fsm = frame_smem_bytes(cur.cap);
-    const int stage = fsm <= kMatchSmemLimit ? 1 : 0;
-    DVM_LAUNCH(match_last_walk_kernel, div_up(max(a.last_n, 1), kWalkThreads), kWalkThreads, stage ? fsm : 0, stream, cur, a, s, stage);
-    DVM_LAUNCH(match_last_kernel, 1, kMatchThreads, use_smem ? smem : 0, stream, cur, a, s, cur_mp, nmatches, use_smem);
+    DVM_LAUNCH_PDL(match_last_walk_kernel, div_up(max(a.last_n, 1), kWalkThreads / 32), kWalkThreads, 0, stream, cur, a, s);
+    DVM_LAUNCH_PDL(match_last_kernel, 1, kMatchThreads, use_smem ? smem : 0, stream, cur, a, s, cur_mp, nmatches, use_smem);
 }
 
 // --------------------------------------------------------------- SearchByProjection(F, mapPoints)
-// phase 1: one thread per in-view map point walks its window once
-__global__ void __launch_bounds__(kWalkThreads) match_map_walk_kernel(FrameDev cur, MatchMapArgs a, MatchScratch s, int use_smem)
+// phase 1: one warp per in-view map point walks its window once
+__global__ void __launch_bounds__(kWalkThreads) match_map_walk_kernel(FrameDev cur, MatchMapArgs a, MatchScratch s)
 {
-    extern __shared__ __align__(128) unsigned char frame_smem[];
-    __shared__ __align__(8) unsigned long long s_bar;
+    pdl_trigger(); pdl_wait();
     const int nq = a.m_ptr ? *a.m_ptr : a.m;
-    if ((int)(blockIdx.x * kWalkThreads) >= nq) return;
-    const FrameLook fl = use_smem ? look_shared_tma(cur, min(*cur.n, cur.cap), frame_smem, &s_bar) : look_global(cur);
-    const int i = blockIdx.x * kWalkThreads + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int i = (blockIdx.x * kWalkThreads + threadIdx.x) >> 5;
     if (i >= nq) return;
+    const FrameLook fl = look_global(cur);
     int lvl;
     float px, py, vcos;
     if (a.use_frustum) { // SearchLocalPoints: isInFrustum decides whether map point i takes part at all
         float R[9];
         quat_to_R_f32(a.fr.pose, R);
-        if (!frustum_eval(a.fr, R, i, px, py, lvl, vcos)) { s.plevels[i] = -1; s.ncand[i] = 0; return; }
+        if (!frustum_eval(a.fr, R, i, px, py, lvl, vcos)) {
+            if (lane == 0) { s.plevels[i] = -1; s.ncand[i] = 0; }
+            return;
+        }
     } else {
         lvl = a.level[i]; px = a.projX[i]; py = a.projY[i]; vcos = a.view_cos[i];
     }
     float r = vcos > 0.998f ? 2.5f : 4.0f; // RadiusByViewingCos
     if (a.th != 1.0f) r = __fmul_rn(r, a.th);
     r = __fmul_rn(r, cur.scale[lvl]);
-    s.pu[i] = px; s.pv[i] = py; s.pr[i] = r; s.plevels[i] = lvl;
+    if (lane == 0) { s.pu[i] = px; s.pv[i] = py; s.pr[i] = r; s.plevels[i] = lvl; }
     uint32_t d[8];
     load_desc(d, a.mp_desc + (size_t)(a.q_index ? a.q_index[i] : i) * 32);
     unsigned long long top[kMatchCacheK];
 #pragma unroll
     for (int p = 0; p < kMatchCacheK; p++) top[p] = ~0ull;
     int nc = 0;
-    walk_area(fl, px, py, r, lvl - 1, lvl, [&](int idx, int oct) {
+    walk_area_warp(fl, px, py, r, lvl - 1, lvl, lane, [&](int idx, int oct, int ord) {
         if (a.cur_map ? a.cur_map[idx] >= 0 : (a.cur_blocked && a.cur_blocked[idx])) return; // blocked from the start
         const int dist = hamming256(d, fl.desc + (size_t)idx * 32);
-        topk_insert(top, pack_cand(dist, nc, oct, idx));
+        topk_insert(top, pack_cand(dist, ord, oct, idx));
         nc++;
     });
-#pragma unroll
-    for (int p = 0; p < kMatchCacheK; p++) s.cache[(size_t)i * kMatchCacheK + p] = top[p];
-    s.ncand[i] = nc;
+    nc = __reduce_add_sync(0xffffffffu, nc);
+    const unsigned long long e = warp_topk_merge(top, lane);
+    if (lane < kMatchCacheK) s.cache[(size_t)i * kMatchCacheK + lane] = e;
+    if (lane == 0) s.ncand[i] = nc;
 }
 
 __global__ void __launch_bounds__(kMatchThreads, 1)
 match_map_kernel(FrameDev cur, MatchMapArgs a, MatchScratch s, int* __restrict__ cur_mp, int* __restrict__ nmatches,
                  int use_smem)
 {
+    pdl_trigger(); pdl_wait();
     extern __shared__ __align__(16) unsigned char claim_smem[];
     __shared__ int s_events;
     const int tid = threadIdx.x;
@@ -490,10 +554,8 @@ void launch_match_map(const FrameDev& cur, const MatchMapArgs& a, const MatchScr
     const size_t smem = claim_smem_bytes(cur.cap);
     const int use_smem = smem <= kMatchSmemLimit ? 1 : 0;
     prepare_match_kernels();
-    const size_t fsm = frame_smem_bytes(cur.cap);
-    const int stage = fsm <= kMatchSmemLimit ? 1 : 0;
-    DVM_LAUNCH(match_map_walk_kernel, div_up(max(a.m, 1), kWalkThreads), kWalkThreads, stage ? fsm : 0, stream, cur, a, s, stage);
-    DVM_LAUNCH(match_map_kernel, 1, kMatchThreads, use_smem ? smem : 0, stream, cur, a, s, cur_mp, nmatches, use_smem);
+    DVM_LAUNCH_PDL(match_map_walk_kernel, div_up(max(a.m, 1), kWalkThreads / 32), kWalkThreads, 0, stream, cur, a, s);
+    DVM_LAUNCH_PDL(match_map_kernel, 1, kMatchThreads, use_smem ? smem : 0, stream, cur, a, s, cur_mp, nmatches, use_smem);
 }
 
 
@@ -505,8 +567,6 @@ static bool prepare_match_kernels()
     if (dev < 0 || dev >= 64 || done[dev].load()) return true;
     cudaFuncSetAttribute(match_last_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMatchSmemLimit);
     cudaFuncSetAttribute(match_map_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMatchSmemLimit);
-    cudaFuncSetAttribute(match_last_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMatchSmemLimit);
-    cudaFuncSetAttribute(match_map_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMatchSmemLimit);
     done[dev].store(true);
     return true;
 }

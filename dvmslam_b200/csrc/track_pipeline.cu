@@ -16,6 +16,7 @@ namespace {
 __global__ void __launch_bounds__(1024) begin_frame_kernel(const float* last, const float* prev, float* prior, int have_prior,
                                                            uint8_t* seen, int map_n, int* cnt)
 {
+    pdl_trigger(); pdl_wait();
     for (int i = threadIdx.x; i < (map_n + 3) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(seen)[i] = 0u;
     if (threadIdx.x < 8) cnt[threadIdx.x] = 0;
     if (threadIdx.x != 0 || have_prior) return;
@@ -55,27 +56,31 @@ __global__ void __launch_bounds__(1024) begin_frame_kernel(const float* last, co
 // Two streams per agent: `es` (the extractor handle's stream) runs the Frame constructor (ExtractORB
 // straight into the frame's buffers + AssignFeaturesToGrid), `stream` runs the dependency chain of the
 // tracked frame.  Frame i+1 does not depend on frame i's pose until the chain starts, so its
-// construction overlaps frame i's chain.  Frames live in a ring of three (current, last, next being
-// built); ev_extracted[slot] / ev_done[slot] order the hand-over between the two streams.
-constexpr int kRing = 3;
+// construction overlaps frame i's chain -- and so does frame i+2's: two extractor handles (the caller's and a
+// clone) alternate on their own streams, so the extraction chain (about as long as the tracking chain) never
+// bounds the frame rate.  Frames live in a ring of four (last, current, two being built); ev_extracted[slot] /
+// ev_done[slot] order the hand-over between the streams.
+constexpr int kRing = 4;
+constexpr int kExtractors = 2;
+constexpr int kMaxPending = 2;   // frames extracted (or being extracted) ahead of the chain
 struct dvm_tracker {
     int device = 0;
     cudaStream_t stream = nullptr;  // tracking chain
-    cudaStream_t es = nullptr;      // extraction (owned by the extractor handle)
-    cudaEvent_t ev_extracted[kRing] = { nullptr, nullptr, nullptr };
-    cudaEvent_t ev_done[kRing] = { nullptr, nullptr, nullptr };
+    cudaStream_t es[kExtractors] = { nullptr, nullptr };   // extraction (owned by the extractor handles)
+    cudaEvent_t ev_extracted[kRing] = { nullptr, nullptr, nullptr, nullptr };
+    cudaEvent_t ev_done[kRing] = { nullptr, nullptr, nullptr, nullptr };
     long long n_extracted = 0;      // frames whose construction has been enqueued
     long long n_tracked = 0;        // frames whose chain has been enqueued (frame 0 = bootstrap)
-    dvm_orb* orb = nullptr;
-    dvm_frame* frames[kRing] = { nullptr, nullptr, nullptr };
+    dvm_orb* orbs[kExtractors] = { nullptr, nullptr };   // [0] the caller's, [1] an owned clone
+    dvm_frame* frames[kRing] = { nullptr, nullptr, nullptr, nullptr };
     int cap = 0, map_n = 0, nlevels = 0;
     float K[4], bounds[4], logScale = 0;
     std::vector<float> inv_sigma2;
     // map snapshot
     float* d_xw = nullptr; uint8_t* d_desc = nullptr; float* d_normal = nullptr; float* d_mind = nullptr; float* d_maxd = nullptr;
     // per-frame association (same ring as the frames)
-    int* d_mp[kRing] = { nullptr, nullptr, nullptr };
-    uint8_t* d_outl[kRing] = { nullptr, nullptr, nullptr };
+    int* d_mp[kRing] = { nullptr, nullptr, nullptr, nullptr };
+    uint8_t* d_outl[kRing] = { nullptr, nullptr, nullptr, nullptr };
     // scratch
     uint8_t* d_seen = nullptr;
     int* d_cur_mp = nullptr; int* d_cur_mp2 = nullptr;
@@ -85,7 +90,7 @@ struct dvm_tracker {
     int* d_res1 = nullptr; int* d_res2 = nullptr;
     uint8_t* d_result = nullptr; // pose[7] float | counts[4] int
     uint8_t* h_result = nullptr; // pinned: [0,48) result read-back, [64,92) prior staging
-    uint8_t* d_img = nullptr; size_t img_cap = 0;
+    uint8_t* d_img[kExtractors] = { nullptr, nullptr }; size_t img_cap[kExtractors] = { 0, 0 };   // H2D staging
 };
 
 static void tracker_free(dvm_tracker* t)
@@ -93,11 +98,12 @@ static void tracker_free(dvm_tracker* t)
     if (!t) return;
     cudaSetDevice(t->device);
     if (t->stream) cudaStreamSynchronize(t->stream);
-    if (t->es) cudaStreamSynchronize(t->es);
+    for (auto e : t->es) if (e) cudaStreamSynchronize(e);
     for (auto f : t->frames) if (f) dvm_frame_destroy(f);
-    void* ptrs[] = { t->d_xw, t->d_desc, t->d_normal, t->d_mind, t->d_maxd, t->d_mp[0], t->d_mp[1], t->d_mp[2], t->d_outl[0],
-                     t->d_outl[1], t->d_outl[2], t->d_seen, t->d_cur_mp, t->d_cur_mp2, t->d_cnt, t->d_pose, t->d_pose_last,
-                     t->d_pose_prev, t->d_res1, t->d_res2, t->d_result, t->d_img };
+    if (t->orbs[1]) dvm_orb_destroy(t->orbs[1]);
+    void* ptrs[] = { t->d_xw, t->d_desc, t->d_normal, t->d_mind, t->d_maxd, t->d_mp[0], t->d_mp[1], t->d_mp[2], t->d_mp[3],
+                     t->d_outl[0], t->d_outl[1], t->d_outl[2], t->d_outl[3], t->d_seen, t->d_cur_mp, t->d_cur_mp2, t->d_cnt,
+                     t->d_pose, t->d_pose_last, t->d_pose_prev, t->d_res1, t->d_res2, t->d_result, t->d_img[0], t->d_img[1] };
     for (void* p : ptrs) cudaFree(p);
     if (t->h_result) cudaFreeHost(t->h_result);
     for (auto e : t->ev_extracted) if (e) cudaEventDestroy(e);
@@ -173,8 +179,12 @@ int dvm_tracker_create(dvm_tracker** out, dvm_orb* orb, const float* K, const fl
     *out = nullptr;
     DVM_REQUIRE(orb && K && bounds && map_n > 0 && map_xw && map_desc && map_normal && map_min_dist && map_max_dist, "null argument");
     dvm_tracker* t = new dvm_tracker;
-    t->orb = orb;
-    t->es = (cudaStream_t)dvm_orb_stream(orb);
+    t->orbs[0] = orb;
+    {
+        const int rc = dvm_orb_clone(orb, &t->orbs[1]);
+        if (rc != DVM_OK) { delete t; return rc; }
+    }
+    for (int e = 0; e < kExtractors; e++) t->es[e] = (cudaStream_t)dvm_orb_stream(t->orbs[e]);
     t->cap = dvm_orb_max_keypoints(orb);
     t->map_n = map_n;
     float sc[16], is2[16];
@@ -255,27 +265,28 @@ static int enqueue_local_map_search(dvm_tracker* t, dvm_frame* cur, int* cur_map
 static int enqueue_extract(dvm_tracker* t, const uint8_t* gray, int gray_is_device, int width, int height, int stride)
 {
     const long long i = t->n_extracted;
-    const int slot = (int)(i % kRing);
-    // the slot was the "last frame" of chain i-2: it is free again once that chain has finished
-    if (i >= 2 && i - 2 < t->n_tracked) DVM_CUDA(cudaStreamWaitEvent(t->es, t->ev_done[(i - 2) % kRing], 0));
-    DVM_REQUIRE(i - 2 < t->n_tracked || i < 2, "extraction may run at most one frame ahead of tracking");
+    const int slot = (int)(i % kRing), e = (int)(i % kExtractors);
+    cudaStream_t es = t->es[e];
+    // the slot was the "last frame" of chain i - (kRing - 1): it is free again once that chain has finished
+    DVM_REQUIRE(i - t->n_tracked < kMaxPending, "too many frames pending extraction");
+    if (i >= kRing - 1) DVM_CUDA(cudaStreamWaitEvent(es, t->ev_done[(i - (kRing - 1)) % kRing], 0));
     const uint8_t* img = gray;
     int istride = stride;
     if (!gray_is_device) {
         const size_t need = (size_t)width * height;
-        if (need > t->img_cap) {
-            DVM_CUDA(cudaStreamSynchronize(t->es));
-            cudaFree(t->d_img); t->d_img = nullptr;
-            DVM_CUDA(cudaMalloc(&t->d_img, need));
-            t->img_cap = need;
+        if (need > t->img_cap[e]) {
+            DVM_CUDA(cudaStreamSynchronize(es));
+            cudaFree(t->d_img[e]); t->d_img[e] = nullptr;
+            DVM_CUDA(cudaMalloc(&t->d_img[e], need));
+            t->img_cap[e] = need;
         }
-        DVM_CUDA(cudaMemcpy2DAsync(t->d_img, width, gray, stride, width, height, cudaMemcpyHostToDevice, t->es));
-        img = t->d_img; istride = width;
+        DVM_CUDA(cudaMemcpy2DAsync(t->d_img[e], width, gray, stride, width, height, cudaMemcpyHostToDevice, es));
+        img = t->d_img[e]; istride = width;
     }
-    int rc = dvm_frame_construct_device(t->frames[slot], t->orb, img, width, height, istride, t->bounds[0], t->bounds[1],
+    int rc = dvm_frame_construct_device(t->frames[slot], t->orbs[e], img, width, height, istride, t->bounds[0], t->bounds[1],
                                         t->bounds[2], t->bounds[3]);
     if (rc != DVM_OK) return rc;
-    DVM_CUDA(cudaEventRecord(t->ev_extracted[slot], t->es));
+    DVM_CUDA(cudaEventRecord(t->ev_extracted[slot], es));
     t->n_extracted = i + 1;
     return DVM_OK;
 }
@@ -285,7 +296,7 @@ int dvm_tracker_bootstrap(dvm_tracker* t, const uint8_t* gray, int width, int he
 {
     DVM_REQUIRE(t && gray && pose_q && pose_t, "null argument");
     DVM_CUDA(cudaSetDevice(t->device));
-    DVM_CUDA(cudaStreamSynchronize(t->es));
+    for (auto e : t->es) DVM_CUDA(cudaStreamSynchronize(e));
     DVM_CUDA(cudaStreamSynchronize(t->stream));
     t->n_extracted = 0;
     t->n_tracked = 0;
@@ -319,7 +330,7 @@ int dvm_tracker_prefetch(dvm_tracker* t, const uint8_t* gray, int gray_is_device
 {
     DVM_REQUIRE(t && gray, "null argument");
     DVM_REQUIRE(t->n_tracked >= 1, "bootstrap the tracker first");
-    DVM_REQUIRE(t->n_extracted == t->n_tracked, "a prefetched frame is already pending");
+    DVM_REQUIRE(t->n_extracted - t->n_tracked < kMaxPending, "two prefetched frames are already pending");
     DVM_CUDA(cudaSetDevice(t->device));
     return enqueue_extract(t, gray, gray_is_device, width, height, stride);
 }
@@ -351,7 +362,7 @@ int dvm_tracker_track(dvm_tracker* t, const uint8_t* gray, int gray_is_device, i
         // staged through the pinned result block's upper half (a stack array may not outlive the async copy)
         DVM_CUDA(cudaMemcpyAsync(t->d_pose, pose, 28, cudaMemcpyHostToDevice, t->stream));
     }
-    DVM_LAUNCH(begin_frame_kernel, 1, 1024, 0, t->stream, t->d_pose_last, t->d_pose_prev, t->d_pose, prior_q ? 1 : 0, t->d_seen,
+    DVM_LAUNCH_PDL(begin_frame_kernel, 1, 1024, 0, t->stream, t->d_pose_last, t->d_pose_prev, t->d_pose, prior_q ? 1 : 0, t->d_seen,
                t->map_n, t->d_cnt);
     // ---- TrackWithMotionModel: SearchByProjection(cur, last, th = 15), retry with 2*th below 20 matches ----
     MatchLastArgs la;

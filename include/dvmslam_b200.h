@@ -64,6 +64,10 @@ typedef struct dvm_orb dvm_orb;
 DVM_API int dvm_orb_create(dvm_orb** out, int device, int nfeatures, float scale_factor, int nlevels,
                            int ini_th_fast, int min_th_fast, int max_width, int max_height);
 DVM_API void dvm_orb_destroy(dvm_orb* h);
+/* A second extractor with the same parameters, own buffers and own stream (an agent keeps several: the
+ * reference constructs two, O3/src/Tracking.cc:575-581; dvm_tracker alternates two so that consecutive frames
+ * are extracted concurrently). */
+DVM_API int dvm_orb_clone(const dvm_orb* src, dvm_orb** out);
 
 /* GetLevels / GetScaleFactors / GetInverseScaleFactors / GetScaleSigmaSquares /
  * GetInverseScaleSigmaSquares (O3/include/ORBextractor.h:57-67) plus the per-level feature quota
@@ -301,10 +305,12 @@ DVM_API int dvm_tracker_track(dvm_tracker* t, const uint8_t* gray, int gray_is_d
 DVM_API int dvm_tracker_result(dvm_tracker* t, float* pose_out, int32_t* counts);
 /* Frame pipelining: ExtractORB does not depend on the previous frame's pose, so the tracker runs it on
  * the extractor's stream while the tracking chain of the previous frame runs on its own stream.
- * dvm_tracker_prefetch enqueues the upload + extraction of the NEXT frame (call it after
- * dvm_tracker_track(..., sync = 0) of the current frame and before dvm_tracker_result); the following
- * dvm_tracker_track call then ignores its image arguments (gray may be NULL) and uses the prefetched
- * frame.  With sync == 0 and no prefetch the same overlap happens whenever the host runs ahead. */
+ * dvm_tracker_prefetch enqueues the upload + extraction of the NEXT frame not yet handed over (call it after
+ * dvm_tracker_track(..., sync = 0) of the current frame and before dvm_tracker_result); at most two frames
+ * may be pending (the tracker alternates two extractors on two streams, so consecutive frames are extracted
+ * concurrently).  A dvm_tracker_track call with pending frames ignores its image arguments (gray may be NULL)
+ * and uses the oldest pending frame.  With sync == 0 and no prefetch the same overlap happens whenever the host
+ * runs ahead. */
 DVM_API int dvm_tracker_prefetch(dvm_tracker* t, const uint8_t* gray, int gray_is_device, int width, int height,
                                  int stride);
 /* The CUDA stream (cudaStream_t) of the tracking chain, for CUDA-event timing by the caller. */
