@@ -4,6 +4,7 @@
 // reference's calls).
 #include "bow_kernels.cuh"
 #include "track_internal.cuh"
+#include <cmath>
 #include <vector>
 
 using namespace dvm;
@@ -161,6 +162,110 @@ int dvm_match_for_initialization(dvm_frame* f2, int n1, const dvm_keypoint* kps1
     const int* r = (const int*)at(a.result);
     *nmatches = r[0];
     f2->last_rounds = r[1];
+    return DVM_OK;
+}
+
+int dvm_match_for_triangulation(dvm_frame* ctx, const dvm_bow_features* kf1, const dvm_keypoint* kps1,
+                                const dvm_bow_features* kf2, const dvm_keypoint* kps2, const float* F12, const float* ep,
+                                const float* scale_factors2, const float* level_sigma2_2, int nlevels, int coarse,
+                                int check_orientation, int32_t* matches12, int* nmatches)
+{
+    DVM_REQUIRE(ctx != nullptr && nmatches != nullptr && F12 && ep && scale_factors2 && level_sigma2_2, "null argument");
+    DVM_REQUIRE(nlevels >= 1 && nlevels <= kTrackMaxLevels, "nlevels out of range");
+    std::vector<uint8_t> seen;
+    int rc = check_side(kf1, seen);
+    if (rc != DVM_OK) return rc;
+    rc = check_side(kf2, seen);
+    if (rc != DVM_OK) return rc;
+    DVM_REQUIRE((kf1->n == 0 || (kps1 && kf1->has_mp && matches12)) && (kf2->n == 0 || (kps2 && kf2->has_mp)), "null keypoints / has_mp");
+    for (int i = 0; i < kf2->n; i++) DVM_REQUIRE(kps2[i].octave >= 0 && kps2[i].octave < nlevels, "octave out of range");
+    DVM_CUDA(cudaSetDevice(ctx->device));
+    const dvm_bow_features* S[2] = { kf1, kf2 };
+    const dvm_keypoint* KP[2] = { kps1, kps2 };
+    size_t in_bytes = 0;
+    for (int k = 0; k < 2; k++) {
+        const size_t n = (size_t)S[k]->n, nn = (size_t)S[k]->n_nodes, tot = nn ? (size_t)S[k]->node_start[nn] : 0;
+        in_bytes += padded({ n * 32, n, nn * 4, (nn + 1) * 4, tot * 4, n * sizeof(dvm_keypoint) });
+    }
+    const size_t out_ints = (size_t)kf1->n + kHistoLength + 2;
+    in_bytes += padded({ out_ints * 4 });
+    rc = dvm_frame_ensure_bytes(ctx, in_bytes, out_ints * 4 + 256);
+    if (rc != DVM_OK) return rc;
+    Stage st(ctx);
+    TriArgs g;
+    memset(&g, 0, sizeof(g));
+    BowSide* D[2] = { &g.a, &g.b };
+    const dvm_keypoint* dk[2];
+    for (int k = 0; k < 2; k++) {
+        const size_t n = (size_t)S[k]->n, nn = (size_t)S[k]->n_nodes, tot = nn ? (size_t)S[k]->node_start[nn] : 0;
+        D[k]->n = S[k]->n; D[k]->n_nodes = S[k]->n_nodes;
+        D[k]->desc = st.add(S[k]->desc, n * 32);
+        D[k]->angle = nullptr;
+        D[k]->valid = st.add(S[k]->has_mp, n);
+        D[k]->node_id = st.add(S[k]->node_id, nn);
+        D[k]->node_start = st.add(S[k]->node_start, nn + 1);
+        D[k]->feat_idx = st.add(S[k]->feat_idx, tot);
+        dk[k] = st.add(KP[k], n);
+    }
+    g.kps1 = dk[0]; g.kps2 = dk[1];
+    memcpy(g.F12, F12, sizeof(g.F12)); g.ep[0] = ep[0]; g.ep[1] = ep[1];
+    for (int l = 0; l < nlevels; l++) { g.scale2[l] = scale_factors2[l]; g.sigma2_2[l] = level_sigma2_2[l]; }
+    g.coarse = coarse ? 1 : 0; g.check_ori = check_orientation;
+    const size_t in_end = st.off;
+    int* d_out = st.add((const int*)nullptr, out_ints);   // matches12 | histo | counters
+    g.matches12 = d_out; g.histo = d_out + kf1->n; g.counters = g.histo + kHistoLength;
+    DVM_CUDA(cudaMemcpyAsync(ctx->d_in, ctx->h_in, in_end, cudaMemcpyHostToDevice, ctx->stream));
+    DVM_CUDA(cudaMemsetAsync(d_out, 0xff, (size_t)kf1->n * 4, ctx->stream));
+    DVM_CUDA(cudaMemsetAsync(g.histo, 0, (kHistoLength + 2) * 4, ctx->stream));
+    launch_triangulation_match(g, ctx->stream);
+    DVM_CUDA(cudaGetLastError());
+    DVM_CUDA(cudaMemcpyAsync(ctx->h_out, d_out, out_ints * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    DVM_CUDA(cudaStreamSynchronize(ctx->stream));
+    const int* h = (const int*)ctx->h_out;
+    if (kf1->n) memcpy(matches12, h, (size_t)kf1->n * 4);
+    *nmatches = h[(size_t)kf1->n + kHistoLength + 1];
+    return DVM_OK;
+}
+
+int dvm_fuse_search(dvm_frame* kf, const float* pose_q, const float* pose_t, const float* K, int m, const float* xw,
+                    const float* normal, const float* min_dist, const float* max_dist, const uint8_t* mp_desc,
+                    const uint8_t* skip, float th, int32_t* best_idx, int32_t* best_dist)
+{
+    DVM_REQUIRE(kf != nullptr && pose_q && pose_t && K && m >= 0, "bad argument");
+    if (m == 0) return DVM_OK;
+    DVM_REQUIRE(xw && normal && min_dist && max_dist && mp_desc && best_idx && best_dist, "null map-point arrays");
+    DVM_CUDA(cudaSetDevice(kf->device));
+    const size_t n = (size_t)m;
+    int rc = dvm_frame_ensure_bytes(kf, padded({ n * 12, n * 12, n * 4, n * 4, n * 32, n, n * 4, n * 4 }), n * 8 + 512);
+    if (rc != DVM_OK) return rc;
+    Stage st(kf);
+    FuseArgs a;
+    memset(&a, 0, sizeof(a));
+    for (int i = 0; i < 4; i++) { a.q[i] = pose_q[i]; a.K[i] = K[i]; }
+    for (int i = 0; i < 3; i++) a.t[i] = pose_t[i];
+    a.nlevels = kf->dev.nlevels;
+    // mfLogScaleFactor = log(mfScaleFactor) (O3/src/KeyFrame.cc: copied from the Frame, O3/src/Frame.cc:401)
+    a.logScale = (float)std::log((double)(kf->dev.nlevels > 1 ? kf->dev.scale[1] : 1.2f));
+    for (int l = 0; l < kf->dev.nlevels; l++) a.inv_sigma2[l] = kf->dev.inv_sigma2[l];
+    a.m = m; a.th = th;
+    a.xw = st.add(xw, n * 3); a.normal = st.add(normal, n * 3);
+    a.min_dist = st.add(min_dist, n); a.max_dist = st.add(max_dist, n);
+    a.mp_desc = st.add(mp_desc, n * 32);
+    a.skip = skip ? st.add(skip, n) : nullptr;
+    const size_t in_end = st.off;
+    const size_t out_begin = (st.off + 255) & ~(size_t)255;
+    a.best_idx = st.add((const int*)nullptr, n);
+    a.best_dist = st.add((const int*)nullptr, n);
+    const size_t out_end = st.off;
+    DVM_CUDA(cudaMemcpyAsync(kf->d_in, kf->h_in, in_end, cudaMemcpyHostToDevice, kf->stream));
+    launch_fuse_search(kf->dev, a, kf->stream);
+    DVM_CUDA(cudaGetLastError());
+    rc = dvm_frame_ensure_bytes(kf, 0, out_end - out_begin);
+    if (rc != DVM_OK) return rc;
+    DVM_CUDA(cudaMemcpyAsync(kf->h_out, kf->d_in + out_begin, out_end - out_begin, cudaMemcpyDeviceToHost, kf->stream));
+    DVM_CUDA(cudaStreamSynchronize(kf->stream));
+    memcpy(best_idx, kf->h_out + ((const uint8_t*)a.best_idx - (kf->d_in + out_begin)), n * 4);
+    memcpy(best_dist, kf->h_out + ((const uint8_t*)a.best_dist - (kf->d_in + out_begin)), n * 4);
     return DVM_OK;
 }
 

@@ -3,6 +3,8 @@
 //   bow_node_kernel / bow_finish_kernel    ORBmatcher::SearchByBoW(KF, Frame)  (O3/src/ORBmatcher.cc:214-393)
 //                                          ORBmatcher::SearchByBoW(KF, KF)     (O3/src/ORBmatcher.cc:709-834)
 //   init_match_kernel                      ORBmatcher::SearchForInitialization (O3/src/ORBmatcher.cc:605-707)
+//   triangulation_kernel                   ORBmatcher::SearchForTriangulation  (O3/src/ORBmatcher.cc:836-1058)
+//   fuse_search_kernel                     ORBmatcher::Fuse, search half       (O3/src/ORBmatcher.cc:1060-1228)
 //
 // SearchByBoW walks the vocabulary nodes the two feature vectors share; inside a node it is a sequential
 // greedy loop (a feature of side 2 taken by an earlier feature of side 1 is skipped), but a feature
@@ -224,6 +226,173 @@ __global__ void __launch_bounds__(kInitThreads, 1) init_match_kernel(FrameDev f2
 void launch_init_match(const FrameDev& f2, const InitMatchArgs& a, cudaStream_t stream)
 {
     DVM_LAUNCH(init_match_kernel, 1, kInitThreads, 0, stream, f2, a);
+}
+
+// --------------------------------------------------------------------------- SearchForTriangulation
+// This fork never marks a feature of keyframe 2 as taken (vbMatched2 stays false), so every feature of
+// keyframe 1 is independent: one warp per shared node walks the node's keyframe-1 features, the lanes share
+// the keyframe-2 features.  The reference keeps a candidate when dist <= min(TH_LOW, bestDist) and the
+// geometric gates pass, i.e. the LAST of the nearest valid candidates wins: the key is
+// distance << 20 | (0xfffff - position) and the warp takes its minimum.
+__global__ void __launch_bounds__(kBowWarps * 32) triangulation_kernel(TriArgs g)
+{
+    const int lane = threadIdx.x & 31;
+    const int ia = blockIdx.x * kBowWarps + (threadIdx.x >> 5);
+    if (ia >= g.a.n_nodes) return;
+    const int ib = find_node(g.b.node_id, g.b.n_nodes, g.a.node_id[ia]);
+    if (ib < 0) return;
+    const int a0 = g.a.node_start[ia], a1 = g.a.node_start[ia + 1];
+    const int b0 = g.b.node_start[ib], nb = g.b.node_start[ib + 1] - b0;
+    for (int p = a0; p < a1; p++) {
+        const int i1 = (int)g.a.feat_idx[p];
+        if (g.a.valid[i1]) continue;
+        const dvm_keypoint kp1 = g.kps1[i1];
+        uint32_t d1[8];
+        load_desc(d1, g.a.desc + (size_t)i1 * 32);
+        // epipolar line of kp1 in image 2: l = x1' F12
+        const float la = __fadd_rn(__fadd_rn(__fmul_rn(kp1.x, g.F12[0]), __fmul_rn(kp1.y, g.F12[3])), g.F12[6]);
+        const float lb = __fadd_rn(__fadd_rn(__fmul_rn(kp1.x, g.F12[1]), __fmul_rn(kp1.y, g.F12[4])), g.F12[7]);
+        const float lc = __fadd_rn(__fadd_rn(__fmul_rn(kp1.x, g.F12[2]), __fmul_rn(kp1.y, g.F12[5])), g.F12[8]);
+        const float den = __fadd_rn(__fmul_rn(la, la), __fmul_rn(lb, lb));
+        unsigned best = ~0u;
+        for (int q = lane; q < nb; q += 32) {
+            const int i2 = (int)g.b.feat_idx[b0 + q];
+            if (g.b.valid[i2]) continue;
+            const int dist = hamming256(d1, g.b.desc + (size_t)i2 * 32);
+            if (dist > kThLow) continue;
+            const float x2 = g.kps2[i2].x, y2 = g.kps2[i2].y;
+            const int oct2 = g.kps2[i2].octave;
+            const float ex = __fsub_rn(g.ep[0], x2), ey = __fsub_rn(g.ep[1], y2);
+            if (__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)) < __fmul_rn(100.f, g.scale2[oct2])) continue;
+            if (!g.coarse) {
+                if (den == 0.f) continue;
+                const float num = __fadd_rn(__fadd_rn(__fmul_rn(la, x2), __fmul_rn(lb, y2)), lc);
+                const float dsqr = __fdiv_rn(__fmul_rn(num, num), den);
+                if (!((double)dsqr < 3.84 * (double)g.sigma2_2[oct2])) continue;
+            }
+            best = min(best, ((unsigned)dist << kPosBits) | (0xfffffu - (unsigned)q));
+        }
+        best = __reduce_min_sync(0xffffffffu, best);
+        if (best != ~0u && lane == 0) {
+            const int q = (int)(0xfffffu - (best & 0xfffffu));
+            const int i2 = (int)g.b.feat_idx[b0 + q];
+            g.matches12[i1] = i2;
+            atomicAdd(&g.counters[0], 1);
+            if (g.check_ori) atomicAdd(&g.histo[rot_bin(kp1.angle, g.kps2[i2].angle)], 1);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(1024) triangulation_finish_kernel(TriArgs g)
+{
+    __shared__ int s_ind[3], s_bad;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        int i1 = -1, i2 = -1, i3 = -1;
+        if (g.check_ori) three_maxima(g.histo, kHistoLength, i1, i2, i3);
+        s_ind[0] = i1; s_ind[1] = i2; s_ind[2] = i3;
+        s_bad = 0;
+    }
+    __syncthreads();
+    if (g.check_ori) {
+        int bad = 0;
+        for (int i1 = tid; i1 < g.a.n; i1 += 1024) {
+            const int i2 = g.matches12[i1];
+            if (i2 < 0) continue;
+            const int bin = rot_bin(g.kps1[i1].angle, g.kps2[i2].angle);
+            if (bin != s_ind[0] && bin != s_ind[1] && bin != s_ind[2]) { g.matches12[i1] = -1; bad++; }
+        }
+        if (bad) atomicAdd(&s_bad, bad);
+    }
+    __syncthreads();
+    if (tid == 0) g.counters[1] = g.counters[0] - s_bad;
+}
+
+void launch_triangulation_match(const TriArgs& g, cudaStream_t stream)
+{
+    if (g.a.n_nodes > 0 && g.b.n_nodes > 0)
+        DVM_LAUNCH(triangulation_kernel, div_up(g.a.n_nodes, kBowWarps), kBowWarps * 32, 0, stream, g);
+    DVM_LAUNCH(triangulation_finish_kernel, 1, 1024, 0, stream, g);
+}
+
+// ---------------------------------------------------------------------------------------- Fuse (search)
+// One warp per map point: the gates of O3/src/ORBmatcher.cc:1100-1150 (depth, image bounds, distance range,
+// viewing angle, predicted level), then the window of KeyFrame::GetFeaturesInArea shared by the lanes.
+// Strict '<' on the distance: the FIRST of the nearest keypoints in traversal order wins.
+constexpr int kFuseWarps = 4;
+
+__device__ inline void quat_transform_f32(float x, float y, float z, float w, const float v[3], float out[3])
+{
+    // Eigen::QuaternionBase::_transformVector, as Sophus::SE3f * point evaluates it
+    float u0 = __fsub_rn(__fmul_rn(y, v[2]), __fmul_rn(z, v[1]));
+    float u1 = __fsub_rn(__fmul_rn(z, v[0]), __fmul_rn(x, v[2]));
+    float u2 = __fsub_rn(__fmul_rn(x, v[1]), __fmul_rn(y, v[0]));
+    u0 = __fadd_rn(u0, u0); u1 = __fadd_rn(u1, u1); u2 = __fadd_rn(u2, u2);
+    out[0] = __fadd_rn(__fadd_rn(v[0], __fmul_rn(w, u0)), __fsub_rn(__fmul_rn(y, u2), __fmul_rn(z, u1)));
+    out[1] = __fadd_rn(__fadd_rn(v[1], __fmul_rn(w, u1)), __fsub_rn(__fmul_rn(z, u0), __fmul_rn(x, u2)));
+    out[2] = __fadd_rn(__fadd_rn(v[2], __fmul_rn(w, u2)), __fsub_rn(__fmul_rn(x, u1), __fmul_rn(y, u0)));
+}
+
+__global__ void __launch_bounds__(kFuseWarps * 32) fuse_search_kernel(FrameDev kf, FuseArgs a)
+{
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * kFuseWarps + (threadIdx.x >> 5);
+    if (i >= a.m) return;
+    int bestIdx = -1, bestDist = 256;
+    do {
+        if (a.skip && a.skip[i]) break;
+        const float qn = __fsqrt_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a.q[0], a.q[0]), __fmul_rn(a.q[1], a.q[1])),
+                                                        __fmul_rn(a.q[2], a.q[2])), __fmul_rn(a.q[3], a.q[3])));
+        const float qx = __fdiv_rn(a.q[0], qn), qy = __fdiv_rn(a.q[1], qn), qz = __fdiv_rn(a.q[2], qn), qw = __fdiv_rn(a.q[3], qn);
+        float Ow[3];
+        { float r[3]; quat_transform_f32(-qx, -qy, -qz, qw, a.t, r); Ow[0] = -r[0]; Ow[1] = -r[1]; Ow[2] = -r[2]; }
+        const float P[3] = { a.xw[3 * i], a.xw[3 * i + 1], a.xw[3 * i + 2] };
+        float pc[3];
+        quat_transform_f32(qx, qy, qz, qw, P, pc);
+        pc[0] = __fadd_rn(pc[0], a.t[0]); pc[1] = __fadd_rn(pc[1], a.t[1]); pc[2] = __fadd_rn(pc[2], a.t[2]);
+        if (pc[2] < 0.0f) break;
+        const float u = __fadd_rn(__fdiv_rn(__fmul_rn(a.K[0], pc[0]), pc[2]), a.K[2]);
+        const float v = __fadd_rn(__fdiv_rn(__fmul_rn(a.K[1], pc[1]), pc[2]), a.K[3]);
+        if (!(u >= kf.minX && u < kf.maxX && v >= kf.minY && v < kf.maxY)) break;
+        const float maxDistance = __fmul_rn(1.2f, a.max_dist[i]), minDistance = __fmul_rn(0.8f, a.min_dist[i]);
+        const float p0 = __fsub_rn(P[0], Ow[0]), p1 = __fsub_rn(P[1], Ow[1]), p2 = __fsub_rn(P[2], Ow[2]);
+        const float dist3D = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(p0, p0), __fmul_rn(p1, p1)), __fmul_rn(p2, p2)));
+        if (dist3D < minDistance || dist3D > maxDistance) break;
+        const float dot = __fadd_rn(__fadd_rn(__fmul_rn(p0, a.normal[3 * i]), __fmul_rn(p1, a.normal[3 * i + 1])),
+                                    __fmul_rn(p2, a.normal[3 * i + 2]));
+        if ((double)dot < 0.5 * (double)dist3D) break;
+        const float ratio = __fdiv_rn(a.max_dist[i], dist3D);
+        int lvl = (int)ceilf(__fdiv_rn((float)log((double)ratio), a.logScale));
+        if (lvl < 0) lvl = 0;
+        else if (lvl >= a.nlevels) lvl = a.nlevels - 1;
+        const float radius = __fmul_rn(a.th, kf.scale[lvl]);
+        uint32_t d[8];
+        load_desc(d, a.mp_desc + (size_t)i * 32);
+        const FrameLook fl = look_global(kf);
+        unsigned long long best = ~0ull;   // distance << 48 | traversal position << 24 | keypoint
+        walk_area_warp(fl, u, v, radius, -1, -1, lane, [&](int idx, int oct, int ord) {
+            if (oct < lvl - 1 || oct > lvl) return;
+            const float ex = __fsub_rn(u, fl.x(idx)), ey = __fsub_rn(v, fl.y(idx));
+            const float e2 = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+            if ((double)__fmul_rn(e2, a.inv_sigma2[oct]) > 5.99) return;
+            const unsigned long long dist = (unsigned long long)hamming256(d, fl.desc + (size_t)idx * 32);
+            if (dist < 256ull) best = min(best, (dist << 48) | ((unsigned long long)min(ord, 0xffffff) << 24) | (unsigned long long)idx);
+        });
+        best = warp_min_u64(best);
+        if (best == ~0ull) break;
+        bestDist = (int)(best >> 48);
+        bestIdx = (int)(best & 0xffffffull);
+    } while (false);
+    if (lane == 0) {
+        const bool ok = bestIdx >= 0 && bestDist <= kThLow;
+        a.best_idx[i] = ok ? bestIdx : -1;
+        a.best_dist[i] = ok ? bestDist : 256;
+    }
+}
+
+void launch_fuse_search(const FrameDev& kf, const FuseArgs& a, cudaStream_t stream)
+{
+    if (a.m > 0) DVM_LAUNCH(fuse_search_kernel, div_up(a.m, kFuseWarps), kFuseWarps * 32, 0, stream, kf, a);
 }
 
 } // namespace dvm

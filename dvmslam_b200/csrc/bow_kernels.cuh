@@ -49,6 +49,34 @@ struct InitMatchArgs {
 
 void launch_init_match(const FrameDev& f2, const InitMatchArgs& a, cudaStream_t stream);
 
+// SearchForTriangulation(pKF1, pKF2, ...) on mono keyframes: BowSide::valid here means "the feature already
+// holds a map point" (such features are skipped on both sides)
+struct TriArgs {
+    BowSide a, b;
+    const dvm_keypoint* kps1;   // pKF1->mvKeysUn
+    const dvm_keypoint* kps2;   // pKF2->mvKeysUn
+    float F12[9], ep[2];
+    float scale2[kTrackMaxLevels], sigma2_2[kTrackMaxLevels];   // pKF2->mvScaleFactors / mvLevelSigma2
+    int coarse, check_ori;
+    int* matches12;   // [a.n] preset to -1
+    int* histo;       // [kHistoLength] preset to 0
+    int* counters;    // [2]: accepted (preset 0), nmatches (out)
+};
+void launch_triangulation_match(const TriArgs& g, cudaStream_t stream);
+
+// the search half of Fuse(pKF, vpMapPoints, th): per map point the keyframe keypoint it would be fused with
+struct FuseArgs {
+    float q[4], t[3], K[4];
+    int nlevels; float logScale;
+    float inv_sigma2[kTrackMaxLevels];
+    int m;
+    const float* xw; const float* normal; const float* min_dist; const float* max_dist;
+    const uint8_t* mp_desc; const uint8_t* skip;
+    float th;
+    int* best_idx; int* best_dist;
+};
+void launch_fuse_search(const FrameDev& kf, const FuseArgs& a, cudaStream_t stream);
+
 // Exhaustive nearest / second-nearest search, batched over blocks (keyframes):
 //   a [ba][na][32], b [bb][nb][32]  ->  key1 / key2 [ba][bb][na]
 // key = distance << 20 | index in the b block; key1 = nearest (first of equal distances), key2 = the

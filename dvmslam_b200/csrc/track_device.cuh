@@ -149,4 +149,46 @@ __device__ inline int rot_bin(float last_angle, float cur_angle)
     return bin;
 }
 
+// ---- one WARP per query: the lanes share the window's candidates, every lane keeps its own sorted
+// top-K, and the K best of the warp are merged by K rounds of a 64-bit warp minimum.  The order key of a
+// candidate is its position in the window's traversal (cells in the reference's order, unfiltered), which
+// is monotone in the reference's visiting order, so (distance, key) ranks candidates exactly as the
+// sequential scan does. ----
+template <class Fn>
+__device__ inline void walk_area_warp(const FrameLook& f, float x, float y, float r, int minLevel, int maxLevel, int lane, Fn fn)
+{
+    const float dxm = __fsub_rn(x, f.minX), dym = __fsub_rn(y, f.minY);
+    const int nMinCellX = max(0, (int)floorf(__fmul_rn(__fsub_rn(dxm, r), f.gwInv)));
+    if (nMinCellX >= kGridCols) return;
+    const int nMaxCellX = min(kGridCols - 1, (int)ceilf(__fmul_rn(__fadd_rn(dxm, r), f.gwInv)));
+    if (nMaxCellX < 0) return;
+    const int nMinCellY = max(0, (int)floorf(__fmul_rn(__fsub_rn(dym, r), f.ghInv)));
+    if (nMinCellY >= kGridRows) return;
+    const int nMaxCellY = min(kGridRows - 1, (int)ceilf(__fmul_rn(__fadd_rn(dym, r), f.ghInv)));
+    if (nMaxCellY < 0) return;
+    const bool bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
+    int base = 0;
+    for (int ix = nMinCellX; ix <= nMaxCellX; ix++) {
+        const int j0 = f.cell_start[ix * kGridRows + nMinCellY], j1 = f.cell_start[ix * kGridRows + nMaxCellY + 1];
+        for (int j = j0 + lane; j < j1; j += 32) {
+            const int idx = f.cell_items[j];
+            const int oct = f.oct(idx);
+            if (bCheckLevels) {
+                if (oct < minLevel) continue;
+                if (maxLevel >= 0 && oct > maxLevel) continue;
+            }
+            const float distx = __fsub_rn(f.x(idx), x), disty = __fsub_rn(f.y(idx), y);
+            if (fabsf(distx) < r && fabsf(disty) < r) fn(idx, oct, base + (j - j0));
+        }
+        base += j1 - j0;
+    }
+}
+
+__device__ inline unsigned long long warp_min_u64(unsigned long long v)
+{
+    const unsigned hi = __reduce_min_sync(0xffffffffu, (unsigned)(v >> 32));
+    const unsigned lo = __reduce_min_sync(0xffffffffu, (unsigned)(v >> 32) == hi ? (unsigned)v : 0xffffffffu);
+    return ((unsigned long long)hi << 32) | lo;
+}
+
 } // namespace dvm

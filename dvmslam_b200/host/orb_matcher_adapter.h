@@ -9,6 +9,7 @@
 #include <cstring>
 #include <list>
 #include <memory>
+#include <utility>
 #include <vector>
 
 #include "dvm_host.h"
@@ -252,6 +253,120 @@ int SearchForInitialization(FrameT& F1, FrameT& F2, std::vector<Point2fT>& vbPre
           "ORBmatcher::SearchForInitialization");
     for (int i = 0; i < n1; i++) { vbPrevMatched[i].x = prev[2 * i]; vbPrevMatched[i].y = prev[2 * i + 1]; }
     return nmatches;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// int ORBmatcher::SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, vector<pair<size_t,size_t>>& vMatchedPairs,
+//                                        const bool bOnlyStereo, const bool bCoarse)             :836-1058
+// Mono keyframes (bOnlyStereo must be false).  The relative pose, the epipole and the fundamental matrix are
+// derived here as the reference does (:841-855; Pinhole::epipolarConstrain, O3/src/CameraModels/Pinhole.cpp:104-110,
+// with the closed-form inverse of the pinhole K instead of Eigen's generic 3x3 inverse).
+// ---------------------------------------------------------------------------------------------------
+template <class KeyFrameT>
+int SearchForTriangulation(KeyFrameT* pKF1, KeyFrameT* pKF2, std::vector<std::pair<size_t, size_t>>& vMatchedPairs,
+                           bool bOnlyStereo, bool bCoarse, bool checkOrientation, dvm_frame* ctx)
+{
+    vMatchedPairs.clear();
+    if (bOnlyStereo) return 0;   // mono keyframes have no stereo observations: every feature is skipped (:896-898)
+    const auto T1w = pKF1->GetPose();
+    const auto T2w = pKF2->GetPose();
+    const auto R1 = T1w.rotationMatrix(), R2 = T2w.rotationMatrix();
+    const auto t1 = T1w.translation(), t2 = T2w.translation();
+    float R12[9], t12[3], Cw[3], C2[3];
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) R12[3 * r + c] = R1(r, 0) * R2(c, 0) + R1(r, 1) * R2(c, 1) + R1(r, 2) * R2(c, 2);   // T1w * Tw2
+    for (int r = 0; r < 3; r++) t12[r] = t1(r) - (R12[3 * r] * t2(0) + R12[3 * r + 1] * t2(1) + R12[3 * r + 2] * t2(2));
+    for (int r = 0; r < 3; r++) Cw[r] = -(R1(0, r) * t1(0) + R1(1, r) * t1(1) + R1(2, r) * t1(2));                       // GetCameraCenter
+    for (int r = 0; r < 3; r++) C2[r] = R2(r, 0) * Cw[0] + R2(r, 1) * Cw[1] + R2(r, 2) * Cw[2] + t2(r);
+    const float ep[2] = { pKF2->fx * C2[0] / C2[2] + pKF2->cx, pKF2->fy * C2[1] / C2[2] + pKF2->cy };
+    // F12 = K1^-T [t12]x R12 K2^-1
+    const float tx[9] = { 0, -t12[2], t12[1], t12[2], 0, -t12[0], -t12[1], t12[0], 0 };
+    float E[9], A[9], F12[9];
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) E[3 * r + c] = tx[3 * r] * R12[c] + tx[3 * r + 1] * R12[3 + c] + tx[3 * r + 2] * R12[6 + c];
+    const float k1it[9] = { 1 / pKF1->fx, 0, 0, 0, 1 / pKF1->fy, 0, -pKF1->cx / pKF1->fx, -pKF1->cy / pKF1->fy, 1 };   // K1^-T
+    const float k2i[9] = { 1 / pKF2->fx, 0, -pKF2->cx / pKF2->fx, 0, 1 / pKF2->fy, -pKF2->cy / pKF2->fy, 0, 0, 1 };    // K2^-1
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) A[3 * r + c] = k1it[3 * r] * E[c] + k1it[3 * r + 1] * E[3 + c] + k1it[3 * r + 2] * E[6 + c];
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) F12[3 * r + c] = A[3 * r] * k2i[c] + A[3 * r + 1] * k2i[3 + c] + A[3 * r + 2] * k2i[6 + c];
+
+    auto flatten = [](KeyFrameT* kf) {
+        FlatFeatures f = flatten_features(kf->mvKeysUn, kf->mDescriptors, kf->mFeatVec,
+                                          static_cast<const std::vector<decltype(kf->GetMapPoint(0))>*>(nullptr));
+        f.has_mp.resize(f.angle.size());
+        for (size_t i = 0; i < f.angle.size(); i++) f.has_mp[i] = kf->GetMapPoint(i) != nullptr;
+        return f;
+    };
+    const FlatFeatures a = flatten(pKF1), b = flatten(pKF2);
+    const dvm_bow_features va = a.view(), vb = b.view();
+    std::vector<int32_t> m12(a.angle.empty() ? 1 : a.angle.size(), -1);
+    int nmatches = 0;
+    check(dvm_match_for_triangulation(ctx, &va, reinterpret_cast<const dvm_keypoint*>(pKF1->mvKeysUn.data()), &vb,
+                                      reinterpret_cast<const dvm_keypoint*>(pKF2->mvKeysUn.data()), F12, ep,
+                                      pKF2->mvScaleFactors.data(), pKF2->mvLevelSigma2.data(),
+                                      static_cast<int>(pKF2->mvScaleFactors.size()), bCoarse ? 1 : 0, checkOrientation ? 1 : 0,
+                                      m12.data(), &nmatches),
+          "ORBmatcher::SearchForTriangulation");
+    vMatchedPairs.reserve(nmatches);
+    for (size_t i = 0; i < a.angle.size(); i++)
+        if (m12[i] >= 0) vMatchedPairs.push_back(std::make_pair(i, static_cast<size_t>(m12[i])));                     // :1049-1054
+    return nmatches;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// int ORBmatcher::Fuse(KeyFrame* pKF, const vector<MapPoint*>& vpMapPoints, const float th, const bool bRight)
+// :1060-1228, bRight = false.  The search runs on the GPU for all map points at once; Replace / AddObservation /
+// AddMapPoint are then applied in vpMapPoints order exactly as the reference's loop does (:1209-1222).
+// ---------------------------------------------------------------------------------------------------
+template <class KeyFrameT, class MapPointT>
+int Fuse(KeyFrameT* pKF, const std::vector<MapPointT*>& vpMapPoints, float th)
+{
+    const int m = static_cast<int>(vpMapPoints.size());
+    std::vector<float> xw(static_cast<size_t>(m) * 3), nrm(static_cast<size_t>(m) * 3), mind(m), maxd(m);
+    std::vector<uint8_t> desc(static_cast<size_t>(m) * 32), skip(m > 0 ? m : 1);
+    for (int i = 0; i < m; i++) {
+        MapPointT* pMP = vpMapPoints[i];
+        skip[i] = !pMP || pMP->isBad() || pMP->IsInKeyFrame(pKF);                                                     // :1086-1098
+        if (skip[i]) continue;
+        const auto p = pMP->GetWorldPos();
+        const auto n = pMP->GetNormal();
+        for (int k = 0; k < 3; k++) { xw[3 * i + k] = p(k); nrm[3 * i + k] = n(k); }
+        // GetMin/MaxDistanceInvariance() = 0.8 * mfMinDistance / 1.2 * mfMaxDistance; the library applies the factors
+        mind[i] = pMP->GetMinDistanceInvariance() / 0.8f;
+        maxd[i] = pMP->GetMaxDistanceInvariance() / 1.2f;
+        const auto d = pMP->GetDescriptor();
+        std::memcpy(&desc[static_cast<size_t>(i) * 32], d.ptr(0), 32);
+    }
+    float q[4], t[3];
+    const auto Tcw = pKF->GetPose();
+    const auto uq = Tcw.unit_quaternion();
+    q[0] = uq.x(); q[1] = uq.y(); q[2] = uq.z(); q[3] = uq.w();
+    const auto tr = Tcw.translation();
+    for (int k = 0; k < 3; k++) t[k] = tr(k);
+    const float K[4] = { pKF->fx, pKF->fy, pKF->cx, pKF->cy };
+    std::vector<int32_t> bestIdx(m > 0 ? m : 1, -1), bestDist(m > 0 ? m : 1, 256);
+    check(dvm_fuse_search(device_frame(*pKF).frame.h, q, t, K, m, xw.data(), nrm.data(), mind.data(), maxd.data(), desc.data(),
+                          skip.data(), th, bestIdx.data(), bestDist.data()),
+          "ORBmatcher::Fuse");
+    int nFused = 0;
+    for (int i = 0; i < m; i++) {
+        if (bestIdx[i] < 0) continue;
+        MapPointT* pMP = vpMapPoints[i];
+        if (pMP->IsInKeyFrame(pKF)) continue;   // the same map point listed twice: added by its first occurrence
+        MapPointT* pMPinKF = pKF->GetMapPoint(bestIdx[i]);
+        if (pMPinKF) {
+            if (!pMPinKF->isBad()) {
+                if (pMPinKF->Observations() > pMP->Observations()) pMP->Replace(pMPinKF);
+                else pMPinKF->Replace(pMP);
+            }
+        } else {
+            pMP->AddObservation(pKF, bestIdx[i]);
+            pKF->AddMapPoint(pMP, bestIdx[i]);
+        }
+        nFused++;
+    }
+    return nFused;
 }
 
 } // namespace dvm_host

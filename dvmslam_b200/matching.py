@@ -28,6 +28,9 @@ def _bind(L):
     L.dvm_match_by_bow.argtypes = [_vp, C.c_int, C.POINTER(_BowFeatures), C.POINTER(_BowFeatures), C.c_float, C.c_int,
                                    _vp, _vp, _ip]
     L.dvm_match_for_initialization.argtypes = [_vp, C.c_int, _vp, _vp, _vp, C.c_int, C.c_float, C.c_int, _vp, _ip]
+    L.dvm_match_for_triangulation.argtypes = [_vp, C.POINTER(_BowFeatures), _vp, C.POINTER(_BowFeatures), _vp, _vp, _vp, _vp,
+                                              _vp, C.c_int, C.c_int, C.c_int, _vp, _ip]
+    L.dvm_fuse_search.argtypes = [_vp, _vp, _vp, _vp, C.c_int] + [_vp] * 6 + [C.c_float, _vp, _vp]
     L.dvm_hamming_create.argtypes = [C.POINTER(_vp), C.c_int, _vp]
     L.dvm_hamming_destroy.argtypes = [_vp]
     L.dvm_hamming_destroy.restype = None
@@ -108,6 +111,63 @@ class BowMatcher:
                                                   int(windowSize), float(self.mfNNratio),
                                                   int(self.mbCheckOrientation), m12.ctypes.data, C.byref(n)))
         return n.value, m12[:len(k1)], pm
+
+
+def fundamental_from_poses(q1, t1, q2, t2, K1, K2):
+    """(F12 row-major float32[9], ep float32[2]) as SearchForTriangulation derives them from the two keyframe poses
+    Tcw (O3/src/ORBmatcher.cc:841-855: T12 = T1w * Tw2, C2 = T2w * Cw, ep = project(C2)) and
+    Pinhole::epipolarConstrain builds F12 = K1^-T [t12]x R12 K2^-1 (O3/src/CameraModels/Pinhole.cpp:104-110).
+    Evaluated in float32 matrix arithmetic; the same numbers go to the oracle and to the GPU."""
+    f = np.float32
+
+    def R_of(q):
+        x, y, z, w = (f(v) for v in np.asarray(q, f) / f(np.linalg.norm(np.asarray(q, f))))
+        return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                         [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                         [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]], f)
+
+    R1, R2 = R_of(q1), R_of(q2)
+    t1, t2 = np.asarray(t1, f), np.asarray(t2, f)
+    R12 = (R1 @ R2.T).astype(f)
+    t12 = (t1 - R12 @ t2).astype(f)
+    Cw = (-(R1.T @ t1)).astype(f)
+    C2 = (R2 @ Cw + t2).astype(f)
+    ep = np.array([K2[0] * C2[0] / C2[2] + K2[2], K2[1] * C2[1] / C2[2] + K2[3]], f)
+    tx = np.array([[0, -t12[2], t12[1]], [t12[2], 0, -t12[0]], [-t12[1], t12[0], 0]], f)
+    Km = lambda K: np.array([[K[0], 0, K[2]], [0, K[1], K[3]], [0, 0, 1]], f)  # noqa: E731
+    F12 = (np.linalg.inv(Km(K1).T).astype(f) @ tx @ R12 @ np.linalg.inv(Km(K2)).astype(f)).astype(f)
+    return np.ascontiguousarray(F12.reshape(9)), ep
+
+
+def SearchForTriangulation(ctx: Frame, kf1: BowFeatures, kps1, kf2: BowFeatures, kps2, F12, ep, scale_factors2,
+                           level_sigma2_2, bCoarse=False, checkOri=True):
+    """ORBmatcher::SearchForTriangulation on mono keyframes -> (nmatches, vMatches12); BowFeatures.has_mp marks the
+    features that already hold a map point."""
+    L = lib()
+    _bind(L)
+    k1, k2 = _c(kps1, KP_DTYPE), _c(kps2, KP_DTYPE)
+    sf, s2 = _c(scale_factors2, np.float32), _c(level_sigma2_2, np.float32)
+    m12 = np.full(max(kf1.n, 1), -1, np.int32)
+    n = C.c_int()
+    sa, sb = kf1.struct(), kf2.struct()
+    check(L.dvm_match_for_triangulation(ctx.h, C.byref(sa), k1.ctypes.data, C.byref(sb), k2.ctypes.data,
+                                        _c(F12, np.float32).ctypes.data, _c(ep, np.float32).ctypes.data, sf.ctypes.data,
+                                        s2.ctypes.data, len(sf), int(bCoarse), int(checkOri), m12.ctypes.data, C.byref(n)))
+    return n.value, m12[:kf1.n]
+
+
+def FuseSearch(kf: Frame, q, t, K, xw, normal, min_dist, max_dist, mp_desc, skip=None, th=3.0):
+    """The search half of ORBmatcher::Fuse(pKF, vpMapPoints, th) -> (best_idx, best_dist) per map point."""
+    L = lib()
+    _bind(L)
+    a = [_c(xw, np.float32), _c(normal, np.float32), _c(min_dist, np.float32), _c(max_dist, np.float32), _c(mp_desc, np.uint8)]
+    m = len(a[2])
+    sk = _c(skip, np.uint8) if skip is not None else None
+    bi, bd = np.full(max(m, 1), -1, np.int32), np.full(max(m, 1), 256, np.int32)
+    check(L.dvm_fuse_search(kf.h, _c(q, np.float32).ctypes.data, _c(t, np.float32).ctypes.data,
+                            _c(K, np.float32).ctypes.data, m, *(x.ctypes.data for x in a),
+                            sk.ctypes.data if sk is not None else None, float(th), bi.ctypes.data, bd.ctypes.data))
+    return bi[:m], bd[:m]
 
 
 class HammingKnn:

@@ -235,6 +235,33 @@ DVM_API int dvm_match_for_initialization(dvm_frame* f2, int n1, const dvm_keypoi
                                          float* prev_matched, int window_size, float nnratio,
                                          int check_orientation, int32_t* matches12, int* nmatches);
 
+/* int ORBmatcher::SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, vector<pair<size_t,size_t>>& vMatchedPairs,
+ * const bool bOnlyStereo = false, const bool bCoarse)  (O3/src/ORBmatcher.cc:836-1058; caller
+ * LocalMapping::CreateNewMapPoints, O3/src/LocalMapping.cc:519), mono keyframes.  In kf1 / kf2 `has_mp[i]` means
+ * GetMapPoint(i) != NULL (such features are skipped; required here).  kps1 / kps2 = mvKeysUn.  F12 (row-major) =
+ * K1^-T [t12]x R12 K2^-1 and ep = camera 1's centre projected into image 2, both as the reference computes them
+ * from the two poses (:841-849, O3/src/CameraModels/Pinhole.cpp:104-110; the host adapter does this);
+ * scale_factors2 / level_sigma2_2 = pKF2->mvScaleFactors / mvLevelSigma2 (nlevels entries).
+ * matches12[kf1->n] receives vMatches12 (the caller builds vMatchedPairs from its entries >= 0). */
+DVM_API int dvm_match_for_triangulation(dvm_frame* ctx, const dvm_bow_features* kf1, const dvm_keypoint* kps1,
+                                        const dvm_bow_features* kf2, const dvm_keypoint* kps2, const float* F12,
+                                        const float* ep, const float* scale_factors2, const float* level_sigma2_2,
+                                        int nlevels, int coarse, int check_orientation, int32_t* matches12,
+                                        int* nmatches);
+
+/* The search half of int ORBmatcher::Fuse(KeyFrame* pKF, const vector<MapPoint*>& vpMapPoints, const float th,
+ * const bool bRight = false)  (O3/src/ORBmatcher.cc:1060-1228; caller LocalMapping::SearchInNeighbors,
+ * O3/src/LocalMapping.cc:818-849).  kf = the keyframe's device twin (mvKeysUn, mDescriptors, grid: an assigned
+ * dvm_frame).  pose_q / pose_t = pKF->GetPose(); K = fx, fy, cx, cy; per map point: world position, GetNormal(),
+ * mfMinDistance / mfMaxDistance (the 0.8 / 1.2 invariance factors are applied inside), descriptor, and
+ * skip[i] = !pMP || isBad() || IsInKeyFrame(pKF).  best_idx[m] / best_dist[m] receive the keypoint each map point
+ * would be fused with (bestDist <= TH_LOW), or -1 / 256.  The search does not read the keyframe's map points, so
+ * the caller applies Replace / AddObservation / AddMapPoint (:1209-1222) afterwards in vpMapPoints order. */
+DVM_API int dvm_fuse_search(dvm_frame* kf, const float* pose_q, const float* pose_t, const float* K, int m,
+                            const float* xw, const float* normal, const float* min_dist, const float* max_dist,
+                            const uint8_t* mp_desc, const uint8_t* skip, float th, int32_t* best_idx,
+                            int32_t* best_dist);
+
 /* ------------------------------------------------------------------------------------------------
  * Exhaustive nearest / second-nearest Hamming search (DescriptorDistance, O3/src/ORBmatcher.cc:1900-1914)
  * -- the inter-agent loop-closure exchange of config C3: every received keyframe's descriptors against

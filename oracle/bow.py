@@ -19,6 +19,9 @@ def _L():
     L.bowo_hamming_knn.argtypes = [_vp, C.c_int, _vp, C.c_int, _vp, _vp, _vp]
     L.bowo_hamming_knn.restype = None
     L.trko_search_for_initialization.argtypes = [C.c_int, _vp, _vp, _vp, _vp, C.c_int, C.c_float, C.c_int, _vp]
+    L.bowo_search_for_triangulation.argtypes = [C.c_int, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp] * 2 + [_vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp]
+    L.trko_fuse_search.argtypes = [_vp, _vp, _vp, _vp, C.c_int, C.c_float, _vp, C.c_int] + [_vp] * 6 + [C.c_float, _vp, _vp]
+    L.trko_fuse_search.restype = None
     L._bow_bound = True
     return L
 
@@ -73,3 +76,37 @@ def search_for_initialization(kps1, desc1, frame2_oracle, prev_matched, window=1
     n = L.trko_search_for_initialization(len(k1), k1.ctypes.data, d1.ctypes.data, frame2_oracle.h, pm.ctypes.data,
                                          int(window), float(nnratio), int(check_ori), m12.ctypes.data)
     return n, m12[:len(k1)], pm
+
+
+def search_for_triangulation(desc1, kps1, has_mp1, fv1, desc2, kps2, has_mp2, fv2, F12, ep, scale_factors2, level_sigma2_2,
+                             coarse=False, check_ori=True):
+    """-> (nmatches, matches12)"""
+    L = _L()
+    args, keep = [], []
+    for d, k, v, fv in ((desc1, kps1, has_mp1, fv1), (desc2, kps2, has_mp2, fv2)):
+        d, k, v = _c(d, np.uint8), _c(k, KP_DTYPE), _c(v, np.uint8)
+        nid, st, idx = _csr(fv)
+        keep += [d, k, v, nid, st, idx]
+        args += [len(k), d.ctypes.data, k.ctypes.data, v.ctypes.data, len(nid), nid.ctypes.data, st.ctypes.data, idx.ctypes.data]
+    n1 = args[0]
+    m12 = np.full(max(n1, 1), -1, np.int32)
+    F12, ep = _c(F12, np.float32), _c(ep, np.float32)
+    sf, s2 = _c(scale_factors2, np.float32), _c(level_sigma2_2, np.float32)
+    n = L.bowo_search_for_triangulation(*args, F12.ctypes.data, ep.ctypes.data, sf.ctypes.data, s2.ctypes.data, int(coarse),
+                                        int(check_ori), m12.ctypes.data)
+    return n, m12[:n1]
+
+
+def fuse_search(frame_oracle, q, t, K, log_scale, inv_sigma2, xw, normal, min_dist, max_dist, mp_desc, skip=None, th=3.0):
+    """frame_oracle: oracle.track.FrameOracle of the keyframe -> (best_idx, best_dist)"""
+    L = _L()
+    a = [_c(xw, np.float32), _c(normal, np.float32), _c(min_dist, np.float32), _c(max_dist, np.float32), _c(mp_desc, np.uint8)]
+    m = len(a[2])
+    sk = _c(skip, np.uint8) if skip is not None else None
+    isg = _c(inv_sigma2, np.float32)
+    bi, bd = np.full(max(m, 1), -1, np.int32), np.full(max(m, 1), 256, np.int32)
+    L.trko_fuse_search(frame_oracle.h, _c(q, np.float32).ctypes.data, _c(t, np.float32).ctypes.data,
+                       _c(K, np.float32).ctypes.data, len(isg), float(log_scale), isg.ctypes.data, m,
+                       *(x.ctypes.data for x in a), sk.ctypes.data if sk is not None else None, float(th), bi.ctypes.data,
+                       bd.ctypes.data)
+    return bi[:m], bd[:m]

@@ -5,6 +5,7 @@
  * (O3/ = /root/reference/src/slam_system/orb_slam3/):
  *   ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&)      O3/src/ORBmatcher.cc:214-393
  *   ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vector<MapPoint*>&)   O3/src/ORBmatcher.cc:709-834
+ *   ORBmatcher::SearchForTriangulation (mono, epipolar gate of Pinhole.cpp)  O3/src/ORBmatcher.cc:836-1058
  *   ORBmatcher::ComputeThreeMaxima                                      O3/src/ORBmatcher.cc:1862-1896
  *   ORBmatcher::DescriptorDistance                                      O3/src/ORBmatcher.cc:1900-1914
  * and the exhaustive nearest / second-nearest Hamming search that the inter-agent exchange (config C3)
@@ -153,6 +154,90 @@ void bowo_hamming_knn(const uint8_t* A, int na, const uint8_t* B, int nb, int* b
         }
         best_idx[i] = bi; best_dist[i] = b1; second_dist[i] = b2;
     }
+}
+
+/* SearchForTriangulation(pKF1, pKF2, vMatchedPairs, bOnlyStereo = false, bCoarse)  (O3/src/ORBmatcher.cc:836-1058),
+ * mono keyframes.  has_mp[i] = GetMapPoint(i) != NULL (such features are skipped on both sides); kps = mvKeysUn as
+ * {x, y, size, angle, response, octave, class_id} records; ep = the projection of camera 1's centre into image 2;
+ * F12 (row-major 3x3) = K1^-T [t12]x R12 K2^-1 as Pinhole::epipolarConstrain builds it
+ * (O3/src/CameraModels/Pinhole.cpp:104-127) -- computed once by the caller and shared with the CUDA path, since
+ * the check 'dsqr < 3.84 * unc' is evaluated in float.  Note that this fork never sets vbMatched2: features of
+ * keyframe 2 can be taken several times, and equal distances go to the LAST candidate ('dist > bestDist' skips).
+ * matches12[n1] receives vMatches12; returns nmatches. */
+struct OKeyPt { float x, y, size, angle, response; int32_t octave, class_id; };
+
+int bowo_search_for_triangulation(int n1, const uint8_t* desc1, const void* kps1_, const uint8_t* has_mp1, int nn1,
+                                  const uint32_t* node1, const int32_t* start1, const uint32_t* idx1, int n2,
+                                  const uint8_t* desc2, const void* kps2_, const uint8_t* has_mp2, int nn2,
+                                  const uint32_t* node2, const int32_t* start2, const uint32_t* idx2, const float* F12,
+                                  const float* ep, const float* scaleFactors2, const float* levelSigma2_2, int bCoarse,
+                                  int checkOri, int* matches12)
+{
+    const OKeyPt* kps1 = (const OKeyPt*)kps1_;
+    const OKeyPt* kps2 = (const OKeyPt*)kps2_;
+    for (int i = 0; i < n1; i++) matches12[i] = -1;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    const float factor = 1.0f / HISTO_LENGTH;
+    int nmatches = 0;
+    int ia = 0, ib = 0;
+    while (ia < nn1 && ib < nn2) {
+        if (node1[ia] == node2[ib]) {
+            for (int p = start1[ia]; p < start1[ia + 1]; p++) {
+                const int i1 = (int)idx1[p];
+                if (has_mp1[i1]) continue;
+                const OKeyPt& kp1 = kps1[i1];
+                const uint8_t* d1 = desc1 + (size_t)i1 * 32;
+                int bestDist = TH_LOW, bestIdx2 = -1;
+                for (int q = start2[ib]; q < start2[ib + 1]; q++) {
+                    const int i2 = (int)idx2[q];
+                    if (has_mp2[i2]) continue;
+                    const int dist = descriptor_distance(d1, desc2 + (size_t)i2 * 32);
+                    if (dist > TH_LOW || dist > bestDist) continue;
+                    const OKeyPt& kp2 = kps2[i2];
+                    const float distex = ep[0] - kp2.x, distey = ep[1] - kp2.y;
+                    if (distex * distex + distey * distey < 100 * scaleFactors2[kp2.octave]) continue;
+                    bool ok = bCoarse != 0;
+                    if (!ok) {
+                        const float a = kp1.x * F12[0] + kp1.y * F12[3] + F12[6];
+                        const float b = kp1.x * F12[1] + kp1.y * F12[4] + F12[7];
+                        const float c = kp1.x * F12[2] + kp1.y * F12[5] + F12[8];
+                        const float num = a * kp2.x + b * kp2.y + c;
+                        const float den = a * a + b * b;
+                        if (den != 0) {
+                            const float dsqr = num * num / den;
+                            ok = dsqr < 3.84 * levelSigma2_2[kp2.octave];   /* double comparison, as in the reference */
+                        }
+                    }
+                    if (ok) { bestIdx2 = i2; bestDist = dist; }
+                }
+                if (bestIdx2 >= 0) {
+                    matches12[i1] = bestIdx2;
+                    nmatches++;
+                    if (checkOri) {
+                        float rot = kp1.angle - kps2[bestIdx2].angle;
+                        if (rot < 0.0) rot += 360.0f;
+                        int bin = (int)std::round(rot * factor);
+                        if (bin == HISTO_LENGTH) bin = 0;
+                        rotHist[bin].push_back(i1);
+                    }
+                }
+            }
+            ia++; ib++;
+        } else if (node1[ia] < node2[ib]) {
+            while (ia < nn1 && node1[ia] < node2[ib]) ia++;
+        } else {
+            while (ib < nn2 && node2[ib] < node1[ia]) ib++;
+        }
+    }
+    if (checkOri) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (int j : rotHist[i]) { matches12[j] = -1; nmatches--; }
+        }
+    }
+    return nmatches;
 }
 
 } // extern "C"

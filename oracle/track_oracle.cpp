@@ -8,6 +8,7 @@
  *   ORBmatcher::SearchByProjection(Frame&, const Frame&, th, mono)  O3/src/ORBmatcher.cc:1553-1748
  *   ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>&, th)  O3/src/ORBmatcher.cc:44-212
  *   ORBmatcher::SearchForInitialization                             O3/src/ORBmatcher.cc:605-707
+ *   ORBmatcher::Fuse (search half, mono)                            O3/src/ORBmatcher.cc:1060-1228
  *   ORBmatcher::ComputeThreeMaxima                                  O3/src/ORBmatcher.cc:1862-1896
  *   Optimizer::PoseOptimization                                     O3/src/Optimizer.cc:744-1028
  *     with g2o's Levenberg-Marquardt (g2o/core/optimization_algorithm_levenberg.cpp:59-188),
@@ -681,6 +682,70 @@ int trko_search_for_initialization(int n1, const void* kps1_, const uint8_t* des
             prev_matched[2 * i1 + 1] = F2.kps[matches12[i1]].y;
         }
     return nmatches;
+}
+
+/* The search half of ORBmatcher::Fuse(pKF, vpMapPoints, th, bRight = false)  (O3/src/ORBmatcher.cc:1060-1228): per map
+ * point the keyframe keypoint it would be fused with (best_idx, best_dist; -1 when a gate rejects it or bestDist >
+ * TH_LOW).  The search does not read the keyframe's map points, so it is independent of the side effects
+ * (Replace / AddObservation / AddMapPoint, :1209-1222), which the caller applies afterwards in vpMapPoints order.
+ * fkf = the keyframe's keypoints/descriptors/grid (KeyFrame::GetFeaturesInArea has no level filter).
+ * skip[i]: !pMP || isBad() || IsInKeyFrame(pKF).  min_dist / max_dist = mfMinDistance / mfMaxDistance.
+ * Conventions: p3Dc = Tcw * p3Dw is Sophus' quaternion form (Eigen's _transformVector), Ow = -(q^-1 * t), float. */
+void trko_fuse_search(void* fkf, const float* q_in, const float* t, const float* K, int nlevels, float logScaleFactor,
+                      const float* invLevelSigma2, int m, const float* xw, const float* normal, const float* min_dist,
+                      const float* max_dist, const uint8_t* mp_desc, const uint8_t* skip, float th, int* best_idx,
+                      int* best_dist)
+{
+    Frame& F = *(Frame*)fkf;
+    const float qn = std::sqrt(q_in[0] * q_in[0] + q_in[1] * q_in[1] + q_in[2] * q_in[2] + q_in[3] * q_in[3]);
+    const float qx = q_in[0] / qn, qy = q_in[1] / qn, qz = q_in[2] / qn, qw = q_in[3] / qn;
+    auto rot = [](float x, float y, float z, float w, const float v[3], float out[3]) {
+        /* Eigen::QuaternionBase::_transformVector: uv = 2 * (q.vec x v); v + w * uv + q.vec x uv */
+        float uv[3] = { y * v[2] - z * v[1], z * v[0] - x * v[2], x * v[1] - y * v[0] };
+        uv[0] += uv[0]; uv[1] += uv[1]; uv[2] += uv[2];
+        out[0] = v[0] + w * uv[0] + (y * uv[2] - z * uv[1]);
+        out[1] = v[1] + w * uv[1] + (z * uv[0] - x * uv[2]);
+        out[2] = v[2] + w * uv[2] + (x * uv[1] - y * uv[0]);
+    };
+    float Ow[3];
+    { float r[3]; rot(-qx, -qy, -qz, qw, t, r); Ow[0] = -r[0]; Ow[1] = -r[1]; Ow[2] = -r[2]; }
+    std::vector<int> idx;
+    for (int i = 0; i < m; i++) {
+        best_idx[i] = -1; best_dist[i] = 256;
+        if (skip && skip[i]) continue;
+        const float* P = xw + 3 * i;
+        float pc[3];
+        rot(qx, qy, qz, qw, P, pc);
+        pc[0] += t[0]; pc[1] += t[1]; pc[2] += t[2];
+        if (pc[2] < 0.0f) continue;
+        const float u = K[0] * pc[0] / pc[2] + K[2], v = K[1] * pc[1] / pc[2] + K[3];     /* Pinhole::project */
+        if (!(u >= F.minX && u < F.maxX && v >= F.minY && v < F.maxY)) continue;          /* KeyFrame::IsInImage */
+        const float maxDistance = 1.2f * max_dist[i], minDistance = 0.8f * min_dist[i];
+        const float PO[3] = { P[0] - Ow[0], P[1] - Ow[1], P[2] - Ow[2] };
+        const float dist3D = std::sqrt(PO[0] * PO[0] + PO[1] * PO[1] + PO[2] * PO[2]);
+        if (dist3D < minDistance || dist3D > maxDistance) continue;
+        const float* Pn = normal + 3 * i;
+        if (PO[0] * Pn[0] + PO[1] * Pn[1] + PO[2] * Pn[2] < 0.5 * dist3D) continue;
+        const float ratio = max_dist[i] / dist3D;
+        int nPredictedLevel = (int)std::ceil((float)std::log((double)ratio) / logScaleFactor);   /* PredictScale */
+        if (nPredictedLevel < 0) nPredictedLevel = 0;
+        else if (nPredictedLevel >= nlevels) nPredictedLevel = nlevels - 1;
+        const float radius = th * F.scaleFactors[nPredictedLevel];
+        features_in_area(F, u, v, radius, -1, -1, idx);
+        if (idx.empty()) continue;
+        const uint8_t* dMP = mp_desc + (size_t)i * 32;
+        int bestDist = 256, bestIdx = -1;
+        for (int k : idx) {
+            const KeyPt& kp = F.kps[k];
+            if (kp.octave < nPredictedLevel - 1 || kp.octave > nPredictedLevel) continue;
+            const float ex = u - kp.x, ey = v - kp.y;
+            const float e2 = ex * ex + ey * ey;
+            if (e2 * invLevelSigma2[kp.octave] > 5.99) continue;
+            const int dist = descriptor_distance(dMP, &F.desc[(size_t)k * 32]);
+            if (dist < bestDist) { bestDist = dist; bestIdx = k; }
+        }
+        if (bestDist <= TH_LOW) { best_idx[i] = bestIdx; best_dist[i] = bestDist; }
+    }
 }
 
 } // extern "C"

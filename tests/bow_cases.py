@@ -49,3 +49,49 @@ def init_pair(extract, k0=1, k1=4, w=640, h=480):
     k2_, d2, _ = extract(S.frame(k1))
     prev = np.stack([k1_["x"], k1_["y"]], 1).astype(np.float32)
     return dict(kps1=k1_, desc1=d1, kps2=k2_, desc2=d2, prev=prev, bounds=(0.0, 0.0, float(w), float(h)))
+
+
+def triangulation_pair(extract, k0=2, k1=6, w=640, h=480, seed=0, mp_frac=0.5):
+    """Two keyframes of the plane stream with their true relative pose: inputs of SearchForTriangulation."""
+    from dvmslam_b200.matching import fundamental_from_poses
+
+    S = synth.PlaneStream(w, h, seed=3, K=(500.0, 500.0, w / 2, h / 2))
+    rng = np.random.default_rng(seed)
+    out = {}
+    poses = []
+    for tag, k in (("1", k0), ("2", k1)):
+        kps, desc, _ = extract(S.frame(k))
+        out["kps" + tag], out["desc" + tag] = kps, desc
+        out["has_mp" + tag] = (rng.random(len(kps)) < mp_frac).astype(np.uint8)
+        out["fv" + tag] = synth.toy_feature_vector(desc)
+        R, t = S.pose(k)
+        poses.append((synth.quat_from_R(np.asarray(R, np.float64)).astype(np.float32), np.asarray(t, np.float32)))
+    K = np.array(S.K, np.float32)
+    out["F12"], out["ep"] = fundamental_from_poses(poses[0][0], poses[0][1], poses[1][0], poses[1][1], K, K)
+    out["K"], out["poses"], out["stream"] = K, poses, S
+    return out
+
+
+def fuse_case(extract, k=4, k_src=1, w=640, h=480, seed=0, n_points=1500):
+    """A keyframe (view k) and map points lifted from another view's keypoints: inputs of Fuse."""
+    S = synth.PlaneStream(w, h, seed=3, K=(500.0, 500.0, w / 2, h / 2))
+    rng = np.random.default_rng(seed)
+    kps, desc, _ = extract(S.frame(k))
+    mk, md, _ = extract(S.frame(k_src))
+    sel = np.sort(rng.permutation(len(mk))[:n_points])
+    X = synth.backproject_to_plane(S, k_src, np.stack([mk["x"][sel], mk["y"][sel]], 1).astype(np.float64)).astype(np.float32)
+    R0, t0 = S.pose(k_src)
+    Ow = -(np.asarray(R0, np.float64).T @ np.asarray(t0, np.float64))
+    PO = X.astype(np.float64) - Ow
+    d = np.linalg.norm(PO, axis=1)
+    normal = (PO / d[:, None]).astype(np.float32)
+    lvl = mk["octave"][sel].astype(np.float64)
+    # MapPoint::UpdateNormalAndDepth: mfMaxDistance = dist * scale[level], mfMinDistance = mfMaxDistance / scale[nLevels - 1]
+    max_d = (d * 1.2 ** lvl).astype(np.float32)
+    min_d = (max_d / np.float32(1.2 ** 7)).astype(np.float32)
+    R, t = S.pose(k)
+    q = synth.quat_from_R(np.asarray(R, np.float64)).astype(np.float32)
+    skip = (rng.random(len(sel)) < 0.1).astype(np.uint8)
+    return dict(kps=kps, desc=desc, q=q, t=np.asarray(t, np.float32), K=np.array(S.K, np.float32), xw=X, normal=normal,
+                min_dist=min_d, max_dist=max_d, mp_desc=np.ascontiguousarray(md[sel]), skip=skip,
+                bounds=(0.0, 0.0, float(w), float(h)))

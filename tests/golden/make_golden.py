@@ -101,6 +101,17 @@ def main():
     n, m12, pm = search_for_initialization(ci["kps1"], ci["desc1"], F2, ci["prev"], 100, 0.9, True)
     out["init_n"], out["init_m12"], out["init_prev"] = np.int32(n), m12, pm
     out["knn"] = np.stack(hamming_knn(c["desc1"], c["desc2"]))
+    from oracle.bow import fuse_search, search_for_triangulation
+
+    ct = bow_cases.triangulation_pair(orc.extract)
+    n, m12 = search_for_triangulation(ct["desc1"], ct["kps1"], ct["has_mp1"], ct["fv1"], ct["desc2"], ct["kps2"], ct["has_mp2"],
+                                      ct["fv2"], ct["F12"], ct["ep"], T["scale"], T["sigma2"])
+    out["tri_n"], out["tri_m12"], out["tri_F12"], out["tri_ep"] = np.int32(n), m12, ct["F12"], ct["ep"]
+    cf = bow_cases.fuse_case(orc.extract)
+    Fk = FrameOracle(cf["kps"], cf["desc"], cf["bounds"], T["scale"])
+    bi, bd = fuse_search(Fk, cf["q"], cf["t"], cf["K"], float(np.float32(np.log(np.float64(T["scale"][1])))), T["inv_sigma2"],
+                         cf["xw"], cf["normal"], cf["min_dist"], cf["max_dist"], cf["mp_desc"], cf["skip"], 3.0)
+    out["fuse_idx"], out["fuse_dist"] = bi, bd
     np.savez_compressed(os.path.join(HERE, "bow_small.npz"), **out)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):

@@ -292,3 +292,90 @@ int hm_local_ba(int nc, float* cam_q, float* cam_t, const uint8_t* cam_fixed, in
 }
 
 } // extern "C"
+
+namespace {
+void fill_keyframe(KeyFrame& K, const dvm_keypoint* kps, const uint8_t* desc, int n, const float* scale, const float* sigma2,
+                   const float* invsig2, int nlevels, const float* q, const float* t, unsigned long id)
+{
+    K.mnId = id; K.N = n;
+    K.mvKeysUn.resize(n);
+    if (n) std::memcpy((void*)K.mvKeysUn.data(), kps, sizeof(dvm_keypoint) * n);
+    K.mDescriptors.create(n > 0 ? n : 1, 32, CV_8U);
+    for (int i = 0; i < n; i++) std::memcpy(K.mDescriptors.ptr(i), desc + (size_t)i * 32, 32);
+    K.mapPoints.assign(n, nullptr);
+    K.mvuRight.assign(n, -1.f);
+    K.mvScaleFactors.assign(scale, scale + nlevels);
+    K.mvLevelSigma2.assign(sigma2, sigma2 + nlevels);
+    K.mvInvLevelSigma2.assign(invsig2, invsig2 + nlevels);
+    K.fx = g_K[0]; K.fy = g_K[1]; K.cx = g_K[2]; K.cy = g_K[3];
+    K.mnMinX = Frame::mnMinX; K.mnMinY = Frame::mnMinY; K.mnMaxX = Frame::mnMaxX; K.mnMaxY = Frame::mnMaxY;
+    set_pose(K.Tcw, q, t);
+}
+} // namespace
+
+extern "C" {
+
+// LocalMapping::CreateNewMapPoints' matcher call.  pairs[2 * cap] receives vMatchedPairs; returns nmatches.
+int hm_search_for_triangulation(const dvm_keypoint* k1, const uint8_t* d1, int n1, const uint8_t* has1, int nn1, const uint32_t* node1,
+                                const int32_t* st1, const uint32_t* idx1, const float* q1, const float* t1, const dvm_keypoint* k2,
+                                const uint8_t* d2, int n2, const uint8_t* has2, int nn2, const uint32_t* node2, const int32_t* st2,
+                                const uint32_t* idx2, const float* q2, const float* t2, const float* scale, const float* sigma2,
+                                const float* invsig2, int nlevels, int coarse, int checkOri, int* pairs, int cap, int* npairs)
+{
+    KeyFrame K1, K2;
+    fill_keyframe(K1, k1, d1, n1, scale, sigma2, invsig2, nlevels, q1, t1, 1);
+    fill_keyframe(K2, k2, d2, n2, scale, sigma2, invsig2, nlevels, q2, t2, 2);
+    K1.mFeatVec = to_fv(nn1, node1, st1, idx1);
+    K2.mFeatVec = to_fv(nn2, node2, st2, idx2);
+    MapPoint some;
+    for (int i = 0; i < n1; i++) if (has1[i]) K1.mapPoints[i] = &some;
+    for (int i = 0; i < n2; i++) if (has2[i]) K2.mapPoints[i] = &some;
+    return guarded([&] {
+        std::vector<std::pair<size_t, size_t>> vp;
+        const int n = dvm_host::SearchForTriangulation(&K1, &K2, vp, false, coarse != 0, checkOri != 0, dvm_host::device_frame(K1).frame.h);
+        *npairs = (int)vp.size();
+        for (size_t i = 0; i < vp.size() && (int)i < cap; i++) { pairs[2 * i] = (int)vp[i].first; pairs[2 * i + 1] = (int)vp[i].second; }
+        return n;
+    });
+}
+
+// LocalMapping::SearchInNeighbors' Fuse call.  kf_has_mp[n]: the keyframe keypoint already holds a map point (with
+// kf_mp_obs[n] observations).  Per listed map point: action[i] = 0 nothing, 1 added to the keyframe at kp[i],
+// 2 it replaced the keyframe's point, 3 it was replaced by the keyframe's point.
+int hm_fuse(const dvm_keypoint* kps, const uint8_t* desc, int n, const float* scale, const float* sigma2, const float* invsig2,
+            int nlevels, const float* q, const float* t, const uint8_t* kf_has_mp, const int* kf_mp_obs, int m, const uint8_t* skip,
+            const float* xw, const float* normal, const float* min_dist, const float* max_dist, const uint8_t* mp_desc,
+            const int* mp_obs, float th, int* action, int* kp)
+{
+    KeyFrame K;
+    fill_keyframe(K, kps, desc, n, scale, sigma2, invsig2, nlevels, q, t, 7);
+    std::vector<std::unique_ptr<MapPoint>> held(n), mps(m);
+    for (int i = 0; i < n; i++)
+        if (kf_has_mp[i]) { held[i].reset(new MapPoint); held[i]->nObs = kf_mp_obs[i]; K.mapPoints[i] = held[i].get(); }
+    std::vector<MapPoint*> vp(m, nullptr);
+    for (int i = 0; i < m; i++) {
+        if (skip[i]) continue;    // null entry of vpMapPoints
+        mps[i].reset(new MapPoint);
+        MapPoint& p = *mps[i];
+        for (int k = 0; k < 3; k++) { p.pos(k) = xw[3 * i + k]; p.normal(k) = normal[3 * i + k]; }
+        p.minDistInv = 0.8f * min_dist[i]; p.maxDistInv = 1.2f * max_dist[i];
+        std::memcpy(p.desc.ptr(0), mp_desc + (size_t)i * 32, 32);
+        p.nObs = mp_obs[i];
+        vp[i] = &p;
+    }
+    return guarded([&] {
+        const int nFused = dvm_host::Fuse(&K, vp, th);
+        for (int i = 0; i < m; i++) {
+            action[i] = 0; kp[i] = -1;
+            if (!vp[i]) continue;
+            if (vp[i]->replacedBy) { action[i] = 3; continue; }
+            for (int k = 0; k < n; k++) {
+                if (K.mapPoints[k] == vp[i]) { action[i] = 1; kp[i] = k; }
+                if (held[k] && held[k]->replacedBy == vp[i]) { action[i] = 2; kp[i] = k; }
+            }
+        }
+        return nFused;
+    });
+}
+
+} // extern "C"

@@ -65,6 +65,15 @@ struct MapPoint {
     std::map<KeyFrame*, std::tuple<int, int>> observations;
     int normalUpdates = 0;
 
+    Vec3 normal;
+    float minDistInv = 0, maxDistInv = 0;   // GetMin/MaxDistanceInvariance()
+    MapPoint* replacedBy = nullptr;
+    Vec3 GetNormal() const { return normal; }
+    float GetMinDistanceInvariance() const { return minDistInv; }
+    float GetMaxDistanceInvariance() const { return maxDistInv; }
+    bool IsInKeyFrame(KeyFrame* kf) const { return observations.count(kf) != 0; }
+    void AddObservation(KeyFrame* kf, int idx) { observations[kf] = std::make_tuple(idx, -1); nObs++; }
+    void Replace(MapPoint* other) { replacedBy = other; bad = true; }
     Vec3 GetWorldPos() const { return pos; }
     void SetWorldPos(const Vec3& p) { pos = p; }
     cv::Mat GetDescriptor() const { return desc; }
@@ -100,9 +109,12 @@ struct KeyFrame {
     unsigned long mnBALocalForKF = ~0ul, mnBAFixedForKF = ~0ul;
     int N = 0, NLeft = -1;
     std::vector<cv::KeyPoint> mvKeysUn;
-    std::vector<float> mvuRight, mvInvLevelSigma2;
+    std::vector<float> mvuRight, mvInvLevelSigma2, mvScaleFactors, mvLevelSigma2;
+    float mnMinX = 0, mnMinY = 0, mnMaxX = 0, mnMaxY = 0;
     cv::Mat mDescriptors;
     std::vector<MapPoint*> mapPoints;
+    MapPoint* GetMapPoint(size_t i) const { return mapPoints[i]; }
+    void AddMapPoint(MapPoint* mp, size_t i) { mapPoints[i] = mp; }
     std::vector<KeyFrame*> covisible;
     FeatureVector mFeatVec;
     SE3f Tcw;

@@ -207,3 +207,62 @@ def test_bow_golden_gpu(ctx):
     h = HammingKnn()
     assert np.array_equal(np.stack(h.knn(c["desc1"], c["desc2"])), g["knn"])
     h.close()
+    from dvmslam_b200.matching import FuseSearch, SearchForTriangulation
+
+    ct = bow_cases.triangulation_pair(orc.extract)
+    n, m12 = SearchForTriangulation(ctx, BowFeatures(ct["desc1"], ct["kps1"]["angle"], ct["has_mp1"], ct["fv1"]), ct["kps1"],
+                                    BowFeatures(ct["desc2"], ct["kps2"]["angle"], ct["has_mp2"], ct["fv2"]), ct["kps2"],
+                                    g["tri_F12"], g["tri_ep"], T["scale"], T["sigma2"])
+    assert n == int(g["tri_n"]) and np.array_equal(m12, g["tri_m12"])
+    cf = bow_cases.fuse_case(orc.extract)
+    Fk = Frame(len(cf["kps"]) + 16, T["scale"], T["inv_sigma2"])
+    Fk.assign(cf["kps"], cf["desc"], cf["bounds"])
+    bi, bd = FuseSearch(Fk, cf["q"], cf["t"], cf["K"], cf["xw"], cf["normal"], cf["min_dist"], cf["max_dist"], cf["mp_desc"],
+                        cf["skip"], 3.0)
+    assert np.array_equal(bi, g["fuse_idx"]) and np.array_equal(bd, g["fuse_dist"])
+    Fk.close()
+
+
+@pytest.mark.parametrize("w,h,nf", [(640, 480, 1000), (1280, 720, 2000)])
+def test_search_for_triangulation(ctx, w, h, nf):
+    from dvmslam_b200.matching import BowFeatures, SearchForTriangulation
+    from oracle.bow import search_for_triangulation
+    from oracle.orb import OrbOracle
+
+    orc = OrbOracle(nf)
+    T = orc.tables()
+    c = bow_cases.triangulation_pair(orc.extract, w=w, h=h)
+    one = dict(c, fv1={4: list(range(len(c["kps1"])))}, fv2={4: list(range(len(c["kps2"])))})   # one node: long candidate lists
+    for case in (c, one):
+        for coarse, ori in ((False, True), (False, False), (True, True)):
+            n0, m0 = search_for_triangulation(case["desc1"], case["kps1"], case["has_mp1"], case["fv1"], case["desc2"], case["kps2"],
+                                              case["has_mp2"], case["fv2"], case["F12"], case["ep"], T["scale"], T["sigma2"], coarse, ori)
+            a = BowFeatures(case["desc1"], case["kps1"]["angle"], case["has_mp1"], case["fv1"])
+            b = BowFeatures(case["desc2"], case["kps2"]["angle"], case["has_mp2"], case["fv2"])
+            n1, m1 = SearchForTriangulation(ctx, a, case["kps1"], b, case["kps2"], case["F12"], case["ep"], T["scale"], T["sigma2"],
+                                            coarse, ori)
+            assert n0 == n1 and np.array_equal(m0, m1), (coarse, ori)
+    assert n0 > 30
+
+
+@pytest.mark.parametrize("w,h,nf,th", [(640, 480, 1000, 3.0), (1280, 720, 2000, 3.0), (1280, 720, 2000, 8.0)])
+def test_fuse_search(w, h, nf, th):
+    from dvmslam_b200.matching import FuseSearch
+    from dvmslam_b200.tracking import Frame
+    from oracle.bow import fuse_search
+    from oracle.orb import OrbOracle
+    from oracle.track import FrameOracle
+
+    orc = OrbOracle(nf)
+    T = orc.tables()
+    c = bow_cases.fuse_case(orc.extract, w=w, h=h, n_points=3000)
+    F0 = FrameOracle(c["kps"], c["desc"], c["bounds"], T["scale"])
+    F1 = Frame(len(c["kps"]) + 16, T["scale"], T["inv_sigma2"])
+    F1.assign(c["kps"], c["desc"], c["bounds"])
+    log_scale = float(np.float32(np.log(np.float64(T["scale"][1]))))
+    i0, d0 = fuse_search(F0, c["q"], c["t"], c["K"], log_scale, T["inv_sigma2"], c["xw"], c["normal"], c["min_dist"], c["max_dist"],
+                         c["mp_desc"], c["skip"], th)
+    i1, d1 = FuseSearch(F1, c["q"], c["t"], c["K"], c["xw"], c["normal"], c["min_dist"], c["max_dist"], c["mp_desc"], c["skip"], th)
+    assert np.array_equal(i0, i1) and np.array_equal(d0, d1)
+    assert (i1 >= 0).sum() > 100
+    F1.close()

@@ -163,3 +163,72 @@ def test_bow_golden():
     assert n == int(g["init_n"]) and np.array_equal(m12, g["init_m12"]) and np.array_equal(pm, g["init_prev"])
     idx, d1, d2 = hamming_knn(c["desc1"], c["desc2"])
     assert np.array_equal(np.stack([idx, d1, d2]), g["knn"])
+    from oracle.bow import fuse_search, search_for_triangulation
+
+    ct = bow_cases.triangulation_pair(orc.extract)
+    assert np.array_equal(ct["F12"], g["tri_F12"]) and np.array_equal(ct["ep"], g["tri_ep"])
+    n, m12 = search_for_triangulation(ct["desc1"], ct["kps1"], ct["has_mp1"], ct["fv1"], ct["desc2"], ct["kps2"], ct["has_mp2"],
+                                      ct["fv2"], g["tri_F12"], g["tri_ep"], T["scale"], T["sigma2"])
+    assert n == int(g["tri_n"]) and np.array_equal(m12, g["tri_m12"])
+    cf = bow_cases.fuse_case(orc.extract)
+    Fk = FrameOracle(cf["kps"], cf["desc"], cf["bounds"], T["scale"])
+    bi, bd = fuse_search(Fk, cf["q"], cf["t"], cf["K"], float(np.float32(np.log(np.float64(T["scale"][1])))), T["inv_sigma2"],
+                         cf["xw"], cf["normal"], cf["min_dist"], cf["max_dist"], cf["mp_desc"], cf["skip"], 3.0)
+    assert np.array_equal(bi, g["fuse_idx"]) and np.array_equal(bd, g["fuse_dist"])
+
+
+def test_triangulation_oracle_properties():
+    """Hand-checkable properties of the SearchForTriangulation restatement on two views of a plane with the
+    true relative pose: matches only between map-point-free features, inside TH_LOW, on the epipolar line."""
+    from oracle.bow import search_for_triangulation
+    from oracle.orb import OrbOracle
+
+    orc = OrbOracle(1000)
+    T = orc.tables()
+    c = bow_cases.triangulation_pair(orc.extract)
+    args = (c["desc1"], c["kps1"], c["has_mp1"], c["fv1"], c["desc2"], c["kps2"], c["has_mp2"], c["fv2"], c["F12"], c["ep"],
+            T["scale"], T["sigma2"])
+    n, m12 = search_for_triangulation(*args)
+    idx = np.nonzero(m12 >= 0)[0]
+    assert n == len(idx) and n > 30
+    assert not c["has_mp1"][idx].any() and not c["has_mp2"][m12[idx]].any()
+    F = c["F12"].reshape(3, 3).astype(np.float64)
+    for i1 in idx:
+        k1, k2 = c["kps1"][i1], c["kps2"][m12[i1]]
+        assert _dist(c["desc1"][i1], c["desc2"][m12[i1]]) <= 50
+        l = np.array([k1["x"], k1["y"], 1.0]) @ F
+        d2 = (l[0] * k2["x"] + l[1] * k2["y"] + l[2]) ** 2 / (l[0] ** 2 + l[1] ** 2)
+        assert d2 < 3.84 * T["sigma2"][k2["octave"]] * 1.001
+    # bCoarse drops the epipolar gate: at least as many raw matches before the orientation filter
+    n_c, _ = search_for_triangulation(*args, coarse=True, check_ori=False)
+    n_f, _ = search_for_triangulation(*args, coarse=False, check_ori=False)
+    assert n_c >= n_f
+    # a wrong geometry (transposed F) rejects most pairs
+    bad = np.ascontiguousarray(c["F12"].reshape(3, 3).T.reshape(9))
+    n_b, _ = search_for_triangulation(*args[:8], bad, *args[9:], check_ori=False)
+    assert n_b < n_f
+
+
+def test_fuse_oracle_properties():
+    from oracle.bow import fuse_search
+    from oracle.orb import OrbOracle
+    from oracle.track import FrameOracle
+
+    orc = OrbOracle(1000)
+    T = orc.tables()
+    c = bow_cases.fuse_case(orc.extract)
+    F = FrameOracle(c["kps"], c["desc"], c["bounds"], T["scale"])
+    bi, bd = fuse_search(F, c["q"], c["t"], c["K"], float(np.log(np.float32(1.2))), T["inv_sigma2"], c["xw"], c["normal"],
+                         c["min_dist"], c["max_dist"], c["mp_desc"], c["skip"], 3.0)
+    ok = bi >= 0
+    assert ok.sum() > 100 and not ok[c["skip"] != 0].any()
+    assert (bd[ok] <= 50).all() and (bd[~ok] == 256).all()
+    for i in np.nonzero(ok)[0][:200]:
+        assert _dist(c["mp_desc"][i], c["desc"][bi[i]]) == bd[i]
+    # everything skipped / a camera looking away: nothing fuses
+    bi2, _ = fuse_search(F, c["q"], c["t"], c["K"], float(np.log(np.float32(1.2))), T["inv_sigma2"], c["xw"], c["normal"],
+                         c["min_dist"], c["max_dist"], c["mp_desc"], np.ones_like(c["skip"]), 3.0)
+    assert (bi2 < 0).all()
+    bi3, _ = fuse_search(F, c["q"], c["t"], c["K"], float(np.log(np.float32(1.2))), T["inv_sigma2"], c["xw"], -c["normal"],
+                         c["min_dist"], c["max_dist"], c["mp_desc"], c["skip"], 3.0)
+    assert (bi3 < 0).all()
