@@ -347,3 +347,37 @@ def keyframe_blocks(n_kf: int, n_feat: int, seed: int, shared_from: np.ndarray |
             dst = rng.choice(n_feat, ns, replace=False)
             out[k, dst] = noisy_copy(shared_from[k, src], flip_p, rng)
     return out
+
+
+def toy_vocabulary(k: int = 10, L: int = 3, seed: int = 0, ragged: bool = False, stop_frac: float = 0.05):
+    """A synthetic DBoW2 vocabulary tree in loadFromTextFile order (breadth first, parents before children):
+    -> dict(k, L, scoring, weighting, parent, is_leaf, desc, weight).  Child descriptors are noisy copies of their
+    parent's so that descents are meaningful; with `ragged` some inner nodes have fewer children and some branches
+    end in a leaf above level L; a few words are stopped (weight 0)."""
+    rng = np.random.default_rng(seed)
+    parent, is_leaf, desc, weight = [], [], [], []
+    frontier = [(0, rng.integers(0, 256, 32, dtype=np.uint8), 0)]   # (node id, descriptor, level)
+    next_id = 1
+    while frontier:
+        new = []
+        for pid, pdesc, lvl in frontier:
+            nchild = k if not ragged else int(rng.integers(2, k + 1))
+            for _ in range(nchild):
+                d = noisy_copy(pdesc[None, :], 0.25 / (lvl + 1), rng)[0]
+                leaf = lvl + 1 == L or (ragged and lvl + 1 >= 2 and rng.random() < 0.15)
+                parent.append(pid); is_leaf.append(int(leaf)); desc.append(d)
+                weight.append(0.0 if (leaf and rng.random() < stop_frac) else (float(rng.uniform(0.5, 9.0)) if leaf else 0.0))
+                if not leaf:
+                    new.append((next_id, d, lvl + 1))
+                next_id += 1
+        frontier = new
+    return dict(k=k, L=L, scoring=0, weighting=0, parent=np.array(parent, np.int64), is_leaf=np.array(is_leaf, np.int64),
+                desc=np.array(desc, np.uint8), weight=np.array(weight, np.float64))
+
+
+def write_vocabulary_text(path: str, v: dict) -> None:
+    """ORBvoc.txt format (DBoW2 saveToTextFile)."""
+    with open(path, "w") as f:
+        f.write(f"{v['k']} {v['L']}  {v['scoring']} {v['weighting']}\n")
+        for p, leaf, d, w in zip(v["parent"], v["is_leaf"], v["desc"], v["weight"]):
+            f.write(f"{int(p)} {int(leaf)} " + " ".join(str(int(x)) for x in d) + f" {float(w)!r}\n")

@@ -263,6 +263,25 @@ DVM_API int dvm_fuse_search(dvm_frame* kf, const float* pose_q, const float* pos
                             int32_t* best_dist);
 
 /* ------------------------------------------------------------------------------------------------
+ * DBoW2 vocabulary transform   -- Frame::ComputeBoW / KeyFrame::ComputeBoW (O3/src/Frame.cc:784-789):
+ * ORBVocabulary::transform(features, mBowVec, mFeatVec, 4)
+ * (O3/Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1025-1146)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct dvm_vocabulary dvm_vocabulary;
+/* The k-ary tree, flat (what loadFromTextFile builds, TemplatedVocabulary.h:1211-1287): node 0 is the root; the
+ * children of node i are children[child_start[i] .. child_start[i+1]) in push_back order; a node without children
+ * is a word with word_id[i] >= 0 and weight[i]; desc[n_nodes * 32] holds the node descriptors; L = m_L. */
+DVM_API int dvm_vocabulary_create(dvm_vocabulary** out, int device, int n_nodes, const int32_t* child_start,
+                                  const int32_t* children, const uint8_t* desc, const double* weight,
+                                  const int32_t* word_id, int L);
+DVM_API void dvm_vocabulary_destroy(dvm_vocabulary* v);
+/* transform(feature, word_id, weight, &nid, levelsup) for n descriptors (host arrays, synchronous).  The caller
+ * assembles BowVector (addWeight / addIfNotExist per feature in index order, then normalize) and FeatureVector
+ * (addFeature(nid, i)) from the three outputs, skipping features with weight <= 0 (stopped words). */
+DVM_API int dvm_vocabulary_transform(dvm_vocabulary* v, const uint8_t* desc, int n, int levelsup, int32_t* word_id,
+                                     double* weight, int32_t* node_id);
+
+/* ------------------------------------------------------------------------------------------------
  * Exhaustive nearest / second-nearest Hamming search (DescriptorDistance, O3/src/ORBmatcher.cc:1900-1914)
  * -- the inter-agent loop-closure exchange of config C3: every received keyframe's descriptors against
  * every local keyframe's, without the vocabulary prefilter (see csrc/hamming.cu).

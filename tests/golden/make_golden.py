@@ -13,6 +13,9 @@
   bow_small.npz       SearchByBoW (both overloads), SearchForInitialization and exhaustive nearest/second-nearest
                       results of the oracle on the seeded cases of tests/bow_cases.py (regression pins, no upstream
                       fixture).
+  dbow_orbvoc.npz     the DBoW2 transform of 240 descriptors through the reference's own ORBvoc.txt (k = 10, L = 6,
+                      1 082 073 nodes): the visited excerpt of the tree (every child of every node on a visited path) and the
+                      oracle's words / nodes / BowVector -- the vocabulary itself does not travel to the GPU box.
 The reference repository holds no fixtures for this path; these are ours.
 """
 import os
@@ -113,6 +116,45 @@ def main():
                          cf["xw"], cf["normal"], cf["min_dist"], cf["max_dist"], cf["mp_desc"], cf["skip"], 3.0)
     out["fuse_idx"], out["fuse_dist"] = bi, bd
     np.savez_compressed(os.path.join(HERE, "bow_small.npz"), **out)
+    # ---- DBoW2 transform on an excerpt of the reference's own vocabulary (ORBvoc.txt, k = 10, L = 6) ----
+    voc_tar = "/root/reference/src/slam_system/orb_slam3/Vocabulary/ORBvoc.txt.tar.gz"
+    if os.path.exists(voc_tar):
+        import tarfile
+        import tempfile
+
+        from dvmslam_b200.vocabulary import flatten_tree, load_text
+        from oracle.dbow import transform, transform_features
+
+        with tempfile.TemporaryDirectory() as tmp:
+            tarfile.open(voc_tar).extractall(tmp)
+            k, L, sc, wt, parent, is_leaf, vdesc, vweight = load_text(os.path.join(tmp, "ORBvoc.txt"))
+        tree = flatten_tree(parent, is_leaf, vdesc, vweight)
+        cs, ch, vd, vw, wid = tree
+        feat = extract_with_cv2(frame, 500)[1][:240]
+        word, w, nid = transform_features(tree, L, feat, 4)
+        bow, fv = transform(tree, L, wt, sc, feat, 4)
+        # keep every node whose parent lies on a visited path (a descent only ever reads those)
+        keep = np.zeros(len(wid), bool)
+        keep[0] = True
+        for i in range(len(feat)):
+            node = 0
+            while cs[node + 1] > cs[node]:
+                kids = ch[cs[node]:cs[node + 1]]
+                keep[kids] = True
+                d = [int(np.unpackbits(feat[i] ^ vd[c]).sum()) for c in kids]
+                node = int(kids[int(np.argmin(d))])
+            assert wid[node] == word[i]
+        new_id = np.cumsum(keep) - 1
+        old = np.nonzero(keep)[0]
+        counts = np.array([int(keep[ch[cs[o]:cs[o + 1]]].sum()) for o in old])
+        p_cs = np.zeros(len(old) + 1, np.int32)
+        p_cs[1:] = np.cumsum(counts)
+        p_ch = np.concatenate([new_id[ch[cs[o]:cs[o + 1]][keep[ch[cs[o]:cs[o + 1]]]]] for o in old]).astype(np.int32)
+        np.savez_compressed(os.path.join(HERE, "dbow_orbvoc.npz"), k=np.int32(k), L=np.int32(L), scoring=np.int32(sc),
+                            weighting=np.int32(wt), child_start=p_cs, children=p_ch, desc=vd[old], weight=vw[old],
+                            word_id=wid[old], orig_node=old.astype(np.int32), feat=feat, word=word, w=w, nid=nid,
+                            bow_word=np.array(list(bow), np.int32), bow_value=np.array(list(bow.values())),
+                            n_nodes_full=np.int32(len(wid)), n_words_full=np.int32(int((wid >= 0).sum())))
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

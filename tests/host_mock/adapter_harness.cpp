@@ -9,6 +9,7 @@
 #include "mock_slam.h"
 #include "optimizer_adapter.h"
 #include "orb_matcher_adapter.h"
+#include "vocabulary_adapter.h"
 
 namespace mock {
 std::mutex MapPoint::mGlobalMutex;
@@ -375,6 +376,54 @@ int hm_fuse(const dvm_keypoint* kps, const uint8_t* desc, int n, const float* sc
             }
         }
         return nFused;
+    });
+}
+
+} // extern "C"
+
+// DBoW2::BowVector / FeatureVector with the reference's method semantics (DBoW2/BowVector.cpp:30-71,
+// DBoW2/FeatureVector.cpp:27-37)
+namespace mock {
+enum LNorm { L1, L2 };
+struct BowVector : std::map<unsigned, double> {
+    void addWeight(unsigned id, double v) { auto it = lower_bound(id); if (it != end() && it->first == id) it->second += v; else insert(it, value_type(id, v)); }
+    void addIfNotExist(unsigned id, double v) { auto it = lower_bound(id); if (it == end() || it->first != id) insert(it, value_type(id, v)); }
+    void normalize(LNorm t)
+    {
+        double norm = 0.0;
+        if (t == L1) for (auto& kv : *this) norm += std::fabs(kv.second);
+        else { for (auto& kv : *this) norm += kv.second * kv.second; norm = std::sqrt(norm); }
+        if (norm > 0.0) for (auto& kv : *this) kv.second /= norm;
+    }
+};
+struct FeatureVectorMap : std::map<unsigned, std::vector<unsigned>> {
+    void addFeature(unsigned id, unsigned i) { (*this)[id].push_back(i); }
+};
+}
+
+extern "C" {
+
+// Frame::ComputeBoW through the adapter: vocabulary from a text file, descriptors as cv::Mat rows
+int hm_compute_bow(const char* voc_path, const uint8_t* desc, int n, int levelsup, int* bow_word, double* bow_value, int* n_bow,
+                   int* fv_node, int* fv_start, int* fv_idx, int* n_fv)
+{
+    return guarded([&] {
+        dvm_host::Vocabulary voc;
+        if (!voc.loadFromTextFile(voc_path)) return -1;
+        std::vector<cv::Mat> feats(n);
+        for (int i = 0; i < n; i++) { feats[i].create(1, 32, CV_8U); std::memcpy(feats[i].ptr(0), desc + (size_t)i * 32, 32); }
+        mock::BowVector v;
+        mock::FeatureVectorMap fv;
+        voc.transform(feats, v, fv, levelsup);
+        int k = 0;
+        for (auto& kv : v) { bow_word[k] = (int)kv.first; bow_value[k] = kv.second; k++; }
+        *n_bow = k;
+        k = 0;
+        int p = 0;
+        fv_start[0] = 0;
+        for (auto& kv : fv) { fv_node[k] = (int)kv.first; for (unsigned i : kv.second) fv_idx[p++] = (int)i; fv_start[++k] = p; }
+        *n_fv = k;
+        return voc.k() * 100 + voc.L();
     });
 }
 

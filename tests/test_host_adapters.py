@@ -378,3 +378,29 @@ def test_fuse_adapter_applies_reference_side_effects(libs):
     assert np.array_equal(action[single], want_action[single])
     assert np.array_equal(kp[single & (want_action != 3)], want_kp[single & (want_action != 3)])
     assert (action[bi < 0] == 0).all()
+
+
+@pytest.mark.gpu
+def test_vocabulary_adapter_matches_oracle(libs, tmp_path):
+    """Frame::ComputeBoW through dvm_host::Vocabulary (text loader, GPU descent, BowVector / FeatureVector filled by the
+    reference's own map methods) against the oracle: identical keys, identical doubles."""
+    from dvmslam_b200.vocabulary import flatten_tree
+    from oracle.dbow import transform
+
+    H, _ = libs
+    v = synth.toy_vocabulary(10, 3, seed=9, ragged=True)
+    p = tmp_path / "voc.txt"
+    synth.write_vocabulary_text(str(p), v)
+    tree = flatten_tree(v["parent"], v["is_leaf"], v["desc"], v["weight"])
+    rng = np.random.default_rng(0)
+    feat = synth.noisy_copy(v["desc"][rng.integers(0, len(v["desc"]), 800)], 0.05, rng)
+    n = len(feat)
+    bw, bv = np.zeros(n, np.int32), np.zeros(n, np.float64)
+    fn, fs, fi = np.zeros(n, np.int32), np.zeros(n + 1, np.int32), np.zeros(n, np.int32)
+    nb, nf = C.c_int(), C.c_int()
+    H.hm_compute_bow.argtypes = [C.c_char_p, _vp, C.c_int, C.c_int, _vp, _vp, _ip, _vp, _vp, _vp, _ip]
+    rc = H.hm_compute_bow(str(p).encode(), _p(feat), n, 2, _p(bw), _p(bv), C.byref(nb), _p(fn), _p(fs), _p(fi), C.byref(nf))
+    assert rc == 10 * 100 + 3, (rc, H.hm_last_error())
+    bow0, fv0 = transform(tree, 3, 0, 0, feat, 2)
+    assert list(bow0.items()) == [(int(bw[i]), float(bv[i])) for i in range(nb.value)]
+    assert list(fv0.items()) == [(int(fn[i]), [int(x) for x in fi[fs[i]:fs[i + 1]]]) for i in range(nf.value)]
