@@ -123,6 +123,7 @@ void launch_features_in_area(const FrameDev& f, float x, float y, float r, int m
 
 // ----------------------------------------------------------------- SearchByProjection(cur, last)
 constexpr int kMatchThreads = 1024;
+constexpr int kRegQ = 2;   // queries per thread kept in registers by the resolution kernels
 constexpr int kNoClaim = 0x7fffffff;
 
 // ---- candidate cache: the window of every query is walked ONCE; its best kMatchCacheK candidates are
@@ -262,41 +263,69 @@ match_last_kernel(FrameDev cur, MatchLastArgs a, MatchScratch s, int* __restrict
     for (int k = tid; k < ncur; k += kMatchThreads) claim_prev[k] = kNoClaim;
     const int nact = compact_active(s.plevels, nq, qlist, warp_sums);
 
+    // the first kRegQ queries of every thread stay in registers across the rounds (index, candidate count, the
+    // four best cache entries, current choice): a round then only touches the claims in shared memory
+    int r_i[kRegQ], r_nc[kRegQ], r_lv[kRegQ], r_choice[kRegQ];
+    ulonglong2 r_e01[kRegQ], r_e23[kRegQ];
+#pragma unroll
+    for (int q = 0; q < kRegQ; q++) {
+        const int j = tid + q * kMatchThreads;
+        r_i[q] = -1; r_nc[q] = 0; r_lv[q] = 0; r_choice[q] = -1;
+        r_e01[q] = make_ulonglong2(~0ull, ~0ull); r_e23[q] = r_e01[q];
+        if (j < nact) {
+            const int i = qlist[j];
+            r_i[q] = i; r_lv[q] = s.plevels[i]; r_nc[q] = s.ncand[i];
+            const unsigned long long* e = s.cache + (size_t)i * kMatchCacheK;
+            r_e01[q] = *reinterpret_cast<const ulonglong2*>(e); r_e23[q] = *reinterpret_cast<const ulonglong2*>(e + 2);
+        }
+    }
+    auto evaluate = [&](int i, int lv, int nc, const ulonglong2& e01, const ulonglong2& e23, const int* claim) -> int {
+        int bestDist = 256, bestIdx = -1;
+        bool found = false;
+        const unsigned long long* e = s.cache + (size_t)i * kMatchCacheK;
+        for (int p = 0; p < kMatchCacheK && p < nc; p++) {
+            const unsigned long long ev = p == 0 ? e01.x : p == 1 ? e01.y : p == 2 ? e23.x : p == 3 ? e23.y : e[p];
+            const int idx = cand_idx(ev);
+            if (claim[idx] < i) continue; // taken by an earlier map point with observations
+            bestDist = cand_dist(ev); bestIdx = idx; found = true;
+            break;
+        }
+        if (!found && nc > kMatchCacheK) { // cache exhausted: full walk against the current claims
+            uint32_t d[8];
+            load_desc(d, desc_of(i));
+            walk_area(fl, s.pu[i], s.pv[i], s.pr[i], lv >> 16, (int)(short)(lv & 0xffff), [&](int idx, int) {
+                if (claim[idx] < i) return;
+                const int dist = hamming256(d, fl.desc + (size_t)idx * 32);
+                if (dist < bestDist) { bestDist = dist; bestIdx = idx; }
+            });
+        }
+        return bestDist <= kThHigh ? bestIdx : -1;
+    };
+
     int rounds = 0;
     while (true) {
         int changed = 0;
-        for (int j = tid; j < nact; j += kMatchThreads) {
+#pragma unroll
+        for (int q = 0; q < kRegQ; q++) {
+            if (r_i[q] < 0) continue;
+            const int pick = evaluate(r_i[q], r_lv[q], r_nc[q], r_e01[q], r_e23[q], claim_prev);
+            if (pick != r_choice[q]) { r_choice[q] = pick; s.choice[r_i[q]] = pick; changed = 1; }
+        }
+        for (int j = tid + kRegQ * kMatchThreads; j < nact; j += kMatchThreads) {
             const int i = qlist[j];
-            const int lv = s.plevels[i];
-            const int nc = s.ncand[i];
-            int bestDist = 256, bestIdx = -1;
-            bool found = false;
             const unsigned long long* e = s.cache + (size_t)i * kMatchCacheK;
-            const ulonglong2 e01 = *reinterpret_cast<const ulonglong2*>(e), e23 = *reinterpret_cast<const ulonglong2*>(e + 2);
-            for (int p = 0; p < kMatchCacheK && p < nc; p++) {
-                const unsigned long long ev = p == 0 ? e01.x : p == 1 ? e01.y : p == 2 ? e23.x : p == 3 ? e23.y : e[p];
-                const int idx = cand_idx(ev);
-                if (claim_prev[idx] < i) continue; // taken by an earlier map point with observations
-                bestDist = cand_dist(ev); bestIdx = idx; found = true;
-                break;
-            }
-            if (!found && nc > kMatchCacheK) { // cache exhausted: full walk against the current claims
-                uint32_t d[8];
-                load_desc(d, desc_of(i));
-                walk_area(fl, s.pu[i], s.pv[i], s.pr[i], lv >> 16, (int)(short)(lv & 0xffff), [&](int idx, int) {
-                    if (claim_prev[idx] < i) return;
-                    const int dist = hamming256(d, fl.desc + (size_t)idx * 32);
-                    if (dist < bestDist) { bestDist = dist; bestIdx = idx; }
-                });
-            }
-            const int pick = bestDist <= kThHigh ? bestIdx : -1;
+            const int pick = evaluate(i, s.plevels[i], s.ncand[i], *reinterpret_cast<const ulonglong2*>(e),
+                                      *reinterpret_cast<const ulonglong2*>(e + 2), claim_prev);
             if (pick != s.choice[i]) { s.choice[i] = pick; changed = 1; }
         }
         rounds++;
         if (!__syncthreads_or(changed)) break;
         for (int k = tid; k < ncur; k += kMatchThreads) claim_next[k] = kNoClaim;
         __syncthreads();
-        for (int j = tid; j < nact; j += kMatchThreads) {
+#pragma unroll
+        for (int q = 0; q < kRegQ; q++)
+            if (r_i[q] >= 0 && r_choice[q] >= 0 && obs_of(r_i[q])) atomicMin(&claim_next[r_choice[q]], r_i[q]);
+        for (int j = tid + kRegQ * kMatchThreads; j < nact; j += kMatchThreads) {
             const int i = qlist[j];
             const int k = s.choice[i];
             if (k >= 0 && obs_of(i)) atomicMin(&claim_next[k], i);
@@ -429,57 +458,84 @@ match_map_kernel(FrameDev cur, MatchMapArgs a, MatchScratch s, int* __restrict__
     if (tid == 0) s_events = 0;
     const int nact = compact_active(s.plevels, nq, qlist, warp_sums); // queries in the frustum, vpMapPoints order
 
+    int r_i[kRegQ], r_nc[kRegQ], r_lv[kRegQ], r_choice[kRegQ];
+    ulonglong2 r_e01[kRegQ], r_e23[kRegQ];
+#pragma unroll
+    for (int q = 0; q < kRegQ; q++) {
+        const int j = tid + q * kMatchThreads;
+        r_i[q] = -1; r_nc[q] = 0; r_lv[q] = 0; r_choice[q] = -1;
+        r_e01[q] = make_ulonglong2(~0ull, ~0ull); r_e23[q] = r_e01[q];
+        if (j < nact) {
+            const int i = qlist[j];
+            r_i[q] = i; r_lv[q] = s.plevels[i]; r_nc[q] = s.ncand[i];
+            const unsigned long long* e = s.cache + (size_t)i * kMatchCacheK;
+            r_e01[q] = *reinterpret_cast<const ulonglong2*>(e); r_e23[q] = *reinterpret_cast<const ulonglong2*>(e + 2);
+        }
+    }
+    auto evaluate = [&](int i, int lvl, int nc, const ulonglong2& e01, const ulonglong2& e23, const int* claim) -> int {
+        int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+        int found = 0;
+        // sorted by (distance, walk order): the first two free entries are the reference's best and
+        // second best (its scan keeps the earliest of equal distances)
+        const unsigned long long* e = s.cache + (size_t)i * kMatchCacheK;
+        for (int p = 0; p < kMatchCacheK && p < nc && found < 2; p++) {
+            const unsigned long long ev = p == 0 ? e01.x : p == 1 ? e01.y : p == 2 ? e23.x : p == 3 ? e23.y : e[p];
+            const int idx = cand_idx(ev);
+            if (claim[idx] < i) continue; // held by a map point with observations
+            if (found == 0) { bestDist = cand_dist(ev); bestLevel = cand_oct(ev); bestIdx = idx; }
+            else { bestDist2 = cand_dist(ev); bestLevel2 = cand_oct(ev); }
+            found++;
+        }
+        if (found < 2 && nc > kMatchCacheK) { // cache exhausted: full walk against the current claims
+            uint32_t d[8];
+            load_desc(d, desc_of(i));
+            bestDist = 256; bestLevel = -1; bestDist2 = 256; bestLevel2 = -1; bestIdx = -1;
+            walk_area(fl, s.pu[i], s.pv[i], s.pr[i], lvl - 1, lvl, [&](int idx, int oct) {
+                if (claim[idx] < i) return;
+                const int dist = hamming256(d, fl.desc + (size_t)idx * 32);
+                if (dist < bestDist) {
+                    bestDist2 = bestDist; bestDist = dist;
+                    bestLevel2 = bestLevel; bestLevel = oct;
+                    bestIdx = idx;
+                } else if (dist < bestDist2) {
+                    bestLevel2 = oct;
+                    bestDist2 = dist;
+                }
+            });
+        }
+        int pick = -1;
+        if (bestDist <= kThHigh) {
+            const float lim = __fmul_rn(a.nnratio, (float)bestDist2);
+            const bool reject = (bestLevel == bestLevel2) && ((float)bestDist > lim);
+            if (!reject && (bestLevel != bestLevel2 || (float)bestDist <= lim)) pick = bestIdx;
+        }
+        return pick;
+    };
+
     int rounds = 0;
     while (true) {
         int changed = 0;
-        for (int j = tid; j < nact; j += kMatchThreads) {
+#pragma unroll
+        for (int q = 0; q < kRegQ; q++) {
+            if (r_i[q] < 0) continue;
+            const int pick = evaluate(r_i[q], r_lv[q], r_nc[q], r_e01[q], r_e23[q], claim_prev);
+            if (pick != r_choice[q]) { r_choice[q] = pick; s.choice[r_i[q]] = pick; changed = 1; }
+        }
+        for (int j = tid + kRegQ * kMatchThreads; j < nact; j += kMatchThreads) {
             const int i = qlist[j];
-            const int lvl = s.plevels[i];
-            const int nc = s.ncand[i];
-            int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
-            int found = 0;
-            // sorted by (distance, walk order): the first two free entries are the reference's best and
-            // second best (its scan keeps the earliest of equal distances)
             const unsigned long long* e = s.cache + (size_t)i * kMatchCacheK;
-            const ulonglong2 e01 = *reinterpret_cast<const ulonglong2*>(e), e23 = *reinterpret_cast<const ulonglong2*>(e + 2);
-            for (int p = 0; p < kMatchCacheK && p < nc && found < 2; p++) {
-                const unsigned long long ev = p == 0 ? e01.x : p == 1 ? e01.y : p == 2 ? e23.x : p == 3 ? e23.y : e[p];
-                const int idx = cand_idx(ev);
-                if (claim_prev[idx] < i) continue; // held by a map point with observations
-                if (found == 0) { bestDist = cand_dist(ev); bestLevel = cand_oct(ev); bestIdx = idx; }
-                else { bestDist2 = cand_dist(ev); bestLevel2 = cand_oct(ev); }
-                found++;
-            }
-            if (found < 2 && nc > kMatchCacheK) { // cache exhausted: full walk against the current claims
-                uint32_t d[8];
-                load_desc(d, desc_of(i));
-                bestDist = 256; bestLevel = -1; bestDist2 = 256; bestLevel2 = -1; bestIdx = -1;
-                walk_area(fl, s.pu[i], s.pv[i], s.pr[i], lvl - 1, lvl, [&](int idx, int oct) {
-                    if (claim_prev[idx] < i) return;
-                    const int dist = hamming256(d, fl.desc + (size_t)idx * 32);
-                    if (dist < bestDist) {
-                        bestDist2 = bestDist; bestDist = dist;
-                        bestLevel2 = bestLevel; bestLevel = oct;
-                        bestIdx = idx;
-                    } else if (dist < bestDist2) {
-                        bestLevel2 = oct;
-                        bestDist2 = dist;
-                    }
-                });
-            }
-            int pick = -1;
-            if (bestDist <= kThHigh) {
-                const float lim = __fmul_rn(a.nnratio, (float)bestDist2);
-                const bool reject = (bestLevel == bestLevel2) && ((float)bestDist > lim);
-                if (!reject && (bestLevel != bestLevel2 || (float)bestDist <= lim)) pick = bestIdx;
-            }
+            const int pick = evaluate(i, s.plevels[i], s.ncand[i], *reinterpret_cast<const ulonglong2*>(e),
+                                      *reinterpret_cast<const ulonglong2*>(e + 2), claim_prev);
             if (pick != s.choice[i]) { s.choice[i] = pick; changed = 1; }
         }
         rounds++;
         if (!__syncthreads_or(changed)) break;
         for (int k = tid; k < ncur; k += kMatchThreads) claim_next[k] = blocked(k) ? -1 : kNoClaim;
         __syncthreads();
-        for (int j = tid; j < nact; j += kMatchThreads) {
+#pragma unroll
+        for (int q = 0; q < kRegQ; q++)
+            if (r_i[q] >= 0 && r_choice[q] >= 0 && obs_of(r_i[q])) atomicMin(&claim_next[r_choice[q]], r_i[q]);
+        for (int j = tid + kRegQ * kMatchThreads; j < nact; j += kMatchThreads) {
             const int i = qlist[j];
             const int k = s.choice[i];
             if (k >= 0 && obs_of(i)) atomicMin(&claim_next[k], i);
