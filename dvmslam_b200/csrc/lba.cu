@@ -221,6 +221,19 @@ constexpr int kClusterCtas = 8;
 constexpr int kPanelLd = 36;   // shared-memory row stride of the panel (doubles): conflict-free 8-byte fragment loads
 constexpr int kDiagLd = kNB + 1;
 
+// Reciprocal square root on the critical path of every column: hardware seed (MUFU.RSQ64H, ~20 bits) and two
+// Newton steps -- within 1-2 ulp for the positive, well-scaled pivots of a damped normal matrix.
+__device__ inline double fast_rsqrt(double d)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    const double h = 0.5 * d;
+    double e = fma(-h * y, y, 0.5);
+    y = fma(y, e, y);
+    e = fma(-h * y, y, 0.5);
+    return fma(y, e, y);
+}
+
 // One warp: Cholesky of the 32x32 block at A (leading dimension ld, lower triangle) held in registers
 // (lane = row, column broadcasts by shuffle), then its inverse (lane = column).  Writes L to Ld and
 // L^-1 to Li (shared, stride kDiagLd); with write_back also L into A and L^-1 (row-major) into Linv_out.
@@ -282,6 +295,81 @@ __device__ __noinline__ bool warp_factor_invert_32(double* __restrict__ A, int l
     return bad;
 }
 
+// The same factorisation + inversion by ALL threads of the CTA (kLbaThreads = 512 = 16 warps): a lone warp cannot
+// hide its own latencies (the one-warp version above runs at ~7 cycles per instruction, 21 us per block, and was
+// 2/3 of the whole solve).  Every thread OWNS two elements of the block and of its inverse in registers for the
+// whole sweep: lane = row, warp w = columns w and w + 16.  Step j:
+//     the warp that owns column j takes the pivot by shuffle, scales its column by rsqrt(pivot) and publishes it
+//     (col[j & 1][:], rinv[j & 1]) | ONE CTA barrier |
+//     a[r][c] -= L[r][j] L[c][j]  (c > j);   X[j][c] = x[j][c] * rinv (by shuffle inside the column's warp),
+//     x[r][c] -= L[r][j] X[j][c]  (r > j)
+// i.e. the right-looking Cholesky step and the column sweep of the triangular inversion share one barrier per
+// step (the published column is double-buffered), and the owner of column j + 1 publishes it before doing its share of
+// step j's inverse updates.  Measured: 21.6 -> 10 us per block (~550 cycles per step; what is left is the FP64 pipe --
+// the triangular masks leave most lanes of the 6 double-precision instructions a warp issues per step idle).
+// `scratch` holds 4 * kNB + 4 doubles.  Same outputs as the warp version.
+// (No __restrict__ here: the published column is exchanged BETWEEN threads, and with restrict-qualified pointers
+// nvcc keeps values read from it across the barriers -- measured: wrong factors.)
+__device__ bool cta_factor_invert_32(double* A, int ld, double* Ld, double* Li, bool write_back, double* Linv_out,
+                                     double* scratch)
+{
+    const int r = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int c0 = w, c1 = w + 16;
+    double* colbuf = scratch;                 // [2][kNB]  L[:, j]
+    double* s_rinv = scratch + 2 * kNB;       // [2]
+    double* s_bad = s_rinv + 2;
+    double a0 = A[(size_t)r * ld + c0], a1 = A[(size_t)r * ld + c1];
+    double x0 = (r == c0) ? 1.0 : 0.0, x1 = (r == c1) ? 1.0 : 0.0;
+    if (threadIdx.x == 0) *s_bad = 0.0;
+    // the warp that owns column j scales it by rsqrt(pivot) and publishes it in buffer j & 1
+    auto publish = [&](int j) {
+        const bool hi = j >= 16;
+        const double djj = __shfl_sync(0xffffffffu, hi ? a1 : a0, j);
+        const bool bad = !(djj > 0) || !isfinite(djj);
+        const double rinv = bad ? 1.0 : fast_rsqrt(djj);
+        if (r >= j) {
+            const double l = (hi ? a1 : a0) * rinv;   // a[j][j] * rinv = sqrt(a[j][j])
+            if (hi) a1 = l; else a0 = l;
+            colbuf[(j & 1) * kNB + r] = l;
+        }
+        if (r == 0) { s_rinv[j & 1] = rinv; if (bad) *s_bad = 1.0; }
+    };
+    if (w == 0) publish(0);
+    for (int j = 0; j < kNB; j++) {
+        __syncthreads();   // column j is published
+        const double* col = colbuf + (j & 1) * kNB;
+        const double rinv = s_rinv[j & 1];
+        const double lr = (r >= j) ? col[r] : 0.0;
+        // Cholesky update of the columns right of j
+        if (c0 > j && r >= c0) a0 -= lr * col[c0];
+        if (c1 > j && r >= c1) a1 -= lr * col[c1];
+        // column j + 1 is complete now: its owner publishes it BEFORE the inverse updates of this step, which keeps
+        // them off the pivot -> rsqrt -> publish -> barrier chain that bounds a step
+        if (j + 1 < kNB && w == ((j + 1) & 15)) publish(j + 1);
+        // inverse: row j is scaled, rows below it are swept (columns <= j)
+        if (c0 <= j) {
+            const double xj = __shfl_sync(0xffffffffu, x0, j) * rinv;
+            if (r == j) x0 = xj; else if (r > j) x0 -= lr * xj;
+        }
+        if (c1 <= j) {
+            const double xj = __shfl_sync(0xffffffffu, x1, j) * rinv;
+            if (r == j) x1 = xj; else if (r > j) x1 -= lr * xj;
+        }
+    }
+    Ld[r * kDiagLd + c0] = (c0 <= r) ? a0 : 0.0;
+    Ld[r * kDiagLd + c1] = (c1 <= r) ? a1 : 0.0;
+    Li[r * kDiagLd + c0] = (c0 <= r) ? x0 : 0.0;
+    Li[r * kDiagLd + c1] = (c1 <= r) ? x1 : 0.0;
+    if (write_back) {
+        if (c0 <= r) A[(size_t)r * ld + c0] = a0;
+        if (c1 <= r) A[(size_t)r * ld + c1] = a1;
+        Linv_out[r * kNB + c0] = (c0 <= r) ? x0 : 0.0;
+        Linv_out[r * kNB + c1] = (c1 <= r) ? x1 : 0.0;
+    }
+    __syncthreads();
+    return *s_bad != 0.0;
+}
+
 __device__ inline size_t chol_smem_doubles(int n) { return (size_t)(n + 8) * kPanelLd + 2 * kNB * kDiagLd + 64 * kNB; }
 
 __device__ bool cluster_cholesky_solve(int n, double* __restrict__ A, const double* __restrict__ b, double* __restrict__ x,
@@ -313,9 +401,10 @@ __device__ bool cluster_cholesky_solve(int n, double* __restrict__ A, const doub
     for (int k0 = 0; k0 < n; k0 += kNB) {
         const int r0 = k0 + kNB;
         // ---- (a) diagonal block: factor + invert, redundantly in every CTA ----
-        if (wid == 0) {
-            const bool bad = warp_factor_invert_32(A + (size_t)k0 * n + k0, n, Ld, Li, rank == 0, Linv_g + (size_t)(k0 / kNB) * kNB * kNB);
-            if (bad && lane == 0) *s_flag = 0;
+        {
+            const bool bad = cta_factor_invert_32(A + (size_t)k0 * n + k0, n, Ld, Li, rank == 0,
+                                                  Linv_g + (size_t)(k0 / kNB) * kNB * kNB, stage);
+            if (bad && tid == 0) *s_flag = 0;
             tk(8);
         }
         __syncthreads();
