@@ -205,8 +205,63 @@ int dvm_frame_construct_device(dvm_frame* f, dvm_orb* orb, const uint8_t* gray_d
     if (rc != DVM_OK) return rc;
     f->host_n = dvm_orb_max_keypoints_current(orb);
     f->dev.cap = f->host_n; // tight bound for this image size: sizes the matchers' shared-memory staging
+    if (f->undistort) launch_undistort(f->d_kps, f->d_n, f->host_n, f->und, (cudaStream_t)dvm_orb_stream(orb));
     launch_grid_build(f->dev, (cudaStream_t)dvm_orb_stream(orb));
     DVM_CUDA(cudaGetLastError());
+    return DVM_OK;
+}
+
+static void fill_undistort(UndistortArgs& u, const float* K, const float* dist5)
+{
+    for (int i = 0; i < 5; i++) u.k[i] = (double)dist5[i];
+    u.fx = K[0]; u.fy = K[1]; u.cx = K[2]; u.cy = K[3];
+}
+
+int dvm_frame_set_distortion(dvm_frame* f, const float* K, const float* dist5)
+{
+    DVM_REQUIRE(f != nullptr, "null frame");
+    // Frame::UndistortKeyPoints is the identity when mDistCoef.at<float>(0) == 0 (O3/src/Frame.cc:792-795)
+    f->undistort = K != nullptr && dist5 != nullptr && dist5[0] != 0.0f;
+    if (f->undistort) fill_undistort(f->und, K, dist5);
+    return DVM_OK;
+}
+
+int dvm_undistort_keypoints(dvm_frame* ctx, dvm_keypoint* kps, int n, const float* K, const float* dist5)
+{
+    DVM_REQUIRE(ctx != nullptr && n >= 0 && K && dist5, "bad argument");
+    DVM_REQUIRE(n == 0 || kps, "null keypoints");
+    if (n == 0 || dist5[0] == 0.0f) return DVM_OK;   // identity, as the reference
+    DVM_CUDA(cudaSetDevice(ctx->device));
+    const size_t bytes = (size_t)n * sizeof(dvm_keypoint);
+    int rc = dvm_frame_ensure_bytes(ctx, bytes + 512, bytes);
+    if (rc != DVM_OK) return rc;
+    memcpy(ctx->h_in, kps, bytes);
+    int* hn = reinterpret_cast<int*>(ctx->h_in + ((bytes + 255) & ~(size_t)255));
+    *hn = n;
+    DVM_CUDA(cudaMemcpyAsync(ctx->d_in, ctx->h_in, ((bytes + 255) & ~(size_t)255) + 4, cudaMemcpyHostToDevice, ctx->stream));
+    UndistortArgs u;
+    fill_undistort(u, K, dist5);
+    launch_undistort(reinterpret_cast<dvm_keypoint*>(ctx->d_in), reinterpret_cast<const int*>(ctx->d_in + ((bytes + 255) & ~(size_t)255)),
+                     n, u, ctx->stream);
+    DVM_CUDA(cudaGetLastError());
+    DVM_CUDA(cudaMemcpyAsync(ctx->h_out, ctx->d_in, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    DVM_CUDA(cudaStreamSynchronize(ctx->stream));
+    memcpy(kps, ctx->h_out, bytes);
+    return DVM_OK;
+}
+
+int dvm_image_bounds(dvm_frame* ctx, const float* K, const float* dist5, int width, int height, float* bounds)
+{
+    DVM_REQUIRE(ctx != nullptr && K && dist5 && bounds && width > 0 && height > 0, "bad argument");
+    if (dist5[0] == 0.0f) { bounds[0] = 0.f; bounds[1] = 0.f; bounds[2] = (float)width; bounds[3] = (float)height; return DVM_OK; }
+    dvm_keypoint c[4];
+    memset(c, 0, sizeof(c));
+    c[0].x = 0.f; c[0].y = 0.f; c[1].x = (float)width; c[1].y = 0.f; c[2].x = 0.f; c[2].y = (float)height;
+    c[3].x = (float)width; c[3].y = (float)height;
+    const int rc = dvm_undistort_keypoints(ctx, c, 4, K, dist5);
+    if (rc != DVM_OK) return rc;
+    bounds[0] = fminf(c[0].x, c[2].x); bounds[2] = fmaxf(c[1].x, c[3].x);    // O3/src/Frame.cc:838-841
+    bounds[1] = fminf(c[0].y, c[1].y); bounds[3] = fmaxf(c[2].y, c[3].y);
     return DVM_OK;
 }
 

@@ -33,6 +33,8 @@ struct dvm_frame {
     size_t h_out_cap = 0;
     int last_rounds = 0;
     int host_n = 0;
+    bool undistort = false;      // k1 != 0: UndistortKeyPoints is not the identity
+    dvm::UndistortArgs und;
 };
 
 

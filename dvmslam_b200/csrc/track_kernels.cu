@@ -79,6 +79,38 @@ __global__ void __launch_bounds__(1024) grid_build_kernel(FrameDev f, const dvm_
     }
 }
 
+// Frame::UndistortKeyPoints: cv::undistortPoints(pts, pts, K, distCoef, Mat(), K) with its default five iterations, in
+// double, operation by operation as OpenCV evaluates it (this file is compiled with -fmad=false; the zero-coefficient
+// terms k4..k6, s1..s4 are kept because they take part in the rounding) -- bit-exact with cv2 4.13 (oracle/cvmodels.c).
+__global__ void __launch_bounds__(256) undistort_kernel(dvm_keypoint* __restrict__ kps, const int* __restrict__ n_ptr, int cap,
+                                                        UndistortArgs a)
+{
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= min(*n_ptr, cap)) return;
+    const double ifx = 1. / a.fx, ify = 1. / a.fy;
+    const double u = (double)kps[i].x, v = (double)kps[i].y;
+    double x = (u - a.cx) * ifx, y = (v - a.cy) * ify;
+    const double x0 = x, y0 = y;
+    const double k5 = 0., k6 = 0., k7 = 0., k8 = 0., k9 = 0., k10 = 0., k11 = 0.;
+    for (int j = 0; j < 5; j++) {
+        const double r2 = x * x + y * y;
+        const double icdist = (1 + ((k7 * r2 + k6) * r2 + k5) * r2) / (1 + ((a.k[4] * r2 + a.k[1]) * r2 + a.k[0]) * r2);
+        if (icdist < 0) { x = (u - a.cx) * ifx; y = (v - a.cy) * ify; break; }
+        const double deltaX = 2 * a.k[2] * x * y + a.k[3] * (r2 + 2 * x * x) + k8 * r2 + k9 * r2 * r2;
+        const double deltaY = a.k[2] * (r2 + 2 * y * y) + 2 * a.k[3] * x * y + k10 * r2 + k11 * r2 * r2;
+        x = (x0 - deltaX) * icdist;
+        y = (y0 - deltaY) * icdist;
+    }
+    const double xx = a.fx * x + 0. * y + a.cx, yy = 0. * x + a.fy * y + a.cy, ww = 1. / (0. * x + 0. * y + 1.);
+    kps[i].x = (float)(xx * ww);
+    kps[i].y = (float)(yy * ww);
+}
+
+void launch_undistort(dvm_keypoint* kps, const int* n_ptr, int cap, const UndistortArgs& a, cudaStream_t stream)
+{
+    DVM_LAUNCH(undistort_kernel, div_up(max(cap, 1), 256), 256, 0, stream, kps, n_ptr, cap, a);
+}
+
 void launch_grid_build(const FrameDev& f, cudaStream_t stream)
 {
     DVM_LAUNCH(grid_build_kernel, 1, 1024, 0, stream, f, (const dvm_keypoint*)nullptr, (const uint8_t*)nullptr, (const int*)nullptr);

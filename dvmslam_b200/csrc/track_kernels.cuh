@@ -124,6 +124,9 @@ struct PoseOptArgs {
     unsigned long long* prof; // [4] or nullptr: ns spent in {edge pass, reduction, solve + update, passes} (DVM_POSE_PROFILE)
 };
 
+// cv::undistortPoints (O3/src/Frame.cc:791-818) applied in place to the x, y of n keypoints (n read from the device)
+struct UndistortArgs { double k[5]; double fx, fy, cx, cy; };
+void launch_undistort(dvm_keypoint* kps, const int* n_ptr, int cap, const UndistortArgs& a, cudaStream_t stream);
 void launch_grid_build(const FrameDev& f, cudaStream_t stream);
 // copies an extractor result (keypoints, descriptors, count) into the frame's buffers and builds the grid, one kernel
 void launch_frame_assign(const FrameDev& f, const dvm_keypoint* src_kps, const uint8_t* src_desc, const int* src_n,

@@ -242,6 +242,13 @@ int dvm_tracker_create(dvm_tracker** out, dvm_orb* orb, const float* K, const fl
 }
 
 void dvm_tracker_destroy(dvm_tracker* t) { tracker_free(t); }
+
+int dvm_tracker_set_distortion(dvm_tracker* t, const float* dist5)
+{
+    DVM_REQUIRE(t != nullptr && dist5 != nullptr, "null argument");
+    for (auto f : t->frames) dvm_frame_set_distortion(f, t->K, dist5);
+    return DVM_OK;
+}
 void* dvm_tracker_stream(const dvm_tracker* t) { return t ? (void*)t->stream : nullptr; }
 
 // SearchLocalPoints: isInFrustum + SearchByProjection(local map) + merge into cur_map, two launches

@@ -29,6 +29,9 @@ def _bind(L):
     L.dvm_match_by_projection_map.argtypes = [_vp, C.c_int] + [_vp] * 6 + [C.c_float, C.c_float, _vp, _vp, _ip]
     L.dvm_match_last_rounds.argtypes = [_vp]
     L.dvm_pose_optimization.argtypes = [_vp, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _ip, _vp]
+    L.dvm_undistort_keypoints.argtypes = [_vp, _vp, C.c_int, _vp, _vp]
+    L.dvm_frame_set_distortion.argtypes = [_vp, _vp, _vp]
+    L.dvm_image_bounds.argtypes = [_vp, _vp, _vp, C.c_int, C.c_int, _vp]
     L._trk_bound = True
 
 
@@ -68,6 +71,19 @@ class Frame:
     def assign_from_orb(self, extractor, bounds):
         check(self.L.dvm_frame_assign_from_orb(self.h, extractor.h, *map(float, bounds)))
         self.n = self.cap
+
+    def UndistortKeyPoints(self, kps, K, dist5):
+        """Frame::UndistortKeyPoints -> mvKeysUn (a copy; the identity when k1 == 0)."""
+        k = _c(kps, KP_DTYPE).copy()
+        check(self.L.dvm_undistort_keypoints(self.h, k.ctypes.data, len(k), _c(K, np.float32).ctypes.data,
+                                             _c(dist5, np.float32).ctypes.data))
+        return k
+
+    def ComputeImageBounds(self, K, dist5, width, height):
+        b = np.zeros(4, np.float32)
+        check(self.L.dvm_image_bounds(self.h, _c(K, np.float32).ctypes.data, _c(dist5, np.float32).ctypes.data, int(width),
+                                      int(height), b.ctypes.data))
+        return tuple(float(x) for x in b)
 
     def GetFeaturesInArea(self, x, y, r, minLevel=-1, maxLevel=-1):
         out = np.zeros(self.cap, np.int32)
@@ -157,7 +173,7 @@ def is_in_frustum(frame: Frame, q, t, K, xw, normal, min_dist, max_dist, skip=No
 class Tracker:
     """dvm_tracker: ExtractORB -> Frame -> TrackWithMotionModel -> TrackLocalMap chained on the GPU."""
 
-    def __init__(self, extractor, K, bounds, world_map):
+    def __init__(self, extractor, K, bounds, world_map, dist_coef=None):
         self.L = lib()
         _bind(self.L)
         L = self.L
@@ -180,6 +196,9 @@ class Tracker:
         check(L.dvm_tracker_create(C.byref(self.h), extractor.h, k[0].ctypes.data, k[1].ctypes.data, len(k[2]),
                                    k[2].ctypes.data, k[3].ctypes.data, k[4].ctypes.data, k[5].ctypes.data,
                                    k[6].ctypes.data))
+        if dist_coef is not None:   # mDistCoef (k1, k2, p1, p2, k3): frames are undistorted on the device
+            L.dvm_tracker_set_distortion.argtypes = [_vp, _vp]
+            check(L.dvm_tracker_set_distortion(self.h, _c(dist_coef, np.float32).ctypes.data))
         self._pose = np.zeros(7, np.float32)
         self._counts = np.zeros(4, np.int32)
 

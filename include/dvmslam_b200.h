@@ -154,6 +154,15 @@ DVM_API int dvm_frame_assign_from_orb(dvm_frame* f, const dvm_orb* orb, float mi
  * (cudaStreamWaitEvent; dvm_tracker does this). */
 DVM_API int dvm_frame_construct_device(dvm_frame* f, dvm_orb* orb, const uint8_t* gray_dev, int width, int height,
                                        int stride, float min_x, float min_y, float max_x, float max_y);
+/* Frame::UndistortKeyPoints (O3/src/Frame.cc:791-818): cv::undistortPoints(pts, pts, K, mDistCoef, Mat(), mK) with
+ * OpenCV's default five iterations, bit-exact with cv2 4.13; dist5 = k1, k2, p1, p2, k3; the identity when k1 == 0,
+ * as in the reference.  In place on the x, y of host keypoints (synchronous). */
+DVM_API int dvm_undistort_keypoints(dvm_frame* ctx, dvm_keypoint* kps, int n, const float* K, const float* dist5);
+/* The same applied inside dvm_frame_construct_device between ExtractORB and AssignFeaturesToGrid (the frame then
+ * holds mvKeysUn); K = NULL or k1 == 0 switches it off. */
+DVM_API int dvm_frame_set_distortion(dvm_frame* f, const float* K, const float* dist5);
+/* Frame::ComputeImageBounds (O3/src/Frame.cc:820-848): bounds = mnMinX, mnMinY, mnMaxX, mnMaxY. */
+DVM_API int dvm_image_bounds(dvm_frame* ctx, const float* K, const float* dist5, int width, int height, float* bounds);
 /* Frame::GetFeaturesInArea(x, y, r, minLevel, maxLevel) (O3/src/Frame.cc:712-770); indices in the
  * reference's order.  *n_out may exceed cap (then only cap entries were written). */
 DVM_API int dvm_frame_features_in_area(dvm_frame* f, float x, float y, float r, int min_level, int max_level,
@@ -334,6 +343,9 @@ DVM_API int dvm_tracker_create(dvm_tracker** out, dvm_orb* orb, const float* K, 
                                const float* map_xw, const uint8_t* map_desc, const float* map_normal,
                                const float* map_min_dist, const float* map_max_dist);
 DVM_API void dvm_tracker_destroy(dvm_tracker* t);
+/* mDistCoef of the agent's camera (k1, k2, p1, p2, k3): every frame the tracker builds is undistorted on the device
+ * (call before dvm_tracker_bootstrap; `bounds` given at creation must then come from dvm_image_bounds). */
+DVM_API int dvm_tracker_set_distortion(dvm_tracker* t, const float* dist5);
 /* Bootstrap: extract `gray` (host image), set the frame's pose (q = x,y,z,w; t) and associate its
  * keypoints with map points by projection + descriptor search around the given pose (what the
  * reference's initialisation / relocalisation leaves behind: a last frame with map points). */

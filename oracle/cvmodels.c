@@ -273,3 +273,36 @@ float cvm_fast_atan2(float y, float x)
     if (y < 0) a = 360.f - a;
     return a;
 }
+
+/* cv::undistortPoints -- call site O3/src/Frame.cc:806 (UndistortKeyPoints) and :836 (ComputeImageBounds).
+ * Model of cvUndistortPointsInternal (calib3d/undistort.dispatch.cpp) for the 5-coefficient radial-tangential
+ * model: normalise with (u - cx) * (1 / fx), five fixed-point iterations
+ *     r2 = x^2 + y^2, icdist = 1 / (1 + ((k3 r2 + k2) r2 + k1) r2),
+ *     dx = 2 p1 x y + p2 (r2 + 2 x^2), dy = p1 (r2 + 2 y^2) + 2 p2 x y,  x = (x0 - dx) icdist, y = (y0 - dy) icdist
+ * all in double, then x' = (fx' x + cx') * (1 / 1), rounded to float.  Bit-exact against cv2 4.13.0 on 15 000 points
+ * and three coefficient sets (tests/golden/undistort.npz).  The k4..k6 / s1..s4 terms are written out with zero
+ * coefficients exactly as OpenCV evaluates them, because they change the rounding of icdist and dx, dy. */
+void cvm_undistort_points(const float* xy, int n, const float* K, const float* dist5, const float* P, float* out)
+{
+    double k[12] = { 0 };
+    for (int i = 0; i < 5; i++) k[i] = (double)dist5[i];
+    const double fx = K[0], fy = K[1], cx = K[2], cy = K[3];
+    const double ifx = 1. / fx, ify = 1. / fy;
+    const double pfx = P[0], pfy = P[1], pcx = P[2], pcy = P[3];
+    for (int i = 0; i < n; i++) {
+        double x = ((double)xy[2 * i] - cx) * ifx, y = ((double)xy[2 * i + 1] - cy) * ify;
+        const double x0 = x, y0 = y;
+        for (int j = 0; j < 5; j++) {
+            const double r2 = x * x + y * y;
+            const double icdist = (1 + ((k[7] * r2 + k[6]) * r2 + k[5]) * r2) / (1 + ((k[4] * r2 + k[1]) * r2 + k[0]) * r2);
+            if (icdist < 0) { x = ((double)xy[2 * i] - cx) * ifx; y = ((double)xy[2 * i + 1] - cy) * ify; break; }
+            const double deltaX = 2 * k[2] * x * y + k[3] * (r2 + 2 * x * x) + k[8] * r2 + k[9] * r2 * r2;
+            const double deltaY = k[2] * (r2 + 2 * y * y) + 2 * k[3] * x * y + k[10] * r2 + k[11] * r2 * r2;
+            x = (x0 - deltaX) * icdist;
+            y = (y0 - deltaY) * icdist;
+        }
+        const double xx = pfx * x + 0. * y + pcx, yy = 0. * x + pfy * y + pcy, ww = 1. / (0. * x + 0. * y + 1.);
+        out[2 * i] = (float)(xx * ww);
+        out[2 * i + 1] = (float)(yy * ww);
+    }
+}

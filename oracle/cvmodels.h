@@ -49,6 +49,9 @@ void cvm_gaussian7_u8(const uint8_t* src, int w, int h, int sstride,
 
 /* cv::fastAtan2(y, x) in degrees, [0,360) */
 float cvm_fast_atan2(float y, float x);
+/* cv::undistortPoints(src, dst, K, distCoeffs(k1,k2,p1,p2,k3), noArray(), P): 5 fixed iterations in double
+ * (default TermCriteria(MAX_ITER, 5, 0.01)), R = I; K, P = fx, fy, cx, cy.  xy / out: n interleaved float pairs. */
+void cvm_undistort_points(const float* xy, int n, const float* K, const float* dist5, const float* P, float* out);
 
 #ifdef __cplusplus
 }

@@ -66,6 +66,9 @@ def full(rep, out, traffic_json, cmd):
                 v, u = r[ix[m]], units[ix[m]]
                 if short.startswith("dram"):
                     cells.append(f"{to_bytes(v, u) / 1e6:.3f} MB")
+                elif short == "us":
+                    t_us = float(v.replace(",", "")) * {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(u, 1.0)
+                    cells.append(f"{t_us:.2f}")
                 else:
                     cells.append(f"{float(v.replace(',', '')):.4g}" if v else "-")
             f.write(f"| {name} | {r[ix['Grid Size']]} x {r[ix['Block Size']]} | " + " | ".join(cells) + " |\n")

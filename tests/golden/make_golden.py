@@ -5,6 +5,7 @@
   cv2_primitives.npz  outputs of the REAL OpenCV primitives the reference calls (cv::resize INTER_LINEAR,
                       cv::GaussianBlur 7x7 sigma 2, cv::FAST 9-16 with NMS, cv::fastAtan2) on small seeded
                       inputs -- the oracle's C models must reproduce them bit for bit;
+  undistort.npz       cv::undistortPoints(pts, K, dist, None, K) of the real cv2 for three coefficient sets;
   orb_small.npz       ORBextractor::operator() outputs (keypoints, descriptors, monoIndex) on a 320x240 frame,
                       produced by the cv2-backed pipeline (oracle/orb.py: extract_with_cv2), i.e. OpenCV
                       primitives + the restated in-tree logic;
@@ -58,6 +59,16 @@ def main():
     np.savez_compressed(os.path.join(HERE, "cv2_primitives.npz"), img=img, resized=resized, blurred=blurred,
                         fast20=fast[20], fast7=fast[7], atan_yx=yx.astype(np.int32), atan_deg=at,
                         cv2_version=np.array(cv2.__version__))
+
+    # ---- cv::undistortPoints (Frame::UndistortKeyPoints / ComputeImageBounds) ----
+    Kc = np.array([[994.3, 0, 638.0], [0, 993.4, 372.6], [0, 0, 1]], np.float32)
+    und_pts = rng.uniform([0, 0], [1280, 720], (3000, 2)).astype(np.float32)
+    und_pts[:4] = [[0, 0], [1280, 0], [0, 720], [1280, 720]]
+    und_dist = np.array([[-0.28, 0.07, 0.0002, -0.0001, 0.0], [0.1, -0.2, 0.001, 0.002, 0.05],
+                         [-0.35, 0.15, -0.001, 0.0005, -0.03]], np.float32)
+    und_out = np.stack([cv2.undistortPoints(und_pts.reshape(-1, 1, 2), Kc, d, None, Kc).reshape(-1, 2) for d in und_dist])
+    np.savez_compressed(os.path.join(HERE, "undistort.npz"), K=np.array([994.3, 993.4, 638.0, 372.6], np.float32), pts=und_pts,
+                        dist=und_dist, out=und_out, cv2_version=np.array(cv2.__version__))
 
     # ---- whole extractor on a small frame ----
     frame = synth.frame(320, 240, seed=11)
