@@ -23,6 +23,7 @@ namespace dvm {
 
 // ------------------------------------------------------------------------------------- SearchByBoW
 constexpr int kBowWarps = 4;
+constexpr int kBowStage = 192;   // side-2 features of a node staged per warp beyond the first 32 (6 KB + 768 B per warp)
 
 __device__ inline int find_node(const uint32_t* ids, int n, uint32_t key)
 {
@@ -49,20 +50,57 @@ __global__ void __launch_bounds__(kBowWarps * 32) bow_node_kernel(BowArgs g)
     const int a0 = g.a.node_start[ia], a1 = g.a.node_start[ia + 1];
     const int b0 = g.b.node_start[ib], nb = g.b.node_start[ib + 1] - b0;
     if (nb <= 0) return;
-    // first chunk of side 2 kept in registers (nodes hold ~20 features at 2000 features / 100 nodes)
+    // side 2 of the node: positions 0..31 in registers, 32..32+kBowStage in this warp's shared memory (descriptor
+    // + feature index, -1 once taken or invalid), anything beyond through L1 -- the sequential loop over side 1
+    // must not wait on global memory per candidate chunk (a 156-feature node took 178 us that way)
+    __shared__ uint4 s_desc[kBowWarps][kBowStage][2];
+    __shared__ int s_r2[kBowWarps][kBowStage];
+    __shared__ float s_ang[kBowWarps][kBowStage];
+    const int wslot = threadIdx.x >> 5;
+    const int nstage = min(max(nb - 32, 0), kBowStage);
+    for (int q = lane; q < nstage; q += 32) {
+        int r2 = (int)g.b.feat_idx[b0 + 32 + q];
+        if (g.kf_kf && g.b.valid && !g.b.valid[r2]) r2 = -1;
+        s_r2[wslot][q] = r2;
+        if (r2 >= 0) {
+            s_ang[wslot][q] = g.check_ori ? g.b.angle[r2] : 0.f;
+            const uint4* dp = reinterpret_cast<const uint4*>(g.b.desc + (size_t)r2 * 32);
+            s_desc[wslot][q][0] = __ldg(dp); s_desc[wslot][q][1] = __ldg(dp + 1);
+        }
+    }
+    __syncwarp();
     int r2_0 = -1;
     uint32_t d2_0[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+    float ang2_0 = 0.f;
     if (lane < nb) {
         r2_0 = (int)g.b.feat_idx[b0 + lane];
         if (g.kf_kf && g.b.valid && !g.b.valid[r2_0]) r2_0 = -1;   // !pMP2 || pMP2->isBad()
-        if (r2_0 >= 0) load_desc(d2_0, g.b.desc + (size_t)r2_0 * 32);
+        if (r2_0 >= 0) { load_desc(d2_0, g.b.desc + (size_t)r2_0 * 32); if (g.check_ori) ang2_0 = g.b.angle[r2_0]; }
     }
     bool taken_0 = false;
+    // the side-1 features of the node are fetched 32 at a time (lane = feature: index, validity, descriptor) and
+    // handed to the whole warp by shuffles, so the sequential loop below never waits on global memory
+    int my_r1 = -1;
+    float my_ang1 = 0.f;
+    uint32_t my_d1[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
     for (int p = a0; p < a1; p++) {
-        const int r1 = (int)g.a.feat_idx[p];
-        if (g.a.valid && !g.a.valid[r1]) continue;
+        if (((p - a0) & 31) == 0) {
+            my_r1 = -1;
+            if (p + lane < a1) {
+                const int r = (int)g.a.feat_idx[p + lane];
+                if (!(g.a.valid && !g.a.valid[r])) {
+                    my_r1 = r; load_desc(my_d1, g.a.desc + (size_t)r * 32);
+                    if (g.check_ori) my_ang1 = g.a.angle[r];
+                }
+            }
+        }
+        const int src = (p - a0) & 31;
+        const int r1 = __shfl_sync(0xffffffffu, my_r1, src);
+        if (r1 < 0) continue;
+        const float ang1 = __shfl_sync(0xffffffffu, my_ang1, src);
         uint32_t d1[8];
-        load_desc(d1, g.a.desc + (size_t)r1 * 32);
+#pragma unroll
+        for (int q = 0; q < 8; q++) d1[q] = __shfl_sync(0xffffffffu, my_d1[q], src);
         unsigned k1 = kNoKey, dist2 = 256;   // lane-local nearest key / second-nearest distance
         if (r2_0 >= 0 && !taken_0) {
             const unsigned dist = __popc(d1[0] ^ d2_0[0]) + __popc(d1[1] ^ d2_0[1]) + __popc(d1[2] ^ d2_0[2]) +
@@ -70,7 +108,16 @@ __global__ void __launch_bounds__(kBowWarps * 32) bow_node_kernel(BowArgs g)
                                   __popc(d1[6] ^ d2_0[6]) + __popc(d1[7] ^ d2_0[7]);
             if (dist < 256) k1 = (dist << kPosBits) | (unsigned)lane;
         }
-        for (int q = 32 + lane; q < nb; q += 32) {   // larger nodes: the rest through L1
+        for (int q = lane; q < nstage; q += 32) {    // larger nodes: the staged part
+            if (s_r2[wslot][q] < 0) continue;
+            const uint4 v0 = s_desc[wslot][q][0], v1 = s_desc[wslot][q][1];
+            const unsigned dist = __popc(d1[0] ^ v0.x) + __popc(d1[1] ^ v0.y) + __popc(d1[2] ^ v0.z) + __popc(d1[3] ^ v0.w) +
+                                  __popc(d1[4] ^ v1.x) + __popc(d1[5] ^ v1.y) + __popc(d1[6] ^ v1.z) + __popc(d1[7] ^ v1.w);
+            const unsigned key = (dist << kPosBits) | (unsigned)(32 + q);
+            if (dist < (k1 >> kPosBits)) { dist2 = k1 >> kPosBits; k1 = key; }
+            else if (dist < dist2) dist2 = dist;
+        }
+        for (int q = 32 + kBowStage + lane; q < nb; q += 32) {   // and whatever does not fit, through L1
             const int r2 = (int)g.b.feat_idx[b0 + q];
             if (g.match21[r2] >= 0) continue;
             if (g.kf_kf && g.b.valid && !g.b.valid[r2]) continue;
@@ -88,12 +135,17 @@ __global__ void __launch_bounds__(kBowWarps * 32) bow_node_kernel(BowArgs g)
             const int q = (int)(best & ((1u << kPosBits) - 1));
             if (q < 32) { if (lane == q) taken_0 = true; }
             const int r2 = __shfl_sync(0xffffffffu, q < 32 ? r2_0 : 0, q & 31);
+            const float a2 = __shfl_sync(0xffffffffu, ang2_0, q & 31);
             if (lane == 0) {
-                const int rr = q < 32 ? r2 : (int)g.b.feat_idx[b0 + q];
+                // partner index and angle from registers / shared memory: no global load on the sequential path
+                const bool staged = q >= 32 && q < 32 + kBowStage;
+                const int rr = q < 32 ? r2 : staged ? s_r2[wslot][q - 32] : (int)g.b.feat_idx[b0 + q];
+                const float ang2 = q < 32 ? a2 : staged ? s_ang[wslot][q - 32] : (g.check_ori ? g.b.angle[rr] : 0.f);
+                if (staged) s_r2[wslot][q - 32] = -1;   // taken
                 g.match21[rr] = r1;
                 g.match12[r1] = rr;
                 atomicAdd(&g.counters[0], 1);
-                if (g.check_ori) atomicAdd(&g.histo[rot_bin(g.a.angle[r1], g.b.angle[rr])], 1);
+                if (g.check_ori) atomicAdd(&g.histo[rot_bin(ang1, ang2)], 1);
             }
             __syncwarp(); // the write to match21 is visible to the lanes that read it for the next feature
         }
@@ -230,25 +282,54 @@ void launch_init_match(const FrameDev& f2, const InitMatchArgs& a, cudaStream_t 
 
 // --------------------------------------------------------------------------- SearchForTriangulation
 // This fork never marks a feature of keyframe 2 as taken (vbMatched2 stays false), so every feature of
-// keyframe 1 is independent: one warp per shared node walks the node's keyframe-1 features, the lanes share
-// the keyframe-2 features.  The reference keeps a candidate when dist <= min(TH_LOW, bestDist) and the
+// keyframe 1 is independent: a warp takes kTriSlots consecutive slots of keyframe 1's feature vector (whatever
+// node they fall in -- a 156-feature node no longer serialises on one warp), the lanes share the keyframe-2
+// features of the slot's node.  The reference keeps a candidate when dist <= min(TH_LOW, bestDist) and the
 // geometric gates pass, i.e. the LAST of the nearest valid candidates wins: the key is
 // distance << 20 | (0xfffff - position) and the warp takes its minimum.
+constexpr int kTriSlots = 16;   // keyframe-1 feature-vector slots per warp
+
 __global__ void __launch_bounds__(kBowWarps * 32) triangulation_kernel(TriArgs g)
 {
     const int lane = threadIdx.x & 31;
-    const int ia = blockIdx.x * kBowWarps + (threadIdx.x >> 5);
-    if (ia >= g.a.n_nodes) return;
-    const int ib = find_node(g.b.node_id, g.b.n_nodes, g.a.node_id[ia]);
-    if (ib < 0) return;
-    const int a0 = g.a.node_start[ia], a1 = g.a.node_start[ia + 1];
-    const int b0 = g.b.node_start[ib], nb = g.b.node_start[ib + 1] - b0;
-    for (int p = a0; p < a1; p++) {
-        const int i1 = (int)g.a.feat_idx[p];
-        if (g.a.valid[i1]) continue;
-        const dvm_keypoint kp1 = g.kps1[i1];
+    const int total = g.a.n_nodes ? g.a.node_start[g.a.n_nodes] : 0;
+    const int p0 = (blockIdx.x * kBowWarps + (threadIdx.x >> 5)) * kTriSlots;
+    if (p0 >= total) return;
+    const int p1 = min(p0 + kTriSlots, total);
+    // the slots' features, lane = slot: index, keypoint, descriptor (features with a map point drop out here)
+    int my_i1 = -1;
+    float my_x = 0.f, my_y = 0.f, my_ang = 0.f;
+    uint32_t my_d1[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+    if (p0 + lane < p1) {
+        const int i = (int)g.a.feat_idx[p0 + lane];
+        if (!g.a.valid[i]) {
+            my_i1 = i; my_x = g.kps1[i].x; my_y = g.kps1[i].y; my_ang = g.kps1[i].angle;
+            load_desc(my_d1, g.a.desc + (size_t)i * 32);
+        }
+    }
+    // node of slot p0: the last node whose start is <= p0 (empty nodes are skipped by the upper bound)
+    int ia;
+    {
+        int lo = 0, hi = g.a.n_nodes;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (g.a.node_start[mid + 1] <= p0) lo = mid + 1; else hi = mid; }
+        ia = lo;
+    }
+    int ib = -2, b0 = 0, nb = 0;   // -2: not looked up yet for the current node
+    for (int p = p0; p < p1; p++) {
+        while (p >= g.a.node_start[ia + 1]) { ia++; ib = -2; }
+        if (ib == -2) {
+            ib = find_node(g.b.node_id, g.b.n_nodes, g.a.node_id[ia]);
+            if (ib >= 0) { b0 = g.b.node_start[ib]; nb = g.b.node_start[ib + 1] - b0; }
+        }
+        const int src = p - p0;
+        const int i1 = __shfl_sync(0xffffffffu, my_i1, src);
+        if (i1 < 0 || ib < 0) continue;
+        dvm_keypoint kp1;
+        kp1.x = __shfl_sync(0xffffffffu, my_x, src); kp1.y = __shfl_sync(0xffffffffu, my_y, src);
+        kp1.angle = __shfl_sync(0xffffffffu, my_ang, src);
         uint32_t d1[8];
-        load_desc(d1, g.a.desc + (size_t)i1 * 32);
+#pragma unroll
+        for (int q = 0; q < 8; q++) d1[q] = __shfl_sync(0xffffffffu, my_d1[q], src);
         // epipolar line of kp1 in image 2: l = x1' F12
         const float la = __fadd_rn(__fadd_rn(__fmul_rn(kp1.x, g.F12[0]), __fmul_rn(kp1.y, g.F12[3])), g.F12[6]);
         const float lb = __fadd_rn(__fadd_rn(__fmul_rn(kp1.x, g.F12[1]), __fmul_rn(kp1.y, g.F12[4])), g.F12[7]);
@@ -310,8 +391,8 @@ __global__ void __launch_bounds__(1024) triangulation_finish_kernel(TriArgs g)
 
 void launch_triangulation_match(const TriArgs& g, cudaStream_t stream)
 {
-    if (g.a.n_nodes > 0 && g.b.n_nodes > 0)
-        DVM_LAUNCH(triangulation_kernel, div_up(g.a.n_nodes, kBowWarps), kBowWarps * 32, 0, stream, g);
+    if (g.a.n_nodes > 0 && g.b.n_nodes > 0 && g.a.n > 0)   // every feature sits in at most one node: <= a.n slots
+        DVM_LAUNCH(triangulation_kernel, div_up(div_up(g.a.n, kTriSlots), kBowWarps), kBowWarps * 32, 0, stream, g);
     DVM_LAUNCH(triangulation_finish_kernel, 1, 1024, 0, stream, g);
 }
 
