@@ -130,7 +130,7 @@ int dvm_match_for_initialization(dvm_frame* f2, int n1, const dvm_keypoint* kps1
     const size_t n = (size_t)n1;
     const size_t out_bytes = n * 8 + n * 4 + 8;   // prev_matched | matches12 | result
     int rc = dvm_frame_ensure_bytes(f2, padded({ n * sizeof(dvm_keypoint), n * 32, out_bytes + 512, n * 4, n * 4, n * 4, n * 4, n * 4,
-                                                 (size_t)f2->cap * 4 }), out_bytes + 512);
+                                                 (size_t)f2->cap * 4, n * 64, n * 4 }), out_bytes + 512);
     if (rc != DVM_OK) return rc;
     Stage st(f2);
     InitMatchArgs a;
@@ -148,6 +148,8 @@ int dvm_match_for_initialization(dvm_frame* f2, int n1, const dvm_keypoint* kps1
     a.cdist_a = st.add((const int*)nullptr, n); a.cdist_b = st.add((const int*)nullptr, n);
     a.next = st.add((const int*)nullptr, n);
     a.head = st.add((const int*)nullptr, (size_t)f2->cap);
+    a.cache = st.add((const unsigned long long*)nullptr, n * 8);
+    a.ncand = st.add((const int*)nullptr, n);
     DVM_CUDA(cudaMemcpyAsync(f2->d_in, f2->h_in, in_end, cudaMemcpyHostToDevice, f2->stream));
     launch_init_match(f2->dev, a, f2->stream);
     DVM_CUDA(cudaGetLastError());

@@ -187,6 +187,54 @@ void launch_bow_match(const BowArgs& g, cudaStream_t stream)
 
 // --------------------------------------------------------------------------- SearchForInitialization
 constexpr int kInitThreads = 1024;
+constexpr int kInitCache = 8;     // nearest candidates kept per query, sorted by (distance, traversal order)
+constexpr int kInitWalkThreads = 128;
+
+__device__ inline unsigned long long init_pack(int dist, int ord, int idx)
+{
+    return ((unsigned long long)(unsigned)dist << 48) | ((unsigned long long)(unsigned)min(ord, 0xffffff) << 24) | (unsigned)idx;
+}
+
+// phase 1 (many CTAs): one warp per keypoint of F1 walks its window in F2 ONCE and keeps the kInitCache nearest
+// candidates; the fixed-point rounds below then only consult this cache (a query whose cached candidates are all
+// skipped while it had more falls back to a full walk)
+__global__ void __launch_bounds__(kInitWalkThreads) init_walk_kernel(FrameDev f2, InitMatchArgs a)
+{
+    const int lane = threadIdx.x & 31;
+    const int i1 = (blockIdx.x * kInitWalkThreads + threadIdx.x) >> 5;
+    if (i1 >= a.n1) return;
+    const int level1 = a.kps1[i1].octave;
+    if (level1 > 0) { if (lane == 0) a.ncand[i1] = -1; return; }     // level1 > 0: continue
+    const FrameLook fl = look_global(f2);
+    uint32_t d1[8];
+    load_desc(d1, a.desc1 + (size_t)i1 * 32);
+    unsigned long long top[kInitCache];
+#pragma unroll
+    for (int p = 0; p < kInitCache; p++) top[p] = ~0ull;
+    int nc = 0;
+    walk_area_warp(fl, a.prev_matched[2 * i1], a.prev_matched[2 * i1 + 1], (float)a.window, level1, level1, lane,
+                   [&](int i2, int, int ord) {
+                       unsigned long long v = init_pack(hamming256(d1, fl.desc + (size_t)i2 * 32), ord, i2);
+#pragma unroll
+                       for (int p = 0; p < kInitCache; p++)
+                           if (v < top[p]) { const unsigned long long t = top[p]; top[p] = v; v = t; }
+                       nc++;
+                   });
+    nc = __reduce_add_sync(0xffffffffu, nc);
+    unsigned long long mine = ~0ull;
+#pragma unroll
+    for (int p = 0; p < kInitCache; p++) {
+        const unsigned long long m = warp_min_u64(top[0]);
+        if (lane == p) mine = m;
+        if (top[0] == m && m != ~0ull) {
+#pragma unroll
+            for (int q = 0; q + 1 < kInitCache; q++) top[q] = top[q + 1];
+            top[kInitCache - 1] = ~0ull;
+        }
+    }
+    if (lane < kInitCache) a.cache[(size_t)i1 * kInitCache + lane] = mine;
+    if (lane == 0) a.ncand[i1] = nc;
+}
 
 __global__ void __launch_bounds__(kInitThreads, 1) init_match_kernel(FrameDev f2, InitMatchArgs a)
 {
@@ -212,20 +260,37 @@ __global__ void __launch_bounds__(kInitThreads, 1) init_match_kernel(FrameDev f2
         int changed = 0;
         for (int i1 = tid; i1 < a.n1; i1 += kInitThreads) {
             int pick = -1, pickDist = 0;
-            if (a.kps1[i1].octave <= 0) {     // level1 > 0: continue
-                uint32_t d1[8];
-                load_desc(d1, a.desc1 + (size_t)i1 * 32);
-                int bestDist = INT_MAX, bestDist2 = INT_MAX, bestIdx2 = -1;
-                const int level1 = a.kps1[i1].octave;
-                walk_area(fl, a.prev_matched[2 * i1], a.prev_matched[2 * i1 + 1], (float)a.window, level1, level1,
-                          [&](int i2, int) {
-                              const int dist = hamming256(d1, fl.desc + (size_t)i2 * 32);
-                              // vMatchedDistance[i2] as the sequential loop sees it at i1
-                              for (int j = a.head[i2]; j >= 0; j = a.next[j])
-                                  if (j < i1 && cdist_prev[j] <= dist) return;
-                              if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestIdx2 = i2; }
-                              else if (dist < bestDist2) bestDist2 = dist;
-                          });
+            const int nc = a.ncand[i1];
+            if (nc > 0) {
+                // vMatchedDistance[i2] as the sequential loop sees it at i1: a candidate is skipped when an earlier
+                // query holds it at a distance <= ours
+                auto skipped = [&](int i2, int dist) {
+                    for (int j = a.head[i2]; j >= 0; j = a.next[j])
+                        if (j < i1 && cdist_prev[j] <= dist) return true;
+                    return false;
+                };
+                int bestDist = INT_MAX, bestDist2 = INT_MAX, bestIdx2 = -1, found = 0;
+                const unsigned long long* e = a.cache + (size_t)i1 * kInitCache;
+                for (int p = 0; p < kInitCache && p < nc && found < 2; p++) {
+                    const unsigned long long ev = e[p];
+                    const int dist = (int)(ev >> 48), i2 = (int)(ev & 0xffffffull);
+                    if (skipped(i2, dist)) continue;
+                    if (found == 0) { bestDist = dist; bestIdx2 = i2; } else bestDist2 = dist;
+                    found++;
+                }
+                if (found < 2 && nc > kInitCache) {   // cache exhausted: full walk against the current claims
+                    uint32_t d1[8];
+                    load_desc(d1, a.desc1 + (size_t)i1 * 32);
+                    bestDist = INT_MAX; bestDist2 = INT_MAX; bestIdx2 = -1;
+                    const int level1 = a.kps1[i1].octave;
+                    walk_area(fl, a.prev_matched[2 * i1], a.prev_matched[2 * i1 + 1], (float)a.window, level1, level1,
+                              [&](int i2, int) {
+                                  const int dist = hamming256(d1, fl.desc + (size_t)i2 * 32);
+                                  if (skipped(i2, dist)) return;
+                                  if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestIdx2 = i2; }
+                                  else if (dist < bestDist2) bestDist2 = dist;
+                              });
+                }
                 if (bestDist <= kThLow && (float)bestDist < __fmul_rn((float)bestDist2, a.nnratio)) { pick = bestIdx2; pickDist = bestDist; }
             }
             choice_next[i1] = pick; cdist_next[i1] = pickDist;
@@ -277,6 +342,7 @@ __global__ void __launch_bounds__(kInitThreads, 1) init_match_kernel(FrameDev f2
 
 void launch_init_match(const FrameDev& f2, const InitMatchArgs& a, cudaStream_t stream)
 {
+    if (a.n1 > 0) DVM_LAUNCH(init_walk_kernel, div_up(a.n1, kInitWalkThreads / 32), kInitWalkThreads, 0, stream, f2, a);
     DVM_LAUNCH(init_match_kernel, 1, kInitThreads, 0, stream, f2, a);
 }
 

@@ -45,6 +45,8 @@ struct InitMatchArgs {
     // scratch
     int* choice_a; int* choice_b; int* cdist_a; int* cdist_b; int* next;  // [n1] each
     int* head;                                                            // [F2 cap]
+    unsigned long long* cache;   // [n1 * 8] nearest candidates per query: distance << 48 | traversal order << 24 | index
+    int* ncand;                  // [n1] candidates in the window (-1: the query does not take part)
 };
 
 void launch_init_match(const FrameDev& f2, const InitMatchArgs& a, cudaStream_t stream);
