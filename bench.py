@@ -454,6 +454,13 @@ def run_ours(args):
                     "frac": achieved / peak, "traffic": ncu_traffic(dom), "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": dom_bytes, "avg_launch_us": stage_us[dom],
                     "stage_us": dict(zip(STAGE_NAMES, stage_us)),
+                    # the HBM-facing stages of the frame with their own algorithmic bytes, measured in
+                    # the same profiled pass; `traffic` = DRAM bytes per launch from the committed ncu capture
+                    "hbm_stages": {STAGE_NAMES[i]: {"algorithmic_bytes": STAGE_BYTES[i],
+                                                    "achieved_GBps": STAGE_BYTES[i] / (stage_us[i] * 1e-6) / 1e9,
+                                                    "frac": STAGE_BYTES[i] / (stage_us[i] * 1e-6) / 1e9 / peak,
+                                                    "traffic": ncu_traffic(i)}
+                                   for i in range(4) if STAGE_BYTES[i] is not None},
                     "frame_us": frame_us, "tracking_us": frame_us - sum(stage_us),
                     "whole_frame": {"algorithmic_bytes": FRAME_BYTES_TOTAL,
                                     "achieved_GBps": FRAME_BYTES_TOTAL * value / world / 1e9}}
