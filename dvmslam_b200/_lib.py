@@ -24,7 +24,8 @@ class DvmError(RuntimeError):
 
 def build(verbose: bool = False) -> None:
     """Compile the CUDA extension for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
-    r = subprocess.run(["make", "-C", os.path.join(_HERE, "csrc")], capture_output=True, text=True)
+    r = subprocess.run(["make", "-j", str(min(8, os.cpu_count() or 1)), "-C", os.path.join(_HERE, "csrc")],
+                       capture_output=True, text=True)
     if verbose or r.returncode != 0:
         print(r.stdout[-4000:])
         print(r.stderr[-4000:])
