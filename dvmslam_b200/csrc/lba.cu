@@ -15,6 +15,7 @@
 //   B1  landmark back-substitution, pose/point update into the trial buffers       (:459-483, se3quat.h:212-240)
 //   B2  errors and robust chi2 at the trial estimate
 #include "common.cuh"
+#include <chrono>
 #include <cooperative_groups.h>
 #include <algorithm>
 #include <cstdlib>
@@ -896,6 +897,7 @@ struct dvm_lba {
     uint8_t* d_buf = nullptr; size_t d_cap = 0;
     uint8_t* h_buf = nullptr; size_t h_cap = 0;
     int* h_abort = nullptr; int* d_abort = nullptr; // mapped pinned
+    std::vector<int> pt_start, cam_start, fill;     // host-side structure scratch, kept between calls
     float last_ms = 0;
 };
 
@@ -983,6 +985,9 @@ int dvm_local_ba(dvm_lba* h, int nc, float* cam_q, float* cam_t, const uint8_t* 
     DVM_REQUIRE(np == 0 || pts, "null point array");
     DVM_REQUIRE(ne == 0 || (edge_cam && edge_pt && edge_obs && edge_inv_sigma2 && edge_bad), "null edge arrays");
     DVM_REQUIRE(K != nullptr, "null intrinsics");
+    const bool hprof = getenv("DVM_LBA_PROFILE") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    const auto ht0 = now();
     // host-side structure building (the analogue of BlockSolver::buildStructure, block_solver.hpp:143-295)
     std::vector<int> cam_col(nc, -1), free_cam;
     int nfixed = 0;
@@ -995,26 +1000,31 @@ int dvm_local_ba(dvm_lba* h, int nc, float* cam_q, float* cam_t, const uint8_t* 
     if (abort_flag && *abort_flag) return DVM_OK;   // :1306-1308
     if (ne == 0 || nf + np == 0) return DVM_OK;
     DVM_REQUIRE(nf <= h->max_free, "more free cameras than dvm_lba_create allowed");
-    for (int e = 0; e < ne; e++)
-        DVM_REQUIRE(edge_cam[e] >= 0 && edge_cam[e] < nc && edge_pt[e] >= 0 && edge_pt[e] < np, "edge index out of range");
-    std::vector<int> pt_start(np + 1, 0), pt_edges(ne), cam_start(nf + 1, 0), cam_edges;
-    for (int e = 0; e < ne; e++) pt_start[edge_pt[e] + 1]++;
-    for (int l = 0; l < np; l++) pt_start[l + 1] += pt_start[l];
+    // one pass over the edges: validation, both histograms, and whether the edges already come grouped by point
+    // (the reference creates them point by point, O3/src/Optimizer.cc:1182-1232, and so does the host adapter)
+    std::vector<int>& pt_start = h->pt_start;
+    std::vector<int>& cam_start = h->cam_start;
+    pt_start.assign((size_t)np + 1, 0);
+    cam_start.assign((size_t)nf + 1, 0);
+    bool by_point = true;
     {
-        std::vector<int> fill(pt_start.begin(), pt_start.end() - 1);
-        for (int e = 0; e < ne; e++) pt_edges[fill[edge_pt[e]]++] = e;
-    }
-    for (int e = 0; e < ne; e++)
-        if (cam_col[edge_cam[e]] >= 0) cam_start[cam_col[edge_cam[e]] + 1]++;
-    for (int c = 0; c < nf; c++) cam_start[c + 1] += cam_start[c];
-    cam_edges.resize(cam_start[nf] > 0 ? cam_start[nf] : 1);
-    {
-        std::vector<int> fill(cam_start.begin(), cam_start.end() - 1);
+        int prev = -1;
+        bool ok = true;
         for (int e = 0; e < ne; e++) {
-            const int cf = cam_col[edge_cam[e]];
-            if (cf >= 0) cam_edges[fill[cf]++] = e;
+            const int c = edge_cam[e], l = edge_pt[e];
+            if ((unsigned)c >= (unsigned)nc || (unsigned)l >= (unsigned)np) { ok = false; break; }
+            pt_start[l + 1]++;
+            const int cf = cam_col[c];
+            if (cf >= 0) cam_start[cf + 1]++;
+            by_point = by_point && l >= prev;
+            prev = l;
         }
+        DVM_REQUIRE(ok, "edge index out of range");
     }
+    for (int l = 0; l < np; l++) pt_start[l + 1] += pt_start[l];
+    for (int c = 0; c < nf; c++) cam_start[c + 1] += cam_start[c];
+    const size_t n_cam_edges = (size_t)std::max(cam_start[nf], 1);
+    const auto ht1 = now();
     DVM_CUDA(cudaSetDevice(h->device));
     const int dimP = 6 * nf;
     const int dimPad = (dimP + kNB - 1) / kNB * kNB;
@@ -1026,7 +1036,7 @@ int dvm_local_ba(dvm_lba* h, int nc, float* cam_q, float* cam_t, const uint8_t* 
     const size_t o_col = take((size_t)nc * 4), o_free = take((size_t)std::max(nf, 1) * 4);
     const size_t o_ecam = take((size_t)ne * 4), o_ept = take((size_t)ne * 4), o_obs = take((size_t)ne * 8), o_info = take((size_t)ne * 4);
     const size_t o_pst = take((size_t)(np + 1) * 4), o_ped = take((size_t)ne * 4);
-    const size_t o_cst = take((size_t)(nf + 1) * 4), o_ced = take(cam_edges.size() * 4);
+    const size_t o_cst = take((size_t)(nf + 1) * 4), o_ced = take(n_cam_edges * 4);
     const size_t upload_bytes = off;
     // work block
     const size_t o_camq1 = take((size_t)nc * 4 * 8), o_camt1 = take((size_t)nc * 3 * 8), o_pts1 = take((size_t)np * 3 * 8);
@@ -1070,10 +1080,27 @@ int dvm_local_ba(dvm_lba* h, int nc, float* cam_q, float* cam_t, const uint8_t* 
         memcpy(hb + o_obs, edge_obs, (size_t)ne * 8);
         memcpy(hb + o_info, edge_inv_sigma2, (size_t)ne * 4);
         memcpy(hb + o_pst, pt_start.data(), (size_t)(np + 1) * 4);
-        memcpy(hb + o_ped, pt_edges.data(), (size_t)ne * 4);
         memcpy(hb + o_cst, cam_start.data(), (size_t)(nf + 1) * 4);
-        memcpy(hb + o_ced, cam_edges.data(), cam_edges.size() * 4);
+        // the two edge lists are filled straight into the pinned upload buffer (stable: ascending edge index per row)
+        int* pt_edges = reinterpret_cast<int*>(hb + o_ped);
+        int* cam_edges = reinterpret_cast<int*>(hb + o_ced);
+        if (by_point) {
+            for (int e = 0; e < ne; e++) pt_edges[e] = e;
+        } else {
+            std::vector<int>& fill = h->fill;
+            fill.assign(pt_start.begin(), pt_start.end() - 1);
+            for (int e = 0; e < ne; e++) pt_edges[fill[edge_pt[e]]++] = e;
+        }
+        {
+            std::vector<int>& fill = h->fill;
+            fill.assign(cam_start.begin(), cam_start.end() - 1);
+            for (int e = 0; e < ne; e++) {
+                const int cf = cam_col[edge_cam[e]];
+                if (cf >= 0) cam_edges[fill[cf]++] = e;
+            }
+        }
     }
+    const auto ht2 = now();
     DVM_CUDA(cudaMemcpyAsync(h->d_buf, hb, upload_bytes, cudaMemcpyHostToDevice, h->stream));
     uint8_t* db = h->d_buf;
     LbaDev P;
@@ -1114,7 +1141,9 @@ int dvm_local_ba(dvm_lba* h, int nc, float* cam_q, float* cam_t, const uint8_t* 
         while (cudaEventQuery(h->ev1) == cudaErrorNotReady)
             if (*abort_flag) *h->h_abort = 1;
     }
+    const auto ht3 = now();
     DVM_CUDA(cudaStreamSynchronize(h->stream));
+    const auto ht4 = now();
     DVM_CUDA(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
     if (getenv("DVM_LBA_PROFILE")) {
         unsigned long long pr[16];
@@ -1137,6 +1166,11 @@ int dvm_local_ba(dvm_lba* h, int nc, float* cam_q, float* cam_t, const uint8_t* 
     memcpy(edge_bad, hb + o_obad, (size_t)ne);
     if (stats) for (int i = 0; i < 4; i++) stats[i] = ost[i];
     *iters_done = (int)ost[0];
+    if (hprof) {
+        auto us = [](auto a, auto b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
+        fprintf(stderr, "[lba host us] structure %.1f staging %.1f enqueue %.1f wait %.1f (kernel %.1f) unpack %.1f\n", us(ht0, ht1),
+                us(ht1, ht2), us(ht2, ht3), us(ht3, ht4), h->last_ms * 1e3, us(ht4, now()));
+    }
     if (!std::isfinite(ost[3])) { set_error("local BA produced a non-finite chi2"); return DVM_ERR_NUMERIC; }
     return DVM_OK;
 }

@@ -50,8 +50,8 @@ class LocalBA:
         ec, ep = _c(edge_cam, np.int32), _c(edge_pt, np.int32)
         eo, ew = _c(edge_obs, np.float32), _c(edge_w, np.float32)
         ne = len(ec)
-        chi2 = np.zeros(max(ne, 1), np.float64)
-        bad = np.zeros(max(ne, 1), np.uint8)
+        chi2 = np.empty(max(ne, 1), np.float64)   # fully written by the call unless it is a no-op (handled below)
+        bad = np.empty(max(ne, 1), np.uint8)
         stats = np.zeros(4, np.float64)
         iters = C.c_int()
         ab = _c([abort], np.uint8) if abort is not None else None   # pbStopFlag: a one-byte bool
@@ -59,6 +59,9 @@ class LocalBA:
                                   ne, ec.ctypes.data, ep.ctypes.data, eo.ctypes.data, ew.ctypes.data,
                                   _c(K, np.float32).ctypes.data, iterations, ab.ctypes.data if ab is not None else None,
                                   chi2.ctypes.data, bad.ctypes.data, stats.ctypes.data, C.byref(iters)))
+        if iters.value < 0:   # no fixed keyframe / stop flag already set: nothing was computed
+            chi2[:] = 0
+            bad[:] = 0
         return dict(cam_q=q, cam_t=t, pts=p, chi2=chi2[:ne], bad=bad[:ne], iters=int(stats[0]), trials=int(stats[1]),
                     chi_first=stats[2], chi_last=stats[3], rc=iters.value, kernel_ms=self.kernel_ms())
 
