@@ -977,6 +977,17 @@ int dvm_local_ba(dvm_lba* h, int nc, float* cam_q, float* cam_t, const uint8_t* 
                  const float* K, int iterations, const volatile uint8_t* abort_flag, double* edge_chi2, uint8_t* edge_bad,
                  double* stats, int* iters_done)
 {
+    // const float thHuberMono = sqrt(5.991), O3/src/Optimizer.cc:1178
+    return dvm_bundle_adjustment(h, nc, cam_q, cam_t, cam_fixed, np, pts, ne, edge_cam, edge_pt, edge_obs, edge_inv_sigma2, K,
+                                 iterations, (float)std::sqrt(5.991), abort_flag, edge_chi2, edge_bad, stats, iters_done);
+}
+
+int dvm_bundle_adjustment(dvm_lba* h, int nc, float* cam_q, float* cam_t, const uint8_t* cam_fixed, int np, float* pts, int ne,
+                          const int32_t* edge_cam, const int32_t* edge_pt, const float* edge_obs,
+                          const float* edge_inv_sigma2, const float* K, int iterations, float huber_delta,
+                          const volatile uint8_t* abort_flag, double* edge_chi2, uint8_t* edge_bad, double* stats,
+                          int* iters_done)
+{
     DVM_REQUIRE(h != nullptr && iters_done != nullptr, "null argument");
     *iters_done = -1;
     if (stats) stats[0] = stats[1] = stats[2] = stats[3] = 0;
@@ -985,6 +996,7 @@ int dvm_local_ba(dvm_lba* h, int nc, float* cam_q, float* cam_t, const uint8_t* 
     DVM_REQUIRE(np == 0 || pts, "null point array");
     DVM_REQUIRE(ne == 0 || (edge_cam && edge_pt && edge_obs && edge_inv_sigma2 && edge_bad), "null edge arrays");
     DVM_REQUIRE(K != nullptr, "null intrinsics");
+    DVM_REQUIRE(huber_delta > 0.0f, "huber_delta must be positive (infinity = no robust kernel)");
     const bool hprof = getenv("DVM_LBA_PROFILE") != nullptr;
     auto now = [] { return std::chrono::steady_clock::now(); };
     const auto ht0 = now();
@@ -1107,7 +1119,7 @@ int dvm_local_ba(dvm_lba* h, int nc, float* cam_q, float* cam_t, const uint8_t* 
     memset(&P, 0, sizeof(P));
     P.nc = nc; P.nf = nf; P.np = np; P.ne = ne; P.dimP = dimP; P.dimPad = dimPad; P.iterations = iterations;
     P.fx = K[0]; P.fy = K[1]; P.cx = K[2]; P.cy = K[3];
-    P.delta = (double)(float)std::sqrt(5.991); // const float thHuberMono = sqrt(5.991), :1178
+    P.delta = (double)huber_delta;   // the caller's float delta; +infinity = no robust kernel
     P.dsqr = P.delta * P.delta;
     P.camq[0] = (double*)(db + o_camq); P.camq[1] = (double*)(db + o_camq1);
     P.camt[0] = (double*)(db + o_camt); P.camt[1] = (double*)(db + o_camt1);

@@ -4,6 +4,8 @@
 // erased and written back afterwards) is the reference's own logic, restated around one GPU call.
 // Mono observations only (mvuRight < 0, no second camera), like the C-ABI.
 #pragma once
+#include <cmath>
+#include <limits>
 #include <list>
 #include <map>
 #include <mutex>
@@ -186,6 +188,85 @@ void LocalBundleAdjustment(dvm_lba* solver, KeyFrameT* pKF, bool* pbStopFlag, Ma
         pts[j]->UpdateNormalAndDepth();
     }
     pMap->IncreaseChangeIndex();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// void Optimizer::BundleAdjustment(const vector<KeyFrame*>& vpKFs, const vector<MapPoint*>& vpMP, int nIterations,
+//                                  bool* pbStopFlag, const unsigned long nLoopKF, const bool bRobust)   :55-356
+// (GlobalBundleAdjustemnt :46-53 passes every keyframe and map point of the map.)  For maps of up to the solver's
+// max_free_cameras keyframes (dense reduced camera system).  Mono observations only.
+// ---------------------------------------------------------------------------------------------------
+template <class KeyFrameT, class MapPointT>
+void BundleAdjustment(dvm_lba* solver, const std::vector<KeyFrameT*>& vpKFs, const std::vector<MapPointT*>& vpMP, int nIterations,
+                      bool* pbStopFlag, unsigned long nLoopKF, bool bRobust)
+{
+    if (vpKFs.empty()) return;
+    auto* pMap = vpKFs[0]->GetMap();
+    std::vector<KeyFrameT*> cams;
+    std::unordered_map<KeyFrameT*, int> camIndex;
+    unsigned long maxKFid = 0;
+    for (KeyFrameT* pKF : vpKFs) {
+        if (pKF->isBad()) continue;                                                       // :105-106
+        camIndex[pKF] = static_cast<int>(cams.size());
+        cams.push_back(pKF);
+        if (pKF->mnId > maxKFid) maxKFid = pKF->mnId;
+    }
+    std::vector<float> cam_q(cams.size() * 4), cam_t(cams.size() * 3);
+    std::vector<uint8_t> cam_fixed(cams.size());
+    for (size_t c = 0; c < cams.size(); c++) {
+        pose_to_floats(cams[c]->GetPose(), &cam_q[4 * c], &cam_t[3 * c]);
+        cam_fixed[c] = cams[c]->mnId == pMap->GetInitKFid();                              // :116
+    }
+    std::vector<MapPointT*> pts;
+    std::vector<float> xyz, edge_obs, edge_w;
+    std::vector<int32_t> edge_cam, edge_pt;
+    for (MapPointT* pMP : vpMP) {
+        if (pMP->isBad()) continue;                                                       // :126-127
+        const size_t first_edge = edge_cam.size();
+        for (const auto& ob : pMP->GetObservations()) {
+            KeyFrameT* pKF = ob.first;
+            if (pKF->isBad() || pKF->mnId > maxKFid) continue;                            // :141-142
+            const auto it = camIndex.find(pKF);
+            if (it == camIndex.end()) continue;                                           // optimizer.vertex(pKF->mnId) == NULL
+            const int leftIndex = std::get<0>(ob.second);
+            if (leftIndex == -1 || !(pKF->mvuRight[leftIndex] < 0)) continue;             // mono observation only
+            const auto& kpUn = pKF->mvKeysUn[leftIndex];
+            edge_cam.push_back(it->second);
+            edge_pt.push_back(static_cast<int32_t>(pts.size()));
+            edge_obs.push_back(kpUn.pt.x); edge_obs.push_back(kpUn.pt.y);
+            edge_w.push_back(pKF->mvInvLevelSigma2[kpUn.octave]);
+        }
+        if (edge_cam.size() == first_edge) continue;                                      // nEdges == 0: vertex removed, :243-247
+        const auto p = pMP->GetWorldPos();
+        for (int k = 0; k < 3; k++) xyz.push_back(p(k));
+        pts.push_back(pMP);
+    }
+    if (edge_cam.empty()) return;
+    const float K[4] = { cams[0]->fx, cams[0]->fy, cams[0]->cx, cams[0]->cy };
+    // const float thHuber2D = sqrt(5.99), :122 -- not LocalBundleAdjustment's sqrt(5.991)
+    const float delta = bRobust ? static_cast<float>(std::sqrt(5.99)) : std::numeric_limits<float>::infinity();
+    std::vector<uint8_t> edge_bad(edge_cam.size());
+    int iters = 0;
+    check(dvm_bundle_adjustment(solver, static_cast<int>(cams.size()), cam_q.data(), cam_t.data(), cam_fixed.data(),
+                                static_cast<int>(pts.size()), xyz.data(), static_cast<int>(edge_cam.size()), edge_cam.data(),
+                                edge_pt.data(), edge_obs.data(), edge_w.data(), K, nIterations, delta,
+                                reinterpret_cast<const volatile uint8_t*>(pbStopFlag), nullptr, edge_bad.data(), nullptr, &iters),
+          "Optimizer::BundleAdjustment");
+    if (iters < 0) return;
+    // recover optimised data, :250-356: the loop keyframe's own map gets the values directly, otherwise they are parked
+    // in mTcwGBA / mPosGBA for the caller's propagation
+    const bool direct = nLoopKF == pMap->GetOriginKF()->mnId;
+    for (size_t c = 0; c < cams.size(); c++) {
+        const auto T = pose_from_floats(cams[c]->GetPose(), &cam_q[4 * c], &cam_t[3 * c]);
+        if (direct) cams[c]->SetPose(T);
+        else { cams[c]->mTcwGBA = T; cams[c]->mnBAGlobalForKF = nLoopKF; }
+    }
+    for (size_t j = 0; j < pts.size(); j++) {
+        auto p = pts[j]->GetWorldPos();
+        for (int k = 0; k < 3; k++) p(k) = xyz[3 * j + k];
+        if (direct) { pts[j]->SetWorldPos(p); pts[j]->UpdateNormalAndDepth(); }
+        else { pts[j]->mPosGBA = p; pts[j]->mnBAGlobalForKF = nLoopKF; }
+    }
 }
 
 } // namespace dvm_host

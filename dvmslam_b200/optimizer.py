@@ -26,6 +26,8 @@ class LocalBA:
         L.dvm_lba_destroy.restype = None
         L.dvm_local_ba.argtypes = [_vp, C.c_int, _vp, _vp, _vp, C.c_int, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, C.c_int,
                                    _vp, _vp, _vp, _vp, _ip]
+        L.dvm_bundle_adjustment.argtypes = [_vp, C.c_int, _vp, _vp, _vp, C.c_int, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, C.c_int,
+                                            C.c_float, _vp, _vp, _vp, _vp, _ip]
         L.dvm_lba_last_kernel_ms.argtypes = [_vp]
         L.dvm_lba_last_kernel_ms.restype = C.c_float
         self.h = _vp()
@@ -42,8 +44,15 @@ class LocalBA:
         except Exception:
             pass
 
+    def BundleAdjustment(self, cam_q, cam_t, cam_fixed, pts, edge_cam, edge_pt, edge_obs, edge_w, K, nIterations=5,
+                         bRobust=True, abort=None):
+        """Optimizer::BundleAdjustment (global BA) for maps of up to max_free_cameras keyframes."""
+        delta = float(np.float32(np.sqrt(5.99))) if bRobust else float("inf")
+        return self.LocalBundleAdjustment(cam_q, cam_t, cam_fixed, pts, edge_cam, edge_pt, edge_obs, edge_w, K, nIterations,
+                                          abort, huber_delta=delta)
+
     def LocalBundleAdjustment(self, cam_q, cam_t, cam_fixed, pts, edge_cam, edge_pt, edge_obs, edge_w, K, iterations=10,
-                              abort=None):
+                              abort=None, huber_delta=None):
         q, t = _c(cam_q, np.float32).copy(), _c(cam_t, np.float32).copy()
         p = _c(pts, np.float32).copy()
         fx = _c(cam_fixed, np.uint8)
@@ -55,10 +64,12 @@ class LocalBA:
         stats = np.zeros(4, np.float64)
         iters = C.c_int()
         ab = _c([abort], np.uint8) if abort is not None else None   # pbStopFlag: a one-byte bool
-        check(self.L.dvm_local_ba(self.h, len(fx), q.ctypes.data, t.ctypes.data, fx.ctypes.data, len(p), p.ctypes.data,
-                                  ne, ec.ctypes.data, ep.ctypes.data, eo.ctypes.data, ew.ctypes.data,
-                                  _c(K, np.float32).ctypes.data, iterations, ab.ctypes.data if ab is not None else None,
-                                  chi2.ctypes.data, bad.ctypes.data, stats.ctypes.data, C.byref(iters)))
+        delta = float(np.float32(np.sqrt(5.991))) if huber_delta is None else float(huber_delta)
+        check(self.L.dvm_bundle_adjustment(self.h, len(fx), q.ctypes.data, t.ctypes.data, fx.ctypes.data, len(p),
+                                           p.ctypes.data, ne, ec.ctypes.data, ep.ctypes.data, eo.ctypes.data,
+                                           ew.ctypes.data, _c(K, np.float32).ctypes.data, iterations, C.c_float(delta),
+                                           ab.ctypes.data if ab is not None else None, chi2.ctypes.data,
+                                           bad.ctypes.data, stats.ctypes.data, C.byref(iters)))
         if iters.value < 0:   # no fixed keyframe / stop flag already set: nothing was computed
             chi2[:] = 0
             bad[:] = 0

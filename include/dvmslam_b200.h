@@ -414,6 +414,17 @@ DVM_API int dvm_local_ba(dvm_lba* h, int nc, float* cam_q, float* cam_t, const u
                          int ne, const int32_t* edge_cam, const int32_t* edge_pt, const float* edge_obs,
                          const float* edge_inv_sigma2, const float* K, int iterations, const volatile uint8_t* abort_flag,
                          double* edge_chi2, uint8_t* edge_bad, double* stats, int* iters_done);
+/* void Optimizer::BundleAdjustment(vpKFs, vpMP, nIterations, pbStopFlag, nLoopKF, bRobust)
+ * (O3/src/Optimizer.cc:55-356; GlobalBundleAdjustemnt :46-53 calls it with every keyframe and map point of the map)
+ * for maps of up to max_free_cameras free keyframes: the same solver with the caller's Huber delta -- the
+ * reference uses (float)sqrt(5.99) here, not LocalBundleAdjustment's sqrt(5.991) -- or INFINITY for bRobust == false.
+ * cam_fixed marks the map's initial keyframe (:116); map points without observation are left out by the caller
+ * (:243-247).  Outputs as dvm_local_ba (the caller writes mTcwGBA / mPosGBA and ignores edge_bad). */
+DVM_API int dvm_bundle_adjustment(dvm_lba* h, int nc, float* cam_q, float* cam_t, const uint8_t* cam_fixed, int np,
+                                  float* pts, int ne, const int32_t* edge_cam, const int32_t* edge_pt,
+                                  const float* edge_obs, const float* edge_inv_sigma2, const float* K, int iterations,
+                                  float huber_delta, const volatile uint8_t* abort_flag, double* edge_chi2,
+                                  uint8_t* edge_bad, double* stats, int* iters_done);
 /* Device time of the last dvm_local_ba kernel in milliseconds (CUDA events on the solver's stream). */
 DVM_API float dvm_lba_last_kernel_ms(const dvm_lba* h);
 

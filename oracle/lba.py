@@ -14,11 +14,14 @@ def _c(a, dt):
     return np.ascontiguousarray(a, dt)
 
 
-def local_ba(cam_q, cam_t, cam_fixed, pts, edge_cam, edge_pt, edge_obs, edge_w, K, iterations=10, abort=None):
-    """Returns dict(cam_q, cam_t, pts, chi2, bad, iters, trials, chi_first, chi_last, rc)."""
+def local_ba(cam_q, cam_t, cam_fixed, pts, edge_cam, edge_pt, edge_obs, edge_w, K, iterations=10, abort=None,
+             huber_delta=None):
+    """Returns dict(cam_q, cam_t, pts, chi2, bad, iters, trials, chi_first, chi_last, rc).  huber_delta: None =
+    LocalBundleAdjustment's float sqrt(5.991); a float = BundleAdjustment's delta (inf = no robust kernel)."""
     L = lib()
-    L.lbao_local_ba.argtypes = [C.c_int, _vp, _vp, _vp, C.c_int, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, C.c_int, _vp,
-                                _vp, _vp, _vp]
+    L.lbao_bundle_adjustment.argtypes = [C.c_int, _vp, _vp, _vp, C.c_int, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, C.c_int,
+                                         C.c_float, _vp, _vp, _vp, _vp]
+    delta = float(np.float32(np.sqrt(5.991))) if huber_delta is None else float(np.float32(huber_delta))
     q, t = _c(cam_q, np.float32).copy(), _c(cam_t, np.float32).copy()
     p = _c(pts, np.float32).copy()
     fx = _c(cam_fixed, np.uint8)
@@ -29,10 +32,11 @@ def local_ba(cam_q, cam_t, cam_fixed, pts, edge_cam, edge_pt, edge_obs, edge_w, 
     bad = np.zeros(max(ne, 1), np.uint8)
     stats = np.zeros(4, np.float64)
     ab = _c([abort], np.int32) if abort is not None else None
-    rc = L.lbao_local_ba(len(fx), q.ctypes.data, t.ctypes.data, fx.ctypes.data, len(p), p.ctypes.data, ne,
-                         ec.ctypes.data, ep.ctypes.data, eo.ctypes.data, ew.ctypes.data, _c(K, np.float32).ctypes.data,
-                         iterations, ab.ctypes.data if ab is not None else None, chi2.ctypes.data, bad.ctypes.data,
-                         stats.ctypes.data)
+    rc = L.lbao_bundle_adjustment(len(fx), q.ctypes.data, t.ctypes.data, fx.ctypes.data, len(p), p.ctypes.data, ne,
+                                  ec.ctypes.data, ep.ctypes.data, eo.ctypes.data, ew.ctypes.data,
+                                  _c(K, np.float32).ctypes.data, iterations, delta,
+                                  ab.ctypes.data if ab is not None else None, chi2.ctypes.data, bad.ctypes.data,
+                                  stats.ctypes.data)
     return dict(cam_q=q, cam_t=t, pts=p, chi2=chi2[:ne], bad=bad[:ne], iters=int(stats[0]), trials=int(stats[1]),
                 chi_first=stats[2], chi_last=stats[3], rc=rc)
 

@@ -220,10 +220,26 @@ extern "C" {
  * Outputs: edge_chi2[ne] (double), edge_bad[ne] (chi2 > 5.991 || depth <= 0 -> observation to
  * erase), stats[4] = {LM iterations run, LM trials, initial robust chi2, final robust chi2}.
  * Returns the number of iterations run, or -1 if nothing was optimised. */
+/* huber_delta: the robust kernel's delta as the caller's float (LocalBundleAdjustment: sqrt(5.991), Optimizer.cc:1178;
+ * BundleAdjustment / GlobalBundleAdjustemnt: sqrt(5.99), :122; bRobust == false: +infinity = no kernel). */
+int lbao_bundle_adjustment(int nc, float* cam_q, float* cam_t, const uint8_t* cam_fixed, int np, float* pts, int ne,
+                           const int* edge_cam, const int* edge_pt, const float* edge_obs, const float* edge_inv_sigma2,
+                           const float* K, int iterations, float huber_delta, const volatile int* abort_flag,
+                           double* edge_chi2_out, uint8_t* edge_bad, double* stats);
+
 int lbao_local_ba(int nc, float* cam_q, float* cam_t, const uint8_t* cam_fixed, int np, float* pts, int ne,
                   const int* edge_cam, const int* edge_pt, const float* edge_obs, const float* edge_inv_sigma2,
                   const float* K, int iterations, const volatile int* abort_flag, double* edge_chi2_out,
                   uint8_t* edge_bad, double* stats)
+{
+    return lbao_bundle_adjustment(nc, cam_q, cam_t, cam_fixed, np, pts, ne, edge_cam, edge_pt, edge_obs, edge_inv_sigma2, K,
+                                  iterations, (float)std::sqrt(5.991), abort_flag, edge_chi2_out, edge_bad, stats);
+}
+
+int lbao_bundle_adjustment(int nc, float* cam_q, float* cam_t, const uint8_t* cam_fixed, int np, float* pts, int ne,
+                           const int* edge_cam, const int* edge_pt, const float* edge_obs, const float* edge_inv_sigma2,
+                           const float* K, int iterations, float huber_delta, const volatile int* abort_flag,
+                           double* edge_chi2_out, uint8_t* edge_bad, double* stats)
 {
     Problem P;
     P.nc = nc; P.np = np; P.ne = ne;
@@ -248,8 +264,7 @@ int lbao_local_ba(int nc, float* cam_q, float* cam_t, const uint8_t* cam_fixed, 
     for (int i = 0; i < 2 * ne; i++) P.obs[i] = edge_obs[i];
     for (int i = 0; i < ne; i++) P.info[i] = edge_inv_sigma2[i];
     P.fx = K[0]; P.fy = K[1]; P.cx = K[2]; P.cy = K[3];
-    const float thHuberMono = (float)std::sqrt(5.991);
-    P.delta = thHuberMono; P.dsqr = P.delta * P.delta;
+    P.delta = huber_delta; P.dsqr = P.delta * P.delta;
 
     const int nf = P.nfree, dimP = 6 * nf, dimL = 3 * np;
     std::vector<double> Hpp((size_t)nf * 36), bp(dimP), Hll((size_t)np * 9), bl(dimL), Hpl((size_t)ne * 18);

@@ -428,3 +428,57 @@ int hm_compute_bow(const char* voc_path, const uint8_t* desc, int n, int levelsu
 }
 
 } // extern "C"
+
+extern "C" {
+
+// Optimizer::BundleAdjustment on a flat scene (every camera a keyframe of the map; the fixed one is the map's initial
+// keyframe).  direct != 0: nLoopKF is the origin keyframe (poses / points written directly), else parked in mTcwGBA / mPosGBA.
+int hm_bundle_adjustment(int nc, float* cam_q, float* cam_t, const uint8_t* cam_fixed, int np, float* pts, int ne, const int* edge_cam,
+                         const int* edge_pt, const float* edge_obs, const int* edge_octave, const float* invsig2, int nlevels,
+                         int iterations, int robust, int direct)
+{
+    Map map;
+    std::vector<std::unique_ptr<KeyFrame>> kfs(nc);
+    std::vector<std::unique_ptr<MapPoint>> mps(np);
+    std::vector<KeyFrame*> vk;
+    std::vector<MapPoint*> vm;
+    for (int c = 0; c < nc; c++) {
+        kfs[c].reset(new KeyFrame);
+        kfs[c]->mnId = 10 + c; kfs[c]->map = &map;
+        kfs[c]->fx = g_K[0]; kfs[c]->fy = g_K[1]; kfs[c]->cx = g_K[2]; kfs[c]->cy = g_K[3];
+        set_pose(kfs[c]->Tcw, cam_q + 4 * c, cam_t + 3 * c);
+        kfs[c]->mvInvLevelSigma2.assign(invsig2, invsig2 + nlevels);
+        if (cam_fixed[c]) map.initKFid = kfs[c]->mnId;
+        vk.push_back(kfs[c].get());
+    }
+    map.originKF = kfs[0].get();
+    for (int j = 0; j < np; j++) {
+        mps[j].reset(new MapPoint);
+        mps[j]->mnId = j; mps[j]->map = &map;
+        for (int k = 0; k < 3; k++) mps[j]->pos(k) = pts[3 * j + k];
+        vm.push_back(mps[j].get());
+    }
+    for (int e = 0; e < ne; e++) {
+        KeyFrame& K = *kfs[edge_cam[e]];
+        cv::KeyPoint k(edge_obs[2 * e], edge_obs[2 * e + 1], 31.f, 0.f, 1.f, edge_octave[e]);
+        K.mvKeysUn.push_back(k); K.mvuRight.push_back(-1.f); K.mapPoints.push_back(mps[edge_pt[e]].get());
+        mps[edge_pt[e]]->observations[&K] = std::make_tuple(K.N, -1);
+        K.N++;
+    }
+    dvm_host::LbaHandle solver;
+    return guarded([&] {
+        dvm_host::check(dvm_lba_create(&solver.h, dvm_host::device_from_env(), 100), "dvm_lba_create");
+        dvm_host::BundleAdjustment<KeyFrame, MapPoint>(solver.h, vk, vm, iterations, nullptr, direct ? kfs[0]->mnId : 999999ul, robust != 0);
+        int parked = 0;
+        for (int c = 0; c < nc; c++) {
+            const SE3f& T = direct ? kfs[c]->Tcw : kfs[c]->mTcwGBA;
+            parked += kfs[c]->mnBAGlobalForKF == 999999ul;
+            for (int k = 0; k < 4; k++) cam_q[4 * c + k] = T.q.q[k];
+            for (int k = 0; k < 3; k++) cam_t[3 * c + k] = T.t.v[k];
+        }
+        for (int j = 0; j < np; j++) for (int k = 0; k < 3; k++) pts[3 * j + k] = direct ? mps[j]->pos(k) : mps[j]->mPosGBA(k);
+        return parked;
+    });
+}
+
+} // extern "C"

@@ -61,7 +61,8 @@ struct MapPoint {
     bool mbTrackInView = false, mbTrackInViewR = false;
     float mTrackProjX = 0, mTrackProjY = 0, mTrackViewCos = 0, mTrackDepth = 0;
     int mnTrackScaleLevel = 0;
-    unsigned long mnBALocalForKF = ~0ul;
+    unsigned long mnBALocalForKF = ~0ul, mnBAGlobalForKF = 0;
+    Vec3 mPosGBA;
     std::map<KeyFrame*, std::tuple<int, int>> observations;
     int normalUpdates = 0;
 
@@ -106,7 +107,8 @@ struct Frame {
 struct KeyFrame {
     float fx = 0, fy = 0, cx = 0, cy = 0;   // per-object constants in the reference (O3/include/KeyFrame.h)
     long unsigned int mnId = 0;
-    unsigned long mnBALocalForKF = ~0ul, mnBAFixedForKF = ~0ul;
+    unsigned long mnBALocalForKF = ~0ul, mnBAFixedForKF = ~0ul, mnBAGlobalForKF = 0;
+    SE3f mTcwGBA;
     int N = 0, NLeft = -1;
     std::vector<cv::KeyPoint> mvKeysUn;
     std::vector<float> mvuRight, mvInvLevelSigma2, mvScaleFactors, mvLevelSigma2;
@@ -137,6 +139,8 @@ struct Map {
     unsigned long initKFid = 0;
     int changeIndex = 0;
     unsigned long GetInitKFid() const { return initKFid; }
+    KeyFrame* originKF = nullptr;
+    KeyFrame* GetOriginKF() const { return originKF; }
     void IncreaseChangeIndex() { changeIndex++; }
 };
 

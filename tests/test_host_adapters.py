@@ -240,6 +240,8 @@ def test_local_ba_adapter_matches_direct_call(libs):
 
     H, _ = libs
     B = synth.ba_scene(12, 4, 600, seed=2)
+    invsig2 = np.array([1.0 / (np.float32(1.2) ** (2 * l)) for l in range(8)], np.float32)
+    B = dict(B, edge_w=invsig2[np.array([int(np.argmin(np.abs(invsig2 - w))) for w in B["edge_w"]])])   # exact table entries
     # the reference's window holds the map points seen by the LOCAL keyframes (:1048-1065); points observed by
     # fixed cameras only never enter it.  Restrict the flat scene to that window so both calls see the same problem.
     free = np.asarray(B["cam_fixed"]) == 0
@@ -270,10 +272,10 @@ def test_local_ba_adapter_matches_direct_call(libs):
     nfree = int((np.asarray(B["cam_fixed"]) == 0).sum())
     nfixed_seen = len(set(np.asarray(B["edge_cam"])[~free[np.asarray(B["edge_cam"])]].tolist()))
     assert list(counts) == [nfixed_seen, nfree, len(pts), ne]
-    if np.array_equal(invsig2[octave], w_exact):
-        assert np.abs(ct - r["cam_t"]).max() < 6e-5 and np.abs(cq - r["cam_q"]).max() < 1e-6
-        assert np.abs(pts - r["pts"]).max() < 1e-4
-        assert (erased != r["bad"]).sum() <= max(2, ne // 500)
+    assert np.array_equal(invsig2[octave], w_exact)
+    assert np.abs(ct - r["cam_t"]).max() < 6e-5 and np.abs(cq - r["cam_q"]).max() < 1e-6
+    assert np.abs(pts - r["pts"]).max() < 1e-4
+    assert (erased != r["bad"]).sum() <= max(2, ne // 500)
     # pbStopFlag already raised: nothing is touched
     cq2, ct2, pts2 = _c(B["cam_q"], np.float32).copy(), _c(B["cam_t"], np.float32).copy(), _c(B["pts"], np.float32).copy()
     rc = H.hm_local_ba(len(cq2), _p(cq2), _p(ct2), _p(_c(B["cam_fixed"], np.uint8)), len(pts2), _p(pts2), ne,
@@ -404,3 +406,31 @@ def test_vocabulary_adapter_matches_oracle(libs, tmp_path):
     bow0, fv0 = transform(tree, 3, 0, 0, feat, 2)
     assert list(bow0.items()) == [(int(bw[i]), float(bv[i])) for i in range(nb.value)]
     assert list(fv0.items()) == [(int(fn[i]), [int(x) for x in fi[fs[i]:fs[i + 1]]]) for i in range(nf.value)]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("direct", [1, 0])
+def test_global_ba_adapter_matches_direct_call(libs, direct):
+    """Optimizer::BundleAdjustment through the adapter (every keyframe and map point of a small map; results written
+    directly or parked in mTcwGBA / mPosGBA) against dvm_bundle_adjustment on the same flat scene."""
+    from dvmslam_b200.optimizer import LocalBA
+
+    H, _ = libs
+    B = synth.ba_scene(20, 1, 700, seed=6)
+    H.hm_set_camera(_p(_c(B["K"], np.float32)), _p(np.array([0, 0, 1280, 720], np.float32)))
+    invsig2 = np.array([1.0 / (np.float32(1.2) ** (2 * l)) for l in range(8)], np.float32)
+    octave = np.array([int(np.argmin(np.abs(invsig2 - w))) for w in B["edge_w"]], np.int32)
+    B = dict(B, edge_w=invsig2[octave])      # the adapter looks mvInvLevelSigma2 up by octave: same floats on both sides
+    s = LocalBA(100)
+    r = s.BundleAdjustment(B["cam_q"], B["cam_t"], B["cam_fixed"], B["pts"], B["edge_cam"], B["edge_pt"], B["edge_obs"],
+                           B["edge_w"], B["K"], nIterations=10, bRobust=True)
+    s.close()
+    cq, ct, pts = _c(B["cam_q"], np.float32).copy(), _c(B["cam_t"], np.float32).copy(), _c(B["pts"], np.float32).copy()
+    rc = H.hm_bundle_adjustment(len(cq), _p(cq), _p(ct), _p(_c(B["cam_fixed"], np.uint8)), len(pts), _p(pts), len(B["edge_cam"]),
+                                _p(_c(B["edge_cam"], np.int32)), _p(_c(B["edge_pt"], np.int32)), _p(_c(B["edge_obs"], np.float32)),
+                                _p(octave), _p(invsig2), 8, 10, 1, direct)
+    assert rc == (0 if direct else len(cq)), (rc, H.hm_last_error())
+    seen = np.zeros(len(pts), bool)
+    seen[np.asarray(B["edge_pt"])] = True                       # points without observation are left out (:243-247)
+    assert np.abs(ct - r["cam_t"]).max() < 6e-5 and np.abs(cq - r["cam_q"]).max() < 1e-6
+    assert np.abs(pts[seen] - r["pts"][seen]).max() < 1e-4

@@ -83,3 +83,25 @@ def test_observation_only_from_fixed_cameras(solver):
     r0 = local_ba(*_args(S))
     r1 = solver.LocalBundleAdjustment(*_args(S))
     _compare(r0, r1, S)
+
+
+@pytest.mark.parametrize("n_free,n_pts,robust,iters", [(40, 1500, True, 10), (96, 3000, True, 20), (30, 800, False, 20)])
+def test_global_bundle_adjustment_matches_oracle(n_free, n_pts, robust, iters):
+    """Optimizer::BundleAdjustment (GlobalBundleAdjustemnt's worker, O3/src/Optimizer.cc:55-356) on maps the dense
+    reduced solve holds (<= 100 free keyframes): one fixed keyframe (the map's initial one), Huber delta
+    (float)sqrt(5.99) or none, nIterations LM iterations; same tolerances as the local BA."""
+    from dvmslam_b200.optimizer import LocalBA
+    from oracle.lba import local_ba
+
+    S = synth.ba_scene(n_free, 1, n_pts, seed=n_free, outlier_frac=0.0 if not robust else 0.05)
+    a = (S["cam_q"], S["cam_t"], S["cam_fixed"], S["pts"], S["edge_cam"], S["edge_pt"], S["edge_obs"], S["edge_w"], S["K"])
+    delta = float(np.float32(np.sqrt(5.99))) if robust else float("inf")
+    r0 = local_ba(*a, iterations=iters, huber_delta=delta)
+    s = LocalBA(100)
+    r1 = s.BundleAdjustment(*a, nIterations=iters, bRobust=robust)
+    s.close()
+    assert r0["iters"] == r1["iters"] and r0["iters"] >= 3
+    assert abs(r1["chi_last"] - r0["chi_last"]) <= 1e-6 * abs(r0["chi_last"]) + 1e-9
+    assert np.abs(r1["cam_t"] - r0["cam_t"]).max() < 6e-5 and np.abs(r1["cam_q"] - r0["cam_q"]).max() < 1e-6
+    assert np.abs(r1["pts"] - r0["pts"]).max() < 1e-4
+    assert r1["chi_last"] < 0.5 * r1["chi_first"]

@@ -58,3 +58,20 @@ def test_noop_conditions():
     assert r["rc"] == -1 and np.array_equal(r["pts"], S["pts"])
     r = local_ba(*_args(S), abort=1)              # pbStopFlag already set
     assert r["rc"] == -1 and np.array_equal(r["cam_t"], S["cam_t"])
+
+
+def test_bundle_adjustment_delta_variants():
+    """The robust-kernel delta is the caller's: sqrt(5.991) (local BA), sqrt(5.99) (global BA), infinity (bRobust =
+    false).  Without outliers and without a kernel the problem is plain least squares and converges to the noise floor."""
+    from oracle.lba import local_ba
+
+    S = synth.ba_scene(10, 1, 300, seed=4, outlier_frac=0.0)
+    a = (S["cam_q"], S["cam_t"], S["cam_fixed"], S["pts"], S["edge_cam"], S["edge_pt"], S["edge_obs"], S["edge_w"], S["K"])
+    r_inf = local_ba(*a, iterations=20, huber_delta=float("inf"))
+    r_gba = local_ba(*a, iterations=20, huber_delta=np.sqrt(5.99))
+    r_lba = local_ba(*a, iterations=20)
+    ne = len(S["edge_cam"])
+    assert r_inf["chi_last"] < 3.0 * ne and r_inf["chi_last"] < 0.2 * r_inf["chi_first"]
+    assert r_gba["chi_last"] <= r_inf["chi_last"] * (1 + 1e-9)             # Huber never exceeds the quadratic cost
+    assert abs(r_gba["chi_last"] - r_lba["chi_last"]) < 1e-2 * r_lba["chi_last"]   # 5.99 vs 5.991: nearly the same kernel
+    assert r_gba["chi_last"] != r_lba["chi_last"]
