@@ -62,6 +62,14 @@ feat = c["desc1"]
 g = med(lambda: voc.transform_features(feat, 4))
 o = med(lambda: od.transform_features(tree, v["L"], feat, 4), 5)
 rows.append((f"DBoW2 descent ({len(feat)} descriptors, k 10, L 5, {len(tree[4])} nodes)", g, o))
+from dvmslam_b200.optimizer import LocalBA
+from oracle.lba import local_ba
+Sg = synth.ba_scene(96, 1, 3000, seed=96)
+ag = (Sg["cam_q"], Sg["cam_t"], Sg["cam_fixed"], Sg["pts"], Sg["edge_cam"], Sg["edge_pt"], Sg["edge_obs"], Sg["edge_w"], Sg["K"])
+sol = LocalBA(100)
+g = med(lambda: sol.BundleAdjustment(*ag, nIterations=20, bRobust=True), 5)
+o = med(lambda: local_ba(*ag, iterations=20, huber_delta=float(np.float32(np.sqrt(5.99)))), 2)
+rows.append((f"BundleAdjustment (global: 96 + 1 keyframes, 3000 points, {len(Sg['edge_cam'])} obs, 20 its)", g, o))
 print(f"{'operator':62s} {'B200 call us':>12s} {'oracle 1 thread us':>18s} {'ratio':>7s}")
 for name, g, o in rows:
     print(f"{name:62s} {g:12.1f} {o:18.1f} {o / g:7.1f}")
