@@ -27,6 +27,8 @@ struct dvm_orb {
     int cur_w = -1, cur_h = -1;
     OrbCfg cfg;
     OrbBuffers buf;
+    OrbTmaps tmaps;                   // TMA descriptors of the levels (FAST cell tiles)
+    const uint8_t* tmap0_img = nullptr; int tmap0_pitch = -1; // what tmaps.map[0] was encoded for
     int oct_smem = 0, oct_smem_prepared = 0;
     // device allocations
     uint8_t* d_pyr = nullptr;
@@ -150,6 +152,10 @@ static int configure(dvm_orb* h, int w, int hgt)
         DVM_CUDA(cudaMemcpy(h->d_xtab, xt.data(), xt.size() * sizeof(ResizeX), cudaMemcpyHostToDevice));
         DVM_CUDA(cudaMemcpy(h->d_ytab, yt.data(), yt.size() * sizeof(ResizeY), cudaMemcpyHostToDevice));
     }
+    // TMA descriptors of the levels (level 0 again per call if the caller's image is read in place)
+    memset(&h->tmaps, 0, sizeof(h->tmaps));
+    for (int l = 0; l < c.nlevels; l++) encode_level_tmap(c, l, h->tmaps);
+    h->tmap0_img = c.lv[0].img; h->tmap0_pitch = c.lv[0].pitch;
     h->cur_w = w;
     h->cur_h = hgt;
     return DVM_OK;
@@ -301,7 +307,11 @@ static int enqueue_pipeline(dvm_orb* h, int lap0, int lap1)
     if (prof) DVM_CUDA(cudaEventRecord(h->ev[0], h->stream));
     for (int l = 1; l < c.nlevels; l++) launch_resize_level(c, h->buf, l, const_cast<uint8_t*>(c.lv[l].img), h->stream);
     if (prof) DVM_CUDA(cudaEventRecord(h->ev[1], h->stream));
-    launch_fast_cells(c, h->buf, h->stream);
+    if (c.lv[0].img != h->tmap0_img || c.lv[0].pitch != h->tmap0_pitch) {   // level 0 may be the caller's image
+        encode_level_tmap(c, 0, h->tmaps);
+        h->tmap0_img = c.lv[0].img; h->tmap0_pitch = c.lv[0].pitch;
+    }
+    launch_fast_cells(c, h->buf, h->tmaps, h->stream);
     if (prof) DVM_CUDA(cudaEventRecord(h->ev[2], h->stream));
     launch_octree(c, h->buf, lap0, lap1, h->oct_smem, h->stream);
     if (prof) DVM_CUDA(cudaEventRecord(h->ev[3], h->stream));

@@ -56,9 +56,11 @@ constexpr int kCellListCap = 1700;
 // minThFAST.  cv::FAST's 3x3 non-max suppression compares scores strictly, with everything outside
 // the sub-image's computed region [3, dim-3) counting as 0; since all scores in one call share one
 // threshold this is "strict local maximum of the arc measure m inside the region, and m > th".
-__global__ void __launch_bounds__(kCellThreads) fast_cells_kernel(const __grid_constant__ OrbCfg cfg, OrbBuffers b)
+__global__ void __launch_bounds__(kCellThreads) fast_cells_kernel(const __grid_constant__ OrbCfg cfg, OrbBuffers b,
+                                                                  const __grid_constant__ OrbTmaps tm)
 {
-    __shared__ uint8_t raw[kCellMaxDim * kCellTilePitch];
+    __shared__ __align__(128) uint8_t raw[kCellMaxDim * kCellTilePitch];
+    __shared__ __align__(8) unsigned long long tma_bar;
     __shared__ uint8_t score[(kCellMaxDim - 6) * kScorePitch];
     __shared__ uint32_t list[kCellListCap];
     __shared__ int s_nlist, s_nini, s_base, s_rank;
@@ -80,18 +82,42 @@ __global__ void __launch_bounds__(kCellThreads) fast_cells_kernel(const __grid_c
     const int cw = sw - 6, ch = sh - 6;
 
     if (threadIdx.x == 0) { s_nlist = 0; s_nini = 0; s_rank = 0; }
-    const uint8_t* src = L.img + (size_t)(kBorder + iniY) * L.pitch + (kBorder + iniX);
-    for (int idx = threadIdx.x; idx < sh * sw; idx += kCellThreads) {
-        const int r = idx / sw, c = idx - r * sw;
-        raw[r * kCellTilePitch + c] = __ldg(src + (size_t)r * L.pitch + c);
+    const uint8_t* tile = raw + (tm.use[level] ? ((kBorder + iniX) & 15) : 0);
+    if (tm.use[level]) {
+        // the cell's tile (kCellTilePitch x (hCell + 6) bytes, zero-filled past the image) by ONE TMA tensor copy.  The
+        // box must start on a 16-byte boundary of the row (an unaligned inner coordinate faults as an illegal instruction),
+        // so it starts at the aligned column below the cell and the kernel reads the tile `xoff` bytes in.
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&tma_bar);
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const uint32_t bytes = (uint32_t)(kCellTilePitch * tm.box_h[level]);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                         ::"r"((uint32_t)__cvta_generic_to_shared(raw)), "l"(reinterpret_cast<uint64_t>(&tm.map[level])),
+                           "r"((kBorder + iniX) & ~15), "r"(kBorder + iniY), "r"(bar) : "memory");
+        }
+        uint32_t done = 0;
+        while (!done)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(bar), "r"(0) : "memory");
+    } else {
+        const uint8_t* src = L.img + (size_t)(kBorder + iniY) * L.pitch + (kBorder + iniX);
+        for (int idx = threadIdx.x; idx < sh * sw; idx += kCellThreads) {
+            const int r = idx / sw, c = idx - r * sw;
+            raw[r * kCellTilePitch + c] = __ldg(src + (size_t)r * L.pitch + c);
+        }
+        __syncthreads();
     }
-    __syncthreads();
 
     // arc measure of every region pixel, two horizontally adjacent pixels per iteration
     const int pw = (cw + 1) >> 1;
     for (int t = threadIdx.x; t < pw * ch; t += kCellThreads) {
         const int ry = t / pw, rx = (t - ry * pw) * 2;
-        const uint8_t* p = raw + (ry + 3) * kCellTilePitch + (rx + 3);
+        const uint8_t* p = tile + (ry + 3) * kCellTilePitch + (rx + 3);
         uint32_t ring[16];
 #pragma unroll
         for (int k = 0; k < 16; k++) {
@@ -147,9 +173,36 @@ __global__ void __launch_bounds__(kCellThreads) fast_cells_kernel(const __grid_c
     }
 }
 
-void launch_fast_cells(const OrbCfg& cfg, const OrbBuffers& b, cudaStream_t stream)
+void launch_fast_cells(const OrbCfg& cfg, const OrbBuffers& b, const OrbTmaps& tm, cudaStream_t stream)
 {
-    DVM_LAUNCH(fast_cells_kernel, cfg.total_cells, kCellThreads, 0, stream, cfg, b);
+    DVM_LAUNCH(fast_cells_kernel, cfg.total_cells, kCellThreads, 0, stream, cfg, b, tm);
+}
+
+bool encode_level_tmap(const OrbCfg& cfg, int level, OrbTmaps& tm)
+{
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = [] {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            fn = nullptr;
+        return (EncodeFn)fn;
+    }();
+    const OrbLevel& L = cfg.lv[level];
+    tm.use[level] = 0;
+    tm.box_h[level] = L.hCell + 6;
+    if (!encode || ((uintptr_t)L.img & 15) != 0 || (L.pitch & 15) != 0) return false;
+    const cuuint64_t dims[2] = { (cuuint64_t)L.w, (cuuint64_t)L.h };
+    const cuuint64_t strides[1] = { (cuuint64_t)L.pitch };
+    const cuuint32_t box[2] = { (cuuint32_t)kCellTilePitch, (cuuint32_t)(L.hCell + 6) };
+    const cuuint32_t estr[2] = { 1, 1 };
+    const CUresult r = encode(&tm.map[level], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(L.img), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    tm.use[level] = r == CUDA_SUCCESS ? 1 : 0;
+    return tm.use[level] != 0;
 }
 
 // ------------------------------------------------------------------------------------------ octree

@@ -1,6 +1,7 @@
 // orb_kernels.cuh -- device-side configuration and kernel entry points of the ORB extractor.
 #pragma once
 #include "common.cuh"
+#include <cuda.h>   // CUtensorMap (the descriptor is encoded through cudaGetDriverEntryPoint: no libcuda link dependency)
 
 namespace dvm {
 
@@ -8,7 +9,7 @@ constexpr int kMaxLevels = 12;
 constexpr int kBorder = 16;        // EDGE_THRESHOLD - 3   (O3/src/ORBextractor.cc:618)
 constexpr int kEdge = 19;          // EDGE_THRESHOLD
 constexpr int kHalfPatch = 15;     // HALF_PATCH_SIZE
-constexpr int kCellTilePitch = 96; // smem pitch of one FAST cell tile (sub-image <= 88 px wide)
+constexpr int kCellTilePitch = 112; // smem pitch of one FAST cell tile (sub-image <= 88 px wide, up to 15 px of TMA alignment slack)
 constexpr int kCellMaxDim = 88;
 
 struct ResizeX { int sx0, sx1; short a0, a1; };       // per destination column
@@ -63,9 +64,21 @@ struct OrbBuffers {
     const int8_t* pattern; // [256*4] device copy of the rBRIEF pattern
 };
 
+// TMA descriptors of the pyramid levels for the FAST cell tiles: a 2-D u8 tensor (width x height, row pitch) per level
+// with a box of kCellTilePitch x (hCell + 6) bytes; a level whose base or pitch is not 16-byte aligned (a caller's
+// image read in place) falls back to ordinary loads.
+struct alignas(64) OrbTmaps {
+    CUtensorMap map[kMaxLevels];
+    int use[kMaxLevels];
+    int box_h[kMaxLevels];
+};
+
 // launches (all on `stream`)
 void launch_resize_level(const OrbCfg& cfg, const OrbBuffers& b, int level, uint8_t* dst, cudaStream_t stream);
-void launch_fast_cells(const OrbCfg& cfg, const OrbBuffers& b, cudaStream_t stream);
+void launch_fast_cells(const OrbCfg& cfg, const OrbBuffers& b, const OrbTmaps& tm, cudaStream_t stream);
+// encodes tm.map[level] for the level image currently in cfg (returns false and clears tm.use[level] when TMA cannot
+// address it)
+bool encode_level_tmap(const OrbCfg& cfg, int level, OrbTmaps& tm);
 int octree_smem_bytes(const OrbCfg& cfg);
 int prepare_octree_kernel(int smem_bytes);
 void launch_octree(const OrbCfg& cfg, const OrbBuffers& b, int lap0, int lap1, int smem_bytes, cudaStream_t stream);
