@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include <chrono>
 #include <cooperative_groups.h>
+#include <math_constants.h>
 #include <algorithm>
 #include <cstdlib>
 #include <vector>
@@ -32,6 +33,8 @@ constexpr int kNB = 32; // Cholesky block size
 
 struct LbaDev {
     int nc, nf, np, ne, dimP, dimPad, iterations; // dimPad = dimP rounded up to the Cholesky block size
+    int iterations2;   // > 0: the welding BA's second pass (no robust kernel, level-0 edges only)
+    uint8_t* level;    // [ne] 1 = edge moved to level 1 before the second pass; null for one-pass calls
     double fx, fy, cx, cy, delta, dsqr;
     double* camq[2]; double* camt[2];
     const int* cam_col; const int* free_cam;
@@ -147,8 +150,8 @@ __device__ inline void se3_update(const double u[6], const double* q_in, const d
     t_out[0] = et[0] + rt[0]; t_out[1] = et[1] + rt[1]; t_out[2] = et[2] + rt[2];
 }
 
-__device__ inline double huber_rho0(const LbaDev& P, double e) { return e <= P.dsqr ? e : 2 * sqrt(e) * P.delta - P.dsqr; }
-__device__ inline double huber_rho1(const LbaDev& P, double e) { return e <= P.dsqr ? 1.0 : P.delta / sqrt(e); }
+__device__ inline double huber_rho0(double delta, double dsqr, double e) { return e <= dsqr ? e : 2 * sqrt(e) * delta - dsqr; }
+__device__ inline double huber_rho1(double delta, double dsqr, double e) { return e <= dsqr ? 1.0 : delta / sqrt(e); }
 
 // camera-frame point and reprojection error of edge e at estimate buffer `cur`
 __device__ inline void edge_residual(const LbaDev& P, int cur, int e, double xc[3], double r[2], Quat* qout)
@@ -542,328 +545,372 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kLbaThrea
         return a;
     };
 
-    for (int it = 0; it < P.iterations && !stop; it++) {
-        if (agree_abort()) break;
-        // ---------------- L1: point-major linearisation ----------------
-        double chi_part = 0, maxd = 0;
-        for (int l = gwarp; l < P.np; l += nwarps) {
-            double h[6] = { 0, 0, 0, 0, 0, 0 }, g[3] = { 0, 0, 0 };
-            const int s = P.pt_start[l], e_end = P.pt_start[l + 1];
-            for (int k = s + lane; k < e_end; k += 32) {
-                const int e = P.pt_edges[k];
-                double xc[3], r[2];
-                Quat Q;
-                edge_residual(P, cur, e, xc, r, &Q);
-                P.err[2 * e] = r[0]; P.err[2 * e + 1] = r[1];
+    // One pass is the reference's optimizer.optimize(iterations).  The welding BA of a map merge (O3/src/Optimizer.cc:
+    // 3257-3675) runs two: optimize(5) with the Huber kernel, then -- unless the stop flag is up -- edges with
+    // chi2 > 5.991 or non-positive depth go to level 1, every edge loses its robust kernel and optimize(10) runs on the
+    // level-0 edges (:3476-3521).  A level-1 edge contributes nothing and keeps the error of the first pass.
+    const int npasses = P.iterations2 > 0 ? 2 : 1;
+    double delta = P.delta, dsqr = P.dsqr;
+    int done_first = 0, excluded = 0;
+    for (int pass = 0; pass < npasses; pass++) {
+        if (pass == 1) {
+            if (agree_abort()) break;
+            done_first = done;
+            int nex = 0;
+            for (int e = gtid; e < P.ne; e += nthreads) {
                 const double om = (double)P.einfo[e];
-                const double chi = r[0] * (om * r[0]) + r[1] * (om * r[1]);
-                chi_part += huber_rho0(P, chi);
-                const double w = huber_rho1(P, chi);
-                const double X = xc[0], Y = xc[1], Z = xc[2];
-                const double pj[6] = { -(P.fx / Z), 0.0, P.fx * X / (Z * Z), 0.0, -(P.fy / Z), P.fy * Y / (Z * Z) };
-                double R[9];
-                quat_to_matrix(Q, R);
-                double A[6];
-#pragma unroll
-                for (int rr = 0; rr < 2; rr++)
-#pragma unroll
-                    for (int kk = 0; kk < 3; kk++)
-                        A[rr * 3 + kk] = pj[rr * 3] * R[kk] + pj[rr * 3 + 1] * R[3 + kk] + pj[rr * 3 + 2] * R[6 + kk];
-                const double wo = w * om;
-                const double r0 = -om * r[0] * w, r1 = -om * r[1] * w;
-                g[0] += A[0] * r0 + A[3] * r1; g[1] += A[1] * r0 + A[4] * r1; g[2] += A[2] * r0 + A[5] * r1;
-                h[0] += A[0] * wo * A[0] + A[3] * wo * A[3];
-                h[1] += A[0] * wo * A[1] + A[3] * wo * A[4];
-                h[2] += A[0] * wo * A[2] + A[3] * wo * A[5];
-                h[3] += A[1] * wo * A[1] + A[4] * wo * A[4];
-                h[4] += A[1] * wo * A[2] + A[4] * wo * A[5];
-                h[5] += A[2] * wo * A[2] + A[5] * wo * A[5];
-                if (P.cam_col[P.ecam[e]] >= 0) {
-                    const double Dv[18] = { 0, Z, -Y, 1, 0, 0, -Z, 0, X, 0, 1, 0, Y, -X, 0, 0, 0, 1 };
-                    double* hp = P.Hpl + (size_t)e * 18;
-#pragma unroll
-                    for (int a = 0; a < 6; a++) {
-                        const double B0 = pj[0] * Dv[a] + pj[1] * Dv[6 + a] + pj[2] * Dv[12 + a];
-                        const double B1 = pj[3] * Dv[a] + pj[4] * Dv[6 + a] + pj[5] * Dv[12 + a];
-#pragma unroll
-                        for (int b2 = 0; b2 < 3; b2++) hp[a * 3 + b2] = B0 * wo * A[b2] + B1 * wo * A[3 + b2];
-                    }
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < 6; i++) h[i] = warp_sum(h[i]);
-#pragma unroll
-            for (int i = 0; i < 3; i++) g[i] = warp_sum(g[i]);
-            if (lane == 0) {
-#pragma unroll
-                for (int i = 0; i < 6; i++) P.Hll[(size_t)l * 6 + i] = h[i];
-#pragma unroll
-                for (int i = 0; i < 3; i++) P.bl[(size_t)l * 3 + i] = g[i];
-                maxd = fmax(maxd, fmax(fabs(h[0]), fmax(fabs(h[3]), fabs(h[5]))));
-            }
-        }
-        {
-            double v[1] = { chi_part };
-            cta_sum<1>(v, warp_buf, red);
-            maxd = warp_max(maxd);
-            if (lane == 0) warp_buf[wid] = maxd;
-            __syncthreads();
-            if (tid == 0) {
-                double m = 0;
-                for (int w2 = 0; w2 < kLbaWarps; w2++) m = fmax(m, warp_buf[w2]);
-                P.part[blockIdx.x * 4 + 0] = red[0];
-                P.part[blockIdx.x * 4 + 2] = m;
-            }
-            __syncthreads();
-        }
-        grid.sync();
-        tick(0);
-        // ---------------- L2: camera-major Hpp, bp ----------------
-        double maxdp = 0;
-        for (int cf = blockIdx.x; cf < P.nf; cf += G) {
-            double acc[27];
-#pragma unroll
-            for (int i = 0; i < 27; i++) acc[i] = 0;
-            const int s = P.cam_start[cf], e_end = P.cam_start[cf + 1];
-            for (int k = s + tid; k < e_end; k += kLbaThreads) {
-                const int e = P.cam_edges[k];
+                const double r0 = P.err[2 * e], r1 = P.err[2 * e + 1];
                 double xc[3], r[2];
                 edge_residual(P, cur, e, xc, r, nullptr);
-                const double om = (double)P.einfo[e];
-                const double chi = r[0] * (om * r[0]) + r[1] * (om * r[1]);
-                const double w = huber_rho1(P, chi);
-                const double X = xc[0], Y = xc[1], Z = xc[2];
-                const double pj[6] = { -(P.fx / Z), 0.0, P.fx * X / (Z * Z), 0.0, -(P.fy / Z), P.fy * Y / (Z * Z) };
-                const double Dv[18] = { 0, Z, -Y, 1, 0, 0, -Z, 0, X, 0, 1, 0, Y, -X, 0, 0, 0, 1 };
-                double B[12];
-#pragma unroll
-                for (int a = 0; a < 6; a++) {
-                    B[a] = pj[0] * Dv[a] + pj[1] * Dv[6 + a] + pj[2] * Dv[12 + a];
-                    B[6 + a] = pj[3] * Dv[a] + pj[4] * Dv[6 + a] + pj[5] * Dv[12 + a];
-                }
-                const double wo = w * om;
-                const double r0 = -om * r[0] * w, r1 = -om * r[1] * w;
-                int idx = 0;
-#pragma unroll
-                for (int a = 0; a < 6; a++) {
-                    acc[21 + a] += B[a] * r0 + B[6 + a] * r1;
-#pragma unroll
-                    for (int b2 = a; b2 < 6; b2++) acc[idx++] += B[a] * wo * B[b2] + B[6 + a] * wo * B[6 + b2];
-                }
-            }
-            cta_sum<27>(acc, warp_buf, red);
-            if (tid < 36) {
-                const int a = tid / 6, b2 = tid % 6;
-                const int lo = min(a, b2), hi = max(a, b2);
-                const int idx = lo * 6 - lo * (lo - 1) / 2 + (hi - lo);
-                P.Hpp[(size_t)cf * 36 + tid] = red[idx];
-            }
-            if (tid < 6) P.bp[cf * 6 + tid] = red[21 + tid];
-            if (tid == 0)
-                for (int a = 0; a < 6; a++) maxdp = fmax(maxdp, fabs(red[a * 6 - a * (a - 1) / 2]));
-            __syncthreads();
-        }
-        if (tid == 0) P.part[blockIdx.x * 4 + 3] = maxdp;
-        grid.sync();
-        tick(1);
-        double currentChi = 0;
-        {
-            double m = 0;
-            for (int b2 = 0; b2 < G; b2++) {
-                currentChi += P.part[b2 * 4 + 0];
-                m = fmax(m, fmax(P.part[b2 * 4 + 2], P.part[b2 * 4 + 3]));
-            }
-            if (it == 0) { lambda = 1e-5 * m; ni = 2; nBad = 0; first_chi = currentChi; }
-        }
-        const double iniChi = currentChi;
-        double rho = 0;
-        int qmax = 0;
-        bool aborted = false;
-        do {
-            const int trial = cur ^ 1;
-            // ---------------- S0: landmark inverses, clear Hs ----------------
-            for (int l = gtid; l < P.np; l += nthreads) {
-                const double* h = P.Hll + (size_t)l * 6;
-                const double d00 = h[0] + lambda, d01 = h[1], d02 = h[2], d11 = h[3] + lambda, d12 = h[4], d22 = h[5] + lambda;
-                const double c00 = d11 * d22 - d12 * d12, c01 = d12 * d02 - d01 * d22, c02 = d01 * d12 - d11 * d02;
-                const double det = d00 * c00 + d01 * c01 + d02 * c02;
-                const double id = 1.0 / det;
-                double* Di = P.Dinv + (size_t)l * 6;
-                const double i00 = c00 * id, i01 = c01 * id, i02 = c02 * id;
-                const double i11 = (d00 * d22 - d02 * d02) * id, i12 = (d02 * d01 - d00 * d12) * id, i22 = (d00 * d11 - d01 * d01) * id;
-                Di[0] = i00; Di[1] = i01; Di[2] = i02; Di[3] = i11; Di[4] = i12; Di[5] = i22;
-                const double* g = P.bl + (size_t)l * 3;
-                double* d = P.db + (size_t)l * 3;
-                d[0] = i00 * g[0] + i01 * g[1] + i02 * g[2];
-                d[1] = i01 * g[0] + i11 * g[1] + i12 * g[2];
-                d[2] = i02 * g[0] + i12 * g[1] + i22 * g[2];
-            }
-            // Hs (lower triangle, padded to dimPad) starts as Hpp + lambda I, identity on the padding
-            for (size_t i = gtid; i < (size_t)P.dimPad * P.dimPad; i += nthreads) {
-                const int r = (int)(i / P.dimPad), c = (int)(i - (size_t)r * P.dimPad);
-                double v = 0.0;
-                if (r >= P.dimP) v = (r == c) ? 1.0 : 0.0;
-                else if (c < P.dimP && r / 6 == c / 6) v = P.Hpp[(size_t)(r / 6) * 36 + (r % 6) * 6 + (c % 6)] + (r == c ? lambda : 0.0);
-                P.Hs[i] = v;
-            }
-            for (int i = gtid; i < P.dimPad; i += nthreads) P.bs[i] = i < P.dimP ? P.bp[i] : 0.0;
-            grid.sync();
-            tick(2);
-            // ---------------- S1: Schur complement, point-major ----------------
-            // For landmark l with observing free cameras {c_i}: Hs(c_i, c_j) -= Hpl_i Dinv Hpl_j^T and
-            // bs(c_i) -= Hpl_i Dinv bl.  One warp per landmark, lanes over the (i, j >= i) pairs; the
-            // 6x6 products are added with FP64 reductions at L2 (no return value needed).
-            for (int l = gwarp; l < P.np; l += nwarps) {
-                const int ps = P.pt_start[l], k = P.pt_start[l + 1] - ps;
-                const double* Di = P.Dinv + (size_t)l * 6;
-                const double* d = P.db + (size_t)l * 3;
-                const double D0 = Di[0], D1 = Di[1], D2 = Di[2], D3 = Di[3], D4 = Di[4], D5 = Di[5];
-                const int npairs = k * (k + 1) / 2;
-                for (int p = lane; p < npairs; p += 32) {
-                    // p -> (i, j) with j <= i  (triangular index)
-                    int i = (int)((sqrt(8.0 * p + 1.0) - 1.0) * 0.5);
-                    while (i * (i + 1) / 2 > p) i--;
-                    while ((i + 1) * (i + 2) / 2 <= p) i++;
-                    const int j = p - i * (i + 1) / 2;
-                    int e1 = P.pt_edges[ps + i], e2 = P.pt_edges[ps + j];
-                    int c1 = P.cam_col[P.ecam[e1]], c2 = P.cam_col[P.ecam[e2]];
-                    if (c1 < 0 || c2 < 0) continue;
-                    if (c1 > c2) { int t = c1; c1 = c2; c2 = t; t = e1; e1 = e2; e2 = t; } // c1 <= c2: block stored at (c2, c1)
-                    const double* B1 = P.Hpl + (size_t)e1 * 18;
-                    const double* B2 = P.Hpl + (size_t)e2 * 18;
-                    double BD[18];
-#pragma unroll
-                    for (int a = 0; a < 6; a++) {
-                        const double b0 = B1[a * 3], b1 = B1[a * 3 + 1], b2 = B1[a * 3 + 2];
-                        BD[a * 3] = b0 * D0 + b1 * D1 + b2 * D2;
-                        BD[a * 3 + 1] = b0 * D1 + b1 * D3 + b2 * D4;
-                        BD[a * 3 + 2] = b0 * D2 + b1 * D4 + b2 * D5;
-                    }
-                    if (i == j) { // once per observation: the gradient part
-#pragma unroll
-                        for (int a = 0; a < 6; a++)
-                            atomicAdd(&P.bs[6 * c1 + a], -(B1[a * 3] * d[0] + B1[a * 3 + 1] * d[1] + B1[a * 3 + 2] * d[2]));
-                    }
-                    double* dst = P.Hs + (size_t)(6 * c2) * P.dimPad + 6 * c1;
-#pragma unroll
-                    for (int b2 = 0; b2 < 6; b2++) {
-                        const double q0 = B2[b2 * 3], q1 = B2[b2 * 3 + 1], q2 = B2[b2 * 3 + 2];
-#pragma unroll
-                        for (int a = 0; a < 6; a++) {
-                            if (i == j && a > b2) continue; // diagonal block: lower triangle only (a <= b2 <-> col <= row)
-                            atomicAdd(&dst[(size_t)b2 * P.dimPad + a], -(BD[a * 3] * q0 + BD[a * 3 + 1] * q1 + BD[a * 3 + 2] * q2));
-                        }
-                    }
-                }
-            }
-            grid.sync();
-            tick(3);
-            // ---------------- C: reduced camera system on one CTA ----------------
-            if (blockIdx.x < kClusterCtas) { // the first cluster
-                bool ok = true;
-                if (P.dimP > 0) ok = cluster_cholesky_solve(P.dimPad, P.Hs, P.bs, P.x, P.Linv, smem, &s_flag, P.prof);
-                if (blockIdx.x == 0 && tid == 0) P.flags[0] = ok ? 1 : 0;
-            }
-            grid.sync();
-            tick(4);
-            const bool ok2 = P.flags[0] != 0;
-            // ---------------- B1: landmark back-substitution and update into the trial buffers ----------------
-            double scale_part = 0;
-            for (int l = gwarp; l < P.np; l += nwarps) {
-                double cl[3] = { 0, 0, 0 };
-                const int s = P.pt_start[l], e_end = P.pt_start[l + 1];
-                for (int k = s + lane; k < e_end; k += 32) {
-                    const int e = P.pt_edges[k];
-                    const int c1 = P.cam_col[P.ecam[e]];
-                    if (c1 < 0) continue;
-                    const double* B1 = P.Hpl + (size_t)e * 18;
-                    const double* xp = P.x + 6 * c1;
-#pragma unroll
-                    for (int a = 0; a < 6; a++) { cl[0] -= B1[a * 3] * xp[a]; cl[1] -= B1[a * 3 + 1] * xp[a]; cl[2] -= B1[a * 3 + 2] * xp[a]; }
-                }
-                cl[0] = warp_sum(cl[0]); cl[1] = warp_sum(cl[1]); cl[2] = warp_sum(cl[2]);
-                if (lane == 0) {
-                    const double* g = P.bl + (size_t)l * 3;
-                    const double* Di = P.Dinv + (size_t)l * 6;
-                    const double c0 = g[0] + cl[0], c1v = g[1] + cl[1], c2v = g[2] + cl[2];
-                    double xl[3];
-                    xl[0] = Di[0] * c0 + Di[1] * c1v + Di[2] * c2v;
-                    xl[1] = Di[1] * c0 + Di[3] * c1v + Di[4] * c2v;
-                    xl[2] = Di[2] * c0 + Di[4] * c1v + Di[5] * c2v;
-                    if (!ok2) { xl[0] = xl[1] = xl[2] = 0.0; }
-#pragma unroll
-                    for (int a = 0; a < 3; a++) {
-                        P.x[P.dimP + 3 * l + a] = xl[a];
-                        P.pts[trial][3 * l + a] = P.pts[cur][3 * l + a] + xl[a];
-                        scale_part += xl[a] * (lambda * xl[a] + g[a]);
-                    }
-                }
-            }
-            for (int c = gtid; c < P.nc; c += nthreads) {
-                const int cf = P.cam_col[c];
-                if (cf >= 0) {
-                    const double* xp = P.x + 6 * cf;
-                    se3_update(xp, P.camq[cur] + 4 * c, P.camt[cur] + 3 * c, P.camq[trial] + 4 * c, P.camt[trial] + 3 * c);
-#pragma unroll
-                    for (int a = 0; a < 6; a++) scale_part += xp[a] * (lambda * xp[a] + P.bp[6 * cf + a]);
-                } else {
-                    for (int a = 0; a < 4; a++) P.camq[trial][4 * c + a] = P.camq[cur][4 * c + a];
-                    for (int a = 0; a < 3; a++) P.camt[trial][3 * c + a] = P.camt[cur][3 * c + a];
-                }
+                const bool out = r0 * (om * r0) + r1 * (om * r1) > 5.991 || !(xc[2] > 0.0);
+                P.level[e] = out ? 1 : 0;
+                nex += out ? 1 : 0;
             }
             {
-                double v[1] = { scale_part };
+                double v[1] = { (double)nex };
                 cta_sum<1>(v, warp_buf, red);
                 if (tid == 0) P.part[blockIdx.x * 4 + 1] = red[0];
             }
             grid.sync();
-            tick(5);
-            // ---------------- B2: errors at the trial estimate ----------------
-            double chi_t = 0;
-            for (int e = gtid; e < P.ne; e += nthreads) {
-                double xc[3], r[2];
-                edge_residual(P, trial, e, xc, r, nullptr);
-                P.err[2 * e] = r[0]; P.err[2 * e + 1] = r[1];
-                const double om = (double)P.einfo[e];
-                chi_t += huber_rho0(P, r[0] * (om * r[0]) + r[1] * (om * r[1]));
+            for (int b2 = 0; b2 < G; b2++) excluded += (int)P.part[b2 * 4 + 1];
+            grid.sync(); // part[] is rewritten by the next pass
+            delta = CUDART_INF; dsqr = CUDART_INF; // (a local copy: writing the parameter struct would move it to the stack)
+            stop = false;
+        }
+        const int iters = pass == 0 ? P.iterations : P.iterations2;
+        for (int it = 0; it < iters && !stop; it++) {
+            if (agree_abort()) break;
+            // ---------------- L1: point-major linearisation ----------------
+            double chi_part = 0, maxd = 0;
+            for (int l = gwarp; l < P.np; l += nwarps) {
+                double h[6] = { 0, 0, 0, 0, 0, 0 }, g[3] = { 0, 0, 0 };
+                const int s = P.pt_start[l], e_end = P.pt_start[l + 1];
+                for (int k = s + lane; k < e_end; k += 32) {
+                    const int e = P.pt_edges[k];
+                    if (P.level && P.level[e]) { // level-1 edge: no contribution to H, b or chi2; its error stays
+                        if (P.cam_col[P.ecam[e]] >= 0) {
+                            double* hp = P.Hpl + (size_t)e * 18;
+#pragma unroll
+                            for (int i = 0; i < 18; i++) hp[i] = 0.0;
+                        }
+                        continue;
+                    }
+                    double xc[3], r[2];
+                    Quat Q;
+                    edge_residual(P, cur, e, xc, r, &Q);
+                    P.err[2 * e] = r[0]; P.err[2 * e + 1] = r[1];
+                    const double om = (double)P.einfo[e];
+                    const double chi = r[0] * (om * r[0]) + r[1] * (om * r[1]);
+                    chi_part += huber_rho0(delta, dsqr, chi);
+                    const double w = huber_rho1(delta, dsqr, chi);
+                    const double X = xc[0], Y = xc[1], Z = xc[2];
+                    const double pj[6] = { -(P.fx / Z), 0.0, P.fx * X / (Z * Z), 0.0, -(P.fy / Z), P.fy * Y / (Z * Z) };
+                    double R[9];
+                    quat_to_matrix(Q, R);
+                    double A[6];
+    #pragma unroll
+                    for (int rr = 0; rr < 2; rr++)
+    #pragma unroll
+                        for (int kk = 0; kk < 3; kk++)
+                            A[rr * 3 + kk] = pj[rr * 3] * R[kk] + pj[rr * 3 + 1] * R[3 + kk] + pj[rr * 3 + 2] * R[6 + kk];
+                    const double wo = w * om;
+                    const double r0 = -om * r[0] * w, r1 = -om * r[1] * w;
+                    g[0] += A[0] * r0 + A[3] * r1; g[1] += A[1] * r0 + A[4] * r1; g[2] += A[2] * r0 + A[5] * r1;
+                    h[0] += A[0] * wo * A[0] + A[3] * wo * A[3];
+                    h[1] += A[0] * wo * A[1] + A[3] * wo * A[4];
+                    h[2] += A[0] * wo * A[2] + A[3] * wo * A[5];
+                    h[3] += A[1] * wo * A[1] + A[4] * wo * A[4];
+                    h[4] += A[1] * wo * A[2] + A[4] * wo * A[5];
+                    h[5] += A[2] * wo * A[2] + A[5] * wo * A[5];
+                    if (P.cam_col[P.ecam[e]] >= 0) {
+                        const double Dv[18] = { 0, Z, -Y, 1, 0, 0, -Z, 0, X, 0, 1, 0, Y, -X, 0, 0, 0, 1 };
+                        double* hp = P.Hpl + (size_t)e * 18;
+    #pragma unroll
+                        for (int a = 0; a < 6; a++) {
+                            const double B0 = pj[0] * Dv[a] + pj[1] * Dv[6 + a] + pj[2] * Dv[12 + a];
+                            const double B1 = pj[3] * Dv[a] + pj[4] * Dv[6 + a] + pj[5] * Dv[12 + a];
+    #pragma unroll
+                            for (int b2 = 0; b2 < 3; b2++) hp[a * 3 + b2] = B0 * wo * A[b2] + B1 * wo * A[3 + b2];
+                        }
+                    }
+                }
+    #pragma unroll
+                for (int i = 0; i < 6; i++) h[i] = warp_sum(h[i]);
+    #pragma unroll
+                for (int i = 0; i < 3; i++) g[i] = warp_sum(g[i]);
+                if (lane == 0) {
+    #pragma unroll
+                    for (int i = 0; i < 6; i++) P.Hll[(size_t)l * 6 + i] = h[i];
+    #pragma unroll
+                    for (int i = 0; i < 3; i++) P.bl[(size_t)l * 3 + i] = g[i];
+                    maxd = fmax(maxd, fmax(fabs(h[0]), fmax(fabs(h[3]), fabs(h[5]))));
+                }
             }
             {
-                double v[1] = { chi_t };
+                double v[1] = { chi_part };
                 cta_sum<1>(v, warp_buf, red);
-                if (tid == 0) P.part[blockIdx.x * 4 + 0] = red[0];
+                maxd = warp_max(maxd);
+                if (lane == 0) warp_buf[wid] = maxd;
+                __syncthreads();
+                if (tid == 0) {
+                    double m = 0;
+                    for (int w2 = 0; w2 < kLbaWarps; w2++) m = fmax(m, warp_buf[w2]);
+                    P.part[blockIdx.x * 4 + 0] = red[0];
+                    P.part[blockIdx.x * 4 + 2] = m;
+                }
+                __syncthreads();
             }
             grid.sync();
-            tick(6);
-            double tempChi = 0, scale = 0;
-            for (int b2 = 0; b2 < G; b2++) { tempChi += P.part[b2 * 4 + 0]; scale += P.part[b2 * 4 + 1]; }
-            if (!ok2) tempChi = 1.7976931348623157e308;
-            rho = currentChi - tempChi;
-            scale += 1e-3;
-            rho /= scale;
-            if (rho > 0 && isfinite(tempChi)) {
-                double alpha = 1. - pow((2 * rho - 1), 3.0);
-                alpha = fmin(alpha, 2. / 3.);
-                lambda *= fmax(1. / 3., alpha);
-                ni = 2;
-                currentChi = tempChi;
-                cur = trial; // discardTop: the trial buffers become the estimate
-            } else {
-                lambda *= ni;
-                ni *= 2; // pop: keep `cur`
+            tick(0);
+            // ---------------- L2: camera-major Hpp, bp ----------------
+            double maxdp = 0;
+            for (int cf = blockIdx.x; cf < P.nf; cf += G) {
+                double acc[27];
+    #pragma unroll
+                for (int i = 0; i < 27; i++) acc[i] = 0;
+                const int s = P.cam_start[cf], e_end = P.cam_start[cf + 1];
+                for (int k = s + tid; k < e_end; k += kLbaThreads) {
+                    const int e = P.cam_edges[k];
+                    if (P.level && P.level[e]) continue;
+                    double xc[3], r[2];
+                    edge_residual(P, cur, e, xc, r, nullptr);
+                    const double om = (double)P.einfo[e];
+                    const double chi = r[0] * (om * r[0]) + r[1] * (om * r[1]);
+                    const double w = huber_rho1(delta, dsqr, chi);
+                    const double X = xc[0], Y = xc[1], Z = xc[2];
+                    const double pj[6] = { -(P.fx / Z), 0.0, P.fx * X / (Z * Z), 0.0, -(P.fy / Z), P.fy * Y / (Z * Z) };
+                    const double Dv[18] = { 0, Z, -Y, 1, 0, 0, -Z, 0, X, 0, 1, 0, Y, -X, 0, 0, 0, 1 };
+                    double B[12];
+    #pragma unroll
+                    for (int a = 0; a < 6; a++) {
+                        B[a] = pj[0] * Dv[a] + pj[1] * Dv[6 + a] + pj[2] * Dv[12 + a];
+                        B[6 + a] = pj[3] * Dv[a] + pj[4] * Dv[6 + a] + pj[5] * Dv[12 + a];
+                    }
+                    const double wo = w * om;
+                    const double r0 = -om * r[0] * w, r1 = -om * r[1] * w;
+                    int idx = 0;
+    #pragma unroll
+                    for (int a = 0; a < 6; a++) {
+                        acc[21 + a] += B[a] * r0 + B[6 + a] * r1;
+    #pragma unroll
+                        for (int b2 = a; b2 < 6; b2++) acc[idx++] += B[a] * wo * B[b2] + B[6 + a] * wo * B[6 + b2];
+                    }
+                }
+                cta_sum<27>(acc, warp_buf, red);
+                if (tid < 36) {
+                    const int a = tid / 6, b2 = tid % 6;
+                    const int lo = min(a, b2), hi = max(a, b2);
+                    const int idx = lo * 6 - lo * (lo - 1) / 2 + (hi - lo);
+                    P.Hpp[(size_t)cf * 36 + tid] = red[idx];
+                }
+                if (tid < 6) P.bp[cf * 6 + tid] = red[21 + tid];
+                if (tid == 0)
+                    for (int a = 0; a < 6; a++) maxdp = fmax(maxdp, fabs(red[a * 6 - a * (a - 1) / 2]));
+                __syncthreads();
             }
-            qmax++;
-            trials++;
-            aborted = agree_abort();
-        } while (rho < 0 && qmax < 10 && !aborted);
-        done++;
-        last_chi = currentChi;
-        if (qmax == 10 || rho == 0) stop = true;
-        else {
-            if ((iniChi - currentChi) * 1e3 < iniChi) nBad++;
-            else nBad = 0;
-            if (nBad >= 3) stop = true;
+            if (tid == 0) P.part[blockIdx.x * 4 + 3] = maxdp;
+            grid.sync();
+            tick(1);
+            double currentChi = 0;
+            {
+                double m = 0;
+                for (int b2 = 0; b2 < G; b2++) {
+                    currentChi += P.part[b2 * 4 + 0];
+                    m = fmax(m, fmax(P.part[b2 * 4 + 2], P.part[b2 * 4 + 3]));
+                }
+                if (it == 0) { lambda = 1e-5 * m; ni = 2; nBad = 0; if (pass == 0) first_chi = currentChi; }
+            }
+            const double iniChi = currentChi;
+            double rho = 0;
+            int qmax = 0;
+            bool aborted = false;
+            do {
+                const int trial = cur ^ 1;
+                // ---------------- S0: landmark inverses, clear Hs ----------------
+                for (int l = gtid; l < P.np; l += nthreads) {
+                    const double* h = P.Hll + (size_t)l * 6;
+                    const double d00 = h[0] + lambda, d01 = h[1], d02 = h[2], d11 = h[3] + lambda, d12 = h[4], d22 = h[5] + lambda;
+                    const double c00 = d11 * d22 - d12 * d12, c01 = d12 * d02 - d01 * d22, c02 = d01 * d12 - d11 * d02;
+                    const double det = d00 * c00 + d01 * c01 + d02 * c02;
+                    const double id = 1.0 / det;
+                    double* Di = P.Dinv + (size_t)l * 6;
+                    const double i00 = c00 * id, i01 = c01 * id, i02 = c02 * id;
+                    const double i11 = (d00 * d22 - d02 * d02) * id, i12 = (d02 * d01 - d00 * d12) * id, i22 = (d00 * d11 - d01 * d01) * id;
+                    Di[0] = i00; Di[1] = i01; Di[2] = i02; Di[3] = i11; Di[4] = i12; Di[5] = i22;
+                    const double* g = P.bl + (size_t)l * 3;
+                    double* d = P.db + (size_t)l * 3;
+                    d[0] = i00 * g[0] + i01 * g[1] + i02 * g[2];
+                    d[1] = i01 * g[0] + i11 * g[1] + i12 * g[2];
+                    d[2] = i02 * g[0] + i12 * g[1] + i22 * g[2];
+                }
+                // Hs (lower triangle, padded to dimPad) starts as Hpp + lambda I, identity on the padding
+                for (size_t i = gtid; i < (size_t)P.dimPad * P.dimPad; i += nthreads) {
+                    const int r = (int)(i / P.dimPad), c = (int)(i - (size_t)r * P.dimPad);
+                    double v = 0.0;
+                    if (r >= P.dimP) v = (r == c) ? 1.0 : 0.0;
+                    else if (c < P.dimP && r / 6 == c / 6) v = P.Hpp[(size_t)(r / 6) * 36 + (r % 6) * 6 + (c % 6)] + (r == c ? lambda : 0.0);
+                    P.Hs[i] = v;
+                }
+                for (int i = gtid; i < P.dimPad; i += nthreads) P.bs[i] = i < P.dimP ? P.bp[i] : 0.0;
+                grid.sync();
+                tick(2);
+                // ---------------- S1: Schur complement, point-major ----------------
+                // For landmark l with observing free cameras {c_i}: Hs(c_i, c_j) -= Hpl_i Dinv Hpl_j^T and
+                // bs(c_i) -= Hpl_i Dinv bl.  One warp per landmark, lanes over the (i, j >= i) pairs; the
+                // 6x6 products are added with FP64 reductions at L2 (no return value needed).
+                for (int l = gwarp; l < P.np; l += nwarps) {
+                    const int ps = P.pt_start[l], k = P.pt_start[l + 1] - ps;
+                    const double* Di = P.Dinv + (size_t)l * 6;
+                    const double* d = P.db + (size_t)l * 3;
+                    const double D0 = Di[0], D1 = Di[1], D2 = Di[2], D3 = Di[3], D4 = Di[4], D5 = Di[5];
+                    const int npairs = k * (k + 1) / 2;
+                    for (int p = lane; p < npairs; p += 32) {
+                        // p -> (i, j) with j <= i  (triangular index)
+                        int i = (int)((sqrt(8.0 * p + 1.0) - 1.0) * 0.5);
+                        while (i * (i + 1) / 2 > p) i--;
+                        while ((i + 1) * (i + 2) / 2 <= p) i++;
+                        const int j = p - i * (i + 1) / 2;
+                        int e1 = P.pt_edges[ps + i], e2 = P.pt_edges[ps + j];
+                        int c1 = P.cam_col[P.ecam[e1]], c2 = P.cam_col[P.ecam[e2]];
+                        if (c1 < 0 || c2 < 0) continue;
+                        if (c1 > c2) { int t = c1; c1 = c2; c2 = t; t = e1; e1 = e2; e2 = t; } // c1 <= c2: block stored at (c2, c1)
+                        const double* B1 = P.Hpl + (size_t)e1 * 18;
+                        const double* B2 = P.Hpl + (size_t)e2 * 18;
+                        double BD[18];
+    #pragma unroll
+                        for (int a = 0; a < 6; a++) {
+                            const double b0 = B1[a * 3], b1 = B1[a * 3 + 1], b2 = B1[a * 3 + 2];
+                            BD[a * 3] = b0 * D0 + b1 * D1 + b2 * D2;
+                            BD[a * 3 + 1] = b0 * D1 + b1 * D3 + b2 * D4;
+                            BD[a * 3 + 2] = b0 * D2 + b1 * D4 + b2 * D5;
+                        }
+                        if (i == j) { // once per observation: the gradient part
+    #pragma unroll
+                            for (int a = 0; a < 6; a++)
+                                atomicAdd(&P.bs[6 * c1 + a], -(B1[a * 3] * d[0] + B1[a * 3 + 1] * d[1] + B1[a * 3 + 2] * d[2]));
+                        }
+                        double* dst = P.Hs + (size_t)(6 * c2) * P.dimPad + 6 * c1;
+    #pragma unroll
+                        for (int b2 = 0; b2 < 6; b2++) {
+                            const double q0 = B2[b2 * 3], q1 = B2[b2 * 3 + 1], q2 = B2[b2 * 3 + 2];
+    #pragma unroll
+                            for (int a = 0; a < 6; a++) {
+                                if (i == j && a > b2) continue; // diagonal block: lower triangle only (a <= b2 <-> col <= row)
+                                atomicAdd(&dst[(size_t)b2 * P.dimPad + a], -(BD[a * 3] * q0 + BD[a * 3 + 1] * q1 + BD[a * 3 + 2] * q2));
+                            }
+                        }
+                    }
+                }
+                grid.sync();
+                tick(3);
+                // ---------------- C: reduced camera system on one CTA ----------------
+                if (blockIdx.x < kClusterCtas) { // the first cluster
+                    bool ok = true;
+                    if (P.dimP > 0) ok = cluster_cholesky_solve(P.dimPad, P.Hs, P.bs, P.x, P.Linv, smem, &s_flag, P.prof);
+                    if (blockIdx.x == 0 && tid == 0) P.flags[0] = ok ? 1 : 0;
+                }
+                grid.sync();
+                tick(4);
+                const bool ok2 = P.flags[0] != 0;
+                // ---------------- B1: landmark back-substitution and update into the trial buffers ----------------
+                double scale_part = 0;
+                for (int l = gwarp; l < P.np; l += nwarps) {
+                    double cl[3] = { 0, 0, 0 };
+                    const int s = P.pt_start[l], e_end = P.pt_start[l + 1];
+                    for (int k = s + lane; k < e_end; k += 32) {
+                        const int e = P.pt_edges[k];
+                        const int c1 = P.cam_col[P.ecam[e]];
+                        if (c1 < 0) continue;
+                        const double* B1 = P.Hpl + (size_t)e * 18;
+                        const double* xp = P.x + 6 * c1;
+    #pragma unroll
+                        for (int a = 0; a < 6; a++) { cl[0] -= B1[a * 3] * xp[a]; cl[1] -= B1[a * 3 + 1] * xp[a]; cl[2] -= B1[a * 3 + 2] * xp[a]; }
+                    }
+                    cl[0] = warp_sum(cl[0]); cl[1] = warp_sum(cl[1]); cl[2] = warp_sum(cl[2]);
+                    if (lane == 0) {
+                        const double* g = P.bl + (size_t)l * 3;
+                        const double* Di = P.Dinv + (size_t)l * 6;
+                        const double c0 = g[0] + cl[0], c1v = g[1] + cl[1], c2v = g[2] + cl[2];
+                        double xl[3];
+                        xl[0] = Di[0] * c0 + Di[1] * c1v + Di[2] * c2v;
+                        xl[1] = Di[1] * c0 + Di[3] * c1v + Di[4] * c2v;
+                        xl[2] = Di[2] * c0 + Di[4] * c1v + Di[5] * c2v;
+                        if (!ok2) { xl[0] = xl[1] = xl[2] = 0.0; }
+    #pragma unroll
+                        for (int a = 0; a < 3; a++) {
+                            P.x[P.dimP + 3 * l + a] = xl[a];
+                            P.pts[trial][3 * l + a] = P.pts[cur][3 * l + a] + xl[a];
+                            scale_part += xl[a] * (lambda * xl[a] + g[a]);
+                        }
+                    }
+                }
+                for (int c = gtid; c < P.nc; c += nthreads) {
+                    const int cf = P.cam_col[c];
+                    if (cf >= 0) {
+                        const double* xp = P.x + 6 * cf;
+                        se3_update(xp, P.camq[cur] + 4 * c, P.camt[cur] + 3 * c, P.camq[trial] + 4 * c, P.camt[trial] + 3 * c);
+    #pragma unroll
+                        for (int a = 0; a < 6; a++) scale_part += xp[a] * (lambda * xp[a] + P.bp[6 * cf + a]);
+                    } else {
+                        for (int a = 0; a < 4; a++) P.camq[trial][4 * c + a] = P.camq[cur][4 * c + a];
+                        for (int a = 0; a < 3; a++) P.camt[trial][3 * c + a] = P.camt[cur][3 * c + a];
+                    }
+                }
+                {
+                    double v[1] = { scale_part };
+                    cta_sum<1>(v, warp_buf, red);
+                    if (tid == 0) P.part[blockIdx.x * 4 + 1] = red[0];
+                }
+                grid.sync();
+                tick(5);
+                // ---------------- B2: errors at the trial estimate ----------------
+                double chi_t = 0;
+                for (int e = gtid; e < P.ne; e += nthreads) {
+                    if (P.level && P.level[e]) continue;
+                    double xc[3], r[2];
+                    edge_residual(P, trial, e, xc, r, nullptr);
+                    P.err[2 * e] = r[0]; P.err[2 * e + 1] = r[1];
+                    const double om = (double)P.einfo[e];
+                    chi_t += huber_rho0(delta, dsqr, r[0] * (om * r[0]) + r[1] * (om * r[1]));
+                }
+                {
+                    double v[1] = { chi_t };
+                    cta_sum<1>(v, warp_buf, red);
+                    if (tid == 0) P.part[blockIdx.x * 4 + 0] = red[0];
+                }
+                grid.sync();
+                tick(6);
+                double tempChi = 0, scale = 0;
+                for (int b2 = 0; b2 < G; b2++) { tempChi += P.part[b2 * 4 + 0]; scale += P.part[b2 * 4 + 1]; }
+                if (!ok2) tempChi = 1.7976931348623157e308;
+                rho = currentChi - tempChi;
+                scale += 1e-3;
+                rho /= scale;
+                if (rho > 0 && isfinite(tempChi)) {
+                    double alpha = 1. - pow((2 * rho - 1), 3.0);
+                    alpha = fmin(alpha, 2. / 3.);
+                    lambda *= fmax(1. / 3., alpha);
+                    ni = 2;
+                    currentChi = tempChi;
+                    cur = trial; // discardTop: the trial buffers become the estimate
+                } else {
+                    lambda *= ni;
+                    ni *= 2; // pop: keep `cur`
+                }
+                qmax++;
+                trials++;
+                aborted = agree_abort();
+            } while (rho < 0 && qmax < 10 && !aborted);
+            done++;
+            last_chi = currentChi;
+            if (qmax == 10 || rho == 0) stop = true;
+            else {
+                if ((iniChi - currentChi) * 1e3 < iniChi) nBad++;
+                else nBad = 0;
+                if (nBad >= 3) stop = true;
+            }
+            if (aborted) stop = true;
         }
-        if (aborted) stop = true;
     }
     // ---------------- outlier test and write-back (O3/src/Optimizer.cc:1313-1386) ----------------
     for (int e = gtid; e < P.ne; e += nthreads) {
@@ -882,6 +929,7 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kLbaThrea
     for (int i = gtid; i < P.np * 3; i += nthreads) P.out_pts[i] = (float)P.pts[cur][i];
     if (gtid == 0) {
         P.out_stats[0] = done; P.out_stats[1] = trials; P.out_stats[2] = first_chi; P.out_stats[3] = last_chi;
+        P.out_stats[4] = done_first; P.out_stats[5] = excluded;
     }
 }
 
@@ -982,16 +1030,16 @@ int dvm_local_ba(dvm_lba* h, int nc, float* cam_q, float* cam_t, const uint8_t* 
                                  iterations, (float)std::sqrt(5.991), abort_flag, edge_chi2, edge_bad, stats, iters_done);
 }
 
-int dvm_bundle_adjustment(dvm_lba* h, int nc, float* cam_q, float* cam_t, const uint8_t* cam_fixed, int np, float* pts, int ne,
-                          const int32_t* edge_cam, const int32_t* edge_pt, const float* edge_obs,
-                          const float* edge_inv_sigma2, const float* K, int iterations, float huber_delta,
-                          const volatile uint8_t* abort_flag, double* edge_chi2, uint8_t* edge_bad, double* stats,
-                          int* iters_done)
+// iterations2 > 0 adds the welding BA's second pass; nstats = entries of `stats` the caller holds (4 or 6)
+static int run_ba(dvm_lba* h, int nc, float* cam_q, float* cam_t, const uint8_t* cam_fixed, int np, float* pts, int ne,
+                  const int32_t* edge_cam, const int32_t* edge_pt, const float* edge_obs, const float* edge_inv_sigma2,
+                  const float* K, int iterations, float huber_delta, int iterations2, const volatile uint8_t* abort_flag,
+                  double* edge_chi2, uint8_t* edge_bad, double* stats, int nstats, int* iters_done)
 {
     DVM_REQUIRE(h != nullptr && iters_done != nullptr, "null argument");
     *iters_done = -1;
-    if (stats) stats[0] = stats[1] = stats[2] = stats[3] = 0;
-    DVM_REQUIRE(nc >= 0 && np >= 0 && ne >= 0 && iterations >= 0, "negative size");
+    if (stats) for (int i = 0; i < nstats; i++) stats[i] = 0;
+    DVM_REQUIRE(nc >= 0 && np >= 0 && ne >= 0 && iterations >= 0 && iterations2 >= 0, "negative size");
     DVM_REQUIRE(nc == 0 || (cam_q && cam_t && cam_fixed), "null camera arrays");
     DVM_REQUIRE(np == 0 || pts, "null point array");
     DVM_REQUIRE(ne == 0 || (edge_cam && edge_pt && edge_obs && edge_inv_sigma2 && edge_bad), "null edge arrays");
@@ -1059,10 +1107,11 @@ int dvm_bundle_adjustment(dvm_lba* h, int nc, float* cam_q, float* cam_t, const 
     const size_t o_linv = take((size_t)std::max(dimPad * kNB, 1) * 8);
     const size_t o_x = take((size_t)(dimPad + np * 3 + 1) * 8);
     const size_t o_part = take((size_t)h->grid * 4 * 8), o_flags = take(4 * 4), o_prof = take(16 * 8);
+    const size_t o_level = take((size_t)std::max(ne, 1));
     // output block (contiguous, one D2H)
     const size_t out_begin = (off + 255) & ~(size_t)255;
     const size_t o_oq = take((size_t)nc * 4 * 4), o_ot = take((size_t)nc * 3 * 4), o_op = take((size_t)np * 3 * 4);
-    const size_t o_ochi = take((size_t)ne * 8), o_obad = take((size_t)ne), o_ostats = take(4 * 8);
+    const size_t o_ochi = take((size_t)ne * 8), o_obad = take((size_t)ne), o_ostats = take(6 * 8);
     const size_t total = off + 256;
     if (total > h->d_cap) {
         DVM_CUDA(cudaStreamSynchronize(h->stream));
@@ -1118,6 +1167,8 @@ int dvm_bundle_adjustment(dvm_lba* h, int nc, float* cam_q, float* cam_t, const 
     LbaDev P;
     memset(&P, 0, sizeof(P));
     P.nc = nc; P.nf = nf; P.np = np; P.ne = ne; P.dimP = dimP; P.dimPad = dimPad; P.iterations = iterations;
+    P.iterations2 = iterations2;
+    P.level = iterations2 > 0 ? db + o_level : nullptr;
     P.fx = K[0]; P.fy = K[1]; P.cx = K[2]; P.cy = K[3];
     P.delta = (double)huber_delta;   // the caller's float delta; +infinity = no robust kernel
     P.dsqr = P.delta * P.delta;
@@ -1142,6 +1193,7 @@ int dvm_bundle_adjustment(dvm_lba* h, int nc, float* cam_q, float* cam_t, const 
     DVM_CUDA(cudaMemsetAsync(db + o_prof, 0, 128, h->stream));
     P.prof = (unsigned long long*)(db + o_prof);
     DVM_CUDA(cudaMemsetAsync(db + o_err, 0, (size_t)ne * 2 * 8, h->stream));
+    if (iterations2 > 0) DVM_CUDA(cudaMemsetAsync(db + o_level, 0, (size_t)ne, h->stream));
     void* args[] = { &P };
     DVM_CUDA(cudaEventRecord(h->ev0, h->stream));
     DVM_CUDA(cudaLaunchCooperativeKernel((void*)lba_kernel, dim3(h->grid), dim3(kLbaThreads), args, h->smem_bytes, h->stream));
@@ -1176,7 +1228,7 @@ int dvm_bundle_adjustment(dvm_lba* h, int nc, float* cam_q, float* cam_t, const 
     memcpy(pts, hb + o_op, (size_t)np * 3 * 4);
     if (edge_chi2) memcpy(edge_chi2, hb + o_ochi, (size_t)ne * 8);
     memcpy(edge_bad, hb + o_obad, (size_t)ne);
-    if (stats) for (int i = 0; i < 4; i++) stats[i] = ost[i];
+    if (stats) for (int i = 0; i < nstats; i++) stats[i] = ost[i];
     *iters_done = (int)ost[0];
     if (hprof) {
         auto us = [](auto a, auto b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
@@ -1185,6 +1237,25 @@ int dvm_bundle_adjustment(dvm_lba* h, int nc, float* cam_q, float* cam_t, const 
     }
     if (!std::isfinite(ost[3])) { set_error("local BA produced a non-finite chi2"); return DVM_ERR_NUMERIC; }
     return DVM_OK;
+}
+
+int dvm_bundle_adjustment(dvm_lba* h, int nc, float* cam_q, float* cam_t, const uint8_t* cam_fixed, int np, float* pts, int ne,
+                          const int32_t* edge_cam, const int32_t* edge_pt, const float* edge_obs,
+                          const float* edge_inv_sigma2, const float* K, int iterations, float huber_delta,
+                          const volatile uint8_t* abort_flag, double* edge_chi2, uint8_t* edge_bad, double* stats,
+                          int* iters_done)
+{
+    return run_ba(h, nc, cam_q, cam_t, cam_fixed, np, pts, ne, edge_cam, edge_pt, edge_obs, edge_inv_sigma2, K, iterations,
+                  huber_delta, 0, abort_flag, edge_chi2, edge_bad, stats, 4, iters_done);
+}
+
+int dvm_merge_ba(dvm_lba* h, int nc, float* cam_q, float* cam_t, const uint8_t* cam_fixed, int np, float* pts, int ne,
+                 const int32_t* edge_cam, const int32_t* edge_pt, const float* edge_obs, const float* edge_inv_sigma2,
+                 const float* K, const volatile uint8_t* abort_flag, double* edge_chi2, uint8_t* edge_bad, double* stats,
+                 int* iters_done)
+{
+    return run_ba(h, nc, cam_q, cam_t, cam_fixed, np, pts, ne, edge_cam, edge_pt, edge_obs, edge_inv_sigma2, K, 5,
+                  (float)std::sqrt(5.99), 10, abort_flag, edge_chi2, edge_bad, stats, 6, iters_done);
 }
 
 } // extern "C"

@@ -269,4 +269,104 @@ void BundleAdjustment(dvm_lba* solver, const std::vector<KeyFrameT*>& vpKFs, con
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// void Optimizer::LocalBundleAdjustment(KeyFrame* pMainKF, vector<KeyFrame*> vpAdjustKF, vector<KeyFrame*> vpFixedKF,
+//                                       bool* pbStopFlag)   :3257-3675
+// The welding BA of a map merge (LoopClosing::MergeLocal).  Mono observations only; both optimisation passes run in one
+// dvm_merge_ba call.  Map points without any edge stay out of the solver (g2o never activates such a vertex) but are
+// still written back, as the reference does.
+// ---------------------------------------------------------------------------------------------------
+template <class KeyFrameT, class MapPointT>
+void LocalBundleAdjustment(dvm_lba* solver, KeyFrameT* pMainKF, std::vector<KeyFrameT*> vpAdjustKF, std::vector<KeyFrameT*> vpFixedKF,
+                           bool* pbStopFlag)
+{
+    auto* pCurrentMap = pMainKF->GetMap();
+    std::vector<KeyFrameT*> cams;
+    std::vector<uint8_t> cam_fixed;
+    std::unordered_map<KeyFrameT*, int> camIndex;
+    std::vector<MapPointT*> vpMPs;
+    unsigned long maxKFid = 0;
+    auto add_keyframe = [&](KeyFrameT* pKFi, bool fixed) {                                // :3283-3348
+        pKFi->mnBALocalForMerge = pMainKF->mnId;
+        camIndex[pKFi] = static_cast<int>(cams.size());
+        cams.push_back(pKFi);
+        cam_fixed.push_back(fixed ? 1 : 0);
+        if (pKFi->mnId > maxKFid) maxKFid = pKFi->mnId;
+        for (MapPointT* pMPi : pKFi->GetMapPoints())
+            if (pMPi && !pMPi->isBad() && pMPi->GetMap() == pCurrentMap && pMPi->mnBALocalForMerge != pMainKF->mnId) {
+                vpMPs.push_back(pMPi);
+                pMPi->mnBALocalForMerge = pMainKF->mnId;
+            }
+    };
+    for (KeyFrameT* pKFi : vpFixedKF)
+        if (!pKFi->isBad() && pKFi->GetMap() == pCurrentMap) add_keyframe(pKFi, true);
+    const size_t nFixed = cams.size();
+    for (KeyFrameT* pKFi : vpAdjustKF)
+        if (!pKFi->isBad() && pKFi->GetMap() == pCurrentMap) add_keyframe(pKFi, false);
+    std::vector<float> cam_q(cams.size() * 4), cam_t(cams.size() * 3);
+    for (size_t c = 0; c < cams.size(); c++) pose_to_floats(cams[c]->GetPose(), &cam_q[4 * c], &cam_t[3 * c]);
+
+    std::vector<MapPointT*> pts;                       // the points that got at least one edge
+    std::vector<float> xyz, edge_obs, edge_w;
+    std::vector<int32_t> edge_cam, edge_pt;
+    std::vector<std::pair<KeyFrameT*, MapPointT*>> edge_owner;
+    for (MapPointT* pMPi : vpMPs) {                                                       // :3370-3466
+        if (pMPi->isBad()) continue;
+        const size_t first_edge = edge_cam.size();
+        for (const auto& ob : pMPi->GetObservations()) {
+            KeyFrameT* pKF = ob.first;
+            const int leftIndex = std::get<0>(ob.second);
+            const auto it = camIndex.find(pKF);
+            if (pKF->isBad() || pKF->mnId > maxKFid || it == camIndex.end() || !pKF->GetMapPoint(leftIndex)) continue;
+            if (!(pKF->mvuRight[leftIndex] < 0)) continue;                                // mono observation only
+            const auto& kpUn = pKF->mvKeysUn[leftIndex];
+            edge_cam.push_back(it->second);
+            edge_pt.push_back(static_cast<int32_t>(pts.size()));
+            edge_obs.push_back(kpUn.pt.x); edge_obs.push_back(kpUn.pt.y);
+            edge_w.push_back(pKF->mvInvLevelSigma2[kpUn.octave]);
+            edge_owner.emplace_back(pKF, pMPi);
+        }
+        if (edge_cam.size() == first_edge) continue;
+        const auto p = pMPi->GetWorldPos();
+        for (int k = 0; k < 3; k++) xyz.push_back(p(k));
+        pts.push_back(pMPi);
+    }
+    if (pbStopFlag && *pbStopFlag) return;                                               // :3468-3470
+    if (edge_cam.empty() || nFixed == 0) return;       // nothing to solve / no gauge: the device solver needs a fixed keyframe
+
+    static_assert(sizeof(bool) == 1, "pbStopFlag is read as one byte");
+    const float K[4] = { pMainKF->fx, pMainKF->fy, pMainKF->cx, pMainKF->cy };
+    std::vector<uint8_t> edge_bad(edge_cam.size());
+    int iters = 0;
+    check(dvm_merge_ba(solver, static_cast<int>(cams.size()), cam_q.data(), cam_t.data(), cam_fixed.data(),
+                       static_cast<int>(pts.size()), xyz.data(), static_cast<int>(edge_cam.size()), edge_cam.data(),
+                       edge_pt.data(), edge_obs.data(), edge_w.data(), K, reinterpret_cast<const volatile uint8_t*>(pbStopFlag),
+                       nullptr, edge_bad.data(), nullptr, &iters),
+          "Optimizer::LocalBundleAdjustment (welding)");
+    if (iters < 0) return;
+
+    // ---- erase the flagged observations and write back, :3523-3674 ----
+    std::unique_lock<std::mutex> lock(pMainKF->GetMap()->mMutexMapUpdate);
+    for (size_t e = 0; e < edge_owner.size(); e++) {
+        MapPointT* pMP = edge_owner[e].second;
+        if (pMP->isBad() || !edge_bad[e]) continue;
+        edge_owner[e].first->EraseMapPointMatch(pMP);
+        pMP->EraseObservation(edge_owner[e].first);
+    }
+    for (KeyFrameT* pKFi : vpAdjustKF) {
+        if (pKFi->isBad()) continue;
+        const auto it = camIndex.find(pKFi);
+        if (it == camIndex.end()) continue;
+        pKFi->SetPose(pose_from_floats(pKFi->GetPose(), &cam_q[4 * it->second], &cam_t[3 * it->second]));
+    }
+    for (size_t j = 0; j < pts.size(); j++) {
+        if (pts[j]->isBad()) continue;
+        auto p = pts[j]->GetWorldPos();
+        for (int k = 0; k < 3; k++) p(k) = xyz[3 * j + k];
+        pts[j]->SetWorldPos(p);
+    }
+    for (MapPointT* pMPi : vpMPs)
+        if (!pMPi->isBad()) pMPi->UpdateNormalAndDepth();
+}
+
 } // namespace dvm_host

@@ -28,6 +28,8 @@ class LocalBA:
                                    _vp, _vp, _vp, _vp, _ip]
         L.dvm_bundle_adjustment.argtypes = [_vp, C.c_int, _vp, _vp, _vp, C.c_int, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, C.c_int,
                                             C.c_float, _vp, _vp, _vp, _vp, _ip]
+        L.dvm_merge_ba.argtypes = [_vp, C.c_int, _vp, _vp, _vp, C.c_int, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                   _ip]
         L.dvm_lba_last_kernel_ms.argtypes = [_vp]
         L.dvm_lba_last_kernel_ms.restype = C.c_float
         self.h = _vp()
@@ -75,6 +77,32 @@ class LocalBA:
             bad[:] = 0
         return dict(cam_q=q, cam_t=t, pts=p, chi2=chi2[:ne], bad=bad[:ne], iters=int(stats[0]), trials=int(stats[1]),
                     chi_first=stats[2], chi_last=stats[3], rc=iters.value, kernel_ms=self.kernel_ms())
+
+    def MergeBundleAdjustment(self, cam_q, cam_t, cam_fixed, pts, edge_cam, edge_pt, edge_obs, edge_w, K, abort=None):
+        """Optimizer::LocalBundleAdjustment(pMainKF, vpAdjustKF, vpFixedKF, pbStopFlag) -- the welding BA of a map merge
+        (O3/src/Optimizer.cc:3257-3675): cam_fixed = 1 for vpFixedKF, 0 for vpAdjustKF.  Returns LocalBundleAdjustment's
+        dict plus iters_first (LM iterations of the Huber pass) and excluded (edges moved to level 1)."""
+        q, t = _c(cam_q, np.float32).copy(), _c(cam_t, np.float32).copy()
+        p = _c(pts, np.float32).copy()
+        fx = _c(cam_fixed, np.uint8)
+        ec, ep = _c(edge_cam, np.int32), _c(edge_pt, np.int32)
+        eo, ew = _c(edge_obs, np.float32), _c(edge_w, np.float32)
+        ne = len(ec)
+        chi2 = np.empty(max(ne, 1), np.float64)
+        bad = np.empty(max(ne, 1), np.uint8)
+        stats = np.zeros(6, np.float64)
+        iters = C.c_int()
+        ab = _c([abort], np.uint8) if abort is not None else None
+        check(self.L.dvm_merge_ba(self.h, len(fx), q.ctypes.data, t.ctypes.data, fx.ctypes.data, len(p), p.ctypes.data, ne,
+                                  ec.ctypes.data, ep.ctypes.data, eo.ctypes.data, ew.ctypes.data,
+                                  _c(K, np.float32).ctypes.data, ab.ctypes.data if ab is not None else None,
+                                  chi2.ctypes.data, bad.ctypes.data, stats.ctypes.data, C.byref(iters)))
+        if iters.value < 0:
+            chi2[:] = 0
+            bad[:] = 0
+        return dict(cam_q=q, cam_t=t, pts=p, chi2=chi2[:ne], bad=bad[:ne], iters=int(stats[0]), trials=int(stats[1]),
+                    chi_first=stats[2], chi_last=stats[3], iters_first=int(stats[4]), excluded=int(stats[5]),
+                    rc=iters.value, kernel_ms=self.kernel_ms())
 
     def kernel_ms(self) -> float:
         return float(self.L.dvm_lba_last_kernel_ms(self.h))

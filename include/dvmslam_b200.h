@@ -425,6 +425,21 @@ DVM_API int dvm_bundle_adjustment(dvm_lba* h, int nc, float* cam_q, float* cam_t
                                   const float* edge_obs, const float* edge_inv_sigma2, const float* K, int iterations,
                                   float huber_delta, const volatile uint8_t* abort_flag, double* edge_chi2,
                                   uint8_t* edge_bad, double* stats, int* iters_done);
+/* void Optimizer::LocalBundleAdjustment(KeyFrame* pMainKF, vector<KeyFrame*> vpAdjustKF, vector<KeyFrame*> vpFixedKF,
+ * bool* pbStopFlag)   (O3/src/Optimizer.cc:3257-3675, mono observations) -- the welding BA of a map merge
+ * (LoopClosing::MergeLocal).  cam_fixed = 1 for vpFixedKF, 0 for vpAdjustKF; at least one fixed keyframe.  Both passes run
+ * in ONE kernel with the estimates kept in double between them, as the reference's optimizer object does:
+ *   pass 1: optimize(5), Huber delta (float)sqrt(5.99) (:3362,3476);
+ *   unless *abort_flag is up: edges with chi2 > 5.991 or depth <= 0 go to level 1, every edge loses its robust kernel,
+ *   pass 2: optimize(10) over the level-0 edges (:3481-3521).
+ * Outputs as dvm_local_ba; edge_chi2 of a level-1 edge is its chi2 after pass 1 (g2o keeps the edge's last error) while
+ * the depth in edge_bad is taken at the final estimate, exactly what the reference's final test reads (:3530-3546).
+ * stats[6] = {LM iterations of both passes, LM trials, initial robust chi2, final chi2 of the last pass, LM iterations of
+ * pass 1, edges moved to level 1}. */
+DVM_API int dvm_merge_ba(dvm_lba* h, int nc, float* cam_q, float* cam_t, const uint8_t* cam_fixed, int np, float* pts,
+                         int ne, const int32_t* edge_cam, const int32_t* edge_pt, const float* edge_obs,
+                         const float* edge_inv_sigma2, const float* K, const volatile uint8_t* abort_flag,
+                         double* edge_chi2, uint8_t* edge_bad, double* stats, int* iters_done);
 /* Device time of the last dvm_local_ba kernel in milliseconds (CUDA events on the solver's stream). */
 DVM_API float dvm_lba_last_kernel_ms(const dvm_lba* h);
 

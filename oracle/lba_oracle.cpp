@@ -174,6 +174,7 @@ struct Problem {
     std::vector<double> obs, info;
     double fx, fy, cx, cy, delta, dsqr;
     std::vector<double> err; /* ne*2: the edges' _error */
+    std::vector<uint8_t> active; /* level-0 edges (all of them unless the welding BA moved some to level 1) */
 };
 
 void edge_project(const Problem& P, const SE3& T, const double* X, double xc[3], double uv[2])
@@ -186,6 +187,7 @@ void edge_project(const Problem& P, const SE3& T, const double* X, double xc[3],
 void compute_errors(Problem& P)
 {
     for (int e = 0; e < P.ne; e++) {
+        if (!P.active[e]) continue; /* computeActiveErrors: a level-1 edge keeps its last _error */
         double xc[3], uv[2];
         edge_project(P, P.cam[P.ecam[e]], &P.pt[3 * P.ept[e]], xc, uv);
         P.err[2 * e] = P.obs[2 * e] - uv[0];
@@ -201,6 +203,7 @@ double robust_chi2(const Problem& P)
 {
     double chi = 0;
     for (int e = 0; e < P.ne; e++) {
+        if (!P.active[e]) continue;
         const double c = edge_chi2(P, e);
         chi += c <= P.dsqr ? c : 2 * std::sqrt(c) * P.delta - P.dsqr;
     }
@@ -236,10 +239,11 @@ int lbao_local_ba(int nc, float* cam_q, float* cam_t, const uint8_t* cam_fixed, 
                                   iterations, (float)std::sqrt(5.991), abort_flag, edge_chi2_out, edge_bad, stats);
 }
 
-int lbao_bundle_adjustment(int nc, float* cam_q, float* cam_t, const uint8_t* cam_fixed, int np, float* pts, int ne,
-                           const int* edge_cam, const int* edge_pt, const float* edge_obs, const float* edge_inv_sigma2,
-                           const float* K, int iterations, float huber_delta, const volatile int* abort_flag,
-                           double* edge_chi2_out, uint8_t* edge_bad, double* stats)
+/* iterations2 > 0: the welding BA's second pass (see lbao_merge_ba); stats then has 6 entries */
+static int run_ba(int nc, float* cam_q, float* cam_t, const uint8_t* cam_fixed, int np, float* pts, int ne,
+                  const int* edge_cam, const int* edge_pt, const float* edge_obs, const float* edge_inv_sigma2,
+                  const float* K, int iterations, float huber_delta, int iterations2, const volatile int* abort_flag,
+                  double* edge_chi2_out, uint8_t* edge_bad, double* stats)
 {
     Problem P;
     P.nc = nc; P.np = np; P.ne = ne;
@@ -253,14 +257,14 @@ int lbao_bundle_adjustment(int nc, float* cam_q, float* cam_t, const uint8_t* ca
         if (!cam_fixed[c]) P.cam_col[c] = P.nfree++;
         else nfixed++;
     }
-    if (stats) stats[0] = stats[1] = stats[2] = stats[3] = 0;
+    if (stats) { stats[0] = stats[1] = stats[2] = stats[3] = 0; if (iterations2 > 0) stats[4] = stats[5] = 0; }
     if (nfixed == 0) return -1;                 /* "LBA aborted": O3/src/Optimizer.cc:1088-1091 */
     if (abort_flag && *abort_flag) return -1;   /* :1306-1308 */
     if (ne == 0 || P.nfree + np == 0) return -1;
     P.pt.resize(3 * np);
     for (int i = 0; i < 3 * np; i++) P.pt[i] = pts[i];
     P.ecam = edge_cam; P.ept = edge_pt;
-    P.obs.resize(2 * ne); P.info.resize(ne); P.err.assign(2 * ne, 0.0);
+    P.obs.resize(2 * ne); P.info.resize(ne); P.err.assign(2 * ne, 0.0); P.active.assign(ne, 1);
     for (int i = 0; i < 2 * ne; i++) P.obs[i] = edge_obs[i];
     for (int i = 0; i < ne; i++) P.info[i] = edge_inv_sigma2[i];
     P.fx = K[0]; P.fy = K[1]; P.cx = K[2]; P.cy = K[3];
@@ -274,16 +278,34 @@ int lbao_bundle_adjustment(int nc, float* cam_q, float* cam_t, const uint8_t* ca
     double first_chi = 0, last_chi = 0;
     auto terminate = [&]() { return abort_flag && *abort_flag; };
 
-    for (int it = 0; it < iterations && !terminate(); it++) {
+    const int nstages = iterations2 > 0 ? 2 : 1;
+    for (int stage = 0; stage < nstages; stage++) {
+    if (stage == 1) {
+        /* O3/src/Optimizer.cc:3476-3521: unless the stop flag is up, edges with chi2 > 5.991 or non-positive depth go
+         * to level 1, EVERY edge loses its robust kernel, initializeOptimization(0), optimize(10) */
+        if (terminate()) break;
+        if (stats) stats[4] = done;
+        int excluded = 0;
+        for (int e = 0; e < ne; e++) {
+            double xc[3], uv[2];
+            edge_project(P, P.cam[P.ecam[e]], &P.pt[3 * P.ept[e]], xc, uv);
+            if (edge_chi2(P, e) > 5.991 || !(xc[2] > 0.0)) { P.active[e] = 0; excluded++; }
+        }
+        if (stats) stats[5] = excluded;
+        P.delta = std::numeric_limits<double>::infinity(); P.dsqr = P.delta;
+    }
+    const int iters = stage == 0 ? iterations : iterations2;
+    for (int it = 0; it < iters && !terminate(); it++) {
         compute_errors(P);
         double currentChi = robust_chi2(P);
         const double iniChi = currentChi;
-        if (it == 0) first_chi = currentChi;
+        if (it == 0 && stage == 0) first_chi = currentChi;
         double tempChi;
         /* buildSystem */
         std::fill(Hpp.begin(), Hpp.end(), 0.0); std::fill(bp.begin(), bp.end(), 0.0);
         std::fill(Hll.begin(), Hll.end(), 0.0); std::fill(bl.begin(), bl.end(), 0.0);
         for (int e = 0; e < ne; e++) {
+            if (!P.active[e]) continue;
             const int c = P.ecam[e], l = P.ept[e], col = P.cam_col[c];
             const SE3& T = P.cam[c];
             double xc[3], uv[2];
@@ -358,7 +380,7 @@ int lbao_bundle_adjustment(int nc, float* cam_q, float* cam_t, const uint8_t* ca
                     for (int a = 0; a < 3; a++) db[a] = Di[a * 3] * bl[3 * l] + Di[a * 3 + 1] * bl[3 * l + 1] + Di[a * 3 + 2] * bl[3 * l + 2];
                     for (int s1 = start[l]; s1 < start[l + 1]; s1++) {
                         const int e1 = order[s1], c1 = P.cam_col[P.ecam[e1]];
-                        if (c1 < 0) continue;
+                        if (c1 < 0 || !P.active[e1]) continue;
                         const double* B1 = &Hpl[(size_t)e1 * 18];
                         double BD[18];
                         for (int a = 0; a < 6; a++)
@@ -367,7 +389,7 @@ int lbao_bundle_adjustment(int nc, float* cam_q, float* cam_t, const uint8_t* ca
                         for (int a = 0; a < 6; a++) bs[6 * c1 + a] -= B1[a * 3] * db[0] + B1[a * 3 + 1] * db[1] + B1[a * 3 + 2] * db[2];
                         for (int s2 = start[l]; s2 < start[l + 1]; s2++) {
                             const int e2 = order[s2], c2 = P.cam_col[P.ecam[e2]];
-                            if (c2 < 0) continue;
+                            if (c2 < 0 || !P.active[e2]) continue;
                             const double* B2 = &Hpl[(size_t)e2 * 18];
                             for (int a = 0; a < 6; a++)
                                 for (int b2 = 0; b2 < 6; b2++)
@@ -383,7 +405,7 @@ int lbao_bundle_adjustment(int nc, float* cam_q, float* cam_t, const uint8_t* ca
                 std::vector<double> cl(bl);
                 for (int e = 0; e < ne; e++) {
                     const int c1 = P.cam_col[P.ecam[e]], l = P.ept[e];
-                    if (c1 < 0) continue;
+                    if (c1 < 0 || !P.active[e]) continue;
                     const double* B1 = &Hpl[(size_t)e * 18];
                     for (int b2 = 0; b2 < 3; b2++)
                         for (int a = 0; a < 6; a++) cl[3 * l + b2] -= B1[a * 3 + b2] * x[6 * c1 + a];
@@ -431,6 +453,7 @@ int lbao_bundle_adjustment(int nc, float* cam_q, float* cam_t, const uint8_t* ca
         else nBad = 0;
         if (nBad >= 3) break;
     }
+    } /* stage */
     /* outlier test on the stored errors + depth at the final estimate (:1313-1329) */
     for (int e = 0; e < ne; e++) {
         const double chi = edge_chi2(P, e);
@@ -448,6 +471,30 @@ int lbao_bundle_adjustment(int nc, float* cam_q, float* cam_t, const uint8_t* ca
     for (int i = 0; i < dimL; i++) pts[i] = (float)P.pt[i];
     if (stats) { stats[0] = done; stats[1] = trials; stats[2] = first_chi; stats[3] = last_chi; }
     return done;
+}
+
+int lbao_bundle_adjustment(int nc, float* cam_q, float* cam_t, const uint8_t* cam_fixed, int np, float* pts, int ne,
+                           const int* edge_cam, const int* edge_pt, const float* edge_obs, const float* edge_inv_sigma2,
+                           const float* K, int iterations, float huber_delta, const volatile int* abort_flag,
+                           double* edge_chi2_out, uint8_t* edge_bad, double* stats)
+{
+    return run_ba(nc, cam_q, cam_t, cam_fixed, np, pts, ne, edge_cam, edge_pt, edge_obs, edge_inv_sigma2, K, iterations,
+                  huber_delta, 0, abort_flag, edge_chi2_out, edge_bad, stats);
+}
+
+/* The welding BA of a map merge: Optimizer::LocalBundleAdjustment(pMainKF, vpAdjustKF, vpFixedKF, pbStopFlag),
+ * O3/src/Optimizer.cc:3257-3675 (mono observations).  optimize(5) with Huber delta (float)sqrt(5.99) (:3362); then,
+ * unless the stop flag is up, edges with chi2 > 5.991 or non-positive depth are moved to level 1, every edge loses its
+ * robust kernel and optimize(10) runs on the level-0 edges (:3476-3521).  The final test (:3530-3546) reads e->chi2()
+ * of EVERY edge -- a level-1 edge still holds the error of the first pass -- and the depth at the final estimate.
+ * stats[6] = {LM iterations of both passes, LM trials, initial robust chi2, final chi2 of the last pass, iterations of
+ * the first pass, edges moved to level 1}. */
+int lbao_merge_ba(int nc, float* cam_q, float* cam_t, const uint8_t* cam_fixed, int np, float* pts, int ne,
+                  const int* edge_cam, const int* edge_pt, const float* edge_obs, const float* edge_inv_sigma2,
+                  const float* K, const volatile int* abort_flag, double* edge_chi2_out, uint8_t* edge_bad, double* stats)
+{
+    return run_ba(nc, cam_q, cam_t, cam_fixed, np, pts, ne, edge_cam, edge_pt, edge_obs, edge_inv_sigma2, K, 5,
+                  (float)std::sqrt(5.99), 10, abort_flag, edge_chi2_out, edge_bad, stats);
 }
 
 /* analytic Jacobians of one edge, for the finite-difference self-check */

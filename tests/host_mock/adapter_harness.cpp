@@ -481,4 +481,51 @@ int hm_bundle_adjustment(int nc, float* cam_q, float* cam_t, const uint8_t* cam_
     });
 }
 
+// Optimizer::LocalBundleAdjustment(pMainKF, vpAdjustKF, vpFixedKF, pbStopFlag) -- the welding BA -- on a flat scene: fixed
+// cameras become vpFixedKF, the others vpAdjustKF (the first of them is pMainKF).  Returns the number of erased
+// observations; *normal_updates = UpdateNormalAndDepth calls.
+int hm_merge_ba(int nc, float* cam_q, float* cam_t, const uint8_t* cam_fixed, int np, float* pts, int ne, const int* edge_cam,
+                const int* edge_pt, const float* edge_obs, const int* edge_octave, const float* invsig2, int nlevels,
+                int* normal_updates)
+{
+    Map map;
+    std::vector<std::unique_ptr<KeyFrame>> kfs(nc);
+    std::vector<std::unique_ptr<MapPoint>> mps(np);
+    std::vector<KeyFrame*> adjust, fixed;
+    for (int c = 0; c < nc; c++) {
+        kfs[c].reset(new KeyFrame);
+        kfs[c]->mnId = 10 + c; kfs[c]->map = &map;
+        kfs[c]->fx = g_K[0]; kfs[c]->fy = g_K[1]; kfs[c]->cx = g_K[2]; kfs[c]->cy = g_K[3];
+        set_pose(kfs[c]->Tcw, cam_q + 4 * c, cam_t + 3 * c);
+        kfs[c]->mvInvLevelSigma2.assign(invsig2, invsig2 + nlevels);
+        (cam_fixed[c] ? fixed : adjust).push_back(kfs[c].get());
+    }
+    for (int j = 0; j < np; j++) {
+        mps[j].reset(new MapPoint);
+        mps[j]->mnId = j; mps[j]->map = &map;
+        for (int k = 0; k < 3; k++) mps[j]->pos(k) = pts[3 * j + k];
+    }
+    for (int e = 0; e < ne; e++) {
+        KeyFrame& K = *kfs[edge_cam[e]];
+        cv::KeyPoint k(edge_obs[2 * e], edge_obs[2 * e + 1], 31.f, 0.f, 1.f, edge_octave[e]);
+        K.mvKeysUn.push_back(k); K.mvuRight.push_back(-1.f); K.mapPoints.push_back(mps[edge_pt[e]].get());
+        mps[edge_pt[e]]->observations[&K] = std::make_tuple(K.N, -1);
+        K.N++;
+    }
+    dvm_host::LbaHandle solver;
+    return guarded([&] {
+        dvm_host::check(dvm_lba_create(&solver.h, dvm_host::device_from_env(), 64), "dvm_lba_create");
+        dvm_host::LocalBundleAdjustment<KeyFrame, MapPoint>(solver.h, adjust[0], adjust, fixed, nullptr);
+        int left = 0, updates = 0;
+        for (int j = 0; j < np; j++) { left += (int)mps[j]->observations.size(); updates += mps[j]->normalUpdates; }
+        for (int c = 0; c < nc; c++) {
+            for (int k = 0; k < 4; k++) cam_q[4 * c + k] = kfs[c]->Tcw.q.q[k];
+            for (int k = 0; k < 3; k++) cam_t[3 * c + k] = kfs[c]->Tcw.t.v[k];
+        }
+        for (int j = 0; j < np; j++) for (int k = 0; k < 3; k++) pts[3 * j + k] = mps[j]->pos(k);
+        *normal_updates = updates;
+        return ne - left;
+    });
+}
+
 } // extern "C"

@@ -61,7 +61,7 @@ struct MapPoint {
     bool mbTrackInView = false, mbTrackInViewR = false;
     float mTrackProjX = 0, mTrackProjY = 0, mTrackViewCos = 0, mTrackDepth = 0;
     int mnTrackScaleLevel = 0;
-    unsigned long mnBALocalForKF = ~0ul, mnBAGlobalForKF = 0;
+    unsigned long mnBALocalForKF = ~0ul, mnBAGlobalForKF = 0, mnBALocalForMerge = ~0ul;
     Vec3 mPosGBA;
     std::map<KeyFrame*, std::tuple<int, int>> observations;
     int normalUpdates = 0;
@@ -107,7 +107,7 @@ struct Frame {
 struct KeyFrame {
     float fx = 0, fy = 0, cx = 0, cy = 0;   // per-object constants in the reference (O3/include/KeyFrame.h)
     long unsigned int mnId = 0;
-    unsigned long mnBALocalForKF = ~0ul, mnBAFixedForKF = ~0ul, mnBAGlobalForKF = 0;
+    unsigned long mnBALocalForKF = ~0ul, mnBAFixedForKF = ~0ul, mnBAGlobalForKF = 0, mnBALocalForMerge = ~0ul;
     SE3f mTcwGBA;
     int N = 0, NLeft = -1;
     std::vector<cv::KeyPoint> mvKeysUn;
@@ -123,6 +123,12 @@ struct KeyFrame {
     bool bad = false;
     Map* map = nullptr;
     std::vector<MapPoint*> GetMapPointMatches() const { return mapPoints; }
+    std::set<MapPoint*> GetMapPoints() const
+    {
+        std::set<MapPoint*> s;
+        for (MapPoint* p : mapPoints) if (p) s.insert(p);
+        return s;
+    }
     std::vector<KeyFrame*> GetVectorCovisibleKeyFrames() const { return covisible; }
     SE3f GetPose() const { return Tcw; }
     void SetPose(const SE3f& T) { Tcw = T; }

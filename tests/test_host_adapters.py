@@ -434,3 +434,41 @@ def test_global_ba_adapter_matches_direct_call(libs, direct):
     seen[np.asarray(B["edge_pt"])] = True                       # points without observation are left out (:243-247)
     assert np.abs(ct - r["cam_t"]).max() < 6e-5 and np.abs(cq - r["cam_q"]).max() < 1e-6
     assert np.abs(pts[seen] - r["pts"][seen]).max() < 1e-4
+
+
+@pytest.mark.gpu
+def test_merge_ba_adapter_matches_direct_call(libs):
+    """Optimizer::LocalBundleAdjustment(pMainKF, vpAdjustKF, vpFixedKF, pbStopFlag) -- the welding BA -- through the adapter
+    against dvm_merge_ba on the same flat scene: same poses and points, flagged observations erased on both sides of the
+    graph, UpdateNormalAndDepth on every map point of the window."""
+    from dvmslam_b200.optimizer import LocalBA
+
+    H, _ = libs
+    B = synth.ba_scene(14, 4, 500, seed=8)
+    H.hm_set_camera(_p(_c(B["K"], np.float32)), _p(np.array([0, 0, 1280, 720], np.float32)))
+    invsig2 = np.array([1.0 / (np.float32(1.2) ** (2 * l)) for l in range(8)], np.float32)
+    octave = np.array([int(np.argmin(np.abs(invsig2 - w))) for w in B["edge_w"]], np.int32)
+    B = dict(B, edge_w=invsig2[octave])
+    s = LocalBA(64)
+    r = s.MergeBundleAdjustment(B["cam_q"], B["cam_t"], B["cam_fixed"], B["pts"], B["edge_cam"], B["edge_pt"], B["edge_obs"],
+                                B["edge_w"], B["K"])
+    s.close()
+    assert r["excluded"] > 0 and r["iters"] > r["iters_first"]
+    cq, ct, pts = _c(B["cam_q"], np.float32).copy(), _c(B["cam_t"], np.float32).copy(), _c(B["pts"], np.float32).copy()
+    upd = C.c_int()
+    H.hm_merge_ba.argtypes = [C.c_int, _vp, _vp, _vp, C.c_int, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, C.c_int, _ip]
+    rc = H.hm_merge_ba(len(cq), _p(cq), _p(ct), _p(_c(B["cam_fixed"], np.uint8)), len(pts), _p(pts), len(B["edge_cam"]),
+                       _p(_c(B["edge_cam"], np.int32)), _p(_c(B["edge_pt"], np.int32)), _p(_c(B["edge_obs"], np.float32)),
+                       _p(octave), _p(invsig2), 8, C.byref(upd))
+    assert rc >= 0, (rc, H.hm_last_error())
+    seen = np.zeros(len(pts), bool)
+    seen[np.asarray(B["edge_pt"])] = True
+    # the adapter orders points and edges as the reference does (std::set / std::map of pointers), the direct call as the
+    # scene lists them: sums differ in the last bits, so a few observations at the 5.991 gate may flip
+    near_gate = int((np.abs(r["chi2"] - 5.991) < 1e-4).sum())
+    assert abs(rc - int(r["bad"].sum())) <= near_gate
+    assert upd.value == int(seen.sum())
+    assert np.abs(ct - r["cam_t"]).max() < 6e-5 and np.abs(cq - r["cam_q"]).max() < 1e-6
+    assert np.abs(pts[seen] - r["pts"][seen]).max() < 1e-4
+    fixed = B["cam_fixed"].astype(bool)
+    assert np.array_equal(ct[fixed], _c(B["cam_t"], np.float32)[fixed])

@@ -105,3 +105,22 @@ def test_global_bundle_adjustment_matches_oracle(n_free, n_pts, robust, iters):
     assert np.abs(r1["cam_t"] - r0["cam_t"]).max() < 6e-5 and np.abs(r1["cam_q"] - r0["cam_q"]).max() < 1e-6
     assert np.abs(r1["pts"] - r0["pts"]).max() < 1e-4
     assert r1["chi_last"] < 0.5 * r1["chi_first"]
+
+
+@pytest.mark.parametrize("nf,nx,npts,seed,outliers", [(12, 3, 600, 1, 0.05), (50, 10, 5000, 0, 0.05), (30, 5, 1500, 2, 0.05),
+                                                      (4, 2, 150, 9, 0.3), (8, 2, 300, 3, 0.0)])
+def test_merge_ba_matches_oracle(solver, nf, nx, npts, seed, outliers):
+    """The welding BA of a map merge (Optimizer::LocalBundleAdjustment(pMainKF, vpAdjustKF, vpFixedKF, pbStopFlag),
+    O3/src/Optimizer.cc:3257-3675): Huber pass of 5, level-1 classification, plain pass of 10 -- one kernel.  Same
+    tolerances as the local BA; the pass structure (iterations of pass 1, number of level-1 edges) must be identical.
+    The 30 % outlier case leaves map points without any level-0 edge in pass 2."""
+    from oracle.lba import merge_ba
+
+    S = synth.ba_scene(nf, nx, npts, seed=seed, outlier_frac=outliers)
+    r0 = merge_ba(*_args(S))
+    r1 = solver.MergeBundleAdjustment(*_args(S))
+    assert (r1["iters_first"], r1["excluded"]) == (r0["iters_first"], r0["excluded"])
+    _compare(r0, r1, S)
+    assert r0["iters"] > r0["iters_first"]
+    r = solver.MergeBundleAdjustment(*_args(S), abort=1)
+    assert r["rc"] == -1 and np.array_equal(r["cam_t"], S["cam_t"])

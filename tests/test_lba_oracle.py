@@ -75,3 +75,29 @@ def test_bundle_adjustment_delta_variants():
     assert r_gba["chi_last"] <= r_inf["chi_last"] * (1 + 1e-9)             # Huber never exceeds the quadratic cost
     assert abs(r_gba["chi_last"] - r_lba["chi_last"]) < 1e-2 * r_lba["chi_last"]   # 5.99 vs 5.991: nearly the same kernel
     assert r_gba["chi_last"] != r_lba["chi_last"]
+
+
+def test_merge_ba_two_passes():
+    """The welding BA (Optimizer.cc:3257-3675): pass 1 is BundleAdjustment's optimize(5) with delta sqrt(5.99); the edges
+    it would flag go to level 1 and keep the error of pass 1; pass 2 runs without a robust kernel on the rest."""
+    from oracle.lba import local_ba, merge_ba
+
+    S = synth.ba_scene(12, 3, 600, seed=1)
+    a = _args(S)
+    r1 = local_ba(*a, iterations=5, huber_delta=np.sqrt(5.99))
+    r = merge_ba(*a)
+    assert r["iters_first"] == r1["iters"] and r["excluded"] == int(r1["bad"].sum()) and r["excluded"] > 0
+    assert r["iters"] > r["iters_first"] and r["chi_first"] == r1["chi_first"]
+    lvl1 = r1["bad"].astype(bool)
+    assert np.array_equal(r["chi2"][lvl1], r1["chi2"][lvl1])            # level-1 edges: stale error
+    assert not np.array_equal(r["chi2"][~lvl1], r1["chi2"][~lvl1])      # level-0 edges moved on
+    # the second pass minimises the plain sum of squares of the level-0 edges: it cannot end above where it started
+    assert r["chi_last"] <= r1["chi2"][~lvl1].sum() * (1 + 1e-12)
+    assert abs(r["chi_last"] - r["chi2"][~lvl1].sum()) < 1e-9 * r["chi_last"]
+    # stop flag up: nothing runs
+    r = merge_ba(*a, abort=1)
+    assert r["rc"] == -1 and np.array_equal(r["pts"], S["pts"])
+    # no outliers, no noise: nothing goes to level 1 and the optimum is the true scene
+    S = synth.ba_scene(8, 2, 300, seed=3, pix_sigma=0.0, outlier_frac=0.0)
+    r = merge_ba(*_args(S))
+    assert r["excluded"] == 0 and r["chi_last"] < 1e-6 * r["chi_first"] and not r["bad"].any()
