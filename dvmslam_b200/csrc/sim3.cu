@@ -1,0 +1,561 @@
+// sim3.cu -- Optimizer::OptimizeSim3 (O3/src/Optimizer.cc:1960-2212) as one sm_100a kernel.
+//
+// One Sim3 vertex (7 DoF, or 6 with bFixScale), fixed point vertices, an EdgeSim3ProjectXYZ / EdgeInverseSim3ProjectXYZ pair
+// per correspondence (O3/include/OptimizableTypes.h:146-206).  The edges define no linearizeOplus, so g2o differentiates
+// them numerically (base_binary_edge.hpp:130-205: central differences, delta 1e-9, through oplus on the vertex); the
+// kernel does the same -- the 14 perturbed estimates are shared by all edges, so they are built once per linearisation --
+// because an analytic Jacobian would follow a (slightly) different LM path than the reference.
+//
+// A few hundred correspondences and a 7x7 system: latency-bound, one CTA.  Every thread carries the estimate and the LM
+// state in registers and derives them from the same shared-memory sums, so the control flow is uniform without
+// broadcasting; the per-correspondence work (28 projections per linearisation) is spread over the threads and reduced
+// with warp shuffles + one shared-memory stage in a fixed order (deterministic).
+#include "common.cuh"
+#include <math_constants.h>
+#include <cmath>
+
+namespace dvm {
+namespace {
+
+constexpr int kSim3Threads = 256;
+constexpr int kSim3Warps = kSim3Threads / 32;
+
+struct Quat { double x, y, z, w; };
+struct Sim3 { Quat r; double t[3]; double s; };
+
+struct Sim3Dev {
+    int n, fix_scale;
+    const float* p1; const float* p2; const float* obs1; const float* obs2; const float* w1; const float* w2;
+    double K1[4], K2[4];
+    double delta, th2;
+    double* err;        // [n*4] the edges' _error: e12 (2), e21 (2)
+    uint8_t* state;     // [n] bit 0: pair still in the graph, bit 1: still carries its Huber kernel
+    double* io;         // [8] q (x,y,z,w), t, s: in/out
+    uint8_t* inlier;    // [n] out
+    double* stats;      // [8] out: iters pass 1, iters pass 2, trials, nBad, first chi2, last chi2, nIn
+};
+
+__device__ inline Quat quat_mul(const Quat& a, const Quat& b)
+{
+    Quat r;
+    r.w = a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z;
+    r.x = a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y;
+    r.y = a.w * b.y + a.y * b.w + a.z * b.x - a.x * b.z;
+    r.z = a.w * b.z + a.z * b.w + a.x * b.y - a.y * b.x;
+    return r;
+}
+__device__ inline void quat_rotate(const Quat& q, const double v[3], double out[3])
+{
+    double uv[3] = { q.y * v[2] - q.z * v[1], q.z * v[0] - q.x * v[2], q.x * v[1] - q.y * v[0] };
+    uv[0] += uv[0]; uv[1] += uv[1]; uv[2] += uv[2];
+    out[0] = v[0] + q.w * uv[0] + (q.y * uv[2] - q.z * uv[1]);
+    out[1] = v[1] + q.w * uv[1] + (q.z * uv[0] - q.x * uv[2]);
+    out[2] = v[2] + q.w * uv[2] + (q.x * uv[1] - q.y * uv[0]);
+}
+__device__ inline Quat quat_from_matrix(const double R[9]) // Eigen::Quaterniond(Matrix3d)
+{
+    Quat q;
+    double t = R[0] + R[4] + R[8];
+    if (t > 0) {
+        t = sqrt(t + 1.0);
+        q.w = 0.5 * t;
+        t = 0.5 / t;
+        q.x = (R[7] - R[5]) * t; q.y = (R[2] - R[6]) * t; q.z = (R[3] - R[1]) * t;
+    } else {
+        int i = 0;
+        if (R[4] > R[0]) i = 1;
+        if (R[8] > R[i * 4]) i = 2;
+        const int j = (i + 1) % 3, k = (j + 1) % 3;
+        t = sqrt(R[i * 4] - R[j * 4] - R[k * 4] + 1.0);
+        double v[3];
+        v[i] = 0.5 * t;
+        t = 0.5 / t;
+        q.w = (R[k * 3 + j] - R[j * 3 + k]) * t;
+        v[j] = (R[j * 3 + i] + R[i * 3 + j]) * t;
+        v[k] = (R[k * 3 + i] + R[i * 3 + k]) * t;
+        q.x = v[0]; q.y = v[1]; q.z = v[2];
+    }
+    return q;
+}
+
+// g2o::Sim3(const Vector7d& update), O3/Thirdparty/g2o/g2o/types/sim3.h
+__device__ Sim3 sim3_exp(const double u[7])
+{
+    const double w0 = u[0], w1 = u[1], w2 = u[2], sigma = u[6];
+    const double theta = sqrt(w0 * w0 + w1 * w1 + w2 * w2);
+    const double O[9] = { 0, -w2, w1, w2, 0, -w0, -w1, w0, 0 };
+    double O2[9], R[9];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) O2[i * 3 + j] = O[i * 3] * O[j] + O[i * 3 + 1] * O[3 + j] + O[i * 3 + 2] * O[6 + j];
+    Sim3 S;
+    S.s = exp(sigma);
+    const double eps = 0.00001;
+    double A, B, C;
+    const bool small_rot = theta < eps;
+    if (small_rot) {
+#pragma unroll
+        for (int i = 0; i < 9; i++) R[i] = ((i % 4 == 0) ? 1.0 : 0.0) + O[i] + O2[i];
+    } else {
+        const double a = sin(theta) / theta, b = (1 - cos(theta)) / (theta * theta);
+#pragma unroll
+        for (int i = 0; i < 9; i++) R[i] = ((i % 4 == 0) ? 1.0 : 0.0) + a * O[i] + b * O2[i];
+    }
+    if (fabs(sigma) < eps) {
+        C = 1;
+        if (small_rot) { A = 1. / 2.; B = 1. / 6.; }
+        else {
+            const double theta2 = theta * theta;
+            A = (1 - cos(theta)) / theta2;
+            B = (theta - sin(theta)) / (theta2 * theta);
+        }
+    } else {
+        C = (S.s - 1) / sigma;
+        if (small_rot) {
+            const double sigma2 = sigma * sigma;
+            A = ((sigma - 1) * S.s + 1) / sigma2;
+            B = ((0.5 * sigma2 - sigma + 1) * S.s) / (sigma2 * sigma);
+        } else {
+            const double a = S.s * sin(theta), b = S.s * cos(theta);
+            const double theta2 = theta * theta, sigma2 = sigma * sigma, c = theta2 + sigma2;
+            A = (a * sigma + (1 - b) * theta) / (theta * c);
+            B = (C - ((b - 1) * sigma + a * theta) / c) * 1. / theta2;
+        }
+    }
+    S.r = quat_from_matrix(R);
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        double acc = 0;
+#pragma unroll
+        for (int j = 0; j < 3; j++) acc += (A * O[i * 3 + j] + B * O2[i * 3 + j] + C * (i == j ? 1.0 : 0.0)) * u[3 + j];
+        S.t[i] = acc;
+    }
+    return S;
+}
+__device__ inline Sim3 sim3_mul(const Sim3& a, const Sim3& b)
+{
+    Sim3 r;
+    r.r = quat_mul(a.r, b.r);
+    double rt[3];
+    quat_rotate(a.r, b.t, rt);
+#pragma unroll
+    for (int i = 0; i < 3; i++) r.t[i] = a.s * rt[i] + a.t[i];
+    r.s = a.s * b.s;
+    return r;
+}
+__device__ inline Sim3 sim3_inverse(const Sim3& a)
+{
+    Sim3 r;
+    r.r = { -a.r.x, -a.r.y, -a.r.z, a.r.w };
+    const double v[3] = { (-1. / a.s) * a.t[0], (-1. / a.s) * a.t[1], (-1. / a.s) * a.t[2] };
+    quat_rotate(r.r, v, r.t);
+    r.s = 1. / a.s;
+    return r;
+}
+// VertexSim3Expmap::oplusImpl
+__device__ inline Sim3 oplus(const Sim3Dev& P, const Sim3& S, const double* update)
+{
+    double u[7];
+#pragma unroll
+    for (int k = 0; k < 7; k++) u[k] = update[k];
+    if (P.fix_scale) u[6] = 0;
+    return sim3_mul(sim3_exp(u), S);
+}
+
+struct Pair { double p1[3], p2[3], o1[2], o2[2]; };
+__device__ inline Pair load_pair(const Sim3Dev& P, int i)
+{
+    Pair c;
+#pragma unroll
+    for (int k = 0; k < 3; k++) { c.p1[k] = (double)P.p1[3 * i + k]; c.p2[k] = (double)P.p2[3 * i + k]; }
+#pragma unroll
+    for (int k = 0; k < 2; k++) { c.o1[k] = (double)P.obs1[2 * i + k]; c.o2[k] = (double)P.obs2[2 * i + k]; }
+    return c;
+}
+// EdgeSim3ProjectXYZ::computeError (e[0..1]) and EdgeInverseSim3ProjectXYZ::computeError (e[2..3])
+__device__ inline void pair_error(const Sim3Dev& P, const Sim3& S, const Sim3& Sinv, const Pair& c, double e[4])
+{
+    double rx[3], x[3];
+    quat_rotate(S.r, c.p2, rx);
+#pragma unroll
+    for (int k = 0; k < 3; k++) x[k] = S.s * rx[k] + S.t[k];
+    e[0] = c.o1[0] - (P.K1[0] * x[0] / x[2] + P.K1[2]);
+    e[1] = c.o1[1] - (P.K1[1] * x[1] / x[2] + P.K1[3]);
+    quat_rotate(Sinv.r, c.p1, rx);
+#pragma unroll
+    for (int k = 0; k < 3; k++) x[k] = Sinv.s * rx[k] + Sinv.t[k];
+    e[2] = c.o2[0] - (P.K2[0] * x[0] / x[2] + P.K2[2]);
+    e[3] = c.o2[1] - (P.K2[1] * x[1] / x[2] + P.K2[3]);
+}
+
+// deterministic CTA sum of NV doubles per thread; the totals land in out[0..NV) (shared) for every thread to read
+template <int NV>
+__device__ inline void cta_sum(double* v, double* warp_buf /*[kSim3Warps*NV]*/, double* out /*[NV]*/)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+        double x = v[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        v[i] = x;
+    }
+    __syncthreads(); // the previous totals have been read
+    if (lane == 0)
+#pragma unroll
+        for (int i = 0; i < NV; i++) warp_buf[wid * NV + i] = v[i];
+    __syncthreads();
+    if (threadIdx.x < NV) {
+        double s = 0;
+        for (int w = 0; w < kSim3Warps; w++) s += warp_buf[w * NV + threadIdx.x];
+        out[threadIdx.x] = s;
+    }
+    __syncthreads();
+}
+
+// symmetric 7x7 solve by LDL^T (LinearSolverDense: Eigen::LDLT, solution only if positive)
+__device__ inline bool solve7(const double* H /*shared, full 7x7*/, double lambda, const double* b, double* x)
+{
+    double L[49], D[7];
+#pragma unroll
+    for (int j = 0; j < 7; j++) {
+        double d = H[j * 7 + j] + lambda;
+#pragma unroll
+        for (int k = 0; k < j; k++) d -= L[j * 7 + k] * L[j * 7 + k] * D[k];
+        if (!(d > 0) || !isfinite(d)) return false;
+        D[j] = d;
+#pragma unroll
+        for (int i = j + 1; i < 7; i++) {
+            double v = H[i * 7 + j];
+#pragma unroll
+            for (int k = 0; k < j; k++) v -= L[i * 7 + k] * L[j * 7 + k] * D[k];
+            L[i * 7 + j] = v / d;
+        }
+    }
+    double y[7];
+#pragma unroll
+    for (int i = 0; i < 7; i++) {
+        double v = b[i];
+#pragma unroll
+        for (int k = 0; k < i; k++) v -= L[i * 7 + k] * y[k];
+        y[i] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < 7; i++) y[i] /= D[i];
+#pragma unroll
+    for (int i = 6; i >= 0; i--) {
+        double v = y[i];
+#pragma unroll
+        for (int k = i + 1; k < 7; k++) v -= L[k * 7 + i] * x[k];
+        x[i] = v;
+    }
+    return true;
+}
+
+__global__ void __launch_bounds__(kSim3Threads, 1) optimize_sim3_kernel(Sim3Dev P)
+{
+    __shared__ double warp_buf[kSim3Warps * 35];
+    __shared__ double tot[35];
+    __shared__ Sim3 pert[28]; // [d]: +delta, [7+d]: its inverse, [14+d]: -delta, [21+d]: its inverse
+    __shared__ double Hs[49], bs[7];
+    const int tid = threadIdx.x;
+    const double dsqr = P.delta * P.delta;
+
+    Sim3 S;
+    S.r = { P.io[0], P.io[1], P.io[2], P.io[3] };
+    S.t[0] = P.io[4]; S.t[1] = P.io[5]; S.t[2] = P.io[6];
+    S.s = P.io[7];
+    for (int i = tid; i < P.n; i += kSim3Threads) { P.state[i] = 3; P.inlier[i] = 1; }
+    __syncthreads();
+
+    auto chi_of = [&](const double* e, double om) { return e[0] * (om * e[0]) + e[1] * (om * e[1]); };
+    // computeActiveErrors + activeRobustChi2 at estimate T: the pairs' errors go to P.err, the robust chi2 to every thread
+    auto errors_and_chi = [&](const Sim3& T) -> double {
+        const Sim3 Tinv = sim3_inverse(T);
+        double part[1] = { 0 };
+        for (int i = tid; i < P.n; i += kSim3Threads) {
+            const uint8_t st = P.state[i];
+            if (!(st & 1)) continue;
+            const Pair c = load_pair(P, i);
+            double e[4];
+            pair_error(P, T, Tinv, c, e);
+#pragma unroll
+            for (int k = 0; k < 4; k++) P.err[4 * i + k] = e[k];
+            const double c1 = chi_of(e, (double)P.w1[i]), c2 = chi_of(e + 2, (double)P.w2[i]);
+            const bool rob = st & 2;
+            part[0] += (!rob || c1 <= dsqr) ? c1 : 2 * sqrt(c1) * P.delta - dsqr;
+            part[0] += (!rob || c2 <= dsqr) ? c2 : 2 * sqrt(c2) * P.delta - dsqr;
+        }
+        cta_sum<1>(part, warp_buf, tot);
+        return tot[0];
+    };
+
+    int trials = 0;
+    double first_chi = 0, last_chi = 0;
+    // optimizer.optimize(iterations): g2o's Levenberg-Marquardt (optimization_algorithm_levenberg.cpp:59-188)
+    auto optimize = [&](int iterations, bool record_first) -> int {
+        double lambda = -1, ni = 2;
+        int nBad = 0, done = 0;
+        for (int it = 0; it < iterations; it++) {
+            double currentChi = errors_and_chi(S);
+            const double iniChi = currentChi;
+            if (it == 0 && record_first) first_chi = currentChi;
+            // the 14 perturbed estimates of the numeric Jacobian and their inverses
+            if (tid < 14) {
+                const int d = tid % 7;
+                double add[7] = { 0, 0, 0, 0, 0, 0, 0 };
+                add[d] = tid < 7 ? 1e-9 : -1e-9;
+                const Sim3 T = oplus(P, S, add);
+                pert[(tid < 7 ? 0 : 14) + d] = T;
+                pert[(tid < 7 ? 7 : 21) + d] = sim3_inverse(T);
+            }
+            __syncthreads();
+            // buildSystem: H (upper triangle, 28) and b (7)
+            double acc[35];
+#pragma unroll
+            for (int k = 0; k < 35; k++) acc[k] = 0;
+            const double scalar = 1.0 / (2 * 1e-9);
+            for (int i = tid; i < P.n; i += kSim3Threads) {
+                const uint8_t st = P.state[i];
+                if (!(st & 1)) continue;
+                const Pair c = load_pair(P, i);
+                double J[4][7];
+#pragma unroll
+                for (int d = 0; d < 7; d++) {
+                    double ep[4], em[4];
+                    pair_error(P, pert[d], pert[7 + d], c, ep);
+                    pair_error(P, pert[14 + d], pert[21 + d], c, em);
+#pragma unroll
+                    for (int r = 0; r < 4; r++) J[r][d] = scalar * (ep[r] - em[r]);
+                }
+                const bool rob = st & 2;
+#pragma unroll
+                for (int half = 0; half < 2; half++) {
+                    const double om = half == 0 ? (double)P.w1[i] : (double)P.w2[i];
+                    const double e0 = P.err[4 * i + 2 * half], e1 = P.err[4 * i + 2 * half + 1];
+                    const double chi = e0 * (om * e0) + e1 * (om * e1);
+                    const double w = (!rob || chi <= dsqr) ? 1.0 : P.delta / sqrt(chi);
+                    const double r0 = -om * e0 * w, r1 = -om * e1 * w;
+                    const double wo = w * om;
+                    int idx = 0;
+#pragma unroll
+                    for (int a = 0; a < 7; a++) {
+                        acc[28 + a] += J[2 * half][a] * r0 + J[2 * half + 1][a] * r1;
+#pragma unroll
+                        for (int b2 = a; b2 < 7; b2++)
+                            acc[idx++] += J[2 * half][a] * wo * J[2 * half][b2] + J[2 * half + 1][a] * wo * J[2 * half + 1][b2];
+                    }
+                }
+            }
+            cta_sum<35>(acc, warp_buf, tot);
+            if (tid < 49) {
+                const int a = tid / 7, b2 = tid % 7;
+                const int lo = min(a, b2), hi = max(a, b2);
+                Hs[tid] = tot[lo * 7 - lo * (lo - 1) / 2 + (hi - lo)];
+            }
+            if (tid < 7) bs[tid] = tot[28 + tid];
+            __syncthreads();
+            if (it == 0) {
+                double mx = 0;
+#pragma unroll
+                for (int j = 0; j < 7; j++) mx = fmax(fabs(Hs[j * 8]), mx);
+                lambda = 1e-5 * mx;
+                ni = 2;
+                nBad = 0;
+            }
+            double bl[7];
+#pragma unroll
+            for (int j = 0; j < 7; j++) bl[j] = bs[j];
+            double rho = 0;
+            int qmax = 0;
+            do {
+                double x[7];
+                const bool ok2 = solve7(Hs, lambda, bl, x);
+                if (!ok2) {
+#pragma unroll
+                    for (int j = 0; j < 7; j++) x[j] = 0;
+                }
+                const Sim3 T = oplus(P, S, x);
+                double tempChi = errors_and_chi(T);
+                if (!ok2) tempChi = 1.7976931348623157e308;
+                rho = currentChi - tempChi;
+                double scale = 0;
+#pragma unroll
+                for (int j = 0; j < 7; j++) scale += x[j] * (lambda * x[j] + bl[j]);
+                scale += 1e-3;
+                rho /= scale;
+                if (rho > 0 && isfinite(tempChi)) {
+                    double alpha = 1. - pow((2 * rho - 1), 3.0);
+                    alpha = fmin(alpha, 2. / 3.);
+                    lambda *= fmax(1. / 3., alpha);
+                    ni = 2;
+                    currentChi = tempChi;
+                    S = T;
+                } else {
+                    lambda *= ni;
+                    ni *= 2;
+                }
+                qmax++;
+                trials++;
+            } while (rho < 0 && qmax < 10);
+            done++;
+            last_chi = currentChi;
+            if (qmax == 10 || rho == 0) break;
+            if ((iniChi - currentChi) * 1e3 < iniChi) nBad++;
+            else nBad = 0;
+            if (nBad >= 3) break;
+        }
+        return done;
+    };
+
+    const int it1 = optimize(5, true);                                  // :2149-2150
+    // inlier check on the stored errors, :2153-2176: outlier pairs leave the graph, the others lose their kernel
+    double cnt[1] = { 0 };
+    for (int i = tid; i < P.n; i += kSim3Threads) {
+        const double* e = P.err + 4 * i;
+        const bool out = chi_of(e, (double)P.w1[i]) > P.th2 || chi_of(e + 2, (double)P.w2[i]) > P.th2;
+        P.state[i] = out ? 0 : 1;
+        if (out) { P.inlier[i] = 0; cnt[0] += 1; }
+    }
+    cta_sum<1>(cnt, warp_buf, tot);
+    const int nBad1 = (int)tot[0];
+    __syncthreads();
+    int it2 = 0, nIn = 0;
+    const bool enough = P.n - nBad1 >= 10;                              // :2183-2184
+    if (enough) {
+        it2 = optimize(nBad1 > 0 ? 10 : 5, false);                      // :2178-2188
+        const Sim3 Sinv = sim3_inverse(S);
+        cnt[0] = 0;
+        for (int i = tid; i < P.n; i += kSim3Threads) {
+            if (!(P.state[i] & 1)) continue;
+            const Pair c = load_pair(P, i);
+            double e[4];
+            pair_error(P, S, Sinv, c, e);                               // e12->computeError(); e21->computeError();
+            if (chi_of(e, (double)P.w1[i]) > P.th2 || chi_of(e + 2, (double)P.w2[i]) > P.th2) P.inlier[i] = 0;
+            else cnt[0] += 1;
+        }
+        cta_sum<1>(cnt, warp_buf, tot);
+        nIn = (int)tot[0];
+    }
+    if (tid == 0) {
+        if (enough) {
+            P.io[0] = S.r.x; P.io[1] = S.r.y; P.io[2] = S.r.z; P.io[3] = S.r.w;
+            P.io[4] = S.t[0]; P.io[5] = S.t[1]; P.io[6] = S.t[2];
+            P.io[7] = S.s;
+        }
+        P.stats[0] = it1; P.stats[1] = it2; P.stats[2] = trials; P.stats[3] = nBad1;
+        P.stats[4] = first_chi; P.stats[5] = last_chi; P.stats[6] = nIn;
+    }
+}
+
+} // namespace
+} // namespace dvm
+
+using namespace dvm;
+
+struct dvm_sim3 {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    uint8_t* d_buf = nullptr;
+    uint8_t* h_buf = nullptr; // pinned
+    size_t cap = 0;
+};
+
+extern "C" {
+
+int dvm_sim3_create(dvm_sim3** out, int device)
+{
+    DVM_REQUIRE(out != nullptr, "null argument");
+    *out = nullptr;
+    const int rc = select_device(device);
+    if (rc != DVM_OK) return rc;
+    dvm_sim3* h = new dvm_sim3;
+    h->device = device;
+    DVM_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    *out = h;
+    return DVM_OK;
+}
+
+void dvm_sim3_destroy(dvm_sim3* h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+    cudaFree(h->d_buf);
+    if (h->h_buf) cudaFreeHost(h->h_buf);
+    delete h;
+}
+
+int dvm_optimize_sim3(dvm_sim3* h, int n, const float* p1c, const float* p2c, const float* obs1, const float* obs2,
+                      const float* inv_sigma2_1, const float* inv_sigma2_2, const float* K1, const float* K2, double* s12_q,
+                      double* s12_t, double* s12_s, float th2, int fix_scale, uint8_t* inlier, int* n_in, double* stats)
+{
+    DVM_REQUIRE(h != nullptr && n_in != nullptr, "null argument");
+    *n_in = 0;
+    if (stats) for (int k = 0; k < 6; k++) stats[k] = 0;
+    DVM_REQUIRE(n >= 0, "negative size");
+    DVM_REQUIRE(K1 && K2 && s12_q && s12_t && s12_s, "null argument");
+    DVM_REQUIRE(n == 0 || (p1c && p2c && obs1 && obs2 && inv_sigma2_1 && inv_sigma2_2 && inlier), "null correspondence arrays");
+    DVM_REQUIRE(th2 > 0.0f, "th2 must be positive");
+    if (n == 0) return DVM_OK;   // no edge: optimize() does nothing and nCorrespondences - nBad < 10 returns 0
+    DVM_CUDA(cudaSetDevice(h->device));
+    size_t off = 0;
+    auto take = [&](size_t bytes) { off = (off + 255) & ~(size_t)255; size_t o = off; off += bytes; return o; };
+    const size_t o_p1 = take((size_t)n * 12), o_p2 = take((size_t)n * 12), o_o1 = take((size_t)n * 8), o_o2 = take((size_t)n * 8);
+    const size_t o_w1 = take((size_t)n * 4), o_w2 = take((size_t)n * 4), o_io = take(8 * 8);
+    const size_t upload = off;
+    const size_t o_err = take((size_t)n * 32), o_state = take((size_t)n);
+    const size_t out_begin = (off + 255) & ~(size_t)255;
+    const size_t o_inl = take((size_t)n), o_stats = take(8 * 8), o_ioo = take(8 * 8);
+    const size_t total = off + 256;
+    if (total > h->cap) {
+        DVM_CUDA(cudaStreamSynchronize(h->stream));
+        cudaFree(h->d_buf); h->d_buf = nullptr;
+        if (h->h_buf) { cudaFreeHost(h->h_buf); h->h_buf = nullptr; }
+        h->cap = 0;
+        const size_t cap = total * 2;
+        DVM_CUDA(cudaMalloc(&h->d_buf, cap));
+        DVM_CUDA(cudaHostAlloc(&h->h_buf, cap, cudaHostAllocDefault));
+        h->cap = cap;
+    }
+    uint8_t* hb = h->h_buf;
+    memcpy(hb + o_p1, p1c, (size_t)n * 12); memcpy(hb + o_p2, p2c, (size_t)n * 12);
+    memcpy(hb + o_o1, obs1, (size_t)n * 8); memcpy(hb + o_o2, obs2, (size_t)n * 8);
+    memcpy(hb + o_w1, inv_sigma2_1, (size_t)n * 4); memcpy(hb + o_w2, inv_sigma2_2, (size_t)n * 4);
+    double* io = reinterpret_cast<double*>(hb + o_io);
+    for (int k = 0; k < 4; k++) io[k] = s12_q[k];
+    for (int k = 0; k < 3; k++) io[4 + k] = s12_t[k];
+    io[7] = *s12_s;
+    DVM_CUDA(cudaMemcpyAsync(h->d_buf, hb, upload, cudaMemcpyHostToDevice, h->stream));
+    uint8_t* db = h->d_buf;
+    Sim3Dev P;
+    memset(&P, 0, sizeof(P));
+    P.n = n; P.fix_scale = fix_scale != 0;
+    P.p1 = (const float*)(db + o_p1); P.p2 = (const float*)(db + o_p2);
+    P.obs1 = (const float*)(db + o_o1); P.obs2 = (const float*)(db + o_o2);
+    P.w1 = (const float*)(db + o_w1); P.w2 = (const float*)(db + o_w2);
+    for (int k = 0; k < 4; k++) { P.K1[k] = K1[k]; P.K2[k] = K2[k]; }
+    P.delta = (double)std::sqrt(th2);   // const float deltaHuber = sqrt(th2), :1997
+    P.th2 = (double)th2;
+    P.err = (double*)(db + o_err); P.state = db + o_state;
+    P.io = (double*)(db + o_ioo); P.inlier = db + o_inl; P.stats = (double*)(db + o_stats);
+    DVM_CUDA(cudaMemcpyAsync(db + o_ioo, db + o_io, 64, cudaMemcpyDeviceToDevice, h->stream));
+    DVM_CUDA(cudaMemsetAsync(db + o_err, 0, (size_t)n * 32, h->stream));
+    DVM_LAUNCH(optimize_sim3_kernel, 1, kSim3Threads, 0, h->stream, P);
+    DVM_CUDA(cudaGetLastError());
+    DVM_CUDA(cudaMemcpyAsync(hb + out_begin, db + out_begin, off - out_begin, cudaMemcpyDeviceToHost, h->stream));
+    DVM_CUDA(cudaStreamSynchronize(h->stream));
+    const double* st = reinterpret_cast<const double*>(hb + o_stats);
+    const double* oo = reinterpret_cast<const double*>(hb + o_ioo);
+    memcpy(inlier, hb + o_inl, (size_t)n);
+    for (int k = 0; k < 4; k++) s12_q[k] = oo[k];
+    for (int k = 0; k < 3; k++) s12_t[k] = oo[4 + k];
+    *s12_s = oo[7];
+    *n_in = (int)st[6];
+    if (stats) for (int k = 0; k < 6; k++) stats[k] = st[k];
+    if (!std::isfinite(st[5])) { set_error("OptimizeSim3 produced a non-finite chi2"); return DVM_ERR_NUMERIC; }
+    return DVM_OK;
+}
+
+} // extern "C"

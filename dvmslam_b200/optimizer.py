@@ -106,3 +106,42 @@ class LocalBA:
 
     def kernel_ms(self) -> float:
         return float(self.L.dvm_lba_last_kernel_ms(self.h))
+
+
+class Sim3Optimizer:
+    """Optimizer::OptimizeSim3 (O3/src/Optimizer.cc:1960-2212) over the C-ABI (dvm_optimize_sim3)."""
+
+    def __init__(self, device: int = 0):
+        self.L = lib()
+        L = self.L
+        L.dvm_sim3_create.argtypes = [C.POINTER(_vp), C.c_int]
+        L.dvm_sim3_destroy.argtypes = [_vp]
+        L.dvm_sim3_destroy.restype = None
+        L.dvm_optimize_sim3.argtypes = [_vp, C.c_int] + [_vp] * 11 + [C.c_float, C.c_int, _vp, _ip, _vp]
+        self.h = _vp()
+        check(L.dvm_sim3_create(C.byref(self.h), device))
+
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            self.L.dvm_sim3_destroy(self.h)
+            self.h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def OptimizeSim3(self, p1c, p2c, obs1, obs2, w1, w2, K1, K2, q, t, s, th2=10.0, bFixScale=False):
+        """Flattened correspondences (see include/dvmslam_b200.h).  Returns dict(q, t, s, inlier, n_in, iters1, iters2,
+        trials, n_bad, chi_first, chi_last)."""
+        a = [_c(x, np.float32) for x in (p1c, p2c, obs1, obs2, w1, w2, K1, K2)]
+        n = len(a[4])
+        qq, tt, ss = _c(q, np.float64).copy(), _c(t, np.float64).copy(), np.array([s], np.float64)
+        inl = np.zeros(max(n, 1), np.uint8)
+        st = np.zeros(6, np.float64)
+        n_in = C.c_int()
+        check(self.L.dvm_optimize_sim3(self.h, n, *[x.ctypes.data for x in a], qq.ctypes.data, tt.ctypes.data, ss.ctypes.data,
+                                       C.c_float(th2), int(bFixScale), inl.ctypes.data, C.byref(n_in), st.ctypes.data))
+        return dict(q=qq, t=tt, s=float(ss[0]), inlier=inl[:n], n_in=n_in.value, iters1=int(st[0]), iters2=int(st[1]),
+                    trials=int(st[2]), n_bad=int(st[3]), chi_first=st[4], chi_last=st[5])

@@ -381,3 +381,56 @@ def write_vocabulary_text(path: str, v: dict) -> None:
         f.write(f"{v['k']} {v['L']}  {v['scoring']} {v['weighting']}\n")
         for p, leaf, d, w in zip(v["parent"], v["is_leaf"], v["desc"], v["weight"]):
             f.write(f"{int(p)} {int(leaf)} " + " ".join(str(int(x)) for x in d) + f" {float(w)!r}\n")
+
+
+def sim3_scene(n: int = 200, seed: int = 0, K=RPI_K, w: int = 1280, h: int = 720, scale: float = 1.3, pix_sigma: float = 1.0,
+               outlier_frac: float = 0.1, perturb=(np.deg2rad(1.0), 0.05, 0.03), not_in_kf2_frac: float = 0.2):
+    """Correspondences for Optimizer::OptimizeSim3: two keyframes of two maps whose frames differ by a similarity.  Point
+    i has camera-frame positions P1c (map 1, keyframe 1) and P2c (map 2, keyframe 2) with P1c = S12 * P2c, keypoints
+    obs1 / obs2 with octave noise and gross outliers; a fraction of the points has no keypoint in keyframe 2 (the
+    reference then uses the normalised projection of P2c as measurement and octave 0, Optimizer.cc:2118-2125).  Returns
+    float32 arrays in dvm_optimize_sim3's layout, the true S12 and a perturbed initial guess (double)."""
+    rng = np.random.default_rng(seed)
+    fx, fy, cx, cy = K
+    # true S12: moderate rotation / translation, the given scale
+    ax = rng.normal(size=3); ax /= np.linalg.norm(ax)
+    ang = np.deg2rad(rng.uniform(5, 25))
+    Kx = np.array([[0, -ax[2], ax[1]], [ax[2], 0, -ax[0]], [-ax[1], ax[0], 0]])
+    R12 = np.eye(3) + np.sin(ang) * Kx + (1 - np.cos(ang)) * Kx @ Kx
+    t12 = rng.uniform(-0.5, 0.5, 3)
+    p2, p1, o1, o2, w1, w2 = [], [], [], [], [], []
+    while len(p2) < n:
+        X2 = np.array([rng.uniform(-3, 3), rng.uniform(-2, 2), rng.uniform(2, 10)])
+        X1 = scale * (R12 @ X2) + t12
+        if X1[2] < 0.5:
+            continue
+        u1, v1 = fx * X1[0] / X1[2] + cx, fy * X1[1] / X1[2] + cy
+        u2, v2 = fx * X2[0] / X2[2] + cx, fy * X2[1] / X2[2] + cy
+        if not (0 <= u1 < w and 0 <= v1 < h and 0 <= u2 < w and 0 <= v2 < h):
+            continue
+        oc1, oc2 = int(rng.integers(0, 8)), int(rng.integers(0, 8))
+        d1 = rng.normal(0, pix_sigma * 1.2 ** oc1, 2)
+        d2 = rng.normal(0, pix_sigma * 1.2 ** oc2, 2)
+        if rng.random() < outlier_frac:
+            d1 = rng.uniform(-60, 60, 2)
+        if rng.random() < not_in_kf2_frac:
+            oc2 = 0
+            ob2 = (np.float32(X2[0]) * (np.float32(1) / np.float32(X2[2])), np.float32(X2[1]) * (np.float32(1) / np.float32(X2[2])))
+        else:
+            ob2 = (u2 + d2[0], v2 + d2[1])
+        p2.append(X2); p1.append(X1)
+        o1.append((u1 + d1[0], v1 + d1[1])); o2.append(ob2)
+        w1.append(np.float32(1.0) / (np.float32(1.2) ** oc1) ** 2)
+        w2.append(np.float32(1.0) / (np.float32(1.2) ** oc2) ** 2)
+    q_true = quat_from_R(R12)
+    # initial guess: exp(noise) * S12
+    dax = rng.normal(size=3); dax /= np.linalg.norm(dax)
+    da = perturb[0]
+    Kd = np.array([[0, -dax[2], dax[1]], [dax[2], 0, -dax[0]], [-dax[1], dax[0], 0]])
+    Rd = np.eye(3) + np.sin(da) * Kd + (1 - np.cos(da)) * Kd @ Kd
+    R0 = Rd @ R12
+    t0 = t12 + rng.normal(0, perturb[1], 3)
+    s0 = scale * (1 + perturb[2])
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    return dict(p1c=f32(p1), p2c=f32(p2), obs1=f32(o1), obs2=f32(o2), w1=f32(w1), w2=f32(w2), K=f32(K),
+                q_true=q_true, t_true=t12, s_true=scale, q0=quat_from_R(R0).astype(np.float64), t0=t0.astype(np.float64), s0=float(s0))

@@ -440,6 +440,30 @@ DVM_API int dvm_merge_ba(dvm_lba* h, int nc, float* cam_q, float* cam_t, const u
                          int ne, const int32_t* edge_cam, const int32_t* edge_pt, const float* edge_obs,
                          const float* edge_inv_sigma2, const float* K, const volatile uint8_t* abort_flag,
                          double* edge_chi2, uint8_t* edge_bad, double* stats, int* iters_done);
+/* ------------------------------------------------------------------------------------------------
+ * int Optimizer::OptimizeSim3(KeyFrame* pKF1, KeyFrame* pKF2, vector<MapPoint*>& vpMatches1, g2o::Sim3& g2oS12,
+ *                             const float th2, const bool bFixScale, Eigen::Matrix<double,7,7>& mAcumHessian,
+ *                             const bool bAllPoints)            (O3/src/Optimizer.cc:1960-2212)
+ * called by LoopClosing::DetectCommonRegionsFromBoW / DetectAndReffineSim3FromLastKF for loop and merge candidates.
+ * The caller flattens the correspondences that receive an edge pair (:2008-2146):
+ *   p1c[n*3], p2c[n*3]: P3D1c = R1w*P1w + t1w and P3D2c = R2w*P2w + t2w as float;
+ *   obs1[n*2]: kpUn1.pt;  obs2[n*2]: kpUn2.pt, or (x/z, y/z) of P3D2c when the point has no keypoint in KF2 (:2118-2125);
+ *   inv_sigma2_1/2[n]: mvInvLevelSigma2[octave] (octave 0 for the projected case);  K1/K2: fx, fy, cx, cy of pCamera1/2;
+ *   s12_q (x,y,z,w) / s12_t / s12_s: g2oS12 in/out as double;  th2 and fix_scale as the reference.
+ * Runs optimize(5) with Huber delta (float)sqrt(th2), drops the pairs with chi2 > th2 on either edge and the robust
+ * kernels of the rest, optimize(10 or 5), and the final inlier test -- g2o's Levenberg-Marquardt with the numeric
+ * (central-difference, delta 1e-9) Jacobians the reference's edges get -- in one kernel launch.
+ * Outputs: inlier[n] = 0 where the reference resets vpMatches1[idx]; *n_in = the return value (0 with s12 untouched when
+ * fewer than 10 correspondences survive the first pass); stats[6] (may be NULL) = {LM iterations pass 1, pass 2, LM
+ * trials, pairs dropped after pass 1, initial robust chi2, final chi2}.  mAcumHessian is zero in the reference (:2191). */
+typedef struct dvm_sim3 dvm_sim3;
+DVM_API int dvm_sim3_create(dvm_sim3** out, int device);
+DVM_API void dvm_sim3_destroy(dvm_sim3* h);
+DVM_API int dvm_optimize_sim3(dvm_sim3* h, int n, const float* p1c, const float* p2c, const float* obs1, const float* obs2,
+                              const float* inv_sigma2_1, const float* inv_sigma2_2, const float* K1, const float* K2,
+                              double* s12_q, double* s12_t, double* s12_s, float th2, int fix_scale, uint8_t* inlier,
+                              int* n_in, double* stats);
+
 /* Device time of the last dvm_local_ba kernel in milliseconds (CUDA events on the solver's stream). */
 DVM_API float dvm_lba_last_kernel_ms(const dvm_lba* h);
 

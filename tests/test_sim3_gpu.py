@@ -1,0 +1,51 @@
+"""GPU parity of Optimizer::OptimizeSim3 against the float64 oracle.  Both differentiate numerically with delta 1e-9 as
+g2o does, which amplifies last-bit differences of sin/cos/exp and of the summation order by 1e9 in the Jacobian, so the
+tolerances are: Sim3 rotation (quaternion components) and scale within 1e-6, translation within 1e-5 m, final chi2 within
+1e-5 relative, same LM iteration counts, and the same inlier set up to pairs whose chi2 lies within 1e-4 relative of th2."""
+import numpy as np
+import pytest
+
+from dvmslam_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _args(S):
+    return (S["p1c"], S["p2c"], S["obs1"], S["obs2"], S["w1"], S["w2"], S["K"], S["K"], S["q0"], S["t0"], S["s0"])
+
+
+@pytest.fixture(scope="module")
+def opt():
+    from dvmslam_b200.optimizer import Sim3Optimizer
+
+    o = Sim3Optimizer()
+    yield o
+    o.close()
+
+
+@pytest.mark.parametrize("n,seed,scale,fix,th2", [(250, 0, 1.3, False, 10.0), (60, 1, 0.8, False, 10.0), (200, 2, 1.0, True, 10.0),
+                                                   (1500, 3, 1.1, False, 10.0), (30, 4, 1.0, True, 7.0), (400, 5, 2.0, False, 10.0)])
+def test_optimize_sim3_matches_oracle(opt, n, seed, scale, fix, th2):
+    from oracle.sim3 import optimize_sim3
+
+    S = synth.sim3_scene(n, seed=seed, scale=scale, perturb=(np.deg2rad(1.0), 0.05, 0.0 if fix else 0.03))
+    r0 = optimize_sim3(*_args(S), th2=th2, fix_scale=fix)
+    r1 = opt.OptimizeSim3(*_args(S), th2=th2, bFixScale=fix)
+    assert (r1["iters1"], r1["iters2"], r1["n_bad"]) == (r0["iters1"], r0["iters2"], r0["n_bad"]), (r0, r1)
+    assert abs(r1["chi_first"] - r0["chi_first"]) <= 1e-9 * r0["chi_first"]
+    assert abs(r1["chi_last"] - r0["chi_last"]) <= 1e-5 * r0["chi_last"]
+    assert np.abs(r1["q"] - r0["q"]).max() < 1e-6 and abs(r1["s"] - r0["s"]) < 1e-6 and np.abs(r1["t"] - r0["t"]).max() < 1e-5
+    if fix:
+        assert r1["s"] == S["s0"]
+    assert abs(r1["n_in"] - r0["n_in"]) <= 1 and int((r0["inlier"] != r1["inlier"]).sum()) <= 1
+    assert r1["n_in"] == int(r1["inlier"].sum()) and r1["n_in"] >= 10
+
+
+def test_too_few_survivors(opt):
+    S = synth.sim3_scene(12, seed=2, outlier_frac=0.6, not_in_kf2_frac=0.3)
+    r = opt.OptimizeSim3(*_args(S), th2=10.0)
+    assert r["n_in"] == 0 and r["iters2"] == 0 and 12 - r["n_bad"] < 10
+    assert np.array_equal(r["q"], S["q0"]) and np.array_equal(r["t"], S["t0"]) and r["s"] == S["s0"]
+    assert int((r["inlier"] == 0).sum()) == r["n_bad"]
+    r = opt.OptimizeSim3(*[a[:0] if i < 6 else a for i, a in enumerate(_args(S))], th2=10.0)
+    assert r["n_in"] == 0
