@@ -59,4 +59,12 @@ struct LbaHandle {
     ~LbaHandle() { dvm_lba_destroy(h); }
 };
 
+struct Sim3Handle {
+    dvm_sim3* h = nullptr;
+    Sim3Handle() = default;
+    Sim3Handle(const Sim3Handle&) = delete;
+    Sim3Handle& operator=(const Sim3Handle&) = delete;
+    ~Sim3Handle() { dvm_sim3_destroy(h); }
+};
+
 } // namespace dvm_host

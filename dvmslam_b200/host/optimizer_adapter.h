@@ -369,4 +369,77 @@ void LocalBundleAdjustment(dvm_lba* solver, KeyFrameT* pMainKF, std::vector<KeyF
         if (!pMPi->isBad()) pMPi->UpdateNormalAndDepth();
 }
 
+// ---------------------------------------------------------------------------------------------------
+// int Optimizer::OptimizeSim3(KeyFrame* pKF1, KeyFrame* pKF2, vector<MapPoint*>& vpMatches1, g2o::Sim3& g2oS12,
+//                             const float th2, const bool bFixScale, Eigen::Matrix<double,7,7>& mAcumHessian,
+//                             const bool bAllPoints)   :1960-2212
+// solver: one dvm_sim3 context per loop-closing thread (dvm_sim3_create).  Sim3T is g2o::Sim3 (rotation(), translation(),
+// scale() with mutable references), Mat77T an Eigen 7x7 (setZero()).  Pinhole cameras (KeyFrame::fx..cy).
+// ---------------------------------------------------------------------------------------------------
+template <class KeyFrameT, class MapPointT, class Sim3T, class Mat77T>
+int OptimizeSim3(dvm_sim3* solver, KeyFrameT* pKF1, KeyFrameT* pKF2, std::vector<MapPointT*>& vpMatches1, Sim3T& g2oS12,
+                 const float th2, const bool bFixScale, Mat77T& mAcumHessian, const bool bAllPoints)
+{
+    const auto R1w = pKF1->GetRotation();
+    const auto t1w = pKF1->GetTranslation();
+    const auto R2w = pKF2->GetRotation();
+    const auto t2w = pKF2->GetTranslation();
+    // Eigen's fixed-size float product R * p + t, coefficient by coefficient
+    auto to_camera = [](const decltype(R1w)& R, const decltype(t1w)& t, const decltype(t1w)& p, float out[3]) {
+        for (int r = 0; r < 3; r++) out[r] = (R(r, 0) * p(0) + R(r, 1) * p(1) + R(r, 2) * p(2)) + t(r);
+    };
+    const int N = static_cast<int>(vpMatches1.size());
+    const std::vector<MapPointT*> vpMapPoints1 = pKF1->GetMapPointMatches();
+    std::vector<float> p1c, p2c, obs1, obs2, w1, w2;
+    std::vector<int> index;
+    for (int i = 0; i < N; i++) {                                                         // :2008-2146
+        if (!vpMatches1[i]) continue;
+        MapPointT* pMP1 = vpMapPoints1[i];
+        MapPointT* pMP2 = vpMatches1[i];
+        const int i2 = std::get<0>(pMP2->GetIndexInKeyFrame(pKF2));
+        if (!pMP1 || !pMP2) continue;                   // the reference only adds an unused fixed vertex here (:2045-2060)
+        if (pMP1->isBad() || pMP2->isBad()) continue;                                     // nBadMPs
+        float P3D1c[3], P3D2c[3];
+        to_camera(R1w, t1w, pMP1->GetWorldPos(), P3D1c);
+        to_camera(R2w, t2w, pMP2->GetWorldPos(), P3D2c);
+        if (i2 < 0 && !bAllPoints) continue;
+        if (P3D2c[2] < 0) continue;
+        const auto& kpUn1 = pKF1->mvKeysUn[i];
+        float o2x, o2y;
+        int octave2;
+        if (i2 >= 0) {
+            const auto& kpUn2 = pKF2->mvKeysUn[i2];
+            o2x = kpUn2.pt.x; o2y = kpUn2.pt.y; octave2 = kpUn2.octave;
+        } else {   // cv::KeyPoint(cv::Point2f(x, y), pMP2->mnTrackScaleLevel): that argument is the SIZE, the octave stays 0
+            const float invz = 1 / P3D2c[2];
+            o2x = P3D2c[0] * invz; o2y = P3D2c[1] * invz; octave2 = 0;
+        }
+        for (int k = 0; k < 3; k++) { p1c.push_back(P3D1c[k]); p2c.push_back(P3D2c[k]); }
+        obs1.push_back(kpUn1.pt.x); obs1.push_back(kpUn1.pt.y);
+        obs2.push_back(o2x); obs2.push_back(o2y);
+        w1.push_back(pKF1->mvInvLevelSigma2[kpUn1.octave]);
+        w2.push_back(pKF2->mvInvLevelSigma2[octave2]);
+        index.push_back(i);
+    }
+    const float K1[4] = { pKF1->fx, pKF1->fy, pKF1->cx, pKF1->cy };
+    const float K2[4] = { pKF2->fx, pKF2->fy, pKF2->cx, pKF2->cy };
+    double q[4] = { g2oS12.rotation().x(), g2oS12.rotation().y(), g2oS12.rotation().z(), g2oS12.rotation().w() };
+    double t[3] = { g2oS12.translation()(0), g2oS12.translation()(1), g2oS12.translation()(2) };
+    double s = g2oS12.scale();
+    std::vector<uint8_t> inlier(index.size() ? index.size() : 1);
+    int nIn = 0;
+    double stats[6] = { 0, 0, 0, 0, 0, 0 };
+    check(dvm_optimize_sim3(solver, static_cast<int>(index.size()), p1c.data(), p2c.data(), obs1.data(), obs2.data(), w1.data(),
+                            w2.data(), K1, K2, q, t, &s, th2, bFixScale ? 1 : 0, inlier.data(), &nIn, stats),
+          "Optimizer::OptimizeSim3");
+    for (size_t e = 0; e < index.size(); e++)
+        if (!inlier[e]) vpMatches1[index[e]] = static_cast<MapPointT*>(nullptr);          // :2160, :2202
+    if (static_cast<int>(index.size()) - static_cast<int>(stats[3]) < 10) return 0;   // nCorrespondences - nBad < 10: g2oS12 untouched (:2183)
+    mAcumHessian.setZero();                                                               // :2191
+    g2oS12.rotation().x() = q[0]; g2oS12.rotation().y() = q[1]; g2oS12.rotation().z() = q[2]; g2oS12.rotation().w() = q[3];
+    for (int k = 0; k < 3; k++) g2oS12.translation()(k) = t[k];
+    g2oS12.scale() = s;
+    return nIn;
+}
+
 } // namespace dvm_host

@@ -70,6 +70,20 @@ sol = LocalBA(100)
 g = med(lambda: sol.BundleAdjustment(*ag, nIterations=20, bRobust=True), 5)
 o = med(lambda: local_ba(*ag, iterations=20, huber_delta=float(np.float32(np.sqrt(5.99)))), 2)
 rows.append((f"BundleAdjustment (global: 96 + 1 keyframes, 3000 points, {len(Sg['edge_cam'])} obs, 20 its)", g, o))
+from oracle.lba import merge_ba
+Sm = synth.ba_scene(30, 10, 3000, seed=30)
+am = (Sm["cam_q"], Sm["cam_t"], Sm["cam_fixed"], Sm["pts"], Sm["edge_cam"], Sm["edge_pt"], Sm["edge_obs"], Sm["edge_w"], Sm["K"])
+g = med(lambda: sol.MergeBundleAdjustment(*am), 5)
+o = med(lambda: merge_ba(*am), 2)
+rows.append((f"welding BA (30 adjust + 10 fixed KFs, {len(Sm['pts'])} points, {len(Sm['edge_cam'])} obs, 5 + 10 its)", g, o))
+from dvmslam_b200.optimizer import Sim3Optimizer
+from oracle.sim3 import optimize_sim3
+Ss = synth.sim3_scene(300, seed=0, scale=1.3)
+as3 = (Ss["p1c"], Ss["p2c"], Ss["obs1"], Ss["obs2"], Ss["w1"], Ss["w2"], Ss["K"], Ss["K"], Ss["q0"], Ss["t0"], Ss["s0"])
+s3 = Sim3Optimizer()
+g = med(lambda: s3.OptimizeSim3(*as3, th2=10.0, bFixScale=False))
+o = med(lambda: optimize_sim3(*as3, th2=10.0, fix_scale=False), 5)
+rows.append(("OptimizeSim3 (300 correspondences, 5 + 10 its, numeric Jacobians)", g, o))
 print(f"{'operator':62s} {'B200 call us':>12s} {'oracle 1 thread us':>18s} {'ratio':>7s}")
 for name, g, o in rows:
     print(f"{name:62s} {g:12.1f} {o:18.1f} {o / g:7.1f}")

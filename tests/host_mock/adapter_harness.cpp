@@ -528,4 +528,52 @@ int hm_merge_ba(int nc, float* cam_q, float* cam_t, const uint8_t* cam_fixed, in
     });
 }
 
+// Optimizer::OptimizeSim3 on flat correspondences: both keyframes sit at the identity of their own map, so a map point's
+// world position is its camera-frame position; point i of KF1 is matched to map point i of map 2, which is observed in
+// KF2 (keypoint i) iff in_kf2[i].  matched[i] = vpMatches1[i] != NULL afterwards; *hessian_zero = mAcumHessian was zeroed.
+int hm_optimize_sim3(int n, const float* p1c, const float* p2c, const float* obs1, const float* obs2, const int* oct1,
+                     const int* oct2, const uint8_t* in_kf2, const float* invsig2, int nlevels, double* q, double* t, double* sc,
+                     float th2, int fix_scale, int all_points, uint8_t* matched, int* hessian_zero)
+{
+    Map map1, map2;
+    KeyFrame kf1, kf2;
+    kf1.map = &map1; kf2.map = &map2; kf1.mnId = 1; kf2.mnId = 2;
+    for (KeyFrame* k : { &kf1, &kf2 }) {
+        k->fx = g_K[0]; k->fy = g_K[1]; k->cx = g_K[2]; k->cy = g_K[3];
+        k->mvInvLevelSigma2.assign(invsig2, invsig2 + nlevels);
+    }
+    std::vector<std::unique_ptr<MapPoint>> m1(n), m2(n);
+    std::vector<MapPoint*> vpMatches1(n);
+    for (int i = 0; i < n; i++) {
+        m1[i].reset(new MapPoint); m2[i].reset(new MapPoint);
+        m1[i]->map = &map1; m2[i]->map = &map2;
+        for (int k = 0; k < 3; k++) { m1[i]->pos(k) = p1c[3 * i + k]; m2[i]->pos(k) = p2c[3 * i + k]; }
+        kf1.mvKeysUn.push_back(cv::KeyPoint(obs1[2 * i], obs1[2 * i + 1], 31.f, 0.f, 1.f, oct1[i]));
+        kf1.mapPoints.push_back(m1[i].get());
+        kf2.mvKeysUn.push_back(cv::KeyPoint(obs2[2 * i], obs2[2 * i + 1], 31.f, 0.f, 1.f, oct2[i]));
+        kf2.mapPoints.push_back(in_kf2[i] ? m2[i].get() : nullptr);
+        if (in_kf2[i]) m2[i]->observations[&kf2] = std::make_tuple(i, -1);
+        vpMatches1[i] = m2[i].get();
+    }
+    kf1.N = kf2.N = n;
+    mock::Sim3 S;
+    for (int k = 0; k < 4; k++) S.r.q[k] = q[k];
+    for (int k = 0; k < 3; k++) S.t.v[k] = t[k];
+    S.s = *sc;
+    mock::Mat77 H;
+    dvm_host::Sim3Handle solver;
+    return guarded([&] {
+        dvm_host::check(dvm_sim3_create(&solver.h, dvm_host::device_from_env()), "dvm_sim3_create");
+        const int nIn = dvm_host::OptimizeSim3<KeyFrame, MapPoint, mock::Sim3, mock::Mat77>(solver.h, &kf1, &kf2, vpMatches1, S, th2,
+                                                                                            fix_scale != 0, H, all_points != 0);
+        for (int i = 0; i < n; i++) matched[i] = vpMatches1[i] != nullptr;
+        for (int k = 0; k < 4; k++) q[k] = S.r.q[k];
+        for (int k = 0; k < 3; k++) t[k] = S.t.v[k];
+        *sc = S.s;
+        *hessian_zero = 1;
+        for (double x : H.m) if (x != 0) *hessian_zero = 0;
+        return nIn;
+    });
+}
+
 } // extern "C"

@@ -46,6 +46,27 @@ struct SE3f {
     }
 };
 
+// g2o::Sim3: rotation() (Eigen::Quaterniond), translation() (Vector3d), scale(), all with mutable access
+struct QuatD {
+    double q[4] = { 0, 0, 0, 1 };
+    double& x() { return q[0]; } double& y() { return q[1]; } double& z() { return q[2]; } double& w() { return q[3]; }
+};
+struct Vec3D {
+    double v[3] = { 0, 0, 0 };
+    double& operator()(int i) { return v[i]; }
+};
+struct Sim3 {
+    QuatD r; Vec3D t; double s = 1;
+    QuatD& rotation() { return r; }
+    Vec3D& translation() { return t; }
+    double& scale() { return s; }
+};
+struct Mat77 {
+    double m[49];
+    Mat77() { for (double& x : m) x = -1; }
+    void setZero() { for (double& x : m) x = 0; }
+};
+
 struct Map;
 struct KeyFrame;
 
@@ -73,6 +94,11 @@ struct MapPoint {
     float GetMinDistanceInvariance() const { return minDistInv; }
     float GetMaxDistanceInvariance() const { return maxDistInv; }
     bool IsInKeyFrame(KeyFrame* kf) const { return observations.count(kf) != 0; }
+    std::tuple<int, int> GetIndexInKeyFrame(KeyFrame* kf) const
+    {
+        const auto it = observations.find(kf);
+        return it == observations.end() ? std::make_tuple(-1, -1) : it->second;
+    }
     void AddObservation(KeyFrame* kf, int idx) { observations[kf] = std::make_tuple(idx, -1); nObs++; }
     void Replace(MapPoint* other) { replacedBy = other; bad = true; }
     Vec3 GetWorldPos() const { return pos; }
@@ -131,6 +157,8 @@ struct KeyFrame {
     }
     std::vector<KeyFrame*> GetVectorCovisibleKeyFrames() const { return covisible; }
     SE3f GetPose() const { return Tcw; }
+    Mat3 GetRotation() const { return Tcw.rotationMatrix(); }
+    Vec3 GetTranslation() const { return Tcw.t; }
     void SetPose(const SE3f& T) { Tcw = T; }
     bool isBad() const { return bad; }
     Map* GetMap() const { return map; }

@@ -472,3 +472,40 @@ def test_merge_ba_adapter_matches_direct_call(libs):
     assert np.abs(pts[seen] - r["pts"][seen]).max() < 1e-4
     fixed = B["cam_fixed"].astype(bool)
     assert np.array_equal(ct[fixed], _c(B["cam_t"], np.float32)[fixed])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("all_points", [1, 0])
+def test_optimize_sim3_adapter_matches_direct_call(libs, all_points):
+    """Optimizer::OptimizeSim3 through the adapter (keyframes, map points, vpMatches1, g2o::Sim3 in/out) against
+    dvm_optimize_sim3 on the same correspondences.  bAllPoints == false leaves out the points without a keypoint in KF2
+    (:2087-2091); with bAllPoints they enter with a normalised measurement and octave 0 (:2118-2125)."""
+    from dvmslam_b200.optimizer import Sim3Optimizer
+
+    H, _ = libs
+    S = synth.sim3_scene(180, seed=7, scale=1.2)
+    H.hm_set_camera(_p(_c(S["K"], np.float32)), _p(np.array([0, 0, 1280, 720], np.float32)))
+    invsig2 = np.array([1.0 / (np.float32(1.2) ** (2 * l)) for l in range(8)], np.float32)
+    oct1 = np.array([int(np.argmin(np.abs(invsig2 - w))) for w in S["w1"]], np.int32)
+    oct2 = np.array([int(np.argmin(np.abs(invsig2 - w))) for w in S["w2"]], np.int32)
+    in_kf2 = (np.abs(S["obs2"]).max(axis=1) >= 3.0).astype(np.uint8)     # the scene's normalised measurements: not in KF2
+    assert 0 < in_kf2.sum() < len(in_kf2)
+    keep = np.ones(len(in_kf2), bool) if all_points else in_kf2.astype(bool)
+    o = Sim3Optimizer()
+    r = o.OptimizeSim3(S["p1c"][keep], S["p2c"][keep], S["obs1"][keep], S["obs2"][keep], invsig2[oct1][keep], invsig2[oct2][keep],
+                       S["K"], S["K"], S["q0"], S["t0"], S["s0"], th2=10.0, bFixScale=False)
+    o.close()
+    q, t, s = S["q0"].copy(), S["t0"].copy(), C.c_double(S["s0"])
+    matched = np.zeros(len(in_kf2), np.uint8)
+    hz = C.c_int(-1)
+    H.hm_optimize_sim3.argtypes = [C.c_int] + [_vp] * 8 + [C.c_int, _vp, _vp, C.POINTER(C.c_double), C.c_float, C.c_int, C.c_int, _vp,
+                                                            _ip]
+    rc = H.hm_optimize_sim3(len(in_kf2), _p(S["p1c"]), _p(S["p2c"]), _p(S["obs1"]), _p(S["obs2"]), _p(oct1), _p(oct2), _p(in_kf2),
+                            _p(invsig2), 8, _p(q), _p(t), C.byref(s), 10.0, 0, all_points, _p(matched), C.byref(hz))
+    assert rc == r["n_in"] and rc >= 10, (rc, r["n_in"], H.hm_last_error())
+    assert hz.value == 1
+    assert np.array_equal(q, r["q"]) and np.array_equal(t, r["t"]) and s.value == r["s"]     # same inputs, same kernel
+    expect = np.zeros(len(in_kf2), np.uint8)
+    expect[keep] = r["inlier"]
+    expect[~keep] = 1                                   # never entered the graph: the match is left alone
+    assert np.array_equal(matched, expect)
