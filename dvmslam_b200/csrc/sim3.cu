@@ -8,7 +8,8 @@
 //
 // A few hundred correspondences and a 7x7 system: latency-bound, one CTA.  Every thread carries the estimate and the LM
 // state in registers and derives them from the same shared-memory sums, so the control flow is uniform without
-// broadcasting; the per-correspondence work (28 projections per linearisation) is spread over the threads and reduced
+// broadcasting; the numeric Jacobians (28 projections per correspondence and linearisation) are spread over the threads one
+// (correspondence, dimension) at a time, the normal equations are accumulated one correspondence per thread and reduced
 // with warp shuffles + one shared-memory stage in a fixed order (deterministic).
 #include "common.cuh"
 #include <math_constants.h>
@@ -17,7 +18,7 @@
 namespace dvm {
 namespace {
 
-constexpr int kSim3Threads = 256;
+constexpr int kSim3Threads = 512;
 constexpr int kSim3Warps = kSim3Threads / 32;
 
 struct Quat { double x, y, z, w; };
@@ -29,6 +30,7 @@ struct Sim3Dev {
     double K1[4], K2[4];
     double delta, th2;
     double* err;        // [n*4] the edges' _error: e12 (2), e21 (2)
+    double* jac;        // [n*28] numeric Jacobians of the pair's four error components (row-major 4 x 7)
     uint8_t* state;     // [n] bit 0: pair still in the graph, bit 1: still carries its Huber kernel
     double* io;         // [8] q (x,y,z,w), t, s: in/out
     uint8_t* inlier;    // [n] out
@@ -311,27 +313,36 @@ __global__ void __launch_bounds__(kSim3Threads, 1) optimize_sim3_kernel(Sim3Dev 
                 pert[(tid < 7 ? 7 : 21) + d] = sim3_inverse(T);
             }
             __syncthreads();
-            // buildSystem: H (upper triangle, 28) and b (7)
+            // buildSystem, phase A: one (pair, dimension) per work item -- the pair's four error components at the two
+            // perturbed estimates of that dimension give one column of its Jacobians
+            const double scalar = 1.0 / (2 * 1e-9);
+            for (int w = tid; w < P.n * 7; w += kSim3Threads) {
+                const int i = w / 7, d = w - 7 * i;
+                if (!(P.state[i] & 1)) continue;
+                const Pair c = load_pair(P, i);
+                double ep[4], em[4];
+                pair_error(P, pert[d], pert[7 + d], c, ep);
+                pair_error(P, pert[14 + d], pert[21 + d], c, em);
+#pragma unroll
+                for (int r = 0; r < 4; r++) P.jac[(size_t)i * 28 + r * 7 + d] = scalar * (ep[r] - em[r]);
+            }
+            __syncthreads();
+            // phase B: one pair per thread -- H (upper triangle, 28) and b (7)
             double acc[35];
 #pragma unroll
             for (int k = 0; k < 35; k++) acc[k] = 0;
-            const double scalar = 1.0 / (2 * 1e-9);
             for (int i = tid; i < P.n; i += kSim3Threads) {
                 const uint8_t st = P.state[i];
                 if (!(st & 1)) continue;
-                const Pair c = load_pair(P, i);
-                double J[4][7];
-#pragma unroll
-                for (int d = 0; d < 7; d++) {
-                    double ep[4], em[4];
-                    pair_error(P, pert[d], pert[7 + d], c, ep);
-                    pair_error(P, pert[14 + d], pert[21 + d], c, em);
-#pragma unroll
-                    for (int r = 0; r < 4; r++) J[r][d] = scalar * (ep[r] - em[r]);
-                }
                 const bool rob = st & 2;
 #pragma unroll
                 for (int half = 0; half < 2; half++) {
+                    double J0[7], J1[7];
+#pragma unroll
+                    for (int a = 0; a < 7; a++) {
+                        J0[a] = P.jac[(size_t)i * 28 + (2 * half) * 7 + a];
+                        J1[a] = P.jac[(size_t)i * 28 + (2 * half + 1) * 7 + a];
+                    }
                     const double om = half == 0 ? (double)P.w1[i] : (double)P.w2[i];
                     const double e0 = P.err[4 * i + 2 * half], e1 = P.err[4 * i + 2 * half + 1];
                     const double chi = e0 * (om * e0) + e1 * (om * e1);
@@ -341,10 +352,9 @@ __global__ void __launch_bounds__(kSim3Threads, 1) optimize_sim3_kernel(Sim3Dev 
                     int idx = 0;
 #pragma unroll
                     for (int a = 0; a < 7; a++) {
-                        acc[28 + a] += J[2 * half][a] * r0 + J[2 * half + 1][a] * r1;
+                        acc[28 + a] += J0[a] * r0 + J1[a] * r1;
 #pragma unroll
-                        for (int b2 = a; b2 < 7; b2++)
-                            acc[idx++] += J[2 * half][a] * wo * J[2 * half][b2] + J[2 * half + 1][a] * wo * J[2 * half + 1][b2];
+                        for (int b2 = a; b2 < 7; b2++) acc[idx++] += J0[a] * wo * J0[b2] + J1[a] * wo * J1[b2];
                     }
                 }
             }
@@ -505,7 +515,7 @@ int dvm_optimize_sim3(dvm_sim3* h, int n, const float* p1c, const float* p2c, co
     const size_t o_p1 = take((size_t)n * 12), o_p2 = take((size_t)n * 12), o_o1 = take((size_t)n * 8), o_o2 = take((size_t)n * 8);
     const size_t o_w1 = take((size_t)n * 4), o_w2 = take((size_t)n * 4), o_io = take(8 * 8);
     const size_t upload = off;
-    const size_t o_err = take((size_t)n * 32), o_state = take((size_t)n);
+    const size_t o_err = take((size_t)n * 32), o_state = take((size_t)n), o_jac = take((size_t)n * 28 * 8);
     const size_t out_begin = (off + 255) & ~(size_t)255;
     const size_t o_inl = take((size_t)n), o_stats = take(8 * 8), o_ioo = take(8 * 8);
     const size_t total = off + 256;
@@ -538,7 +548,7 @@ int dvm_optimize_sim3(dvm_sim3* h, int n, const float* p1c, const float* p2c, co
     for (int k = 0; k < 4; k++) { P.K1[k] = K1[k]; P.K2[k] = K2[k]; }
     P.delta = (double)std::sqrt(th2);   // const float deltaHuber = sqrt(th2), :1997
     P.th2 = (double)th2;
-    P.err = (double*)(db + o_err); P.state = db + o_state;
+    P.err = (double*)(db + o_err); P.state = db + o_state; P.jac = (double*)(db + o_jac);
     P.io = (double*)(db + o_ioo); P.inlier = db + o_inl; P.stats = (double*)(db + o_stats);
     DVM_CUDA(cudaMemcpyAsync(db + o_ioo, db + o_io, 64, cudaMemcpyDeviceToDevice, h->stream));
     DVM_CUDA(cudaMemsetAsync(db + o_err, 0, (size_t)n * 32, h->stream));
