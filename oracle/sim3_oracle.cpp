@@ -10,8 +10,20 @@
  *   O3/Thirdparty/g2o/g2o/core/optimization_algorithm_levenberg.cpp:59-188, sparse_optimizer.cpp:349-413   LM
  *   O3/Thirdparty/g2o/g2o/solvers/linear_solver_dense.h   dense LDL^T of the 7x7 system
  *
- * Parity unpinned: the reference holds no fixture for this function; self-checks in tests/test_sim3_oracle.py
- * (recovery of a planted Sim3, fixed-scale column, outlier removal). */
+ *   O3/src/Optimizer.cc:1389-1651, O3/Thirdparty/g2o/g2o/types/types_seven_dof_expmap.h:93-117   the solve of
+ *                                                 OptimizeEssentialGraph (EdgeSim3 pose graph; ORACLE ONLY so far)
+ *
+ * A property of the reference worth knowing (sim3.h, both in Sim3(update) and in log()): in the small-rotation branch
+ * with |sigma| >= 1e-5 the coefficient B = ((0.5 sigma^2 - sigma + 1) s) / sigma^3 has no finite limit (it is ~1/sigma^3),
+ * so W = A Omega + B Omega^2 + C I is dominated by B Omega^2 whenever the rotation is small but not zero (log(): below
+ * 4.5e-3 rad).  log() then returns an upsilon that is blind to the two translation directions orthogonal to omega: after
+ * the first LM iteration of an essential-graph optimisation (errors spread thinly over the edges, scales no longer 1) H is
+ * singular to working precision, and with lambda = 1e-16 the next iteration's ten trials all fail and g2o terminates.
+ * The restatement keeps the formula as it is: that behaviour IS the reference's.
+ *
+ * Parity unpinned: the reference holds no fixture for these functions; self-checks in tests/test_sim3_oracle.py
+ * (recovery of a planted Sim3, fixed-scale column, outlier removal, exp/log round trip, loop-error distribution). */
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <limits>
@@ -139,6 +151,96 @@ void sim3_map(const Sim3& S, const double X[3], double out[3])
     double rx[3];
     quat_rotate(S.r, X, rx);
     for (int i = 0; i < 3; i++) out[i] = S.s * rx[i] + S.t[i];
+}
+
+void quat_to_matrix(const Quat& q, double R[9]) /* Eigen toRotationMatrix */
+{
+    const double tx = 2 * q.x, ty = 2 * q.y, tz = 2 * q.z;
+    const double twx = tx * q.w, twy = ty * q.w, twz = tz * q.w;
+    const double txx = tx * q.x, txy = ty * q.x, txz = tz * q.x;
+    const double tyy = ty * q.y, tyz = tz * q.y, tzz = tz * q.z;
+    R[0] = 1 - (tyy + tzz); R[1] = txy - twz; R[2] = txz + twy;
+    R[3] = txy + twz; R[4] = 1 - (txx + tzz); R[5] = tyz - twx;
+    R[6] = txz - twy; R[7] = tyz + twx; R[8] = 1 - (txx + tyy);
+}
+/* W.lu().solve(t): 3x3 LU with partial pivoting (Eigen::PartialPivLU) */
+void lu_solve3(const double W[9], const double t[3], double x[3])
+{
+    double A[9], b[3] = { t[0], t[1], t[2] };
+    for (int i = 0; i < 9; i++) A[i] = W[i];
+    int piv[3] = { 0, 1, 2 };
+    for (int k = 0; k < 3; k++) {
+        int best = k;
+        for (int r = k + 1; r < 3; r++)
+            if (std::fabs(A[piv[r] * 3 + k]) > std::fabs(A[piv[best] * 3 + k])) best = r;
+        std::swap(piv[k], piv[best]);
+        const double* pk = &A[piv[k] * 3];
+        for (int r = k + 1; r < 3; r++) {
+            double* pr = &A[piv[r] * 3];
+            const double f = pr[k] / pk[k];
+            pr[k] = f;
+            for (int c = k + 1; c < 3; c++) pr[c] -= f * pk[c];
+        }
+    }
+    double y[3];
+    for (int k = 0; k < 3; k++) {
+        double v = b[piv[k]];
+        for (int c = 0; c < k; c++) v -= A[piv[k] * 3 + c] * y[c];
+        y[k] = v;
+    }
+    for (int k = 2; k >= 0; k--) {
+        double v = y[k];
+        for (int c = k + 1; c < 3; c++) v -= A[piv[k] * 3 + c] * x[c];
+        x[k] = v / A[piv[k] * 3 + k];
+    }
+}
+/* g2o::Sim3::log(), sim3.h */
+void sim3_log(const Sim3& S, double res[7])
+{
+    const double sigma = std::log(S.s);
+    double R[9];
+    quat_to_matrix(S.r, R);
+    const double d = 0.5 * (R[0] + R[4] + R[8] - 1);
+    const double eps = 0.00001;
+    const double dR[3] = { R[7] - R[5], R[2] - R[6], R[3] - R[1] };   /* deltaR(R) */
+    double omega[3], A, B, C;
+    auto set_omega = [&](double f) { for (int i = 0; i < 3; i++) omega[i] = f * dR[i]; };
+    if (std::fabs(sigma) < eps) {
+        C = 1;
+        if (d > 1 - eps) { set_omega(0.5); A = 1. / 2.; B = 1. / 6.; }
+        else {
+            const double theta = std::acos(d), theta2 = theta * theta;
+            set_omega(theta / (2 * std::sqrt(1 - d * d)));
+            A = (1 - std::cos(theta)) / theta2;
+            B = (theta - std::sin(theta)) / (theta2 * theta);
+        }
+    } else {
+        C = (S.s - 1) / sigma;
+        if (d > 1 - eps) {
+            const double sigma2 = sigma * sigma;
+            set_omega(0.5);
+            A = ((sigma - 1) * S.s + 1) / sigma2;
+            B = ((0.5 * sigma2 - sigma + 1) * S.s) / (sigma2 * sigma);
+        } else {
+            const double theta = std::acos(d);
+            set_omega(theta / (2 * std::sqrt(1 - d * d)));
+            const double theta2 = theta * theta;
+            const double a = S.s * std::sin(theta), b = S.s * std::cos(theta), c = theta2 + sigma * sigma;
+            A = (a * sigma + (1 - b) * theta) / (theta * c);
+            B = (C - ((b - 1) * sigma + a * theta) / c) * 1. / theta2;
+        }
+    }
+    const double O[9] = { 0, -omega[2], omega[1], omega[2], 0, -omega[0], -omega[1], omega[0], 0 };
+    double W[9];
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) {
+            const double O2 = O[i * 3] * O[j] + O[i * 3 + 1] * O[3 + j] + O[i * 3 + 2] * O[6 + j];
+            W[i * 3 + j] = A * O[i * 3 + j] + B * O2 + C * (i == j ? 1.0 : 0.0);
+        }
+    double ups[3];
+    lu_solve3(W, S.t, ups);
+    for (int i = 0; i < 3; i++) { res[i] = omega[i]; res[3 + i] = ups[i]; }
+    res[6] = sigma;
 }
 
 struct Problem {
@@ -362,5 +464,175 @@ int sim3o_optimize_sim3(int n, const float* p1c, const float* p2c, const float* 
     if (stats) { stats[1] = it2; stats[2] = trials; stats[5] = last; }
     return nIn;
 }
+
+/* Optimizer::OptimizeEssentialGraph's solve (O3/src/Optimizer.cc:1389-1651) on the flattened pose graph the caller
+ * assembles (:1423-1592): nv Sim3 vertices (g2o::VertexSim3Expmap, estimate Scw as q (x,y,z,w), t, s), `fixed` = the
+ * map's initial keyframe (:1447), ne EdgeSim3 edges with vertex 0 = vi, vertex 1 = vj and measurement Sji, information
+ * identity, no robust kernel; error = log(Sji * Siw * Sjw^-1) (types_seven_dof_expmap.h:99-106) with g2o's numeric
+ * Jacobians for both vertices; Levenberg-Marquardt with setUserLambdaInit(lambda_init) (1e-16, :1400) for `iterations`
+ * (20, :1594) iterations; the reduced system is dense here (the reference uses a sparse LDL^T: same solution).
+ * sim3[nv*8] in/out.  stats[4] = {LM iterations, LM trials, initial chi2, final chi2}.  Returns iterations run.
+ * NO PRODUCT KERNEL EXISTS FOR THIS YET: the restatement is the head start for it. */
+int sim3o_optimize_essential_graph(int nv, double* sim3, const uint8_t* fixed, int ne, const int* vi, const int* vj,
+                                   const double* meas, int fix_scale, int iterations, double lambda_init, double* stats)
+{
+    std::vector<Sim3> V(nv), M(ne);
+    auto load = [](const double* p) { Sim3 S; S.r = { p[0], p[1], p[2], p[3] }; S.t[0] = p[4]; S.t[1] = p[5]; S.t[2] = p[6]; S.s = p[7]; return S; };
+    for (int v = 0; v < nv; v++) V[v] = load(sim3 + 8 * v);
+    for (int e = 0; e < ne; e++) M[e] = load(meas + 8 * e);
+    std::vector<int> col(nv, -1);
+    int nf = 0;
+    for (int v = 0; v < nv; v++) if (!fixed[v]) col[v] = nf++;
+    const int dim = 7 * nf;
+    Problem Pfs; Pfs.fix_scale = fix_scale != 0;   /* oplus only reads fix_scale */
+    auto edge_error = [&](int e, const Sim3& Si, const Sim3& Sj, double err[7]) {
+        sim3_log(sim3_mul(sim3_mul(M[e], Si), sim3_inverse(Sj)), err);
+    };
+    std::vector<double> err(7 * (size_t)ne);
+    auto compute_errors = [&]() {
+        double chi = 0;
+        for (int e = 0; e < ne; e++) {
+            edge_error(e, V[vi[e]], V[vj[e]], &err[7 * e]);
+            for (int k = 0; k < 7; k++) chi += err[7 * e + k] * err[7 * e + k];
+        }
+        return chi;
+    };
+    if (stats) stats[0] = stats[1] = stats[2] = stats[3] = 0;
+    std::vector<double> H((size_t)dim * dim), b(dim), Hl, x(dim);
+    double lambda = -1, ni = 2;
+    int nBad = 0, done = 0, trials = 0;
+    const double delta = 1e-9, scalar = 1.0 / (2 * delta);
+    for (int it = 0; it < iterations; it++) {
+        double currentChi = compute_errors();
+        const double iniChi = currentChi;
+        if (it == 0 && stats) stats[2] = currentChi;
+        std::fill(H.begin(), H.end(), 0.0); std::fill(b.begin(), b.end(), 0.0);
+        for (int e = 0; e < ne; e++) {
+            const int a = vi[e], c = vj[e];
+            double Ji[49], Jj[49];   /* 7 x 7, row-major: d(error row) / d(update column) */
+            for (int side = 0; side < 2; side++) {
+                const int v = side == 0 ? a : c;
+                if (col[v] < 0) continue;
+                double* J = side == 0 ? Ji : Jj;
+                for (int d = 0; d < 7; d++) {
+                    double add[7] = { 0, 0, 0, 0, 0, 0, 0 }, ep[7], em[7];
+                    add[d] = delta;
+                    const Sim3 Vp = oplus(Pfs, V[v], add);
+                    add[d] = -delta;
+                    const Sim3 Vm = oplus(Pfs, V[v], add);
+                    if (side == 0) { edge_error(e, Vp, V[c], ep); edge_error(e, Vm, V[c], em); }
+                    else { edge_error(e, V[a], Vp, ep); edge_error(e, V[a], Vm, em); }
+                    for (int r = 0; r < 7; r++) J[r * 7 + d] = scalar * (ep[r] - em[r]);
+                }
+            }
+            const double* er = &err[7 * e];
+            auto add_block = [&](int cr, int cc, const double* Jr, const double* Jc) {
+                for (int p = 0; p < 7; p++)
+                    for (int q = 0; q < 7; q++) {
+                        double sacc = 0;
+                        for (int r = 0; r < 7; r++) sacc += Jr[r * 7 + p] * Jc[r * 7 + q];
+                        H[(size_t)(7 * cr + p) * dim + 7 * cc + q] += sacc;
+                    }
+            };
+            if (col[a] >= 0) {
+                add_block(col[a], col[a], Ji, Ji);
+                for (int p = 0; p < 7; p++) { double sacc = 0; for (int r = 0; r < 7; r++) sacc += Ji[r * 7 + p] * (-er[r]); b[7 * col[a] + p] += sacc; }
+            }
+            if (col[c] >= 0) {
+                add_block(col[c], col[c], Jj, Jj);
+                for (int p = 0; p < 7; p++) { double sacc = 0; for (int r = 0; r < 7; r++) sacc += Jj[r * 7 + p] * (-er[r]); b[7 * col[c] + p] += sacc; }
+            }
+            if (col[a] >= 0 && col[c] >= 0 && a != c) { add_block(col[a], col[c], Ji, Jj); add_block(col[c], col[a], Jj, Ji); }
+        }
+        if (it == 0) {
+            if (lambda_init > 0) lambda = lambda_init;   /* computeLambdaInit with setUserLambdaInit */
+            else {
+                double mx = 0;
+                for (int j = 0; j < dim; j++) mx = std::max(std::fabs(H[(size_t)j * dim + j]), mx);
+                lambda = 1e-5 * mx;
+            }
+            ni = 2;
+            nBad = 0;
+        }
+        double rho = 0;
+        int qmax = 0;
+        do {
+            const std::vector<Sim3> backup = V;
+            Hl = H;
+            for (int j = 0; j < dim; j++) Hl[(size_t)j * dim + j] += lambda;
+            /* dense unpivoted LDL^T */
+            bool ok2 = true;
+            {
+                std::vector<double> D(dim);
+                for (int j = 0; j < dim && ok2; j++) {
+                    double dj = Hl[(size_t)j * dim + j];
+                    for (int k = 0; k < j; k++) dj -= Hl[(size_t)j * dim + k] * Hl[(size_t)j * dim + k] * D[k];
+                    if (!(dj > 0) || !std::isfinite(dj)) { ok2 = false; break; }
+                    D[j] = dj;
+                    for (int i = j + 1; i < dim; i++) {
+                        double v = Hl[(size_t)i * dim + j];
+                        for (int k = 0; k < j; k++) v -= Hl[(size_t)i * dim + k] * Hl[(size_t)j * dim + k] * D[k];
+                        Hl[(size_t)i * dim + j] = v / dj;
+                    }
+                }
+                if (ok2) {
+                    std::vector<double> y(dim);
+                    for (int i = 0; i < dim; i++) { double v = b[i]; for (int k = 0; k < i; k++) v -= Hl[(size_t)i * dim + k] * y[k]; y[i] = v; }
+                    for (int i = 0; i < dim; i++) y[i] /= D[i];
+                    for (int i = dim - 1; i >= 0; i--) { double v = y[i]; for (int k = i + 1; k < dim; k++) v -= Hl[(size_t)k * dim + i] * x[k]; x[i] = v; }
+                } else std::fill(x.begin(), x.end(), 0.0);
+            }
+            for (int v = 0; v < nv; v++)
+                if (col[v] >= 0) V[v] = oplus(Pfs, V[v], &x[7 * col[v]]);
+            double tempChi = compute_errors();
+            if (!ok2) tempChi = std::numeric_limits<double>::max();
+            rho = currentChi - tempChi;
+            double scale = 0;
+            for (int j = 0; j < dim; j++) scale += x[j] * (lambda * x[j] + b[j]);
+            scale += 1e-3;
+            rho /= scale;
+            if (rho > 0 && std::isfinite(tempChi)) {
+                double alpha = 1. - std::pow((2 * rho - 1), 3);
+                alpha = std::min(alpha, 2. / 3.);
+                lambda *= std::max(1. / 3., alpha);
+                ni = 2;
+                currentChi = tempChi;
+            } else {
+                lambda *= ni;
+                ni *= 2;
+                V = backup;
+            }
+            qmax++;
+            trials++;
+        } while (rho < 0 && qmax < 10);
+        done++;
+        if (stats) stats[3] = currentChi;
+        if (qmax == 10 || rho == 0) break;
+        if ((iniChi - currentChi) * 1e3 < iniChi) nBad++;
+        else nBad = 0;
+        if (nBad >= 3) break;
+    }
+    for (int v = 0; v < nv; v++) {
+        double* p = sim3 + 8 * v;
+        p[0] = V[v].r.x; p[1] = V[v].r.y; p[2] = V[v].r.z; p[3] = V[v].r.w;
+        p[4] = V[v].t[0]; p[5] = V[v].t[1]; p[6] = V[v].t[2]; p[7] = V[v].s;
+    }
+    if (stats) { stats[0] = done; stats[1] = trials; }
+    return done;
+}
+
+/* g2o::Sim3 exp / log, exposed for the round-trip self-check */
+void sim3o_exp(const double* u, double* out8)
+{
+    const Sim3 S = sim3_exp(u);
+    out8[0] = S.r.x; out8[1] = S.r.y; out8[2] = S.r.z; out8[3] = S.r.w;
+    out8[4] = S.t[0]; out8[5] = S.t[1]; out8[6] = S.t[2]; out8[7] = S.s;
+}
+void sim3o_log(const double* in8, double* u)
+{
+    Sim3 S; S.r = { in8[0], in8[1], in8[2], in8[3] }; S.t[0] = in8[4]; S.t[1] = in8[5]; S.t[2] = in8[6]; S.s = in8[7];
+    sim3_log(S, u);
+}
+
 
 } // extern "C"
