@@ -225,7 +225,7 @@ def run_reference(args):
         return
     cores = os.cpu_count() or 1
     agents = max(1, min(args.gpus, cores))
-    per_step = 4  # tracked frames per agent per step: a bounded sample of the same workload
+    per_step = 16  # tracked frames per agent per step: a bounded sample of the same workload
     for _ in range(args.warmup and 1):
         cpu_oracle_fps(agents, 1)
     t = time.perf_counter()
@@ -236,9 +236,11 @@ def run_reference(args):
     all_fps = cpu_oracle_fps(cores, 2) if cores > agents else v
     all_lba = cpu_lba_iters_per_sec(cores, 1) if cores > agents else lba_v
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1), "higher_is_better": True,
+            "warmup": args.warmup, "ms_per_step": 1e3 * per_step * agents / v, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": WORKLOAD, "frames_per_step": per_step * agents, "local_map_points": MAP_POINTS},
+            # every step also rebuilds the agent's map and synthesises its frames (untimed, as in our arm)
+            "wall_ms_per_step": 1e3 * wall / max(args.steps, 1),
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": agents, "kind": "port",
                              "sample": f"{agents} agent(s), one oracle process (thread) per agent, {per_step} tracked "
                                        f"frames/agent/step x {args.steps} steps"},
