@@ -17,6 +17,9 @@
   dbow_orbvoc.npz     the DBoW2 transform of 240 descriptors through the reference's own ORBvoc.txt (k = 10, L = 6,
                       1 082 073 nodes): the visited excerpt of the tree (every child of every node on a visited path) and the
                       oracle's words / nodes / BowVector -- the vocabulary itself does not travel to the GPU box.
+  keyframe_ops.npz    welding BA, OptimizeSim3 and essential-graph results of the oracle on small seeded scenes
+                      (regression pins, no upstream fixture); `python tests/golden/make_golden.py keyframe` remakes this
+                      file alone (it needs neither cv2 nor /root/reference).
 The reference repository holds no fixtures for this path; these are ours.
 """
 import os
@@ -29,7 +32,35 @@ sys.path.insert(0, ROOT)
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
+def keyframe_ops():
+    from dvmslam_b200 import synth
+    from oracle.lba import merge_ba
+    from oracle.sim3 import optimize_essential_graph, optimize_sim3
+    from tests.sim3_cases import loop_graph
+
+    B = synth.ba_scene(8, 3, 200, seed=11)
+    m = merge_ba(B["cam_q"], B["cam_t"], B["cam_fixed"], B["pts"], B["edge_cam"], B["edge_pt"], B["edge_obs"], B["edge_w"], B["K"])
+    S = synth.sim3_scene(80, seed=11, scale=1.25)
+    s3 = optimize_sim3(S["p1c"], S["p2c"], S["obs1"], S["obs2"], S["w1"], S["w2"], S["K"], S["K"], S["q0"], S["t0"], S["s0"], 10.0, False)
+    est, fixed, vi, vj, meas, _ = loop_graph(16, seed=2)
+    eg = optimize_essential_graph(est, fixed, vi, vj, meas)
+    egf = optimize_essential_graph(est, fixed, vi, vj, meas, fix_scale=True)
+    np.savez_compressed(os.path.join(HERE, "keyframe_ops.npz"),
+                        merge_cam_q=m["cam_q"], merge_cam_t=m["cam_t"], merge_pts=m["pts"], merge_bad=m["bad"],
+                        merge_counts=np.array([m["iters"], m["iters_first"], m["excluded"], m["trials"]], np.int32),
+                        merge_chi=np.array([m["chi_first"], m["chi_last"]]),
+                        sim3_q=s3["q"], sim3_t=s3["t"], sim3_s=np.float64(s3["s"]), sim3_inlier=s3["inlier"],
+                        sim3_counts=np.array([s3["n_in"], s3["iters1"], s3["iters2"], s3["n_bad"]], np.int32),
+                        eg_sim3=eg["sim3"], eg_counts=np.array([eg["iters"], eg["trials"]], np.int32),
+                        eg_chi=np.array([eg["chi_first"], eg["chi_last"]]),
+                        egf_sim3=egf["sim3"], egf_counts=np.array([egf["iters"], egf["trials"]], np.int32))
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "keyframe":
+        keyframe_ops()
+        return
+    keyframe_ops()
     import cv2
 
     from dvmslam_b200 import synth

@@ -87,6 +87,33 @@ def test_oracle_tracking_and_ba_reproduce_golden():
     assert np.allclose(ba["cam_t"], g["ba_cam_t"], atol=1e-6) and np.allclose(ba["pts"], g["ba_pts"], atol=1e-5)
 
 
+def test_oracle_keyframe_operators_reproduce_golden():
+    """Welding BA, OptimizeSim3 and the essential-graph solve of the oracle against their committed outputs (regression
+    pins).  The Sim3 paths differentiate numerically with delta 1e-9, so a different libm may move them by ~1e-7."""
+    from oracle.lba import merge_ba
+    from oracle.sim3 import optimize_essential_graph, optimize_sim3
+    from tests.sim3_cases import loop_graph
+
+    g = np.load(os.path.join(G, "keyframe_ops.npz"))
+    B = synth.ba_scene(8, 3, 200, seed=11)
+    m = merge_ba(B["cam_q"], B["cam_t"], B["cam_fixed"], B["pts"], B["edge_cam"], B["edge_pt"], B["edge_obs"], B["edge_w"], B["K"])
+    assert [m["iters"], m["iters_first"], m["excluded"], m["trials"]] == list(g["merge_counts"])
+    assert np.array_equal(m["bad"], g["merge_bad"]) and np.allclose([m["chi_first"], m["chi_last"]], g["merge_chi"], rtol=1e-9)
+    assert np.allclose(m["cam_t"], g["merge_cam_t"], atol=1e-6) and np.allclose(m["cam_q"], g["merge_cam_q"], atol=1e-7)
+    assert np.allclose(m["pts"], g["merge_pts"], atol=1e-5)
+    S = synth.sim3_scene(80, seed=11, scale=1.25)
+    s3 = optimize_sim3(S["p1c"], S["p2c"], S["obs1"], S["obs2"], S["w1"], S["w2"], S["K"], S["K"], S["q0"], S["t0"], S["s0"], 10.0, False)
+    assert [s3["n_in"], s3["iters1"], s3["iters2"], s3["n_bad"]] == list(g["sim3_counts"])
+    assert np.array_equal(s3["inlier"], g["sim3_inlier"])
+    assert np.allclose(s3["q"], g["sim3_q"], atol=1e-6) and np.allclose(s3["t"], g["sim3_t"], atol=1e-5) and abs(s3["s"] - float(g["sim3_s"])) < 1e-6
+    est, fixed, vi, vj, meas, _ = loop_graph(16, seed=2)
+    eg = optimize_essential_graph(est, fixed, vi, vj, meas)
+    assert eg["iters"] == int(g["eg_counts"][0]) and np.allclose(eg["sim3"], g["eg_sim3"], atol=1e-6)
+    assert np.allclose([eg["chi_first"], eg["chi_last"]], g["eg_chi"], rtol=1e-4)
+    egf = optimize_essential_graph(est, fixed, vi, vj, meas, fix_scale=True)
+    assert egf["iters"] == int(g["egf_counts"][0]) and np.allclose(egf["sim3"], g["egf_sim3"], atol=1e-6)
+
+
 @pytest.mark.gpu
 def test_gpu_extractor_reproduces_golden():
     from dvmslam_b200.extractor import ORBextractor
