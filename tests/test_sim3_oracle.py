@@ -86,3 +86,67 @@ def test_essential_graph_fixed_scale_and_edge_order():
     p = np.random.default_rng(0).permutation(len(vi))
     rp = optimize_essential_graph(est, fixed, vi[p], vj[p], meas[p], fix_scale=True)
     assert rp["iters"] == r["iters"] and np.abs(rp["sim3"] - r["sim3"]).max() < 1e-6
+
+
+def test_optimize_sim3_ends_at_the_least_squares_optimum():
+    """Independent check of the restated Sim3 algebra: when the final test drops nobody, the second pass is plain weighted
+    least squares over the pairs that survived the first pass, so scipy's optimum over exp(u) * S12 (own residual code,
+    rotation-vector parametrisation) must coincide with the oracle's result."""
+    from scipy.optimize import least_squares
+    from scipy.spatial.transform import Rotation
+
+    S = synth.sim3_scene(120, seed=5, scale=1.15, outlier_frac=0.05, not_in_kf2_frac=0.1)
+    r = optimize_sim3(*_args(S), th2=10.0, fix_scale=False)
+    assert r["n_in"] + r["n_bad"] == 120 and r["n_in"] > 60
+    keep = r["inlier"].astype(bool)
+    fx, fy, cx, cy = [float(v) for v in S["K"]]
+    p1, p2 = S["p1c"][keep].astype(np.float64), S["p2c"][keep].astype(np.float64)
+    o1, o2 = S["obs1"][keep].astype(np.float64), S["obs2"][keep].astype(np.float64)
+    w1, w2 = np.sqrt(S["w1"][keep].astype(np.float64)), np.sqrt(S["w2"][keep].astype(np.float64))
+
+    def residuals(p):
+        R = Rotation.from_rotvec(p[:3]).as_matrix()
+        t, s = p[3:6], np.exp(p[6])
+        x1 = s * p2 @ R.T + t                          # S12 * X2
+        x2 = (p1 - t) @ R / s                          # S12^-1 * X1
+        e1 = o1 - np.stack([fx * x1[:, 0] / x1[:, 2] + cx, fy * x1[:, 1] / x1[:, 2] + cy], 1)
+        e2 = o2 - np.stack([fx * x2[:, 0] / x2[:, 2] + cx, fy * x2[:, 1] / x2[:, 2] + cy], 1)
+        return np.concatenate([(e1 * w1[:, None]).ravel(), (e2 * w2[:, None]).ravel()])
+
+    q = r["q"]
+    p0 = np.concatenate([Rotation.from_quat(q).as_rotvec(), r["t"], [np.log(r["s"])]])
+    sol = least_squares(residuals, p0, method="lm", xtol=1e-14, ftol=1e-14, gtol=1e-14)
+    assert abs(np.sum(residuals(p0) ** 2) - r["chi_last"]) < 1e-6 * r["chi_last"]      # same cost function
+    assert np.sum(sol.fun ** 2) <= r["chi_last"] * (1 + 1e-12)
+    assert r["chi_last"] - np.sum(sol.fun ** 2) < 1e-4 * r["chi_last"]                # ... and the oracle sits at its minimum
+    assert np.abs(sol.x - p0).max() < 1e-4
+
+
+def test_sim3_exp_against_the_matrix_exponential_and_the_g2o_quirk():
+    """g2o::Sim3(update) is the closed form of expm([[Omega + sigma I, upsilon], [0, 0]]) = [[s R, t], [0, 1]]: checked
+    against scipy for general updates.  In its small-rotation branch with |sigma| >= 1e-5 the coefficient B is ~1/sigma^3
+    instead of its finite limit (sim3.h; see the header of oracle/sim3_oracle.cpp): the restatement must reproduce that
+    deviation, not fix it."""
+    from scipy.linalg import expm
+    from scipy.spatial.transform import Rotation
+    from oracle.sim3 import sim3_exp
+
+    def matrix_of(u):
+        w, v, sg = np.asarray(u[:3], float), np.asarray(u[3:6], float), float(u[6])
+        A = np.zeros((4, 4))
+        A[:3, :3] = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]]) + sg * np.eye(3)
+        A[:3, 3] = v
+        return expm(A)
+
+    rng = np.random.default_rng(1)
+    for _ in range(30):
+        u = np.concatenate([rng.normal(0, 0.5, 3), rng.normal(0, 2.0, 3), [rng.normal(0, 0.3)]])
+        S, T = sim3_exp(u), matrix_of(u)
+        sR = S[7] * Rotation.from_quat(S[:4]).as_matrix()
+        assert np.abs(sR - T[:3, :3]).max() < 1e-12 and np.abs(S[4:7] - T[:3, 3]).max() < 1e-11
+    for u in ([0.3, -0.2, 0.1, 1.0, 2.0, 3.0, 0.0], [0, 0, 0, 1.0, 2.0, 3.0, 0.2], [0, 0, 0, 1.0, 2.0, 3.0, 0.0]):   # regular special branches
+        S, T = sim3_exp(u), matrix_of(u)
+        assert np.abs(S[4:7] - T[:3, 3]).max() < 1e-11
+    u = [3e-6, -4e-6, 0.0, 1.0, 2.0, 3.0, 1e-3]          # theta = 5e-6 < 1e-5, sigma = 1e-3: B = ~1e9, B * theta^2 = ~0.025
+    S, T = sim3_exp(u), matrix_of(u)
+    assert 1e-3 < np.abs(S[4:7] - T[:3, 3]).max() < 1.0
