@@ -101,3 +101,44 @@ def test_merge_ba_two_passes():
     S = synth.ba_scene(8, 2, 300, seed=3, pix_sigma=0.0, outlier_frac=0.0)
     r = merge_ba(*_args(S))
     assert r["excluded"] == 0 and r["chi_last"] < 1e-6 * r["chi_first"] and not r["bad"].any()
+
+
+def test_merge_ba_second_pass_reaches_the_least_squares_optimum():
+    """Independent check of the two-pass flow: pass 2 is plain least squares over the level-0 edges, so scipy started from
+    the oracle's result (own residual code: rotation-vector increments on the free poses, additive points) must not find a
+    noticeably lower cost."""
+    from scipy.optimize import least_squares
+    from scipy.spatial.transform import Rotation
+    from oracle.lba import local_ba, merge_ba
+
+    S = synth.ba_scene(5, 2, 60, seed=13)
+    a = _args(S)
+    r = merge_ba(*a)
+    lvl0 = ~local_ba(*a, iterations=5, huber_delta=np.sqrt(5.99))["bad"].astype(bool)
+    assert r["excluded"] == int((~lvl0).sum())
+    ec, ep = S["edge_cam"][lvl0], S["edge_pt"][lvl0]
+    obs, w = S["edge_obs"][lvl0].astype(np.float64), np.sqrt(S["edge_w"][lvl0].astype(np.float64))
+    fx, fy, cx, cy = [float(v) for v in S["K"]]
+    free = np.nonzero(S["cam_fixed"] == 0)[0]
+    R0 = Rotation.from_quat(r["cam_q"].astype(np.float64)).as_matrix()
+    t0 = r["cam_t"].astype(np.float64)
+    P0 = r["pts"].astype(np.float64)
+
+    def residuals(x):
+        R, t = R0.copy(), t0.copy()
+        for k, c in enumerate(free):
+            dR = Rotation.from_rotvec(x[6 * k:6 * k + 3]).as_matrix()
+            R[c] = dR @ R0[c]
+            t[c] = dR @ t0[c] + x[6 * k + 3:6 * k + 6]
+        P = P0 + x[6 * len(free):].reshape(-1, 3)
+        Xc = np.einsum("eij,ej->ei", R[ec], P[ep]) + t[ec]
+        uv = np.stack([fx * Xc[:, 0] / Xc[:, 2] + cx, fy * Xc[:, 1] / Xc[:, 2] + cy], 1)
+        return ((obs - uv) * w[:, None]).ravel()
+
+    x0 = np.zeros(6 * len(free) + P0.size)
+    c0 = float(np.sum(residuals(x0) ** 2))
+    # the outputs are float32: the cost at the rounded result is the oracle's final chi2 up to that rounding
+    assert abs(c0 - r["chi_last"]) < 1e-3 * r["chi_last"]
+    sol = least_squares(residuals, x0, method="trf", xtol=1e-12, ftol=1e-12, gtol=1e-12, max_nfev=50)
+    c1 = float(np.sum(sol.fun ** 2))
+    assert c1 <= c0 and c0 - c1 < 2e-3 * c0
