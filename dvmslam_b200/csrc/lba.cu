@@ -238,70 +238,9 @@ __device__ inline double fast_rsqrt(double d)
     return fma(y, e, y);
 }
 
-// One warp: Cholesky of the 32x32 block at A (leading dimension ld, lower triangle) held in registers
-// (lane = row, column broadcasts by shuffle), then its inverse (lane = column).  Writes L to Ld and
-// L^-1 to Li (shared, stride kDiagLd); with write_back also L into A and L^-1 (row-major) into Linv_out.
-// Kept out of line so that its 64-register row does not compete with the caller's live state.
-__device__ __noinline__ bool warp_factor_invert_32(double* __restrict__ A, int ld, double* __restrict__ Ld,
-                                                   double* __restrict__ Li, bool write_back, double* __restrict__ Linv_out)
-{
-    const int lane = threadIdx.x & 31;
-    double row[kNB];
-#pragma unroll
-    for (int c = 0; c < kNB; c++) row[c] = A[(size_t)lane * ld + c];
-    bool bad = false;
-    double my_rinv = 1.0; // 1 / L[lane][lane]
-#pragma unroll
-    for (int j = 0; j < kNB; j++) {
-        const double djj = __shfl_sync(0xffffffffu, row[j], j);
-        bad = bad || !(djj > 0) || !isfinite(djj);
-        // IEEE sqrt and division are ~600-cycle software sequences and sit on the critical path of every
-        // column: one rsqrt (1-2 ulp) replaces both, well inside the solver's tolerance
-        const double rinv = bad ? 1.0 : rsqrt(djj);
-        const double lij = row[j] * rinv;
-        if (lane == j) { row[j] = djj * rinv; my_rinv = rinv; }
-        else if (lane > j) row[j] = lij;
-        // column j is exchanged through shared memory (Li is free until the inverse is written): the
-        // 31 broadcast loads pipeline, where 31 dependent shuffle pairs would serialise
-        Li[j * kDiagLd + lane] = row[j];
-        __syncwarp();
-#pragma unroll
-        for (int k = j + 1; k < kNB; k++) {
-            const double lkj = Li[j * kDiagLd + k];
-            if (lane >= k) row[k] -= lij * lkj;
-        }
-    }
-    __syncwarp();
-#pragma unroll
-    for (int c = 0; c < kNB; c++) {
-        Ld[lane * kDiagLd + c] = (c <= lane) ? row[c] : 0.0;
-        if (write_back && c <= lane) A[(size_t)lane * ld + c] = row[c];
-    }
-    __syncwarp();
-    // inverse of the lower-triangular block: lane = column j of L^-1, forward substitution on e_j
-    double xi[kNB];
-#pragma unroll
-    for (int i = 0; i < kNB; i++) {
-        double s0 = (i == lane) ? 1.0 : 0.0, s1 = 0.0;
-#pragma unroll
-        for (int k = 0; k < i; k += 2) {
-            s0 -= Ld[i * kDiagLd + k] * xi[k];
-            if (k + 1 < i) s1 -= Ld[i * kDiagLd + k + 1] * xi[k + 1];
-        }
-        const double ri = __shfl_sync(0xffffffffu, my_rinv, i); // outside the select: every lane must take part
-        xi[i] = (i >= lane) ? (s0 + s1) * ri : 0.0;
-    }
-#pragma unroll
-    for (int i = 0; i < kNB; i++) {
-        Li[i * kDiagLd + lane] = xi[i];
-        if (write_back) Linv_out[i * kNB + lane] = xi[i];
-    }
-    return bad;
-}
-
-// The same factorisation + inversion by ALL threads of the CTA (kLbaThreads = 512 = 16 warps): a lone warp cannot
-// hide its own latencies (the one-warp version above runs at ~7 cycles per instruction, 21 us per block, and was
-// 2/3 of the whole solve).  Every thread OWNS two elements of the block and of its inverse in registers for the
+// Factorisation + inversion of a 32x32 diagonal block by ALL threads of the CTA (kLbaThreads = 512 = 16 warps): a lone
+// warp cannot hide its own latencies (a one-warp version with the block in registers ran at ~7 cycles per instruction,
+// 21 us per block, and was 2/3 of the whole solve; DESIGN.md, negative results).  Every thread OWNS two elements of the block and of its inverse in registers for the
 // whole sweep: lane = row, warp w = columns w and w + 16.  Step j:
 //     the warp that owns column j takes the pivot by shuffle, scales its column by rsqrt(pivot) and publishes it
 //     (col[j & 1][:], rinv[j & 1]) | ONE CTA barrier |
@@ -374,7 +313,6 @@ __device__ bool cta_factor_invert_32(double* A, int ld, double* Ld, double* Li, 
     return *s_bad != 0.0;
 }
 
-__device__ inline size_t chol_smem_doubles(int n) { return (size_t)(n + 8) * kPanelLd + 2 * kNB * kDiagLd + 64 * kNB; }
 
 __device__ bool cluster_cholesky_solve(int n, double* __restrict__ A, const double* __restrict__ b, double* __restrict__ x,
                                        double* __restrict__ Linv_g, double* smem, int* s_flag, unsigned long long* prof)
