@@ -1,6 +1,7 @@
 // track_device.cuh -- device helpers shared by the matcher kernels (track_kernels.cu, bow_kernels.cu):
-// descriptor distance, the views through which a kernel reads a Frame (global memory or a TMA-staged
-// shared-memory copy), Frame::GetFeaturesInArea as a window walk, the rotation histogram.
+// descriptor distance, the view through which a kernel reads a Frame, Frame::GetFeaturesInArea as a window walk (one
+// thread or one warp per query), the rotation histogram.  (Staging the whole frame in every CTA's shared memory by TMA
+// bulk copies was measured and dropped: DESIGN.md, negative results.)
 #pragma once
 #include "track_kernels.cuh"
 
@@ -43,54 +44,6 @@ __device__ inline FrameLook look_global(const FrameDev& f)
     v.cell_start = f.cell_start; v.cell_items = f.cell_items;
     v.kbase = reinterpret_cast<const char*>(f.kps); v.kstride = (int)sizeof(dvm_keypoint); v.oct_off = 20;
     v.desc = f.desc;
-    v.minX = f.minX; v.minY = f.minY; v.gwInv = f.gwInv; v.ghInv = f.ghInv;
-    return v;
-}
-
-// ---- frame staged in shared memory by TMA bulk copies (cp.async.bulk, one mbarrier) ----
-__host__ __device__ inline size_t frame_smem_bytes(int cap) { return (size_t)cap * (32 + 12 + 4) + (size_t)(kGridCells + 4) * 4; }
-__device__ inline uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-// all threads of the CTA call this; returns once descriptors, {x,y,octave} records and the CSR grid of
-// the frame are in `smem` (layout: desc | kxyo | cell_start | cell_items, every part 16-byte aligned)
-__device__ inline FrameLook look_shared_tma(const FrameDev& f, int n, unsigned char* smem, unsigned long long* bar)
-{
-    unsigned char* sdesc = smem;
-    unsigned char* skxyo = sdesc + (size_t)f.cap * 32;
-    unsigned char* scell = skxyo + (size_t)f.cap * 12;
-    unsigned char* sitems = scell + (size_t)(kGridCells + 4) * 4;
-    const uint32_t b = smem_u32(bar);
-    if (threadIdx.x == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(b), "r"(1));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const uint32_t bytes_desc = (uint32_t)n * 32u;
-        const uint32_t bytes_kxyo = min(((uint32_t)n * 12u + 15u) & ~15u, (uint32_t)f.cap * 12u);
-        const uint32_t bytes_cell = (uint32_t)(kGridCells + 4) * 4u;
-        const uint32_t bytes_items = min(((uint32_t)n * 4u + 15u) & ~15u, (uint32_t)f.cap * 4u);
-        const uint32_t total = bytes_desc + bytes_kxyo + bytes_cell + bytes_items;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(total) : "memory");
-        auto bulk = [&](unsigned char* dst, const void* src, uint32_t bytes) {
-            if (bytes == 0) return;
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(b) : "memory");
-        };
-        bulk(sdesc, f.desc, bytes_desc);
-        bulk(skxyo, f.kxyo, bytes_kxyo);
-        bulk(scell, f.cell_start, bytes_cell);
-        bulk(sitems, f.cell_items, bytes_items);
-    }
-    uint32_t done = 0;
-    while (!done) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done) : "r"(b), "r"(0) : "memory");
-    }
-    FrameLook v;
-    v.cell_start = reinterpret_cast<const int*>(scell); v.cell_items = reinterpret_cast<const int*>(sitems);
-    v.kbase = reinterpret_cast<const char*>(skxyo); v.kstride = 12; v.oct_off = 8;
-    v.desc = sdesc;
     v.minX = f.minX; v.minY = f.minY; v.gwInv = f.gwInv; v.ghInv = f.ghInv;
     return v;
 }
