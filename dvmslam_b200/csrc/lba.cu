@@ -30,6 +30,13 @@ namespace {
 constexpr int kLbaThreads = 512;
 constexpr int kLbaWarps = kLbaThreads / 32;
 constexpr int kNB = 32; // Cholesky block size
+// Per-CTA partial sums exchanged through global memory between grid barriers.  Every WRITER has its own slot: the
+// linearisation's chi2 (written right at the top of the next LM iteration, with no grid barrier after the previous
+// trial's decision was read) must not share a slot with the trial chi2 that decision reads -- with a shared slot a CTA
+// without landmarks (np < warps in the grid) overwrote it while slower warps were still summing it, and those warps
+// then took a different accept/stop decision than the rest of the grid.
+constexpr int kPartStride = 8;
+constexpr int kPartLinChi = 0, kPartScale = 1, kPartMaxHll = 2, kPartMaxHpp = 3, kPartTrialChi = 4, kPartExcluded = 5;
 
 struct LbaDev {
     int nc, nf, np, ne, dimP, dimPad, iterations; // dimPad = dimP rounded up to the Cholesky block size
@@ -44,7 +51,7 @@ struct LbaDev {
     const int* cam_start; const int* cam_edges;
     double* err; double* Hpl; double* Hll; double* bl; double* Dinv; double* db;
     double* Hpp; double* bp; double* Hs; double* bs; double* x; double* Linv;
-    double* part;  // [gridDim * 4]
+    double* part;  // [gridDim * kPartStride], slots: see kPart*
     int* flags;    // [0] Cholesky ok
     const volatile int* abort_flag;
     float* out_camq; float* out_camt; float* out_pts; double* out_chi2; uint8_t* out_bad; double* out_stats;
@@ -507,11 +514,10 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kLbaThrea
             {
                 double v[1] = { (double)nex };
                 cta_sum<1>(v, warp_buf, red);
-                if (tid == 0) P.part[blockIdx.x * 4 + 1] = red[0];
+                if (tid == 0) P.part[blockIdx.x * kPartStride + kPartExcluded] = red[0];
             }
             grid.sync();
-            for (int b2 = 0; b2 < G; b2++) excluded += (int)P.part[b2 * 4 + 1];
-            grid.sync(); // part[] is rewritten by the next pass
+            for (int b2 = 0; b2 < G; b2++) excluded += (int)P.part[b2 * kPartStride + kPartExcluded];
             delta = CUDART_INF; dsqr = CUDART_INF; // (a local copy: writing the parameter struct would move it to the stack)
             stop = false;
         }
@@ -593,8 +599,8 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kLbaThrea
                 if (tid == 0) {
                     double m = 0;
                     for (int w2 = 0; w2 < kLbaWarps; w2++) m = fmax(m, warp_buf[w2]);
-                    P.part[blockIdx.x * 4 + 0] = red[0];
-                    P.part[blockIdx.x * 4 + 2] = m;
+                    P.part[blockIdx.x * kPartStride + kPartLinChi] = red[0];
+                    P.part[blockIdx.x * kPartStride + kPartMaxHll] = m;
                 }
                 __syncthreads();
             }
@@ -646,15 +652,15 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kLbaThrea
                     for (int a = 0; a < 6; a++) maxdp = fmax(maxdp, fabs(red[a * 6 - a * (a - 1) / 2]));
                 __syncthreads();
             }
-            if (tid == 0) P.part[blockIdx.x * 4 + 3] = maxdp;
+            if (tid == 0) P.part[blockIdx.x * kPartStride + kPartMaxHpp] = maxdp;
             grid.sync();
             tick(1);
             double currentChi = 0;
             {
                 double m = 0;
                 for (int b2 = 0; b2 < G; b2++) {
-                    currentChi += P.part[b2 * 4 + 0];
-                    m = fmax(m, fmax(P.part[b2 * 4 + 2], P.part[b2 * 4 + 3]));
+                    currentChi += P.part[b2 * kPartStride + kPartLinChi];
+                    m = fmax(m, fmax(P.part[b2 * kPartStride + kPartMaxHll], P.part[b2 * kPartStride + kPartMaxHpp]));
                 }
                 if (it == 0) { lambda = 1e-5 * m; ni = 2; nBad = 0; if (pass == 0) first_chi = currentChi; }
             }
@@ -797,7 +803,7 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kLbaThrea
                 {
                     double v[1] = { scale_part };
                     cta_sum<1>(v, warp_buf, red);
-                    if (tid == 0) P.part[blockIdx.x * 4 + 1] = red[0];
+                    if (tid == 0) P.part[blockIdx.x * kPartStride + kPartScale] = red[0];
                 }
                 grid.sync();
                 tick(5);
@@ -814,12 +820,12 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kLbaThrea
                 {
                     double v[1] = { chi_t };
                     cta_sum<1>(v, warp_buf, red);
-                    if (tid == 0) P.part[blockIdx.x * 4 + 0] = red[0];
+                    if (tid == 0) P.part[blockIdx.x * kPartStride + kPartTrialChi] = red[0];
                 }
                 grid.sync();
                 tick(6);
                 double tempChi = 0, scale = 0;
-                for (int b2 = 0; b2 < G; b2++) { tempChi += P.part[b2 * 4 + 0]; scale += P.part[b2 * 4 + 1]; }
+                for (int b2 = 0; b2 < G; b2++) { tempChi += P.part[b2 * kPartStride + kPartTrialChi]; scale += P.part[b2 * kPartStride + kPartScale]; }
                 if (!ok2) tempChi = 1.7976931348623157e308;
                 rho = currentChi - tempChi;
                 scale += 1e-3;
@@ -1044,7 +1050,7 @@ static int run_ba(dvm_lba* h, int nc, float* cam_q, float* cam_t, const uint8_t*
     const size_t o_hs = take((size_t)std::max((dimPad + 8) * dimPad, 1) * 8), o_bs = take((size_t)std::max(dimPad, 1) * 8);
     const size_t o_linv = take((size_t)std::max(dimPad * kNB, 1) * 8);
     const size_t o_x = take((size_t)(dimPad + np * 3 + 1) * 8);
-    const size_t o_part = take((size_t)h->grid * 4 * 8), o_flags = take(4 * 4), o_prof = take(16 * 8);
+    const size_t o_part = take((size_t)h->grid * kPartStride * 8), o_flags = take(4 * 4), o_prof = take(16 * 8);
     const size_t o_level = take((size_t)std::max(ne, 1));
     // output block (contiguous, one D2H)
     const size_t out_begin = (off + 255) & ~(size_t)255;
@@ -1057,6 +1063,7 @@ static int run_ba(dvm_lba* h, int nc, float* cam_q, float* cam_t, const uint8_t*
         if (h->h_buf) { cudaFreeHost(h->h_buf); h->h_buf = nullptr; }
         const size_t cap = total + total / 4;
         DVM_CUDA(cudaMalloc(&h->d_buf, cap));
+        DVM_CUDA(cudaMemsetAsync(h->d_buf, 0, cap, h->stream)); // the alignment gaps of the output block travel in its one D2H copy
         DVM_CUDA(cudaHostAlloc(&h->h_buf, cap, cudaHostAllocDefault));
         h->d_cap = h->h_cap = cap;
     }
