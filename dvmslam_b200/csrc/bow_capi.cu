@@ -61,6 +61,7 @@ struct dvm_hamming {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     KnnScratch scratch;
+    int mode = 0;   // dvm_hamming_set_mode
     uint8_t* d_buf = nullptr; size_t d_cap = 0;   // host-call staging: a | b | key1 | key2
     uint8_t* h_buf = nullptr; size_t h_cap = 0;
 };
@@ -294,7 +295,7 @@ void dvm_hamming_destroy(dvm_hamming* h)
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    cudaFree(h->scratch.part[0]); cudaFree(h->scratch.part[1]); cudaFree(h->d_buf);
+    cudaFree(h->scratch.part[0]); cudaFree(h->scratch.part[1]); cudaFree(h->scratch.expanded); cudaFree(h->d_buf);
     if (h->h_buf) cudaFreeHost(h->h_buf);
     if (h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -310,7 +311,14 @@ int dvm_hamming_knn_device(dvm_hamming* h, const uint8_t* a_dev, int ba, int na,
     KnnArgs k;
     k.a = a_dev; k.ba = ba; k.na = na; k.b = b_dev; k.bb = bb; k.nb = nb;
     k.key1 = key1_dev; k.key2 = key2_dev; k.counts = counts_dev; k.th_low = th_low; k.nnratio = nnratio;
-    return launch_hamming_knn(k, h->scratch, h->stream);
+    return launch_hamming_knn(k, h->scratch, h->stream, h->mode);
+}
+
+int dvm_hamming_set_mode(dvm_hamming* h, int mode)
+{
+    DVM_REQUIRE(h != nullptr && mode >= 0 && mode <= 3, "mode must be 0..3");
+    h->mode = mode;
+    return DVM_OK;
 }
 
 int dvm_hamming_sync(dvm_hamming* h)

@@ -91,7 +91,14 @@ struct KnnArgs {
     int* counts;   // preset to 0 by the launcher
     int th_low; float nnratio;
 };
-struct KnnScratch { uint32_t* part[2] = { nullptr, nullptr }; size_t cap = 0; }; // per-split partial keys
-int launch_hamming_knn(const KnnArgs& k, KnnScratch& scratch, cudaStream_t stream);
+struct KnnScratch {
+    uint32_t* part[2] = { nullptr, nullptr }; size_t cap = 0;   // per-split partial keys (POPC path)
+    uint8_t* expanded = nullptr; size_t exp_cap = 0;            // descriptors as +1 / -1 bytes (tensor-core path)
+};
+// mode: 0 = by size (tensor cores for batched keyframe blocks, POPC for small calls), 1 = POPC, 2 = tensor cores,
+//       3 = tensor cores without the accumulator read-out (MMA-only timing probe, writes nothing)
+int launch_hamming_knn(const KnnArgs& k, KnnScratch& scratch, cudaStream_t stream, int mode = 0);
+bool hamming_tc_applicable(const KnnArgs& k);
+int launch_hamming_knn_tc(const KnnArgs& k, KnnScratch& scratch, cudaStream_t stream, int epilogue);
 
 } // namespace dvm

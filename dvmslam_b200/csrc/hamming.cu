@@ -121,10 +121,14 @@ __global__ void __launch_bounds__(256) hamming_merge_kernel(KnnArgs k, int nspli
     }
 }
 
-int launch_hamming_knn(const KnnArgs& k, KnnScratch& sc, cudaStream_t stream)
+int launch_hamming_knn(const KnnArgs& k, KnnScratch& sc, cudaStream_t stream, int mode)
 {
     const int pairs = k.ba * k.bb;
     if (pairs <= 0 || k.na <= 0) return DVM_OK;
+    if (mode >= 2 || (mode == 0 && hamming_tc_applicable(k))) {
+        if (k.na < 1 || k.nb < 1) { set_error("the tensor-core Hamming path needs non-empty blocks"); return DVM_ERR_INVALID; }
+        return launch_hamming_knn_tc(k, sc, stream, mode == 3 ? 0 : 1);
+    }
     if (k.counts) DVM_CUDA(cudaMemsetAsync(k.counts, 0, (size_t)pairs * sizeof(int), stream));
     const int groups = div_up(k.na, kKnnThreads * kKnnRows);
     // enough CTAs to fill the 148 SMs several times over: split the b block when the batch is small

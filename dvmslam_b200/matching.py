@@ -38,6 +38,7 @@ def _bind(L):
     L.dvm_hamming_knn_device.argtypes = [_vp, _vp, C.c_int, C.c_int, _vp, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int,
                                          C.c_float]
     L.dvm_hamming_sync.argtypes = [_vp]
+    L.dvm_hamming_set_mode.argtypes = [_vp, C.c_int]
     L._bow_bound = True
 
 
@@ -211,3 +212,7 @@ class HammingKnn:
 
     def sync(self):
         check(self.L.dvm_hamming_sync(self.h))
+
+    def set_mode(self, mode: int):
+        """0 = by size, 1 = popcount kernel, 2 = tcgen05 int8 kernel, 3 = tensor pipe only (timing probe, no outputs)."""
+        check(self.L.dvm_hamming_set_mode(self.h, int(mode)))

@@ -313,6 +313,11 @@ DVM_API int dvm_hamming_knn_device(dvm_hamming* h, const uint8_t* a_dev, int ba,
                                    int nb, uint32_t* key1_dev, uint32_t* key2_dev, int32_t* counts_dev, int th_low,
                                    float nnratio);
 DVM_API int dvm_hamming_sync(dvm_hamming* h);
+/* Kernel selection of dvm_hamming_knn[_device]: 0 (default) = by size -- batched keyframe blocks go to the tcgen05 int8
+ * kernel (csrc/hamming_tc.cu: a . b = 256 - 2 * distance over +1 / -1 bytes, exact in int32), small calls to the
+ * popcount kernel; 1 = popcount; 2 = tensor cores; 3 = tensor cores without the accumulator read-out (a timing probe of
+ * the MMA pipeline alone: writes no outputs).  Results of modes 0, 1 and 2 are bit-identical. */
+DVM_API int dvm_hamming_set_mode(dvm_hamming* h, int mode);
 
 /* ------------------------------------------------------------------------------------------------
  * Optimizer::PoseOptimization   (O3/src/Optimizer.cc:744-1028, mono observations)

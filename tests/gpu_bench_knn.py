@@ -13,6 +13,8 @@ B = torch.from_numpy(synth.keyframe_blocks(KB, N, seed=2)).cuda()
 k1 = torch.empty((KA, KB, N), dtype=torch.int32, device="cuda"); k2 = torch.empty_like(k1)
 cnt = torch.empty((KA, KB), dtype=torch.int32, device="cuda")
 h = HammingKnn(stream=torch.cuda.current_stream().cuda_stream)
+MODE = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+h.set_mode(MODE)
 def run():
     h.knn_device(A.data_ptr(), KA, N, B.data_ptr(), KB, N, k1.data_ptr(), k2.data_ptr(), cnt.data_ptr(), 50, 0.75)
 for _ in range(3): run()
@@ -24,6 +26,7 @@ for _ in range(reps): run()
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / reps
 pairs = KA * KB * N * N
+print(f"mode {MODE}: {2 * pairs * 256 / ms * 1e-9:.1f} Tops/s (int8 MAC x2)")
 print(f"knn {KA}x{KB} keyframes x {N}^2: {ms:.3f} ms  {pairs / ms / 1e6:.1f} G descriptor pairs/s  "
       f"{pairs * 8 / ms / 1e6 / 148 / 1.965:.2f} popc32/clk/SM  {KA * KB / ms * 1e3:.0f} keyframe pairs/s")
 # single keyframe pair (split path)

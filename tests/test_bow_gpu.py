@@ -266,3 +266,49 @@ def test_fuse_search(w, h, nf, th):
     assert np.array_equal(i0, i1) and np.array_equal(d0, d1)
     assert (i1 >= 0).sum() > 100
     F1.close()
+
+
+@pytest.mark.parametrize("KA,NA,KB,NB", [(1, 128, 1, 128), (2, 300, 3, 257), (1, 1, 1, 1), (3, 2000, 2, 2000), (1, 513, 2, 129),
+                                         (2, 256, 1, 3000)])
+def test_hamming_tensor_core_matches_popcount_and_oracle(KA, NA, KB, NB):
+    """The tcgen05 int8 formulation (a . b = 256 - 2 * distance over +1 / -1 bytes) against the popcount kernel and the
+    oracle: keys (distance << 20 | first nearest index), second-smallest keys and accept counts bit-identical, with
+    duplicated rows (ties -> first index), all-ones against all-zeros rows (distance 256 never matches), ragged sizes
+    (rows and columns past the last full 128-tile) and blocks that are not multiples of the tile."""
+    import torch
+
+    from dvmslam_b200.matching import HammingKnn
+    from oracle.bow import hamming_knn
+
+    rng = np.random.default_rng(KA * 1000 + NB)
+    A = rng.integers(0, 256, (KA, NA, 32), dtype=np.uint8)
+    B = rng.integers(0, 256, (KB, NB, 32), dtype=np.uint8)
+    if NB > 4:
+        for j in range(KB):
+            take = rng.integers(0, NA, max(1, NA // 3))
+            B[j, rng.integers(0, NB, len(take))] = A[j % KA, take] ^ (rng.random((len(take), 32)) < 0.02).astype(np.uint8)
+            B[j, NB - 1] = B[j, NB // 2]          # a tie across tiles: the lower index wins
+            B[j, 1] = B[j, 0]
+        A[0, 0] = 0xFF
+        B[0, 2] = 0x00                            # distance 256
+    a, b = torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda()
+    out = {}
+    h = HammingKnn(stream=torch.cuda.current_stream().cuda_stream)
+    for mode in (1, 2):
+        k1 = torch.full((KA, KB, NA), -1, dtype=torch.int32, device="cuda")
+        k2 = torch.full_like(k1, -1)
+        cnt = torch.full((KA, KB), -1, dtype=torch.int32, device="cuda")
+        h.set_mode(mode)
+        h.knn_device(a.data_ptr(), KA, NA, b.data_ptr(), KB, NB, k1.data_ptr(), k2.data_ptr(), cnt.data_ptr(), 50, 0.75)
+        h.sync()
+        out[mode] = (k1.cpu().numpy().view(np.uint32), k2.cpu().numpy().view(np.uint32), cnt.cpu().numpy())
+    h.close()
+    for x, y in zip(out[1], out[2]):
+        assert np.array_equal(x, y)
+    k1, k2, cnt = out[2]
+    for i in range(KA):
+        for j in range(KB):
+            idx, d1, d2 = hamming_knn(A[i], B[j])
+            assert np.array_equal(np.minimum(k1[i, j] >> 20, 256), d1)
+            assert np.array_equal(np.where(d1 < 256, k1[i, j] & 0xFFFFF, -1), idx)
+            assert np.array_equal(np.minimum(k2[i, j] >> 20, 256), d2)
