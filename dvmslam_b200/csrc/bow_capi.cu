@@ -316,7 +316,7 @@ int dvm_hamming_knn_device(dvm_hamming* h, const uint8_t* a_dev, int ba, int na,
 
 int dvm_hamming_set_mode(dvm_hamming* h, int mode)
 {
-    DVM_REQUIRE(h != nullptr && mode >= 0 && mode <= 3, "mode must be 0..3");
+    DVM_REQUIRE(h != nullptr && mode >= 0 && mode <= 4, "mode must be 0..4");
     h->mode = mode;
     return DVM_OK;
 }

@@ -96,7 +96,7 @@ struct KnnScratch {
     uint8_t* expanded = nullptr; size_t exp_cap = 0;            // descriptors as +1 / -1 bytes (tensor-core path)
 };
 // mode: 0 = by size (tensor cores for batched keyframe blocks, POPC for small calls), 1 = POPC, 2 = tensor cores,
-//       3 = tensor cores without the accumulator read-out (MMA-only timing probe, writes nothing)
+//       3 / 4 = timing probes of the tensor-core kernel that write nothing (3: TMA + MMA only, 4: + TMEM read-out)
 int launch_hamming_knn(const KnnArgs& k, KnnScratch& scratch, cudaStream_t stream, int mode = 0);
 bool hamming_tc_applicable(const KnnArgs& k);
 int launch_hamming_knn_tc(const KnnArgs& k, KnnScratch& scratch, cudaStream_t stream, int epilogue);

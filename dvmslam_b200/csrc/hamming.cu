@@ -127,7 +127,7 @@ int launch_hamming_knn(const KnnArgs& k, KnnScratch& sc, cudaStream_t stream, in
     if (pairs <= 0 || k.na <= 0) return DVM_OK;
     if (mode >= 2 || (mode == 0 && hamming_tc_applicable(k))) {
         if (k.na < 1 || k.nb < 1) { set_error("the tensor-core Hamming path needs non-empty blocks"); return DVM_ERR_INVALID; }
-        return launch_hamming_knn_tc(k, sc, stream, mode == 3 ? 0 : 1);
+        return launch_hamming_knn_tc(k, sc, stream, mode == 3 ? 0 : mode == 4 ? 2 : 1);
     }
     if (k.counts) DVM_CUDA(cudaMemsetAsync(k.counts, 0, (size_t)pairs * sizeof(int), stream));
     const int groups = div_up(k.na, kKnnThreads * kKnnRows);

@@ -214,5 +214,5 @@ class HammingKnn:
         check(self.L.dvm_hamming_sync(self.h))
 
     def set_mode(self, mode: int):
-        """0 = by size, 1 = popcount kernel, 2 = tcgen05 int8 kernel, 3 = tensor pipe only (timing probe, no outputs)."""
+        """0 = by size, 1 = popcount kernel, 2 = tcgen05 int8 kernel, 3 / 4 = timing probes without outputs (MMA only / + TMEM read-out)."""
         check(self.L.dvm_hamming_set_mode(self.h, int(mode)))

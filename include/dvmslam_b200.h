@@ -315,8 +315,8 @@ DVM_API int dvm_hamming_knn_device(dvm_hamming* h, const uint8_t* a_dev, int ba,
 DVM_API int dvm_hamming_sync(dvm_hamming* h);
 /* Kernel selection of dvm_hamming_knn[_device]: 0 (default) = by size -- batched keyframe blocks go to the tcgen05 int8
  * kernel (csrc/hamming_tc.cu: a . b = 256 - 2 * distance over +1 / -1 bytes, exact in int32), small calls to the
- * popcount kernel; 1 = popcount; 2 = tensor cores; 3 = tensor cores without the accumulator read-out (a timing probe of
- * the MMA pipeline alone: writes no outputs).  Results of modes 0, 1 and 2 are bit-identical. */
+ * popcount kernel; 1 = popcount; 2 = tensor cores; 3 / 4 = timing probes that write no outputs (3: TMA + MMA pipeline
+ * alone, 4: plus the TMEM read-out without the key bookkeeping).  Results of modes 0, 1 and 2 are bit-identical. */
 DVM_API int dvm_hamming_set_mode(dvm_hamming* h, int mode);
 
 /* ------------------------------------------------------------------------------------------------
