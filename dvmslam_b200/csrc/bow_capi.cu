@@ -2,6 +2,8 @@
 // Host-array entry points stage their flat inputs in the frame's pinned buffer, upload them with one
 // copy, run the kernels on the frame's stream and read the results back (synchronous, like the
 // reference's calls).
+#include "sophus_f32.cuh"
+#include "glibc_logf.h"
 #include "bow_kernels.cuh"
 #include "track_internal.cuh"
 #include <cmath>
@@ -248,7 +250,7 @@ int dvm_fuse_search(dvm_frame* kf, const float* pose_q, const float* pose_t, con
     for (int i = 0; i < 3; i++) a.t[i] = pose_t[i];
     a.nlevels = kf->dev.nlevels;
     // mfLogScaleFactor = log(mfScaleFactor) (O3/src/KeyFrame.cc: copied from the Frame, O3/src/Frame.cc:401)
-    a.logScale = (float)std::log((double)(kf->dev.nlevels > 1 ? kf->dev.scale[1] : 1.2f));
+    a.logScale = dvm_glibc_logf(kf->dev.nlevels > 1 ? kf->dev.scale[1] : 1.2f)   /* mfLogScaleFactor = log(mfScaleFactor) on floats, Frame.cc:401 */;
     for (int l = 0; l < kf->dev.nlevels; l++) a.inv_sigma2[l] = kf->dev.inv_sigma2[l];
     a.m = m; a.th = th;
     a.xw = st.add(xw, n * 3); a.normal = st.add(normal, n * 3);
@@ -269,6 +271,30 @@ int dvm_fuse_search(dvm_frame* kf, const float* pose_q, const float* pose_t, con
     DVM_CUDA(cudaStreamSynchronize(kf->stream));
     memcpy(best_idx, kf->h_out + ((const uint8_t*)a.best_idx - (kf->d_in + out_begin)), n * 4);
     memcpy(best_dist, kf->h_out + ((const uint8_t*)a.best_dist - (kf->d_in + out_begin)), n * 4);
+    return DVM_OK;
+}
+
+int dvm_fundamental_from_poses(const float* q1, const float* t1, const float* q2, const float* t2, const float* K1,
+                               const float* K2, float* F12, float* ep)
+{
+    DVM_REQUIRE(q1 && t1 && q2 && t2 && K1 && K2 && F12 && ep, "null argument");
+    float qw2[4], tw2[3], q12[4], t12[3], qw1[4], Cw[3], C2[3], R12[9];
+    so::se3_inverse(q2, t2, qw2, tw2);                 // Tw2 = pKF2->GetPoseInverse()
+    so::se3_mul(q1, t1, qw2, tw2, q12, t12);           // T12 = T1w * Tw2
+    so::quat_to_matrix(q12, R12);
+    so::se3_inverse(q1, t1, qw1, Cw);                  // Cw = pKF1->GetCameraCenter()
+    so::se3_apply(q2, t2, Cw, C2);                     // C2 = T2w * Cw
+    ep[0] = so::fa(so::fd(so::fm(K2[0], C2[0]), C2[2]), K2[2]);
+    ep[1] = so::fa(so::fd(so::fm(K2[1], C2[1]), C2[2]), K2[3]);
+    const float t12x[9] = { 0.f, -t12[2], t12[1], t12[2], 0.f, -t12[0], -t12[1], t12[0], 0.f };   // Sophus::SO3f::hat
+    const float K1T[9] = { K1[0], 0.f, 0.f, 0.f, K1[1], 0.f, K1[2], K1[3], 1.f };                 // toK_().transpose()
+    const float K2m[9] = { K2[0], 0.f, K2[2], 0.f, K2[1], K2[3], 0.f, 0.f, 1.f };
+    float K1Ti[9], K2i[9], A[9], B[9];
+    so::mat_inverse(K1T, K1Ti);
+    so::mat_inverse(K2m, K2i);
+    so::mat_mul(K1Ti, t12x, A);
+    so::mat_mul(A, R12, B);
+    so::mat_mul(B, K2i, F12);
     return DVM_OK;
 }
 

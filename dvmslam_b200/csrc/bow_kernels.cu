@@ -17,6 +17,7 @@
 // iterated from "nothing matched" on one CTA; at a fixed point the rule holds for i1 = 0, 1, 2, ... in
 // turn, which is the reference's loop.
 #include "bow_kernels.cuh"
+#include "sophus_f32.cuh"
 #include "track_device.cuh"
 
 namespace dvm {
@@ -468,18 +469,6 @@ void launch_triangulation_match(const TriArgs& g, cudaStream_t stream)
 // Strict '<' on the distance: the FIRST of the nearest keypoints in traversal order wins.
 constexpr int kFuseWarps = 4;
 
-__device__ inline void quat_transform_f32(float x, float y, float z, float w, const float v[3], float out[3])
-{
-    // Eigen::QuaternionBase::_transformVector, as Sophus::SE3f * point evaluates it
-    float u0 = __fsub_rn(__fmul_rn(y, v[2]), __fmul_rn(z, v[1]));
-    float u1 = __fsub_rn(__fmul_rn(z, v[0]), __fmul_rn(x, v[2]));
-    float u2 = __fsub_rn(__fmul_rn(x, v[1]), __fmul_rn(y, v[0]));
-    u0 = __fadd_rn(u0, u0); u1 = __fadd_rn(u1, u1); u2 = __fadd_rn(u2, u2);
-    out[0] = __fadd_rn(__fadd_rn(v[0], __fmul_rn(w, u0)), __fsub_rn(__fmul_rn(y, u2), __fmul_rn(z, u1)));
-    out[1] = __fadd_rn(__fadd_rn(v[1], __fmul_rn(w, u1)), __fsub_rn(__fmul_rn(z, u0), __fmul_rn(x, u2)));
-    out[2] = __fadd_rn(__fadd_rn(v[2], __fmul_rn(w, u2)), __fsub_rn(__fmul_rn(x, u1), __fmul_rn(y, u0)));
-}
-
 __global__ void __launch_bounds__(kFuseWarps * 32) fuse_search_kernel(FrameDev kf, FuseArgs a)
 {
     const int lane = threadIdx.x & 31;
@@ -488,30 +477,23 @@ __global__ void __launch_bounds__(kFuseWarps * 32) fuse_search_kernel(FrameDev k
     int bestIdx = -1, bestDist = 256;
     do {
         if (a.skip && a.skip[i]) break;
-        const float qn = __fsqrt_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a.q[0], a.q[0]), __fmul_rn(a.q[1], a.q[1])),
-                                                        __fmul_rn(a.q[2], a.q[2])), __fmul_rn(a.q[3], a.q[3])));
-        const float qx = __fdiv_rn(a.q[0], qn), qy = __fdiv_rn(a.q[1], qn), qz = __fdiv_rn(a.q[2], qn), qw = __fdiv_rn(a.q[3], qn);
-        float Ow[3];
-        { float r[3]; quat_transform_f32(-qx, -qy, -qz, qw, a.t, r); Ow[0] = -r[0]; Ow[1] = -r[1]; Ow[2] = -r[2]; }
+        // Tcw = pKF->GetPose() as stored; Ow = pKF->GetCameraCenter() = translation of Tcw.inverse() (KeyFrame.cc:224-257)
+        float qi[4], Ow[3];
+        so::se3_inverse(a.q, a.t, qi, Ow);
         const float P[3] = { a.xw[3 * i], a.xw[3 * i + 1], a.xw[3 * i + 2] };
         float pc[3];
-        quat_transform_f32(qx, qy, qz, qw, P, pc);
-        pc[0] = __fadd_rn(pc[0], a.t[0]); pc[1] = __fadd_rn(pc[1], a.t[1]); pc[2] = __fadd_rn(pc[2], a.t[2]);
+        so::se3_apply(a.q, a.t, P, pc);                                         // p3Dc = Tcw * p3Dw (:1107)
         if (pc[2] < 0.0f) break;
         const float u = __fadd_rn(__fdiv_rn(__fmul_rn(a.K[0], pc[0]), pc[2]), a.K[2]);
         const float v = __fadd_rn(__fdiv_rn(__fmul_rn(a.K[1], pc[1]), pc[2]), a.K[3]);
         if (!(u >= kf.minX && u < kf.maxX && v >= kf.minY && v < kf.maxY)) break;
         const float maxDistance = __fmul_rn(1.2f, a.max_dist[i]), minDistance = __fmul_rn(0.8f, a.min_dist[i]);
-        const float p0 = __fsub_rn(P[0], Ow[0]), p1 = __fsub_rn(P[1], Ow[1]), p2 = __fsub_rn(P[2], Ow[2]);
-        const float dist3D = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(p0, p0), __fmul_rn(p1, p1)), __fmul_rn(p2, p2)));
+        const float PO[3] = { __fsub_rn(P[0], Ow[0]), __fsub_rn(P[1], Ow[1]), __fsub_rn(P[2], Ow[2]) };
+        const float dist3D = so::norm3(PO);
         if (dist3D < minDistance || dist3D > maxDistance) break;
-        const float dot = __fadd_rn(__fadd_rn(__fmul_rn(p0, a.normal[3 * i]), __fmul_rn(p1, a.normal[3 * i + 1])),
-                                    __fmul_rn(p2, a.normal[3 * i + 2]));
-        if ((double)dot < 0.5 * (double)dist3D) break;
-        const float ratio = __fdiv_rn(a.max_dist[i], dist3D);
-        int lvl = (int)ceilf(__fdiv_rn((float)log((double)ratio), a.logScale));
-        if (lvl < 0) lvl = 0;
-        else if (lvl >= a.nlevels) lvl = a.nlevels - 1;
+        const float Pn[3] = { a.normal[3 * i], a.normal[3 * i + 1], a.normal[3 * i + 2] };
+        if ((double)so::dot3(PO, Pn) < 0.5 * (double)dist3D) break;
+        const int lvl = so::predict_scale(a.max_dist[i], dist3D, a.logScale, a.nlevels);
         const float radius = __fmul_rn(a.th, kf.scale[lvl]);
         uint32_t d[8];
         load_desc(d, a.mp_desc + (size_t)i * 32);

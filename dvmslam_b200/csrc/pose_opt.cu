@@ -506,7 +506,13 @@ __global__ void __cluster_dims__(kPoseCtas, 1, 1) __launch_bounds__(kPoseThreads
     }
     if (tid == 0) {
         if (nedges >= 3) {
-            a.pose[0] = (float)T.r.x; a.pose[1] = (float)T.r.y; a.pose[2] = (float)T.r.z; a.pose[3] = (float)T.r.w;
+            // pFrame->SetPose(Sophus::SE3<float>(rotation().cast<float>(), translation().cast<float>())), Optimizer.cc:1021-1024:
+            // the SE3f constructor normalises the float quaternion (so3.hpp:480-487; 4-float norm (x^2 + z^2) + (y^2 + w^2))
+            {
+                const float qx = (float)T.r.x, qy = (float)T.r.y, qz = (float)T.r.z, qw = (float)T.r.w;
+                const float qn = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(qx, qx), __fmul_rn(qz, qz)), __fadd_rn(__fmul_rn(qy, qy), __fmul_rn(qw, qw))));
+                a.pose[0] = __fdiv_rn(qx, qn); a.pose[1] = __fdiv_rn(qy, qn); a.pose[2] = __fdiv_rn(qz, qn); a.pose[3] = __fdiv_rn(qw, qn);
+            }
             a.pose[4] = (float)T.t[0]; a.pose[5] = (float)T.t[1]; a.pose[6] = (float)T.t[2];
         }
         a.result[0] = nedges >= 3 ? nedges - nBadEdges : 0;

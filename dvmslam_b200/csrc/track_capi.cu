@@ -314,12 +314,12 @@ static int finish_match(dvm_frame* f, int32_t* cur_mp, int* nmatches)
     return DVM_OK;
 }
 
-int dvm_match_by_projection_last(dvm_frame* cur, const float* Rcw, const float* tcw, const float* K, int last_n,
+int dvm_match_by_projection_last(dvm_frame* cur, const float* qcw, const float* tcw, const float* K, int last_n,
                                  const uint8_t* has_mp, const uint8_t* outlier, const float* Xw, const uint8_t* mp_desc,
                                  const uint8_t* mp_obs_pos, const int32_t* last_octave, const float* last_angle,
                                  float th, int check_orientation, int32_t* cur_mp, int* nmatches)
 {
-    DVM_REQUIRE(cur != nullptr && Rcw && tcw && K && cur_mp && nmatches, "null argument");
+    DVM_REQUIRE(cur != nullptr && qcw && tcw && K && cur_mp && nmatches, "null argument");
     DVM_REQUIRE(last_n >= 0, "negative count");
     DVM_REQUIRE(last_n == 0 || (has_mp && outlier && Xw && mp_desc && mp_obs_pos && last_octave && last_angle), "null last-frame arrays");
     DVM_CUDA(cudaSetDevice(cur->device));
@@ -330,7 +330,7 @@ int dvm_match_by_projection_last(dvm_frame* cur, const float* Rcw, const float* 
     if (rc != DVM_OK) return rc;
     MatchLastArgs a;
     memset(&a, 0, sizeof(a));
-    memcpy(a.R, Rcw, sizeof(a.R)); memcpy(a.t, tcw, sizeof(a.t)); memcpy(a.K, K, sizeof(a.K));
+    memcpy(a.q, qcw, sizeof(a.q)); memcpy(a.t, tcw, sizeof(a.t)); memcpy(a.K, K, sizeof(a.K));
     a.last_n = last_n; a.th = th; a.check_ori = check_orientation;
     Packer p(cur);
     a.has_mp = p.add(has_mp, n);

@@ -126,11 +126,11 @@ __global__ void __launch_bounds__(256) frustum_kernel(FrustumArgs a)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= a.m) return;
-    float R[9];
-    quat_to_R_f32(a.pose, R);
+    FrustumPose fp;
+    frustum_pose(a.pose, fp);
     float u, v, vc;
     int lvl;
-    const bool vis = frustum_eval(a, R, k, u, v, lvl, vc);
+    const bool vis = frustum_eval(a, fp, k, u, v, lvl, vc);
     a.in_view[k] = vis ? 1 : 0; a.px[k] = u; a.py[k] = v; a.level[k] = lvl; a.view_cos[k] = vc;
 }
 void launch_frustum(const FrustumArgs& a, cudaStream_t stream) { DVM_LAUNCH(frustum_kernel, div_up(a.m, 256), 256, 0, stream, a); }
@@ -224,9 +224,7 @@ __global__ void __launch_bounds__(kWalkThreads) match_last_walk_kernel(FrameDev 
     if (i >= nq) return;
     const FrameLook fl = look_global(cur);
     if (a.pose) { // pose prior held on the device
-        float Rm[9];
-        quat_to_R_f32(a.pose, Rm);
-        for (int k = 0; k < 9; k++) a.R[k] = Rm[k];
+        a.q[0] = a.pose[0]; a.q[1] = a.pose[1]; a.q[2] = a.pose[2]; a.q[3] = a.pose[3];
         a.t[0] = a.pose[4]; a.t[1] = a.pose[5]; a.t[2] = a.pose[6];
     }
     const int mi = a.mp_index ? a.mp_index[i] : (a.has_mp[i] ? i : -1);
@@ -235,10 +233,11 @@ __global__ void __launch_bounds__(kWalkThreads) match_last_walk_kernel(FrameDev 
 #pragma unroll
     for (int p = 0; p < kMatchCacheK; p++) top[p] = ~0ull;
     if (mi >= 0 && !a.outlier[i]) {
-        const float X = a.Xw[3 * mi], Y = a.Xw[3 * mi + 1], Z = a.Xw[3 * mi + 2];
-        const float xc = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a.R[0], X), __fmul_rn(a.R[1], Y)), __fmul_rn(a.R[2], Z)), a.t[0]);
-        const float yc = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a.R[3], X), __fmul_rn(a.R[4], Y)), __fmul_rn(a.R[5], Z)), a.t[1]);
-        const float zc = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a.R[6], X), __fmul_rn(a.R[7], Y)), __fmul_rn(a.R[8], Z)), a.t[2]);
+        // x3Dc = Tcw * x3Dw (O3/src/ORBmatcher.cc:1577): Sophus' quaternion action, not a matrix product
+        const float Pw[3] = { a.Xw[3 * mi], a.Xw[3 * mi + 1], a.Xw[3 * mi + 2] };
+        float Pc[3];
+        so::se3_apply(a.q, a.t, Pw, Pc);
+        const float xc = Pc[0], yc = Pc[1], zc = Pc[2];
         const float invzc = (float)(1.0 / (double)zc);
         if (!(invzc < 0)) {
             const float u = __fadd_rn(__fdiv_rn(__fmul_rn(a.K[0], xc), zc), a.K[2]);
@@ -436,9 +435,9 @@ __global__ void __launch_bounds__(kWalkThreads) match_map_walk_kernel(FrameDev c
     int lvl;
     float px, py, vcos;
     if (a.use_frustum) { // SearchLocalPoints: isInFrustum decides whether map point i takes part at all
-        float R[9];
-        quat_to_R_f32(a.fr.pose, R);
-        if (!frustum_eval(a.fr, R, i, px, py, lvl, vcos)) {
+        FrustumPose fp;
+        frustum_pose(a.fr.pose, fp);
+        if (!frustum_eval(a.fr, fp, i, px, py, lvl, vcos)) {
             if (lane == 0) { s.plevels[i] = -1; s.ncand[i] = 0; }
             return;
         }

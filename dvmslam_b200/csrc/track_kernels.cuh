@@ -1,6 +1,7 @@
 // track_kernels.cuh -- device structures and launchers of the per-frame tracking operators
 // (Frame grid, projection matchers, pose-only optimisation).
 #pragma once
+#include "sophus_f32.cuh"
 #include "common.cuh"
 
 namespace dvm {
@@ -28,7 +29,7 @@ struct FrameDev {
 
 // SearchByProjection(CurrentFrame, LastFrame): flat last-frame inputs (device pointers)
 struct MatchLastArgs {
-    float R[9], t[3], K[4];
+    float q[4], t[3], K[4];   // Tcw as the frame's SE3f holds it: unit quaternion (x, y, z, w), translation
     int last_n;
     const uint8_t* has_mp;
     const uint8_t* outlier;
@@ -43,7 +44,7 @@ struct MatchLastArgs {
     const int* n_ptr;              // last_n read from the device
     const int* mp_index;           // per last keypoint: index into Xw / mp_desc (map arrays), -1 = no map point
     const dvm_keypoint* last_kps;  // octave / angle source instead of the two arrays
-    const float* pose;             // qx,qy,qz,qw,tx,ty,tz on the device instead of R,t
+    const float* pose;             // qx,qy,qz,qw,tx,ty,tz on the device instead of q,t
     const int* guard;              // skip the whole search if *guard >= 20 (the 2*th retry, Tracking.cc:2614)
     int* map_out;                  // [cur cap] with mp_index: map point now held by each current keypoint (-1 none)
 };
@@ -137,55 +138,40 @@ void launch_match_last(const FrameDev& cur, const MatchLastArgs& a, const MatchS
 void launch_match_map(const FrameDev& cur, const MatchMapArgs& a, const MatchScratch& s, int* cur_mp, int* nmatches,
                       cudaStream_t stream);
 int launch_pose_opt(const PoseOptArgs& a, cudaStream_t stream);
-// quaternion (x,y,z,w, float) -> row-major rotation matrix, Eigen's toRotationMatrix in float32 after
-// normalisation: the convention shared with oracle/track_oracle.cpp (trko_is_in_frustum)
-__device__ inline void quat_to_R_f32(const float* q_in, float R[9])
+// Frame::isInFrustum (mono branch, O3/src/Frame.cc:575-636) + MapPoint::PredictScale (O3/src/MapPoint.cc:573-587) for map
+// point k.  pose = qx,qy,qz,qw,tx,ty,tz of the frame's SE3f as stored; R = toRotationMatrix(q) and Ow = translation of
+// Tcw.inverse() are what Frame::UpdatePoseMatrices (:553-559) caches (FrustumPose, computed once per thread).
+struct FrustumPose { float R[9], t[3], Ow[3]; };
+__device__ inline void frustum_pose(const float* pose, FrustumPose& fp)
 {
-    const float n = __fsqrt_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(q_in[0], q_in[0]), __fmul_rn(q_in[1], q_in[1])),
-                                                   __fmul_rn(q_in[2], q_in[2])), __fmul_rn(q_in[3], q_in[3])));
-    const float x = __fdiv_rn(q_in[0], n), y = __fdiv_rn(q_in[1], n), z = __fdiv_rn(q_in[2], n), w = __fdiv_rn(q_in[3], n);
-    const float tx = __fmul_rn(2.f, x), ty = __fmul_rn(2.f, y), tz = __fmul_rn(2.f, z);
-    const float twx = __fmul_rn(tx, w), twy = __fmul_rn(ty, w), twz = __fmul_rn(tz, w);
-    const float txx = __fmul_rn(tx, x), txy = __fmul_rn(ty, x), txz = __fmul_rn(tz, x);
-    const float tyy = __fmul_rn(ty, y), tyz = __fmul_rn(tz, y), tzz = __fmul_rn(tz, z);
-    R[0] = __fsub_rn(1.f, __fadd_rn(tyy, tzz)); R[1] = __fsub_rn(txy, twz); R[2] = __fadd_rn(txz, twy);
-    R[3] = __fadd_rn(txy, twz); R[4] = __fsub_rn(1.f, __fadd_rn(txx, tzz)); R[5] = __fsub_rn(tyz, twx);
-    R[6] = __fsub_rn(txz, twy); R[7] = __fadd_rn(tyz, twx); R[8] = __fsub_rn(1.f, __fadd_rn(txx, tyy));
+    const float q[4] = { pose[0], pose[1], pose[2], pose[3] };
+    fp.t[0] = pose[4]; fp.t[1] = pose[5]; fp.t[2] = pose[6];
+    so::quat_to_matrix(q, fp.R);
+    float qi[4];
+    so::se3_inverse(q, fp.t, qi, fp.Ow);
 }
-
-// Frame::isInFrustum (mono branch, O3/src/Frame.cc:575-636) + MapPoint::PredictScale (O3/src/MapPoint.cc:573-587)
-// for map point k with rotation R (row-major) and translation pose[4..6]; returns visibility
-__device__ inline bool frustum_eval(const FrustumArgs& a, const float R[9], int k, float& u, float& v, int& lvl, float& vc)
+__device__ inline bool frustum_eval(const FrustumArgs& a, const FrustumPose& fp, int k, float& u, float& v, int& lvl, float& vc)
 {
     u = -1.f; v = -1.f; vc = 0.f; lvl = -1;
     if (a.skip && a.skip[k]) return false;
-    const float t0 = a.pose[4], t1 = a.pose[5], t2 = a.pose[6];
-    const float X = a.xw[3 * k], Y = a.xw[3 * k + 1], Z = a.xw[3 * k + 2];
-    const float xc = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(R[0], X), __fmul_rn(R[1], Y)), __fmul_rn(R[2], Z)), t0);
-    const float yc = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(R[3], X), __fmul_rn(R[4], Y)), __fmul_rn(R[5], Z)), t1);
-    const float zc = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(R[6], X), __fmul_rn(R[7], Y)), __fmul_rn(R[8], Z)), t2);
+    const float P[3] = { a.xw[3 * k], a.xw[3 * k + 1], a.xw[3 * k + 2] };
+    float Pc[3];
+    so::mat_vec(fp.R, P, Pc);                                   // Pc = mRcw * P + mtcw
+    const float xc = __fadd_rn(Pc[0], fp.t[0]), yc = __fadd_rn(Pc[1], fp.t[1]), zc = __fadd_rn(Pc[2], fp.t[2]);
     if (zc < 0.0f) return false;
     const float pu = __fadd_rn(__fdiv_rn(__fmul_rn(a.K[0], xc), zc), a.K[2]);
     const float pv = __fadd_rn(__fdiv_rn(__fmul_rn(a.K[1], yc), zc), a.K[3]);
     if ((pu < a.bounds[0] || pu > a.bounds[2]) || (pv < a.bounds[1] || pv > a.bounds[3])) return false;
     u = pu; v = pv;
     const float maxD = __fmul_rn(1.2f, a.max_dist[k]), minD = __fmul_rn(0.8f, a.min_dist[k]);
-    float Ow[3];
-#pragma unroll
-    for (int i = 0; i < 3; i++)
-        Ow[i] = __fadd_rn(__fadd_rn(__fmul_rn(R[i], -t0), __fmul_rn(R[3 + i], -t1)), __fmul_rn(R[6 + i], -t2));
-    const float p0 = __fsub_rn(X, Ow[0]), p1 = __fsub_rn(Y, Ow[1]), p2 = __fsub_rn(Z, Ow[2]);
-    const float dist = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(p0, p0), __fmul_rn(p1, p1)), __fmul_rn(p2, p2)));
+    const float PO[3] = { __fsub_rn(P[0], fp.Ow[0]), __fsub_rn(P[1], fp.Ow[1]), __fsub_rn(P[2], fp.Ow[2]) };
+    const float dist = so::norm3(PO);
     if (dist < minD || dist > maxD) return false;
-    const float dot = __fadd_rn(__fadd_rn(__fmul_rn(p0, a.normal[3 * k]), __fmul_rn(p1, a.normal[3 * k + 1])),
-                                __fmul_rn(p2, a.normal[3 * k + 2]));
-    const float c = __fdiv_rn(dot, dist);
+    const float Pn[3] = { a.normal[3 * k], a.normal[3 * k + 1], a.normal[3 * k + 2] };
+    const float c = __fdiv_rn(so::dot3(PO, Pn), dist);
     if (c < a.cosLimit) return false;
-    const float ratio = __fdiv_rn(a.max_dist[k], dist);
-    int nScale = (int)ceilf(__fdiv_rn((float)log((double)ratio), a.logScale));
-    if (nScale < 0) nScale = 0;
-    else if (nScale >= a.nlevels) nScale = a.nlevels - 1;
-    lvl = nScale; vc = c;
+    lvl = so::predict_scale(a.max_dist[k], dist, a.logScale, a.nlevels);
+    vc = c;
     return true;
 }
 

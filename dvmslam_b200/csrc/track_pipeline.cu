@@ -3,6 +3,8 @@
 // SearchByProjection(local map) -> PoseOptimization without host round trips
 // (call order of Tracking::TrackWithMotionModel / TrackLocalMap / SearchLocalPoints,
 //  O3/src/Tracking.cc:2584-2666, 2668-2768, 3041-3106).
+#include "sophus_f32.cuh"
+#include "glibc_logf.h"
 #include "track_internal.cuh"
 #include <cmath>
 #include <vector>
@@ -11,7 +13,10 @@ using namespace dvm;
 
 namespace {
 
-// prior = mVelocity * last, mVelocity = last * prev^-1 (Tracking.cc:1968-1971, 2598), in double then float
+// The constant-velocity prior of Tracking::TrackWithMotionModel in the reference's own float32 Sophus arithmetic:
+// mVelocity = mCurrentFrame.GetPose() * mLastFrame.GetPose().inverse() after a tracked frame (Tracking.cc:1990-1991),
+// then mCurrentFrame.SetPose(mVelocity * mLastFrame.GetPose()) for the next one (:2598).  `last` / `prev` are the two
+// most recent poses (qx,qy,qz,qw,tx,ty,tz) as their SE3f would hold them.
 // Also the per-frame reset of the "seen in this frame" marks and the counters (one launch instead of three).
 __global__ void __launch_bounds__(1024) begin_frame_kernel(const float* last, const float* prev, float* prior, int have_prior,
                                                            uint8_t* seen, int map_n, int* cnt)
@@ -20,34 +25,14 @@ __global__ void __launch_bounds__(1024) begin_frame_kernel(const float* last, co
     for (int i = threadIdx.x; i < (map_n + 3) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(seen)[i] = 0u;
     if (threadIdx.x < 8) cnt[threadIdx.x] = 0;
     if (threadIdx.x != 0 || have_prior) return;
-    auto qmul = [](const double* a, const double* b, double* r) {
-        r[3] = a[3] * b[3] - a[0] * b[0] - a[1] * b[1] - a[2] * b[2];
-        r[0] = a[3] * b[0] + a[0] * b[3] + a[1] * b[2] - a[2] * b[1];
-        r[1] = a[3] * b[1] + a[1] * b[3] + a[2] * b[0] - a[0] * b[2];
-        r[2] = a[3] * b[2] + a[2] * b[3] + a[0] * b[1] - a[1] * b[0];
-    };
-    auto qrot = [](const double* q, const double* v, double* o) {
-        double uv[3] = { q[1] * v[2] - q[2] * v[1], q[2] * v[0] - q[0] * v[2], q[0] * v[1] - q[1] * v[0] };
-        uv[0] += uv[0]; uv[1] += uv[1]; uv[2] += uv[2];
-        o[0] = v[0] + q[3] * uv[0] + (q[1] * uv[2] - q[2] * uv[1]);
-        o[1] = v[1] + q[3] * uv[1] + (q[2] * uv[0] - q[0] * uv[2]);
-        o[2] = v[2] + q[3] * uv[2] + (q[0] * uv[1] - q[1] * uv[0]);
-    };
-    double ql[4], tl[3], qp[4], tp[3];
+    float ql[4], tl[3], qp[4], tp[3], qpi[4], tpi[3], qv[4], tv[3], qo[4], to[3];
     for (int i = 0; i < 4; i++) { ql[i] = last[i]; qp[i] = prev[i]; }
     for (int i = 0; i < 3; i++) { tl[i] = last[4 + i]; tp[i] = prev[4 + i]; }
-    // V = L * P^-1:  qv = ql * conj(qp), tv = tl - qv * tp ;  prior = V * L
-    double qpc[4] = { -qp[0], -qp[1], -qp[2], qp[3] }, qv[4], tmp[3], tv[3], qo[4], to[3];
-    qmul(ql, qpc, qv);
-    qrot(qv, tp, tmp);
-    for (int i = 0; i < 3; i++) tv[i] = tl[i] - tmp[i];
-    qmul(qv, ql, qo);
-    qrot(qv, tl, tmp);
-    for (int i = 0; i < 3; i++) to[i] = tmp[i] + tv[i];
-    double n = sqrt(qo[0] * qo[0] + qo[1] * qo[1] + qo[2] * qo[2] + qo[3] * qo[3]);
-    if (qo[3] < 0) n = -n;
-    for (int i = 0; i < 4; i++) prior[i] = (float)(qo[i] / n);
-    for (int i = 0; i < 3; i++) prior[4 + i] = (float)to[i];
+    so::se3_inverse(qp, tp, qpi, tpi);            // LastTwc
+    so::se3_mul(ql, tl, qpi, tpi, qv, tv);        // mVelocity
+    so::se3_mul(qv, tv, ql, tl, qo, to);          // mVelocity * mLastFrame.GetPose()
+    for (int i = 0; i < 4; i++) prior[i] = qo[i];
+    for (int i = 0; i < 3; i++) prior[4 + i] = to[i];
 }
 
 } // namespace
@@ -153,7 +138,7 @@ int dvm_frame_is_in_frustum(dvm_frame* f, const float* pose_q, const float* pose
     FrustumArgs a;
     const float bounds[4] = { f->dev.minX, f->dev.minY, f->dev.maxX, f->dev.maxY };
     // mfLogScaleFactor = log(mfScaleFactor), O3/src/Frame.cc:401 (scale[1] is the per-level factor)
-    const float logScale = (float)std::log((double)(f->dev.nlevels > 1 ? f->dev.scale[1] : 1.2f));
+    const float logScale = dvm_glibc_logf(f->dev.nlevels > 1 ? f->dev.scale[1] : 1.2f);
     fill_frustum_args(a, (const float*)(f->d_in + o_pose), K, bounds, f->dev.nlevels, logScale, viewing_cos_limit);
     a.m = m;
     a.xw = (const float*)(f->d_in + o_xw); a.normal = (const float*)(f->d_in + o_nrm);
@@ -190,7 +175,7 @@ int dvm_tracker_create(dvm_tracker** out, dvm_orb* orb, const float* K, const fl
     float sc[16], is2[16];
     dvm_orb_tables(orb, &t->nlevels, sc, nullptr, nullptr, is2, nullptr);
     t->inv_sigma2.assign(is2, is2 + t->nlevels);
-    t->logScale = (float)std::log((double)(t->nlevels > 1 ? sc[1] : 1.2f));
+    t->logScale = dvm_glibc_logf(t->nlevels > 1 ? sc[1] : 1.2f);
     for (int i = 0; i < 4; i++) { t->K[i] = K[i]; t->bounds[i] = bounds[i]; }
     cudaGetDevice(&t->device);
 #define DVM_TCREATE(call)                                                                      \

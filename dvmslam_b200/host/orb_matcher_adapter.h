@@ -72,13 +72,11 @@ int SearchByProjectionLast(FrameT& Cur, const FrameT& Last, float th, bool check
 {
     DeviceFrame& dev = device_frame(Cur);
     const auto Tcw = Cur.GetPose();
-    const auto R = Tcw.rotationMatrix();
+    // the pose goes over as the SE3f holds it: the library applies Sophus' quaternion action (x3Dc = Tcw * x3Dw, :1577)
+    const auto uq = Tcw.unit_quaternion();
     const auto t = Tcw.translation();
-    float Rcw[9], tcw[3];
-    for (int r = 0; r < 3; r++) {
-        for (int c = 0; c < 3; c++) Rcw[3 * r + c] = R(r, c);
-        tcw[r] = t(r);
-    }
+    const float qcw[4] = { uq.x(), uq.y(), uq.z(), uq.w() };
+    const float tcw[3] = { t(0), t(1), t(2) };
     const float K[4] = { Cur.fx, Cur.fy, Cur.cx, Cur.cy };
     const int n = Last.N;
     std::vector<uint8_t> has_mp(n), outlier(n), obs_pos(n), desc(static_cast<size_t>(n) * 32);
@@ -99,7 +97,7 @@ int SearchByProjectionLast(FrameT& Cur, const FrameT& Last, float th, bool check
     }
     std::vector<int32_t> cur_mp(Cur.N > 0 ? Cur.N : 1, -1);
     int nmatches = 0;
-    check(dvm_match_by_projection_last(dev.frame.h, Rcw, tcw, K, n, has_mp.data(), outlier.data(), Xw.data(), desc.data(),
+    check(dvm_match_by_projection_last(dev.frame.h, qcw, tcw, K, n, has_mp.data(), outlier.data(), Xw.data(), desc.data(),
                                        obs_pos.data(), octave.data(), angle.data(), th, checkOrientation ? 1 : 0,
                                        cur_mp.data(), &nmatches),
           "ORBmatcher::SearchByProjection(Frame&, const Frame&)");
@@ -259,8 +257,8 @@ int SearchForInitialization(FrameT& F1, FrameT& F2, std::vector<Point2fT>& vbPre
 // int ORBmatcher::SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, vector<pair<size_t,size_t>>& vMatchedPairs,
 //                                        const bool bOnlyStereo, const bool bCoarse)             :836-1058
 // Mono keyframes (bOnlyStereo must be false).  The relative pose, the epipole and the fundamental matrix are
-// derived here as the reference does (:841-855; Pinhole::epipolarConstrain, O3/src/CameraModels/Pinhole.cpp:104-110,
-// with the closed-form inverse of the pinhole K instead of Eigen's generic 3x3 inverse).
+// derived by dvm_fundamental_from_poses as the reference does (:841-860; Pinhole::epipolarConstrain,
+// O3/src/CameraModels/Pinhole.cpp:104-110) -- same float32 operations in the same order.
 // ---------------------------------------------------------------------------------------------------
 template <class KeyFrameT>
 int SearchForTriangulation(KeyFrameT* pKF1, KeyFrameT* pKF2, std::vector<std::pair<size_t, size_t>>& vMatchedPairs,
@@ -270,26 +268,14 @@ int SearchForTriangulation(KeyFrameT* pKF1, KeyFrameT* pKF2, std::vector<std::pa
     if (bOnlyStereo) return 0;   // mono keyframes have no stereo observations: every feature is skipped (:896-898)
     const auto T1w = pKF1->GetPose();
     const auto T2w = pKF2->GetPose();
-    const auto R1 = T1w.rotationMatrix(), R2 = T2w.rotationMatrix();
-    const auto t1 = T1w.translation(), t2 = T2w.translation();
-    float R12[9], t12[3], Cw[3], C2[3];
-    for (int r = 0; r < 3; r++)
-        for (int c = 0; c < 3; c++) R12[3 * r + c] = R1(r, 0) * R2(c, 0) + R1(r, 1) * R2(c, 1) + R1(r, 2) * R2(c, 2);   // T1w * Tw2
-    for (int r = 0; r < 3; r++) t12[r] = t1(r) - (R12[3 * r] * t2(0) + R12[3 * r + 1] * t2(1) + R12[3 * r + 2] * t2(2));
-    for (int r = 0; r < 3; r++) Cw[r] = -(R1(0, r) * t1(0) + R1(1, r) * t1(1) + R1(2, r) * t1(2));                       // GetCameraCenter
-    for (int r = 0; r < 3; r++) C2[r] = R2(r, 0) * Cw[0] + R2(r, 1) * Cw[1] + R2(r, 2) * Cw[2] + t2(r);
-    const float ep[2] = { pKF2->fx * C2[0] / C2[2] + pKF2->cx, pKF2->fy * C2[1] / C2[2] + pKF2->cy };
-    // F12 = K1^-T [t12]x R12 K2^-1
-    const float tx[9] = { 0, -t12[2], t12[1], t12[2], 0, -t12[0], -t12[1], t12[0], 0 };
-    float E[9], A[9], F12[9];
-    for (int r = 0; r < 3; r++)
-        for (int c = 0; c < 3; c++) E[3 * r + c] = tx[3 * r] * R12[c] + tx[3 * r + 1] * R12[3 + c] + tx[3 * r + 2] * R12[6 + c];
-    const float k1it[9] = { 1 / pKF1->fx, 0, 0, 0, 1 / pKF1->fy, 0, -pKF1->cx / pKF1->fx, -pKF1->cy / pKF1->fy, 1 };   // K1^-T
-    const float k2i[9] = { 1 / pKF2->fx, 0, -pKF2->cx / pKF2->fx, 0, 1 / pKF2->fy, -pKF2->cy / pKF2->fy, 0, 0, 1 };    // K2^-1
-    for (int r = 0; r < 3; r++)
-        for (int c = 0; c < 3; c++) A[3 * r + c] = k1it[3 * r] * E[c] + k1it[3 * r + 1] * E[3 + c] + k1it[3 * r + 2] * E[6 + c];
-    for (int r = 0; r < 3; r++)
-        for (int c = 0; c < 3; c++) F12[3 * r + c] = A[3 * r] * k2i[c] + A[3 * r + 1] * k2i[3 + c] + A[3 * r + 2] * k2i[6 + c];
+    // T12 = T1w * Tw2, the epipole and F12 = K1^-T [t12]x R12 K2^-1 in the reference's float32 Sophus / Eigen arithmetic
+    const auto q1 = T1w.unit_quaternion(), q2 = T2w.unit_quaternion();
+    const auto tr1 = T1w.translation(), tr2 = T2w.translation();
+    const float qa[4] = { q1.x(), q1.y(), q1.z(), q1.w() }, ta[3] = { tr1(0), tr1(1), tr1(2) };
+    const float qb[4] = { q2.x(), q2.y(), q2.z(), q2.w() }, tb[3] = { tr2(0), tr2(1), tr2(2) };
+    const float K1[4] = { pKF1->fx, pKF1->fy, pKF1->cx, pKF1->cy }, K2[4] = { pKF2->fx, pKF2->fy, pKF2->cx, pKF2->cy };
+    float F12[9], ep[2];
+    check(dvm_fundamental_from_poses(qa, ta, qb, tb, K1, K2, F12, ep), "ORBmatcher::SearchForTriangulation (relative pose)");
 
     auto flatten = [](KeyFrameT* kf) {
         FlatFeatures f = flatten_features(kf->mvKeysUn, kf->mDescriptors, kf->mFeatVec,
@@ -332,9 +318,12 @@ int Fuse(KeyFrameT* pKF, const std::vector<MapPointT*>& vpMapPoints, float th)
         const auto p = pMP->GetWorldPos();
         const auto n = pMP->GetNormal();
         for (int k = 0; k < 3; k++) { xw[3 * i + k] = p(k); nrm[3 * i + k] = n(k); }
-        // GetMin/MaxDistanceInvariance() = 0.8 * mfMinDistance / 1.2 * mfMaxDistance; the library applies the factors
-        mind[i] = pMP->GetMinDistanceInvariance() / 0.8f;
-        maxd[i] = pMP->GetMaxDistanceInvariance() / 1.2f;
+        // mfMinDistance / mfMaxDistance themselves: the library forms 0.8f * min and 1.2f * max for the range gate as
+        // Get{Min,Max}DistanceInvariance do and feeds mfMaxDistance to PredictScale (MapPoint.cc:547-587).  The members
+        // are protected in the reference; INTEGRATION.md adds the two one-line getters used here (dividing the
+        // invariance values by 0.8f / 1.2f does not give the members back bit for bit).
+        mind[i] = pMP->GetMinDistance();
+        maxd[i] = pMP->GetMaxDistance();
         const auto d = pMP->GetDescriptor();
         std::memcpy(&desc[static_cast<size_t>(i) * 32], d.ptr(0), 32);
     }
@@ -353,6 +342,7 @@ int Fuse(KeyFrameT* pKF, const std::vector<MapPointT*>& vpMapPoints, float th)
     for (int i = 0; i < m; i++) {
         if (bestIdx[i] < 0) continue;
         MapPointT* pMP = vpMapPoints[i];
+        if (pMP->isBad()) continue;             // replaced by an earlier iteration of this loop (:1086-1090 re-evaluated per iteration)
         if (pMP->IsInKeyFrame(pKF)) continue;   // the same map point listed twice: added by its first occurrence
         MapPointT* pMPinKF = pKF->GetMapPoint(bestIdx[i]);
         if (pMPinKF) {

@@ -115,29 +115,16 @@ class BowMatcher:
 
 
 def fundamental_from_poses(q1, t1, q2, t2, K1, K2):
-    """(F12 row-major float32[9], ep float32[2]) as SearchForTriangulation derives them from the two keyframe poses
-    Tcw (O3/src/ORBmatcher.cc:841-855: T12 = T1w * Tw2, C2 = T2w * Cw, ep = project(C2)) and
-    Pinhole::epipolarConstrain builds F12 = K1^-T [t12]x R12 K2^-1 (O3/src/CameraModels/Pinhole.cpp:104-110).
-    Evaluated in float32 matrix arithmetic; the same numbers go to the oracle and to the GPU."""
-    f = np.float32
-
-    def R_of(q):
-        x, y, z, w = (f(v) for v in np.asarray(q, f) / f(np.linalg.norm(np.asarray(q, f))))
-        return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
-                         [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
-                         [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]], f)
-
-    R1, R2 = R_of(q1), R_of(q2)
-    t1, t2 = np.asarray(t1, f), np.asarray(t2, f)
-    R12 = (R1 @ R2.T).astype(f)
-    t12 = (t1 - R12 @ t2).astype(f)
-    Cw = (-(R1.T @ t1)).astype(f)
-    C2 = (R2 @ Cw + t2).astype(f)
-    ep = np.array([K2[0] * C2[0] / C2[2] + K2[2], K2[1] * C2[1] / C2[2] + K2[3]], f)
-    tx = np.array([[0, -t12[2], t12[1]], [t12[2], 0, -t12[0]], [-t12[1], t12[0], 0]], f)
-    Km = lambda K: np.array([[K[0], 0, K[2]], [0, K[1], K[3]], [0, 0, 1]], f)  # noqa: E731
-    F12 = (np.linalg.inv(Km(K1).T).astype(f) @ tx @ R12 @ np.linalg.inv(Km(K2)).astype(f)).astype(f)
-    return np.ascontiguousarray(F12.reshape(9)), ep
+    """(F12 row-major float32[9], ep float32[2]) as SearchForTriangulation derives them from the two keyframe poses Tcw
+    (O3/src/ORBmatcher.cc:841-860) and Pinhole::epipolarConstrain rebuilds F12 = K1^-T [t12]x R12 K2^-1
+    (O3/src/CameraModels/Pinhole.cpp:104-110), in the reference's float32 Sophus / Eigen arithmetic
+    (dvm_fundamental_from_poses; host arithmetic inside the library)."""
+    L = lib()
+    L.dvm_fundamental_from_poses.argtypes = [_vp] * 8
+    a = [_c(x, np.float32) for x in (q1, t1, q2, t2, K1, K2)]
+    F12, ep = np.zeros(9, np.float32), np.zeros(2, np.float32)
+    check(L.dvm_fundamental_from_poses(*(x.ctypes.data for x in a), F12.ctypes.data, ep.ctypes.data))
+    return F12, ep
 
 
 def SearchForTriangulation(ctx: Frame, kf1: BowFeatures, kps1, kf2: BowFeatures, kps2, F12, ep, scale_factors2,

@@ -179,8 +179,9 @@ def tracking_case(stream: "PlaneStream", k: int, extract, n_local: int = 4000, s
     sel = rng.permutation(len(mk))[:n_local]
     sel.sort()
     Xm = backproject_to_plane(stream, k0, np.stack([mk["x"][sel], mk["y"][sel]], 1).astype(np.float64))
+    qp = quat_from_R(Rp.astype(np.float64)).astype(np.float32)   # the prior as an SE3f would hold it
     return dict(last_kps=lk, last_desc=ld, cur_kps=ck, cur_desc=cd, cur_img=cur_img, last_Xw=Xw, has_mp=has_mp,
-                outlier=outlier, obs_pos=obs_pos, Rcw_prior=Rp, tcw_prior=tp, Rcw_true=Rcw, tcw_true=tcw,
+                outlier=outlier, obs_pos=obs_pos, Rcw_prior=Rp, qcw_prior=qp, tcw_prior=tp, Rcw_true=Rcw, tcw_true=tcw,
                 K=np.array(stream.K, np.float32), map_Xw=Xm, map_desc=md[sel].copy(), map_octave=mk["octave"][sel].copy(),
                 bounds=(0.0, 0.0, float(stream.w), float(stream.h)))
 

@@ -107,10 +107,12 @@ class ORBmatcher:
         self.L = lib()
         _bind(self.L)
 
-    def SearchByProjectionLast(self, cur: Frame, Rcw, tcw, K, has_mp, outlier, Xw, mp_desc, obs_pos, last_octave,
+    def SearchByProjectionLast(self, cur: Frame, qcw, tcw, K, has_mp, outlier, Xw, mp_desc, obs_pos, last_octave,
                                last_angle, th):
-        """SearchByProjection(CurrentFrame, LastFrame, th, bMono=True) -> (nmatches, cur_mp)."""
-        a = [_c(Rcw, np.float32), _c(tcw, np.float32), _c(K, np.float32)]
+        """SearchByProjection(CurrentFrame, LastFrame, th, bMono=True) -> (nmatches, cur_mp).  qcw (x, y, z, w) / tcw:
+        CurrentFrame.GetPose() as its SE3f holds it."""
+        a = [_c(qcw, np.float32), _c(tcw, np.float32), _c(K, np.float32)]
+        assert a[0].shape == (4,), "the pose is a quaternion (x, y, z, w), not a rotation matrix"
         b = [_c(has_mp, np.uint8), _c(outlier, np.uint8), _c(Xw, np.float32), _c(mp_desc, np.uint8),
              _c(obs_pos, np.uint8), _c(last_octave, np.int32), _c(last_angle, np.float32)]
         cur_mp = np.full(cur.cap, -1, np.int32)

@@ -180,10 +180,12 @@ DVM_API int dvm_frame_grid_cell(dvm_frame* f, int ix, int iy, int32_t* out, int 
  * (O3/src/ORBmatcher.cc:1553-1748).  One entry per last-frame keypoint i: has_mp (mvpMapPoints[i] !=
  * NULL), outlier (mvbOutlier[i]), Xw (GetWorldPos), mp_desc (GetDescriptor, 32 B), mp_obs_pos
  * (Observations() > 0), last_octave (mvKeys[i].octave), last_angle (mvKeysUn[i].angle).
- * Rcw (row-major 3x3), tcw: CurrentFrame.GetPose(); K = fx, fy, cx, cy.
+ * qcw (x, y, z, w), tcw: CurrentFrame.GetPose() as the SE3f holds it -- unit_quaternion().coeffs() and translation(),
+ * used as they are (no renormalisation): the projection is Sophus' quaternion action x3Dc = Tcw * x3Dw (:1577;
+ * O3/Thirdparty/Sophus/sophus/so3.hpp:358-367), not a rotation-matrix product.  K = fx, fy, cx, cy.
  * cur_mp[cur n] receives, per current keypoint, the last-frame index whose map point it now holds
  * (CurrentFrame.mvpMapPoints, which the caller cleared before the call); *nmatches = return value. */
-DVM_API int dvm_match_by_projection_last(dvm_frame* cur, const float* Rcw, const float* tcw, const float* K,
+DVM_API int dvm_match_by_projection_last(dvm_frame* cur, const float* qcw, const float* tcw, const float* K,
                                          int last_n, const uint8_t* has_mp, const uint8_t* outlier, const float* Xw,
                                          const uint8_t* mp_desc, const uint8_t* mp_obs_pos,
                                          const int32_t* last_octave, const float* last_angle, float th,
@@ -243,6 +245,16 @@ DVM_API int dvm_match_by_bow(dvm_frame* ctx, int kf_kf, const dvm_bow_features* 
 DVM_API int dvm_match_for_initialization(dvm_frame* f2, int n1, const dvm_keypoint* kps1_un, const uint8_t* desc1,
                                          float* prev_matched, int window_size, float nnratio,
                                          int check_orientation, int32_t* matches12, int* nmatches);
+
+/* The relative geometry SearchForTriangulation derives from the two keyframe poses before it matches
+ * (O3/src/ORBmatcher.cc:841-860, mono keyframes), in the reference's own float32 arithmetic: T12 = T1w * T2w.inverse()
+ * (Sophus' normalising quaternion product and inverse, O3/Thirdparty/Sophus/sophus/{so3,se3}.hpp), R12 / t12 of it, the
+ * fundamental matrix Pinhole::epipolarConstrain rebuilds for every candidate pair, F12 = K1^-T [t12]x R12 K2^-1 with
+ * Eigen's 3x3 inverse and left-to-right products (O3/src/CameraModels/Pinhole.cpp:104-110), and the epipole ep =
+ * project(T2w * Cw).  q1 / q2 = (x, y, z, w) and t1 / t2 of pKF1->GetPose() / pKF2->GetPose() as stored; K = fx, fy, cx,
+ * cy.  Host arithmetic only (no GPU): F12[9] row-major and ep[2] are the arguments of dvm_match_for_triangulation. */
+DVM_API int dvm_fundamental_from_poses(const float* q1, const float* t1, const float* q2, const float* t2, const float* K1,
+                                       const float* K2, float* F12, float* ep);
 
 /* int ORBmatcher::SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, vector<pair<size_t,size_t>>& vMatchedPairs,
  * const bool bOnlyStereo = false, const bool bCoarse)  (O3/src/ORBmatcher.cc:836-1058; caller

@@ -97,6 +97,18 @@ def search_for_triangulation(desc1, kps1, has_mp1, fv1, desc2, kps2, has_mp2, fv
     return n, m12[:n1]
 
 
+def fundamental_from_poses(q1, t1, q2, t2, K1, K2):
+    """(F12 row-major float32[9], ep float32[2]) from the two keyframe poses Tcw as stored, in the reference's float32
+    arithmetic (Sophus products / inverse, Eigen 3x3 inverse and products; bowo_fundamental_from_poses)."""
+    L = _L()
+    L.bowo_fundamental_from_poses.argtypes = [_vp] * 8
+    L.bowo_fundamental_from_poses.restype = None
+    a = [_c(x, np.float32) for x in (q1, t1, q2, t2, K1, K2)]
+    F12, ep = np.zeros(9, np.float32), np.zeros(2, np.float32)
+    L.bowo_fundamental_from_poses(*(x.ctypes.data for x in a), F12.ctypes.data, ep.ctypes.data)
+    return F12, ep
+
+
 def fuse_search(frame_oracle, q, t, K, log_scale, inv_sigma2, xw, normal, min_dist, max_dist, mp_desc, skip=None, th=3.0):
     """frame_oracle: oracle.track.FrameOracle of the keyframe -> (best_idx, best_dist)"""
     L = _L()

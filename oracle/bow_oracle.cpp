@@ -18,6 +18,7 @@
  * Parity status: UNPINNED against the reference (no tests or fixtures upstream; ORBmatcher.cc does not
  * compile without OpenCV/DBoW2/the map data model).
  */
+#include "sophus_order.h"
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -238,6 +239,37 @@ int bowo_search_for_triangulation(int n1, const uint8_t* desc1, const void* kps1
         }
     }
     return nmatches;
+}
+
+
+/* The relative geometry SearchForTriangulation works with (O3/src/ORBmatcher.cc:841-860, mono keyframes): from the two
+ * keyframe poses Tcw as stored (q = x, y, z, w; t), T12 = T1w * Tw2 with Tw2 = T2w.inverse() (Sophus: normalising
+ * quaternion product, so3.hpp:325-340), R12 = T12.rotationMatrix(), t12 = T12.translation(); the epipole
+ * ep = project(T2w * Cw) with Cw = T1w.inverse().translation(); and the fundamental matrix
+ * Pinhole::epipolarConstrain rebuilds for every candidate pair (O3/src/CameraModels/Pinhole.cpp:104-110):
+ * F12 = K1.transpose().inverse() * hat(t12) * R12 * K2.inverse(), Eigen's 3x3 inverse and left-to-right coefficient
+ * products.  F12 row-major [9], ep [2]. */
+void bowo_fundamental_from_poses(const float* q1, const float* t1, const float* q2, const float* t2, const float* K1,
+                                 const float* K2, float* F12, float* ep)
+{
+    float qw2[4], tw2[3], q12[4], t12[3], qw1[4], Cw[3], C2[3];
+    so::se3_inverse(q2, t2, qw2, tw2);
+    so::se3_mul(q1, t1, qw2, tw2, q12, t12);
+    float R12[9];
+    so::quat_to_matrix(q12, R12);
+    so::se3_inverse(q1, t1, qw1, Cw);
+    so::se3_apply(q2, t2, Cw, C2);
+    ep[0] = K2[0] * C2[0] / C2[2] + K2[2];
+    ep[1] = K2[1] * C2[1] / C2[2] + K2[3];
+    const float t12x[9] = { 0.f, -t12[2], t12[1], t12[2], 0.f, -t12[0], -t12[1], t12[0], 0.f };
+    const float K1T[9] = { K1[0], 0.f, 0.f, 0.f, K1[1], 0.f, K1[2], K1[3], 1.f };   /* toK_() transposed */
+    const float K2m[9] = { K2[0], 0.f, K2[2], 0.f, K2[1], K2[3], 0.f, 0.f, 1.f };
+    float K1Ti[9], K2i[9], A[9], B[9];
+    so::mat_inverse(K1T, K1Ti);
+    so::mat_inverse(K2m, K2i);
+    so::mat_mul(K1Ti, t12x, A);
+    so::mat_mul(A, R12, B);
+    so::mat_mul(B, K2i, F12);
 }
 
 } // extern "C"

@@ -96,6 +96,8 @@ public:
     template <typename T> const T& at(int y, int x) const { return *(const T*)(data + (size_t)y * step + x); }
     uchar* ptr(int y = 0) { return data + (size_t)y * step; }
     const uchar* ptr(int y = 0) const { return data + (size_t)y * step; }
+    template <typename T> T* ptr(int y = 0) { return (T*)(data + (size_t)y * step); }
+    template <typename T> const T* ptr(int y = 0) const { return (const T*)(data + (size_t)y * step); }
     Mat operator()(const Rect& r) const { Mat m = *this; m.data = data + (size_t)r.y * step + r.x; m.rows = r.height; m.cols = r.width; return m; }
     Mat rowRange(int a, int b) const { return (*this)(Rect(0, a, cols, b - a)); }
     Mat colRange(int a, int b) const { return (*this)(Rect(a, 0, b - a, rows)); }

@@ -59,10 +59,12 @@ class FrameOracle:
         n = self.L.trko_features_in_area(self.h, x, y, r, min_level, max_level, buf.ctypes.data, len(buf))
         return buf[:n].copy()
 
-    def search_by_projection_last(self, Rcw, tcw, K, has_mp, outlier, Xw, mp_desc, obs_pos, last_octave, last_angle,
+    def search_by_projection_last(self, qcw, tcw, K, has_mp, outlier, Xw, mp_desc, obs_pos, last_octave, last_angle,
                                   th, check_ori=True):
+        """qcw (x, y, z, w), tcw: the current frame's pose as its SE3f holds it."""
         cur_mp = np.full(max(self.n, 1), -1, np.int32)
-        a = [_c(Rcw, np.float32), _c(tcw, np.float32), _c(K, np.float32)]
+        a = [_c(qcw, np.float32), _c(tcw, np.float32), _c(K, np.float32)]
+        assert a[0].shape == (4,)
         b = [_c(has_mp, np.uint8), _c(outlier, np.uint8), _c(Xw, np.float32), _c(mp_desc, np.uint8),
              _c(obs_pos, np.uint8), _c(last_octave, np.int32), _c(last_angle, np.float32)]
         n = self.L.trko_search_by_projection_last(self.h, *(x.ctypes.data for x in a), len(b[0]),
@@ -123,19 +125,6 @@ class TrackerOracle:
         self.extract, self.T, self.K, self.bounds, self.map = extract, tables, np.asarray(K, np.float32), bounds, world_map
         self.last = None
 
-    @staticmethod
-    def _R(q):
-        q = np.asarray(q, np.float32)
-        n = np.float32(np.sqrt(np.float32(np.float32(np.float32(q[0] * q[0] + q[1] * q[1]) + q[2] * q[2]) + q[3] * q[3])))
-        x, y, z, w = (q / n).astype(np.float32)
-        f = np.float32
-        tx, ty, tz = f(2) * x, f(2) * y, f(2) * z
-        twx, twy, twz = tx * w, ty * w, tz * w
-        txx, txy, txz = tx * x, ty * x, tz * x
-        tyy, tyz, tzz = ty * y, tz * y, tz * z
-        return np.array([f(1) - (tyy + tzz), txy - twz, txz + twy, txy + twz, f(1) - (txx + tzz), tyz - twx,
-                         txz - twy, tyz + twx, f(1) - (txx + tyy)], np.float32)
-
     def _local_map_search(self, F, q, t, cur_map, th, nnratio, seen):
         M = self.map
         inv, px, py, lv, vc = is_in_frustum(q, t, self.K, self.bounds, len(self.T["scale"]), self.T["scale"][1],
@@ -162,11 +151,10 @@ class TrackerOracle:
         M, L = self.map, self.last
         kps, desc, _ = self.extract(img)
         F = FrameOracle(kps, desc, self.bounds, self.T["scale"])
-        R = self._R(prior_q)
         lm = L["mp"]
         has = (lm >= 0).astype(np.uint8)
         lidx = np.where(lm >= 0, lm, 0)
-        args = (R, prior_t, self.K, has, L["outlier"], M["xw"][lidx], M["desc"][lidx], np.ones(len(lm), np.uint8),
+        args = (prior_q, prior_t, self.K, has, L["outlier"], M["xw"][lidx], M["desc"][lidx], np.ones(len(lm), np.uint8),
                 L["kps"]["octave"], L["kps"]["angle"])
         nm, cur_mp = F.search_by_projection_last(*args, 15.0)
         if nm < 20:

@@ -23,6 +23,7 @@
  * mono path only (Nleft == -1, mvuRight < 0); the 6x6 solve is an unpivoted LDL^T in double
  * (the reference uses Eigen::LDLT, which pivots: results agree to rounding, tolerance in tests).
  */
+#include "sophus_order.h"
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
@@ -415,11 +416,12 @@ int trko_features_in_area(void* f, float x, float y, float r, int minLevel, int 
 int trko_descriptor_distance(const uint8_t* a, const uint8_t* b) { return descriptor_distance(a, b); }
 
 /* SearchByProjection(CurrentFrame, LastFrame, th, bMono = true).
+ * qcw (x, y, z, w) / tcw: the current frame's pose as its SE3f holds it (used as is, not renormalised).
  * Last frame, one entry per keypoint i: has_mp, outlier, world position, the map point's
  * descriptor, whether the map point has Observations() > 0, and the last frame's keypoint
  * octave / angle.  cur_mp[cur.n] (in: all -1) receives the last-frame index matched to each current
  * keypoint.  Returns nmatches. */
-int trko_search_by_projection_last(void* fcur, const float* Rcw, const float* tcw, const float* K, int lastN,
+int trko_search_by_projection_last(void* fcur, const float* qcw, const float* tcw, const float* K, int lastN,
                                    const uint8_t* has_mp, const uint8_t* outlier, const float* Xw,
                                    const uint8_t* mp_desc, const uint8_t* mp_obs_pos, const int* last_octave,
                                    const float* last_angle, float th, int checkOri, int* cur_mp)
@@ -432,10 +434,9 @@ int trko_search_by_projection_last(void* fcur, const float* Rcw, const float* tc
     for (int i = 0; i < C.n; i++) cur_mp[i] = -1;
     for (int i = 0; i < lastN; i++) {
         if (!has_mp[i] || outlier[i]) continue;
-        const float X = Xw[3 * i], Y = Xw[3 * i + 1], Z = Xw[3 * i + 2];
-        const float xc = ((Rcw[0] * X + Rcw[1] * Y) + Rcw[2] * Z) + tcw[0];
-        const float yc = ((Rcw[3] * X + Rcw[4] * Y) + Rcw[5] * Z) + tcw[1];
-        const float zc = ((Rcw[6] * X + Rcw[7] * Y) + Rcw[8] * Z) + tcw[2];
+        float x3Dc[3];
+        so::se3_apply(qcw, tcw, Xw + 3 * i, x3Dc);   /* x3Dc = Tcw * x3Dw (:1577): Sophus' quaternion action */
+        const float xc = x3Dc[0], yc = x3Dc[1], zc = x3Dc[2];
         const float invzc = (float)(1.0 / zc);
         if (invzc < 0) continue;
         const float u = K[0] * xc / zc + K[2];
@@ -522,55 +523,40 @@ int trko_search_by_projection_map(void* fcur, int M, const float* projX, const f
     return nmatches;
 }
 
-/* Frame::isInFrustum (mono branch, O3/src/Frame.cc:576-636) + MapPoint::PredictScale
- * (O3/src/MapPoint.cc:573-587) over a batch.  Conventions fixed by this oracle: Rcw is the float
- * rotation matrix of the (normalised) float quaternion, Eigen's toRotationMatrix formula; products are
- * ((a*x + b*y) + c*z) + t; Ow = R^T * (-t); log() is taken in double and rounded to float. */
-void trko_is_in_frustum(const float* q_in, const float* t, const float* K, const float* bounds, int nlevels,
+/* Frame::isInFrustum (mono branch, O3/src/Frame.cc:576-636) + MapPoint::PredictScale (O3/src/MapPoint.cc:573-587)
+ * over a batch.  The pose (q, t) is the frame's SE3f as stored; Frame::UpdatePoseMatrices (:553-559) derives
+ * mRcw = toRotationMatrix(q), mtcw = t and mOw = translation of Tcw.inverse() (Sophus: normalised conjugate quaternion
+ * applied to -t).  Pc = mRcw * P + mtcw is Eigen's coefficient product (x0 + (x1 + x2)), PO.norm() / PO.dot(Pn) use the
+ * same 3-term order; min_dist / max_dist are mfMinDistance / mfMaxDistance. */
+void trko_is_in_frustum(const float* q, const float* t, const float* K, const float* bounds, int nlevels,
                         float scaleFactor, int m, const float* xw, const float* normal, const float* min_dist,
                         const float* max_dist, const uint8_t* skip, float cosLimit, uint8_t* in_view, float* px,
                         float* py, int* level, float* viewCos)
 {
-    float q[4] = { q_in[0], q_in[1], q_in[2], q_in[3] };
-    const float qn = std::sqrt(((q[0] * q[0] + q[1] * q[1]) + q[2] * q[2]) + q[3] * q[3]);
-    for (int i = 0; i < 4; i++) q[i] = q[i] / qn;
-    float R[9];
-    {
-        const float tx = 2 * q[0], ty = 2 * q[1], tz = 2 * q[2];
-        const float twx = tx * q[3], twy = ty * q[3], twz = tz * q[3];
-        const float txx = tx * q[0], txy = ty * q[0], txz = tz * q[0];
-        const float tyy = ty * q[1], tyz = tz * q[1], tzz = tz * q[2];
-        R[0] = 1 - (tyy + tzz); R[1] = txy - twz; R[2] = txz + twy;
-        R[3] = txy + twz; R[4] = 1 - (txx + tzz); R[5] = tyz - twx;
-        R[6] = txz - twy; R[7] = tyz + twx; R[8] = 1 - (txx + tyy);
-    }
-    float Ow[3];
-    for (int i = 0; i < 3; i++) Ow[i] = (R[i] * (-t[0]) + R[3 + i] * (-t[1])) + R[6 + i] * (-t[2]);
-    const float logScale = (float)std::log((double)scaleFactor);
+    float R[9], qi[4], Ow[3];
+    so::quat_to_matrix(q, R);
+    so::se3_inverse(q, t, qi, Ow);
+    const float logScale = std::log(scaleFactor);   /* Frame.cc:399 mfLogScaleFactor = log(mfScaleFactor) on floats */
     for (int k = 0; k < m; k++) {
         in_view[k] = 0; px[k] = -1; py[k] = -1; level[k] = -1; viewCos[k] = 0;
         if (skip && skip[k]) continue;
-        const float X = xw[3 * k], Y = xw[3 * k + 1], Z = xw[3 * k + 2];
-        const float xc = ((R[0] * X + R[1] * Y) + R[2] * Z) + t[0];
-        const float yc = ((R[3] * X + R[4] * Y) + R[5] * Z) + t[1];
-        const float zc = ((R[6] * X + R[7] * Y) + R[8] * Z) + t[2];
-        if (zc < 0.0f) continue;
-        const float u = K[0] * xc / zc + K[2];
-        const float v = K[1] * yc / zc + K[3];
+        const float* P = xw + 3 * k;
+        float Pc[3];
+        so::mat_vec(R, P, Pc);
+        for (int i = 0; i < 3; i++) Pc[i] = Pc[i] + t[i];
+        if (Pc[2] < 0.0f) continue;
+        const float u = K[0] * Pc[0] / Pc[2] + K[2];
+        const float v = K[1] * Pc[1] / Pc[2] + K[3];
         if (u < bounds[0] || u > bounds[2]) continue;
         if (v < bounds[1] || v > bounds[3]) continue;
         px[k] = u; py[k] = v;
         const float maxD = 1.2f * max_dist[k], minD = 0.8f * min_dist[k];
-        const float PO[3] = { X - Ow[0], Y - Ow[1], Z - Ow[2] };
-        const float dist = std::sqrt((PO[0] * PO[0] + PO[1] * PO[1]) + PO[2] * PO[2]);
+        const float PO[3] = { P[0] - Ow[0], P[1] - Ow[1], P[2] - Ow[2] };
+        const float dist = so::norm3(PO);
         if (dist < minD || dist > maxD) continue;
-        const float vc = ((PO[0] * normal[3 * k] + PO[1] * normal[3 * k + 1]) + PO[2] * normal[3 * k + 2]) / dist;
+        const float vc = so::dot3(PO, normal + 3 * k) / dist;
         if (vc < cosLimit) continue;
-        const float ratio = max_dist[k] / dist;
-        int nScale = (int)std::ceil((float)std::log((double)ratio) / logScale);
-        if (nScale < 0) nScale = 0;
-        else if (nScale >= nlevels) nScale = nlevels - 1;
-        in_view[k] = 1; level[k] = nScale; viewCos[k] = vc;
+        in_view[k] = 1; level[k] = so::predict_scale(max_dist[k], dist, logScale, nlevels); viewCos[k] = vc;
     }
 }
 
@@ -617,7 +603,10 @@ int trko_pose_optimization(float* pose_q, float* pose_t, const float* K, int n, 
         }
         if (n < 10) break;
     }
+    /* pFrame->SetPose(Sophus::SE3<float>(rotation().cast<float>(), translation().cast<float>())), Optimizer.cc:1021-1024:
+     * the SE3f constructor normalises the float quaternion */
     pose_q[0] = (float)T.r.x; pose_q[1] = (float)T.r.y; pose_q[2] = (float)T.r.z; pose_q[3] = (float)T.r.w;
+    so::quat_normalize(pose_q);
     pose_t[0] = (float)T.t[0]; pose_t[1] = (float)T.t[1]; pose_t[2] = (float)T.t[2];
     return n - nBad;
 }
@@ -690,46 +679,32 @@ int trko_search_for_initialization(int n1, const void* kps1_, const uint8_t* des
  * (Replace / AddObservation / AddMapPoint, :1209-1222), which the caller applies afterwards in vpMapPoints order.
  * fkf = the keyframe's keypoints/descriptors/grid (KeyFrame::GetFeaturesInArea has no level filter).
  * skip[i]: !pMP || isBad() || IsInKeyFrame(pKF).  min_dist / max_dist = mfMinDistance / mfMaxDistance.
- * Conventions: p3Dc = Tcw * p3Dw is Sophus' quaternion form (Eigen's _transformVector), Ow = -(q^-1 * t), float. */
-void trko_fuse_search(void* fkf, const float* q_in, const float* t, const float* K, int nlevels, float logScaleFactor,
+ * The pose (q, t) is the keyframe's SE3f as stored: p3Dc = Tcw * p3Dw is Sophus' quaternion action, Ow =
+ * pKF->GetCameraCenter() = translation of Tcw.inverse() (KeyFrame.cc:224-257). */
+void trko_fuse_search(void* fkf, const float* q, const float* t, const float* K, int nlevels, float logScaleFactor,
                       const float* invLevelSigma2, int m, const float* xw, const float* normal, const float* min_dist,
                       const float* max_dist, const uint8_t* mp_desc, const uint8_t* skip, float th, int* best_idx,
                       int* best_dist)
 {
     Frame& F = *(Frame*)fkf;
-    const float qn = std::sqrt(q_in[0] * q_in[0] + q_in[1] * q_in[1] + q_in[2] * q_in[2] + q_in[3] * q_in[3]);
-    const float qx = q_in[0] / qn, qy = q_in[1] / qn, qz = q_in[2] / qn, qw = q_in[3] / qn;
-    auto rot = [](float x, float y, float z, float w, const float v[3], float out[3]) {
-        /* Eigen::QuaternionBase::_transformVector: uv = 2 * (q.vec x v); v + w * uv + q.vec x uv */
-        float uv[3] = { y * v[2] - z * v[1], z * v[0] - x * v[2], x * v[1] - y * v[0] };
-        uv[0] += uv[0]; uv[1] += uv[1]; uv[2] += uv[2];
-        out[0] = v[0] + w * uv[0] + (y * uv[2] - z * uv[1]);
-        out[1] = v[1] + w * uv[1] + (z * uv[0] - x * uv[2]);
-        out[2] = v[2] + w * uv[2] + (x * uv[1] - y * uv[0]);
-    };
-    float Ow[3];
-    { float r[3]; rot(-qx, -qy, -qz, qw, t, r); Ow[0] = -r[0]; Ow[1] = -r[1]; Ow[2] = -r[2]; }
+    float qi[4], Ow[3];
+    so::se3_inverse(q, t, qi, Ow);
     std::vector<int> idx;
     for (int i = 0; i < m; i++) {
         best_idx[i] = -1; best_dist[i] = 256;
         if (skip && skip[i]) continue;
         const float* P = xw + 3 * i;
         float pc[3];
-        rot(qx, qy, qz, qw, P, pc);
-        pc[0] += t[0]; pc[1] += t[1]; pc[2] += t[2];
+        so::se3_apply(q, t, P, pc);
         if (pc[2] < 0.0f) continue;
         const float u = K[0] * pc[0] / pc[2] + K[2], v = K[1] * pc[1] / pc[2] + K[3];     /* Pinhole::project */
         if (!(u >= F.minX && u < F.maxX && v >= F.minY && v < F.maxY)) continue;          /* KeyFrame::IsInImage */
         const float maxDistance = 1.2f * max_dist[i], minDistance = 0.8f * min_dist[i];
         const float PO[3] = { P[0] - Ow[0], P[1] - Ow[1], P[2] - Ow[2] };
-        const float dist3D = std::sqrt(PO[0] * PO[0] + PO[1] * PO[1] + PO[2] * PO[2]);
+        const float dist3D = so::norm3(PO);
         if (dist3D < minDistance || dist3D > maxDistance) continue;
-        const float* Pn = normal + 3 * i;
-        if (PO[0] * Pn[0] + PO[1] * Pn[1] + PO[2] * Pn[2] < 0.5 * dist3D) continue;
-        const float ratio = max_dist[i] / dist3D;
-        int nPredictedLevel = (int)std::ceil((float)std::log((double)ratio) / logScaleFactor);   /* PredictScale */
-        if (nPredictedLevel < 0) nPredictedLevel = 0;
-        else if (nPredictedLevel >= nlevels) nPredictedLevel = nlevels - 1;
+        if (so::dot3(PO, normal + 3 * i) < 0.5 * dist3D) continue;
+        const int nPredictedLevel = so::predict_scale(max_dist[i], dist3D, logScaleFactor, nlevels);   /* PredictScale */
         const float radius = th * F.scaleFactors[nPredictedLevel];
         features_in_area(F, u, v, radius, -1, -1, idx);
         if (idx.empty()) continue;

@@ -53,7 +53,7 @@ def init_pair(extract, k0=1, k1=4, w=640, h=480):
 
 def triangulation_pair(extract, k0=2, k1=6, w=640, h=480, seed=0, mp_frac=0.5):
     """Two keyframes of the plane stream with their true relative pose: inputs of SearchForTriangulation."""
-    from dvmslam_b200.matching import fundamental_from_poses
+    from oracle.bow import fundamental_from_poses
 
     S = synth.PlaneStream(w, h, seed=3, K=(500.0, 500.0, w / 2, h / 2))
     rng = np.random.default_rng(seed)

@@ -114,7 +114,7 @@ def main():
     case = synth.tracking_case(S, 4, orc.extract, n_local=1500)
     F = FrameOracle(case["cur_kps"], case["cur_desc"], case["bounds"], T["scale"])
     lk = case["last_kps"]
-    n, cur_mp = F.search_by_projection_last(case["Rcw_prior"], case["tcw_prior"], case["K"], case["has_mp"],
+    n, cur_mp = F.search_by_projection_last(case["qcw_prior"], case["tcw_prior"], case["K"], case["has_mp"],
                                             case["outlier"], case["last_Xw"], case["last_desc"], case["obs_pos"],
                                             lk["octave"], lk["angle"], 15.0)
     idx = np.nonzero(cur_mp >= 0)[0]

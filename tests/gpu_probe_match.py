@@ -15,7 +15,7 @@ F1.assign(case["cur_kps"], case["cur_desc"], case["bounds"])
 lk = case["last_kps"]
 mt = ORBmatcher(0.9, True)
 for th in (15.0, 30.0):
-    args = (case["Rcw_prior"], case["tcw_prior"], case["K"], case["has_mp"], case["outlier"], case["last_Xw"],
+    args = (case["qcw_prior"], case["tcw_prior"], case["K"], case["has_mp"], case["outlier"], case["last_Xw"],
             case["last_desc"], case["obs_pos"], lk["octave"], lk["angle"], th)
     mt.SearchByProjectionLast(F1, *args)
     t = time.perf_counter()

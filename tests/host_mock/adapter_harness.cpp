@@ -359,7 +359,7 @@ int hm_fuse(const dvm_keypoint* kps, const uint8_t* desc, int n, const float* sc
         mps[i].reset(new MapPoint);
         MapPoint& p = *mps[i];
         for (int k = 0; k < 3; k++) { p.pos(k) = xw[3 * i + k]; p.normal(k) = normal[3 * i + k]; }
-        p.minDistInv = 0.8f * min_dist[i]; p.maxDistInv = 1.2f * max_dist[i];
+        p.minDistInv = 0.8f * min_dist[i]; p.maxDistInv = 1.2f * max_dist[i]; p.minDist = min_dist[i]; p.maxDist = max_dist[i];
         std::memcpy(p.desc.ptr(0), mp_desc + (size_t)i * 32, 32);
         p.nObs = mp_obs[i];
         vp[i] = &p;

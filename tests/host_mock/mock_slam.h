@@ -93,6 +93,9 @@ struct MapPoint {
     Vec3 GetNormal() const { return normal; }
     float GetMinDistanceInvariance() const { return minDistInv; }
     float GetMaxDistanceInvariance() const { return maxDistInv; }
+    float minDist = 0, maxDist = 0;         // mfMinDistance / mfMaxDistance and the getters INTEGRATION.md adds
+    float GetMinDistance() const { return minDist; }
+    float GetMaxDistance() const { return maxDist; }
     bool IsInKeyFrame(KeyFrame* kf) const { return observations.count(kf) != 0; }
     std::tuple<int, int> GetIndexInKeyFrame(KeyFrame* kf) const
     {

@@ -69,7 +69,7 @@ def test_oracle_tracking_and_ba_reproduce_golden():
     S, orc, T, case = _track_case()
     F = FrameOracle(case["cur_kps"], case["cur_desc"], case["bounds"], T["scale"])
     lk = case["last_kps"]
-    n, cur_mp = F.search_by_projection_last(case["Rcw_prior"], case["tcw_prior"], case["K"], case["has_mp"],
+    n, cur_mp = F.search_by_projection_last(case["qcw_prior"], case["tcw_prior"], case["K"], case["has_mp"],
                                             case["outlier"], case["last_Xw"], case["last_desc"], case["obs_pos"],
                                             lk["octave"], lk["angle"], 15.0)
     assert n == int(g["nmatches"]) and np.array_equal(cur_mp, g["cur_mp"])
@@ -135,7 +135,7 @@ def test_gpu_tracking_and_ba_reproduce_golden():
     F = Frame(len(case["cur_kps"]) + 8, T["scale"], T["inv_sigma2"])
     F.assign(case["cur_kps"], case["cur_desc"], case["bounds"])
     lk = case["last_kps"]
-    n, cur_mp = ORBmatcher(0.9, True).SearchByProjectionLast(F, case["Rcw_prior"], case["tcw_prior"], case["K"],
+    n, cur_mp = ORBmatcher(0.9, True).SearchByProjectionLast(F, case["qcw_prior"], case["tcw_prior"], case["K"],
                                                              case["has_mp"], case["outlier"], case["last_Xw"],
                                                              case["last_desc"], case["obs_pos"], lk["octave"],
                                                              lk["angle"], 15.0)

@@ -56,7 +56,7 @@ def test_search_by_projection_last(world, k, th):
     case = world["cases"][k]
     F0, F1 = _frames(world, case)
     lk = case["last_kps"]
-    args = (case["Rcw_prior"], case["tcw_prior"], case["K"], case["has_mp"], case["outlier"], case["last_Xw"],
+    args = (case["qcw_prior"], case["tcw_prior"], case["K"], case["has_mp"], case["outlier"], case["last_Xw"],
             case["last_desc"], case["obs_pos"], lk["octave"], lk["angle"], th)
     n0, m0 = F0.search_by_projection_last(*args)
     for ori in (True, False):
@@ -81,7 +81,7 @@ def test_search_by_projection_last_heavy_contention(world):
     Xw = case["last_Xw"].copy()
     Xw[:, :2] = Xw[rng.integers(0, 40, len(Xw)), :2] + rng.normal(0, 0.01, (len(Xw), 2)).astype(np.float32)
     obs = (rng.random(len(Xw)) < 0.7).astype(np.uint8)
-    args = (case["Rcw_prior"], case["tcw_prior"], case["K"], np.ones_like(case["has_mp"]), np.zeros_like(case["outlier"]),
+    args = (case["qcw_prior"], case["tcw_prior"], case["K"], np.ones_like(case["has_mp"]), np.zeros_like(case["outlier"]),
             Xw, case["last_desc"], obs, lk["octave"], lk["angle"], 30.0)
     n0, m0 = F0.search_by_projection_last(*args)
     mt = ORBmatcher(0.9, True)
@@ -131,7 +131,7 @@ def test_pose_optimization(world, k):
     case = world["cases"][k]
     F0, F1 = _frames(world, case)
     lk, ck = case["last_kps"], case["cur_kps"]
-    n, cur_mp = F0.search_by_projection_last(case["Rcw_prior"], case["tcw_prior"], case["K"], case["has_mp"],
+    n, cur_mp = F0.search_by_projection_last(case["qcw_prior"], case["tcw_prior"], case["K"], case["has_mp"],
                                              case["outlier"], case["last_Xw"], case["last_desc"], case["obs_pos"],
                                              lk["octave"], lk["angle"], 15.0)
     idx = np.nonzero(cur_mp >= 0)[0]
