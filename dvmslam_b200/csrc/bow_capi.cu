@@ -232,28 +232,23 @@ int dvm_match_for_triangulation(dvm_frame* ctx, const dvm_bow_features* kf1, con
     return DVM_OK;
 }
 
-int dvm_fuse_search(dvm_frame* kf, const float* pose_q, const float* pose_t, const float* K, int m, const float* xw,
-                    const float* normal, const float* min_dist, const float* max_dist, const uint8_t* mp_desc,
-                    const uint8_t* skip, float th, int32_t* best_idx, int32_t* best_dist)
+// stages the candidate arrays, runs fuse_search_kernel with the preset flags of `a` and reads best_idx / best_dist back
+static int run_proj_search(dvm_frame* kf, FuseArgs a, int m, const float* xw, const float* normal, const float* min_dist,
+                           const float* max_dist, const uint8_t* mp_desc, const uint8_t* skip, float th, int32_t* best_idx,
+                           int32_t* best_dist)
 {
-    DVM_REQUIRE(kf != nullptr && pose_q && pose_t && K && m >= 0, "bad argument");
-    if (m == 0) return DVM_OK;
-    DVM_REQUIRE(xw && normal && min_dist && max_dist && mp_desc && best_idx && best_dist, "null map-point arrays");
     DVM_CUDA(cudaSetDevice(kf->device));
     const size_t n = (size_t)m;
     int rc = dvm_frame_ensure_bytes(kf, padded({ n * 12, n * 12, n * 4, n * 4, n * 32, n, n * 4, n * 4 }), n * 8 + 512);
     if (rc != DVM_OK) return rc;
     Stage st(kf);
-    FuseArgs a;
-    memset(&a, 0, sizeof(a));
-    for (int i = 0; i < 4; i++) { a.q[i] = pose_q[i]; a.K[i] = K[i]; }
-    for (int i = 0; i < 3; i++) a.t[i] = pose_t[i];
     a.nlevels = kf->dev.nlevels;
-    // mfLogScaleFactor = log(mfScaleFactor) (O3/src/KeyFrame.cc: copied from the Frame, O3/src/Frame.cc:401)
-    a.logScale = dvm_glibc_logf(kf->dev.nlevels > 1 ? kf->dev.scale[1] : 1.2f)   /* mfLogScaleFactor = log(mfScaleFactor) on floats, Frame.cc:401 */;
+    // mfLogScaleFactor = log(mfScaleFactor) on floats (O3/src/Frame.cc:401, copied into the KeyFrame)
+    a.logScale = dvm_glibc_logf(kf->dev.nlevels > 1 ? kf->dev.scale[1] : 1.2f);
     for (int l = 0; l < kf->dev.nlevels; l++) a.inv_sigma2[l] = kf->dev.inv_sigma2[l];
     a.m = m; a.th = th;
-    a.xw = st.add(xw, n * 3); a.normal = st.add(normal, n * 3);
+    a.xw = st.add(xw, n * 3);
+    a.normal = normal ? st.add(normal, n * 3) : nullptr;
     a.min_dist = st.add(min_dist, n); a.max_dist = st.add(max_dist, n);
     a.mp_desc = st.add(mp_desc, n * 32);
     a.skip = skip ? st.add(skip, n) : nullptr;
@@ -270,8 +265,125 @@ int dvm_fuse_search(dvm_frame* kf, const float* pose_q, const float* pose_t, con
     DVM_CUDA(cudaMemcpyAsync(kf->h_out, kf->d_in + out_begin, out_end - out_begin, cudaMemcpyDeviceToHost, kf->stream));
     DVM_CUDA(cudaStreamSynchronize(kf->stream));
     memcpy(best_idx, kf->h_out + ((const uint8_t*)a.best_idx - (kf->d_in + out_begin)), n * 4);
-    memcpy(best_dist, kf->h_out + ((const uint8_t*)a.best_dist - (kf->d_in + out_begin)), n * 4);
+    if (best_dist) memcpy(best_dist, kf->h_out + ((const uint8_t*)a.best_dist - (kf->d_in + out_begin)), n * 4);
     return DVM_OK;
+}
+
+int dvm_fuse_search(dvm_frame* kf, const float* pose_q, const float* pose_t, const float* K, int m, const float* xw,
+                    const float* normal, const float* min_dist, const float* max_dist, const uint8_t* mp_desc,
+                    const uint8_t* skip, float th, int32_t* best_idx, int32_t* best_dist)
+{
+    DVM_REQUIRE(kf != nullptr && pose_q && pose_t && K && m >= 0, "bad argument");
+    if (m == 0) return DVM_OK;
+    DVM_REQUIRE(xw && normal && min_dist && max_dist && mp_desc && best_idx && best_dist, "null map-point arrays");
+    FuseArgs a;
+    memset(&a, 0, sizeof(a));
+    for (int i = 0; i < 4; i++) { a.q[i] = pose_q[i]; a.K[i] = K[i]; }
+    for (int i = 0; i < 3; i++) a.t[i] = pose_t[i];
+    a.check_normal = 1; a.check_chi = 1; a.accept_th = kThLow;
+    return run_proj_search(kf, a, m, xw, normal, min_dist, max_dist, mp_desc, skip, th, best_idx, best_dist);
+}
+
+int dvm_fuse_search_sim3(dvm_frame* kf, const float* sim3_q, const float* sim3_t, const float* K, int m, const float* xw,
+                         const float* normal, const float* min_dist, const float* max_dist, const uint8_t* mp_desc,
+                         const uint8_t* skip, float th, int32_t* best_idx, int32_t* best_dist)
+{
+    DVM_REQUIRE(kf != nullptr && sim3_q && sim3_t && K && m >= 0, "bad argument");
+    if (m == 0) return DVM_OK;
+    DVM_REQUIRE(xw && normal && min_dist && max_dist && mp_desc && best_idx && best_dist, "null map-point arrays");
+    FuseArgs a;
+    memset(&a, 0, sizeof(a));
+    so::sim3_to_se3(sim3_q, sim3_t, a.q, a.t);   // Tcw = SE3f(Scw.rotationMatrix(), Scw.translation() / Scw.scale()), :1245
+    for (int i = 0; i < 4; i++) a.K[i] = K[i];
+    a.check_normal = 1; a.check_chi = 0; a.accept_th = kThLow;
+    return run_proj_search(kf, a, m, xw, normal, min_dist, max_dist, mp_desc, skip, th, best_idx, best_dist);
+}
+
+int dvm_match_by_sim3(dvm_frame* kf1, dvm_frame* kf2, const float* q1, const float* t1, const float* q2, const float* t2,
+                      const float* s12_q, const float* s12_t, const float* K, const uint8_t* skip1, const float* xw1,
+                      const float* min_dist1, const float* max_dist1, const uint8_t* mp_desc1, const uint8_t* skip2,
+                      const float* xw2, const float* min_dist2, const float* max_dist2, const uint8_t* mp_desc2, float th,
+                      int32_t* match12, int* nfound)
+{
+    DVM_REQUIRE(kf1 && kf2 && q1 && t1 && q2 && t2 && s12_q && s12_t && K && match12 && nfound, "null argument");
+    const int n1 = kf1->host_n, n2 = kf2->host_n;
+    *nfound = 0;
+    for (int i = 0; i < n1; i++) match12[i] = -1;
+    if (n1 == 0 || n2 == 0) return DVM_OK;
+    DVM_REQUIRE(skip1 && xw1 && min_dist1 && max_dist1 && mp_desc1 && skip2 && xw2 && min_dist2 && max_dist2 && mp_desc2,
+                "null map-point arrays");
+    float s21_q[4], s21_t[3];
+    so::sim3_inverse(s12_q, s12_t, s21_q, s21_t);   // Sophus::Sim3f S21 = S12.inverse(), :1359
+    std::vector<int32_t> m1(n1), m2(n2);
+    FuseArgs a;
+    memset(&a, 0, sizeof(a));
+    for (int i = 0; i < 4; i++) a.K[i] = K[i];   // both directions project with pKF1's intrinsics (:1349-1352)
+    a.chain_sim3 = 1; a.proj_invz = 1; a.dist_camera = 1; a.accept_th = kThHigh;
+    // keyframe 1's map points into keyframe 2: p3Dc2 = S21 * (T1w * p3Dw)
+    for (int i = 0; i < 4; i++) { a.q[i] = q1[i]; a.sq[i] = s21_q[i]; }
+    for (int i = 0; i < 3; i++) { a.t[i] = t1[i]; a.st[i] = s21_t[i]; }
+    int rc = run_proj_search(kf2, a, n1, xw1, nullptr, min_dist1, max_dist1, mp_desc1, skip1, th, m1.data(), nullptr);
+    if (rc != DVM_OK) return rc;
+    // keyframe 2's map points into keyframe 1: p3Dc1 = S12 * (T2w * p3Dw)
+    for (int i = 0; i < 4; i++) { a.q[i] = q2[i]; a.sq[i] = s12_q[i]; }
+    for (int i = 0; i < 3; i++) { a.t[i] = t2[i]; a.st[i] = s12_t[i]; }
+    rc = run_proj_search(kf1, a, n2, xw2, nullptr, min_dist2, max_dist2, mp_desc2, skip2, th, m2.data(), nullptr);
+    if (rc != DVM_OK) return rc;
+    int found = 0;
+    for (int i1 = 0; i1 < n1; i1++) {   // the agreement check, :1539-1549
+        const int idx2 = m1[i1];
+        if (idx2 >= 0 && m2[idx2] == i1) { match12[i1] = idx2; found++; }
+    }
+    *nfound = found;
+    return DVM_OK;
+}
+
+int dvm_match_by_projection_sim3(dvm_frame* kf, const float* sim3_q, const float* sim3_t, const float* K, int m, const float* xw,
+                                 const float* normal, const float* min_dist, const float* max_dist, const uint8_t* mp_desc,
+                                 const uint8_t* skip, const uint8_t* kp_matched, int th, float ratio_hamming, int32_t* kp_point,
+                                 int* nmatches)
+{
+    DVM_REQUIRE(kf != nullptr && sim3_q && sim3_t && K && m >= 0 && kp_point && nmatches, "bad argument");
+    *nmatches = 0;
+    const int nk = kf->host_n;
+    for (int k = 0; k < nk; k++) kp_point[k] = -1;
+    if (m == 0 || nk == 0) return DVM_OK;
+    DVM_REQUIRE(xw && normal && min_dist && max_dist && mp_desc && kp_matched, "null arrays");
+    DVM_CUDA(cudaSetDevice(kf->device));
+    const size_t n = (size_t)m;
+    int rc = dvm_frame_ensure_bytes(kf, padded({ n * 12, n * 12, n * 4, n * 4, n * 32, n, n * 4, n * 4, n * 4, (size_t)nk }),
+                                    (size_t)(kf->cap + 8) * sizeof(int));
+    if (rc != DVM_OK) return rc;
+    rc = dvm_frame_ensure_query_cap(kf, m);
+    if (rc != DVM_OK) return rc;
+    Stage st(kf);
+    FuseArgs a;
+    memset(&a, 0, sizeof(a));
+    so::sim3_to_se3(sim3_q, sim3_t, a.q, a.t);   // :403
+    for (int i = 0; i < 4; i++) a.K[i] = K[i];
+    a.check_normal = 1; a.gate_only = 1;
+    a.nlevels = kf->dev.nlevels;
+    a.logScale = dvm_glibc_logf(kf->dev.nlevels > 1 ? kf->dev.scale[1] : 1.2f);
+    a.m = m; a.th = (float)th;
+    a.xw = st.add(xw, n * 3); a.normal = st.add(normal, n * 3);
+    a.min_dist = st.add(min_dist, n); a.max_dist = st.add(max_dist, n);
+    const uint8_t* d_desc = st.add(mp_desc, n * 32);
+    a.mp_desc = d_desc;
+    a.skip = skip ? st.add(skip, n) : nullptr;
+    const uint8_t* d_blocked = st.add(kp_matched, (size_t)nk);
+    a.gate_u = st.add((const float*)nullptr, n); a.gate_v = st.add((const float*)nullptr, n);
+    a.gate_level = st.add((const int*)nullptr, n);
+    DVM_CUDA(cudaMemcpyAsync(kf->d_in, kf->h_in, st.off, cudaMemcpyHostToDevice, kf->stream));
+    launch_fuse_search(kf->dev, a, kf->stream);                  // the projection gates, one warp per candidate
+    MatchMapArgs ma;
+    memset(&ma, 0, sizeof(ma));
+    ma.m = m; ma.th = (float)th; ma.nnratio = 1.f;
+    ma.projX = a.gate_u; ma.projY = a.gate_v; ma.level = a.gate_level;
+    ma.mp_desc = d_desc; ma.cur_blocked = d_blocked;
+    ma.sim3_mode = 1;
+    ma.accept_limit = (float)kThLow * ratio_hamming;            // bestDist <= TH_LOW * ratioHamming, :487
+    launch_match_map(kf->dev, ma, kf->ms, kf->d_cur_mp, kf->d_cur_mp + kf->cap, kf->stream);   // sequential-greedy outcome
+    return dvm_frame_finish_match(kf, kp_point, nmatches);
 }
 
 int dvm_fundamental_from_poses(const float* q1, const float* t1, const float* q2, const float* t2, const float* K1,

@@ -474,38 +474,57 @@ __global__ void __launch_bounds__(kFuseWarps * 32) fuse_search_kernel(FrameDev k
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * kFuseWarps + (threadIdx.x >> 5);
     if (i >= a.m) return;
-    int bestIdx = -1, bestDist = 256;
+    int bestIdx = -1, bestDist = 256, lvl = -1;
+    float u = 0.f, v = 0.f;
     do {
         if (a.skip && a.skip[i]) break;
-        // Tcw = pKF->GetPose() as stored; Ow = pKF->GetCameraCenter() = translation of Tcw.inverse() (KeyFrame.cc:224-257)
-        float qi[4], Ow[3];
-        so::se3_inverse(a.q, a.t, qi, Ow);
         const float P[3] = { a.xw[3 * i], a.xw[3 * i + 1], a.xw[3 * i + 2] };
         float pc[3];
-        so::se3_apply(a.q, a.t, P, pc);                                         // p3Dc = Tcw * p3Dw (:1107)
+        so::se3_apply(a.q, a.t, P, pc);                                         // p3Dc = Tcw * p3Dw
+        if (a.chain_sim3) { float p2[3]; so::sim3_apply(a.sq, a.st, pc, p2); pc[0] = p2[0]; pc[1] = p2[1]; pc[2] = p2[2]; }
         if (pc[2] < 0.0f) break;
-        const float u = __fadd_rn(__fdiv_rn(__fmul_rn(a.K[0], pc[0]), pc[2]), a.K[2]);
-        const float v = __fadd_rn(__fdiv_rn(__fmul_rn(a.K[1], pc[1]), pc[2]), a.K[3]);
-        if (!(u >= kf.minX && u < kf.maxX && v >= kf.minY && v < kf.maxY)) break;
+        if (a.proj_invz) {
+            const float invz = (float)(1.0 / (double)pc[2]);
+            u = __fadd_rn(__fmul_rn(a.K[0], __fmul_rn(pc[0], invz)), a.K[2]);
+            v = __fadd_rn(__fmul_rn(a.K[1], __fmul_rn(pc[1], invz)), a.K[3]);
+        } else {                                                                // Pinhole::project
+            u = __fadd_rn(__fdiv_rn(__fmul_rn(a.K[0], pc[0]), pc[2]), a.K[2]);
+            v = __fadd_rn(__fdiv_rn(__fmul_rn(a.K[1], pc[1]), pc[2]), a.K[3]);
+        }
+        if (!(u >= kf.minX && u < kf.maxX && v >= kf.minY && v < kf.maxY)) break;   // KeyFrame::IsInImage
         const float maxDistance = __fmul_rn(1.2f, a.max_dist[i]), minDistance = __fmul_rn(0.8f, a.min_dist[i]);
-        const float PO[3] = { __fsub_rn(P[0], Ow[0]), __fsub_rn(P[1], Ow[1]), __fsub_rn(P[2], Ow[2]) };
-        const float dist3D = so::norm3(PO);
+        float dist3D;
+        if (a.dist_camera) dist3D = so::norm3(pc);
+        else {
+            // Ow = pKF->GetCameraCenter() = translation of Tcw.inverse() (KeyFrame.cc:224-257)
+            float qi[4], Ow[3];
+            so::se3_inverse(a.q, a.t, qi, Ow);
+            const float PO[3] = { __fsub_rn(P[0], Ow[0]), __fsub_rn(P[1], Ow[1]), __fsub_rn(P[2], Ow[2]) };
+            dist3D = so::norm3(PO);
+            if (dist3D < minDistance || dist3D > maxDistance) break;
+            if (a.check_normal) {
+                const float Pn[3] = { a.normal[3 * i], a.normal[3 * i + 1], a.normal[3 * i + 2] };
+                if ((double)so::dot3(PO, Pn) < 0.5 * (double)dist3D) break;
+            }
+        }
         if (dist3D < minDistance || dist3D > maxDistance) break;
-        const float Pn[3] = { a.normal[3 * i], a.normal[3 * i + 1], a.normal[3 * i + 2] };
-        if ((double)so::dot3(PO, Pn) < 0.5 * (double)dist3D) break;
-        const int lvl = so::predict_scale(a.max_dist[i], dist3D, a.logScale, a.nlevels);
+        lvl = so::predict_scale(a.max_dist[i], dist3D, a.logScale, a.nlevels);
+        if (a.gate_only) break;
         const float radius = __fmul_rn(a.th, kf.scale[lvl]);
         uint32_t d[8];
         load_desc(d, a.mp_desc + (size_t)i * 32);
         const FrameLook fl = look_global(kf);
         unsigned long long best = ~0ull;   // distance << 48 | traversal position << 24 | keypoint
+        const int level = lvl;
         walk_area_warp(fl, u, v, radius, -1, -1, lane, [&](int idx, int oct, int ord) {
-            if (oct < lvl - 1 || oct > lvl) return;
-            const float ex = __fsub_rn(u, fl.x(idx)), ey = __fsub_rn(v, fl.y(idx));
-            const float e2 = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
-            if ((double)__fmul_rn(e2, a.inv_sigma2[oct]) > 5.99) return;
+            if (oct < level - 1 || oct > level) return;
+            if (a.check_chi) {
+                const float ex = __fsub_rn(u, fl.x(idx)), ey = __fsub_rn(v, fl.y(idx));
+                const float e2 = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+                if ((double)__fmul_rn(e2, a.inv_sigma2[oct]) > 5.99) return;
+            }
             const unsigned long long dist = (unsigned long long)hamming256(d, fl.desc + (size_t)idx * 32);
-            if (dist < 256ull) best = min(best, (dist << 48) | ((unsigned long long)min(ord, 0xffffff) << 24) | (unsigned long long)idx);
+            best = min(best, (dist << 48) | ((unsigned long long)min(ord, 0xffffff) << 24) | (unsigned long long)idx);
         });
         best = warp_min_u64(best);
         if (best == ~0ull) break;
@@ -513,7 +532,8 @@ __global__ void __launch_bounds__(kFuseWarps * 32) fuse_search_kernel(FrameDev k
         bestIdx = (int)(best & 0xffffffull);
     } while (false);
     if (lane == 0) {
-        const bool ok = bestIdx >= 0 && bestDist <= kThLow;
+        if (a.gate_only) { a.gate_u[i] = u; a.gate_v[i] = v; a.gate_level[i] = lvl; return; }
+        const bool ok = bestIdx >= 0 && bestDist <= a.accept_th;
         a.best_idx[i] = ok ? bestIdx : -1;
         a.best_dist[i] = ok ? bestDist : 256;
     }

@@ -66,9 +66,20 @@ struct TriArgs {
 };
 void launch_triangulation_match(const TriArgs& g, cudaStream_t stream);
 
-// the search half of Fuse(pKF, vpMapPoints, th): per map point the keyframe keypoint it would be fused with
+// Project-and-search, one warp per map point: the common core of Fuse(pKF, vpMapPoints, th) (:1060-1228), Fuse(pKF, Scw,
+// ...) (:1236-1345), one direction of SearchBySim3 (:1347-1551) and the gate pass of SearchByProjection(pKF, Scw, ...)
+// (:395-603).  The point goes through the SE3 (q, t) -- and then through the Sim3 (sq, st) when chain_sim3 is set -- is
+// gated (depth, KeyFrame::IsInImage, scale-invariance range, viewing angle), its level predicted, and the keypoints of the
+// window th * scale[level] with octave in [level - 1, level] compared; the first of the nearest wins.
 struct FuseArgs {
     float q[4], t[3], K[4];
+    int chain_sim3; float sq[4], st[3];   // SearchBySim3: p = S * (T * P)
+    int proj_invz;        // SearchBySim3's u = fx * (x * (float)(1.0 / z)) + cx instead of Pinhole::project
+    int dist_camera;      // SearchBySim3: the distance is |p| in the target camera frame, not |P - Ow|
+    int check_normal;     // viewing-angle gate PO . Pn < 0.5 * dist
+    int check_chi;        // Fuse(pKF, vpMapPoints, th) only: reprojection error gate e^2 * invSigma2 > 5.99
+    int accept_th;        // TH_LOW (50) or TH_HIGH (100)
+    int gate_only;        // SearchByProjection(pKF, Scw, ...): no search; gate_u / gate_v / gate_level receive the projection
     int nlevels; float logScale;
     float inv_sigma2[kTrackMaxLevels];
     int m;
@@ -76,6 +87,7 @@ struct FuseArgs {
     const uint8_t* mp_desc; const uint8_t* skip;
     float th;
     int* best_idx; int* best_dist;
+    float* gate_u; float* gate_v; int* gate_level;   // gate_level[i] = -1 when the point is rejected
 };
 void launch_fuse_search(const FrameDev& kf, const FuseArgs& a, cudaStream_t stream);
 

@@ -299,7 +299,9 @@ int dvm_frame_grid_cell(dvm_frame* f, int ix, int iy, int32_t* out, int cap, int
     return DVM_OK;
 }
 
-static int finish_match(dvm_frame* f, int32_t* cur_mp, int* nmatches)
+} // extern "C"
+
+int dvm_frame_finish_match(dvm_frame* f, int32_t* cur_mp, int* nmatches)
 {
     DVM_CUDA(cudaGetLastError());
     DVM_CUDA(cudaMemcpyAsync(f->d_cur_mp + f->cap + 1, f->ms.iters, sizeof(int), cudaMemcpyDeviceToDevice, f->stream));
@@ -313,6 +315,8 @@ static int finish_match(dvm_frame* f, int32_t* cur_mp, int* nmatches)
     f->last_rounds = h[f->cap + 1];
     return DVM_OK;
 }
+
+extern "C" {
 
 int dvm_match_by_projection_last(dvm_frame* cur, const float* qcw, const float* tcw, const float* K, int last_n,
                                  const uint8_t* has_mp, const uint8_t* outlier, const float* Xw, const uint8_t* mp_desc,
@@ -346,7 +350,7 @@ int dvm_match_by_projection_last(dvm_frame* cur, const float* qcw, const float* 
     }
     DVM_CUDA(cudaMemcpyAsync(cur->d_in, cur->h_in, p.off, cudaMemcpyHostToDevice, cur->stream));
     launch_match_last(cur->dev, a, cur->ms, cur->d_cur_mp, cur->d_cur_mp + cur->cap, cur->stream);
-    return finish_match(cur, cur_mp, nmatches);
+    return dvm_frame_finish_match(cur, cur_mp, nmatches);
 }
 
 int dvm_match_by_projection_map(dvm_frame* cur, int m, const float* proj_x, const float* proj_y, const int32_t* level,
@@ -376,7 +380,7 @@ int dvm_match_by_projection_map(dvm_frame* cur, int m, const float* proj_x, cons
     a.cur_blocked = cur_blocked ? p.add(cur_blocked, nc) : nullptr;
     DVM_CUDA(cudaMemcpyAsync(cur->d_in, cur->h_in, p.off, cudaMemcpyHostToDevice, cur->stream));
     launch_match_map(cur->dev, a, cur->ms, cur->d_cur_mp, cur->d_cur_mp + cur->cap, cur->stream);
-    return finish_match(cur, cur_mp, nmatches);
+    return dvm_frame_finish_match(cur, cur_mp, nmatches);
 }
 
 int dvm_match_last_rounds(dvm_frame* cur) { return cur ? cur->last_rounds : DVM_ERR_INVALID; }

@@ -40,3 +40,5 @@ struct dvm_frame {
 
 int dvm_frame_ensure_query_cap(dvm_frame* f, int nq);
 int dvm_frame_ensure_bytes(dvm_frame* f, size_t in_bytes, size_t out_bytes);
+// reads cur_mp[host_n] / nmatches of the last matcher launch back (synchronises the frame's stream)
+int dvm_frame_finish_match(dvm_frame* f, int32_t* cur_mp, int* nmatches);

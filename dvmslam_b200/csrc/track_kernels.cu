@@ -442,11 +442,19 @@ __global__ void __launch_bounds__(kWalkThreads) match_map_walk_kernel(FrameDev c
             return;
         }
     } else {
-        lvl = a.level[i]; px = a.projX[i]; py = a.projY[i]; vcos = a.view_cos[i];
+        lvl = a.level[i]; px = a.projX[i]; py = a.projY[i]; vcos = a.sim3_mode ? 0.f : a.view_cos[i];
+        if (a.sim3_mode && lvl < 0) { // rejected by the projection gates
+            if (lane == 0) { s.plevels[i] = -1; s.ncand[i] = 0; }
+            return;
+        }
     }
-    float r = vcos > 0.998f ? 2.5f : 4.0f; // RadiusByViewingCos
-    if (a.th != 1.0f) r = __fmul_rn(r, a.th);
-    r = __fmul_rn(r, cur.scale[lvl]);
+    float r;
+    if (a.sim3_mode) r = __fmul_rn(a.th, cur.scale[lvl]);   // const float radius = th * pKF->mvScaleFactors[nPredictedLevel]
+    else {
+        r = vcos > 0.998f ? 2.5f : 4.0f; // RadiusByViewingCos
+        if (a.th != 1.0f) r = __fmul_rn(r, a.th);
+        r = __fmul_rn(r, cur.scale[lvl]);
+    }
     if (lane == 0) { s.pu[i] = px; s.pv[i] = py; s.pr[i] = r; s.plevels[i] = lvl; }
     uint32_t d[8];
     load_desc(d, a.mp_desc + (size_t)(a.q_index ? a.q_index[i] : i) * 32);
@@ -535,6 +543,7 @@ match_map_kernel(FrameDev cur, MatchMapArgs a, MatchScratch s, int* __restrict__
             });
         }
         int pick = -1;
+        if (a.sim3_mode) return ((float)bestDist <= a.accept_limit && bestDist < 256) ? bestIdx : -1;
         if (bestDist <= kThHigh) {
             const float lim = __fmul_rn(a.nnratio, (float)bestDist2);
             const bool reject = (bestLevel == bestLevel2) && ((float)bestDist > lim);

@@ -82,6 +82,11 @@ struct MatchMapArgs {
     int use_frustum;
     FrustumArgs fr;
     int* merge_into;            // [cur cap] or nullptr: keypoints matched by this call receive their map index here
+    // ---- SearchByProjection(pKF, Scw, vpPoints, vpMatched, th, ratioHamming) (O3/src/ORBmatcher.cc:395-603): level[i] < 0
+    // = candidate rejected by the projection gates; radius th * scale[level] (no viewing-cosine factor); the nearest free
+    // keypoint is accepted when (float)bestDist <= accept_limit (TH_LOW * ratioHamming), no second-best test ----
+    int sim3_mode;
+    float accept_limit;
 };
 
 struct MatchScratch {

@@ -203,3 +203,54 @@ class HammingKnn:
     def set_mode(self, mode: int):
         """0 = by size, 1 = popcount kernel, 2 = tcgen05 int8 kernel, 3 / 4 = timing probes without outputs (MMA only / + TMEM read-out)."""
         check(self.L.dvm_hamming_set_mode(self.h, int(mode)))
+
+
+def _points(xw, normal, min_dist, max_dist, mp_desc, skip):
+    a = [_c(xw, np.float32), None if normal is None else _c(normal, np.float32), _c(min_dist, np.float32), _c(max_dist, np.float32),
+         _c(mp_desc, np.uint8)]
+    return a, (_c(skip, np.uint8) if skip is not None else None), len(a[2])
+
+
+def _ptr(a):
+    return a.ctypes.data if a is not None else None
+
+
+def SearchByProjectionSim3(kf: Frame, sim3_q, sim3_t, K, xw, normal, min_dist, max_dist, mp_desc, skip, kp_matched, th, ratioHamming=1.0):
+    """ORBmatcher::SearchByProjection(pKF, Scw, vpPoints, vpMatched, th, ratioHamming) -> (nmatches, kp_point[kf n]): the
+    candidate index newly written to vpMatched[k], -1 where unchanged."""
+    L = lib()
+    a, sk, m = _points(xw, normal, min_dist, max_dist, mp_desc, skip)
+    km = _c(kp_matched, np.uint8)
+    out = np.full(max(kf.n, 1), -1, np.int32)
+    n = C.c_int()
+    sq, st, Kc = _c(sim3_q, np.float32), _c(sim3_t, np.float32), _c(K, np.float32)
+    L.dvm_match_by_projection_sim3.argtypes = [_vp, _vp, _vp, _vp, C.c_int] + [_vp] * 7 + [C.c_int, C.c_float, _vp, _vp]
+    check(L.dvm_match_by_projection_sim3(kf.h, _ptr(sq), _ptr(st), _ptr(Kc), m, *(_ptr(x) for x in a), _ptr(sk), _ptr(km), int(th),
+                                         float(ratioHamming), _ptr(out), C.addressof(n)))
+    return n.value, out[:kf.n]
+
+
+def FuseSearchSim3(kf: Frame, sim3_q, sim3_t, K, xw, normal, min_dist, max_dist, mp_desc, skip=None, th=3.0):
+    """The search half of ORBmatcher::Fuse(pKF, Scw, vpPoints, th, vpReplacePoint) -> (best_idx, best_dist)."""
+    L = lib()
+    a, sk, m = _points(xw, normal, min_dist, max_dist, mp_desc, skip)
+    bi, bd = np.full(max(m, 1), -1, np.int32), np.full(max(m, 1), 256, np.int32)
+    sq, st, Kc = _c(sim3_q, np.float32), _c(sim3_t, np.float32), _c(K, np.float32)
+    L.dvm_fuse_search_sim3.argtypes = [_vp, _vp, _vp, _vp, C.c_int] + [_vp] * 6 + [C.c_float, _vp, _vp]
+    check(L.dvm_fuse_search_sim3(kf.h, _ptr(sq), _ptr(st), _ptr(Kc), m, *(_ptr(x) for x in a), _ptr(sk), float(th), _ptr(bi), _ptr(bd)))
+    return bi[:m], bd[:m]
+
+
+def SearchBySim3(kf1: Frame, kf2: Frame, q1, t1, q2, t2, s12_q, s12_t, K, side1, side2, th=7.5):
+    """ORBmatcher::SearchBySim3(pKF1, pKF2, vpMatches12, S12, th) -> (nFound, match12).  side = (skip, xw, min_dist, max_dist,
+    mp_desc), one entry per keypoint of the keyframe."""
+    L = lib()
+    p = [_c(x, np.float32) for x in (q1, t1, q2, t2, s12_q, s12_t, K)]
+    sides = []
+    for sk, xw, mn, mx, d in (side1, side2):
+        sides += [_c(sk, np.uint8), _c(xw, np.float32), _c(mn, np.float32), _c(mx, np.float32), _c(d, np.uint8)]
+    m12 = np.full(max(kf1.n, 1), -1, np.int32)
+    n = C.c_int()
+    L.dvm_match_by_sim3.argtypes = [_vp] * 19 + [C.c_float, _vp, _vp]
+    check(L.dvm_match_by_sim3(kf1.h, kf2.h, *(_ptr(x) for x in p), *(_ptr(x) for x in sides), float(th), _ptr(m12), C.addressof(n)))
+    return n.value, m12[:kf1.n]

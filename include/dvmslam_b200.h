@@ -246,6 +246,42 @@ DVM_API int dvm_match_for_initialization(dvm_frame* f2, int n1, const dvm_keypoi
                                          float* prev_matched, int window_size, float nnratio,
                                          int check_orientation, int32_t* matches12, int* nmatches);
 
+/* ---- Sim3-guided matchers of loop closing / map merging (LoopClosing::DetectCommonRegionsFromBoW / ...FromLastKF,
+ * O3/src/LoopClosing.cc:823-847 and callers of FindMatchesByProjection).  A Sophus::Sim3f goes over as sim3_q =
+ * quaternion().coeffs() (x, y, z, w; squared norm = scale) and sim3_t = translation(), used as stored.  Map points as in
+ * dvm_fuse_search: world position, GetNormal(), mfMinDistance / mfMaxDistance (the members), descriptor. */
+
+/* int ORBmatcher::SearchByProjection(KeyFrame* pKF, Sophus::Sim3f& Scw, const vector<MapPoint*>& vpPoints,
+ * vector<MapPoint*>& vpMatched, int th, float ratioHamming)  (O3/src/ORBmatcher.cc:395-494) and its overload with
+ * vpPointsKFs / vpMatchedKF (:496-603, same matching; the caller copies the keyframe pointers by index).  skip[i] = isBad()
+ * or the point is already in vpMatched; kp_matched[kf n] = vpMatched[k] != NULL on entry.  kp_point[kf n] receives the index
+ * i of the candidate the call writes into vpMatched[k] (-1: unchanged); *nmatches the return value.  Sequential semantics
+ * kept: a keypoint taken by an earlier candidate is not available to a later one. */
+DVM_API int dvm_match_by_projection_sim3(dvm_frame* kf, const float* sim3_q, const float* sim3_t, const float* K, int m,
+                                         const float* xw, const float* normal, const float* min_dist, const float* max_dist,
+                                         const uint8_t* mp_desc, const uint8_t* skip, const uint8_t* kp_matched, int th,
+                                         float ratio_hamming, int32_t* kp_point, int* nmatches);
+
+/* int ORBmatcher::SearchBySim3(KeyFrame* pKF1, KeyFrame* pKF2, vector<MapPoint*>& vpMatches12, const Sophus::Sim3f& S12,
+ * const float th)  (:1347-1551).  kf1 / kf2 = the keyframes' device twins; q / t = GetPose() of each; s12_q / s12_t = S12;
+ * K = pKF1's fx, fy, cx, cy (the reference projects both directions with them, :1349-1352).  Side s, one entry per
+ * keypoint: skip (no map point, isBad(), or already matched: vbAlreadyMatched, :1370-1381), the map point's world position,
+ * mfMinDistance / mfMaxDistance and descriptor.  match12[kf1 n] receives the keypoint of keyframe 2 whose map point
+ * the call writes to vpMatches12[i1] (-1: unchanged); *nfound the return value. */
+DVM_API int dvm_match_by_sim3(dvm_frame* kf1, dvm_frame* kf2, const float* q1, const float* t1, const float* q2,
+                              const float* t2, const float* s12_q, const float* s12_t, const float* K, const uint8_t* skip1,
+                              const float* xw1, const float* min_dist1, const float* max_dist1, const uint8_t* mp_desc1,
+                              const uint8_t* skip2, const float* xw2, const float* min_dist2, const float* max_dist2,
+                              const uint8_t* mp_desc2, float th, int32_t* match12, int* nfound);
+
+/* The search half of int ORBmatcher::Fuse(KeyFrame* pKF, Sophus::Sim3f& Scw, const vector<MapPoint*>& vpPoints, float th,
+ * vector<MapPoint*>& vpReplacePoint)  (:1236-1345; caller LoopClosing::SearchAndFuse).  skip[i] = isBad() or the point is
+ * among pKF->GetMapPoints().  best_idx[m] / best_dist[m]: the keypoint each candidate is fused with (bestDist <= TH_LOW) or
+ * -1 / 256; the caller then sets vpReplacePoint[i] = pKF->GetMapPoint(best_idx) or adds the observation (:1330-1340). */
+DVM_API int dvm_fuse_search_sim3(dvm_frame* kf, const float* sim3_q, const float* sim3_t, const float* K, int m,
+                                 const float* xw, const float* normal, const float* min_dist, const float* max_dist,
+                                 const uint8_t* mp_desc, const uint8_t* skip, float th, int32_t* best_idx, int32_t* best_dist);
+
 /* The relative geometry SearchForTriangulation derives from the two keyframe poses before it matches
  * (O3/src/ORBmatcher.cc:841-860, mono keyframes), in the reference's own float32 arithmetic: T12 = T1w * T2w.inverse()
  * (Sophus' normalising quaternion product and inverse, O3/Thirdparty/Sophus/sophus/{so3,se3}.hpp), R12 / t12 of it, the

@@ -122,3 +122,51 @@ def fuse_search(frame_oracle, q, t, K, log_scale, inv_sigma2, xw, normal, min_di
                        *(x.ctypes.data for x in a), sk.ctypes.data if sk is not None else None, float(th), bi.ctypes.data,
                        bd.ctypes.data)
     return bi[:m], bd[:m]
+
+
+def _pts(xw, normal, min_dist, max_dist, mp_desc, skip):
+    a = [_c(xw, np.float32), _c(normal, np.float32), _c(min_dist, np.float32), _c(max_dist, np.float32), _c(mp_desc, np.uint8)]
+    sk = _c(skip, np.uint8) if skip is not None else None
+    return a, sk, len(a[2])
+
+
+def search_by_projection_sim3(frame_oracle, sq, st, K, log_scale, nlevels, xw, normal, min_dist, max_dist, mp_desc, skip, kp_matched,
+                              th, ratio_hamming=1.0):
+    """SearchByProjection(pKF, Scw, vpPoints, vpMatched, th, ratioHamming) -> (nmatches, kp_point[kf n])."""
+    L = _L()
+    L.trko_search_by_projection_sim3.argtypes = [_vp, _vp, _vp, _vp, C.c_int, C.c_float, C.c_int] + [_vp] * 7 + [C.c_int, C.c_float, _vp]
+    a, sk, m = _pts(xw, normal, min_dist, max_dist, mp_desc, skip)
+    km = _c(kp_matched, np.uint8)
+    out = np.full(max(frame_oracle.n, 1), -1, np.int32)
+    n = L.trko_search_by_projection_sim3(frame_oracle.h, _c(sq, np.float32).ctypes.data, _c(st, np.float32).ctypes.data,
+                                         _c(K, np.float32).ctypes.data, int(nlevels), float(log_scale), m, *(x.ctypes.data for x in a),
+                                         sk.ctypes.data if sk is not None else None, km.ctypes.data, int(th), float(ratio_hamming),
+                                         out.ctypes.data)
+    return n, out[:frame_oracle.n]
+
+
+def fuse_search_sim3(frame_oracle, sq, st, K, log_scale, nlevels, xw, normal, min_dist, max_dist, mp_desc, skip=None, th=3.0):
+    """The search half of Fuse(pKF, Scw, vpPoints, th, vpReplacePoint) -> (best_idx, best_dist)."""
+    L = _L()
+    L.trko_fuse_search_sim3.argtypes = [_vp, _vp, _vp, _vp, C.c_int, C.c_float, C.c_int] + [_vp] * 6 + [C.c_float, _vp, _vp]
+    L.trko_fuse_search_sim3.restype = None
+    a, sk, m = _pts(xw, normal, min_dist, max_dist, mp_desc, skip)
+    bi, bd = np.full(max(m, 1), -1, np.int32), np.full(max(m, 1), 256, np.int32)
+    L.trko_fuse_search_sim3(frame_oracle.h, _c(sq, np.float32).ctypes.data, _c(st, np.float32).ctypes.data, _c(K, np.float32).ctypes.data,
+                            int(nlevels), float(log_scale), m, *(x.ctypes.data for x in a), sk.ctypes.data if sk is not None else None,
+                            float(th), bi.ctypes.data, bd.ctypes.data)
+    return bi[:m], bd[:m]
+
+
+def search_by_sim3(f1, f2, q1, t1, q2, t2, s12q, s12t, K, log_scale, nlevels, side1, side2, th=7.5):
+    """SearchBySim3(pKF1, pKF2, vpMatches12, S12, th) -> (nFound, match12).  side = (skip, xw, min_dist, max_dist, mp_desc)."""
+    L = _L()
+    L.trko_search_by_sim3.argtypes = [_vp] * 9 + [C.c_int, C.c_float] + [_vp] * 10 + [C.c_float, _vp]
+    p = [_c(x, np.float32) for x in (q1, t1, q2, t2, s12q, s12t, K)]
+    sides = []
+    for sk, xw, mn, mx, d in (side1, side2):
+        sides += [_c(sk, np.uint8), _c(xw, np.float32), _c(mn, np.float32), _c(mx, np.float32), _c(d, np.uint8)]
+    m12 = np.full(max(f1.n, 1), -1, np.int32)
+    n = L.trko_search_by_sim3(f1.h, f2.h, *(x.ctypes.data for x in p), int(nlevels), float(log_scale), *(x.ctypes.data for x in sides),
+                              float(th), m12.ctypes.data)
+    return n, m12[:f1.n]

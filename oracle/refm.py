@@ -48,6 +48,9 @@ def _L():
         L.refm_frame_set_featvec.argtypes = [_vp, C.c_int, _vp, _vp, _vp]
         L.refm_frame_set_featvec.restype = None
         L.refm_fuse.argtypes = [_vp, _vp, _vp, C.c_int] + [_vp] * 6 + [C.c_float, _vp]
+        L.refm_search_by_projection_sim3.argtypes = [_vp, _vp, _vp, C.c_int] + [_vp] * 7 + [C.c_int, C.c_float, _vp]
+        L.refm_fuse_sim3.argtypes = [_vp, _vp, _vp, C.c_int] + [_vp] * 6 + [C.c_float, _vp]
+        L.refm_search_by_sim3.argtypes = [_vp] * 18 + [C.c_float, _vp]
         _LIB = L
     return _LIB
 
@@ -119,6 +122,38 @@ class RefFrame:
         q, t = _c(q, np.float32), _c(t, np.float32)
         n = self.L.refm_fuse(self.h, _p(q), _p(t), m, *(_p(x) for x in a), _p(sk), float(th), _p(bi))
         return n, bi[:m]
+
+
+def _pts(xw, normal, min_dist, max_dist, mp_desc, skip):
+    a = [_c(xw, np.float32), _c(normal, np.float32), _c(min_dist, np.float32), _c(max_dist, np.float32), _c(mp_desc, np.uint8)]
+    return a, (_c(skip, np.uint8) if skip is not None else None), len(a[2])
+
+
+def search_by_projection_sim3(kf: RefFrame, sq, st, xw, normal, min_dist, max_dist, mp_desc, skip, kp_matched, th, ratio_hamming=1.0):
+    a, sk, m = _pts(xw, normal, min_dist, max_dist, mp_desc, skip)
+    km = _c(kp_matched, np.uint8)
+    out = np.full(max(kf.n, 1), -1, np.int32)
+    sq, st = _c(sq, np.float32), _c(st, np.float32)
+    n = _L().refm_search_by_projection_sim3(kf.h, _p(sq), _p(st), m, *(_p(x) for x in a), _p(sk), _p(km), int(th), float(ratio_hamming), _p(out))
+    return n, out[:kf.n]
+
+
+def fuse_sim3(kf: RefFrame, sq, st, xw, normal, min_dist, max_dist, mp_desc, skip=None, th=3.0):
+    a, sk, m = _pts(xw, normal, min_dist, max_dist, mp_desc, skip)
+    bi = np.full(max(m, 1), -1, np.int32)
+    sq, st = _c(sq, np.float32), _c(st, np.float32)
+    n = _L().refm_fuse_sim3(kf.h, _p(sq), _p(st), m, *(_p(x) for x in a), _p(sk), float(th), _p(bi))
+    return n, bi[:m]
+
+
+def search_by_sim3(f1: RefFrame, f2: RefFrame, q1, t1, q2, t2, s12q, s12t, side1, side2, th=7.5):
+    p = [_c(x, np.float32) for x in (q1, t1, q2, t2, s12q, s12t)]
+    sides = []
+    for sk, xw, mn, mx, d in (side1, side2):
+        sides += [_c(sk, np.uint8), _c(xw, np.float32), _c(mn, np.float32), _c(mx, np.float32), _c(d, np.uint8)]
+    m12 = np.full(max(f1.n, 1), -1, np.int32)
+    n = _L().refm_search_by_sim3(f1.h, f2.h, *(_p(x) for x in p), *(_p(x) for x in sides), float(th), _p(m12))
+    return n, m12[:f1.n]
 
 
 def descriptor_distance(a, b):

@@ -374,4 +374,99 @@ int refm_fuse(void* fkf, const float* q, const float* t, int m, const float* xw,
     return n;
 }
 
+
+/* SearchByProjection(pKF, Scw, vpPoints, vpMatched, th, ratioHamming), :395-494.  sq / st: Scw.quaternion() / translation().
+ * kp_matched[kf n]: vpMatched[k] != NULL on entry; kp_point[kf n] receives the candidate index newly written to vpMatched[k]. */
+int refm_search_by_projection_sim3(void* fkf, const float* sq, const float* st, int m, const float* xw, const float* normal,
+                                   const float* min_dist, const float* max_dist, const uint8_t* mp_desc, const uint8_t* skip,
+                                   const uint8_t* kp_matched, int th, float ratioHamming, int* kp_point)
+{
+    RefFrame* R = (RefFrame*)fkf;
+    KeyFrame* kf = R->keyframe();
+    Sophus::Sim3f Scw(Eigen::Quaternionf(sq[3], sq[0], sq[1], sq[2]), Eigen::Vector3f(st[0], st[1], st[2]));
+    MapPoint occupied;
+    std::vector<std::unique_ptr<MapPoint>> pts(m);
+    std::vector<MapPoint*> v(m);
+    for (int i = 0; i < m; i++) {
+        pts[i].reset(new MapPoint);
+        MapPoint* p = v[i] = pts[i].get();
+        p->mnFlatIndex = i;
+        p->mWorldPos = Eigen::Vector3f(xw[3 * i], xw[3 * i + 1], xw[3 * i + 2]);
+        p->mNormalVector = Eigen::Vector3f(normal[3 * i], normal[3 * i + 1], normal[3 * i + 2]);
+        p->mfMinDistance = min_dist[i]; p->mfMaxDistance = max_dist[i];
+        p->mDescriptor = desc_row(mp_desc + (size_t)i * 32);
+        p->mbBad = skip && skip[i];
+    }
+    std::vector<MapPoint*> matched(kf->N, nullptr);
+    for (int k = 0; k < kf->N; k++) if (kp_matched[k]) matched[k] = &occupied;
+    ORBmatcher matcher(0.75f, true);
+    const int n = matcher.SearchByProjection(kf, Scw, v, matched, th, ratioHamming);
+    for (int k = 0; k < kf->N; k++) kp_point[k] = (matched[k] && matched[k] != &occupied) ? matched[k]->mnFlatIndex : -1;
+    return n;
+}
+
+/* Fuse(pKF, Scw, vpPoints, th, vpReplacePoint), :1236-1345.  The keyframe holds no map points on entry, so every fused
+ * candidate is added (AddObservation / AddMapPoint) or, when an earlier candidate took the keypoint, reported through
+ * vpReplacePoint; best_idx[i] = the keypoint either way. */
+int refm_fuse_sim3(void* fkf, const float* sq, const float* st, int m, const float* xw, const float* normal, const float* min_dist,
+                   const float* max_dist, const uint8_t* mp_desc, const uint8_t* skip, float th, int* best_idx)
+{
+    RefFrame* R = (RefFrame*)fkf;
+    KeyFrame* kf = R->keyframe();
+    std::fill(kf->mvpMapPoints.begin(), kf->mvpMapPoints.end(), nullptr);
+    Sophus::Sim3f Scw(Eigen::Quaternionf(sq[3], sq[0], sq[1], sq[2]), Eigen::Vector3f(st[0], st[1], st[2]));
+    std::vector<std::unique_ptr<MapPoint>> pts(m);
+    std::vector<MapPoint*> v(m), repl(m, nullptr);
+    for (int i = 0; i < m; i++) {
+        pts[i].reset(new MapPoint);
+        MapPoint* p = v[i] = pts[i].get();
+        p->mnFlatIndex = i;
+        p->mWorldPos = Eigen::Vector3f(xw[3 * i], xw[3 * i + 1], xw[3 * i + 2]);
+        p->mNormalVector = Eigen::Vector3f(normal[3 * i], normal[3 * i + 1], normal[3 * i + 2]);
+        p->mfMinDistance = min_dist[i]; p->mfMaxDistance = max_dist[i];
+        p->mDescriptor = desc_row(mp_desc + (size_t)i * 32);
+        p->nObs = 1;
+        p->mbBad = skip && skip[i];
+    }
+    ORBmatcher matcher;
+    const int n = matcher.Fuse(kf, Scw, v, th, repl);
+    std::vector<int> first_at(m, -1);
+    for (int i = 0; i < m; i++) {
+        const auto it = pts[i]->mObservations.find(kf);
+        if (it != pts[i]->mObservations.end()) first_at[i] = std::get<0>(it->second);
+    }
+    for (int i = 0; i < m; i++) best_idx[i] = first_at[i] >= 0 ? first_at[i] : (repl[i] ? first_at[repl[i]->mnFlatIndex] : -1);
+    return n;
+}
+
+/* SearchBySim3(pKF1, pKF2, vpMatches12, S12, th), :1347-1551.  has_s[i] = keypoint i of keyframe s holds a (good) map point. */
+int refm_search_by_sim3(void* f1, void* f2, const float* q1, const float* t1, const float* q2, const float* t2, const float* s12q,
+                        const float* s12t, const uint8_t* skip1, const float* xw1, const float* min1, const float* max1,
+                        const uint8_t* desc1, const uint8_t* skip2, const float* xw2, const float* min2, const float* max2,
+                        const uint8_t* desc2, float th, int* match12)
+{
+    RefFrame *R1 = (RefFrame*)f1, *R2 = (RefFrame*)f2;
+    KeyFrame *k1 = R1->keyframe(), *k2 = R2->keyframe();
+    k1->SetPose(pose_of(q1, t1)); k2->SetPose(pose_of(q2, t2));
+    auto fill = [](RefFrame* R, KeyFrame* kf, const uint8_t* skip, const float* xw, const float* mind, const float* maxd, const uint8_t* desc) {
+        for (int i = 0; i < kf->N; i++) {
+            kf->mvpMapPoints[i] = nullptr;
+            if (skip[i]) continue;
+            MapPoint* p = R->new_point(i);
+            p->mWorldPos = Eigen::Vector3f(xw[3 * i], xw[3 * i + 1], xw[3 * i + 2]);
+            p->mfMinDistance = mind[i]; p->mfMaxDistance = maxd[i];
+            p->mDescriptor = desc_row(desc + (size_t)i * 32);
+            kf->mvpMapPoints[i] = p;
+        }
+    };
+    fill(R1, k1, skip1, xw1, min1, max1, desc1);
+    fill(R2, k2, skip2, xw2, min2, max2, desc2);
+    Sophus::Sim3f S12(Eigen::Quaternionf(s12q[3], s12q[0], s12q[1], s12q[2]), Eigen::Vector3f(s12t[0], s12t[1], s12t[2]));
+    std::vector<MapPoint*> vm(k1->N, nullptr);
+    ORBmatcher matcher(0.75f, true);
+    const int n = matcher.SearchBySim3(k1, k2, vm, S12, th);
+    for (int i = 0; i < k1->N; i++) match12[i] = vm[i] ? vm[i]->mnFlatIndex : -1;
+    return n;
+}
+
 } // extern "C"

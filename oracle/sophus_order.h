@@ -97,6 +97,62 @@ inline void mat_inverse(const float M[9], float I[9])
     for (int r = 0; r < 3; r++)
         for (int c = 0; c < 3; c++) I[3 * r + c] = (r == 0 ? c0[c] : cof(c, r)) * invdet;
 }
+/* Eigen/src/Geometry/Quaternion.h, quaternionbase_assign_impl<Other,3,3>: quaternion <- rotation matrix (row-major R) */
+inline void quat_from_matrix(const float R[9], float q[4])
+{
+    float t = R[0] + (R[4] + R[8]);
+    if (t > 0.f) {
+        t = std::sqrt(t + 1.0f);
+        q[3] = 0.5f * t;
+        t = 0.5f / t;
+        q[0] = (R[7] - R[5]) * t; q[1] = (R[2] - R[6]) * t; q[2] = (R[3] - R[1]) * t;
+    } else {
+        int i = 0;
+        if (R[4] > R[0]) i = 1;
+        if (R[8] > R[4 * i]) i = 2;
+        const int j = (i + 1) % 3, k = (j + 1) % 3;
+        t = std::sqrt(R[4 * i] - R[4 * j] - R[4 * k] + 1.0f);
+        q[i] = 0.5f * t;
+        t = 0.5f / t;
+        q[3] = (R[3 * k + j] - R[3 * j + k]) * t;
+        q[j] = (R[3 * j + i] + R[3 * i + j]) * t;
+        q[k] = (R[3 * k + i] + R[3 * i + k]) * t;
+    }
+}
+/* Sophus::Sim3f as (RxSO3 quaternion with |q|^2 = scale, translation).  scale(): rxso3.hpp:349-350 */
+inline float sim3_scale(const float sq[4]) { return (sq[0] * sq[0] + sq[2] * sq[2]) + (sq[1] * sq[1] + sq[3] * sq[3]); }
+/* RxSO3::operator*(point), rxso3.hpp:262-273, then + t (sim3.hpp:226-230) */
+inline void sim3_apply(const float sq[4], const float st[3], const float p[3], float o[3])
+{
+    const float scale = sim3_scale(sq);
+    float c2[3], c[3];
+    cross3(sq, p, c2);
+    c2[0] += c2[0]; c2[1] += c2[1]; c2[2] += c2[2];
+    cross3(sq, c2, c);
+    for (int i = 0; i < 3; i++) o[i] = (scale * p[i] + (sq[3] * c2[i] + c[i])) + st[i];
+}
+/* Sim3::inverse(), sim3.hpp:129-132: RxSO3(quaternion().inverse()) (Eigen: conjugate / squaredNorm) applied to -t */
+inline void sim3_inverse(const float sq[4], const float st[3], float iq[4], float it[3])
+{
+    const float n2 = sim3_scale(sq);
+    iq[0] = -sq[0] / n2; iq[1] = -sq[1] / n2; iq[2] = -sq[2] / n2; iq[3] = sq[3] / n2;
+    const float mt[3] = { st[0] * -1.f, st[1] * -1.f, st[2] * -1.f };
+    float z[3] = { 0.f, 0.f, 0.f };
+    sim3_apply(iq, z, mt, it);
+    /* sim3_apply adds a zero translation: x + 0.f == x for every finite x (and -0.f + 0.f = 0.f, compared equal) */
+}
+/* Tcw = Sophus::SE3f(Scw.rotationMatrix(), Scw.translation() / Scw.scale()) (O3/src/ORBmatcher.cc:403,505,1245):
+ * rotationMatrix() normalises a copy of the quaternion (rxso3.hpp:341-345), SE3f(R, t) converts the matrix back to a
+ * quaternion without normalising (so3.hpp:469-474) */
+inline void sim3_to_se3(const float sq[4], const float st[3], float q[4], float t[3])
+{
+    float nq[4] = { sq[0], sq[1], sq[2], sq[3] }, R[9];
+    quat_normalize(nq);
+    quat_to_matrix(nq, R);
+    quat_from_matrix(R, q);
+    const float s = sim3_scale(sq);
+    for (int i = 0; i < 3; i++) t[i] = st[i] / s;
+}
 /* MapPoint::PredictScale, O3/src/MapPoint.cc:557-587: ceil(log(ratio) / mfLogScaleFactor) in float (std::log(float)) */
 inline int predict_scale(float maxDistance, float dist, float logScaleFactor, int nlevels)
 {

@@ -23,6 +23,7 @@
  * mono path only (Nleft == -1, mvuRight < 0); the 6x6 solve is an unpivoted LDL^T in double
  * (the reference uses Eigen::LDLT, which pivots: results agree to rounding, tolerance in tests).
  */
+#include <climits>
 #include "sophus_order.h"
 #include <algorithm>
 #include <cmath>
@@ -721,6 +722,165 @@ void trko_fuse_search(void* fkf, const float* q, const float* t, const float* K,
         }
         if (bestDist <= TH_LOW) { best_idx[i] = bestIdx; best_dist[i] = bestDist; }
     }
+}
+
+
+/* ---- Sim3-guided matchers of loop closing / map merging (LoopClosing::DetectCommonRegionsFromBoW, O3/src/LoopClosing.cc:823-847) ----
+ * Common to all: the candidate map point is projected into a keyframe (its keypoints / grid = fkf), gated by depth,
+ * image bounds (KeyFrame::IsInImage), the scale-invariance range and -- except in SearchBySim3 -- the viewing angle; the
+ * keypoints in a window of radius th * scale[predicted level] with octave in [level - 1, level] are compared and the first
+ * of the nearest wins.  min_dist / max_dist are mfMinDistance / mfMaxDistance. */
+namespace {
+struct ProjGate { float u, v; int level; };
+/* the gates of O3/src/ORBmatcher.cc:421-454 (= :524-563, :1264-1297): returns false when the point is rejected */
+bool sim3_project_gate(const Frame& F, const float q[4], const float t[3], const float Ow[3], const float* K, int nlevels,
+                       float logScale, const float* P, const float* Pn, float minD, float maxD, ProjGate& g)
+{
+    float pc[3];
+    so::se3_apply(q, t, P, pc);
+    if (pc[2] < 0.0f) return false;
+    g.u = K[0] * pc[0] / pc[2] + K[2];
+    g.v = K[1] * pc[1] / pc[2] + K[3];
+    if (!(g.u >= F.minX && g.u < F.maxX && g.v >= F.minY && g.v < F.maxY)) return false;
+    const float maxDistance = 1.2f * maxD, minDistance = 0.8f * minD;
+    const float PO[3] = { P[0] - Ow[0], P[1] - Ow[1], P[2] - Ow[2] };
+    const float dist = so::norm3(PO);
+    if (dist < minDistance || dist > maxDistance) return false;
+    if (so::dot3(PO, Pn) < 0.5 * dist) return false;
+    g.level = so::predict_scale(maxD, dist, logScale, nlevels);
+    return true;
+}
+} // namespace
+
+/* int ORBmatcher::SearchByProjection(KeyFrame* pKF, Sophus::Sim3f& Scw, const vector<MapPoint*>& vpPoints,
+ * vector<MapPoint*>& vpMatched, int th, float ratioHamming)  (:395-494; the overload with vpPointsKFs, :496-603, matches
+ * identically).  sq / st: Scw.quaternion() (x, y, z, w; |q|^2 = scale) and Scw.translation().  skip[i]: isBad() or already
+ * in vpMatched.  kp_matched[kf n]: in = vpMatched[k] != NULL, out = unchanged for those, else the index of the candidate
+ * now held (-1 none) in kp_point.  Sequential: a keypoint taken by an earlier candidate is not available to later ones. */
+int trko_search_by_projection_sim3(void* fkf, const float* sq, const float* st, const float* K, int nlevels, float logScale,
+                                   int m, const float* xw, const float* normal, const float* min_dist, const float* max_dist,
+                                   const uint8_t* mp_desc, const uint8_t* skip, const uint8_t* kp_matched, int th,
+                                   float ratioHamming, int* kp_point)
+{
+    Frame& F = *(Frame*)fkf;
+    float q[4], t[3], qi[4], Ow[3];
+    so::sim3_to_se3(sq, st, q, t);
+    so::se3_inverse(q, t, qi, Ow);
+    std::vector<uint8_t> taken(kp_matched, kp_matched + F.n);
+    for (int k = 0; k < F.n; k++) kp_point[k] = -1;
+    int nmatches = 0;
+    std::vector<int> idx;
+    for (int i = 0; i < m; i++) {
+        if (skip && skip[i]) continue;
+        ProjGate g;
+        if (!sim3_project_gate(F, q, t, Ow, K, nlevels, logScale, xw + 3 * i, normal + 3 * i, min_dist[i], max_dist[i], g)) continue;
+        const float radius = th * F.scaleFactors[g.level];
+        features_in_area(F, g.u, g.v, radius, -1, -1, idx);
+        if (idx.empty()) continue;
+        const uint8_t* dMP = mp_desc + (size_t)i * 32;
+        int bestDist = 256, bestIdx = -1;
+        for (int k : idx) {
+            if (taken[k]) continue;
+            const int lv = F.kps[k].octave;
+            if (lv < g.level - 1 || lv > g.level) continue;
+            const int dist = descriptor_distance(dMP, &F.desc[(size_t)k * 32]);
+            if (dist < bestDist) { bestDist = dist; bestIdx = k; }
+        }
+        if (bestDist <= TH_LOW * ratioHamming) { taken[bestIdx] = 1; kp_point[bestIdx] = i; nmatches++; }
+    }
+    return nmatches;
+}
+
+/* The search half of int ORBmatcher::Fuse(KeyFrame* pKF, Sophus::Sim3f& Scw, const vector<MapPoint*>& vpPoints, float th,
+ * vector<MapPoint*>& vpReplacePoint)  (:1236-1345): per candidate the keypoint it is fused with (-1 none).  skip[i]:
+ * isBad() or already among pKF->GetMapPoints().  No chi-square gate here (unlike Fuse(pKF, vpMapPoints, th)). */
+void trko_fuse_search_sim3(void* fkf, const float* sq, const float* st, const float* K, int nlevels, float logScale, int m,
+                           const float* xw, const float* normal, const float* min_dist, const float* max_dist,
+                           const uint8_t* mp_desc, const uint8_t* skip, float th, int* best_idx, int* best_dist)
+{
+    Frame& F = *(Frame*)fkf;
+    float q[4], t[3], qi[4], Ow[3];
+    so::sim3_to_se3(sq, st, q, t);
+    so::se3_inverse(q, t, qi, Ow);
+    std::vector<int> idx;
+    for (int i = 0; i < m; i++) {
+        best_idx[i] = -1; best_dist[i] = 256;
+        if (skip && skip[i]) continue;
+        ProjGate g;
+        if (!sim3_project_gate(F, q, t, Ow, K, nlevels, logScale, xw + 3 * i, normal + 3 * i, min_dist[i], max_dist[i], g)) continue;
+        const float radius = th * F.scaleFactors[g.level];
+        features_in_area(F, g.u, g.v, radius, -1, -1, idx);
+        if (idx.empty()) continue;
+        const uint8_t* dMP = mp_desc + (size_t)i * 32;
+        int bestDist = INT_MAX, bestIdx = -1;
+        for (int k : idx) {
+            const int lv = F.kps[k].octave;
+            if (lv < g.level - 1 || lv > g.level) continue;
+            const int dist = descriptor_distance(dMP, &F.desc[(size_t)k * 32]);
+            if (dist < bestDist) { bestDist = dist; bestIdx = k; }
+        }
+        if (bestDist <= TH_LOW) { best_idx[i] = bestIdx; best_dist[i] = bestDist; }
+    }
+}
+
+/* int ORBmatcher::SearchBySim3(KeyFrame* pKF1, KeyFrame* pKF2, vector<MapPoint*>& vpMatches12, const Sophus::Sim3f& S12,
+ * float th)  (:1347-1551).  Both directions project with pKF1's intrinsics (:1349-1352, the reference's choice) in the
+ * u = fx * (x * invz) + cx form with invz = 1.0 / z taken in double; the distance is the norm of the point in the target
+ * camera frame; no viewing-angle gate; TH_HIGH; a pair is kept when the two directions agree.
+ * Side s (1, 2): n_s keypoints of keyframe s with the map point behind each (skip_s[i]: no map point, bad, or already
+ * matched -- vbAlreadyMatched), its world position, distance range and descriptor.  match12[n1]: keypoint of keyframe 2
+ * whose map point feature i1 is matched with (-1 none).  Returns nFound. */
+int trko_search_by_sim3(void* f1, void* f2, const float* q1, const float* t1, const float* q2, const float* t2,
+                        const float* s12q, const float* s12t, const float* K, int nlevels, float logScale,
+                        const uint8_t* skip1, const float* xw1, const float* min1, const float* max1, const uint8_t* desc1,
+                        const uint8_t* skip2, const float* xw2, const float* min2, const float* max2, const uint8_t* desc2,
+                        float th, int* match12)
+{
+    Frame &F1 = *(Frame*)f1, &F2 = *(Frame*)f2;
+    float s21q[4], s21t[3];
+    so::sim3_inverse(s12q, s12t, s21q, s21t);
+    auto direction = [&](const Frame& Fsrc, const Frame& Fdst, const float* qs, const float* ts, const float* sq, const float* st,
+                         const uint8_t* skip, const float* xw, const float* mind, const float* maxd, const uint8_t* desc,
+                         std::vector<int>& out) {
+        out.assign(Fsrc.n, -1);
+        std::vector<int> idx;
+        for (int i = 0; i < Fsrc.n; i++) {
+            if (skip[i]) continue;
+            float pa[3], pb[3];
+            so::se3_apply(qs, ts, xw + 3 * i, pa);
+            so::sim3_apply(sq, st, pa, pb);
+            if (pb[2] < 0.0) continue;
+            const float invz = (float)(1.0 / pb[2]);
+            const float x = pb[0] * invz, y = pb[1] * invz;
+            const float u = K[0] * x + K[2], v = K[1] * y + K[3];
+            if (!(u >= Fdst.minX && u < Fdst.maxX && v >= Fdst.minY && v < Fdst.maxY)) continue;
+            const float maxDistance = 1.2f * maxd[i], minDistance = 0.8f * mind[i];
+            const float dist3D = so::norm3(pb);
+            if (dist3D < minDistance || dist3D > maxDistance) continue;
+            const int level = so::predict_scale(maxd[i], dist3D, logScale, nlevels);
+            const float radius = th * Fdst.scaleFactors[level];
+            features_in_area(Fdst, u, v, radius, -1, -1, idx);
+            if (idx.empty()) continue;
+            int bestDist = INT_MAX, bestIdx = -1;
+            for (int k : idx) {
+                const int lv = Fdst.kps[k].octave;
+                if (lv < level - 1 || lv > level) continue;
+                const int dist = descriptor_distance(desc + (size_t)i * 32, &Fdst.desc[(size_t)k * 32]);
+                if (dist < bestDist) { bestDist = dist; bestIdx = k; }
+            }
+            if (bestDist <= TH_HIGH) out[i] = bestIdx;
+        }
+    };
+    std::vector<int> m1, m2;
+    direction(F1, F2, q1, t1, s21q, s21t, skip1, xw1, min1, max1, desc1, m1);
+    direction(F2, F1, q2, t2, s12q, s12t, skip2, xw2, min2, max2, desc2, m2);
+    int nFound = 0;
+    for (int i1 = 0; i1 < F1.n; i1++) {
+        match12[i1] = -1;
+        const int idx2 = m1[i1];
+        if (idx2 >= 0 && m2[idx2] == i1) { match12[i1] = idx2; nFound++; }
+    }
+    return nFound;
 }
 
 } // extern "C"

@@ -95,3 +95,67 @@ def fuse_case(extract, k=4, k_src=1, w=640, h=480, seed=0, n_points=1500):
     return dict(kps=kps, desc=desc, q=q, t=np.asarray(t, np.float32), K=np.array(S.K, np.float32), xw=X, normal=normal,
                 min_dist=min_d, max_dist=max_d, mp_desc=np.ascontiguousarray(md[sel]), skip=skip,
                 bounds=(0.0, 0.0, float(w), float(h)))
+
+
+def _lift(S, k_src, mk, sel):
+    """Keypoints `sel` of view k_src lifted to the plane, with normals and distance ranges as UpdateNormalAndDepth leaves them."""
+    X = synth.backproject_to_plane(S, k_src, np.stack([mk["x"][sel], mk["y"][sel]], 1).astype(np.float64))
+    R0, t0 = S.pose(k_src)
+    Ow = -(np.asarray(R0, np.float64).T @ np.asarray(t0, np.float64))
+    PO = X - Ow
+    d = np.linalg.norm(PO, axis=1)
+    max_d = d * 1.2 ** mk["octave"][sel].astype(np.float64)
+    return X, (PO / d[:, None]), max_d / 1.2 ** 7, max_d
+
+
+def sim3_quat(R, s):
+    """RxSO3 quaternion (x, y, z, w) of scale s: |q|^2 = s (Sophus::Sim3f::quaternion())."""
+    return (synth.quat_from_R(np.asarray(R, np.float64)) * np.sqrt(s)).astype(np.float32)
+
+
+def sim3_projection_case(extract, k=4, k_src=1, w=640, h=480, seed=0, n_points=1500, scale=1.3):
+    """A keyframe (view k) and candidate map points of ANOTHER map whose frame differs from the keyframe's world by a
+    similarity: inputs of SearchByProjection(pKF, Scw, ...) and Fuse(pKF, Scw, ...).  With Scw = (s, R, s t) the reference's
+    Tcw = SE3(Scw.rotationMatrix(), Scw.translation() / Scw.scale()) is the keyframe's pose."""
+    S = synth.PlaneStream(w, h, seed=3, K=(500.0, 500.0, w / 2, h / 2))
+    rng = np.random.default_rng(seed)
+    kps, desc, _ = extract(S.frame(k))
+    mk, md, _ = extract(S.frame(k_src))
+    sel = np.sort(rng.permutation(len(mk))[:n_points])
+    X, normal, min_d, max_d = _lift(S, k_src, mk, sel)
+    R, t = S.pose(k)
+    sq = sim3_quat(R, scale)
+    st = (np.asarray(t, np.float64) * scale).astype(np.float32)
+    skip = (rng.random(len(sel)) < 0.1).astype(np.uint8)
+    kp_matched = (rng.random(len(kps)) < 0.2).astype(np.uint8)
+    return dict(kps=kps, desc=desc, sq=sq, st=st, K=np.array(S.K, np.float32), xw=X.astype(np.float32),
+                normal=normal.astype(np.float32), min_dist=min_d.astype(np.float32), max_dist=max_d.astype(np.float32),
+                mp_desc=np.ascontiguousarray(md[sel]), skip=skip, kp_matched=kp_matched, bounds=(0.0, 0.0, float(w), float(h)))
+
+
+def search_by_sim3_case(extract, k1=2, k2=6, w=640, h=480, seed=0, c=1.7, mp_frac=0.8):
+    """Two keyframes of two maps (map B = map A scaled by c) with a map point behind most keypoints and the similarity
+    S12 (camera 2 -> camera 1): inputs of SearchBySim3."""
+    S = synth.PlaneStream(w, h, seed=3, K=(500.0, 500.0, w / 2, h / 2))
+    rng = np.random.default_rng(seed)
+    out = {"K": np.array(S.K, np.float32), "bounds": (0.0, 0.0, float(w), float(h))}
+    Rs, ts = [], []
+    for tag, k, unit in (("1", k1, 1.0), ("2", k2, c)):
+        kps, desc, _ = extract(S.frame(k))
+        sel = np.arange(len(kps))
+        X, _, min_d, max_d = _lift(S, k, kps, sel)
+        R, t = S.pose(k)
+        Rs.append(np.asarray(R, np.float64)); ts.append(np.asarray(t, np.float64))
+        out["kps" + tag], out["desc" + tag] = kps, desc
+        out["skip" + tag] = (rng.random(len(kps)) > mp_frac).astype(np.uint8)
+        out["xw" + tag] = (X * unit).astype(np.float32)
+        out["min" + tag], out["max" + tag] = (min_d * unit).astype(np.float32), (max_d * unit).astype(np.float32)
+        # the map point's descriptor: the keypoint's own with a few flipped bits (another observation is the representative)
+        out["mpdesc" + tag] = synth.noisy_copy(desc, 0.02, rng)
+        out["q" + tag] = synth.quat_from_R(np.asarray(R, np.float64)).astype(np.float32)
+        out["t" + tag] = (np.asarray(t, np.float64) * unit).astype(np.float32)
+    R12 = Rs[0] @ Rs[1].T
+    t12 = ts[0] - R12 @ ts[1]
+    out["s12q"] = sim3_quat(R12, 1.0 / c)
+    out["s12t"] = t12.astype(np.float32)
+    return out

@@ -312,3 +312,71 @@ def test_hamming_tensor_core_matches_popcount_and_oracle(KA, NA, KB, NB):
             assert np.array_equal(np.minimum(k1[i, j] >> 20, 256), d1)
             assert np.array_equal(np.where(d1 < 256, k1[i, j] & 0xFFFFF, -1), idx)
             assert np.array_equal(np.minimum(k2[i, j] >> 20, 256), d2)
+
+
+def _kf(c, T, tag=""):
+    from dvmslam_b200.tracking import Frame
+    from oracle.track import FrameOracle
+
+    kps, desc = c["kps" + tag], c["desc" + tag]
+    F0 = FrameOracle(kps, desc, c["bounds"], T["scale"])
+    F1 = Frame(len(kps) + 16, T["scale"], T["inv_sigma2"])
+    F1.assign(kps, desc, c["bounds"])
+    return F0, F1
+
+
+@pytest.mark.parametrize("w,h,nf,th,ratio", [(640, 480, 1000, 8, 1.5), (1280, 720, 2000, 4, 1.0), (640, 480, 1000, 30, 1.0)])
+def test_search_by_projection_sim3(w, h, nf, th, ratio):
+    """SearchByProjection(pKF, Scw, vpPoints, vpMatched, th, ratioHamming) (O3/src/ORBmatcher.cc:395-603): gate pass +
+    sequential-greedy resolution on the GPU against the oracle (pinned to the reference in tests/test_ref_matchers.py);
+    th = 30 packs many candidates onto each keypoint."""
+    from dvmslam_b200.matching import SearchByProjectionSim3
+    from oracle.bow import search_by_projection_sim3
+    from oracle.orb import OrbOracle
+
+    orc = OrbOracle(nf)
+    T = orc.tables()
+    c = bow_cases.sim3_projection_case(orc.extract, w=w, h=h, n_points=3000)
+    F0, F1 = _kf(c, T)
+    pts = (c["xw"], c["normal"], c["min_dist"], c["max_dist"], c["mp_desc"], c["skip"], c["kp_matched"])
+    n0, k0 = search_by_projection_sim3(F0, c["sq"], c["st"], c["K"], float(np.log(np.float32(T["scale"][1]))), 8, *pts, th, ratio)
+    n1, k1 = SearchByProjectionSim3(F1, c["sq"], c["st"], c["K"], *pts, th, ratio)
+    assert n0 == n1 and np.array_equal(k0, k1)
+    assert n0 > 100
+    F1.close()
+
+
+@pytest.mark.parametrize("w,h,nf,th", [(640, 480, 1000, 3.0), (1280, 720, 2000, 4.0)])
+def test_fuse_search_sim3(w, h, nf, th):
+    from dvmslam_b200.matching import FuseSearchSim3
+    from oracle.bow import fuse_search_sim3
+    from oracle.orb import OrbOracle
+
+    orc = OrbOracle(nf)
+    T = orc.tables()
+    c = bow_cases.sim3_projection_case(orc.extract, w=w, h=h, n_points=3000, scale=0.7)
+    F0, F1 = _kf(c, T)
+    pts = (c["xw"], c["normal"], c["min_dist"], c["max_dist"], c["mp_desc"], c["skip"])
+    i0, d0 = fuse_search_sim3(F0, c["sq"], c["st"], c["K"], float(np.log(np.float32(T["scale"][1]))), 8, *pts, th)
+    i1, d1 = FuseSearchSim3(F1, c["sq"], c["st"], c["K"], *pts, th)
+    assert np.array_equal(i0, i1) and np.array_equal(d0, d1) and (i1 >= 0).sum() > 100
+    F1.close()
+
+
+@pytest.mark.parametrize("w,h,nf,th", [(640, 480, 1000, 7.5), (1280, 720, 2000, 7.5)])
+def test_search_by_sim3(w, h, nf, th):
+    from dvmslam_b200.matching import SearchBySim3
+    from oracle.bow import search_by_sim3
+    from oracle.orb import OrbOracle
+
+    orc = OrbOracle(nf)
+    T = orc.tables()
+    c = bow_cases.search_by_sim3_case(orc.extract, w=w, h=h)
+    (A0, A1), (B0, B1) = _kf(c, T, "1"), _kf(c, T, "2")
+    sides = [(c["skip" + s], c["xw" + s], c["min" + s], c["max" + s], c["mpdesc" + s]) for s in "12"]
+    poses = (c["q1"], c["t1"], c["q2"], c["t2"], c["s12q"], c["s12t"])
+    n0, m0 = search_by_sim3(A0, B0, *poses, c["K"], float(np.log(np.float32(T["scale"][1]))), 8, *sides, th)
+    n1, m1 = SearchBySim3(A1, B1, *poses, c["K"], *sides, th)
+    assert n0 == n1 and np.array_equal(m0, m1) and n0 > 50
+    A1.close()
+    B1.close()

@@ -234,3 +234,65 @@ def test_fuse(w, h, nf, th):
     n1, i1 = FR.fuse(c["q"], c["t"], c["xw"], c["normal"], c["min_dist"], c["max_dist"], c["mp_desc"], c["skip"], th)
     assert np.array_equal(i0, i1)
     assert n1 == (i0 >= 0).sum() > 100
+
+
+def _log_scale(T):
+    return float(np.log(np.float32(T["scale"][1])))
+
+
+@pytest.mark.parametrize("w,h,nf,th,ratio", [(640, 480, 1000, 8, 1.5), (1280, 720, 2000, 4, 1.0), (640, 480, 1000, 30, 1.0)])
+def test_search_by_projection_sim3(w, h, nf, th, ratio):
+    """SearchByProjection(pKF, Scw, vpPoints, vpMatched, th, ratioHamming), O3/src/ORBmatcher.cc:395-494 (and the overload with
+    vpPointsKFs, :496-603, whose matching is the same): which keypoint ends up holding which candidate."""
+    from oracle.bow import search_by_projection_sim3
+    from oracle.orb import OrbOracle
+    from oracle.track import FrameOracle
+
+    orc = OrbOracle(nf)
+    T = orc.tables()
+    c = bow_cases.sim3_projection_case(orc.extract, w=w, h=h, n_points=3000)
+    F0 = FrameOracle(c["kps"], c["desc"], c["bounds"], T["scale"])
+    FR = refm.RefFrame(c["kps"], c["desc"], c["bounds"], T["scale"], c["K"])
+    pts = (c["xw"], c["normal"], c["min_dist"], c["max_dist"], c["mp_desc"], c["skip"], c["kp_matched"])
+    n0, k0 = search_by_projection_sim3(F0, c["sq"], c["st"], c["K"], _log_scale(T), 8, *pts, th, ratio)
+    n1, k1 = refm.search_by_projection_sim3(FR, c["sq"], c["st"], *pts, th, ratio)
+    assert n0 == n1 and np.array_equal(k0, k1)
+    assert n0 > 100 and not (k0[c["kp_matched"] != 0] >= 0).any()
+
+
+@pytest.mark.parametrize("w,h,nf,th", [(640, 480, 1000, 3.0), (1280, 720, 2000, 4.0)])
+def test_fuse_sim3(w, h, nf, th):
+    """Fuse(pKF, Scw, vpPoints, th, vpReplacePoint), O3/src/ORBmatcher.cc:1236-1345."""
+    from oracle.bow import fuse_search_sim3
+    from oracle.orb import OrbOracle
+    from oracle.track import FrameOracle
+
+    orc = OrbOracle(nf)
+    T = orc.tables()
+    c = bow_cases.sim3_projection_case(orc.extract, w=w, h=h, n_points=3000, scale=0.7)
+    F0 = FrameOracle(c["kps"], c["desc"], c["bounds"], T["scale"])
+    FR = refm.RefFrame(c["kps"], c["desc"], c["bounds"], T["scale"], c["K"])
+    pts = (c["xw"], c["normal"], c["min_dist"], c["max_dist"], c["mp_desc"], c["skip"])
+    i0, d0 = fuse_search_sim3(F0, c["sq"], c["st"], c["K"], _log_scale(T), 8, *pts, th)
+    n1, i1 = refm.fuse_sim3(FR, c["sq"], c["st"], *pts, th)
+    assert np.array_equal(i0, i1) and n1 == (i0 >= 0).sum() > 100
+
+
+@pytest.mark.parametrize("w,h,nf,th", [(640, 480, 1000, 7.5), (1280, 720, 2000, 7.5)])
+def test_search_by_sim3(w, h, nf, th):
+    """SearchBySim3(pKF1, pKF2, vpMatches12, S12, th), O3/src/ORBmatcher.cc:1347-1551."""
+    from oracle.bow import search_by_sim3
+    from oracle.orb import OrbOracle
+    from oracle.track import FrameOracle
+
+    orc = OrbOracle(nf)
+    T = orc.tables()
+    c = bow_cases.search_by_sim3_case(orc.extract, w=w, h=h)
+    F = [FrameOracle(c["kps" + s], c["desc" + s], c["bounds"], T["scale"]) for s in "12"]
+    R = [refm.RefFrame(c["kps" + s], c["desc" + s], c["bounds"], T["scale"], c["K"]) for s in "12"]
+    sides = [(c["skip" + s], c["xw" + s], c["min" + s], c["max" + s], c["mpdesc" + s]) for s in "12"]
+    poses = (c["q1"], c["t1"], c["q2"], c["t2"], c["s12q"], c["s12t"])
+    n0, m0 = search_by_sim3(F[0], F[1], *poses, c["K"], _log_scale(T), 8, *sides, th)
+    n1, m1 = refm.search_by_sim3(R[0], R[1], *poses, *sides, th)
+    assert n0 == n1 and np.array_equal(m0, m1)
+    assert n0 > 50
