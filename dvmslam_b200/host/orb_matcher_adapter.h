@@ -10,6 +10,7 @@
 #include <list>
 #include <memory>
 #include <utility>
+#include <set>
 #include <vector>
 
 #include "dvm_host.h"
@@ -350,6 +351,168 @@ int Fuse(KeyFrameT* pKF, const std::vector<MapPointT*>& vpMapPoints, float th)
                 if (pMPinKF->Observations() > pMP->Observations()) pMP->Replace(pMPinKF);
                 else pMPinKF->Replace(pMP);
             }
+        } else {
+            pMP->AddObservation(pKF, bestIdx[i]);
+            pKF->AddMapPoint(pMP, bestIdx[i]);
+        }
+        nFused++;
+    }
+    return nFused;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Sim3-guided matchers of LoopClosing (O3/src/LoopClosing.cc:823-847 and FindMatchesByProjection).  A Sophus::Sim3f goes to
+// the library as quaternion().coeffs() (x, y, z, w; squared norm = scale) + translation(), as stored.
+// ---------------------------------------------------------------------------------------------------
+namespace detail {
+template <class Sim3T>
+inline void flatten_sim3(const Sim3T& S, float q[4], float t[3])
+{
+    const auto sq = S.quaternion();
+    const auto st = S.translation();
+    q[0] = sq.x(); q[1] = sq.y(); q[2] = sq.z(); q[3] = sq.w();
+    for (int k = 0; k < 3; k++) t[k] = st(k);
+}
+template <class SE3T>
+inline void flatten_se3(const SE3T& T, float q[4], float t[3])
+{
+    const auto uq = T.unit_quaternion();
+    const auto tr = T.translation();
+    q[0] = uq.x(); q[1] = uq.y(); q[2] = uq.z(); q[3] = uq.w();
+    for (int k = 0; k < 3; k++) t[k] = tr(k);
+}
+// world position, normal, mfMinDistance / mfMaxDistance (getters added by INTEGRATION.md) and descriptor of one map point
+struct FlatPoints {
+    std::vector<float> xw, nrm, mind, maxd;
+    std::vector<uint8_t> desc, skip;
+    explicit FlatPoints(size_t m) : xw(m * 3), nrm(m * 3), mind(m), maxd(m), desc(m * 32), skip(m ? m : 1) { }
+    template <class MapPointT>
+    void set(size_t i, MapPointT* pMP)
+    {
+        const auto p = pMP->GetWorldPos();
+        const auto n = pMP->GetNormal();
+        for (int k = 0; k < 3; k++) { xw[3 * i + k] = p(k); nrm[3 * i + k] = n(k); }
+        mind[i] = pMP->GetMinDistance();
+        maxd[i] = pMP->GetMaxDistance();
+        const auto d = pMP->GetDescriptor();
+        std::memcpy(&desc[i * 32], d.ptr(0), 32);
+    }
+};
+} // namespace detail
+
+// int ORBmatcher::SearchByProjection(KeyFrame* pKF, Sophus::Sim3f& Scw, const vector<MapPoint*>& vpPoints,
+//                                    vector<MapPoint*>& vpMatched, int th, float ratioHamming)          :395-494
+template <class KeyFrameT, class Sim3T, class MapPointT>
+int SearchByProjection(KeyFrameT* pKF, Sim3T& Scw, const std::vector<MapPointT*>& vpPoints, std::vector<MapPointT*>& vpMatched, int th,
+                       float ratioHamming = 1.0f)
+{
+    const size_t m = vpPoints.size();
+    std::set<MapPointT*> spAlreadyFound(vpMatched.begin(), vpMatched.end());                  // :406-407
+    spAlreadyFound.erase(static_cast<MapPointT*>(nullptr));
+    detail::FlatPoints P(m);
+    for (size_t i = 0; i < m; i++) {
+        MapPointT* pMP = vpPoints[i];
+        P.skip[i] = pMP->isBad() || spAlreadyFound.count(pMP);                                // :416-417
+        if (!P.skip[i]) P.set(i, pMP);
+    }
+    std::vector<uint8_t> taken(vpMatched.size() ? vpMatched.size() : 1);
+    for (size_t k = 0; k < vpMatched.size(); k++) taken[k] = vpMatched[k] != nullptr;
+    float sq[4], st[3];
+    detail::flatten_sim3(Scw, sq, st);
+    const float K[4] = { pKF->fx, pKF->fy, pKF->cx, pKF->cy };
+    std::vector<int32_t> kp_point(vpMatched.size() ? vpMatched.size() : 1, -1);
+    int nmatches = 0;
+    check(dvm_match_by_projection_sim3(device_frame(*pKF).frame.h, sq, st, K, static_cast<int>(m), P.xw.data(), P.nrm.data(),
+                                       P.mind.data(), P.maxd.data(), P.desc.data(), P.skip.data(), taken.data(), th, ratioHamming,
+                                       kp_point.data(), &nmatches),
+          "ORBmatcher::SearchByProjection(KeyFrame*, Sim3f&, ...)");
+    for (size_t k = 0; k < vpMatched.size(); k++)
+        if (kp_point[k] >= 0) vpMatched[k] = vpPoints[kp_point[k]];                           // :487-489
+    return nmatches;
+}
+
+// The overload that also reports the keyframe each matched point came from                             :496-603
+template <class KeyFrameT, class Sim3T, class MapPointT>
+int SearchByProjection(KeyFrameT* pKF, Sim3T& Scw, const std::vector<MapPointT*>& vpPoints, const std::vector<KeyFrameT*>& vpPointsKFs,
+                       std::vector<MapPointT*>& vpMatched, std::vector<KeyFrameT*>& vpMatchedKF, int th, float ratioHamming = 1.0f)
+{
+    const std::vector<MapPointT*> before = vpMatched;
+    const int n = SearchByProjection(pKF, Scw, vpPoints, vpMatched, th, ratioHamming);
+    for (size_t k = 0; k < vpMatched.size(); k++) {
+        if (vpMatched[k] == before[k]) continue;
+        for (size_t i = 0; i < vpPoints.size(); i++)
+            if (vpPoints[i] == vpMatched[k]) { vpMatchedKF[k] = vpPointsKFs[i]; break; }     // :596-598 (first occurrence wins)
+    }
+    return n;
+}
+
+// int ORBmatcher::SearchBySim3(KeyFrame* pKF1, KeyFrame* pKF2, vector<MapPoint*>& vpMatches12, const Sophus::Sim3f& S12,
+//                              const float th)                                                         :1347-1551
+template <class KeyFrameT, class Sim3T, class MapPointT>
+int SearchBySim3(KeyFrameT* pKF1, KeyFrameT* pKF2, std::vector<MapPointT*>& vpMatches12, const Sim3T& S12, float th)
+{
+    const std::vector<MapPointT*> vp1 = pKF1->GetMapPointMatches(), vp2 = pKF2->GetMapPointMatches();
+    const int N1 = static_cast<int>(vp1.size()), N2 = static_cast<int>(vp2.size());
+    std::vector<uint8_t> matched1(N1 ? N1 : 1, 0), matched2(N2 ? N2 : 1, 0);
+    for (int i = 0; i < N1; i++) {                                                           // :1370-1381
+        MapPointT* pMP = vpMatches12[i];
+        if (!pMP) continue;
+        matched1[i] = 1;
+        const int idx2 = std::get<0>(pMP->GetIndexInKeyFrame(pKF2));
+        if (idx2 >= 0 && idx2 < N2) matched2[idx2] = 1;
+    }
+    detail::FlatPoints A(N1), B(N2);
+    for (int i = 0; i < N1; i++) {
+        A.skip[i] = !vp1[i] || matched1[i] || vp1[i]->isBad();                                // :1389-1394
+        if (!A.skip[i]) A.set(i, vp1[i]);
+    }
+    for (int i = 0; i < N2; i++) {
+        B.skip[i] = !vp2[i] || matched2[i] || vp2[i]->isBad();                                // :1465-1470
+        if (!B.skip[i]) B.set(i, vp2[i]);
+    }
+    float q1[4], t1[3], q2[4], t2[3], sq[4], st[3];
+    detail::flatten_se3(pKF1->GetPose(), q1, t1);
+    detail::flatten_se3(pKF2->GetPose(), q2, t2);
+    detail::flatten_sim3(S12, sq, st);
+    const float K[4] = { pKF1->fx, pKF1->fy, pKF1->cx, pKF1->cy };
+    std::vector<int32_t> m12(N1 ? N1 : 1, -1);
+    int nFound = 0;
+    check(dvm_match_by_sim3(device_frame(*pKF1).frame.h, device_frame(*pKF2).frame.h, q1, t1, q2, t2, sq, st, K, A.skip.data(),
+                            A.xw.data(), A.mind.data(), A.maxd.data(), A.desc.data(), B.skip.data(), B.xw.data(), B.mind.data(),
+                            B.maxd.data(), B.desc.data(), th, m12.data(), &nFound),
+          "ORBmatcher::SearchBySim3");
+    for (int i = 0; i < N1; i++)
+        if (m12[i] >= 0) vpMatches12[i] = vp2[m12[i]];                                        // :1545
+    return nFound;
+}
+
+// int ORBmatcher::Fuse(KeyFrame* pKF, Sophus::Sim3f& Scw, const vector<MapPoint*>& vpPoints, float th,
+//                      vector<MapPoint*>& vpReplacePoint)                                              :1236-1345
+template <class KeyFrameT, class Sim3T, class MapPointT>
+int Fuse(KeyFrameT* pKF, Sim3T& Scw, const std::vector<MapPointT*>& vpPoints, float th, std::vector<MapPointT*>& vpReplacePoint)
+{
+    const size_t m = vpPoints.size();
+    const std::set<MapPointT*> spAlreadyFound = pKF->GetMapPoints();                          // :1249
+    detail::FlatPoints P(m);
+    for (size_t i = 0; i < m; i++) {
+        MapPointT* pMP = vpPoints[i];
+        P.skip[i] = pMP->isBad() || spAlreadyFound.count(pMP);                                // :1260-1261
+        if (!P.skip[i]) P.set(i, pMP);
+    }
+    float sq[4], st[3];
+    detail::flatten_sim3(Scw, sq, st);
+    const float K[4] = { pKF->fx, pKF->fy, pKF->cx, pKF->cy };
+    std::vector<int32_t> bestIdx(m ? m : 1, -1), bestDist(m ? m : 1, 256);
+    check(dvm_fuse_search_sim3(device_frame(*pKF).frame.h, sq, st, K, static_cast<int>(m), P.xw.data(), P.nrm.data(), P.mind.data(),
+                               P.maxd.data(), P.desc.data(), P.skip.data(), th, bestIdx.data(), bestDist.data()),
+          "ORBmatcher::Fuse(KeyFrame*, Sim3f&, ...)");
+    int nFused = 0;
+    for (size_t i = 0; i < m; i++) {                                                          // :1328-1341 in vpPoints order
+        if (bestIdx[i] < 0) continue;
+        MapPointT* pMP = vpPoints[i];
+        MapPointT* pMPinKF = pKF->GetMapPoint(bestIdx[i]);
+        if (pMPinKF) {
+            if (!pMPinKF->isBad()) vpReplacePoint[i] = pMPinKF;
         } else {
             pMP->AddObservation(pKF, bestIdx[i]);
             pKF->AddMapPoint(pMP, bestIdx[i]);

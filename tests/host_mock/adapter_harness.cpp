@@ -379,6 +379,100 @@ int hm_fuse(const dvm_keypoint* kps, const uint8_t* desc, int n, const float* sc
     });
 }
 
+
+// ---- Sim3-guided matchers through the adapters (results flattened to candidate / keypoint indices) ----
+static void fill_points(std::vector<std::unique_ptr<MapPoint>>& mps, std::vector<MapPoint*>& vp, int m, const uint8_t* bad, const float* xw,
+                        const float* normal, const float* min_dist, const float* max_dist, const uint8_t* mp_desc)
+{
+    mps.resize(m); vp.assign(m, nullptr);
+    for (int i = 0; i < m; i++) {
+        mps[i].reset(new MapPoint);
+        MapPoint& p = *mps[i];
+        p.mnId = (unsigned long)i;
+        for (int k = 0; k < 3; k++) { p.pos(k) = xw[3 * i + k]; if (normal) p.normal(k) = normal[3 * i + k]; }
+        p.minDist = min_dist[i]; p.maxDist = max_dist[i];
+        std::memcpy(p.desc.ptr(0), mp_desc + (size_t)i * 32, 32);
+        p.bad = bad && bad[i];
+        vp[i] = &p;
+    }
+}
+
+int hm_search_by_projection_sim3(const dvm_keypoint* kps, const uint8_t* desc, int n, const float* scale, const float* sigma2,
+                                 const float* invsig2, int nlevels, const float* sq, const float* st, int m, const uint8_t* bad,
+                                 const float* xw, const float* normal, const float* min_dist, const float* max_dist,
+                                 const uint8_t* mp_desc, const uint8_t* kp_matched, int th, float ratio, int* kp_point)
+{
+    KeyFrame K;
+    const float I[4] = { 0, 0, 0, 1 }, Z[3] = { 0, 0, 0 };
+    fill_keyframe(K, kps, desc, n, scale, sigma2, invsig2, nlevels, I, Z, 21);
+    std::vector<std::unique_ptr<MapPoint>> mps;
+    std::vector<MapPoint*> vp;
+    fill_points(mps, vp, m, bad, xw, normal, min_dist, max_dist, mp_desc);
+    MapPoint occupied;
+    std::vector<MapPoint*> matched(n, nullptr);
+    for (int k = 0; k < n; k++) if (kp_matched[k]) matched[k] = &occupied;
+    mock::Sim3f S;
+    for (int k = 0; k < 4; k++) S.q.q[k] = sq[k];
+    for (int k = 0; k < 3; k++) S.t(k) = st[k];
+    return guarded([&] {
+        const int r = dvm_host::SearchByProjection(&K, S, vp, matched, th, ratio);
+        for (int k = 0; k < n; k++) kp_point[k] = (matched[k] && matched[k] != &occupied) ? (int)matched[k]->mnId : -1;
+        return r;
+    });
+}
+
+int hm_fuse_sim3(const dvm_keypoint* kps, const uint8_t* desc, int n, const float* scale, const float* sigma2, const float* invsig2,
+                 int nlevels, const float* sq, const float* st, int m, const uint8_t* bad, const float* xw, const float* normal,
+                 const float* min_dist, const float* max_dist, const uint8_t* mp_desc, float th, int* best_idx)
+{
+    KeyFrame K;
+    const float I[4] = { 0, 0, 0, 1 }, Z[3] = { 0, 0, 0 };
+    fill_keyframe(K, kps, desc, n, scale, sigma2, invsig2, nlevels, I, Z, 22);
+    std::vector<std::unique_ptr<MapPoint>> mps;
+    std::vector<MapPoint*> vp;
+    fill_points(mps, vp, m, bad, xw, normal, min_dist, max_dist, mp_desc);
+    std::vector<MapPoint*> repl(m, nullptr);
+    mock::Sim3f S;
+    for (int k = 0; k < 4; k++) S.q.q[k] = sq[k];
+    for (int k = 0; k < 3; k++) S.t(k) = st[k];
+    return guarded([&] {
+        const int r = dvm_host::Fuse(&K, S, vp, th, repl);
+        for (int i = 0; i < m; i++) {
+            best_idx[i] = -1;
+            const auto it = vp[i]->observations.find(&K);
+            if (it != vp[i]->observations.end()) best_idx[i] = std::get<0>(it->second);
+            else if (repl[i]) best_idx[i] = std::get<0>(repl[i]->observations.find(&K)->second);
+        }
+        return r;
+    });
+}
+
+int hm_search_by_sim3(const dvm_keypoint* kps1, const uint8_t* desc1, int n1, const dvm_keypoint* kps2, const uint8_t* desc2, int n2,
+                      const float* scale, const float* sigma2, const float* invsig2, int nlevels, const float* q1, const float* t1,
+                      const float* q2, const float* t2, const float* sq, const float* st, const uint8_t* skip1, const float* xw1,
+                      const float* min1, const float* max1, const uint8_t* mpd1, const uint8_t* skip2, const float* xw2,
+                      const float* min2, const float* max2, const uint8_t* mpd2, float th, int* match12)
+{
+    KeyFrame A, B;
+    fill_keyframe(A, kps1, desc1, n1, scale, sigma2, invsig2, nlevels, q1, t1, 23);
+    fill_keyframe(B, kps2, desc2, n2, scale, sigma2, invsig2, nlevels, q2, t2, 24);
+    std::vector<std::unique_ptr<MapPoint>> m1, m2;
+    std::vector<MapPoint*> v1, v2;
+    fill_points(m1, v1, n1, nullptr, xw1, nullptr, min1, max1, mpd1);
+    fill_points(m2, v2, n2, nullptr, xw2, nullptr, min2, max2, mpd2);
+    for (int i = 0; i < n1; i++) A.mapPoints[i] = skip1[i] ? nullptr : v1[i];
+    for (int i = 0; i < n2; i++) B.mapPoints[i] = skip2[i] ? nullptr : v2[i];
+    std::vector<MapPoint*> vm(n1, nullptr);
+    mock::Sim3f S;
+    for (int k = 0; k < 4; k++) S.q.q[k] = sq[k];
+    for (int k = 0; k < 3; k++) S.t(k) = st[k];
+    return guarded([&] {
+        const int r = dvm_host::SearchBySim3(&A, &B, vm, S, th);
+        for (int i = 0; i < n1; i++) match12[i] = vm[i] ? (int)vm[i]->mnId : -1;
+        return r;
+    });
+}
+
 } // extern "C"
 
 // DBoW2::BowVector / FeatureVector with the reference's method semantics (DBoW2/BowVector.cpp:30-71,

@@ -46,6 +46,13 @@ struct SE3f {
     }
 };
 
+// Sophus::Sim3<float>: quaternion() (squared norm = scale), translation()
+struct Sim3f {
+    Quat q; Vec3 t;
+    Quat quaternion() const { return q; }
+    Vec3 translation() const { return t; }
+};
+
 // g2o::Sim3: rotation() (Eigen::Quaterniond), translation() (Vector3d), scale(), all with mutable access
 struct QuatD {
     double q[4] = { 0, 0, 0, 1 };

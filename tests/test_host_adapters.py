@@ -508,3 +508,52 @@ def test_optimize_sim3_adapter_matches_direct_call(libs, all_points):
     expect[keep] = r["inlier"]
     expect[~keep] = 1                                   # never entered the graph: the match is left alone
     assert np.array_equal(matched, expect)
+
+
+@pytest.mark.gpu
+def test_sim3_matcher_adapters_match_oracle(libs):
+    """LoopClosing's Sim3-guided matchers through the C++ adapters (reference signatures over mock types): the vpMatched /
+    vpMatches12 / fused-keypoint results equal the oracle's, which tests/test_ref_matchers.py pins to the reference source."""
+    from oracle.bow import fuse_search_sim3, search_by_projection_sim3, search_by_sim3
+    from oracle.orb import OrbOracle
+    from oracle.track import FrameOracle
+    from tests import bow_cases
+
+    H, _ = libs
+    orc = OrbOracle(1000)
+    T = orc.tables()
+    ls = float(np.log(np.float32(T["scale"][1])))
+    tabs = (_p(T["scale"]), _p(T["sigma2"]), _p(T["inv_sigma2"]), 8)
+    c = bow_cases.sim3_projection_case(orc.extract, n_points=2500)
+    H.hm_set_camera(_p(c["K"]), _p(np.array(c["bounds"], np.float32)))
+    n = len(c["kps"])
+    d = _c(c["desc"], np.uint8)
+    F0 = FrameOracle(c["kps"], c["desc"], c["bounds"], T["scale"])
+    pts = (c["xw"], c["normal"], c["min_dist"], c["max_dist"], c["mp_desc"])
+    m = len(c["xw"])
+    kp_point = np.zeros(n, np.int32)
+    r = H.hm_search_by_projection_sim3(_p(c["kps"]), _p(d), n, *tabs, _p(c["sq"]), _p(c["st"]), m, _p(c["skip"]), *(_p(x) for x in pts),
+                                       _p(c["kp_matched"]), 8, C.c_float(1.5), _p(kp_point))
+    assert r >= 0, H.hm_last_error()
+    n0, k0 = search_by_projection_sim3(F0, c["sq"], c["st"], c["K"], ls, 8, *pts, c["skip"], c["kp_matched"], 8, 1.5)
+    assert r == n0 and np.array_equal(kp_point, k0) and n0 > 100
+    best = np.zeros(m, np.int32)
+    r = H.hm_fuse_sim3(_p(c["kps"]), _p(d), n, *tabs, _p(c["sq"]), _p(c["st"]), m, _p(c["skip"]), *(_p(x) for x in pts), C.c_float(3.0),
+                       _p(best))
+    assert r >= 0, H.hm_last_error()
+    i0, _ = fuse_search_sim3(F0, c["sq"], c["st"], c["K"], ls, 8, *pts, c["skip"], 3.0)
+    assert np.array_equal(best, i0) and r == (i0 >= 0).sum() > 100
+
+    s = bow_cases.search_by_sim3_case(orc.extract)
+    n1, n2 = len(s["kps1"]), len(s["kps2"])
+    d1, d2 = _c(s["desc1"], np.uint8), _c(s["desc2"], np.uint8)
+    m12 = np.zeros(n1, np.int32)
+    side = lambda t: (_p(s["skip" + t]), _p(s["xw" + t]), _p(s["min" + t]), _p(s["max" + t]), _p(_c(s["mpdesc" + t], np.uint8)))  # noqa: E731
+    r = H.hm_search_by_sim3(_p(s["kps1"]), _p(d1), n1, _p(s["kps2"]), _p(d2), n2, *tabs, _p(s["q1"]), _p(s["t1"]), _p(s["q2"]), _p(s["t2"]),
+                            _p(s["s12q"]), _p(s["s12t"]), *side("1"), *side("2"), C.c_float(7.5), _p(m12))
+    assert r >= 0, H.hm_last_error()
+    A0 = FrameOracle(s["kps1"], s["desc1"], s["bounds"], T["scale"])
+    B0 = FrameOracle(s["kps2"], s["desc2"], s["bounds"], T["scale"])
+    sides = [(s["skip" + t], s["xw" + t], s["min" + t], s["max" + t], s["mpdesc" + t]) for t in "12"]
+    n0, m0 = search_by_sim3(A0, B0, s["q1"], s["t1"], s["q2"], s["t2"], s["s12q"], s["s12t"], s["K"], ls, 8, *sides, 7.5)
+    assert r == n0 and np.array_equal(m12, m0) and n0 > 50
