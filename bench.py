@@ -61,6 +61,29 @@ def ncu_traffic(stage):
         return None
 
 
+def ncu_traffic_of(kernel):
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(kernel)
+    except Exception:
+        return None
+
+
+def measured_peak_bf16():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
+    except Exception:
+        return 1590.0   # fallback of B200_PROFILING.md
+
+
+def measured_peak_fp64():
+    """FP64 tensor-pipe (DMMA m8n8k4) peak measured by tools/dmma_peak.cu on this pool's B200 (profiles/r2_a_fp64_peak.jsonl)."""
+    try:
+        rows = [json.loads(l) for l in open(os.path.join(ROOT, "profiles", "r2_a_fp64_peak.jsonl")) if l.strip()]
+        return max(r["dmma_tflops"] for r in rows), "measured (tools/dmma_peak.cu, profiles/r2_a_fp64_peak.jsonl)"
+    except Exception:
+        return 37.0, "nominal"
+
+
 def measured_peak_hbm():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -138,6 +161,11 @@ def make_frames(seed: int, n: int, stream=None) -> np.ndarray:
     return out
 
 
+def bench_config():
+    return {"workload": WORKLOAD, "frames_per_step": FRAMES_PER_STEP, "local_map_points": MAP_POINTS,
+            "l2": f"{RESIDENT_FRAMES} distinct resident frames ({RESIDENT_FRAMES * W * H >> 20} MB) cycled: inputs larger than L2"}
+
+
 def lba_scene(seed: int = 0):
     from dvmslam_b200 import synth
 
@@ -198,6 +226,76 @@ def cpu_lba_iters_per_sec(cores: int, reps: int = 1):
     return sum(n / dt for dt, n in res)
 
 
+def cpu_stage_times(frame: np.ndarray, reps: int = 3):
+    """Per-stage CPU time (ms per 1280x720 frame, single thread) of the OpenCV primitives the reference's front end calls --
+    the resize chain of ComputePyramid, cv::FAST (threshold 20, NMS) and the 7x7 GaussianBlur over the 8 pyramid levels -- for
+    the C models the CPU arm runs (oracle/cvmodels.c, bit-exact with cv2) AND for cv2's own SIMD code on the same images, so
+    that the distance of the port from the real library is on record.  cv2 may be absent on a box: then only the models."""
+    import ctypes as C
+
+    from oracle import lib as oracle_lib
+
+    L = oracle_lib()
+
+    class KP(C.Structure):
+        _fields_ = [("x", C.c_int), ("y", C.c_int), ("r", C.c_int)]
+
+    try:
+        import cv2
+
+        cv2.setNumThreads(1)
+    except Exception:
+        cv2 = None
+    P = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    sizes = [(W, H)]
+    inv = np.float32(1)
+    for _ in range(7):
+        inv = inv * (np.float32(1) / np.float32(1.2))
+        sizes.append((int(np.rint(np.float32(W) * inv)), int(np.rint(np.float32(H) * inv))))
+    out = {}
+    buf = (KP * 400000)()
+
+    def timed(fn):
+        best = 1e9
+        for _ in range(reps):
+            t = time.perf_counter()
+            fn()
+            best = min(best, time.perf_counter() - t)
+        return 1e3 * best
+
+    levels = [frame]
+
+    def chain_port():
+        lv = [frame]
+        for (w, h) in sizes[1:]:
+            o = np.empty((h, w), np.uint8)
+            L.cvm_resize_linear_u8(P(lv[-1]), lv[-1].shape[1], lv[-1].shape[0], lv[-1].shape[1], P(o), w, h, w)
+            lv.append(o)
+        levels[:] = lv
+
+    out["resize_chain"] = {"port_ms": timed(chain_port)}
+    out["fast_th20_nms"] = {"port_ms": timed(lambda: [L.cvm_fast_detect(P(l), l.shape[1], l.shape[0], l.shape[1], 20, buf, 400000) for l in levels])}
+
+    def blur_port():
+        for l in levels:
+            o = np.empty_like(l)
+            L.cvm_gaussian7_u8(P(l), l.shape[1], l.shape[0], l.shape[1], P(o), l.shape[1])
+
+    out["gaussian_blur_7x7"] = {"port_ms": timed(blur_port)}
+    if cv2 is not None:
+        def chain_cv():
+            lv = [frame]
+            for (w, h) in sizes[1:]:
+                lv.append(cv2.resize(lv[-1], (w, h), interpolation=cv2.INTER_LINEAR))
+
+        det = cv2.FastFeatureDetector_create(20, True, cv2.FAST_FEATURE_DETECTOR_TYPE_9_16)
+        out["resize_chain"]["cv2_ms"] = timed(chain_cv)
+        out["fast_th20_nms"]["cv2_ms"] = timed(lambda: [det.detect(l) for l in levels])
+        out["gaussian_blur_7x7"]["cv2_ms"] = timed(lambda: [cv2.GaussianBlur(l, (7, 7), 2, sigmaY=2, borderType=cv2.BORDER_REFLECT_101) for l in levels])
+        out["cv2_version"] = cv2.__version__
+    return out
+
+
 def cpu_oracle_fps(cores: int, frames_per_core: int, reps: int = 1):
     """frames/sec of the CPU oracle (restated reference front end) using `cores` processes."""
     import multiprocessing as mp
@@ -238,7 +336,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * per_step * agents / v, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_step": per_step * agents, "local_map_points": MAP_POINTS},
+            # the same config block as our arm (the CPU arm times a bounded SAMPLE of that workload per step: cpu_baseline.sample)
+            "config": bench_config(),
             # every step also rebuilds the agent's map and synthesises its frames (untimed, as in our arm)
             "wall_ms_per_step": 1e3 * wall / max(args.steps, 1),
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": agents, "kind": "port",
@@ -374,6 +473,17 @@ def run_ours(args):
     ext.set_profiling(False)
     stage_us = [1e3 * float(m) / max(nprof, 1) for m in stage_ms]
 
+    # ---- per-segment device time of the tracking chain (the critical path), CUDA events on the chain's stream ----
+    bootstrap()
+    trk.set_profiling(True)
+    for i in range(FRAMES_PER_STEP):
+        trk.track((base + ((1 + i) % RESIDENT_FRAMES) * frame_bytes, W, H, W), sync=False)
+    nchain, chain_ms = trk.get_profile()
+    _, _, c_prof = trk.result()
+    trk.set_profiling(False)
+    CHAIN_NAMES = ["prior_and_reset", "search_by_projection_last", "pose_optimization_1", "search_local_points", "pose_optimization_2"]
+    chain_us = [1e3 * float(m) / max(nchain, 1) for m in chain_ms]
+
     # ---- local BA (config C4) ----
     lba = None
     if rank == 0 or world > 1:
@@ -400,15 +510,18 @@ def run_ours(args):
                "achieved_GBps_kernel": 29e6 * its / (kern_ms * 1e-3) / 1e9}
         solver.close()
 
-    # ---- inter-agent loop-closure exchange step (config C3): all-to-all of new keyframe descriptor blocks +
-    # exhaustive Hamming matching against the local keyframe database; at N = 1 the matching alone ----
+    # ---- inter-agent loop-closure exchange step (config C3): dvm_exchange_round = grouped ncclSend / ncclRecv of the new
+    # keyframe descriptor blocks to the owner of each agent pair + exhaustive Hamming matching (tcgen05 int8 kernel)
+    # against the local keyframe database; at N = 1 the matching alone.  Every agent's keyframe k shares 30 % of its
+    # descriptors (with bit noise) with agent 0's keyframe k, so the candidate SET is known: it is checked, not counted ----
     from dvmslam_b200.exchange import LoopClosureExchange, pair_owner
+    from dvmslam_b200.matching import HammingKnn
 
-    base = synth.keyframe_blocks(C3_KEYFRAMES, NFEAT, seed=100)
-    own = base if rank == 0 else synth.keyframe_blocks(C3_KEYFRAMES, NFEAT, seed=100 + rank, shared_from=base)
+    base_kf = synth.keyframe_blocks(C3_KEYFRAMES, NFEAT, seed=100)
+    own = base_kf if rank == 0 else synth.keyframe_blocks(C3_KEYFRAMES, NFEAT, seed=100 + rank, shared_from=base_kf)
     own_dev = torch.from_numpy(own).cuda()
     x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    xms, ncand, nl0 = [], 0, launch_count()
+    xms, mms, ncand, cand_ok, nl0 = [], [], 0, True, launch_count()
     for rep in range(4):   # first repetition = warm-up (NCCL channel setup, buffer growth)
         ex = LoopClosureExchange(n_feat=NFEAT, max_keyframes=C3_KEYFRAMES, device=torch.device("cuda", local_rank),
                                  owner="balanced")
@@ -417,55 +530,111 @@ def run_ours(args):
         x0.record()
         if world > 1:
             cands = ex.exchange()
+            got = {(p, a, b) for p, a, b, _ in cands}
+            want = {(p, k, k) for p in range(world) if p != rank and pair_owner(rank, p, "balanced") == rank
+                    for k in range(C3_KEYFRAMES)}
+            cand_ok = cand_ok and got == want
         else:
-            cnt = ex.match_counts(ex.db[:ex.n_kf], ex.db[:ex.n_kf])
+            cnt = ex.match_counts(own_dev)
             cands = np.argwhere(cnt >= ex.min_matches)
+            cand_ok = cand_ok and {tuple(c) for c in cands} == {(k, k) for k in range(C3_KEYFRAMES)}
         x1.record()
         torch.cuda.synchronize()
         if rep:
             xms.append(x0.elapsed_time(x1))
+            mms.append(ex.last_match_ms)
             ncand = len(cands)
         ex.close()
     xt = torch.tensor([float(np.mean(xms))], device="cuda")
+    okt = torch.tensor([1.0 if cand_ok else 0.0], device="cuda")
     if dist is not None:
         dist.all_reduce(xt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
     kf_pairs = C3_KEYFRAMES * C3_KEYFRAMES * (world * (world - 1) // 2 if world > 1 else 1)
-    my_pairs = sum(1 for p in range(world) if p != rank and pair_owner(rank, p, "balanced") == rank) if world > 1 else 1
     exchange = {"value": kf_pairs / (float(xt.item()) * 1e-3), "unit": "keyframe pairs/s", "ms_per_round": float(xt.item()),
                 "workload": f"C3: {C3_KEYFRAMES} keyframes x {NFEAT} descriptors per agent, every agent pair matched once "
-                            f"(balanced ownership), {'all-to-all over NCCL + ' if world > 1 else ''}exhaustive Hamming",
+                            f"(balanced ownership), {'grouped ncclSend/ncclRecv + ' if world > 1 else ''}exhaustive Hamming "
+                            "(tcgen05 int8) through dvm_exchange_*",
                 "descriptor_pairs_per_s": kf_pairs * NFEAT * NFEAT / (float(xt.item()) * 1e-3),
-                # popcount-bound: 8 POPC per descriptor pair; the quarter-rate pipe issues 16 lanes/clk/SM
-                "popc_per_clk_per_sm_rank0": my_pairs * C3_KEYFRAMES ** 2 * NFEAT * NFEAT * 8 / (float(np.mean(xms)) * 1e-3)
-                                             / 148 / 1.965e9,
+                "match_kernel_ms_rank0": float(np.mean(mms)),
                 "bytes_exchanged_per_rank": C3_KEYFRAMES * NFEAT * 32 if world > 1 else 0,
-                "candidates_rank0": int(ncand), "gpu_launches": int(launch_count() - nl0)}
+                "candidates_rank0": int(ncand), "candidate_sets_correct_all_ranks": bool(okt.item() > 0.5),
+                "gpu_launches": int(launch_count() - nl0)}
+    # ---- the Hamming kernel alone (64 x 64 keyframe pairs of 2000 x 2000 descriptors), for its tensor-pipe roofline ----
+    hk = HammingKnn(stream=torch.cuda.current_stream().cuda_stream)
+    k1 = torch.empty((C3_KEYFRAMES, C3_KEYFRAMES, NFEAT), dtype=torch.int32, device="cuda")
+    k2 = torch.empty_like(k1)
+    cn = torch.empty((C3_KEYFRAMES, C3_KEYFRAMES), dtype=torch.int32, device="cuda")
+    ham_ms = {}
+    for mode in (2, 3, 1):   # tcgen05 kernel, its MMA-only probe, the popcount kernel it replaced
+        hk.set_mode(mode)
+        for it in range(2 if mode != 1 else 1):
+            hk.knn_device(own_dev.data_ptr(), C3_KEYFRAMES, NFEAT, own_dev.data_ptr(), C3_KEYFRAMES, NFEAT, k1.data_ptr(),
+                          k2.data_ptr(), cn.data_ptr(), 50, 0.75)
+        torch.cuda.synchronize()
+        reps_h = 5 if mode != 1 else 2
+        x0.record()
+        for it in range(reps_h):
+            hk.knn_device(own_dev.data_ptr(), C3_KEYFRAMES, NFEAT, own_dev.data_ptr(), C3_KEYFRAMES, NFEAT, k1.data_ptr(),
+                          k2.data_ptr(), cn.data_ptr(), 50, 0.75)
+        x1.record()
+        torch.cuda.synchronize()
+        ham_ms[mode] = x0.elapsed_time(x1) / reps_h
+    hk.close()
+    del k1, k2, cn
 
     if rank == 0:
         frames = args.steps * FRAMES_PER_STEP
         value = world * frames / (ms_total * 1e-3)
         e2e = world * frames / e2e_total
         peak, peak_src = measured_peak_hbm()
-        dom = int(np.argmax(stage_us))
-        dom_bytes = STAGE_BYTES[dom]
-        if dom_bytes is None:  # octree: candidates read + selection written; latency-bound by construction
-            dom_bytes = 4 * 40000 + 4 * NFEAT
-        achieved = dom_bytes / (stage_us[dom] * 1e-6) / 1e9
         frame_us = 1e3 * ms_total / frames
-        roofline = {"bound": "hbm", "kernel": STAGE_NAMES[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": ncu_traffic(dom), "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": dom_bytes, "avg_launch_us": stage_us[dom],
-                    "stage_us": dict(zip(STAGE_NAMES, stage_us)),
+        # The kernel with the largest share of the critical path: the frame rate is bounded by the tracking chain (pose k ->
+        # prior k + 1), extraction runs ahead on its own streams.  PoseOptimization (two launches per frame) is that kernel:
+        # one 8-CTA cluster running 4 x 10 dependent LM passes over ~1000 edges, i.e. latency-bound by construction.  Its
+        # algorithmic bytes: 24 B per edge (world point 12 + keypoint 8 + weight 4), read once.
+        pose_us = 0.5 * (chain_us[2] + chain_us[4])
+        pose_edges = max(int(c_prof[1]), 1)
+        pose_bytes = 24 * pose_edges
+        pose_gbs = pose_bytes / (pose_us * 1e-6) / 1e9
+        roofline = {"bound": "latency", "kernel": "pose_opt_kernel", "achieved": pose_gbs, "peak": peak, "unit": "GB/s",
+                    "frac": pose_gbs / peak, "traffic": ncu_traffic_of("pose_opt_kernel"), "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": pose_bytes, "avg_launch_us": pose_us, "launches_per_frame": 2,
+                    "share_of_chain": (chain_us[2] + chain_us[4]) / max(sum(chain_us), 1e-9),
+                    "note": "critical-path kernel; bound by its dependent LM passes (40 per launch), not by HBM",
+                    "chain_us": dict(zip(CHAIN_NAMES, chain_us)), "chain_us_total": sum(chain_us), "frame_us": frame_us,
+                    "extraction_stage_us": dict(zip(STAGE_NAMES, stage_us)),
                     # the HBM-facing stages of the frame with their own algorithmic bytes, measured in
-                    # the same profiled pass; `traffic` = DRAM bytes per launch from the committed ncu capture
+                    # the profiled extraction pass; `traffic` = DRAM bytes per launch from the committed ncu capture
                     "hbm_stages": {STAGE_NAMES[i]: {"algorithmic_bytes": STAGE_BYTES[i],
                                                     "achieved_GBps": STAGE_BYTES[i] / (stage_us[i] * 1e-6) / 1e9,
                                                     "frac": STAGE_BYTES[i] / (stage_us[i] * 1e-6) / 1e9 / peak,
                                                     "traffic": ncu_traffic(i)}
                                    for i in range(4) if STAGE_BYTES[i] is not None},
-                    "frame_us": frame_us, "tracking_us": frame_us - sum(stage_us),
                     "whole_frame": {"algorithmic_bytes": FRAME_BYTES_TOTAL,
-                                    "achieved_GBps": FRAME_BYTES_TOTAL * value / world / 1e9}}
+                                    "achieved_GBps": FRAME_BYTES_TOTAL * value / world / 1e9,
+                                    "frac": FRAME_BYTES_TOTAL * value / world / 1e9 / peak}}
+        # ---- per-leg rooflines ----
+        fp64_peak, fp64_src = measured_peak_fp64()
+        if lba is not None:
+            # ~75 MFLOP of FP64 per LM iteration at C4 (linearise + Schur ~65, reduced solve ~9)
+            lba_tf = 75e6 * lba["kernel_iters_per_s"] / 1e12
+            lba["roofline"] = {"bound": "latency", "kernel": "lba_kernel", "achieved": lba_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+                               "frac": lba_tf / fp64_peak, "peak_source": fp64_src,
+                               "algorithmic_flop_per_iteration": 75e6, "algorithmic_bytes_per_iteration": 29e6,
+                               "achieved_GBps": 29e6 * lba["kernel_iters_per_s"] / 1e9,
+                               "traffic": ncu_traffic_of("lba_kernel"),
+                               "note": "FP64 (DMMA m8n8k4 in the reduced solve); a 300 x 300 system is ~9 MFLOP: the kernel is "
+                                       "bound by its dependent phases, not by the FP64 pipe"}
+        int8_peak = 2.0 * measured_peak_bf16()
+        ham_ops = 2.0 * 256 * (C3_KEYFRAMES * NFEAT) ** 2
+        roofline_hamming = {"bound": "tensor", "kernel": "hamming_tc_kernel", "achieved": ham_ops / (ham_ms[2] * 1e-3) / 1e12,
+                            "peak": int8_peak, "unit": "TOP/s", "frac": ham_ops / (ham_ms[2] * 1e-3) / 1e12 / int8_peak,
+                            "peak_source": "2 x measured bf16 cuBLAS peak (MEASURED_PEAKS.json): the int8 tcgen05 rate is twice bf16's",
+                            "ms": ham_ms[2], "mma_only_probe_ms": ham_ms[3], "popcount_kernel_ms": ham_ms[1],
+                            "workload": f"{C3_KEYFRAMES} x {C3_KEYFRAMES} keyframe pairs of {NFEAT} x {NFEAT} descriptors, 256-bit",
+                            "descriptor_pairs_per_s": (C3_KEYFRAMES * NFEAT) ** 2 / (ham_ms[2] * 1e-3),
+                            "traffic": ncu_traffic_of("hamming_tc_kernel")}
         cpu = None
         if world == 1:
             tc = time.perf_counter()
@@ -474,19 +643,20 @@ def run_ours(args):
             cpu_lba = cpu_lba_iters_per_sec(1, cpu_bas)
             cpu = {"value": cpu_fps, "unit": UNIT, "cores": 1, "kind": "port",
                    "sample": f"{cpu_frames} tracked frames of the same stream + {cpu_bas} C4 local BAs, single thread, "
-                             f"{time.perf_counter() - tc:.1f} s including map and frame synthesis", "lba_iters_per_s": cpu_lba}
+                             f"{time.perf_counter() - tc:.1f} s including map and frame synthesis", "lba_iters_per_s": cpu_lba,
+                   # whole-level primitives on one frame of the stream: the C models of the port beside cv2's own code
+                   "opencv_primitives_ms_per_frame": cpu_stage_times(frames_np[1])}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "u8 (extract/match) + f64 (pose, BA)",
                 "data": "synthetic",
-                "config": {"workload": WORKLOAD, "frames_per_step": FRAMES_PER_STEP, "local_map_points": MAP_POINTS,
-                           "l2": f"{RESIDENT_FRAMES} distinct resident frames ({RESIDENT_FRAMES * frame_bytes >> 20} MB) "
-                                 "cycled: inputs larger than L2"},
+                "config": bench_config(),
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": FRAMES_PER_STEP * frame_bytes,
                         "d2h_bytes_per_step": FRAMES_PER_STEP * 48, "tracked_ok_frac": tracked_ok,
                         "median_inliers": float(np.median(inliers)) if inliers else 0.0},
                 "gpu_launches": int(launches), "clocks": clock_info, "roofline": roofline, "cpu_baseline": cpu,
-                "lba": lba, "exchange": exchange, "last_counts_device_run": list(c_dev)}
+                "lba": lba, "exchange": exchange, "roofline_hamming": roofline_hamming,
+                "last_counts_device_run": list(c_dev)}
         print(json.dumps(line), flush=True)
     trk.close()
     ext.close()

@@ -93,7 +93,9 @@ int dvm_frame_create(dvm_frame** out, int device, void* cuda_stream, int max_key
 {
     DVM_REQUIRE(out != nullptr, "null output handle");
     *out = nullptr;
-    DVM_REQUIRE(max_keypoints > 0 && nlevels >= 1 && nlevels <= kTrackMaxLevels, "max_keypoints/nlevels out of range");
+    // the matchers' candidate keys carry the keypoint index in 16 bits (pack_cand, track_kernels.cu)
+    DVM_REQUIRE(max_keypoints > 0 && max_keypoints <= 65532 && nlevels >= 1 && nlevels <= kTrackMaxLevels,
+                "max_keypoints (1..65532) / nlevels out of range");
     DVM_REQUIRE(scale_factors != nullptr && inv_level_sigma2 != nullptr, "null scale tables");
     int rc = select_device(device);
     if (rc != DVM_OK) return rc;

@@ -76,6 +76,11 @@ struct dvm_tracker {
     uint8_t* d_result = nullptr; // pose[7] float | counts[4] int
     uint8_t* h_result = nullptr; // pinned: [0,48) result read-back, [64,92) prior staging
     uint8_t* d_img[kExtractors] = { nullptr, nullptr }; size_t img_cap[kExtractors] = { 0, 0 };   // H2D staging
+    // per-segment device time of the chain (dvm_tracker_set_profiling): events between the operators of a tracked frame
+    bool profiling = false;
+    cudaEvent_t pev[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+    double prof_ms[5] = { 0, 0, 0, 0, 0 };
+    long long prof_frames = 0;
 };
 
 static void tracker_free(dvm_tracker* t)
@@ -93,6 +98,7 @@ static void tracker_free(dvm_tracker* t)
     if (t->h_result) cudaFreeHost(t->h_result);
     for (auto e : t->ev_extracted) if (e) cudaEventDestroy(e);
     for (auto e : t->ev_done) if (e) cudaEventDestroy(e);
+    for (auto e : t->pev) if (e) cudaEventDestroy(e);
     if (t->stream) cudaStreamDestroy(t->stream);
     delete t;
 }
@@ -236,6 +242,26 @@ int dvm_tracker_set_distortion(dvm_tracker* t, const float* dist5)
 }
 void* dvm_tracker_stream(const dvm_tracker* t) { return t ? (void*)t->stream : nullptr; }
 
+int dvm_tracker_set_profiling(dvm_tracker* t, int on)
+{
+    DVM_REQUIRE(t != nullptr, "null handle");
+    DVM_CUDA(cudaSetDevice(t->device));
+    for (auto& e : t->pev)
+        if (on && !e) DVM_CUDA(cudaEventCreate(&e));
+    t->profiling = on != 0;
+    for (double& v : t->prof_ms) v = 0;
+    t->prof_frames = 0;
+    return DVM_OK;
+}
+
+int dvm_tracker_get_profile(const dvm_tracker* t, double* segment_ms, long long* frames)
+{
+    DVM_REQUIRE(t != nullptr && segment_ms && frames, "null argument");
+    for (int i = 0; i < 5; i++) segment_ms[i] = t->prof_ms[i];
+    *frames = t->prof_frames;
+    return DVM_OK;
+}
+
 // SearchLocalPoints: isInFrustum + SearchByProjection(local map) + merge into cur_map, two launches
 static int enqueue_local_map_search(dvm_tracker* t, dvm_frame* cur, int* cur_map, float th, float nnratio)
 {
@@ -354,8 +380,11 @@ int dvm_tracker_track(dvm_tracker* t, const uint8_t* gray, int gray_is_device, i
         // staged through the pinned result block's upper half (a stack array may not outlive the async copy)
         DVM_CUDA(cudaMemcpyAsync(t->d_pose, pose, 28, cudaMemcpyHostToDevice, t->stream));
     }
+    auto mark = [&](int i) { if (t->profiling) cudaEventRecord(t->pev[i], t->stream); };
+    mark(0);
     DVM_LAUNCH_PDL(begin_frame_kernel, 1, 1024, 0, t->stream, t->d_pose_last, t->d_pose_prev, t->d_pose, prior_q ? 1 : 0, t->d_seen,
                t->map_n, t->d_cnt);
+    mark(1);
     // ---- TrackWithMotionModel: SearchByProjection(cur, last, th = 15), retry with 2*th below 20 matches ----
     MatchLastArgs la;
     memset(&la, 0, sizeof(la));
@@ -368,6 +397,7 @@ int dvm_tracker_track(dvm_tracker* t, const uint8_t* gray, int gray_is_device, i
     launch_match_last(cur->dev, la, cur->ms, t->d_cur_mp, t->d_cnt + 1, t->stream);
     la.th = 30.0f; la.guard = t->d_cnt + 1;
     launch_match_last(cur->dev, la, cur->ms, t->d_cur_mp, t->d_cnt + 1, t->stream);
+    mark(2);
     // ---- PoseOptimization + discard outliers (fused tail) ----
     PoseOptArgs pa;
     memset(&pa, 0, sizeof(pa));
@@ -378,9 +408,11 @@ int dvm_tracker_track(dvm_tracker* t, const uint8_t* gray, int gray_is_device, i
     pa.seen = t->d_seen; pa.map_index_rw = t->d_mp[ci];
     rc = launch_pose_opt(pa, t->stream);
     if (rc != DVM_OK) return rc;
+    mark(3);
     // ---- TrackLocalMap: SearchLocalPoints (isInFrustum, th = 1, nnratio 0.8) + PoseOptimization ----
     rc = enqueue_local_map_search(t, cur, t->d_mp[ci], 1.0f, 0.8f);
     if (rc != DVM_OK) return rc;
+    mark(4);
     pa.result = t->d_res2;
     pa.seen = nullptr; pa.map_index_rw = nullptr;
     pa.pose_last = t->d_pose_last; pa.pose_prev = t->d_pose_prev;
@@ -388,9 +420,19 @@ int dvm_tracker_track(dvm_tracker* t, const uint8_t* gray, int gray_is_device, i
     pa.nm_last = t->d_cnt + 1; pa.res_first = t->d_res1;
     rc = launch_pose_opt(pa, t->stream);
     if (rc != DVM_OK) return rc;
+    mark(5);
     DVM_CUDA(cudaGetLastError());
     DVM_CUDA(cudaEventRecord(t->ev_done[ci], t->stream));
     t->n_tracked = fi + 1;
+    if (t->profiling) {
+        DVM_CUDA(cudaEventSynchronize(t->pev[5]));
+        for (int i = 0; i < 5; i++) {
+            float ms = 0;
+            DVM_CUDA(cudaEventElapsedTime(&ms, t->pev[i], t->pev[i + 1]));
+            t->prof_ms[i] += ms;
+        }
+        t->prof_frames++;
+    }
     if (sync) return dvm_tracker_result(t, pose_out, counts);
     return DVM_OK;
 }

@@ -8,6 +8,7 @@
 // read through L2; the upper levels stay cache-resident, so a frame costs about L dependent L2 round trips.
 // The BowVector / FeatureVector maps are assembled from the per-feature results by the caller (ordered maps,
 // sequential double sums in feature order: dvmslam_b200/vocabulary.py, host/vocabulary_adapter.h).
+#include <mutex>
 #include "common.cuh"
 #include <vector>
 
@@ -68,6 +69,10 @@ struct dvm_vocabulary {
     int* d_child_start = nullptr; int* d_children = nullptr; uint8_t* d_desc = nullptr; double* d_weight = nullptr;
     int* d_word_id = nullptr;
     uint8_t* d_buf = nullptr; uint8_t* h_buf = nullptr; size_t cap = 0;   // per-call staging: features | word | nid | weight
+    // The reference shares ONE vocabulary between the tracking and the local-mapping thread (Frame::ComputeBoW from
+    // Tracking.cc:2463 / 3279 and KeyFrame::ComputeBoW from LocalMapping.cc:320 / 375 run concurrently): transform()
+    // calls are serialised here because they share the staging buffers and the stream.
+    std::mutex mtx;
 };
 
 static void vocab_free(dvm_vocabulary* v)
@@ -136,6 +141,7 @@ int dvm_vocabulary_transform(dvm_vocabulary* v, const uint8_t* desc, int n, int 
     DVM_REQUIRE(v != nullptr && n >= 0, "bad argument");
     if (n == 0) return DVM_OK;
     DVM_REQUIRE(desc && word_id && weight && node_id, "null arrays");
+    std::lock_guard<std::mutex> lock(v->mtx);
     DVM_CUDA(cudaSetDevice(v->device));
     const size_t sn = (size_t)n;
     const size_t o_w = sn * 32, o_word = o_w + sn * 8, o_nid = o_word + sn * 4, total = o_nid + sn * 4;

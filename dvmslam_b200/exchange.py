@@ -1,159 +1,220 @@
-"""Inter-agent loop-closure detection step (BASELINE.json config C3), one agent per rank/GPU.
+"""Inter-agent loop-closure detection step (BASELINE.json config C3), one agent per rank/GPU -- ctypes mirror of
+dvm_exchange_* (include/dvmslam_b200.h, csrc/exchange.cu).
 
-Reference behaviour this replaces (W/ = src/slam_system/): every agent pushes the BoW vectors of its
-new keyframes to its peers (`sendNewKeyFrameBows`, W/src/orb_slam3_wrapper.cpp:457-534; at least
-MIN_BOW_SHARE_SIZE new keyframes, each keyframe sent to a peer once), and the agent with the LOWER id of
-a pair looks for merge candidates among its own keyframes (`receiveNewKeyFrameBows` :536-600,
-`isLeadNodeInGroup` :1238-1243) before descriptors are compared by SearchByBoW
-(O3/src/ORBmatcher.cc:709-834) inside place recognition.
+Reference behaviour this replaces (W/ = src/slam_system/): every agent pushes the BoW vectors of its new keyframes to its
+peers (`sendNewKeyFrameBows`, W/src/orb_slam3_wrapper.cpp:457-534; at least MIN_BOW_SHARE_SIZE new keyframes, each keyframe
+sent to a peer once), and the agent with the LOWER id of a pair looks for merge candidates among its own keyframes
+(`receiveNewKeyFrameBows` :536-618, `isLeadNodeInGroup` :1238-1243).
 
-B200-native form: the keyframes' descriptor blocks u8[K, N, 32] live in HBM; the one real
-exchange step is an all-to-all (`torch.distributed.all_to_all_single`: NCCL over NVLink on GPUs, gloo in
-the CPU tests) in which each rank sends its not-yet-sent blocks to the ranks that own the pair; the owner
-compares every received keyframe with every keyframe of its database by exhaustive nearest /
-second-nearest Hamming search (dvm_hamming_knn_device) and reports the keyframe pairs whose number of
-accepted descriptor matches reaches `min_matches`.  Control decisions stay on the host, as in the
-reference.  There is no CPU matcher in the product: without CUDA tensors a `matcher` has to be injected
-(the CPU tests inject the oracle to exercise the exchange logic).
+All of the step lives in the library: the plan (who sends what to whom), grouped ncclSend / ncclRecv of the descriptor blocks
+straight out of the HBM-resident database over NVLink, the exhaustive Hamming search (tcgen05 int8 kernel) of every received
+keyframe against the local database, thresholds and ordering of the candidates.  This module only distributes the
+ncclUniqueId (over torch.distributed's store -- the reference's agents would use their DDS channel) and exposes the calls.
+
+Without GPUs the library has no matcher and no transport of its own: the CPU tests inject both through dvm_exchange_hooks
+(`matcher=` here, the all-to-all carried by torch.distributed's gloo backend) and so exercise the library's host logic.
 """
 from __future__ import annotations
 
+import ctypes as C
 from typing import Callable, List, Optional, Tuple
 
 import numpy as np
-import torch
-import torch.distributed as dist
+
+from ._lib import check, lib
 
 MIN_BOW_SHARE_SIZE = 5   # W/src/orb_slam3_wrapper.cpp:37: fewer new keyframes than this are not worth a message
 N_BOW_MATCHES = 20       # O3/src/LoopClosing.cc:647,751: descriptor matches a candidate pair needs
+_vp = C.c_void_p
+
+_ALLTOALL = C.CFUNCTYPE(C.c_int, _vp, _vp, C.POINTER(C.c_size_t), _vp, C.POINTER(C.c_size_t))
+_MATCH = C.CFUNCTYPE(C.c_int, _vp, _vp, C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.c_float, _vp)
+
+
+class _Hooks(C.Structure):
+    _fields_ = [("ctx", _vp), ("alltoall", _ALLTOALL), ("match_counts", _MATCH)]
 
 
 def pair_owner(i: int, j: int, policy: str = "lead") -> int:
-    """The rank that matches the keyframes of agents i and j.  "lead": the lower id, the reference's rule
-    (only the lead node attempts a merge).  "balanced": the lower id when the ids differ by an odd number,
-    else the higher one, so that every rank owns about (world - 1) / 2 pairs."""
+    """The rank that matches the keyframes of agents i and j.  "lead": the lower id, the reference's rule (only the lead
+    node attempts a merge).  "balanced": the lower id when the ids differ by an odd number, else the higher one, so that
+    every rank owns about (world - 1) / 2 pairs.  (Mirrors pair_owner in csrc/exchange.cu.)"""
     lo, hi = min(i, j), max(i, j)
     if policy == "lead" or (hi - lo) % 2 == 1:
         return lo
     return hi
 
 
+def _bind(L):
+    if getattr(L, "_exchange_bound", False):
+        return
+    L.dvm_exchange_unique_id.argtypes = [_vp]
+    L.dvm_exchange_create.argtypes = [C.POINTER(_vp), C.c_int, C.c_int, C.c_int, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp]
+    L.dvm_exchange_destroy.argtypes = [_vp]
+    L.dvm_exchange_destroy.restype = None
+    L.dvm_exchange_set_policy.argtypes = [_vp, C.c_int, C.c_float, C.c_int, C.c_int]
+    L.dvm_exchange_add_keyframes.argtypes = [_vp, _vp, C.c_int, C.c_int, _vp]
+    L.dvm_exchange_keyframes.argtypes = [_vp]
+    L.dvm_exchange_database.argtypes = [_vp]
+    L.dvm_exchange_database.restype = _vp
+    L.dvm_exchange_match_counts.argtypes = [_vp, _vp, C.c_int, _vp]
+    L.dvm_exchange_round.argtypes = [_vp, _vp, C.c_int, _vp]
+    L.dvm_exchange_last_bytes_sent.argtypes = [_vp]
+    L.dvm_exchange_last_bytes_sent.restype = C.c_size_t
+    L.dvm_exchange_last_match_ms.argtypes = [_vp]
+    L.dvm_exchange_last_match_ms.restype = C.c_float
+    L._exchange_bound = True
+
+
 class LoopClosureExchange:
-    def __init__(self, n_feat: int = 2000, max_keyframes: int = 1024, device: Optional[torch.device] = None,
-                 group=None, matcher: Optional[Callable] = None, th_low: int = 50, nnratio: float = 0.75,
+    def __init__(self, n_feat: int = 2000, max_keyframes: int = 1024, device=None, group=None,
+                 matcher: Optional[Callable] = None, th_low: int = 50, nnratio: float = 0.75,
                  min_matches: int = N_BOW_MATCHES, min_share: int = MIN_BOW_SHARE_SIZE, owner: str = "lead"):
+        import torch
+        import torch.distributed as dist
+
+        self.L = lib()
+        _bind(self.L)
         self.group = group
-        self.owner = owner
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
-        self.device = torch.device(device) if device is not None else torch.device("cpu")
         self.n_feat, self.cap = n_feat, max_keyframes
-        self.th_low, self.nnratio, self.min_matches, self.min_share = th_low, nnratio, min_matches, min_share
-        self.db = torch.empty((max_keyframes, n_feat, 32), dtype=torch.uint8, device=self.device)
-        self.n_kf = 0
-        self.sent_upto = [0] * self.world      # per peer: keyframes [0, sent_upto) were already sent
-        self._recv_upto = [0] * self.world     # per peer: keyframes received so far (= the next one's id there)
-        self._matcher = matcher
-        self._knn = None
-        self.last_bytes_sent = 0
-        if matcher is None:
-            if self.device.type != "cuda":
-                raise RuntimeError("LoopClosureExchange: no CUDA device and no matcher injected -- there is no CPU "
-                                   "fallback for the Hamming search")
-            from .matching import HammingKnn
+        self.device = torch.device(device) if device is not None else torch.device("cpu")
+        self.h = _vp()
+        self._keep = []
+        hooks_ptr = None
+        ident = None
+        if matcher is not None:
+            hooks_ptr = self._make_hooks(matcher)
+        elif self.device.type != "cuda":
+            raise RuntimeError("LoopClosureExchange: no CUDA device and no matcher injected -- there is no CPU fallback for "
+                               "the Hamming search")
+        elif self.world > 1:
+            buf = np.zeros(128, np.uint8)
+            if self.rank == 0:
+                check(self.L.dvm_exchange_unique_id(buf.ctypes.data))
+            obj = [buf.tobytes()]
+            dist.broadcast_object_list(obj, src=0, group=group)   # the ncclUniqueId travels over the host-side channel
+            ident = np.frombuffer(obj[0], np.uint8).copy()
+            self._keep.append(ident)
+        stream = torch.cuda.current_stream(self.device).cuda_stream if self.device.type == "cuda" else None
+        check(self.L.dvm_exchange_create(C.byref(self.h), self.device.index or 0, self.rank, self.world,
+                                         ident.ctypes.data if ident is not None else None, n_feat, max_keyframes,
+                                         1 if owner == "balanced" else 0, _vp(stream) if stream else None, hooks_ptr))
+        check(self.L.dvm_exchange_set_policy(self.h, th_low, nnratio, min_matches, min_share))
+        self.min_matches = min_matches
 
-            self._knn = HammingKnn(self.device.index or 0, torch.cuda.current_stream(self.device).cuda_stream)
+    # ------------------------------------------------------------------ test hooks (CPU, gloo)
+    def _make_hooks(self, matcher):
+        import torch
+        import torch.distributed as dist
+
+        world, group, n_feat = self.world, self.group, self.n_feat
+
+        def alltoall(ctx, send, send_bytes, recv, recv_bytes):
+            try:
+                sb = [send_bytes[p] for p in range(world)]
+                rb = [recv_bytes[p] for p in range(world)]
+                if sum(sb):
+                    s = torch.from_numpy(np.ctypeslib.as_array(C.cast(send, C.POINTER(C.c_uint8)), (sum(sb),)).copy())
+                else:
+                    s = torch.empty(0, dtype=torch.uint8)
+                r = torch.empty(sum(rb), dtype=torch.uint8)
+                dist.all_to_all_single(r, s, rb, sb, group=group)
+                if sum(rb):
+                    C.memmove(recv, r.numpy().ctypes.data, sum(rb))
+                return 0
+            except Exception:   # pragma: no cover
+                import traceback
+
+                traceback.print_exc()
+                return 1
+
+        def match_counts(ctx, a, ka, db, kb, nf, th_low, nnratio, counts):
+            try:
+                A = np.ctypeslib.as_array(C.cast(a, C.POINTER(C.c_uint8)), (ka, nf, 32))
+                B = np.ctypeslib.as_array(C.cast(db, C.POINTER(C.c_uint8)), (kb, nf, 32))
+                out = np.asarray(matcher(torch.from_numpy(A.copy()), torch.from_numpy(B.copy()), th_low, nnratio), np.int32).reshape(ka, kb)
+                C.memmove(counts, np.ascontiguousarray(out).ctypes.data, ka * kb * 4)
+                return 0
+            except Exception:   # pragma: no cover
+                import traceback
+
+                traceback.print_exc()
+                return 1
+
+        del n_feat
+        cb_a, cb_m = _ALLTOALL(alltoall), _MATCH(match_counts)
+        hooks = _Hooks(None, cb_a, cb_m)
+        self._keep += [cb_a, cb_m, hooks]
+        return C.byref(hooks)
 
     # ------------------------------------------------------------------ database
+    @property
+    def n_kf(self) -> int:
+        return int(self.L.dvm_exchange_keyframes(self.h))
+
+    @property
+    def db_ptr(self) -> int:
+        """Device pointer (host pointer with hooks) of the database u8[max_keyframes][n_feat][32]."""
+        return int(self.L.dvm_exchange_database(self.h) or 0)
+
+    @property
+    def last_bytes_sent(self) -> int:
+        return int(self.L.dvm_exchange_last_bytes_sent(self.h))
+
+    @property
+    def last_match_ms(self) -> float:
+        """Device time of the last match_counts call (CUDA events on the exchange's stream)."""
+        return float(self.L.dvm_exchange_last_match_ms(self.h))
+
     def add_keyframes(self, desc_blocks) -> range:
-        """Appends keyframes (u8[K, n_feat, 32], numpy or torch) to this agent's database; returns their ids."""
+        """Appends keyframes (u8[K, n_feat, 32], numpy or torch, host or device) to this agent's database; returns their ids."""
+        import torch
+
         t = torch.as_tensor(desc_blocks)
         if t.dtype != torch.uint8 or t.dim() != 3 or tuple(t.shape[1:]) != (self.n_feat, 32):
             raise ValueError(f"expected u8[K, {self.n_feat}, 32], got {t.dtype} {tuple(t.shape)}")
-        k = t.shape[0]
-        if self.n_kf + k > self.cap:
+        t = t.contiguous()
+        if self.n_kf + t.shape[0] > self.cap:
             raise ValueError("keyframe database is full")
-        self.db[self.n_kf:self.n_kf + k].copy_(t, non_blocking=True)
-        ids = range(self.n_kf, self.n_kf + k)
-        self.n_kf += k
-        return ids
+        first = C.c_int()
+        check(self.L.dvm_exchange_add_keyframes(self.h, _vp(t.data_ptr()), int(t.shape[0]), int(t.is_cuda), C.addressof(first)))
+        if t.is_cuda:
+            torch.cuda.current_stream(t.device).synchronize()
+        return range(first.value, first.value + int(t.shape[0]))
 
     # ------------------------------------------------------------------ the exchange step
-    def _plan(self) -> Tuple[List[int], List[int]]:
-        """send counts per peer (only to the owner of the pair, only unsent keyframes, only when enough are new)."""
-        send = [0] * self.world
-        for p in range(self.world):
-            if p == self.rank or pair_owner(self.rank, p, self.owner) != p:
-                continue
-            new = self.n_kf - self.sent_upto[p]
-            send[p] = new if new >= self.min_share else 0
-        counts = torch.tensor(send, dtype=torch.int64, device=self.device)
-        recv = torch.empty_like(counts)
-        if self.world > 1:
-            dist.all_to_all_single(recv, counts, group=self.group)
-        else:
-            recv.copy_(counts)
-        return send, [int(x) for x in recv.tolist()]
-
     def exchange(self) -> List[Tuple[int, int, int, int]]:
-        """One exchange + matching round.  Returns merge candidates (peer rank, peer keyframe id, own
-        keyframe id, accepted descriptor matches), best first, for the pairs this rank owns."""
-        send, recv = self._plan()
-        row = self.n_feat * 32
-        # the keyframes not yet sent differ per peer only by their start: pack [start_p, n_kf) per peer
-        parts = [self.db[self.sent_upto[p]:self.sent_upto[p] + send[p]] for p in range(self.world)]
-        sendbuf = torch.cat(parts).reshape(-1) if sum(send) else torch.empty(0, dtype=torch.uint8, device=self.device)
-        recvbuf = torch.empty(sum(recv) * row, dtype=torch.uint8, device=self.device)
-        if self.world > 1:
-            dist.all_to_all_single(recvbuf, sendbuf, [r * row for r in recv], [s * row for s in send], group=self.group)
-        self.last_bytes_sent = int(sendbuf.numel())
-        for p in range(self.world):
-            self.sent_upto[p] += send[p]
-        # ids of the received keyframes in the sender's numbering: the sender's sent_upto[self.rank] before this round
-        peer_first = self._peer_first_ids(recv)
-        out: List[Tuple[int, int, int, int]] = []
-        off = 0
-        for p in range(self.world):
-            k = recv[p]
-            if k == 0:
-                continue
-            blocks = recvbuf[off * row:(off + k) * row].view(k, self.n_feat, 32)
-            off += k
-            if self.n_kf == 0:
-                continue
-            counts = self.match_counts(blocks, self.db[:self.n_kf])
-            ia, ib = np.nonzero(counts >= self.min_matches)
-            out += [(p, peer_first[p] + int(a), int(b), int(counts[a, b])) for a, b in zip(ia, ib)]
-        out.sort(key=lambda c: (-c[3], c[0], c[1], c[2]))
+        """One exchange + matching round (collective).  Returns merge candidates (peer rank, peer keyframe id, own keyframe
+        id, accepted descriptor matches), best first, for the pairs this rank owns."""
+        cap = 4096
+        while True:
+            buf = np.zeros((cap, 4), np.int32)
+            n = C.c_int()
+            check(self.L.dvm_exchange_round(self.h, buf.ctypes.data, cap, C.addressof(n)))
+            if n.value <= cap:
+                return [tuple(int(v) for v in row) for row in buf[:n.value]]
+            raise RuntimeError(f"{n.value} candidates exceed the buffer of {cap}")   # a round cannot be repeated
+
+    def match_counts(self, a_blocks, b_blocks=None) -> np.ndarray:
+        """int32[ka, n_kf]: per keyframe pair, the descriptors of a whose nearest descriptor in the DATABASE keyframe is
+        accepted (distance <= th_low and < nnratio * second-nearest distance).  b_blocks is accepted for symmetry with the
+        earlier interface and must be the database."""
+        import torch
+
+        a = torch.as_tensor(a_blocks).contiguous()
+        out = np.zeros((a.shape[0], self.n_kf), np.int32)
+        check(self.L.dvm_exchange_match_counts(self.h, _vp(a.data_ptr()), int(a.shape[0]), out.ctypes.data))
         return out
 
-    def _peer_first_ids(self, recv: List[int]) -> List[int]:
-        first = list(self._recv_upto)
-        for p in range(self.world):
-            self._recv_upto[p] += recv[p]
-        return first
-
-    # ------------------------------------------------------------------ matching
-    def match_counts(self, a_blocks: torch.Tensor, b_blocks: torch.Tensor) -> np.ndarray:
-        """int32[ka, kb]: per keyframe pair, the descriptors of a whose nearest descriptor in b is accepted
-        (distance <= th_low and < nnratio * second-nearest distance)."""
-        ka, kb = a_blocks.shape[0], b_blocks.shape[0]
-        if self._matcher is not None:
-            return np.asarray(self._matcher(a_blocks, b_blocks, self.th_low, self.nnratio), np.int32).reshape(ka, kb)
-        a, b = a_blocks.contiguous(), b_blocks.contiguous()
-        # keys are scratch here (only the counts leave the GPU); chunk the batch so they stay small
-        chunk = max(1, min(ka, (64 << 20) // max(1, kb * self.n_feat * 8)))
-        counts = torch.empty((ka, kb), dtype=torch.int32, device=a.device)
-        k1 = torch.empty((chunk, kb, self.n_feat), dtype=torch.int32, device=a.device)
-        k2 = torch.empty_like(k1)
-        for s in range(0, ka, chunk):
-            n = min(chunk, ka - s)
-            self._knn.knn_device(a[s:].data_ptr(), n, self.n_feat, b.data_ptr(), kb, self.n_feat, k1.data_ptr(),
-                                 k2.data_ptr(), counts[s:].data_ptr(), self.th_low, self.nnratio)
-        self._knn.sync()
-        return counts.cpu().numpy()
-
     def close(self):
-        if self._knn is not None:
-            self._knn.close()
-            self._knn = None
+        if getattr(self, "h", None) and self.h.value:
+            self.L.dvm_exchange_destroy(self.h)
+            self.h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -254,6 +254,18 @@ class Tracker:
             return self._pose[:4].copy(), self._pose[4:].copy(), tuple(int(c) for c in self._counts)
         return None
 
+    def set_profiling(self, on: bool):
+        self.L.dvm_tracker_set_profiling.argtypes = [_vp, C.c_int]
+        check(self.L.dvm_tracker_set_profiling(self.h, int(on)))
+
+    def get_profile(self):
+        """(frames, [ms per segment]): prior/reset, SearchByProjection(last), PoseOptimization, SearchLocalPoints, PoseOptimization."""
+        seg = np.zeros(5, np.float64)
+        n = C.c_longlong()
+        self.L.dvm_tracker_get_profile.argtypes = [_vp, _vp, _vp]
+        check(self.L.dvm_tracker_get_profile(self.h, seg.ctypes.data, C.addressof(n)))
+        return int(n.value), seg
+
     def result(self):
         check(self.L.dvm_tracker_result(self.h, self._pose.ctypes.data, self._counts.ctypes.data))
         return self._pose[:4].copy(), self._pose[4:].copy(), tuple(int(c) for c in self._counts)

@@ -368,6 +368,50 @@ DVM_API int dvm_hamming_sync(dvm_hamming* h);
 DVM_API int dvm_hamming_set_mode(dvm_hamming* h, int mode);
 
 /* ------------------------------------------------------------------------------------------------
+ * Inter-agent loop-closure exchange (BASELINE.json config C3), one agent per rank / GPU.  Replaces the keyframe push of
+ * OrbSlam3Wrapper::sendNewKeyFrameBows / receiveNewKeyFrameBows (src/slam_system/src/orb_slam3_wrapper.cpp:457-618):
+ * every agent sends the descriptor blocks of its not-yet-sent keyframes (at least MIN_BOW_SHARE_SIZE of them, :37) to
+ * the rank that owns the agent pair -- the lower id, the reference's lead-node rule (isLeadNodeInGroup, :1238-1243), or
+ * a balanced assignment -- over grouped ncclSend / ncclRecv (NVLink / NVSwitch), and the owner matches every received
+ * keyframe against its whole database with the exhaustive Hamming search (csrc/exchange.cu, csrc/hamming_tc.cu).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct dvm_exchange dvm_exchange;
+/* Test hooks (host logic without GPUs): with hooks the database lives in host memory, `alltoall` carries both exchanges
+ * (send: one contiguous buffer, send_bytes[world] / recv_bytes[world] per peer, recv: contiguous in rank order) and
+ * `match_counts` fills counts[ka][kb] = accepted descriptor matches of block a[i] against db[j].  Return 0 on success.
+ * The library has no CPU matcher of its own. */
+typedef struct dvm_exchange_hooks {
+    void* ctx;
+    int (*alltoall)(void* ctx, const void* send, const size_t* send_bytes, void* recv, const size_t* recv_bytes);
+    int (*match_counts)(void* ctx, const uint8_t* a, int ka, const uint8_t* db, int kb, int n_feat, int th_low, float nnratio,
+                        int32_t* counts);
+} dvm_exchange_hooks;
+/* ncclGetUniqueId into id128[128]: rank 0 calls it and hands the bytes to its peers over its own channel. */
+DVM_API int dvm_exchange_unique_id(uint8_t* id128);
+/* One handle per agent.  world > 1 creates the NCCL communicator from id128 (collective: every rank calls it).
+ * balanced_ownership = 0: the lower agent id of a pair matches (the reference's rule); 1: pairs are spread over the ranks.
+ * cuda_stream: stream to work on, or NULL for a private one.  hooks: NULL in production. */
+DVM_API int dvm_exchange_create(dvm_exchange** out, int device, int rank, int world, const uint8_t* id128, int n_feat,
+                                int max_keyframes, int balanced_ownership, void* cuda_stream, const dvm_exchange_hooks* hooks);
+DVM_API void dvm_exchange_destroy(dvm_exchange* x);
+/* th_low / nnratio: a descriptor match is accepted when best <= th_low and best < nnratio * second best (defaults 50,
+ * 0.75); min_matches: accepted matches a keyframe pair needs to be reported (default 20 = nBoWMatches,
+ * O3/src/LoopClosing.cc:647,751); min_share: fewer new keyframes than this are held back (default 5). */
+DVM_API int dvm_exchange_set_policy(dvm_exchange* x, int th_low, float nnratio, int min_matches, int min_share);
+/* Appends n_kf keyframes (u8[n_kf][n_feat][32], host or device memory) to this agent's database; *first_id = id of the first. */
+DVM_API int dvm_exchange_add_keyframes(dvm_exchange* x, const uint8_t* desc, int n_kf, int desc_is_device, int* first_id);
+DVM_API int dvm_exchange_keyframes(const dvm_exchange* x);
+DVM_API const uint8_t* dvm_exchange_database(const dvm_exchange* x);
+/* counts[ka][keyframes()] (host) = accepted descriptor matches of the ka blocks at `a` (device memory; host with hooks)
+ * against every keyframe of the database. */
+DVM_API int dvm_exchange_match_counts(dvm_exchange* x, const uint8_t* a, int ka, int32_t* counts);
+/* One exchange + matching round (collective over the ranks).  candidates[cap][4] receives (peer rank, peer keyframe id,
+ * own keyframe id, accepted matches), best first, for the pairs this rank owns; *n_candidates the total found. */
+DVM_API int dvm_exchange_round(dvm_exchange* x, int32_t* candidates, int cap, int* n_candidates);
+DVM_API size_t dvm_exchange_last_bytes_sent(const dvm_exchange* x);
+DVM_API float dvm_exchange_last_match_ms(const dvm_exchange* x);
+
+/* ------------------------------------------------------------------------------------------------
  * Optimizer::PoseOptimization   (O3/src/Optimizer.cc:744-1028, mono observations)
  * ---------------------------------------------------------------------------------------------- */
 /* pose_q (x,y,z,w of Tcw.unit_quaternion()) and pose_t (Tcw.translation()) are in/out (float, like
@@ -426,6 +470,12 @@ DVM_API int dvm_tracker_prefetch(dvm_tracker* t, const uint8_t* gray, int gray_i
                                  int stride);
 /* The CUDA stream (cudaStream_t) of the tracking chain, for CUDA-event timing by the caller. */
 DVM_API void* dvm_tracker_stream(const dvm_tracker* t);
+/* Device time of the tracked-frame chain by segment (a measurement aid: with profiling on, every dvm_tracker_track
+ * call records CUDA events between the operators and waits for the frame).  segment_ms[5] accumulates, in the chain's
+ * order: constant-velocity prior + per-frame reset | SearchByProjection(cur, last) incl. the 2*th retry |
+ * PoseOptimization | SearchLocalPoints (isInFrustum + SearchByProjection(F, map points)) | PoseOptimization. */
+DVM_API int dvm_tracker_set_profiling(dvm_tracker* t, int on);
+DVM_API int dvm_tracker_get_profile(const dvm_tracker* t, double* segment_ms, long long* frames);
 /* Current frame's association after the last track call, for parity tests: cur_map[n] = map point
  * index per keypoint (-1 none), outlier[n] = mvbOutlier. */
 DVM_API int dvm_tracker_debug_matches(dvm_tracker* t, int32_t* cur_map, uint8_t* outlier, int cap, int* n_out);

@@ -34,7 +34,7 @@ def test_match_counts_single_gpu():
     B = synth.keyframe_blocks(7, N, seed=2, shared_from=np.concatenate([A, A[:2]]))
     ex = LoopClosureExchange(n_feat=N, max_keyframes=16, device=torch.device("cuda", 0))
     ex.add_keyframes(B)
-    got = ex.match_counts(torch.from_numpy(A).cuda(), ex.db[:ex.n_kf])
+    got = ex.match_counts(torch.from_numpy(A).cuda())
     want = _oracle_counts(A, B, 50, 0.75)
     assert np.array_equal(got, want)
     assert (np.diag(got[:5, :5]) > 400).all() and got[0, 5] > 400 and got[0, 1] < 20
