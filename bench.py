@@ -522,9 +522,9 @@ def run_ours(args):
     own_dev = torch.from_numpy(own).cuda()
     x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     xms, mms, ncand, cand_ok, nl0 = [], [], 0, True, launch_count()
-    for rep in range(4):   # first repetition = warm-up (NCCL channel setup, buffer growth)
-        ex = LoopClosureExchange(n_feat=NFEAT, max_keyframes=C3_KEYFRAMES, device=torch.device("cuda", local_rank),
-                                 owner="balanced")
+    ex = LoopClosureExchange(n_feat=NFEAT, max_keyframes=C3_KEYFRAMES, device=torch.device("cuda", local_rank), owner="balanced")
+    for rep in range(4):   # first repetition = warm-up (NCCL connection setup, buffer growth)
+        ex.reset()         # a new session on the same communicator: empty database, nothing sent yet
         ex.add_keyframes(own_dev)
         barrier()
         x0.record()
@@ -544,7 +544,7 @@ def run_ours(args):
             xms.append(x0.elapsed_time(x1))
             mms.append(ex.last_match_ms)
             ncand = len(cands)
-        ex.close()
+    ex.close()
     xt = torch.tensor([float(np.mean(xms))], device="cuda")
     okt = torch.tensor([1.0 if cand_ok else 0.0], device="cuda")
     if dist is not None:
@@ -561,7 +561,7 @@ def run_ours(args):
                 "candidates_rank0": int(ncand), "candidate_sets_correct_all_ranks": bool(okt.item() > 0.5),
                 "gpu_launches": int(launch_count() - nl0)}
     # ---- the Hamming kernel alone (64 x 64 keyframe pairs of 2000 x 2000 descriptors), for its tensor-pipe roofline ----
-    hk = HammingKnn(stream=torch.cuda.current_stream().cuda_stream)
+    hk = HammingKnn(local_rank, stream=torch.cuda.current_stream().cuda_stream)
     k1 = torch.empty((C3_KEYFRAMES, C3_KEYFRAMES, NFEAT), dtype=torch.int32, device="cuda")
     k2 = torch.empty_like(k1)
     cn = torch.empty((C3_KEYFRAMES, C3_KEYFRAMES), dtype=torch.int32, device="cuda")

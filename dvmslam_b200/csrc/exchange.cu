@@ -220,6 +220,17 @@ int dvm_exchange_add_keyframes(dvm_exchange* x, const uint8_t* desc, int n_kf, i
     return DVM_OK;
 }
 
+int dvm_exchange_reset(dvm_exchange* x)
+{
+    DVM_REQUIRE(x != nullptr, "null handle");
+    if (x->device >= 0) { DVM_CUDA(cudaSetDevice(x->device)); DVM_CUDA(cudaStreamSynchronize(x->stream)); }
+    x->n_kf = 0;
+    std::fill(x->sent_upto.begin(), x->sent_upto.end(), 0);
+    std::fill(x->recv_upto.begin(), x->recv_upto.end(), 0);
+    x->last_bytes_sent = 0;
+    return DVM_OK;
+}
+
 int dvm_exchange_keyframes(const dvm_exchange* x) { return x ? x->n_kf : DVM_ERR_INVALID; }
 const uint8_t* dvm_exchange_database(const dvm_exchange* x) { return x ? x->db : nullptr; }
 size_t dvm_exchange_last_bytes_sent(const dvm_exchange* x) { return x ? x->last_bytes_sent : 0; }

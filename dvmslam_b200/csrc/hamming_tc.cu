@@ -396,10 +396,12 @@ int launch_hamming_knn_tc(const KnnArgs& k, KnnScratch& sc, cudaStream_t stream,
     }
     uint8_t* ea = sc.expanded;
     uint8_t* eb = sc.expanded + ((abytes + 1023) & ~(size_t)1023);
-    static bool attr_set = false;
-    if (!attr_set) {
+    int dev = 0, sms = kNumSMs;
+    DVM_CUDA(cudaGetDevice(&dev));
+    static std::atomic<unsigned long long> attr_set{ 0 };   // function attributes are per device
+    if (dev < 64 && !(attr_set.load() >> dev & 1ull)) {
         DVM_CUDA(cudaFuncSetAttribute(hamming_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
-        attr_set = true;
+        attr_set.fetch_or(1ull << dev);
     }
     CUtensorMap map_a, map_b;
     if (!encode_desc_map(&map_a, ea, k.na, k.ba) || !encode_desc_map(&map_b, eb, k.nb, k.bb)) {
@@ -419,8 +421,6 @@ int launch_hamming_knn_tc(const KnnArgs& k, KnnScratch& sc, cudaStream_t stream,
     g.ntiles = div_up(k.nb, kTcCols);
     g.items = k.ba * k.bb * g.mblocks;
     g.epilogue = epilogue;
-    int dev = 0, sms = kNumSMs;
-    cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = std::min(g.items, sms);
     DVM_LAUNCH(hamming_tc_kernel, grid, kTcThreads, kTcSmemBytes, stream, map_a, map_b, g);

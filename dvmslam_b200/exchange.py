@@ -55,6 +55,7 @@ def _bind(L):
     L.dvm_exchange_set_policy.argtypes = [_vp, C.c_int, C.c_float, C.c_int, C.c_int]
     L.dvm_exchange_add_keyframes.argtypes = [_vp, _vp, C.c_int, C.c_int, _vp]
     L.dvm_exchange_keyframes.argtypes = [_vp]
+    L.dvm_exchange_reset.argtypes = [_vp]
     L.dvm_exchange_database.argtypes = [_vp]
     L.dvm_exchange_database.restype = _vp
     L.dvm_exchange_match_counts.argtypes = [_vp, _vp, C.c_int, _vp]
@@ -207,6 +208,11 @@ class LoopClosureExchange:
         out = np.zeros((a.shape[0], self.n_kf), np.int32)
         check(self.L.dvm_exchange_match_counts(self.h, _vp(a.data_ptr()), int(a.shape[0]), out.ctypes.data))
         return out
+
+    def reset(self):
+        """Empties the database and forgets what was sent / received (collective in effect: every rank does the same); the
+        communicator stays."""
+        check(self.L.dvm_exchange_reset(self.h))
 
     def close(self):
         if getattr(self, "h", None) and self.h.value:

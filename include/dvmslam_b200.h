@@ -400,6 +400,8 @@ DVM_API void dvm_exchange_destroy(dvm_exchange* x);
 DVM_API int dvm_exchange_set_policy(dvm_exchange* x, int th_low, float nnratio, int min_matches, int min_share);
 /* Appends n_kf keyframes (u8[n_kf][n_feat][32], host or device memory) to this agent's database; *first_id = id of the first. */
 DVM_API int dvm_exchange_add_keyframes(dvm_exchange* x, const uint8_t* desc, int n_kf, int desc_is_device, int* first_id);
+/* Empties the database and the sent / received bookkeeping; the communicator stays (every rank must do the same). */
+DVM_API int dvm_exchange_reset(dvm_exchange* x);
 DVM_API int dvm_exchange_keyframes(const dvm_exchange* x);
 DVM_API const uint8_t* dvm_exchange_database(const dvm_exchange* x);
 /* counts[ka][keyframes()] (host) = accepted descriptor matches of the ka blocks at `a` (device memory; host with hooks)
