@@ -1,0 +1,239 @@
+// chol_device.cuh -- device pieces shared by the dense SPD solvers of the optimisation kernels (lba.cu: the reduced camera
+// system on one 8-CTA cluster; grid_cholesky_solve below: the same factorisation spread over a whole cooperative grid for
+// systems too large for one SM's shared memory -- global bundle adjustment over hundreds of keyframes, essential graph).
+#pragma once
+#include "common.cuh"
+#include <cooperative_groups.h>
+
+namespace dvm {
+
+constexpr int kCholThreads = 512;            // every kernel using these helpers runs 512-thread CTAs (16 warps)
+constexpr int kCholWarps = kCholThreads / 32;
+constexpr int kNB = 32;                      // Cholesky block size
+constexpr int kPanelLd = 36;   // shared-memory row stride of a panel (doubles): conflict-free 8-byte fragment loads
+constexpr int kDiagLd = kNB + 1;
+
+// D = C - A * B for one m8n8k4 FP64 tensor-core tile step (a: A[r=lane/4][k=lane%4], b: B[k=lane%4][c=lane/4])
+__device__ inline void dmma_m8n8k4(double& c0, double& c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// Reciprocal square root on the critical path of every column: hardware seed (MUFU.RSQ64H, ~20 bits) and two
+// Newton steps -- within 1-2 ulp for the positive, well-scaled pivots of a damped normal matrix.
+__device__ inline double fast_rsqrt(double d)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    const double h = 0.5 * d;
+    double e = fma(-h * y, y, 0.5);
+    y = fma(y, e, y);
+    e = fma(-h * y, y, 0.5);
+    return fma(y, e, y);
+}
+
+// Factorisation + inversion of a 32x32 diagonal block by ALL threads of the CTA (kCholThreads = 512 = 16 warps): a lone
+// warp cannot hide its own latencies (a one-warp version with the block in registers ran at ~7 cycles per instruction,
+// 21 us per block, and was 2/3 of the whole solve; DESIGN.md, negative results).  Every thread OWNS two elements of the block and of its inverse in registers for the
+// whole sweep: lane = row, warp w = columns w and w + 16.  Step j:
+//     the warp that owns column j takes the pivot by shuffle, scales its column by rsqrt(pivot) and publishes it
+//     (col[j & 1][:], rinv[j & 1]) | ONE CTA barrier |
+//     a[r][c] -= L[r][j] L[c][j]  (c > j);   X[j][c] = x[j][c] * rinv (by shuffle inside the column's warp),
+//     x[r][c] -= L[r][j] X[j][c]  (r > j)
+// i.e. the right-looking Cholesky step and the column sweep of the triangular inversion share one barrier per
+// step (the published column is double-buffered), and the owner of column j + 1 publishes it before doing its share of
+// step j's inverse updates.  Measured: 21.6 -> 10 us per block (~550 cycles per step; what is left is the FP64 pipe --
+// the triangular masks leave most lanes of the 6 double-precision instructions a warp issues per step idle).
+// `scratch` holds 4 * kNB + 4 doubles.  Same outputs as the warp version.
+// (No __restrict__ here: the published column is exchanged BETWEEN threads, and with restrict-qualified pointers
+// nvcc keeps values read from it across the barriers -- measured: wrong factors.)
+__device__ bool cta_factor_invert_32(double* A, int ld, double* Ld, double* Li, bool write_back, double* Linv_out,
+                                     double* scratch)
+{
+    const int r = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int c0 = w, c1 = w + 16;
+    double* colbuf = scratch;                 // [2][kNB]  L[:, j]
+    double* s_rinv = scratch + 2 * kNB;       // [2]
+    double* s_bad = s_rinv + 2;
+    double a0 = A[(size_t)r * ld + c0], a1 = A[(size_t)r * ld + c1];
+    double x0 = (r == c0) ? 1.0 : 0.0, x1 = (r == c1) ? 1.0 : 0.0;
+    if (threadIdx.x == 0) *s_bad = 0.0;
+    // the warp that owns column j scales it by rsqrt(pivot) and publishes it in buffer j & 1
+    auto publish = [&](int j) {
+        const bool hi = j >= 16;
+        const double djj = __shfl_sync(0xffffffffu, hi ? a1 : a0, j);
+        const bool bad = !(djj > 0) || !isfinite(djj);
+        const double rinv = bad ? 1.0 : fast_rsqrt(djj);
+        if (r >= j) {
+            const double l = (hi ? a1 : a0) * rinv;   // a[j][j] * rinv = sqrt(a[j][j])
+            if (hi) a1 = l; else a0 = l;
+            colbuf[(j & 1) * kNB + r] = l;
+        }
+        if (r == 0) { s_rinv[j & 1] = rinv; if (bad) *s_bad = 1.0; }
+    };
+    if (w == 0) publish(0);
+    for (int j = 0; j < kNB; j++) {
+        __syncthreads();   // column j is published
+        const double* col = colbuf + (j & 1) * kNB;
+        const double rinv = s_rinv[j & 1];
+        const double lr = (r >= j) ? col[r] : 0.0;
+        // Cholesky update of the columns right of j
+        if (c0 > j && r >= c0) a0 -= lr * col[c0];
+        if (c1 > j && r >= c1) a1 -= lr * col[c1];
+        // column j + 1 is complete now: its owner publishes it BEFORE the inverse updates of this step, which keeps
+        // them off the pivot -> rsqrt -> publish -> barrier chain that bounds a step
+        if (j + 1 < kNB && w == ((j + 1) & 15)) publish(j + 1);
+        // inverse: row j is scaled, rows below it are swept (columns <= j)
+        if (c0 <= j) {
+            const double xj = __shfl_sync(0xffffffffu, x0, j) * rinv;
+            if (r == j) x0 = xj; else if (r > j) x0 -= lr * xj;
+        }
+        if (c1 <= j) {
+            const double xj = __shfl_sync(0xffffffffu, x1, j) * rinv;
+            if (r == j) x1 = xj; else if (r > j) x1 -= lr * xj;
+        }
+    }
+    Ld[r * kDiagLd + c0] = (c0 <= r) ? a0 : 0.0;
+    Ld[r * kDiagLd + c1] = (c1 <= r) ? a1 : 0.0;
+    Li[r * kDiagLd + c0] = (c0 <= r) ? x0 : 0.0;
+    Li[r * kDiagLd + c1] = (c1 <= r) ? x1 : 0.0;
+    if (write_back) {
+        if (c0 <= r) A[(size_t)r * ld + c0] = a0;
+        if (c1 <= r) A[(size_t)r * ld + c1] = a1;
+        Linv_out[r * kNB + c0] = (c0 <= r) ? x0 : 0.0;
+        Linv_out[r * kNB + c1] = (c1 <= r) ? x1 : 0.0;
+    }
+    __syncthreads();
+    return *s_bad != 0.0;
+}
+
+
+
+// ---- dense SPD solve A x = b on a whole cooperative grid ------------------------------------------------------------
+// Blocked right-looking Cholesky (lower triangle, kNB = 32) of the n x n matrix A (n a multiple of 32: the caller pads with
+// an identity block; leading dimension n; n + 8 rows, the right-hand side rides along as row n so that after the
+// factorisation it holds y = L^-1 b).  Per block column, three grid barriers:
+//   (a) CTA 0 factors and inverts the 32 x 32 diagonal block (cta_factor_invert_32) and publishes L11, L11^-1;
+//   (b) the panel rows below it, in chunks of 64 rows dealt round-robin to the CTAs:  L21 = A21 * L11^-T;
+//   (c) the trailing update A22 -= L21 L21^T in 64 x 64 tiles dealt round-robin, both panel slices staged in shared
+//       memory, 8 x 8 sub-tiles on the FP64 tensor pipe (DMMA m8n8k4), lower triangle only.
+// Then CTA 0 solves L^T x = y block by block.  *g_ok (global) is 1 on success, 0 when a pivot was not positive / finite
+// (x is then zero).  The caller must grid.sync() before reading x.  smem: kGridCholSmemDoubles doubles.
+constexpr int kGridCholSmemDoubles = 2 * kNB * kDiagLd + 64 * kNB + 2 * 64 * kPanelLd + 4 * kNB + 8;
+
+__device__ inline void grid_cholesky_solve(cooperative_groups::grid_group& grid, int n, double* A, const double* b, double* x,
+                                           double* Linv_g, int* g_ok, double* smem)
+{
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int G = gridDim.x, cta = blockIdx.x;
+    double* Ld = smem;                            // [kNB][kDiagLd]
+    double* Li = Ld + kNB * kDiagLd;              // [kNB][kDiagLd]
+    double* stage = Li + kNB * kDiagLd;           // [64][kNB]
+    double* Pi = stage + 64 * kNB;                // [64][kPanelLd]
+    double* Pj = Pi + 64 * kPanelLd;              // [64][kPanelLd]
+    double* scratch = Pj + 64 * kPanelLd;         // [4 * kNB + 8]
+    const int M = n + 8;
+    if (cta == 0) {
+        for (int i = tid; i < 8 * n; i += kCholThreads) A[(size_t)n * n + i] = (i < n) ? b[i] : 0.0;
+        if (tid == 0) *g_ok = 1;
+    }
+    grid.sync();
+    for (int k0 = 0; k0 < n; k0 += kNB) {
+        const int r0 = k0 + kNB;
+        // ---- (a) diagonal block ----
+        if (cta == 0) {
+            const bool bad = cta_factor_invert_32(A + (size_t)k0 * n + k0, n, Ld, Li, true, Linv_g + (size_t)(k0 / kNB) * kNB * kNB, scratch);
+            if (bad && tid == 0) *g_ok = 0;
+        }
+        grid.sync();
+        // ---- (b) panel: L21 = A21 * L11^-T ----
+        const int mrows = M - r0;
+        if (cta * 64 < mrows) {
+            const double* Lg = Linv_g + (size_t)(k0 / kNB) * kNB * kNB;
+            for (int t = tid; t < kNB * kNB; t += kCholThreads) Li[(t >> 5) * kDiagLd + (t & 31)] = Lg[t];
+            __syncthreads();
+            for (int base = r0 + cta * 64; base < M; base += G * 64) {
+                const int cnt = min(64, M - base);
+                for (int t = tid; t < cnt * kNB; t += kCholThreads) stage[t] = A[(size_t)(base + (t >> 5)) * n + k0 + (t & 31)];
+                __syncthreads();
+                for (int t = tid; t < cnt * kNB; t += kCholThreads) {
+                    const int r = t >> 5, c = t & 31;
+                    double acc = 0.0;
+                    for (int k = 0; k <= c; k++) acc += stage[r * kNB + k] * Li[c * kDiagLd + k];
+                    A[(size_t)(base + r) * n + k0 + c] = acc;
+                }
+                __syncthreads();
+            }
+        }
+        grid.sync();
+        // ---- (c) trailing update in 64 x 64 tiles ----
+        const int mcols = n - r0;
+        if (mcols > 0) {
+            const int mt = (mcols + 63) / 64, mrt = (mrows + 63) / 64;
+            for (int t = cta; t < mrt * mt; t += G) {
+                const int I = t / mt, J = t - I * mt;
+                if (J > I) continue;   // strictly above the diagonal
+                const int ri = r0 + I * 64, rj = r0 + J * 64;
+                __syncthreads();
+                for (int e = tid; e < 64 * kNB; e += kCholThreads) {
+                    const int r = e >> 5, c = e & 31;
+                    Pi[r * kPanelLd + c] = (ri + r < M) ? A[(size_t)(ri + r) * n + k0 + c] : 0.0;
+                    Pj[r * kPanelLd + c] = (rj + r < n) ? A[(size_t)(rj + r) * n + k0 + c] : 0.0;
+                }
+                __syncthreads();
+                for (int sub = wid; sub < 64; sub += kCholWarps) {
+                    const int si = sub >> 3, sj = sub & 7;
+                    if (I == J && sj > si) continue;
+                    const int ar = si * 8 + (lane >> 2), bc = sj * 8 + (lane >> 2);
+                    double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+                    for (int kk = 0; kk < kNB; kk += 4)
+                        dmma_m8n8k4(c0, c1, Pi[ar * kPanelLd + kk + (lane & 3)], Pj[bc * kPanelLd + kk + (lane & 3)]);
+                    const int row = ri + ar, col = rj + sj * 8 + (lane & 3) * 2;
+                    if (row < M) {
+                        double* dst = A + (size_t)row * n + col;
+                        if (col < n && col <= row) dst[0] -= c0;
+                        if (col + 1 < n && col + 1 <= row) dst[1] -= c1;
+                    }
+                }
+            }
+        }
+        grid.sync();
+    }
+    // ---- backward substitution L^T x = y on CTA 0 (y = row n of A; x doubles as the work vector) ----
+    if (cta == 0) {
+        const bool ok = *g_ok != 0;
+        double* part = stage;         // [16][kNB]
+        double* rhs = scratch;        // [kNB]
+        for (int i = tid; i < n; i += kCholThreads) x[i] = A[(size_t)n * n + i];
+        __syncthreads();
+        for (int k0 = n - kNB; k0 >= 0; k0 -= kNB) {
+            {
+                const int c = tid & 31, g = tid >> 5;
+                double acc = 0.0;
+                for (int i = k0 + kNB + g; i < n; i += kCholWarps) acc += A[(size_t)i * n + k0 + c] * x[i];
+                part[g * kNB + c] = acc;
+            }
+            __syncthreads();
+            if (tid < kNB) {
+                double acc = x[k0 + tid];
+                for (int g = 0; g < kCholWarps; g++) acc -= part[g * kNB + tid];
+                rhs[tid] = acc;
+            }
+            __syncthreads();
+            if (tid < kNB) {   // x_k = L_kk^-T rhs
+                const double* Lg = Linv_g + (size_t)(k0 / kNB) * kNB * kNB;
+                double acc = 0.0;
+                for (int c = tid; c < kNB; c++) acc += Lg[c * kNB + tid] * rhs[c];
+                x[k0 + tid] = acc;
+            }
+            __syncthreads();
+        }
+        if (!ok) for (int i = tid; i < n; i += kCholThreads) x[i] = 0.0;
+        __syncthreads();
+    }
+}
+
+} // namespace dvm

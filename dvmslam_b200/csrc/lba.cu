@@ -15,6 +15,7 @@
 //   B1  landmark back-substitution, pose/point update into the trial buffers       (:459-483, se3quat.h:212-240)
 //   B2  errors and robust chi2 at the trial estimate
 #include "common.cuh"
+#include "chol_device.cuh"
 #include <chrono>
 #include <cooperative_groups.h>
 #include <math_constants.h>
@@ -27,9 +28,8 @@ using namespace dvm;
 
 namespace {
 
-constexpr int kLbaThreads = 512;
+constexpr int kLbaThreads = kCholThreads;
 constexpr int kLbaWarps = kLbaThreads / 32;
-constexpr int kNB = 32; // Cholesky block size
 // Per-CTA partial sums exchanged through global memory between grid barriers.  Every WRITER has its own slot: the
 // linearisation's chi2 (written right at the top of the next LM iteration, with no grid barrier after the previous
 // trial's decision was read) must not share a slot with the trial chi2 that decision reads -- with a shared slot a CTA
@@ -41,6 +41,7 @@ constexpr int kPartLinChi = 0, kPartScale = 1, kPartMaxHll = 2, kPartMaxHpp = 3,
 struct LbaDev {
     int nc, nf, np, ne, dimP, dimPad, iterations; // dimPad = dimP rounded up to the Cholesky block size
     int iterations2;   // > 0: the welding BA's second pass (no robust kernel, level-0 edges only)
+    int grid_chol;     // reduced system too large for one cluster's shared memory: factor it on the whole grid
     uint8_t* level;    // [ne] 1 = edge moved to level 1 before the second pass; null for one-pass calls
     double fx, fy, cx, cy, delta, dsqr;
     double* camq[2]; double* camt[2];
@@ -209,14 +210,6 @@ __device__ inline double warp_max(double s)
     return s;
 }
 
-// D = C - A * B for one m8n8k4 FP64 tensor-core tile step (a: A[r=lane/4][k=lane%4], b: B[k=lane%4][c=lane/4])
-__device__ inline void dmma_m8n8k4(double& c0, double& c1, double a, double b)
-{
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                 : "+d"(c0), "+d"(c1)
-                 : "d"(a), "d"(b));
-}
-
 // ---- dense SPD solve Hs x = bs on ONE 8-CTA CLUSTER ------------------------------------------------
 // Blocked right-looking Cholesky (lower triangle, kNB = 32) of the n x n reduced camera matrix A
 // (n a multiple of 32: the caller pads with an identity block), with the right-hand side carried as an
@@ -229,96 +222,8 @@ __device__ inline void dmma_m8n8k4(double& c0, double& c1, double a, double b)
 //       of the 8x8 trailing tiles  A22 -= L21 L21^T  on the FP64 tensor pipe (DMMA m8n8k4).
 // A has n + 8 rows of leading dimension n.  Linv_g [n/32][32*32] receives the inverted diagonal blocks.
 constexpr int kClusterCtas = 8;
-constexpr int kPanelLd = 36;   // shared-memory row stride of the panel (doubles): conflict-free 8-byte fragment loads
-constexpr int kDiagLd = kNB + 1;
-
-// Reciprocal square root on the critical path of every column: hardware seed (MUFU.RSQ64H, ~20 bits) and two
-// Newton steps -- within 1-2 ulp for the positive, well-scaled pivots of a damped normal matrix.
-__device__ inline double fast_rsqrt(double d)
-{
-    double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
-    const double h = 0.5 * d;
-    double e = fma(-h * y, y, 0.5);
-    y = fma(y, e, y);
-    e = fma(-h * y, y, 0.5);
-    return fma(y, e, y);
-}
-
-// Factorisation + inversion of a 32x32 diagonal block by ALL threads of the CTA (kLbaThreads = 512 = 16 warps): a lone
-// warp cannot hide its own latencies (a one-warp version with the block in registers ran at ~7 cycles per instruction,
-// 21 us per block, and was 2/3 of the whole solve; DESIGN.md, negative results).  Every thread OWNS two elements of the block and of its inverse in registers for the
-// whole sweep: lane = row, warp w = columns w and w + 16.  Step j:
-//     the warp that owns column j takes the pivot by shuffle, scales its column by rsqrt(pivot) and publishes it
-//     (col[j & 1][:], rinv[j & 1]) | ONE CTA barrier |
-//     a[r][c] -= L[r][j] L[c][j]  (c > j);   X[j][c] = x[j][c] * rinv (by shuffle inside the column's warp),
-//     x[r][c] -= L[r][j] X[j][c]  (r > j)
-// i.e. the right-looking Cholesky step and the column sweep of the triangular inversion share one barrier per
-// step (the published column is double-buffered), and the owner of column j + 1 publishes it before doing its share of
-// step j's inverse updates.  Measured: 21.6 -> 10 us per block (~550 cycles per step; what is left is the FP64 pipe --
-// the triangular masks leave most lanes of the 6 double-precision instructions a warp issues per step idle).
-// `scratch` holds 4 * kNB + 4 doubles.  Same outputs as the warp version.
-// (No __restrict__ here: the published column is exchanged BETWEEN threads, and with restrict-qualified pointers
-// nvcc keeps values read from it across the barriers -- measured: wrong factors.)
-__device__ bool cta_factor_invert_32(double* A, int ld, double* Ld, double* Li, bool write_back, double* Linv_out,
-                                     double* scratch)
-{
-    const int r = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int c0 = w, c1 = w + 16;
-    double* colbuf = scratch;                 // [2][kNB]  L[:, j]
-    double* s_rinv = scratch + 2 * kNB;       // [2]
-    double* s_bad = s_rinv + 2;
-    double a0 = A[(size_t)r * ld + c0], a1 = A[(size_t)r * ld + c1];
-    double x0 = (r == c0) ? 1.0 : 0.0, x1 = (r == c1) ? 1.0 : 0.0;
-    if (threadIdx.x == 0) *s_bad = 0.0;
-    // the warp that owns column j scales it by rsqrt(pivot) and publishes it in buffer j & 1
-    auto publish = [&](int j) {
-        const bool hi = j >= 16;
-        const double djj = __shfl_sync(0xffffffffu, hi ? a1 : a0, j);
-        const bool bad = !(djj > 0) || !isfinite(djj);
-        const double rinv = bad ? 1.0 : fast_rsqrt(djj);
-        if (r >= j) {
-            const double l = (hi ? a1 : a0) * rinv;   // a[j][j] * rinv = sqrt(a[j][j])
-            if (hi) a1 = l; else a0 = l;
-            colbuf[(j & 1) * kNB + r] = l;
-        }
-        if (r == 0) { s_rinv[j & 1] = rinv; if (bad) *s_bad = 1.0; }
-    };
-    if (w == 0) publish(0);
-    for (int j = 0; j < kNB; j++) {
-        __syncthreads();   // column j is published
-        const double* col = colbuf + (j & 1) * kNB;
-        const double rinv = s_rinv[j & 1];
-        const double lr = (r >= j) ? col[r] : 0.0;
-        // Cholesky update of the columns right of j
-        if (c0 > j && r >= c0) a0 -= lr * col[c0];
-        if (c1 > j && r >= c1) a1 -= lr * col[c1];
-        // column j + 1 is complete now: its owner publishes it BEFORE the inverse updates of this step, which keeps
-        // them off the pivot -> rsqrt -> publish -> barrier chain that bounds a step
-        if (j + 1 < kNB && w == ((j + 1) & 15)) publish(j + 1);
-        // inverse: row j is scaled, rows below it are swept (columns <= j)
-        if (c0 <= j) {
-            const double xj = __shfl_sync(0xffffffffu, x0, j) * rinv;
-            if (r == j) x0 = xj; else if (r > j) x0 -= lr * xj;
-        }
-        if (c1 <= j) {
-            const double xj = __shfl_sync(0xffffffffu, x1, j) * rinv;
-            if (r == j) x1 = xj; else if (r > j) x1 -= lr * xj;
-        }
-    }
-    Ld[r * kDiagLd + c0] = (c0 <= r) ? a0 : 0.0;
-    Ld[r * kDiagLd + c1] = (c1 <= r) ? a1 : 0.0;
-    Li[r * kDiagLd + c0] = (c0 <= r) ? x0 : 0.0;
-    Li[r * kDiagLd + c1] = (c1 <= r) ? x1 : 0.0;
-    if (write_back) {
-        if (c0 <= r) A[(size_t)r * ld + c0] = a0;
-        if (c1 <= r) A[(size_t)r * ld + c1] = a1;
-        Linv_out[r * kNB + c0] = (c0 <= r) ? x0 : 0.0;
-        Linv_out[r * kNB + c1] = (c1 <= r) ? x1 : 0.0;
-    }
-    __syncthreads();
-    return *s_bad != 0.0;
-}
+constexpr int kLbaClusterFree = 100;   // free keyframes whose reduced system (600 unknowns) fits one SM's shared-memory panel
+constexpr int kLbaMaxFree = 2000;
 
 
 __device__ bool cluster_cholesky_solve(int n, double* __restrict__ A, const double* __restrict__ b, double* __restrict__ x,
@@ -748,7 +653,9 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kLbaThrea
                 grid.sync();
                 tick(3);
                 // ---------------- C: reduced camera system on one CTA ----------------
-                if (blockIdx.x < kClusterCtas) { // the first cluster
+                if (P.grid_chol) {   // hundreds of free keyframes (global BA): blocked Cholesky over every SM
+                    grid_cholesky_solve(grid, P.dimPad, P.Hs, P.bs, P.x, P.Linv, &P.flags[0], smem);
+                } else if (blockIdx.x < kClusterCtas) { // the first cluster
                     bool ok = true;
                     if (P.dimP > 0) ok = cluster_cholesky_solve(P.dimPad, P.Hs, P.bs, P.x, P.Linv, smem, &s_flag, P.prof);
                     if (blockIdx.x == 0 && tid == 0) P.flags[0] = ok ? 1 : 0;
@@ -912,7 +819,7 @@ int dvm_lba_create(dvm_lba** out, int device, int max_free_cameras)
 {
     DVM_REQUIRE(out != nullptr, "null output handle");
     *out = nullptr;
-    DVM_REQUIRE(max_free_cameras >= 1 && max_free_cameras <= 100, "max_free_cameras must be in 1..100");
+    DVM_REQUIRE(max_free_cameras >= 1 && max_free_cameras <= kLbaMaxFree, "max_free_cameras must be in 1..2000");
     int rc = select_device(device);
     if (rc != DVM_OK) return rc;
     dvm_lba* h = new dvm_lba;
@@ -934,8 +841,11 @@ int dvm_lba_create(dvm_lba** out, int device, int max_free_cameras)
     *h->h_abort = 0;
     DVM_LCREATE(cudaHostGetDevicePointer(&h->d_abort, h->h_abort, 0));
     // shared memory: max(Schur row [nf*36+6], Cholesky panel [n*kNB] + diag [kNB*(kNB+1)]) doubles
-    const size_t n = ((size_t)6 * max_free_cameras + kNB - 1) / kNB * kNB;
-    h->smem_bytes = ((n + 8) * kPanelLd + 2 * kNB * kDiagLd + 64 * kNB) * sizeof(double);
+    // up to kLbaClusterFree free keyframes the reduced system is factored by ONE cluster with its panel in shared memory
+    // (local BA: lowest latency); above that by the whole grid (grid_cholesky_solve), whose shared memory need is fixed
+    const size_t n = ((size_t)6 * std::min(max_free_cameras, kLbaClusterFree) + kNB - 1) / kNB * kNB;
+    h->smem_bytes = std::max(((n + 8) * kPanelLd + 2 * kNB * kDiagLd + 64 * kNB) * sizeof(double),
+                             (size_t)kGridCholSmemDoubles * sizeof(double));
     DVM_REQUIRE(h->smem_bytes <= 227 * 1024, "max_free_cameras needs more shared memory than one SM has");
     DVM_LCREATE(cudaFuncSetAttribute(lba_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
     {   // persistent CTAs in clusters of 8: as many clusters as can be co-resident (cooperative launch)
@@ -1042,30 +952,36 @@ static int run_ba(dvm_lba* h, int nc, float* cam_q, float* cam_t, const uint8_t*
     const size_t o_pst = take((size_t)(np + 1) * 4), o_ped = take((size_t)ne * 4);
     const size_t o_cst = take((size_t)(nf + 1) * 4), o_ced = take(n_cam_edges * 4);
     const size_t upload_bytes = off;
-    // work block
+    // output block (contiguous, one D2H); the pinned host mirror spans [0, out_end) only
+    const size_t out_begin = (off + 255) & ~(size_t)255;
+    const size_t o_oq = take((size_t)nc * 4 * 4), o_ot = take((size_t)nc * 3 * 4), o_op = take((size_t)np * 3 * 4);
+    const size_t o_ochi = take((size_t)ne * 8), o_obad = take((size_t)ne), o_ostats = take(6 * 8);
+    const size_t out_end = off;
+    // work block (device only)
     const size_t o_camq1 = take((size_t)nc * 4 * 8), o_camt1 = take((size_t)nc * 3 * 8), o_pts1 = take((size_t)np * 3 * 8);
     const size_t o_err = take((size_t)ne * 2 * 8), o_hpl = take((size_t)ne * 18 * 8);
     const size_t o_hll = take((size_t)np * 6 * 8), o_bl = take((size_t)np * 3 * 8), o_dinv = take((size_t)np * 6 * 8), o_db = take((size_t)np * 3 * 8);
     const size_t o_hpp = take((size_t)std::max(nf, 1) * 36 * 8), o_bp = take((size_t)std::max(dimP, 1) * 8);
-    const size_t o_hs = take((size_t)std::max((dimPad + 8) * dimPad, 1) * 8), o_bs = take((size_t)std::max(dimPad, 1) * 8);
+    const size_t o_hs = take((size_t)std::max((size_t)(dimPad + 8) * dimPad, (size_t)1) * 8), o_bs = take((size_t)std::max(dimPad, 1) * 8);
     const size_t o_linv = take((size_t)std::max(dimPad * kNB, 1) * 8);
     const size_t o_x = take((size_t)(dimPad + np * 3 + 1) * 8);
     const size_t o_part = take((size_t)h->grid * kPartStride * 8), o_flags = take(4 * 4), o_prof = take(16 * 8);
     const size_t o_level = take((size_t)std::max(ne, 1));
-    // output block (contiguous, one D2H)
-    const size_t out_begin = (off + 255) & ~(size_t)255;
-    const size_t o_oq = take((size_t)nc * 4 * 4), o_ot = take((size_t)nc * 3 * 4), o_op = take((size_t)np * 3 * 4);
-    const size_t o_ochi = take((size_t)ne * 8), o_obad = take((size_t)ne), o_ostats = take(6 * 8);
     const size_t total = off + 256;
     if (total > h->d_cap) {
         DVM_CUDA(cudaStreamSynchronize(h->stream));
         cudaFree(h->d_buf); h->d_buf = nullptr;
-        if (h->h_buf) { cudaFreeHost(h->h_buf); h->h_buf = nullptr; }
         const size_t cap = total + total / 4;
         DVM_CUDA(cudaMalloc(&h->d_buf, cap));
-        DVM_CUDA(cudaMemsetAsync(h->d_buf, 0, cap, h->stream)); // the alignment gaps of the output block travel in its one D2H copy
+        DVM_CUDA(cudaMemsetAsync(h->d_buf, 0, std::min(cap, out_end + 4096), h->stream)); // the alignment gaps of the output block travel in its one D2H copy
+        h->d_cap = cap;
+    }
+    if (out_end + 256 > h->h_cap) {
+        DVM_CUDA(cudaStreamSynchronize(h->stream));
+        if (h->h_buf) { cudaFreeHost(h->h_buf); h->h_buf = nullptr; }
+        const size_t cap = out_end + out_end / 4 + 4096;
         DVM_CUDA(cudaHostAlloc(&h->h_buf, cap, cudaHostAllocDefault));
-        h->d_cap = h->h_cap = cap;
+        h->h_cap = cap;
     }
     // ---- stage inputs (float -> double conversions as the reference's .cast<double>()) ----
     uint8_t* hb = h->h_buf;
@@ -1113,6 +1029,7 @@ static int run_ba(dvm_lba* h, int nc, float* cam_q, float* cam_t, const uint8_t*
     memset(&P, 0, sizeof(P));
     P.nc = nc; P.nf = nf; P.np = np; P.ne = ne; P.dimP = dimP; P.dimPad = dimPad; P.iterations = iterations;
     P.iterations2 = iterations2;
+    P.grid_chol = nf > kLbaClusterFree ? 1 : 0;
     P.level = iterations2 > 0 ? db + o_level : nullptr;
     P.fx = K[0]; P.fy = K[1]; P.cx = K[2]; P.cy = K[3];
     P.delta = (double)huber_delta;   // the caller's float delta; +infinity = no robust kernel
@@ -1144,7 +1061,7 @@ static int run_ba(dvm_lba* h, int nc, float* cam_q, float* cam_t, const uint8_t*
     DVM_CUDA(cudaLaunchCooperativeKernel((void*)lba_kernel, dim3(h->grid), dim3(kLbaThreads), args, h->smem_bytes, h->stream));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     DVM_CUDA(cudaEventRecord(h->ev1, h->stream));
-    const size_t out_bytes = off - out_begin;
+    const size_t out_bytes = out_end - out_begin;
     DVM_CUDA(cudaMemcpyAsync(hb + out_begin, db + out_begin, out_bytes, cudaMemcpyDeviceToHost, h->stream));
     if (abort_flag) { // mirror the caller's pbStopFlag into mapped memory while the kernel runs
         while (cudaEventQuery(h->ev1) == cudaErrorNotReady)

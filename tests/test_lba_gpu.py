@@ -85,7 +85,8 @@ def test_observation_only_from_fixed_cameras(solver):
     _compare(r0, r1, S)
 
 
-@pytest.mark.parametrize("n_free,n_pts,robust,iters", [(40, 1500, True, 10), (96, 3000, True, 20), (30, 800, False, 20)])
+@pytest.mark.parametrize("n_free,n_pts,robust,iters", [(40, 1500, True, 10), (96, 3000, True, 20), (30, 800, False, 20),
+                                                        (200, 4000, True, 10), (101, 1200, False, 6)])
 def test_global_bundle_adjustment_matches_oracle(n_free, n_pts, robust, iters):
     """Optimizer::BundleAdjustment (GlobalBundleAdjustemnt's worker, O3/src/Optimizer.cc:55-356) on maps the dense
     reduced solve holds (<= 100 free keyframes): one fixed keyframe (the map's initial one), Huber delta
@@ -97,7 +98,7 @@ def test_global_bundle_adjustment_matches_oracle(n_free, n_pts, robust, iters):
     a = (S["cam_q"], S["cam_t"], S["cam_fixed"], S["pts"], S["edge_cam"], S["edge_pt"], S["edge_obs"], S["edge_w"], S["K"])
     delta = float(np.float32(np.sqrt(5.99))) if robust else float("inf")
     r0 = local_ba(*a, iterations=iters, huber_delta=delta)
-    s = LocalBA(100)
+    s = LocalBA(max(100, n_free))   # above 100 free keyframes the reduced system is factored by the whole grid
     r1 = s.BundleAdjustment(*a, nIterations=iters, bRobust=robust)
     s.close()
     assert r0["iters"] == r1["iters"] and r0["iters"] >= 3
