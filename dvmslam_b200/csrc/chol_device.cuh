@@ -49,7 +49,7 @@ __device__ inline double fast_rsqrt(double d)
 // `scratch` holds 4 * kNB + 4 doubles.  Same outputs as the warp version.
 // (No __restrict__ here: the published column is exchanged BETWEEN threads, and with restrict-qualified pointers
 // nvcc keeps values read from it across the barriers -- measured: wrong factors.)
-__device__ bool cta_factor_invert_32(double* A, int ld, double* Ld, double* Li, bool write_back, double* Linv_out,
+__device__ inline bool cta_factor_invert_32(double* A, int ld, double* Ld, double* Li, bool write_back, double* Linv_out,
                                      double* scratch)
 {
     const int r = threadIdx.x & 31, w = threadIdx.x >> 5;

@@ -43,7 +43,8 @@ struct LbaDev {
     int iterations2;   // > 0: the welding BA's second pass (no robust kernel, level-0 edges only)
     int grid_chol;     // reduced system too large for one cluster's shared memory: factor it on the whole grid
     uint8_t* level;    // [ne] 1 = edge moved to level 1 before the second pass; null for one-pass calls
-    double fx, fy, cx, cy, delta, dsqr;
+    const double* camK;   // [nc][4] fx, fy, cx, cy of every camera (e->pCamera = pKFi->mpCamera, O3/src/Optimizer.cc:1219)
+    double delta, dsqr;
     double* camq[2]; double* camt[2];
     const int* cam_col; const int* free_cam;
     double* pts[2];
@@ -171,8 +172,9 @@ __device__ inline void edge_residual(const LbaDev& P, int cur, int e, double xc[
     const double X[3] = { P.pts[cur][3 * l], P.pts[cur][3 * l + 1], P.pts[cur][3 * l + 2] };
     quat_rotate(Q, X, xc);
     xc[0] += t[0]; xc[1] += t[1]; xc[2] += t[2];
-    r[0] = (double)P.eobs[2 * e] - (P.fx * xc[0] / xc[2] + P.cx);
-    r[1] = (double)P.eobs[2 * e + 1] - (P.fy * xc[1] / xc[2] + P.cy);
+    const double* kc = P.camK + 4 * c;
+    r[0] = (double)P.eobs[2 * e] - (kc[0] * xc[0] / xc[2] + kc[2]);
+    r[1] = (double)P.eobs[2 * e + 1] - (kc[1] * xc[1] / xc[2] + kc[3]);
     if (qout) *qout = Q;
 }
 
@@ -453,7 +455,8 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kLbaThrea
                     chi_part += huber_rho0(delta, dsqr, chi);
                     const double w = huber_rho1(delta, dsqr, chi);
                     const double X = xc[0], Y = xc[1], Z = xc[2];
-                    const double pj[6] = { -(P.fx / Z), 0.0, P.fx * X / (Z * Z), 0.0, -(P.fy / Z), P.fy * Y / (Z * Z) };
+                    const double fx = P.camK[4 * P.ecam[e]], fy = P.camK[4 * P.ecam[e] + 1];
+                    const double pj[6] = { -(fx / Z), 0.0, fx * X / (Z * Z), 0.0, -(fy / Z), fy * Y / (Z * Z) };
                     double R[9];
                     quat_to_matrix(Q, R);
                     double A[6];
@@ -527,7 +530,8 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kLbaThrea
                     const double chi = r[0] * (om * r[0]) + r[1] * (om * r[1]);
                     const double w = huber_rho1(delta, dsqr, chi);
                     const double X = xc[0], Y = xc[1], Z = xc[2];
-                    const double pj[6] = { -(P.fx / Z), 0.0, P.fx * X / (Z * Z), 0.0, -(P.fy / Z), P.fy * Y / (Z * Z) };
+                    const double fx = P.camK[4 * P.ecam[e]], fy = P.camK[4 * P.ecam[e] + 1];
+                    const double pj[6] = { -(fx / Z), 0.0, fx * X / (Z * Z), 0.0, -(fy / Z), fy * Y / (Z * Z) };
                     const double Dv[18] = { 0, Z, -Y, 1, 0, 0, -Z, 0, X, 0, 1, 0, Y, -X, 0, 0, 0, 1 };
                     double B[12];
     #pragma unroll
@@ -797,6 +801,7 @@ struct dvm_lba {
     uint8_t* h_buf = nullptr; size_t h_cap = 0;
     int* h_abort = nullptr; int* d_abort = nullptr; // mapped pinned
     std::vector<int> pt_start, cam_start, fill;     // host-side structure scratch, kept between calls
+    std::vector<float> next_cam_K;                  // dvm_lba_set_camera_intrinsics: [nc][4] for the next call
     float last_ms = 0;
 };
 
@@ -874,6 +879,13 @@ void dvm_lba_destroy(dvm_lba* h) { lba_free(h); }
 
 float dvm_lba_last_kernel_ms(const dvm_lba* h) { return h ? h->last_ms : -1.f; }
 
+int dvm_lba_set_camera_intrinsics(dvm_lba* h, int nc, const float* cam_K)
+{
+    DVM_REQUIRE(h != nullptr && nc >= 0 && (nc == 0 || cam_K), "bad argument");
+    h->next_cam_K.assign(cam_K, cam_K + (size_t)nc * 4);
+    return DVM_OK;
+}
+
 int dvm_local_ba(dvm_lba* h, int nc, float* cam_q, float* cam_t, const uint8_t* cam_fixed, int np, float* pts, int ne,
                  const int32_t* edge_cam, const int32_t* edge_pt, const float* edge_obs, const float* edge_inv_sigma2,
                  const float* K, int iterations, const volatile uint8_t* abort_flag, double* edge_chi2, uint8_t* edge_bad,
@@ -947,7 +959,7 @@ static int run_ba(dvm_lba* h, int nc, float* cam_q, float* cam_t, const uint8_t*
     auto take = [&](size_t bytes) { off = (off + 255) & ~(size_t)255; size_t o = off; off += bytes; return o; };
     // uploaded block
     const size_t o_camq = take((size_t)nc * 4 * 8), o_camt = take((size_t)nc * 3 * 8), o_pts = take((size_t)np * 3 * 8);
-    const size_t o_col = take((size_t)nc * 4), o_free = take((size_t)std::max(nf, 1) * 4);
+    const size_t o_col = take((size_t)nc * 4), o_free = take((size_t)std::max(nf, 1) * 4), o_camk = take((size_t)std::max(nc, 1) * 4 * 8);
     const size_t o_ecam = take((size_t)ne * 4), o_ept = take((size_t)ne * 4), o_obs = take((size_t)ne * 8), o_info = take((size_t)ne * 4);
     const size_t o_pst = take((size_t)(np + 1) * 4), o_ped = take((size_t)ne * 4);
     const size_t o_cst = take((size_t)(nf + 1) * 4), o_ced = take(n_cam_edges * 4);
@@ -995,6 +1007,13 @@ static int run_ba(dvm_lba* h, int nc, float* cam_q, float* cam_t, const uint8_t*
             for (int i = 0; i < 3; i++) t[3 * c + i] = cam_t[3 * c + i];
         }
         for (int i = 0; i < np * 3; i++) p[i] = pts[i];
+        {   // intrinsics per camera: the caller's K for all, or the per-camera table set for this call
+            double* kc = (double*)(hb + o_camk);
+            const bool per_cam = (int)h->next_cam_K.size() == nc * 4 && nc > 0;
+            for (int c = 0; c < nc; c++)
+                for (int i = 0; i < 4; i++) kc[4 * c + i] = per_cam ? (double)h->next_cam_K[4 * c + i] : (double)K[i];
+            h->next_cam_K.clear();
+        }
         memcpy(hb + o_col, cam_col.data(), (size_t)nc * 4);
         memcpy(hb + o_free, free_cam.data(), (size_t)nf * 4);
         memcpy(hb + o_ecam, edge_cam, (size_t)ne * 4);
@@ -1031,7 +1050,7 @@ static int run_ba(dvm_lba* h, int nc, float* cam_q, float* cam_t, const uint8_t*
     P.iterations2 = iterations2;
     P.grid_chol = nf > kLbaClusterFree ? 1 : 0;
     P.level = iterations2 > 0 ? db + o_level : nullptr;
-    P.fx = K[0]; P.fy = K[1]; P.cx = K[2]; P.cy = K[3];
+    P.camK = (const double*)(db + o_camk);
     P.delta = (double)huber_delta;   // the caller's float delta; +infinity = no robust kernel
     P.dsqr = P.delta * P.delta;
     P.camq[0] = (double*)(db + o_camq); P.camq[1] = (double*)(db + o_camq1);

@@ -11,18 +11,18 @@
 // broadcasting; the numeric Jacobians (28 projections per correspondence and linearisation) are spread over the threads one
 // (correspondence, dimension) at a time, the normal equations are accumulated one correspondence per thread and reduced
 // with warp shuffles + one shared-memory stage in a fixed order (deterministic).
+#include "sim3_math.cuh"
 #include "common.cuh"
 #include <math_constants.h>
 #include <cmath>
 
 namespace dvm {
+using namespace sim3m;
 namespace {
 
 constexpr int kSim3Threads = 512;
 constexpr int kSim3Warps = kSim3Threads / 32;
 
-struct Quat { double x, y, z, w; };
-struct Sim3 { Quat r; double t[3]; double s; };
 
 struct Sim3Dev {
     int n, fix_scale;
@@ -37,124 +37,6 @@ struct Sim3Dev {
     double* stats;      // [8] out: iters pass 1, iters pass 2, trials, nBad, first chi2, last chi2, nIn
 };
 
-__device__ inline Quat quat_mul(const Quat& a, const Quat& b)
-{
-    Quat r;
-    r.w = a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z;
-    r.x = a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y;
-    r.y = a.w * b.y + a.y * b.w + a.z * b.x - a.x * b.z;
-    r.z = a.w * b.z + a.z * b.w + a.x * b.y - a.y * b.x;
-    return r;
-}
-__device__ inline void quat_rotate(const Quat& q, const double v[3], double out[3])
-{
-    double uv[3] = { q.y * v[2] - q.z * v[1], q.z * v[0] - q.x * v[2], q.x * v[1] - q.y * v[0] };
-    uv[0] += uv[0]; uv[1] += uv[1]; uv[2] += uv[2];
-    out[0] = v[0] + q.w * uv[0] + (q.y * uv[2] - q.z * uv[1]);
-    out[1] = v[1] + q.w * uv[1] + (q.z * uv[0] - q.x * uv[2]);
-    out[2] = v[2] + q.w * uv[2] + (q.x * uv[1] - q.y * uv[0]);
-}
-__device__ inline Quat quat_from_matrix(const double R[9]) // Eigen::Quaterniond(Matrix3d)
-{
-    Quat q;
-    double t = R[0] + R[4] + R[8];
-    if (t > 0) {
-        t = sqrt(t + 1.0);
-        q.w = 0.5 * t;
-        t = 0.5 / t;
-        q.x = (R[7] - R[5]) * t; q.y = (R[2] - R[6]) * t; q.z = (R[3] - R[1]) * t;
-    } else {
-        int i = 0;
-        if (R[4] > R[0]) i = 1;
-        if (R[8] > R[i * 4]) i = 2;
-        const int j = (i + 1) % 3, k = (j + 1) % 3;
-        t = sqrt(R[i * 4] - R[j * 4] - R[k * 4] + 1.0);
-        double v[3];
-        v[i] = 0.5 * t;
-        t = 0.5 / t;
-        q.w = (R[k * 3 + j] - R[j * 3 + k]) * t;
-        v[j] = (R[j * 3 + i] + R[i * 3 + j]) * t;
-        v[k] = (R[k * 3 + i] + R[i * 3 + k]) * t;
-        q.x = v[0]; q.y = v[1]; q.z = v[2];
-    }
-    return q;
-}
-
-// g2o::Sim3(const Vector7d& update), O3/Thirdparty/g2o/g2o/types/sim3.h
-__device__ Sim3 sim3_exp(const double u[7])
-{
-    const double w0 = u[0], w1 = u[1], w2 = u[2], sigma = u[6];
-    const double theta = sqrt(w0 * w0 + w1 * w1 + w2 * w2);
-    const double O[9] = { 0, -w2, w1, w2, 0, -w0, -w1, w0, 0 };
-    double O2[9], R[9];
-#pragma unroll
-    for (int i = 0; i < 3; i++)
-#pragma unroll
-        for (int j = 0; j < 3; j++) O2[i * 3 + j] = O[i * 3] * O[j] + O[i * 3 + 1] * O[3 + j] + O[i * 3 + 2] * O[6 + j];
-    Sim3 S;
-    S.s = exp(sigma);
-    const double eps = 0.00001;
-    double A, B, C;
-    const bool small_rot = theta < eps;
-    if (small_rot) {
-#pragma unroll
-        for (int i = 0; i < 9; i++) R[i] = ((i % 4 == 0) ? 1.0 : 0.0) + O[i] + O2[i];
-    } else {
-        const double a = sin(theta) / theta, b = (1 - cos(theta)) / (theta * theta);
-#pragma unroll
-        for (int i = 0; i < 9; i++) R[i] = ((i % 4 == 0) ? 1.0 : 0.0) + a * O[i] + b * O2[i];
-    }
-    if (fabs(sigma) < eps) {
-        C = 1;
-        if (small_rot) { A = 1. / 2.; B = 1. / 6.; }
-        else {
-            const double theta2 = theta * theta;
-            A = (1 - cos(theta)) / theta2;
-            B = (theta - sin(theta)) / (theta2 * theta);
-        }
-    } else {
-        C = (S.s - 1) / sigma;
-        if (small_rot) {
-            const double sigma2 = sigma * sigma;
-            A = ((sigma - 1) * S.s + 1) / sigma2;
-            B = ((0.5 * sigma2 - sigma + 1) * S.s) / (sigma2 * sigma);
-        } else {
-            const double a = S.s * sin(theta), b = S.s * cos(theta);
-            const double theta2 = theta * theta, sigma2 = sigma * sigma, c = theta2 + sigma2;
-            A = (a * sigma + (1 - b) * theta) / (theta * c);
-            B = (C - ((b - 1) * sigma + a * theta) / c) * 1. / theta2;
-        }
-    }
-    S.r = quat_from_matrix(R);
-#pragma unroll
-    for (int i = 0; i < 3; i++) {
-        double acc = 0;
-#pragma unroll
-        for (int j = 0; j < 3; j++) acc += (A * O[i * 3 + j] + B * O2[i * 3 + j] + C * (i == j ? 1.0 : 0.0)) * u[3 + j];
-        S.t[i] = acc;
-    }
-    return S;
-}
-__device__ inline Sim3 sim3_mul(const Sim3& a, const Sim3& b)
-{
-    Sim3 r;
-    r.r = quat_mul(a.r, b.r);
-    double rt[3];
-    quat_rotate(a.r, b.t, rt);
-#pragma unroll
-    for (int i = 0; i < 3; i++) r.t[i] = a.s * rt[i] + a.t[i];
-    r.s = a.s * b.s;
-    return r;
-}
-__device__ inline Sim3 sim3_inverse(const Sim3& a)
-{
-    Sim3 r;
-    r.r = { -a.r.x, -a.r.y, -a.r.z, a.r.w };
-    const double v[3] = { (-1. / a.s) * a.t[0], (-1. / a.s) * a.t[1], (-1. / a.s) * a.t[2] };
-    quat_rotate(r.r, v, r.t);
-    r.s = 1. / a.s;
-    return r;
-}
 // VertexSim3Expmap::oplusImpl
 __device__ inline Sim3 oplus(const Sim3Dev& P, const Sim3& S, const double* update)
 {

@@ -17,6 +17,20 @@
 #include "orb_matcher_adapter.h"
 
 namespace dvm_host {
+namespace detail {
+// e->pCamera = pKFi->mpCamera (O3/src/Optimizer.cc:1219): every keyframe's own intrinsics go to the solver (merged maps
+// mix keyframes of agents with different calibrations)
+template <class KeyFrameT>
+inline void set_camera_intrinsics(dvm_lba* solver, const std::vector<KeyFrameT*>& cams)
+{
+    std::vector<float> camK(cams.size() * 4);
+    for (size_t c = 0; c < cams.size(); c++) {
+        camK[4 * c] = cams[c]->fx; camK[4 * c + 1] = cams[c]->fy; camK[4 * c + 2] = cams[c]->cx; camK[4 * c + 3] = cams[c]->cy;
+    }
+    check(dvm_lba_set_camera_intrinsics(solver, static_cast<int>(cams.size()), camK.data()), "Optimizer (camera intrinsics)");
+}
+} // namespace detail
+
 
 // pose <-> (qx, qy, qz, qw, tx, ty, tz) through the accessors Sophus::SE3f / Eigen offer
 template <class PoseT>
@@ -161,7 +175,8 @@ void LocalBundleAdjustment(dvm_lba* solver, KeyFrameT* pKF, bool* pbStopFlag, Ma
     // pbStopFlag (a bool set by the tracking thread, O3/src/LocalMapping.cc:359) is polled by the library while
     // the solver runs and forwarded to the device, like g2o's forceStopFlag
     static_assert(sizeof(bool) == 1, "pbStopFlag is read as one byte");
-    const float K[4] = { pKF->fx, pKF->fy, pKF->cx, pKF->cy };   // KeyFrame::fx.. are per-object constants
+    const float K[4] = { pKF->fx, pKF->fy, pKF->cx, pKF->cy };
+    detail::set_camera_intrinsics(solver, cams);
     std::vector<uint8_t> edge_bad(edge_cam.size() ? edge_cam.size() : 1);
     int iters = 0;
     check(dvm_local_ba(solver, static_cast<int>(cams.size()), cam_q.data(), cam_t.data(), cam_fixed.data(),
@@ -243,6 +258,7 @@ void BundleAdjustment(dvm_lba* solver, const std::vector<KeyFrameT*>& vpKFs, con
     }
     if (edge_cam.empty()) return;
     const float K[4] = { cams[0]->fx, cams[0]->fy, cams[0]->cx, cams[0]->cy };
+    detail::set_camera_intrinsics(solver, cams);
     // const float thHuber2D = sqrt(5.99), :122 -- not LocalBundleAdjustment's sqrt(5.991)
     const float delta = bRobust ? static_cast<float>(std::sqrt(5.99)) : std::numeric_limits<float>::infinity();
     std::vector<uint8_t> edge_bad(edge_cam.size());
@@ -336,6 +352,7 @@ void LocalBundleAdjustment(dvm_lba* solver, KeyFrameT* pMainKF, std::vector<KeyF
 
     static_assert(sizeof(bool) == 1, "pbStopFlag is read as one byte");
     const float K[4] = { pMainKF->fx, pMainKF->fy, pMainKF->cx, pMainKF->cy };
+    detail::set_camera_intrinsics(solver, cams);
     std::vector<uint8_t> edge_bad(edge_cam.size());
     int iters = 0;
     check(dvm_merge_ba(solver, static_cast<int>(cams.size()), cam_q.data(), cam_t.data(), cam_fixed.data(),

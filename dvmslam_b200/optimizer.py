@@ -104,6 +104,13 @@ class LocalBA:
                     chi_first=stats[2], chi_last=stats[3], iters_first=int(stats[4]), excluded=int(stats[5]),
                     rc=iters.value, kernel_ms=self.kernel_ms())
 
+    def set_camera_intrinsics(self, cam_K):
+        """cam_K[nc][4] = fx, fy, cx, cy of every camera for the NEXT bundle-adjustment call (each edge is projected with its
+        own keyframe's camera, O3/src/Optimizer.cc:1219)."""
+        k = _c(cam_K, np.float32)
+        self.L.dvm_lba_set_camera_intrinsics.argtypes = [_vp, C.c_int, _vp]
+        check(self.L.dvm_lba_set_camera_intrinsics(self.h, len(k), k.ctypes.data))
+
     def kernel_ms(self) -> float:
         return float(self.L.dvm_lba_last_kernel_ms(self.h))
 
@@ -145,3 +152,44 @@ class Sim3Optimizer:
                                        C.c_float(th2), int(bFixScale), inl.ctypes.data, C.byref(n_in), st.ctypes.data))
         return dict(q=qq, t=tt, s=float(ss[0]), inlier=inl[:n], n_in=n_in.value, iters1=int(st[0]), iters2=int(st[1]),
                     trials=int(st[2]), n_bad=int(st[3]), chi_first=st[4], chi_last=st[5])
+
+
+class EssentialGraphOptimizer:
+    """The solve of Optimizer::OptimizeEssentialGraph (O3/src/Optimizer.cc:1389-1651) over the C-ABI
+    (dvm_optimize_essential_graph): Sim3 pose graph, numeric Jacobians, LM with lambda_init 1e-16, 20 iterations."""
+
+    def __init__(self, device: int = 0):
+        self.L = lib()
+        L = self.L
+        L.dvm_essential_graph_create.argtypes = [C.POINTER(_vp), C.c_int]
+        L.dvm_essential_graph_destroy.argtypes = [_vp]
+        L.dvm_essential_graph_destroy.restype = None
+        L.dvm_optimize_essential_graph.argtypes = [_vp, C.c_int, _vp, _vp, C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, C.c_double, _vp]
+        L.dvm_essential_graph_last_kernel_ms.argtypes = [_vp]
+        L.dvm_essential_graph_last_kernel_ms.restype = C.c_float
+        self.h = _vp()
+        check(L.dvm_essential_graph_create(C.byref(self.h), device))
+
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            self.L.dvm_essential_graph_destroy(self.h)
+            self.h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def OptimizeEssentialGraph(self, sim3, fixed, vi, vj, meas, bFixScale=False, iterations=20, lambda_init=1e-16):
+        """sim3 [nv, 8] (q xyzw, t, s) = Scw; edges (vi, vj, Sji [ne, 8]).  Returns dict(sim3, iters, trials, chi_first,
+        chi_last, kernel_ms)."""
+        S = _c(sim3, np.float64).copy()
+        fx = _c(fixed, np.uint8)
+        a, b = _c(vi, np.int32), _c(vj, np.int32)
+        m = _c(meas, np.float64)
+        st = np.zeros(4)
+        check(self.L.dvm_optimize_essential_graph(self.h, len(S), S.ctypes.data, fx.ctypes.data, len(a), a.ctypes.data, b.ctypes.data,
+                                                  m.ctypes.data, int(bFixScale), int(iterations), float(lambda_init), st.ctypes.data))
+        return dict(sim3=S, iters=int(st[0]), trials=int(st[1]), chi_first=st[2], chi_last=st[3],
+                    kernel_ms=float(self.L.dvm_essential_graph_last_kernel_ms(self.h)))

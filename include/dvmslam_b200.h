@@ -501,6 +501,12 @@ typedef struct dvm_lba dvm_lba;
 DVM_API int dvm_lba_create(dvm_lba** out, int device, int max_free_cameras);
 DVM_API void dvm_lba_destroy(dvm_lba* h);
 
+/* Intrinsics per camera for the NEXT dvm_local_ba / dvm_bundle_adjustment / dvm_merge_ba call on this handle (consumed by
+ * it): cam_K[nc][4] = fx, fy, cx, cy of every camera, as the reference projects each edge with its own keyframe's camera
+ * (e->pCamera = pKFi->mpCamera, O3/src/Optimizer.cc:1219) -- merged maps mix keyframes of agents with different
+ * calibrations.  Without it (or when nc does not match) every camera uses the call's K. */
+DVM_API int dvm_lba_set_camera_intrinsics(dvm_lba* h, int nc, const float* cam_K);
+
 /* The flattened local window that LocalBundleAdjustment assembles (O3/src/Optimizer.cc:1033-1304):
  *   cam_q[nc*4] (x,y,z,w) / cam_t[nc*3]: keyframe poses Tcw as float (KeyFrame::GetPose), in/out;
  *   cam_fixed[nc]: 1 for lFixedCameras and for the map's initial keyframe (vSE3->setFixed);
@@ -571,6 +577,25 @@ DVM_API int dvm_optimize_sim3(dvm_sim3* h, int n, const float* p1c, const float*
 
 /* Device time of the last dvm_local_ba kernel in milliseconds (CUDA events on the solver's stream). */
 DVM_API float dvm_lba_last_kernel_ms(const dvm_lba* h);
+
+/* ------------------------------------------------------------------------------------------------
+ * The solve of Optimizer::OptimizeEssentialGraph (O3/src/Optimizer.cc:1389-1651; the 4-DoF variant of :1653 differs only
+ * in its vertex / edge types and is not covered) on a flattened pose graph: Sim3 vertices, EdgeSim3 constraints with
+ * identity information, g2o's numeric Jacobians, Levenberg-Marquardt with setUserLambdaInit(lambda_init = 1e-16) for
+ * `iterations` (20) iterations -- one cooperative kernel, the reduced system factored densely over the whole GPU
+ * (csrc/essential_graph.cu).  sim3[nv][8] = Scw of every keyframe as (q x,y,z,w; t; s), in/out; fixed[nv] (the initial /
+ * loop keyframe: vSim3->setFixed(true), :1448-1449); edges (vi, vj, meas[ne][8]): vertex(0) = vi, vertex(1) = vj,
+ * measurement Sji (:1479-1592).  fix_scale = bFixScale (true for mono after inertial initialisation; false here).
+ * stats[4] = LM iterations, trials, initial chi2, final chi2.  The caller writes the poses back and corrects the map
+ * points (:1602-1650).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct dvm_essential_graph dvm_essential_graph;
+DVM_API int dvm_essential_graph_create(dvm_essential_graph** out, int device);
+DVM_API void dvm_essential_graph_destroy(dvm_essential_graph* h);
+DVM_API int dvm_optimize_essential_graph(dvm_essential_graph* h, int nv, double* sim3, const uint8_t* fixed, int ne,
+                                         const int32_t* vi, const int32_t* vj, const double* meas, int fix_scale,
+                                         int iterations, double lambda_init, double* stats);
+DVM_API float dvm_essential_graph_last_kernel_ms(const dvm_essential_graph* h);
 
 #ifdef __cplusplus
 }

@@ -14,6 +14,15 @@ def _c(a, dt):
     return np.ascontiguousarray(a, dt)
 
 
+def set_camera_intrinsics(cam_K):
+    """cam_K[nc][4] for the NEXT local_ba / merge_ba call of the oracle (mirrors dvm_lba_set_camera_intrinsics)."""
+    L = lib()
+    L.lbao_set_camera_intrinsics.argtypes = [C.c_int, _vp]
+    L.lbao_set_camera_intrinsics.restype = None
+    k = _c(cam_K, np.float32)
+    L.lbao_set_camera_intrinsics(len(k), k.ctypes.data)
+
+
 def local_ba(cam_q, cam_t, cam_fixed, pts, edge_cam, edge_pt, edge_obs, edge_w, K, iterations=10, abort=None,
              huber_delta=None):
     """Returns dict(cam_q, cam_t, pts, chi2, bad, iters, trials, chi_first, chi_last, rc).  huber_delta: None =

@@ -173,23 +173,29 @@ struct Problem {
     const int* ecam; const int* ept;
     std::vector<double> obs, info;
     double fx, fy, cx, cy, delta, dsqr;
+    std::vector<double> camK; /* [nc][4]: every camera's own intrinsics (e->pCamera = pKFi->mpCamera, Optimizer.cc:1219) */
     std::vector<double> err; /* ne*2: the edges' _error */
     std::vector<uint8_t> active; /* level-0 edges (all of them unless the welding BA moved some to level 1) */
 };
 
-void edge_project(const Problem& P, const SE3& T, const double* X, double xc[3], double uv[2])
+std::vector<float> g_next_cam_K;   /* lbao_set_camera_intrinsics: per-camera K for the next call (mirrors dvm_lba_set_camera_intrinsics) */
+
+void edge_project(const Problem& P, const SE3& T, const double* X, double xc[3], double uv[2], int cam = -1)
 {
     quat_rotate(T.r, X, xc);
     xc[0] += T.t[0]; xc[1] += T.t[1]; xc[2] += T.t[2];
-    uv[0] = P.fx * xc[0] / xc[2] + P.cx;
-    uv[1] = P.fy * xc[1] / xc[2] + P.cy;
+    const bool per = cam >= 0 && !P.camK.empty();
+    const double fx = per ? P.camK[4 * cam] : P.fx, fy = per ? P.camK[4 * cam + 1] : P.fy;
+    const double cx = per ? P.camK[4 * cam + 2] : P.cx, cy = per ? P.camK[4 * cam + 3] : P.cy;
+    uv[0] = fx * xc[0] / xc[2] + cx;
+    uv[1] = fy * xc[1] / xc[2] + cy;
 }
 void compute_errors(Problem& P)
 {
     for (int e = 0; e < P.ne; e++) {
         if (!P.active[e]) continue; /* computeActiveErrors: a level-1 edge keeps its last _error */
         double xc[3], uv[2];
-        edge_project(P, P.cam[P.ecam[e]], &P.pt[3 * P.ept[e]], xc, uv);
+        edge_project(P, P.cam[P.ecam[e]], &P.pt[3 * P.ept[e]], xc, uv, P.ecam[e]);
         P.err[2 * e] = P.obs[2 * e] - uv[0];
         P.err[2 * e + 1] = P.obs[2 * e + 1] - uv[1];
     }
@@ -268,6 +274,8 @@ static int run_ba(int nc, float* cam_q, float* cam_t, const uint8_t* cam_fixed, 
     for (int i = 0; i < 2 * ne; i++) P.obs[i] = edge_obs[i];
     for (int i = 0; i < ne; i++) P.info[i] = edge_inv_sigma2[i];
     P.fx = K[0]; P.fy = K[1]; P.cx = K[2]; P.cy = K[3];
+    if ((int)g_next_cam_K.size() == 4 * nc) P.camK.assign(g_next_cam_K.begin(), g_next_cam_K.end());
+    g_next_cam_K.clear();
     P.delta = huber_delta; P.dsqr = P.delta * P.delta;
 
     const int nf = P.nfree, dimP = 6 * nf, dimL = 3 * np;
@@ -309,10 +317,11 @@ static int run_ba(int nc, float* cam_q, float* cam_t, const uint8_t* cam_fixed, 
             const int c = P.ecam[e], l = P.ept[e], col = P.cam_col[c];
             const SE3& T = P.cam[c];
             double xc[3], uv[2];
-            edge_project(P, T, &P.pt[3 * l], xc, uv);
+            edge_project(P, T, &P.pt[3 * l], xc, uv, c);
             const double X = xc[0], Y = xc[1], Z = xc[2];
+            const double fxc = P.camK.empty() ? P.fx : P.camK[4 * c], fyc = P.camK.empty() ? P.fy : P.camK[4 * c + 1];
             /* projectJac = -pCamera->projectJac(xyz_trans) */
-            const double pj[6] = { -(P.fx / Z), -0.0, -(-P.fx * X / (Z * Z)), -0.0, -(P.fy / Z), -(-P.fy * Y / (Z * Z)) };
+            const double pj[6] = { -(fxc / Z), -0.0, -(-fxc * X / (Z * Z)), -0.0, -(fyc / Z), -(-fyc * Y / (Z * Z)) };
             double R[9];
             quat_to_matrix(T.r, R);
             double A[6], B[12]; /* A: 2x3 wrt the point, B: 2x6 wrt the pose */
@@ -496,6 +505,9 @@ int lbao_merge_ba(int nc, float* cam_q, float* cam_t, const uint8_t* cam_fixed, 
     return run_ba(nc, cam_q, cam_t, cam_fixed, np, pts, ne, edge_cam, edge_pt, edge_obs, edge_inv_sigma2, K, 5,
                   (float)std::sqrt(5.99), 10, abort_flag, edge_chi2_out, edge_bad, stats);
 }
+
+/* per-camera intrinsics camK[nc][4] for the NEXT lbao_bundle_adjustment / lbao_merge_ba call */
+void lbao_set_camera_intrinsics(int nc, const float* camK) { g_next_cam_K.assign(camK, camK + (size_t)4 * nc); }
 
 /* analytic Jacobians of one edge, for the finite-difference self-check */
 void lbao_edge_jacobians(const float* q, const float* t, const float* X, const float* K, double* A /*2x3*/, double* B /*2x6*/)

@@ -49,3 +49,34 @@ def test_too_few_survivors(opt):
     assert int((r["inlier"] == 0).sum()) == r["n_bad"]
     r = opt.OptimizeSim3(*[a[:0] if i < 6 else a for i, a in enumerate(_args(S))], th2=10.0)
     assert r["n_in"] == 0
+
+
+@pytest.mark.parametrize("n,seed,fix_scale,extra", [(16, 2, False, 0), (24, 0, False, 6), (40, 3, True, 10), (90, 5, False, 30)])
+def test_essential_graph_matches_oracle(n, seed, fix_scale, extra):
+    """The device solve of OptimizeEssentialGraph (Sim3 pose graph, numeric Jacobians with delta 1e-9, LM from lambda 1e-16,
+    dense Cholesky over the whole grid) against the oracle on closed trajectories with drift: same LM iteration and trial
+    counts, chi2 to 1e-5 relative (+ an absolute floor: the converged chi2 is ~1e-20 of the initial one and the numeric
+    Jacobians amplify last-bit differences by 1e9), poses to 1e-6.  `extra` adds covisibility-style edges between nearby
+    keyframes (a denser reduced system); n = 90 is a 630-unknown system (20 block columns of the Cholesky)."""
+    from dvmslam_b200.optimizer import EssentialGraphOptimizer
+    from oracle.sim3 import optimize_essential_graph
+    from tests.sim3_cases import loop_graph, sim3_inv, sim3_mul
+
+    est, fixed, vi, vj, meas, true = loop_graph(n, seed=seed)
+    rng = np.random.default_rng(seed)
+    vi, vj, meas = list(vi), list(vj), list(meas)
+    for _ in range(extra):
+        a = int(rng.integers(0, n))
+        b = (a + int(rng.integers(2, 5))) % n
+        vi.append(a); vj.append(b); meas.append(sim3_mul(est[b], sim3_inv(est[a])))
+    vi, vj, meas = np.array(vi, np.int32), np.array(vj, np.int32), np.array(meas)
+    r0 = optimize_essential_graph(est, fixed, vi, vj, meas, fix_scale=fix_scale)
+    opt = EssentialGraphOptimizer()
+    r1 = opt.OptimizeEssentialGraph(est, fixed, vi, vj, meas, bFixScale=fix_scale)
+    opt.close()
+    assert abs(r1["chi_first"] - r0["chi_first"]) <= 1e-9 * r0["chi_first"]
+    assert r0["chi_last"] < 0.5 * r0["chi_first"]
+    assert (r1["iters"], r1["trials"]) == (r0["iters"], r0["trials"]), (r0["iters"], r0["trials"], r1["iters"], r1["trials"])
+    assert abs(r1["chi_last"] - r0["chi_last"]) <= 1e-5 * r0["chi_last"] + 1e-12 * r0["chi_first"]
+    assert np.abs(r1["sim3"] - r0["sim3"]).max() < 1e-6
+    assert np.array_equal(r1["sim3"][0], est[0])   # the fixed keyframe is untouched
