@@ -263,6 +263,120 @@ def ba_scene(n_free: int = 50, n_fixed: int = 10, n_points: int = 5000, seed: in
                 q_true=q_true, t_true=t_true, pts_true=P)
 
 
+def ba_scene_large(n_free: int = 399, n_fixed: int = 1, n_points: int = 20000, seed: int = 0, K=RPI_K, w: int = 1280, h: int = 720,
+                   max_obs: int = 12, pix_sigma: float = 1.0, outlier_frac: float = 0.02, pose_noise=(0.02, np.deg2rad(0.5)),
+                   point_noise: float = 0.05):
+    """The geometry of ba_scene for MERGED maps (config C5: hundreds of keyframes), generated with array operations instead of
+    per-point loops (not stream-compatible with ba_scene's seeds).  Same layout of the returned arrays; edges grouped by point."""
+    rng = np.random.default_rng(seed)
+    fx, fy, cx, cy = K
+    nc = n_free + n_fixed
+    ang = rng.permutation(np.sort(rng.uniform(0, 2 * np.pi, nc)))
+    C = np.stack([6.0 * np.cos(ang), rng.uniform(-0.5, 0.5, nc), 6.0 * np.sin(ang)], 1)
+    z = -C / np.linalg.norm(C, axis=1, keepdims=True)
+    x = np.cross(np.array([0.0, 1.0, 0.0]), z)
+    x /= np.linalg.norm(x, axis=1, keepdims=True)
+    y = np.cross(z, x)
+    Rs = np.stack([x, y, z], 1)                     # [nc, 3, 3] rows = camera axes
+    ts = -np.einsum("cij,cj->ci", Rs, C)
+    P = rng.uniform(-3.0, 3.0, (n_points, 3))
+    e_cam, e_pt, e_u, e_v = [], [], [], []
+    for lo in range(0, n_points, 2048):             # chunks bound the [points, cameras] temporaries
+        Pc = P[lo:lo + 2048]
+        Xc = np.einsum("cij,pj->pci", Rs, Pc) + ts[None]
+        u = fx * Xc[..., 0] / Xc[..., 2] + cx
+        v = fy * Xc[..., 1] / Xc[..., 2] + cy
+        vis = (Xc[..., 2] >= 0.5) & (u >= 0) & (u < w) & (v >= 0) & (v < h)
+        key = np.where(vis, rng.random(vis.shape), 2.0)       # keep at most max_obs random visible cameras per point
+        kth = np.sort(key, axis=1)[:, min(max_obs, nc) - 1][:, None]
+        keep = vis & (key <= kth)
+        pi, ci = np.nonzero(keep)
+        e_pt.append(pi + lo); e_cam.append(ci); e_u.append(u[pi, ci]); e_v.append(v[pi, ci])
+    e_pt, e_cam = np.concatenate(e_pt), np.concatenate(e_cam).astype(np.int32)
+    ne = len(e_pt)
+    octv = rng.integers(0, 8, ne)
+    sig = pix_sigma * 1.2 ** octv
+    noise = rng.normal(0, 1, (ne, 2)) * sig[:, None]
+    out = rng.random(ne) < outlier_frac
+    noise[out] = rng.uniform(-50, 50, (int(out.sum()), 2))
+    obs = (np.stack([np.concatenate(e_u), np.concatenate(e_v)], 1) + noise).astype(np.float32)
+    e_w = (np.float32(1.0) / (np.float32(1.2) ** octv.astype(np.float32)) ** 2).astype(np.float32)
+    seen = np.unique(e_pt)
+    remap = -np.ones(n_points, np.int64)
+    remap[seen] = np.arange(len(seen))
+    e_pt = remap[e_pt].astype(np.int32)
+    P = P[seen]
+    q = np.zeros((nc, 4), np.float32)
+    t = np.zeros((nc, 3), np.float32)
+    for c in range(nc):
+        R, tt = Rs[c], ts[c]
+        if c < n_free:
+            wv = rng.normal(0, 1, 3)
+            wv *= pose_noise[1] / np.linalg.norm(wv)
+            th = np.linalg.norm(wv)
+            Kx = np.array([[0, -wv[2], wv[1]], [wv[2], 0, -wv[0]], [-wv[1], wv[0], 0]])
+            R = (np.eye(3) + np.sin(th) / th * Kx + (1 - np.cos(th)) / th ** 2 * Kx @ Kx) @ R
+            tt = tt + rng.normal(0, pose_noise[0] / np.sqrt(3), 3)
+        q[c], t[c] = quat_from_R(R), tt
+    fixed = np.zeros(nc, np.uint8)
+    fixed[n_free:] = 1
+    pts = (P + rng.normal(0, point_noise / np.sqrt(3), P.shape)).astype(np.float32)
+    return dict(cam_q=q, cam_t=t, cam_fixed=fixed, pts=pts, edge_cam=e_cam, edge_pt=e_pt, edge_obs=obs.reshape(-1), edge_w=e_w,
+                K=np.array(K, np.float32), pts_true=P)
+
+
+def sim3_mul(a, b):
+    """Sim3 product on (q xyzw, t, s) rows, g2o::Sim3::operator*."""
+    def qmul(p, q):
+        x1, y1, z1, w1 = p
+        x2, y2, z2, w2 = q
+        return np.array([w1 * x2 + x1 * w2 + y1 * z2 - z1 * y2, w1 * y2 + y1 * w2 + z1 * x2 - x1 * z2,
+                         w1 * z2 + z1 * w2 + x1 * y2 - y1 * x2, w1 * w2 - x1 * x2 - y1 * y2 - z1 * z2])
+
+    def rot(q, v):
+        uv = 2 * np.cross(q[:3], v)
+        return v + q[3] * uv + np.cross(q[:3], uv)
+    return np.concatenate([qmul(a[:4], b[:4]), a[7] * rot(a[:4], b[4:7]) + a[4:7], [a[7] * b[7]]])
+
+
+def sim3_inv(a):
+    qc = np.array([-a[0], -a[1], -a[2], a[3]])
+    v = (-1.0 / a[7]) * a[4:7]
+    uv = 2 * np.cross(qc[:3], v)
+    return np.concatenate([qc, v + qc[3] * uv + np.cross(qc[:3], uv), [1.0 / a[7]]])
+
+
+def _sim3_from(rotvec, t, log_s):
+    th = np.linalg.norm(rotvec)
+    q = np.array([0.0, 0.0, 0.0, 1.0]) if th < 1e-12 else np.concatenate([np.sin(th / 2) * np.asarray(rotvec) / th, [np.cos(th / 2)]])
+    return np.concatenate([q, np.asarray(t, np.float64), [np.exp(log_s)]])
+
+
+def loop_pose_graph(n: int = 400, seed: int = 0, drift=(0.002, 0.005, 0.0015), covis_edges: int = 2):
+    """Config C5's essential graph: `n` keyframes of a closed trajectory (8 agents x 50 keyframes after the merge), estimates
+    with accumulating similarity drift, spanning-tree edges taken from the drifted estimates, `covis_edges` extra edges
+    per keyframe to earlier neighbours (covisibility >= 100) and one loop edge from the truth.
+    -> (sim3 [n, 8] Scw estimates, fixed [n], vi, vj, meas [ne, 8] = Sji, truth [n, 8])."""
+    rng = np.random.default_rng(seed)
+    true = [_sim3_from([0, 2 * np.pi * k / n, 0], [3 * np.cos(2 * np.pi * k / n), 0.1 * np.sin(6 * np.pi * k / n), 3 * np.sin(2 * np.pi * k / n)], 0.0)
+            for k in range(n)]
+    est = [true[0].copy()]
+    D = _sim3_from([0, 0, 0], [0, 0, 0], 0.0)
+    for k in range(1, n):
+        D = sim3_mul(_sim3_from(rng.normal(0, drift[0], 3), rng.normal(0, drift[1], 3), rng.normal(0, drift[2])), D)
+        est.append(sim3_mul(D, true[k]))
+    vi, vj, meas = [], [], []
+    for k in range(1, n):                       # vertex(0) = child k, vertex(1) = parent k - 1, Sji = Sjw * Swi
+        vi.append(k); vj.append(k - 1); meas.append(sim3_mul(est[k - 1], sim3_inv(est[k])))
+        for d in range(2, 2 + covis_edges):
+            if k - d >= 0:
+                vi.append(k); vj.append(k - d); meas.append(sim3_mul(est[k - d], sim3_inv(est[k])))
+    vi.append(n - 1); vj.append(0); meas.append(sim3_mul(true[0], sim3_inv(true[n - 1])))   # the loop closure
+    fixed = np.zeros(n, np.uint8)
+    fixed[0] = 1
+    return np.array(est), fixed, np.array(vi, np.int32), np.array(vj, np.int32), np.array(meas), np.array(true)
+
+
 class OrbitStream(PlaneStream):
     """Bounded variant of the C2 stream for long runs: the camera sways over the same textured plane
     (x = A sin, yaw = B sin, period `period` frames) so that frame `period` equals frame 0 and the
