@@ -12,6 +12,7 @@
 #include <tuple>
 #include <unordered_map>
 #include <utility>
+#include <set>
 #include <vector>
 
 #include "orb_matcher_adapter.h"
@@ -457,6 +458,180 @@ int OptimizeSim3(dvm_sim3* solver, KeyFrameT* pKF1, KeyFrameT* pKF2, std::vector
     for (int k = 0; k < 3; k++) g2oS12.translation()(k) = t[k];
     g2oS12.scale() = s;
     return nIn;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// void Optimizer::OptimizeEssentialGraph(Map* pMap, KeyFrame* pLoopKF, KeyFrame* pCurKF,
+//        const LoopClosing::KeyFrameAndPose& NonCorrectedSim3, const LoopClosing::KeyFrameAndPose& CorrectedSim3,
+//        const map<KeyFrame*, set<KeyFrame*>>& LoopConnections, const bool& bFixScale)                     :1389-1651
+// The graph is flattened exactly as the reference assembles it (vertices :1419-1452; loop-connection edges :1460-1488;
+// per keyframe the spanning-tree edge :1507-1528, earlier loop edges :1530-1552, covisibility >= 100 edges :1554-1585;
+// inertial edges are out of scope with the rest of the IMU path), solved on the device, and written back: keyframe poses
+// Sim3 -> SE3 [R, t / s] (:1602-1615) and map points through their reference keyframe (:1619-1647).
+// solver: one dvm_essential_graph context per loop-closing thread.  KeyFrameAndPoseT = map<KeyFrame*, g2o::Sim3>.
+// ---------------------------------------------------------------------------------------------------
+namespace detail {
+struct S3 {   // g2o::Sim3 arithmetic in double on the host (g2o/types/sim3.h: operator*, inverse, map)
+    double q[4], t[3], s;
+    static void rot(const double q[4], const double v[3], double o[3])
+    {
+        double uv[3] = { q[1] * v[2] - q[2] * v[1], q[2] * v[0] - q[0] * v[2], q[0] * v[1] - q[1] * v[0] };
+        uv[0] += uv[0]; uv[1] += uv[1]; uv[2] += uv[2];
+        o[0] = v[0] + q[3] * uv[0] + (q[1] * uv[2] - q[2] * uv[1]);
+        o[1] = v[1] + q[3] * uv[1] + (q[2] * uv[0] - q[0] * uv[2]);
+        o[2] = v[2] + q[3] * uv[2] + (q[0] * uv[1] - q[1] * uv[0]);
+    }
+    S3 operator*(const S3& b) const
+    {
+        S3 r;
+        r.q[3] = q[3] * b.q[3] - q[0] * b.q[0] - q[1] * b.q[1] - q[2] * b.q[2];
+        r.q[0] = q[3] * b.q[0] + q[0] * b.q[3] + q[1] * b.q[2] - q[2] * b.q[1];
+        r.q[1] = q[3] * b.q[1] + q[1] * b.q[3] + q[2] * b.q[0] - q[0] * b.q[2];
+        r.q[2] = q[3] * b.q[2] + q[2] * b.q[3] + q[0] * b.q[1] - q[1] * b.q[0];
+        double rt[3];
+        rot(q, b.t, rt);
+        for (int i = 0; i < 3; i++) r.t[i] = s * rt[i] + t[i];
+        r.s = s * b.s;
+        return r;
+    }
+    S3 inverse() const
+    {
+        S3 r;
+        r.q[0] = -q[0]; r.q[1] = -q[1]; r.q[2] = -q[2]; r.q[3] = q[3];
+        const double v[3] = { (-1. / s) * t[0], (-1. / s) * t[1], (-1. / s) * t[2] };
+        rot(r.q, v, r.t);
+        r.s = 1. / s;
+        return r;
+    }
+    void map(const double p[3], double o[3]) const
+    {
+        double rp[3];
+        rot(q, p, rp);
+        for (int i = 0; i < 3; i++) o[i] = s * rp[i] + t[i];
+    }
+    template <class Sim3T> static S3 from(const Sim3T& g)
+    {
+        S3 r;
+        Sim3T& m = const_cast<Sim3T&>(g);
+        r.q[0] = m.rotation().x(); r.q[1] = m.rotation().y(); r.q[2] = m.rotation().z(); r.q[3] = m.rotation().w();
+        for (int i = 0; i < 3; i++) r.t[i] = m.translation()(i);
+        r.s = m.scale();
+        return r;
+    }
+};
+} // namespace detail
+
+template <class MapT, class KeyFrameT, class KeyFrameAndPoseT>
+void OptimizeEssentialGraph(dvm_essential_graph* solver, MapT* pMap, KeyFrameT* pLoopKF, KeyFrameT* pCurKF,
+                            const KeyFrameAndPoseT& NonCorrectedSim3, const KeyFrameAndPoseT& CorrectedSim3,
+                            const std::map<KeyFrameT*, std::set<KeyFrameT*>>& LoopConnections, const bool& bFixScale)
+{
+    using detail::S3;
+    const std::vector<KeyFrameT*> vpKFs = pMap->GetAllKeyFrames();
+    const auto vpMPs = pMap->GetAllMapPoints();
+    const unsigned int nMaxKFid = pMap->GetMaxKFid();
+    std::vector<S3> vScw(nMaxKFid + 1), vCorrectedSwc(nMaxKFid + 1);
+    std::vector<int> vertex_of(nMaxKFid + 1, -1);     // keyframe id -> vertex index of the flattened graph
+    const int minFeat = 100;
+    std::vector<double> sim3;
+    std::vector<uint8_t> fixed;
+    std::vector<KeyFrameT*> vertex_kf;
+    for (KeyFrameT* pKF : vpKFs) {                                                        // :1419-1452
+        if (pKF->isBad()) continue;
+        const int nIDi = static_cast<int>(pKF->mnId);
+        const auto it = CorrectedSim3.find(pKF);
+        S3 Siw;
+        if (it != CorrectedSim3.end()) Siw = S3::from(it->second);
+        else {   // g2o::Sim3 Siw(Tcw.unit_quaternion(), Tcw.translation(), 1.0) of the pose cast to double
+            const auto Tcw = pKF->GetPose();
+            const auto uq = Tcw.unit_quaternion();
+            const auto tr = Tcw.translation();
+            Siw.q[0] = uq.x(); Siw.q[1] = uq.y(); Siw.q[2] = uq.z(); Siw.q[3] = uq.w();
+            for (int k = 0; k < 3; k++) Siw.t[k] = tr(k);
+            Siw.s = 1.0;
+        }
+        vScw[nIDi] = Siw;
+        vertex_of[nIDi] = static_cast<int>(vertex_kf.size());
+        vertex_kf.push_back(pKF);
+        for (int k = 0; k < 4; k++) sim3.push_back(Siw.q[k]);
+        for (int k = 0; k < 3; k++) sim3.push_back(Siw.t[k]);
+        sim3.push_back(Siw.s);
+        fixed.push_back(pKF->mnId == pMap->GetInitKFid());
+    }
+    std::vector<int32_t> vi, vj;
+    std::vector<double> meas;
+    auto add_edge = [&](long unsigned int idi, long unsigned int idj, const S3& Sji) {     // vertex(0) = i, vertex(1) = j
+        if (vertex_of[idi] < 0 || vertex_of[idj] < 0) return;   // optimizer.vertex(id) of a bad keyframe is null in the reference
+        vi.push_back(vertex_of[idi]); vj.push_back(vertex_of[idj]);
+        for (int k = 0; k < 4; k++) meas.push_back(Sji.q[k]);
+        for (int k = 0; k < 3; k++) meas.push_back(Sji.t[k]);
+        meas.push_back(Sji.s);
+    };
+    std::set<std::pair<long unsigned int, long unsigned int>> sInsertedEdges;
+    for (const auto& mit : LoopConnections) {                                             // :1460-1488
+        KeyFrameT* pKF = mit.first;
+        const long unsigned int nIDi = pKF->mnId;
+        const S3 Swi = vScw[nIDi].inverse();
+        for (KeyFrameT* pKFj : mit.second) {
+            const long unsigned int nIDj = pKFj->mnId;
+            if ((nIDi != pCurKF->mnId || nIDj != pLoopKF->mnId) && pKF->GetWeight(pKFj) < minFeat) continue;
+            add_edge(nIDi, nIDj, vScw[nIDj] * Swi);
+            sInsertedEdges.insert(std::make_pair(std::min(nIDi, nIDj), std::max(nIDi, nIDj)));
+        }
+    }
+    auto non_corrected = [&](KeyFrameT* k) {   // Sjw = NonCorrectedSim3[k] if present, else vScw[k]
+        const auto it = NonCorrectedSim3.find(k);
+        return it != NonCorrectedSim3.end() ? S3::from(it->second) : vScw[k->mnId];
+    };
+    for (KeyFrameT* pKF : vpKFs) {                                                        // :1491-1592
+        const long unsigned int nIDi = pKF->mnId;
+        const S3 Swi = non_corrected(pKF).inverse();
+        KeyFrameT* pParentKF = pKF->GetParent();
+        if (pParentKF) add_edge(nIDi, pParentKF->mnId, non_corrected(pParentKF) * Swi);  // spanning tree
+        for (KeyFrameT* pLKF : pKF->GetLoopEdges())                                       // earlier loop edges
+            if (pLKF->mnId < pKF->mnId) add_edge(nIDi, pLKF->mnId, non_corrected(pLKF) * Swi);
+        for (KeyFrameT* pKFn : pKF->GetCovisiblesByWeight(minFeat)) {                     // covisibility graph
+            if (pKFn && pKFn != pParentKF && !pKF->hasChild(pKFn)) {
+                if (!pKFn->isBad() && pKFn->mnId < pKF->mnId) {
+                    if (sInsertedEdges.count(std::make_pair(std::min(pKF->mnId, pKFn->mnId), std::max(pKF->mnId, pKFn->mnId)))) continue;
+                    add_edge(nIDi, pKFn->mnId, non_corrected(pKFn) * Swi);
+                }
+            }
+        }
+    }
+    double stats[4];
+    check(dvm_optimize_essential_graph(solver, static_cast<int>(vertex_kf.size()), sim3.data(), fixed.data(), static_cast<int>(vi.size()),
+                                       vi.data(), vj.data(), meas.data(), bFixScale ? 1 : 0, 20, 1e-16, stats),
+          "Optimizer::OptimizeEssentialGraph");
+    std::unique_lock<std::mutex> lock(pMap->mMutexMapUpdate);
+    for (size_t v = 0; v < vertex_kf.size(); v++) {                                       // :1602-1615
+        KeyFrameT* pKFi = vertex_kf[v];
+        S3 C;
+        for (int k = 0; k < 4; k++) C.q[k] = sim3[8 * v + k];
+        for (int k = 0; k < 3; k++) C.t[k] = sim3[8 * v + 4 + k];
+        C.s = sim3[8 * v + 7];
+        vCorrectedSwc[pKFi->mnId] = C.inverse();
+        // Sophus::SE3f Tiw(CorrectedSiw.rotation().cast<float>(), CorrectedSiw.translation().cast<float>() / s)
+        float qf[4], tf[3];
+        for (int k = 0; k < 4; k++) qf[k] = static_cast<float>(C.q[k]);
+        for (int k = 0; k < 3; k++) tf[k] = static_cast<float>(C.t[k]) / static_cast<float>(C.s);   // Vector3f / scalar
+        pKFi->SetPose(pose_from_floats(pKFi->GetPose(), qf, tf));
+    }
+    for (auto* pMP : vpMPs) {                                                             // :1619-1647
+        if (pMP->isBad()) continue;
+        const long unsigned int nIDr = pMP->mnCorrectedByKF == pCurKF->mnId ? pMP->mnCorrectedReference
+                                                                               : pMP->GetReferenceKeyFrame()->mnId;
+        const auto p = pMP->GetWorldPos();
+        const double P[3] = { p(0), p(1), p(2) };
+        double a[3], b[3];
+        vScw[nIDr].map(P, a);
+        vCorrectedSwc[nIDr].map(a, b);
+        auto np = p;
+        for (int k = 0; k < 3; k++) np(k) = static_cast<float>(b[k]);
+        pMP->SetWorldPos(np);
+        pMP->UpdateNormalAndDepth();
+    }
+    pMap->IncreaseChangeIndex();
 }
 
 } // namespace dvm_host

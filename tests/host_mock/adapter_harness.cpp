@@ -473,6 +473,57 @@ int hm_search_by_sim3(const dvm_keypoint* kps1, const uint8_t* desc1, int n1, co
     });
 }
 
+
+// OptimizeEssentialGraph through the adapter on a chain of n keyframes (parent of k = k - 1, keyframe 0 = the map's initial
+// keyframe and the loop keyframe, keyframe n - 1 = the current keyframe with its Sim3 correction and a loop connection to 0;
+// covis[k] >= 100 adds a covisibility edge k -> k - 2).  poses[n][7] = q, t in/out; points[m][3] in/out, point_ref[m] = id of the
+// point's reference keyframe.
+int hm_optimize_essential_graph(int n, float* poses, const double* corrected_last, const double* noncorrected_last, const int* covis,
+                                int m, float* points, const int* point_ref, int fix_scale)
+{
+    Map map;
+    std::vector<std::unique_ptr<KeyFrame>> kfs(n);
+    for (int k = 0; k < n; k++) {
+        kfs[k].reset(new KeyFrame);
+        kfs[k]->mnId = (unsigned long)k; kfs[k]->map = &map;
+        set_pose(kfs[k]->Tcw, poses + 7 * k, poses + 7 * k + 4);
+        map.keyframes.push_back(kfs[k].get());
+    }
+    for (int k = 1; k < n; k++) {
+        kfs[k]->parent = kfs[k - 1].get();
+        kfs[k - 1]->children.insert(kfs[k].get());
+        if (k >= 2 && covis[k] >= 100) { kfs[k]->weights[kfs[k - 2].get()] = covis[k]; kfs[k - 2]->weights[kfs[k].get()] = covis[k]; }
+    }
+    map.initKFid = 0;
+    std::vector<std::unique_ptr<MapPoint>> mps(m);
+    for (int i = 0; i < m; i++) {
+        mps[i].reset(new MapPoint);
+        for (int k = 0; k < 3; k++) mps[i]->pos(k) = points[3 * i + k];
+        mps[i]->refKF = kfs[point_ref[i]].get();
+        map.mappoints.push_back(mps[i].get());
+    }
+    auto to_sim3 = [](const double* p) { mock::Sim3 S; for (int k = 0; k < 4; k++) S.r.q[k] = p[k]; for (int k = 0; k < 3; k++) S.t.v[k] = p[4 + k]; S.s = p[7]; return S; };
+    std::map<KeyFrame*, mock::Sim3> corrected, noncorrected;
+    corrected[kfs[n - 1].get()] = to_sim3(corrected_last);
+    noncorrected[kfs[n - 1].get()] = to_sim3(noncorrected_last);
+    std::map<KeyFrame*, std::set<KeyFrame*>> loopConnections;
+    loopConnections[kfs[n - 1].get()].insert(kfs[0].get());
+    dvm_essential_graph* solver = nullptr;
+    const int rc = guarded([&] {
+        dvm_host::check(dvm_essential_graph_create(&solver, dvm_host::device_from_env()), "dvm_essential_graph_create");
+        dvm_host::OptimizeEssentialGraph(solver, &map, kfs[0].get(), kfs[n - 1].get(), noncorrected, corrected, loopConnections, fix_scale != 0);
+        for (int k = 0; k < n; k++) {
+            for (int i = 0; i < 4; i++) poses[7 * k + i] = kfs[k]->Tcw.q.q[i];
+            for (int i = 0; i < 3; i++) poses[7 * k + 4 + i] = kfs[k]->Tcw.t(i);
+        }
+        for (int i = 0; i < m; i++)
+            for (int k = 0; k < 3; k++) points[3 * i + k] = mps[i]->pos(k);
+        return map.changeIndex;
+    });
+    dvm_essential_graph_destroy(solver);
+    return rc;
+}
+
 } // extern "C"
 
 // DBoW2::BowVector / FeatureVector with the reference's method semantics (DBoW2/BowVector.cpp:30-71,

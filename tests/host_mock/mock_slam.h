@@ -3,6 +3,7 @@
 // O3/include/{Frame,KeyFrame,MapPoint,Map}.h), so the adapters can be compiled and driven without Eigen,
 // Sophus, DBoW2 and the rest of ORB-SLAM3.
 #pragma once
+#include <algorithm>
 #include <map>
 #include <mutex>
 #include <opencv2/opencv.hpp>
@@ -120,6 +121,10 @@ struct MapPoint {
     std::map<KeyFrame*, std::tuple<int, int>> GetObservations() const { return observations; }
     void EraseObservation(KeyFrame* kf) { observations.erase(kf); }
     void UpdateNormalAndDepth() { normalUpdates++; }
+    // loop-closing bookkeeping read by OptimizeEssentialGraph
+    unsigned long mnCorrectedByKF = ~0ul, mnCorrectedReference = 0;
+    KeyFrame* refKF = nullptr;
+    KeyFrame* GetReferenceKeyFrame() const { return refKF; }
 };
 
 typedef std::map<unsigned int, std::vector<unsigned int>> FeatureVector;   // DBoW2::FeatureVector
@@ -176,6 +181,20 @@ struct KeyFrame {
     {
         for (auto& p : mapPoints) if (p == mp) p = nullptr;
     }
+    // spanning tree / loop edges / covisibility graph as OptimizeEssentialGraph reads them
+    KeyFrame* parent = nullptr;
+    std::set<KeyFrame*> children, loopEdges;
+    std::map<KeyFrame*, int> weights;
+    KeyFrame* GetParent() const { return parent; }
+    std::set<KeyFrame*> GetLoopEdges() const { return loopEdges; }
+    bool hasChild(KeyFrame* k) const { return children.count(k) != 0; }
+    int GetWeight(KeyFrame* k) const { const auto it = weights.find(k); return it == weights.end() ? 0 : it->second; }
+    std::vector<KeyFrame*> GetCovisiblesByWeight(int w) const
+    {
+        std::vector<KeyFrame*> v;
+        for (const auto& kv : weights) if (kv.second >= w) v.push_back(kv.first);
+        return v;
+    }
 };
 
 struct Map {
@@ -186,6 +205,11 @@ struct Map {
     KeyFrame* originKF = nullptr;
     KeyFrame* GetOriginKF() const { return originKF; }
     void IncreaseChangeIndex() { changeIndex++; }
+    std::vector<KeyFrame*> keyframes;
+    std::vector<MapPoint*> mappoints;
+    std::vector<KeyFrame*> GetAllKeyFrames() const { return keyframes; }
+    std::vector<MapPoint*> GetAllMapPoints() const { return mappoints; }
+    unsigned long GetMaxKFid() const { unsigned long m = 0; for (auto* k : keyframes) m = std::max(m, (unsigned long)k->mnId); return m; }
 };
 
 } // namespace mock

@@ -557,3 +557,62 @@ def test_sim3_matcher_adapters_match_oracle(libs):
     sides = [(s["skip" + t], s["xw" + t], s["min" + t], s["max" + t], s["mpdesc" + t]) for t in "12"]
     n0, m0 = search_by_sim3(A0, B0, s["q1"], s["t1"], s["q2"], s["t2"], s["s12q"], s["s12t"], s["K"], ls, 8, *sides, 7.5)
     assert r == n0 and np.array_equal(m12, m0) and n0 > 50
+
+
+@pytest.mark.gpu
+def test_essential_graph_adapter(libs):
+    """Optimizer::OptimizeEssentialGraph through the adapter on a chain of mock keyframes with a Sim3-corrected current
+    keyframe, a loop connection and covisibility edges: the adapter must assemble the graph the reference's way (vertex
+    estimates from CorrectedSim3 / poses, loop-connection edge from the corrected poses, spanning-tree / covisibility edges
+    from the non-corrected ones), solve it on the device and write keyframe poses ([R, t / s]) and map points back -- equal
+    to the same graph flattened here and sent through the C-ABI."""
+    from dvmslam_b200.optimizer import EssentialGraphOptimizer
+
+    H, _ = libs
+    n = 30
+    est, fixed, _, _, _, true = synth.loop_pose_graph(n, seed=5, covis_edges=0)
+    poses = np.concatenate([est[:, :4], est[:, 4:7] / est[:, 7:8]], 1).astype(np.float32)   # keyframe poses are SE3: [R, t / s]
+    S = np.concatenate([poses.astype(np.float64), np.ones((n, 1))], 1)                      # ... read back as Sim3 of scale 1
+    corrected_last = true[n - 1].copy()
+    corrected_last[4:7] *= 1.1
+    corrected_last[7] = 1.1                                                                 # the loop closure's Sim3 (scale drift)
+    noncorrected_last = S[n - 1].copy()
+    covis = np.zeros(n, np.int32)
+    covis[5::3] = 150
+    covis[6::5] = 40                                                                        # below minFeat: no edge
+    rng = np.random.default_rng(0)
+    m = 200
+    pts = rng.uniform(-3, 3, (m, 3)).astype(np.float32)
+    ref = rng.integers(0, n, m).astype(np.int32)
+    # ---- the same graph, flattened as the reference assembles it ----
+    V = S.copy()
+    V[n - 1] = corrected_last
+    vi, vj, meas = [n - 1], [0], [synth.sim3_mul(V[0], synth.sim3_inv(V[n - 1]))]           # loop connection (cur -> loop keyframe)
+    nonc = S.copy()
+    nonc[n - 1] = noncorrected_last
+    for k in range(n):
+        Swi = synth.sim3_inv(nonc[k])
+        if k >= 1:
+            vi.append(k); vj.append(k - 1); meas.append(synth.sim3_mul(nonc[k - 1], Swi))
+        if k >= 2 and covis[k] >= 100:
+            vi.append(k); vj.append(k - 2); meas.append(synth.sim3_mul(nonc[k - 2], Swi))
+    fx = np.zeros(n, np.uint8)
+    fx[0] = 1
+    opt = EssentialGraphOptimizer()
+    r = opt.OptimizeEssentialGraph(V, fx, np.array(vi, np.int32), np.array(vj, np.int32), np.array(meas))
+    opt.close()
+    C = r["sim3"]
+    want_q = C[:, :4].astype(np.float32)
+    want_t = (C[:, 4:7].astype(np.float32) / C[:, 7:8].astype(np.float32)).astype(np.float32)
+    want_pts = np.zeros_like(pts)
+    for i in range(m):
+        a = synth.sim3_mul(V[ref[i]], np.concatenate([[0, 0, 0, 1.0], pts[i].astype(np.float64), [1.0]]))[4:7]
+        b = synth.sim3_mul(synth.sim3_inv(C[ref[i]]), np.concatenate([[0, 0, 0, 1.0], a, [1.0]]))[4:7]
+        want_pts[i] = b.astype(np.float32)
+    got_poses, got_pts = poses.copy(), pts.copy()
+    rc = H.hm_optimize_essential_graph(n, _p(got_poses), _p(corrected_last), _p(noncorrected_last), _p(covis), m, _p(got_pts), _p(ref), 0)
+    assert rc == 1, H.hm_last_error()           # Map::IncreaseChangeIndex called once
+    assert r["iters"] >= 1 and r["chi_last"] < r["chi_first"]
+    assert np.allclose(got_poses[:, :4], want_q, atol=1e-6) and np.allclose(got_poses[:, 4:], want_t, atol=1e-5)
+    assert np.allclose(got_pts, want_pts, atol=1e-4)
+    assert np.abs(got_poses - poses).max() > 1e-3   # the correction moved the trajectory
