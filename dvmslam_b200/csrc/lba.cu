@@ -925,7 +925,9 @@ static int run_ba(dvm_lba* h, int nc, float* cam_q, float* cam_t, const uint8_t*
     if (nfixed == 0) return DVM_OK;                 // "LBA aborted": no fixed keyframe (:1088-1091)
     if (abort_flag && *abort_flag) return DVM_OK;   // :1306-1308
     if (ne == 0 || nf + np == 0) return DVM_OK;
-    DVM_REQUIRE(nf <= h->max_free, "more free cameras than dvm_lba_create allowed");
+    // max_free_cameras of dvm_lba_create is a sizing hint, not a limit: a window with more free keyframes than the
+    // shared-memory panel of the one-cluster solve was sized for goes to the grid-wide solve
+    if (nf > kLbaMaxFree) { set_error("%d free keyframes exceed the dense reduced-camera solver's limit of %d", nf, kLbaMaxFree); return DVM_ERR_CAPACITY; }
     // one pass over the edges: validation, both histograms, and whether the edges already come grouped by point
     // (the reference creates them point by point, O3/src/Optimizer.cc:1182-1232, and so does the host adapter)
     std::vector<int>& pt_start = h->pt_start;
@@ -1048,7 +1050,11 @@ static int run_ba(dvm_lba* h, int nc, float* cam_q, float* cam_t, const uint8_t*
     memset(&P, 0, sizeof(P));
     P.nc = nc; P.nf = nf; P.np = np; P.ne = ne; P.dimP = dimP; P.dimPad = dimPad; P.iterations = iterations;
     P.iterations2 = iterations2;
-    P.grid_chol = nf > kLbaClusterFree ? 1 : 0;
+    {
+        const size_t n = (size_t)((6 * nf + kNB - 1) / kNB * kNB);
+        const size_t cluster_need = ((n + 8) * kPanelLd + 2 * kNB * kDiagLd + 64 * kNB) * sizeof(double);
+        P.grid_chol = (nf > kLbaClusterFree || cluster_need > h->smem_bytes) ? 1 : 0;
+    }
     P.level = iterations2 > 0 ? db + o_level : nullptr;
     P.camK = (const double*)(db + o_camk);
     P.delta = (double)huber_delta;   // the caller's float delta; +infinity = no robust kernel

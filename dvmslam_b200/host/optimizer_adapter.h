@@ -5,6 +5,7 @@
 // Mono observations only (mvuRight < 0, no second camera), like the C-ABI.
 #pragma once
 #include <cmath>
+#include <cstdio>
 #include <limits>
 #include <list>
 #include <map>
@@ -18,6 +19,21 @@
 #include "orb_matcher_adapter.h"
 
 namespace dvm_host {
+namespace detail {
+// The BA adapters run on worker threads of the reference (LocalMapping, the detached GBA thread of LoopClosing) where nothing
+// catches exceptions.  A window beyond the dense solver's capacity (DVM_ERR_CAPACITY: more than 2000 free keyframes) is
+// reported and treated like an aborted optimisation -- the map is left untouched -- instead of terminating the process.
+inline bool ba_ok(int rc, const char* what)
+{
+    if (rc == DVM_ERR_CAPACITY) {
+        std::fprintf(stderr, "dvmslam_b200: %s skipped: %s\n", what, dvm_last_error());
+        return false;
+    }
+    check(rc, what);
+    return true;
+}
+} // namespace detail
+
 namespace detail {
 // e->pCamera = pKFi->mpCamera (O3/src/Optimizer.cc:1219): every keyframe's own intrinsics go to the solver (merged maps
 // mix keyframes of agents with different calibrations)
@@ -180,12 +196,12 @@ void LocalBundleAdjustment(dvm_lba* solver, KeyFrameT* pKF, bool* pbStopFlag, Ma
     detail::set_camera_intrinsics(solver, cams);
     std::vector<uint8_t> edge_bad(edge_cam.size() ? edge_cam.size() : 1);
     int iters = 0;
-    check(dvm_local_ba(solver, static_cast<int>(cams.size()), cam_q.data(), cam_t.data(), cam_fixed.data(),
+    if (!detail::ba_ok(dvm_local_ba(solver, static_cast<int>(cams.size()), cam_q.data(), cam_t.data(), cam_fixed.data(),
                        static_cast<int>(pts.size()), xyz.data(), static_cast<int>(edge_cam.size()), edge_cam.data(),
                        edge_pt.data(), edge_obs.data(), edge_w.data(), K, 10,
                        reinterpret_cast<const volatile uint8_t*>(pbStopFlag), nullptr, edge_bad.data(),
                        nullptr, &iters),
-          "Optimizer::LocalBundleAdjustment");
+          "Optimizer::LocalBundleAdjustment")) return;
     if (iters < 0) return;
 
     // ---- cull and write back, :1313-1387 ----
@@ -210,7 +226,7 @@ void LocalBundleAdjustment(dvm_lba* solver, KeyFrameT* pKF, bool* pbStopFlag, Ma
 // void Optimizer::BundleAdjustment(const vector<KeyFrame*>& vpKFs, const vector<MapPoint*>& vpMP, int nIterations,
 //                                  bool* pbStopFlag, const unsigned long nLoopKF, const bool bRobust)   :55-356
 // (GlobalBundleAdjustemnt :46-53 passes every keyframe and map point of the map.)  For maps of up to the solver's
-// max_free_cameras keyframes (dense reduced camera system).  Mono observations only.
+// 2000 free keyframes (dense reduced camera system; larger maps are reported and left untouched).  Mono observations only.
 // ---------------------------------------------------------------------------------------------------
 template <class KeyFrameT, class MapPointT>
 void BundleAdjustment(dvm_lba* solver, const std::vector<KeyFrameT*>& vpKFs, const std::vector<MapPointT*>& vpMP, int nIterations,
@@ -264,11 +280,11 @@ void BundleAdjustment(dvm_lba* solver, const std::vector<KeyFrameT*>& vpKFs, con
     const float delta = bRobust ? static_cast<float>(std::sqrt(5.99)) : std::numeric_limits<float>::infinity();
     std::vector<uint8_t> edge_bad(edge_cam.size());
     int iters = 0;
-    check(dvm_bundle_adjustment(solver, static_cast<int>(cams.size()), cam_q.data(), cam_t.data(), cam_fixed.data(),
+    if (!detail::ba_ok(dvm_bundle_adjustment(solver, static_cast<int>(cams.size()), cam_q.data(), cam_t.data(), cam_fixed.data(),
                                 static_cast<int>(pts.size()), xyz.data(), static_cast<int>(edge_cam.size()), edge_cam.data(),
                                 edge_pt.data(), edge_obs.data(), edge_w.data(), K, nIterations, delta,
                                 reinterpret_cast<const volatile uint8_t*>(pbStopFlag), nullptr, edge_bad.data(), nullptr, &iters),
-          "Optimizer::BundleAdjustment");
+          "Optimizer::BundleAdjustment")) return;
     if (iters < 0) return;
     // recover optimised data, :250-356: the loop keyframe's own map gets the values directly, otherwise they are parked
     // in mTcwGBA / mPosGBA for the caller's propagation
@@ -356,11 +372,11 @@ void LocalBundleAdjustment(dvm_lba* solver, KeyFrameT* pMainKF, std::vector<KeyF
     detail::set_camera_intrinsics(solver, cams);
     std::vector<uint8_t> edge_bad(edge_cam.size());
     int iters = 0;
-    check(dvm_merge_ba(solver, static_cast<int>(cams.size()), cam_q.data(), cam_t.data(), cam_fixed.data(),
+    if (!detail::ba_ok(dvm_merge_ba(solver, static_cast<int>(cams.size()), cam_q.data(), cam_t.data(), cam_fixed.data(),
                        static_cast<int>(pts.size()), xyz.data(), static_cast<int>(edge_cam.size()), edge_cam.data(),
                        edge_pt.data(), edge_obs.data(), edge_w.data(), K, reinterpret_cast<const volatile uint8_t*>(pbStopFlag),
                        nullptr, edge_bad.data(), nullptr, &iters),
-          "Optimizer::LocalBundleAdjustment (welding)");
+          "Optimizer::LocalBundleAdjustment (welding)")) return;
     if (iters < 0) return;
 
     // ---- erase the flagged observations and write back, :3523-3674 ----

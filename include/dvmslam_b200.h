@@ -496,8 +496,11 @@ DVM_API int dvm_frame_is_in_frustum(dvm_frame* f, const float* pose_q, const flo
  * ---------------------------------------------------------------------------------------------- */
 typedef struct dvm_lba dvm_lba;
 
-/* One solver context per agent/GPU; buffers grow on demand.  max_free_cameras bounds the reduced
- * camera system (6 * max_free_cameras unknowns, dense). */
+/* One solver context per agent/GPU; buffers grow on demand.  max_free_cameras (1..2000) is a SIZING HINT for the
+ * one-cluster solve of the dense reduced camera system (6 unknowns per free keyframe), not a limit: windows of up to 100 free
+ * keyframes that fit the hint are factored by one 8-CTA cluster from shared memory (local BA: lowest latency), anything
+ * larger -- global BA over hundreds of keyframes -- by a blocked Cholesky over the whole GPU.  Calls with more than 2000
+ * free keyframes return DVM_ERR_CAPACITY (a 12000 x 12000 dense system; the reference's sparse solver has no such bound). */
 DVM_API int dvm_lba_create(dvm_lba** out, int device, int max_free_cameras);
 DVM_API void dvm_lba_destroy(dvm_lba* h);
 
@@ -527,7 +530,7 @@ DVM_API int dvm_local_ba(dvm_lba* h, int nc, float* cam_q, float* cam_t, const u
                          double* edge_chi2, uint8_t* edge_bad, double* stats, int* iters_done);
 /* void Optimizer::BundleAdjustment(vpKFs, vpMP, nIterations, pbStopFlag, nLoopKF, bRobust)
  * (O3/src/Optimizer.cc:55-356; GlobalBundleAdjustemnt :46-53 calls it with every keyframe and map point of the map)
- * for maps of up to max_free_cameras free keyframes: the same solver with the caller's Huber delta -- the
+ * for maps of up to 2000 free keyframes: the same solver with the caller's Huber delta -- the
  * reference uses (float)sqrt(5.99) here, not LocalBundleAdjustment's sqrt(5.991) -- or INFINITY for bRobust == false.
  * cam_fixed marks the map's initial keyframe (:116); map points without observation are left out by the caller
  * (:243-247).  Outputs as dvm_local_ba (the caller writes mTcwGBA / mPosGBA and ignores edge_bad). */
