@@ -521,11 +521,21 @@ __global__ void __cluster_dims__(kPoseCtas, 1, 1) __launch_bounds__(kPoseThreads
         a.result[3] = total_trials;
         if (a.prof) { a.prof[0] = pr_edges; a.prof[1] = pr_reduce; a.prof[2] = pr_solve; a.prof[3] = pr_pass; }
         if (a.out_pose) { // frame hand-over: pose history for the constant-velocity prior + result block
+            float cur[7], prev[7];
             for (int i = 0; i < 7; i++) {
-                const float v = a.pose[i];
-                a.pose_prev[i] = a.pose_last[i];
-                a.pose_last[i] = v;
-                a.out_pose[i] = v;
+                cur[i] = a.pose[i];
+                prev[i] = a.pose_last[i];
+                a.pose_prev[i] = prev[i];
+                a.pose_last[i] = cur[i];
+                a.out_pose[i] = cur[i];
+            }
+            if (a.next_prior) { // mVelocity = Tcw * LastTwc, next prior = mVelocity * Tcw, in the reference's float32 Sophus arithmetic
+                float qpi[4], tpi[3], qv[4], tv[3], qo[4], to[3];
+                so::se3_inverse(prev, prev + 4, qpi, tpi);
+                so::se3_mul(cur, cur + 4, qpi, tpi, qv, tv);
+                so::se3_mul(qv, tv, cur, cur + 4, qo, to);
+                for (int i = 0; i < 4; i++) a.next_prior[i] = qo[i];
+                for (int i = 0; i < 3; i++) a.next_prior[4 + i] = to[i];
             }
             a.out_counts[0] = n;
             a.out_counts[1] = *a.nm_last;
@@ -533,6 +543,8 @@ __global__ void __cluster_dims__(kPoseCtas, 1, 1) __launch_bounds__(kPoseThreads
             a.out_counts[3] = nedges >= 3 ? nedges - nBadEdges : nedges; // mnMatchesInliers
         }
     }
+    if (a.seen_reset)
+        for (int i = tid; i < (a.seen_n + 3) / 4; i += kPoseStride) reinterpret_cast<uint32_t*>(a.seen_reset)[i] = 0u;
     cooperative_groups::this_cluster().sync(); // no CTA may exit while peers can still write into its shared memory
 }
 

@@ -12,7 +12,7 @@ static void frame_free(dvm_frame* f)
     cudaSetDevice(f->device);
     cudaFree(f->d_kps); cudaFree(f->d_desc); cudaFree(f->d_n); cudaFree(f->d_cell_start); cudaFree(f->d_cell_items); cudaFree(f->d_kxyo);
     cudaFree(f->d_in); cudaFree(f->ms.pu); cudaFree(f->ms.pv); cudaFree(f->ms.pr); cudaFree(f->ms.plevels);
-    cudaFree(f->ms.choice); cudaFree(f->ms.cache); cudaFree(f->ms.ncand); cudaFree(f->ms.qlist); cudaFree(f->ms.claim_a); cudaFree(f->ms.claim_b); cudaFree(f->ms.iters);
+    cudaFree(f->ms.choice); cudaFree(f->ms.cache); cudaFree(f->ms.ncand); cudaFree(f->ms.qmeta); cudaFree(f->ms.cache8); cudaFree(f->ms.claim_a); cudaFree(f->ms.claim_b); cudaFree(f->ms.iters);
     cudaFree(f->d_cur_mp); cudaFree(f->d_err);
     if (f->h_in) cudaFreeHost(f->h_in);
     if (f->h_out) cudaFreeHost(f->h_out);
@@ -24,11 +24,12 @@ static void frame_free(dvm_frame* f)
 int dvm_frame_ensure_query_cap(dvm_frame* f, int nq)
 {
     if (nq <= f->q_cap) return DVM_OK;
+    DVM_REQUIRE(nq < (1 << 20), "more than 2^20 queries in one projection search");   // claim words carry 20 index bits
     const int cap = nq + nq / 4 + 256;
     DVM_CUDA(cudaStreamSynchronize(f->stream));
     cudaFree(f->ms.pu); cudaFree(f->ms.pv); cudaFree(f->ms.pr); cudaFree(f->ms.plevels); cudaFree(f->ms.choice);
-    cudaFree(f->ms.cache); cudaFree(f->ms.ncand); cudaFree(f->ms.qlist);
-    f->ms.qlist = nullptr;
+    cudaFree(f->ms.cache); cudaFree(f->ms.ncand); cudaFree(f->ms.qmeta); cudaFree(f->ms.cache8);
+    f->ms.qmeta = nullptr; f->ms.cache8 = nullptr;
     f->ms.pu = f->ms.pv = f->ms.pr = nullptr; f->ms.plevels = f->ms.choice = nullptr; f->ms.cache = nullptr; f->ms.ncand = nullptr;
     DVM_CUDA(cudaMalloc(&f->ms.pu, cap * sizeof(float)));
     DVM_CUDA(cudaMalloc(&f->ms.pv, cap * sizeof(float)));
@@ -37,7 +38,8 @@ int dvm_frame_ensure_query_cap(dvm_frame* f, int nq)
     DVM_CUDA(cudaMalloc(&f->ms.choice, cap * sizeof(int)));
     DVM_CUDA(cudaMalloc(&f->ms.cache, (size_t)cap * kMatchCacheK * sizeof(unsigned long long)));
     DVM_CUDA(cudaMalloc(&f->ms.ncand, cap * sizeof(int)));
-    DVM_CUDA(cudaMalloc(&f->ms.qlist, cap * sizeof(int)));
+    DVM_CUDA(cudaMalloc(&f->ms.qmeta, cap * sizeof(int4)));
+    DVM_CUDA(cudaMalloc(&f->ms.cache8, (size_t)cap * kMatchCacheK * sizeof(unsigned)));
     f->q_cap = cap;
     return DVM_OK;
 }
@@ -127,17 +129,19 @@ int dvm_frame_create(dvm_frame** out, int device, void* cuda_stream, int max_key
     DVM_FCREATE(cudaMemset(f->d_cell_start, 0, (kGridCells + 4) * sizeof(int)));
     DVM_FCREATE(cudaMalloc(&f->d_cell_items, f->cap * sizeof(int)));
     DVM_FCREATE(cudaMemset(f->d_cell_items, 0, f->cap * sizeof(int)));
-    DVM_FCREATE(cudaMalloc(&f->d_kxyo, (size_t)f->cap * 3 * sizeof(int)));
-    DVM_FCREATE(cudaMemset(f->d_kxyo, 0, (size_t)f->cap * 3 * sizeof(int)));
+    DVM_FCREATE(cudaMalloc(&f->d_kxyo, (size_t)f->cap * 4 * sizeof(int)));
+    DVM_FCREATE(cudaMemset(f->d_kxyo, 0, (size_t)f->cap * 4 * sizeof(int)));
     DVM_FCREATE(cudaMalloc(&f->ms.claim_a, f->cap * sizeof(int)));
     DVM_FCREATE(cudaMalloc(&f->ms.claim_b, f->cap * sizeof(int)));
-    DVM_FCREATE(cudaMalloc(&f->ms.iters, sizeof(int)));
+    DVM_FCREATE(cudaMalloc(&f->ms.iters, 4 * sizeof(int)));
+    DVM_FCREATE(cudaMemset(f->ms.iters, 0, 4 * sizeof(int)));
+    f->ms.qcount = f->ms.iters + 1;
     DVM_FCREATE(cudaMalloc(&f->d_cur_mp, (f->cap + 8) * sizeof(int)));
 #undef DVM_FCREATE
     FrameDev& d = f->dev;
     memset(&d, 0, sizeof(d));
     d.kps = f->d_kps; d.desc = f->d_desc; d.n = f->d_n; d.cap = f->cap;
-    d.cell_start = f->d_cell_start; d.cell_items = f->d_cell_items; d.kxyo = f->d_kxyo;
+    d.cell_start = f->d_cell_start; d.cell_items = f->d_cell_items; d.cell_rec = reinterpret_cast<int4*>(f->d_kxyo);
     d.nlevels = nlevels;
     for (int i = 0; i < nlevels; i++) { d.scale[i] = scale_factors[i]; d.inv_sigma2[i] = inv_level_sigma2[i]; }
     *out = f;

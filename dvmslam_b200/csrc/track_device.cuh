@@ -29,6 +29,7 @@ __device__ inline void load_desc(uint32_t a[8], const uint8_t* d)
 struct FrameLook {
     const int* cell_start;
     const int* cell_items;
+    const int4* cell_rec;   // per grid position j: {x bits, y bits, octave, keypoint index} (grid_build_kernel)
     const char* kbase;   // keypoint records: x at +0, y at +4, octave at +oct_off
     int kstride, oct_off;
     const uint8_t* desc;
@@ -41,7 +42,7 @@ struct FrameLook {
 __device__ inline FrameLook look_global(const FrameDev& f)
 {
     FrameLook v;
-    v.cell_start = f.cell_start; v.cell_items = f.cell_items;
+    v.cell_start = f.cell_start; v.cell_items = f.cell_items; v.cell_rec = f.cell_rec;
     v.kbase = reinterpret_cast<const char*>(f.kps); v.kstride = (int)sizeof(dvm_keypoint); v.oct_off = 20;
     v.desc = f.desc;
     v.minX = f.minX; v.minY = f.minY; v.gwInv = f.gwInv; v.ghInv = f.ghInv;
@@ -67,13 +68,13 @@ __device__ inline void walk_area(const FrameLook& f, float x, float y, float r, 
         // cells of one grid column are contiguous: one range covers iy = nMinCellY .. nMaxCellY
         const int j0 = f.cell_start[ix * kGridRows + nMinCellY], j1 = f.cell_start[ix * kGridRows + nMaxCellY + 1];
         for (int j = j0; j < j1; j++) {
-            const int idx = f.cell_items[j];
-            const int oct = f.oct(idx);
+            const int4 rec = f.cell_rec[j];
+            const int idx = rec.w, oct = rec.z;
             if (bCheckLevels) {
                 if (oct < minLevel) continue;
                 if (maxLevel >= 0 && oct > maxLevel) continue;
             }
-            const float distx = __fsub_rn(f.x(idx), x), disty = __fsub_rn(f.y(idx), y);
+            const float distx = __fsub_rn(__int_as_float(rec.x), x), disty = __fsub_rn(__int_as_float(rec.y), y);
             if (fabsf(distx) < r && fabsf(disty) < r) fn(idx, oct);
         }
     }
@@ -106,7 +107,10 @@ __device__ inline int rot_bin(float last_angle, float cur_angle)
 // top-K, and the K best of the warp are merged by K rounds of a 64-bit warp minimum.  The order key of a
 // candidate is its position in the window's traversal (cells in the reference's order, unfiltered), which
 // is monotone in the reference's visiting order, so (distance, key) ranks candidates exactly as the
-// sequential scan does. ----
+// sequential scan does.
+// The grid columns of the window are NOT walked one after the other (each would be a dependent chain of loads for a
+// handful of keypoints): lane c fetches the item range of column c, a warp scan concatenates the ranges, and the lanes
+// then stride over the concatenation -- one pass of cell_start -> cell_rec -> descriptor for the whole window. ----
 template <class Fn>
 __device__ inline void walk_area_warp(const FrameLook& f, float x, float y, float r, int minLevel, int maxLevel, int lane, Fn fn)
 {
@@ -120,20 +124,44 @@ __device__ inline void walk_area_warp(const FrameLook& f, float x, float y, floa
     const int nMaxCellY = min(kGridRows - 1, (int)ceilf(__fmul_rn(__fadd_rn(dym, r), f.ghInv)));
     if (nMaxCellY < 0) return;
     const bool bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
+    const int ncols = nMaxCellX - nMinCellX + 1;
     int base = 0;
-    for (int ix = nMinCellX; ix <= nMaxCellX; ix++) {
-        const int j0 = f.cell_start[ix * kGridRows + nMinCellY], j1 = f.cell_start[ix * kGridRows + nMaxCellY + 1];
-        for (int j = j0 + lane; j < j1; j += 32) {
-            const int idx = f.cell_items[j];
-            const int oct = f.oct(idx);
+    for (int c0 = 0; c0 < ncols; c0 += 32) {
+        int j0 = 0, cnt = 0;
+        if (c0 + lane < ncols) { // cells of one grid column are contiguous: one range covers iy = nMinCellY .. nMaxCellY
+            const int ix = nMinCellX + c0 + lane;
+            j0 = f.cell_start[ix * kGridRows + nMinCellY];
+            cnt = f.cell_start[ix * kGridRows + nMaxCellY + 1] - j0;
+        }
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        const int excl = incl - cnt;
+        for (int tb = 0; tb < total; tb += 32) {
+            const int t = tb + lane;
+            int col = 0; // number of columns that end at or before position t = the column position t lies in
+#pragma unroll
+            for (int sft = 16; sft >= 1; sft >>= 1) {
+                const int probe = __shfl_sync(0xffffffffu, incl, col + sft - 1);
+                if (probe <= t) col += sft;
+            }
+            col = min(col, 31);
+            const int cj0 = __shfl_sync(0xffffffffu, j0, col), cex = __shfl_sync(0xffffffffu, excl, col);
+            if (t >= total) continue;
+            const int4 rec = f.cell_rec[cj0 + (t - cex)];
+            const int idx = rec.w, oct = rec.z;
             if (bCheckLevels) {
                 if (oct < minLevel) continue;
                 if (maxLevel >= 0 && oct > maxLevel) continue;
             }
-            const float distx = __fsub_rn(f.x(idx), x), disty = __fsub_rn(f.y(idx), y);
-            if (fabsf(distx) < r && fabsf(disty) < r) fn(idx, oct, base + (j - j0));
+            const float distx = __fsub_rn(__int_as_float(rec.x), x), disty = __fsub_rn(__int_as_float(rec.y), y);
+            if (fabsf(distx) < r && fabsf(disty) < r) fn(idx, oct, base + t);
         }
-        base += j1 - j0;
+        base += total;
     }
 }
 

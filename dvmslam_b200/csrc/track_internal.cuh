@@ -24,7 +24,7 @@ struct dvm_frame {
     size_t in_cap = 0;
     uint8_t* h_in = nullptr;   // pinned staging for uploads
     size_t h_in_cap = 0;
-    MatchScratch ms;
+    MatchScratch ms = {};
     int q_cap = 0;
     int* d_cur_mp = nullptr;   // [cap + 8]: cur_mp, then {nmatches}
     double* d_err = nullptr;

@@ -41,7 +41,6 @@ __global__ void __launch_bounds__(1024) grid_build_kernel(FrameDev f, const dvm_
     __syncthreads();
     for (int i = tid; i < n; i += 1024) {
         const dvm_keypoint* kp = f.kps + i;
-        f.kxyo[3 * i] = __float_as_int(kp->x); f.kxyo[3 * i + 1] = __float_as_int(kp->y); f.kxyo[3 * i + 2] = kp->octave;
         const int px = (int)roundf(__fmul_rn(__fsub_rn(kp->x, f.minX), f.gwInv));
         const int py = (int)roundf(__fmul_rn(__fsub_rn(kp->y, f.minY), f.ghInv));
         if (px < 0 || px >= kGridCols || py < 0 || py >= kGridRows) continue;
@@ -76,6 +75,13 @@ __global__ void __launch_bounds__(1024) grid_build_kernel(FrameDev f, const dvm_
             while (k >= j0 && f.cell_items[k] > v) { f.cell_items[k + 1] = f.cell_items[k]; k--; }
             f.cell_items[k + 1] = v;
         }
+    }
+    __syncthreads();
+    // what a window walk needs of the keypoint at grid position j, in one 16-byte record
+    for (int j = tid; j < total; j += 1024) {
+        const int i = f.cell_items[j];
+        const dvm_keypoint* kp = f.kps + i;
+        f.cell_rec[j] = make_int4(__float_as_int(kp->x), __float_as_int(kp->y), kp->octave, i);
     }
 }
 
@@ -154,9 +160,9 @@ void launch_features_in_area(const FrameDev& f, float x, float y, float r, int m
 }
 
 // ----------------------------------------------------------------- SearchByProjection(cur, last)
-constexpr int kMatchThreads = 1024;
-constexpr int kRegQ = 2;   // queries per thread kept in registers by the resolution kernels
-constexpr int kNoClaim = 0x7fffffff;
+constexpr int kMatchThreads = 512;   // one CTA; 128 registers per thread keep kRegQ queries each without spilling
+constexpr int kRegQ = 8;   // queries per thread kept in registers by the resolution kernels
+constexpr int kMoreWords = 7 * kRegQ * kMatchThreads;   // shared-memory words for their candidates two to eight
 
 // ---- candidate cache: the window of every query is walked ONCE; its best kMatchCacheK candidates are
 // kept sorted by (Hamming distance, walk order) -- the reference's preference order: strict '<' keeps
@@ -169,6 +175,14 @@ __device__ inline unsigned long long pack_cand(int dist, int ord, int oct, int i
 __device__ inline int cand_idx(unsigned long long e) { return (int)(e & 0xffffu); }
 __device__ inline int cand_oct(unsigned long long e) { return (int)((e >> 16) & 0xffu); }
 __device__ inline int cand_dist(unsigned long long e) { return (int)(e >> 48); }
+// the same candidate in 32 bits for the registers of the resolution kernels: distance:9 | octave:7 | keypoint:16
+__device__ inline unsigned cand_short(unsigned long long e)
+{
+    return e == ~0ull ? 0xffffffffu : ((unsigned)cand_dist(e) << 23) | ((unsigned)(cand_oct(e) & 0x7f) << 16) | (unsigned)cand_idx(e);
+}
+__device__ inline int short_idx(unsigned c) { return (int)(c & 0xffffu); }
+__device__ inline int short_oct(unsigned c) { return (int)((c >> 16) & 0x7fu); }
+__device__ inline int short_dist(unsigned c) { return (int)(c >> 23); }
 
 __device__ inline void topk_insert(unsigned long long (&top)[kMatchCacheK], unsigned long long v)
 {
@@ -176,7 +190,6 @@ __device__ inline void topk_insert(unsigned long long (&top)[kMatchCacheK], unsi
     for (int p = 0; p < kMatchCacheK; p++)
         if (v < top[p]) { const unsigned long long t = top[p]; top[p] = v; v = t; }
 }
-
 
 // merges the lanes' sorted top-K lists; lane p < K returns the p-th best of the warp (~0 when absent)
 __device__ inline unsigned long long warp_topk_merge(unsigned long long (&top)[kMatchCacheK], int lane)
@@ -186,7 +199,8 @@ __device__ inline unsigned long long warp_topk_merge(unsigned long long (&top)[k
     for (int p = 0; p < kMatchCacheK; p++) {
         const unsigned long long m = warp_min_u64(top[0]);
         if (lane == p) mine = m;
-        if (top[0] == m && m != ~0ull) { // keys are unique: exactly one lane pops
+        if (m == ~0ull) break; // nothing left in any lane (warp-uniform)
+        if (top[0] == m) { // keys are unique: exactly one lane pops
 #pragma unroll
             for (int q = 0; q + 1 < kMatchCacheK; q++) top[q] = top[q + 1];
             top[kMatchCacheK - 1] = ~0ull;
@@ -197,229 +211,390 @@ __device__ inline unsigned long long warp_topk_merge(unsigned long long (&top)[k
 
 constexpr int kWalkThreads = 128;
 
-// ordered list of the queries that take part (plevels != -1) in shared memory; returns their number
-__device__ inline int compact_active(const int* __restrict__ plevels, int nq, int* qlist, int* warp_sums)
+// phase stamps for DVM_MATCH_PROFILE (thread 0 of a one-CTA kernel; min / max over the CTAs of a walk)
+__device__ inline unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ inline void prof_stamp(unsigned long long* prof, int slot) { if (prof && threadIdx.x == 0) prof[slot] = gtimer(); }
+__device__ inline void prof_walk_begin(unsigned long long* prof) { if (prof && threadIdx.x == 0) atomicMin(&prof[0], gtimer()); }
+__device__ inline void prof_walk_end(unsigned long long* prof) { if (prof && threadIdx.x == 0) atomicMax(&prof[1], gtimer()); }
+
+// ---- claims of the greedy rounds.  claim[k] = the smallest index among the queries (with observations) that chose keypoint
+// k, 0xffffffff while nobody has.  Shared-memory atomics are what a round costs (two cycles per lane on the one SM this
+// runs on), so a query claims only when its choice CHANGES, in place, while the others read: the choices move down the
+// candidate lists and the holders' indices only fall, the process is monotone and ends in the unique state in which
+// every query holds its best candidate not held by an earlier one -- the sequential outcome -- whatever the interleaving.
+// The one non-monotone event is a query that gives up a keypoint it holds (the second-best test of
+// SearchByProjection(F, map points) can turn against a candidate when the runner-up changes): the claim array is then
+// rebuilt from the current choices before the next round.  A round that changes no choice ends the iteration.
+// The common case -- the answer is among a query's first candidates -- is a few dozen instructions on registers and shared
+// memory; everything else (the full walk, queries beyond the register-resident ones) sits behind one call that is not
+// inlined. ----
+constexpr unsigned kNoClaim = 0xffffffffu;
+__device__ inline bool held_before(const unsigned* claim, int idx, int i) { return claim[idx] < (unsigned)i; }
+constexpr int kIdxBits = 20;                       // query index | candidate count << 20 in one register
+constexpr int kIdxMask = (1 << kIdxBits) - 1;
+
+// what the slow path needs, gathered once per kernel (lives in local memory: its address is passed to a call)
+struct SlowCtx {
+    FrameLook fl;
+    const unsigned long long* cache;
+    const float* pu; const float* pv; const float* pr;
+    const uint8_t* q_desc;      // descriptors of the queries ...
+    const int* q_desc_index;    // ... indexed through this table when it is not null
+    const int* cur_map;         // SearchByProjection(F, map points): keypoints blocked from the start
+    const uint8_t* cur_blocked;
+    unsigned long long* prof;
+};
+
+// One query of SearchByProjection(cur, last) (O3/src/ORBmatcher.cc:1570-1640): projects the map point of last-frame
+// keypoint i with the pose prior, walks its window once (whole warp) and appends the query -- its index, level window,
+// candidate count, angle and its kMatchCacheK best candidates -- to the compact list the resolution kernel reads.
+__device__ inline void last_walk_query(const FrameDev& cur, const MatchLastArgs& a, const MatchScratch& s, const FrameLook& fl,
+                                       const float* q, const float* t, float th, int i, int lane)
 {
-    const int ipt = div_up(max(nq, 1), kMatchThreads);
-    const int i0 = min((int)threadIdx.x * ipt, nq), i1 = min(i0 + ipt, nq);
-    int c = 0;
-    for (int i = i0; i < i1; i++) c += (plevels[i] != -1);
-    int total;
-    int off = block_exclusive_scan(c, warp_sums, &total);
-    for (int i = i0; i < i1; i++)
-        if (plevels[i] != -1) qlist[off++] = i;
-    __syncthreads();
-    return total;
+    const int mi = a.mp_index ? a.mp_index[i] : (a.has_mp[i] ? i : -1);
+    if (mi < 0 || a.outlier[i]) return;
+    // x3Dc = Tcw * x3Dw (O3/src/ORBmatcher.cc:1577): Sophus' quaternion action, not a matrix product
+    const float Pw[3] = { a.Xw[3 * mi], a.Xw[3 * mi + 1], a.Xw[3 * mi + 2] };
+    float Pc[3];
+    so::se3_apply(q, t, Pw, Pc);
+    const float xc = Pc[0], yc = Pc[1], zc = Pc[2];
+    const float invzc = (float)(1.0 / (double)zc);
+    if (invzc < 0) return;
+    const float u = __fadd_rn(__fdiv_rn(__fmul_rn(a.K[0], xc), zc), a.K[2]);
+    const float v = __fadd_rn(__fdiv_rn(__fmul_rn(a.K[1], yc), zc), a.K[3]);
+    if ((u < cur.minX || u > cur.maxX) || (v < cur.minY || v > cur.maxY)) return;
+    // the conditions above depend on the query only: the whole warp is here together
+    int slot = 0;
+    if (lane == 0) slot = atomicAdd(s.qcount, 1);
+    const int oct = a.last_kps ? a.last_kps[i].octave : a.octave[i];
+    const float ang = a.last_kps ? a.last_kps[i].angle : a.angle[i];
+    const float r = __fmul_rn(th, cur.scale[oct]);
+    if (lane == 0) { s.pu[i] = u; s.pv[i] = v; s.pr[i] = r; }
+    uint32_t d[8];
+    load_desc(d, a.mp_desc + (size_t)mi * 32);
+    unsigned long long top[kMatchCacheK];
+#pragma unroll
+    for (int p = 0; p < kMatchCacheK; p++) top[p] = ~0ull;
+    int nc = 0;
+    walk_area_warp(fl, u, v, r, oct - 1, oct + 1, lane, [&](int idx, int o, int ord) {
+        const int dist = hamming256(d, fl.desc + (size_t)idx * 32);
+        topk_insert(top, pack_cand(dist, ord, o, idx));
+        nc++;
+    });
+    nc = __reduce_add_sync(0xffffffffu, nc);
+    const unsigned long long e = warp_topk_merge(top, lane);
+    slot = __shfl_sync(0xffffffffu, slot, 0);
+    if (lane < kMatchCacheK) s.cache[(size_t)slot * kMatchCacheK + lane] = e;
+    if (lane < kMatchCacheK) s.cache8[(size_t)slot * kMatchCacheK + lane] = cand_short(e);
+    if (lane == 0) s.qmeta[slot] = make_int4(i, ((oct - 1) << 16) | ((oct + 1) & 0xffff), nc, __float_as_int(ang));
 }
 
-// ---- SearchByProjection(cur, last), phase 1: one WARP per last-frame keypoint projects its map point
-// with the pose prior and walks its window once (many CTAs; the frame is read through L1/L2) ----
+// ---- SearchByProjection(cur, last), phase 1: one WARP per last-frame keypoint (many CTAs; the frame is read through
+// L1/L2) ----
 __global__ void __launch_bounds__(kWalkThreads) match_last_walk_kernel(FrameDev cur, MatchLastArgs a, MatchScratch s)
 {
     pdl_trigger(); pdl_wait();
     if (a.guard && *a.guard >= 20) return; // enough matches at th: the wider retry is not run
+    prof_walk_begin(s.prof);
     const int nq = a.n_ptr ? *a.n_ptr : a.last_n;
     const int lane = threadIdx.x & 31;
     const int i = (blockIdx.x * kWalkThreads + threadIdx.x) >> 5;
-    if (i >= nq) return;
-    const FrameLook fl = look_global(cur);
-    if (a.pose) { // pose prior held on the device
-        a.q[0] = a.pose[0]; a.q[1] = a.pose[1]; a.q[2] = a.pose[2]; a.q[3] = a.pose[3];
-        a.t[0] = a.pose[4]; a.t[1] = a.pose[5]; a.t[2] = a.pose[6];
-    }
-    const int mi = a.mp_index ? a.mp_index[i] : (a.has_mp[i] ? i : -1);
-    int lv = -1, nc = 0;
-    unsigned long long top[kMatchCacheK];
-#pragma unroll
-    for (int p = 0; p < kMatchCacheK; p++) top[p] = ~0ull;
-    if (mi >= 0 && !a.outlier[i]) {
-        // x3Dc = Tcw * x3Dw (O3/src/ORBmatcher.cc:1577): Sophus' quaternion action, not a matrix product
-        const float Pw[3] = { a.Xw[3 * mi], a.Xw[3 * mi + 1], a.Xw[3 * mi + 2] };
-        float Pc[3];
-        so::se3_apply(a.q, a.t, Pw, Pc);
-        const float xc = Pc[0], yc = Pc[1], zc = Pc[2];
-        const float invzc = (float)(1.0 / (double)zc);
-        if (!(invzc < 0)) {
-            const float u = __fadd_rn(__fdiv_rn(__fmul_rn(a.K[0], xc), zc), a.K[2]);
-            const float v = __fadd_rn(__fdiv_rn(__fmul_rn(a.K[1], yc), zc), a.K[3]);
-            if (!(u < cur.minX || u > cur.maxX) && !(v < cur.minY || v > cur.maxY)) {
-                const int oct = a.last_kps ? a.last_kps[i].octave : a.octave[i];
-                const float r = __fmul_rn(a.th, cur.scale[oct]);
-                if (lane == 0) { s.pu[i] = u; s.pv[i] = v; s.pr[i] = r; }
-                lv = ((oct - 1) << 16) | ((oct + 1) & 0xffff);
-                uint32_t d[8];
-                load_desc(d, a.mp_desc + (size_t)mi * 32);
-                walk_area_warp(fl, u, v, r, oct - 1, oct + 1, lane, [&](int idx, int o, int ord) {
-                    const int dist = hamming256(d, fl.desc + (size_t)idx * 32);
-                    topk_insert(top, pack_cand(dist, ord, o, idx));
-                    nc++;
-                });
-            }
+    if (i < nq) {
+        const FrameLook fl = look_global(cur);
+        if (a.pose) { // pose prior held on the device
+            a.q[0] = a.pose[0]; a.q[1] = a.pose[1]; a.q[2] = a.pose[2]; a.q[3] = a.pose[3];
+            a.t[0] = a.pose[4]; a.t[1] = a.pose[5]; a.t[2] = a.pose[6];
         }
+        last_walk_query(cur, a, s, fl, a.q, a.t, a.th, i, lane);
     }
-    // the branch conditions above depend on the query only: the whole warp is here together
-    if (lane == 0) s.plevels[i] = lv;
-    if (lv != -1) {
-        nc = __reduce_add_sync(0xffffffffu, nc);
-        const unsigned long long e = warp_topk_merge(top, lane);
-        if (lane < kMatchCacheK) s.cache[(size_t)i * kMatchCacheK + lane] = e;
-        if (lane == 0) s.ncand[i] = nc;
+    prof_walk_end(s.prof);
+}
+
+// slow path of one query of SearchByProjection(cur, last): all cached candidates, then the full walk
+__device__ __noinline__ int slow_pick_last(const SlowCtx* c, int j, int i, int lv, int nc, const unsigned* claim)
+{
+    if (c->prof) atomicAdd(&c->prof[10], 1ull);
+    const unsigned long long* e = c->cache + (size_t)j * kMatchCacheK;
+    for (int p = 0; p < kMatchCacheK && p < nc; p++) {
+        const unsigned long long ev = e[p];
+        if (held_before(claim, cand_idx(ev), i)) continue; // taken by an earlier map point with observations
+        return cand_dist(ev) <= kThHigh ? cand_idx(ev) : -1;
     }
+    if (nc <= kMatchCacheK) return -1;
+    if (c->prof) atomicAdd(&c->prof[8], 1ull);
+    int bestDist = 256, bestIdx = -1; // cache exhausted: full walk against the current claims
+    uint32_t d[8];
+    load_desc(d, c->q_desc + (size_t)(c->q_desc_index ? c->q_desc_index[i] : i) * 32);
+    walk_area(c->fl, c->pu[i], c->pv[i], c->pr[i], lv >> 16, (int)(short)(lv & 0xffff), [&](int idx, int) {
+        if (held_before(claim, idx, i)) return;
+        const int dist = hamming256(d, c->fl.desc + (size_t)idx * 32);
+        if (dist < bestDist) { bestDist = dist; bestIdx = idx; }
+    });
+    return bestDist <= kThHigh ? bestIdx : -1;
 }
 
 // ---- phase 2: the sequential-greedy outcome as a Jacobi fixed point on ONE CTA (claims in shared
-// memory), then the rotation-consistency check ----
+// memory), then the rotation-consistency check.  With a.retry_th > 0 the kernel also holds Tracking's retry
+// (Tracking.cc:2614-2621): fewer than 20 matches -> the CTA walks every query again with the wider window (a rare,
+// nearly-lost frame: one CTA is enough) and resolves once more; the outputs of the second pass replace the first's. ----
+template <bool kClaimsInSmem>
 __global__ void __launch_bounds__(kMatchThreads, 1)
-match_last_kernel(FrameDev cur, MatchLastArgs a, MatchScratch s, int* __restrict__ cur_mp, int* __restrict__ nmatches,
-                  int use_smem)
+match_last_kernel(FrameDev cur, MatchLastArgs a, MatchScratch s, int* __restrict__ cur_mp, int* __restrict__ nmatches)
 {
     pdl_trigger(); pdl_wait();
     extern __shared__ __align__(16) unsigned char claim_smem[];
     __shared__ int histo[kHistoLength];
-    __shared__ int s_ind[3], s_events, s_bad;
-    const int tid = threadIdx.x;
+    __shared__ int s_events, s_bad;
+    const int tid = threadIdx.x, lane = tid & 31;
     if (a.guard && *a.guard >= 20) return; // enough matches at th: the wider retry is not run
+    prof_stamp(s.prof, 2);
     const int ncur = min(*cur.n, cur.cap);
-    const int nq = a.n_ptr ? *a.n_ptr : a.last_n;
-    const FrameLook fl = look_global(cur);
-    auto desc_of = [&](int i) { return a.mp_desc + (size_t)(a.mp_index ? a.mp_index[i] : i) * 32; };
+    SlowCtx sc;
+    sc.fl = look_global(cur);
+    sc.cache = s.cache; sc.pu = s.pu; sc.pv = s.pv; sc.pr = s.pr;
+    sc.q_desc = a.mp_desc; sc.q_desc_index = a.mp_index; sc.cur_map = nullptr; sc.cur_blocked = nullptr; sc.prof = s.prof;
+    const bool all_obs = a.obs_pos == nullptr;   // every query blocks later ones (the tracker): a keypoint's chooser is unique
     auto obs_of = [&](int i) { return a.obs_pos ? a.obs_pos[i] != 0 : true; };
-    auto angle_of = [&](int i) { return a.last_kps ? a.last_kps[i].angle : a.angle[i]; };
+    // shared memory: candidates two to eight of the register-resident queries, the claim array, the owner array
+    unsigned* more = reinterpret_cast<unsigned*>(claim_smem);
+    unsigned* claim = kClaimsInSmem ? more + kMoreWords : reinterpret_cast<unsigned*>(s.claim_a);
+    int* owner = kClaimsInSmem ? reinterpret_cast<int*>(more + kMoreWords + cur.cap) : s.claim_b;
 
-    __shared__ int warp_sums[33];
-    int* claim_prev = use_smem ? reinterpret_cast<int*>(claim_smem) : s.claim_a;
-    int* claim_next = use_smem ? reinterpret_cast<int*>(claim_smem) + cur.cap : s.claim_b;
-    int* qlist = s.qlist;
-    for (int i = tid; i < nq; i += kMatchThreads) s.choice[i] = -1;
-    for (int k = tid; k < ncur; k += kMatchThreads) claim_prev[k] = kNoClaim;
-    const int nact = compact_active(s.plevels, nq, qlist, warp_sums);
-
-    // the first kRegQ queries of every thread stay in registers across the rounds (index, candidate count, the
-    // four best cache entries, current choice): a round then only touches the claims in shared memory
-    int r_i[kRegQ], r_nc[kRegQ], r_lv[kRegQ], r_choice[kRegQ];
-    ulonglong2 r_e01[kRegQ], r_e23[kRegQ];
-#pragma unroll
-    for (int q = 0; q < kRegQ; q++) {
-        const int j = tid + q * kMatchThreads;
-        r_i[q] = -1; r_nc[q] = 0; r_lv[q] = 0; r_choice[q] = -1;
-        r_e01[q] = make_ulonglong2(~0ull, ~0ull); r_e23[q] = r_e01[q];
-        if (j < nact) {
-            const int i = qlist[j];
-            r_i[q] = i; r_lv[q] = s.plevels[i]; r_nc[q] = s.ncand[i];
-            const unsigned long long* e = s.cache + (size_t)i * kMatchCacheK;
-            r_e01[q] = *reinterpret_cast<const ulonglong2*>(e); r_e23[q] = *reinterpret_cast<const ulonglong2*>(e + 2);
-        }
-    }
-    auto evaluate = [&](int i, int lv, int nc, const ulonglong2& e01, const ulonglong2& e23, const int* claim) -> int {
-        int bestDist = 256, bestIdx = -1;
-        bool found = false;
-        const unsigned long long* e = s.cache + (size_t)i * kMatchCacheK;
-        for (int p = 0; p < kMatchCacheK && p < nc; p++) {
-            const unsigned long long ev = p == 0 ? e01.x : p == 1 ? e01.y : p == 2 ? e23.x : p == 3 ? e23.y : e[p];
-            const int idx = cand_idx(ev);
-            if (claim[idx] < i) continue; // taken by an earlier map point with observations
-            bestDist = cand_dist(ev); bestIdx = idx; found = true;
-            break;
-        }
-        if (!found && nc > kMatchCacheK) { // cache exhausted: full walk against the current claims
-            uint32_t d[8];
-            load_desc(d, desc_of(i));
-            walk_area(fl, s.pu[i], s.pv[i], s.pr[i], lv >> 16, (int)(short)(lv & 0xffff), [&](int idx, int) {
-                if (claim[idx] < i) return;
-                const int dist = hamming256(d, fl.desc + (size_t)idx * 32);
-                if (dist < bestDist) { bestDist = dist; bestIdx = idx; }
-            });
-        }
-        return bestDist <= kThHigh ? bestIdx : -1;
-    };
-
-    int rounds = 0;
-    while (true) {
-        int changed = 0;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        const int nact = *reinterpret_cast<volatile int*>(s.qcount);
+        // the first kRegQ queries of every thread stay in registers across the rounds -- index and candidate count in one
+        // word, the best candidate, the current choice; candidates two to eight wait in shared memory: a round's common case
+        // (the best candidate is free, nothing changes) is a dozen instructions
+        int r_in[kRegQ], r_choice[kRegQ];   // r_in: index | min(candidates, 255) << 20, or -1
+        unsigned r_c0[kRegQ];
 #pragma unroll
         for (int q = 0; q < kRegQ; q++) {
-            if (r_i[q] < 0) continue;
-            const int pick = evaluate(r_i[q], r_lv[q], r_nc[q], r_e01[q], r_e23[q], claim_prev);
-            if (pick != r_choice[q]) { r_choice[q] = pick; s.choice[r_i[q]] = pick; changed = 1; }
-        }
-        for (int j = tid + kRegQ * kMatchThreads; j < nact; j += kMatchThreads) {
-            const int i = qlist[j];
-            const unsigned long long* e = s.cache + (size_t)i * kMatchCacheK;
-            const int pick = evaluate(i, s.plevels[i], s.ncand[i], *reinterpret_cast<const ulonglong2*>(e),
-                                      *reinterpret_cast<const ulonglong2*>(e + 2), claim_prev);
-            if (pick != s.choice[i]) { s.choice[i] = pick; changed = 1; }
-        }
-        rounds++;
-        if (!__syncthreads_or(changed)) break;
-        for (int k = tid; k < ncur; k += kMatchThreads) claim_next[k] = kNoClaim;
-        __syncthreads();
-#pragma unroll
-        for (int q = 0; q < kRegQ; q++)
-            if (r_i[q] >= 0 && r_choice[q] >= 0 && obs_of(r_i[q])) atomicMin(&claim_next[r_choice[q]], r_i[q]);
-        for (int j = tid + kRegQ * kMatchThreads; j < nact; j += kMatchThreads) {
-            const int i = qlist[j];
-            const int k = s.choice[i];
-            if (k >= 0 && obs_of(i)) atomicMin(&claim_next[k], i);
-        }
-        __syncthreads();
-        int* t = claim_prev; claim_prev = claim_next; claim_next = t;
-    }
-
-    // every accepted query is one write "CurrentFrame.mvpMapPoints[k] = pMP" (+ one histogram entry)
-    if (tid < kHistoLength) histo[tid] = 0;
-    if (tid == 0) { s_events = 0; s_bad = 0; }
-    int* owner = claim_next;   // last writer of each keypoint
-    int* nulled = claim_prev;  // keypoint cleared by the rotation check
-    __syncthreads();
-    for (int k = tid; k < ncur; k += kMatchThreads) { owner[k] = -1; nulled[k] = 0; }
-    __syncthreads();
-    for (int j = tid; j < nact; j += kMatchThreads) {
-        const int i = qlist[j];
-        const int k = s.choice[i];
-        if (k < 0) continue;
-        atomicMax(&owner[k], i);
-        atomicAdd(&s_events, 1);
-        if (a.check_ori) atomicAdd(&histo[rot_bin(angle_of(i), cur.kps[k].angle)], 1);
-    }
-    __syncthreads();
-    if (tid == 0) {
-        int i1 = -1, i2 = -1, i3 = -1;
-        if (a.check_ori) three_maxima(histo, kHistoLength, i1, i2, i3);
-        s_ind[0] = i1; s_ind[1] = i2; s_ind[2] = i3;
-    }
-    __syncthreads();
-    if (a.check_ori) {
-        for (int j = tid; j < nact; j += kMatchThreads) {
-            const int i = qlist[j];
-            const int k = s.choice[i];
-            if (k < 0) continue;
-            const int bin = rot_bin(angle_of(i), cur.kps[k].angle);
-            if (bin != s_ind[0] && bin != s_ind[1] && bin != s_ind[2]) {
-                nulled[k] = 1;
-                atomicAdd(&s_bad, 1);
+            const int j = tid + q * kMatchThreads;
+            r_in[q] = -1; r_c0[q] = ~0u; r_choice[q] = -1;
+            if (j < nact) {
+                const int4 m = s.qmeta[j];
+                const uint4 c = reinterpret_cast<const uint4*>(s.cache8)[2 * j], c2 = reinterpret_cast<const uint4*>(s.cache8)[2 * j + 1];
+                r_in[q] = m.x | (min(m.z, 255) << kIdxBits);
+                r_c0[q] = c.x;
+                unsigned* mo = more + 7 * j;
+                mo[0] = c.y; mo[1] = c.z; mo[2] = c.w; mo[3] = c2.x; mo[4] = c2.y; mo[5] = c2.z; mo[6] = c2.w;
             }
         }
+        for (int k = tid; k < ncur; k += kMatchThreads) claim[k] = kNoClaim;
+        for (int j = tid + kRegQ * kMatchThreads; j < nact; j += kMatchThreads) s.choice[j] = -1;
+        if (tid < kHistoLength) histo[tid] = 0;
+        if (tid == 0) { s_events = 0; s_bad = 0; }
+        __syncthreads();
+        prof_stamp(s.prof, 4);
+        if (s.prof && tid == 0) s.prof[9] = (unsigned long long)nact;
+        auto accept = [&](unsigned c) { return short_dist(c) <= kThHigh ? short_idx(c) : -1; };
+
+        int rounds = 0;
+        while (true) {
+            int changed = 0;
+            unsigned redo = 0u;
+#pragma unroll
+            for (int q = 0; q < kRegQ; q++) {
+                if (r_in[q] < 0) continue;
+                const int i = r_in[q] & kIdxMask, nc = r_in[q] >> kIdxBits;
+                int pick = -1;
+                if (nc > 0) {
+                    if (!held_before(claim, short_idx(r_c0[q]), i)) pick = accept(r_c0[q]);
+                    else if (nc > 1) { redo |= 1u << q; continue; }
+                }
+                if (pick != r_choice[q]) {
+                    r_choice[q] = pick; changed = 1;
+                    if (pick >= 0 && obs_of(i)) atomicMin(&claim[pick], (unsigned)i);
+                }
+            }
+#pragma unroll 1
+            while (redo) { // the best candidate is taken: the next ones (one copy of this code for all register slots)
+                const int q = __ffs(redo) - 1;
+                redo &= redo - 1u;
+                const int j = tid + q * kMatchThreads;
+                int rin = r_in[0];
+#pragma unroll
+                for (int qq = 1; qq < kRegQ; qq++) rin = qq == q ? r_in[qq] : rin;
+                const int i = rin & kIdxMask, nc = rin >> kIdxBits;
+                int pick = -1;
+                bool decided = false;
+                for (int p = 1; p < kMatchCacheK && p < nc; p++) {
+                    const unsigned c = more[7 * j + p - 1];
+                    if (held_before(claim, short_idx(c), i)) continue;
+                    pick = accept(c); decided = true;
+                    break;
+                }
+                if (!decided && nc > kMatchCacheK) pick = slow_pick_last(&sc, j, i, s.qmeta[j].y, s.qmeta[j].z, claim);
+                int prev = r_choice[0];
+#pragma unroll
+                for (int qq = 1; qq < kRegQ; qq++) prev = qq == q ? r_choice[qq] : prev;
+                if (pick != prev) {
+                    changed = 1;
+#pragma unroll
+                    for (int qq = 0; qq < kRegQ; qq++) r_choice[qq] = qq == q ? pick : r_choice[qq];
+                    if (pick >= 0 && obs_of(i)) atomicMin(&claim[pick], (unsigned)i);
+                }
+            }
+#pragma unroll 1
+            for (int j = tid + kRegQ * kMatchThreads; j < nact; j += kMatchThreads) {
+                const int4 m = s.qmeta[j];
+                const int pick = slow_pick_last(&sc, j, m.x, m.y, m.z, claim);
+                if (pick != s.choice[j]) {
+                    s.choice[j] = pick; changed = 1;
+                    if (pick >= 0 && obs_of(m.x)) atomicMin(&claim[pick], (unsigned)m.x);
+                }
+            }
+            rounds++;
+            if (s.prof && tid == 0 && rounds <= 12) s.prof[16 + rounds] = gtimer();
+            // (a query leaves a keypoint only for one an earlier query took from it: no claim is ever given up here)
+            if (!__syncthreads_or(changed)) break;
+            if (s.prof && tid == 0 && rounds <= 12) s.prof[32 + rounds] = gtimer();
+            if (rounds > nact + 8) break; // (the fixed point is reached within one round per query; never seen, kept as a fuse)
+        }
+        prof_stamp(s.prof, 5);
+
+        // every accepted query is one write "CurrentFrame.mvpMapPoints[k] = pMP" (+ one histogram entry); the last writer of a
+        // keypoint owns it.  With observations everywhere the chooser of a keypoint is unique and the claim array IS the owner.
+        if (!all_obs) {
+            for (int k = tid; k < ncur; k += kMatchThreads) owner[k] = -1;
+            __syncthreads();
+        }
+        int r_bin[kRegQ];
+        int events = 0;
+#pragma unroll
+        for (int q = 0; q < kRegQ; q++) {
+            r_bin[q] = -1;
+            const bool has = r_in[q] >= 0 && r_choice[q] >= 0;
+            if (has) {
+                events++;
+                if (!all_obs) atomicMax(&owner[r_choice[q]], r_in[q] & kIdxMask);
+                if (a.check_ori) r_bin[q] = rot_bin(__int_as_float(s.qmeta[tid + q * kMatchThreads].w), cur.kps[r_choice[q]].angle);
+            }
+            if (a.check_ori) { // one shared-memory atomic per distinct bin of the warp
+                const unsigned peers = __match_any_sync(0xffffffffu, r_bin[q]);
+                if (r_bin[q] >= 0 && lane == __ffs(peers) - 1) atomicAdd(&histo[r_bin[q]], __popc(peers));
+            }
+        }
+#pragma unroll 1
+        for (int j = tid + kRegQ * kMatchThreads; j < nact; j += kMatchThreads) {
+            const int k = s.choice[j];
+            if (k < 0) continue;
+            const int4 m = s.qmeta[j];
+            events++;
+            if (!all_obs) atomicMax(&owner[k], m.x);
+            if (a.check_ori) atomicAdd(&histo[rot_bin(__int_as_float(m.w), cur.kps[k].angle)], 1);
+        }
+        events = __reduce_add_sync(0xffffffffu, events);
+        if (lane == 0 && events) atomicAdd(&s_events, events);
+        __syncthreads();
+        prof_stamp(s.prof, 6);
+        int* own = all_obs ? reinterpret_cast<int*>(claim) : owner;   // kNoClaim reads as -1
+        if (a.check_ori) {
+            // ComputeThreeMaxima by every warp for itself: the sequential scan with its strict comparisons keeps the three
+            // largest positive bins, equal counts in index order -- three warp maxima of count << 5 | (31 - bin)
+            unsigned key = (lane < kHistoLength && histo[lane] > 0) ? ((unsigned)histo[lane] << 5) | (unsigned)(31 - lane) : 0u;
+            int ind[3], mx[3];
+#pragma unroll
+            for (int m = 0; m < 3; m++) {
+                const unsigned best = __reduce_max_sync(0xffffffffu, key);
+                ind[m] = best ? 31 - (int)(best & 31u) : -1;
+                mx[m] = (int)(best >> 5);
+                if (key == best) key = 0u;
+            }
+            if ((float)mx[1] < __fmul_rn(0.1f, (float)mx[0])) { ind[1] = -1; ind[2] = -1; }
+            else if ((float)mx[2] < __fmul_rn(0.1f, (float)mx[0])) ind[2] = -1;
+            // a keypoint whose match falls outside the three bins is cleared, whoever wrote it last (ORBmatcher.cc:1733-1741)
+            int bad = 0;
+            auto drop = [&](int k, int bin) {
+                if (bin != ind[0] && bin != ind[1] && bin != ind[2]) { bad++; atomicOr(reinterpret_cast<unsigned*>(&own[k]), 0x40000000u); }
+            };
+#pragma unroll
+            for (int q = 0; q < kRegQ; q++)
+                if (r_bin[q] >= 0) drop(r_choice[q], r_bin[q]);
+#pragma unroll 1
+            for (int j = tid + kRegQ * kMatchThreads; j < nact; j += kMatchThreads) {
+                const int k = s.choice[j];
+                if (k >= 0) drop(k, rot_bin(__int_as_float(s.qmeta[j].w), cur.kps[k].angle));
+            }
+            bad = __reduce_add_sync(0xffffffffu, bad);
+            if (lane == 0 && bad) atomicAdd(&s_bad, bad);
+            __syncthreads();
+        }
+        // own[k]: -1 nobody, index | 0x40000000 cleared by the rotation check, index otherwise
+        for (int k = tid; k < cur.cap; k += kMatchThreads) {
+            const int o = k < ncur ? own[k] : -1;
+            const int keep = (o < 0 || (o & 0x40000000)) ? -1 : o;
+            if (k < ncur) cur_mp[k] = keep;
+            if (a.map_out) a.map_out[k] = keep >= 0 ? a.mp_index[keep] : -1; // CurrentFrame.mvpMapPoints as map indices
+        }
+        const int found = s_events - s_bad;
+        if (tid == 0) { *nmatches = found; *s.iters = rounds; *s.qcount = 0; }
+        prof_stamp(s.prof, 7);
+        if (attempt == 1 || !(a.retry_th > 0.f) || found >= 20) break;
+        // ---- nmatches < 20: SearchByProjection(cur, last, 2 * th) (Tracking.cc:2614-2621), walked by this CTA ----
+        __syncthreads(); // own / s_events were read by everybody; the reset of qcount is ordered before the appends
+        {
+            const int nq = a.n_ptr ? *a.n_ptr : a.last_n;
+            float q4[4], t3[3];
+            for (int c = 0; c < 4; c++) q4[c] = a.pose ? a.pose[c] : a.q[c];
+            for (int c = 0; c < 3; c++) t3[c] = a.pose ? a.pose[4 + c] : a.t[c];
+            for (int i = tid >> 5; i < nq; i += kMatchThreads / 32) last_walk_query(cur, a, s, sc.fl, q4, t3, a.retry_th, i, lane);
+        }
+        __threadfence_block();
+        __syncthreads();
     }
-    __syncthreads();
-    for (int k = tid; k < ncur; k += kMatchThreads) cur_mp[k] = nulled[k] ? -1 : owner[k];
-    if (a.map_out) // CurrentFrame.mvpMapPoints as map indices (device-resident tracker)
-        for (int k = tid; k < cur.cap; k += kMatchThreads)
-            a.map_out[k] = (k < ncur && !nulled[k] && owner[k] >= 0) ? a.mp_index[owner[k]] : -1;
-    if (tid == 0) { *nmatches = s_events - s_bad; *s.iters = rounds; }
 }
 
 constexpr size_t kMatchSmemLimit = 200 * 1024;
 static bool prepare_match_kernels(); // raises the dynamic shared memory limit of both matcher kernels once
 __host__ inline size_t claim_smem_bytes(int cap) { return (size_t)cap * 8; }
+__host__ inline size_t match_smem_bytes(int use_smem, int cap) { return kMoreWords * 4 + (use_smem ? claim_smem_bytes(cap) : 0); }
 
-void launch_match_last(const FrameDev& cur, const MatchLastArgs& a, const MatchScratch& s, int* cur_mp, int* nmatches,
+// DVM_MATCH_PROFILE: prints the phase times of every matcher launch (synchronises: diagnostics only)
+struct MatchProfile {
+    unsigned long long* d = nullptr;
+    bool on = false;
+    MatchProfile() { on = getenv("DVM_MATCH_PROFILE") != nullptr; }
+    void arm(MatchScratch& s, cudaStream_t st)
+    {
+        if (!on) return;
+        if (!d) cudaMalloc(&d, 64 * 8);
+        cudaMemsetAsync(d, 0, 64 * 8, st);
+        cudaMemsetAsync(d, 0xff, 8, st);
+        s.prof = d;
+    }
+    void report(const char* what, const MatchScratch& s, cudaStream_t st)
+    {
+        if (!on) return;
+        unsigned long long p[64];
+        int rounds = 0;
+        cudaStreamSynchronize(st);
+        cudaMemcpy(p, d, sizeof(p), cudaMemcpyDeviceToHost);
+        cudaMemcpy(&rounds, s.iters, 4, cudaMemcpyDeviceToHost);
+        if (p[2] == 0) { fprintf(stderr, "[%s] skipped\n", what); return; }
+        auto us = [&](int a, int b) { return p[a] && p[b] ? (double)(long long)(p[b] - p[a]) * 1e-3 : -1.0; };
+        fprintf(stderr, "[%s us] walk %.1f gap %.1f | stage %.1f rounds(%d) %.1f owner %.1f tail %.1f | total %.1f | active %llu slow calls %llu full walks %llu\n",
+                what, us(0, 1), us(1, 2), us(2, 4), rounds, us(4, 5), p[6] ? us(5, 6) : 0.0, p[6] ? us(6, 7) : us(5, 7), us(0, 7), p[9], p[10], p[8]);
+        fprintf(stderr, "    rounds (work / barrier wait, us):");
+        for (int r = 1; r <= 12 && p[16 + r]; r++)
+            fprintf(stderr, " %.2f/%.2f", (double)(long long)(p[16 + r] - (r == 1 ? p[4] : p[32 + r - 1])) * 1e-3,
+                    p[32 + r] ? (double)(long long)(p[32 + r] - p[16 + r]) * 1e-3 : 0.0);
+        fprintf(stderr, "\n");
+    }
+};
+static MatchProfile g_match_profile;
+
+void launch_match_last(const FrameDev& cur, const MatchLastArgs& a, const MatchScratch& s_in, int* cur_mp, int* nmatches,
                        cudaStream_t stream)
 {
-    const size_t smem = claim_smem_bytes(cur.cap);
-    const int use_smem = smem <= kMatchSmemLimit ? 1 : 0;
+    const int use_smem = match_smem_bytes(1, cur.cap) <= kMatchSmemLimit ? 1 : 0;
     prepare_match_kernels();
+    MatchScratch s = s_in;
+    g_match_profile.arm(s, stream);
     DVM_LAUNCH_PDL(match_last_walk_kernel, div_up(max(a.last_n, 1), kWalkThreads / 32), kWalkThreads, 0, stream, cur, a, s);
-    DVM_LAUNCH_PDL(match_last_kernel, 1, kMatchThreads, use_smem ? smem : 0, stream, cur, a, s, cur_mp, nmatches, use_smem);
+    if (use_smem) DVM_LAUNCH_PDL(match_last_kernel<true>, 1, kMatchThreads, match_smem_bytes(1, cur.cap), stream, cur, a, s, cur_mp, nmatches);
+    else DVM_LAUNCH_PDL(match_last_kernel<false>, 1, kMatchThreads, match_smem_bytes(0, cur.cap), stream, cur, a, s, cur_mp, nmatches);
+    g_match_profile.report("match-last", s, stream);
 }
 
 // --------------------------------------------------------------- SearchByProjection(F, mapPoints)
@@ -427,6 +602,8 @@ void launch_match_last(const FrameDev& cur, const MatchLastArgs& a, const MatchS
 __global__ void __launch_bounds__(kWalkThreads) match_map_walk_kernel(FrameDev cur, MatchMapArgs a, MatchScratch s)
 {
     pdl_trigger(); pdl_wait();
+    prof_walk_begin(s.prof);
+    struct Stamp { unsigned long long* p; __device__ ~Stamp() { prof_walk_end(p); } } stamp_end{ s.prof };
     const int nq = a.m_ptr ? *a.m_ptr : a.m;
     const int lane = threadIdx.x & 31;
     const int i = (blockIdx.x * kWalkThreads + threadIdx.x) >> 5;
@@ -437,17 +614,13 @@ __global__ void __launch_bounds__(kWalkThreads) match_map_walk_kernel(FrameDev c
     if (a.use_frustum) { // SearchLocalPoints: isInFrustum decides whether map point i takes part at all
         FrustumPose fp;
         frustum_pose(a.fr.pose, fp);
-        if (!frustum_eval(a.fr, fp, i, px, py, lvl, vcos)) {
-            if (lane == 0) { s.plevels[i] = -1; s.ncand[i] = 0; }
-            return;
-        }
+        if (!frustum_eval(a.fr, fp, i, px, py, lvl, vcos)) return;
     } else {
         lvl = a.level[i]; px = a.projX[i]; py = a.projY[i]; vcos = a.sim3_mode ? 0.f : a.view_cos[i];
-        if (a.sim3_mode && lvl < 0) { // rejected by the projection gates
-            if (lane == 0) { s.plevels[i] = -1; s.ncand[i] = 0; }
-            return;
-        }
+        if (a.sim3_mode && lvl < 0) return; // rejected by the projection gates
     }
+    int slot = 0;
+    if (lane == 0) slot = atomicAdd(s.qcount, 1);
     float r;
     if (a.sim3_mode) r = __fmul_rn(a.th, cur.scale[lvl]);   // const float radius = th * pKF->mvScaleFactors[nPredictedLevel]
     else {
@@ -455,7 +628,7 @@ __global__ void __launch_bounds__(kWalkThreads) match_map_walk_kernel(FrameDev c
         if (a.th != 1.0f) r = __fmul_rn(r, a.th);
         r = __fmul_rn(r, cur.scale[lvl]);
     }
-    if (lane == 0) { s.pu[i] = px; s.pv[i] = py; s.pr[i] = r; s.plevels[i] = lvl; }
+    if (lane == 0) { s.pu[i] = px; s.pv[i] = py; s.pr[i] = r; }
     uint32_t d[8];
     load_desc(d, a.mp_desc + (size_t)(a.q_index ? a.q_index[i] : i) * 32);
     unsigned long long top[kMatchCacheK];
@@ -470,146 +643,253 @@ __global__ void __launch_bounds__(kWalkThreads) match_map_walk_kernel(FrameDev c
     });
     nc = __reduce_add_sync(0xffffffffu, nc);
     const unsigned long long e = warp_topk_merge(top, lane);
-    if (lane < kMatchCacheK) s.cache[(size_t)i * kMatchCacheK + lane] = e;
-    if (lane == 0) s.ncand[i] = nc;
+    slot = __shfl_sync(0xffffffffu, slot, 0);
+    if (lane < kMatchCacheK) s.cache[(size_t)slot * kMatchCacheK + lane] = e;
+    if (lane < kMatchCacheK) s.cache8[(size_t)slot * kMatchCacheK + lane] = cand_short(e);
+    if (lane == 0) s.qmeta[slot] = make_int4(i, lvl, nc, 0);
 }
 
+// the acceptance rule of SearchByProjection(F, vpMapPoints) (ORBmatcher.cc:150-170) / of the Sim3-guided search (:470-480)
+__device__ inline int map_decide(const MatchMapArgs& a, int bestDist, int bestLevel, int bestDist2, int bestLevel2, int bestIdx)
+{
+    if (a.sim3_mode) return ((float)bestDist <= a.accept_limit && bestDist < 256) ? bestIdx : -1;
+    if (bestDist <= kThHigh) {
+        const float lim = __fmul_rn(a.nnratio, (float)bestDist2);
+        const bool reject = (bestLevel == bestLevel2) && ((float)bestDist > lim);
+        if (!reject && (bestLevel != bestLevel2 || (float)bestDist <= lim)) return bestIdx;
+    }
+    return -1;
+}
+struct MapDecide { int sim3_mode; float accept_limit, nnratio; };
+__device__ inline int map_decide(const MapDecide& a, int bestDist, int bestLevel, int bestDist2, int bestLevel2, int bestIdx)
+{
+    if (a.sim3_mode) return ((float)bestDist <= a.accept_limit && bestDist < 256) ? bestIdx : -1;
+    if (bestDist <= kThHigh) {
+        const float lim = __fmul_rn(a.nnratio, (float)bestDist2);
+        const bool reject = (bestLevel == bestLevel2) && ((float)bestDist > lim);
+        if (!reject && (bestLevel != bestLevel2 || (float)bestDist <= lim)) return bestIdx;
+    }
+    return -1;
+}
+
+// slow path of one query of SearchByProjection(F, vpMapPoints): all cached candidates, then the full walk
+__device__ __noinline__ int slow_pick_map(const SlowCtx* c, const MapDecide* md, int j, int i, int lvl, int nc, const unsigned* claim)
+{
+    if (c->prof) atomicAdd(&c->prof[10], 1ull);
+    int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+    int found = 0;
+    // sorted by (distance, walk order): the first two free entries are the reference's best and
+    // second best (its scan keeps the earliest of equal distances)
+    const unsigned long long* e = c->cache + (size_t)j * kMatchCacheK;
+    for (int p = 0; p < kMatchCacheK && p < nc && found < 2; p++) {
+        const unsigned long long ev = e[p];
+        const int idx = cand_idx(ev);
+        if (held_before(claim, idx, i)) continue; // held by a map point with observations
+        if (found == 0) { bestDist = cand_dist(ev); bestLevel = cand_oct(ev); bestIdx = idx; }
+        else { bestDist2 = cand_dist(ev); bestLevel2 = cand_oct(ev); }
+        found++;
+    }
+    if (found < 2 && nc > kMatchCacheK) { // cache exhausted: full walk against the current claims
+        if (c->prof) atomicAdd(&c->prof[8], 1ull);
+        uint32_t d[8];
+        load_desc(d, c->q_desc + (size_t)(c->q_desc_index ? c->q_desc_index[i] : i) * 32);
+        bestDist = 256; bestLevel = -1; bestDist2 = 256; bestLevel2 = -1; bestIdx = -1;
+        walk_area(c->fl, c->pu[i], c->pv[i], c->pr[i], lvl - 1, lvl, [&](int idx, int oct) {
+            if (c->cur_map ? c->cur_map[idx] >= 0 : (c->cur_blocked && c->cur_blocked[idx])) return;
+            if (held_before(claim, idx, i)) return;
+            const int dist = hamming256(d, c->fl.desc + (size_t)idx * 32);
+            if (dist < bestDist) {
+                bestDist2 = bestDist; bestDist = dist;
+                bestLevel2 = bestLevel; bestLevel = oct;
+                bestIdx = idx;
+            } else if (dist < bestDist2) {
+                bestLevel2 = oct;
+                bestDist2 = dist;
+            }
+        });
+    }
+    return map_decide(*md, bestDist, bestLevel, bestDist2, bestLevel2, bestIdx);
+}
+
+template <bool kClaimsInSmem>
 __global__ void __launch_bounds__(kMatchThreads, 1)
-match_map_kernel(FrameDev cur, MatchMapArgs a, MatchScratch s, int* __restrict__ cur_mp, int* __restrict__ nmatches,
-                 int use_smem)
+match_map_kernel(FrameDev cur, MatchMapArgs a, MatchScratch s, int* __restrict__ cur_mp, int* __restrict__ nmatches)
 {
     pdl_trigger(); pdl_wait();
     extern __shared__ __align__(16) unsigned char claim_smem[];
-    __shared__ int s_events;
-    const int tid = threadIdx.x;
+    __shared__ int s_events, s_dirty;
+    const int tid = threadIdx.x, lane = tid & 31;
+    prof_stamp(s.prof, 2);
     const int ncur = min(*cur.n, cur.cap);
-    const int nq = a.m_ptr ? *a.m_ptr : a.m;
-    const FrameLook fl = look_global(cur);
-    auto desc_of = [&](int i) { return a.mp_desc + (size_t)(a.q_index ? a.q_index[i] : i) * 32; };
+    const int nact = *s.qcount; // queries in the frustum (any order: the greedy priority is the query index itself)
+    SlowCtx sc;
+    sc.fl = look_global(cur);
+    sc.cache = s.cache; sc.pu = s.pu; sc.pv = s.pv; sc.pr = s.pr;
+    sc.q_desc = a.mp_desc; sc.q_desc_index = a.q_index; sc.cur_map = a.cur_map; sc.cur_blocked = a.cur_blocked; sc.prof = s.prof;
+    MapDecide md;
+    md.sim3_mode = a.sim3_mode; md.accept_limit = a.accept_limit; md.nnratio = a.nnratio;
+    const bool all_obs = a.obs_pos == nullptr;
     auto obs_of = [&](int i) { return a.obs_pos ? a.obs_pos[i] != 0 : true; };
-    auto blocked = [&](int k) { return a.cur_map ? a.cur_map[k] >= 0 : (a.cur_blocked && a.cur_blocked[k]); };
-    __shared__ int warp_sums[33];
-    int* claim_prev = use_smem ? reinterpret_cast<int*>(claim_smem) : s.claim_a;
-    int* claim_next = use_smem ? reinterpret_cast<int*>(claim_smem) + cur.cap : s.claim_b;
-    int* qlist = s.qlist;
-    for (int i = tid; i < nq; i += kMatchThreads) s.choice[i] = -1;
-    for (int k = tid; k < ncur; k += kMatchThreads) claim_prev[k] = blocked(k) ? -1 : kNoClaim;
-    if (tid == 0) s_events = 0;
-    const int nact = compact_active(s.plevels, nq, qlist, warp_sums); // queries in the frustum, vpMapPoints order
+    unsigned* more = reinterpret_cast<unsigned*>(claim_smem);
+    unsigned* claim = kClaimsInSmem ? more + kMoreWords : reinterpret_cast<unsigned*>(s.claim_a);
+    int* owner = kClaimsInSmem ? reinterpret_cast<int*>(more + kMoreWords + cur.cap) : s.claim_b;
 
-    int r_i[kRegQ], r_nc[kRegQ], r_lv[kRegQ], r_choice[kRegQ];
-    ulonglong2 r_e01[kRegQ], r_e23[kRegQ];
+    // register-resident queries: index | candidate count, the two best candidates, the choice; candidates three to eight
+    // in shared memory (a round's common case -- the two best are free, nothing changes -- touches registers and the claims only)
+    int r_in[kRegQ], r_choice[kRegQ];
+    unsigned r_c0[kRegQ], r_c1[kRegQ];
 #pragma unroll
     for (int q = 0; q < kRegQ; q++) {
         const int j = tid + q * kMatchThreads;
-        r_i[q] = -1; r_nc[q] = 0; r_lv[q] = 0; r_choice[q] = -1;
-        r_e01[q] = make_ulonglong2(~0ull, ~0ull); r_e23[q] = r_e01[q];
+        r_in[q] = -1; r_c0[q] = ~0u; r_c1[q] = ~0u; r_choice[q] = -1;
         if (j < nact) {
-            const int i = qlist[j];
-            r_i[q] = i; r_lv[q] = s.plevels[i]; r_nc[q] = s.ncand[i];
-            const unsigned long long* e = s.cache + (size_t)i * kMatchCacheK;
-            r_e01[q] = *reinterpret_cast<const ulonglong2*>(e); r_e23[q] = *reinterpret_cast<const ulonglong2*>(e + 2);
+            const int4 m = s.qmeta[j];
+            const uint4 c = reinterpret_cast<const uint4*>(s.cache8)[2 * j], c2 = reinterpret_cast<const uint4*>(s.cache8)[2 * j + 1];
+            r_in[q] = m.x | (min(m.z, 255) << kIdxBits);
+            r_c0[q] = c.x; r_c1[q] = c.y;
+            unsigned* mo = more + 7 * j;
+            mo[0] = c.y; mo[1] = c.z; mo[2] = c.w; mo[3] = c2.x; mo[4] = c2.y; mo[5] = c2.z; mo[6] = c2.w;
         }
     }
-    auto evaluate = [&](int i, int lvl, int nc, const ulonglong2& e01, const ulonglong2& e23, const int* claim) -> int {
-        int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
-        int found = 0;
-        // sorted by (distance, walk order): the first two free entries are the reference's best and
-        // second best (its scan keeps the earliest of equal distances)
-        const unsigned long long* e = s.cache + (size_t)i * kMatchCacheK;
-        for (int p = 0; p < kMatchCacheK && p < nc && found < 2; p++) {
-            const unsigned long long ev = p == 0 ? e01.x : p == 1 ? e01.y : p == 2 ? e23.x : p == 3 ? e23.y : e[p];
-            const int idx = cand_idx(ev);
-            if (claim[idx] < i) continue; // held by a map point with observations
-            if (found == 0) { bestDist = cand_dist(ev); bestLevel = cand_oct(ev); bestIdx = idx; }
-            else { bestDist2 = cand_dist(ev); bestLevel2 = cand_oct(ev); }
-            found++;
-        }
-        if (found < 2 && nc > kMatchCacheK) { // cache exhausted: full walk against the current claims
-            uint32_t d[8];
-            load_desc(d, desc_of(i));
-            bestDist = 256; bestLevel = -1; bestDist2 = 256; bestLevel2 = -1; bestIdx = -1;
-            walk_area(fl, s.pu[i], s.pv[i], s.pr[i], lvl - 1, lvl, [&](int idx, int oct) {
-                if (claim[idx] < i) return;
-                const int dist = hamming256(d, fl.desc + (size_t)idx * 32);
-                if (dist < bestDist) {
-                    bestDist2 = bestDist; bestDist = dist;
-                    bestLevel2 = bestLevel; bestLevel = oct;
-                    bestIdx = idx;
-                } else if (dist < bestDist2) {
-                    bestLevel2 = oct;
-                    bestDist2 = dist;
-                }
-            });
-        }
-        int pick = -1;
-        if (a.sim3_mode) return ((float)bestDist <= a.accept_limit && bestDist < 256) ? bestIdx : -1;
-        if (bestDist <= kThHigh) {
-            const float lim = __fmul_rn(a.nnratio, (float)bestDist2);
-            const bool reject = (bestLevel == bestLevel2) && ((float)bestDist > lim);
-            if (!reject && (bestLevel != bestLevel2 || (float)bestDist <= lim)) pick = bestIdx;
-        }
-        return pick;
+    for (int k = tid; k < ncur; k += kMatchThreads) claim[k] = kNoClaim;
+    if (tid == 0) { s_events = 0; s_dirty = 0; }
+    for (int j = tid + kRegQ * kMatchThreads; j < nact; j += kMatchThreads) s.choice[j] = -1;
+    __syncthreads();
+    prof_stamp(s.prof, 4);
+    if (s.prof && tid == 0) s.prof[9] = (unsigned long long)nact;
+    const MapDecide mdr = { a.sim3_mode, a.accept_limit, a.nnratio };   // register copy (md's address goes to the slow path)
+    // best / second best as packed candidates (~0 = none) -> the reference's acceptance rule
+    auto decide = [&](unsigned first, unsigned second) {
+        return map_decide(mdr, first == ~0u ? 256 : short_dist(first), first == ~0u ? -1 : short_oct(first),
+                          second == ~0u ? 256 : short_dist(second), second == ~0u ? -1 : short_oct(second),
+                          first == ~0u ? -1 : short_idx(first));
+    };
+    // a changed choice: claim the new keypoint; giving up a keypoint this query HOLDS is the one non-monotone event
+    // (the claim array is then rebuilt)
+    int dirty = 0;
+    auto move_to = [&](int i, int prev, int pick) {
+        if (!obs_of(i)) return;
+        if (prev >= 0 && claim[prev] == (unsigned)i) dirty = 1;
+        if (pick >= 0) atomicMin(&claim[pick], (unsigned)i);
     };
 
     int rounds = 0;
     while (true) {
         int changed = 0;
+        unsigned redo = 0u;
 #pragma unroll
         for (int q = 0; q < kRegQ; q++) {
-            if (r_i[q] < 0) continue;
-            const int pick = evaluate(r_i[q], r_lv[q], r_nc[q], r_e01[q], r_e23[q], claim_prev);
-            if (pick != r_choice[q]) { r_choice[q] = pick; s.choice[r_i[q]] = pick; changed = 1; }
+            if (r_in[q] < 0) continue;
+            const int i = r_in[q] & kIdxMask, nc = r_in[q] >> kIdxBits;
+            const bool f0 = nc > 0 && !held_before(claim, short_idx(r_c0[q]), i);
+            const bool f1 = nc > 1 && !held_before(claim, short_idx(r_c1[q]), i);
+            if (!(f0 && f1) && nc > 2) { redo |= 1u << q; continue; }
+            const int pick = decide(f0 ? r_c0[q] : (f1 ? r_c1[q] : ~0u), (f0 && f1) ? r_c1[q] : ~0u);
+            if (pick != r_choice[q]) { move_to(i, r_choice[q], pick); r_choice[q] = pick; changed = 1; }
         }
+#pragma unroll 1
+        while (redo) { // one of the two best candidates is held: look further (one copy of this code for all register slots)
+            const int q = __ffs(redo) - 1;
+            redo &= redo - 1u;
+            const int j = tid + q * kMatchThreads;
+            int rin = r_in[0];
+            unsigned c0 = r_c0[0];
+#pragma unroll
+            for (int qq = 1; qq < kRegQ; qq++) { rin = qq == q ? r_in[qq] : rin; c0 = qq == q ? r_c0[qq] : c0; }
+            const int i = rin & kIdxMask, nc = rin >> kIdxBits;
+            unsigned first = ~0u, second = ~0u;
+            for (int p = 0; p < kMatchCacheK && p < nc && second == ~0u; p++) {
+                const unsigned c = p == 0 ? c0 : more[7 * j + p - 1];
+                if (held_before(claim, short_idx(c), i)) continue;
+                if (first == ~0u) first = c; else second = c;
+            }
+            int pick;
+            if (second == ~0u && nc > kMatchCacheK) pick = slow_pick_map(&sc, &md, j, i, s.qmeta[j].y, s.qmeta[j].z, claim);
+            else pick = decide(first, second);
+            int prev = r_choice[0];
+#pragma unroll
+            for (int qq = 1; qq < kRegQ; qq++) prev = qq == q ? r_choice[qq] : prev;
+            if (pick != prev) {
+                move_to(i, prev, pick);
+                changed = 1;
+#pragma unroll
+                for (int qq = 0; qq < kRegQ; qq++) r_choice[qq] = qq == q ? pick : r_choice[qq];
+            }
+        }
+#pragma unroll 1
         for (int j = tid + kRegQ * kMatchThreads; j < nact; j += kMatchThreads) {
-            const int i = qlist[j];
-            const unsigned long long* e = s.cache + (size_t)i * kMatchCacheK;
-            const int pick = evaluate(i, s.plevels[i], s.ncand[i], *reinterpret_cast<const ulonglong2*>(e),
-                                      *reinterpret_cast<const ulonglong2*>(e + 2), claim_prev);
-            if (pick != s.choice[i]) { s.choice[i] = pick; changed = 1; }
+            const int4 m = s.qmeta[j];
+            const int pick = slow_pick_map(&sc, &md, j, m.x, m.y, m.z, claim);
+            const int prev = s.choice[j];
+            if (pick != prev) { move_to(m.x, prev, pick); s.choice[j] = pick; changed = 1; }
         }
         rounds++;
+        if (s.prof && tid == 0 && rounds <= 12) s.prof[16 + rounds] = gtimer();
+        if (dirty) s_dirty = 1;
         if (!__syncthreads_or(changed)) break;
-        for (int k = tid; k < ncur; k += kMatchThreads) claim_next[k] = blocked(k) ? -1 : kNoClaim;
-        __syncthreads();
+        if (s.prof && tid == 0 && rounds <= 12) s.prof[32 + rounds] = gtimer();
+        if (rounds > nact + 8) break; // (the fixed point is reached within one round per query; never seen, kept as a fuse)
+        if (s_dirty) { // a held keypoint was given up: rebuild the claims from the current choices
+            dirty = 0;
+            for (int k = tid; k < ncur; k += kMatchThreads) claim[k] = kNoClaim;
+            __syncthreads();
+            if (tid == 0) s_dirty = 0;
 #pragma unroll
-        for (int q = 0; q < kRegQ; q++)
-            if (r_i[q] >= 0 && r_choice[q] >= 0 && obs_of(r_i[q])) atomicMin(&claim_next[r_choice[q]], r_i[q]);
-        for (int j = tid + kRegQ * kMatchThreads; j < nact; j += kMatchThreads) {
-            const int i = qlist[j];
-            const int k = s.choice[i];
-            if (k >= 0 && obs_of(i)) atomicMin(&claim_next[k], i);
+            for (int q = 0; q < kRegQ; q++)
+                if (r_in[q] >= 0 && r_choice[q] >= 0 && obs_of(r_in[q] & kIdxMask)) atomicMin(&claim[r_choice[q]], (unsigned)(r_in[q] & kIdxMask));
+#pragma unroll 1
+            for (int j = tid + kRegQ * kMatchThreads; j < nact; j += kMatchThreads) {
+                const int k = s.choice[j];
+                const int i = s.qmeta[j].x;
+                if (k >= 0 && obs_of(i)) atomicMin(&claim[k], (unsigned)i);
+            }
+            __syncthreads();
         }
+    }
+    prof_stamp(s.prof, 5);
+    // the last writer of a keypoint owns it; with observations everywhere the chooser is unique and the claims are the owners
+    if (!all_obs) {
+        for (int k = tid; k < ncur; k += kMatchThreads) owner[k] = -1;
         __syncthreads();
-        int* t = claim_prev; claim_prev = claim_next; claim_next = t;
     }
-    int* owner = claim_next;
-    __syncthreads();
-    for (int k = tid; k < ncur; k += kMatchThreads) owner[k] = -1;
-    __syncthreads();
-    for (int j = tid; j < nact; j += kMatchThreads) {
-        const int i = qlist[j];
-        const int k = s.choice[i];
+    int events = 0;
+#pragma unroll
+    for (int q = 0; q < kRegQ; q++) {
+        if (r_in[q] < 0 || r_choice[q] < 0) continue;
+        events++;
+        if (!all_obs) atomicMax(&owner[r_choice[q]], r_in[q] & kIdxMask);
+    }
+#pragma unroll 1
+    for (int j = tid + kRegQ * kMatchThreads; j < nact; j += kMatchThreads) {
+        const int k = s.choice[j];
         if (k < 0) continue;
-        atomicMax(&owner[k], i);
-        atomicAdd(&s_events, 1);
+        events++;
+        if (!all_obs) atomicMax(&owner[k], s.qmeta[j].x);
     }
+    events = __reduce_add_sync(0xffffffffu, events);
+    if (lane == 0 && events) atomicAdd(&s_events, events);
     __syncthreads();
+    const int* own = all_obs ? reinterpret_cast<const int*>(claim) : owner;   // kNoClaim reads as -1
     for (int k = tid; k < ncur; k += kMatchThreads) {
-        cur_mp[k] = owner[k];
-        if (a.merge_into && owner[k] >= 0) a.merge_into[k] = a.q_index ? a.q_index[owner[k]] : owner[k];
+        const int o = own[k];
+        cur_mp[k] = o;
+        if (a.merge_into && o >= 0) a.merge_into[k] = a.q_index ? a.q_index[o] : o;
     }
-    if (tid == 0) { *nmatches = s_events; *s.iters = rounds; }
+    if (tid == 0) { *nmatches = s_events; *s.iters = rounds; *s.qcount = 0; }
+    prof_stamp(s.prof, 7);
 }
 
-void launch_match_map(const FrameDev& cur, const MatchMapArgs& a, const MatchScratch& s, int* cur_mp, int* nmatches,
+void launch_match_map(const FrameDev& cur, const MatchMapArgs& a, const MatchScratch& s_in, int* cur_mp, int* nmatches,
                       cudaStream_t stream)
 {
-    const size_t smem = claim_smem_bytes(cur.cap);
-    const int use_smem = smem <= kMatchSmemLimit ? 1 : 0;
+    const int use_smem = match_smem_bytes(1, cur.cap) <= kMatchSmemLimit ? 1 : 0;
     prepare_match_kernels();
+    MatchScratch s = s_in;
+    g_match_profile.arm(s, stream);
     DVM_LAUNCH_PDL(match_map_walk_kernel, div_up(max(a.m, 1), kWalkThreads / 32), kWalkThreads, 0, stream, cur, a, s);
-    DVM_LAUNCH_PDL(match_map_kernel, 1, kMatchThreads, use_smem ? smem : 0, stream, cur, a, s, cur_mp, nmatches, use_smem);
+    if (use_smem) DVM_LAUNCH_PDL(match_map_kernel<true>, 1, kMatchThreads, match_smem_bytes(1, cur.cap), stream, cur, a, s, cur_mp, nmatches);
+    else DVM_LAUNCH_PDL(match_map_kernel<false>, 1, kMatchThreads, match_smem_bytes(0, cur.cap), stream, cur, a, s, cur_mp, nmatches);
+    g_match_profile.report("match-map", s, stream);
 }
 
 
@@ -619,8 +899,10 @@ static bool prepare_match_kernels()
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || done[dev].load()) return true;
-    cudaFuncSetAttribute(match_last_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMatchSmemLimit);
-    cudaFuncSetAttribute(match_map_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMatchSmemLimit);
+    cudaFuncSetAttribute(match_last_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMatchSmemLimit);
+    cudaFuncSetAttribute(match_map_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMatchSmemLimit);
+    cudaFuncSetAttribute(match_last_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMatchSmemLimit);
+    cudaFuncSetAttribute(match_map_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMatchSmemLimit);
     done[dev].store(true);
     return true;
 }

@@ -21,7 +21,7 @@ struct FrameDev {
     float minX, minY, maxX, maxY, gwInv, ghInv;
     int* cell_start;       // [kGridCells + 1] (allocated kGridCells + 4)
     int* cell_items;       // [cap]
-    int* kxyo;             // [cap * 3] compact {x bits, y bits, octave} records written by the grid build
+    int4* cell_rec;        // [cap] per grid position j (the order of cell_items): {x bits, y bits, octave, keypoint index}
     int nlevels;
     float scale[kTrackMaxLevels];       // mvScaleFactors
     float inv_sigma2[kTrackMaxLevels];  // mvInvLevelSigma2
@@ -45,7 +45,9 @@ struct MatchLastArgs {
     const int* mp_index;           // per last keypoint: index into Xw / mp_desc (map arrays), -1 = no map point
     const dvm_keypoint* last_kps;  // octave / angle source instead of the two arrays
     const float* pose;             // qx,qy,qz,qw,tx,ty,tz on the device instead of q,t
-    const int* guard;              // skip the whole search if *guard >= 20 (the 2*th retry, Tracking.cc:2614)
+    const int* guard;              // skip the whole search if *guard >= 20 (the 2*th retry as a second launch)
+    float retry_th;                // > 0: fewer than 20 matches -> the resolution kernel itself searches again with this th
+                                   // (Tracking.cc:2614-2621) and its second result replaces the first
     int* map_out;                  // [cur cap] with mp_index: map point now held by each current keypoint (-1 none)
 };
 
@@ -93,14 +95,18 @@ struct MatchScratch {
     float* pu;      // [cap_q] projected u
     float* pv;      // [cap_q]
     float* pr;      // [cap_q] radius
-    int* plevels;   // [cap_q] minLevel << 16 | (maxLevel & 0xffff), or -1 when the query is skipped
-    int* choice;    // [cap_q] chosen keypoint per query
+    int* plevels;   // [cap_q] (unused by the projection matchers since the compact list carries the level window)
+    int* choice;    // [cap_q] chosen keypoint per compact slot (slots beyond the register-resident ones)
     int* claim_a;   // [cap_kp]
     int* claim_b;   // [cap_kp]
     int* iters;     // [1] fixed-point rounds used (diagnostic)
-    unsigned long long* cache; // [cap_q * kMatchCacheK] best candidates of each query, sorted by (distance, walk order)
-    int* ncand;     // [cap_q] candidates seen by the window walk
-    int* qlist;     // [cap_q] ordered list of the queries that take part
+    unsigned long long* cache; // [cap_q * kMatchCacheK] best candidates of each compact slot, sorted by (distance, walk order)
+    int* ncand;     // [cap_q] (unused by the projection matchers)
+    unsigned* cache8; // [cap_q * kMatchCacheK] the same candidates in 32 bits each (distance:9 | octave:7 | keypoint:16)
+    int4* qmeta;    // [cap_q] compact list of the queries that take part, in the order the walk's warps append them:
+                    // {query index, level window, candidates seen, 0}; cache rows are in the same compact order
+    int* qcount;    // [1] length of the compact list: bumped by the walk, reset to 0 by the resolution kernel
+    unsigned long long* prof; // [16] or nullptr: %globaltimer stamps of the kernel phases (DVM_MATCH_PROFILE, diagnostics)
 };
 constexpr int kMatchCacheK = 8;
 
@@ -127,6 +133,9 @@ struct PoseOptArgs {
     int* map_index_rw;
     // frame hand-over after TrackLocalMap: pose history for the constant-velocity prior and the result block
     float* pose_last; float* pose_prev; float* out_pose; int* out_counts; const int* nm_last; const int* res_first;
+    // ... and the start of the NEXT frame, so that its chain begins with the projection search: the constant-velocity prior
+    // mVelocity * mLastFrame.GetPose() (Tracking.cc:1990-1991,2598) written over `pose`, the "seen in this frame" marks cleared
+    float* next_prior; uint8_t* seen_reset; int seen_n;
     unsigned long long* prof; // [4] or nullptr: ns spent in {edge pass, reduction, solve + update, passes} (DVM_POSE_PROFILE)
 };
 

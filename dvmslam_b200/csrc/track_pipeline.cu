@@ -382,8 +382,10 @@ int dvm_tracker_track(dvm_tracker* t, const uint8_t* gray, int gray_is_device, i
     }
     auto mark = [&](int i) { if (t->profiling) cudaEventRecord(t->pev[i], t->stream); };
     mark(0);
-    DVM_LAUNCH_PDL(begin_frame_kernel, 1, 1024, 0, t->stream, t->d_pose_last, t->d_pose_prev, t->d_pose, prior_q ? 1 : 0, t->d_seen,
-               t->map_n, t->d_cnt);
+    // every later frame finds its prior and the cleared marks already there: the previous chain's last kernel left them
+    if (fi == 1)
+        DVM_LAUNCH_PDL(begin_frame_kernel, 1, 1024, 0, t->stream, t->d_pose_last, t->d_pose_prev, t->d_pose, prior_q ? 1 : 0, t->d_seen,
+                   t->map_n, t->d_cnt);
     mark(1);
     // ---- TrackWithMotionModel: SearchByProjection(cur, last, th = 15), retry with 2*th below 20 matches ----
     MatchLastArgs la;
@@ -392,10 +394,9 @@ int dvm_tracker_track(dvm_tracker* t, const uint8_t* gray, int gray_is_device, i
     la.mp_index = t->d_mp[li]; la.outlier = t->d_outl[li];
     la.Xw = t->d_xw; la.mp_desc = t->d_desc; la.obs_pos = nullptr; la.last_kps = last->d_kps;
     la.pose = t->d_pose; la.th = 15.0f; la.check_ori = 1;
+    la.retry_th = 30.0f;   // the 2 * th retry runs inside the resolution kernel when it is needed
     la.map_out = t->d_mp[ci];
     for (int i = 0; i < 4; i++) la.K[i] = t->K[i];
-    launch_match_last(cur->dev, la, cur->ms, t->d_cur_mp, t->d_cnt + 1, t->stream);
-    la.th = 30.0f; la.guard = t->d_cnt + 1;
     launch_match_last(cur->dev, la, cur->ms, t->d_cur_mp, t->d_cnt + 1, t->stream);
     mark(2);
     // ---- PoseOptimization + discard outliers (fused tail) ----
@@ -418,6 +419,7 @@ int dvm_tracker_track(dvm_tracker* t, const uint8_t* gray, int gray_is_device, i
     pa.pose_last = t->d_pose_last; pa.pose_prev = t->d_pose_prev;
     pa.out_pose = (float*)t->d_result; pa.out_counts = (int*)(t->d_result + 32);
     pa.nm_last = t->d_cnt + 1; pa.res_first = t->d_res1;
+    pa.next_prior = t->d_pose; pa.seen_reset = t->d_seen; pa.seen_n = t->map_n;
     rc = launch_pose_opt(pa, t->stream);
     if (rc != DVM_OK) return rc;
     mark(5);

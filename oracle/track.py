@@ -24,6 +24,7 @@ def _L():
     L.trko_search_by_projection_last.argtypes = [_vp, _vp, _vp, _vp, C.c_int] + [_vp] * 7 + [C.c_float, C.c_int, _vp]
     L.trko_search_by_projection_map.argtypes = [_vp, C.c_int] + [_vp] * 6 + [C.c_float, C.c_float, _vp, _vp]
     L.trko_pose_optimization.argtypes = [_vp, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp]
+    L.trko_velocity_prior.argtypes = [_vp, _vp, _vp]
     L._trk_bound = True
     return L
 
@@ -102,6 +103,17 @@ def descriptor_distance(a, b):
     return _L().trko_descriptor_distance(_c(a, np.uint8).ctypes.data, _c(b, np.uint8).ctypes.data)
 
 
+def velocity_prior(last_q, last_t, prev_q, prev_t):
+    """mVelocity * mLastFrame.GetPose() with mVelocity = last * prev^-1 (Tracking.cc:1990-1991,2598), float32 Sophus order.
+    Returns (q[4] f32, t[3] f32)."""
+    L = _L()
+    last = np.concatenate([_c(last_q, np.float32), _c(last_t, np.float32)])
+    prev = np.concatenate([_c(prev_q, np.float32), _c(prev_t, np.float32)])
+    out = np.zeros(7, np.float32)
+    L.trko_velocity_prior(last.ctypes.data, prev.ctypes.data, out.ctypes.data)
+    return out[:4].copy(), out[4:].copy()
+
+
 def pose_optimization(q, t, K, Xw, kp_xy, inv_sigma2):
     """Returns (n_inliers, q[4] f32, t[3] f32, outlier[n] u8, (lm_iterations, lm_trials))."""
     L = _L()
@@ -157,6 +169,7 @@ class TrackerOracle:
         args = (prior_q, prior_t, self.K, has, L["outlier"], M["xw"][lidx], M["desc"][lidx], np.ones(len(lm), np.uint8),
                 L["kps"]["octave"], L["kps"]["angle"])
         nm, cur_mp = F.search_by_projection_last(*args, 15.0)
+        self.retried = nm < 20   # Tracking.cc:2614-2621
         if nm < 20:
             nm, cur_mp = F.search_by_projection_last(*args, 30.0)
         cur_map = np.where(cur_mp >= 0, lm[np.where(cur_mp >= 0, cur_mp, 0)], -1).astype(np.int64)

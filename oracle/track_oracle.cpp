@@ -883,4 +883,16 @@ int trko_search_by_sim3(void* f1, void* f2, const float* q1, const float* t1, co
     return nFound;
 }
 
+/* The constant-velocity prior of Tracking::TrackWithMotionModel in the reference's float32 Sophus arithmetic:
+ * mVelocity = mCurrentFrame.GetPose() * mLastFrame.GetPose().inverse() once a frame is tracked (O3/src/Tracking.cc:1990-1991)
+ * and mCurrentFrame.SetPose(mVelocity * mLastFrame.GetPose()) for the next one (:2598).  last / prev = the two most recent
+ * poses (qx,qy,qz,qw,tx,ty,tz); prior receives the seven floats of the predicted pose. */
+void trko_velocity_prior(const float* last, const float* prev, float* prior)
+{
+    float qpi[4], tpi[3], qv[4], tv[3];
+    so::se3_inverse(prev, prev + 4, qpi, tpi);
+    so::se3_mul(last, last + 4, qpi, tpi, qv, tv);
+    so::se3_mul(qv, tv, last, last + 4, prior, prior + 4);
+}
+
 } // extern "C"

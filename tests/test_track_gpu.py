@@ -232,6 +232,57 @@ def test_tracker_pipeline_matches_oracle_chain():
     ext.close()
 
 
+def test_tracker_device_prior_and_wide_retry():
+    """Two paths that live inside the chain's kernels: (1) the constant-velocity prior mVelocity * Tcw that the last kernel
+    of a frame leaves for the next one (free-running mode, no prior from the host) against the oracle chain fed with
+    the oracle's float32 Sophus restatement of the same product; (2) Tracking's retry with the doubled window
+    (Tracking.cc:2614-2621), forced by a prior that is three degrees off, which the resolution kernel runs itself."""
+    from dvmslam_b200.extractor import ORBextractor
+    from dvmslam_b200.tracking import Tracker
+    from oracle.orb import OrbOracle
+    from oracle.track import TrackerOracle, velocity_prior
+
+    S = synth.OrbitStream(seed=3, period=320)
+    orc = OrbOracle(2000)
+    T = orc.tables()
+    M = synth.plane_map(S, orc.extract, [0, 40, 80, 120], T["scale"], 6000)
+    bounds = (0.0, 0.0, 1280.0, 720.0)
+    t0 = TrackerOracle(orc.extract, T, S.K, bounds, M)
+    ext = ORBextractor(2000, 1.2, 8, 20, 7, max_width=1280, max_height=720)
+    t1 = Tracker(ext, S.K, bounds, M)
+    R, t = S.pose(0)
+    q = synth.quat_from_R(R).astype(np.float32)
+    assert t0.bootstrap(S.frame(0), q, t) == t1.bootstrap(S.frame(0), q, t)
+    hist = [(q, np.asarray(t, np.float32))] * 2          # (last, prev) as the device holds them after the bootstrap
+    for k in range(1, 7):
+        img = S.frame(k)
+        pq, pt = velocity_prior(hist[0][0], hist[0][1], hist[1][0], hist[1][1])
+        r0 = t0.track(img, pq, pt)
+        q1, tt1, c1 = t1.track(img)                      # no prior from the host
+        cm, ol = t1.debug_matches()
+        assert c1 == tuple(int(c) for c in r0["counts"]), (k, c1, r0["counts"])
+        assert np.array_equal(cm, r0["cur_map"]) and np.array_equal(ol, r0["outlier"]), k
+        assert np.abs(tt1 - r0["t"]).max() < POSE_T_TOL and np.abs(q1 - r0["q"]).max() < POSE_Q_TOL, k
+        hist = [(q1, tt1), hist[0]]                      # the device's own results: its next prior is built from these
+        t0.last["q"], t0.last["t"] = q1, tt1
+    # a prior rotated by 40 degrees: most projections leave the image, fewer than 20 matches at th = 15, the retry at
+    # th = 30 runs (found with the CPU oracle).  The poses that follow are optimised over wrong associations (ill-conditioned),
+    # so only the search itself is compared: keypoint count and nmatches of the search that was kept.
+    good_q, good_t = hist[0]
+    a = np.deg2rad(40.0)
+    dq = np.array([0.0, np.sin(a / 2), 0.0, np.cos(a / 2)])
+    qd = good_q.astype(np.float64)
+    w0, v0, w1, v1 = dq[3], dq[:3], qd[3], qd[:3]
+    off = np.concatenate([w0 * v1 + w1 * v0 + np.cross(v0, v1), [w0 * w1 - v0 @ v1]]).astype(np.float32)
+    img = S.frame(7)
+    r0 = t0.track(img, off, good_t)
+    q1, tt1, c1 = t1.track(img, off, good_t)
+    assert t0.retried, "the oracle chain did not take the retry: the case does not test it"
+    assert c1[:2] == tuple(int(c) for c in r0["counts"][:2]) and c1[1] >= 20, (c1, r0["counts"])
+    t1.close()
+    ext.close()
+
+
 def test_tracker_prefetch_overlap_is_identical():
     """dvm_tracker_prefetch (next frame's upload + extraction on the extractor's stream while the current
     frame's chain runs) must not change any result: same poses, counts and associations as the plain
