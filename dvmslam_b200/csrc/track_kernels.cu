@@ -160,8 +160,8 @@ void launch_features_in_area(const FrameDev& f, float x, float y, float r, int m
 }
 
 // ----------------------------------------------------------------- SearchByProjection(cur, last)
-constexpr int kMatchThreads = 512;   // one CTA; 128 registers per thread keep kRegQ queries each without spilling
-constexpr int kRegQ = 8;   // queries per thread kept in registers by the resolution kernels
+constexpr int kMatchThreads = 1024;  // one CTA of 32 warps: a round is bound by the serial path of one warp, so few queries per thread
+constexpr int kRegQ = 4;   // queries per thread kept in registers by the resolution kernels
 constexpr int kMoreWords = 7 * kRegQ * kMatchThreads;   // shared-memory words for their candidates two to eight
 
 // ---- candidate cache: the window of every query is walked ONCE; its best kMatchCacheK candidates are
@@ -232,6 +232,7 @@ constexpr unsigned kNoClaim = 0xffffffffu;
 __device__ inline bool held_before(const unsigned* claim, int idx, int i) { return claim[idx] < (unsigned)i; }
 constexpr int kIdxBits = 20;                       // query index | candidate count << 20 in one register
 constexpr int kIdxMask = (1 << kIdxBits) - 1;
+constexpr unsigned kWatchNone = 0xffffu, kWatchAlways = 0xfffeu;   // watched-keypoint markers (keypoint indices stay below 65532)
 
 // what the slow path needs, gathered once per kernel (lives in local memory: its address is passed to a call)
 struct SlowCtx {
@@ -362,15 +363,17 @@ match_last_kernel(FrameDev cur, MatchLastArgs a, MatchScratch s, int* __restrict
 
     for (int attempt = 0; attempt < 2; attempt++) {
         const int nact = *reinterpret_cast<volatile int*>(s.qcount);
-        // the first kRegQ queries of every thread stay in registers across the rounds -- index and candidate count in one
-        // word, the best candidate, the current choice; candidates two to eight wait in shared memory: a round's common case
-        // (the best candidate is free, nothing changes) is a dozen instructions
+        // the first kRegQ queries of every thread stay in registers across the rounds: index and candidate count in one
+        // word, the best candidate, the current choice and the WATCHED keypoint -- the first candidate no earlier query
+        // holds.  Keypoints held by earlier queries stay held (the process is monotone), so between two evaluations the only
+        // thing that can change a query's answer is its watched keypoint being taken: a round costs one shared-memory load
+        // and a compare per query, and the (few) queries that lost their keypoint are re-evaluated by one copy of the scan.
         int r_in[kRegQ], r_choice[kRegQ];   // r_in: index | min(candidates, 255) << 20, or -1
-        unsigned r_c0[kRegQ];
+        unsigned r_c0[kRegQ], r_watch[kRegQ];
 #pragma unroll
         for (int q = 0; q < kRegQ; q++) {
             const int j = tid + q * kMatchThreads;
-            r_in[q] = -1; r_c0[q] = ~0u; r_choice[q] = -1;
+            r_in[q] = -1; r_c0[q] = ~0u; r_choice[q] = -1; r_watch[q] = kWatchNone;
             if (j < nact) {
                 const int4 m = s.qmeta[j];
                 const uint4 c = reinterpret_cast<const uint4*>(s.cache8)[2 * j], c2 = reinterpret_cast<const uint4*>(s.cache8)[2 * j + 1];
@@ -378,6 +381,11 @@ match_last_kernel(FrameDev cur, MatchLastArgs a, MatchScratch s, int* __restrict
                 r_c0[q] = c.x;
                 unsigned* mo = more + 7 * j;
                 mo[0] = c.y; mo[1] = c.z; mo[2] = c.w; mo[3] = c2.x; mo[4] = c2.y; mo[5] = c2.z; mo[6] = c2.w;
+                // first evaluation, nothing claimed yet: the best candidate
+                if (m.z > 0) {
+                    r_watch[q] = (unsigned)short_idx(c.x);
+                    r_choice[q] = short_dist(c.x) <= kThHigh ? short_idx(c.x) : -1;
+                }
             }
         }
         for (int k = tid; k < ncur; k += kMatchThreads) claim[k] = kNoClaim;
@@ -385,53 +393,55 @@ match_last_kernel(FrameDev cur, MatchLastArgs a, MatchScratch s, int* __restrict
         if (tid < kHistoLength) histo[tid] = 0;
         if (tid == 0) { s_events = 0; s_bad = 0; }
         __syncthreads();
+#pragma unroll
+        for (int q = 0; q < kRegQ; q++)
+            if (r_choice[q] >= 0 && obs_of(r_in[q] & kIdxMask)) atomicMin(&claim[r_choice[q]], (unsigned)(r_in[q] & kIdxMask));
+        __syncthreads();
         prof_stamp(s.prof, 4);
         if (s.prof && tid == 0) s.prof[9] = (unsigned long long)nact;
-        auto accept = [&](unsigned c) { return short_dist(c) <= kThHigh ? short_idx(c) : -1; };
 
-        int rounds = 0;
+        int rounds = 1;
         while (true) {
             int changed = 0;
             unsigned redo = 0u;
 #pragma unroll
             for (int q = 0; q < kRegQ; q++) {
-                if (r_in[q] < 0) continue;
-                const int i = r_in[q] & kIdxMask, nc = r_in[q] >> kIdxBits;
-                int pick = -1;
-                if (nc > 0) {
-                    if (!held_before(claim, short_idx(r_c0[q]), i)) pick = accept(r_c0[q]);
-                    else if (nc > 1) { redo |= 1u << q; continue; }
-                }
-                if (pick != r_choice[q]) {
-                    r_choice[q] = pick; changed = 1;
-                    if (pick >= 0 && obs_of(i)) atomicMin(&claim[pick], (unsigned)i);
-                }
+                // (inactive slots watch nothing; kWatchAlways = the answer came from the full walk: evaluate every round)
+                const unsigned w = r_watch[q];
+                const bool stale = w == kWatchAlways || (w != kWatchNone && claim[w] < (unsigned)(r_in[q] & kIdxMask));
+                if (stale) redo |= 1u << q;
             }
 #pragma unroll 1
-            while (redo) { // the best candidate is taken: the next ones (one copy of this code for all register slots)
+            while (redo) { // the watched keypoint was taken by an earlier query: scan the candidates again
                 const int q = __ffs(redo) - 1;
                 redo &= redo - 1u;
                 const int j = tid + q * kMatchThreads;
                 int rin = r_in[0];
+                unsigned c0 = r_c0[0];
 #pragma unroll
-                for (int qq = 1; qq < kRegQ; qq++) rin = qq == q ? r_in[qq] : rin;
+                for (int qq = 1; qq < kRegQ; qq++) { rin = qq == q ? r_in[qq] : rin; c0 = qq == q ? r_c0[qq] : c0; }
                 const int i = rin & kIdxMask, nc = rin >> kIdxBits;
                 int pick = -1;
+                unsigned watch = kWatchNone;
                 bool decided = false;
-                for (int p = 1; p < kMatchCacheK && p < nc; p++) {
-                    const unsigned c = more[7 * j + p - 1];
+                for (int p = 0; p < kMatchCacheK && p < nc; p++) {
+                    const unsigned c = p == 0 ? c0 : more[7 * j + p - 1];
                     if (held_before(claim, short_idx(c), i)) continue;
-                    pick = accept(c); decided = true;
+                    pick = short_dist(c) <= kThHigh ? short_idx(c) : -1;
+                    watch = (unsigned)short_idx(c); decided = true;
                     break;
                 }
-                if (!decided && nc > kMatchCacheK) pick = slow_pick_last(&sc, j, i, s.qmeta[j].y, s.qmeta[j].z, claim);
+                if (!decided && nc > kMatchCacheK) {
+                    pick = slow_pick_last(&sc, j, i, s.qmeta[j].y, s.qmeta[j].z, claim);
+                    watch = kWatchAlways;
+                }
                 int prev = r_choice[0];
 #pragma unroll
                 for (int qq = 1; qq < kRegQ; qq++) prev = qq == q ? r_choice[qq] : prev;
+#pragma unroll
+                for (int qq = 0; qq < kRegQ; qq++) { r_choice[qq] = qq == q ? pick : r_choice[qq]; r_watch[qq] = qq == q ? watch : r_watch[qq]; }
                 if (pick != prev) {
                     changed = 1;
-#pragma unroll
-                    for (int qq = 0; qq < kRegQ; qq++) r_choice[qq] = qq == q ? pick : r_choice[qq];
                     if (pick >= 0 && obs_of(i)) atomicMin(&claim[pick], (unsigned)i);
                 }
             }
@@ -576,8 +586,8 @@ struct MatchProfile {
         fprintf(stderr, "[%s us] walk %.1f gap %.1f | stage %.1f rounds(%d) %.1f owner %.1f tail %.1f | total %.1f | active %llu slow calls %llu full walks %llu\n",
                 what, us(0, 1), us(1, 2), us(2, 4), rounds, us(4, 5), p[6] ? us(5, 6) : 0.0, p[6] ? us(6, 7) : us(5, 7), us(0, 7), p[9], p[10], p[8]);
         fprintf(stderr, "    rounds (work / barrier wait, us):");
-        for (int r = 1; r <= 12 && p[16 + r]; r++)
-            fprintf(stderr, " %.2f/%.2f", (double)(long long)(p[16 + r] - (r == 1 ? p[4] : p[32 + r - 1])) * 1e-3,
+        for (int r = 2; r <= 12 && p[16 + r]; r++)
+            fprintf(stderr, " %.2f/%.2f", (double)(long long)(p[16 + r] - (r == 2 ? p[4] : p[32 + r - 1])) * 1e-3,
                     p[32 + r] ? (double)(long long)(p[32 + r] - p[16 + r]) * 1e-3 : 0.0);
         fprintf(stderr, "\n");
     }
@@ -734,29 +744,12 @@ match_map_kernel(FrameDev cur, MatchMapArgs a, MatchScratch s, int* __restrict__
     unsigned* claim = kClaimsInSmem ? more + kMoreWords : reinterpret_cast<unsigned*>(s.claim_a);
     int* owner = kClaimsInSmem ? reinterpret_cast<int*>(more + kMoreWords + cur.cap) : s.claim_b;
 
-    // register-resident queries: index | candidate count, the two best candidates, the choice; candidates three to eight
-    // in shared memory (a round's common case -- the two best are free, nothing changes -- touches registers and the claims only)
+    // register-resident queries: index | candidate count, the best candidate, the choice and the two WATCHED keypoints -- the
+    // first two candidates that no earlier query holds, which are all the acceptance rule looks at.  Held keypoints stay held
+    // (monotone process), so a round is two shared-memory loads and compares per query; a query is evaluated again only when
+    // one of its watched keypoints was taken (or after the rare rebuild of the claims, which re-evaluates everybody).
     int r_in[kRegQ], r_choice[kRegQ];
-    unsigned r_c0[kRegQ], r_c1[kRegQ];
-#pragma unroll
-    for (int q = 0; q < kRegQ; q++) {
-        const int j = tid + q * kMatchThreads;
-        r_in[q] = -1; r_c0[q] = ~0u; r_c1[q] = ~0u; r_choice[q] = -1;
-        if (j < nact) {
-            const int4 m = s.qmeta[j];
-            const uint4 c = reinterpret_cast<const uint4*>(s.cache8)[2 * j], c2 = reinterpret_cast<const uint4*>(s.cache8)[2 * j + 1];
-            r_in[q] = m.x | (min(m.z, 255) << kIdxBits);
-            r_c0[q] = c.x; r_c1[q] = c.y;
-            unsigned* mo = more + 7 * j;
-            mo[0] = c.y; mo[1] = c.z; mo[2] = c.w; mo[3] = c2.x; mo[4] = c2.y; mo[5] = c2.z; mo[6] = c2.w;
-        }
-    }
-    for (int k = tid; k < ncur; k += kMatchThreads) claim[k] = kNoClaim;
-    if (tid == 0) { s_events = 0; s_dirty = 0; }
-    for (int j = tid + kRegQ * kMatchThreads; j < nact; j += kMatchThreads) s.choice[j] = -1;
-    __syncthreads();
-    prof_stamp(s.prof, 4);
-    if (s.prof && tid == 0) s.prof[9] = (unsigned long long)nact;
+    unsigned r_c0[kRegQ], r_watch[kRegQ];   // r_watch: first | second << 16
     const MapDecide mdr = { a.sim3_mode, a.accept_limit, a.nnratio };   // register copy (md's address goes to the slow path)
     // best / second best as packed candidates (~0 = none) -> the reference's acceptance rule
     auto decide = [&](unsigned first, unsigned second) {
@@ -764,6 +757,33 @@ match_map_kernel(FrameDev cur, MatchMapArgs a, MatchScratch s, int* __restrict__
                           second == ~0u ? 256 : short_dist(second), second == ~0u ? -1 : short_oct(second),
                           first == ~0u ? -1 : short_idx(first));
     };
+#pragma unroll
+    for (int q = 0; q < kRegQ; q++) {
+        const int j = tid + q * kMatchThreads;
+        r_in[q] = -1; r_c0[q] = ~0u; r_choice[q] = -1; r_watch[q] = kWatchNone | (kWatchNone << 16);
+        if (j < nact) {
+            const int4 m = s.qmeta[j];
+            const uint4 c = reinterpret_cast<const uint4*>(s.cache8)[2 * j], c2 = reinterpret_cast<const uint4*>(s.cache8)[2 * j + 1];
+            r_in[q] = m.x | (min(m.z, 255) << kIdxBits);
+            r_c0[q] = c.x;
+            unsigned* mo = more + 7 * j;
+            mo[0] = c.y; mo[1] = c.z; mo[2] = c.w; mo[3] = c2.x; mo[4] = c2.y; mo[5] = c2.z; mo[6] = c2.w;
+            // first evaluation, nothing claimed yet: the two best candidates
+            const unsigned first = m.z > 0 ? c.x : ~0u, second = m.z > 1 ? c.y : ~0u;
+            r_watch[q] = (first == ~0u ? kWatchNone : (unsigned)short_idx(first)) | ((second == ~0u ? kWatchNone : (unsigned)short_idx(second)) << 16);
+            r_choice[q] = decide(first, second);
+        }
+    }
+    for (int k = tid; k < ncur; k += kMatchThreads) claim[k] = kNoClaim;
+    if (tid == 0) { s_events = 0; s_dirty = 0; }
+    for (int j = tid + kRegQ * kMatchThreads; j < nact; j += kMatchThreads) s.choice[j] = -1;
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < kRegQ; q++)
+        if (r_choice[q] >= 0 && obs_of(r_in[q] & kIdxMask)) atomicMin(&claim[r_choice[q]], (unsigned)(r_in[q] & kIdxMask));
+    __syncthreads();
+    prof_stamp(s.prof, 4);
+    if (s.prof && tid == 0) s.prof[9] = (unsigned long long)nact;
     // a changed choice: claim the new keypoint; giving up a keypoint this query HOLDS is the one non-monotone event
     // (the claim array is then rebuilt)
     int dirty = 0;
@@ -773,22 +793,22 @@ match_map_kernel(FrameDev cur, MatchMapArgs a, MatchScratch s, int* __restrict__
         if (pick >= 0) atomicMin(&claim[pick], (unsigned)i);
     };
 
-    int rounds = 0;
+    int rounds = 1;
+    bool everybody = false;   // after a rebuild of the claims
     while (true) {
         int changed = 0;
         unsigned redo = 0u;
 #pragma unroll
         for (int q = 0; q < kRegQ; q++) {
-            if (r_in[q] < 0) continue;
-            const int i = r_in[q] & kIdxMask, nc = r_in[q] >> kIdxBits;
-            const bool f0 = nc > 0 && !held_before(claim, short_idx(r_c0[q]), i);
-            const bool f1 = nc > 1 && !held_before(claim, short_idx(r_c1[q]), i);
-            if (!(f0 && f1) && nc > 2) { redo |= 1u << q; continue; }
-            const int pick = decide(f0 ? r_c0[q] : (f1 ? r_c1[q] : ~0u), (f0 && f1) ? r_c1[q] : ~0u);
-            if (pick != r_choice[q]) { move_to(i, r_choice[q], pick); r_choice[q] = pick; changed = 1; }
+            const unsigned w0 = r_watch[q] & 0xffffu, w1 = r_watch[q] >> 16;
+            const unsigned i = (unsigned)(r_in[q] & kIdxMask);
+            const bool stale = w0 == kWatchAlways || (w0 != kWatchNone && claim[w0] < i) || (w1 != kWatchNone && claim[w1] < i) ||
+                               (everybody && r_in[q] >= 0);
+            if (stale) redo |= 1u << q;
         }
+        everybody = false;
 #pragma unroll 1
-        while (redo) { // one of the two best candidates is held: look further (one copy of this code for all register slots)
+        while (redo) { // a watched keypoint was taken by an earlier query: scan the candidates again
             const int q = __ffs(redo) - 1;
             redo &= redo - 1u;
             const int j = tid + q * kMatchThreads;
@@ -804,17 +824,20 @@ match_map_kernel(FrameDev cur, MatchMapArgs a, MatchScratch s, int* __restrict__
                 if (first == ~0u) first = c; else second = c;
             }
             int pick;
-            if (second == ~0u && nc > kMatchCacheK) pick = slow_pick_map(&sc, &md, j, i, s.qmeta[j].y, s.qmeta[j].z, claim);
-            else pick = decide(first, second);
+            unsigned watch;
+            if (second == ~0u && nc > kMatchCacheK) {
+                pick = slow_pick_map(&sc, &md, j, i, s.qmeta[j].y, s.qmeta[j].z, claim);
+                watch = kWatchAlways | (kWatchNone << 16);
+            } else {
+                pick = decide(first, second);
+                watch = (first == ~0u ? kWatchNone : (unsigned)short_idx(first)) | ((second == ~0u ? kWatchNone : (unsigned)short_idx(second)) << 16);
+            }
             int prev = r_choice[0];
 #pragma unroll
             for (int qq = 1; qq < kRegQ; qq++) prev = qq == q ? r_choice[qq] : prev;
-            if (pick != prev) {
-                move_to(i, prev, pick);
-                changed = 1;
 #pragma unroll
-                for (int qq = 0; qq < kRegQ; qq++) r_choice[qq] = qq == q ? pick : r_choice[qq];
-            }
+            for (int qq = 0; qq < kRegQ; qq++) { r_choice[qq] = qq == q ? pick : r_choice[qq]; r_watch[qq] = qq == q ? watch : r_watch[qq]; }
+            if (pick != prev) { move_to(i, prev, pick); changed = 1; }
         }
 #pragma unroll 1
         for (int j = tid + kRegQ * kMatchThreads; j < nact; j += kMatchThreads) {
@@ -829,8 +852,9 @@ match_map_kernel(FrameDev cur, MatchMapArgs a, MatchScratch s, int* __restrict__
         if (!__syncthreads_or(changed)) break;
         if (s.prof && tid == 0 && rounds <= 12) s.prof[32 + rounds] = gtimer();
         if (rounds > nact + 8) break; // (the fixed point is reached within one round per query; never seen, kept as a fuse)
-        if (s_dirty) { // a held keypoint was given up: rebuild the claims from the current choices
+        if (s_dirty) { // a held keypoint was given up: rebuild the claims from the current choices, then look at everybody again
             dirty = 0;
+            everybody = true;
             for (int k = tid; k < ncur; k += kMatchThreads) claim[k] = kNoClaim;
             __syncthreads();
             if (tid == 0) s_dirty = 0;

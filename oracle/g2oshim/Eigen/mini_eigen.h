@@ -296,8 +296,9 @@ public:
     using Base::operator=; /* (none in base; kept for symmetry) */
     Matrix() { }
     explicit Matrix(int n) { if (R == Dynamic && C == 1) s_.resize(n, 1); else if (C == Dynamic && R == 1) s_.resize(1, n); else if (R == Dynamic && C == Dynamic) s_.resize(n, n); else if (R * C == 1) s_.data()[0] = (T)n; }
-    Matrix(int r, int c) { if (R == Dynamic || C == Dynamic) s_.resize(r, c); else { assert(R * C == 2); s_.data()[0] = (T)r; s_.data()[1] = (T)c; } }
-    Matrix(T a, T b) { static_assert(R * C == 2 || R == Dynamic || C == Dynamic, "2-coefficient constructor"); init2(a, b, std::integral_constant<bool, (R == Dynamic || C == Dynamic)>()); }
+    /* two arguments: (rows, cols) of a dynamic matrix, the two coefficients of a fixed 2-vector */
+    template <class A, class B, class = typename std::enable_if<std::is_arithmetic<A>::value && std::is_arithmetic<B>::value>::type>
+    Matrix(A a, B b) { init2(a, b, std::integral_constant<bool, (R == Dynamic || C == Dynamic)>()); }
     Matrix(T a, T b, T c) { s_.data()[0] = a; s_.data()[1] = b; s_.data()[2] = c; }
     Matrix(T a, T b, T c, T d) { s_.data()[0] = a; s_.data()[1] = b; s_.data()[2] = c; s_.data()[3] = d; }
     explicit Matrix(const T* p) { std::memcpy(s_.data(), p, sizeof(T) * R * C); }
@@ -337,8 +338,8 @@ public:
     static Matrix UnitY() { Matrix m; m.setZero(); m.coeffRef(1) = 1; return m; }
     static Matrix UnitZ() { Matrix m; m.setZero(); m.coeffRef(2) = 1; return m; }
 private:
-    void init2(T a, T b, std::false_type) { s_.data()[0] = a; s_.data()[1] = b; }
-    void init2(T a, T b, std::true_type) { s_.resize((int)a, (int)b); }
+    template <class A, class B> void init2(A a, B b, std::false_type) { s_.data()[0] = (T)a; s_.data()[1] = (T)b; }
+    template <class A, class B> void init2(A a, B b, std::true_type) { s_.resize((int)a, (int)b); }
 };
 
 /* ---- Map: a view over caller memory ---- */

@@ -19,7 +19,8 @@ public:
     SM& m;
     explicit SparseSelfAdjointView(SM& m_) : m(m_) { }
     template <class P> SparseSelfAdjointView twistedBy(const P&) const { return *this; }
-    template <class O, int U2> SparseSelfAdjointView& operator=(const SparseSelfAdjointView<O, U2>& o) { m = o.m; return *this; }
+    SparseSelfAdjointView(const SparseSelfAdjointView& o) : m(o.m) { }
+    SparseSelfAdjointView& operator=(const SparseSelfAdjointView& o) { m = o.m; return *this; }
 };
 
 template <class T, int Options, class I> class SparseMatrix {
