@@ -114,6 +114,58 @@ __device__ inline SE3d se3_mul(const SE3d& a, const SE3d& b)
     return r;
 }
 
+// VertexSE3Expmap::oplusImpl: exp(u) * T (g2o/types/types_six_dof_expmap.h:71-74) as ONE dependent chain instead of the
+// three the reference's call sequence has (quaternion of exp, its normalisation, product, normalisation).  With
+// exp(u) = (R_e, V v), R_e = I + A*O + B*O^2 and its quaternion q_e = (A*w, 2 - B*theta^2) / sqrt(trace + 1):
+//   rotation     normalize(q_e (x) T.r): the scale of q_e drops out of the normalisation, so its own square root is skipped;
+//   translation  R_e * T.t + V v with R_e p = p + A*(w x p) + B*(w x (w x p)), independent of the quaternion chain.
+// Same value as se3_mul(se3_exp(u), T) up to rounding (1e-16), about 20 dependent FP64 operations shorter.
+__device__ inline SE3d se3_left_update(const double u[6], const SE3d& T)
+{
+    const double w0 = u[0], w1 = u[1], w2 = u[2];
+    const double th2 = w0 * w0 + w1 * w1 + w2 * w2;
+    double A = 1.0, B = 1.0, Bv = 1.0, C = 1.0;
+    if (!(th2 < 1e-10) && th2 < 0.25) {
+        const double x = th2;
+        A = 1.0 + x * (-1.0 / 6 + x * (1.0 / 120 + x * (-1.0 / 5040 + x * (1.0 / 362880 + x * (-1.0 / 39916800 + x * (1.0 / 6227020800.0 + x * (-1.0 / 1307674368000.0)))))));
+        B = 0.5 + x * (-1.0 / 24 + x * (1.0 / 720 + x * (-1.0 / 40320 + x * (1.0 / 3628800 + x * (-1.0 / 479001600 + x * (1.0 / 87178291200.0 + x * (-1.0 / 20922789888000.0)))))));
+        C = 1.0 / 6 + x * (-1.0 / 120 + x * (1.0 / 5040 + x * (-1.0 / 362880 + x * (1.0 / 39916800 + x * (-1.0 / 6227020800.0 + x * (1.0 / 1307674368000.0 + x * (-1.0 / 355687428096000.0)))))));
+        Bv = B;
+    } else if (!(th2 < 1e-10)) {
+        const double inv = fast_rsqrt(th2), theta = th2 * inv;
+        double sn, cs;
+        sincos(theta, &sn, &cs);
+        A = sn * inv;
+        B = (1.0 - cs) * inv * inv;
+        Bv = B;
+        C = (theta - sn) * inv * inv * inv;
+    }
+    SE3d R;
+    // below theta = 1e-5 the reference takes A = B = 1 in R_e (se3quat.h:222-226): q_e = (w, 2 - theta^2) / sqrt(trace + 1) there too
+    Quat qe;
+    qe.x = A * w0; qe.y = A * w1; qe.z = A * w2; qe.w = 2.0 - B * th2;
+    R.r = quat_mul(qe, T.r);
+    quat_normalize(R.r);
+    const double p0 = T.t[0], p1 = T.t[1], p2 = T.t[2];
+    const double a0 = w1 * p2 - w2 * p1, a1 = w2 * p0 - w0 * p2, a2 = w0 * p1 - w1 * p0;        // w x p
+    const double b0 = w1 * a2 - w2 * a1, b1 = w2 * a0 - w0 * a2, b2 = w0 * a1 - w1 * a0;        // w x (w x p)
+    const double v0 = u[3], v1 = u[4], v2 = u[5];
+    const double c0 = w1 * v2 - w2 * v1, c1 = w2 * v0 - w0 * v2, c2 = w0 * v1 - w1 * v0;        // w x v
+    const double d0 = w1 * c2 - w2 * c1, d1 = w2 * c0 - w0 * c2, d2 = w0 * c1 - w1 * c0;        // w x (w x v)
+    // the point is moved by the (normalised) QUATERNION of exp(u) (SE3Quat::operator*, se3quat.h:105-111).  For theta >= 1e-5
+    // that is R_e itself; below it R_e = I + O + O^2 is not a rotation and its normalised quaternion
+    // (w, 2 - theta^2) / n turns by p + (2 s / n^2) (w x p) + (2 / n^2) (w x (w x p)) with s = 2 - theta^2, n^2 = theta^2 + s^2
+    double Ar = A, Br = B;
+    if (th2 < 1e-10) {
+        const double sq = 2.0 - th2, in2 = fast_rcp(th2 + sq * sq);
+        Ar = 2.0 * sq * in2; Br = 2.0 * in2;
+    }
+    R.t[0] = (p0 + Ar * a0 + Br * b0) + (v0 + Bv * c0 + C * d0);
+    R.t[1] = (p1 + Ar * a1 + Br * b1) + (v1 + Bv * c1 + C * d1);
+    R.t[2] = (p2 + Ar * a2 + Br * b2) + (v2 + Bv * c2 + C * d2);
+    return R;
+}
+
 // Symmetric positive-definite 6x6 solve by 3x3 blocks (rotation block A11, translation block A22):
 //   S = A22 - A12^T A11^-1 A12,  x2 = S^-1 (b2 - A12^T A11^-1 b1),  x1 = A11^-1 b1 - A11^-1 A12 x2
 // with closed-form (adjugate) 3x3 inverses.  Same solution as the LDL^T the reference's dense solver
@@ -280,23 +332,46 @@ __global__ void __cluster_dims__(kPoseCtas, 1, 1) __launch_bounds__(kPoseThreads
     }
     cooperative_groups::this_cluster().sync(); // nobody sends before every CTA has initialised its barriers
 
-    // ---- gather this thread's edges into registers ----
+    // ---- gather this CTA's edges into registers, compacted ----
+    // Potential edge k of the frame belongs to CTA (k % kPoseStride) / kPoseThreads.  Only a part of the keypoints carries a
+    // map point, so the CTA first packs its valid ones (block scan, order kept) and thread p then takes entries p,
+    // p + 128, ...: with at most 128 valid edges per CTA -- a tracked frame of 2000 keypoints -- every thread holds ONE edge
+    // and the second register slot is skipped by whole warps in each of the ~25 dependent passes.
     // state: bit0 excluded (level 1), bit1 robust kernel removed, bit2 not an edge
+    __shared__ int s_list[EPT * kPoseThreads];
+    __shared__ int s_scan[33];
     double X[EPT][3], ox[EPT], oy[EPT], om[EPT], e0[EPT], e1[EPT];
-    int st[EPT], mis[EPT];
+    int st[EPT], mis[EPT], kk[EPT];
     double acc[kPoseNV];
 #pragma unroll
     for (int i = 0; i < kPoseNV; i++) acc[i] = 0;
+    {
+        unsigned vmask = 0u;
+        int mine = 0;
 #pragma unroll
-    for (int s = 0; s < EPT; s++) {
-        const int k = tid + s * kPoseStride;
-        st[s] = 4; mis[s] = -1;
-        X[s][0] = X[s][1] = X[s][2] = 0; ox[s] = oy[s] = om[s] = 0; e0[s] = e1[s] = 0;
-        if (k < n) {
-            const int mi = a.map_index ? a.map_index[k] : k;
-            const bool valid = a.map_index ? mi >= 0 : (a.valid ? a.valid[k] != 0 : true);
-            if (valid) {
-                st[s] = 0; mis[s] = mi;
+        for (int s = 0; s < EPT; s++) {
+            const int k = tid + s * kPoseStride;
+            if (k < n) {
+                const bool valid = a.map_index ? a.map_index[k] >= 0 : (a.valid ? a.valid[k] != 0 : true);
+                if (valid) { vmask |= 1u << s; mine++; }
+                else a.outlier[k] = 0; // not an edge
+            }
+        }
+        int total;
+        int off = block_exclusive_scan(mine, s_scan, &total);
+#pragma unroll
+        for (int s = 0; s < EPT; s++)
+            if (vmask & (1u << s)) s_list[off++] = tid + s * kPoseStride;
+        __syncthreads();
+#pragma unroll
+        for (int s = 0; s < EPT; s++) {
+            const int slot = threadIdx.x + s * kPoseThreads;
+            st[s] = 4; mis[s] = -1; kk[s] = -1;
+            X[s][0] = X[s][1] = X[s][2] = 0; ox[s] = oy[s] = om[s] = 0; e0[s] = e1[s] = 0;
+            if (slot < total) {
+                const int k = s_list[slot];
+                const int mi = a.map_index ? a.map_index[k] : k;
+                st[s] = 0; mis[s] = mi; kk[s] = k;
                 const float* xp = a.Xw + 3 * (size_t)mi;
                 X[s][0] = (double)xp[0]; X[s][1] = (double)xp[1]; X[s][2] = (double)xp[2];
                 if (a.kps) {
@@ -432,7 +507,7 @@ __global__ void __cluster_dims__(kPoseCtas, 1, 1) __launch_bounds__(kPoseThreads
 #pragma unroll
                         for (int j = 0; j < 6; j++) x[j] = 0;
                     }
-                    T = se3_mul(se3_exp(x), T);
+                    T = se3_left_update(x, T);
                     linearize_at(T); // computeActiveErrors at the trial (+ speculative buildSystem)
                     double tempChi = acc[27];
                     if (!ok2) tempChi = 1.7976931348623157e308;
@@ -495,10 +570,10 @@ __global__ void __cluster_dims__(kPoseCtas, 1, 1) __launch_bounds__(kPoseThreads
     }
 #pragma unroll
     for (int s = 0; s < EPT; s++) {
-        const int k = tid + s * kPoseStride;
-        if (k >= n) continue;
-        int out = (st[s] & 4) ? 0 : (st[s] & 1);
-        if (a.seen && !(st[s] & 4)) { // "discard outliers": Tracking.cc:2634-2654
+        const int k = kk[s];
+        if (k < 0) continue;
+        int out = st[s] & 1;
+        if (a.seen) { // "discard outliers": Tracking.cc:2634-2654
             a.seen[mis[s]] = 1;
             if (out) { a.map_index_rw[k] = -1; out = 0; }
         }

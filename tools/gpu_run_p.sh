@@ -1,0 +1,10 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 240 python -m pytest tests/test_track_gpu.py tests/test_host_adapters.py -m gpu -q -x --timeout 60 > gpurun_out/r2p_pytest.log 2>&1; tail -8 gpurun_out/r2p_pytest.log
+DVM_POSE_PROFILE=1 timeout 120 python tests/gpu_profile_track.py 3 0 2>&1 | tail -7
+timeout 300 python bench.py --steps 10 --warmup 3 > gpurun_out/r2p_bench.json 2> gpurun_out/r2p_bench.err; python - <<'PY'
+import json
+d = json.loads(open("gpurun_out/r2p_bench.json").read().strip().splitlines()[-1])
+print("value", d["value"], "e2e", d["e2e"]["value"], "chain", d["roofline"].get("chain_us"), "frame_us", d["roofline"].get("frame_us"))
+PY
+tail -3 gpurun_out/r2p_bench.err
