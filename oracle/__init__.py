@@ -7,7 +7,12 @@ Parity status: the reference holds no tests or golden vectors for this path
 (SURVEY.md section 8c).  The oracle is pinned instead against (1) the cv2 4.13.0
 primitives the reference calls (tests/test_oracle_cv2.py, golden vectors under
 tests/golden/ made by tests/golden/make_golden.py) and (2) the reference's own
-ORBextractor.cc compiled against oracle/cvshim into oracle/_ref/ (`make ref`).
+sources compiled unmodified where they lie into oracle/_ref/ (`make ref`):
+ORBextractor.cc against oracle/cvshim (tests/test_ref_build.py), ORBmatcher.cc with
+the Frame / KeyFrame / MapPoint / Pinhole bodies it calls against oracle/slamshim
+(tests/test_ref_matchers.py), and the optimisation functions of Optimizer.cc with
+OptimizableTypes.cpp and the vendored g2o against the mini Eigen of oracle/g2oshim
+(tests/test_ref_optimizer.py).
 """
 from __future__ import annotations
 
@@ -20,7 +25,7 @@ _LIB = None
 
 
 def build(ref: bool = False) -> None:
-    subprocess.run(["make", "-C", _HERE] + (["ref"] if ref else []), check=True, capture_output=True)
+    subprocess.run(["make", "-C", _HERE, "-j8"] + (["ref"] if ref else []), check=True, capture_output=True)
 
 
 def lib() -> ctypes.CDLL:
