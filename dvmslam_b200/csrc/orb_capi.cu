@@ -39,6 +39,8 @@ struct dvm_orb {
     size_t cand_total = 0;
     ResizeX* d_xtab = nullptr;
     ResizeY* d_ytab = nullptr;
+    int* d_pyr_col = nullptr; int* d_pyr_row = nullptr; size_t pyr_col_cap = 0, pyr_row_cap = 0;
+    bool fused_pyramid = true;
     size_t xtab_cap = 0, ytab_cap = 0;
     uint8_t* d_out = nullptr; // [counts 16 B | status 16 B | kps | desc]
     size_t out_bytes = 0;
@@ -65,7 +67,7 @@ static void free_all(dvm_orb* h)
 {
     if (!h) return;
     cudaSetDevice(h->device);
-    cudaFree(h->d_pyr); cudaFree(h->d_dbg); cudaFree(h->d_xtab); cudaFree(h->d_ytab); cudaFree(h->d_out);
+    cudaFree(h->d_pyr); cudaFree(h->d_dbg); cudaFree(h->d_xtab); cudaFree(h->d_ytab); cudaFree(h->d_pyr_col); cudaFree(h->d_pyr_row); cudaFree(h->d_out);
     cudaFree(h->d_pattern);
     cudaFree(h->buf.cand); cudaFree(h->buf.cand_count); cudaFree(h->buf.pnode); cudaFree(h->buf.sel);
     cudaFree(h->buf.sel_count); cudaFree(h->buf.work_kp); cudaFree(h->buf.work_meta); cudaFree(h->buf.ticket);
@@ -77,6 +79,7 @@ static void free_all(dvm_orb* h)
 
 // Per-size geometry: level sizes, cell grid, octree roots, resize tables.  Mirrors the integer /
 // float expressions of ComputePyramid, ComputeKeyPointsOctTree and DistributeOctTree.
+constexpr int kPyrMaxSpanHost = 192;   // = kPyrMaxSpan of orb_kernels.cu (table slices in shared memory)
 static int configure(dvm_orb* h, int w, int hgt)
 {
     if (w == h->cur_w && hgt == h->cur_h) return DVM_OK;
@@ -147,7 +150,65 @@ static int configure(dvm_orb* h, int w, int hgt)
         int rc = prepare_octree_kernel(h->oct_smem);
         if (rc != DVM_OK) return rc;
     }
+    // ---- plan of the one-launch pyramid: per tile column / row of the last level, the region of every level ----
+    std::vector<int> colr, rowr;
+    h->fused_pyramid = c.nlevels >= 2;
+    if (c.nlevels >= 2) {
+        const int L = c.nlevels - 1;
+        OrbPyrPlan& P = c.pyr;
+        P.ntx = (c.lv[L].w + kPyrTileW - 1) / kPyrTileW;
+        P.nty = (c.lv[L].h + kPyrTileH - 1) / kPyrTileH;
+        auto plan_axis = [&](bool is_x, int ntiles, int tile, std::vector<int>& out, int* maxlen) {
+            out.assign((size_t)ntiles * kMaxLevels * 3, 0);
+            auto dim = [&](int l) { return is_x ? c.lv[l].w : c.lv[l].h; };
+            auto s0 = [&](int l, int d) { return is_x ? xt[c.lv[l].xtab_off + d].sx0 : yt[c.lv[l].ytab_off + d].sy0; };   // first tap of pixel d of level l
+            auto s1 = [&](int l, int d) { return is_x ? xt[c.lv[l].xtab_off + d].sx1 : yt[c.lv[l].ytab_off + d].sy1; };
+            std::vector<int> start((size_t)(ntiles + 1) * kMaxLevels, 0);
+            for (int i = 0; i <= ntiles; i++) {   // first pixel of tile i's region at every level (tile ntiles = one past the end)
+                int d = std::min(i * tile, dim(L));
+                start[(size_t)i * kMaxLevels + L] = d;
+                for (int l = L - 1; l >= 0; l--) {
+                    d = d >= dim(l + 1) ? dim(l) : s0(l + 1, d);
+                    start[(size_t)i * kMaxLevels + l] = d;
+                }
+            }
+            for (int l = 0; l < kMaxLevels; l++) maxlen[l] = 0;
+            for (int i = 0; i < ntiles; i++) {
+                int need1 = 0;
+                for (int l = L; l >= 0; l--) {
+                    const int first = start[(size_t)i * kMaxLevels + l];
+                    const int own1 = (i + 1 == ntiles ? dim(l) : start[(size_t)(i + 1) * kMaxLevels + l]) - 1;
+                    need1 = l == L ? own1 : std::max(own1, s1(l + 1, need1));
+                    int* e = &out[((size_t)i * kMaxLevels + l) * 3];
+                    e[0] = first; e[1] = own1; e[2] = need1;
+                    maxlen[l] = std::max(maxlen[l], need1 - first + 1);
+                }
+            }
+        };
+        int mw[kMaxLevels], mh[kMaxLevels];
+        plan_axis(true, P.ntx, kPyrTileW, colr, mw);
+        plan_axis(false, P.nty, kPyrTileH, rowr, mh);
+        int off = 0;
+        for (int l = 1; l <= L; l++) {
+            P.spitch[l] = (mw[l] + 3) & ~3;
+            P.soff[l] = off;
+            off += P.spitch[l] * mh[l];
+            off = (off + 15) & ~15;
+        }
+        P.smem_bytes = off;
+        bool span_ok = true;
+        for (int l = 1; l <= L; l++) span_ok = span_ok && mw[l] <= kPyrMaxSpanHost && mh[l] <= kPyrMaxSpanHost;
+        if (off > 200 * 1024 || !span_ok) h->fused_pyramid = false;   // (other scale factors / level counts: keep the per-level launches)
+        else if (off > 48 * 1024) prepare_pyramid_kernel(off);
+    }
     DVM_CUDA(cudaStreamSynchronize(h->stream)); // nothing in flight may still read the old tables
+    if (!colr.empty()) {
+        if (colr.size() > h->pyr_col_cap) { cudaFree(h->d_pyr_col); h->d_pyr_col = nullptr; DVM_CUDA(cudaMalloc(&h->d_pyr_col, colr.size() * 4)); h->pyr_col_cap = colr.size(); }
+        if (rowr.size() > h->pyr_row_cap) { cudaFree(h->d_pyr_row); h->d_pyr_row = nullptr; DVM_CUDA(cudaMalloc(&h->d_pyr_row, rowr.size() * 4)); h->pyr_row_cap = rowr.size(); }
+        DVM_CUDA(cudaMemcpy(h->d_pyr_col, colr.data(), colr.size() * 4, cudaMemcpyHostToDevice));
+        DVM_CUDA(cudaMemcpy(h->d_pyr_row, rowr.data(), rowr.size() * 4, cudaMemcpyHostToDevice));
+        h->buf.pyr_col = h->d_pyr_col; h->buf.pyr_row = h->d_pyr_row;
+    }
     if (!xt.empty()) {
         DVM_CUDA(cudaMemcpy(h->d_xtab, xt.data(), xt.size() * sizeof(ResizeX), cudaMemcpyHostToDevice));
         DVM_CUDA(cudaMemcpy(h->d_ytab, yt.data(), yt.size() * sizeof(ResizeY), cudaMemcpyHostToDevice));
@@ -305,7 +366,8 @@ static int enqueue_pipeline(dvm_orb* h, int lap0, int lap1)
     const OrbCfg& c = h->cfg;
     const bool prof = h->profiling;
     if (prof) DVM_CUDA(cudaEventRecord(h->ev[0], h->stream));
-    for (int l = 1; l < c.nlevels; l++) launch_resize_level(c, h->buf, l, const_cast<uint8_t*>(c.lv[l].img), h->stream);
+    if (h->fused_pyramid) launch_pyramid(c, h->buf, h->stream);
+    else for (int l = 1; l < c.nlevels; l++) launch_resize_level(c, h->buf, l, const_cast<uint8_t*>(c.lv[l].img), h->stream);
     if (prof) DVM_CUDA(cudaEventRecord(h->ev[1], h->stream));
     if (c.lv[0].img != h->tmap0_img || c.lv[0].pitch != h->tmap0_pitch) {   // level 0 may be the caller's image
         encode_level_tmap(c, 0, h->tmaps);

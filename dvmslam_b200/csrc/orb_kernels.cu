@@ -1,6 +1,7 @@
 // orb_kernels.cu -- sm_100a kernels of the ORB extractor (reference: O3/src/ORBextractor.cc).
 //
-//   resize_linear_kernel   cv::resize INTER_LINEAR chain        (ComputePyramid, :957-976)
+//   pyramid_kernel         cv::resize INTER_LINEAR chain, all levels in one launch (ComputePyramid, :957-976);
+//                          resize_linear_kernel = one level (debug / fallback)
 //   fast_cells_kernel      per-cell FAST-9-16 + 3x3 NMS + 20->7 threshold fallback, one CTA per
 //                          ~35 px cell                           (ComputeKeyPointsOctTree, :612-692)
 //   octree_kernel          DistributeOctTree, one CTA per level; the last CTA also lays out the
@@ -40,6 +41,94 @@ void launch_resize_level(const OrbCfg& cfg, const OrbBuffers& b, int level, uint
     dim3 block(32, 8), grid(div_up(D.w, 32), div_up(D.h, 8));
     DVM_LAUNCH(resize_linear_kernel, grid, block, 0, stream, S.img, S.pitch, dst, D.w, D.h, D.pitch,
                b.xtab + D.xtab_off, b.ytab + D.ytab_off);
+}
+
+// ---- the whole chain in one launch ----
+struct PyrLevels {
+    const uint8_t* src0; int pitch0;          // level 0
+    uint8_t* dst[kMaxLevels]; int pitch[kMaxLevels];
+    int xoff[kMaxLevels], yoff[kMaxLevels];   // resize tables of level l
+};
+
+constexpr int kPyrThreads = 512;   // two CTAs per SM
+constexpr int kPyrMaxSpan = 192;   // widest / tallest region of one tile at level 1 (tile 32 x 16 at level 7 of a 1.2 pyramid: 108 x 60)
+
+__global__ void __launch_bounds__(kPyrThreads, 2) pyramid_kernel(OrbPyrPlan plan, PyrLevels lv, int nlevels, const ResizeX* __restrict__ xtab,
+                                                              const ResizeY* __restrict__ ytab, const int* __restrict__ colr,
+                                                              const int* __restrict__ rowr)
+{
+    extern __shared__ uint8_t pyr_smem[];
+    __shared__ int s_rng[kMaxLevels][6];
+    __shared__ ResizeX s_xt[kPyrMaxSpan];
+    __shared__ ResizeY s_yt[kPyrMaxSpan];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    if (threadIdx.x < nlevels * 6) {
+        const int l = threadIdx.x / 6, k = threadIdx.x % 6;
+        s_rng[l][k] = k < 3 ? colr[(blockIdx.x * kMaxLevels + l) * 3 + k] : rowr[(blockIdx.y * kMaxLevels + l) * 3 + k - 3];
+    }
+    __syncthreads();
+    for (int l = 1; l < nlevels; l++) {
+        const int x0 = s_rng[l][0], ox1 = s_rng[l][1], nx1 = s_rng[l][2], y0 = s_rng[l][3], oy1 = s_rng[l][4], ny1 = s_rng[l][5];
+        const int px0 = s_rng[l - 1][0], py0 = s_rng[l - 1][3];
+        // this level's table slices: one dependent load less per pixel
+        for (int i = threadIdx.x; i <= nx1 - x0; i += kPyrThreads) s_xt[i] = xtab[lv.xoff[l] + x0 + i];
+        for (int i = threadIdx.x; i <= ny1 - y0; i += kPyrThreads) s_yt[i] = ytab[lv.yoff[l] + y0 + i];
+        __syncthreads();
+        const uint8_t* src = l == 1 ? lv.src0 : pyr_smem + plan.soff[l - 1];
+        const int sp = l == 1 ? lv.pitch0 : plan.spitch[l - 1];
+        const int sx_org = l == 1 ? 0 : px0, sy_org = l == 1 ? 0 : py0;
+        uint8_t* buf = pyr_smem + plan.soff[l];
+        const int bp = plan.spitch[l];
+        uint8_t* dst = lv.dst[l];
+        const int dp = lv.pitch[l];
+        const int rw = nx1 - x0 + 1;
+        for (int ly = ty; ly <= ny1 - y0; ly += kPyrThreads / 32) {
+            const ResizeY Y = s_yt[ly];
+            const uint8_t* S0 = src + ((Y.sy0 - sy_org) * sp - sx_org);   // (32-bit offsets: a level is far below 2 GB)
+            const uint8_t* S1 = src + ((Y.sy1 - sy_org) * sp - sx_org);
+            const int dy = y0 + ly;
+            uint8_t* drow = dst + dy * dp + x0;
+            // the arithmetic of resize_linear_kernel (cv::resize, 8-bit fixed point, 11-bit coefficients), two pixels per
+            // iteration so that their loads are in flight together
+            auto pixel = [&](const ResizeX& X) {
+                const int R0 = S0[X.sx0] * X.a0 + S0[X.sx1] * X.a1;
+                const int R1 = S1[X.sx0] * X.a0 + S1[X.sx1] * X.a1;
+                const int v = (((Y.b0 * (R0 >> 4)) >> 16) + ((Y.b1 * (R1 >> 4)) >> 16) + 2) >> 2;
+                return (uint8_t)min(max(v, 0), 255);
+            };
+            for (int lx = tx; lx < rw; lx += 64) {
+                const bool second = lx + 32 < rw;
+                const ResizeX Xa = s_xt[lx], Xb = s_xt[second ? lx + 32 : lx];
+                const uint8_t va = pixel(Xa), vb = pixel(Xb);
+                buf[ly * bp + lx] = va;
+                if (x0 + lx <= ox1 && dy <= oy1) drow[lx] = va;
+                if (second) {
+                    buf[ly * bp + lx + 32] = vb;
+                    if (x0 + lx + 32 <= ox1 && dy <= oy1) drow[lx + 32] = vb;
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+void prepare_pyramid_kernel(int smem_bytes)
+{
+    cudaFuncSetAttribute(pyramid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+}
+
+void launch_pyramid(const OrbCfg& cfg, const OrbBuffers& b, cudaStream_t stream)
+{
+    if (cfg.nlevels < 2) return;
+    PyrLevels lv;
+    memset(&lv, 0, sizeof(lv));
+    lv.src0 = cfg.lv[0].img; lv.pitch0 = cfg.lv[0].pitch;
+    for (int l = 1; l < cfg.nlevels; l++) {
+        lv.dst[l] = const_cast<uint8_t*>(cfg.lv[l].img); lv.pitch[l] = cfg.lv[l].pitch;
+        lv.xoff[l] = cfg.lv[l].xtab_off; lv.yoff[l] = cfg.lv[l].ytab_off;
+    }
+    DVM_LAUNCH(pyramid_kernel, dim3(cfg.pyr.ntx, cfg.pyr.nty), kPyrThreads, cfg.pyr.smem_bytes, stream, cfg.pyr, lv, cfg.nlevels, b.xtab, b.ytab,
+               b.pyr_col, b.pyr_row);
 }
 
 // -------------------------------------------------------------------------------------- FAST cells

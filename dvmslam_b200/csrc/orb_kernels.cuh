@@ -32,12 +32,26 @@ struct OrbLevel {
     int xtab_off, ytab_off; // resize tables (levels >= 1)
 };
 
+// The whole resize chain in ONE launch (pyramid_kernel): a CTA owns a tile of the LAST level and computes, level by level in
+// shared memory, the region of every level that tile depends on -- the chain dependency of ComputePyramid (level l from
+// level l-1, O3/src/ORBextractor.cc:967) stays inside the CTA -- and writes the part of each level it owns.  Per tile
+// column / row and level: first pixel of the region, last pixel it owns, last pixel it needs (host-built from the
+// resize tables).
+constexpr int kPyrTileW = 32, kPyrTileH = 8;   // 12 x 26 = 312 tiles at 720p: two CTAs per SM hide each other's load latency
+struct OrbPyrPlan {
+    int ntx, nty;                 // tiles of the last level
+    int soff[kMaxLevels];         // shared-memory offset of each level's region buffer
+    int spitch[kMaxLevels];       // and its pitch (max region width over the tiles)
+    int smem_bytes;
+};
+
 struct OrbCfg {
     int nlevels;
     int total_cells;
     int ini_th, min_th;
     int max_kp;           // sum of node_cap
     OrbLevel lv[kMaxLevels];
+    OrbPyrPlan pyr;
 };
 
 // packed keypoint: response << 24 | y << 12 | x   (x, y relative to the 16-px border origin)
@@ -61,6 +75,8 @@ struct OrbBuffers {
     uint8_t* out_desc;     // [max_kp * 32]
     const ResizeX* xtab;
     const ResizeY* ytab;
+    const int* pyr_col;    // [ntx][kMaxLevels][3] = {first, last owned, last needed} column of each level's region
+    const int* pyr_row;    // [nty][kMaxLevels][3]
     const int8_t* pattern; // [256*4] device copy of the rBRIEF pattern
 };
 
@@ -75,6 +91,8 @@ struct alignas(64) OrbTmaps {
 
 // launches (all on `stream`)
 void launch_resize_level(const OrbCfg& cfg, const OrbBuffers& b, int level, uint8_t* dst, cudaStream_t stream);
+void launch_pyramid(const OrbCfg& cfg, const OrbBuffers& b, cudaStream_t stream);   // levels 1 .. nlevels-1 in one launch
+void prepare_pyramid_kernel(int smem_bytes);
 void launch_fast_cells(const OrbCfg& cfg, const OrbBuffers& b, const OrbTmaps& tm, cudaStream_t stream);
 // encodes tm.map[level] for the level image currently in cfg (returns false and clears tm.use[level] when TMA cannot
 // address it)
