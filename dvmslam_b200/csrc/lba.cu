@@ -58,6 +58,11 @@ struct LbaDev {
     const volatile int* abort_flag;
     float* out_camq; float* out_camt; float* out_pts; double* out_chi2; uint8_t* out_bad; double* out_stats;
     unsigned long long* prof; // [8] ns per phase (L1, L2, S0, S1, C, B1, B2, other), written by thread 0
+    // edges grouped by point (as the reference creates them): the two CSR structures are built by the kernel itself
+    int build;             // 1 = build pt_start / pt_edges / cam_start / cam_edges in the prologue
+    int* pt_start_w; int* pt_edges_w; int* cam_start_w; int* cam_edges_w;
+    int* cnt;              // [nf][warps of the grid] per-chunk camera counts, then their exclusive prefix
+    int* cam_tot;          // [nf + 1]
 };
 
 // ---- SE3 helpers (same formulas as the pose-only optimiser; g2o/types/se3quat.h) ----
@@ -396,6 +401,80 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kLbaThrea
         grid.sync();
         return a;
     };
+
+    // ---- structure (the analogue of BlockSolver::buildStructure, block_solver.hpp:143-295) on the device, for edges
+    // that come grouped by point: rows by point are runs of the edge array; rows by free camera are a STABLE counting
+    // sort (ascending edge index inside a row, so that every sum over a row has a fixed order): every warp owns a
+    // contiguous chunk of edges, counts its edges per camera, a per-camera scan over the chunks gives each (camera,
+    // chunk) its base, and the warps then place their edges in order.
+    if (P.build) {
+        const int C = (P.ne + nwarps - 1) / nwarps;
+        for (size_t i = gtid; i < (size_t)P.nf * nwarps; i += nthreads) P.cnt[i] = 0;
+        for (int e = gtid; e < P.ne; e += nthreads) {
+            const int l = P.ept[e], prev = e > 0 ? P.ept[e - 1] : -1;
+            for (int k = prev + 1; k <= l; k++) P.pt_start_w[k] = e;
+            if (e == P.ne - 1) for (int k = l + 1; k <= P.np; k++) P.pt_start_w[k] = P.ne;
+            P.pt_edges_w[e] = e;
+        }
+        grid.sync();
+        {
+            const int e0 = gwarp * C, e1 = min(e0 + C, P.ne);
+            for (int eb = e0; eb < e1; eb += 32) {
+                const int e = eb + lane;
+                const int cf = e < e1 ? P.cam_col[P.ecam[e]] : -1;
+                const unsigned peers = __match_any_sync(0xffffffffu, cf);
+                if (cf >= 0 && lane == __ffs(peers) - 1) atomicAdd(&P.cnt[(size_t)cf * nwarps + gwarp], __popc(peers));
+            }
+        }
+        grid.sync();
+        for (int cf = gwarp; cf < P.nf; cf += nwarps) { // exclusive prefix over the chunks, one warp per camera
+            int* row = P.cnt + (size_t)cf * nwarps;
+            int run = 0;
+            for (int b0 = 0; b0 < nwarps; b0 += 32) {
+                const int v = b0 + lane < nwarps ? row[b0 + lane] : 0;
+                int incl = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                if (b0 + lane < nwarps) row[b0 + lane] = run + incl - v;
+                run += __shfl_sync(0xffffffffu, incl, 31);
+            }
+            if (lane == 0) P.cam_tot[cf] = run;
+        }
+        grid.sync();
+        if (blockIdx.x == 0 && wid == 0) { // row starts: exclusive prefix of the totals (nf <= 2000)
+            int run = 0;
+            for (int b0 = 0; b0 < P.nf; b0 += 32) {
+                const int v = b0 + lane < P.nf ? P.cam_tot[b0 + lane] : 0;
+                int incl = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                if (b0 + lane < P.nf) P.cam_start_w[b0 + lane] = run + incl - v;
+                run += __shfl_sync(0xffffffffu, incl, 31);
+            }
+            if (lane == 0) P.cam_start_w[P.nf] = run;
+        }
+        grid.sync();
+        {
+            const int e0 = gwarp * C, e1 = min(e0 + C, P.ne);
+            for (int eb = e0; eb < e1; eb += 32) {
+                const int e = eb + lane;
+                const int cf = e < e1 ? P.cam_col[P.ecam[e]] : -1;
+                const unsigned peers = __match_any_sync(0xffffffffu, cf);
+                const int leader = __ffs(peers) - 1;
+                int base = 0;
+                if (cf >= 0 && lane == leader) base = atomicAdd(&P.cnt[(size_t)cf * nwarps + gwarp], __popc(peers)); // running base of this chunk
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (cf >= 0) P.cam_edges_w[P.cam_start_w[cf] + base + __popc(peers & ((1u << lane) - 1u))] = e;
+            }
+        }
+        grid.sync();
+    }
 
     // One pass is the reference's optimizer.optimize(iterations).  The welding BA of a map merge (O3/src/Optimizer.cc:
     // 3257-3675) runs two: optimize(5) with the Huber kernel, then -- unless the stop flag is up -- edges with
@@ -932,26 +1011,32 @@ static int run_ba(dvm_lba* h, int nc, float* cam_q, float* cam_t, const uint8_t*
     // (the reference creates them point by point, O3/src/Optimizer.cc:1182-1232, and so does the host adapter)
     std::vector<int>& pt_start = h->pt_start;
     std::vector<int>& cam_start = h->cam_start;
-    pt_start.assign((size_t)np + 1, 0);
-    cam_start.assign((size_t)nf + 1, 0);
     bool by_point = true;
-    {
+    {   // validation, and whether the edges come grouped by point: then the device builds both structures itself
         int prev = -1;
-        bool ok = true;
+        unsigned bad = 0;
         for (int e = 0; e < ne; e++) {
             const int c = edge_cam[e], l = edge_pt[e];
-            if ((unsigned)c >= (unsigned)nc || (unsigned)l >= (unsigned)np) { ok = false; break; }
-            pt_start[l + 1]++;
-            const int cf = cam_col[c];
-            if (cf >= 0) cam_start[cf + 1]++;
+            bad |= (unsigned)((unsigned)c >= (unsigned)nc) | (unsigned)((unsigned)l >= (unsigned)np);
             by_point = by_point && l >= prev;
             prev = l;
         }
-        DVM_REQUIRE(ok, "edge index out of range");
+        DVM_REQUIRE(bad == 0, "edge index out of range");
     }
-    for (int l = 0; l < np; l++) pt_start[l + 1] += pt_start[l];
-    for (int c = 0; c < nf; c++) cam_start[c + 1] += cam_start[c];
-    const size_t n_cam_edges = (size_t)std::max(cam_start[nf], 1);
+    static const bool host_structure = getenv("DVM_LBA_HOST_STRUCTURE") != nullptr;   // (diagnostics: force the host build)
+    const bool device_build = by_point && !host_structure;
+    if (!device_build) {
+        pt_start.assign((size_t)np + 1, 0);
+        cam_start.assign((size_t)nf + 1, 0);
+        for (int e = 0; e < ne; e++) {
+            pt_start[edge_pt[e] + 1]++;
+            const int cf = cam_col[edge_cam[e]];
+            if (cf >= 0) cam_start[cf + 1]++;
+        }
+        for (int l = 0; l < np; l++) pt_start[l + 1] += pt_start[l];
+        for (int c = 0; c < nf; c++) cam_start[c + 1] += cam_start[c];
+    }
+    const size_t n_cam_edges = (size_t)std::max(ne, 1);
     const auto ht1 = now();
     DVM_CUDA(cudaSetDevice(h->device));
     const int dimP = 6 * nf;
@@ -965,7 +1050,7 @@ static int run_ba(dvm_lba* h, int nc, float* cam_q, float* cam_t, const uint8_t*
     const size_t o_ecam = take((size_t)ne * 4), o_ept = take((size_t)ne * 4), o_obs = take((size_t)ne * 8), o_info = take((size_t)ne * 4);
     const size_t o_pst = take((size_t)(np + 1) * 4), o_ped = take((size_t)ne * 4);
     const size_t o_cst = take((size_t)(nf + 1) * 4), o_ced = take(n_cam_edges * 4);
-    const size_t upload_bytes = off;
+    const size_t upload_bytes = device_build ? o_pst : off;
     // output block (contiguous, one D2H); the pinned host mirror spans [0, out_end) only
     const size_t out_begin = (off + 255) & ~(size_t)255;
     const size_t o_oq = take((size_t)nc * 4 * 4), o_ot = take((size_t)nc * 3 * 4), o_op = take((size_t)np * 3 * 4);
@@ -981,6 +1066,7 @@ static int run_ba(dvm_lba* h, int nc, float* cam_q, float* cam_t, const uint8_t*
     const size_t o_x = take((size_t)(dimPad + np * 3 + 1) * 8);
     const size_t o_part = take((size_t)h->grid * kPartStride * 8), o_flags = take(4 * 4), o_prof = take(16 * 8);
     const size_t o_level = take((size_t)std::max(ne, 1));
+    const size_t o_cnt = take(device_build ? (size_t)std::max(nf, 1) * h->grid * kLbaWarps * 4 : 4), o_ctot = take((size_t)(nf + 1) * 4);
     const size_t total = off + 256;
     if (total > h->d_cap) {
         DVM_CUDA(cudaStreamSynchronize(h->stream));
@@ -1022,24 +1108,26 @@ static int run_ba(dvm_lba* h, int nc, float* cam_q, float* cam_t, const uint8_t*
         memcpy(hb + o_ept, edge_pt, (size_t)ne * 4);
         memcpy(hb + o_obs, edge_obs, (size_t)ne * 8);
         memcpy(hb + o_info, edge_inv_sigma2, (size_t)ne * 4);
-        memcpy(hb + o_pst, pt_start.data(), (size_t)(np + 1) * 4);
-        memcpy(hb + o_cst, cam_start.data(), (size_t)(nf + 1) * 4);
-        // the two edge lists are filled straight into the pinned upload buffer (stable: ascending edge index per row)
-        int* pt_edges = reinterpret_cast<int*>(hb + o_ped);
-        int* cam_edges = reinterpret_cast<int*>(hb + o_ced);
-        if (by_point) {
-            for (int e = 0; e < ne; e++) pt_edges[e] = e;
-        } else {
-            std::vector<int>& fill = h->fill;
-            fill.assign(pt_start.begin(), pt_start.end() - 1);
-            for (int e = 0; e < ne; e++) pt_edges[fill[edge_pt[e]]++] = e;
-        }
-        {
-            std::vector<int>& fill = h->fill;
-            fill.assign(cam_start.begin(), cam_start.end() - 1);
-            for (int e = 0; e < ne; e++) {
-                const int cf = cam_col[edge_cam[e]];
-                if (cf >= 0) cam_edges[fill[cf]++] = e;
+        if (!device_build) {
+            memcpy(hb + o_pst, pt_start.data(), (size_t)(np + 1) * 4);
+            memcpy(hb + o_cst, cam_start.data(), (size_t)(nf + 1) * 4);
+            // the two edge lists are filled straight into the pinned upload buffer (stable: ascending edge index per row)
+            int* pt_edges = reinterpret_cast<int*>(hb + o_ped);
+            int* cam_edges = reinterpret_cast<int*>(hb + o_ced);
+            if (by_point) {
+                for (int e = 0; e < ne; e++) pt_edges[e] = e;
+            } else {
+                std::vector<int>& fill = h->fill;
+                fill.assign(pt_start.begin(), pt_start.end() - 1);
+                for (int e = 0; e < ne; e++) pt_edges[fill[edge_pt[e]]++] = e;
+            }
+            {
+                std::vector<int>& fill = h->fill;
+                fill.assign(cam_start.begin(), cam_start.end() - 1);
+                for (int e = 0; e < ne; e++) {
+                    const int cf = cam_col[edge_cam[e]];
+                    if (cf >= 0) cam_edges[fill[cf]++] = e;
+                }
             }
         }
     }
@@ -1067,6 +1155,9 @@ static int run_ba(dvm_lba* h, int nc, float* cam_q, float* cam_t, const uint8_t*
     P.eobs = (const float*)(db + o_obs); P.einfo = (const float*)(db + o_info);
     P.pt_start = (const int*)(db + o_pst); P.pt_edges = (const int*)(db + o_ped);
     P.cam_start = (const int*)(db + o_cst); P.cam_edges = (const int*)(db + o_ced);
+    P.build = device_build ? 1 : 0;
+    P.pt_start_w = (int*)(db + o_pst); P.pt_edges_w = (int*)(db + o_ped); P.cam_start_w = (int*)(db + o_cst); P.cam_edges_w = (int*)(db + o_ced);
+    P.cnt = (int*)(db + o_cnt); P.cam_tot = (int*)(db + o_ctot);
     P.err = (double*)(db + o_err); P.Hpl = (double*)(db + o_hpl); P.Hll = (double*)(db + o_hll);
     P.bl = (double*)(db + o_bl); P.Dinv = (double*)(db + o_dinv); P.db = (double*)(db + o_db);
     P.Hpp = (double*)(db + o_hpp); P.bp = (double*)(db + o_bp); P.Hs = (double*)(db + o_hs); P.bs = (double*)(db + o_bs);

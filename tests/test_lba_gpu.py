@@ -47,6 +47,28 @@ def test_local_ba_matches_oracle(solver, nf, nx, npts, seed):
     assert r1["chi_last"] < r1["chi_first"]
 
 
+def test_edges_in_any_order(solver):
+    """Edges grouped by point (as the reference creates them) have their two CSR structures built by the kernel itself;
+    any other order goes through the host-built structures.  Both must give the oracle's result for that order."""
+    from oracle.lba import local_ba
+
+    S = synth.ba_scene(12, 4, 600, seed=7)
+    assert np.all(np.diff(S["edge_pt"]) >= 0)
+    _compare(local_ba(*_args(S)), solver.LocalBundleAdjustment(*_args(S)), S)
+    perm = np.random.default_rng(0).permutation(len(S["edge_pt"]))
+    T = dict(S)
+    for k in ("edge_cam", "edge_pt", "edge_obs", "edge_w"):
+        T[k] = np.ascontiguousarray(S[k][perm])
+    assert not np.all(np.diff(T["edge_pt"]) >= 0)
+    _compare(local_ba(*_args(T)), solver.LocalBundleAdjustment(*_args(T)), T)
+    # points without any observation in between (empty rows) and a leading gap
+    U = dict(S)
+    keep = (S["edge_pt"] % 7 != 3) & (S["edge_pt"] > 4)
+    for k in ("edge_cam", "edge_pt", "edge_obs", "edge_w"):
+        U[k] = np.ascontiguousarray(S[k][keep])
+    _compare(local_ba(*_args(U)), solver.LocalBundleAdjustment(*_args(U)), U)
+
+
 def test_zero_noise_and_fixed_poses_untouched(solver):
     S = synth.ba_scene(10, 3, 400, seed=2, pix_sigma=0.0, outlier_frac=0.0)
     r1 = solver.LocalBundleAdjustment(*_args(S))
