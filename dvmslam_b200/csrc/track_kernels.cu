@@ -253,7 +253,12 @@ __device__ inline void last_walk_query(const FrameDev& cur, const MatchLastArgs&
                                        const float* q, const float* t, float th, int i, int lane)
 {
     const int mi = a.mp_index ? a.mp_index[i] : (a.has_mp[i] ? i : -1);
-    if (mi < 0 || a.outlier[i]) return;
+    const bool is_outlier = a.outlier[i] != 0;
+    const int oct = a.last_kps ? a.last_kps[i].octave : a.octave[i];        // (loaded with the first round trip)
+    const float ang = a.last_kps ? a.last_kps[i].angle : a.angle[i];
+    if (mi < 0 || is_outlier) return;
+    uint32_t d[8];
+    load_desc(d, a.mp_desc + (size_t)mi * 32);                              // (with the second, next to the position)
     // x3Dc = Tcw * x3Dw (O3/src/ORBmatcher.cc:1577): Sophus' quaternion action, not a matrix product
     const float Pw[3] = { a.Xw[3 * mi], a.Xw[3 * mi + 1], a.Xw[3 * mi + 2] };
     float Pc[3];
@@ -267,12 +272,8 @@ __device__ inline void last_walk_query(const FrameDev& cur, const MatchLastArgs&
     // the conditions above depend on the query only: the whole warp is here together
     int slot = 0;
     if (lane == 0) slot = atomicAdd(s.qcount, 1);
-    const int oct = a.last_kps ? a.last_kps[i].octave : a.octave[i];
-    const float ang = a.last_kps ? a.last_kps[i].angle : a.angle[i];
     const float r = __fmul_rn(th, cur.scale[oct]);
     if (lane == 0) { s.pu[i] = u; s.pv[i] = v; s.pr[i] = r; }
-    uint32_t d[8];
-    load_desc(d, a.mp_desc + (size_t)mi * 32);
     unsigned long long top[kMatchCacheK];
 #pragma unroll
     for (int p = 0; p < kMatchCacheK; p++) top[p] = ~0ull;
@@ -621,6 +622,8 @@ __global__ void __launch_bounds__(kWalkThreads) match_map_walk_kernel(FrameDev c
     const FrameLook fl = look_global(cur);
     int lvl;
     float px, py, vcos;
+    uint32_t d[8];   // (loaded before the gates: its latency overlaps theirs)
+    load_desc(d, a.mp_desc + (size_t)(a.q_index ? a.q_index[i] : i) * 32);
     if (a.use_frustum) { // SearchLocalPoints: isInFrustum decides whether map point i takes part at all
         FrustumPose fp;
         frustum_pose(a.fr.pose, fp);
@@ -639,8 +642,6 @@ __global__ void __launch_bounds__(kWalkThreads) match_map_walk_kernel(FrameDev c
         r = __fmul_rn(r, cur.scale[lvl]);
     }
     if (lane == 0) { s.pu[i] = px; s.pv[i] = py; s.pr[i] = r; }
-    uint32_t d[8];
-    load_desc(d, a.mp_desc + (size_t)(a.q_index ? a.q_index[i] : i) * 32);
     unsigned long long top[kMatchCacheK];
 #pragma unroll
     for (int p = 0; p < kMatchCacheK; p++) top[p] = ~0ull;

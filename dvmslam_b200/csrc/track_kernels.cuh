@@ -167,8 +167,12 @@ __device__ inline void frustum_pose(const float* pose, FrustumPose& fp)
 __device__ inline bool frustum_eval(const FrustumArgs& a, const FrustumPose& fp, int k, float& u, float& v, int& lvl, float& vc)
 {
     u = -1.f; v = -1.f; vc = 0.f; lvl = -1;
-    if (a.skip && a.skip[k]) return false;
+    // everything the gates may need is loaded up front (one round trip to L2 instead of one per gate passed)
+    const bool skipped = a.skip && a.skip[k];
     const float P[3] = { a.xw[3 * k], a.xw[3 * k + 1], a.xw[3 * k + 2] };
+    const float max_dist_k = a.max_dist[k], min_dist_k = a.min_dist[k];
+    const float Pn[3] = { a.normal[3 * k], a.normal[3 * k + 1], a.normal[3 * k + 2] };
+    if (skipped) return false;
     float Pc[3];
     so::mat_vec(fp.R, P, Pc);                                   // Pc = mRcw * P + mtcw
     const float xc = __fadd_rn(Pc[0], fp.t[0]), yc = __fadd_rn(Pc[1], fp.t[1]), zc = __fadd_rn(Pc[2], fp.t[2]);
@@ -177,14 +181,13 @@ __device__ inline bool frustum_eval(const FrustumArgs& a, const FrustumPose& fp,
     const float pv = __fadd_rn(__fdiv_rn(__fmul_rn(a.K[1], yc), zc), a.K[3]);
     if ((pu < a.bounds[0] || pu > a.bounds[2]) || (pv < a.bounds[1] || pv > a.bounds[3])) return false;
     u = pu; v = pv;
-    const float maxD = __fmul_rn(1.2f, a.max_dist[k]), minD = __fmul_rn(0.8f, a.min_dist[k]);
+    const float maxD = __fmul_rn(1.2f, max_dist_k), minD = __fmul_rn(0.8f, min_dist_k);
     const float PO[3] = { __fsub_rn(P[0], fp.Ow[0]), __fsub_rn(P[1], fp.Ow[1]), __fsub_rn(P[2], fp.Ow[2]) };
     const float dist = so::norm3(PO);
     if (dist < minD || dist > maxD) return false;
-    const float Pn[3] = { a.normal[3 * k], a.normal[3 * k + 1], a.normal[3 * k + 2] };
     const float c = __fdiv_rn(so::dot3(PO, Pn), dist);
     if (c < a.cosLimit) return false;
-    lvl = so::predict_scale(a.max_dist[k], dist, a.logScale, a.nlevels);
+    lvl = so::predict_scale(max_dist_k, dist, a.logScale, a.nlevels);
     vc = c;
     return true;
 }
