@@ -44,8 +44,11 @@ __device__ inline double fast_rsqrt(double d)
 //     x[r][c] -= L[r][j] X[j][c]  (r > j)
 // i.e. the right-looking Cholesky step and the column sweep of the triangular inversion share one barrier per
 // step (the published column is double-buffered), and the owner of column j + 1 publishes it before doing its share of
-// step j's inverse updates.  Measured: 21.6 -> 10 us per block (~550 cycles per step; what is left is the FP64 pipe --
-// the triangular masks leave most lanes of the 6 double-precision instructions a warp issues per step idle).
+// step j's inverse updates.  Measured (tools/chol_probe.cu, cycles per 32 x 32 block): one warp 40 000; this scheme
+// 18 900; with the validity test of the pivot off the chain 16 300; with the loop unrolled and the pivots carried by every
+// lane 14 200 (this code).  A dependent FP64 operation costs ~24 cycles here and a 512-thread barrier ~55, so a step cannot
+// go far below 300 cycles; variants that did NOT help: four warps owning eight columns each (15 000), a named barrier the
+// publisher only arrives at (18 100), the inverse on warps of its own (16 000), a third-order rsqrt (slower).
 // `scratch` holds 4 * kNB + 4 doubles.  Same outputs as the warp version.
 // (No __restrict__ here: the published column is exchanged BETWEEN threads, and with restrict-qualified pointers
 // nvcc keeps values read from it across the barriers -- measured: wrong factors.)
@@ -58,34 +61,39 @@ __device__ inline bool cta_factor_invert_32(double* A, int ld, double* Ld, doubl
     double* s_rinv = scratch + 2 * kNB;       // [2]
     double* s_bad = s_rinv + 2;
     double a0 = A[(size_t)r * ld + c0], a1 = A[(size_t)r * ld + c1];
+    // the pivots of the two owned columns, carried by EVERY lane (one more multiply-add per step, but the pivot -> rsqrt ->
+    // publish -> barrier chain that bounds a step starts without a shuffle)
+    double d0 = A[(size_t)c0 * ld + c0], d1 = A[(size_t)c1 * ld + c1];
     double x0 = (r == c0) ? 1.0 : 0.0, x1 = (r == c1) ? 1.0 : 0.0;
-    if (threadIdx.x == 0) *s_bad = 0.0;
-    // the warp that owns column j scales it by rsqrt(pivot) and publishes it in buffer j & 1
+    if (threadIdx.x == 0) *s_bad = 0.0;   // (thread 0 is also the lane that raises it for column 0)
+    // the warp that owns column j scales it by rsqrt(pivot) and publishes it in buffer j & 1.  A pivot that is not positive
+    // and finite only raises the flag (off the chain): the factor is garbage from there on and the callers discard it.
     auto publish = [&](int j) {
         const bool hi = j >= 16;
-        const double djj = __shfl_sync(0xffffffffu, hi ? a1 : a0, j);
-        const bool bad = !(djj > 0) || !isfinite(djj);
-        const double rinv = bad ? 1.0 : fast_rsqrt(djj);
-        if (r >= j) {
-            const double l = (hi ? a1 : a0) * rinv;   // a[j][j] * rinv = sqrt(a[j][j])
-            if (hi) a1 = l; else a0 = l;
-            colbuf[(j & 1) * kNB + r] = l;
-        }
-        if (r == 0) { s_rinv[j & 1] = rinv; if (bad) *s_bad = 1.0; }
+        const double djj = hi ? d1 : d0;
+        const double rinv = fast_rsqrt(djj);
+        const double l = (hi ? a1 : a0) * rinv;   // a[j][j] * rinv = sqrt(a[j][j])
+        if (hi) a1 = l; else a0 = l;
+        if (r >= j) colbuf[(j & 1) * kNB + r] = l;
+        if (r == 0) { s_rinv[j & 1] = rinv; if (!(djj > 0) || !isfinite(djj)) *s_bad = 1.0; }
     };
     if (w == 0) publish(0);
+#pragma unroll
     for (int j = 0; j < kNB; j++) {
         __syncthreads();   // column j is published
         const double* col = colbuf + (j & 1) * kNB;
-        const double rinv = s_rinv[j & 1];
         const double lr = (r >= j) ? col[r] : 0.0;
+        const double l0 = col[c0], l1 = col[c1];
         // Cholesky update of the columns right of j
-        if (c0 > j && r >= c0) a0 -= lr * col[c0];
-        if (c1 > j && r >= c1) a1 -= lr * col[c1];
+        if (c0 > j && r >= c0) a0 -= lr * l0;
+        if (c1 > j && r >= c1) a1 -= lr * l1;
+        if (c0 > j) d0 -= l0 * l0;
+        if (c1 > j) d1 -= l1 * l1;
         // column j + 1 is complete now: its owner publishes it BEFORE the inverse updates of this step, which keeps
         // them off the pivot -> rsqrt -> publish -> barrier chain that bounds a step
         if (j + 1 < kNB && w == ((j + 1) & 15)) publish(j + 1);
         // inverse: row j is scaled, rows below it are swept (columns <= j)
+        const double rinv = s_rinv[j & 1];
         if (c0 <= j) {
             const double xj = __shfl_sync(0xffffffffu, x0, j) * rinv;
             if (r == j) x0 = xj; else if (r > j) x0 -= lr * xj;
@@ -110,6 +118,24 @@ __device__ inline bool cta_factor_invert_32(double* A, int ld, double* Ld, doubl
 }
 
 
+
+// sum_{k < len} a[k] * b[k] with four partial sums (a dependent FP64 multiply-add costs ~24 cycles: one running sum over a
+// 32-long row is a 770-cycle chain)
+__device__ inline double tri_dot4(const double* a, const double* b, int len)
+{
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int k = 0;
+    for (; k + 3 < len; k += 4) {
+        s0 += a[k] * b[k];
+        s1 += a[k + 1] * b[k + 1];
+        s2 += a[k + 2] * b[k + 2];
+        s3 += a[k + 3] * b[k + 3];
+    }
+    if (k < len) s0 += a[k] * b[k];
+    if (k + 1 < len) s1 += a[k + 1] * b[k + 1];
+    if (k + 2 < len) s2 += a[k + 2] * b[k + 2];
+    return (s0 + s1) + (s2 + s3);
+}
 
 // ---- dense SPD solve A x = b on a whole cooperative grid ------------------------------------------------------------
 // Blocked right-looking Cholesky (lower triangle, kNB = 32) of the n x n matrix A (n a multiple of 32: the caller pads with
@@ -160,9 +186,7 @@ __device__ inline void grid_cholesky_solve(cooperative_groups::grid_group& grid,
                 __syncthreads();
                 for (int t = tid; t < cnt * kNB; t += kCholThreads) {
                     const int r = t >> 5, c = t & 31;
-                    double acc = 0.0;
-                    for (int k = 0; k <= c; k++) acc += stage[r * kNB + k] * Li[c * kDiagLd + k];
-                    A[(size_t)(base + r) * n + k0 + c] = acc;
+                    A[(size_t)(base + r) * n + k0 + c] = tri_dot4(stage + r * kNB, Li + c * kDiagLd, c + 1);
                 }
                 __syncthreads();
             }
@@ -212,22 +236,32 @@ __device__ inline void grid_cholesky_solve(cooperative_groups::grid_group& grid,
         for (int k0 = n - kNB; k0 >= 0; k0 -= kNB) {
             {
                 const int c = tid & 31, g = tid >> 5;
-                double acc = 0.0;
-                for (int i = k0 + kNB + g; i < n; i += kCholWarps) acc += A[(size_t)i * n + k0 + c] * x[i];
-                part[g * kNB + c] = acc;
+                double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+                int i = k0 + kNB + g;
+                for (; i + 3 * kCholWarps < n; i += 4 * kCholWarps) {
+                    acc0 += A[(size_t)i * n + k0 + c] * x[i];
+                    acc1 += A[(size_t)(i + kCholWarps) * n + k0 + c] * x[i + kCholWarps];
+                    acc2 += A[(size_t)(i + 2 * kCholWarps) * n + k0 + c] * x[i + 2 * kCholWarps];
+                    acc3 += A[(size_t)(i + 3 * kCholWarps) * n + k0 + c] * x[i + 3 * kCholWarps];
+                }
+                for (; i < n; i += kCholWarps) acc0 += A[(size_t)i * n + k0 + c] * x[i];
+                part[g * kNB + c] = (acc0 + acc1) + (acc2 + acc3);
             }
             __syncthreads();
             if (tid < kNB) {
-                double acc = x[k0 + tid];
-                for (int g = 0; g < kCholWarps; g++) acc -= part[g * kNB + tid];
-                rhs[tid] = acc;
+                double s4[4] = { 0.0, 0.0, 0.0, 0.0 };
+#pragma unroll
+                for (int g = 0; g < kCholWarps; g++) s4[g & 3] += part[g * kNB + tid];
+                rhs[tid] = x[k0 + tid] - ((s4[0] + s4[1]) + (s4[2] + s4[3]));
             }
             __syncthreads();
             if (tid < kNB) {   // x_k = L_kk^-T rhs
                 const double* Lg = Linv_g + (size_t)(k0 / kNB) * kNB * kNB;
-                double acc = 0.0;
-                for (int c = tid; c < kNB; c++) acc += Lg[c * kNB + tid] * rhs[c];
-                x[k0 + tid] = acc;
+                double s4[4] = { 0.0, 0.0, 0.0, 0.0 };
+#pragma unroll 8
+                for (int c = 0; c < kNB; c++)
+                    if (c >= tid) s4[c & 3] += Lg[c * kNB + tid] * rhs[c];
+                x[k0 + tid] = (s4[0] + s4[1]) + (s4[2] + s4[3]);
             }
             __syncthreads();
         }

@@ -63,7 +63,16 @@ struct LbaDev {
     int* pt_start_w; int* pt_edges_w; int* cam_start_w; int* cam_edges_w;
     int* cnt;              // [nf][warps of the grid] per-chunk camera counts, then their exclusive prefix
     int* cam_tot;          // [nf + 1]
+    // observation pairs grouped by camera pair (built by the prologue): bin (c2, c1 <= c2) = c2 (c2 + 1) / 2 + c1 holds every
+    // pair of edges (e1 on free camera c1, e2 on free camera c2) that see the same landmark; e1 == e2 in the diagonal bins
+    // The lists are cut into work items of at most kPairChunk pairs: items[i] = { first, end, c1, c2 }; flags[2] = their number.
+    int nbins;
+    int* pair_start;       // [nbins + 1]
+    int* pair_fill;        // [nbins]
+    int4* pairs;           // { e1, e2, landmark, - }
+    int4* items;
 };
+constexpr int kPairChunk = 64;
 
 // ---- SE3 helpers (same formulas as the pose-only optimiser; g2o/types/se3quat.h) ----
 struct Quat { double x, y, z, w; };
@@ -222,11 +231,12 @@ __device__ inline double warp_max(double s)
 // (n a multiple of 32: the caller pads with an identity block), with the right-hand side carried as an
 // extra matrix row (row n): after the factorisation that row holds y = L^-1 b, so only the backward
 // substitution L^T x = y remains.  Per block column:
-//   (a) every CTA factors the 32x32 diagonal block redundantly in registers of one warp (lane = row,
-//       shuffles for the column broadcasts) and inverts it (lane = column) -- no broadcast needed;
+//   (a) the 32x32 diagonal block arrives factored and inverted (cta_factor_invert_32) from CTA 0, which did it one block
+//       column AHEAD, beside the previous trailing update;
 //   (b) the panel rows are split over the 8 CTAs:  L21 = A21 * L11^-T  as a small GEMM with the inverse;
-//   (c) after a cluster barrier every CTA stages the whole panel in shared memory and takes its share
-//       of the 8x8 trailing tiles  A22 -= L21 L21^T  on the FP64 tensor pipe (DMMA m8n8k4).
+//   (c) after a cluster barrier CTA 0 updates, factors and inverts the next diagonal block while the other seven stage the
+//       whole panel in shared memory and share the 8x8 trailing tiles  A22 -= L21 L21^T  on the FP64 tensor pipe
+//       (DMMA m8n8k4).
 // A has n + 8 rows of leading dimension n.  Linv_g [n/32][32*32] receives the inverted diagonal blocks.
 constexpr int kClusterCtas = 8;
 constexpr int kLbaClusterFree = 100;   // free keyframes whose reduced system (600 unknowns) fits one SM's shared-memory panel
@@ -259,47 +269,102 @@ __device__ bool cluster_cholesky_solve(int n, double* __restrict__ A, const doub
     if (rank == 0)
         for (int i = tid; i < 8 * n; i += kLbaThreads) A[(size_t)n * n + i] = (i < n) ? b[i] : 0.0;
     cluster.sync();
+    // block 0 has no predecessor to hide behind
+    if (rank == 0) {
+        const bool bad = cta_factor_invert_32(A, n, Ld, Li, true, Linv_g, stage);
+        if (bad && tid == 0) *s_flag = 0;
+    }
+    tk(8);
+    cluster.sync();
     for (int k0 = 0; k0 < n; k0 += kNB) {
         const int r0 = k0 + kNB;
-        // ---- (a) diagonal block: factor + invert, redundantly in every CTA ----
-        {
-            const bool bad = cta_factor_invert_32(A + (size_t)k0 * n + k0, n, Ld, Li, rank == 0,
-                                                  Linv_g + (size_t)(k0 / kNB) * kNB * kNB, stage);
-            if (bad && tid == 0) *s_flag = 0;
-            tk(8);
+        // ---- (a) the inverted diagonal block: CTA 0 still holds it from its factorisation, the others fetch it ----
+        if (rank != 0) {
+            const double* Lg = Linv_g + (size_t)(k0 / kNB) * kNB * kNB;
+            for (int t = tid; t < kNB * kNB; t += kLbaThreads) Li[(t >> 5) * kDiagLd + (t & 31)] = Lg[t];
         }
         __syncthreads();
         tk(9);
         // ---- (b) panel rows of this CTA: L21 = A21 * L11^-T ----
         const int mrows = M - r0;
-        const int chunk = (mrows + kClusterCtas - 1) / kClusterCtas;
-        const int i0 = r0 + rank * chunk, i1 = min(i0 + chunk, M);
+        const int mcols = n - r0;
+        // CTA 0 takes the 32 panel rows of the next diagonal block -- they stay in its shared memory (Pn) -- and fetches that
+        // block now, under the latency of the panel loads; the other seven CTAs share the rows below
+        int i0, i1;
+        if (mcols > 0) {
+            const int chunk = (mrows - kNB + kClusterCtas - 2) / (kClusterCtas - 1);
+            i0 = rank == 0 ? r0 : r0 + kNB + (rank - 1) * chunk;
+            i1 = rank == 0 ? r0 + kNB : min(i0 + chunk, M);
+        } else {   // last block column: only the right-hand-side rows are left
+            const int chunk = (mrows + kClusterCtas - 1) / kClusterCtas;
+            i0 = r0 + rank * chunk;
+            i1 = min(i0 + chunk, M);
+        }
+        double* Pn = panel;                       // [kNB][kDiagLd]  panel rows r0 .. r0 + 31
+        double* Dn = panel + kNB * kDiagLd;       // [kNB][kDiagLd]  the next diagonal block
+        const bool own_next = rank == 0 && mcols > 0;
+        double dnext[2] = { 0.0, 0.0 };
+        if (rank == 0 && mcols > 0) {
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int r = tid & 31, c = (tid >> 5) + 16 * h;
+                if (c <= r) dnext[h] = A[(size_t)(r0 + r) * n + r0 + c];
+            }
+        }
         for (int base = i0; base < i1; base += 64) {
             const int cnt = min(64, i1 - base);
             for (int t = tid; t < cnt * kNB; t += kLbaThreads) stage[t] = A[(size_t)(base + (t >> 5)) * n + k0 + (t & 31)];
             __syncthreads();
             for (int t = tid; t < cnt * kNB; t += kLbaThreads) {
                 const int r = t >> 5, c = t & 31;
-                double acc = 0.0;
-                for (int k = 0; k <= c; k++) acc += stage[r * kNB + k] * Li[c * kDiagLd + k];
+                const double acc = tri_dot4(stage + r * kNB, Li + c * kDiagLd, c + 1);
                 A[(size_t)(base + r) * n + k0 + c] = acc;
+                if (own_next && base + r - r0 < kNB) Pn[(base + r - r0) * kDiagLd + c] = acc;
             }
             __syncthreads();
         }
         tk(10);
         cluster.sync();
         tk(11);
-        // ---- (c) trailing update ----
-        const int mcols = n - r0;
-        if (mcols > 0) {
+        // ---- (c) trailing update, with the NEXT diagonal block taken out of it: CTA 0 brings that block up to date from the
+        // first 32 panel rows, factors and inverts it while the other seven CTAs update the rest of the trailing matrix, so the
+        // 32 dependent pivot steps of a block (the longest chain of the solve) run beside the tensor-pipe work instead of
+        // before it (look-ahead of one block column) ----
+        if (mcols > 0 && rank == 0) {
+            {
+                const int r = tid & 31;
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int c = (tid >> 5) + 16 * h;
+                    double v = 0.0;
+                    if (c <= r) {
+                        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+                        for (int k = 0; k < kNB; k += 4) {
+                            s0 += Pn[r * kDiagLd + k] * Pn[c * kDiagLd + k];
+                            s1 += Pn[r * kDiagLd + k + 1] * Pn[c * kDiagLd + k + 1];
+                            s2 += Pn[r * kDiagLd + k + 2] * Pn[c * kDiagLd + k + 2];
+                            s3 += Pn[r * kDiagLd + k + 3] * Pn[c * kDiagLd + k + 3];
+                        }
+                        v = dnext[h] - ((s0 + s1) + (s2 + s3));
+                    }
+                    Dn[r * kDiagLd + c] = v;
+                }
+            }
+            __syncthreads();
+            tk(12);
+            const bool bad = cta_factor_invert_32(Dn, kDiagLd, Ld, Li, true, Linv_g + (size_t)(r0 / kNB) * kNB * kNB, stage);
+            if (bad && tid == 0) *s_flag = 0;
+            tk(13);
+        } else if (mcols > 0) {
             for (int t = tid; t < mrows * kNB; t += kLbaThreads)
                 panel[(size_t)(t >> 5) * kPanelLd + (t & 31)] = A[(size_t)(r0 + (t >> 5)) * n + k0 + (t & 31)];
             __syncthreads();
-            tk(12);
             const int mtc = mcols / 8;
             const int tri = mtc * (mtc + 1) / 2;
             const int ntiles = tri + mtc; // + the right-hand-side row group against every column tile
-            for (int t = rank * kLbaWarps + wid; t < ntiles; t += kClusterCtas * kLbaWarps) {
+            // tiles 0 .. 9 (ti < 4) are the next diagonal block: CTA 0's
+            for (int t = 10 + (rank - 1) * kLbaWarps + wid; t < ntiles; t += (kClusterCtas - 1) * kLbaWarps) {
                 int ti, tj;
                 if (t < tri) {
                     ti = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
@@ -321,7 +386,6 @@ __device__ bool cluster_cholesky_solve(int n, double* __restrict__ A, const doub
                 if (cc + 1 <= ar) dst[1] -= c1;
             }
         }
-        tk(13);
         cluster.sync();
         tk(14);
     }
@@ -336,23 +400,32 @@ __device__ bool cluster_cholesky_solve(int n, double* __restrict__ A, const doub
         for (int k0 = n - kNB; k0 >= 0; k0 -= kNB) {
             // rhs[c] = y[k0+c] - sum_{i >= k0+32} L[i][k0+c] * x[i]
             {
+                // (two partial sums per thread and trees below: a dependent FP64 operation costs ~24 cycles)
                 const int c = tid & 31, g = tid >> 5;
-                double acc = 0.0;
-                for (int i = k0 + kNB + g; i < n; i += kLbaWarps) acc += A[(size_t)i * n + k0 + c] * y[i];
-                part[g * kNB + c] = acc;
+                double acc0 = 0.0, acc1 = 0.0;
+                int i = k0 + kNB + g;
+                for (; i + kLbaWarps < n; i += 2 * kLbaWarps) {
+                    acc0 += A[(size_t)i * n + k0 + c] * y[i];
+                    acc1 += A[(size_t)(i + kLbaWarps) * n + k0 + c] * y[i + kLbaWarps];
+                }
+                if (i < n) acc0 += A[(size_t)i * n + k0 + c] * y[i];
+                part[g * kNB + c] = acc0 + acc1;
             }
             __syncthreads();
             if (tid < kNB) {
-                double acc = y[k0 + tid];
-                for (int g = 0; g < kLbaWarps; g++) acc -= part[g * kNB + tid];
-                rhs[tid] = acc;
+                double s4[4] = { 0.0, 0.0, 0.0, 0.0 };
+#pragma unroll
+                for (int g = 0; g < kLbaWarps; g++) s4[g & 3] += part[g * kNB + tid];
+                rhs[tid] = y[k0 + tid] - ((s4[0] + s4[1]) + (s4[2] + s4[3]));
             }
             __syncthreads();
             if (tid < kNB) { // x_k = L_kk^-T rhs
                 const double* Lg = Linv_g + (size_t)(k0 / kNB) * kNB * kNB;
-                double acc = 0.0;
-                for (int c = tid; c < kNB; c++) acc += Lg[c * kNB + tid] * rhs[c];
-                y[k0 + tid] = acc;
+                double s4[4] = { 0.0, 0.0, 0.0, 0.0 };
+#pragma unroll 8
+                for (int c = 0; c < kNB; c++)
+                    if (c >= tid) s4[c & 3] += Lg[c * kNB + tid] * rhs[c];
+                y[k0 + tid] = (s4[0] + s4[1]) + (s4[2] + s4[3]);
             }
             __syncthreads();
         }
@@ -473,6 +546,77 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kLbaThrea
                 if (cf >= 0) P.cam_edges_w[P.cam_start_w[cf] + base + __popc(peers & ((1u << lane) - 1u))] = e;
             }
         }
+        grid.sync();
+    }
+
+    // ---- the Schur complement's work lists: every pair of observations of one landmark from free cameras, grouped by
+    // camera pair (counting sort: count, scan on CTA 0, place).  With them S1 below sums each 6 x 6 block of the reduced
+    // system in registers and writes it once, instead of one FP64 atomic per product term (12 M per trial at C4 size).
+    {
+        __shared__ int s_wsum[kLbaWarps], s_wsum_i[kLbaWarps];
+        const int nb = P.nbins;
+        for (int i = gtid; i <= nb; i += nthreads) P.pair_start[i] = 0;
+        grid.sync();
+        auto for_each_pair = [&](auto&& f) {
+            for (int l = gwarp; l < P.np; l += nwarps) {
+                const int ps = P.pt_start[l], k = P.pt_start[l + 1] - ps;
+                const int npairs = k * (k + 1) / 2;
+                for (int p = lane; p < npairs; p += 32) {
+                    int i = (int)((sqrt(8.0 * p + 1.0) - 1.0) * 0.5);
+                    while (i * (i + 1) / 2 > p) i--;
+                    while ((i + 1) * (i + 2) / 2 <= p) i++;
+                    const int j = p - i * (i + 1) / 2;
+                    int e1 = P.pt_edges[ps + i], e2 = P.pt_edges[ps + j];
+                    int c1 = P.cam_col[P.ecam[e1]], c2 = P.cam_col[P.ecam[e2]];
+                    if (c1 < 0 || c2 < 0) continue;
+                    if (c1 > c2) { int t = c1; c1 = c2; c2 = t; t = e1; e1 = e2; e2 = t; }
+                    f(c2 * (c2 + 1) / 2 + c1, e1, e2);
+                }
+            }
+        };
+        for_each_pair([&](int bin, int, int) { atomicAdd(&P.pair_start[bin + 1], 1); });
+        grid.sync();
+        if (blockIdx.x == 0) {   // scans of the counts (pair_start[b + 1] = end of bin b) and of the bins' item counts
+            int run = 0, run_items = 0;
+            for (int b0 = 0; b0 < nb; b0 += kLbaThreads) {
+                const int b = b0 + tid;
+                const int v = b < nb ? P.pair_start[b + 1] : 0;
+                const int vi = (v + kPairChunk - 1) / kPairChunk;
+                int incl = v, incl_i = vi;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                    const int ti = __shfl_up_sync(0xffffffffu, incl_i, o);
+                    if (lane >= o) { incl += t; incl_i += ti; }
+                }
+                if (lane == 31) { s_wsum[wid] = incl; s_wsum_i[wid] = incl_i; }
+                __syncthreads();
+                int before = 0, total = 0, before_i = 0, total_i = 0;
+#pragma unroll
+                for (int w2 = 0; w2 < kLbaWarps; w2++) {
+                    const int t = s_wsum[w2], ti = s_wsum_i[w2];
+                    if (w2 < wid) { before += t; before_i += ti; }
+                    total += t; total_i += ti;
+                }
+                if (b < nb) {
+                    const int first = run + before + incl - v;
+                    P.pair_start[b + 1] = first + v;
+                    P.pair_fill[b] = first;
+                    int c2 = (int)((sqrt(8.0 * b + 1.0) - 1.0) * 0.5);
+                    while (c2 * (c2 + 1) / 2 > b) c2--;
+                    while ((c2 + 1) * (c2 + 2) / 2 <= b) c2++;
+                    const int c1 = b - c2 * (c2 + 1) / 2;
+                    int4* it = P.items + run_items + before_i + incl_i - vi;
+                    for (int ch = 0; ch < vi; ch++) it[ch] = make_int4(first + ch * kPairChunk, min(first + (ch + 1) * kPairChunk, first + v), c1, c2);
+                }
+                run += total;
+                run_items += total_i;
+                __syncthreads();
+            }
+            if (tid == 0) P.flags[2] = run_items;
+        }
+        grid.sync();
+        for_each_pair([&](int bin, int e1, int e2) { P.pairs[atomicAdd(&P.pair_fill[bin], 1)] = make_int4(e1, e2, P.ept[e1], 0); });
         grid.sync();
     }
 
@@ -686,50 +830,75 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kLbaThrea
                 for (int i = gtid; i < P.dimPad; i += nthreads) P.bs[i] = i < P.dimP ? P.bp[i] : 0.0;
                 grid.sync();
                 tick(2);
-                // ---------------- S1: Schur complement, point-major ----------------
-                // For landmark l with observing free cameras {c_i}: Hs(c_i, c_j) -= Hpl_i Dinv Hpl_j^T and
-                // bs(c_i) -= Hpl_i Dinv bl.  One warp per landmark, lanes over the (i, j >= i) pairs; the
-                // 6x6 products are added with FP64 reductions at L2 (no return value needed).
-                for (int l = gwarp; l < P.np; l += nwarps) {
-                    const int ps = P.pt_start[l], k = P.pt_start[l + 1] - ps;
-                    const double* Di = P.Dinv + (size_t)l * 6;
-                    const double* d = P.db + (size_t)l * 3;
-                    const double D0 = Di[0], D1 = Di[1], D2 = Di[2], D3 = Di[3], D4 = Di[4], D5 = Di[5];
-                    const int npairs = k * (k + 1) / 2;
-                    for (int p = lane; p < npairs; p += 32) {
-                        // p -> (i, j) with j <= i  (triangular index)
-                        int i = (int)((sqrt(8.0 * p + 1.0) - 1.0) * 0.5);
-                        while (i * (i + 1) / 2 > p) i--;
-                        while ((i + 1) * (i + 2) / 2 <= p) i++;
-                        const int j = p - i * (i + 1) / 2;
-                        int e1 = P.pt_edges[ps + i], e2 = P.pt_edges[ps + j];
-                        int c1 = P.cam_col[P.ecam[e1]], c2 = P.cam_col[P.ecam[e2]];
-                        if (c1 < 0 || c2 < 0) continue;
-                        if (c1 > c2) { int t = c1; c1 = c2; c2 = t; t = e1; e1 = e2; e2 = t; } // c1 <= c2: block stored at (c2, c1)
-                        const double* B1 = P.Hpl + (size_t)e1 * 18;
-                        const double* B2 = P.Hpl + (size_t)e2 * 18;
-                        double BD[18];
-    #pragma unroll
-                        for (int a = 0; a < 6; a++) {
-                            const double b0 = B1[a * 3], b1 = B1[a * 3 + 1], b2 = B1[a * 3 + 2];
-                            BD[a * 3] = b0 * D0 + b1 * D1 + b2 * D2;
-                            BD[a * 3 + 1] = b0 * D1 + b1 * D3 + b2 * D4;
-                            BD[a * 3 + 2] = b0 * D2 + b1 * D4 + b2 * D5;
+                // ---------------- S1: Schur complement, camera-pair-major ----------------
+                // Hs(c2, c1) -= sum over the landmarks seen by both of Hpl_2 Dinv Hpl_1^T, bs(c) -= sum Hpl Dinv bl.  One warp
+                // per work item (<= 64 observation pairs of one camera pair); its two half-warps take the left and the right
+                // three columns of the 6 x 6 block, 16 pairs per step, sums in registers, one butterfly, and 36 additions
+                // at L2 per item instead of 36 per pair.
+                {
+                    const int half = lane >> 4, sub = lane & 15;
+                    const int nitems = P.flags[2];
+                    for (int item = gwarp; item < nitems; item += nwarps) {
+                        const int4 it = P.items[item];
+                        const int c1 = it.z, c2 = it.w;
+                        const bool diag = c1 == c2;
+                        // the item's pairs first: their loads are in flight together
+                        int4 pe[kPairChunk / 16];
+#pragma unroll
+                        for (int u = 0; u < kPairChunk / 16; u++) {
+                            const int t = it.x + sub + 16 * u;
+                            pe[u] = t < it.y ? P.pairs[t] : make_int4(-1, -1, -1, 0);
                         }
-                        if (i == j) { // once per observation: the gradient part
-    #pragma unroll
-                            for (int a = 0; a < 6; a++)
-                                atomicAdd(&P.bs[6 * c1 + a], -(B1[a * 3] * d[0] + B1[a * 3 + 1] * d[1] + B1[a * 3 + 2] * d[2]));
-                        }
-                        double* dst = P.Hs + (size_t)(6 * c2) * P.dimPad + 6 * c1;
-    #pragma unroll
-                        for (int b2 = 0; b2 < 6; b2++) {
-                            const double q0 = B2[b2 * 3], q1 = B2[b2 * 3 + 1], q2 = B2[b2 * 3 + 2];
-    #pragma unroll
-                            for (int a = 0; a < 6; a++) {
-                                if (i == j && a > b2) continue; // diagonal block: lower triangle only (a <= b2 <-> col <= row)
-                                atomicAdd(&dst[(size_t)b2 * P.dimPad + a], -(BD[a * 3] * q0 + BD[a * 3 + 1] * q1 + BD[a * 3 + 2] * q2));
+                        double acc[18], g[3] = { 0.0, 0.0, 0.0 };
+#pragma unroll
+                        for (int v = 0; v < 18; v++) acc[v] = 0.0;
+#pragma unroll
+                        for (int u = 0; u < kPairChunk / 16; u++) {
+                            if (pe[u].x < 0) continue;
+                            const int l = pe[u].z;
+                            const double* Di = P.Dinv + (size_t)l * 6;
+                            const double D0 = Di[0], D1 = Di[1], D2 = Di[2], D3 = Di[3], D4 = Di[4], D5 = Di[5];
+                            const double* B1 = P.Hpl + (size_t)pe[u].x * 18 + half * 9;   // rows 3 * half .. 3 * half + 2
+                            const double* B2 = P.Hpl + (size_t)pe[u].y * 18;
+                            double BD[9];
+#pragma unroll
+                            for (int a = 0; a < 3; a++) {
+                                const double b0 = B1[a * 3], b1 = B1[a * 3 + 1], b2 = B1[a * 3 + 2];
+                                BD[a * 3] = b0 * D0 + b1 * D1 + b2 * D2;
+                                BD[a * 3 + 1] = b0 * D1 + b1 * D3 + b2 * D4;
+                                BD[a * 3 + 2] = b0 * D2 + b1 * D4 + b2 * D5;
                             }
+                            if (diag) { // once per observation: the gradient part
+                                const double* d = P.db + (size_t)l * 3;
+                                const double d0 = d[0], d1 = d[1], d2 = d[2];
+#pragma unroll
+                                for (int a = 0; a < 3; a++) g[a] += B1[a * 3] * d0 + B1[a * 3 + 1] * d1 + B1[a * 3 + 2] * d2;
+                            }
+#pragma unroll
+                            for (int b2 = 0; b2 < 6; b2++) {
+                                const double q0 = B2[b2 * 3], q1 = B2[b2 * 3 + 1], q2 = B2[b2 * 3 + 2];
+#pragma unroll
+                                for (int a = 0; a < 3; a++) acc[b2 * 3 + a] += BD[a * 3] * q0 + BD[a * 3 + 1] * q1 + BD[a * 3 + 2] * q2;
+                            }
+                        }
+#pragma unroll
+                        for (int o = 8; o > 0; o >>= 1) {
+#pragma unroll
+                            for (int v = 0; v < 18; v++) acc[v] += __shfl_xor_sync(0xffffffffu, acc[v], o);
+#pragma unroll
+                            for (int a = 0; a < 3; a++) g[a] += __shfl_xor_sync(0xffffffffu, g[a], o);
+                        }
+                        double* dst = P.Hs + (size_t)(6 * c2) * P.dimPad + 6 * c1 + 3 * half;
+#pragma unroll
+                        for (int v = 0; v < 18; v++) {
+                            const int b2 = v / 3, a = v % 3;
+                            // diagonal block: lower triangle only (column <= row)
+                            if (sub == (v & 15) && (!diag || 3 * half + a <= b2)) atomicAdd(&dst[(size_t)b2 * P.dimPad + a], -acc[v]);
+                        }
+                        if (diag) {
+#pragma unroll
+                            for (int a = 0; a < 3; a++)
+                                if (sub == a) atomicAdd(&P.bs[6 * c1 + 3 * half + a], -g[a]);
                         }
                     }
                 }
@@ -1012,15 +1181,20 @@ static int run_ba(dvm_lba* h, int nc, float* cam_q, float* cam_t, const uint8_t*
     std::vector<int>& pt_start = h->pt_start;
     std::vector<int>& cam_start = h->cam_start;
     bool by_point = true;
+    size_t pairs_cap = 0;   // capacity of the Schur complement's pair lists: sum over the landmarks of k (k + 1) / 2 (k = observations)
     {   // validation, and whether the edges come grouped by point: then the device builds both structures itself
         int prev = -1;
         unsigned bad = 0;
+        size_t run = 0;
         for (int e = 0; e < ne; e++) {
             const int c = edge_cam[e], l = edge_pt[e];
             bad |= (unsigned)((unsigned)c >= (unsigned)nc) | (unsigned)((unsigned)l >= (unsigned)np);
             by_point = by_point && l >= prev;
+            if (l != prev) { pairs_cap += run * (run + 1) / 2; run = 0; }
+            run++;
             prev = l;
         }
+        pairs_cap += run * (run + 1) / 2;
         DVM_REQUIRE(bad == 0, "edge index out of range");
     }
     static const bool host_structure = getenv("DVM_LBA_HOST_STRUCTURE") != nullptr;   // (diagnostics: force the host build)
@@ -1033,9 +1207,16 @@ static int run_ba(dvm_lba* h, int nc, float* cam_q, float* cam_t, const uint8_t*
             const int cf = cam_col[edge_cam[e]];
             if (cf >= 0) cam_start[cf + 1]++;
         }
-        for (int l = 0; l < np; l++) pt_start[l + 1] += pt_start[l];
+        pairs_cap = 0;
+        for (int l = 0; l < np; l++) {
+            const size_t k = (size_t)pt_start[l + 1];
+            pairs_cap += k * (k + 1) / 2;
+            pt_start[l + 1] += pt_start[l];
+        }
         for (int c = 0; c < nf; c++) cam_start[c + 1] += cam_start[c];
     }
+    if (pairs_cap >= ((size_t)1 << 31)) { set_error("the landmarks' observation pairs (%zu) exceed the Schur complement's work list", pairs_cap); return DVM_ERR_CAPACITY; }
+    const size_t nbins = (size_t)nf * (nf + 1) / 2;
     const size_t n_cam_edges = (size_t)std::max(ne, 1);
     const auto ht1 = now();
     DVM_CUDA(cudaSetDevice(h->device));
@@ -1067,6 +1248,8 @@ static int run_ba(dvm_lba* h, int nc, float* cam_q, float* cam_t, const uint8_t*
     const size_t o_part = take((size_t)h->grid * kPartStride * 8), o_flags = take(4 * 4), o_prof = take(16 * 8);
     const size_t o_level = take((size_t)std::max(ne, 1));
     const size_t o_cnt = take(device_build ? (size_t)std::max(nf, 1) * h->grid * kLbaWarps * 4 : 4), o_ctot = take((size_t)(nf + 1) * 4);
+    const size_t o_pstart = take((nbins + 1) * 4), o_pfill = take(std::max(nbins, (size_t)1) * 4), o_pairs = take(std::max(pairs_cap, (size_t)1) * 16),
+                 o_items = take((pairs_cap / kPairChunk + nbins + 1) * 16);
     const size_t total = off + 256;
     if (total > h->d_cap) {
         DVM_CUDA(cudaStreamSynchronize(h->stream));
@@ -1158,6 +1341,7 @@ static int run_ba(dvm_lba* h, int nc, float* cam_q, float* cam_t, const uint8_t*
     P.build = device_build ? 1 : 0;
     P.pt_start_w = (int*)(db + o_pst); P.pt_edges_w = (int*)(db + o_ped); P.cam_start_w = (int*)(db + o_cst); P.cam_edges_w = (int*)(db + o_ced);
     P.cnt = (int*)(db + o_cnt); P.cam_tot = (int*)(db + o_ctot);
+    P.nbins = (int)nbins; P.pair_start = (int*)(db + o_pstart); P.pair_fill = (int*)(db + o_pfill); P.pairs = (int4*)(db + o_pairs); P.items = (int4*)(db + o_items);
     P.err = (double*)(db + o_err); P.Hpl = (double*)(db + o_hpl); P.Hll = (double*)(db + o_hll);
     P.bl = (double*)(db + o_bl); P.Dinv = (double*)(db + o_dinv); P.db = (double*)(db + o_db);
     P.Hpp = (double*)(db + o_hpp); P.bp = (double*)(db + o_bp); P.Hs = (double*)(db + o_hs); P.bs = (double*)(db + o_bs);
@@ -1190,7 +1374,7 @@ static int run_ba(dvm_lba* h, int nc, float* cam_q, float* cam_t, const uint8_t*
     if (getenv("DVM_LBA_PROFILE")) {
         unsigned long long pr[16];
         cudaMemcpy(pr, db + o_prof, 128, cudaMemcpyDeviceToHost);
-        fprintf(stderr, "[chol us] factor %.1f inverse %.1f trsm %.1f sync %.1f stage %.1f tiles %.1f sync %.1f backsub %.1f\n", pr[8] * 1e-3,
+        fprintf(stderr, "[chol us, CTA 0] first factor %.1f fetch Linv %.1f trsm %.1f sync %.1f next-diagonal update %.1f look-ahead factor %.1f wait for the trailing tiles %.1f backsub %.1f\n", pr[8] * 1e-3,
                 pr[9] * 1e-3, pr[10] * 1e-3, pr[11] * 1e-3, pr[12] * 1e-3, pr[13] * 1e-3, pr[14] * 1e-3, pr[15] * 1e-3);
         fprintf(stderr, "[lba phases us] L1 %.1f L2 %.1f S0 %.1f S1 %.1f C %.1f B1 %.1f B2 %.1f total %.1f\n", pr[0] * 1e-3, pr[1] * 1e-3,
                 pr[2] * 1e-3, pr[3] * 1e-3, pr[4] * 1e-3, pr[5] * 1e-3, pr[6] * 1e-3, h->last_ms * 1e3);
