@@ -11,7 +11,7 @@ constexpr int kCholThreads = 512;            // every kernel using these helpers
 constexpr int kCholWarps = kCholThreads / 32;
 constexpr int kNB = 32;                      // Cholesky block size
 constexpr int kPanelLd = 36;   // shared-memory row stride of a panel (doubles): conflict-free 8-byte fragment loads
-constexpr int kDiagLd = kNB + 1;
+constexpr int kDiagLd = kPanelLd;   // diagonal block and its inverse: also read as tensor-core fragments
 
 // D = C - A * B for one m8n8k4 FP64 tensor-core tile step (a: A[r=lane/4][k=lane%4], b: B[k=lane%4][c=lane/4])
 __device__ inline void dmma_m8n8k4(double& c0, double& c1, double a, double b)
@@ -119,22 +119,25 @@ __device__ inline bool cta_factor_invert_32(double* A, int ld, double* Ld, doubl
 
 
 
-// sum_{k < len} a[k] * b[k] with four partial sums (a dependent FP64 multiply-add costs ~24 cycles: one running sum over a
-// 32-long row is a 770-cycle chain)
-__device__ inline double tri_dot4(const double* a, const double* b, int len)
+// out[rows x 32] = S[rows x 32] * Linv^T on the FP64 tensor pipe (the panel step L21 = A21 * L11^-T as a product with the
+// inverted diagonal block).  S is staged in shared memory with row stride kPanelLd, Linv with kDiagLd; rows is a multiple
+// of 8; every warp takes 8 x 8 output tiles and hands store(row, col, v(row, col), v(row, col + 1)) its two results per
+// lane.  Linv is lower triangular, so column tile tc only needs k < 8 (tc + 1).
+// (One thread per output with two shared-memory loads per multiply-add was bound by the shared-memory pipe: 2.7 us for a
+// 32 x 32 panel; as tensor-core fragments every loaded value feeds 8 multiply-adds.)
+template <class Store>
+__device__ inline void panel_times_inverse_t(const double* S, int rows, const double* Linv, Store&& store)
 {
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    int k = 0;
-    for (; k + 3 < len; k += 4) {
-        s0 += a[k] * b[k];
-        s1 += a[k + 1] * b[k + 1];
-        s2 += a[k + 2] * b[k + 2];
-        s3 += a[k + 3] * b[k + 3];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int ntiles = (rows >> 3) * (kNB / 8);
+    for (int t = wid; t < ntiles; t += kCholWarps) {
+        const int tr = t >> 2, tc = t & 3;
+        const int ar = tr * 8 + (lane >> 2), bc = tc * 8 + (lane >> 2);
+        double c0 = 0.0, c1 = 0.0;
+        for (int kk = 0; kk < (tc + 1) * 8; kk += 4)
+            dmma_m8n8k4(c0, c1, S[ar * kPanelLd + kk + (lane & 3)], Linv[bc * kDiagLd + kk + (lane & 3)]);
+        store(ar, tc * 8 + (lane & 3) * 2, c0, c1);
     }
-    if (k < len) s0 += a[k] * b[k];
-    if (k + 1 < len) s1 += a[k + 1] * b[k + 1];
-    if (k + 2 < len) s2 += a[k + 2] * b[k + 2];
-    return (s0 + s1) + (s2 + s3);
 }
 
 // ---- dense SPD solve A x = b on a whole cooperative grid ------------------------------------------------------------
@@ -147,7 +150,7 @@ __device__ inline double tri_dot4(const double* a, const double* b, int len)
 //       memory, 8 x 8 sub-tiles on the FP64 tensor pipe (DMMA m8n8k4), lower triangle only.
 // Then CTA 0 solves L^T x = y block by block.  *g_ok (global) is 1 on success, 0 when a pivot was not positive / finite
 // (x is then zero).  The caller must grid.sync() before reading x.  smem: kGridCholSmemDoubles doubles.
-constexpr int kGridCholSmemDoubles = 2 * kNB * kDiagLd + 64 * kNB + 2 * 64 * kPanelLd + 4 * kNB + 8;
+constexpr int kGridCholSmemDoubles = 2 * kNB * kDiagLd + 64 * kPanelLd + 2 * 64 * kPanelLd + 4 * kNB + 8;
 
 __device__ inline void grid_cholesky_solve(cooperative_groups::grid_group& grid, int n, double* A, const double* b, double* x,
                                            double* Linv_g, int* g_ok, double* smem)
@@ -156,8 +159,8 @@ __device__ inline void grid_cholesky_solve(cooperative_groups::grid_group& grid,
     const int G = gridDim.x, cta = blockIdx.x;
     double* Ld = smem;                            // [kNB][kDiagLd]
     double* Li = Ld + kNB * kDiagLd;              // [kNB][kDiagLd]
-    double* stage = Li + kNB * kDiagLd;           // [64][kNB]
-    double* Pi = stage + 64 * kNB;                // [64][kPanelLd]
+    double* stage = Li + kNB * kDiagLd;           // [64][kPanelLd]
+    double* Pi = stage + 64 * kPanelLd;           // [64][kPanelLd]
     double* Pj = Pi + 64 * kPanelLd;              // [64][kPanelLd]
     double* scratch = Pj + 64 * kPanelLd;         // [4 * kNB + 8]
     const int M = n + 8;
@@ -182,12 +185,12 @@ __device__ inline void grid_cholesky_solve(cooperative_groups::grid_group& grid,
             __syncthreads();
             for (int base = r0 + cta * 64; base < M; base += G * 64) {
                 const int cnt = min(64, M - base);
-                for (int t = tid; t < cnt * kNB; t += kCholThreads) stage[t] = A[(size_t)(base + (t >> 5)) * n + k0 + (t & 31)];
+                for (int t = tid; t < cnt * kNB; t += kCholThreads) stage[(t >> 5) * kPanelLd + (t & 31)] = A[(size_t)(base + (t >> 5)) * n + k0 + (t & 31)];
                 __syncthreads();
-                for (int t = tid; t < cnt * kNB; t += kCholThreads) {
-                    const int r = t >> 5, c = t & 31;
-                    A[(size_t)(base + r) * n + k0 + c] = tri_dot4(stage + r * kNB, Li + c * kDiagLd, c + 1);
-                }
+                panel_times_inverse_t(stage, cnt, Li, [&](int r, int c, double v0, double v1) {
+                    double* dst = A + (size_t)(base + r) * n + k0 + c;
+                    dst[0] = v0; dst[1] = v1;
+                });
                 __syncthreads();
             }
         }

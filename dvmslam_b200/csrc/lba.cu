@@ -73,6 +73,10 @@ struct LbaDev {
     int4* items;
 };
 constexpr int kPairChunk = 64;
+// Hpl block of an edge (6 x 3, camera rows x landmark columns): rows 0-2 and rows 3-5 as two 16-byte aligned groups of
+// 9 (+1 padding) doubles, so that the Schur complement's half-warps read theirs with 128-bit loads
+constexpr int kHplStride = 20;
+__device__ __forceinline__ int hpl_idx(int a, int k) { return (a / 3) * 10 + (a % 3) * 3 + k; }
 
 // ---- SE3 helpers (same formulas as the pose-only optimiser; g2o/types/se3quat.h) ----
 struct Quat { double x, y, z, w; };
@@ -262,7 +266,7 @@ __device__ bool cluster_cholesky_solve(int n, double* __restrict__ A, const doub
     double* panel = smem;                                 // [(n + 8)][kPanelLd]
     double* Ld = panel + (size_t)(n + 8) * kPanelLd;      // [kNB][kDiagLd]  factored diagonal block
     double* Li = Ld + kNB * kDiagLd;                      // [kNB][kDiagLd]  its inverse
-    double* stage = Li + kNB * kDiagLd;                   // [64][kNB]       this CTA's panel rows before the TRSM
+    double* stage = Li + kNB * kDiagLd;                   // [64][kPanelLd]  this CTA's panel rows before the TRSM
     const int M = n + 8;                                  // rows including the right-hand-side row group
     if (tid == 0) *s_flag = 1;
     // right-hand side as row n, zero rows n+1 .. n+7
@@ -292,35 +296,36 @@ __device__ bool cluster_cholesky_solve(int n, double* __restrict__ A, const doub
         // block now, under the latency of the panel loads; the other seven CTAs share the rows below
         int i0, i1;
         if (mcols > 0) {
-            const int chunk = (mrows - kNB + kClusterCtas - 2) / (kClusterCtas - 1);
+            const int chunk = ((mrows - kNB + kClusterCtas - 2) / (kClusterCtas - 1) + 7) & ~7;   // whole 8-row tiles
             i0 = rank == 0 ? r0 : r0 + kNB + (rank - 1) * chunk;
             i1 = rank == 0 ? r0 + kNB : min(i0 + chunk, M);
         } else {   // last block column: only the right-hand-side rows are left
-            const int chunk = (mrows + kClusterCtas - 1) / kClusterCtas;
+            const int chunk = 8;
             i0 = r0 + rank * chunk;
             i1 = min(i0 + chunk, M);
         }
         double* Pn = panel;                       // [kNB][kDiagLd]  panel rows r0 .. r0 + 31
         double* Dn = panel + kNB * kDiagLd;       // [kNB][kDiagLd]  the next diagonal block
         const bool own_next = rank == 0 && mcols > 0;
+        // (in the layout of the tensor-core tile warp `wid` computes below: 10 lower 8 x 8 tiles of the 32 x 32 block)
         double dnext[2] = { 0.0, 0.0 };
-        if (rank == 0 && mcols > 0) {
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-                const int r = tid & 31, c = (tid >> 5) + 16 * h;
-                if (c <= r) dnext[h] = A[(size_t)(r0 + r) * n + r0 + c];
-            }
+        const int dti = wid < 1 ? 0 : wid < 3 ? 1 : wid < 6 ? 2 : 3, dtj = wid - dti * (dti + 1) / 2;
+        const int drow = dti * 8 + (lane >> 2), dcol = dtj * 8 + (lane & 3) * 2;
+        if (rank == 0 && mcols > 0 && wid < 10) {
+            if (dcol <= drow) dnext[0] = A[(size_t)(r0 + drow) * n + r0 + dcol];
+            if (dcol + 1 <= drow) dnext[1] = A[(size_t)(r0 + drow) * n + r0 + dcol + 1];
         }
         for (int base = i0; base < i1; base += 64) {
             const int cnt = min(64, i1 - base);
-            for (int t = tid; t < cnt * kNB; t += kLbaThreads) stage[t] = A[(size_t)(base + (t >> 5)) * n + k0 + (t & 31)];
+            for (int t = tid; t < cnt * kNB; t += kLbaThreads) stage[(t >> 5) * kPanelLd + (t & 31)] = A[(size_t)(base + (t >> 5)) * n + k0 + (t & 31)];
             __syncthreads();
-            for (int t = tid; t < cnt * kNB; t += kLbaThreads) {
-                const int r = t >> 5, c = t & 31;
-                const double acc = tri_dot4(stage + r * kNB, Li + c * kDiagLd, c + 1);
-                A[(size_t)(base + r) * n + k0 + c] = acc;
-                if (own_next && base + r - r0 < kNB) Pn[(base + r - r0) * kDiagLd + c] = acc;
-            }
+            tk(16);
+            panel_times_inverse_t(stage, cnt, Li, [&](int r, int c, double v0, double v1) {
+                double* dst = A + (size_t)(base + r) * n + k0 + c;
+                dst[0] = v0; dst[1] = v1;
+                if (own_next) { Pn[(base + r - r0) * kDiagLd + c] = v0; Pn[(base + r - r0) * kDiagLd + c + 1] = v1; }
+            });
+            tk(17);
             __syncthreads();
         }
         tk(10);
@@ -331,25 +336,18 @@ __device__ bool cluster_cholesky_solve(int n, double* __restrict__ A, const doub
         // 32 dependent pivot steps of a block (the longest chain of the solve) run beside the tensor-pipe work instead of
         // before it (look-ahead of one block column) ----
         if (mcols > 0 && rank == 0) {
-            {
-                const int r = tid & 31;
+            if (wid < 10) {   // D = A(next diagonal block) - Pn Pn^T, lower tiles, on the tensor pipe
+                double c0 = 0.0, c1 = 0.0;
 #pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const int c = (tid >> 5) + 16 * h;
-                    double v = 0.0;
-                    if (c <= r) {
-                        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-#pragma unroll
-                        for (int k = 0; k < kNB; k += 4) {
-                            s0 += Pn[r * kDiagLd + k] * Pn[c * kDiagLd + k];
-                            s1 += Pn[r * kDiagLd + k + 1] * Pn[c * kDiagLd + k + 1];
-                            s2 += Pn[r * kDiagLd + k + 2] * Pn[c * kDiagLd + k + 2];
-                            s3 += Pn[r * kDiagLd + k + 3] * Pn[c * kDiagLd + k + 3];
-                        }
-                        v = dnext[h] - ((s0 + s1) + (s2 + s3));
-                    }
-                    Dn[r * kDiagLd + c] = v;
-                }
+                for (int kk = 0; kk < kNB; kk += 4)
+                    dmma_m8n8k4(c0, c1, Pn[drow * kDiagLd + kk + (lane & 3)], Pn[(dtj * 8 + (lane >> 2)) * kDiagLd + kk + (lane & 3)]);
+                Dn[drow * kDiagLd + dcol] = dcol <= drow ? dnext[0] - c0 : 0.0;
+                Dn[drow * kDiagLd + dcol + 1] = dcol + 1 <= drow ? dnext[1] - c1 : 0.0;
+            } else {          // the six tiles above the diagonal
+                const int u = wid - 10;
+                const int uti = u < 3 ? 0 : u < 5 ? 1 : 2, utj = u < 3 ? u + 1 : u < 5 ? u - 1 : 3;
+                Dn[(uti * 8 + (lane >> 2)) * kDiagLd + utj * 8 + (lane & 3) * 2] = 0.0;
+                Dn[(uti * 8 + (lane >> 2)) * kDiagLd + utj * 8 + (lane & 3) * 2 + 1] = 0.0;
             }
             __syncthreads();
             tk(12);
@@ -663,9 +661,9 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kLbaThrea
                     const int e = P.pt_edges[k];
                     if (P.level && P.level[e]) { // level-1 edge: no contribution to H, b or chi2; its error stays
                         if (P.cam_col[P.ecam[e]] >= 0) {
-                            double* hp = P.Hpl + (size_t)e * 18;
+                            double* hp = P.Hpl + (size_t)e * kHplStride;
 #pragma unroll
-                            for (int i = 0; i < 18; i++) hp[i] = 0.0;
+                            for (int i = 0; i < kHplStride; i++) hp[i] = 0.0;
                         }
                         continue;
                     }
@@ -699,13 +697,13 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kLbaThrea
                     h[5] += A[2] * wo * A[2] + A[5] * wo * A[5];
                     if (P.cam_col[P.ecam[e]] >= 0) {
                         const double Dv[18] = { 0, Z, -Y, 1, 0, 0, -Z, 0, X, 0, 1, 0, Y, -X, 0, 0, 0, 1 };
-                        double* hp = P.Hpl + (size_t)e * 18;
+                        double* hp = P.Hpl + (size_t)e * kHplStride;
     #pragma unroll
                         for (int a = 0; a < 6; a++) {
                             const double B0 = pj[0] * Dv[a] + pj[1] * Dv[6 + a] + pj[2] * Dv[12 + a];
                             const double B1 = pj[3] * Dv[a] + pj[4] * Dv[6 + a] + pj[5] * Dv[12 + a];
     #pragma unroll
-                            for (int b2 = 0; b2 < 3; b2++) hp[a * 3 + b2] = B0 * wo * A[b2] + B1 * wo * A[3 + b2];
+                            for (int b2 = 0; b2 < 3; b2++) hp[hpl_idx(a, b2)] = B0 * wo * A[b2] + B1 * wo * A[3 + b2];
                         }
                     }
                 }
@@ -856,10 +854,18 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kLbaThrea
                         for (int u = 0; u < kPairChunk / 16; u++) {
                             if (pe[u].x < 0) continue;
                             const int l = pe[u].z;
-                            const double* Di = P.Dinv + (size_t)l * 6;
-                            const double D0 = Di[0], D1 = Di[1], D2 = Di[2], D3 = Di[3], D4 = Di[4], D5 = Di[5];
-                            const double* B1 = P.Hpl + (size_t)pe[u].x * 18 + half * 9;   // rows 3 * half .. 3 * half + 2
-                            const double* B2 = P.Hpl + (size_t)pe[u].y * 18;
+                            const double2* Di = reinterpret_cast<const double2*>(P.Dinv + (size_t)l * 6);
+                            const double2 Da = Di[0], Db = Di[1], Dc = Di[2];
+                            const double D0 = Da.x, D1 = Da.y, D2 = Db.x, D3 = Db.y, D4 = Dc.x, D5 = Dc.y;
+                            double B1[10], B2[20];   // rows 3 * half .. 3 * half + 2 of the first block, the whole second block
+                            {
+                                const double2* q1 = reinterpret_cast<const double2*>(P.Hpl + (size_t)pe[u].x * kHplStride + half * 10);
+                                const double2* q2 = reinterpret_cast<const double2*>(P.Hpl + (size_t)pe[u].y * kHplStride);
+#pragma unroll
+                                for (int i = 0; i < 5; i++) { const double2 v = q1[i]; B1[2 * i] = v.x; B1[2 * i + 1] = v.y; }
+#pragma unroll
+                                for (int i = 0; i < 10; i++) { const double2 v = q2[i]; B2[2 * i] = v.x; B2[2 * i + 1] = v.y; }
+                            }
                             double BD[9];
 #pragma unroll
                             for (int a = 0; a < 3; a++) {
@@ -876,7 +882,7 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kLbaThrea
                             }
 #pragma unroll
                             for (int b2 = 0; b2 < 6; b2++) {
-                                const double q0 = B2[b2 * 3], q1 = B2[b2 * 3 + 1], q2 = B2[b2 * 3 + 2];
+                                const double q0 = B2[hpl_idx(b2, 0)], q1 = B2[hpl_idx(b2, 1)], q2 = B2[hpl_idx(b2, 2)];
 #pragma unroll
                                 for (int a = 0; a < 3; a++) acc[b2 * 3 + a] += BD[a * 3] * q0 + BD[a * 3 + 1] * q1 + BD[a * 3 + 2] * q2;
                             }
@@ -924,10 +930,10 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kLbaThrea
                         const int e = P.pt_edges[k];
                         const int c1 = P.cam_col[P.ecam[e]];
                         if (c1 < 0) continue;
-                        const double* B1 = P.Hpl + (size_t)e * 18;
+                        const double* B1 = P.Hpl + (size_t)e * kHplStride;
                         const double* xp = P.x + 6 * c1;
     #pragma unroll
-                        for (int a = 0; a < 6; a++) { cl[0] -= B1[a * 3] * xp[a]; cl[1] -= B1[a * 3 + 1] * xp[a]; cl[2] -= B1[a * 3 + 2] * xp[a]; }
+                        for (int a = 0; a < 6; a++) { cl[0] -= B1[hpl_idx(a, 0)] * xp[a]; cl[1] -= B1[hpl_idx(a, 1)] * xp[a]; cl[2] -= B1[hpl_idx(a, 2)] * xp[a]; }
                     }
                     cl[0] = warp_sum(cl[0]); cl[1] = warp_sum(cl[1]); cl[2] = warp_sum(cl[2]);
                     if (lane == 0) {
@@ -1097,7 +1103,7 @@ int dvm_lba_create(dvm_lba** out, int device, int max_free_cameras)
     // up to kLbaClusterFree free keyframes the reduced system is factored by ONE cluster with its panel in shared memory
     // (local BA: lowest latency); above that by the whole grid (grid_cholesky_solve), whose shared memory need is fixed
     const size_t n = ((size_t)6 * std::min(max_free_cameras, kLbaClusterFree) + kNB - 1) / kNB * kNB;
-    h->smem_bytes = std::max(((n + 8) * kPanelLd + 2 * kNB * kDiagLd + 64 * kNB) * sizeof(double),
+    h->smem_bytes = std::max(((n + 8) * kPanelLd + 2 * kNB * kDiagLd + 64 * kPanelLd) * sizeof(double),
                              (size_t)kGridCholSmemDoubles * sizeof(double));
     DVM_REQUIRE(h->smem_bytes <= 227 * 1024, "max_free_cameras needs more shared memory than one SM has");
     DVM_LCREATE(cudaFuncSetAttribute(lba_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
@@ -1239,13 +1245,13 @@ static int run_ba(dvm_lba* h, int nc, float* cam_q, float* cam_t, const uint8_t*
     const size_t out_end = off;
     // work block (device only)
     const size_t o_camq1 = take((size_t)nc * 4 * 8), o_camt1 = take((size_t)nc * 3 * 8), o_pts1 = take((size_t)np * 3 * 8);
-    const size_t o_err = take((size_t)ne * 2 * 8), o_hpl = take((size_t)ne * 18 * 8);
+    const size_t o_err = take((size_t)ne * 2 * 8), o_hpl = take((size_t)ne * kHplStride * 8);
     const size_t o_hll = take((size_t)np * 6 * 8), o_bl = take((size_t)np * 3 * 8), o_dinv = take((size_t)np * 6 * 8), o_db = take((size_t)np * 3 * 8);
     const size_t o_hpp = take((size_t)std::max(nf, 1) * 36 * 8), o_bp = take((size_t)std::max(dimP, 1) * 8);
     const size_t o_hs = take((size_t)std::max((size_t)(dimPad + 8) * dimPad, (size_t)1) * 8), o_bs = take((size_t)std::max(dimPad, 1) * 8);
     const size_t o_linv = take((size_t)std::max(dimPad * kNB, 1) * 8);
     const size_t o_x = take((size_t)(dimPad + np * 3 + 1) * 8);
-    const size_t o_part = take((size_t)h->grid * kPartStride * 8), o_flags = take(4 * 4), o_prof = take(16 * 8);
+    const size_t o_part = take((size_t)h->grid * kPartStride * 8), o_flags = take(4 * 4), o_prof = take(32 * 8);
     const size_t o_level = take((size_t)std::max(ne, 1));
     const size_t o_cnt = take(device_build ? (size_t)std::max(nf, 1) * h->grid * kLbaWarps * 4 : 4), o_ctot = take((size_t)(nf + 1) * 4);
     const size_t o_pstart = take((nbins + 1) * 4), o_pfill = take(std::max(nbins, (size_t)1) * 4), o_pairs = take(std::max(pairs_cap, (size_t)1) * 16),
@@ -1323,7 +1329,7 @@ static int run_ba(dvm_lba* h, int nc, float* cam_q, float* cam_t, const uint8_t*
     P.iterations2 = iterations2;
     {
         const size_t n = (size_t)((6 * nf + kNB - 1) / kNB * kNB);
-        const size_t cluster_need = ((n + 8) * kPanelLd + 2 * kNB * kDiagLd + 64 * kNB) * sizeof(double);
+        const size_t cluster_need = ((n + 8) * kPanelLd + 2 * kNB * kDiagLd + 64 * kPanelLd) * sizeof(double);
         P.grid_chol = (nf > kLbaClusterFree || cluster_need > h->smem_bytes) ? 1 : 0;
     }
     P.level = iterations2 > 0 ? db + o_level : nullptr;
@@ -1352,7 +1358,7 @@ static int run_ba(dvm_lba* h, int nc, float* cam_q, float* cam_t, const uint8_t*
     *h->h_abort = 0;
     P.abort_flag = abort_flag ? h->d_abort : nullptr;
     DVM_CUDA(cudaMemsetAsync(db + o_flags, 0, 16, h->stream));
-    DVM_CUDA(cudaMemsetAsync(db + o_prof, 0, 128, h->stream));
+    DVM_CUDA(cudaMemsetAsync(db + o_prof, 0, 256, h->stream));
     P.prof = (unsigned long long*)(db + o_prof);
     DVM_CUDA(cudaMemsetAsync(db + o_err, 0, (size_t)ne * 2 * 8, h->stream));
     if (iterations2 > 0) DVM_CUDA(cudaMemsetAsync(db + o_level, 0, (size_t)ne, h->stream));
@@ -1372,8 +1378,9 @@ static int run_ba(dvm_lba* h, int nc, float* cam_q, float* cam_t, const uint8_t*
     const auto ht4 = now();
     DVM_CUDA(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
     if (getenv("DVM_LBA_PROFILE")) {
-        unsigned long long pr[16];
-        cudaMemcpy(pr, db + o_prof, 128, cudaMemcpyDeviceToHost);
+        unsigned long long pr[32];
+        cudaMemcpy(pr, db + o_prof, 256, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[chol us, CTA 0, inside trsm] panel rows loaded %.1f multiplied %.1f\n", pr[16] * 1e-3, pr[17] * 1e-3);
         fprintf(stderr, "[chol us, CTA 0] first factor %.1f fetch Linv %.1f trsm %.1f sync %.1f next-diagonal update %.1f look-ahead factor %.1f wait for the trailing tiles %.1f backsub %.1f\n", pr[8] * 1e-3,
                 pr[9] * 1e-3, pr[10] * 1e-3, pr[11] * 1e-3, pr[12] * 1e-3, pr[13] * 1e-3, pr[14] * 1e-3, pr[15] * 1e-3);
         fprintf(stderr, "[lba phases us] L1 %.1f L2 %.1f S0 %.1f S1 %.1f C %.1f B1 %.1f B2 %.1f total %.1f\n", pr[0] * 1e-3, pr[1] * 1e-3,
