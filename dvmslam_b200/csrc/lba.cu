@@ -389,25 +389,39 @@ __device__ bool cluster_cholesky_solve(int n, double* __restrict__ A, const doub
     }
     const bool ok = *s_flag != 0;
     // ---- backward substitution L^T x = y on CTA 0 (y = row n of A) ----
+    // Per block column (last to first): the inverted diagonal block is fetched into shared memory while the 16 warps sum
+    // L(below, block)^T x(below) -- the loads of a warp are issued four rows at a time, a multiply-add waiting for its
+    // operand would otherwise hold back the next load (in-order issue: one L2 round trip per row).
     if (rank == 0) {
         double* y = panel;          // [n]
         double* part = panel + n;   // [16][kNB] partial sums
         double* rhs = part + 16 * kNB;
+        double* LgS = rhs + kNB;    // [kNB][kNB + 1]   (runs on into the dead diagonal-block buffers when n = 32)
         for (int i = tid; i < n; i += kLbaThreads) y[i] = A[(size_t)n * n + i];
         __syncthreads();
         for (int k0 = n - kNB; k0 >= 0; k0 -= kNB) {
-            // rhs[c] = y[k0+c] - sum_{i >= k0+32} L[i][k0+c] * x[i]
             {
-                // (two partial sums per thread and trees below: a dependent FP64 operation costs ~24 cycles)
+                const double* Lg = Linv_g + (size_t)(k0 / kNB) * kNB * kNB;
+                const double g0 = Lg[tid], g1 = Lg[tid + kLbaThreads];
                 const int c = tid & 31, g = tid >> 5;
-                double acc0 = 0.0, acc1 = 0.0;
+                double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
                 int i = k0 + kNB + g;
-                for (; i + kLbaWarps < n; i += 2 * kLbaWarps) {
-                    acc0 += A[(size_t)i * n + k0 + c] * y[i];
-                    acc1 += A[(size_t)(i + kLbaWarps) * n + k0 + c] * y[i + kLbaWarps];
+                for (; i + 3 * kLbaWarps < n; i += 4 * kLbaWarps) {
+                    const double a0 = A[(size_t)i * n + k0 + c], a1 = A[(size_t)(i + kLbaWarps) * n + k0 + c];
+                    const double a2 = A[(size_t)(i + 2 * kLbaWarps) * n + k0 + c], a3 = A[(size_t)(i + 3 * kLbaWarps) * n + k0 + c];
+                    acc0 += a0 * y[i]; acc1 += a1 * y[i + kLbaWarps]; acc2 += a2 * y[i + 2 * kLbaWarps]; acc3 += a3 * y[i + 3 * kLbaWarps];
                 }
-                if (i < n) acc0 += A[(size_t)i * n + k0 + c] * y[i];
-                part[g * kNB + c] = acc0 + acc1;
+                {
+                    const bool h0 = i < n, h1 = i + kLbaWarps < n, h2 = i + 2 * kLbaWarps < n;
+                    const double a0 = h0 ? A[(size_t)i * n + k0 + c] : 0.0, a1 = h1 ? A[(size_t)(i + kLbaWarps) * n + k0 + c] : 0.0;
+                    const double a2 = h2 ? A[(size_t)(i + 2 * kLbaWarps) * n + k0 + c] : 0.0;
+                    if (h0) acc0 += a0 * y[i];
+                    if (h1) acc1 += a1 * y[i + kLbaWarps];
+                    if (h2) acc2 += a2 * y[i + 2 * kLbaWarps];
+                }
+                part[g * kNB + c] = (acc0 + acc1) + (acc2 + acc3);
+                LgS[(tid >> 5) * (kNB + 1) + (tid & 31)] = g0;
+                LgS[((tid + kLbaThreads) >> 5) * (kNB + 1) + (tid & 31)] = g1;
             }
             __syncthreads();
             if (tid < kNB) {
@@ -418,11 +432,10 @@ __device__ bool cluster_cholesky_solve(int n, double* __restrict__ A, const doub
             }
             __syncthreads();
             if (tid < kNB) { // x_k = L_kk^-T rhs
-                const double* Lg = Linv_g + (size_t)(k0 / kNB) * kNB * kNB;
                 double s4[4] = { 0.0, 0.0, 0.0, 0.0 };
-#pragma unroll 8
+#pragma unroll
                 for (int c = 0; c < kNB; c++)
-                    if (c >= tid) s4[c & 3] += Lg[c * kNB + tid] * rhs[c];
+                    if (c >= tid) s4[c & 3] += LgS[c * (kNB + 1) + tid] * rhs[c];
                 y[k0 + tid] = (s4[0] + s4[1]) + (s4[2] + s4[3]);
             }
             __syncthreads();
