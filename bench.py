@@ -401,16 +401,28 @@ def run_ours(args):
 
     inliers = []
 
+    dev_pending = [0]
+
     def step_device(s):
+        # the same hand-over as the host loop below (two frames ahead on the extraction streams), images already in HBM
         for i in range(FRAMES_PER_STEP):
             k = (1 + s * FRAMES_PER_STEP + i) % RESIDENT_FRAMES
-            trk.track((base + k * frame_bytes, W, H, W), sync=False)
+            if dev_pending[0] == 0:
+                trk.track((base + k * frame_bytes, W, H, W), sync=False)
+            else:
+                trk.track(None, sync=False)
+                dev_pending[0] -= 1
+            while dev_pending[0] < 2:
+                kk = (k + 1 + dev_pending[0]) % RESIDENT_FRAMES
+                trk.prefetch((base + kk * frame_bytes, W, H, W))
+                dev_pending[0] += 1
 
     pending = [0]  # frames whose upload + extraction is already enqueued (dvm_tracker_prefetch; at most two)
 
     def step_host(s):
         # a camera-driven loop: frames k+1 and k+2 are handed to the two extraction streams while frame k's chain
-        # runs; every frame's pose and counts are read back to the host before the next frame is tracked
+        # runs; every frame's pose and counts reach the host (the chain's last kernel writes them into a pinned ring) and
+        # are read one frame behind the enqueue, so the GPU is never idle between two frames of the agent
         for i in range(FRAMES_PER_STEP):
             k = (1 + s * FRAMES_PER_STEP + i) % RESIDENT_FRAMES
             if pending[0] == 0:
@@ -421,8 +433,11 @@ def run_ours(args):
             while pending[0] < 2:
                 trk.prefetch(host_np[(k + 1 + pending[0]) % RESIDENT_FRAMES])
                 pending[0] += 1
-            _, _, c = trk.result()
-            inliers.append(c[3])
+            if i > 0:
+                _, _, c = trk.result(lag=1)
+                inliers.append(c[3])
+        _, _, c = trk.result()
+        inliers.append(c[3])
 
     # ---- device-resident throughput (`value`) ----
     bootstrap()

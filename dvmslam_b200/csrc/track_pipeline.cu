@@ -74,7 +74,9 @@ struct dvm_tracker {
     float* d_pose_last = nullptr; float* d_pose_prev = nullptr;
     int* d_res1 = nullptr; int* d_res2 = nullptr;
     uint8_t* d_result = nullptr; // pose[7] float | counts[4] int
-    uint8_t* h_result = nullptr; // pinned: [0,48) result read-back, [64,92) prior staging
+    uint8_t* h_result = nullptr; // pinned: [64,92) prior staging
+    uint8_t* h_ring = nullptr;   // pinned + mapped, [kRing][64]: pose[7] float | counts[4] int of frame i in slot i % kRing, written by
+    uint8_t* d_ring = nullptr;   // the chain's last kernel straight into host memory (its device alias): no read-back copy
     uint8_t* d_img[kExtractors] = { nullptr, nullptr }; size_t img_cap[kExtractors] = { 0, 0 };   // H2D staging
     // per-segment device time of the chain (dvm_tracker_set_profiling): events between the operators of a tracked frame
     bool profiling = false;
@@ -96,6 +98,7 @@ static void tracker_free(dvm_tracker* t)
                      t->d_pose, t->d_pose_last, t->d_pose_prev, t->d_res1, t->d_res2, t->d_result, t->d_img[0], t->d_img[1] };
     for (void* p : ptrs) cudaFree(p);
     if (t->h_result) cudaFreeHost(t->h_result);
+    if (t->h_ring) cudaFreeHost(t->h_ring);
     for (auto e : t->ev_extracted) if (e) cudaEventDestroy(e);
     for (auto e : t->ev_done) if (e) cudaEventDestroy(e);
     for (auto e : t->pev) if (e) cudaEventDestroy(e);
@@ -227,6 +230,9 @@ int dvm_tracker_create(dvm_tracker** out, dvm_orb* orb, const float* K, const fl
     DVM_TCREATE(cudaMalloc(&t->d_res1, 16)); DVM_TCREATE(cudaMalloc(&t->d_res2, 16));
     DVM_TCREATE(cudaMalloc(&t->d_result, 64)); DVM_TCREATE(cudaMemset(t->d_result, 0, 64));
     DVM_TCREATE(cudaHostAlloc(&t->h_result, 128, cudaHostAllocDefault));
+    DVM_TCREATE(cudaHostAlloc(&t->h_ring, kRing * 64, cudaHostAllocMapped));
+    memset(t->h_ring, 0, kRing * 64);
+    DVM_TCREATE(cudaHostGetDevicePointer(&t->d_ring, t->h_ring, 0));
 #undef DVM_TCREATE
     *out = t;
     return DVM_OK;
@@ -318,6 +324,7 @@ int dvm_tracker_bootstrap(dvm_tracker* t, const uint8_t* gray, int width, int he
     DVM_CUDA(cudaStreamSynchronize(t->stream));
     t->n_extracted = 0;
     t->n_tracked = 0;
+    memset(t->h_ring, 0, kRing * 64);   // (every stream is idle here)
     int rc = enqueue_extract(t, gray, 0, width, height, stride);
     if (rc != DVM_OK) return rc;
     dvm_frame* cur = t->frames[0];
@@ -417,7 +424,7 @@ int dvm_tracker_track(dvm_tracker* t, const uint8_t* gray, int gray_is_device, i
     pa.result = t->d_res2;
     pa.seen = nullptr; pa.map_index_rw = nullptr;
     pa.pose_last = t->d_pose_last; pa.pose_prev = t->d_pose_prev;
-    pa.out_pose = (float*)t->d_result; pa.out_counts = (int*)(t->d_result + 32);
+    pa.out_pose = (float*)(t->d_ring + 64 * ci); pa.out_counts = (int*)(t->d_ring + 64 * ci + 32);
     pa.nm_last = t->d_cnt + 1; pa.res_first = t->d_res1;
     pa.next_prior = t->d_pose; pa.seen_reset = t->d_seen; pa.seen_n = t->map_n;
     rc = launch_pose_opt(pa, t->stream);
@@ -439,16 +446,20 @@ int dvm_tracker_track(dvm_tracker* t, const uint8_t* gray, int gray_is_device, i
     return DVM_OK;
 }
 
-int dvm_tracker_result(dvm_tracker* t, float* pose_out, int32_t* counts)
+int dvm_tracker_result_lag(dvm_tracker* t, int lag, float* pose_out, int32_t* counts)
 {
     DVM_REQUIRE(t != nullptr, "null handle");
+    DVM_REQUIRE(lag >= 0 && lag <= kRing - 2, "lag out of range (the result ring keeps the last three frames)");
+    DVM_REQUIRE(t->n_tracked - 1 - lag >= 0, "no such frame yet");
     DVM_CUDA(cudaSetDevice(t->device));
-    DVM_CUDA(cudaMemcpyAsync(t->h_result, t->d_result, 48, cudaMemcpyDeviceToHost, t->stream));
-    DVM_CUDA(cudaStreamSynchronize(t->stream));
-    if (pose_out) memcpy(pose_out, t->h_result, 28);
-    if (counts) memcpy(counts, t->h_result + 32, 16);
+    const int slot = (int)((t->n_tracked - 1 - lag) % kRing);
+    DVM_CUDA(cudaEventSynchronize(t->ev_done[slot]));   // that frame's chain only: later frames keep running
+    if (pose_out) memcpy(pose_out, t->h_ring + 64 * slot, 28);
+    if (counts) memcpy(counts, t->h_ring + 64 * slot + 32, 16);
     return DVM_OK;
 }
+
+int dvm_tracker_result(dvm_tracker* t, float* pose_out, int32_t* counts) { return dvm_tracker_result_lag(t, 0, pose_out, counts); }
 
 int dvm_tracker_debug_matches(dvm_tracker* t, int32_t* cur_map, uint8_t* outlier, int cap, int* n_out)
 {

@@ -185,6 +185,7 @@ class Tracker:
         L.dvm_tracker_bootstrap.argtypes = [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _ip]
         L.dvm_tracker_track.argtypes = [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_int, _vp, _vp]
         L.dvm_tracker_result.argtypes = [_vp, _vp, _vp]
+        L.dvm_tracker_result_lag.argtypes = [_vp, C.c_int, _vp, _vp]
         L.dvm_tracker_prefetch.argtypes = [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int]
         L.dvm_tracker_stream.argtypes = [_vp]
         L.dvm_tracker_stream.restype = _vp
@@ -266,8 +267,9 @@ class Tracker:
         check(self.L.dvm_tracker_get_profile(self.h, seg.ctypes.data, C.addressof(n)))
         return int(n.value), seg
 
-    def result(self):
-        check(self.L.dvm_tracker_result(self.h, self._pose.ctypes.data, self._counts.ctypes.data))
+    def result(self, lag=0):
+        """Pose and counts of the frame `lag` frames before the last one handed to track(); waits for that frame only."""
+        check(self.L.dvm_tracker_result_lag(self.h, int(lag), self._pose.ctypes.data, self._counts.ctypes.data))
         return self._pose[:4].copy(), self._pose[4:].copy(), tuple(int(c) for c in self._counts)
 
     def debug_matches(self):

@@ -460,6 +460,12 @@ DVM_API int dvm_tracker_track(dvm_tracker* t, const uint8_t* gray, int gray_is_d
                               int stride, const float* prior_q, const float* prior_t, int sync, float* pose_out,
                               int32_t* counts);
 DVM_API int dvm_tracker_result(dvm_tracker* t, float* pose_out, int32_t* counts);
+/* The result of the frame `lag` frames before the last one handed to dvm_tracker_track (lag 0 = dvm_tracker_result;
+ * lag <= 2).  It waits for THAT frame's chain only, so a caller that enqueues frame k + 1 first and then reads frame k
+ * (lag = 1) gets every frame's pose without ever leaving the GPU idle between two frames: the chain's last kernel
+ * writes pose and counts straight into a pinned, mapped ring (the role of mCurrentFrame.GetPose() /
+ * mnMatchesInliers after Tracking::Track, O3/src/Tracking.cc:2057-2150). */
+DVM_API int dvm_tracker_result_lag(dvm_tracker* t, int lag, float* pose_out, int32_t* counts);
 /* Frame pipelining: ExtractORB does not depend on the previous frame's pose, so the tracker runs it on
  * the extractor's stream while the tracking chain of the previous frame runs on its own stream.
  * dvm_tracker_prefetch enqueues the upload + extraction of the NEXT frame not yet handed over (call it after

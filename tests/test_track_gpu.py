@@ -318,3 +318,40 @@ def test_tracker_prefetch_overlap_is_identical():
         tr.close()
     for e in exts:
         e.close()
+
+
+def test_tracker_results_read_one_frame_behind():
+    """dvm_tracker_result_lag: frame k + 1 is enqueued before frame k's pose and counts are read from the pinned result
+    ring; every frame's result must be the one the synchronous loop returns, and lag 0 must still be the last frame."""
+    from dvmslam_b200.extractor import ORBextractor
+    from dvmslam_b200.tracking import Tracker
+
+    S = synth.OrbitStream(seed=2, period=320)
+    bounds = (0.0, 0.0, 1280.0, 720.0)
+    exts = [ORBextractor(2000, 1.2, 8, 20, 7, max_width=1280, max_height=720) for _ in range(2)]
+    T = exts[0].tables()
+    M = synth.plane_map(S, lambda im: exts[0](im), [0, 40, 80, 120], T["scale"], 6000)
+    trk = [Tracker(e, S.K, bounds, M) for e in exts]
+    R, t = S.pose(0)
+    q = synth.quat_from_R(R).astype(np.float32)
+    frames = [S.frame(k) for k in range(0, 9)]
+    for tr in trk:
+        assert tr.bootstrap(frames[0], q, t) > 50
+    ref = [trk[0].track(frames[k]) for k in range(1, 8)]
+    got = []
+    for k in range(1, 8):
+        trk[1].track(None if k > 1 else frames[k], sync=False)
+        trk[1].prefetch(frames[k + 1])
+        if k > 1:
+            got.append(trk[1].result(lag=1))
+    got.append(trk[1].result())
+    assert len(got) == len(ref)
+    for k, (g, r) in enumerate(zip(got, ref)):
+        assert g[2] == r[2], (k, g[2], r[2])
+        assert np.array_equal(g[0], r[0]) and np.array_equal(g[1], r[1]), k
+    with pytest.raises(Exception):
+        trk[1].result(lag=3)
+    for tr in trk:
+        tr.close()
+    for e in exts:
+        e.close()
