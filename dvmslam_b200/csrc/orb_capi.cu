@@ -38,6 +38,8 @@ struct dvm_orb {
     size_t dbg_bytes = 0;
     size_t cand_total = 0;
     ResizeX* d_xtab = nullptr;
+    ResizeX4* d_x4tab = nullptr;
+    size_t x4_cap = 0;
     ResizeY* d_ytab = nullptr;
     int* d_pyr_col = nullptr; int* d_pyr_row = nullptr; size_t pyr_col_cap = 0, pyr_row_cap = 0;
     bool fused_pyramid = true;
@@ -67,7 +69,7 @@ static void free_all(dvm_orb* h)
 {
     if (!h) return;
     cudaSetDevice(h->device);
-    cudaFree(h->d_pyr); cudaFree(h->d_dbg); cudaFree(h->d_xtab); cudaFree(h->d_ytab); cudaFree(h->d_pyr_col); cudaFree(h->d_pyr_row); cudaFree(h->d_out);
+    cudaFree(h->d_pyr); cudaFree(h->d_dbg); cudaFree(h->d_xtab); cudaFree(h->d_x4tab); cudaFree(h->d_ytab); cudaFree(h->d_pyr_col); cudaFree(h->d_pyr_row); cudaFree(h->d_out);
     cudaFree(h->d_pattern);
     cudaFree(h->buf.cand); cudaFree(h->buf.cand_count); cudaFree(h->buf.pnode); cudaFree(h->buf.sel);
     cudaFree(h->buf.sel_count); cudaFree(h->buf.work_kp); cudaFree(h->buf.work_meta); cudaFree(h->buf.ticket);
@@ -139,6 +141,43 @@ static int configure(dvm_orb* h, int w, int hgt)
             }
         }
     }
+    // groups of four destination columns for the vectorised pyramid (see ResizeX4)
+    std::vector<ResizeX4> x4;
+    bool vec_ok = true;
+    for (int l = 1; l < h->nlevels; l++) {
+        OrbLevel& L = c.lv[l];
+        L.x4_off = (int)x4.size();
+        const ResizeX* X = xt.data() + L.xtab_off;
+        for (int g = 0; g * 4 < L.w; g++) {
+            ResizeX4 e;
+            memset(&e, 0, sizeof(e));
+            int o0[4], o1[4];
+            const int bw = X[std::min(4 * g, L.w - 1)].sx0 >> 2;
+            for (int p2 = 0; p2 < 4; p2++) {
+                const ResizeX& t = X[std::min(4 * g + p2, L.w - 1)];
+                o0[p2] = t.sx0 - 4 * bw; o1[p2] = t.sx1 - 4 * bw;
+                e.c[p2] = (uint32_t)(uint16_t)t.a0 | ((uint32_t)(uint16_t)t.a1 << 16);
+                vec_ok = vec_ok && t.a0 >= 0 && t.a1 >= 0;
+            }
+            uint32_t sel = 0, win = 0;
+            for (int pr = 0; pr < 2; pr++) {
+                const int a = 2 * pr, b2 = 2 * pr + 1;
+                const int lo = std::min(std::min(o0[a], o1[a]), std::min(o0[b2], o1[b2]));
+                const int hi = std::max(std::max(o0[a], o1[a]), std::max(o0[b2], o1[b2]));
+                const int wsh = lo >= 4 ? 4 : 0;
+                vec_ok = vec_ok && lo >= 0 && hi - wsh <= 7 && hi <= 11;
+                const uint32_t sl = (uint32_t)((o0[a] - wsh) & 7) | (uint32_t)((o1[a] - wsh) & 7) << 4 | (uint32_t)((o0[b2] - wsh) & 7) << 8 |
+                                    (uint32_t)((o1[b2] - wsh) & 7) << 12;
+                sel |= sl << (16 * pr);
+                if (wsh) win |= 1u << (16 + pr);
+            }
+            e.sel = sel;
+            e.base = (uint32_t)bw | win;
+            vec_ok = vec_ok && bw < 65536;
+            x4.push_back(e);
+        }
+    }
+    DVM_REQUIRE(x4.size() <= h->x4_cap, "resize table too small");
     c.total_cells = cells;
     c.max_kp = sel_off;
     DVM_REQUIRE((size_t)cand_off <= h->cand_total, "candidate buffer too small");
@@ -168,7 +207,8 @@ static int configure(dvm_orb* h, int w, int hgt)
                 int d = std::min(i * tile, dim(L));
                 start[(size_t)i * kMaxLevels + L] = d;
                 for (int l = L - 1; l >= 0; l--) {
-                    d = d >= dim(l + 1) ? dim(l) : s0(l + 1, d);
+                    // (columns: a region starts on a multiple of 4, so that a thread's four pixels are one aligned word)
+                    d = d >= dim(l + 1) ? dim(l) : (is_x ? s0(l + 1, d) & ~3 : s0(l + 1, d));
                     start[(size_t)i * kMaxLevels + l] = d;
                 }
             }
@@ -179,6 +219,7 @@ static int configure(dvm_orb* h, int w, int hgt)
                     const int first = start[(size_t)i * kMaxLevels + l];
                     const int own1 = (i + 1 == ntiles ? dim(l) : start[(size_t)(i + 1) * kMaxLevels + l]) - 1;
                     need1 = l == L ? own1 : std::max(own1, s1(l + 1, need1));
+                    if (is_x) need1 = std::min(dim(l) - 1, first + ((need1 - first + 4) & ~3) - 1);   // whole groups of four columns
                     int* e = &out[((size_t)i * kMaxLevels + l) * 3];
                     e[0] = first; e[1] = own1; e[2] = need1;
                     maxlen[l] = std::max(maxlen[l], need1 - first + 1);
@@ -196,6 +237,7 @@ static int configure(dvm_orb* h, int w, int hgt)
             off = (off + 15) & ~15;
         }
         P.smem_bytes = off;
+        P.vec_ok = vec_ok ? 1 : 0;
         bool span_ok = true;
         for (int l = 1; l <= L; l++) span_ok = span_ok && mw[l] <= kPyrMaxSpanHost && mh[l] <= kPyrMaxSpanHost;
         if (off > 200 * 1024 || !span_ok) h->fused_pyramid = false;   // (other scale factors / level counts: keep the per-level launches)
@@ -212,6 +254,7 @@ static int configure(dvm_orb* h, int w, int hgt)
     if (!xt.empty()) {
         DVM_CUDA(cudaMemcpy(h->d_xtab, xt.data(), xt.size() * sizeof(ResizeX), cudaMemcpyHostToDevice));
         DVM_CUDA(cudaMemcpy(h->d_ytab, yt.data(), yt.size() * sizeof(ResizeY), cudaMemcpyHostToDevice));
+        if (!x4.empty()) DVM_CUDA(cudaMemcpy(h->d_x4tab, x4.data(), x4.size() * sizeof(ResizeX4), cudaMemcpyHostToDevice));
     }
     // TMA descriptors of the levels (level 0 again per call if the caller's image is read in place)
     memset(&h->tmaps, 0, sizeof(h->tmaps));
@@ -281,23 +324,25 @@ int dvm_orb_create(dvm_orb** out, int device, int nfeatures, float scale_factor,
 
     DVM_CREATE_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     // pyramid: every level at its maximum size, rows padded to 128 B
-    size_t off = 0, xt_n = 0, yt_n = 0, cand = 0;
+    size_t off = 0, xt_n = 0, yt_n = 0, x4_n = 0, cand = 0;
     for (int l = 0; l < nlevels; l++) {
         int lw, lh;
         level_size(h, max_width, max_height, l, &lw, &lh);
         h->lvl_off[l] = off;
         off += align_up(lw, 128) * (size_t)(lh + 1) + 256;
         xt_n += lw + 8; yt_n += lh + 8;
+        x4_n += lw / 4 + 4;
         cand += (size_t)(lw / 2 + 64) * (lh / 2 + 64);
     }
     h->pyr_bytes = off;
     h->dbg_bytes = align_up(max_width, 128) * (size_t)max_height;
     h->cand_total = cand;
-    h->xtab_cap = xt_n; h->ytab_cap = yt_n;
+    h->xtab_cap = xt_n; h->ytab_cap = yt_n; h->x4_cap = x4_n;
     DVM_CREATE_CUDA(cudaMalloc(&h->d_pyr, h->pyr_bytes));
     DVM_CREATE_CUDA(cudaMalloc(&h->d_dbg, h->dbg_bytes));
     DVM_CREATE_CUDA(cudaMalloc(&h->d_xtab, xt_n * sizeof(ResizeX)));
     DVM_CREATE_CUDA(cudaMalloc(&h->d_ytab, yt_n * sizeof(ResizeY)));
+    DVM_CREATE_CUDA(cudaMalloc(&h->d_x4tab, x4_n * sizeof(ResizeX4)));
     DVM_CREATE_CUDA(cudaMalloc(&h->d_pattern, sizeof(kPatternHost)));
     DVM_CREATE_CUDA(cudaMemcpy(h->d_pattern, kPatternHost, sizeof(kPatternHost), cudaMemcpyHostToDevice));
     OrbBuffers& b = h->buf;
@@ -323,6 +368,7 @@ int dvm_orb_create(dvm_orb** out, int device, int nfeatures, float scale_factor,
     b.out_desc = h->d_out + 32 + (size_t)h->max_kp * sizeof(dvm_keypoint);
     b.xtab = h->d_xtab;
     b.ytab = h->d_ytab;
+    b.x4tab = h->d_x4tab;
     b.pattern = h->d_pattern;
 #undef DVM_CREATE_CUDA
     *out = h;

@@ -14,6 +14,11 @@ constexpr int kCellMaxDim = 88;
 
 struct ResizeX { int sx0, sx1; short a0, a1; };       // per destination column
 struct ResizeY { int sy0, sy1; short b0, b1; };       // per destination row
+// Four destination columns 4g .. 4g + 3 at once (the vectorised pyramid): the taps of the four pixels lie within 12 source
+// bytes from the 4-byte aligned word `base`; sel holds two PRMT selectors (pixels 0-1 in the low half, 2-3 in the high half),
+// each picking the bytes (tap0, tap1, tap0, tap1) of its two pixels out of the word pair (w0, w1) or -- window bit set --
+// (w1, w2); c[p] = a0 | a1 << 16 feeds IDP.2A with those bytes.
+struct ResizeX4 { uint32_t sel, base /* word index | winA << 16 | winB << 17 */, c[4], pad[2]; };
 
 struct OrbLevel {
     const uint8_t* img;   // level image (level 0 may alias the caller's device image)
@@ -30,6 +35,7 @@ struct OrbLevel {
     float scale;            // mvScaleFactor[level]
     float size;             // (int)(31 * scale)
     int xtab_off, ytab_off; // resize tables (levels >= 1)
+    int x4_off;             // ResizeX4 table of this level (groups of four columns)
 };
 
 // The whole resize chain in ONE launch (pyramid_kernel): a CTA owns a tile of the LAST level and computes, level by level in
@@ -43,6 +49,7 @@ struct OrbPyrPlan {
     int soff[kMaxLevels];         // shared-memory offset of each level's region buffer
     int spitch[kMaxLevels];       // and its pitch (max region width over the tiles)
     int smem_bytes;
+    int vec_ok;                   // the four-pixels-per-thread kernel applies (tap windows fit, regions 4-aligned)
 };
 
 struct OrbCfg {
@@ -75,6 +82,7 @@ struct OrbBuffers {
     uint8_t* out_desc;     // [max_kp * 32]
     const ResizeX* xtab;
     const ResizeY* ytab;
+    const ResizeX4* x4tab; // per level, per group of four columns
     const int* pyr_col;    // [ntx][kMaxLevels][3] = {first, last owned, last needed} column of each level's region
     const int* pyr_row;    // [nty][kMaxLevels][3]
     const int8_t* pattern; // [256*4] device copy of the rBRIEF pattern
