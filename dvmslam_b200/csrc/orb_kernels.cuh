@@ -43,7 +43,7 @@ struct OrbLevel {
 // level l-1, O3/src/ORBextractor.cc:967) stays inside the CTA -- and writes the part of each level it owns.  Per tile
 // column / row and level: first pixel of the region, last pixel it owns, last pixel it needs (host-built from the
 // resize tables).
-constexpr int kPyrTileW = 32, kPyrTileH = 8;   // 12 x 26 = 312 tiles at 720p: two CTAs per SM hide each other's load latency
+constexpr int kPyrTileW = 32, kPyrTileH = 16;  // 12 x 13 = 156 tiles at 720p: ONE wave (312 tiles of 32 x 8 were two waves of ~10 us, each bounded by its seven dependent levels)
 struct OrbPyrPlan {
     int ntx, nty;                 // tiles of the last level
     int soff[kMaxLevels];         // shared-memory offset of each level's region buffer
