@@ -49,7 +49,7 @@ STAGE_BYTES = [2781331 + 1931488, 2853088, None, 5706176 + 1498000 + 1024000 + 1
 FRAME_BYTES_TOTAL = 15914083
 
 
-STAGE_KERNELS = ["pyramid_kernel", "fast_cells_kernel", "octree_kernel", "describe_kernel"]
+STAGE_KERNELS = ["pyramid4_kernel", "fast_cells_kernel", "octree_kernel", "describe_kernel"]
 
 
 def ncu_traffic(stage):
