@@ -160,3 +160,28 @@ def test_tables_match_oracle():
         ext.close()
         for key in ("scale", "inv_scale", "sigma2", "inv_sigma2", "per_level"):
             assert np.array_equal(T0[key], T1[key]), (nf, key)
+
+
+def test_unaligned_device_image_takes_the_byte_gather_pyramid(extractors):
+    """A caller's image read in place from an odd address with an odd pitch (a cv::Mat ROI): the word-load pyramid kernel does
+    not apply, the byte-gather one must give the same levels, candidates and selection."""
+    import torch
+    from oracle.orb import OrbOracle
+
+    w, h, stride = 640, 480, 701
+    img = synth.frame(w, h, 21)
+    orc = OrbOracle(1000)
+    orc.extract(img)
+    ext = _get(extractors, 1000, 640, 480)
+    buf = torch.zeros(h * stride + 16, dtype=torch.uint8, device="cuda")
+    view = buf[1:1 + h * stride].view(h, stride)
+    view[:, :w] = torch.from_numpy(img).cuda()
+    torch.cuda.synchronize()
+    ext.extract_device(buf.data_ptr() + 1, w, h, stride)
+    ext.sync()
+    for l in range(8):
+        assert np.array_equal(orc.level_image(l), ext.level_image(l)), f"pyramid level {l}"
+    for l in range(8):
+        s0 = orc.level_selected(l)
+        ref = np.stack([s0["x"].astype(int), s0["y"].astype(int), s0["response"].astype(int)], 1)
+        assert np.array_equal(ref, ext.level_keypoints(l, 1)), f"octree selection level {l}"
