@@ -506,7 +506,9 @@ typedef struct dvm_lba dvm_lba;
  * one-cluster solve of the dense reduced camera system (6 unknowns per free keyframe), not a limit: windows of up to 100 free
  * keyframes that fit the hint are factored by one 8-CTA cluster from shared memory (local BA: lowest latency), anything
  * larger -- global BA over hundreds of keyframes -- by a blocked Cholesky over the whole GPU.  Calls with more than 2000
- * free keyframes return DVM_ERR_CAPACITY (a 12000 x 12000 dense system; the reference's sparse solver has no such bound). */
+ * free keyframes return DVM_ERR_CAPACITY (a 12000 x 12000 dense system; the reference's sparse solver has no such bound), and
+ * so do maps whose landmarks have 2^31 or more observation pairs in total (sum over the landmarks of k (k + 1) / 2 for k
+ * observations: the Schur complement's work lists hold one 16-byte entry per pair). */
 DVM_API int dvm_lba_create(dvm_lba** out, int device, int max_free_cameras);
 DVM_API void dvm_lba_destroy(dvm_lba* h);
 
