@@ -43,7 +43,9 @@ def load_text(path):
         try:
             import pandas as pd
 
-            rows = pd.read_csv(f, sep=r"\s+", header=None).to_numpy(np.float64)
+            # round_trip: the weights must be the doubles the reference's `ssnode >> weight` (strtod, correctly rounded) reads; the
+            # default fast converter is off by an ulp now and then (found by tests/test_ref_dbow.py)
+            rows = pd.read_csv(f, sep=r"\s+", header=None, float_precision="round_trip").to_numpy(np.float64)
         except ImportError:
             rows = np.loadtxt(f, dtype=np.float64, ndmin=2)
     return (k, L, scoring, weighting, rows[:, 0].astype(np.int64), rows[:, 1].astype(np.int64),

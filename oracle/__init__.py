@@ -12,7 +12,8 @@ ORBextractor.cc against oracle/cvshim (tests/test_ref_build.py), ORBmatcher.cc w
 the Frame / KeyFrame / MapPoint / Pinhole bodies it calls against oracle/slamshim
 (tests/test_ref_matchers.py), and the optimisation functions of Optimizer.cc with
 OptimizableTypes.cpp and the vendored g2o against the mini Eigen of oracle/g2oshim
-(tests/test_ref_optimizer.py).
+(tests/test_ref_optimizer.py), and the vendored DBoW2 (the ORBVocabulary) against the stand-in
+opencv2/core of oracle/dbowshim (tests/test_ref_dbow.py).
 """
 from __future__ import annotations
 
