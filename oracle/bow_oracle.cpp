@@ -15,8 +15,10 @@
  * CSR form: node ids ascending (the map's iteration order), node_start[n_nodes + 1], feat_idx in each
  * node's push_back order.  The mono path only (Nleft == -1, no second camera).
  *
- * Parity status: UNPINNED against the reference (no tests or fixtures upstream; ORBmatcher.cc does not
- * compile without OpenCV/DBoW2/the map data model).
+ * Parity status: PINNED to the reference source.  The reference has no tests or fixtures for this path, so its own
+ * ORBmatcher.cc (with the Frame / KeyFrame / MapPoint / Pinhole bodies it calls and DBoW2's FeatureVector / BowVector) is
+ * compiled unmodified into oracle/_ref/libref_matcher.so (oracle/Makefile `ref`, shims in oracle/slamshim + oracle/cvshim)
+ * and tests/test_ref_matchers.py requires every matcher's index arrays to be identical to this restatement's.
  */
 #include "sophus_order.h"
 #include <cmath>

@@ -15,7 +15,13 @@
  * Convention where the reference leaves a value undefined: a feature that reaches a leaf above the requested
  * level (nid never assigned, :1140-1141) reports that leaf as its node.
  *
- * Parity status: UNPINNED (DBoW2 needs OpenCV to build; the reference holds no fixture for it).
+ * Parity status: PINNED to the reference source.  The reference's vendored DBoW2 (TemplatedVocabulary<FORB::TDescriptor,
+ * FORB>, FORB.cpp, BowVector.cpp, FeatureVector.cpp, ScoringObject.cpp) is compiled unmodified over a stand-in
+ * <opencv2/core/core.hpp> into oracle/_ref/libref_dbow.so (oracle/Makefile `ref`, oracle/dbowshim); tests/test_ref_dbow.py
+ * requires word ids, weights, node ids, BowVector (identical doubles) and FeatureVector to be equal on toy vocabularies of
+ * every weighting and on the reference's own ORBvoc.txt loaded by the reference's own loadFromTextFile.  Excluded: the two
+ * undefined behaviours of the reference named in that test (the loader's artefact node after a final newline; the
+ * uninitialised node id of a leaf above the requested level, for which the convention above applies).
  */
 #include <cmath>
 #include <cstdint>

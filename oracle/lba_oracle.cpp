@@ -12,8 +12,11 @@
  *   SparseOptimizer::optimize                       g2o/core/sparse_optimizer.cpp:349-413
  *   VertexSE3Expmap / VertexSBAPointXYZ oplus       g2o/types/types_six_dof_expmap.h:71-74, g2o/types/types_sba.h:49-52
  *
- * Parity status: UNPINNED against the reference (no tests/fixtures upstream; g2o needs Eigen, which
- * is not installed).  Differences by construction, all at rounding level: the reduced camera system
+ * Parity status: PINNED to the reference source.  The reference has no tests or fixtures for this path, so its own
+ * Optimizer::LocalBundleAdjustment (local mapping and welding BA) and BundleAdjustment, its edge types and its vendored g2o
+ * are compiled unmodified over a mini Eigen into oracle/_ref/libref_opt.so (oracle/Makefile `ref`, oracle/g2oshim) and
+ * tests/test_ref_optimizer.py requires float32-identical poses, points within 2.4e-7 m and identical erased-observation
+ * sets up to C4 size.  Differences by construction, all at rounding level: the reduced camera system
  * is solved with an unpivoted dense LDL^T (reference: Eigen::SimplicialLDLT with AMD ordering);
  * summation order over edges is the input order (reference: allocation/id order).  Self-checks in
  * tests/test_lba_oracle.py: finite-difference Jacobians, zero-noise convergence, chi2 monotonicity.

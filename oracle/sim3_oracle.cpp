@@ -21,7 +21,10 @@
  * singular to working precision, and with lambda = 1e-16 the next iteration's ten trials all fail and g2o terminates.
  * The restatement keeps the formula as it is: that behaviour IS the reference's.
  *
- * Parity unpinned: the reference holds no fixture for these functions; self-checks in tests/test_sim3_oracle.py
+ * Parity status: PINNED to the reference source.  The reference holds no fixture for these functions, so its own
+ * Optimizer::OptimizeSim3 and OptimizeEssentialGraph (bodies cut out of Optimizer.cc at build time) run on its vendored g2o
+ * in oracle/_ref/libref_opt.so (oracle/Makefile `ref`, oracle/g2oshim); tests/test_ref_optimizer.py requires the same Sim3
+ * (1e-6), inlier sets, iteration counts and corrected keyframe / map-point poses.  Self-checks in tests/test_sim3_oracle.py
  * (recovery of a planted Sim3, fixed-scale column, outlier removal, exp/log round trip, loop-error distribution). */
 #include <algorithm>
 #include <cmath>

@@ -17,9 +17,11 @@
  *     EdgeSE3ProjectXYZOnlyPose (O3/include/OptimizableTypes.h:32-57, O3/src/OptimizableTypes.cpp:51-63)
  *     and Pinhole::project / projectJac (O3/src/CameraModels/Pinhole.cpp:38-79).
  *
- * Parity status: UNPINNED against the reference (it has no tests or fixtures for this path, and
- * neither ORBmatcher.cc nor Optimizer.cc compiles without OpenCV/Eigen/the full map data model).
- * Conventions fixed here: float32 projection evaluated as ((R0*X + R1*Y) + R2*Z) + t, no FMA; the
+ * Parity status: PINNED to the reference source.  The reference has no tests or fixtures for this path, so its own
+ * ORBmatcher.cc (+ the Frame / MapPoint / Pinhole bodies it calls) and Optimizer::PoseOptimization (+ vendored g2o) are
+ * compiled unmodified into oracle/_ref/libref_matcher.so / libref_opt.so (oracle/Makefile `ref`); tests/test_ref_matchers.py
+ * requires identical match index arrays, tests/test_ref_optimizer.py float32-identical poses and identical outlier flags.
+ * Conventions fixed here: float32 transforms in Sophus' evaluation order (oracle/sophus_order.h), no FMA; the
  * mono path only (Nleft == -1, mvuRight < 0); the 6x6 solve is an unpivoted LDL^T in double
  * (the reference uses Eigen::LDLT, which pivots: results agree to rounding, tolerance in tests).
  */

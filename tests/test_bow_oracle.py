@@ -1,7 +1,7 @@
 """Self-checks of the descriptor-matcher oracle (oracle/bow_oracle.cpp, trko_search_for_initialization):
 hand-computable cases and a literal pure-Python restatement of the reference loops on small inputs.
-The reference holds no fixture for these: parity unpinned, regression-pinned by
-tests/golden/bow_small.npz."""
+The reference holds no fixture for these; the restatement is pinned to the reference's own ORBmatcher.cc
+in tests/test_ref_matchers.py and regression-pinned by tests/golden/bow_small.npz."""
 import os
 
 import numpy as np
