@@ -760,6 +760,7 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kLbaThrea
     #pragma unroll
                             for (int b2 = 0; b2 < 3; b2++) hp[hpl_idx(a, b2)] = B0 * wo * A[b2] + B1 * wo * A[3 + b2];
                         }
+                        hp[9] = 0.0; hp[19] = 0.0;   // the padding is loaded (never used) by the Schur phase's 128-bit reads: keep it defined
                     }
                 }
     #pragma unroll
