@@ -28,7 +28,7 @@ def main(so, out):
             op = m.group(1)
             cur["_n"] += 1
             for k in SPECIAL + OTHER:
-                if op == k or op.startswith(k + ".") or (k in ("BAR.SYNC", "BAR.RED", "BAR.ARV") and op.startswith(k)):
+                if op == k or op.startswith(k + ".") or op.startswith(k + "_") or (k in ("BAR.SYNC", "BAR.RED", "BAR.ARV") and op.startswith(k)):
                     cur[k] += 1
                     break
     demangled = subprocess.run(["c++filt"], input="\n".join(kernels), capture_output=True, text=True).stdout.splitlines()
@@ -39,7 +39,7 @@ def main(so, out):
                 "`DMMA` = FP64 tensor-core MMA, `IDP` = integer dot product (dp2a / dp4a), `PRMT` = byte permute.\n\n"
                 "| kernel | instructions | tensor / TMA / TMEM / cluster / dot | other |\n|---|---|---|---|\n")
         for (name, c), dn in sorted(zip(kernels.items(), demangled), key=lambda x: x[1]):
-            short = re.sub(r"\(.*", "", dn).replace("(anonymous namespace)::", "").replace("dvm::", "").replace("void ", "")
+            short = re.sub(r"\(.*", "", dn.replace("(anonymous namespace)::", "")).replace("dvm::", "").replace("void ", "")
             sp = ", ".join(f"{k} {c[k]}" for k in SPECIAL if c[k]) or "-"
             ot = ", ".join(f"{k} {c[k]}" for k in OTHER if c[k])
             f.write(f"| `{short}` | {c['_n']} | {sp} | {ot} |\n")
