@@ -99,7 +99,7 @@ def test_full_orbvoc_through_the_reference_loader_matches_the_golden(tmp_path):
     import tarfile
 
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", "dbow_orbvoc.npz"))
-    tarfile.open(VOC_TAR).extractall(tmp_path)
+    tarfile.open(VOC_TAR).extractall(tmp_path, filter="data")
     ref = refdbow.RefVocabulary(str(tmp_path / "ORBvoc.txt"))
     assert (ref.k, ref.L, ref.scoring, ref.weighting) == (int(g["k"]), int(g["L"]), int(g["scoring"]), int(g["weighting"]))
     # (ORBvoc.txt ends with a newline: the reference's loader appends its artefact node, see _both)
